@@ -1,0 +1,119 @@
+"""Generate tests/golden/*.npz by EXECUTING the reference's own source files (imported from /root/reference,
+never copied) under the numpy shim of jax/flax in oracle/jax_shim/.   TEST INFRASTRUCTURE ONLY.
+
+Run in the build container (the GPU box has no /root/reference):   python oracle/gen_golden.py
+The committed .npz fixtures are what tests/ read; this script documents how they were made.
+
+Reference entry points executed:
+  multi_modal_transformers/tokenizers/token_compression.py:54-129  bipartite_soft_matching, merge, merge_wavg
+  multi_modal_transformers/tokenizers/token_sequencer.py:186-334   TokenSequence.generate_attention_mask,
+                                                                   get_modality_idx
+"""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+OUT = os.path.join(HERE, "..", "tests", "golden")
+
+
+def _load(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def main():
+    sys.path.insert(0, os.path.join(HERE, "jax_shim"))
+    sys.path.insert(0, REF)
+    import jax.numpy as jnp  # the shim
+
+    tc = _load("ref_token_compression", f"{REF}/multi_modal_transformers/tokenizers/token_compression.py")
+    ts = _load("ref_token_sequencer", f"{REF}/multi_modal_transformers/tokenizers/token_sequencer.py")
+    os.makedirs(OUT, exist_ok=True)
+
+    # ---------------- matching + merge ----------------
+    rng = np.random.default_rng(20261018)
+    cases = [
+        # name, B, T, Dm, C, r, class_token, distill_token, kind
+        ("small", 2, 16, 8, 4, 3, False, False, "normal"),
+        ("oddT", 3, 75, 16, 8, 10, False, False, "normal"),
+        ("octo_lit", 2, 74, 256, 32, 16, False, False, "normal"),
+        ("clamp", 2, 10, 4, 4, 99, False, False, "normal"),
+        ("cls", 2, 33, 8, 4, 5, True, False, "normal"),
+        ("distill", 2, 32, 8, 4, 5, False, True, "normal"),
+        ("cls_distill", 2, 41, 8, 4, 7, True, True, "normal"),
+        ("ties", 2, 24, 2, 4, 5, False, False, "ties"),
+        ("all_to_one", 1, 32, 4, 4, 8, False, False, "all_to_one"),
+        ("c2_layer0", 1, 536, 64, 16, 16, False, False, "normal"),
+    ]
+    out = {}
+    names = []
+    for name, B, T, Dm, C, r, cls, dis, kind in cases:
+        if kind == "normal":
+            metric = rng.standard_normal((B, T, Dm)).astype(np.float32)
+        elif kind == "ties":  # few distinct directions -> many exactly tied scores
+            dirs = np.array([[1, 0], [0, 1], [-1, 0], [3, 4]], np.float32)
+            metric = dirs[rng.integers(0, 4, size=(B, T))]
+        elif kind == "all_to_one":  # every even token's best match is odd token 3
+            metric = rng.standard_normal((B, T, Dm)).astype(np.float32) * 0.01
+            metric[:, ::2, :] += np.array([1, 0, 0, 0], np.float32)
+            metric[:, 7, :] = np.array([5, 0, 0, 0], np.float32)
+        x = rng.standard_normal((B, T, C)).astype(np.float32)
+        merge = tc.bipartite_soft_matching(jnp.asarray(metric), r, cls, dis)
+        x1, s1 = tc.merge_wavg(merge, jnp.asarray(x))
+        xsum = merge(jnp.asarray(x), mode="sum")
+        # second round on the merged output (sizes now non-trivial), re-using the first T1 metric rows
+        T1 = x1.shape[1]
+        metric2 = rng.standard_normal((B, T1, Dm)).astype(np.float32)
+        merge2 = tc.bipartite_soft_matching(jnp.asarray(metric2), r, cls, dis)
+        x2, s2 = tc.merge_wavg(merge2, x1, s1)
+        # the closure's indices (token_compression.py:84-88) -- read from the closure cells of `merge`
+        cells = dict(zip(merge.__code__.co_freevars, [c.cell_contents for c in merge.__closure__]))
+        cells2 = dict(zip(merge2.__code__.co_freevars, [c.cell_contents for c in merge2.__closure__]))
+        names.append(name)
+        out[f"{name}/cfg"] = np.array([B, T, Dm, C, r, int(cls), int(dis)], np.int32)
+        out[f"{name}/metric"] = metric
+        out[f"{name}/x"] = x
+        out[f"{name}/x1"] = np.asarray(x1)
+        out[f"{name}/s1"] = np.asarray(s1)
+        out[f"{name}/xsum"] = np.asarray(xsum)
+        out[f"{name}/unm_idx"] = np.asarray(cells["unm_idx"])[..., 0].astype(np.int32)
+        out[f"{name}/src_idx"] = np.asarray(cells["src_idx"])[..., 0].astype(np.int32)
+        out[f"{name}/dst_idx"] = np.asarray(cells["dst_idx"])[..., 0].astype(np.int32)
+        out[f"{name}/metric2"] = metric2
+        out[f"{name}/x2"] = np.asarray(x2)
+        out[f"{name}/s2"] = np.asarray(s2)
+        out[f"{name}/src_idx2"] = np.asarray(cells2["src_idx"])[..., 0].astype(np.int32)
+        out[f"{name}/dst_idx2"] = np.asarray(cells2["dst_idx"])[..., 0].astype(np.int32)
+    out["names"] = np.array(names)
+    np.savez_compressed(os.path.join(OUT, "token_compression.npz"), **out)
+    print("token_compression.npz:", names)
+
+    # ---------------- token sequence masks ----------------
+    seqs = {
+        "octo_base": "[TaskDescriptionPrefix{16}] [Image{25};Readout{4}]*2",
+        "main_demo": "[TaskDescriptionPrefix{20}] [Image{10};Readout{10}]*2",
+        "w3": "[TaskDescriptionPrefix{4}] [Image{6};Readout{2}]*3",
+        "text": "[Text{5}] [Image{3};Readout{2}]*2",
+        "c2": "[TaskDescriptionPrefix{16}] [Image{256};Readout{4}]*2",
+    }
+    mo = {"names": np.array(list(seqs))}
+    for name, s in seqs.items():
+        seq = ts.TokenSequence(s)
+        mask = np.asarray(seq.generate_attention_mask(repeats=1, layer=0))[0]
+        mo[f"{name}/seq"] = np.array(s)
+        mo[f"{name}/mask"] = np.packbits(mask.astype(np.uint8), axis=-1)
+        mo[f"{name}/T"] = np.array(mask.shape[0], np.int32)
+        mo[f"{name}/readout_idx"] = np.asarray(seq.get_modality_idx("readouts")).astype(np.int32)
+    np.savez_compressed(os.path.join(OUT, "token_sequencer.npz"), **mo)
+    print("token_sequencer.npz:", list(seqs))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,459 @@
+"""CPU oracle for the ToMe transformer block  --  TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` leg may import
+this file.  The product package (`multi_modal_transformers_tokenmerge_b200`) never does.
+
+It restates, line by line, the reference's algorithm for the hot path (paths relative to
+/root/reference/multi_modal_transformers/):
+
+  * matching / merge  ............ tokenizers/token_compression.py:54-129   (numpy fp32, sequential loops)
+  * block / MLP / stack .......... attention_blocks/attention.py:20-119      (torch CPU, autograd gives grads)
+  * MHA projections .............. attention_blocks/tome_attention.py:137-164, 259-299
+  * hyper-parameters, LN axes .... model_configs/attention_blocks/vanilla_decoder.yaml:1-59
+  * mask rules ................... tokenizers/token_sequencer.py:55-183, 199-253, 313-334
+  * mask use / readout gather .... models/octo/octo.py:66-68, 116-126
+
+Third-party arithmetic that is NOT under /root/reference and is restated from its published behaviour:
+flax ^0.8.2 (`dot_product_attention`, `DenseGeneral`, `LayerNorm(use_fast_variance=True)`, `Dropout`),
+jax ^0.4.26 (`argsort` stable, `argmax` first-max, `.at[].add`), see pyproject.toml:27-47.
+
+Parity pinning: the matching/merge functions are checked against golden vectors produced by EXECUTING the
+reference's own `token_compression.py` / `token_sequencer.py` under a numpy shim of jax (oracle/gen_golden.py ->
+tests/golden/*.npz) and against the hand-checked vector of SURVEY.md Appendix B.  The block-level pieces that do
+not exist in runnable form in the reference (ToMe placement, `unmerge`, proportional `log size` bias -- the
+reference's tome_attention.py is a SyntaxError and has no tests) are DEFINED here following the ToMe paper;
+for those rows parity is "unpinned by the reference" and this file is the only pin.
+"""
+from __future__ import annotations
+
+import math
+import re
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+# --------------------------------------------------------------------------------------------------------
+# 1. bipartite soft matching + merge   (token_compression.py:54-129)
+# --------------------------------------------------------------------------------------------------------
+
+
+@dataclass
+class MatchPlan:
+    """Everything `bipartite_soft_matching` closes over (token_compression.py:84-88) plus the scores."""
+
+    t: int
+    r: int
+    distill_token: bool
+    scores: Optional[np.ndarray]  # [B,Ta,Tb] fp32 (None when r == 0)
+    node_max: Optional[np.ndarray]  # [B,Ta] fp32
+    node_idx: Optional[np.ndarray]  # [B,Ta] int32
+    edge_idx: Optional[np.ndarray]  # [B,Ta] int32  (full ranking, value desc / index desc)
+    unm_idx: Optional[np.ndarray]  # [B,Ta-r] int32
+    src_idx: Optional[np.ndarray]  # [B,r] int32
+    dst_idx: Optional[np.ndarray]  # [B,r] int32
+
+
+def clamp_r(t: int, r: int, class_token: bool = False, distill_token: bool = False) -> int:
+    """token_compression.py:60-67."""
+    protected = int(bool(class_token)) + int(bool(distill_token))
+    return max(0, min(int(r), (t - protected) // 2))
+
+
+def similarity_scores(metric: np.ndarray, class_token=False, distill_token=False) -> np.ndarray:
+    """token_compression.py:72-80: L2-normalise (no epsilon), even/odd split, a @ b^T, protect rows/cols."""
+    metric = np.asarray(metric, dtype=np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        metric = metric / np.sqrt(np.sum(metric * metric, axis=-1, keepdims=True, dtype=np.float32))
+    a, b = metric[..., ::2, :], metric[..., 1::2, :]
+    scores = np.matmul(a, np.swapaxes(b, -1, -2)).astype(np.float32)
+    if class_token:
+        scores[..., 0, :] = -np.inf
+    if distill_token:
+        scores[..., :, 0] = -np.inf
+    return scores
+
+
+def plan_from_scores(scores: np.ndarray, t: int, r: int, distill_token: bool = False) -> MatchPlan:
+    """token_compression.py:82-88 given fp32 scores [B,Ta,Tb]; `r` must already be clamped."""
+    scores = np.asarray(scores, dtype=np.float32)
+    node_max = scores.max(axis=-1)
+    node_idx = scores.argmax(axis=-1).astype(np.int32)  # first maximum (NaN counts as maximum, like XLA)
+    # jnp.argsort is stable ascending with NaNs last; [:, ::-1] => value descending, ties by index descending
+    edge_idx = np.argsort(node_max, axis=-1, kind="stable")[:, ::-1].astype(np.int32)
+    unm_idx = edge_idx[:, r:]
+    src_idx = edge_idx[:, :r]
+    dst_idx = np.take_along_axis(node_idx, src_idx, axis=-1)
+    return MatchPlan(t, r, distill_token, scores, node_max, node_idx, edge_idx, unm_idx, src_idx, dst_idx)
+
+
+def bipartite_soft_matching(metric, r, class_token=False, distill_token=False, scores_override=None) -> MatchPlan:
+    """token_compression.py:54-112.  `r <= 0` returns an identity plan (the reference returns a tuple there,
+    which `merge_wavg` cannot call -- SURVEY Appendix C; identity is the documented fix).
+    `scores_override` lets a test inject the GPU's fp32 scores so index parity is judged on identical scores."""
+    t = int(np.shape(metric)[1])
+    r = clamp_r(t, r, class_token, distill_token)
+    if r <= 0:
+        return MatchPlan(t, 0, distill_token, None, None, None, None, None, None, None)
+    scores = similarity_scores(metric, class_token, distill_token) if scores_override is None else scores_override
+    return plan_from_scores(scores, t, r, distill_token)
+
+
+def merge(plan: MatchPlan, x: np.ndarray, mode: str = "sum") -> np.ndarray:
+    """The closure `merge` of token_compression.py:90-109 (fp32, sequential scatter in rank order)."""
+    if plan.r == 0:
+        return x
+    x = np.asarray(x)
+    n, t, c = x.shape
+    xe, xo = x[:, ::2, :], x[:, 1::2, :]
+    unm = np.take_along_axis(xe, plan.unm_idx[..., None], axis=1)
+    src = np.take_along_axis(xe, plan.src_idx[..., None], axis=1)
+    dst = np.array(xo, copy=True)
+    if mode == "sum":
+        bidx = np.arange(n)
+        for i in range(plan.r):  # token_compression.py:100-101, one dependent scatter-add per edge
+            dst[bidx, plan.dst_idx[:, i], :] += src[:, i, :]
+    if plan.distill_token:
+        return np.concatenate([unm[:, :1], dst[:, :1], unm[:, 1:], dst[:, 1:]], axis=1)
+    return np.concatenate([unm, dst], axis=1)
+
+
+def merge_wavg(plan: MatchPlan, x: np.ndarray, size: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray]:
+    """token_compression.py:114-129."""
+    if size is None:
+        size = np.ones_like(x[..., 0, None])
+    x = merge(plan, x * size, mode="sum")
+    size = merge(plan, size, mode="sum")
+    x = x / size
+    return x, size
+
+
+def row_map(plan: MatchPlan) -> np.ndarray:
+    """For every input row t of the layer, the row of the merged output it lands in.  [B,T] int32.
+    (Derived from the concatenation order of token_compression.py:103-108.)"""
+    assert plan.r > 0
+    b = plan.edge_idx.shape[0]
+    t = plan.t
+    ta, tb = (t + 1) // 2, t // 2
+    r = plan.r
+    rank = np.empty((b, ta), dtype=np.int32)
+    np.put_along_axis(rank, plan.edge_idx, np.broadcast_to(np.arange(ta, dtype=np.int32), (b, ta)), axis=1)
+    out = np.empty((b, t), dtype=np.int32)
+    n_unm = ta - r
+
+    def pos_unm(i):  # i-th unmerged token
+        if plan.distill_token:
+            return np.where(i == 0, 0, i + 1)
+        return i
+
+    def pos_dst(j):
+        if plan.distill_token:
+            return np.where(j == 0, 1, n_unm + j)
+        return n_unm + j
+
+    node = plan.node_idx
+    ev = np.where(rank >= r, pos_unm(rank - r), pos_dst(node))
+    out[:, ::2] = ev
+    out[:, 1::2] = pos_dst(np.arange(tb, dtype=np.int32))[None, :]
+    return out
+
+
+def unmerge(plan: MatchPlan, xm: np.ndarray) -> np.ndarray:
+    """ToMe-paper `unmerge` (NOT in the reference): every original row copies its merged row."""
+    if plan.r == 0:
+        return xm
+    rm = row_map(plan)
+    return np.take_along_axis(np.asarray(xm), rm[..., None], axis=1)
+
+
+# --------------------------------------------------------------------------------------------------------
+# 2. token-sequence grammar -> groups, allow table, dense mask, readout indices  (token_sequencer.py)
+# --------------------------------------------------------------------------------------------------------
+
+KIND_TDP, KIND_TEXT, KIND_IMAGE, KIND_READOUT = 0, 1, 2, 3
+_KIND_BY_NAME = {"TaskDescriptionPrefix": KIND_TDP, "Text": KIND_TEXT, "Image": KIND_IMAGE, "Readout": KIND_READOUT}
+_MODALITY = {KIND_TDP: "text", KIND_TEXT: "text", KIND_IMAGE: "images", KIND_READOUT: "readouts"}
+
+
+def parse_token_sequence(seq: str) -> List[Tuple[int, int, int]]:
+    """token_sequencer.py:199-253 (no compression string): list of (kind, num_tokens, timestep)."""
+    blocks = re.findall(r"\[(.*?)\]", seq)
+    reps = []
+    for rep in re.findall(r"(?<=\])(.*?)(?=\[|$)", seq):
+        reps.append(1 if rep.strip() == "" else int(re.findall(r"\*(\d+)", rep)[0]))
+    out, ts = [], 0
+    for block, rep in zip(blocks, reps):
+        groups = re.split(r";", block)
+        for _ in range(rep):
+            for g in groups:
+                name = re.search(r"^(.*?)\{", g).group(1).strip()
+                out.append((_KIND_BY_NAME[name], int(re.search(r"\d+", g).group()), ts))
+            ts += 1
+    return out
+
+
+def allow_rule(qk: int, qt: int, kk: int, kt: int) -> int:
+    """Rule table of token_sequencer.py:55-183.  0 = masked, 1 = all-ones, 2 = causal-within-set (Text intra)."""
+    same = (qt == kt) and (kk == qk)  # isinstance(key, type(query)) and same timestep -> intra rule
+    if qk == KIND_TDP:  # :94-113   (TDP subclasses Text: isinstance(TDP-key, Text-query) is also "intra")
+        return 1 if same else 0
+    if qk == KIND_TEXT:  # :55-91
+        if (qt == kt) and kk in (KIND_TEXT, KIND_TDP):  # isinstance(tokenset, Text) incl. subclass TDP
+            return 2
+        if kk == KIND_READOUT:
+            return 0
+        return 1 if kt <= qt else 0
+    if qk == KIND_IMAGE:  # :116-148
+        if same:
+            return 1
+        if kk == KIND_READOUT:
+            return 0
+        return 1 if kt <= qt else 0
+    if qk == KIND_READOUT:  # :151-183
+        if same:
+            return 1
+        if kk == KIND_READOUT:
+            return 0
+        return 1 if kt <= qt else 0
+    raise ValueError(qk)
+
+
+def sequence_groups(seq: str):
+    """-> (group_id[T] uint8, pos_in_group[T] int32, allow[G,G] uint8, readout_idx[n] int32)."""
+    sets = parse_token_sequence(seq)
+    gid, pos = [], []
+    for g, (_, n, _) in enumerate(sets):
+        gid += [g] * n
+        pos += list(range(n))
+    G = len(sets)
+    allow = np.zeros((G, G), dtype=np.uint8)
+    for i, (qk, _, qt) in enumerate(sets):
+        for j, (kk, _, kt) in enumerate(sets):
+            allow[i, j] = allow_rule(qk, qt, kk, kt)
+    ro, cur = [], 0
+    for kind, n, _ in sets:  # token_sequencer.py:323-334
+        if _MODALITY[kind] == "readouts":
+            ro += list(range(cur, cur + n))
+        cur += n
+    return np.asarray(gid, np.uint8), np.asarray(pos, np.int32), allow, np.asarray(ro, np.int32)
+
+
+def dense_mask(gid_q, pos_q, gid_k, pos_k, allow) -> np.ndarray:
+    """[.., Tq, Tk] bool mask from group ids (token_sequencer.py:313-321 expanded)."""
+    a = allow[np.asarray(gid_q)[..., :, None], np.asarray(gid_k)[..., None, :]]
+    causal_ok = np.asarray(pos_k)[..., None, :] <= np.asarray(pos_q)[..., :, None]
+    return (a == 1) | ((a == 2) & causal_ok)
+
+
+# --------------------------------------------------------------------------------------------------------
+# 3. block / stack in torch (CPU, fp32 or fp64); autograd supplies the reference gradients
+# --------------------------------------------------------------------------------------------------------
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def layer_norm(x, scale, bias, eps=1e-6, axis="seq"):
+    """flax.linen.LayerNorm as configured in vanilla_decoder.yaml:7-13: reduction_axes=[1] (TOKENS), feature
+    axis -1 for scale/bias, use_fast_variance (var = max(0, E[x^2]-E[x]^2)).  axis="feature" is the
+    conventional last-axis LayerNorm (opt-in, not what the reference config says)."""
+    torch = _torch()
+    ax = 1 if axis == "seq" else -1
+    mu = x.mean(dim=ax, keepdim=True)
+    var = torch.clamp((x * x).mean(dim=ax, keepdim=True) - mu * mu, min=0.0)
+    return (x - mu) * torch.rsqrt(var + eps) * scale + bias
+
+
+def attention(q, k, v, mask=None, bias=None, drop_keep=None):
+    """flax dot_product_attention (restated): q,k,v [B,T,H,D]; mask bool broadcastable to [B,H,Tq,Tk];
+    bias added to logits before masking; masked logits -> finfo.min; softmax; optional dropout keep-mask
+    (already scaled) on the weights; returns [B,T,H,D]."""
+    torch = _torch()
+    d = q.shape[-1]
+    logits = torch.einsum("bqhd,bkhd->bhqk", q / math.sqrt(d), k)
+    if bias is not None:
+        logits = logits + bias
+    if mask is not None:
+        logits = torch.where(mask, logits, torch.full_like(logits, torch.finfo(logits.dtype).min))
+    w = torch.softmax(logits, dim=-1)
+    if drop_keep is not None:
+        w = w * drop_keep
+    return torch.einsum("bhqk,bkhd->bqhd", w, v)
+
+
+def merge_wavg_torch(plan: MatchPlan, x, size):
+    """merge_wavg with autograd support; same sequential scatter order as token_compression.py:100-101."""
+    torch = _torch()
+    if plan.r == 0:
+        return x, size
+
+    def _merge(z):
+        ze, zo = z[:, ::2, :], z[:, 1::2, :]
+        unm_i = torch.as_tensor(plan.unm_idx, dtype=torch.long)[..., None].expand(-1, -1, z.shape[-1])
+        src_i = torch.as_tensor(plan.src_idx, dtype=torch.long)[..., None].expand(-1, -1, z.shape[-1])
+        unm = torch.gather(ze, 1, unm_i)
+        src = torch.gather(ze, 1, src_i)
+        dst = zo
+        n = z.shape[0]
+        bidx = torch.arange(n)
+        dsti = torch.as_tensor(plan.dst_idx, dtype=torch.long)
+        for i in range(plan.r):
+            dst = dst.index_put((bidx, dsti[:, i]), src[:, i, :], accumulate=True)
+        if plan.distill_token:
+            return torch.cat([unm[:, :1], dst[:, :1], unm[:, 1:], dst[:, 1:]], dim=1)
+        return torch.cat([unm, dst], dim=1)
+
+    xs = _merge(x * size)
+    s2 = _merge(size)
+    return xs / s2, s2
+
+
+@dataclass
+class BlockParams:
+    """One block's parameters in the Flax tree layout.  Kernels are [in, out]."""
+
+    ln1_scale: "object"
+    ln1_bias: "object"
+    wq: "object"  # [C, H*D]  (flax: query/kernel [C,H,D] flattened)
+    bq: "object"  # [H*D]
+    wk: "object"
+    bk: "object"
+    wv: "object"
+    bv: "object"
+    wo: "object"  # [H*D, C]   (flax: out/kernel [H,D,C] flattened)
+    bo: "object"  # [C]
+    ln2_scale: "object"
+    ln2_bias: "object"
+    w1: "object"  # [C, Dff]
+    b1: "object"
+    w2: "object"  # [Dff, C]
+    b2: "object"
+
+    def tensors(self):
+        return [getattr(self, f) for f in self.__dataclass_fields__]
+
+
+@dataclass
+class LayerTrace:
+    plan: MatchPlan
+    t_in: int
+
+
+def tome_block(p: BlockParams, x, size, gid, pos, allow, *, num_heads, r, ln_axis="seq", prop_attn=True,
+               class_token=False, distill_token=False, scores_override=None, trace: Optional[list] = None):
+    """ToMeEncoder1DBlock with the ToMe-paper placement (reference shell attention.py:52-69):
+
+        x = x + attn(LN(x), mask(groups), bias = log size)       # dropout 0 (parity mode)
+        metric = mean_heads(key);  plan = bipartite_soft_matching(metric, r)
+        x, size = merge_wavg(plan, x, size);  groups follow the merge (dst keeps its own group/pos)
+        x = x + MLP(LN'(x))
+
+    x [B,T,C] torch; size [B,T,1] torch; gid/pos numpy [B,T]; returns (x, size, gid, pos)."""
+    torch = _torch()
+    B, T, C = x.shape
+    H = num_heads
+    h = layer_norm(x, p.ln1_scale, p.ln1_bias, axis=ln_axis)
+    q = (h @ p.wq + p.bq).reshape(B, T, H, -1)
+    k = (h @ p.wk + p.bk).reshape(B, T, H, -1)
+    v = (h @ p.wv + p.bv).reshape(B, T, H, -1)
+    mask = torch.as_tensor(dense_mask(gid, pos, gid, pos, allow))[:, None, :, :]
+    bias = torch.log(size[:, None, None, :, 0]) if prop_attn else None
+    o = attention(q, k, v, mask=mask, bias=bias).reshape(B, T, -1)
+    x = x + (o @ p.wo + p.bo)
+    # --- ToMe (intended call site tome_attention.py:249-256): metric = keys reduced over heads
+    metric = k.detach().mean(dim=2).to(torch.float32).numpy()
+    plan = bipartite_soft_matching(metric, r, class_token, distill_token, scores_override=scores_override)
+    if trace is not None:
+        trace.append(LayerTrace(plan, T))
+    if plan.r > 0:
+        x, size = merge_wavg_torch(plan, x, size)
+        rm = row_map(plan)
+        t2 = T - plan.r
+        gid2 = np.zeros((B, t2), dtype=gid.dtype)
+        pos2 = np.zeros((B, t2), dtype=pos.dtype)
+        # a merged row keeps the group/position of its destination (odd) token; unmerged rows keep their own
+        keep = np.ones((B, T), dtype=bool)
+        keep[:, ::2] = False
+        ta = (T + 1) // 2
+        rank = np.empty((B, ta), dtype=np.int32)
+        np.put_along_axis(rank, plan.edge_idx, np.broadcast_to(np.arange(ta, dtype=np.int32), (B, ta)), axis=1)
+        keep[:, ::2] = rank >= plan.r
+        bi, ti = np.nonzero(keep)
+        gid2[bi, rm[bi, ti]] = gid[bi, ti]
+        pos2[bi, rm[bi, ti]] = pos[bi, ti]
+        gid, pos = gid2, pos2
+    y = layer_norm(x, p.ln2_scale, p.ln2_bias, axis=ln_axis)
+    y = torch.relu(y @ p.w1 + p.b1)  # attention.py:32-33 (dropout at :34,:37 is identity in parity mode)
+    y = y @ p.w2 + p.b2
+    return x + y, size, gid, pos
+
+
+def tome_stack(params: Sequence[BlockParams], pos_embedding, x, gid, pos, allow, *, num_heads, r,
+               ln_axis="seq", prop_attn=True, scores_override: Optional[Sequence] = None,
+               trace: Optional[list] = None):
+    """StackedEncoder1DBlock (attention.py:94-119) unrolled, with shrinking T.  Returns
+    (x_final [B,T_L,C], size, origin_row [B,T0] = row of x_final each ORIGINAL token ended up in)."""
+    torch = _torch()
+    B, T0, C = x.shape
+    x = x + pos_embedding
+    size = torch.ones(B, T0, 1, dtype=x.dtype)
+    gid = np.broadcast_to(gid, (B, T0)).copy()
+    pos = np.broadcast_to(pos, (B, T0)).copy()
+    origin = np.broadcast_to(np.arange(T0, dtype=np.int32), (B, T0)).copy()
+    for li, p in enumerate(params):
+        tr: list = []
+        so = None if scores_override is None else scores_override[li]
+        x, size, gid, pos = tome_block(p, x, size, gid, pos, allow, num_heads=num_heads, r=r, ln_axis=ln_axis,
+                                       prop_attn=prop_attn, scores_override=so, trace=tr)
+        plan = tr[0].plan
+        if plan.r > 0:
+            origin = np.take_along_axis(row_map(plan), origin, axis=1)
+        if trace is not None:
+            trace.append(tr[0])
+    return x, size, origin
+
+
+def readout_loss(x_final, origin, readout_idx, target):
+    """Stand-in for octo.py:123-124 + :167-174: gather the rows the readout tokens ended up in (unmerge to the
+    original positions, then jnp.take), mean squared error against `target` [B, n_readout, C]."""
+    torch = _torch()
+    rows = torch.as_tensor(origin[:, readout_idx], dtype=torch.long)  # [B, n]
+    out = torch.gather(x_final, 1, rows[..., None].expand(-1, -1, x_final.shape[-1]))
+    return ((out - target) ** 2).mean(), out
+
+
+# --------------------------------------------------------------------------------------------------------
+# 4. synthetic parameters (initialisers of vanilla_decoder.yaml:25-29,38-42; attention.py:98)
+# --------------------------------------------------------------------------------------------------------
+
+
+def init_block_params(rng: np.random.Generator, C: int, H: int, D: int, Dff: int, dtype=np.float32) -> dict:
+    """he_normal kernels (std = sqrt(2/fan_in)), normal(0.01) biases, LN scale 1 / bias 0.  numpy dict."""
+
+    def he(fan_in, shape):
+        return (rng.standard_normal(shape) * math.sqrt(2.0 / fan_in)).astype(dtype)
+
+    def nb(shape):
+        return (rng.standard_normal(shape) * 0.01).astype(dtype)
+
+    hd = H * D
+    return dict(
+        ln1_scale=np.ones(C, dtype), ln1_bias=np.zeros(C, dtype),
+        wq=he(C, (C, hd)), bq=nb(hd), wk=he(C, (C, hd)), bk=nb(hd), wv=he(C, (C, hd)), bv=nb(hd),
+        wo=he(hd, (hd, C)), bo=nb(C),
+        ln2_scale=np.ones(C, dtype), ln2_bias=np.zeros(C, dtype),
+        w1=he(C, (C, Dff)), b1=nb(Dff), w2=he(Dff, (Dff, C)), b2=nb(C),
+    )
+
+
+def block_params_to_torch(d: dict, dtype=None, requires_grad=False) -> BlockParams:
+    torch = _torch()
+    kw = {}
+    for k, v in d.items():
+        t = torch.tensor(np.asarray(v), dtype=dtype or torch.float32)
+        t.requires_grad_(requires_grad)
+        kw[k] = t
+    return BlockParams(**kw)

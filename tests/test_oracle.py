@@ -1,0 +1,114 @@
+"""Pins the CPU oracle (oracle/tome_oracle.py) against
+  (1) golden vectors produced by executing the reference's own token_compression.py / token_sequencer.py
+      under a numpy shim of jax (oracle/gen_golden.py -> tests/golden/*.npz), and
+  (2) the hand-checked vector of SURVEY.md Appendix B,
+plus the invariants of SURVEY §8c.  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import tome_oracle as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TC = np.load(os.path.join(GOLD, "token_compression.npz"))
+TS = np.load(os.path.join(GOLD, "token_sequencer.npz"))
+
+
+@pytest.mark.parametrize("name", [str(n) for n in TC["names"]])
+def test_matching_and_merge_against_reference_golden(name):
+    B, T, Dm, C, r, cls, dis = [int(v) for v in TC[f"{name}/cfg"]]
+    metric, x = TC[f"{name}/metric"], TC[f"{name}/x"]
+    plan = O.bipartite_soft_matching(metric, r, bool(cls), bool(dis))
+    assert plan.r == O.clamp_r(T, r, cls, dis)
+    np.testing.assert_array_equal(plan.src_idx, TC[f"{name}/src_idx"])
+    np.testing.assert_array_equal(plan.dst_idx, TC[f"{name}/dst_idx"])
+    np.testing.assert_array_equal(plan.unm_idx, TC[f"{name}/unm_idx"])
+    x1, s1 = O.merge_wavg(plan, x)
+    np.testing.assert_array_equal(s1, TC[f"{name}/s1"])
+    np.testing.assert_array_equal(x1, TC[f"{name}/x1"])  # same fp32 op order -> bit exact
+    np.testing.assert_array_equal(O.merge(plan, x, "sum"), TC[f"{name}/xsum"])
+    plan2 = O.bipartite_soft_matching(TC[f"{name}/metric2"], r, bool(cls), bool(dis))
+    np.testing.assert_array_equal(plan2.src_idx, TC[f"{name}/src_idx2"])
+    np.testing.assert_array_equal(plan2.dst_idx, TC[f"{name}/dst_idx2"])
+    x2, s2 = O.merge_wavg(plan2, x1, s1)
+    np.testing.assert_array_equal(s2, TC[f"{name}/s2"])
+    np.testing.assert_array_equal(x2, TC[f"{name}/x2"])
+    # invariants: token mass and size conservation through two merges
+    assert np.all(s2.sum(axis=1) == T)
+    np.testing.assert_allclose((s2 * x2).sum(axis=1), x.sum(axis=1), rtol=2e-4, atol=2e-4)
+
+
+def test_appendix_b_golden_vector():
+    metric = np.array([[[1, 0], [1, 0], [0, 1], [3, 4], [1, 0], [0, 2], [4, 3], [-1, 0]]], np.float32)
+    x = np.stack([2 * np.arange(8), 2 * np.arange(8) + 1], -1)[None].astype(np.float32)
+    plan = O.bipartite_soft_matching(metric, 2)
+    np.testing.assert_allclose(plan.scores[0], [[1, .6, 0, -1], [0, .8, 1, 0], [1, .6, 0, -1], [.8, .96, .6, -.8]],
+                               atol=1e-6)
+    np.testing.assert_array_equal(plan.node_idx[0], [0, 2, 0, 1])
+    np.testing.assert_array_equal(plan.edge_idx[0], [2, 1, 0, 3])
+    np.testing.assert_array_equal(plan.src_idx[0], [2, 1])
+    np.testing.assert_array_equal(plan.dst_idx[0], [0, 2])
+    np.testing.assert_array_equal(plan.unm_idx[0], [0, 3])
+    x1, s1 = O.merge_wavg(plan, x)
+    np.testing.assert_array_equal(x1[0], [[0, 1], [12, 13], [5, 6], [6, 7], [7, 8], [14, 15]])
+    np.testing.assert_array_equal(s1[0, :, 0], [1, 1, 2, 1, 2, 1])
+    # unmerge: every original row reads its merged row
+    um = O.unmerge(plan, x1)
+    np.testing.assert_array_equal(um[0, :, 0], [0, 5, 7, 6, 5, 7, 12, 14])
+    np.testing.assert_array_equal(O.row_map(plan)[0], [0, 2, 4, 3, 2, 4, 1, 5])
+
+
+def test_r0_is_identity_and_unmerge_roundtrip():
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((2, 9, 4)).astype(np.float32)
+    plan = O.bipartite_soft_matching(x, 0)
+    x1, s1 = O.merge_wavg(plan, x)
+    np.testing.assert_array_equal(x1, x)
+    assert np.all(s1 == 1)
+    for dis in (False, True):
+        plan = O.bipartite_soft_matching(rng.standard_normal((2, 9, 4)).astype(np.float32), 3, False, dis)
+        rm = O.row_map(plan)
+        # row_map is consistent with merge(): a one-hot "which output row am I in" check
+        eye = np.broadcast_to(np.eye(9, dtype=np.float32), (2, 9, 9)).copy()
+        merged = O.merge(plan, eye, "sum")  # [2, 6, 9]: merged[b,row,t] = 1 iff token t landed in row
+        for b in range(2):
+            for t in range(9):
+                assert merged[b, rm[b, t], t] == 1 and merged[b, :, t].sum() == 1
+
+
+@pytest.mark.parametrize("name", [str(n) for n in TS["names"]])
+def test_mask_groups_against_reference_golden(name):
+    seq = str(TS[f"{name}/seq"])
+    T = int(TS[f"{name}/T"])
+    gid, pos, allow, ro = O.sequence_groups(seq)
+    assert gid.shape[0] == T
+    mask = np.unpackbits(TS[f"{name}/mask"], axis=-1)[:, :T].astype(bool)
+    np.testing.assert_array_equal(O.dense_mask(gid, pos, gid, pos, allow), mask)
+    np.testing.assert_array_equal(ro, TS[f"{name}/readout_idx"])
+
+
+def test_octo_base_table_matches_survey():
+    gid, pos, allow, ro = O.sequence_groups("[TaskDescriptionPrefix{16}] [Image{25};Readout{4}]*2")
+    np.testing.assert_array_equal(allow, [[1, 0, 0, 0, 0], [1, 1, 0, 0, 0], [1, 1, 1, 0, 0], [1, 1, 0, 1, 0],
+                                          [1, 1, 0, 1, 1]])
+    assert gid.shape[0] == 74 and list(ro) == [41, 42, 43, 44, 70, 71, 72, 73]
+
+
+def test_block_oracle_runs_and_grads_flow():
+    import torch
+    rng = np.random.default_rng(1)
+    C, H, D, Dff, B = 32, 2, 16, 64, 2
+    gid, pos, allow, ro = O.sequence_groups("[TaskDescriptionPrefix{4}] [Image{10};Readout{2}]*2")
+    T = gid.shape[0]
+    params = [O.block_params_to_torch(O.init_block_params(rng, C, H, D, Dff), requires_grad=True) for _ in range(2)]
+    x = torch.tensor(rng.standard_normal((B, T, C)).astype(np.float32))
+    pe = torch.tensor((rng.standard_normal((1, T, C)) * 0.02).astype(np.float32), requires_grad=True)
+    tr = []
+    xf, size, origin = O.tome_stack(params, pe, x, gid, pos, allow, num_heads=H, r=3, trace=tr)
+    assert xf.shape == (B, T - 6, C) and float(size.sum()) == B * T
+    y = torch.tensor(rng.standard_normal((B, len(ro), C)).astype(np.float32))
+    loss, _ = O.readout_loss(xf, origin, ro, y)
+    loss.backward()
+    assert all(t.grad is not None and torch.isfinite(t.grad).all() for p in params for t in p.tensors())
+    assert pe.grad is not None
