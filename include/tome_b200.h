@@ -1,0 +1,295 @@
+/* tome_b200.h -- C ABI of the B200-native ToMe transformer block.
+ *
+ * This is the drop-in boundary.  The reference has NO native layer: its interface for this
+ * path is a set of Python/JAX functions and Flax modules (paths relative to
+ * /root/reference/multi_modal_transformers/).  Each entry point below names the reference lines whose arithmetic
+ * it replaces; the Python mirror of the reference API (package multi_modal_transformers_tokenmerge_b200) and an
+ * XLA-FFI shim bind exactly these symbols.
+ *
+ * Conventions
+ *   - every pointer is DEVICE memory owned by the caller unless the name ends in _host; the library allocates
+ *     nothing, keeps no state except a thread-local error string, and never synchronises the stream;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and the call returns at once;
+ *   - return value: TOME_OK (0) or an error code; the text is available from tome_last_error();
+ *     nothing throws or aborts across this boundary;
+ *   - activations are bf16 (TOME_BF16) or fp32 (TOME_F32) where a dtype field exists; token sizes, LayerNorm
+ *     statistics, log-sum-exp, biases and gradients of parameters are always fp32; indices are int32;
+ *   - strides and leading dimensions are in ELEMENTS.
+ */
+#ifndef TOME_B200_H
+#define TOME_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TOME_ABI_VERSION 3
+
+enum tome_status { TOME_OK = 0, TOME_ERR_INVALID = 1, TOME_ERR_CUDA = 2, TOME_ERR_UNSUPPORTED = 3 };
+enum tome_dtype { TOME_BF16 = 0, TOME_F32 = 1 };
+enum tome_major { TOME_MAJOR_K = 0, TOME_MAJOR_MN = 1 };
+enum tome_merge_mode { TOME_MERGE_SUM = 0, TOME_MERGE_WAVG = 1 };
+
+const char* tome_last_error(void);
+int tome_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 1. Bipartite soft matching          tokenizers/token_compression.py:54-112
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* r = min(r, (tokens - protected) / 2), clamped at 0            token_compression.py:60-67 */
+int tome_clamp_r(int tokens, int r, int class_token, int distill_token);
+
+/* Where the matching metric comes from.  metric[b,t,d] = (1/heads) * sum_h src[b,t,h,d]; with heads == 1 this is a
+ * plain [B,T,Dm] tensor (the `metric` argument of bipartite_soft_matching); with heads > 1 it is "keys averaged
+ * over heads" read in place from a packed qkv buffer (intended call site tome_attention.py:249-256). */
+typedef struct {
+  int batch, tokens, dim, heads;
+  int dtype; /* tome_dtype of src */
+  long long batch_stride, token_stride, head_stride;
+  int class_token, distill_token;
+} tome_metric_desc_t;
+
+/* L2-normalise rows (no epsilon), split even/odd, scores = a b^T in fp32, protect row/column 0, then
+ * node_max[b,i] = max_j scores, node_idx[b,i] = first arg max.                       token_compression.py:72-83
+ * node_max f32 [B,Ta], node_idx i32 [B,Ta]  (Ta = ceil(T/2), Tb = floor(T/2)).
+ * scores_out: optional f32 [B,Ta,Tb] dump of the exact fp32 scores the arg max was taken from (parity protocol:
+ * "indices bit-exact from the same fp32 scores"); pass NULL on the fast path and the scores never touch HBM. */
+int tome_sim_argmax(const tome_metric_desc_t* desc, const void* src, float* node_max, int32_t* node_idx,
+                    float* scores_out, void* stream);
+
+/* The index set bipartite_soft_matching closes over (token_compression.py:84-88) plus derived maps the merge
+ * kernels use.  All int32, device. */
+typedef struct {
+  int32_t* edge_idx; /* [B,Ta]   argsort(node_max) reversed: value descending, ties by index descending;
+                                 edge_idx[:, :r] = src_idx, edge_idx[:, r:] = unm_idx                       */
+  int32_t* dst_idx;  /* [B,r]    node_idx[src_idx]                                                          */
+  int32_t* row_map;  /* [B,T]    row of the merged output that input token t lands in (unmerge gather map)  */
+  int32_t* dst_off;  /* [B,Tb+1] CSR offsets: sources merged into odd token j are dst_src[dst_off[j]..)     */
+  int32_t* dst_src;  /* [B,r]    even-set indices grouped by destination, in rank order inside a group      */
+} tome_plan_t;
+
+typedef struct {
+  int batch, tokens, r; /* r already clamped (tome_clamp_r), r >= 1 */
+  int distill_token;
+} tome_plan_shape_t;
+
+/* Edge ranking and index split.                                                       token_compression.py:84-88 */
+int tome_select_topr(const tome_plan_shape_t* shape, const float* node_max, const int32_t* node_idx,
+                     const tome_plan_t* plan, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 2. Merge / unmerge                   tokenizers/token_compression.py:90-129
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int batch, tokens, channels, r;
+  int distill_token;
+  int dtype; /* of x / x_out / dy / dx */
+  int mode;  /* TOME_MERGE_SUM: merge(x, "sum") :90-109;  TOME_MERGE_WAVG: merge_wavg :114-129 */
+} tome_merge_shape_t;
+
+/* x [B,T,C] -> x_out [B,T-r,C].  WAVG: x_out = merge(x*size)/merge(size), size_out = merge(size), fp32 arithmetic in
+ * the reference's order (sources added to their destination sequentially in rank order).  size / size_out are
+ * f32 [B,T] / [B,T-r]; size == NULL means all ones (token_compression.py:121-122).  SUM ignores both.
+ * gid/pos (optional, may be NULL): per-token group id (u8) and position-in-group (i32) carried through the merge:
+ * an output row keeps the group/position of its unmerged or destination token. */
+int tome_merge_fwd(const tome_merge_shape_t* shape, const tome_plan_t* plan, const void* x, const float* size,
+                   void* x_out, float* size_out, const uint8_t* gid, const int32_t* pos, uint8_t* gid_out,
+                   int32_t* pos_out, void* stream);
+
+/* Backward of tome_merge_fwd w.r.t. x (autodiff of token_compression.py:95-108,125-127):
+ * dx[b,t] = w * dy[b,row_map[b,t]],  w = size[b,t] / size_out[b,row] for WAVG, 1 for SUM.
+ * With mode SUM this is also the ToMe-paper `unmerge` (not in the reference). */
+int tome_merge_bwd(const tome_merge_shape_t* shape, const tome_plan_t* plan, const float* size, const float* size_out,
+                   const void* dy, void* dx, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 3. Dense layers                      attention_blocks/tome_attention.py:145-164,287-299; attention.py:32-37
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* C[M,N] = epilogue(A[M,K] * B[N,K]^T), bf16 operands, fp32 accumulation (tcgen05, accumulators in TMEM).
+ * An operand is K-major (row index = M or N, K contiguous) or MN-major (row index = K, M or N contiguous), so the
+ * Flax kernel layout [in, out] serves forward (B MN-major), dgrad (B K-major) and wgrad (A, B MN-major) as is.
+ * epilogue, in order: + bias[N]; ReLU; * (gate > 0 ? gate_scale : 0); dropout; + residual; cast to c_dtype.
+ * k_splits > 1 (fp32 C only) splits the reduction and sums the partials in a fixed order (weight gradients);
+ * k_splits == 0 lets the library choose; with accumulate != 0 the result is ADDED to C (fp32 C only). */
+typedef struct {
+  int m, n, k;
+  const void* a; long long lda; int a_major;
+  const void* b; long long ldb; int b_major;
+  void* c; long long ldc; int c_dtype;
+  const float* bias;
+  const void* residual; long long ldr; /* bf16 [M, ldr] */
+  const void* gate; long long ldg;     /* bf16 [M, ldg] */
+  float gate_scale;
+  int relu;
+  float dropout_rate; uint64_t dropout_seed; uint32_t dropout_site;
+  int k_splits;
+  int accumulate;
+} tome_gemm_args_t;
+
+size_t tome_gemm_workspace_bytes(const tome_gemm_args_t* args);
+int tome_gemm_bf16(const tome_gemm_args_t* args, void* workspace, size_t workspace_bytes, void* stream);
+
+/* out[n] (+)= sum_m x[m,n]   (bias gradients).  x bf16 [M, ldx]; out f32 [N].  workspace: f32 [ws_rows, N] with
+ * ws_rows = tome_colsum_workspace_rows(m). */
+int tome_colsum_workspace_rows(int m);
+int tome_colsum_bf16(int m, int n, const void* x, long long ldx, float* out, int accumulate, float* workspace,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 4. LayerNorm as configured          model_configs/attention_blocks/vanilla_decoder.yaml:7-13
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* axis = 1: statistics over TOKENS for every (batch, feature) -- what reduction_axes=[1] says;
+ * axis = 2: conventional statistics over features for every (batch, token) (opt-in).
+ * var = max(0, E[x^2] - E[x]^2) (use_fast_variance), y = (x - mean) * rsqrt(var + eps) * gamma + beta.
+ * x,y bf16 [B,T,C]; gamma,beta f32 [C]; mean,rstd f32 [B,C] (axis 1) or [B,T] (axis 2). */
+int tome_layernorm_fwd(int batch, int tokens, int channels, int axis, float eps, const void* x, const float* gamma,
+                       const float* beta, void* y, float* mean, float* rstd, void* stream);
+
+/* dx = LN backward (+ dres if not NULL, the residual branch's gradient); dgamma/dbeta f32 [C] are ACCUMULATED
+ * into (caller zeroes them at the start of a step).  partial: f32 workspace [2, B, C] (axis 1) or
+ * [2, tome_colsum_workspace_rows(B*T), C] (axis 2). */
+int tome_layernorm_bwd(int batch, int tokens, int channels, int axis, const void* x, const void* dy,
+                       const float* gamma, const float* mean, const float* rstd, const void* dres, void* dx,
+                       float* dgamma, float* dbeta, float* partial, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 5. Attention                         flax dot_product_attention reached from tome_attention.py:259-285;
+ *                                      mask rules tokenizers/token_sequencer.py:55-183,313-321
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int batch, tokens, heads, head_dim; /* head_dim: 64 */
+  /* q,k,v,out: element (b,t,h,d) at  ptr[b*batch_stride + t*token_stride + h*head_dim + d], bf16 */
+  long long q_batch_stride, q_token_stride;
+  long long k_batch_stride, k_token_stride;
+  long long v_batch_stride, v_token_stride;
+  long long o_batch_stride, o_token_stride;
+  float scale; /* 1/sqrt(head_dim): query scaling of dot_product_attention */
+  /* block-causal mask as a group table instead of [B,H,T,T] booleans (octo.py:66-68,119):
+   * allow[gid[b,q]*num_groups + gid[b,k]] = 0 masked, 1 visible, 2 visible iff pos[b,k] <= pos[b,q].
+   * gid == NULL: no mask.  masked logits become -FLT_MAX (finite, like flax's finfo.min), so a fully masked row
+   * yields the uniform distribution, not NaN. */
+  const uint8_t* gid;   /* [B,T] */
+  const int32_t* pos;   /* [B,T] */
+  const uint8_t* allow; /* [G,G], G <= 32 */
+  int num_groups;
+  /* proportional attention (ToMe paper; not in the reference): logits += log(size[b,k]) */
+  const float* size; /* [B,T] or NULL */
+} tome_attn_desc_t;
+
+/* out [B,T,H,D] bf16, lse f32 [B,H,T] (natural-log sum-exp of the biased, masked, scaled logits) */
+int tome_attention_fwd(const tome_attn_desc_t* desc, const void* q, const void* k, const void* v, void* out,
+                       float* lse, void* stream);
+
+/* dq,dk,dv share the layout of q,k,v (their own strides given in dqkv_*); delta f32 [B,H,T] workspace;
+ * dq_accum f32 [B,T,H*D] workspace (zeroed by the call). */
+typedef struct {
+  long long dq_batch_stride, dq_token_stride;
+  long long dk_batch_stride, dk_token_stride;
+  long long dv_batch_stride, dv_token_stride;
+  long long do_batch_stride, do_token_stride;
+} tome_attn_grad_strides_t;
+int tome_attention_bwd(const tome_attn_desc_t* desc, const tome_attn_grad_strides_t* gs, const void* q, const void* k,
+                       const void* v, const void* out, const float* lse, const void* dout, void* dq, void* dk,
+                       void* dv, float* delta, float* dq_accum, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 6. Small fused steps around the block
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* y[b,t,:] = x[b,t,:] + pos_embedding[t,:]     attention.py:97-100 (x f32 or bf16 -> y bf16) */
+int tome_add_pos_embedding(int batch, int tokens, int channels, const void* x, int x_dtype, const float* pos_embedding,
+                           void* y, void* stream);
+/* dpe[t,:] += sum_b dy[b,t,:]  (f32 accumulate) */
+int tome_pos_embedding_bwd(int batch, int tokens, int channels, const void* dy, float* dpe, void* stream);
+
+/* origin[b,i] <- row of the final sequence that original token readout_idx[i] ended up in: chains the per-layer
+ * row maps (row_maps_host: host array of `layers` device pointers, entry l is i32 [B, tokens_host[l]] or NULL when
+ * layer l merged nothing).  Replaces unmerge + jnp.take(embeddings, readout_idx) of octo.py:123-124. */
+int tome_chain_row_maps(int batch, int layers, const int32_t* const* row_maps_host, const int* tokens_host,
+                        const int32_t* readout_idx, int n_readout, int32_t* origin, void* stream);
+
+/* Synthetic stand-in for octo.py:167-174: out[b,i,:] = x[b,origin[b,i],:]; loss = mean((out - target)^2);
+ * writes dx (bf16 [B,T,C], zero except gathered rows, summed where two readouts share a row), loss f32 [1 + B]
+ * (loss[0] = the mean; loss[1..B] = per-row partial sums, reduced in a fixed order), and optionally the gathered
+ * rows `out` f32 [B,n,C]. target f32 [B,n,C]. */
+int tome_readout_mse(int batch, int tokens, int channels, int n_readout, const void* x, const int32_t* origin,
+                     const float* target, float* loss, void* dx, float* out, void* stream);
+
+/* AdamW on an fp32 master vector with a bf16 working copy refreshed in the same pass (bf16_copy may be NULL).
+ * grad_scale multiplies the gradient first (1/world_size after a sum all-reduce). */
+int tome_adamw_step(long long n, float* param, const float* grad, float* m, float* v, void* bf16_copy, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, float grad_scale, int step, void* stream);
+
+/* dst_bf16[i] = (bf16) src_f32[i] */
+int tome_cast_f32_to_bf16(long long n, const float* src, void* dst, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 7. The whole stack: StackedEncoder1DBlock of ToMeEncoder1DBlock, unrolled with shrinking T
+ *    attention.py:41-119, tome_attention.py:305-383, placement per SURVEY.md A.7
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int batch, tokens, channels, heads, head_dim, mlp_dim, layers;
+  int r;              /* tokens merged per layer (clamped per layer) */
+  int ln_axis;        /* 1 = tokens (reference yaml), 2 = features */
+  float ln_eps;       /* 1e-6 */
+  int prop_attn;      /* logits += log(size) */
+  int class_token, distill_token;
+  int num_groups;     /* 0: no mask */
+  int n_readout;
+  float dropout_rate; /* hidden dropout after out-proj, ReLU and dense_out (attention.py:34,37,60); 0 in parity mode */
+  uint64_t dropout_seed;
+} tome_stack_cfg_t;
+
+/* Per-layer parameter offsets (elements) into one flat fp32 vector (master weights / gradients / Adam moments)
+ * and the same offsets into a flat bf16 working copy.  Kernels are stored [in, out] (Flax layout):
+ * wqkv [C, 3*H*D] = concat(query, key, value kernels), wo [H*D, C], w1 [C, Dff], w2 [Dff, C].
+ * Layout of one layer: ln1_scale[C] ln1_bias[C] wqkv bqkv[3HD] wo bo[C] ln2_scale[C] ln2_bias[C] w1 b1[Dff] w2 b2[C];
+ * the vector starts with pos_embedding [T0, C].  tome_stack_param_count gives the total. */
+long long tome_stack_param_count(const tome_stack_cfg_t* cfg);
+long long tome_stack_layer_offset(const tome_stack_cfg_t* cfg, int layer); /* offset of ln1_scale of `layer` */
+
+/* bytes of activation workspace the executor needs (saved activations for backward + scratch) */
+size_t tome_stack_workspace_bytes(const tome_stack_cfg_t* cfg);
+
+typedef struct {
+  const float* params_f32;    /* flat fp32 (biases, LN, pos-embedding are read from here) */
+  const void* params_bf16;    /* flat bf16 copy (GEMM operands) */
+  const void* x;              /* [B,T0,C] input embeddings */
+  int x_dtype;
+  const uint8_t* gid;         /* [T0] group ids (same for every batch row at layer 0) or NULL */
+  const int32_t* pos;         /* [T0] */
+  const uint8_t* allow;       /* [G,G] */
+  const int32_t* readout_idx; /* [n_readout] original positions of the readout tokens */
+  const float* target;        /* [B,n_readout,C] (loss) or NULL */
+  void* workspace; size_t workspace_bytes;
+  /* outputs */
+  void* x_final;              /* bf16 [B,T_L,C] (points into workspace when NULL is passed: see tome_stack_final) */
+  float* readout;             /* f32 [B,n_readout,C] or NULL */
+  float* loss;                /* f32 [1 + B] (see tome_readout_mse) */
+  float* grads_f32;           /* flat fp32 gradient vector (backward; accumulated into, caller zeroes) */
+  void* const* layer_done_events; /* optional host array [layers+1] of cudaEvent_t recorded as each layer's (and
+                                     finally the pos-embedding's) gradients become final, for all-reduce overlap */
+} tome_stack_io_t;
+
+int tome_stack_forward(const tome_stack_cfg_t* cfg, const tome_stack_io_t* io, void* stream);
+/* runs loss gradient + full backward; tome_stack_forward must have run on the same workspace */
+int tome_stack_backward(const tome_stack_cfg_t* cfg, const tome_stack_io_t* io, void* stream);
+/* device pointers into the workspace, valid after forward: final tokens/sizes and per-layer plan dumps (tests) */
+int tome_stack_tokens_at(const tome_stack_cfg_t* cfg, int layer); /* T entering `layer`; layer == layers: final T */
+const void* tome_stack_final_x(const tome_stack_cfg_t* cfg, const tome_stack_io_t* io);
+const float* tome_stack_final_size(const tome_stack_cfg_t* cfg, const tome_stack_io_t* io);
+const int32_t* tome_stack_layer_edge_idx(const tome_stack_cfg_t* cfg, const tome_stack_io_t* io, int layer);
+const int32_t* tome_stack_layer_dst_idx(const tome_stack_cfg_t* cfg, const tome_stack_io_t* io, int layer);
+const float* tome_stack_layer_node_max(const tome_stack_cfg_t* cfg, const tome_stack_io_t* io, int layer);
+const int32_t* tome_stack_layer_node_idx(const tome_stack_cfg_t* cfg, const tome_stack_io_t* io, int layer);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOME_B200_H */

@@ -1,0 +1,159 @@
+"""ctypes binding of include/tome_b200.h (the C-ABI drop-in boundary).
+
+There is NO fallback: if libtome_b200.so is missing or a call fails, this raises.  The structures below mirror the
+header field for field; `tests/test_abi.py` checks that every symbol the header declares is exported.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libtome_b200.so")
+
+TOME_OK, TOME_ERR_INVALID, TOME_ERR_CUDA, TOME_ERR_UNSUPPORTED = 0, 1, 2, 3
+TOME_BF16, TOME_F32 = 0, 1
+TOME_MAJOR_K, TOME_MAJOR_MN = 0, 1
+TOME_MERGE_SUM, TOME_MERGE_WAVG = 0, 1
+ABI_VERSION = 3
+
+vp, ll, i32, f32, u64, u32 = C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_uint64, C.c_uint32
+
+
+class TomeError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"tome_b200 error {code}: {msg}")
+        self.code = code
+
+
+class MetricDesc(C.Structure):
+    _fields_ = [("batch", i32), ("tokens", i32), ("dim", i32), ("heads", i32), ("dtype", i32),
+                ("batch_stride", ll), ("token_stride", ll), ("head_stride", ll),
+                ("class_token", i32), ("distill_token", i32)]
+
+
+class Plan(C.Structure):
+    _fields_ = [("edge_idx", vp), ("dst_idx", vp), ("row_map", vp), ("dst_off", vp), ("dst_src", vp)]
+
+
+class PlanShape(C.Structure):
+    _fields_ = [("batch", i32), ("tokens", i32), ("r", i32), ("distill_token", i32)]
+
+
+class MergeShape(C.Structure):
+    _fields_ = [("batch", i32), ("tokens", i32), ("channels", i32), ("r", i32), ("distill_token", i32),
+                ("dtype", i32), ("mode", i32)]
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [("m", i32), ("n", i32), ("k", i32),
+                ("a", vp), ("lda", ll), ("a_major", i32),
+                ("b", vp), ("ldb", ll), ("b_major", i32),
+                ("c", vp), ("ldc", ll), ("c_dtype", i32),
+                ("bias", vp),
+                ("residual", vp), ("ldr", ll),
+                ("gate", vp), ("ldg", ll),
+                ("gate_scale", f32), ("relu", i32),
+                ("dropout_rate", f32), ("dropout_seed", u64), ("dropout_site", u32),
+                ("k_splits", i32), ("accumulate", i32)]
+
+
+class AttnDesc(C.Structure):
+    _fields_ = [("batch", i32), ("tokens", i32), ("heads", i32), ("head_dim", i32),
+                ("q_batch_stride", ll), ("q_token_stride", ll), ("k_batch_stride", ll), ("k_token_stride", ll),
+                ("v_batch_stride", ll), ("v_token_stride", ll), ("o_batch_stride", ll), ("o_token_stride", ll),
+                ("scale", f32),
+                ("gid", vp), ("pos", vp), ("allow", vp), ("num_groups", i32),
+                ("size", vp)]
+
+
+class AttnGradStrides(C.Structure):
+    _fields_ = [("dq_batch_stride", ll), ("dq_token_stride", ll), ("dk_batch_stride", ll), ("dk_token_stride", ll),
+                ("dv_batch_stride", ll), ("dv_token_stride", ll), ("do_batch_stride", ll), ("do_token_stride", ll)]
+
+
+class StackCfg(C.Structure):
+    _fields_ = [("batch", i32), ("tokens", i32), ("channels", i32), ("heads", i32), ("head_dim", i32),
+                ("mlp_dim", i32), ("layers", i32), ("r", i32), ("ln_axis", i32), ("ln_eps", f32),
+                ("prop_attn", i32), ("class_token", i32), ("distill_token", i32), ("num_groups", i32),
+                ("n_readout", i32), ("dropout_rate", f32), ("dropout_seed", u64)]
+
+
+class StackIO(C.Structure):
+    _fields_ = [("params_f32", vp), ("params_bf16", vp), ("x", vp), ("x_dtype", i32),
+                ("gid", vp), ("pos", vp), ("allow", vp), ("readout_idx", vp), ("target", vp),
+                ("workspace", vp), ("workspace_bytes", C.c_size_t),
+                ("x_final", vp), ("readout", vp), ("loss", vp), ("grads_f32", vp),
+                ("layer_done_events", C.POINTER(vp))]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """The loaded shared library.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found: build it with `python -m multi_modal_transformers_tokenmerge_b200.build` "
+                "(or __graft_entry__.build()).  There is no CPU or PyTorch fallback for this package.")
+        L = C.CDLL(LIB_PATH)
+        L.tome_last_error.restype = C.c_char_p
+        L.tome_abi_version.restype = i32
+        if L.tome_abi_version() != ABI_VERSION:
+            raise ImportError(f"libtome_b200.so has ABI {L.tome_abi_version()}, python binding expects {ABI_VERSION}: rebuild")
+        for name in ("tome_gemm_workspace_bytes", "tome_stack_workspace_bytes"):
+            if hasattr(L, name):
+                getattr(L, name).restype = C.c_size_t
+        for name in ("tome_stack_param_count", "tome_stack_layer_offset"):
+            if hasattr(L, name):
+                getattr(L, name).restype = ll
+        for name in ("tome_stack_final_x", "tome_stack_final_size", "tome_stack_layer_edge_idx", "tome_stack_layer_dst_idx",
+                     "tome_stack_layer_node_max", "tome_stack_layer_node_idx"):
+            if hasattr(L, name):
+                getattr(L, name).restype = vp
+        P = C.POINTER
+        sig = {
+            "tome_clamp_r": [i32, i32, i32, i32],
+            "tome_sim_argmax": [P(MetricDesc), vp, vp, vp, vp, vp],
+            "tome_select_topr": [P(PlanShape), vp, vp, P(Plan), vp],
+            "tome_merge_fwd": [P(MergeShape), P(Plan), vp, vp, vp, vp, vp, vp, vp, vp, vp],
+            "tome_merge_bwd": [P(MergeShape), P(Plan), vp, vp, vp, vp, vp],
+            "tome_gemm_workspace_bytes": [P(GemmArgs)],
+            "tome_gemm_bf16": [P(GemmArgs), vp, C.c_size_t, vp],
+            "tome_colsum_workspace_rows": [i32],
+            "tome_colsum_bf16": [i32, i32, vp, ll, vp, i32, vp, vp],
+            "tome_layernorm_fwd": [i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp],
+            "tome_layernorm_bwd": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+            "tome_attention_fwd": [P(AttnDesc), vp, vp, vp, vp, vp, vp],
+            "tome_attention_bwd": [P(AttnDesc), P(AttnGradStrides), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+            "tome_add_pos_embedding": [i32, i32, i32, vp, i32, vp, vp, vp],
+            "tome_pos_embedding_bwd": [i32, i32, i32, vp, vp, vp],
+            "tome_chain_row_maps": [i32, i32, P(vp), P(i32), vp, i32, vp, vp],
+            "tome_readout_mse": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp],
+            "tome_adamw_step": [ll, vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, f32, i32, vp],
+            "tome_cast_f32_to_bf16": [ll, vp, vp, vp],
+            "tome_stack_param_count": [P(StackCfg)],
+            "tome_stack_layer_offset": [P(StackCfg), i32],
+            "tome_stack_workspace_bytes": [P(StackCfg)],
+            "tome_stack_forward": [P(StackCfg), P(StackIO), vp],
+            "tome_stack_backward": [P(StackCfg), P(StackIO), vp],
+            "tome_stack_tokens_at": [P(StackCfg), i32],
+            "tome_stack_final_x": [P(StackCfg), P(StackIO)],
+            "tome_stack_final_size": [P(StackCfg), P(StackIO)],
+            "tome_stack_layer_edge_idx": [P(StackCfg), P(StackIO), i32],
+            "tome_stack_layer_dst_idx": [P(StackCfg), P(StackIO), i32],
+            "tome_stack_layer_node_max": [P(StackCfg), P(StackIO), i32],
+            "tome_stack_layer_node_idx": [P(StackCfg), P(StackIO), i32],
+        }
+        for name, args in sig.items():
+            if hasattr(L, name):
+                getattr(L, name).argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != TOME_OK:
+        raise TomeError(rc, lib().tome_last_error().decode())

@@ -1,0 +1,412 @@
+// K7: persistent warp-specialised tcgen05 GEMM with fused epilogues (projections, MLP, dgrad, wgrad).
+//
+//   C[M,N] = epilogue( A (M x K)  *  B (N x K)^T )       bf16 operands, fp32 accumulation in TMEM
+//
+// Either operand may be stored K-major (row = M/N index, K contiguous) or MN-major (row = K index, M/N
+// contiguous), so the Flax parameter layout kernel[in, out] serves forward (B MN-major), dgrad (B K-major) and
+// wgrad (A and B MN-major, reduction over the B*T rows) without any transposed copies in HBM.
+//
+// Replaces (reference, via XLA): DenseGeneral query/key/value tome_attention.py:145-164, out :287-299,
+// MLPBlock Dense layers attention.py:32-37, and their autodiff.
+//
+// Roles (192 threads, 1 CTA per SM, persistent over a static round-robin tile schedule):
+//   warp 0      TMA producer        global -> smem ring (STAGES x {A 16 KB, B BN*128 B}), 128B swizzle
+//   warp 1      UMMA issuer         one thread issues tcgen05.mma 128 x BN x 16, accumulators double-buffered in TMEM
+//   warps 2..5  epilogue            tcgen05.ld (thread = row, 32 columns at a time) -> bias/ReLU/dropout/residual
+//                                   -> 128-bit global stores; overlaps the next tile's main loop
+#include "common.cuh"
+#include "host_util.h"
+
+namespace tome {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+struct GemmEpilogue {
+  void* c;             // [M, ldc] bf16 or fp32
+  const float* bias;   // [N] or null
+  const void* residual;  // bf16 [M, ldr] or null (added last)
+  const void* gate;    // bf16 [M, ldg] or null:  acc *= (gate > 0 ? gate_scale : 0)   (ReLU / dropout backward)
+  long long ldc, ldr, ldg;
+  float gate_scale;
+  int relu;
+  int c_is_f32;
+  DropoutCfg drop;     // applied after ReLU, before residual
+  long long split_stride;  // elements between split-K partial outputs (c_is_f32 only)
+  int accumulate;          // c_is_f32 only: C += result
+};
+
+struct GemmShape {
+  int m, n, k;
+  int m_tiles, n_tiles, k_splits, kb_per_split, kb_total;
+};
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN <= 128) ? 6 : 4;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual 1 KB alignment
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                 const GemmShape s, const GemmEpilogue e) {
+  using L = GemmSmem<BN>;
+  constexpr int STAGES = L::STAGES;
+  constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages
+  static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = s.m_tiles * s.n_tiles * s.k_splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================= TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int split = tile % s.k_splits;
+        const int n_blk = (tile / s.k_splits) % s.n_tiles;
+        const int m_blk = tile / (s.k_splits * s.n_tiles);
+        const int m0 = m_blk * GEMM_BM, n0 = n_blk * BN;
+        const int kb0 = split * s.kb_per_split;
+        const int kb1 = min(kb0 + s.kb_per_split, s.kb_total);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          const int k0 = kb * GEMM_BK;
+          if (!A_MN) {
+            tma_load_2d(sa, &tma_a, &full_bar[stage], k0, m0);  // box {64 k, 128 m}
+          } else {
+#pragma unroll
+            for (int j = 0; j < GEMM_BM / 64; ++j)  // box {64 m, 64 k} per 64-wide M atom
+              tma_load_2d(sa + j * 8192, &tma_a, &full_bar[stage], m0 + 64 * j, k0);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tma_b, &full_bar[stage], k0, n0);  // box {64 k, BN n}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tma_b, &full_bar[stage], n0 + 64 * j, k0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================= UMMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int split = tile % s.k_splits;
+        const int kb0 = split * s.kb_per_split;
+        const int kb1 = min(kb0 + s.kb_per_split, s.kb_total);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            const uint64_t da = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================================================================= epilogue (warps 2..5)
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int row_in_tile = quad * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int split = tile % s.k_splits;
+      const int n_blk = (tile / s.k_splits) % s.n_tiles;
+      const int m_blk = tile / (s.k_splits * s.n_tiles);
+      const long long row = (long long)m_blk * GEMM_BM + row_in_tile;
+      const int n0 = n_blk * BN;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_x32(t_addr + c0, v);
+        tmem_ld_wait();
+        const int col = n0 + c0;
+        if (row < s.m && col < s.n) {
+          float acc_f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc_f[i] = __uint_as_float(v[i]);
+          const int ncols = min(32, s.n - col);  // multiple of 8 (host checks n % 8 == 0)
+          if (e.bias) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              if (i < ncols) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col + i));
+                acc_f[i] += b4.x; acc_f[i + 1] += b4.y; acc_f[i + 2] += b4.z; acc_f[i + 3] += b4.w;
+              }
+            }
+          }
+          if (e.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc_f[i] = fmaxf(acc_f[i], 0.f);
+          }
+          if (e.gate) {
+            const uint4* g = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(e.gate) + row * e.ldg + col);
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              if (i < ncols) {
+                const uint4 gv = __ldg(g + i / 8);
+                const uint32_t w[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  acc_f[i + 2 * j] *= (bf16_lo(w[j]) > 0.f) ? e.gate_scale : 0.f;
+                  acc_f[i + 2 * j + 1] *= (bf16_hi(w[j]) > 0.f) ? e.gate_scale : 0.f;
+                }
+              }
+            }
+          }
+          if (e.drop.thresh16) {
+            const uint64_t ebase = (uint64_t)row * (uint64_t)s.n + (uint64_t)col;  // n % 8 == 0 -> 8-aligned
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              if (i < ncols) {
+                const uint32_t keep = dropout_keep8(e.drop, (ebase + i) >> 3);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc_f[i + j] = ((keep >> j) & 1u) ? acc_f[i + j] * e.drop.inv_keep : 0.f;
+              }
+            }
+          }
+          if (e.residual) {
+            const uint4* r = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(e.residual) + row * e.ldr + col);
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              if (i < ncols) {
+                const uint4 rv = __ldg(r + i / 8);
+                const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  acc_f[i + 2 * j] += bf16_lo(w[j]);
+                  acc_f[i + 2 * j + 1] += bf16_hi(w[j]);
+                }
+              }
+            }
+          }
+          if (e.c_is_f32) {
+            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.c) + (long long)split * e.split_stride + row * e.ldc + col);
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              if (i < ncols) {
+                float4 ov = make_float4(acc_f[i], acc_f[i + 1], acc_f[i + 2], acc_f[i + 3]);
+                if (e.accumulate) {
+                  const float4 old = o[i / 4];
+                  ov.x += old.x; ov.y += old.y; ov.z += old.z; ov.w += old.w;
+                }
+                o[i / 4] = ov;
+              }
+          } else {
+            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.c) + row * e.ldc + col);
+#pragma unroll
+            for (int i = 0; i < 32; i += 8)
+              if (i < ncols)
+                o[i / 8] = make_uint4(pack_bf16(acc_f[i], acc_f[i + 1]), pack_bf16(acc_f[i + 2], acc_f[i + 3]),
+                                      pack_bf16(acc_f[i + 4], acc_f[i + 5]), pack_bf16(acc_f[i + 6], acc_f[i + 7]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// sum split-K partials: out[i] = sum_s part[s*stride + i]      (fp32, deterministic order)
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, long long n4,
+                                     long long stride4, int splits, int accumulate) {
+  const float4* p = reinterpret_cast<const float4*>(part);
+  float4* o = reinterpret_cast<float4*>(out);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 a = p[i];
+    for (int s = 1; s < splits; ++s) {
+      const float4 b = p[i + s * stride4];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (accumulate) {
+      const float4 b = o[i];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    o[i] = a;
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& s, const GemmEpilogue& e,
+                       cudaStream_t stream) {
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    TOME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::TOTAL));
+    attr_set = true;
+  }
+  const int num_tiles = s.m_tiles * s.n_tiles * s.k_splits;
+  const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
+  kern<<<grid, GEMM_THREADS, GemmSmem<BN>::TOTAL, stream>>>(ta, tb, s, e);
+  TOME_CUDA(cudaGetLastError());
+  return TOME_OK;
+}
+
+}  // namespace tome
+
+using namespace tome;
+
+static int pick_splits(const tome_gemm_args_t* a, int bn) {
+  if (a->k_splits > 0) return a->k_splits;
+  if (a->c_dtype != TOME_F32) return 1;  // split-K only for fp32 outputs (weight gradients)
+  const int tiles = ceil_div(a->m, GEMM_BM) * ceil_div(a->n, bn);
+  const int kb = ceil_div(a->k, GEMM_BK);
+  int s = kNumSMs / (tiles > 0 ? tiles : 1);
+  if (s < 1) s = 1;
+  if (s > kb / 8) s = kb / 8 > 0 ? kb / 8 : 1;  // keep >= 8 k-blocks per split
+  if (s > 64) s = 64;
+  return s;
+}
+
+extern "C" size_t tome_gemm_workspace_bytes(const tome_gemm_args_t* a) {
+  if (!a) return 0;
+  const int splits = pick_splits(a, 128);
+  if (splits <= 1) return 0;
+  return (size_t)splits * (size_t)a->m * (size_t)a->ldc * sizeof(float);
+}
+
+extern "C" int tome_gemm_bf16(const tome_gemm_args_t* a, void* workspace, size_t workspace_bytes, void* stream_) {
+  clear_error();
+  cudaStream_t stream = (cudaStream_t)stream_;
+  TOME_CHECK(a != nullptr, TOME_ERR_INVALID, "gemm: null args");
+  TOME_CHECK(a->m > 0 && a->n > 0 && a->k > 0, TOME_ERR_INVALID, "gemm: m,n,k must be positive (%d,%d,%d)", a->m, a->n, a->k);
+  TOME_CHECK(a->a && a->b && a->c, TOME_ERR_INVALID, "gemm: null operand pointer");
+  TOME_CHECK(a->n % 8 == 0, TOME_ERR_INVALID, "gemm: n (%d) must be a multiple of 8", a->n);
+  TOME_CHECK(a->lda % 8 == 0 && a->ldb % 8 == 0, TOME_ERR_INVALID, "gemm: lda/ldb must be multiples of 8 elements (16 B)");
+  TOME_CHECK(a->c_dtype == TOME_BF16 || a->c_dtype == TOME_F32, TOME_ERR_INVALID, "gemm: c_dtype must be bf16 or f32");
+  TOME_CHECK(a->ldc % (a->c_dtype == TOME_F32 ? 4 : 8) == 0, TOME_ERR_INVALID, "gemm: ldc must keep rows 16-byte aligned");
+  TOME_CHECK(!a->residual || a->ldr % 8 == 0, TOME_ERR_INVALID, "gemm: ldr must be a multiple of 8");
+  TOME_CHECK(!a->gate || a->ldg % 8 == 0, TOME_ERR_INVALID, "gemm: ldg must be a multiple of 8");
+  TOME_CHECK(a->dropout_rate >= 0.f && a->dropout_rate < 1.f, TOME_ERR_INVALID, "gemm: dropout_rate must be in [0,1)");
+
+  const int bn = 128;
+  GemmShape s;
+  s.m = a->m; s.n = a->n; s.k = a->k;
+  s.m_tiles = ceil_div(a->m, GEMM_BM);
+  s.n_tiles = ceil_div(a->n, bn);
+  s.kb_total = ceil_div(a->k, GEMM_BK);
+  s.k_splits = pick_splits(a, bn);
+  s.kb_per_split = ceil_div(s.kb_total, s.k_splits);
+  s.k_splits = ceil_div(s.kb_total, s.kb_per_split);  // drop empty splits
+
+  GemmEpilogue e;
+  e.c = a->c; e.bias = a->bias; e.residual = a->residual; e.gate = a->gate;
+  e.ldc = a->ldc; e.ldr = a->ldr; e.ldg = a->ldg;
+  e.gate_scale = a->gate_scale; e.relu = a->relu; e.c_is_f32 = (a->c_dtype == TOME_F32);
+  e.drop.thresh16 = (uint32_t)(a->dropout_rate * 65536.0f + 0.5f);
+  e.drop.inv_keep = 1.0f / (1.0f - (float)e.drop.thresh16 / 65536.0f);
+  e.drop.seed_lo = (uint32_t)a->dropout_seed; e.drop.seed_hi = (uint32_t)(a->dropout_seed >> 32);
+  e.drop.site = a->dropout_site;
+  e.split_stride = 0;
+  e.accumulate = a->accumulate;
+  TOME_CHECK(!a->accumulate || e.c_is_f32, TOME_ERR_INVALID, "gemm: accumulate requires an fp32 output");
+  if (s.k_splits > 1) {
+    TOME_CHECK(e.c_is_f32, TOME_ERR_INVALID, "gemm: split-K requires an fp32 output");
+    TOME_CHECK(!a->bias && !a->residual && !a->gate && !a->relu && e.drop.thresh16 == 0, TOME_ERR_INVALID,
+               "gemm: split-K supports a plain epilogue only");
+    const size_t need = (size_t)s.k_splits * (size_t)a->m * (size_t)a->ldc * sizeof(float);
+    TOME_CHECK(workspace && workspace_bytes >= need, TOME_ERR_INVALID, "gemm: split-K workspace too small (%zu < %zu)",
+               workspace_bytes, need);
+    e.c = workspace;
+    e.split_stride = (long long)a->m * a->ldc;
+    e.accumulate = 0;  // partials are plain; the reduce kernel adds into C
+  }
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (a->a_major == TOME_MAJOR_K) rc = make_tmap_2d_bf16(&ta, a->a, a->m, a->k, a->lda, GEMM_BM);
+  else rc = make_tmap_2d_bf16(&ta, a->a, a->k, a->m, a->lda, GEMM_BK);
+  if (rc) return rc;
+  if (a->b_major == TOME_MAJOR_K) rc = make_tmap_2d_bf16(&tb, a->b, a->n, a->k, a->ldb, bn);
+  else rc = make_tmap_2d_bf16(&tb, a->b, a->k, a->n, a->ldb, GEMM_BK);
+  if (rc) return rc;
+
+  const bool amn = a->a_major == TOME_MAJOR_MN, bmn = a->b_major == TOME_MAJOR_MN;
+  if (!amn && !bmn) rc = launch_gemm<128, false, false>(ta, tb, s, e, stream);
+  else if (!amn && bmn) rc = launch_gemm<128, false, true>(ta, tb, s, e, stream);
+  else if (amn && !bmn) rc = launch_gemm<128, true, false>(ta, tb, s, e, stream);
+  else rc = launch_gemm<128, true, true>(ta, tb, s, e, stream);
+  if (rc) return rc;
+
+  if (s.k_splits > 1) {
+    const long long n4 = (long long)a->m * a->ldc / 4;
+    int blocks = (int)((n4 + 255) / 256);
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float*>(workspace),
+                                                     reinterpret_cast<float*>(a->c), n4, n4, s.k_splits, a->accumulate);
+    TOME_CUDA(cudaGetLastError());
+  }
+  return TOME_OK;
+}

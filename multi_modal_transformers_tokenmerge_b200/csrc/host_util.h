@@ -1,0 +1,39 @@
+// Host-side helpers shared by the C-ABI translation units: error reporting (thread-local string, never throws
+// across the ABI) and TMA tensor-map encoding through the driver entry point (no link-time libcuda dependency).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/tome_b200.h"
+
+namespace tome {
+
+int set_error(int code, const char* fmt, ...);  // returns code
+void clear_error();
+
+#define TOME_CHECK(cond, code, ...)                        \
+  do {                                                     \
+    if (!(cond)) return ::tome::set_error(code, __VA_ARGS__); \
+  } while (0)
+
+#define TOME_CUDA(expr)                                                                                   \
+  do {                                                                                                    \
+    cudaError_t _e = (expr);                                                                              \
+    if (_e != cudaSuccess)                                                                                \
+      return ::tome::set_error(TOME_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                               __LINE__);                                                                 \
+  } while (0)
+
+// Row-major bf16 matrix [rows, cols] with leading dimension ld (elements), described as a 2-D TMA tensor with a
+// {64 x box_rows} box and 128-byte swizzle.  cols*2 and ld*2 must be multiples of 16 bytes.
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+// [d2, d1, d0] bf16 tensor (d0 contiguous; strides in elements), box {64, box_d1, 1}, 128-byte swizzle.
+int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,
+                      uint64_t stride2, uint32_t box_d1);
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace tome

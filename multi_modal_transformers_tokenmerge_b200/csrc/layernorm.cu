@@ -1,0 +1,427 @@
+// K8: LayerNorm exactly as the reference configures it (vanilla_decoder.yaml:7-13): reduction_axes=[1] -- the
+// statistics run over the TOKEN axis for every (batch, feature) pair -- scale/bias per feature, epsilon 1e-6,
+// flax's fast variance max(0, E[x^2] - E[x]^2).  axis = 2 is the conventional per-token LayerNorm (opt-in).
+//
+// HBM-bound.  axis 1: one CTA owns a (batch, 64-feature) slab = T rows x 128 bytes; 8 threads x 16 bytes cover a
+// row segment (one full 128-byte line), 32 row groups stride over T.  The slab (T x 128 B <= 1 MB) is read twice, the
+// second time from L2.  Also here: column sums (bias gradients) with the same slab walk.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace tome {
+
+constexpr int LN_THREADS = 256;
+constexpr int LN_RG = 32;     // row groups
+constexpr int LN_SLAB = 64;   // features per CTA (8 threads x 8 bf16)
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+
+// ------------------------------------------------------------------------------------------------ axis 1 forward
+__global__ void __launch_bounds__(LN_THREADS)
+ln_seq_fwd_kernel(int T, int C, float eps, const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ mean,
+                  float* __restrict__ rstd) {
+  __shared__ float s_sum[LN_RG][LN_SLAB + 1];
+  __shared__ float s_sq[LN_RG][LN_SLAB + 1];
+  __shared__ float s_mean[LN_SLAB], s_rstd[LN_SLAB];
+  const int b = blockIdx.y, c0 = blockIdx.x * LN_SLAB;
+  const int ct = threadIdx.x & 7, rg = threadIdx.x >> 3;
+  const int c = c0 + ct * 8;
+  const bool active = c < C;
+  const __nv_bfloat16* xb = x + (long long)b * T * C + c;
+  float sum[8], sq[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum[i] = sq[i] = 0.f;
+  if (active) {
+    for (int t = rg; t < T; t += LN_RG) {
+      float f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(xb + (long long)t * C)), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        sum[i] += f[i];
+        sq[i] = fmaf(f[i], f[i], sq[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    s_sum[rg][ct * 8 + i] = sum[i];
+    s_sq[rg][ct * 8 + i] = sq[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < LN_SLAB) {
+    float a = 0.f, q = 0.f;
+    for (int g = 0; g < LN_RG; ++g) {
+      a += s_sum[g][threadIdx.x];
+      q += s_sq[g][threadIdx.x];
+    }
+    const float mu = a / (float)T;
+    const float var = fmaxf(q / (float)T - mu * mu, 0.f);
+    const float rs = rsqrtf(var + eps);
+    s_mean[threadIdx.x] = mu;
+    s_rstd[threadIdx.x] = rs;
+    if (c0 + threadIdx.x < C) {
+      mean[(long long)b * C + c0 + threadIdx.x] = mu;
+      rstd[(long long)b * C + c0 + threadIdx.x] = rs;
+    }
+  }
+  __syncthreads();
+  if (!active) return;
+  float mu[8], sc[8], sh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    mu[i] = s_mean[ct * 8 + i];
+    sc[i] = s_rstd[ct * 8 + i] * gamma[c + i];
+    sh[i] = beta[c + i];
+  }
+  __nv_bfloat16* yb = y + (long long)b * T * C + c;
+  for (int t = rg; t < T; t += LN_RG) {
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(xb + (long long)t * C)), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i] - mu[i], sc[i], sh[i]);
+    *reinterpret_cast<uint4*>(yb + (long long)t * C) = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ axis 1 backward
+// per (b, c):  A = sum_t dy,  Bq = sum_t dy * xhat;   dx = rstd*gamma*(dy - A/T - xhat*Bq/T) (+ dres)
+// partial[0][b][c] = A (-> dbeta), partial[1][b][c] = Bq (-> dgamma); reduced over b by reduce_rows_kernel.
+__global__ void __launch_bounds__(LN_THREADS)
+ln_seq_bwd_kernel(int B, int T, int C, const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                  const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+                  const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx, float* __restrict__ partial) {
+  __shared__ float s_a[LN_RG][LN_SLAB + 1];
+  __shared__ float s_b[LN_RG][LN_SLAB + 1];
+  __shared__ float s_A[LN_SLAB], s_B[LN_SLAB];
+  const int b = blockIdx.y, c0 = blockIdx.x * LN_SLAB;
+  const int ct = threadIdx.x & 7, rg = threadIdx.x >> 3;
+  const int c = c0 + ct * 8;
+  const bool active = c < C;
+  const long long base = (long long)b * T * C + c;
+  float mu[8], rs[8];
+  float sa[8], sb[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sa[i] = sb[i] = 0.f;
+    mu[i] = active ? mean[(long long)b * C + c + i] : 0.f;
+    rs[i] = active ? rstd[(long long)b * C + c + i] : 0.f;
+  }
+  if (active) {
+    for (int t = rg; t < T; t += LN_RG) {
+      float fx[8], fd[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x + base + (long long)t * C)), fx);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(dy + base + (long long)t * C)), fd);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        sa[i] += fd[i];
+        sb[i] = fmaf(fd[i], (fx[i] - mu[i]) * rs[i], sb[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    s_a[rg][ct * 8 + i] = sa[i];
+    s_b[rg][ct * 8 + i] = sb[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < LN_SLAB) {
+    float a = 0.f, q = 0.f;
+    for (int g = 0; g < LN_RG; ++g) {
+      a += s_a[g][threadIdx.x];
+      q += s_b[g][threadIdx.x];
+    }
+    s_A[threadIdx.x] = a;
+    s_B[threadIdx.x] = q;
+    if (c0 + threadIdx.x < C) {
+      partial[(long long)b * C + c0 + threadIdx.x] = a;
+      partial[(long long)(B + b) * C + c0 + threadIdx.x] = q;
+    }
+  }
+  __syncthreads();
+  if (!active) return;
+  const float inv_t = 1.0f / (float)T;
+  float k0[8], k1[8], k2[8];  // dx = k0*dy + k1*xhat + k2
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float g = rs[i] * gamma[c + i];
+    k0[i] = g;
+    k1[i] = -g * s_B[ct * 8 + i] * inv_t;
+    k2[i] = -g * s_A[ct * 8 + i] * inv_t;
+  }
+  for (int t = rg; t < T; t += LN_RG) {
+    float fx[8], fd[8], o[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + base + (long long)t * C)), fx);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy + base + (long long)t * C)), fd);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = fmaf(k0[i], fd[i], fmaf(k1[i], (fx[i] - mu[i]) * rs[i], k2[i]));
+    if (dres) {
+      float fr[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(dres + base + (long long)t * C)), fr);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] += fr[i];
+    }
+    *reinterpret_cast<uint4*>(dx + base + (long long)t * C) = pack8(o);
+  }
+}
+
+// out[n] (+)= sum_r ws[r, n]      (fp32, fixed order)
+__global__ void reduce_rows_kernel(int R, int N, const float* __restrict__ ws, float* __restrict__ out, int accumulate) {
+  __shared__ float s[8][33];
+  const int n = blockIdx.x * 32 + (threadIdx.x & 31), rgp = threadIdx.x >> 5;
+  float a = 0.f;
+  if (n < N)
+    for (int r = rgp; r < R; r += 8) a += ws[(long long)r * N + n];
+  s[rgp][threadIdx.x & 31] = a;
+  __syncthreads();
+  if (rgp == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += s[g][threadIdx.x & 31];
+    out[n] = accumulate ? out[n] + t : t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ column sums
+// ws[chunk, n] = sum over the rows of this chunk of x[m, n]
+__global__ void __launch_bounds__(LN_THREADS)
+colsum_partial_kernel(int M, int N, long long ldx, int rows_per_chunk, const __nv_bfloat16* __restrict__ x,
+                      float* __restrict__ ws) {
+  __shared__ float s_sum[LN_RG][LN_SLAB + 1];
+  const int chunk = blockIdx.y, c0 = blockIdx.x * LN_SLAB;
+  const int ct = threadIdx.x & 7, rg = threadIdx.x >> 3;
+  const int c = c0 + ct * 8;
+  const int m0 = chunk * rows_per_chunk, m1 = min(M, m0 + rows_per_chunk);
+  float sum[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum[i] = 0.f;
+  if (c < N) {
+    for (int m = m0 + rg; m < m1; m += LN_RG) {
+      float f[8];
+      unpack8(ld_nc_v4(x + (long long)m * ldx + c), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sum[i] += f[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s_sum[rg][ct * 8 + i] = sum[i];
+  __syncthreads();
+  if (threadIdx.x < LN_SLAB && c0 + threadIdx.x < N) {
+    float a = 0.f;
+    for (int g = 0; g < LN_RG; ++g) a += s_sum[g][threadIdx.x];
+    ws[(long long)chunk * N + c0 + threadIdx.x] = a;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ axis 2 (features)
+// one warp per token row
+__global__ void __launch_bounds__(256)
+ln_feat_fwd_kernel(long long rows, int C, float eps, const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ mean,
+                   float* __restrict__ rstd) {
+  const long long row = blockIdx.x * 8ll + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const __nv_bfloat16* xr = x + row * C;
+  float a = 0.f, q = 0.f;
+  for (int c = lane * 8; c < C; c += 256) {
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(xr + c)), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      a += f[i];
+      q = fmaf(f[i], f[i], q);
+    }
+  }
+  a = warp_sum(a);
+  q = warp_sum(q);
+  const float mu = a / (float)C;
+  const float rs = rsqrtf(fmaxf(q / (float)C - mu * mu, 0.f) + eps);
+  if (lane == 0) {
+    mean[row] = mu;
+    rstd[row] = rs;
+  }
+  for (int c = lane * 8; c < C; c += 256) {
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(xr + c)), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = fmaf((f[i] - mu) * rs, gamma[c + i], beta[c + i]);
+    *reinterpret_cast<uint4*>(y + row * C + c) = pack8(f);
+  }
+}
+
+// dx = rstd * (g - mean_c(g) - xhat * mean_c(g * xhat)),  g = dy * gamma.   Per-chunk dgamma/dbeta partials in ws.
+__global__ void __launch_bounds__(256)
+ln_feat_bwd_kernel(long long rows, int C, const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                   const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+                   const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx) {
+  const long long row = blockIdx.x * 8ll + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float mu = mean[row], rs = rstd[row];
+  float a = 0.f, q = 0.f;
+  for (int c = lane * 8; c < C; c += 256) {
+    float fx[8], fd[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + row * C + c)), fx);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy + row * C + c)), fd);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float g = fd[i] * gamma[c + i];
+      a += g;
+      q = fmaf(g, (fx[i] - mu) * rs, q);
+    }
+  }
+  a = warp_sum(a) / (float)C;
+  q = warp_sum(q) / (float)C;
+  for (int c = lane * 8; c < C; c += 256) {
+    float fx[8], fd[8], o[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + row * C + c)), fx);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy + row * C + c)), fd);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = rs * (fd[i] * gamma[c + i] - a - (fx[i] - mu) * rs * q);
+    if (dres) {
+      float fr[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(dres + row * C + c)), fr);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] += fr[i];
+    }
+    *reinterpret_cast<uint4*>(dx + row * C + c) = pack8(o);
+  }
+}
+
+// ws[0][chunk][c] = sum_rows dy ; ws[1][chunk][c] = sum_rows dy * xhat      (axis-2 dbeta / dgamma partials)
+__global__ void __launch_bounds__(LN_THREADS)
+ln_feat_param_grad_kernel(long long rows, int C, int rows_per_chunk, int n_chunks, const __nv_bfloat16* __restrict__ x,
+                          const __nv_bfloat16* __restrict__ dy, const float* __restrict__ mean,
+                          const float* __restrict__ rstd, float* __restrict__ ws) {
+  __shared__ float s_a[LN_RG][LN_SLAB + 1];
+  __shared__ float s_b[LN_RG][LN_SLAB + 1];
+  const int chunk = blockIdx.y, c0 = blockIdx.x * LN_SLAB;
+  const int ct = threadIdx.x & 7, rg = threadIdx.x >> 3;
+  const int c = c0 + ct * 8;
+  const long long m0 = (long long)chunk * rows_per_chunk;
+  const long long m1 = m0 + rows_per_chunk < rows ? m0 + rows_per_chunk : rows;
+  float sa[8], sb[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sa[i] = sb[i] = 0.f;
+  if (c < C) {
+    for (long long m = m0 + rg; m < m1; m += LN_RG) {
+      float fx[8], fd[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x + m * C + c)), fx);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(dy + m * C + c)), fd);
+      const float mu = mean[m], rs = rstd[m];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        sa[i] += fd[i];
+        sb[i] = fmaf(fd[i], (fx[i] - mu) * rs, sb[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    s_a[rg][ct * 8 + i] = sa[i];
+    s_b[rg][ct * 8 + i] = sb[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < LN_SLAB && c0 + threadIdx.x < C) {
+    float a = 0.f, q = 0.f;
+    for (int g = 0; g < LN_RG; ++g) {
+      a += s_a[g][threadIdx.x];
+      q += s_b[g][threadIdx.x];
+    }
+    ws[(long long)chunk * C + c0 + threadIdx.x] = a;
+    ws[(long long)(n_chunks + chunk) * C + c0 + threadIdx.x] = q;
+  }
+}
+
+static inline int colsum_rows(long long m) {
+  long long r = (m + 63) / 64;
+  if (r > 256) r = 256;
+  return (int)(r < 1 ? 1 : r);
+}
+
+}  // namespace tome
+
+using namespace tome;
+
+extern "C" int tome_colsum_workspace_rows(int m) { return colsum_rows(m); }
+
+extern "C" int tome_colsum_bf16(int m, int n, const void* x, long long ldx, float* out, int accumulate, float* workspace,
+                                void* stream_) {
+  clear_error();
+  cudaStream_t stream = (cudaStream_t)stream_;
+  TOME_CHECK(m > 0 && n > 0 && x && out && workspace, TOME_ERR_INVALID, "colsum: bad argument");
+  TOME_CHECK(n % 8 == 0 && ldx % 8 == 0, TOME_ERR_INVALID, "colsum: n and ldx must be multiples of 8");
+  const int chunks = colsum_rows(m);
+  const int rpc = ceil_div(m, chunks);
+  dim3 grid(ceil_div(n, LN_SLAB), chunks);
+  colsum_partial_kernel<<<grid, LN_THREADS, 0, stream>>>(m, n, ldx, rpc, reinterpret_cast<const __nv_bfloat16*>(x), workspace);
+  TOME_CUDA(cudaGetLastError());
+  reduce_rows_kernel<<<ceil_div(n, 32), 256, 0, stream>>>(chunks, n, workspace, out, accumulate);
+  TOME_CUDA(cudaGetLastError());
+  return TOME_OK;
+}
+
+extern "C" int tome_layernorm_fwd(int batch, int tokens, int channels, int axis, float eps, const void* x,
+                                  const float* gamma, const float* beta, void* y, float* mean, float* rstd, void* stream_) {
+  clear_error();
+  cudaStream_t stream = (cudaStream_t)stream_;
+  TOME_CHECK(batch > 0 && tokens > 0 && channels > 0, TOME_ERR_INVALID, "layernorm_fwd: bad shape");
+  TOME_CHECK(channels % 8 == 0, TOME_ERR_INVALID, "layernorm_fwd: channels (%d) must be a multiple of 8", channels);
+  TOME_CHECK(x && gamma && beta && y && mean && rstd, TOME_ERR_INVALID, "layernorm_fwd: null argument");
+  TOME_CHECK(axis == 1 || axis == 2, TOME_ERR_INVALID, "layernorm_fwd: axis must be 1 (tokens) or 2 (features)");
+  const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
+  if (axis == 1) {
+    TOME_CHECK(batch <= 65535, TOME_ERR_INVALID, "layernorm_fwd: batch too large");
+    dim3 grid(ceil_div(channels, LN_SLAB), batch);
+    ln_seq_fwd_kernel<<<grid, LN_THREADS, 0, stream>>>(tokens, channels, eps, xp, gamma, beta, yp, mean, rstd);
+  } else {
+    const long long rows = (long long)batch * tokens;
+    ln_feat_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(rows, channels, eps, xp, gamma, beta, yp, mean, rstd);
+  }
+  TOME_CUDA(cudaGetLastError());
+  return TOME_OK;
+}
+
+extern "C" int tome_layernorm_bwd(int batch, int tokens, int channels, int axis, const void* x, const void* dy,
+                                  const float* gamma, const float* mean, const float* rstd, const void* dres, void* dx,
+                                  float* dgamma, float* dbeta, float* partial, void* stream_) {
+  clear_error();
+  cudaStream_t stream = (cudaStream_t)stream_;
+  TOME_CHECK(batch > 0 && tokens > 0 && channels > 0 && channels % 8 == 0, TOME_ERR_INVALID, "layernorm_bwd: bad shape");
+  TOME_CHECK(x && dy && gamma && mean && rstd && dx && dgamma && dbeta && partial, TOME_ERR_INVALID,
+             "layernorm_bwd: null argument");
+  TOME_CHECK(axis == 1 || axis == 2, TOME_ERR_INVALID, "layernorm_bwd: axis must be 1 (tokens) or 2 (features)");
+  const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+  const __nv_bfloat16* dyp = reinterpret_cast<const __nv_bfloat16*>(dy);
+  const __nv_bfloat16* drp = reinterpret_cast<const __nv_bfloat16*>(dres);
+  __nv_bfloat16* dxp = reinterpret_cast<__nv_bfloat16*>(dx);
+  int chunks;
+  if (axis == 1) {
+    TOME_CHECK(batch <= 65535, TOME_ERR_INVALID, "layernorm_bwd: batch too large");
+    dim3 grid(ceil_div(channels, LN_SLAB), batch);
+    ln_seq_bwd_kernel<<<grid, LN_THREADS, 0, stream>>>(batch, tokens, channels, xp, dyp, gamma, mean, rstd, drp, dxp, partial);
+    chunks = batch;
+  } else {
+    const long long rows = (long long)batch * tokens;
+    ln_feat_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(rows, channels, xp, dyp, gamma, mean, rstd, drp, dxp);
+    TOME_CUDA(cudaGetLastError());
+    chunks = colsum_rows(rows);
+    const int rpc = (int)((rows + chunks - 1) / chunks);
+    dim3 grid(ceil_div(channels, LN_SLAB), chunks);
+    ln_feat_param_grad_kernel<<<grid, LN_THREADS, 0, stream>>>(rows, channels, rpc, chunks, xp, dyp, mean, rstd, partial);
+  }
+  TOME_CUDA(cudaGetLastError());
+  reduce_rows_kernel<<<ceil_div(channels, 32), 256, 0, stream>>>(chunks, channels, partial, dbeta, 1);
+  reduce_rows_kernel<<<ceil_div(channels, 32), 256, 0, stream>>>(chunks, channels, partial + (long long)chunks * channels,
+                                                                 dgamma, 1);
+  TOME_CUDA(cudaGetLastError());
+  return TOME_OK;
+}

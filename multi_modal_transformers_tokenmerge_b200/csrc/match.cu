@@ -1,0 +1,318 @@
+// K1 + K2: bipartite soft matching.
+//
+//   tome_sim_argmax   token_compression.py:72-83   L2-normalise, even/odd split, scores = a b^T, row max / arg max
+//   tome_select_topr  token_compression.py:84-88   edge ranking (value desc, index desc on ties), index split,
+//                                                  plus the derived maps the merge kernels consume
+//
+// Both are exact-index kernels: all comparisons are done on fp32 values with the reference's tie rules
+// (arg max = first maximum; ranking = stable ascending argsort reversed; NaN ranks above everything, as in XLA /
+// numpy), so indices are bit-exact given the same fp32 scores.  The similarity product is fp32 FMA on CUDA cores
+// on purpose: it is 0.1 % of the block's FLOPs and fp32 keeps the arg max aligned with the fp32
+// reference; the scores tile lives in registers and never reaches HBM unless scores_out is given.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace tome {
+
+// "candidate (v, j) beats the current best (bv, bj)" for a row arg max: larger value, NaN largest, first index wins.
+__device__ __forceinline__ bool argmax_better(float v, int j, float bv, int bj) {
+  const bool nv = v != v, nb = bv != bv;
+  if (nv || nb) return nv && (!nb || j < bj);
+  return v > bv || (v == bv && j < bj);
+}
+
+constexpr int SIM_TILE = 64;
+constexpr int SIM_THREADS = 256;
+
+template <typename T>
+__device__ __forceinline__ float2 load2(const T* p);
+template <>
+__device__ __forceinline__ float2 load2<float>(const float* p) {
+  return *reinterpret_cast<const float2*>(p);
+}
+template <>
+__device__ __forceinline__ float2 load2<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+}
+
+// Load `SIM_TILE` metric rows (token = 2*row + parity) into smem as normalised fp32 rows of pitch dim+1.
+template <typename T>
+__device__ __forceinline__ void load_rows_normalised(float* dst, const T* src, const tome_metric_desc_t& d, int b,
+                                                     int row0, int nrows_total, int parity) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pitch = d.dim + 1;
+  const float inv_h = 1.0f / (float)d.heads;
+  for (int rr = warp; rr < SIM_TILE; rr += SIM_THREADS / 32) {
+    const int row = row0 + rr;
+    float* drow = dst + rr * pitch;
+    if (row >= nrows_total) {
+      for (int c = lane; c < d.dim; c += 32) drow[c] = 0.f;
+      continue;
+    }
+    const T* base = src + (long long)b * d.batch_stride + (long long)(2 * row + parity) * d.token_stride;
+    float ss = 0.f;
+    for (int c = 2 * lane; c < d.dim; c += 64) {
+      float2 acc = make_float2(0.f, 0.f);
+      for (int h = 0; h < d.heads; ++h) {
+        const float2 v = load2<T>(base + (long long)h * d.head_stride + c);
+        acc.x += v.x;
+        acc.y += v.y;
+      }
+      if (d.heads > 1) {  // jnp.mean over heads = sum / H
+        acc.x *= inv_h;
+        acc.y *= inv_h;
+      }
+      drow[c] = acc.x;
+      drow[c + 1] = acc.y;
+      ss += acc.x * acc.x + acc.y * acc.y;
+    }
+    ss = warp_sum(ss);
+    const float nrm = sqrtf(ss);  // no epsilon (token_compression.py:72): a zero row becomes NaN
+    for (int c = 2 * lane; c < d.dim; c += 64) {
+      drow[c] = drow[c] / nrm;
+      drow[c + 1] = drow[c + 1] / nrm;
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SIM_THREADS)
+sim_argmax_kernel(const tome_metric_desc_t d, const T* __restrict__ src, float* __restrict__ node_max,
+                  int32_t* __restrict__ node_idx, float* __restrict__ scores_out) {
+  extern __shared__ float sm[];
+  const int pitch = d.dim + 1;
+  float* sa = sm;
+  float* sb = sm + SIM_TILE * pitch;
+  const int b = blockIdx.y;
+  const int ta = (d.tokens + 1) / 2, tb = d.tokens / 2;
+  const int a0 = blockIdx.x * SIM_TILE;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+
+  load_rows_normalised<T>(sa, src, d, b, a0, ta, 0);
+
+  float best_v[4];
+  int best_j[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    best_v[i] = -INFINITY;
+    best_j[i] = 0x7fffffff;
+  }
+
+  for (int b0 = 0; b0 < tb; b0 += SIM_TILE) {
+    __syncthreads();  // previous tile fully consumed (and sa visible on the first pass)
+    load_rows_normalised<T>(sb, src, d, b, b0, tb, 1);
+    __syncthreads();
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int c = 0; c < d.dim; ++c) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = sa[(ty + 16 * i) * pitch + c];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = sb[(tx + 16 * j) * pitch + c];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int ai = a0 + ty + 16 * i;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int bj = b0 + tx + 16 * j;
+        if (ai < ta && bj < tb) {
+          float s = acc[i][j];
+          if ((d.class_token && ai == 0) || (d.distill_token && bj == 0)) s = -INFINITY;  // :77-80
+          if (scores_out) scores_out[((long long)b * ta + ai) * tb + bj] = s;
+          if (argmax_better(s, bj, best_v[i], best_j[i])) {
+            best_v[i] = s;
+            best_j[i] = bj;
+          }
+        }
+      }
+    }
+  }
+  // reduce over the 16 tx lanes that share an a-row (contiguous half-warp)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best_v[i], o);
+      const int oj = __shfl_xor_sync(0xffffffffu, best_j[i], o);
+      if (argmax_better(ov, oj, best_v[i], best_j[i])) {
+        best_v[i] = ov;
+        best_j[i] = oj;
+      }
+    }
+    const int ai = a0 + ty + 16 * i;
+    if (tx == 0 && ai < ta) {
+      node_max[(long long)b * ta + ai] = best_v[i];
+      node_idx[(long long)b * ta + ai] = best_j[i] == 0x7fffffff ? 0 : best_j[i];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K2
+// rank order of jnp.argsort(node_max)[:, ::-1]: j precedes i iff key_j "greater" (NaN greatest), ties: larger index.
+__device__ __forceinline__ bool rank_before(float vj, int j, float vi, int i) {
+  const bool nj = vj != vj, ni = vi != vi;
+  if (nj || ni) return nj && (!ni || j > i);
+  return vj > vi || (vj == vi && j > i);
+}
+
+constexpr int SEL_THREADS = 1024;
+
+__global__ void __launch_bounds__(SEL_THREADS)
+select_topr_kernel(const tome_plan_shape_t s, const float* __restrict__ node_max, const int32_t* __restrict__ node_idx,
+                   const tome_plan_t p) {
+  extern __shared__ int sel_sm[];
+  const int T = s.tokens, r = s.r;
+  const int ta = (T + 1) / 2, tb = T / 2;
+  float* vals = reinterpret_cast<float*>(sel_sm);  // [ta]
+  int* nidx = sel_sm + ta;                         // [ta]
+  int* rnk = nidx + ta;                            // [ta]   rank of even token i
+  int* edge = rnk + ta;                            // [ta]   edge[rank] = i
+  int* dstr = edge + ta;                           // [r]    destination of rank i
+  int* cnt = dstr + r;                             // [tb+1] counts then exclusive offsets
+  int* part = cnt + tb + 1;                        // [SEL_THREADS] scan partials
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+
+  for (int i = tid; i < ta; i += nt) {
+    vals[i] = node_max[(long long)b * ta + i];
+    nidx[i] = node_idx[(long long)b * ta + i];
+  }
+  for (int j = tid; j <= tb; j += nt) cnt[j] = 0;
+  __syncthreads();
+  for (int i = tid; i < ta; i += nt) {
+    const float vi = vals[i];
+    int rk = 0;
+    for (int j = 0; j < ta; ++j) rk += rank_before(vals[j], j, vi, i) ? 1 : 0;
+    rnk[i] = rk;
+    edge[rk] = i;
+    p.edge_idx[(long long)b * ta + rk] = i;
+  }
+  __syncthreads();
+  for (int i = tid; i < r; i += nt) {
+    const int d = nidx[edge[i]];
+    dstr[i] = d;
+    p.dst_idx[(long long)b * r + i] = d;
+    atomicAdd(&cnt[d], 1);
+  }
+  __syncthreads();
+  // exclusive scan of cnt[0..tb) -> offsets; cnt[tb] = r
+  {
+    const int per = (tb + nt - 1) / nt;
+    const int lo = tid * per, hi = min(lo + per, tb);
+    int sum = 0;
+    for (int j = lo; j < hi; ++j) sum += cnt[j];
+    part[tid] = sum;
+    __syncthreads();
+    for (int o = 1; o < nt; o <<= 1) {
+      const int add = tid >= o ? part[tid - o] : 0;
+      __syncthreads();
+      part[tid] += add;
+      __syncthreads();
+    }
+    int run = part[tid] - sum;  // exclusive prefix of this thread's chunk
+    for (int j = lo; j < hi; ++j) {
+      const int c = cnt[j];
+      cnt[j] = run;
+      run += c;
+    }
+    if (tid == 0) cnt[tb] = r;
+    __syncthreads();
+  }
+  for (int j = tid; j <= tb; j += nt) p.dst_off[(long long)b * (tb + 1) + j] = cnt[j];
+  // placement: sources of one destination keep their rank order (the reference adds them in that order, :100-101)
+  for (int i = tid; i < r; i += nt) {
+    const int d = dstr[i];
+    int k = 0;
+    for (int i2 = 0; i2 < i; ++i2) k += (dstr[i2] == d) ? 1 : 0;
+    p.dst_src[(long long)b * r + cnt[d] + k] = edge[i];
+  }
+  // row map: where every input token lands in the concatenation [unm | dst] (:103-108)
+  const int n_unm = ta - r;
+  for (int t = tid; t < T; t += nt) {
+    int row;
+    const int h = t >> 1;
+    if (t & 1) {
+      row = s.distill_token ? (h == 0 ? 1 : n_unm + h) : n_unm + h;
+    } else {
+      const int rk = rnk[h];
+      if (rk >= r) {
+        const int u = rk - r;
+        row = s.distill_token ? (u == 0 ? 0 : u + 1) : u;
+      } else {
+        const int j = nidx[h];
+        row = s.distill_token ? (j == 0 ? 1 : n_unm + j) : n_unm + j;
+      }
+    }
+    p.row_map[(long long)b * T + t] = row;
+  }
+}
+
+}  // namespace tome
+
+using namespace tome;
+
+extern "C" int tome_clamp_r(int tokens, int r, int class_token, int distill_token) {
+  const int prot = (class_token ? 1 : 0) + (distill_token ? 1 : 0);
+  int m = (tokens - prot) / 2;
+  if (r > m) r = m;
+  return r > 0 ? r : 0;
+}
+
+extern "C" int tome_sim_argmax(const tome_metric_desc_t* d, const void* src, float* node_max, int32_t* node_idx,
+                               float* scores_out, void* stream_) {
+  clear_error();
+  cudaStream_t stream = (cudaStream_t)stream_;
+  TOME_CHECK(d && src && node_max && node_idx, TOME_ERR_INVALID, "sim_argmax: null argument");
+  TOME_CHECK(d->batch > 0 && d->tokens >= 2 && d->heads >= 1, TOME_ERR_INVALID,
+             "sim_argmax: need batch > 0, tokens >= 2, heads >= 1 (got %d, %d, %d)", d->batch, d->tokens, d->heads);
+  TOME_CHECK(d->dim >= 2 && d->dim % 2 == 0 && d->dim <= 512, TOME_ERR_INVALID,
+             "sim_argmax: metric dim must be even and in [2, 512] (got %d)", d->dim);
+  TOME_CHECK(d->dtype == TOME_BF16 || d->dtype == TOME_F32, TOME_ERR_INVALID, "sim_argmax: dtype must be bf16 or f32");
+  TOME_CHECK(d->token_stride % 2 == 0 && d->batch_stride % 2 == 0 && d->head_stride % 2 == 0, TOME_ERR_INVALID,
+             "sim_argmax: strides must be even (vector loads)");
+  TOME_CHECK(d->batch <= 65535, TOME_ERR_INVALID, "sim_argmax: batch too large for one launch");
+  const int ta = (d->tokens + 1) / 2;
+  const size_t smem = (size_t)2 * SIM_TILE * (d->dim + 1) * sizeof(float);
+  dim3 grid(ceil_div(ta, SIM_TILE), d->batch);
+  if (d->dtype == TOME_BF16) {
+    auto kern = sim_argmax_kernel<__nv_bfloat16>;
+    TOME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, SIM_THREADS, smem, stream>>>(*d, reinterpret_cast<const __nv_bfloat16*>(src), node_max, node_idx,
+                                              scores_out);
+  } else {
+    auto kern = sim_argmax_kernel<float>;
+    TOME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, SIM_THREADS, smem, stream>>>(*d, reinterpret_cast<const float*>(src), node_max, node_idx, scores_out);
+  }
+  TOME_CUDA(cudaGetLastError());
+  return TOME_OK;
+}
+
+extern "C" int tome_select_topr(const tome_plan_shape_t* s, const float* node_max, const int32_t* node_idx,
+                                const tome_plan_t* plan, void* stream_) {
+  clear_error();
+  cudaStream_t stream = (cudaStream_t)stream_;
+  TOME_CHECK(s && node_max && node_idx && plan, TOME_ERR_INVALID, "select_topr: null argument");
+  TOME_CHECK(plan->edge_idx && plan->dst_idx && plan->row_map && plan->dst_off && plan->dst_src, TOME_ERR_INVALID,
+             "select_topr: every plan buffer must be provided");
+  TOME_CHECK(s->batch > 0 && s->tokens >= 2, TOME_ERR_INVALID, "select_topr: need batch > 0 and tokens >= 2");
+  const int ta = (s->tokens + 1) / 2, tb = s->tokens / 2;
+  TOME_CHECK(s->r >= 1 && s->r <= tb && s->r <= ta, TOME_ERR_INVALID,
+             "select_topr: r (%d) must be clamped to [1, %d] first (tome_clamp_r; r == 0 is the identity, no plan needed)",
+             s->r, tb);
+  const size_t smem = sizeof(int) * ((size_t)4 * ta + s->r + tb + 1 + SEL_THREADS);
+  TOME_CHECK(smem <= 220 * 1024, TOME_ERR_UNSUPPORTED, "select_topr: tokens (%d) too large for the shared-memory ranking",
+             s->tokens);
+  TOME_CUDA(cudaFuncSetAttribute(select_topr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  select_topr_kernel<<<s->batch, SEL_THREADS, smem, stream>>>(*s, node_max, node_idx, *plan);
+  TOME_CUDA(cudaGetLastError());
+  return TOME_OK;
+}

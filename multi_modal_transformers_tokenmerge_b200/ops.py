@@ -1,0 +1,245 @@
+"""Thin torch-tensor wrappers over the C ABI (include/tome_b200.h).
+
+torch is plumbing only here: device memory, the current stream, dtype bookkeeping.  Every function launches the
+hand-written sm_100a kernels through `libtome_b200.so`; nothing falls back to torch ops or to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.bfloat16:
+        return L.TOME_BF16
+    if t.dtype == torch.float32:
+        return L.TOME_F32
+    raise TypeError(f"unsupported dtype {t.dtype} (bf16 or fp32)")
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("multi_modal_transformers_tokenmerge_b200 runs on CUDA (sm_100a) only: got a CPU tensor. "
+                               "There is no CPU fallback.")
+
+
+def clamp_r(tokens: int, r: int, class_token: bool = False, distill_token: bool = False) -> int:
+    """token_compression.py:60-67 (pure host arithmetic; does not need the GPU)."""
+    return int(L.lib().tome_clamp_r(int(tokens), int(r), int(bool(class_token)), int(bool(distill_token))))
+
+
+# ------------------------------------------------------------------------------------------------ matching
+@dataclass
+class MatchPlan:
+    """Device-resident index set of one bipartite matching (token_compression.py:84-88)."""
+
+    batch: int
+    tokens: int
+    r: int
+    distill_token: bool
+    node_max: torch.Tensor  # [B,Ta] f32
+    node_idx: torch.Tensor  # [B,Ta] i32
+    edge_idx: torch.Tensor  # [B,Ta] i32
+    dst_idx: torch.Tensor   # [B,r] i32
+    row_map: torch.Tensor   # [B,T] i32
+    dst_off: torch.Tensor   # [B,Tb+1] i32
+    dst_src: torch.Tensor   # [B,r] i32
+    scores: Optional[torch.Tensor] = None
+
+    @property
+    def src_idx(self):
+        return self.edge_idx[:, : self.r]
+
+    @property
+    def unm_idx(self):
+        return self.edge_idx[:, self.r:]
+
+    def c_plan(self) -> L.Plan:
+        return L.Plan(self.edge_idx.data_ptr(), self.dst_idx.data_ptr(), self.row_map.data_ptr(),
+                      self.dst_off.data_ptr(), self.dst_src.data_ptr())
+
+
+def sim_argmax(src: torch.Tensor, *, heads: int = 1, dim: Optional[int] = None, batch_stride=None, token_stride=None,
+               head_stride=None, tokens=None, batch=None, class_token=False, distill_token=False, dump_scores=False,
+               offset_elems: int = 0):
+    """K1.  `src` is either a [B,T,Dm] metric (heads=1) or a packed buffer addressed by the given strides."""
+    _need_cuda(src)
+    if heads == 1 and dim is None:
+        assert src.dim() == 3 and src.is_contiguous()
+        batch, tokens, dim = src.shape
+        batch_stride, token_stride, head_stride = tokens * dim, dim, 0
+    ta, tb = (tokens + 1) // 2, tokens // 2
+    node_max = torch.empty(batch, ta, dtype=torch.float32, device=src.device)
+    node_idx = torch.empty(batch, ta, dtype=torch.int32, device=src.device)
+    scores = torch.empty(batch, ta, tb, dtype=torch.float32, device=src.device) if dump_scores else None
+    d = L.MetricDesc(batch, tokens, dim, heads, _dt(src), batch_stride, token_stride, head_stride,
+                     int(bool(class_token)), int(bool(distill_token)))
+    base = C.c_void_p(src.data_ptr() + offset_elems * src.element_size())
+    L.check(L.lib().tome_sim_argmax(C.byref(d), base, _ptr(node_max), _ptr(node_idx), _ptr(scores), _stream()))
+    return node_max, node_idx, scores
+
+
+def select_topr(node_max: torch.Tensor, node_idx: torch.Tensor, tokens: int, r: int, distill_token=False) -> MatchPlan:
+    """K2.  `r` must already be clamped and >= 1."""
+    _need_cuda(node_max, node_idx)
+    b = node_max.shape[0]
+    ta, tb = (tokens + 1) // 2, tokens // 2
+    dev = node_max.device
+    i32 = torch.int32
+    plan = MatchPlan(b, tokens, r, bool(distill_token), node_max, node_idx,
+                     torch.empty(b, ta, dtype=i32, device=dev), torch.empty(b, r, dtype=i32, device=dev),
+                     torch.empty(b, tokens, dtype=i32, device=dev), torch.empty(b, tb + 1, dtype=i32, device=dev),
+                     torch.empty(b, r, dtype=i32, device=dev))
+    shp = L.PlanShape(b, tokens, r, int(bool(distill_token)))
+    cp = plan.c_plan()
+    L.check(L.lib().tome_select_topr(C.byref(shp), _ptr(node_max), _ptr(node_idx), C.byref(cp), _stream()))
+    return plan
+
+
+def merge_fwd(plan: MatchPlan, x: torch.Tensor, size: Optional[torch.Tensor], mode: int, gid=None, pos=None):
+    """K3.  x [B,T,C] (bf16/fp32, contiguous); size f32 [B,T] or None.  Returns (x_out, size_out, gid_out, pos_out)."""
+    _need_cuda(x, size)
+    assert x.is_contiguous() and x.dim() == 3
+    b, t, c = x.shape
+    assert t == plan.tokens and b == plan.batch
+    to = t - plan.r
+    x_out = torch.empty(b, to, c, dtype=x.dtype, device=x.device)
+    size_out = torch.empty(b, to, dtype=torch.float32, device=x.device) if mode == L.TOME_MERGE_WAVG else None
+    gid_out = torch.empty(b, to, dtype=torch.uint8, device=x.device) if gid is not None else None
+    pos_out = torch.empty(b, to, dtype=torch.int32, device=x.device) if pos is not None else None
+    shp = L.MergeShape(b, t, c, plan.r, int(plan.distill_token), _dt(x), mode)
+    cp = plan.c_plan()
+    L.check(L.lib().tome_merge_fwd(C.byref(shp), C.byref(cp), _ptr(x), _ptr(size), _ptr(x_out), _ptr(size_out),
+                                   _ptr(gid), _ptr(pos), _ptr(gid_out), _ptr(pos_out), _stream()))
+    return x_out, size_out, gid_out, pos_out
+
+
+def merge_bwd(plan: MatchPlan, dy: torch.Tensor, size: Optional[torch.Tensor], size_out: Optional[torch.Tensor], mode: int):
+    """K4.  dy [B,T-r,C] -> dx [B,T,C].  mode SUM == ToMe `unmerge`."""
+    _need_cuda(dy)
+    assert dy.is_contiguous()
+    b, to, c = dy.shape
+    t = plan.tokens
+    dx = torch.empty(b, t, c, dtype=dy.dtype, device=dy.device)
+    shp = L.MergeShape(b, t, c, plan.r, int(plan.distill_token), _dt(dy), mode)
+    cp = plan.c_plan()
+    L.check(L.lib().tome_merge_bwd(C.byref(shp), C.byref(cp), _ptr(size), _ptr(size_out), _ptr(dy), _ptr(dx), _stream()))
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------ dense
+def gemm(a: torch.Tensor, b: torch.Tensor, *, m: int, n: int, k: int, a_major=L.TOME_MAJOR_K, b_major=L.TOME_MAJOR_K,
+         lda=None, ldb=None, out: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16, bias=None, residual=None,
+         gate=None, gate_scale=1.0, relu=False, dropout_rate=0.0, dropout_seed=0, dropout_site=0, k_splits=0,
+         accumulate=False) -> torch.Tensor:
+    """C[M,N] = epilogue(A * B^T) on tcgen05.  a/b are 2-D bf16 tensors whose rows are M/N (K-major) or K (MN-major)."""
+    _need_cuda(a, b)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    lda = a.stride(0) if lda is None else lda
+    ldb = b.stride(0) if ldb is None else ldb
+    if out is None:
+        out = torch.empty(m, n, dtype=out_dtype, device=a.device)
+    args = L.GemmArgs(m, n, k, a.data_ptr(), lda, a_major, b.data_ptr(), ldb, b_major, out.data_ptr(), out.stride(0),
+                      _dt(out), None if bias is None else bias.data_ptr(),
+                      None if residual is None else residual.data_ptr(), 0 if residual is None else residual.stride(0),
+                      None if gate is None else gate.data_ptr(), 0 if gate is None else gate.stride(0),
+                      float(gate_scale), int(relu), float(dropout_rate), int(dropout_seed), int(dropout_site),
+                      int(k_splits), int(accumulate))
+    ws_bytes = L.lib().tome_gemm_workspace_bytes(C.byref(args))
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=a.device) if ws_bytes else None
+    L.check(L.lib().tome_gemm_bf16(C.byref(args), _ptr(ws), ws_bytes, _stream()))
+    return out
+
+
+def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate=False) -> torch.Tensor:
+    _need_cuda(x)
+    m, n = x.shape
+    rows = L.lib().tome_colsum_workspace_rows(m)
+    ws = torch.empty(rows, n, dtype=torch.float32, device=x.device)
+    if out is None:
+        out = torch.empty(n, dtype=torch.float32, device=x.device)
+    L.check(L.lib().tome_colsum_bf16(m, n, _ptr(x), x.stride(0), _ptr(out), int(accumulate), _ptr(ws), _stream()))
+    return out
+
+
+def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-6, axis: int = 1):
+    _need_cuda(x)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    b, t, c = x.shape
+    y = torch.empty_like(x)
+    stat_shape = (b, c) if axis == 1 else (b, t)
+    mean = torch.empty(stat_shape, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(stat_shape, dtype=torch.float32, device=x.device)
+    L.check(L.lib().tome_layernorm_fwd(b, t, c, axis, eps, _ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(mean),
+                                       _ptr(rstd), _stream()))
+    return y, mean, rstd
+
+
+def layernorm_bwd(x, dy, gamma, mean, rstd, dgamma, dbeta, dres=None, axis: int = 1):
+    _need_cuda(x, dy)
+    b, t, c = x.shape
+    dx = torch.empty_like(x)
+    rows = b if axis == 1 else L.lib().tome_colsum_workspace_rows(b * t)
+    partial = torch.empty(2, rows, c, dtype=torch.float32, device=x.device)
+    L.check(L.lib().tome_layernorm_bwd(b, t, c, axis, _ptr(x), _ptr(dy), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dres),
+                                       _ptr(dx), _ptr(dgamma), _ptr(dbeta), _ptr(partial), _stream()))
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def _attn_desc(q, k, v, out, scale, gid, pos, allow, size):
+    b, t, h, d = q.shape
+    for x in (q, k, v, out):
+        assert x.dtype == torch.bfloat16 and x.stride(3) == 1 and x.stride(2) == d, "heads must be packed [.., H, D]"
+    g = 0 if allow is None else allow.shape[0]
+    return L.AttnDesc(b, t, h, d, q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
+                      out.stride(0), out.stride(1), float(scale),
+                      None if gid is None else gid.data_ptr(), None if pos is None else pos.data_ptr(),
+                      None if allow is None else allow.data_ptr(), g, None if size is None else size.data_ptr())
+
+
+def attention_fwd(q, k, v, *, gid=None, pos=None, allow=None, size=None, scale=None):
+    """q,k,v: [B,T,H,D] bf16 views (may be slices of a packed qkv buffer).  Returns (out [B,T,H,D], lse [B,H,T])."""
+    _need_cuda(q, k, v)
+    b, t, h, d = q.shape
+    scale = 1.0 / math.sqrt(d) if scale is None else scale
+    out = torch.empty(b, t, h, d, dtype=torch.bfloat16, device=q.device)
+    lse = torch.empty(b, h, t, dtype=torch.float32, device=q.device)
+    desc = _attn_desc(q, k, v, out, scale, gid, pos, allow, size)
+    L.check(L.lib().tome_attention_fwd(C.byref(desc), _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse), _stream()))
+    return out, lse
+
+
+def attention_bwd(q, k, v, out, lse, dout, *, gid=None, pos=None, allow=None, size=None, scale=None, dqkv=None):
+    """Returns (dq, dk, dv) [B,T,H,D] bf16 (views of one packed [B,T,3,H,D] buffer unless dqkv views are given)."""
+    _need_cuda(q, k, v, out, dout)
+    b, t, h, d = q.shape
+    scale = 1.0 / math.sqrt(d) if scale is None else scale
+    if dqkv is None:
+        buf = torch.empty(b, t, 3, h, d, dtype=torch.bfloat16, device=q.device)
+        dq, dk, dv = buf[:, :, 0], buf[:, :, 1], buf[:, :, 2]
+    else:
+        dq, dk, dv = dqkv
+    desc = _attn_desc(q, k, v, out, scale, gid, pos, allow, size)
+    gs = L.AttnGradStrides(dq.stride(0), dq.stride(1), dk.stride(0), dk.stride(1), dv.stride(0), dv.stride(1),
+                           dout.stride(0), dout.stride(1))
+    delta = torch.empty(b, h, t, dtype=torch.float32, device=q.device)
+    dq_acc = torch.empty(b, t, h * d, dtype=torch.float32, device=q.device)
+    L.check(L.lib().tome_attention_bwd(C.byref(desc), C.byref(gs), _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse),
+                                       _ptr(dout), _ptr(dq), _ptr(dk), _ptr(dv), _ptr(delta), _ptr(dq_acc), _stream()))
+    return dq, dk, dv

@@ -1,0 +1,284 @@
+"""Parity of every CUDA kernel against the CPU oracle, through the C ABI (ctypes).  Needs a B200: `-m gpu`.
+
+Bars (north star): indices and token sizes BIT-EXACT given the same fp32 scores; merged rows bit-exact in fp32 (same
+association as the reference's sequential scatter); dense / attention / LayerNorm outputs within the bf16 tolerance
+stated in each test."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import tome_oracle as O  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from multi_modal_transformers_tokenmerge_b200 import _lib, ops as _ops
+    _lib.lib()  # raises if the CUDA library is missing: no silent fallback
+    return _ops
+
+
+def dev(a, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(a)).cuda()
+    return t if dtype is None else t.to(dtype)
+
+
+def gpu_match(ops, metric_t, r, cls=False, dis=False, **kw):
+    T = kw.get("tokens", metric_t.shape[1])
+    r = ops.clamp_r(T, r, cls, dis)
+    nm, ni, sc = ops.sim_argmax(metric_t, class_token=cls, distill_token=dis, dump_scores=True, **kw)
+    plan = ops.select_topr(nm, ni, T, r, dis) if r > 0 else None
+    return r, nm, ni, sc, plan
+
+
+def check_plan_exact(plan, oplan):
+    np.testing.assert_array_equal(plan.node_idx.cpu().numpy(), oplan.node_idx)
+    np.testing.assert_array_equal(plan.node_max.cpu().numpy(), oplan.node_max)
+    np.testing.assert_array_equal(plan.edge_idx.cpu().numpy(), oplan.edge_idx)
+    np.testing.assert_array_equal(plan.dst_idx.cpu().numpy(), oplan.dst_idx)
+    np.testing.assert_array_equal(plan.row_map.cpu().numpy(), O.row_map(oplan))
+
+
+TC = np.load(os.path.join(GOLD, "token_compression.npz"))
+
+
+@pytest.mark.parametrize("name", [str(n) for n in TC["names"]])
+def test_matching_and_merge_golden(ops, name):
+    """GPU matching + merge on the inputs of the reference-generated goldens.  Indices are compared with the oracle
+    run on the GPU's own fp32 scores (bit-exact), the scores with the golden-producing arithmetic (1e-5), and, when
+    the GPU indices equal the golden ones, merged rows / sizes with the reference's outputs bit for bit."""
+    B, T, Dm, C, r, cls, dis = [int(v) for v in TC[f"{name}/cfg"]]
+    metric, x = TC[f"{name}/metric"], TC[f"{name}/x"]
+    rc, nm, ni, sc, plan = gpu_match(ops, dev(metric), r, bool(cls), bool(dis))
+    assert rc == O.clamp_r(T, r, cls, dis)
+    ref_scores = O.similarity_scores(metric, cls, dis)
+    got = sc.cpu().numpy()
+    fin = np.isfinite(ref_scores)
+    np.testing.assert_array_equal(np.isfinite(got), fin)
+    np.testing.assert_allclose(got[fin], ref_scores[fin], atol=1e-5, rtol=0)
+    oplan = O.plan_from_scores(got, T, rc, bool(dis))
+    check_plan_exact(plan, oplan)
+    # merge (fp32): bit-exact against the oracle on the same indices
+    x1, s1, _, _ = ops.merge_fwd(plan, dev(x), None, 1)
+    ox1, os1 = O.merge_wavg(oplan, x)
+    np.testing.assert_array_equal(x1.cpu().numpy(), ox1)
+    np.testing.assert_array_equal(s1.cpu().numpy(), os1[..., 0])
+    xs, _, _, _ = ops.merge_fwd(plan, dev(x), None, 0)
+    np.testing.assert_array_equal(xs.cpu().numpy(), O.merge(oplan, x, "sum"))
+    same_idx = np.array_equal(oplan.src_idx, TC[f"{name}/src_idx"]) and np.array_equal(oplan.dst_idx, TC[f"{name}/dst_idx"])
+    if name not in ("ties",):  # exact ties can legitimately resolve differently when scores differ in the last ulp
+        assert same_idx, "GPU scores led to different merge indices than the reference run"
+    if same_idx:
+        np.testing.assert_array_equal(x1.cpu().numpy(), TC[f"{name}/x1"])
+        np.testing.assert_array_equal(s1.cpu().numpy(), TC[f"{name}/s1"][..., 0])
+        np.testing.assert_array_equal(xs.cpu().numpy(), TC[f"{name}/xsum"])
+    # second round with non-trivial sizes
+    metric2 = TC[f"{name}/metric2"]
+    T1 = T - rc
+    rc2, _, _, sc2, plan2 = gpu_match(ops, dev(metric2), r, bool(cls), bool(dis))
+    oplan2 = O.plan_from_scores(sc2.cpu().numpy(), T1, rc2, bool(dis))
+    check_plan_exact(plan2, oplan2)
+    x2, s2, _, _ = ops.merge_fwd(plan2, x1, s1, 1)
+    ox2, os2 = O.merge_wavg(oplan2, ox1, os1)
+    np.testing.assert_array_equal(x2.cpu().numpy(), ox2)
+    np.testing.assert_array_equal(s2.cpu().numpy(), os2[..., 0])
+    assert np.all(s2.sum(dim=1).cpu().numpy() == T)
+    # unmerge == gather through row_map; merge backward == size-weighted gather
+    um = ops.merge_bwd(plan2, x2, None, None, 0)
+    np.testing.assert_array_equal(um.cpu().numpy(), O.unmerge(oplan2, ox2))
+
+
+@pytest.mark.parametrize("T,r,H,D,C", [(536, 16, 6, 64, 384), (75, 10, 2, 32, 64), (1024, 256, 12, 64, 768)])
+def test_matching_from_packed_keys_and_bf16_merge(ops, T, r, H, D, C):
+    """metric = keys averaged over heads, read in place from a packed bf16 qkv buffer (the block's call site);
+    bf16 merge vs oracle on the bf16-rounded inputs (fp32 arithmetic, one final rounding): bit-exact."""
+    rng = np.random.default_rng(7)
+    B = 3
+    qkv = torch.tensor(rng.standard_normal((B, T, 3, H, D)).astype(np.float32)).cuda().bfloat16()
+    nm, ni, sc = ops.sim_argmax(qkv, heads=H, dim=D, batch=B, tokens=T, batch_stride=T * 3 * H * D,
+                                token_stride=3 * H * D, head_stride=D, dump_scores=True, offset_elems=H * D)
+    kmean = qkv[:, :, 1].float().mean(dim=2).cpu().numpy()
+    np.testing.assert_allclose(sc.cpu().numpy(), O.similarity_scores(kmean), atol=2e-5, rtol=0)
+    plan = ops.select_topr(nm, ni, T, r)
+    oplan = O.plan_from_scores(sc.cpu().numpy(), T, r)
+    check_plan_exact(plan, oplan)
+    x = torch.tensor(rng.standard_normal((B, T, C)).astype(np.float32)).cuda().bfloat16()
+    size = torch.tensor(rng.integers(1, 5, size=(B, T)).astype(np.float32)).cuda()
+    gid = torch.tensor(rng.integers(0, 5, size=(B, T)).astype(np.uint8)).cuda()
+    pos = torch.tensor(rng.integers(0, 99, size=(B, T)).astype(np.int32)).cuda()
+    x1, s1, g1, p1 = ops.merge_fwd(plan, x, size, 1, gid, pos)
+    ox1, os1 = O.merge_wavg(oplan, x.float().cpu().numpy(), size.cpu().numpy()[..., None])
+    np.testing.assert_array_equal(x1.float().cpu().numpy(), torch.tensor(ox1).bfloat16().float().numpy())
+    np.testing.assert_array_equal(s1.cpu().numpy(), os1[..., 0])
+    # group / position carried: a row keeps the metadata of its unmerged or destination token
+    rm = O.row_map(oplan)
+    keep = np.ones((B, T), bool)
+    rank = np.empty((B, (T + 1) // 2), np.int32)
+    np.put_along_axis(rank, oplan.edge_idx, np.broadcast_to(np.arange((T + 1) // 2, dtype=np.int32), rank.shape), axis=1)
+    keep[:, ::2] = rank >= r
+    bi, ti = np.nonzero(keep)
+    g_ref = np.zeros((B, T - r), np.uint8)
+    p_ref = np.zeros((B, T - r), np.int32)
+    g_ref[bi, rm[bi, ti]] = gid.cpu().numpy()[bi, ti]
+    p_ref[bi, rm[bi, ti]] = pos.cpu().numpy()[bi, ti]
+    np.testing.assert_array_equal(g1.cpu().numpy(), g_ref)
+    np.testing.assert_array_equal(p1.cpu().numpy(), p_ref)
+    # backward: dx = size_t / size'_row * dy[row]
+    dy = torch.tensor(rng.standard_normal((B, T - r, C)).astype(np.float32)).cuda()
+    dx = ops.merge_bwd(plan, dy, size, s1, 1)
+    w = size.cpu().numpy() / np.take_along_axis(s1.cpu().numpy(), rm, axis=1)
+    ref = np.take_along_axis(dy.cpu().numpy(), rm[..., None], axis=1) * w[..., None]
+    np.testing.assert_array_equal(dx.cpu().numpy(), ref.astype(np.float32))
+
+
+def test_matching_edge_cases(ops):
+    """NaN rows (zero metric rows: no epsilon in the reference normalisation), all-equal scores, r = T//2."""
+    T, Dm = 12, 4
+    metric = np.ones((2, T, Dm), np.float32)
+    metric[1, 4] = 0.0  # zero row -> NaN scores for that even token
+    rc, nm, ni, sc, plan = gpu_match(ops, dev(metric), T // 2)
+    oplan = O.plan_from_scores(sc.cpu().numpy(), T, rc)
+    got_nan = np.isnan(sc.cpu().numpy())
+    np.testing.assert_array_equal(got_nan, np.isnan(O.similarity_scores(metric)))
+    np.testing.assert_array_equal(plan.node_idx.cpu().numpy(), oplan.node_idx)
+    np.testing.assert_array_equal(plan.edge_idx.cpu().numpy(), oplan.edge_idx)
+    np.testing.assert_array_equal(plan.dst_idx.cpu().numpy(), oplan.dst_idx)
+
+
+# ------------------------------------------------------------------------------------------------ dense
+@pytest.mark.parametrize("m,n,k", [(256, 128, 64), (1000, 384, 384), (130, 1152, 384), (4096, 1536, 384), (384, 1536, 2000)])
+@pytest.mark.parametrize("a_mn,b_mn", [(False, True), (False, False), (True, True)])
+def test_gemm_tcgen05(ops, m, n, k, a_mn, b_mn):
+    """bf16 x bf16 -> fp32 accumulate.  Tolerance: |err| <= 2e-2 * sqrt(k)/16 absolute on N(0,1) operands (bf16 output
+    rounding 2^-8 relative + accumulation order)."""
+    if a_mn and m % 8:
+        pytest.skip("MN-major A needs m % 8 == 0")
+    rng = np.random.default_rng(m + n + k)
+    A = torch.tensor(rng.standard_normal((m, k)).astype(np.float32)).cuda().bfloat16()
+    Bm = torch.tensor(rng.standard_normal((n, k)).astype(np.float32)).cuda().bfloat16()
+    a_t = A.t().contiguous() if a_mn else A
+    b_t = Bm.t().contiguous() if b_mn else Bm
+    ref = A.float() @ Bm.float().t()
+    out = ops.gemm(a_t, b_t, m=m, n=n, k=k, a_major=int(a_mn), b_major=int(b_mn), out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    err = (out - ref).abs().max().item()
+    assert err <= 1e-3 * math.sqrt(k), f"fp32-out gemm err {err}"
+    out16 = ops.gemm(a_t, b_t, m=m, n=n, k=k, a_major=int(a_mn), b_major=int(b_mn))
+    rel = ((out16.float() - ref).abs() / (ref.abs() + math.sqrt(k))).max().item()
+    assert rel <= 1e-2, f"bf16-out gemm rel err {rel}"
+
+
+def test_gemm_epilogues_and_splitk(ops):
+    rng = np.random.default_rng(3)
+    m, n, k = 700, 384, 192
+    A = torch.tensor(rng.standard_normal((m, k)).astype(np.float32)).cuda().bfloat16()
+    W = torch.tensor(rng.standard_normal((k, n)).astype(np.float32) * 0.1).cuda().bfloat16()  # flax [in, out]
+    bias = torch.tensor(rng.standard_normal(n).astype(np.float32)).cuda()
+    res = torch.tensor(rng.standard_normal((m, n)).astype(np.float32)).cuda().bfloat16()
+    gate = torch.tensor(rng.standard_normal((m, n)).astype(np.float32)).cuda().bfloat16()
+    base = A.float() @ W.float()
+    out = ops.gemm(A, W, m=m, n=n, k=k, b_major=1, bias=bias, relu=True, residual=res)
+    ref = torch.relu(base + bias) + res.float()
+    assert ((out.float() - ref).abs() / (ref.abs() + 1)).max().item() <= 1e-2
+    out = ops.gemm(A, W, m=m, n=n, k=k, b_major=1, gate=gate, gate_scale=0.5)
+    ref = base * (gate.float() > 0) * 0.5
+    assert ((out.float() - ref).abs() / (ref.abs() + 1)).max().item() <= 1e-2
+    # wgrad shape: dW[k, n] = A^T[k, m] * G[m, n], both operands MN-major, split-K, accumulate into fp32
+    G = res
+    dW = torch.ones(k, n, dtype=torch.float32, device="cuda")
+    ops.gemm(A, G, m=k, n=n, k=m, a_major=1, b_major=1, out=dW, k_splits=3, accumulate=True)
+    ref = 1.0 + A.float().t() @ G.float()
+    assert (dW - ref).abs().max().item() <= 2e-3 * math.sqrt(m)
+    dW2 = ops.gemm(A, G, m=k, n=n, k=m, a_major=1, b_major=1, out_dtype=torch.float32, k_splits=0)
+    assert (dW2 - (ref - 1.0)).abs().max().item() <= 2e-3 * math.sqrt(m)
+    # dropout: kept fraction and scaling; identical mask for identical (seed, site)
+    o1 = ops.gemm(A, W, m=m, n=n, k=k, b_major=1, dropout_rate=0.25, dropout_seed=11, dropout_site=2)
+    o2 = ops.gemm(A, W, m=m, n=n, k=k, b_major=1, dropout_rate=0.25, dropout_seed=11, dropout_site=2)
+    assert torch.equal(o1, o2)
+    kept = (o1 != 0).float().mean().item()
+    assert abs(kept - 0.75) < 0.01
+    sel = o1 != 0
+    assert ((o1.float()[sel] * 0.75 - base[sel]).abs() / (base[sel].abs() + 1)).max().item() <= 2e-2
+    # bias gradient: column sums
+    cs = ops.colsum(res)
+    assert (cs - res.float().sum(0)).abs().max().item() <= 1e-2
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm
+@pytest.mark.parametrize("axis", [1, 2])
+@pytest.mark.parametrize("B,T,C", [(3, 74, 768), (4, 536, 384), (2, 33, 40)])
+def test_layernorm_fwd_bwd(ops, axis, B, T, C):
+    """vs oracle.layer_norm (flax LayerNorm as configured; axis 1 = tokens) + autograd.  bf16 I/O: 2e-2 abs."""
+    rng = np.random.default_rng(B * T + C)
+    x = torch.tensor((rng.standard_normal((B, T, C)) * 2 + 0.5).astype(np.float32)).cuda().bfloat16()
+    g = torch.tensor((1 + 0.1 * rng.standard_normal(C)).astype(np.float32)).cuda()
+    bta = torch.tensor((0.1 * rng.standard_normal(C)).astype(np.float32)).cuda()
+    y, mean, rstd = ops.layernorm_fwd(x, g, bta, 1e-6, axis)
+    xr = x.float().cpu().requires_grad_(True)
+    gr = g.cpu().requires_grad_(True)
+    br = bta.cpu().requires_grad_(True)
+    yr = O.layer_norm(xr, gr, br, 1e-6, "seq" if axis == 1 else "feature")
+    assert (y.float().cpu() - yr).abs().max().item() <= 3e-2
+    dy = torch.tensor(rng.standard_normal((B, T, C)).astype(np.float32)).cuda().bfloat16()
+    dres = torch.tensor(rng.standard_normal((B, T, C)).astype(np.float32)).cuda().bfloat16()
+    yr.backward(dy.float().cpu())
+    dgamma = torch.zeros(C, device="cuda")
+    dbeta = torch.zeros(C, device="cuda")
+    dx = ops.layernorm_bwd(x, dy, g, mean, rstd, dgamma, dbeta, dres, axis)
+    ref_dx = xr.grad + dres.float().cpu()
+    assert (dx.float().cpu() - ref_dx).abs().max().item() <= 3e-2 * max(1.0, ref_dx.abs().max().item() / 4)
+    scale = math.sqrt(B * T)
+    assert (dgamma.cpu() - gr.grad).abs().max().item() <= 3e-2 * scale
+    assert (dbeta.cpu() - br.grad).abs().max().item() <= 3e-2 * scale
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def _attn_ref(q, k, v, gid, pos, allow, size):
+    mask = None if gid is None else torch.as_tensor(O.dense_mask(gid, pos, gid, pos, allow))[:, None]
+    bias = None if size is None else torch.log(torch.as_tensor(size))[:, None, None, :]
+    return O.attention(q, k, v, mask=mask, bias=bias)
+
+
+@pytest.mark.parametrize("T,H,masked,sized", [(74, 3, True, True), (536, 6, True, True), (128, 2, False, False),
+                                              (300, 4, True, False), (1000, 2, False, True)])
+def test_attention_fwd(ops, T, H, masked, sized):
+    """tcgen05 flash attention with group-table mask and log(size) bias vs oracle.attention (flax semantics) in fp32
+    on the same bf16-rounded inputs.  Tolerance 2e-2 abs on outputs of O(1) (bf16 P and bf16 output rounding)."""
+    rng = np.random.default_rng(T + H)
+    B, D = 2, 64
+    qkv = torch.tensor(rng.standard_normal((B, T, 3, H, D)).astype(np.float32)).cuda().bfloat16()
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    gid = pos = allow = size = None
+    if masked:
+        n_img = (T - 16) // 2 - 4
+        seq = f"[TaskDescriptionPrefix{{16}}] [Image{{{n_img}}};Readout{{4}}]*2"
+        g1, p1, allow, _ = O.sequence_groups(seq)
+        pad = T - g1.shape[0]
+        g1 = np.concatenate([g1, np.full(pad, g1[-1], np.uint8)])
+        p1 = np.concatenate([p1, np.arange(pad, dtype=np.int32)])
+        gid = np.stack([g1, rng.permutation(g1)])  # batch row 1: scrambled order, as after a merge
+        pos = np.stack([p1, rng.integers(0, 50, size=T).astype(np.int32)])
+    if sized:
+        size = rng.integers(1, 6, size=(B, T)).astype(np.float32)
+    out, lse = ops.attention_fwd(q, k, v, gid=None if gid is None else dev(gid), pos=None if pos is None else dev(pos),
+                                 allow=None if allow is None else dev(allow), size=None if size is None else dev(size))
+    torch.cuda.synchronize()
+    ref = _attn_ref(q.float().cpu(), k.float().cpu(), v.float().cpu(), gid, pos, allow, size)
+    err = (out.float().cpu() - ref).abs().max().item()
+    assert err <= 2e-2, f"attention fwd err {err}"
+    # lse against a direct computation
+    logits = torch.einsum("bqhd,bkhd->bhqk", q.float().cpu() / 8.0, k.float().cpu())
+    if size is not None:
+        logits = logits + torch.log(torch.as_tensor(size))[:, None, None, :]
+    if gid is not None:
+        m = torch.as_tensor(O.dense_mask(gid, pos, gid, pos, allow))[:, None]
+        logits = torch.where(m, logits, torch.full_like(logits, -1e30))
+    assert (lse.cpu() - torch.logsumexp(logits, -1)).abs().max().item() <= 2e-2
