@@ -186,8 +186,8 @@ typedef struct {
 int tome_attention_fwd(const tome_attn_desc_t* desc, const void* q, const void* k, const void* v, void* out,
                        float* lse, void* stream);
 
-/* dq,dk,dv share the layout of q,k,v (their own strides given in dqkv_*); delta f32 [B,H,T] workspace;
- * dq_accum f32 [B,T,H*D] workspace (zeroed by the call). */
+/* dq,dk,dv share the layout of q,k,v (their own strides below); delta f32 [B,H,T] workspace;
+ * scratch: at least 8*B*T bytes (per-token mask words); gradients are produced without atomics or fp32 staging. */
 typedef struct {
   long long dq_batch_stride, dq_token_stride;
   long long dk_batch_stride, dk_token_stride;
@@ -196,7 +196,7 @@ typedef struct {
 } tome_attn_grad_strides_t;
 int tome_attention_bwd(const tome_attn_desc_t* desc, const tome_attn_grad_strides_t* gs, const void* q, const void* k,
                        const void* v, const void* out, const float* lse, const void* dout, void* dq, void* dk,
-                       void* dv, float* delta, float* dq_accum, void* stream);
+                       void* dv, float* delta, float* scratch, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * 6. Small fused steps around the block

@@ -320,7 +320,8 @@ using namespace tome;
 
 static int pick_splits(const tome_gemm_args_t* a, int bn) {
   if (a->k_splits > 0) return a->k_splits;
-  if (a->c_dtype != TOME_F32) return 1;  // split-K only for fp32 outputs (weight gradients)
+  if (a->c_dtype != TOME_F32 || a->ldc != a->n) return 1;  // split-K only for dense fp32 outputs (weight gradients)
+  if (a->bias || a->residual || a->gate || a->relu || a->dropout_rate > 0.f) return 1;
   const int tiles = ceil_div(a->m, GEMM_BM) * ceil_div(a->n, bn);
   const int kb = ceil_div(a->k, GEMM_BK);
   int s = kNumSMs / (tiles > 0 ? tiles : 1);
@@ -374,6 +375,7 @@ extern "C" int tome_gemm_bf16(const tome_gemm_args_t* a, void* workspace, size_t
   TOME_CHECK(!a->accumulate || e.c_is_f32, TOME_ERR_INVALID, "gemm: accumulate requires an fp32 output");
   if (s.k_splits > 1) {
     TOME_CHECK(e.c_is_f32, TOME_ERR_INVALID, "gemm: split-K requires an fp32 output");
+    TOME_CHECK(a->ldc == a->n, TOME_ERR_INVALID, "gemm: split-K requires a dense output (ldc == n)");
     TOME_CHECK(!a->bias && !a->residual && !a->gate && !a->relu && e.drop.thresh16 == 0, TOME_ERR_INVALID,
                "gemm: split-K supports a plain epilogue only");
     const size_t need = (size_t)s.k_splits * (size_t)a->m * (size_t)a->ldc * sizeof(float);

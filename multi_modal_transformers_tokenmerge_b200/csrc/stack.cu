@@ -1,0 +1,488 @@
+// The whole stack as one native executor: StackedEncoder1DBlock of ToMeEncoder1DBlock, unrolled because the token
+// count shrinks by r per layer (an nn.scan carry cannot do that: SURVEY.md 3.3).
+//
+//   x = x + pos_embedding                                                       attention.py:97-100
+//   per layer:  h   = LN1(x)                                                    attention.py:58
+//               qkv = h Wqkv + b ; o = attention(q, k, v, group mask, log size) tome_attention.py:145-164, 259-285
+//               x1  = x + dropout(o Wo + bo)                                    :287-299, attention.py:60-63
+//               metric = mean_heads(k) -> match -> x1m, size = merge_wavg(x1)   tome_attention.py:249-256 (intent),
+//                                                                               token_compression.py:54-129
+//               y   = x1m + dropout(W2 dropout(relu(W1 LN2(x1m) + b1)) + b2)    attention.py:66-69, :32-37
+//   readout rows gathered through the chained row maps, synthetic MSE loss      octo.py:123-124, 167-174
+//
+// Host code only: it sequences the kernels of this library on one stream and owns the layout of the activation
+// workspace (everything saved for backward lives there; the library allocates nothing).  Every launch has static
+// shapes, so a whole step can be captured in a CUDA graph by the caller.
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "host_util.h"
+
+namespace tome {
+
+struct LayerShape {
+  int t_in, r, t_out;
+};
+
+struct LayerBufs {
+  // saved for backward
+  __nv_bfloat16 *x_in, *h, *qkv, *attn_o, *x1m, *h2, *m1, *x_out;
+  float *ln1_mean, *ln1_rstd, *ln2_mean, *ln2_rstd, *lse;
+  float *size_in, *size_out;  // size_in == nullptr at layer 0 (all ones)
+  uint8_t *gid_in, *gid_out;
+  int32_t *pos_in, *pos_out;
+  float* node_max;
+  int32_t* node_idx;
+  tome_plan_t plan;
+};
+
+struct StackLayout {
+  std::vector<LayerShape> shapes;
+  std::vector<LayerBufs> L;
+  __nv_bfloat16 *x1_scratch, *g0, *g1, *g2, *g3, *big;
+  float *delta, *attn_scratch, *ws_gemm, *ws_colsum, *ws_ln;
+  int32_t* origin;
+  size_t ws_gemm_bytes;
+  size_t total;
+};
+
+struct ParamOffsets {
+  long long ln1_scale, ln1_bias, wqkv, bqkv, wo, bo, ln2_scale, ln2_bias, w1, b1, w2, b2, end;
+};
+
+static ParamOffsets layer_offsets(const tome_stack_cfg_t* c, int layer) {
+  const long long C = c->channels, HD = (long long)c->heads * c->head_dim, F = c->mlp_dim;
+  const long long per = C + C + C * 3 * HD + 3 * HD + HD * C + C + C + C + C * F + F + F * C + C;
+  ParamOffsets o;
+  long long p = (long long)c->tokens * C + per * layer;
+  o.ln1_scale = p; p += C;
+  o.ln1_bias = p; p += C;
+  o.wqkv = p; p += C * 3 * HD;
+  o.bqkv = p; p += 3 * HD;
+  o.wo = p; p += HD * C;
+  o.bo = p; p += C;
+  o.ln2_scale = p; p += C;
+  o.ln2_bias = p; p += C;
+  o.w1 = p; p += C * F;
+  o.b1 = p; p += F;
+  o.w2 = p; p += F * C;
+  o.b2 = p; p += C;
+  o.end = p;
+  return o;
+}
+
+static int check_cfg(const tome_stack_cfg_t* c) {
+  TOME_CHECK(c != nullptr, TOME_ERR_INVALID, "stack: null config");
+  TOME_CHECK(c->batch > 0 && c->tokens >= 2 && c->layers >= 1 && c->layers <= 64, TOME_ERR_INVALID,
+             "stack: need batch > 0, tokens >= 2, 1 <= layers <= 64");
+  TOME_CHECK(c->channels % 8 == 0 && c->mlp_dim % 8 == 0 && c->channels > 0 && c->mlp_dim > 0, TOME_ERR_INVALID,
+             "stack: channels and mlp_dim must be positive multiples of 8");
+  TOME_CHECK(c->head_dim == 64, TOME_ERR_UNSUPPORTED, "stack: head_dim %d not supported (this build: 64)", c->head_dim);
+  TOME_CHECK(c->heads > 0, TOME_ERR_INVALID, "stack: heads must be positive");
+  TOME_CHECK(c->ln_axis == 1 || c->ln_axis == 2, TOME_ERR_INVALID, "stack: ln_axis must be 1 (tokens) or 2 (features)");
+  TOME_CHECK(c->r >= 0, TOME_ERR_INVALID, "stack: r must be >= 0");
+  TOME_CHECK(c->num_groups >= 0 && c->num_groups <= 32, TOME_ERR_INVALID, "stack: num_groups must be in [0, 32]");
+  TOME_CHECK(c->dropout_rate >= 0.f && c->dropout_rate < 1.f, TOME_ERR_INVALID, "stack: dropout_rate must be in [0, 1)");
+  TOME_CHECK(c->n_readout >= 0, TOME_ERR_INVALID, "stack: n_readout must be >= 0");
+  return TOME_OK;
+}
+
+static std::vector<LayerShape> layer_shapes(const tome_stack_cfg_t* c) {
+  std::vector<LayerShape> s(c->layers);
+  int t = c->tokens;
+  for (int l = 0; l < c->layers; ++l) {
+    s[l].t_in = t;
+    s[l].r = tome_clamp_r(t, c->r, c->class_token, c->distill_token);
+    s[l].t_out = t - s[l].r;
+    t = s[l].t_out;
+  }
+  return s;
+}
+
+struct Bump {
+  uint8_t* base;
+  size_t off = 0;
+  template <typename T>
+  T* take(size_t count) {
+    off = (off + 255) & ~size_t(255);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * sizeof(T);
+    return p;
+  }
+};
+
+// One function computes the layout for both the size query (base == nullptr) and the real pointers.
+static StackLayout make_layout(const tome_stack_cfg_t* c, void* workspace) {
+  StackLayout S;
+  S.shapes = layer_shapes(c);
+  S.L.resize(c->layers);
+  Bump b{reinterpret_cast<uint8_t*>(workspace)};
+  const size_t B = c->batch, C = c->channels, HD = (size_t)c->heads * c->head_dim, F = c->mlp_dim, T0 = c->tokens;
+  const size_t wide = 3 * HD > F ? 3 * HD : F;
+  __nv_bfloat16* x_prev = b.take<__nv_bfloat16>(B * T0 * C);  // x0 = x + pos_embedding
+  float* size_prev = nullptr;
+  uint8_t* gid_prev = c->num_groups ? b.take<uint8_t>(B * T0) : nullptr;
+  int32_t* pos_prev = c->num_groups ? b.take<int32_t>(B * T0) : nullptr;
+  for (int l = 0; l < c->layers; ++l) {
+    LayerBufs& Lb = S.L[l];
+    const size_t T = S.shapes[l].t_in, To = S.shapes[l].t_out, r = S.shapes[l].r;
+    const size_t ta = (T + 1) / 2, tb = T / 2;
+    const size_t st_in = c->ln_axis == 1 ? B * C : B * T, st_out = c->ln_axis == 1 ? B * C : B * To;
+    Lb.x_in = x_prev;
+    Lb.size_in = size_prev;
+    Lb.gid_in = gid_prev;
+    Lb.pos_in = pos_prev;
+    Lb.ln1_mean = b.take<float>(st_in);
+    Lb.ln1_rstd = b.take<float>(st_in);
+    Lb.h = b.take<__nv_bfloat16>(B * T * C);
+    Lb.qkv = b.take<__nv_bfloat16>(B * T * 3 * HD);
+    Lb.attn_o = b.take<__nv_bfloat16>(B * T * HD);
+    Lb.lse = b.take<float>(B * c->heads * T);
+    Lb.x1m = b.take<__nv_bfloat16>(B * To * C);
+    memset(&Lb.plan, 0, sizeof(Lb.plan));
+    Lb.node_max = nullptr;
+    Lb.node_idx = nullptr;
+    if (r > 0) {
+      Lb.node_max = b.take<float>(B * ta);
+      Lb.node_idx = b.take<int32_t>(B * ta);
+      Lb.plan.edge_idx = b.take<int32_t>(B * ta);
+      Lb.plan.dst_idx = b.take<int32_t>(B * r);
+      Lb.plan.row_map = b.take<int32_t>(B * T);
+      Lb.plan.dst_off = b.take<int32_t>(B * (tb + 1));
+      Lb.plan.dst_src = b.take<int32_t>(B * r);
+      Lb.size_out = b.take<float>(B * To);
+      Lb.gid_out = c->num_groups ? b.take<uint8_t>(B * To) : nullptr;
+      Lb.pos_out = c->num_groups ? b.take<int32_t>(B * To) : nullptr;
+    } else {
+      Lb.size_out = Lb.size_in;
+      Lb.gid_out = Lb.gid_in;
+      Lb.pos_out = Lb.pos_in;
+    }
+    Lb.ln2_mean = b.take<float>(st_out);
+    Lb.ln2_rstd = b.take<float>(st_out);
+    Lb.h2 = b.take<__nv_bfloat16>(B * To * C);
+    Lb.m1 = b.take<__nv_bfloat16>(B * To * F);
+    Lb.x_out = b.take<__nv_bfloat16>(B * To * C);
+    x_prev = Lb.x_out;
+    size_prev = Lb.size_out;
+    gid_prev = Lb.gid_out;
+    pos_prev = Lb.pos_out;
+  }
+  S.x1_scratch = b.take<__nv_bfloat16>(B * T0 * C);
+  S.g0 = b.take<__nv_bfloat16>(B * T0 * C);
+  S.g1 = b.take<__nv_bfloat16>(B * T0 * C);
+  S.g2 = b.take<__nv_bfloat16>(B * T0 * C);
+  S.g3 = b.take<__nv_bfloat16>(B * T0 * HD);
+  S.big = b.take<__nv_bfloat16>(B * T0 * wide);
+  S.delta = b.take<float>(B * c->heads * T0);
+  S.attn_scratch = b.take<float>(B * T0 * 2);
+  // split-K workspace: the largest weight gradient, at most 64 splits are ever chosen but 148 tiles bound the product
+  size_t wmax = C * 3 * HD;
+  if (C * F > wmax) wmax = C * F;
+  if (HD * C > wmax) wmax = HD * C;
+  S.ws_gemm_bytes = wmax * sizeof(float) * 64;
+  S.ws_gemm = b.take<float>(wmax * 64);
+  S.ws_colsum = b.take<float>(256 * wide);
+  const size_t ln_rows = c->ln_axis == 1 ? B : 256;
+  S.ws_ln = b.take<float>(2 * ln_rows * C);
+  S.origin = b.take<int32_t>(B * (c->n_readout > 0 ? c->n_readout : 1));
+  S.total = (b.off + 255) & ~size_t(255);
+  return S;
+}
+
+__global__ void broadcast_groups_kernel(int B, int T, const uint8_t* __restrict__ gid, const int32_t* __restrict__ pos,
+                                        uint8_t* __restrict__ gid_out, int32_t* __restrict__ pos_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * T) {
+    gid_out[i] = gid[i % T];
+    pos_out[i] = pos[i % T];
+  }
+}
+
+// dy_eff = dy * keep / (1 - rate), same Philox stream as the GEMM epilogue (element index = row * n + col)
+__global__ void dropout_apply_kernel(long long n8, const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                     DropoutCfg d) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 v = ld_nc_v4(reinterpret_cast<const uint4*>(x) + i);
+    const uint32_t keep = dropout_keep8(d, (uint64_t)i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float lo = ((keep >> (2 * j)) & 1u) ? bf16_lo(w[j]) * d.inv_keep : 0.f;
+      const float hi = ((keep >> (2 * j + 1)) & 1u) ? bf16_hi(w[j]) * d.inv_keep : 0.f;
+      o[j] = pack_bf16(lo, hi);
+    }
+    reinterpret_cast<uint4*>(y)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+static DropoutCfg make_drop(const tome_stack_cfg_t* c, uint32_t site) {
+  DropoutCfg d;
+  d.thresh16 = (uint32_t)(c->dropout_rate * 65536.0f + 0.5f);
+  d.inv_keep = 1.0f / (1.0f - (float)d.thresh16 / 65536.0f);
+  d.seed_lo = (uint32_t)c->dropout_seed;
+  d.seed_hi = (uint32_t)(c->dropout_seed >> 32);
+  d.site = site;
+  return d;
+}
+
+#define RC(expr)                 \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != TOME_OK) return _rc; \
+  } while (0)
+
+static int gemm(const tome_stack_cfg_t* c, const StackLayout& S, cudaStream_t st, int m, int n, int k, const void* a,
+                long long lda, int a_major, const void* b, long long ldb, int b_major, void* out, long long ldc, int c_dtype,
+                const float* bias, int relu, const void* residual, const void* gate, float gate_scale, int drop_site,
+                int accumulate) {
+  tome_gemm_args_t g;
+  memset(&g, 0, sizeof(g));
+  g.m = m; g.n = n; g.k = k;
+  g.a = a; g.lda = lda; g.a_major = a_major;
+  g.b = b; g.ldb = ldb; g.b_major = b_major;
+  g.c = out; g.ldc = ldc; g.c_dtype = c_dtype;
+  g.bias = bias; g.relu = relu;
+  g.residual = residual; g.ldr = n;
+  g.gate = gate; g.ldg = n; g.gate_scale = gate_scale;
+  if (drop_site >= 0 && c->dropout_rate > 0.f) {
+    g.dropout_rate = c->dropout_rate;
+    g.dropout_seed = c->dropout_seed;
+    g.dropout_site = (uint32_t)drop_site;
+  }
+  g.k_splits = 0;
+  g.accumulate = accumulate;
+  return tome_gemm_bf16(&g, S.ws_gemm, S.ws_gemm_bytes, st);
+}
+
+}  // namespace tome
+
+using namespace tome;
+
+extern "C" long long tome_stack_param_count(const tome_stack_cfg_t* c) {
+  if (check_cfg(c)) return -1;
+  return layer_offsets(c, c->layers).ln1_scale;
+}
+extern "C" long long tome_stack_layer_offset(const tome_stack_cfg_t* c, int layer) {
+  if (check_cfg(c) || layer < 0 || layer > c->layers) return -1;
+  return layer_offsets(c, layer).ln1_scale;
+}
+extern "C" size_t tome_stack_workspace_bytes(const tome_stack_cfg_t* c) {
+  if (check_cfg(c)) return 0;
+  return make_layout(c, nullptr).total;
+}
+extern "C" int tome_stack_tokens_at(const tome_stack_cfg_t* c, int layer) {
+  if (check_cfg(c) || layer < 0 || layer > c->layers) return -1;
+  auto s = layer_shapes(c);
+  return layer == c->layers ? s.back().t_out : s[layer].t_in;
+}
+
+static int check_io(const tome_stack_cfg_t* c, const tome_stack_io_t* io, const StackLayout& S, bool backward) {
+  TOME_CHECK(io != nullptr, TOME_ERR_INVALID, "stack: null io");
+  TOME_CHECK(io->params_f32 && io->params_bf16 && io->x && io->workspace, TOME_ERR_INVALID, "stack: null params / x / workspace");
+  TOME_CHECK(io->workspace_bytes >= S.total, TOME_ERR_INVALID, "stack: workspace too small (%zu < %zu)", io->workspace_bytes, S.total);
+  TOME_CHECK(((uintptr_t)io->workspace & 255) == 0, TOME_ERR_INVALID, "stack: workspace must be 256-byte aligned");
+  TOME_CHECK(c->num_groups == 0 || (io->gid && io->pos && io->allow), TOME_ERR_INVALID, "stack: a group mask needs gid, pos and allow");
+  TOME_CHECK(c->n_readout == 0 || io->readout_idx, TOME_ERR_INVALID, "stack: readout_idx missing");
+  if (backward) TOME_CHECK(io->grads_f32 && io->target && io->loss && c->n_readout > 0, TOME_ERR_INVALID,
+                           "stack_backward: needs grads_f32, target, loss and n_readout > 0");
+  return TOME_OK;
+}
+
+extern "C" int tome_stack_forward(const tome_stack_cfg_t* c, const tome_stack_io_t* io, void* stream_) {
+  clear_error();
+  cudaStream_t st = (cudaStream_t)stream_;
+  RC(check_cfg(c));
+  StackLayout S = make_layout(c, io ? io->workspace : nullptr);
+  RC(check_io(c, io, S, false));
+  const int B = c->batch, C = c->channels, H = c->heads, D = c->head_dim, HD = H * D, F = c->mlp_dim;
+  const float* pf = io->params_f32;
+  const __nv_bfloat16* pw = reinterpret_cast<const __nv_bfloat16*>(io->params_bf16);
+
+  RC(tome_add_pos_embedding(B, c->tokens, C, io->x, io->x_dtype, pf, S.L[0].x_in, st));
+  if (c->num_groups) {
+    const int n = B * c->tokens;
+    broadcast_groups_kernel<<<ceil_div(n, 256), 256, 0, st>>>(B, c->tokens, io->gid, io->pos, S.L[0].gid_in, S.L[0].pos_in);
+    TOME_CUDA(cudaGetLastError());
+  }
+  for (int l = 0; l < c->layers; ++l) {
+    const LayerBufs& Lb = S.L[l];
+    const ParamOffsets o = layer_offsets(c, l);
+    const int T = S.shapes[l].t_in, r = S.shapes[l].r, To = S.shapes[l].t_out;
+    const int M = B * T, Mo = B * To;
+    RC(tome_layernorm_fwd(B, T, C, c->ln_axis, c->ln_eps, Lb.x_in, pf + o.ln1_scale, pf + o.ln1_bias, Lb.h, Lb.ln1_mean,
+                          Lb.ln1_rstd, st));
+    RC(gemm(c, S, st, M, 3 * HD, C, Lb.h, C, TOME_MAJOR_K, pw + o.wqkv, 3 * HD, TOME_MAJOR_MN, Lb.qkv, 3 * HD, TOME_BF16,
+            pf + o.bqkv, 0, nullptr, nullptr, 1.f, -1, 0));
+    tome_attn_desc_t ad;
+    memset(&ad, 0, sizeof(ad));
+    ad.batch = B; ad.tokens = T; ad.heads = H; ad.head_dim = D;
+    ad.q_batch_stride = ad.k_batch_stride = ad.v_batch_stride = (long long)T * 3 * HD;
+    ad.q_token_stride = ad.k_token_stride = ad.v_token_stride = 3 * HD;
+    ad.o_batch_stride = (long long)T * HD; ad.o_token_stride = HD;
+    ad.scale = 1.0f / sqrtf((float)D);
+    if (c->num_groups) { ad.gid = Lb.gid_in; ad.pos = Lb.pos_in; ad.allow = io->allow; ad.num_groups = c->num_groups; }
+    ad.size = c->prop_attn ? Lb.size_in : nullptr;
+    RC(tome_attention_fwd(&ad, Lb.qkv, Lb.qkv + HD, Lb.qkv + 2 * HD, Lb.attn_o, Lb.lse, st));
+    __nv_bfloat16* x1 = r > 0 ? S.x1_scratch : Lb.x1m;
+    RC(gemm(c, S, st, M, C, HD, Lb.attn_o, HD, TOME_MAJOR_K, pw + o.wo, C, TOME_MAJOR_MN, x1, C, TOME_BF16, pf + o.bo, 0,
+            Lb.x_in, nullptr, 1.f, 3 * l + 0, 0));
+    if (r > 0) {
+      tome_metric_desc_t md;
+      md.batch = B; md.tokens = T; md.dim = D; md.heads = H; md.dtype = TOME_BF16;
+      md.batch_stride = (long long)T * 3 * HD; md.token_stride = 3 * HD; md.head_stride = D;
+      md.class_token = c->class_token; md.distill_token = c->distill_token;
+      RC(tome_sim_argmax(&md, Lb.qkv + HD, Lb.node_max, Lb.node_idx, nullptr, st));
+      tome_plan_shape_t ps{B, T, r, c->distill_token};
+      RC(tome_select_topr(&ps, Lb.node_max, Lb.node_idx, &Lb.plan, st));
+      tome_merge_shape_t ms{B, T, C, r, c->distill_token, TOME_BF16, TOME_MERGE_WAVG};
+      RC(tome_merge_fwd(&ms, &Lb.plan, x1, Lb.size_in, Lb.x1m, Lb.size_out, Lb.gid_in, Lb.pos_in, Lb.gid_out, Lb.pos_out, st));
+    }
+    RC(tome_layernorm_fwd(B, To, C, c->ln_axis, c->ln_eps, Lb.x1m, pf + o.ln2_scale, pf + o.ln2_bias, Lb.h2, Lb.ln2_mean,
+                          Lb.ln2_rstd, st));
+    RC(gemm(c, S, st, Mo, F, C, Lb.h2, C, TOME_MAJOR_K, pw + o.w1, F, TOME_MAJOR_MN, Lb.m1, F, TOME_BF16, pf + o.b1, 1, nullptr,
+            nullptr, 1.f, 3 * l + 1, 0));
+    RC(gemm(c, S, st, Mo, C, F, Lb.m1, F, TOME_MAJOR_K, pw + o.w2, C, TOME_MAJOR_MN, Lb.x_out, C, TOME_BF16, pf + o.b2, 0, Lb.x1m,
+            nullptr, 1.f, 3 * l + 2, 0));
+  }
+  const int TL = S.shapes.back().t_out;
+  if (io->x_final)
+    TOME_CUDA(cudaMemcpyAsync(io->x_final, S.L.back().x_out, (size_t)B * TL * C * 2, cudaMemcpyDeviceToDevice, st));
+  if (c->n_readout > 0) {
+    const int32_t* maps[64];
+    int toks[64];
+    for (int l = 0; l < c->layers; ++l) {
+      maps[l] = S.shapes[l].r > 0 ? S.L[l].plan.row_map : nullptr;
+      toks[l] = S.shapes[l].t_in;
+    }
+    RC(tome_chain_row_maps(B, c->layers, maps, toks, io->readout_idx, c->n_readout, S.origin, st));
+    if (io->readout || (io->target && io->loss))
+      RC(tome_readout_mse(B, TL, C, c->n_readout, S.L.back().x_out, S.origin, (io->target && io->loss) ? io->target : nullptr,
+                          (io->target && io->loss) ? io->loss : nullptr, nullptr, io->readout, st));
+  }
+  return TOME_OK;
+}
+
+extern "C" int tome_stack_backward(const tome_stack_cfg_t* c, const tome_stack_io_t* io, void* stream_) {
+  clear_error();
+  cudaStream_t st = (cudaStream_t)stream_;
+  RC(check_cfg(c));
+  StackLayout S = make_layout(c, io ? io->workspace : nullptr);
+  RC(check_io(c, io, S, true));
+  const int B = c->batch, C = c->channels, H = c->heads, D = c->head_dim, HD = H * D, F = c->mlp_dim;
+  const float* pf = io->params_f32;
+  const __nv_bfloat16* pw = reinterpret_cast<const __nv_bfloat16*>(io->params_bf16);
+  float* gr = io->grads_f32;
+  const bool drop = c->dropout_rate > 0.f;
+  const float inv_keep = drop ? make_drop(c, 0).inv_keep : 1.0f;
+  const int TL = S.shapes.back().t_out;
+
+  __nv_bfloat16 *g0 = S.g0, *g1 = S.g1, *g2 = S.g2, *g3 = S.g3;
+  // dL/dx_final (and the loss value again, harmless) from the readout rows
+  RC(tome_readout_mse(B, TL, C, c->n_readout, S.L.back().x_out, S.origin, io->target, io->loss, g0, nullptr, st));
+
+  auto masked = [&](const __nv_bfloat16* src, __nv_bfloat16* dst, long long n, int site) -> const __nv_bfloat16* {
+    if (!drop) return src;
+    const long long n8 = n / 8;
+    long long blocks = (n8 + 255) / 256;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    dropout_apply_kernel<<<(unsigned)blocks, 256, 0, st>>>(n8, src, dst, make_drop(c, (uint32_t)site));
+    return dst;
+  };
+
+  for (int l = c->layers - 1; l >= 0; --l) {
+    const LayerBufs& Lb = S.L[l];
+    const ParamOffsets o = layer_offsets(c, l);
+    const int T = S.shapes[l].t_in, r = S.shapes[l].r, To = S.shapes[l].t_out;
+    const int M = B * T, Mo = B * To;
+    // ---- MLP: y = x1m + drop2(m1 W2 + b2),  m1 = drop1(relu(h2 W1 + b1))          d_out in g0
+    const __nv_bfloat16* dy2 = masked(g0, g2, (long long)Mo * C, 3 * l + 2);
+    RC(tome_colsum_bf16(Mo, C, dy2, C, gr + o.b2, 1, S.ws_colsum, st));
+    RC(gemm(c, S, st, F, C, Mo, Lb.m1, F, TOME_MAJOR_MN, dy2, C, TOME_MAJOR_MN, gr + o.w2, C, TOME_F32, nullptr, 0, nullptr,
+            nullptr, 1.f, -1, 1));
+    RC(gemm(c, S, st, Mo, F, C, dy2, C, TOME_MAJOR_K, pw + o.w2, C, TOME_MAJOR_K, S.big, F, TOME_BF16, nullptr, 0, nullptr, Lb.m1,
+            inv_keep, -1, 0));  // dm1 (pre-activation): relu and dropout masks both read off the saved m1
+    RC(tome_colsum_bf16(Mo, F, S.big, F, gr + o.b1, 1, S.ws_colsum, st));
+    RC(gemm(c, S, st, C, F, Mo, Lb.h2, C, TOME_MAJOR_MN, S.big, F, TOME_MAJOR_MN, gr + o.w1, F, TOME_F32, nullptr, 0, nullptr,
+            nullptr, 1.f, -1, 1));
+    RC(gemm(c, S, st, Mo, C, F, S.big, F, TOME_MAJOR_K, pw + o.w1, F, TOME_MAJOR_K, g1, C, TOME_BF16, nullptr, 0, nullptr, nullptr,
+            1.f, -1, 0));  // dh2
+    // ---- LN2 (+ residual gradient d_out) -> dx1m in g2
+    RC(tome_layernorm_bwd(B, To, C, c->ln_axis, Lb.x1m, g1, pf + o.ln2_scale, Lb.ln2_mean, Lb.ln2_rstd, g0, g2,
+                          gr + o.ln2_scale, gr + o.ln2_bias, S.ws_ln, st));
+    // ---- merge backward -> dx1 in g0
+    const __nv_bfloat16* dx1;
+    if (r > 0) {
+      tome_merge_shape_t ms{B, T, C, r, c->distill_token, TOME_BF16, TOME_MERGE_WAVG};
+      RC(tome_merge_bwd(&ms, &Lb.plan, Lb.size_in, Lb.size_out, g2, g0, st));
+      dx1 = g0;
+    } else {
+      dx1 = g2;
+      __nv_bfloat16* t = g0; g0 = g2; g2 = t;  // keep "dx1 lives in g0"
+    }
+    // ---- out projection: x1 = x + drop0(o Wo + bo)
+    const __nv_bfloat16* dyo = masked(dx1, g1, (long long)M * C, 3 * l + 0);
+    RC(tome_colsum_bf16(M, C, dyo, C, gr + o.bo, 1, S.ws_colsum, st));
+    RC(gemm(c, S, st, HD, C, M, Lb.attn_o, HD, TOME_MAJOR_MN, dyo, C, TOME_MAJOR_MN, gr + o.wo, C, TOME_F32, nullptr, 0, nullptr,
+            nullptr, 1.f, -1, 1));
+    RC(gemm(c, S, st, M, HD, C, dyo, C, TOME_MAJOR_K, pw + o.wo, C, TOME_MAJOR_K, g3, HD, TOME_BF16, nullptr, 0, nullptr, nullptr,
+            1.f, -1, 0));  // d attn_o
+    // ---- attention backward -> dqkv in big
+    tome_attn_desc_t ad;
+    memset(&ad, 0, sizeof(ad));
+    ad.batch = B; ad.tokens = T; ad.heads = H; ad.head_dim = D;
+    ad.q_batch_stride = ad.k_batch_stride = ad.v_batch_stride = (long long)T * 3 * HD;
+    ad.q_token_stride = ad.k_token_stride = ad.v_token_stride = 3 * HD;
+    ad.o_batch_stride = (long long)T * HD; ad.o_token_stride = HD;
+    ad.scale = 1.0f / sqrtf((float)D);
+    if (c->num_groups) { ad.gid = Lb.gid_in; ad.pos = Lb.pos_in; ad.allow = io->allow; ad.num_groups = c->num_groups; }
+    ad.size = c->prop_attn ? Lb.size_in : nullptr;
+    tome_attn_grad_strides_t gs;
+    gs.dq_batch_stride = gs.dk_batch_stride = gs.dv_batch_stride = (long long)T * 3 * HD;
+    gs.dq_token_stride = gs.dk_token_stride = gs.dv_token_stride = 3 * HD;
+    gs.do_batch_stride = (long long)T * HD; gs.do_token_stride = HD;
+    RC(tome_attention_bwd(&ad, &gs, Lb.qkv, Lb.qkv + HD, Lb.qkv + 2 * HD, Lb.attn_o, Lb.lse, g3, S.big, S.big + HD,
+                          S.big + 2 * HD, S.delta, S.attn_scratch, st));
+    // ---- qkv projection
+    RC(tome_colsum_bf16(M, 3 * HD, S.big, 3 * HD, gr + o.bqkv, 1, S.ws_colsum, st));
+    RC(gemm(c, S, st, C, 3 * HD, M, Lb.h, C, TOME_MAJOR_MN, S.big, 3 * HD, TOME_MAJOR_MN, gr + o.wqkv, 3 * HD, TOME_F32, nullptr, 0,
+            nullptr, nullptr, 1.f, -1, 1));
+    RC(gemm(c, S, st, M, C, 3 * HD, S.big, 3 * HD, TOME_MAJOR_K, pw + o.wqkv, 3 * HD, TOME_MAJOR_K, g1, C, TOME_BF16, nullptr, 0,
+            nullptr, nullptr, 1.f, -1, 0));  // dh
+    // ---- LN1 (+ residual gradient dx1) -> dx_in in g2, which becomes the next d_out (g0)
+    RC(tome_layernorm_bwd(B, T, C, c->ln_axis, Lb.x_in, g1, pf + o.ln1_scale, Lb.ln1_mean, Lb.ln1_rstd, dx1, g2,
+                          gr + o.ln1_scale, gr + o.ln1_bias, S.ws_ln, st));
+    {
+      __nv_bfloat16* t = g0; g0 = g2; g2 = t;
+    }
+    if (l == 0) RC(tome_pos_embedding_bwd(B, c->tokens, C, g0, gr, st));
+    if (io->layer_done_events && io->layer_done_events[l])
+      TOME_CUDA(cudaEventRecord((cudaEvent_t)io->layer_done_events[l], st));
+  }
+  if (io->layer_done_events && io->layer_done_events[c->layers])
+    TOME_CUDA(cudaEventRecord((cudaEvent_t)io->layer_done_events[c->layers], st));
+  return TOME_OK;
+}
+
+#define ACCESSOR(name, type, expr)                                                             \
+  extern "C" type name(const tome_stack_cfg_t* c, const tome_stack_io_t* io, int layer) {      \
+    if (check_cfg(c) || !io || layer < 0 || layer >= c->layers) return nullptr;                \
+    StackLayout S = make_layout(c, io->workspace);                                             \
+    return expr;                                                                               \
+  }
+ACCESSOR(tome_stack_layer_edge_idx, const int32_t*, S.L[layer].plan.edge_idx)
+ACCESSOR(tome_stack_layer_dst_idx, const int32_t*, S.L[layer].plan.dst_idx)
+ACCESSOR(tome_stack_layer_node_max, const float*, S.L[layer].node_max)
+ACCESSOR(tome_stack_layer_node_idx, const int32_t*, S.L[layer].node_idx)
+
+extern "C" const void* tome_stack_final_x(const tome_stack_cfg_t* c, const tome_stack_io_t* io) {
+  if (check_cfg(c) || !io) return nullptr;
+  return make_layout(c, io->workspace).L.back().x_out;
+}
+extern "C" const float* tome_stack_final_size(const tome_stack_cfg_t* c, const tome_stack_io_t* io) {
+  if (check_cfg(c) || !io) return nullptr;
+  return make_layout(c, io->workspace).L.back().size_out;
+}

@@ -74,11 +74,21 @@ def similarity_scores(metric: np.ndarray, class_token=False, distill_token=False
     return scores
 
 
+def plan_from_node(node_max: np.ndarray, node_idx: np.ndarray, t: int, r: int, distill_token: bool = False) -> MatchPlan:
+    """token_compression.py:84-88 given the row max / arg max (used when the test follows the GPU's matching
+    decisions layer by layer: the ranking and index split are still recomputed here)."""
+    return _plan_from_node(None, np.asarray(node_max, np.float32), np.asarray(node_idx, np.int32), t, r, distill_token)
+
+
 def plan_from_scores(scores: np.ndarray, t: int, r: int, distill_token: bool = False) -> MatchPlan:
     """token_compression.py:82-88 given fp32 scores [B,Ta,Tb]; `r` must already be clamped."""
     scores = np.asarray(scores, dtype=np.float32)
     node_max = scores.max(axis=-1)
     node_idx = scores.argmax(axis=-1).astype(np.int32)  # first maximum (NaN counts as maximum, like XLA)
+    return _plan_from_node(scores, node_max, node_idx, t, r, distill_token)
+
+
+def _plan_from_node(scores, node_max, node_idx, t, r, distill_token):
     # jnp.argsort is stable ascending with NaNs last; [:, ::-1] => value descending, ties by index descending
     edge_idx = np.argsort(node_max, axis=-1, kind="stable")[:, ::-1].astype(np.int32)
     unm_idx = edge_idx[:, r:]
@@ -87,7 +97,8 @@ def plan_from_scores(scores: np.ndarray, t: int, r: int, distill_token: bool = F
     return MatchPlan(t, r, distill_token, scores, node_max, node_idx, edge_idx, unm_idx, src_idx, dst_idx)
 
 
-def bipartite_soft_matching(metric, r, class_token=False, distill_token=False, scores_override=None) -> MatchPlan:
+def bipartite_soft_matching(metric, r, class_token=False, distill_token=False, scores_override=None,
+                            node_override=None) -> MatchPlan:
     """token_compression.py:54-112.  `r <= 0` returns an identity plan (the reference returns a tuple there,
     which `merge_wavg` cannot call -- SURVEY Appendix C; identity is the documented fix).
     `scores_override` lets a test inject the GPU's fp32 scores so index parity is judged on identical scores."""
@@ -95,6 +106,8 @@ def bipartite_soft_matching(metric, r, class_token=False, distill_token=False, s
     r = clamp_r(t, r, class_token, distill_token)
     if r <= 0:
         return MatchPlan(t, 0, distill_token, None, None, None, None, None, None, None)
+    if node_override is not None:
+        return plan_from_node(node_override[0], node_override[1], t, r, distill_token)
     scores = similarity_scores(metric, class_token, distill_token) if scores_override is None else scores_override
     return plan_from_scores(scores, t, r, distill_token)
 
@@ -342,8 +355,17 @@ class LayerTrace:
     t_in: int
 
 
+def _round_st(t, dtype):
+    """Round activations to `dtype` with a straight-through gradient: lets the fp32 oracle take the SAME ReLU / merge
+    decisions as a kernel pipeline that stores its activations in bf16 (the arithmetic itself stays fp32)."""
+    if dtype is None:
+        return t
+    return t + (t.to(dtype).to(t.dtype) - t).detach()
+
+
 def tome_block(p: BlockParams, x, size, gid, pos, allow, *, num_heads, r, ln_axis="seq", prop_attn=True,
-               class_token=False, distill_token=False, scores_override=None, trace: Optional[list] = None):
+               class_token=False, distill_token=False, scores_override=None, node_override=None,
+               trace: Optional[list] = None, act_dtype=None):
     """ToMeEncoder1DBlock with the ToMe-paper placement (reference shell attention.py:52-69):
 
         x = x + attn(LN(x), mask(groups), bias = log size)       # dropout 0 (parity mode)
@@ -355,21 +377,24 @@ def tome_block(p: BlockParams, x, size, gid, pos, allow, *, num_heads, r, ln_axi
     torch = _torch()
     B, T, C = x.shape
     H = num_heads
-    h = layer_norm(x, p.ln1_scale, p.ln1_bias, axis=ln_axis)
-    q = (h @ p.wq + p.bq).reshape(B, T, H, -1)
-    k = (h @ p.wk + p.bk).reshape(B, T, H, -1)
-    v = (h @ p.wv + p.bv).reshape(B, T, H, -1)
+    rd = lambda t: _round_st(t, act_dtype)  # noqa: E731
+    h = rd(layer_norm(x, p.ln1_scale, p.ln1_bias, axis=ln_axis))
+    q = rd(h @ p.wq + p.bq).reshape(B, T, H, -1)
+    k = rd(h @ p.wk + p.bk).reshape(B, T, H, -1)
+    v = rd(h @ p.wv + p.bv).reshape(B, T, H, -1)
     mask = torch.as_tensor(dense_mask(gid, pos, gid, pos, allow))[:, None, :, :]
     bias = torch.log(size[:, None, None, :, 0]) if prop_attn else None
-    o = attention(q, k, v, mask=mask, bias=bias).reshape(B, T, -1)
-    x = x + (o @ p.wo + p.bo)
+    o = rd(attention(q, k, v, mask=mask, bias=bias).reshape(B, T, -1))
+    x = rd(x + (o @ p.wo + p.bo))
     # --- ToMe (intended call site tome_attention.py:249-256): metric = keys reduced over heads
     metric = k.detach().mean(dim=2).to(torch.float32).numpy()
-    plan = bipartite_soft_matching(metric, r, class_token, distill_token, scores_override=scores_override)
+    plan = bipartite_soft_matching(metric, r, class_token, distill_token, scores_override=scores_override,
+                                   node_override=node_override)
     if trace is not None:
         trace.append(LayerTrace(plan, T))
     if plan.r > 0:
         x, size = merge_wavg_torch(plan, x, size)
+        x = rd(x)
         rm = row_map(plan)
         t2 = T - plan.r
         gid2 = np.zeros((B, t2), dtype=gid.dtype)
@@ -385,20 +410,20 @@ def tome_block(p: BlockParams, x, size, gid, pos, allow, *, num_heads, r, ln_axi
         gid2[bi, rm[bi, ti]] = gid[bi, ti]
         pos2[bi, rm[bi, ti]] = pos[bi, ti]
         gid, pos = gid2, pos2
-    y = layer_norm(x, p.ln2_scale, p.ln2_bias, axis=ln_axis)
-    y = torch.relu(y @ p.w1 + p.b1)  # attention.py:32-33 (dropout at :34,:37 is identity in parity mode)
+    y = rd(layer_norm(x, p.ln2_scale, p.ln2_bias, axis=ln_axis))
+    y = rd(torch.relu(y @ p.w1 + p.b1))  # attention.py:32-33 (dropout at :34,:37 is identity in parity mode)
     y = y @ p.w2 + p.b2
-    return x + y, size, gid, pos
+    return rd(x + y), size, gid, pos
 
 
 def tome_stack(params: Sequence[BlockParams], pos_embedding, x, gid, pos, allow, *, num_heads, r,
                ln_axis="seq", prop_attn=True, scores_override: Optional[Sequence] = None,
-               trace: Optional[list] = None):
+               node_override: Optional[Sequence] = None, trace: Optional[list] = None, act_dtype=None):
     """StackedEncoder1DBlock (attention.py:94-119) unrolled, with shrinking T.  Returns
     (x_final [B,T_L,C], size, origin_row [B,T0] = row of x_final each ORIGINAL token ended up in)."""
     torch = _torch()
     B, T0, C = x.shape
-    x = x + pos_embedding
+    x = _round_st(x + pos_embedding, act_dtype)
     size = torch.ones(B, T0, 1, dtype=x.dtype)
     gid = np.broadcast_to(gid, (B, T0)).copy()
     pos = np.broadcast_to(pos, (B, T0)).copy()
@@ -406,8 +431,10 @@ def tome_stack(params: Sequence[BlockParams], pos_embedding, x, gid, pos, allow,
     for li, p in enumerate(params):
         tr: list = []
         so = None if scores_override is None else scores_override[li]
+        no = None if node_override is None else node_override[li]
         x, size, gid, pos = tome_block(p, x, size, gid, pos, allow, num_heads=num_heads, r=r, ln_axis=ln_axis,
-                                       prop_attn=prop_attn, scores_override=so, trace=tr)
+                                       prop_attn=prop_attn, scores_override=so, node_override=no, trace=tr,
+                                       act_dtype=act_dtype)
         plan = tr[0].plan
         if plan.r > 0:
             origin = np.take_along_axis(row_map(plan), origin, axis=1)

@@ -216,7 +216,8 @@ def test_gemm_epilogues_and_splitk(ops):
 @pytest.mark.parametrize("axis", [1, 2])
 @pytest.mark.parametrize("B,T,C", [(3, 74, 768), (4, 536, 384), (2, 33, 40)])
 def test_layernorm_fwd_bwd(ops, axis, B, T, C):
-    """vs oracle.layer_norm (flax LayerNorm as configured; axis 1 = tokens) + autograd.  bf16 I/O: 2e-2 abs."""
+    """vs oracle.layer_norm (flax LayerNorm as configured; axis 1 = tokens) + autograd.  bf16 I/O: forward 3e-2 abs,
+    dx / dgamma / dbeta within 1e-2 relative L2."""
     rng = np.random.default_rng(B * T + C)
     x = torch.tensor((rng.standard_normal((B, T, C)) * 2 + 0.5).astype(np.float32)).cuda().bfloat16()
     g = torch.tensor((1 + 0.1 * rng.standard_normal(C)).astype(np.float32)).cuda()
@@ -234,10 +235,10 @@ def test_layernorm_fwd_bwd(ops, axis, B, T, C):
     dbeta = torch.zeros(C, device="cuda")
     dx = ops.layernorm_bwd(x, dy, g, mean, rstd, dgamma, dbeta, dres, axis)
     ref_dx = xr.grad + dres.float().cpu()
-    assert (dx.float().cpu() - ref_dx).abs().max().item() <= 3e-2 * max(1.0, ref_dx.abs().max().item() / 4)
-    scale = math.sqrt(B * T)
-    assert (dgamma.cpu() - gr.grad).abs().max().item() <= 3e-2 * scale
-    assert (dbeta.cpu() - br.grad).abs().max().item() <= 3e-2 * scale
+    rel = lambda a, b: ((a.double() - b.double()).norm() / b.double().norm()).item()  # noqa: E731
+    assert rel(dx.float().cpu(), ref_dx) <= 1e-2
+    assert rel(dgamma.cpu(), gr.grad) <= 1e-2
+    assert rel(dbeta.cpu(), br.grad) <= 1e-2
 
 
 # ------------------------------------------------------------------------------------------------ attention

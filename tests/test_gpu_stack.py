@@ -1,0 +1,208 @@
+"""Parity of attention backward and of the whole native stack (forward, loss, every gradient) against the CPU oracle
+(torch-CPU fp32 restatement + autograd).  Needs a B200: `-m gpu`.
+
+Protocol (north star): the oracle follows the GPU's per-layer matching decisions (node_max / node_idx are fed to the
+oracle, which recomputes ranking + index split itself and must reproduce the GPU's edge / dst indices bit-exactly);
+outputs and gradients are compared within the bf16 tolerance written in each test."""
+import math
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import tome_oracle as O  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from multi_modal_transformers_tokenmerge_b200 import _lib, engine, ops
+    _lib.lib()
+    return ops, engine
+
+
+def rel_err(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+@pytest.mark.parametrize("T,H,masked,sized", [(74, 3, True, True), (536, 6, True, True), (128, 2, False, False),
+                                              (200, 2, True, False), (333, 4, False, True)])
+def test_attention_bwd(pkg, T, H, masked, sized):
+    """dq/dk/dv vs autograd of oracle.attention on the same bf16-rounded inputs; relative L2 error <= 2e-2 per tensor
+    (bf16 P / dS operands and bf16 gradient outputs)."""
+    ops, _ = pkg
+    rng = np.random.default_rng(T * 7 + H)
+    B, D = 2, 64
+    qkv = torch.tensor(rng.standard_normal((B, T, 3, H, D)).astype(np.float32)).cuda().bfloat16()
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    gid = pos = allow = size = None
+    if masked:
+        n_img = (T - 16) // 2 - 4
+        g1, p1, allow, _ = O.sequence_groups(f"[TaskDescriptionPrefix{{16}}] [Image{{{n_img}}};Readout{{4}}]*2")
+        pad = T - g1.shape[0]
+        g1 = np.concatenate([g1, np.full(pad, g1[-1], np.uint8)])
+        p1 = np.concatenate([p1, np.arange(pad, dtype=np.int32)])
+        gid = np.stack([g1, rng.permutation(g1)])
+        pos = np.stack([p1, rng.integers(0, 50, size=T).astype(np.int32)])
+    if sized:
+        size = rng.integers(1, 6, size=(B, T)).astype(np.float32)
+    dv_ = lambda a: None if a is None else torch.as_tensor(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    kw = dict(gid=dv_(gid), pos=dv_(pos), allow=dv_(allow), size=dv_(size))
+    out, lse = ops.attention_fwd(q, k, v, **kw)
+    dout = torch.tensor(rng.standard_normal((B, T, H, D)).astype(np.float32)).cuda().bfloat16()
+    dq, dk, dvv = ops.attention_bwd(q, k, v, out, lse, dout, **kw)
+    torch.cuda.synchronize()
+    qr, kr, vr = (t.float().cpu().requires_grad_(True) for t in (q, k, v))
+    mask = None if gid is None else torch.as_tensor(O.dense_mask(gid, pos, gid, pos, allow))[:, None]
+    bias = None if size is None else torch.log(torch.as_tensor(size))[:, None, None, :]
+    ref = O.attention(qr, kr, vr, mask=mask, bias=bias)
+    ref.backward(dout.float().cpu())
+    for name, got, want in (("dq", dq, qr.grad), ("dk", dk, kr.grad), ("dv", dvv, vr.grad)):
+        e = rel_err(got.float().cpu(), want)
+        assert e <= 2e-2, f"{name}: rel err {e}"
+
+
+def _build(pkg, B, W, P, C, H, Dff, Lyr, r, ln_axis, seed=0, n_ro=2, n_tdp=4):
+    ops, engine = pkg
+    rng = np.random.default_rng(seed)
+    seq = f"[TaskDescriptionPrefix{{{n_tdp}}}] [Image{{{P}}};Readout{{{n_ro}}}]*{W}"
+    gid, pos, allow, ro = O.sequence_groups(seq)
+    T = gid.shape[0]
+    D = 64
+    layers = [O.init_block_params(rng, C, H, D, Dff) for _ in range(Lyr)]
+    for d in layers:  # non-trivial LN affine so their gradients are exercised
+        for k_ in ("ln1_scale", "ln2_scale"):
+            d[k_] = (d[k_] + 0.1 * rng.standard_normal(C)).astype(np.float32)
+        for k_ in ("ln1_bias", "ln2_bias"):
+            d[k_] = (0.1 * rng.standard_normal(C)).astype(np.float32)
+    pe = (rng.standard_normal((1, T, C)) * 0.02).astype(np.float32)
+    x = rng.standard_normal((B, T, C)).astype(np.float32)
+    y = rng.standard_normal((B, len(ro), C)).astype(np.float32)
+    cfg = engine.StackConfig(batch=B, tokens=T, channels=C, heads=H, head_dim=D, mlp_dim=Dff, layers=Lyr, r=r,
+                             ln_axis=ln_axis, num_groups=allow.shape[0], n_readout=len(ro))
+    eng = engine.ToMeStackEngine(cfg, gid=gid, pos=pos, allow=allow, readout_idx=ro)
+    eng.load_params(pe[0], layers)
+    return eng, cfg, layers, pe, x, y, (gid, pos, allow, ro)
+
+
+def _oracle_run(eng, cfg, layers, pe, x, y, groups, node_override, act_dtype=None):
+    gid, pos, allow, ro = groups
+    # the oracle sees exactly the bf16-rounded weights the GPU GEMMs consume (biases / LN params stay fp32)
+    v = eng.param_views(eng.params_bf16.float().cpu())
+    vf = eng.param_views(eng.params.cpu())
+    params = []
+    for l in range(cfg.layers):
+        d = {}
+        hd = cfg.heads * cfg.head_dim
+        src, srcf = v["layers"][l], vf["layers"][l]
+        d.update(ln1_scale=srcf["ln1_scale"], ln1_bias=srcf["ln1_bias"], ln2_scale=srcf["ln2_scale"], ln2_bias=srcf["ln2_bias"])
+        d.update(wq=src["wqkv"][:, :hd], wk=src["wqkv"][:, hd:2 * hd], wv=src["wqkv"][:, 2 * hd:],
+                 bq=srcf["bqkv"][:hd], bk=srcf["bqkv"][hd:2 * hd], bv=srcf["bqkv"][2 * hd:])
+        d.update(wo=src["wo"], bo=srcf["bo"], w1=src["w1"], b1=srcf["b1"], w2=src["w2"], b2=srcf["b2"])
+        params.append(O.BlockParams(**{k_: t.clone().contiguous().requires_grad_(True) for k_, t in d.items()}))
+    pet = vf["pos_embedding"].clone()[None].requires_grad_(True)
+    xt = torch.tensor(x)
+    tr = []
+    xf, size, origin = O.tome_stack(params, pet, xt, gid, pos, allow, num_heads=cfg.heads, r=cfg.r,
+                                    ln_axis="seq" if cfg.ln_axis == 1 else "feature", node_override=node_override, trace=tr,
+                                    act_dtype=act_dtype)
+    loss, out = O.readout_loss(xf, origin, ro, torch.tensor(y))
+    loss.backward()
+    return params, pet, xf, size, origin, loss, out, tr
+
+
+# (ln_axis, r, layers, b1 shift, tolerance on the forward, tolerance on every parameter gradient)
+#  * b1 + 8 opens every ReLU gate and ln_axis = 2 avoids the token-axis cancellation, so those rows measure the
+#    kernels themselves: gradients within 2e-2 relative L2 of the fp32 oracle (observed <= 6e-3);
+#  * the reference-literal rows (ReLU active, LayerNorm over tokens) are dominated by two effects that are properties
+#    of bf16 storage, not of the kernels: a ReLU gate whose pre-activation is within bf16 rounding of zero flips
+#    (relative L2 error = sqrt(fraction flipped), ~0.4 % of gates -> ~6 %), and with reduction_axes=[1] the token sums
+#    in the weight gradients cancel (sum_t xhat = 0), which amplifies rounding noise.  Observed <= 0.17; bar 0.25.
+CASES = [(2, 4, 2, 8.0, 1e-2, 2e-2), (2, 0, 1, 8.0, 1e-2, 2e-2), (2, 6, 3, 8.0, 1e-2, 2e-2), (1, 4, 2, 8.0, 1e-2, 0.12),
+         (1, 4, 2, 0.0, 3e-2, 0.25), (2, 4, 2, 0.0, 3e-2, 0.25), (1, 0, 1, 0.0, 3e-2, 0.25), (1, 6, 3, 0.0, 3e-2, 0.25)]
+
+
+@pytest.mark.parametrize("ln_axis,r,Lyr,b1_shift,tol_fwd,tol_grad", CASES)
+def test_stack_forward_backward_vs_oracle(pkg, ln_axis, r, Lyr, b1_shift, tol_fwd, tol_grad):
+    """Whole stack vs the oracle (fp32 arithmetic, activations rounded to bf16 at the points where the kernels store
+    them): merge indices bit-exact (the oracle recomputes ranking + split from the GPU's node_max / node_idx), token
+    sizes bit-exact, final tokens / readout / loss and every parameter gradient within the tolerances of CASES."""
+    B, W, P, C, H, Dff = 2, 2, 24, 128, 2, 256
+    eng, cfg, layers, pe, x, y, groups = _build(pkg, B, W, P, C, H, Dff, Lyr, r, ln_axis)
+    if b1_shift:
+        for d in layers:
+            d["b1"] = d["b1"] + np.float32(b1_shift)
+        eng.load_params(pe[0], layers)
+    xd, yd = torch.tensor(x).cuda(), torch.tensor(y).cuda()
+    eng.zero_grad()
+    eng.forward(xd, yd)
+    eng.backward()
+    torch.cuda.synchronize()
+    node_override, plans = [], []
+    for l in range(Lyr):
+        pl = eng.layer_plan(l)
+        plans.append(pl)
+        node_override.append(None if pl is None else (pl[0].cpu().numpy(), pl[1].cpu().numpy()))
+    params, pet, xf, size, origin, loss, out, tr = _oracle_run(eng, cfg, layers, pe, x, y, groups, node_override,
+                                                               torch.bfloat16)
+    for l in range(Lyr):
+        if plans[l] is None:
+            continue
+        np.testing.assert_array_equal(plans[l][2].cpu().numpy(), tr[l].plan.edge_idx)
+        np.testing.assert_array_equal(plans[l][3].cpu().numpy(), tr[l].plan.dst_idx)
+    fs = eng.final_size()
+    if fs is not None:
+        np.testing.assert_array_equal(fs.cpu().numpy(), size.detach().numpy()[..., 0])
+    assert rel_err(eng.final_x().float().cpu(), xf.detach()) <= tol_fwd
+    assert rel_err(eng.readout.cpu(), out.detach()) <= tol_fwd
+    assert abs(eng.loss[0].item() - loss.item()) <= tol_fwd * abs(loss.item())
+    g = eng.param_views(eng.grads.cpu())
+    assert rel_err(g["pos_embedding"], pet.grad[0]) <= tol_grad
+    for l in range(Lyr):
+        p, gl = params[l], g["layers"][l]
+        ref = dict(ln1_scale=p.ln1_scale.grad, ln1_bias=p.ln1_bias.grad, ln2_scale=p.ln2_scale.grad, ln2_bias=p.ln2_bias.grad,
+                   wqkv=torch.cat([p.wq.grad, p.wk.grad, p.wv.grad], 1), bqkv=torch.cat([p.bq.grad, p.bk.grad, p.bv.grad]),
+                   wo=p.wo.grad, bo=p.bo.grad, w1=p.w1.grad, b1=p.b1.grad, w2=p.w2.grad, b2=p.b2.grad)
+        for name, want in ref.items():
+            e = rel_err(gl[name], want)
+            assert e <= tol_grad, f"layer {l} grad {name}: rel err {e}"
+
+
+def test_stack_octo_small_shape_runs_and_trains(pkg):
+    """C2-shaped stack at a small batch: T0 = 536 -> 344 over 12 layers (r = 16), sizes conserve T0, loss falls under
+    AdamW, dropout path runs and is reproducible for a fixed seed."""
+    ops, engine = pkg
+    gid, pos, allow, ro = O.sequence_groups("[TaskDescriptionPrefix{16}] [Image{256};Readout{4}]*2")
+    B, T, C, H, Dff, Lyr, r = 4, 536, 384, 6, 1536, 12, 16
+    cfg = engine.StackConfig(batch=B, tokens=T, channels=C, heads=H, head_dim=64, mlp_dim=Dff, layers=Lyr, r=r,
+                             num_groups=allow.shape[0], n_readout=len(ro))
+    eng = engine.ToMeStackEngine(cfg, gid=gid, pos=pos, allow=allow, readout_idx=ro)
+    eng.init_params(1)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(B, T, C, device="cuda", generator=g)
+    y = torch.randn(B, len(ro), C, device="cuda", generator=g)
+    losses = []
+    for _ in range(8):
+        eng.zero_grad()
+        eng.forward(x, y)
+        eng.backward()
+        eng.adamw_step(lr=3e-4)
+        losses.append(eng.loss[0].item())
+    assert eng.tokens_at(Lyr) == 344
+    assert torch.all(eng.final_size().sum(dim=1) == T)
+    assert all(math.isfinite(v) for v in losses) and losses[-1] < losses[0], losses
+    cfg2 = engine.StackConfig(**{**cfg.__dict__, "dropout_rate": 0.1, "dropout_seed": 5})
+    e2 = engine.ToMeStackEngine(cfg2, gid=gid, pos=pos, allow=allow, readout_idx=ro)
+    e2.init_params(1)
+    vals = []
+    for _ in range(2):
+        e2.zero_grad()
+        e2.forward(x, y)
+        e2.backward()
+        torch.cuda.synchronize()
+        vals.append((e2.loss[0].item(), e2.grads.norm().item()))
+    assert vals[0] == vals[1] and math.isfinite(vals[0][1])
