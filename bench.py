@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py -- ToMe-transformer train samples/s (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W                  # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W # the reference's algorithm on the host CPU
+
+A "step" is one full training step of the octo-small-style ToMe stack (BASELINE.json configs[1]: batch 256 per GPU,
+T0 = 536 tokens, 12 layers, r = 16 / layer, block-causal readout mask, bf16) on synthetic embeddings: zero grads,
+forward, synthetic readout loss, full backward, (N > 1: overlapped NCCL gradient all-reduce), AdamW.
+One JSON line is printed by rank 0.  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEQ = "[TaskDescriptionPrefix{16}] [Image{256};Readout{4}]*2"   # T0 = 536 (form of octo_base.yaml:10)
+CONFIGS = {
+    # BASELINE.json configs[1]: octo-small train step bf16, batch 256 / GPU, r = 16
+    "octo_small": dict(channels=384, heads=6, head_dim=64, mlp_dim=1536, layers=12, r=16, batch=256),
+    # BASELINE.json configs[2] per-GPU shard: octo-base, 256 / GPU (2048 on 8 GPUs), r = 32
+    "octo_base": dict(channels=768, heads=12, head_dim=64, mlp_dim=3072, layers=12, r=32, batch=256),
+}
+METRIC = "ToMe-transformer train samples/sec"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+def flops_per_sample(c, T0):
+    """Algorithmic block FLOPs: forward, x3 for a train step."""
+    C, Dff, D, r = c["channels"], c["mlp_dim"], c["head_dim"], c["r"]
+    T, tot = T0, 0.0
+    for _ in range(c["layers"]):
+        rr = min(r, T // 2)
+        tot += 6 * T * C * C + 4 * T * T * C + 2 * T * C * C + 2 * ((T + 1) // 2) * (T // 2) * D + 4 * (T - rr) * C * Dff
+        T -= rr
+    return tot
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([v.strip() for v in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        mx = max(float(r[1]) for r in self.rows if len(r) >= 7)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm / cpu baseline
+def cpu_reference_steps(cfgname, steps, warmup, sample_batch):
+    """The reference's algorithm for this path, restated (oracle/tome_oracle.py: sequential scatter loop, double merge
+    call, dense [B,H,T,T] mask, fp32) as a torch-CPU train step with autograd + SGD, all host threads.  JAX/Flax are
+    not installable here (no wheels, no network), so this is the port ("kind": "port"), not the JAX program."""
+    import numpy as np
+    import torch
+    from oracle import tome_oracle as O
+
+    c = CONFIGS[cfgname]
+    gid, pos, allow, ro = O.sequence_groups(SEQ)
+    T0 = gid.shape[0]
+    rng = np.random.default_rng(1)
+    params = [O.block_params_to_torch(O.init_block_params(rng, c["channels"], c["heads"], c["head_dim"], c["mlp_dim"]),
+                                      requires_grad=True) for _ in range(c["layers"])]
+    pe = torch.tensor((rng.standard_normal((1, T0, c["channels"])) * 0.02).astype(np.float32), requires_grad=True)
+    x = torch.tensor(np.random.default_rng(0).standard_normal((sample_batch, T0, c["channels"])).astype(np.float32))
+    y = torch.tensor(np.random.default_rng(2).standard_normal((sample_batch, len(ro), c["channels"])).astype(np.float32))
+    leaves = [t for p in params for t in p.tensors()] + [pe]
+    opt = torch.optim.SGD(leaves, lr=1e-4)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        xf, size, origin = O.tome_stack(params, pe, x, gid, pos, allow, num_heads=c["heads"], r=c["r"])
+        loss, _ = O.readout_loss(xf, origin, ro, y)
+        loss.backward()
+        opt.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sample_batch * len(times) / sum(times), sum(times) / len(times), torch.get_num_threads(), T0
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    sb = 2 if (args.steps + args.warmup) <= 12 else 1
+    sps, sec, cores, T0 = cpu_reference_steps(args.config, args.steps, args.warmup, sb)
+    c = CONFIGS[args.config]
+    sample = f"{sb} samples/step of the {args.config} workload (T0={T0}, {c['layers']} layers, r={c['r']}), fp32, train step"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.config} ToMe stack train step, restated reference on host CPU", "sample_batch": sb},
+        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------ this repo's arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="tome_b200", choices=["tome_b200", "reference"])
+    ap.add_argument("--config", default="octo_small", choices=list(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override (default: the config's 256)")
+    ap.add_argument("--dropout", type=float, default=0.1, help="hidden dropout rate (vanilla_decoder.yaml:17,50)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "tome_b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from multi_modal_transformers_tokenmerge_b200 import _lib as L
+    from multi_modal_transformers_tokenmerge_b200.engine import StackConfig, ToMeStackEngine
+    from multi_modal_transformers_tokenmerge_b200.parallel import DataParallelTrainer
+    from multi_modal_transformers_tokenmerge_b200.tokenizers.token_sequencer import sequence_groups
+
+    lib = L.lib()  # raises if the CUDA library is missing: the product path has no fallback
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    c = dict(CONFIGS[args.config])
+    if args.batch:
+        c["batch"] = args.batch
+    gid, pos, allow, ro = sequence_groups(SEQ)
+    T0, B, C = len(gid), c["batch"], c["channels"]
+    cfg = StackConfig(batch=B, tokens=T0, channels=C, heads=c["heads"], head_dim=c["head_dim"], mlp_dim=c["mlp_dim"],
+                      layers=c["layers"], r=c["r"], ln_axis=1, num_groups=allow.shape[0], n_readout=len(ro),
+                      dropout_rate=args.dropout, dropout_seed=1234 + rank)
+    eng = ToMeStackEngine(cfg, gid=gid, pos=pos, allow=allow, readout_idx=ro)
+    eng.init_params(seed=1)  # same weights on every rank
+    trainer = DataParallelTrainer(eng)
+    g = torch.Generator(device="cuda").manual_seed(100 + rank)
+    x = torch.randn(B, T0, C, device="cuda", generator=g).bfloat16()      # synthetic block inputs (embeddings)
+    y = torch.randn(B, len(ro), C, device="cuda", generator=g)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, fn):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    step = lambda: trainer.train_step(x, y, lr=1e-4)  # noqa: E731
+    for _ in range(args.warmup):
+        step()
+    lib.tome_launch_count(1)
+    with ClockSampler(local) as clk:
+        ms = timed(args.steps, step)
+    launches = int(lib.tome_launch_count(1))
+    loss_dev = float(eng.loss[0].item())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the public API: pinned host inputs -> H2D -> step -> D2H loss, every step ----
+    xh = [torch.randn(B, T0, C).bfloat16().pin_memory() for _ in range(2)]
+    yh = [torch.randn(B, len(ro), C).pin_memory() for _ in range(2)]
+    xd = [torch.empty_like(x) for _ in range(2)]
+    yd = [torch.empty_like(y) for _ in range(2)]
+    loss_h = torch.zeros(1).pin_memory()
+    copy_stream = torch.cuda.Stream()
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    state = {"i": 0}
+
+    def prefetch(i):
+        s = i & 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[s])
+            xd[s].copy_(xh[s], non_blocking=True)
+            yd[s].copy_(yh[s], non_blocking=True)
+            ready[s].record(copy_stream)
+
+    def e2e_step():
+        i = state["i"]
+        s = i & 1
+        if i == 0:
+            prefetch(0)
+        prefetch(i + 1)                       # next step's inputs stream in under this step's compute
+        torch.cuda.current_stream().wait_event(ready[s])
+        trainer.train_step(xd[s], yd[s], lr=1e-4)
+        consumed[s].record()
+        loss_h.copy_(eng.loss[:1], non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the step's result is read on the host every step
+        state["i"] = i + 1
+
+    for ev in consumed:
+        ev.record()
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(args.steps, e2e_step)
+    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+    h2d = xh[0].numel() * 2 + yh[0].numel() * 4
+    d2h = 4
+
+    # ---- roofline pass: same step, every op bracketed by CUDA events on its own stream ----
+    P = peaks()
+    L.check(lib.tome_profile_enable(4096))
+    nprof = 2
+    for _ in range(nprof):
+        step()
+    torch.cuda.synchronize()
+    prof = L.profile_collect()
+    lib.tome_profile_disable()
+    tot_ms = sum(v[0] for v in prof.values())
+    kernels = {}
+    for k_, (kms, work, cnt) in prof.items():
+        if cnt == 0:
+            continue
+        ent = {"ms_per_step": kms / nprof, "share": kms / tot_ms, "ops_per_step": cnt // nprof}
+        if k_ in ("gemm", "attn_fwd", "attn_bwd", "sim_argmax") and kms > 0:
+            ent["tflops"] = work / (kms * 1e-3) / 1e12
+        elif work > 0 and kms > 0:
+            ent["gbs"] = work / (kms * 1e-3) / 1e9
+        kernels[k_] = ent
+    gms, gwork, gcnt = prof["gemm"]
+    roof = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)", "achieved": gwork / (gms * 1e-3) / 1e12,
+            "peak": P["tf_sust"], "unit": "TFLOP/s", "frac": gwork / (gms * 1e-3) / 1e12 / P["tf_sust"], "traffic": None,
+            "peak_source": f"{P['src']} bf16_tflops_sustained", "launches_per_step": gcnt // nprof,
+            "avg_launch_us": gms / gcnt * 1e3, "share_of_step": gms / tot_ms}
+    mms, mwork, mcnt = prof["merge_fwd"]
+    merge_roof = {"bound": "hbm", "kernel": "merge_fwd_kernel", "achieved": mwork / (mms * 1e-3) / 1e9, "peak": P["hbm"],
+                  "unit": "GB/s", "frac": mwork / (mms * 1e-3) / 1e9 / P["hbm"], "traffic": None,
+                  "peak_source": f"{P['src']} hbm_gbs", "avg_launch_us": mms / mcnt * 1e3} if mcnt else None
+
+    out = None
+    if rank == 0:
+        fl = flops_per_sample(c, T0) * 3
+        out = {
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"{args.config} ToMe stack train step (BASELINE.json configs[1] shape)", "global_batch": B * world,
+                       "per_gpu_batch": B, "tokens": T0, "layers": c["layers"], "channels": C, "heads": c["heads"],
+                       "mlp_dim": c["mlp_dim"], "r_per_layer": c["r"], "mask": "block-causal group table", "ln_axis": "tokens",
+                       "hidden_dropout": args.dropout, "attention_dropout": 0.0, "optimizer": "AdamW fp32 master",
+                       "parallelism": f"dp{world}", "l2_policy": "inputs and activations (>= 1 GB/step) exceed the 126 MB L2"},
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "merge_roofline": merge_roof,
+            "kernels": kernels, "model_tflops": value / world * fl / 1e12, "loss": loss_dev,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            sps, sec, cores, _ = cpu_reference_steps(args.config, 3, 1, 2)
+            out["cpu_baseline"] = {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
+                                   "sample": f"3 train steps of 2 samples of the same workload (fp32, torch-CPU restatement of the "
+                                             f"reference), {sec:.1f} s/step"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -289,6 +289,20 @@ const int32_t* tome_stack_layer_dst_idx(const tome_stack_cfg_t* cfg, const tome_
 const float* tome_stack_layer_node_max(const tome_stack_cfg_t* cfg, const tome_stack_io_t* io, int layer);
 const int32_t* tome_stack_layer_node_idx(const tome_stack_cfg_t* cfg, const tome_stack_io_t* io, int layer);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * 8. Launch accounting and per-op timing (measurement aid; off by default, never on the product path's hot loop)
+ * ------------------------------------------------------------------------------------------------------------ */
+enum tome_prof_tag { TOME_PROF_GEMM = 0, TOME_PROF_ATTN_FWD, TOME_PROF_ATTN_BWD, TOME_PROF_MERGE_FWD, TOME_PROF_MERGE_BWD,
+                     TOME_PROF_SIM, TOME_PROF_SELECT, TOME_PROF_LN, TOME_PROF_COLSUM, TOME_PROF_OTHER, TOME_PROF_NTAGS };
+/* number of kernels this library has launched in this process (reset != 0 zeroes the counter after reading) */
+long long tome_launch_count(int reset);
+/* bracket every op with a pair of CUDA events on its own stream (up to max_records ops) */
+int tome_profile_enable(int max_records);
+int tome_profile_disable(void);
+/* per tag: total milliseconds, total algorithmic work (FLOPs for GEMM / attention / sim, bytes for merge / LN /
+ * colsum), number of ops; clears the records.  Arrays must hold TOME_PROF_NTAGS entries. */
+int tome_profile_collect(int n_tags, float* ms, double* work, int* count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -106,7 +106,7 @@ def lib() -> C.CDLL:
         for name in ("tome_gemm_workspace_bytes", "tome_stack_workspace_bytes"):
             if hasattr(L, name):
                 getattr(L, name).restype = C.c_size_t
-        for name in ("tome_stack_param_count", "tome_stack_layer_offset"):
+        for name in ("tome_stack_param_count", "tome_stack_layer_offset", "tome_launch_count"):
             if hasattr(L, name):
                 getattr(L, name).restype = ll
         for name in ("tome_stack_final_x", "tome_stack_final_size", "tome_stack_layer_edge_idx", "tome_stack_layer_dst_idx",
@@ -134,6 +134,10 @@ def lib() -> C.CDLL:
             "tome_readout_mse": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp],
             "tome_adamw_step": [ll, vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, f32, i32, vp],
             "tome_cast_f32_to_bf16": [ll, vp, vp, vp],
+            "tome_launch_count": [i32],
+            "tome_profile_enable": [i32],
+            "tome_profile_disable": [],
+            "tome_profile_collect": [i32, P(f32), P(C.c_double), P(i32)],
             "tome_stack_param_count": [P(StackCfg)],
             "tome_stack_layer_offset": [P(StackCfg), i32],
             "tome_stack_workspace_bytes": [P(StackCfg)],
@@ -152,6 +156,18 @@ def lib() -> C.CDLL:
                 getattr(L, name).argtypes = args
         _lib = L
     return _lib
+
+
+PROF_TAGS = ["gemm", "attn_fwd", "attn_bwd", "merge_fwd", "merge_bwd", "sim_argmax", "select_topr", "layernorm", "colsum",
+             "other"]
+
+
+def profile_collect() -> dict:
+    """{tag: (ms, work, count)} of the ops recorded since tome_profile_enable / the last collect."""
+    n = len(PROF_TAGS)
+    ms, work, cnt = (f32 * n)(), (C.c_double * n)(), (i32 * n)()
+    check(lib().tome_profile_collect(n, ms, work, cnt))
+    return {PROF_TAGS[i]: (float(ms[i]), float(work[i]), int(cnt[i])) for i in range(n)}
 
 
 def check(rc: int) -> None:

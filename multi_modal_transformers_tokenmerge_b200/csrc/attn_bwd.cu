@@ -521,6 +521,7 @@ extern "C" int tome_attention_bwd(const tome_attn_desc_t* d, const tome_attn_gra
                            gs->dv_batch_stride, gs->dv_token_stride, gs->do_batch_stride, gs->do_token_stride};
   for (int i = 0; i < 8; ++i) TOME_CHECK(st[i] % 8 == 0, TOME_ERR_INVALID, "attention_bwd: strides must be multiples of 8");
   const int B = d->batch, T = d->tokens, H = d->heads;
+  ProfScope prof(PROF_ATTN_BWD, 10.0 * d->batch * d->heads * (double)d->tokens * d->tokens * d->head_dim, 3, stream);
   // dq_accum doubles as scratch for the per-token mask words (first B*T*8 bytes); no fp32 dQ accumulation is needed.
   uint2* mwords = d->gid ? reinterpret_cast<uint2*>(dq_accum) : nullptr;
   {

@@ -326,6 +326,7 @@ extern "C" int tome_attention_fwd(const tome_attn_desc_t* d, const void* q, cons
   TOME_CHECK(((uintptr_t)out & 15) == 0, TOME_ERR_INVALID, "attention_fwd: out must be 16-byte aligned");
   CUtensorMap tq, tk, tv;
   const uint64_t hd = (uint64_t)d->heads * d->head_dim;
+  ProfScope prof(PROF_ATTN_FWD, 4.0 * d->batch * d->heads * (double)d->tokens * d->tokens * d->head_dim, 1, stream);
   if (int rc = make_tmap_3d_bf16(&tq, q, hd, d->tokens, d->batch, d->q_token_stride, d->q_batch_stride, ATT_BM)) return rc;
   if (int rc = make_tmap_3d_bf16(&tk, k, hd, d->tokens, d->batch, d->k_token_stride, d->k_batch_stride, ATT_BN)) return rc;
   if (int rc = make_tmap_3d_bf16(&tv, v, hd, d->tokens, d->batch, d->v_token_stride, d->v_batch_stride, ATT_BN)) return rc;

@@ -396,6 +396,7 @@ extern "C" int tome_gemm_bf16(const tome_gemm_args_t* a, void* workspace, size_t
   if (rc) return rc;
 
   const bool amn = a->a_major == TOME_MAJOR_MN, bmn = a->b_major == TOME_MAJOR_MN;
+  ProfScope prof(PROF_GEMM, 2.0 * a->m * (double)a->n * a->k, s.k_splits > 1 ? 2 : 1, stream);
   if (!amn && !bmn) rc = launch_gemm<128, false, false>(ta, tb, s, e, stream);
   else if (!amn && bmn) rc = launch_gemm<128, false, true>(ta, tb, s, e, stream);
   else if (amn && !bmn) rc = launch_gemm<128, true, false>(ta, tb, s, e, stream);

@@ -3,6 +3,8 @@
 
 #include <string.h>
 
+#include <vector>
+
 namespace tome {
 
 static thread_local char g_err[512] = {0};
@@ -64,6 +66,77 @@ int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t 
 }
 
 }  // namespace tome
+
+namespace tome {
+struct Profiler {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;  // 2 per record
+  std::vector<int> tag;
+  std::vector<double> work;
+  int n = 0, cap = 0;
+  long long launches = 0;
+};
+static Profiler g_prof;  // one process drives one GPU (one rank per process); not thread-safe by design
+
+ProfScope::ProfScope(int tag, double work, int kernels, cudaStream_t stream) : st(stream), rec(false) {
+  g_prof.launches += kernels;
+  if (g_prof.on && g_prof.n < g_prof.cap) {
+    g_prof.tag[g_prof.n] = tag;
+    g_prof.work[g_prof.n] = work;
+    cudaEventRecord(g_prof.ev[2 * g_prof.n], st);
+    rec = true;
+  }
+}
+ProfScope::~ProfScope() {
+  if (rec) {
+    cudaEventRecord(g_prof.ev[2 * g_prof.n + 1], st);
+    ++g_prof.n;
+  }
+}
+}  // namespace tome
+
+extern "C" long long tome_launch_count(int reset) {
+  const long long v = tome::g_prof.launches;
+  if (reset) tome::g_prof.launches = 0;
+  return v;
+}
+extern "C" int tome_profile_enable(int max_records) {
+  using namespace tome;
+  clear_error();
+  TOME_CHECK(max_records > 0, TOME_ERR_INVALID, "profile_enable: max_records must be positive");
+  while ((int)g_prof.ev.size() < 2 * max_records) {
+    cudaEvent_t e;
+    TOME_CUDA(cudaEventCreate(&e));
+    g_prof.ev.push_back(e);
+  }
+  g_prof.tag.assign(max_records, 0);
+  g_prof.work.assign(max_records, 0.0);
+  g_prof.cap = max_records;
+  g_prof.n = 0;
+  g_prof.on = true;
+  return TOME_OK;
+}
+extern "C" int tome_profile_disable(void) {
+  tome::g_prof.on = false;
+  return TOME_OK;
+}
+// Synchronises the recorded events; per tag: total milliseconds, total algorithmic work, number of ops.
+extern "C" int tome_profile_collect(int n_tags, float* ms, double* work, int* count) {
+  using namespace tome;
+  clear_error();
+  TOME_CHECK(n_tags >= PROF_NTAGS && ms && work && count, TOME_ERR_INVALID, "profile_collect: need %d tag slots", (int)PROF_NTAGS);
+  for (int i = 0; i < n_tags; ++i) { ms[i] = 0.f; work[i] = 0.0; count[i] = 0; }
+  for (int i = 0; i < g_prof.n; ++i) {
+    float t = 0.f;
+    TOME_CUDA(cudaEventSynchronize(g_prof.ev[2 * i + 1]));
+    TOME_CUDA(cudaEventElapsedTime(&t, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]));
+    ms[g_prof.tag[i]] += t;
+    work[g_prof.tag[i]] += g_prof.work[i];
+    count[g_prof.tag[i]] += 1;
+  }
+  g_prof.n = 0;
+  return TOME_OK;
+}
 
 extern "C" const char* tome_last_error(void) { return tome::g_err; }
 extern "C" int tome_abi_version(void) { return TOME_ABI_VERSION; }

@@ -36,4 +36,14 @@ int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t 
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// ---- launch accounting + optional per-op CUDA-event timing (bench.py's roofline pass; off by default) ----
+enum ProfTag { PROF_GEMM = 0, PROF_ATTN_FWD, PROF_ATTN_BWD, PROF_MERGE_FWD, PROF_MERGE_BWD, PROF_SIM, PROF_SELECT,
+               PROF_LN, PROF_COLSUM, PROF_OTHER, PROF_NTAGS };
+struct ProfScope {  // RAII around one C-ABI op: `kernels` launches doing `work` algorithmic FLOPs or bytes
+  cudaStream_t st;
+  bool rec;
+  ProfScope(int tag, double work, int kernels, cudaStream_t stream);
+  ~ProfScope();
+};
+
 }  // namespace tome

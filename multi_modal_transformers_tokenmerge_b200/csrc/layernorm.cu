@@ -359,6 +359,7 @@ extern "C" int tome_colsum_bf16(int m, int n, const void* x, long long ldx, floa
   TOME_CHECK(m > 0 && n > 0 && x && out && workspace, TOME_ERR_INVALID, "colsum: bad argument");
   TOME_CHECK(n % 8 == 0 && ldx % 8 == 0, TOME_ERR_INVALID, "colsum: n and ldx must be multiples of 8");
   const int chunks = colsum_rows(m);
+  ProfScope prof(PROF_COLSUM, (double)m * n * 2.0, 2, stream);
   const int rpc = ceil_div(m, chunks);
   dim3 grid(ceil_div(n, LN_SLAB), chunks);
   colsum_partial_kernel<<<grid, LN_THREADS, 0, stream>>>(m, n, ldx, rpc, reinterpret_cast<const __nv_bfloat16*>(x), workspace);
@@ -378,6 +379,7 @@ extern "C" int tome_layernorm_fwd(int batch, int tokens, int channels, int axis,
   TOME_CHECK(axis == 1 || axis == 2, TOME_ERR_INVALID, "layernorm_fwd: axis must be 1 (tokens) or 2 (features)");
   const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
+  ProfScope prof(PROF_LN, 2.0 * batch * (double)tokens * channels * 2.0, 1, stream);
   if (axis == 1) {
     TOME_CHECK(batch <= 65535, TOME_ERR_INVALID, "layernorm_fwd: batch too large");
     dim3 grid(ceil_div(channels, LN_SLAB), batch);
@@ -403,6 +405,7 @@ extern "C" int tome_layernorm_bwd(int batch, int tokens, int channels, int axis,
   const __nv_bfloat16* dyp = reinterpret_cast<const __nv_bfloat16*>(dy);
   const __nv_bfloat16* drp = reinterpret_cast<const __nv_bfloat16*>(dres);
   __nv_bfloat16* dxp = reinterpret_cast<__nv_bfloat16*>(dx);
+  ProfScope prof(PROF_LN, (dres ? 4.0 : 3.0) * batch * (double)tokens * channels * 2.0, axis == 1 ? 3 : 4, stream);
   int chunks;
   if (axis == 1) {
     TOME_CHECK(batch <= 65535, TOME_ERR_INVALID, "layernorm_bwd: batch too large");

@@ -281,6 +281,7 @@ extern "C" int tome_sim_argmax(const tome_metric_desc_t* d, const void* src, flo
   TOME_CHECK(d->batch <= 65535, TOME_ERR_INVALID, "sim_argmax: batch too large for one launch");
   const int ta = (d->tokens + 1) / 2;
   const size_t smem = (size_t)2 * SIM_TILE * (d->dim + 1) * sizeof(float);
+  ProfScope prof(PROF_SIM, 2.0 * d->batch * ((d->tokens + 1) / 2) * (double)(d->tokens / 2) * d->dim, 1, stream);
   dim3 grid(ceil_div(ta, SIM_TILE), d->batch);
   if (d->dtype == TOME_BF16) {
     auto kern = sim_argmax_kernel<__nv_bfloat16>;
@@ -312,6 +313,7 @@ extern "C" int tome_select_topr(const tome_plan_shape_t* s, const float* node_ma
   TOME_CHECK(smem <= 220 * 1024, TOME_ERR_UNSUPPORTED, "select_topr: tokens (%d) too large for the shared-memory ranking",
              s->tokens);
   TOME_CUDA(cudaFuncSetAttribute(select_topr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope prof(PROF_SELECT, 0.0, 1, stream);
   select_topr_kernel<<<s->batch, SEL_THREADS, smem, stream>>>(*s, node_max, node_idx, *plan);
   TOME_CUDA(cudaGetLastError());
   return TOME_OK;

@@ -174,6 +174,9 @@ extern "C" int tome_merge_fwd(const tome_merge_shape_t* s, const tome_plan_t* pl
   TOME_CHECK((((uintptr_t)x | (uintptr_t)x_out) & 15) == 0, TOME_ERR_INVALID, "merge_fwd: x / x_out must be 16-byte aligned");
   const int n = s->dtype == TOME_BF16 ? 8 : 4;
   const long long items = (long long)s->batch * (s->tokens - s->r) * (s->channels / n);
+  const double esz = s->dtype == TOME_BF16 ? 2.0 : 4.0;
+  ProfScope prof(PROF_MERGE_FWD, (double)s->batch * ((double)s->tokens * s->channels * esz + 4.0 * s->tokens +
+                 4.0 * ((s->tokens + 1) / 2 + s->r) + (double)(s->tokens - s->r) * s->channels * esz + 4.0 * (s->tokens - s->r)), 1, stream);
   const int grid = merge_grid(items);
   const bool wavg = s->mode == TOME_MERGE_WAVG;
 #define LAUNCH(TT, W)                                                                                              \
@@ -198,6 +201,8 @@ extern "C" int tome_merge_bwd(const tome_merge_shape_t* s, const tome_plan_t* pl
   TOME_CHECK((((uintptr_t)dy | (uintptr_t)dx) & 15) == 0, TOME_ERR_INVALID, "merge_bwd: dy / dx must be 16-byte aligned");
   const int n = s->dtype == TOME_BF16 ? 8 : 4;
   const long long items = (long long)s->batch * s->tokens * (s->channels / n);
+  const double esz = s->dtype == TOME_BF16 ? 2.0 : 4.0;
+  ProfScope prof(PROF_MERGE_BWD, (double)s->batch * ((double)(s->tokens - s->r) * s->channels * esz + (double)s->tokens * s->channels * esz + 4.0 * s->tokens), 1, stream);
   const int grid = merge_grid(items);
 #define LAUNCH(TT, W)                                                                                               \
   merge_bwd_kernel<TT, W><<<grid, MERGE_THREADS, 0, stream>>>(*s, plan->row_map, size, size_out,                    \

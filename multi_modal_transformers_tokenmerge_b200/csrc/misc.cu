@@ -140,6 +140,7 @@ extern "C" int tome_add_pos_embedding(int batch, int tokens, int channels, const
   TOME_CHECK(x && pos_embedding && y, TOME_ERR_INVALID, "add_pos_embedding: null argument");
   TOME_CHECK(x_dtype == TOME_BF16 || x_dtype == TOME_F32, TOME_ERR_INVALID, "add_pos_embedding: bad dtype");
   const long long tc8 = (long long)tokens * channels / 8, n8 = tc8 * batch;
+  ProfScope prof(PROF_OTHER, 0.0, 1, stream);
   if (x_dtype == TOME_F32)
     add_pos_kernel<true><<<ew_grid(n8, 256), 256, 0, stream>>>(n8, tc8, x, pos_embedding, reinterpret_cast<__nv_bfloat16*>(y));
   else
@@ -154,6 +155,7 @@ extern "C" int tome_pos_embedding_bwd(int batch, int tokens, int channels, const
   TOME_CHECK(batch > 0 && tokens > 0 && channels > 0 && channels % 8 == 0 && dy && dpe, TOME_ERR_INVALID,
              "pos_embedding_bwd: bad argument");
   const long long tc8 = (long long)tokens * channels / 8;
+  ProfScope prof(PROF_OTHER, 0.0, 1, stream);
   pos_bwd_kernel<<<(unsigned)((tc8 + 127) / 128), 128, 0, stream>>>(batch, tc8, reinterpret_cast<const __nv_bfloat16*>(dy), dpe);
   TOME_CUDA(cudaGetLastError());
   return TOME_OK;
@@ -172,6 +174,7 @@ extern "C" int tome_chain_row_maps(int batch, int layers, const int32_t* const* 
     a.tokens[l] = l < layers ? tokens_host[l] : 0;
   }
   const int n = batch * n_readout;
+  ProfScope prof(PROF_OTHER, 0.0, 1, stream);
   chain_kernel<<<ceil_div(n, 128), 128, 0, stream>>>(batch, layers, a, readout_idx, n_readout, origin);
   TOME_CUDA(cudaGetLastError());
   return TOME_OK;
@@ -183,6 +186,7 @@ extern "C" int tome_readout_mse(int batch, int tokens, int channels, int n_reado
   cudaStream_t stream = (cudaStream_t)stream_;
   TOME_CHECK(batch > 0 && tokens > 0 && channels > 0 && n_readout > 0 && x && origin, TOME_ERR_INVALID, "readout_mse: bad argument");
   TOME_CHECK(!(loss || dx) || target, TOME_ERR_INVALID, "readout_mse: loss / dx need a target");
+  ProfScope prof(PROF_OTHER, 0.0, loss ? 2 : 1, stream);
   if (dx) TOME_CUDA(cudaMemsetAsync(dx, 0, (size_t)batch * tokens * channels * 2, stream));
   readout_mse_kernel<<<batch, 256, 0, stream>>>(batch, tokens, channels, n_readout, reinterpret_cast<const __nv_bfloat16*>(x),
                                                 origin, target, loss, reinterpret_cast<__nv_bfloat16*>(dx), out);
@@ -200,6 +204,7 @@ extern "C" int tome_adamw_step(long long n, float* param, const float* grad, flo
   clear_error();
   cudaStream_t stream = (cudaStream_t)stream_;
   TOME_CHECK(n > 0 && param && grad && m && v && step >= 1, TOME_ERR_INVALID, "adamw_step: bad argument");
+  ProfScope prof(PROF_OTHER, 0.0, 1, stream);
   const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
   adamw_kernel<<<ew_grid(n, 256), 256, 0, stream>>>(n, param, grad, m, v, reinterpret_cast<__nv_bfloat16*>(bf16_copy), lr, beta1,
                                                     beta2, eps, weight_decay, grad_scale, bc1, bc2);
@@ -211,6 +216,7 @@ extern "C" int tome_cast_f32_to_bf16(long long n, const float* src, void* dst, v
   clear_error();
   cudaStream_t stream = (cudaStream_t)stream_;
   TOME_CHECK(n > 0 && src && dst, TOME_ERR_INVALID, "cast: bad argument");
+  ProfScope prof(PROF_OTHER, 0.0, 1, stream);
   cast_kernel<<<ew_grid(n, 256), 256, 0, stream>>>(n, src, reinterpret_cast<__nv_bfloat16*>(dst));
   TOME_CUDA(cudaGetLastError());
   return TOME_OK;

@@ -305,6 +305,7 @@ extern "C" int tome_stack_forward(const tome_stack_cfg_t* c, const tome_stack_io
   RC(tome_add_pos_embedding(B, c->tokens, C, io->x, io->x_dtype, pf, S.L[0].x_in, st));
   if (c->num_groups) {
     const int n = B * c->tokens;
+    ProfScope prof(PROF_OTHER, 0.0, 1, st);
     broadcast_groups_kernel<<<ceil_div(n, 256), 256, 0, st>>>(B, c->tokens, io->gid, io->pos, S.L[0].gid_in, S.L[0].pos_in);
     TOME_CUDA(cudaGetLastError());
   }
@@ -389,6 +390,7 @@ extern "C" int tome_stack_backward(const tome_stack_cfg_t* c, const tome_stack_i
     const long long n8 = n / 8;
     long long blocks = (n8 + 255) / 256;
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    ProfScope prof(PROF_OTHER, 0.0, 1, st);
     dropout_apply_kernel<<<(unsigned)blocks, 256, 0, st>>>(n8, src, dst, make_drop(c, (uint32_t)site));
     return dst;
   };
