@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TOME_ABI_VERSION 3
+#define TOME_ABI_VERSION 4
 
 enum tome_status { TOME_OK = 0, TOME_ERR_INVALID = 1, TOME_ERR_CUDA = 2, TOME_ERR_UNSUPPORTED = 3 };
 enum tome_dtype { TOME_BF16 = 0, TOME_F32 = 1 };
@@ -129,6 +129,7 @@ typedef struct {
   float dropout_rate; uint64_t dropout_seed; uint32_t dropout_site;
   int k_splits;
   int accumulate;
+  int no_multicast; /* debugging aid: 1 disables the CTA-pair TMA multicast of the B operand */
 } tome_gemm_args_t;
 
 size_t tome_gemm_workspace_bytes(const tome_gemm_args_t* args);

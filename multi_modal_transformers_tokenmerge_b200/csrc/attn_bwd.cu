@@ -27,6 +27,8 @@ struct AttnBwdParams {
   float scale, scale_log2;
   const uint8_t* gid;
   const int32_t* pos;
+  const uint8_t* allow;
+  int num_groups;
   const uint2* mwords;  // [B,T] (m_all, m_causal) or null
   const float* size;
   const float* lse;     // [B,H,T]
@@ -81,7 +83,7 @@ constexpr int DKV_BQ = 64;   // queries per tile
 constexpr int DKV_KV_BYTES = DKV_BK * AB_D * 2;  // 16 KB
 constexpr int DKV_Q_BYTES = DKV_BQ * AB_D * 2;   // 8 KB
 constexpr int DKV_PT_BYTES = DKV_BK * DKV_BQ * 2;  // 16 KB
-constexpr int DKV_META = 2 * DKV_BQ * 20;          // lse2, delta, m_all, m_causal, pos  x 2 parities
+constexpr int DKV_META = 2 * DKV_BQ * 12 + 2 * 2 * 32 * 2 * 4;  // lse2, delta, pos x 2 parities; query-visibility words (all, causal) per key group x 2 parities
 constexpr int DKV_SMEM = 2 * DKV_KV_BYTES + 2 * 2 * DKV_Q_BYTES + 2 * DKV_PT_BYTES + DKV_META + 256 + 1024;
 
 __global__ void __launch_bounds__(AB_THREADS, 2)
@@ -97,10 +99,10 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   uint8_t* s_dst = s_pt + DKV_PT_BYTES;           // dS^T
   float* s_lse = reinterpret_cast<float*>(s_dst + DKV_PT_BYTES);  // [2][64]
   float* s_delta = s_lse + 2 * DKV_BQ;
-  uint32_t* s_mall = reinterpret_cast<uint32_t*>(s_delta + 2 * DKV_BQ);
-  uint32_t* s_mcau = s_mall + 2 * DKV_BQ;
-  int* s_posq = reinterpret_cast<int*>(s_mcau + 2 * DKV_BQ);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_posq + 2 * DKV_BQ);
+  int* s_posq = reinterpret_cast<int*>(s_delta + 2 * DKV_BQ);
+  uint32_t* s_qvis = reinterpret_cast<uint32_t*>(s_posq + 2 * DKV_BQ);  // [2][32 key groups][2] queries that see the group
+  uint32_t* s_qvisc = s_qvis + 2 * 32 * 2;                              // [2][32][2] ... iff pos_k <= pos_q
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_qvisc + 2 * 32 * 2);
   uint64_t* kv_full = bars;        // 1
   uint64_t* q_full = bars + 1;     // [2]
   uint64_t* q_empty = bars + 3;    // [2]
@@ -208,9 +210,9 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     }
     for (int i = 0; i < n_q; ++i) {
       const int par = i & 1;
-      if (row < DKV_BQ) {  // per-query metadata of this tile
+      if (row < DKV_BQ) {  // per-query metadata of this tile (warps 0 and 1: one query per thread)
         const int q = i * DKV_BQ + row;
-        float l2 = INFINITY, dl = 0.f;
+        float l2 = INFINITY, dl = 0.f;    // queries past T: exp2(s - inf) = 0
         uint32_t ma = 0xffffffffu, mc = 0;
         int pq = 0;
         if (q < T) {
@@ -225,30 +227,57 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         }
         s_lse[par * DKV_BQ + row] = l2;
         s_delta[par * DKV_BQ + row] = dl;
-        s_mall[par * DKV_BQ + row] = ma;
-        s_mcau[par * DKV_BQ + row] = mc;
-        s_posq[par * DKV_BQ + row] = pq;
+        if (has_mask) {
+          s_posq[par * DKV_BQ + row] = pq;
+          for (int g = 0; g < p.num_groups; ++g) {  // bit q of word (g, warp): query q sees keys of group g
+            const uint32_t wa = __ballot_sync(0xffffffffu, (ma >> g) & 1u);
+            const uint32_t wc = __ballot_sync(0xffffffffu, (mc >> g) & 1u);
+            if (lane == 0) {
+              s_qvis[(par * 32 + g) * 2 + warp] = wa;
+              s_qvisc[(par * 32 + g) * 2 + warp] = wc;
+            }
+          }
+        }
       }
       named_bar_sync_b(1, DKV_BK);
+      uint32_t vw[2] = {0xffffffffu, 0xffffffffu}, vc[2] = {0u, 0u};
+      if (has_mask) {
+        vw[0] = s_qvis[(par * 32 + gk) * 2];
+        vw[1] = s_qvis[(par * 32 + gk) * 2 + 1];
+        vc[0] = s_qvisc[(par * 32 + gk) * 2];
+        vc[1] = s_qvisc[(par * 32 + gk) * 2 + 1];
+      }
+      if (!k_valid) vw[0] = vw[1] = vc[0] = vc[1] = 0u;  // rows past T contribute nothing
+      const float4* lse4 = reinterpret_cast<const float4*>(s_lse + par * DKV_BQ);
+      const float4* del4 = reinterpret_cast<const float4*>(s_delta + par * DKV_BQ);
       mbar_wait(st_full, i & 1);
       tc_fence_after();
       if (i >= 1) mbar_wait(pd_free, (i - 1) & 1);  // previous P^T / dS^T fully consumed by the tensor core
-#pragma unroll 1
-      for (int c0 = 0; c0 < DKV_BQ; c0 += 32) {
+#pragma unroll
+      for (int cq = 0; cq < DKV_BQ / 32; ++cq) {
+        const int c0 = cq * 32;
         uint32_t sv[32], dv[32];
         tmem_ld_x32(tm_st + lane_sel + c0, sv);
         tmem_ld_x32(tm_dpt + lane_sel + c0, dv);
+        uint32_t word = vw[cq];
+        if (vc[cq]) {  // rare (Text sets): fold the causal rule into the visibility word
+          for (int c = 0; c < 32; ++c)
+            if (((vc[cq] >> c) & 1u) && pk <= s_posq[par * DKV_BQ + c0 + c]) word |= 1u << c;
+        }
         tmem_ld_wait();
         float pv[32], ds[32];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const int qi = par * DKV_BQ + c0 + c;
-          float s2 = fmaf(__uint_as_float(sv[c]), p.scale_log2, bias2);
-          bool ok = k_valid;
-          if (has_mask) ok = ok && (((s_mall[qi] >> gk) & 1u) || (((s_mcau[qi] >> gk) & 1u) && pk <= s_posq[qi]));
-          const float pe = ok ? exp2f(s2 - s_lse[qi]) : 0.f;
-          pv[c] = pe;
-          ds[c] = pe * (__uint_as_float(dv[c]) - s_delta[qi]) * p.scale;
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 l4 = lse4[cq * 8 + c4], d4 = del4[cq * 8 + c4];
+          const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dl4[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int c = c4 * 4 + u;
+            const float s2 = fmaf(__uint_as_float(sv[c]), p.scale_log2, bias2);
+            const float pe = ((word >> c) & 1u) ? fast_exp2(s2 - lv[u]) : 0.f;
+            pv[c] = pe;
+            ds[c] = pe * p.scale * (__uint_as_float(dv[c]) - dl4[u]);
+          }
         }
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
@@ -306,7 +335,7 @@ constexpr int DQ_BK = 64;   // keys per tile
 constexpr int DQ_Q_BYTES = DQ_BQ * AB_D * 2;   // 16 KB
 constexpr int DQ_K_BYTES = DQ_BK * AB_D * 2;   // 8 KB
 constexpr int DQ_DS_BYTES = DQ_BQ * DQ_BK * 2;  // 16 KB
-constexpr int DQ_META = 2 * DQ_BK * 12;
+constexpr int DQ_META = 2 * DQ_BK * 8 + 2 * 2 * 32 * 2 * 4 + 2 * 32 * 4;  // bias2, pos x 2 parities; key-visibility words per query group; column words
 constexpr int DQ_SMEM = 2 * DQ_Q_BYTES + 2 * 2 * DQ_K_BYTES + DQ_DS_BYTES + DQ_META + 256 + 1024;
 
 __global__ void __launch_bounds__(AB_THREADS, 2)
@@ -320,9 +349,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   uint8_t* s_kv = s_do + DQ_Q_BYTES;             // stage s: K at s*16K, V at s*16K + 8K
   uint8_t* s_ds = s_kv + 2 * 2 * DQ_K_BYTES;     // dS [128 queries][64 keys] bf16 K-major swizzled
   float* s_bias = reinterpret_cast<float*>(s_ds + DQ_DS_BYTES);  // [2][64]
-  int* s_gid = reinterpret_cast<int*>(s_bias + 2 * DQ_BK);
-  int* s_pos = s_gid + 2 * DQ_BK;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_pos + 2 * DQ_BK);
+  int* s_pos = reinterpret_cast<int*>(s_bias + 2 * DQ_BK);
+  uint32_t* s_vis = reinterpret_cast<uint32_t*>(s_pos + 2 * DQ_BK);  // [2][32 query groups][2] keys visible to the group
+  uint32_t* s_visc = s_vis + 2 * 32 * 2;                             // [2][32][2] ... iff pos_k <= pos_q
+  uint32_t* s_colw = s_visc + 2 * 32 * 2;                            // [32] query groups that see key group g (code 1)
+  uint32_t* s_colc = s_colw + 32;                                    // [32] (code 2)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_colc + 32);
   uint64_t* q_full = bars;          // Q and dO
   uint64_t* kv_full = bars + 1;     // [2]
   uint64_t* kv_empty = bars + 3;    // [2]
@@ -354,6 +386,18 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     tma_prefetch_desc(&tm_do);
   }
   if (warp == 5) tmem_alloc(tmem_slot, AB_TMEM_COLS);
+  if (threadIdx.x < 32) {  // transpose the mask words: which query groups may see keys of group g
+    uint32_t cw = 0, cc = 0;
+    const int g = threadIdx.x;
+    if (p.allow != nullptr && g < p.num_groups)
+      for (int qg = 0; qg < p.num_groups; ++qg) {
+        const int a = p.allow[qg * p.num_groups + g];
+        cw |= (a == 1 ? 1u : 0u) << qg;
+        cc |= (a == 2 ? 1u : 0u) << qg;
+      }
+    s_colw[g] = cw;
+    s_colc[g] = cc;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -416,57 +460,80 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const bool has_mask = p.mwords != nullptr;
     const bool q_valid = q < T;
     float lse2 = INFINITY, dl = 0.f;
-    uint32_t m_all = 0xffffffffu, m_causal = 0u;
-    int pos_q = 0;
+    int gq = 0, pos_q = 0;
     if (q_valid) {
       lse2 = p.lse[((long long)b * p.heads + h) * T + q] * 1.4426950408889634f;
       dl = p.delta[((long long)b * p.heads + h) * T + q];
       if (has_mask) {
-        const uint2 w = p.mwords[(long long)b * T + q];
-        m_all = w.x;
-        m_causal = w.y;
+        gq = p.gid[(long long)b * T + q];
         pos_q = p.pos[(long long)b * T + q];
       }
     }
     for (int j = 0; j < n_k; ++j) {
       const int par = j & 1;
-      if (row < DQ_BK) {
+      if (row < DQ_BK) {  // per-key metadata (warps 0 and 1: one key per thread)
         const int kk = j * DQ_BK + row;
-        float bias2 = -INFINITY;  // keys past T contribute nothing
-        int gk = 0, pk = 0;
+        float bias2 = -INFINITY;  // keys past T contribute nothing (and stay "visible" so the -inf survives)
+        uint32_t cw = 0xffffffffu, cc = 0u;
+        int pk = 0;
         if (kk < T) {
           bias2 = p.size ? log2f(p.size[(long long)b * T + kk]) : 0.f;
           if (has_mask) {
-            gk = p.gid[(long long)b * T + kk];
+            const int gk = p.gid[(long long)b * T + kk];
+            cw = s_colw[gk];
+            cc = s_colc[gk];
             pk = p.pos[(long long)b * T + kk];
           }
         }
         s_bias[par * DQ_BK + row] = bias2;
-        s_gid[par * DQ_BK + row] = gk;
-        s_pos[par * DQ_BK + row] = pk;
+        if (has_mask) {
+          s_pos[par * DQ_BK + row] = pk;
+          for (int g = 0; g < p.num_groups; ++g) {
+            const uint32_t wa = __ballot_sync(0xffffffffu, (cw >> g) & 1u);
+            const uint32_t wc = __ballot_sync(0xffffffffu, (cc >> g) & 1u);
+            if (lane == 0) {
+              s_vis[(par * 32 + g) * 2 + warp] = wa;
+              s_visc[(par * 32 + g) * 2 + warp] = wc;
+            }
+          }
+        }
       }
       named_bar_sync_b(1, DQ_BQ);
+      uint32_t vw[2] = {0xffffffffu, 0xffffffffu}, vc[2] = {0u, 0u};
+      if (has_mask) {
+        vw[0] = s_vis[(par * 32 + gq) * 2];
+        vw[1] = s_vis[(par * 32 + gq) * 2 + 1];
+        vc[0] = s_visc[(par * 32 + gq) * 2];
+        vc[1] = s_visc[(par * 32 + gq) * 2 + 1];
+      }
+      const float4* bias4 = reinterpret_cast<const float4*>(s_bias + par * DQ_BK);
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       if (j >= 1) mbar_wait(ds_free, (j - 1) & 1);
-#pragma unroll 1
-      for (int c0 = 0; c0 < DQ_BK; c0 += 32) {
+#pragma unroll
+      for (int cq = 0; cq < DQ_BK / 32; ++cq) {
+        const int c0 = cq * 32;
         uint32_t sv[32], dv[32];
         tmem_ld_x32(tm_s + lane_sel + c0, sv);
         tmem_ld_x32(tm_dp + lane_sel + c0, dv);
+        uint32_t word = vw[cq];
+        if (vc[cq]) {
+          for (int c = 0; c < 32; ++c)
+            if (((vc[cq] >> c) & 1u) && s_pos[par * DQ_BK + c0 + c] <= pos_q) word |= 1u << c;
+        }
         tmem_ld_wait();
         float ds[32];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const int ki = par * DQ_BK + c0 + c;
-          const float s2 = fmaf(__uint_as_float(sv[c]), p.scale_log2, s_bias[ki]);
-          bool ok = true;
-          if (has_mask) {
-            const int g = s_gid[ki];
-            ok = ((m_all >> g) & 1u) || (((m_causal >> g) & 1u) && s_pos[ki] <= pos_q);
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 b4 = bias4[cq * 8 + c4];
+          const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int c = c4 * 4 + u;
+            const float s2 = fmaf(__uint_as_float(sv[c]), p.scale_log2, bv[u]);
+            const float pe = ((word >> c) & 1u) ? fast_exp2(s2 - lse2) : 0.f;
+            ds[c] = pe * p.scale * (__uint_as_float(dv[c]) - dl);
           }
-          const float pe = ok ? exp2f(s2 - lse2) : 0.f;
-          ds[c] = pe * (__uint_as_float(dv[c]) - dl) * p.scale;
         }
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
@@ -536,7 +603,7 @@ extern "C" int tome_attention_bwd(const tome_attn_desc_t* d, const tome_attn_gra
   AttnBwdParams p;
   p.batch = B; p.tokens = T; p.heads = H;
   p.scale = d->scale; p.scale_log2 = d->scale * 1.4426950408889634f;
-  p.gid = d->gid; p.pos = d->pos; p.mwords = mwords; p.size = d->size; p.lse = lse; p.delta = delta;
+  p.gid = d->gid; p.pos = d->pos; p.allow = d->gid ? d->allow : nullptr; p.num_groups = d->num_groups; p.mwords = mwords; p.size = d->size; p.lse = lse; p.delta = delta;
   p.dq = reinterpret_cast<__nv_bfloat16*>(dq); p.dq_bs = gs->dq_batch_stride; p.dq_ts = gs->dq_token_stride;
   p.dk = reinterpret_cast<__nv_bfloat16*>(dk); p.dk_bs = gs->dk_batch_stride; p.dk_ts = gs->dk_token_stride;
   p.dv = reinterpret_cast<__nv_bfloat16*>(dv); p.dv_bs = gs->dv_batch_stride; p.dv_ts = gs->dv_token_stride;

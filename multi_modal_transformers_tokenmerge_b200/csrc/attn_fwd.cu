@@ -5,9 +5,13 @@
 // One CTA = one (batch, head, 128-query tile); 2 CTAs per SM interleave (TMEM 256 columns each).
 //   warp 4      TMA producer: Q once, then K_0 V_0 K_1 V_1 ... (128 keys x 64 each) through a 3-slot ring, 128B swizzle
 //   warp 5      UMMA issuer:  S = Q K_j^T (128x128x64) -> TMEM cols [0,128);  O_j = P_j V_j (128x64x128) -> cols [128,192)
-//   warps 0..3  softmax: thread = query row.  S is read from TMEM twice (row max, then exp2), P_j is written to
-//               shared memory as the bf16 K-major A operand of the second MMA, O is kept in fp32 REGISTERS and
-//               rescaled there (O = O * alpha + O_j), so TMEM never needs a correction pass.
+//   warps 0..3  softmax: thread = query row.  Pass 1 reads S from TMEM, applies scale + log-size bias + mask, takes
+//               the row max and writes the finished logits back to TMEM; pass 2 re-reads them, exponentiates and
+//               writes P_j to shared memory as the bf16 K-major A operand of the second MMA.  O is kept in fp32
+//               REGISTERS and rescaled there (O = O * alpha + O_j), so TMEM never needs a correction pass.
+//               The mask costs one bit test per element: per key tile the 128 threads publish, by warp ballots, one
+//               128-bit "visible keys" word set per QUERY GROUP (the mask depends on a query only through its
+//               group), and the log-size bias is fetched four keys per shared-memory read.
 // Logits are kept in the log2 domain: s2 = (q.k) * scale * log2(e) + log2(size_k); masked -> -FLT_MAX (finite, as
 // flax's finfo.min), keys past T -> -inf.
 #include <float.h>
@@ -25,7 +29,7 @@ constexpr int ATT_Q_BYTES = ATT_BM * ATT_D * 2;         // 16 KB
 constexpr int ATT_KV_BYTES = ATT_BN * ATT_D * 2;        // 16 KB each for K and V
 constexpr int ATT_P_BYTES = ATT_BM * ATT_BN * 2;        // 32 KB (two 64-key K-blocks of 16 KB)
 constexpr int ATT_SLOTS = 3;  // ring of 16 KB slots; items are loaded in the order K_0 V_0 K_1 V_1 ...
-constexpr int ATT_SMEM_META = 2 * ATT_BN * (4 + 4 + 4);  // bias2 f32, pos i32, gid (as i32) x 2 parities
+constexpr int ATT_SMEM_META = 2 * ATT_BN * (4 + 4 + 4) + 2 * 32 * 4 * 4 * 2 + 2 * 32 * 4 + 16;  // bias2/pos/gid x 2 parities, visible-key words (all, causal) per group x 2 parities, column words
 constexpr int ATT_SMEM = ATT_Q_BYTES + ATT_SLOTS * ATT_KV_BYTES + ATT_P_BYTES + ATT_SMEM_META + 256 + 1024;
 constexpr uint32_t ATT_TMEM_COLS = 256;
 
@@ -57,7 +61,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   float* s_bias = reinterpret_cast<float*>(s_p + ATT_P_BYTES);  // [2][128]
   int* s_pos = reinterpret_cast<int*>(s_bias + 2 * ATT_BN);     // [2][128]
   int* s_gid = s_pos + 2 * ATT_BN;                              // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_gid + 2 * ATT_BN);
+  uint32_t* s_vis = reinterpret_cast<uint32_t*>(s_gid + 2 * ATT_BN);  // [2][32 groups][4] keys visible to a query group
+  uint32_t* s_visc = s_vis + 2 * 32 * 4;                        // [2][32][4] keys visible iff pos_k <= pos_q
+  uint32_t* s_colw = s_visc + 2 * 32 * 4;                       // [32] query groups that see key group g (code 1)
+  uint32_t* s_colc = s_colw + 32;                               // [32] ... (code 2)
+  uint32_t* s_anyc = s_colc + 32;                               // [1]  some rule is causal
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_anyc + 4);
   uint64_t* q_full = bars;                // 1
   uint64_t* kv_full = bars + 1;           // [3]
   uint64_t* kv_empty = bars + 4;          // [3]
@@ -88,6 +97,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     tma_prefetch_desc(&tm_v);
   }
   if (warp == 5) tmem_alloc(tmem_slot, ATT_TMEM_COLS);
+  if (threadIdx.x < 32) {  // transpose the allow table: which query groups may see keys of group g
+    uint32_t cw = 0, cc = 0;
+    const int g = threadIdx.x;
+    if (p.gid != nullptr && g < p.num_groups)
+      for (int qg = 0; qg < p.num_groups; ++qg) {
+        const int a = p.allow[qg * p.num_groups + g];
+        cw |= (a == 1 ? 1u : 0u) << qg;
+        cc |= (a == 2 ? 1u : 0u) << qg;
+      }
+    s_colw[g] = cw;
+    s_colc[g] = cc;
+    const uint32_t any = __ballot_sync(0xffffffffu, cc != 0);
+    if (g == 0) s_anyc[0] = any;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -153,17 +176,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int q = qt * ATT_BM + row;
     const uint32_t lane_sel = ((uint32_t)(warp * 32)) << 16;
     const bool has_mask = p.gid != nullptr;
-    uint32_t m_all = 0xffffffffu, m_causal = 0u;
-    int pos_q = 0;
+    const bool any_causal = has_mask && s_anyc[0] != 0;
+    int gq = 0, pos_q = 0;
     if (has_mask && q < T) {
-      const int gq = p.gid[(long long)b * T + q];
+      gq = p.gid[(long long)b * T + q];
       pos_q = p.pos[(long long)b * T + q];
-      m_all = 0u;
-      for (int g = 0; g < p.num_groups; ++g) {
-        const int a = p.allow[gq * p.num_groups + g];
-        m_all |= (a == 1 ? 1u : 0u) << g;
-        m_causal |= (a == 2 ? 1u : 0u) << g;
-      }
     }
     float o_acc[ATT_D];
 #pragma unroll
@@ -172,53 +189,78 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
     for (int j = 0; j < n_kv; ++j) {
       const int par = j & 1;
-      {  // per-key metadata of this tile (each softmax thread loads one key)
+      {  // per-key metadata of this tile: thread `row` owns key j*128 + row
         const int kk = j * ATT_BN + row;
-        float bias2 = 0.f;
-        int pk = 0, gk = 0;
+        float bias2 = -INFINITY;           // keys past T: logit -inf (and "visible", so the mask keeps the -inf)
+        uint32_t cw = 0xffffffffu, cc = 0u;
+        int pk = 0;
         if (kk < T) {
-          if (p.size) bias2 = log2f(p.size[(long long)b * T + kk]);
+          bias2 = p.size ? log2f(p.size[(long long)b * T + kk]) : 0.f;
           if (has_mask) {
+            const int gk = p.gid[(long long)b * T + kk];
+            cw = s_colw[gk];
+            cc = s_colc[gk];
             pk = p.pos[(long long)b * T + kk];
-            gk = p.gid[(long long)b * T + kk];
           }
         }
         s_bias[par * ATT_BN + row] = bias2;
-        s_pos[par * ATT_BN + row] = pk;
-        s_gid[par * ATT_BN + row] = gk;
+        if (has_mask) {
+          for (int g = 0; g < p.num_groups; ++g) {
+            const uint32_t w = __ballot_sync(0xffffffffu, (cw >> g) & 1u);
+            if (lane == 0) s_vis[(par * 32 + g) * 4 + warp] = w;
+          }
+          if (any_causal) {
+            s_pos[par * ATT_BN + row] = pk;
+            for (int g = 0; g < p.num_groups; ++g) {
+              const uint32_t w = __ballot_sync(0xffffffffu, (cc >> g) & 1u);
+              if (lane == 0) s_visc[(par * 32 + g) * 4 + warp] = w;
+            }
+          }
+        }
       }
       named_bar_sync(1, ATT_BM);
-      const float* bias_t = s_bias + par * ATT_BN;
-      const int* pos_t = s_pos + par * ATT_BN;
-      const int* gid_t = s_gid + par * ATT_BN;
-      const int n_valid = min(ATT_BN, T - j * ATT_BN);
+      const float4* bias4 = reinterpret_cast<const float4*>(s_bias + par * ATT_BN);
+      uint4 vis = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu), visc = make_uint4(0u, 0u, 0u, 0u);
+      if (has_mask) {
+        vis = *reinterpret_cast<const uint4*>(s_vis + (par * 32 + gq) * 4);
+        if (any_causal) visc = *reinterpret_cast<const uint4*>(s_visc + (par * 32 + gq) * 4);
+      }
+      const bool causal_row = (visc.x | visc.y | visc.z | visc.w) != 0u;
 
       mbar_wait(s_full, j & 1);
       tc_fence_after();
 
-      auto logit = [&](float raw, int c) -> float {
-        float s2 = fmaf(raw, p.scale_log2, bias_t[c]);
-        if (has_mask) {
-          const int g = gid_t[c];
-          const bool ok = ((m_all >> g) & 1u) || (((m_causal >> g) & 1u) && pos_t[c] <= pos_q);
-          s2 = ok ? s2 : -FLT_MAX;
-        }
-        if (c >= n_valid) s2 = -INFINITY;
-        return s2;
-      };
-
-      // pass 1: row maximum
+      // pass 1: finished logits (log2 domain) back to TMEM + row maximum
       float m_tile = -INFINITY;
 #pragma unroll 1
-      for (int c0 = 0; c0 < ATT_BN; c0 += 32) {
+      for (int cq = 0; cq < ATT_BN / 32; ++cq) {
         uint32_t v[32];
-        tmem_ld_x32(tmem_s + lane_sel + c0, v);
+        tmem_ld_x32(tmem_s + lane_sel + cq * 32, v);
+        uint32_t vw = cq == 0 ? vis.x : cq == 1 ? vis.y : cq == 2 ? vis.z : vis.w;
+        if (causal_row) {  // rare (Text sets): fold the causal rule into the visibility word
+          const uint32_t cwd = cq == 0 ? visc.x : cq == 1 ? visc.y : cq == 2 ? visc.z : visc.w;
+          for (int i = 0; i < 32; ++i)
+            if (((cwd >> i) & 1u) && s_pos[par * ATT_BN + cq * 32 + i] <= pos_q) vw |= 1u << i;
+        }
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) m_tile = fmaxf(m_tile, logit(__uint_as_float(v[i]), c0 + i));
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 bb = bias4[cq * 8 + i4];
+          const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i4 * 4 + u;
+            float s2 = fmaf(__uint_as_float(v[i]), p.scale_log2, bv[u]);
+            if (has_mask) s2 = ((vw >> i) & 1u) ? s2 : -FLT_MAX;
+            m_tile = fmaxf(m_tile, s2);
+            v[i] = __float_as_uint(s2);
+          }
+        }
+        tmem_st_x32(tmem_s + lane_sel + cq * 32, v);
       }
+      tmem_st_wait();
       const float m_new = fmaxf(m_run, m_tile);  // finite: tile 0 always holds key 0
-      const float alpha = exp2f(m_run - m_new);  // first tile: exp2(-inf) = 0
+      const float alpha = fast_exp2(m_run - m_new);  // first tile: exp2(-inf) = 0
 
       // fold O_{j-1} (its MMA completed before S_j's commit fired) into the register accumulator
       if (j > 0) {
@@ -245,7 +287,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         float pv[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          pv[i] = exp2f(logit(__uint_as_float(v[i]), c0 + i) - m_new);
+          pv[i] = fast_exp2(__uint_as_float(v[i]) - m_new);
           l_tile += pv[i];
         }
         uint8_t* prow = s_p + (c0 >> 6) * 16384 + row * 128;
@@ -260,7 +302,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       l_run = fmaf(l_run, alpha, l_tile);
       m_run = m_new;
       fence_proxy_async_smem();  // P visible to the tensor core (async proxy)
-      tc_fence_before();         // our TMEM reads of S_j / O_{j-1} are ordered before the MMAs that overwrite them
+      tc_fence_before();         // our TMEM accesses of S_j / O_{j-1} are ordered before the MMAs that overwrite them
       mbar_arrive(p_ready);
     }
     // last tile's O

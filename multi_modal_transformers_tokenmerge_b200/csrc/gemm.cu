@@ -12,8 +12,14 @@
 // Roles (192 threads, 1 CTA per SM, persistent over a static round-robin tile schedule):
 //   warp 0      TMA producer        global -> smem ring (STAGES x {A 16 KB, B BN*128 B}), 128B swizzle
 //   warp 1      UMMA issuer         one thread issues tcgen05.mma 128 x BN x 16, accumulators double-buffered in TMEM
-//   warps 2..5  epilogue            tcgen05.ld (thread = row, 32 columns at a time) -> bias/ReLU/dropout/residual
-//                                   -> 128-bit global stores; overlaps the next tile's main loop
+//   warps 2..9  epilogue            two warps per TMEM lane quadrant, each owning half of the tile's columns:
+//                                   tcgen05.ld (thread = row, 32 columns at a time) -> bias/ReLU/gate/dropout/residual
+//                                   -> 128-bit global stores; overlaps the next tile's main loop.  Everything the
+//                                   epilogue reads from memory (bias tile -> shared memory, residual / gate rows ->
+//                                   registers) is fetched BEFORE it waits for the accumulator, so no global-load
+//                                   latency sits between the MMA's completion and the stores.
+#include <string.h>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -21,7 +27,9 @@ namespace tome {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
+
 
 struct GemmEpilogue {
   void* c;             // [M, ldc] bf16 or fp32
@@ -40,6 +48,7 @@ struct GemmEpilogue {
 struct GemmShape {
   int m, n, k;
   int m_tiles, n_tiles, k_splits, kb_per_split, kb_total;
+  int m_items;  // m_tiles, or ceil(m_tiles / 2) when CTA pairs share the B operand
 };
 
 template <int BN>
@@ -47,50 +56,61 @@ struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN <= 128) ? 6 : 4;
-  static constexpr int BAR_BYTES = 256;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual 1 KB alignment
+  static constexpr int STAGES = (BN <= 128) ? 6 : (BN <= 192) ? 5 : 4;  // 6 x 32 KB, 5 x 40 KB, 4 x 48 KB
+  static constexpr int STORE_BYTES = GEMM_EPI_WARPS * 2048;  // per epilogue warp: 32 rows x 64 B staging tile for TMA stores
+  static constexpr int BAR_BYTES = 256 + 2 * BN * 4;  // barriers + double-buffered bias tile
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + STORE_BYTES + BAR_BYTES + 1024;  // +1024: manual 1 KB alignment
 };
 
-template <int BN, bool A_MN, bool B_MN>
+// MC: clusters of two CTAs work on vertically adjacent tiles (same n_blk); each CTA fetches half of the shared B tile
+// and TMA-multicasts it into both CTAs, halving the L2 -> SM traffic of B (the K = C = 384 projections are bound by
+// that traffic, not by the tensor pipe).  A stage is reusable once BOTH CTAs' MMAs have drained it.
+template <int BN, bool A_MN, bool B_MN, bool MC>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                 const GemmShape s, const GemmEpilogue e) {
+                 const __grid_constant__ CUtensorMap tma_c, const GemmShape s, const GemmEpilogue e) {
   using L = GemmSmem<BN>;
   constexpr int STAGES = L::STAGES;
-  constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages
-  static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two");
+  constexpr uint32_t TMEM_COLS = BN <= 64 ? 128 : BN <= 128 ? 256 : 512;  // two accumulator stages of BN columns
+  static_assert(2 * BN <= 512 && BN % 64 == 0, "two BN-column accumulators must fit the 512 TMEM columns");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES);
+  uint8_t* s_store = smem + STAGES * L::STAGE_BYTES;  // 1 KB aligned (stage sizes are multiples of 1 KB)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_store + L::STORE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* s_bias = reinterpret_cast<float*>(s_store + L::STORE_BYTES + 256);  // [2][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = s.m_tiles * s.n_tiles * s.k_splits;
+  const int num_tiles = s.m_items * s.n_tiles * s.k_splits;  // work items (tile, or vertical tile pair)
+  const uint32_t crank = MC ? cluster_ctarank() : 0u;
+  const int first_item = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int item_step = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    if (!e.c_is_f32) tma_prefetch_desc(&tma_c);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], MC ? 2 : 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], GEMM_EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();  // the peer's barriers exist before anything is multicast at them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -99,10 +119,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = first_item; tile < num_tiles; tile += item_step) {
         const int split = tile % s.k_splits;
         const int n_blk = (tile / s.k_splits) % s.n_tiles;
-        const int m_blk = tile / (s.k_splits * s.n_tiles);
+        const int m_blk = (tile / (s.k_splits * s.n_tiles)) * (MC ? 2 : 1) + (int)crank;
         const int m0 = m_blk * GEMM_BM, n0 = n_blk * BN;
         const int kb0 = split * s.kb_per_split;
         const int kb1 = min(kb0 + s.kb_per_split, s.kb_total);
@@ -119,11 +139,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             for (int j = 0; j < GEMM_BM / 64; ++j)  // box {64 m, 64 k} per 64-wide M atom
               tma_load_2d(sa + j * 8192, &tma_a, &full_bar[stage], m0 + 64 * j, k0);
           }
-          if (!B_MN) {
-            tma_load_2d(sb, &tma_b, &full_bar[stage], k0, n0);  // box {64 k, BN n}
-          } else {
+          if (!MC) {
+            if (!B_MN) {
+              tma_load_2d(sb, &tma_b, &full_bar[stage], k0, n0);  // box {64 k, BN n}
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tma_b, &full_bar[stage], n0 + 64 * j, k0);
+              for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tma_b, &full_bar[stage], n0 + 64 * j, k0);
+            }
+          } else {  // this CTA's share of B, multicast to both CTAs of the pair
+            if (!B_MN) {
+              tma_load_2d_mc(sb + crank * (BN / 2) * 128, &tma_b, &full_bar[stage], k0, n0 + (int)crank * (BN / 2), (uint16_t)3);  // box {64 k, BN/2 n}
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                if ((j & 1) == (int)crank) tma_load_2d_mc(sb + j * 8192, &tma_b, &full_bar[stage], n0 + 64 * j, k0, (uint16_t)3);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -137,7 +167,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = first_item; tile < num_tiles; tile += item_step) {
         const int split = tile % s.k_splits;
         const int kb0 = split * s.kb_per_split;
         const int kb1 = min(kb0 + s.kb_per_split, s.kb_total);
@@ -155,7 +185,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
             umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (MC) umma_commit_mc(&empty_bar[stage], (uint16_t)3);  // both CTAs' producers may refill this stage
+          else umma_commit(&empty_bar[stage]);                     // smem slot reusable once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
@@ -163,86 +194,105 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       }
     }
   } else {
-    // ================================================================= epilogue (warps 2..5)
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // ================================================================= epilogue (warps 2..9)
+    constexpr int HALF = BN / 2;                 // columns per epilogue warp
+    constexpr int NCH = HALF / 32;               // 32-column chunks per warp
+    const int ew = warp - 2;
+    const int quad = warp & 3;                   // TMEM lane quadrant this warp may access
+    const int half = ew >> 2;                    // which half of the tile's columns
     const int row_in_tile = quad * 32 + lane;
+    const int etid = threadIdx.x - 64;           // 0..255
+    const __nv_bfloat16* resid = reinterpret_cast<const __nv_bfloat16*>(e.residual);
+    const __nv_bfloat16* gate = reinterpret_cast<const __nv_bfloat16*>(e.gate);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = first_item; tile < num_tiles; tile += item_step) {
       const int split = tile % s.k_splits;
       const int n_blk = (tile / s.k_splits) % s.n_tiles;
-      const int m_blk = tile / (s.k_splits * s.n_tiles);
+      const int m_blk = (tile / (s.k_splits * s.n_tiles)) * (MC ? 2 : 1) + (int)crank;
       const long long row = (long long)m_blk * GEMM_BM + row_in_tile;
       const int n0 = n_blk * BN;
+      const int cbase = n0 + half * HALF;
+      const bool row_ok = row < s.m;
+      // ---- prefetch everything the epilogue reads, while the tensor core is still working on this tile
+      if (e.bias && etid < BN) s_bias[acc * BN + etid] = (n0 + etid < s.n) ? __ldg(e.bias + n0 + etid) : 0.f;
+      // one prefetch array serves the residual or, when there is no residual, the gate (the library's own callers
+      // never pass both; if both are given the gate is read inside the loop)
+      const __nv_bfloat16* pre_src = resid ? resid : gate;
+      const long long pre_ld = resid ? e.ldr : e.ldg;
+      uint4 pre[NCH][4];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int col = cbase + c * 32 + i * 8;
+          pre[c][i] = (pre_src && row_ok && col < s.n) ? __ldg(reinterpret_cast<const uint4*>(pre_src + row * pre_ld + col))
+                                                      : make_uint4(0u, 0u, 0u, 0u);
+        }
+      asm volatile("bar.sync 1, %0;" ::"r"(32 * GEMM_EPI_WARPS) : "memory");  // bias tile visible to all epilogue warps
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      const uint32_t t_addr = tmem_base + acc * BN + half * HALF + ((uint32_t)(quad * 32) << 16);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
         uint32_t v[32];
-        tmem_ld_x32(t_addr + c0, v);
+        tmem_ld_x32(t_addr + c * 32, v);
         tmem_ld_wait();
-        const int col = n0 + c0;
-        if (row < s.m && col < s.n) {
-          float acc_f[32];
+        const int col = cbase + c * 32;
+        const bool active = row_ok && col < s.n;  // rows / columns past the edge are computed but never stored
+        float acc_f[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc_f[i] = __uint_as_float(v[i]);
-          const int ncols = min(32, s.n - col);  // multiple of 8 (host checks n % 8 == 0)
-          if (e.bias) {
+        for (int i = 0; i < 32; ++i) acc_f[i] = __uint_as_float(v[i]);
+        const int ncols = min(32, s.n - col);  // multiple of 8 (host checks n % 8 == 0); <= 0 past the edge
+        if (e.bias) {
+          const float4* b4p = reinterpret_cast<const float4*>(s_bias + acc * BN + half * HALF + c * 32);
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              if (i < ncols) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col + i));
-                acc_f[i] += b4.x; acc_f[i + 1] += b4.y; acc_f[i + 2] += b4.z; acc_f[i + 3] += b4.w;
-              }
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = b4p[i / 4];
+            acc_f[i] += b4.x; acc_f[i + 1] += b4.y; acc_f[i + 2] += b4.z; acc_f[i + 3] += b4.w;
+          }
+        }
+        if (e.relu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc_f[i] = fmaxf(acc_f[i], 0.f);
+        }
+        if (gate) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 gq = pre[c][i / 8];
+            if (resid && active && i < ncols) gq = __ldg(reinterpret_cast<const uint4*>(gate + row * e.ldg + col + i));
+            const uint32_t w[4] = {gq.x, gq.y, gq.z, gq.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              acc_f[i + 2 * j] *= (bf16_lo(w[j]) > 0.f) ? e.gate_scale : 0.f;
+              acc_f[i + 2 * j + 1] *= (bf16_hi(w[j]) > 0.f) ? e.gate_scale : 0.f;
             }
           }
-          if (e.relu) {
+        }
+        if (e.drop.thresh16 && active) {
+          const uint64_t ebase = (uint64_t)row * (uint64_t)s.n + (uint64_t)col;  // n % 8 == 0 -> 8-aligned
 #pragma unroll
-            for (int i = 0; i < 32; ++i) acc_f[i] = fmaxf(acc_f[i], 0.f);
-          }
-          if (e.gate) {
-            const uint4* g = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(e.gate) + row * e.ldg + col);
+          for (int i = 0; i < 32; i += 8) {
+            if (i < ncols) {
+              const uint32_t keep = dropout_keep8(e.drop, (ebase + i) >> 3);
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              if (i < ncols) {
-                const uint4 gv = __ldg(g + i / 8);
-                const uint32_t w[4] = {gv.x, gv.y, gv.z, gv.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  acc_f[i + 2 * j] *= (bf16_lo(w[j]) > 0.f) ? e.gate_scale : 0.f;
-                  acc_f[i + 2 * j + 1] *= (bf16_hi(w[j]) > 0.f) ? e.gate_scale : 0.f;
-                }
-              }
+              for (int j = 0; j < 8; ++j) acc_f[i + j] = ((keep >> j) & 1u) ? acc_f[i + j] * e.drop.inv_keep : 0.f;
             }
           }
-          if (e.drop.thresh16) {
-            const uint64_t ebase = (uint64_t)row * (uint64_t)s.n + (uint64_t)col;  // n % 8 == 0 -> 8-aligned
+        }
+        if (resid) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              if (i < ncols) {
-                const uint32_t keep = dropout_keep8(e.drop, (ebase + i) >> 3);
+          for (int i = 0; i < 32; i += 8) {
+            const uint32_t w[4] = {pre[c][i / 8].x, pre[c][i / 8].y, pre[c][i / 8].z, pre[c][i / 8].w};
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc_f[i + j] = ((keep >> j) & 1u) ? acc_f[i + j] * e.drop.inv_keep : 0.f;
-              }
+            for (int j = 0; j < 4; ++j) {
+              acc_f[i + 2 * j] += bf16_lo(w[j]);
+              acc_f[i + 2 * j + 1] += bf16_hi(w[j]);
             }
           }
-          if (e.residual) {
-            const uint4* r = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(e.residual) + row * e.ldr + col);
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              if (i < ncols) {
-                const uint4 rv = __ldg(r + i / 8);
-                const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  acc_f[i + 2 * j] += bf16_lo(w[j]);
-                  acc_f[i + 2 * j + 1] += bf16_hi(w[j]);
-                }
-              }
-            }
-          }
-          if (e.c_is_f32) {
+        }
+        if (e.c_is_f32) {
+          if (active) {
             float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.c) + (long long)split * e.split_stride + row * e.ldc + col);
 #pragma unroll
             for (int i = 0; i < 32; i += 4)
@@ -254,13 +304,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 }
                 o[i / 4] = ov;
               }
-          } else {
-            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.c) + row * e.ldc + col);
+          }
+        } else {
+          // bf16: stage this warp's 32 rows x 32 columns in shared memory (64-byte swizzled rows) and hand the box to
+          // TMA, which writes whole lines and clips rows >= M / columns >= N.
+          uint8_t* stg = s_store + ew * 2048;
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous box has left smem
+          __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 32; i += 8)
-              if (i < ncols)
-                o[i / 8] = make_uint4(pack_bf16(acc_f[i], acc_f[i + 1]), pack_bf16(acc_f[i + 2], acc_f[i + 3]),
-                                      pack_bf16(acc_f[i + 4], acc_f[i + 5]), pack_bf16(acc_f[i + 6], acc_f[i + 7]));
+          for (int i = 0; i < 32; i += 8) {
+            const int chunk = i / 8;
+            *reinterpret_cast<uint4*>(stg + lane * 64 + ((chunk ^ ((lane >> 1) & 3)) << 4)) =
+                make_uint4(pack_bf16(acc_f[i], acc_f[i + 1]), pack_bf16(acc_f[i + 2], acc_f[i + 3]),
+                           pack_bf16(acc_f[i + 4], acc_f[i + 5]), pack_bf16(acc_f[i + 6], acc_f[i + 7]));
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            const int row0 = m_blk * GEMM_BM + quad * 32;
+            if (col < s.n && row0 < s.m) {
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                           ::"l"(&tma_c), "r"(smem_u32(stg)), "r"(col), "r"(row0) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
       }
@@ -269,10 +335,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all of this warp's TMA stores are complete
   }
 
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();  // the peer may still multicast into this CTA's smem / arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -298,25 +366,48 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __re
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& s, const GemmEpilogue& e,
+template <int BN, bool A_MN, bool B_MN, bool MC>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmShape& s, const GemmEpilogue& e,
                        cudaStream_t stream) {
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, MC>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     TOME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::TOTAL));
     attr_set = true;
   }
-  const int num_tiles = s.m_tiles * s.n_tiles * s.k_splits;
-  const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
-  kern<<<grid, GEMM_THREADS, GemmSmem<BN>::TOTAL, stream>>>(ta, tb, s, e);
-  TOME_CUDA(cudaGetLastError());
+  const int items = s.m_items * s.n_tiles * s.k_splits;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = GemmSmem<BN>::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  if (MC) {
+    const int clusters = items < kNumSMs / 2 ? items : kNumSMs / 2;
+    cfg.gridDim = dim3(2 * clusters);
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  } else {
+    cfg.gridDim = dim3(items < kNumSMs ? items : kNumSMs);
+  }
+  TOME_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, s, e));
   return TOME_OK;
 }
 
 }  // namespace tome
 
 using namespace tome;
+
+static int pick_bn(int n) {  // fewest N tiles, then the narrower tile
+  const int t256 = ceil_div(n, 256), t192 = ceil_div(n, 192), t128 = ceil_div(n, 128);
+  if (t128 <= t192 && t128 <= t256) return 128;
+  if (t192 <= t256) return 192;
+  return 256;
+}
 
 static int pick_splits(const tome_gemm_args_t* a, int bn) {
   if (a->k_splits > 0) return a->k_splits;
@@ -333,7 +424,7 @@ static int pick_splits(const tome_gemm_args_t* a, int bn) {
 
 extern "C" size_t tome_gemm_workspace_bytes(const tome_gemm_args_t* a) {
   if (!a) return 0;
-  const int splits = pick_splits(a, 128);
+  const int splits = pick_splits(a, pick_bn(a->n));
   if (splits <= 1) return 0;
   return (size_t)splits * (size_t)a->m * (size_t)a->ldc * sizeof(float);
 }
@@ -352,7 +443,7 @@ extern "C" int tome_gemm_bf16(const tome_gemm_args_t* a, void* workspace, size_t
   TOME_CHECK(!a->gate || a->ldg % 8 == 0, TOME_ERR_INVALID, "gemm: ldg must be a multiple of 8");
   TOME_CHECK(a->dropout_rate >= 0.f && a->dropout_rate < 1.f, TOME_ERR_INVALID, "gemm: dropout_rate must be in [0,1)");
 
-  const int bn = 128;
+  const int bn = pick_bn(a->n);
   GemmShape s;
   s.m = a->m; s.n = a->n; s.k = a->k;
   s.m_tiles = ceil_div(a->m, GEMM_BM);
@@ -361,6 +452,9 @@ extern "C" int tome_gemm_bf16(const tome_gemm_args_t* a, void* workspace, size_t
   s.k_splits = pick_splits(a, bn);
   s.kb_per_split = ceil_div(s.kb_total, s.k_splits);
   s.k_splits = ceil_div(s.kb_total, s.kb_per_split);  // drop empty splits
+  // CTA pairs sharing B: worth it unless an odd, small tile count would leave a large share of dummy tiles
+  const bool mc = a->no_multicast == 0 && s.m_tiles >= 2 && (s.m_tiles % 2 == 0 || s.m_tiles >= 16);
+  s.m_items = mc ? ceil_div(s.m_tiles, 2) : s.m_tiles;
 
   GemmEpilogue e;
   e.c = a->c; e.bias = a->bias; e.residual = a->residual; e.gate = a->gate;
@@ -391,16 +485,36 @@ extern "C" int tome_gemm_bf16(const tome_gemm_args_t* a, void* workspace, size_t
   if (a->a_major == TOME_MAJOR_K) rc = make_tmap_2d_bf16(&ta, a->a, a->m, a->k, a->lda, GEMM_BM);
   else rc = make_tmap_2d_bf16(&ta, a->a, a->k, a->m, a->lda, GEMM_BK);
   if (rc) return rc;
-  if (a->b_major == TOME_MAJOR_K) rc = make_tmap_2d_bf16(&tb, a->b, a->n, a->k, a->ldb, bn);
+  if (a->b_major == TOME_MAJOR_K) rc = make_tmap_2d_bf16(&tb, a->b, a->n, a->k, a->ldb, mc ? bn / 2 : bn);
   else rc = make_tmap_2d_bf16(&tb, a->b, a->k, a->n, a->ldb, GEMM_BK);
   if (rc) return rc;
 
+  CUtensorMap tc;
+  memset(&tc, 0, sizeof(tc));
+  if (!e.c_is_f32) {  // bf16 outputs leave through TMA stores: box {32 columns, 32 rows}, 64-byte swizzle
+    rc = make_tmap_2d_bf16_store32(&tc, a->c, a->m, a->n, a->ldc);
+    if (rc) return rc;
+  }
   const bool amn = a->a_major == TOME_MAJOR_MN, bmn = a->b_major == TOME_MAJOR_MN;
   ProfScope prof(PROF_GEMM, 2.0 * a->m * (double)a->n * a->k, s.k_splits > 1 ? 2 : 1, stream);
-  if (!amn && !bmn) rc = launch_gemm<128, false, false>(ta, tb, s, e, stream);
-  else if (!amn && bmn) rc = launch_gemm<128, false, true>(ta, tb, s, e, stream);
-  else if (amn && !bmn) rc = launch_gemm<128, true, false>(ta, tb, s, e, stream);
-  else rc = launch_gemm<128, true, true>(ta, tb, s, e, stream);
+#define TOME_GEMM_DISPATCH(BN_)                                                      \
+  do {                                                                              \
+    if (mc) {                                                                             \
+      if (!amn && !bmn) rc = launch_gemm<BN_, false, false, true>(ta, tb, tc, s, e, stream);    \
+      else if (!amn && bmn) rc = launch_gemm<BN_, false, true, true>(ta, tb, tc, s, e, stream); \
+      else if (amn && !bmn) rc = launch_gemm<BN_, true, false, true>(ta, tb, tc, s, e, stream); \
+      else rc = launch_gemm<BN_, true, true, true>(ta, tb, tc, s, e, stream);                   \
+    } else {                                                                              \
+      if (!amn && !bmn) rc = launch_gemm<BN_, false, false, false>(ta, tb, tc, s, e, stream);    \
+      else if (!amn && bmn) rc = launch_gemm<BN_, false, true, false>(ta, tb, tc, s, e, stream); \
+      else if (amn && !bmn) rc = launch_gemm<BN_, true, false, false>(ta, tb, tc, s, e, stream); \
+      else rc = launch_gemm<BN_, true, true, false>(ta, tb, tc, s, e, stream);                   \
+    }                                                                                     \
+  } while (0)
+  if (bn == 128) TOME_GEMM_DISPATCH(128);
+  else if (bn == 192) TOME_GEMM_DISPATCH(192);
+  else TOME_GEMM_DISPATCH(256);
+#undef TOME_GEMM_DISPATCH
   if (rc) return rc;
 
   if (s.k_splits > 1) {

@@ -35,13 +35,13 @@ static EncodeTiledFn get_encode() {
 }
 
 static int encode(CUtensorMap* out, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
-                  const cuuint32_t* box) {
+                  const cuuint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = get_encode();
   TOME_CHECK(fn != nullptr, TOME_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   TOME_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, TOME_ERR_INVALID, "TMA base pointer must be 16-byte aligned");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_b, box,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   TOME_CHECK(r == CUDA_SUCCESS, TOME_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu x %llu)",
              (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1]);
@@ -54,6 +54,14 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   cuuint64_t strides[1] = {ld * 2};
   cuuint32_t box[2] = {64, box_rows};
   return encode(out, base, 2, dims, strides, box);
+}
+
+int make_tmap_2d_bf16_store32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld) {
+  TOME_CHECK((ld * 2) % 16 == 0, TOME_ERR_INVALID, "TMA row pitch must be a multiple of 16 bytes (ld=%llu)", (unsigned long long)ld);
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {32, 32};
+  return encode(out, base, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
 int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,

@@ -30,6 +30,8 @@ void clear_error();
 // Row-major bf16 matrix [rows, cols] with leading dimension ld (elements), described as a 2-D TMA tensor with a
 // {64 x box_rows} box and 128-byte swizzle.  cols*2 and ld*2 must be multiples of 16 bytes.
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+// Same matrix as a TMA STORE target: box {32 columns, 32 rows}, 64-byte swizzle (one epilogue warp's chunk).
+int make_tmap_2d_bf16_store32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld);
 // [d2, d1, d0] bf16 tensor (d0 contiguous; strides in elements), box {64, box_d1, 1}, 128-byte swizzle.
 int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,
                       uint64_t stride2, uint32_t box_d1);

@@ -35,52 +35,52 @@ __device__ __forceinline__ float2 load2<__nv_bfloat16>(const __nv_bfloat16* p) {
   return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
 }
 
-// Load `SIM_TILE` metric rows (token = 2*row + parity) into smem as normalised fp32 rows of pitch dim+1.
+// Load `SIM_TILE` metric rows (token = 2*row + parity) into smem as normalised fp32 rows, zero-padded to a multiple of 4
+// columns, pitch = padded dim + 4 floats (16-byte aligned rows; consecutive rows start 4 banks apart).
 template <typename T>
 __device__ __forceinline__ void load_rows_normalised(float* dst, const T* src, const tome_metric_desc_t& d, int b,
                                                      int row0, int nrows_total, int parity) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pitch = d.dim + 1;
+  // 4 threads per row, all 64 rows of the tile in flight at once (one memory-latency chain per tile)
+  const int rr = threadIdx.x >> 2, part = threadIdx.x & 3;
+  const int dpad = (d.dim + 3) & ~3, pitch = dpad + 4;
   const float inv_h = 1.0f / (float)d.heads;
-  for (int rr = warp; rr < SIM_TILE; rr += SIM_THREADS / 32) {
-    const int row = row0 + rr;
-    float* drow = dst + rr * pitch;
-    if (row >= nrows_total) {
-      for (int c = lane; c < d.dim; c += 32) drow[c] = 0.f;
-      continue;
+  const int row = row0 + rr;
+  float* drow = dst + rr * pitch;
+  const bool valid = row < nrows_total;  // rows past the end become zero rows; every lane still takes the shuffles
+  const T* base = src + (long long)b * d.batch_stride + (long long)(2 * (valid ? row : 0) + parity) * d.token_stride;
+  float ss = 0.f;
+  for (int c = 2 * part; c < d.dim; c += 8) {
+    float2 acc = make_float2(0.f, 0.f);
+    for (int h = 0; h < (valid ? d.heads : 0); ++h) {
+      const float2 v = load2<T>(base + (long long)h * d.head_stride + c);
+      acc.x += v.x;
+      acc.y += v.y;
     }
-    const T* base = src + (long long)b * d.batch_stride + (long long)(2 * row + parity) * d.token_stride;
-    float ss = 0.f;
-    for (int c = 2 * lane; c < d.dim; c += 64) {
-      float2 acc = make_float2(0.f, 0.f);
-      for (int h = 0; h < d.heads; ++h) {
-        const float2 v = load2<T>(base + (long long)h * d.head_stride + c);
-        acc.x += v.x;
-        acc.y += v.y;
-      }
-      if (d.heads > 1) {  // jnp.mean over heads = sum / H
-        acc.x *= inv_h;
-        acc.y *= inv_h;
-      }
-      drow[c] = acc.x;
-      drow[c + 1] = acc.y;
-      ss += acc.x * acc.x + acc.y * acc.y;
+    if (d.heads > 1) {  // jnp.mean over heads = sum / H
+      acc.x *= inv_h;
+      acc.y *= inv_h;
     }
-    ss = warp_sum(ss);
-    const float nrm = sqrtf(ss);  // no epsilon (token_compression.py:72): a zero row becomes NaN
-    for (int c = 2 * lane; c < d.dim; c += 64) {
-      drow[c] = drow[c] / nrm;
-      drow[c + 1] = drow[c + 1] / nrm;
-    }
+    drow[c] = acc.x;
+    drow[c + 1] = acc.y;
+    ss += acc.x * acc.x + acc.y * acc.y;
   }
+  ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+  ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+  const float nrm = valid ? sqrtf(ss) : 1.0f;  // no epsilon (token_compression.py:72): a zero row becomes NaN
+  for (int c = 2 * part; c < d.dim; c += 8) {
+    drow[c] = drow[c] / nrm;
+    drow[c + 1] = drow[c + 1] / nrm;
+  }
+  if (part < dpad - d.dim) drow[d.dim + part] = 0.f;
 }
 
 template <typename T>
 __global__ void __launch_bounds__(SIM_THREADS)
 sim_argmax_kernel(const tome_metric_desc_t d, const T* __restrict__ src, float* __restrict__ node_max,
                   int32_t* __restrict__ node_idx, float* __restrict__ scores_out) {
-  extern __shared__ float sm[];
-  const int pitch = d.dim + 1;
+  extern __shared__ float4 sm4[];
+  float* sm = reinterpret_cast<float*>(sm4);
+  const int dpad = (d.dim + 3) & ~3, pitch = dpad + 4;
   float* sa = sm;
   float* sb = sm + SIM_TILE * pitch;
   const int b = blockIdx.y;
@@ -107,16 +107,21 @@ sim_argmax_kernel(const tome_metric_desc_t d, const T* __restrict__ src, float* 
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int c = 0; c < d.dim; ++c) {
-      float av[4], bv[4];
+    for (int c = 0; c < dpad; c += 4) {  // one 128-bit shared-memory read feeds 4 k-steps: 8 LDS.128 per 64 FMAs
+      float4 av[4], bv[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) av[i] = sa[(ty + 16 * i) * pitch + c];
+      for (int i = 0; i < 4; ++i) av[i] = *reinterpret_cast<const float4*>(sa + (ty + 16 * i) * pitch + c);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bv[j] = sb[(tx + 16 * j) * pitch + c];
+      for (int j = 0; j < 4; ++j) bv[j] = *reinterpret_cast<const float4*>(sb + (tx + 16 * j) * pitch + c);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) {  // ascending k, one accumulator: the order of a plain dot product
+          acc[i][j] = fmaf(av[i].x, bv[j].x, acc[i][j]);
+          acc[i][j] = fmaf(av[i].y, bv[j].y, acc[i][j]);
+          acc[i][j] = fmaf(av[i].z, bv[j].z, acc[i][j]);
+          acc[i][j] = fmaf(av[i].w, bv[j].w, acc[i][j]);
+        }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -280,7 +285,7 @@ extern "C" int tome_sim_argmax(const tome_metric_desc_t* d, const void* src, flo
              "sim_argmax: strides must be even (vector loads)");
   TOME_CHECK(d->batch <= 65535, TOME_ERR_INVALID, "sim_argmax: batch too large for one launch");
   const int ta = (d->tokens + 1) / 2;
-  const size_t smem = (size_t)2 * SIM_TILE * (d->dim + 1) * sizeof(float);
+  const size_t smem = (size_t)2 * SIM_TILE * (((d->dim + 3) & ~3) + 4) * sizeof(float);
   ProfScope prof(PROF_SIM, 2.0 * d->batch * ((d->tokens + 1) / 2) * (double)(d->tokens / 2) * d->dim, 1, stream);
   dim3 grid(ceil_div(ta, SIM_TILE), d->batch);
   if (d->dtype == TOME_BF16) {

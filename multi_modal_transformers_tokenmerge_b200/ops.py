@@ -146,7 +146,7 @@ def merge_bwd(plan: MatchPlan, dy: torch.Tensor, size: Optional[torch.Tensor], s
 def gemm(a: torch.Tensor, b: torch.Tensor, *, m: int, n: int, k: int, a_major=L.TOME_MAJOR_K, b_major=L.TOME_MAJOR_K,
          lda=None, ldb=None, out: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16, bias=None, residual=None,
          gate=None, gate_scale=1.0, relu=False, dropout_rate=0.0, dropout_seed=0, dropout_site=0, k_splits=0,
-         accumulate=False) -> torch.Tensor:
+         accumulate=False, no_multicast=False) -> torch.Tensor:
     """C[M,N] = epilogue(A * B^T) on tcgen05.  a/b are 2-D bf16 tensors whose rows are M/N (K-major) or K (MN-major)."""
     _need_cuda(a, b)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
@@ -159,7 +159,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, m: int, n: int, k: int, a_major=L.
                       None if residual is None else residual.data_ptr(), 0 if residual is None else residual.stride(0),
                       None if gate is None else gate.data_ptr(), 0 if gate is None else gate.stride(0),
                       float(gate_scale), int(relu), float(dropout_rate), int(dropout_seed), int(dropout_site),
-                      int(k_splits), int(accumulate))
+                      int(k_splits), int(accumulate), int(no_multicast))
     ws_bytes = L.lib().tome_gemm_workspace_bytes(C.byref(args))
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=a.device) if ws_bytes else None
     L.check(L.lib().tome_gemm_bf16(C.byref(args), _ptr(ws), ws_bytes, _stream()))
