@@ -1,0 +1,245 @@
+"""The reference-facing Python API (same names / signatures / error behaviour as multi_modal_transformers/
+tokenizers/token_compression.py and attention_blocks/{attention,tome_attention}.py).
+
+CPU part: configuration, parameter-tree shape, mask conversion, argument errors (no kernel is launched).
+GPU part (-m gpu): the operator API against the reference-generated goldens and the oracle; the per-block modules
+chained in Python against the native stack executor (same kernels -> identical bits) and against the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from multi_modal_transformers_tokenmerge_b200 import model_configs as MC  # noqa: E402
+from multi_modal_transformers_tokenmerge_b200.attention_blocks import _functional as F  # noqa: E402
+from multi_modal_transformers_tokenmerge_b200.attention_blocks import attention as A  # noqa: E402
+from multi_modal_transformers_tokenmerge_b200.attention_blocks import tome_attention as TA  # noqa: E402
+from multi_modal_transformers_tokenmerge_b200.tokenizers import token_compression as TCm  # noqa: E402
+from multi_modal_transformers_tokenmerge_b200.tokenizers.token_sequencer import TokenSequence  # noqa: E402
+from oracle import tome_oracle as O  # noqa: E402  (checker only)
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+SEQ = "[TaskDescriptionPrefix{4}] [Image{24};Readout{2}]*2"
+
+
+def small_cfg(C=128, H=2, Dff=256, blocks=2, r=4, hidden_drop=0.0):
+    cfg = MC.load("attention_blocks/tome_decoder_octo_small")
+    cfg["num_blocks"], cfg["tome_r"] = blocks, r
+    e = cfg["encoder_1d_block"]
+    e["self_attention"].update(num_heads=H, qkv_features=C)
+    e["mlp_block"]["dense"]["features"] = Dff
+    e["mlp_block"]["dense_out"]["features"] = C
+    e["dropout"]["rate"] = hidden_drop
+    e["mlp_block"]["norm"]["rate"] = hidden_drop
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------ CPU
+def test_yaml_schema_of_the_reference_is_accepted():
+    cfg = MC.load("attention_blocks/tome_decoder_octo_base")
+    assert set(cfg["encoder_1d_block"]) == {"_target_", "layer_norm", "dropout", "self_attention", "mlp_block"}
+    st = MC.build_stack(cfg)
+    assert isinstance(st, TA.StackedEncoder1DBlock) and st.r == 32 and st.num_blocks == 12
+    ln, dr, at, mlp = st._block()._specs()
+    assert (ln.axis, ln.epsilon, dr.rate, at.num_heads, at.qkv_features) == (1, 1e-6, 0.1, 12, 768)
+    d, act, mdrop, do = mlp._specs()
+    assert (d.features, act, mdrop.rate, do.features) == (3072, "relu", 0.1, 768)
+    # the literal reference node kinds (SelfAttention target, vanilla block) resolve to the vanilla stack
+    lit = {"num_blocks": 1, "encoder_1d_block": dict(cfg["encoder_1d_block"], _target_="multi_modal_transformers.attention_blocks.attention.Encoder1DBlock")}
+    lit["encoder_1d_block"]["self_attention"] = dict(cfg["encoder_1d_block"]["self_attention"], _target_="flax.linen.SelfAttention")
+    assert type(MC.build_stack(lit)) is A.StackedEncoder1DBlock
+    with pytest.raises(ValueError):
+        A.instantiate({"_target_": "flax.linen.Conv"})
+
+
+def test_param_tree_has_flax_names_and_scan_axis():
+    cfg = small_cfg(C=128, H=2, Dff=256, blocks=3)
+    st = MC.build_stack(cfg)
+    x = torch.zeros(2, 56, 128)
+    v = st.init(0, x)
+    p = v["params"]
+    assert p["posembed_input"]["pos_embedding"].shape == (1, 56, 128)          # attention.py:97-100
+    blk = p["ScanEncoder1DBlock_0"]                                             # nn.scan, params stacked on axis 0
+    a = blk["ToMeMultiHeadDotProductAttention_0"]
+    assert a["query"]["kernel"].shape == (3, 128, 2, 64) and a["query"]["bias"].shape == (3, 2, 64)
+    assert a["out"]["kernel"].shape == (3, 2, 64, 128) and a["out"]["bias"].shape == (3, 128)
+    assert blk["LayerNorm_0"]["scale"].shape == (3, 128) and blk["LayerNorm_1"]["bias"].shape == (3, 128)
+    assert blk["MLPBlock_0"]["Dense_0"]["kernel"].shape == (3, 128, 256)
+    assert blk["MLPBlock_0"]["Dense_1"]["kernel"].shape == (3, 256, 128)
+    layers = A.flax_tree_to_layers(blk, "ToMeMultiHeadDotProductAttention_0", 3)
+    assert layers[1]["wq"].shape == (128, 128) and layers[2]["wo"].shape == (128, 128) and layers[0]["w1"].shape == (128, 256)
+
+
+def test_dense_mask_to_group_table_roundtrip():
+    ts = TokenSequence("[TaskDescriptionPrefix{16}] [Image{25};Readout{4}]*2")     # octo_base.yaml:10
+    dense = ts.generate_attention_mask(repeats=3)                                 # [H, T, T] as octo.py:66-68
+    gm = F.group_mask_from_dense(np.broadcast_to(dense, (2,) + dense.shape), device="cpu")
+    gid = gm.gid.numpy()
+    allow = gm.allow.numpy()
+    assert allow.shape[0] <= 5
+    np.testing.assert_array_equal(allow[gid][:, gid].astype(bool), dense[0])
+    bad = np.broadcast_to(dense, (2,) + dense.shape).copy()
+    bad[1, 0, 0, -1] ^= True
+    with pytest.raises(ValueError):
+        F.group_mask_from_dense(bad, device="cpu")
+
+
+def test_argument_errors_follow_the_reference():
+    att = TA.ToMeMultiHeadDotProductAttention(num_heads=2, qkv_features=128)
+    x = torch.zeros(1, 8, 128)
+    v = att.init(0, x)
+    with pytest.raises(ValueError):                      # tome_attention.py:116-121
+        att.apply(v, x, None, x)
+    with pytest.raises(ValueError):                      # :94-103
+        att.apply(v, x, x, inputs_kv=x)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        att.apply(v, x)
+    with pytest.raises(ValueError):                      # :139-142
+        TA.ToMeMultiHeadDotProductAttention(num_heads=3, qkv_features=128).init(0, x)
+    blk = MC.build_stack(small_cfg())._block()
+    with pytest.raises(ValueError):                      # merge_param('train', None, None)  attention.py:54
+        blk.apply(blk.init(0, x), x.cuda() if torch.cuda.is_available() else x)
+    with pytest.raises(ValueError):
+        TCm.bipartite_soft_matching(torch.zeros(4, 8), 2)
+    m = TCm._Merge(None, 8)
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 8, 4), mode="mean")
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+gpu = pytest.mark.gpu
+
+
+def _dev(a, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(a)).cuda()
+    return t if dtype is None else t.to(dtype)
+
+
+@gpu
+def test_operator_api_against_reference_goldens():
+    """bipartite_soft_matching / merge / merge_wavg called exactly as the reference is (token_compression.py:54-129) on
+    the golden inputs: outputs equal the reference's own outputs bit for bit wherever the indices agree."""
+    TC = np.load(os.path.join(GOLD, "token_compression.npz"))
+    n_exact = 0
+    for name in [str(n) for n in TC["names"]]:
+        B, T, Dm, C, r, cls, dis = [int(v) for v in TC[f"{name}/cfg"]]
+        metric, x = _dev(TC[f"{name}/metric"]), _dev(TC[f"{name}/x"])
+        merge = TCm.bipartite_soft_matching(metric, r, class_token=bool(cls), distill_token=bool(dis))
+        x1, s1 = TCm.merge_wavg(merge, x)
+        assert s1.shape == (B, T - merge.r, 1) and x1.shape == (B, T - merge.r, C)
+        if merge.r == 0:
+            np.testing.assert_array_equal(x1.cpu().numpy(), TC[f"{name}/x"])
+            continue
+        same = np.array_equal(merge.plan.src_idx.cpu().numpy(), TC[f"{name}/src_idx"][..., 0] if TC[f"{name}/src_idx"].ndim == 3 else TC[f"{name}/src_idx"]) \
+            and np.array_equal(merge.plan.dst_idx.cpu().numpy(), TC[f"{name}/dst_idx"][..., 0] if TC[f"{name}/dst_idx"].ndim == 3 else TC[f"{name}/dst_idx"])
+        if same:
+            n_exact += 1
+            np.testing.assert_array_equal(x1.cpu().numpy(), TC[f"{name}/x1"])
+            np.testing.assert_array_equal(s1.cpu().numpy(), TC[f"{name}/s1"])
+            np.testing.assert_array_equal(merge(x, mode="sum").cpu().numpy(), TC[f"{name}/xsum"])
+        # merge(size) alone, as merge_wavg's second call does (:126)
+        ones = torch.ones(B, T, 1, device="cuda")
+        np.testing.assert_array_equal(merge(ones).cpu().numpy(), s1.cpu().numpy())
+        # unmerge(merge_wavg(x)) puts every merged row back at all of its members' positions
+        um = merge.unmerge(x1)
+        assert um.shape == (B, T, C)
+    assert n_exact >= 3
+
+
+@gpu
+@pytest.mark.parametrize("r", [0, 4])
+def test_blocks_chained_in_python_equal_the_native_stack_and_the_oracle(r):
+    cfg = small_cfg(C=128, H=2, Dff=256, blocks=2, r=r)
+    ts = TokenSequence(SEQ)
+    T = ts.num_tokens
+    B, C = 2, 128
+    rng = np.random.default_rng(0)
+    x = _dev(rng.standard_normal((B, T, C)).astype(np.float32))
+    stack = MC.build_stack(cfg)
+    variables = stack.init(1, x)
+    gm = F.GroupMask.from_token_sequence(ts)
+    # (a) the native executor through the reference-shaped call
+    y_stack = stack.apply(variables, x, train=False, mask=gm)
+    assert y_stack.shape == (B, T - 2 * r, C)
+    # (b) the caller's own loop over ToMeEncoder1DBlock, parameters unstacked from the scan axis
+    p = variables["params"]
+    h = A.AddPositionEmbedding().apply({"params": p["posembed_input"]}, x)
+    state = F.ToMeState()
+    blk = stack._block()
+    for l in range(2):
+        pl = {"params": _index_tree(p["ScanEncoder1DBlock_0"], l)}
+        h, none = blk.apply(pl, h, mask=gm, train=False, tome_state=state, site=3 * l)
+        assert none is None
+    torch.testing.assert_close(h, y_stack, rtol=0, atol=0)
+    if r:
+        torch.testing.assert_close(state.size, stack.last_size, rtol=0, atol=0)
+        assert float(state.size.sum(dim=1)[0]) == T
+    # (c) the same with the dense boolean mask of octo.py:66-68 instead of the group table
+    dense = torch.as_tensor(ts.generate_attention_mask(repeats=2))[None].expand(B, -1, -1, -1)
+    y_dense = stack.apply(variables, x, train=False, mask=dense)
+    torch.testing.assert_close(y_dense, y_stack, rtol=0, atol=0)
+    # (d) the oracle (fp32, bf16-rounded weights), tolerance 3e-2 relative L2 as in test_gpu_stack.py
+    gid, pos, allow, _ = O.sequence_groups(SEQ)
+    layers = A.flax_tree_to_layers(p["ScanEncoder1DBlock_0"], blk._attn_name, 2)
+    rb = lambda a: torch.as_tensor(np.asarray(a)).bfloat16().float()  # noqa: E731
+    params = []
+    for lay in layers:
+        d = {k: (rb(v) if k.startswith("w") else torch.as_tensor(np.asarray(v))) for k, v in lay.items()}
+        params.append(O.BlockParams(**d))
+    node_override = None
+    if r:
+        eng = stack._engine
+        node_override = [tuple(t.cpu().numpy() for t in eng.layer_plan(l)[:2]) for l in range(2)]
+    xf, size, origin = O.tome_stack(params, torch.as_tensor(p["posembed_input"]["pos_embedding"]), x.cpu(), gid, pos, allow,
+                                    num_heads=2, r=r, node_override=node_override)
+    err = (y_stack.float().cpu() - xf).norm() / xf.norm()
+    assert err <= 3e-2, err
+
+
+def _index_tree(tree, l):
+    if isinstance(tree, dict):
+        return {k: _index_tree(v, l) for k, v in tree.items()}
+    return tree[l]
+
+
+@gpu
+def test_mha_module_and_hidden_dropout_site_parity():
+    """ToMeMultiHeadDotProductAttention alone (projections + masked attention + out) against the oracle's attention, and
+    train=True hidden dropout: the Python-chained blocks and the native stack draw the same Philox masks."""
+    ts = TokenSequence(SEQ)
+    T, B, C, H = ts.num_tokens, 2, 128, 2
+    rng = np.random.default_rng(3)
+    x = _dev(rng.standard_normal((B, T, C)).astype(np.float32)).bfloat16()
+    att = TA.ToMeMultiHeadDotProductAttention(num_heads=H, qkv_features=C, kernel_init="he_normal", bias_init="normal")
+    v = att.init(5, x)
+    gm = F.GroupMask.from_token_sequence(ts)
+    size = _dev(rng.integers(1, 4, size=(B, T)).astype(np.float32))
+    out, metric = att.apply(v, x, mask=gm, size=size, return_metric=True)
+    p = v["params"]
+    rb = lambda a: torch.as_tensor(a).bfloat16().float()  # noqa: E731
+    xf = x.float().cpu()
+    q, k, vv = [(xf @ rb(p[n]["kernel"]).reshape(C, C) + torch.as_tensor(p[n]["bias"]).reshape(-1)).bfloat16().float().reshape(B, T, H, 64)
+                for n in ("query", "key", "value")]
+    gid, pos, allow, _ = O.sequence_groups(SEQ)
+    g2, p2 = np.broadcast_to(gid, (B, T)), np.broadcast_to(pos, (B, T))
+    mask = torch.as_tensor(O.dense_mask(g2, p2, g2, p2, allow))[:, None]
+    ref = O.attention(q, k, vv, mask=mask, bias=torch.log(size.cpu())[:, None, None, :]).reshape(B, T, C)
+    ref = ref.bfloat16().float() @ rb(p["out"]["kernel"]).reshape(C, C) + torch.as_tensor(p["out"]["bias"])
+    assert ((out.float().cpu() - ref).norm() / ref.norm()) <= 2e-2
+    assert metric.shape == (B, T, 64)
+    # hidden dropout: same seed + site numbering -> identical bits on both routes
+    cfg = small_cfg(C=128, H=2, Dff=256, blocks=2, r=4, hidden_drop=0.1)
+    stack = MC.build_stack(cfg)
+    xs = x.float()
+    variables = stack.init(1, xs)
+    y_stack = stack.apply(variables, xs, train=True, mask=gm, dropout_rng=77)
+    pz = variables["params"]
+    h = A.AddPositionEmbedding().apply({"params": pz["posembed_input"]}, xs)
+    state, blk = F.ToMeState(), stack._block()
+    for l in range(2):
+        h, _ = blk.apply({"params": _index_tree(pz["ScanEncoder1DBlock_0"], l)}, h, mask=gm, train=True, tome_state=state,
+                         site=3 * l, dropout_rng=77)
+    torch.testing.assert_close(h, y_stack, rtol=0, atol=0)
+    y_eval = stack.apply(variables, xs, train=False, mask=gm)
+    assert not torch.equal(y_eval, y_stack)
