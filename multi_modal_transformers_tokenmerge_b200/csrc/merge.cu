@@ -112,6 +112,145 @@ merge_fwd_kernel(const tome_merge_shape_t s, const tome_plan_t p, const T* __res
   }
 }
 
+// ------------------------------------------------------------------------------------------------ K3, bulk-copy version
+// A CTA owns `rows` consecutive output rows of one batch element.
+//   1. threads < rows: resolve which input token each output row keeps (edge_idx / odd position), its size, its CSR
+//      source range; produce size_out / gid_out / pos_out for the row.
+//   2. one cp.async.bulk (global -> shared) per kept row, all completing on one mbarrier: the gather runs in the copy
+//      engine with rows * row_bytes in flight per CTA and no register staging.
+//   3. rows that need arithmetic (size != 1, or sources merged into them) are patched in shared memory; their source
+//      rows are read straight from global (r of T rows).
+//   4. the run of output rows is contiguous in x_out: ONE cp.async.bulk (shared -> global) writes it.
+struct MergeRowMeta {
+  int keep_tok;
+  int e0, e1;
+  float size_keep;  // size of the kept token
+  float size_sum;   // size_out of the row
+};
+
+template <typename T, bool WAVG>
+__global__ void __launch_bounds__(MERGE_THREADS)
+merge_fwd_bulk_kernel(const tome_merge_shape_t s, const tome_plan_t p, const T* __restrict__ x,
+                      const float* __restrict__ size, T* __restrict__ x_out, float* __restrict__ size_out,
+                      const uint8_t* __restrict__ gid, const int32_t* __restrict__ pos, uint8_t* __restrict__ gid_out,
+                      int32_t* __restrict__ pos_out, int rows_per_cta) {
+  constexpr int N = Vec<T>::N;
+  extern __shared__ __align__(128) uint8_t smem_merge[];
+  const int Tn = s.tokens, r = s.r, C = s.channels;
+  const int ta = (Tn + 1) / 2, tb = Tn / 2, n_unm = ta - r, To = Tn - r;
+  const int row_bytes = C * (int)sizeof(T);
+  const int b = blockIdx.y;
+  const int row0 = blockIdx.x * rows_per_cta;
+  const int nrows = min(rows_per_cta, To - row0);
+  uint8_t* s_rows = smem_merge;
+  MergeRowMeta* s_meta = reinterpret_cast<MergeRowMeta*>(smem_merge + (size_t)rows_per_cta * row_bytes);
+  int* s_fix = reinterpret_cast<int*>(s_meta + rows_per_cta);  // [rows_per_cta] rows that need arithmetic
+  int* s_nfix = s_fix + rows_per_cta;
+  uint64_t* bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_nfix + 1) + 7) & ~uintptr_t(7));
+
+  const T* xb = x + (long long)b * Tn * C;
+  const float* sb = size ? size + (long long)b * Tn : nullptr;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+    *s_nfix = 0;
+  }
+  __syncthreads();
+  if (tid == 0) mbar_expect_tx(bar, (uint32_t)(nrows * row_bytes));
+  if (tid < nrows) {
+    const int prow = row0 + tid;
+    int u = -1, j = -1;
+    if (!s.distill_token) {
+      if (prow < n_unm) u = prow; else j = prow - n_unm;
+    } else {
+      if (prow == 0) u = 0;
+      else if (prow == 1) j = 0;
+      else if (prow <= n_unm) u = prow - 1;
+      else j = prow - n_unm;
+    }
+    MergeRowMeta m;
+    m.e0 = m.e1 = 0;
+    if (u >= 0) {
+      m.keep_tok = 2 * p.edge_idx[(long long)b * ta + r + u];
+    } else {
+      m.keep_tok = 2 * j + 1;
+      m.e0 = p.dst_off[(long long)b * (tb + 1) + j];
+      m.e1 = p.dst_off[(long long)b * (tb + 1) + j + 1];
+    }
+    // the copy first: everything below overlaps it
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(s_rows + (size_t)tid * row_bytes)), "l"(xb + (long long)m.keep_tok * C), "r"(row_bytes),
+                   "r"(smem_u32(bar))
+                 : "memory");
+    m.size_keep = sb ? sb[m.keep_tok] : 1.0f;
+    float sacc = m.size_keep;
+    for (int e = m.e0; e < m.e1; ++e) sacc = __fadd_rn(sacc, sb ? sb[2 * p.dst_src[(long long)b * r + e]] : 1.0f);
+    m.size_sum = sacc;
+    s_meta[tid] = m;
+    if ((WAVG && m.size_keep != 1.0f) || m.e1 > m.e0) s_fix[atomicAdd(s_nfix, 1)] = tid;
+    if (size_out) size_out[(long long)b * To + prow] = sacc;
+    if (gid_out) gid_out[(long long)b * To + prow] = gid[(long long)b * Tn + m.keep_tok];
+    if (pos_out) pos_out[(long long)b * To + prow] = pos[(long long)b * Tn + m.keep_tok];
+  }
+  __syncthreads();  // s_meta / s_fix visible; (thread 0's expect_tx preceded every copy: it is first in program order of warp 0, and the phase cannot complete before its arrival)
+  mbar_wait(bar, 0);
+
+  const int nfix = *s_nfix;
+  if (nfix > 0) {
+    const int vpr = C / N;
+    for (int item = tid; item < nfix * vpr; item += MERGE_THREADS) {
+      const int fr = s_fix[item / vpr], v = item % vpr;
+      const MergeRowMeta m = s_meta[fr];
+      T* srow = reinterpret_cast<T*>(s_rows + (size_t)fr * row_bytes) + v * N;
+      float acc[N];
+      {
+        const uint4 q = *reinterpret_cast<const uint4*>(srow);
+        if constexpr (N == 8) {
+          acc[0] = bf16_lo(q.x); acc[1] = bf16_hi(q.x); acc[2] = bf16_lo(q.y); acc[3] = bf16_hi(q.y);
+          acc[4] = bf16_lo(q.z); acc[5] = bf16_hi(q.z); acc[6] = bf16_lo(q.w); acc[7] = bf16_hi(q.w);
+        } else {
+          acc[0] = __uint_as_float(q.x); acc[1] = __uint_as_float(q.y); acc[2] = __uint_as_float(q.z); acc[3] = __uint_as_float(q.w);
+        }
+      }
+      if (WAVG) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) acc[i] = __fmul_rn(acc[i], m.size_keep);
+      }
+      for (int e = m.e0; e < m.e1; ++e) {
+        const int tok = 2 * p.dst_src[(long long)b * r + e];
+        float f[N];
+        Vec<T>::load(xb + (long long)tok * C + v * N, f);
+        const float sz = sb ? sb[tok] : 1.0f;
+#pragma unroll
+        for (int i = 0; i < N; ++i) acc[i] = __fadd_rn(acc[i], WAVG ? __fmul_rn(f[i], sz) : f[i]);  // no FMA contraction
+      }
+      if (WAVG) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) acc[i] = __fdiv_rn(acc[i], m.size_sum);
+      }
+      uint4 o;
+      if constexpr (N == 8) {
+        o = make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
+      } else {
+        o = make_uint4(__float_as_uint(acc[0]), __float_as_uint(acc[1]), __float_as_uint(acc[2]), __float_as_uint(acc[3]));
+      }
+      *reinterpret_cast<uint4*>(srow) = o;
+    }
+    fence_proxy_async_smem();  // patched rows visible to the bulk store (async proxy)
+    __syncthreads();
+  }
+  if (tid == 0) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(x_out + ((long long)b * To + row0) * C), "r"(smem_u32(s_rows)), "r"(nrows * row_bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must outlive the store's reads
+  }
+}
+
+static int g_merge_rows_override = 0;  // tuning aid for scripts/bench_kernels.py (0 = choose automatically)
+
 template <typename T, bool WAVG>
 __global__ void __launch_bounds__(MERGE_THREADS)
 merge_bwd_kernel(const tome_merge_shape_t s, const int32_t* __restrict__ row_map, const float* __restrict__ size,
@@ -177,8 +316,34 @@ extern "C" int tome_merge_fwd(const tome_merge_shape_t* s, const tome_plan_t* pl
   const double esz = s->dtype == TOME_BF16 ? 2.0 : 4.0;
   ProfScope prof(PROF_MERGE_FWD, (double)s->batch * ((double)s->tokens * s->channels * esz + 4.0 * s->tokens +
                  4.0 * ((s->tokens + 1) / 2 + s->r) + (double)(s->tokens - s->r) * s->channels * esz + 4.0 * (s->tokens - s->r)), 1, stream);
-  const int grid = merge_grid(items);
   const bool wavg = s->mode == TOME_MERGE_WAVG;
+  const int row_bytes = s->channels * (int)esz;
+  if (row_bytes <= 32768 && s->batch <= 65535) {
+    // bulk-copy path: rows * row_bytes ~ 24 KB per CTA, so 8 CTAs (~190 KB in flight) fit one SM
+    int rows = g_merge_rows_override > 0 ? g_merge_rows_override : 24576 / row_bytes;
+    if (rows < 1) rows = 1;
+    if (rows > 128) rows = 128;
+    if (rows > s->tokens - s->r) rows = s->tokens - s->r;
+    const size_t smem = (size_t)rows * row_bytes + (size_t)rows * (sizeof(MergeRowMeta) + sizeof(int)) + sizeof(int) + 24;
+    dim3 grid2(ceil_div(s->tokens - s->r, rows), s->batch);
+#define LAUNCHB(TT, W)                                                                                                  \
+  do {                                                                                                                  \
+    static size_t smem_set = 0;                                                                                         \
+    if (smem > 48 * 1024 && smem > smem_set) {                                                                          \
+      TOME_CUDA(cudaFuncSetAttribute(merge_fwd_bulk_kernel<TT, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      smem_set = smem;                                                                                                  \
+    }                                                                                                                   \
+    merge_fwd_bulk_kernel<TT, W><<<grid2, MERGE_THREADS, smem, stream>>>(*s, *plan, reinterpret_cast<const TT*>(x), size, \
+                                                                         reinterpret_cast<TT*>(x_out), size_out, gid, pos, \
+                                                                         gid_out, pos_out, rows);                       \
+  } while (0)
+    if (s->dtype == TOME_BF16) { if (wavg) LAUNCHB(__nv_bfloat16, true); else LAUNCHB(__nv_bfloat16, false); }
+    else { if (wavg) LAUNCHB(float, true); else LAUNCHB(float, false); }
+#undef LAUNCHB
+    TOME_CUDA(cudaGetLastError());
+    return TOME_OK;
+  }
+  const int grid = merge_grid(items);  // rows wider than 32 KB: thread-per-vector kernel
 #define LAUNCH(TT, W)                                                                                              \
   merge_fwd_kernel<TT, W><<<grid, MERGE_THREADS, 0, stream>>>(*s, *plan, reinterpret_cast<const TT*>(x), size,     \
                                                               reinterpret_cast<TT*>(x_out), size_out, gid, pos,   \
@@ -189,6 +354,9 @@ extern "C" int tome_merge_fwd(const tome_merge_shape_t* s, const tome_plan_t* pl
   TOME_CUDA(cudaGetLastError());
   return TOME_OK;
 }
+
+/* tuning aid (not part of the public header): force the bulk kernel's rows per CTA; 0 restores the default */
+extern "C" void tome_merge_set_rows_per_cta(int rows) { g_merge_rows_override = rows; }
 
 extern "C" int tome_merge_bwd(const tome_merge_shape_t* s, const tome_plan_t* plan, const float* size,
                               const float* size_out, const void* dy, void* dx, void* stream_) {

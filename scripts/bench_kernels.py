@@ -45,8 +45,15 @@ def bench_merge():
         size = torch.ones(B, T, device="cuda")
         ta = (T + 1) // 2
         by = B * (T * C * 2 + 4 * T + 4 * (ta + r) + (T - r) * C * 2 + 4 * (T - r))
-        t = timeit(lambda: ops.merge_fwd(plan, x, size, 1))
-        print(f"merge_fwd  B{B} T{T} C{C} r{r}: {t*1e6:8.1f} us  {by/t/1e9:7.1f} GB/s  frac {by/t/1e9/PEAKS['hbm_gbs']:.3f}")
+        from multi_modal_transformers_tokenmerge_b200 import _lib
+        for rows in ([0] if "sweep" not in sys.argv else [0, 8, 16, 32, 48, 64]):
+            _lib.lib().tome_merge_set_rows_per_cta(rows)
+            t = timeit(lambda: ops.merge_fwd(plan, x, size, 1))
+            print(f"merge_fwd  B{B} T{T} C{C} r{r} rows/cta {rows}: {t*1e6:8.1f} us  {by/t/1e9:7.1f} GB/s  frac {by/t/1e9/PEAKS['hbm_gbs']:.3f}")
+        _lib.lib().tome_merge_set_rows_per_cta(0)
+        size2 = torch.randint(1, 4, (B, T), device="cuda").float()   # sizes != 1: every row takes the arithmetic path
+        t = timeit(lambda: ops.merge_fwd(plan, x, size2, 1))
+        print(f"merge_fwd  (all rows patched) : {t*1e6:8.1f} us  {by/t/1e9:7.1f} GB/s  frac {by/t/1e9/PEAKS['hbm_gbs']:.3f}")
         x1, s1, _, _ = ops.merge_fwd(plan, x, size, 1)
         dy = torch.randn_like(x1)
         by2 = B * ((T - r) * C * 2 + T * C * 2 + 4 * T)
@@ -113,6 +120,6 @@ def bench_ln():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["merge", "gemm", "attn", "ln"]
+    which = [a for a in sys.argv[1:] if a != "sweep"] or ["merge", "gemm", "attn", "ln"]
     for w in which:
         globals()["bench_" + w]()
