@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TOME_ABI_VERSION 4
+#define TOME_ABI_VERSION 5
 
 enum tome_status { TOME_OK = 0, TOME_ERR_INVALID = 1, TOME_ERR_CUDA = 2, TOME_ERR_UNSUPPORTED = 3 };
 enum tome_dtype { TOME_BF16 = 0, TOME_F32 = 1 };
@@ -183,21 +183,26 @@ typedef struct {
   const float* size; /* [B,T] or NULL */
 } tome_attn_desc_t;
 
-/* out [B,T,H,D] bf16, lse f32 [B,H,T] (natural-log sum-exp of the biased, masked, scaled logits) */
+/* out [B,T,H,D] bf16, lse f32 [B,H,T] (natural-log sum-exp of the biased, masked, scaled logits).
+ * workspace: tome_attention_workspace_bytes(desc) bytes of 16-byte-aligned device scratch (per-tile mask words and
+ * log2(size) bias, built once per call and streamed into the kernel by bulk copies); contents need not be kept. */
+size_t tome_attention_workspace_bytes(const tome_attn_desc_t* desc);
 int tome_attention_fwd(const tome_attn_desc_t* desc, const void* q, const void* k, const void* v, void* out,
-                       float* lse, void* stream);
+                       float* lse, void* workspace, size_t workspace_bytes, void* stream);
 
-/* dq,dk,dv share the layout of q,k,v (their own strides below); delta f32 [B,H,T] workspace;
- * scratch: at least 8*B*T bytes (per-token mask words); gradients are produced without atomics or fp32 staging. */
+/* dq,dk,dv share the layout of q,k,v (their own strides below).  workspace: tome_attention_bwd_workspace_bytes(desc)
+ * bytes of 256-byte-aligned device scratch (delta = rowsum(dO*O), per-tile mask words); gradients are produced
+ * without atomics or fp32 staging. */
 typedef struct {
   long long dq_batch_stride, dq_token_stride;
   long long dk_batch_stride, dk_token_stride;
   long long dv_batch_stride, dv_token_stride;
   long long do_batch_stride, do_token_stride;
 } tome_attn_grad_strides_t;
+size_t tome_attention_bwd_workspace_bytes(const tome_attn_desc_t* desc);
 int tome_attention_bwd(const tome_attn_desc_t* desc, const tome_attn_grad_strides_t* gs, const void* q, const void* k,
                        const void* v, const void* out, const float* lse, const void* dout, void* dq, void* dk,
-                       void* dv, float* delta, float* scratch, void* stream);
+                       void* dv, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * 6. Small fused steps around the block

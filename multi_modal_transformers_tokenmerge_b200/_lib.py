@@ -15,7 +15,7 @@ TOME_OK, TOME_ERR_INVALID, TOME_ERR_CUDA, TOME_ERR_UNSUPPORTED = 0, 1, 2, 3
 TOME_BF16, TOME_F32 = 0, 1
 TOME_MAJOR_K, TOME_MAJOR_MN = 0, 1
 TOME_MERGE_SUM, TOME_MERGE_WAVG = 0, 1
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 vp, ll, i32, f32, u64, u32 = C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_uint64, C.c_uint32
 
@@ -103,7 +103,8 @@ def lib() -> C.CDLL:
         L.tome_abi_version.restype = i32
         if L.tome_abi_version() != ABI_VERSION:
             raise ImportError(f"libtome_b200.so has ABI {L.tome_abi_version()}, python binding expects {ABI_VERSION}: rebuild")
-        for name in ("tome_gemm_workspace_bytes", "tome_stack_workspace_bytes"):
+        for name in ("tome_gemm_workspace_bytes", "tome_stack_workspace_bytes", "tome_attention_workspace_bytes",
+                     "tome_attention_bwd_workspace_bytes"):
             if hasattr(L, name):
                 getattr(L, name).restype = C.c_size_t
         for name in ("tome_stack_param_count", "tome_stack_layer_offset", "tome_launch_count"):
@@ -126,8 +127,10 @@ def lib() -> C.CDLL:
             "tome_colsum_bf16": [i32, i32, vp, ll, vp, i32, vp, vp],
             "tome_layernorm_fwd": [i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp],
             "tome_layernorm_bwd": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
-            "tome_attention_fwd": [P(AttnDesc), vp, vp, vp, vp, vp, vp],
-            "tome_attention_bwd": [P(AttnDesc), P(AttnGradStrides), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+            "tome_attention_workspace_bytes": [P(AttnDesc)],
+            "tome_attention_bwd_workspace_bytes": [P(AttnDesc)],
+            "tome_attention_fwd": [P(AttnDesc), vp, vp, vp, vp, vp, vp, C.c_size_t, vp],
+            "tome_attention_bwd": [P(AttnDesc), P(AttnGradStrides), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp],
             "tome_add_pos_embedding": [i32, i32, i32, vp, i32, vp, vp, vp],
             "tome_pos_embedding_bwd": [i32, i32, i32, vp, vp, vp],
             "tome_chain_row_maps": [i32, i32, P(vp), P(i32), vp, i32, vp, vp],

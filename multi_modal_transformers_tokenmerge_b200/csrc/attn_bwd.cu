@@ -576,21 +576,34 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 
 using namespace tome;
 
+static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+extern "C" size_t tome_attention_bwd_workspace_bytes(const tome_attn_desc_t* d) {
+  if (!d || d->batch <= 0 || d->tokens <= 0 || d->heads <= 0) return 0;
+  const size_t bht = (size_t)d->batch * d->heads * d->tokens;
+  return align256(bht * sizeof(float)) + align256((size_t)d->batch * d->tokens * sizeof(uint2));
+}
+
 extern "C" int tome_attention_bwd(const tome_attn_desc_t* d, const tome_attn_grad_strides_t* gs, const void* q, const void* k,
                                   const void* v, const void* out, const float* lse, const void* dout, void* dq, void* dk,
-                                  void* dv, float* delta, float* dq_accum, void* stream_) {
+                                  void* dv, void* workspace, size_t workspace_bytes, void* stream_) {
   clear_error();
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int rc = check_attn_desc(d, "attention_bwd")) return rc;
-  TOME_CHECK(gs && q && k && v && out && lse && dout && dq && dk && dv && delta && dq_accum, TOME_ERR_INVALID,
+  TOME_CHECK(gs && q && k && v && out && lse && dout && dq && dk && dv && workspace, TOME_ERR_INVALID,
              "attention_bwd: null argument");
+  TOME_CHECK(((uintptr_t)workspace & 255) == 0, TOME_ERR_INVALID, "attention_bwd: workspace must be 256-byte aligned");
+  TOME_CHECK(workspace_bytes >= tome_attention_bwd_workspace_bytes(d), TOME_ERR_INVALID,
+             "attention_bwd: workspace too small (%zu < %zu, see tome_attention_bwd_workspace_bytes)", workspace_bytes,
+             tome_attention_bwd_workspace_bytes(d));
   const long long st[8] = {gs->dq_batch_stride, gs->dq_token_stride, gs->dk_batch_stride, gs->dk_token_stride,
                            gs->dv_batch_stride, gs->dv_token_stride, gs->do_batch_stride, gs->do_token_stride};
   for (int i = 0; i < 8; ++i) TOME_CHECK(st[i] % 8 == 0, TOME_ERR_INVALID, "attention_bwd: strides must be multiples of 8");
   const int B = d->batch, T = d->tokens, H = d->heads;
   ProfScope prof(PROF_ATTN_BWD, 10.0 * d->batch * d->heads * (double)d->tokens * d->tokens * d->head_dim, 3, stream);
-  // dq_accum doubles as scratch for the per-token mask words (first B*T*8 bytes); no fp32 dQ accumulation is needed.
-  uint2* mwords = d->gid ? reinterpret_cast<uint2*>(dq_accum) : nullptr;
+  float* delta = reinterpret_cast<float*>(workspace);
+  uint2* mwords = d->gid ? reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(workspace) + align256((size_t)B * H * T * sizeof(float)))
+                         : nullptr;
   {
     const long long total = (long long)B * T * H * 8;
     attn_bwd_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(

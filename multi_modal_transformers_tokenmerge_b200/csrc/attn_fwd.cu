@@ -2,78 +2,93 @@
 // log(size) key bias.  Replaces flax dot_product_attention as reached from tome_attention.py:259-285 with the mask of
 // token_sequencer.py:313-321 -- without ever materialising [B,H,T,T] logits, weights or booleans.
 //
-// One CTA = one (batch, head, 128-query tile); 2 CTAs per SM interleave (TMEM 256 columns each).
-//   warp 4      TMA producer: Q once, then K_0 V_0 K_1 V_1 ... (128 keys x 64 each) through a 3-slot ring, 128B swizzle
-//   warp 5      UMMA issuer:  S = Q K_j^T (128x128x64) -> TMEM cols [0,128);  O_j = P_j V_j (128x64x128) -> cols [128,192)
-//   warps 0..3  softmax: thread = query row.  Pass 1 reads S from TMEM, applies scale + log-size bias + mask, takes
-//               the row max and writes the finished logits back to TMEM; pass 2 re-reads them, exponentiates and
-//               writes P_j to shared memory as the bf16 K-major A operand of the second MMA.  O is kept in fp32
-//               REGISTERS and rescaled there (O = O * alpha + O_j), so TMEM never needs a correction pass.
-//               The mask costs one bit test per element: per key tile the 128 threads publish, by warp ballots, one
-//               128-bit "visible keys" word set per QUERY GROUP (the mask depends on a query only through its
-//               group), and the log-size bias is fetched four keys per shared-memory read.
+// One CTA = one (batch, head, 128-query tile); 2 CTAs per SM (256 TMEM columns each).  Key tiles are 64 wide, so a
+// softmax thread holds one whole row of a tile (64 fp32 logits) in registers and touches every logit exactly once:
+//   warp 4      TMA producer: Q once, then K_0 K_1 V_0 K_2 V_1 ... (64 keys x 64 each) through a 6-slot ring, 128B
+//               swizzle; and, through a 4-slot ring, each key tile's METADATA block (attn_meta.cuh: log2(size) bias,
+//               positions, one 64-bit "visible keys" word per QUERY GROUP -- the mask depends on a query only through
+//               its group, so it costs the softmax one bit test per logit), one cp.async.bulk per tile
+//   warp 5      UMMA issuer:  S_j = Q K_j^T (128x64x64) into a DOUBLE-BUFFERED TMEM accumulator (S_{j+1} is computed
+//               while the softmax warps work on S_j); O += P_j V_j (128x64x64) accumulates IN TMEM across key tiles
+//   warps 0..3  softmax, thread = query row: S_j (TMEM) -> registers, scale + bias (packed f32x2 FMA), mask, row max,
+//               exp2, row sum, P_j -> bf16 K-major A operand in shared memory (double-buffered).
+//               The running maximum is LAZY: O and l are rescaled only when a row's maximum grows by more than 2^8,
+//               which after the first tile is rare, so the usual tile needs no TMEM correction pass at all; when a
+//               warp does need one it multiplies its 32 rows of O in TMEM by alpha (tcgen05.ld / st) before it
+//               publishes P_j -- the PV MMA that reads O next is only issued after that.
 // Logits are kept in the log2 domain: s2 = (q.k) * scale * log2(e) + log2(size_k); masked -> -FLT_MAX (finite, as
 // flax's finfo.min), keys past T -> -inf.
 #include <float.h>
 
+#include "attn_meta.cuh"
 #include "common.cuh"
 #include "host_util.h"
 
 namespace tome {
 
 constexpr int ATT_BM = 128;   // queries per CTA
-constexpr int ATT_BN = 128;   // keys per tile
+constexpr int ATT_BN = 64;    // keys per tile
 constexpr int ATT_D = 64;
 constexpr int ATT_THREADS = 192;
 constexpr int ATT_Q_BYTES = ATT_BM * ATT_D * 2;         // 16 KB
-constexpr int ATT_KV_BYTES = ATT_BN * ATT_D * 2;        // 16 KB each for K and V
-constexpr int ATT_P_BYTES = ATT_BM * ATT_BN * 2;        // 32 KB (two 64-key K-blocks of 16 KB)
-constexpr int ATT_SLOTS = 3;  // ring of 16 KB slots; items are loaded in the order K_0 V_0 K_1 V_1 ...
-constexpr int ATT_SMEM_META = 2 * ATT_BN * (4 + 4 + 4) + 2 * 32 * 4 * 4 * 2 + 2 * 32 * 4 + 16;  // bias2/pos/gid x 2 parities, visible-key words (all, causal) per group x 2 parities, column words
-constexpr int ATT_SMEM = ATT_Q_BYTES + ATT_SLOTS * ATT_KV_BYTES + ATT_P_BYTES + ATT_SMEM_META + 256 + 1024;
-constexpr uint32_t ATT_TMEM_COLS = 256;
+constexpr int ATT_KV_BYTES = ATT_BN * ATT_D * 2;        // 8 KB each for K and V
+constexpr int ATT_P_BYTES = ATT_BM * ATT_BN * 2;        // 16 KB, x2 buffers
+constexpr int ATT_SLOTS = 6;  // ring of 8 KB slots; items are loaded in the order K_0 K_1 V_0 K_2 V_1 ...
+constexpr int ATT_MSLOTS = 4; // metadata ring
+constexpr int ATT_META_SLOT = ATTN_META_KEY_BYTES;  // bias2 | vis[32][2] | visc[32][2] | pos
+static_assert(ATT_BN == ATTN_META_TILE, "key tiles and metadata tiles must coincide");
+constexpr int ATT_SMEM = ATT_Q_BYTES + ATT_SLOTS * ATT_KV_BYTES + 2 * ATT_P_BYTES + ATT_MSLOTS * ATT_META_SLOT + 512 + 1024;
+constexpr uint32_t ATT_TMEM_COLS = 256;  // S0 [0,64) S1 [64,128) O [128,192)
+constexpr float ATT_LAZY_LOG2 = 8.0f;    // rescale O only when the row maximum grows by more than 2^8
 
 struct AttnFwdParams {
   int batch, tokens, heads;
   float scale_log2;  // scale * log2(e)
-  const uint8_t* gid;
+  const uint8_t* gid;   // null: no mask
   const int32_t* pos;
-  const uint8_t* allow;
-  int num_groups;
-  const float* size;
+  const uint8_t* meta;  // [B][n_kv][ATTN_META_BYTES]
   __nv_bfloat16* out;
   long long o_batch_stride, o_token_stride;
   float* lse;
 };
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+// TMEM -> 32 consecutive fp32 registers of a larger per-thread array (indices are compile-time after unrolling)
+template <int OFF, int N>
+__device__ __forceinline__ void tmem_ld_f32x32(uint32_t taddr, float (&r)[N]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=f"(r[OFF + 0]), "=f"(r[OFF + 1]), "=f"(r[OFF + 2]), "=f"(r[OFF + 3]), "=f"(r[OFF + 4]), "=f"(r[OFF + 5]),
+        "=f"(r[OFF + 6]), "=f"(r[OFF + 7]), "=f"(r[OFF + 8]), "=f"(r[OFF + 9]), "=f"(r[OFF + 10]), "=f"(r[OFF + 11]),
+        "=f"(r[OFF + 12]), "=f"(r[OFF + 13]), "=f"(r[OFF + 14]), "=f"(r[OFF + 15]), "=f"(r[OFF + 16]), "=f"(r[OFF + 17]),
+        "=f"(r[OFF + 18]), "=f"(r[OFF + 19]), "=f"(r[OFF + 20]), "=f"(r[OFF + 21]), "=f"(r[OFF + 22]), "=f"(r[OFF + 23]),
+        "=f"(r[OFF + 24]), "=f"(r[OFF + 25]), "=f"(r[OFF + 26]), "=f"(r[OFF + 27]), "=f"(r[OFF + 28]), "=f"(r[OFF + 29]),
+        "=f"(r[OFF + 30]), "=f"(r[OFF + 31])
+      : "r"(taddr)
+      : "memory");
 }
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const AttnFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1 KB alignment by pointer arithmetic on the __shared__ array itself, so every access below stays LDS/STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_q = smem;
-  uint8_t* s_kv = s_q + ATT_Q_BYTES;                        // slot i at i * 16 KB
-  uint8_t* s_p = s_kv + ATT_SLOTS * ATT_KV_BYTES;
-  float* s_bias = reinterpret_cast<float*>(s_p + ATT_P_BYTES);  // [2][128]
-  int* s_pos = reinterpret_cast<int*>(s_bias + 2 * ATT_BN);     // [2][128]
-  int* s_gid = s_pos + 2 * ATT_BN;                              // [2][128]
-  uint32_t* s_vis = reinterpret_cast<uint32_t*>(s_gid + 2 * ATT_BN);  // [2][32 groups][4] keys visible to a query group
-  uint32_t* s_visc = s_vis + 2 * 32 * 4;                        // [2][32][4] keys visible iff pos_k <= pos_q
-  uint32_t* s_colw = s_visc + 2 * 32 * 4;                       // [32] query groups that see key group g (code 1)
-  uint32_t* s_colc = s_colw + 32;                               // [32] ... (code 2)
-  uint32_t* s_anyc = s_colc + 32;                               // [1]  some rule is causal
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_anyc + 4);
-  uint64_t* q_full = bars;                // 1
-  uint64_t* kv_full = bars + 1;           // [3]
-  uint64_t* kv_empty = bars + 4;          // [3]
-  uint64_t* s_full = bars + 7;            // 1   S_j ready in TMEM
-  uint64_t* p_ready = bars + 8;           // 1   P_j in smem, S_j and O_{j-1} consumed (128 arrivals)
-  uint64_t* o_full = bars + 9;            // 1   O_j ready in TMEM
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint8_t* s_kv = s_q + ATT_Q_BYTES;                        // slot i at i * 8 KB
+  uint8_t* s_p = s_kv + ATT_SLOTS * ATT_KV_BYTES;           // buffer i at i * 16 KB
+  uint8_t* s_meta = s_p + 2 * ATT_P_BYTES;                  // metadata slot i at i * ATT_META_SLOT
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_meta + ATT_MSLOTS * ATT_META_SLOT);
+  uint64_t* q_full = bars;                 // 1
+  uint64_t* kv_full = bars + 1;            // [6]
+  uint64_t* kv_empty = bars + 7;           // [6]
+  uint64_t* s_full = bars + 13;            // [2]  S_j ready in TMEM buffer j&1
+  uint64_t* p_ready = bars + 15;           // [2]  P_j in smem buffer j&1, S_j consumed, O corrected (128 arrivals)
+  uint64_t* pv_done = bars + 17;           // [2]  O += P_j V_j retired: P buffer j&1 reusable, O readable
+  uint64_t* meta_full = bars + 19;         // [4]  bulk copy of the tile's metadata block landed
+  uint64_t* meta_empty = bars + 23;        // [4]  128 arrivals (softmax threads)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -86,9 +101,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_ready, ATT_BM);
-    mbar_init(o_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_ready[i], ATT_BM);
+      mbar_init(&pv_done[i], 1);
+    }
+    for (int i = 0; i < ATT_MSLOTS; ++i) {
+      mbar_init(&meta_full[i], 1);
+      mbar_init(&meta_empty[i], ATT_BM);
+    }
     fence_barrier_init();
   }
   if (warp == 4 && lane == 0) {
@@ -97,37 +118,36 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     tma_prefetch_desc(&tm_v);
   }
   if (warp == 5) tmem_alloc(tmem_slot, ATT_TMEM_COLS);
-  if (threadIdx.x < 32) {  // transpose the allow table: which query groups may see keys of group g
-    uint32_t cw = 0, cc = 0;
-    const int g = threadIdx.x;
-    if (p.gid != nullptr && g < p.num_groups)
-      for (int qg = 0; qg < p.num_groups; ++qg) {
-        const int a = p.allow[qg * p.num_groups + g];
-        cw |= (a == 1 ? 1u : 0u) << qg;
-        cc |= (a == 2 ? 1u : 0u) << qg;
-      }
-    s_colw[g] = cw;
-    s_colc[g] = cc;
-    const uint32_t any = __ballot_sync(0xffffffffu, cc != 0);
-    if (g == 0) s_anyc[0] = any;
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base;         // 128 columns
-  const uint32_t tmem_o = tmem_base + 128;   // 64 columns
+  const uint32_t tmem_o = tmem_base + 128;   // 64 columns; S buffers at +0 and +64
+  const bool has_mask = p.gid != nullptr;
 
   if (warp == 4) {
-    // ================================================================= TMA producer
+    // ================================================================= TMA producer: K/V ring + metadata ring
     if (lane == 0) {
-      mbar_expect_tx(q_full, ATT_Q_BYTES);
-      tma_load_3d(s_q, &tm_q, q_full, h * ATT_D, qt * ATT_BM, b);
-      for (int item = 0; item < 2 * n_kv; ++item) {
+      int item = 0;
+      auto load_item = [&](bool is_v, int tile) {  // ring order K_0 K_1 V_0 K_2 V_1 ... K_{n-1} V_{n-2} V_{n-1}
         const int slot = item % ATT_SLOTS, use = item / ATT_SLOTS;
         mbar_wait(&kv_empty[slot], (use & 1) ^ 1);
         mbar_expect_tx(&kv_full[slot], ATT_KV_BYTES);
-        tma_load_3d(s_kv + slot * ATT_KV_BYTES, (item & 1) ? &tm_v : &tm_k, &kv_full[slot], h * ATT_D, (item >> 1) * ATT_BN, b);
+        tma_load_3d(s_kv + slot * ATT_KV_BYTES, is_v ? &tm_v : &tm_k, &kv_full[slot], h * ATT_D, tile * ATT_BN, b);
+        ++item;
+      };
+      const uint32_t meta_bytes = has_mask ? ATTN_META_KEY_BYTES : 256u;  // without a mask only the bias is read
+      const uint8_t* meta_b = p.meta + (size_t)b * n_kv * ATTN_META_BYTES;
+      mbar_expect_tx(q_full, ATT_Q_BYTES);
+      tma_load_3d(s_q, &tm_q, q_full, h * ATT_D, qt * ATT_BM, b);
+      load_item(false, 0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int ms = j % ATT_MSLOTS;
+        mbar_wait(&meta_empty[ms], ((j / ATT_MSLOTS) & 1) ^ 1);
+        mbar_expect_tx(&meta_full[ms], meta_bytes);
+        bulk_g2s(s_meta + ms * ATT_META_SLOT, meta_b + (size_t)j * ATTN_META_BYTES, meta_bytes, &meta_full[ms]);
+        if (j + 1 < n_kv) load_item(false, j + 1);
+        load_item(true, j);
       }
     }
   } else if (warp == 5) {
@@ -136,38 +156,36 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BM, ATT_BN, false, false);  // Q K-major, K K-major
       constexpr uint32_t idesc_o = make_idesc_bf16(ATT_BM, ATT_D, false, true);    // P K-major, V MN-major
       const uint32_t aq = smem_u32(s_q), ap = smem_u32(s_p);
+      const int n_items = 2 * n_kv;
+      auto issue_s = [&](int t) {  // S_t = Q K_t^T into TMEM buffer t&1
+        const int item = t == 0 ? 0 : 2 * t - 1, slot = item % ATT_SLOTS;
+        mbar_wait(&kv_full[slot], (item / ATT_SLOTS) & 1);
+        tc_fence_after();
+        const uint32_t ak = smem_u32(s_kv + slot * ATT_KV_BYTES);
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; ++k)
+          umma_bf16(tmem_base + (t & 1) * ATT_BN, make_smem_desc(aq + k * 32, 16, 1024), make_smem_desc(ak + k * 32, 16, 1024),
+                    idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(&s_full[t & 1]);
+        umma_commit(&kv_empty[slot]);
+      };
       mbar_wait(q_full, 0);
-      // issue order: S_0 | (wait P_0) S_1, O_0 | (wait P_1) S_2, O_1 | ...   S and O_tmp are single-buffered:
-      // p_ready(j-1) certifies that S_{j-1} and O_{j-2} were consumed and P_{j-1} is in shared memory.
-      for (int j = 0; j <= n_kv; ++j) {
-        if (j >= 1) {
-          mbar_wait(p_ready, (j - 1) & 1);
-          tc_fence_after();
-        }
-        if (j < n_kv) {  // S_j = Q K_j^T
-          const int item = 2 * j, slot = item % ATT_SLOTS;
-          mbar_wait(&kv_full[slot], (item / ATT_SLOTS) & 1);
-          tc_fence_after();
-          const uint32_t ak = smem_u32(s_kv + slot * ATT_KV_BYTES);
+      issue_s(0);
+      if (n_kv > 1) issue_s(1);
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(&p_ready[j & 1], (j >> 1) & 1);  // P_j in smem, S_j consumed, O corrected
+        tc_fence_after();
+        const int item = j == n_kv - 1 ? n_items - 1 : 2 * j + 2, slot = item % ATT_SLOTS;
+        mbar_wait(&kv_full[slot], (item / ATT_SLOTS) & 1);
+        tc_fence_after();
+        const uint32_t av = smem_u32(s_kv + slot * ATT_KV_BYTES), apj = ap + (j & 1) * ATT_P_BYTES;
 #pragma unroll
-          for (int k = 0; k < ATT_D / 16; ++k)
-            umma_bf16(tmem_s, make_smem_desc(aq + k * 32, 16, 1024), make_smem_desc(ak + k * 32, 16, 1024), idesc_s,
-                      k > 0 ? 1u : 0u);
-          umma_commit(s_full);
-          umma_commit(&kv_empty[slot]);
-        }
-        if (j >= 1) {  // O_{j-1} = P_{j-1} V_{j-1}
-          const int item = 2 * (j - 1) + 1, slot = item % ATT_SLOTS;
-          mbar_wait(&kv_full[slot], (item / ATT_SLOTS) & 1);
-          tc_fence_after();
-          const uint32_t av = smem_u32(s_kv + slot * ATT_KV_BYTES);
-#pragma unroll
-          for (int k = 0; k < ATT_BN / 16; ++k)
-            umma_bf16(tmem_o, make_smem_desc(ap + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                      make_smem_desc(av + k * 2048, 8192, 1024), idesc_o, k > 0 ? 1u : 0u);
-          umma_commit(o_full);
-          umma_commit(&kv_empty[slot]);
-        }
+        for (int k = 0; k < ATT_BN / 16; ++k)  // O += P_j V_j
+          umma_bf16(tmem_o, make_smem_desc(apj + k * 32, 16, 1024), make_smem_desc(av + k * 2048, 8192, 1024), idesc_o,
+                    (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&pv_done[j & 1]);
+        umma_commit(&kv_empty[slot]);
+        if (j + 2 < n_kv) issue_s(j + 2);
       }
     }
   } else {
@@ -175,159 +193,140 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int row = threadIdx.x;                 // 0..127 == TMEM lane
     const int q = qt * ATT_BM + row;
     const uint32_t lane_sel = ((uint32_t)(warp * 32)) << 16;
-    const bool has_mask = p.gid != nullptr;
-    const bool any_causal = has_mask && s_anyc[0] != 0;
+    const bool warp_active = qt * ATT_BM + warp * 32 < T;  // a warp whose 32 rows are all past T only keeps the barriers moving
     int gq = 0, pos_q = 0;
     if (has_mask && q < T) {
       gq = p.gid[(long long)b * T + q];
       pos_q = p.pos[(long long)b * T + q];
     }
-    float o_acc[ATT_D];
-#pragma unroll
-    for (int i = 0; i < ATT_D; ++i) o_acc[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    const float2 scale2 = make_float2(p.scale_log2, p.scale_log2);
 
     for (int j = 0; j < n_kv; ++j) {
-      const int par = j & 1;
-      {  // per-key metadata of this tile: thread `row` owns key j*128 + row
-        const int kk = j * ATT_BN + row;
-        float bias2 = -INFINITY;           // keys past T: logit -inf (and "visible", so the mask keeps the -inf)
-        uint32_t cw = 0xffffffffu, cc = 0u;
-        int pk = 0;
-        if (kk < T) {
-          bias2 = p.size ? log2f(p.size[(long long)b * T + kk]) : 0.f;
-          if (has_mask) {
-            const int gk = p.gid[(long long)b * T + kk];
-            cw = s_colw[gk];
-            cc = s_colc[gk];
-            pk = p.pos[(long long)b * T + kk];
-          }
-        }
-        s_bias[par * ATT_BN + row] = bias2;
-        if (has_mask) {
-          for (int g = 0; g < p.num_groups; ++g) {
-            const uint32_t w = __ballot_sync(0xffffffffu, (cw >> g) & 1u);
-            if (lane == 0) s_vis[(par * 32 + g) * 4 + warp] = w;
-          }
-          if (any_causal) {
-            s_pos[par * ATT_BN + row] = pk;
-            for (int g = 0; g < p.num_groups; ++g) {
-              const uint32_t w = __ballot_sync(0xffffffffu, (cc >> g) & 1u);
-              if (lane == 0) s_visc[(par * 32 + g) * 4 + warp] = w;
-            }
-          }
-        }
+      const int ms = j % ATT_MSLOTS;
+      const uint8_t* mb = s_meta + ms * ATT_META_SLOT;
+      mbar_wait(&meta_full[ms], (j / ATT_MSLOTS) & 1);
+      if (!warp_active) {
+        mbar_wait(&s_full[j & 1], (j >> 1) & 1);   // pacing only: S_{j+2} is not issued before p_ready(j) completes
+        mbar_arrive(&meta_empty[ms]);
+        mbar_arrive(&p_ready[j & 1]);
+        continue;
       }
-      named_bar_sync(1, ATT_BM);
-      const float4* bias4 = reinterpret_cast<const float4*>(s_bias + par * ATT_BN);
-      uint4 vis = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu), visc = make_uint4(0u, 0u, 0u, 0u);
+      const float4* bias4 = reinterpret_cast<const float4*>(mb);
+      uint32_t vw0 = 0xffffffffu, vw1 = 0xffffffffu;
+      bool masked_tile = false;
       if (has_mask) {
-        vis = *reinterpret_cast<const uint4*>(s_vis + (par * 32 + gq) * 4);
-        if (any_causal) visc = *reinterpret_cast<const uint4*>(s_visc + (par * 32 + gq) * 4);
-      }
-      const bool causal_row = (visc.x | visc.y | visc.z | visc.w) != 0u;
-
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-
-      // pass 1: finished logits (log2 domain) back to TMEM + row maximum
-      float m_tile = -INFINITY;
-#pragma unroll 1
-      for (int cq = 0; cq < ATT_BN / 32; ++cq) {
-        uint32_t v[32];
-        tmem_ld_x32(tmem_s + lane_sel + cq * 32, v);
-        uint32_t vw = cq == 0 ? vis.x : cq == 1 ? vis.y : cq == 2 ? vis.z : vis.w;
-        if (causal_row) {  // rare (Text sets): fold the causal rule into the visibility word
-          const uint32_t cwd = cq == 0 ? visc.x : cq == 1 ? visc.y : cq == 2 ? visc.z : visc.w;
-          for (int i = 0; i < 32; ++i)
-            if (((cwd >> i) & 1u) && s_pos[par * ATT_BN + cq * 32 + i] <= pos_q) vw |= 1u << i;
-        }
-        tmem_ld_wait();
-#pragma unroll
-        for (int i4 = 0; i4 < 8; ++i4) {
-          const float4 bb = bias4[cq * 8 + i4];
-          const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = i4 * 4 + u;
-            float s2 = fmaf(__uint_as_float(v[i]), p.scale_log2, bv[u]);
-            if (has_mask) s2 = ((vw >> i) & 1u) ? s2 : -FLT_MAX;
-            m_tile = fmaxf(m_tile, s2);
-            v[i] = __float_as_uint(s2);
+        const uint2 vv = *reinterpret_cast<const uint2*>(mb + ATTN_META_OFF_VIS + gq * 8);
+        const uint2 vc = *reinterpret_cast<const uint2*>(mb + ATTN_META_OFF_VISC + gq * 8);
+        vw0 = vv.x; vw1 = vv.y;
+        if (vc.x | vc.y) {  // rare (Text sets): fold the causal rule into the visibility words
+          const int* m_pos = reinterpret_cast<const int*>(mb + ATTN_META_OFF_POS);
+          for (int i = 0; i < 32; ++i) {
+            if (((vc.x >> i) & 1u) && m_pos[i] <= pos_q) vw0 |= 1u << i;
+            if (((vc.y >> i) & 1u) && m_pos[32 + i] <= pos_q) vw1 |= 1u << i;
           }
         }
-        tmem_st_x32(tmem_s + lane_sel + cq * 32, v);
+        masked_tile = !__all_sync(0xffffffffu, (vw0 & vw1) == 0xffffffffu);  // warp-uniform: skip the selects when nothing is masked
       }
-      tmem_st_wait();
-      const float m_new = fmaxf(m_run, m_tile);  // finite: tile 0 always holds key 0
-      const float alpha = fast_exp2(m_run - m_new);  // first tile: exp2(-inf) = 0
 
-      // fold O_{j-1} (its MMA completed before S_j's commit fired) into the register accumulator
-      if (j > 0) {
-        mbar_wait(o_full, (j - 1) & 1);
-        tc_fence_after();
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      float s[ATT_BN];
+      const uint32_t ts = tmem_base + (j & 1) * ATT_BN + lane_sel;
+      tmem_ld_f32x32<0>(ts, s);
+      tmem_ld_f32x32<32>(ts + 32, s);
+      tmem_ld_wait();
+
+      // s2 = s * scale*log2e + log2(size_k)     (packed f32x2 FMA: two logits per instruction)
 #pragma unroll
-        for (int c0 = 0; c0 < ATT_D; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_x32(tmem_o + lane_sel + c0, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o_acc[c0 + i] = fmaf(o_acc[c0 + i], alpha_prev, __uint_as_float(v[i]));
-        }
+      for (int i4 = 0; i4 < ATT_BN / 4; ++i4) {
+        const float4 bb = bias4[i4];
+        const float2 t0 = __ffma2_rn(make_float2(s[4 * i4], s[4 * i4 + 1]), scale2, make_float2(bb.x, bb.y));
+        const float2 t1 = __ffma2_rn(make_float2(s[4 * i4 + 2], s[4 * i4 + 3]), scale2, make_float2(bb.z, bb.w));
+        s[4 * i4] = t0.x; s[4 * i4 + 1] = t0.y; s[4 * i4 + 2] = t1.x; s[4 * i4 + 3] = t1.y;
       }
-      alpha_prev = alpha;
-
-      // pass 2: P = exp2(s2 - m_new) -> bf16, K-major 128B-swizzled A operand in shared memory
-      float l_tile = 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < ATT_BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_x32(tmem_s + lane_sel + c0, v);
-        tmem_ld_wait();
-        float pv[32];
+      mbar_arrive(&meta_empty[ms]);  // last read of this tile's metadata
+      if (masked_tile) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          pv[i] = fast_exp2(__uint_as_float(v[i]) - m_new);
-          l_tile += pv[i];
-        }
-        uint8_t* prow = s_p + (c0 >> 6) * 16384 + row * 128;
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {  // 4 chunks of 8 keys = 16 bytes
-          const int chunk = ((c0 & 63) >> 3) + ch;
-          const uint4 w = make_uint4(pack_bf16(pv[ch * 8 + 0], pv[ch * 8 + 1]), pack_bf16(pv[ch * 8 + 2], pv[ch * 8 + 3]),
-                                     pack_bf16(pv[ch * 8 + 4], pv[ch * 8 + 5]), pack_bf16(pv[ch * 8 + 6], pv[ch * 8 + 7]));
-          *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) = w;
+          s[i] = ((vw0 >> i) & 1u) ? s[i] : -FLT_MAX;
+          s[32 + i] = ((vw1 >> i) & 1u) ? s[32 + i] : -FLT_MAX;
         }
       }
-      l_run = fmaf(l_run, alpha, l_tile);
-      m_run = m_new;
+      float m_tile = fmaxf(s[0], s[1]);
+#pragma unroll
+      for (int i = 2; i < ATT_BN; i += 2) m_tile = fmaxf(m_tile, fmaxf(s[i], s[i + 1]));
+      // m_tile >= -FLT_MAX: every tile holds at least one key < T, whose logit is finite or -FLT_MAX
+
+      if (j == 0) {
+        m_run = m_tile;
+      } else {
+        const float m_new = fmaxf(m_run, m_tile);
+        const bool need = (m_new - m_run) > ATT_LAZY_LOG2;
+        if (__any_sync(0xffffffffu, need)) {  // rare after the first tiles: correct this warp's 32 rows of O in TMEM
+          const float alpha = need ? fast_exp2(m_run - m_new) : 1.0f;
+          if (need) m_run = m_new;
+          l_run *= alpha;
+          mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);  // O holds tiles 0..j-1
+          tc_fence_after();
+#pragma unroll
+          for (int c0 = 0; c0 < ATT_D; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_x32(tmem_o + lane_sel + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_x32(tmem_o + lane_sel + c0, v);
+          }
+          tmem_st_wait();
+        }
+      }
+
+      // P = exp2(s2 - m_run) -> bf16, K-major 128B-swizzled A operand in shared memory buffer j&1
+      if (j >= 2) mbar_wait(&pv_done[j & 1], ((j - 2) >> 1) & 1);  // P V_{j-2} has finished reading this buffer
+      const float2 nm2 = make_float2(-m_run, -m_run);
+      float2 l2 = make_float2(0.f, 0.f);
+      uint8_t* prow = s_p + (j & 1) * ATT_P_BYTES + row * 128;
+#pragma unroll
+      for (int ch = 0; ch < ATT_BN / 8; ++ch) {  // 8 chunks of 8 keys = 16 bytes
+        uint32_t w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float2 d = __fadd2_rn(make_float2(s[ch * 8 + 2 * u], s[ch * 8 + 2 * u + 1]), nm2);
+          const float2 e = make_float2(fast_exp2(d.x), fast_exp2(d.y));
+          l2 = __fadd2_rn(l2, e);
+          w[u] = pack_bf16(e.x, e.y);
+        }
+        *reinterpret_cast<uint4*>(prow + ((ch ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      l_run += l2.x + l2.y;
       fence_proxy_async_smem();  // P visible to the tensor core (async proxy)
-      tc_fence_before();         // our TMEM accesses of S_j / O_{j-1} are ordered before the MMAs that overwrite them
-      mbar_arrive(p_ready);
+      tc_fence_before();         // our TMEM reads of S_j / writes of O are ordered before the MMAs that follow
+      mbar_arrive(&p_ready[j & 1]);
     }
-    // last tile's O
-    mbar_wait(o_full, (n_kv - 1) & 1);
+    // O is final once the last P V retires
+    mbar_wait(&pv_done[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);
     tc_fence_after();
-#pragma unroll
-    for (int c0 = 0; c0 < ATT_D; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld_x32(tmem_o + lane_sel + c0, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) o_acc[c0 + i] = fmaf(o_acc[c0 + i], alpha_prev, __uint_as_float(v[i]));
-    }
-    if (q < T) {
+    if (warp_active) {
       const float inv_l = 1.0f / l_run;
-      __nv_bfloat16* orow = p.out + (long long)b * p.o_batch_stride + (long long)q * p.o_token_stride + h * ATT_D;
+      __nv_bfloat16* orow = p.out + (long long)b * p.o_batch_stride + (long long)(q < T ? q : 0) * p.o_token_stride + h * ATT_D;
 #pragma unroll
-      for (int i = 0; i < ATT_D; i += 8) {
-        const uint4 w = make_uint4(pack_bf16(o_acc[i] * inv_l, o_acc[i + 1] * inv_l),
-                                   pack_bf16(o_acc[i + 2] * inv_l, o_acc[i + 3] * inv_l),
-                                   pack_bf16(o_acc[i + 4] * inv_l, o_acc[i + 5] * inv_l),
-                                   pack_bf16(o_acc[i + 6] * inv_l, o_acc[i + 7] * inv_l));
-        *reinterpret_cast<uint4*>(orow + i) = w;
+      for (int c0 = 0; c0 < ATT_D; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_x32(tmem_o + lane_sel + c0, v);   // warp-collective: rows past T take part and only skip the stores
+        tmem_ld_wait();
+        if (q < T) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            const uint4 w = make_uint4(pack_bf16(__uint_as_float(v[i]) * inv_l, __uint_as_float(v[i + 1]) * inv_l),
+                                       pack_bf16(__uint_as_float(v[i + 2]) * inv_l, __uint_as_float(v[i + 3]) * inv_l),
+                                       pack_bf16(__uint_as_float(v[i + 4]) * inv_l, __uint_as_float(v[i + 5]) * inv_l),
+                                       pack_bf16(__uint_as_float(v[i + 6]) * inv_l, __uint_as_float(v[i + 7]) * inv_l));
+            *reinterpret_cast<uint4*>(orow + c0 + i) = w;
+          }
+        }
       }
-      if (p.lse) p.lse[((long long)b * p.heads + h) * T + q] = (m_run + log2f(l_run)) * 0.6931471805599453f;
+      if (q < T && p.lse) p.lse[((long long)b * p.heads + h) * T + q] = (m_run + log2f(l_run)) * 0.6931471805599453f;
     }
   }
 
@@ -337,6 +336,56 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     tc_fence_after();
     tmem_dealloc(tmem_base, ATT_TMEM_COLS);
   }
+}
+
+// ------------------------------------------------------------------------------------------------ metadata (attn_meta.cuh)
+__global__ void __launch_bounds__(ATTN_META_TILE)
+attn_meta_kernel(int T, const uint8_t* __restrict__ gid, const int32_t* __restrict__ pos, const uint8_t* __restrict__ allow,
+                 int G, const float* __restrict__ size, uint8_t* __restrict__ meta) {
+  const int tile = blockIdx.x, b = blockIdx.y, t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int idx = tile * ATTN_META_TILE + t;
+  const bool valid = idx < T;
+  uint8_t* m = meta + ((size_t)b * gridDim.x + tile) * ATTN_META_BYTES;
+  reinterpret_cast<float*>(m)[t] = valid ? (size ? log2f(size[(long long)b * T + idx]) : 0.f) : -INFINITY;
+  uint32_t cw = 0xffffffffu, cc = 0u, rw = 0xffffffffu, rc = 0u;  // tokens past T: "visible" (the -inf bias / +inf lse removes them)
+  int ps = 0;
+  if (gid != nullptr && valid) {
+    const int g = gid[(long long)b * T + idx];
+    ps = pos[(long long)b * T + idx];
+    cw = cc = rw = rc = 0u;
+    for (int o = 0; o < G; ++o) {
+      const int a_col = allow[o * G + g];  // query group o looking at this token as a KEY
+      const int a_row = allow[g * G + o];  // this token as a QUERY looking at key group o
+      cw |= (a_col == 1 ? 1u : 0u) << o;
+      cc |= (a_col == 2 ? 1u : 0u) << o;
+      rw |= (a_row == 1 ? 1u : 0u) << o;
+      rc |= (a_row == 2 ? 1u : 0u) << o;
+    }
+  }
+  reinterpret_cast<int*>(m + ATTN_META_OFF_POS)[t] = ps;
+  uint32_t* vis = reinterpret_cast<uint32_t*>(m + ATTN_META_OFF_VIS);
+  uint32_t* visc = reinterpret_cast<uint32_t*>(m + ATTN_META_OFF_VISC);
+  uint32_t* qvis = reinterpret_cast<uint32_t*>(m + ATTN_META_OFF_QVIS);
+  uint32_t* qvisc = reinterpret_cast<uint32_t*>(m + ATTN_META_OFF_QVISC);
+  for (int g = 0; g < 32; ++g) {
+    const uint32_t w0 = __ballot_sync(0xffffffffu, (cw >> g) & 1u), w1 = __ballot_sync(0xffffffffu, (cc >> g) & 1u);
+    const uint32_t w2 = __ballot_sync(0xffffffffu, (rw >> g) & 1u), w3 = __ballot_sync(0xffffffffu, (rc >> g) & 1u);
+    if (lane == 0) {
+      vis[g * 2 + warp] = w0;
+      visc[g * 2 + warp] = w1;
+      qvis[g * 2 + warp] = w2;
+      qvisc[g * 2 + warp] = w3;
+    }
+  }
+}
+
+int launch_attn_meta(int B, int T, const uint8_t* gid, const int32_t* pos, const uint8_t* allow, int G, const float* size,
+                     uint8_t* meta, cudaStream_t stream) {
+  TOME_CHECK(meta != nullptr && ((uintptr_t)meta & 15) == 0, TOME_ERR_INVALID, "attention: workspace must be non-null and 16-byte aligned");
+  dim3 grid((T + ATTN_META_TILE - 1) / ATTN_META_TILE, B);
+  attn_meta_kernel<<<grid, ATTN_META_TILE, 0, stream>>>(T, gid, pos, allow, G, size, meta);
+  TOME_CUDA(cudaGetLastError());
+  return TOME_OK;
 }
 
 }  // namespace tome
@@ -359,23 +408,33 @@ int check_attn_desc(const tome_attn_desc_t* d, const char* who) {
 }
 }  // namespace tome
 
+extern "C" size_t tome_attention_workspace_bytes(const tome_attn_desc_t* d) {
+  if (!d || d->batch <= 0 || d->tokens <= 0) return 0;
+  return attn_meta_bytes(d->batch, d->tokens);
+}
+
 extern "C" int tome_attention_fwd(const tome_attn_desc_t* d, const void* q, const void* k, const void* v, void* out,
-                                  float* lse, void* stream_) {
+                                  float* lse, void* workspace, size_t workspace_bytes, void* stream_) {
   clear_error();
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int rc = check_attn_desc(d, "attention_fwd")) return rc;
   TOME_CHECK(q && k && v && out, TOME_ERR_INVALID, "attention_fwd: null tensor");
   TOME_CHECK(((uintptr_t)out & 15) == 0, TOME_ERR_INVALID, "attention_fwd: out must be 16-byte aligned");
+  TOME_CHECK(workspace && workspace_bytes >= attn_meta_bytes(d->batch, d->tokens), TOME_ERR_INVALID,
+             "attention_fwd: workspace too small (%zu < %zu, see tome_attention_workspace_bytes)", workspace_bytes,
+             attn_meta_bytes(d->batch, d->tokens));
   CUtensorMap tq, tk, tv;
   const uint64_t hd = (uint64_t)d->heads * d->head_dim;
-  ProfScope prof(PROF_ATTN_FWD, 4.0 * d->batch * d->heads * (double)d->tokens * d->tokens * d->head_dim, 1, stream);
+  ProfScope prof(PROF_ATTN_FWD, 4.0 * d->batch * d->heads * (double)d->tokens * d->tokens * d->head_dim, 2, stream);
+  if (int rc = launch_attn_meta(d->batch, d->tokens, d->gid, d->pos, d->allow, d->num_groups, d->size,
+                                reinterpret_cast<uint8_t*>(workspace), stream)) return rc;
   if (int rc = make_tmap_3d_bf16(&tq, q, hd, d->tokens, d->batch, d->q_token_stride, d->q_batch_stride, ATT_BM)) return rc;
   if (int rc = make_tmap_3d_bf16(&tk, k, hd, d->tokens, d->batch, d->k_token_stride, d->k_batch_stride, ATT_BN)) return rc;
   if (int rc = make_tmap_3d_bf16(&tv, v, hd, d->tokens, d->batch, d->v_token_stride, d->v_batch_stride, ATT_BN)) return rc;
   AttnFwdParams p;
   p.batch = d->batch; p.tokens = d->tokens; p.heads = d->heads;
   p.scale_log2 = d->scale * 1.4426950408889634f;
-  p.gid = d->gid; p.pos = d->pos; p.allow = d->allow; p.num_groups = d->num_groups; p.size = d->size;
+  p.gid = d->gid; p.pos = d->pos; p.meta = reinterpret_cast<const uint8_t*>(workspace);
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.o_batch_stride = d->o_batch_stride; p.o_token_stride = d->o_token_stride;
   p.lse = lse;

@@ -1,0 +1,40 @@
+// Per-token-tile attention metadata, computed ONCE per (batch, 64-token tile) by attn_meta_kernel and then streamed
+// into shared memory by cp.async.bulk (1 copy per tile, completion on an mbarrier) in the forward, dQ and dK/dV
+// kernels.  Before this existed every CTA -- one per (batch, head, 128-row tile), i.e. 30x redundantly at the bench
+// shape -- rebuilt the same words from gid / pos / size / allow with dependent global loads on its critical path,
+// and that latency chain, not the tensor pipe or MUFU, paced the kernels (profiles/r01c_attn_fwd_v2_meta_bound.txt).
+//
+// Block layout (ATTN_META_BYTES per (b, tile); token t of the tile is bit t&31 of word t>>5):
+//   +0     bias2[64]    f32   log2(size_k), 0 when size == NULL, -inf for tokens past T
+//   +256   vis[32][2]   u32   vis[g]  : KEYS of this tile visible to QUERY group g          (allow == 1)
+//   +512   visc[32][2]  u32   visc[g] : keys visible to query group g iff pos_k <= pos_q    (allow == 2)
+//   +768   pos[64]      i32
+//   +1024  qvis[32][2]  u32   qvis[g] : QUERIES of this tile that see KEY group g           (allow == 1)
+//   +1280  qvisc[32][2] u32   ... iff pos_k <= pos_q                                        (allow == 2)
+// Tokens past T are "visible" everywhere: the -inf bias (keys) or +inf lse (queries) removes them.
+#pragma once
+#include "common.cuh"
+
+namespace tome {
+
+constexpr int ATTN_META_TILE = 64;
+constexpr int ATTN_META_BYTES = 1536;
+constexpr int ATTN_META_KEY_BYTES = 1024;   // bias2 | vis | visc | pos : what a query-row kernel needs per key tile
+constexpr int ATTN_META_OFF_VIS = 256, ATTN_META_OFF_VISC = 512, ATTN_META_OFF_POS = 768, ATTN_META_OFF_QVIS = 1024,
+              ATTN_META_OFF_QVISC = 1280;
+
+inline size_t attn_meta_bytes(int batch, int tokens) {
+  return (size_t)batch * ((tokens + ATTN_META_TILE - 1) / ATTN_META_TILE) * ATTN_META_BYTES;
+}
+// launches attn_meta_kernel (attn_fwd.cu); meta must be 16-byte aligned
+int launch_attn_meta(int B, int T, const uint8_t* gid, const int32_t* pos, const uint8_t* allow, int G, const float* size,
+                     uint8_t* meta, cudaStream_t stream);
+
+// global -> shared bulk copy completing on an mbarrier (bytes % 16 == 0, both addresses 16-byte aligned)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+}  // namespace tome

@@ -26,21 +26,23 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Bounded wait: a protocol bug must fault (trap) instead of hanging the GPU box.
+// Bounded wait: a protocol bug must fault (trap) instead of hanging the GPU box.  try_wait carries a suspend-time
+// hint, so a waiting thread sleeps in hardware until the phase completes (or ~8 us pass) instead of spinning on the
+// issue port its CTA's working warps need; the spin bound is therefore counted in units of that time-out.
 #ifndef TOME_MBAR_SPIN_LIMIT
-#define TOME_MBAR_SPIN_LIMIT (1ll << 26)
+#define TOME_MBAR_SPIN_LIMIT (1 << 22)
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
-  long long spins = 0;
+  int spins = 0;
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(8192u)
         : "memory");
     if (done) break;
     if (++spins > TOME_MBAR_SPIN_LIMIT) __trap();

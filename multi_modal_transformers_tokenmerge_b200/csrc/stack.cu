@@ -42,7 +42,9 @@ struct StackLayout {
   std::vector<LayerShape> shapes;
   std::vector<LayerBufs> L;
   __nv_bfloat16 *x1_scratch, *g0, *g1, *g2, *g3, *big;
-  float *delta, *attn_scratch, *ws_gemm, *ws_colsum, *ws_ln;
+  float *ws_gemm, *ws_colsum, *ws_ln;
+  uint8_t* ws_attn;
+  size_t ws_attn_bytes;
   int32_t* origin;
   size_t ws_gemm_bytes;
   size_t total;
@@ -176,8 +178,14 @@ static StackLayout make_layout(const tome_stack_cfg_t* c, void* workspace) {
   S.g2 = b.take<__nv_bfloat16>(B * T0 * C);
   S.g3 = b.take<__nv_bfloat16>(B * T0 * HD);
   S.big = b.take<__nv_bfloat16>(B * T0 * wide);
-  S.delta = b.take<float>(B * c->heads * T0);
-  S.attn_scratch = b.take<float>(B * T0 * 2);
+  {  // attention scratch (forward: per-tile metadata; backward: delta + metadata), sized for the widest layer
+    tome_attn_desc_t ad;
+    memset(&ad, 0, sizeof(ad));
+    ad.batch = c->batch; ad.tokens = c->tokens; ad.heads = c->heads; ad.head_dim = c->head_dim;
+    const size_t f = tome_attention_workspace_bytes(&ad), bw = tome_attention_bwd_workspace_bytes(&ad);
+    S.ws_attn_bytes = f > bw ? f : bw;
+    S.ws_attn = b.take<uint8_t>(S.ws_attn_bytes);
+  }
   // split-K workspace: the largest weight gradient, at most 64 splits are ever chosen but 148 tiles bound the product
   size_t wmax = C * 3 * HD;
   if (C * F > wmax) wmax = C * F;
@@ -327,7 +335,7 @@ extern "C" int tome_stack_forward(const tome_stack_cfg_t* c, const tome_stack_io
     ad.scale = 1.0f / sqrtf((float)D);
     if (c->num_groups) { ad.gid = Lb.gid_in; ad.pos = Lb.pos_in; ad.allow = io->allow; ad.num_groups = c->num_groups; }
     ad.size = c->prop_attn ? Lb.size_in : nullptr;
-    RC(tome_attention_fwd(&ad, Lb.qkv, Lb.qkv + HD, Lb.qkv + 2 * HD, Lb.attn_o, Lb.lse, st));
+    RC(tome_attention_fwd(&ad, Lb.qkv, Lb.qkv + HD, Lb.qkv + 2 * HD, Lb.attn_o, Lb.lse, S.ws_attn, S.ws_attn_bytes, st));
     __nv_bfloat16* x1 = r > 0 ? S.x1_scratch : Lb.x1m;
     RC(gemm(c, S, st, M, C, HD, Lb.attn_o, HD, TOME_MAJOR_K, pw + o.wo, C, TOME_MAJOR_MN, x1, C, TOME_BF16, pf + o.bo, 0,
             Lb.x_in, nullptr, 1.f, 3 * l + 0, 0));
@@ -447,7 +455,7 @@ extern "C" int tome_stack_backward(const tome_stack_cfg_t* c, const tome_stack_i
     gs.dq_token_stride = gs.dk_token_stride = gs.dv_token_stride = 3 * HD;
     gs.do_batch_stride = (long long)T * HD; gs.do_token_stride = HD;
     RC(tome_attention_bwd(&ad, &gs, Lb.qkv, Lb.qkv + HD, Lb.qkv + 2 * HD, Lb.attn_o, Lb.lse, g3, S.big, S.big + HD,
-                          S.big + 2 * HD, S.delta, S.attn_scratch, st));
+                          S.big + 2 * HD, S.ws_attn, S.ws_attn_bytes, st));
     // ---- qkv projection
     RC(tome_colsum_bf16(M, 3 * HD, S.big, 3 * HD, gr + o.bqkv, 1, S.ws_colsum, st));
     RC(gemm(c, S, st, C, 3 * HD, M, Lb.h, C, TOME_MAJOR_MN, S.big, 3 * HD, TOME_MAJOR_MN, gr + o.wqkv, 3 * HD, TOME_F32, nullptr, 0,

@@ -202,6 +202,13 @@ def layernorm_bwd(x, dy, gamma, mean, rstd, dgamma, dbeta, dres=None, axis: int 
 
 
 # ------------------------------------------------------------------------------------------------ attention
+def _scratch(nbytes: int, device) -> torch.Tensor:
+    """uint8 device scratch of `nbytes` whose data pointer is 256-byte aligned (torch's allocator aligns to 512)."""
+    t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+    assert t.data_ptr() % 256 == 0
+    return t
+
+
 def _attn_desc(q, k, v, out, scale, gid, pos, allow, size):
     b, t, h, d = q.shape
     for x in (q, k, v, out):
@@ -221,7 +228,9 @@ def attention_fwd(q, k, v, *, gid=None, pos=None, allow=None, size=None, scale=N
     out = torch.empty(b, t, h, d, dtype=torch.bfloat16, device=q.device)
     lse = torch.empty(b, h, t, dtype=torch.float32, device=q.device)
     desc = _attn_desc(q, k, v, out, scale, gid, pos, allow, size)
-    L.check(L.lib().tome_attention_fwd(C.byref(desc), _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse), _stream()))
+    ws = _scratch(L.lib().tome_attention_workspace_bytes(C.byref(desc)), q.device)
+    L.check(L.lib().tome_attention_fwd(C.byref(desc), _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse), _ptr(ws), ws.numel(),
+                                       _stream()))
     return out, lse
 
 
@@ -238,8 +247,7 @@ def attention_bwd(q, k, v, out, lse, dout, *, gid=None, pos=None, allow=None, si
     desc = _attn_desc(q, k, v, out, scale, gid, pos, allow, size)
     gs = L.AttnGradStrides(dq.stride(0), dq.stride(1), dk.stride(0), dk.stride(1), dv.stride(0), dv.stride(1),
                            dout.stride(0), dout.stride(1))
-    delta = torch.empty(b, h, t, dtype=torch.float32, device=q.device)
-    dq_acc = torch.empty(b, t, h * d, dtype=torch.float32, device=q.device)
+    ws = _scratch(L.lib().tome_attention_bwd_workspace_bytes(C.byref(desc)), q.device)
     L.check(L.lib().tome_attention_bwd(C.byref(desc), C.byref(gs), _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse),
-                                       _ptr(dout), _ptr(dq), _ptr(dk), _ptr(dv), _ptr(delta), _ptr(dq_acc), _stream()))
+                                       _ptr(dout), _ptr(dq), _ptr(dk), _ptr(dv), _ptr(ws), ws.numel(), _stream()))
     return dq, dk, dv

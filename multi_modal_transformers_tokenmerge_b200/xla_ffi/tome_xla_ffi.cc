@@ -101,25 +101,26 @@ static tome_attn_desc_t AttnDesc(const ffi::AnyBuffer& qkv, const ffi::Buffer<ff
   a.size = size.typed_data();
   return a;
 }
+// workspace: a u8 Result buffer of tome_attention_workspace_bytes(desc) bytes that XLA allocates (tome_jax.py sizes it)
 static ffi::Error AttnFwd(cudaStream_t s, ffi::AnyBuffer qkv, ffi::Buffer<ffi::U8> gid, ffi::Buffer<ffi::S32> pos,
                           ffi::Buffer<ffi::U8> allow, ffi::Buffer<ffi::F32> size, ffi::Result<ffi::AnyBuffer> out,
-                          ffi::Result<ffi::Buffer<ffi::F32>> lse, float scale) {
+                          ffi::Result<ffi::Buffer<ffi::F32>> lse, ffi::Result<ffi::Buffer<ffi::U8>> workspace, float scale) {
   tome_attn_desc_t a = AttnDesc(qkv, gid, pos, allow, size, scale);
   const uint16_t* base = reinterpret_cast<const uint16_t*>(qkv.untyped_data());
   const long long hd = (long long)a.heads * a.head_dim;
-  return Status(tome_attention_fwd(&a, base, base + hd, base + 2 * hd, out->untyped_data(), lse->typed_data(), s));
+  return Status(tome_attention_fwd(&a, base, base + hd, base + 2 * hd, out->untyped_data(), lse->typed_data(),
+                                   workspace->typed_data(), workspace->element_count(), s));
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(TomeAttentionFwd, AttnFwd,
                               ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<ffi::AnyBuffer>()
                                   .Arg<ffi::Buffer<ffi::U8>>().Arg<ffi::Buffer<ffi::S32>>().Arg<ffi::Buffer<ffi::U8>>()
                                   .Arg<ffi::Buffer<ffi::F32>>().Ret<ffi::AnyBuffer>().Ret<ffi::Buffer<ffi::F32>>()
-                                  .Attr<float>("scale"));
+                                  .Ret<ffi::Buffer<ffi::U8>>().Attr<float>("scale"));
 
-// ---- tome_attention_bwd: -> dqkv bf16 [B,T,3,H,D]; delta / scratch are Result buffers XLA allocates for us
+// ---- tome_attention_bwd: -> dqkv bf16 [B,T,3,H,D]; the workspace is a Result buffer XLA allocates for us
 static ffi::Error AttnBwd(cudaStream_t s, ffi::AnyBuffer qkv, ffi::AnyBuffer out, ffi::Buffer<ffi::F32> lse, ffi::AnyBuffer dout,
                           ffi::Buffer<ffi::U8> gid, ffi::Buffer<ffi::S32> pos, ffi::Buffer<ffi::U8> allow, ffi::Buffer<ffi::F32> size,
-                          ffi::Result<ffi::AnyBuffer> dqkv, ffi::Result<ffi::Buffer<ffi::F32>> delta,
-                          ffi::Result<ffi::Buffer<ffi::F32>> scratch, float scale) {
+                          ffi::Result<ffi::AnyBuffer> dqkv, ffi::Result<ffi::Buffer<ffi::U8>> workspace, float scale) {
   tome_attn_desc_t a = AttnDesc(qkv, gid, pos, allow, size, scale);
   tome_attn_grad_strides_t g{a.q_batch_stride, a.q_token_stride, a.q_batch_stride, a.q_token_stride, a.q_batch_stride, a.q_token_stride,
                              a.o_batch_stride, a.o_token_stride};
@@ -127,14 +128,13 @@ static ffi::Error AttnBwd(cudaStream_t s, ffi::AnyBuffer qkv, ffi::AnyBuffer out
   uint16_t* dbase = reinterpret_cast<uint16_t*>(dqkv->untyped_data());
   const long long hd = (long long)a.heads * a.head_dim;
   return Status(tome_attention_bwd(&a, &g, base, base + hd, base + 2 * hd, out.untyped_data(), lse.typed_data(), dout.untyped_data(),
-                                   dbase, dbase + hd, dbase + 2 * hd, delta->typed_data(), scratch->typed_data(), s));
+                                   dbase, dbase + hd, dbase + 2 * hd, workspace->typed_data(), workspace->element_count(), s));
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(TomeAttentionBwd, AttnBwd,
                               ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>()
                                   .Arg<ffi::Buffer<ffi::F32>>().Arg<ffi::AnyBuffer>().Arg<ffi::Buffer<ffi::U8>>()
                                   .Arg<ffi::Buffer<ffi::S32>>().Arg<ffi::Buffer<ffi::U8>>().Arg<ffi::Buffer<ffi::F32>>()
-                                  .Ret<ffi::AnyBuffer>().Ret<ffi::Buffer<ffi::F32>>().Ret<ffi::Buffer<ffi::F32>>()
-                                  .Attr<float>("scale"));
+                                  .Ret<ffi::AnyBuffer>().Ret<ffi::Buffer<ffi::U8>>().Attr<float>("scale"));
 
 // ---- tome_gemm_bf16 as a Dense layer: y = epilogue(x [M,K] * kernel [K,N] + bias)       attention.py:32-37
 static ffi::Error Dense(cudaStream_t s, ffi::AnyBuffer x, ffi::AnyBuffer kernel, ffi::Buffer<ffi::F32> bias, ffi::AnyBuffer residual,

@@ -94,12 +94,27 @@ def bench_attn():
         t = timeit(lambda: ops.attention_fwd(q, k, v, size=size), iters=5)
         fl = 4.0 * B * H * T * T * 64
         print(f"attn_fwd B{B} T{T} H{H}: {t*1e6:9.1f} us {fl/t/1e12:7.1f} TF/s")
+        # block-causal group mask in a scrambled token order (as after a merge)
+        from multi_modal_transformers_tokenmerge_b200.tokenizers.token_sequencer import sequence_groups
+        import numpy as np
+        n_img = (T - 16) // 2 - 4
+        g1, p1, allow, _ = sequence_groups(f"[TaskDescriptionPrefix{{16}}] [Image{{{n_img}}};Readout{{4}}]*2")
+        rng = np.random.default_rng(0)
+        gm = torch.tensor(np.stack([rng.permutation(g1) for _ in range(B)])).cuda()
+        pm = torch.tensor(np.broadcast_to(p1, (B, len(g1))).copy()).cuda()
+        am = torch.tensor(allow).cuda()
+        if gm.shape[1] == T:
+            t = timeit(lambda: ops.attention_fwd(q, k, v, size=size, gid=gm, pos=pm, allow=am), iters=5)
+            print(f"attn_fwd B{B} T{T} H{H} masked: {t*1e6:9.1f} us {fl/t/1e12:7.1f} TF/s")
         if hasattr(ops, "attention_bwd"):
             try:
                 out, lse = ops.attention_fwd(q, k, v, size=size)
                 do = torch.randn_like(out)
                 t = timeit(lambda: ops.attention_bwd(q, k, v, out, lse, do, size=size), iters=5)
                 print(f"attn_bwd B{B} T{T} H{H}: {t*1e6:9.1f} us {2.5*fl/t/1e12:7.1f} TF/s")
+                if gm.shape[1] == T:
+                    t = timeit(lambda: ops.attention_bwd(q, k, v, out, lse, do, size=size, gid=gm, pos=pm, allow=am), iters=5)
+                    print(f"attn_bwd B{B} T{T} H{H} masked: {t*1e6:9.1f} us {2.5*fl/t/1e12:7.1f} TF/s")
             except Exception as ex:  # not built yet
                 print("attn_bwd unavailable:", ex)
 

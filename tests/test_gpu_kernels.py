@@ -283,3 +283,33 @@ def test_attention_fwd(ops, T, H, masked, sized):
         m = torch.as_tensor(O.dense_mask(gid, pos, gid, pos, allow))[:, None]
         logits = torch.where(m, logits, torch.full_like(logits, -1e30))
     assert (lse.cpu() - torch.logsumexp(logits, -1)).abs().max().item() <= 2e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T,growth", [(536, 6.0), (200, 20.0), (1000, -4.0)])
+def test_attention_fwd_lazy_rescale(ops, T, growth):
+    """The forward kernel keeps O in TMEM and rescales it only when a row maximum grows by more than 2^8.  Keys whose
+    magnitude grows (or shrinks) tile by tile force that correction path on every tile (or on none); both must match
+    the oracle.  Also covers a causal (code 2) group table, where visibility depends on positions."""
+    rng = np.random.default_rng(7)
+    B, H, D = 2, 2, 64
+    qkv = rng.standard_normal((B, T, 3, H, D)).astype(np.float32)
+    ramp = 1.0 + np.maximum(0.0, growth * (np.arange(T) // 64)) if growth > 0 else 1.0 + (-growth) * ((T - 1 - np.arange(T)) // 64)
+    qkv[:, :, 1] *= ramp[None, :, None, None]
+    qkv = torch.tensor(qkv).cuda().bfloat16()
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    gid = rng.integers(0, 3, size=(B, T)).astype(np.uint8)
+    pos = rng.integers(0, 40, size=(B, T)).astype(np.int32)
+    allow = np.array([[1, 0, 2], [1, 1, 0], [2, 1, 2]], np.uint8)   # code 2: visible iff pos_k <= pos_q
+    gid[:, 0] = 0   # every group sees group-0 keys (directly or causally at pos 0): no fully masked row
+    pos[:, 0] = 0
+    out, lse = ops.attention_fwd(q, k, v, gid=dev(gid), pos=dev(pos), allow=dev(allow))
+    torch.cuda.synchronize()
+    ref = _attn_ref(q.float().cpu(), k.float().cpu(), v.float().cpu(), gid, pos, allow, None)
+    err = (out.float().cpu() - ref).abs().max().item()
+    assert err <= 3e-2, f"attention fwd (rescale path) err {err}"
+    logits = torch.einsum("bqhd,bkhd->bhqk", q.float().cpu() / 8.0, k.float().cpu())
+    m = torch.as_tensor(O.dense_mask(gid, pos, gid, pos, allow))[:, None]
+    logits = torch.where(m, logits, torch.full_like(logits, -1e30))
+    ref_lse = torch.logsumexp(logits, -1)
+    assert ((lse.cpu() - ref_lse).abs() / ref_lse.abs().clamp_min(1.0)).max().item() <= 2e-2
