@@ -169,6 +169,19 @@ __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&r)[
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// same load, straight into fp32 registers
+__device__ __forceinline__ void tmem_ld_f32x32(uint32_t taddr, float (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]), "=f"(r[8]),
+        "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15]), "=f"(r[16]),
+        "=f"(r[17]), "=f"(r[18]), "=f"(r[19]), "=f"(r[20]), "=f"(r[21]), "=f"(r[22]), "=f"(r[23]), "=f"(r[24]),
+        "=f"(r[25]), "=f"(r[26]), "=f"(r[27]), "=f"(r[28]), "=f"(r[29]), "=f"(r[30]), "=f"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
 
 // ------------------------------------------------------------------------------------------------ 128-bit access
 __device__ __forceinline__ uint4 ld_nc_v4(const void* p) {  // streaming read, do not allocate in L1
@@ -191,38 +204,51 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 }
 
 // ------------------------------------------------------------------------------------------------ dropout RNG
-// Philox4x32-10 keyed by (seed, site); one call -> 8 x 16-bit uniforms for elements [8*ctr, 8*ctr+8).
-// keep iff u16 >= thresh16 where thresh16 = round(rate * 65536); forward and backward kernels call the same
-// function with the same (seed, site, ctr), so no mask tensor is ever stored.
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += W0;
-    key.y += W1;
-  }
-  return ctr;
-}
+// Counter-based and stateless, so forward and backward regenerate the same mask and no mask tensor is ever stored.
+// An element (row, col) of a row-major [M, N] tensor belongs to the STREAM (row, col / 32): two independent 32-bit
+// hashes of (seed, site, row, chunk) give the start state x0 and an odd increment c of a 32-bit LCG, and element
+// e = col % 32 of the chunk is kept iff the top 16 bits of x_{e+1} (x_{k+1} = A x_k + c) are >= thresh16.
+// One multiply-add and one compare per element: this runs in the GEMM epilogue, thread = row, 32 columns at a time,
+// where the previous Philox4x32-10 (~10 integer ops per element) made the epilogue, not the tensor pipe, the
+// bottleneck of every dropout GEMM (profiles/r01b_gemm_ncu_summary.txt).  Jump-ahead constants let a consumer that
+// owns 8 elements start in the middle of a chunk.  (Flax's threefry stream cannot be reproduced either way.)
 struct DropoutCfg {
-  uint32_t thresh16;  // 0 => dropout disabled
+  uint32_t thresh16;  // 0 => dropout disabled; keep iff u16 >= thresh16, thresh16 = round(rate * 65536)
   float inv_keep;     // 1 / (1 - thresh16/65536)
   uint32_t seed_lo, seed_hi;
   uint32_t site;  // distinguishes call sites / layers
 };
-// returns 8 bits: bit j set => element 8*ctr+j is KEPT
-__device__ __forceinline__ uint32_t dropout_keep8(const DropoutCfg& d, uint64_t ctr) {
-  const uint4 r = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), d.site, 0u),
-                                make_uint2(d.seed_lo, d.seed_hi));
-  uint32_t m = 0;
-  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    m |= ((w[j] & 0xFFFFu) >= d.thresh16 ? 1u : 0u) << (2 * j);
-    m |= ((w[j] >> 16) >= d.thresh16 ? 1u : 0u) << (2 * j + 1);
+constexpr uint32_t DROP_A = 0x915F77F5u;  // LCG multiplier (A % 8 == 5: full period for any odd increment)
+__host__ __device__ constexpr uint32_t drop_pow(int n) { uint32_t r = 1; for (int i = 0; i < n; ++i) r *= DROP_A; return r; }
+__host__ __device__ constexpr uint32_t drop_geo(int n) { uint32_t r = 0, a = 1; for (int i = 0; i < n; ++i) { r += a; a *= DROP_A; } return r; }  // 1 + A + ... + A^(n-1)
+__device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
+  x ^= x >> 16; x *= 0x21f0aaadu; x ^= x >> 15; x *= 0x735a2d97u; x ^= x >> 15;
+  return x;
+}
+struct DropStream {
+  uint32_t x, c;
+  __device__ __forceinline__ uint32_t next() { x = x * DROP_A + c; return x; }   // word of the next element; top 16 bits are the uniform
+  __device__ __forceinline__ void skip8(int n8) {  // jump over 8 * n8 elements (n8 in 0..3)
+    const uint32_t pa = n8 == 0 ? 1u : n8 == 1 ? drop_pow(8) : n8 == 2 ? drop_pow(16) : drop_pow(24);
+    const uint32_t ge = n8 == 0 ? 0u : n8 == 1 ? drop_geo(8) : n8 == 2 ? drop_geo(16) : drop_geo(24);
+    x = x * pa + c * ge;
   }
+};
+__device__ __forceinline__ DropStream drop_stream(const DropoutCfg& d, uint32_t row, uint32_t chunk) {
+  const uint32_t k = d.seed_lo ^ (d.site * 0x9E3779B9u);
+  DropStream s;
+  s.x = lowbias32(row * 0x9E3779B1u + chunk * 0x85EBCA77u + k);
+  s.c = lowbias32((row ^ d.seed_hi) * 0xC2B2AE35u + chunk * 0x27D4EB2Fu + (k ^ 0x5bd1e995u)) | 1u;
+  return s;
+}
+// 8 bits: bit j set => element (row, col + j) is KEPT; col % 8 == 0
+__device__ __forceinline__ uint32_t dropout_keep8(const DropoutCfg& d, uint32_t row, uint32_t col) {
+  DropStream s = drop_stream(d, row, col >> 5);
+  s.skip8((col >> 3) & 3);
+  const uint32_t thr = d.thresh16 << 16;
+  uint32_t m = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m |= (s.next() >= thr ? 1u : 0u) << j;
   return m;
 }
 

@@ -65,7 +65,12 @@ struct GemmSmem {
 // MC: clusters of two CTAs work on vertically adjacent tiles (same n_blk); each CTA fetches half of the shared B tile
 // and TMA-multicasts it into both CTAs, halving the L2 -> SM traffic of B (the K = C = 384 projections are bound by
 // that traffic, not by the tensor pipe).  A stage is reusable once BOTH CTAs' MMAs have drained it.
-template <int BN, bool A_MN, bool B_MN, bool MC>
+// EPI < 0: every epilogue option is a run-time flag (any combination, fp32 or bf16 output, split-K).
+// EPI >= 0: bit set of EPI_* -- the options are compile-time, the output is bf16 through TMA stores, and the inner loops
+// carry no flag tests or per-8-column edge tests.  The stack's own GEMMs all take one of these paths.
+constexpr int EPI_GENERIC = -1, EPI_BIAS = 1, EPI_RELU = 2, EPI_GATE = 4, EPI_DROP = 8, EPI_RESID = 16;
+
+template <int BN, bool A_MN, bool B_MN, bool MC, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const __grid_constant__ CUtensorMap tma_c, const GemmShape s, const GemmEpilogue e) {
@@ -75,7 +80,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   static_assert(2 * BN <= 512 && BN % 64 == 0, "two BN-column accumulators must fit the 512 TMEM columns");
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1 KB alignment by pointer arithmetic on the __shared__ array itself, so the epilogue's accesses stay LDS/STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_store = smem + STAGES * L::STAGE_BYTES;  // 1 KB aligned (stage sizes are multiples of 1 KB)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_store + L::STORE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -206,6 +212,120 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const __nv_bfloat16* gate = reinterpret_cast<const __nv_bfloat16*>(e.gate);
     int acc = 0;
     uint32_t acc_phase = 0;
+    if constexpr (EPI >= 0) {
+      // ============================================================= specialised epilogues (bf16 out, k_splits == 1)
+      constexpr bool kBias = (EPI & EPI_BIAS) != 0, kRelu = (EPI & EPI_RELU) != 0, kGate = (EPI & EPI_GATE) != 0,
+                     kDrop = (EPI & EPI_DROP) != 0, kResid = (EPI & EPI_RESID) != 0;
+      static_assert(!(kGate && kResid) && !(kGate && kDrop), "gate is the backward of relu/dropout: it never meets them");
+      const bool drop_on = kDrop && e.drop.thresh16 != 0;   // warp-uniform: rate 0 (parity / eval) skips the RNG
+      const uint32_t thr32 = e.drop.thresh16 << 16;
+      const float2 gs2 = make_float2(e.gate_scale, e.gate_scale);
+      for (int tile = first_item; tile < num_tiles; tile += item_step) {
+        const int n_blk = tile % s.n_tiles;
+        const int m_blk = (tile / s.n_tiles) * (MC ? 2 : 1) + (int)crank;
+        const long long row = (long long)m_blk * GEMM_BM + row_in_tile;
+        const int n0 = n_blk * BN;
+        const int cbase = n0 + half * HALF;
+        const bool row_ok = row < s.m;
+        // ---- everything the epilogue reads from memory is fetched while the tensor core still works on this tile
+        if (kBias && etid < BN) s_bias[acc * BN + etid] = (n0 + etid < s.n) ? __ldg(e.bias + n0 + etid) : 0.f;
+        uint4 pre[(kResid || kGate) ? NCH : 1][4];
+        if constexpr (kResid || kGate) {
+          const __nv_bfloat16* src = kResid ? resid : gate;
+          const long long ld = kResid ? e.ldr : e.ldg;
+#pragma unroll
+          for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int col = cbase + c * 32 + i * 8;
+              pre[c][i] = (row_ok && col < s.n) ? __ldg(reinterpret_cast<const uint4*>(src + row * ld + col)) : make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        if (kBias) asm volatile("bar.sync 1, %0;" ::"r"(32 * GEMM_EPI_WARPS) : "memory");  // bias tile visible to all epilogue warps
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + acc * BN + half * HALF + ((uint32_t)(quad * 32) << 16);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          float v[32];
+          tmem_ld_f32x32(t_addr + c * 32, v);
+          tmem_ld_wait();
+          const int col = cbase + c * 32;
+          if constexpr (kBias) {
+            const float4* b4p = reinterpret_cast<const float4*>(s_bias + acc * BN + half * HALF + c * 32);
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b4 = b4p[i / 4];
+              const float2 t0 = __fadd2_rn(make_float2(v[i], v[i + 1]), make_float2(b4.x, b4.y));
+              const float2 t1 = __fadd2_rn(make_float2(v[i + 2], v[i + 3]), make_float2(b4.z, b4.w));
+              v[i] = t0.x; v[i + 1] = t0.y; v[i + 2] = t1.x; v[i + 3] = t1.y;
+            }
+          }
+          if constexpr (kGate) {  // acc *= (gate > 0 ? gate_scale : 0): the sign/zero test runs on the raw bf16 bits
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const uint32_t w = reinterpret_cast<const uint32_t*>(&pre[c][i / 8])[(i / 2) & 3];
+              const float2 t = __fmul2_rn(make_float2(v[i], v[i + 1]), gs2);
+              v[i] = ((int)(w << 16) > 0) ? t.x : 0.f;
+              v[i + 1] = ((int)w > 0xffff) ? t.y : 0.f;
+            }
+          }
+          if (drop_on) {
+            DropStream ds = drop_stream(e.drop, (uint32_t)row, (uint32_t)col >> 5);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float mult = ds.next() >= thr32 ? e.drop.inv_keep : 0.f;
+              if constexpr (kResid) {
+                const uint32_t w = reinterpret_cast<const uint32_t*>(&pre[c][i / 8])[(i / 2) & 3];
+                v[i] = fmaf(v[i], mult, (i & 1) ? bf16_hi(w) : bf16_lo(w));
+              } else {
+                v[i] *= mult;
+              }
+            }
+          } else if constexpr (kResid) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const uint32_t w = reinterpret_cast<const uint32_t*>(&pre[c][i / 8])[(i / 2) & 3];
+              const float2 t = __fadd2_rn(make_float2(v[i], v[i + 1]), make_float2(bf16_lo(w), bf16_hi(w)));
+              v[i] = t.x; v[i + 1] = t.y;
+            }
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+            if constexpr (kRelu) {  // relu commutes with the (non-negative) dropout factor and with rounding: apply it packed
+              __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&pk[i]);
+              h = __hmax2(h, __floats2bfloat162_rn(0.f, 0.f));
+              pk[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
+          }
+          // stage this warp's 32 rows x 32 columns in shared memory (64-byte swizzled rows) and hand the box to TMA,
+          // which writes whole lines and clips rows >= M / columns >= N
+          uint8_t* stg = s_store + ew * 2048;
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous box has left smem
+          __syncwarp();
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch)
+            *reinterpret_cast<uint4*>(stg + lane * 64 + ((ch ^ ((lane >> 1) & 3)) << 4)) =
+                make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            const int row0 = m_blk * GEMM_BM + quad * 32;
+            if (col < s.n && row0 < s.m) {
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                           ::"l"(&tma_c), "r"(smem_u32(stg)), "r"(col), "r"(row0) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    } else
     for (int tile = first_item; tile < num_tiles; tile += item_step) {
       const int split = tile % s.k_splits;
       const int n_blk = (tile / s.k_splits) % s.n_tiles;
@@ -270,11 +390,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           }
         }
         if (e.drop.thresh16 && active) {
-          const uint64_t ebase = (uint64_t)row * (uint64_t)s.n + (uint64_t)col;  // n % 8 == 0 -> 8-aligned
 #pragma unroll
           for (int i = 0; i < 32; i += 8) {
             if (i < ncols) {
-              const uint32_t keep = dropout_keep8(e.drop, (ebase + i) >> 3);
+              const uint32_t keep = dropout_keep8(e.drop, (uint32_t)row, (uint32_t)(col + i));
 #pragma unroll
               for (int j = 0; j < 8; ++j) acc_f[i + j] = ((keep >> j) & 1u) ? acc_f[i + j] * e.drop.inv_keep : 0.f;
             }
@@ -366,10 +485,10 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __re
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, bool MC>
+template <int BN, bool A_MN, bool B_MN, bool MC, int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmShape& s, const GemmEpilogue& e,
                        cudaStream_t stream) {
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, MC>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, MC, EPI>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     TOME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::TOTAL));
@@ -497,23 +616,61 @@ extern "C" int tome_gemm_bf16(const tome_gemm_args_t* a, void* workspace, size_t
   }
   const bool amn = a->a_major == TOME_MAJOR_MN, bmn = a->b_major == TOME_MAJOR_MN;
   ProfScope prof(PROF_GEMM, 2.0 * a->m * (double)a->n * a->k, s.k_splits > 1 ? 2 : 1, stream);
-#define TOME_GEMM_DISPATCH(BN_)                                                      \
-  do {                                                                              \
-    if (mc) {                                                                             \
-      if (!amn && !bmn) rc = launch_gemm<BN_, false, false, true>(ta, tb, tc, s, e, stream);    \
-      else if (!amn && bmn) rc = launch_gemm<BN_, false, true, true>(ta, tb, tc, s, e, stream); \
-      else if (amn && !bmn) rc = launch_gemm<BN_, true, false, true>(ta, tb, tc, s, e, stream); \
-      else rc = launch_gemm<BN_, true, true, true>(ta, tb, tc, s, e, stream);                   \
-    } else {                                                                              \
-      if (!amn && !bmn) rc = launch_gemm<BN_, false, false, false>(ta, tb, tc, s, e, stream);    \
-      else if (!amn && bmn) rc = launch_gemm<BN_, false, true, false>(ta, tb, tc, s, e, stream); \
-      else if (amn && !bmn) rc = launch_gemm<BN_, true, false, false>(ta, tb, tc, s, e, stream); \
-      else rc = launch_gemm<BN_, true, true, false>(ta, tb, tc, s, e, stream);                   \
-    }                                                                                     \
+  // which epilogue: a compile-time specialisation when the combination is one the stack uses, else the generic one
+  int epi = EPI_GENERIC;
+  if (!e.c_is_f32 && s.k_splits == 1 && !a->accumulate) {
+    const int flags = (a->bias ? EPI_BIAS : 0) | (a->relu ? EPI_RELU : 0) | (a->gate ? EPI_GATE : 0) |
+                      (e.drop.thresh16 ? EPI_DROP : 0) | (a->residual ? EPI_RESID : 0);
+    if (!amn && bmn) {  // forward layers: A = activations (K-major), B = Flax kernel [in, out] (MN-major)
+      if (flags == EPI_BIAS) epi = EPI_BIAS;
+      else if (flags == (EPI_BIAS | EPI_RESID) || flags == (EPI_BIAS | EPI_DROP | EPI_RESID)) epi = EPI_BIAS | EPI_DROP | EPI_RESID;
+      else if (flags == (EPI_BIAS | EPI_RELU) || flags == (EPI_BIAS | EPI_RELU | EPI_DROP)) epi = EPI_BIAS | EPI_RELU | EPI_DROP;
+    } else if (!amn && !bmn) {  // data gradients: B = the same kernel read K-major
+      if (flags == 0) epi = 0;
+      else if (flags == EPI_GATE) epi = EPI_GATE;
+    }
+  }
+#define TOME_GEMM_LAYOUTS(BN_, EPI_)                                                                \
+  do {                                                                                              \
+    if (mc) {                                                                                       \
+      if (!amn && !bmn) rc = launch_gemm<BN_, false, false, true, EPI_>(ta, tb, tc, s, e, stream);  \
+      else if (!amn && bmn) rc = launch_gemm<BN_, false, true, true, EPI_>(ta, tb, tc, s, e, stream); \
+      else if (amn && !bmn) rc = launch_gemm<BN_, true, false, true, EPI_>(ta, tb, tc, s, e, stream); \
+      else rc = launch_gemm<BN_, true, true, true, EPI_>(ta, tb, tc, s, e, stream);                 \
+    } else {                                                                                        \
+      if (!amn && !bmn) rc = launch_gemm<BN_, false, false, false, EPI_>(ta, tb, tc, s, e, stream); \
+      else if (!amn && bmn) rc = launch_gemm<BN_, false, true, false, EPI_>(ta, tb, tc, s, e, stream); \
+      else if (amn && !bmn) rc = launch_gemm<BN_, true, false, false, EPI_>(ta, tb, tc, s, e, stream); \
+      else rc = launch_gemm<BN_, true, true, false, EPI_>(ta, tb, tc, s, e, stream);                \
+    }                                                                                               \
+  } while (0)
+#define TOME_GEMM_FWD(BN_, EPI_)                                                                    \
+  do {                                                                                              \
+    if (mc) rc = launch_gemm<BN_, false, true, true, EPI_>(ta, tb, tc, s, e, stream);               \
+    else rc = launch_gemm<BN_, false, true, false, EPI_>(ta, tb, tc, s, e, stream);                 \
+  } while (0)
+#define TOME_GEMM_DGRAD(BN_, EPI_)                                                                  \
+  do {                                                                                              \
+    if (mc) rc = launch_gemm<BN_, false, false, true, EPI_>(ta, tb, tc, s, e, stream);              \
+    else rc = launch_gemm<BN_, false, false, false, EPI_>(ta, tb, tc, s, e, stream);                \
+  } while (0)
+#define TOME_GEMM_DISPATCH(BN_)                                                                     \
+  do {                                                                                              \
+    switch (epi) {                                                                                  \
+      case EPI_BIAS: TOME_GEMM_FWD(BN_, EPI_BIAS); break;                                           \
+      case EPI_BIAS | EPI_DROP | EPI_RESID: TOME_GEMM_FWD(BN_, EPI_BIAS | EPI_DROP | EPI_RESID); break; \
+      case EPI_BIAS | EPI_RELU | EPI_DROP: TOME_GEMM_FWD(BN_, EPI_BIAS | EPI_RELU | EPI_DROP); break; \
+      case 0: TOME_GEMM_DGRAD(BN_, 0); break;                                                       \
+      case EPI_GATE: TOME_GEMM_DGRAD(BN_, EPI_GATE); break;                                         \
+      default: TOME_GEMM_LAYOUTS(BN_, EPI_GENERIC); break;                                          \
+    }                                                                                               \
   } while (0)
   if (bn == 128) TOME_GEMM_DISPATCH(128);
   else if (bn == 192) TOME_GEMM_DISPATCH(192);
   else TOME_GEMM_DISPATCH(256);
+#undef TOME_GEMM_LAYOUTS
+#undef TOME_GEMM_FWD
+#undef TOME_GEMM_DGRAD
 #undef TOME_GEMM_DISPATCH
   if (rc) return rc;
 

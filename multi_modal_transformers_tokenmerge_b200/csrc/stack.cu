@@ -209,12 +209,13 @@ __global__ void broadcast_groups_kernel(int B, int T, const uint8_t* __restrict_
   }
 }
 
-// dy_eff = dy * keep / (1 - rate), same Philox stream as the GEMM epilogue (element index = row * n + col)
-__global__ void dropout_apply_kernel(long long n8, const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
-                                     DropoutCfg d) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+// dy_eff = dy * keep / (1 - rate), same stream as the GEMM epilogue (element (row, col) of the [rows, n] tensor)
+__global__ void dropout_apply_kernel(long long n8_total, int n8_per_row, const __nv_bfloat16* __restrict__ x,
+                                     __nv_bfloat16* __restrict__ y, DropoutCfg d) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8_total; i += (long long)gridDim.x * blockDim.x) {
     const uint4 v = ld_nc_v4(reinterpret_cast<const uint4*>(x) + i);
-    const uint32_t keep = dropout_keep8(d, (uint64_t)i);
+    const uint32_t row = (uint32_t)(i / n8_per_row), col = (uint32_t)(i - (long long)row * n8_per_row) * 8u;
+    const uint32_t keep = dropout_keep8(d, row, col);
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
     uint32_t o[4];
 #pragma unroll
@@ -393,13 +394,13 @@ extern "C" int tome_stack_backward(const tome_stack_cfg_t* c, const tome_stack_i
   // dL/dx_final (and the loss value again, harmless) from the readout rows
   RC(tome_readout_mse(B, TL, C, c->n_readout, S.L.back().x_out, S.origin, io->target, io->loss, g0, nullptr, st));
 
-  auto masked = [&](const __nv_bfloat16* src, __nv_bfloat16* dst, long long n, int site) -> const __nv_bfloat16* {
+  auto masked = [&](const __nv_bfloat16* src, __nv_bfloat16* dst, long long rows, int ncols, int site) -> const __nv_bfloat16* {
     if (!drop) return src;
-    const long long n8 = n / 8;
+    const long long n8 = rows * ncols / 8;
     long long blocks = (n8 + 255) / 256;
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
     ProfScope prof(PROF_OTHER, 0.0, 1, st);
-    dropout_apply_kernel<<<(unsigned)blocks, 256, 0, st>>>(n8, src, dst, make_drop(c, (uint32_t)site));
+    dropout_apply_kernel<<<(unsigned)blocks, 256, 0, st>>>(n8, ncols / 8, src, dst, make_drop(c, (uint32_t)site));
     return dst;
   };
 
@@ -409,7 +410,7 @@ extern "C" int tome_stack_backward(const tome_stack_cfg_t* c, const tome_stack_i
     const int T = S.shapes[l].t_in, r = S.shapes[l].r, To = S.shapes[l].t_out;
     const int M = B * T, Mo = B * To;
     // ---- MLP: y = x1m + drop2(m1 W2 + b2),  m1 = drop1(relu(h2 W1 + b1))          d_out in g0
-    const __nv_bfloat16* dy2 = masked(g0, g2, (long long)Mo * C, 3 * l + 2);
+    const __nv_bfloat16* dy2 = masked(g0, g2, Mo, C, 3 * l + 2);
     RC(tome_colsum_bf16(Mo, C, dy2, C, gr + o.b2, 1, S.ws_colsum, st));
     RC(gemm(c, S, st, F, C, Mo, Lb.m1, F, TOME_MAJOR_MN, dy2, C, TOME_MAJOR_MN, gr + o.w2, C, TOME_F32, nullptr, 0, nullptr,
             nullptr, 1.f, -1, 1));
@@ -434,7 +435,7 @@ extern "C" int tome_stack_backward(const tome_stack_cfg_t* c, const tome_stack_i
       __nv_bfloat16* t = g0; g0 = g2; g2 = t;  // keep "dx1 lives in g0"
     }
     // ---- out projection: x1 = x + drop0(o Wo + bo)
-    const __nv_bfloat16* dyo = masked(dx1, g1, (long long)M * C, 3 * l + 0);
+    const __nv_bfloat16* dyo = masked(dx1, g1, M, C, 3 * l + 0);
     RC(tome_colsum_bf16(M, C, dyo, C, gr + o.bo, 1, S.ws_colsum, st));
     RC(gemm(c, S, st, HD, C, M, Lb.attn_o, HD, TOME_MAJOR_MN, dyo, C, TOME_MAJOR_MN, gr + o.wo, C, TOME_F32, nullptr, 0, nullptr,
             nullptr, 1.f, -1, 1));

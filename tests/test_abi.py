@@ -74,7 +74,7 @@ def test_validation_errors_are_reported_not_thrown(lib):
     assert lib.tome_merge_fwd(C.byref(shp), C.byref(plan), None, None, None, None, None, None, None, None, None) == L.TOME_ERR_INVALID
     assert b"mode" in lib.tome_last_error()
     d = L.AttnDesc(1, 8, 1, 256, 0, 0, 0, 0, 0, 0, 0, 0, 1.0, None, None, None, 0, None)  # head_dim 256 not built
-    assert lib.tome_attention_fwd(C.byref(d), None, None, None, None, None, None) == L.TOME_ERR_UNSUPPORTED
+    assert lib.tome_attention_fwd(C.byref(d), None, None, None, None, None, None, 0, None) == L.TOME_ERR_UNSUPPORTED
 
 
 def test_product_path_has_no_cpu_fallback():
