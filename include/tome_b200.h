@@ -57,9 +57,13 @@ typedef struct {
  * node_max[b,i] = max_j scores, node_idx[b,i] = first arg max.                       token_compression.py:72-83
  * node_max f32 [B,Ta], node_idx i32 [B,Ta]  (Ta = ceil(T/2), Tb = floor(T/2)).
  * scores_out: optional f32 [B,Ta,Tb] dump of the exact fp32 scores the arg max was taken from (parity protocol:
- * "indices bit-exact from the same fp32 scores"); pass NULL on the fast path and the scores never touch HBM. */
+ * "indices bit-exact from the same fp32 scores"); pass NULL on the fast path and the scores never touch HBM.
+ * workspace: optional, tome_sim_argmax_workspace_bytes(desc) bytes, 16-byte aligned.  With it the rows are
+ * normalised once into fp32 planes and the score kernel streams them; with NULL every
+ * CTA normalises the rows it needs itself.  Both normalise first; the workspace path sums even and odd k separately (packed FMAs). */
+size_t tome_sim_argmax_workspace_bytes(const tome_metric_desc_t* desc);
 int tome_sim_argmax(const tome_metric_desc_t* desc, const void* src, float* node_max, int32_t* node_idx,
-                    float* scores_out, void* stream);
+                    float* scores_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* The index set bipartite_soft_matching closes over (token_compression.py:84-88) plus derived maps the merge
  * kernels use.  All int32, device. */

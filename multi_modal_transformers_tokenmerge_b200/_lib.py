@@ -103,7 +103,7 @@ def lib() -> C.CDLL:
         L.tome_abi_version.restype = i32
         if L.tome_abi_version() != ABI_VERSION:
             raise ImportError(f"libtome_b200.so has ABI {L.tome_abi_version()}, python binding expects {ABI_VERSION}: rebuild")
-        for name in ("tome_gemm_workspace_bytes", "tome_stack_workspace_bytes", "tome_attention_workspace_bytes",
+        for name in ("tome_gemm_workspace_bytes", "tome_stack_workspace_bytes", "tome_attention_workspace_bytes", "tome_sim_argmax_workspace_bytes",
                      "tome_attention_bwd_workspace_bytes"):
             if hasattr(L, name):
                 getattr(L, name).restype = C.c_size_t
@@ -117,7 +117,8 @@ def lib() -> C.CDLL:
         P = C.POINTER
         sig = {
             "tome_clamp_r": [i32, i32, i32, i32],
-            "tome_sim_argmax": [P(MetricDesc), vp, vp, vp, vp, vp],
+            "tome_sim_argmax_workspace_bytes": [P(MetricDesc)],
+            "tome_sim_argmax": [P(MetricDesc), vp, vp, vp, vp, vp, C.c_size_t, vp],
             "tome_select_topr": [P(PlanShape), vp, vp, P(Plan), vp],
             "tome_merge_fwd": [P(MergeShape), P(Plan), vp, vp, vp, vp, vp, vp, vp, vp, vp],
             "tome_merge_bwd": [P(MergeShape), P(Plan), vp, vp, vp, vp, vp],

@@ -161,6 +161,208 @@ sim_argmax_kernel(const tome_metric_desc_t d, const T* __restrict__ src, float* 
   }
 }
 
+// ------------------------------------------------------------------------------------------------ K1, workspace path
+// The kernel above re-reads and re-normalises every b row once per 64-row a tile (5x at T = 536) with the head mean, the
+// square root and the divisions on its critical path: 229 us per layer for 2.4 GFLOP (profiles/r01b_launches_summary.csv).
+// With a workspace the normalisation happens ONCE (metric_norm_kernel: head mean, L2 norm, fp32, a rows and b rows in
+// separate contiguous planes) and the score kernel only streams 16 KB tiles through a cp.async double buffer into the
+// 4x4-per-thread fp32 loop, now on packed f32x2 FMAs (even-k and odd-k partial sums, added at the end).
+// generic version: one warp per token row, 2 columns per lane per step (any even dim <= 512, any even strides)
+template <typename T>
+__global__ void __launch_bounds__(256)
+metric_norm_kernel(const tome_metric_desc_t d, const T* __restrict__ src, float* __restrict__ plane_a,
+                   float* __restrict__ plane_b) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long tok = (long long)blockIdx.x * 8 + warp;   // b * T + t
+  if (tok >= (long long)d.batch * d.tokens) return;
+  const int b = (int)(tok / d.tokens), t = (int)(tok % d.tokens);
+  const int dpad = (d.dim + 3) & ~3;
+  const int ta = (d.tokens + 1) / 2, tb = d.tokens / 2;
+  const T* base = src + (long long)b * d.batch_stride + (long long)t * d.token_stride;
+  float* out = (t & 1) ? plane_b + ((long long)b * tb + (t >> 1)) * dpad : plane_a + ((long long)b * ta + (t >> 1)) * dpad;
+  const float inv_h = 1.0f / (float)d.heads;
+  float ss = 0.f;
+  for (int c = 2 * lane; c < d.dim; c += 64) {  // pass 1: head mean -> out (un-normalised), sum of squares
+    float2 acc = make_float2(0.f, 0.f);
+    for (int h = 0; h < d.heads; ++h) {
+      const float2 v = load2<T>(base + (long long)h * d.head_stride + c);
+      acc.x += v.x;
+      acc.y += v.y;
+    }
+    if (d.heads > 1) {  // jnp.mean over heads = sum / H
+      acc.x *= inv_h;
+      acc.y *= inv_h;
+    }
+    ss += acc.x * acc.x + acc.y * acc.y;
+    *reinterpret_cast<float2*>(out + c) = acc;
+  }
+  ss = warp_sum(ss);
+  const float nrm = sqrtf(ss);  // no epsilon (token_compression.py:72): a zero row becomes NaN
+  for (int c = 2 * lane; c < dpad; c += 64) {   // pass 2: each lane rescales what it wrote
+    float2 v = c < d.dim ? *reinterpret_cast<float2*>(out + c) : make_float2(0.f, 0.f);
+    *reinterpret_cast<float2*>(out + c) = c < d.dim ? make_float2(v.x / nrm, v.y / nrm) : v;
+  }
+}
+
+// bf16, dim == 64, 16-byte aligned rows (the stack's case): 8 lanes per token row, one 128-bit load per head per lane
+__global__ void __launch_bounds__(256)
+metric_norm64_kernel(const tome_metric_desc_t d, const __nv_bfloat16* __restrict__ src, float* __restrict__ plane_a,
+                     float* __restrict__ plane_b) {
+  const long long tok = ((long long)blockIdx.x * 256 + threadIdx.x) >> 3;   // b * T + t
+  const int sub = threadIdx.x & 7;
+  const bool valid = tok < (long long)d.batch * d.tokens;   // every lane stays for the shuffles
+  const long long tk = valid ? tok : 0;
+  const int b = (int)(tk / d.tokens), t = (int)(tk % d.tokens);
+  const int ta = (d.tokens + 1) / 2, tb = d.tokens / 2;
+  const __nv_bfloat16* base = src + (long long)b * d.batch_stride + (long long)t * d.token_stride + sub * 8;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int h = 0; h < d.heads; ++h) {
+    const uint4 v = ld_nc_v4(base + (long long)h * d.head_stride);
+    acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
+    acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z); acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
+  }
+  float ss = 0.f;
+  const float inv_h = 1.0f / (float)d.heads;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (d.heads > 1) acc[i] *= inv_h;
+    ss += acc[i] * acc[i];
+  }
+  ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+  ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+  ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+  const float nrm = sqrtf(ss);
+  if (valid) {
+    float* out = ((t & 1) ? plane_b + ((long long)b * tb + (t >> 1)) * 64 : plane_a + ((long long)b * ta + (t >> 1)) * 64) + sub * 8;
+    reinterpret_cast<float4*>(out)[0] = make_float4(acc[0] / nrm, acc[1] / nrm, acc[2] / nrm, acc[3] / nrm);
+    reinterpret_cast<float4*>(out)[1] = make_float4(acc[4] / nrm, acc[5] / nrm, acc[6] / nrm, acc[7] / nrm);
+  }
+}
+
+__device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src, bool valid) {
+  const uint32_t n = valid ? 16u : 0u;  // src-size 0: the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(n) : "memory");
+}
+
+// tile of SIM_TILE normalised rows (plane row r0 + i, dpad floats each) -> smem rows of pitch dpad + 4
+__device__ __forceinline__ void load_tile_async(float* dst, const float* plane, int r0, int nrows, int dpad) {
+  const int pitch = dpad + 4, vpr = dpad >> 2;
+  for (int i = threadIdx.x; i < SIM_TILE * vpr; i += SIM_THREADS) {
+    const int rr = i / vpr, v = i - rr * vpr;
+    const bool ok = r0 + rr < nrows;
+    cp_async_16(dst + rr * pitch + 4 * v, plane + (long long)(ok ? r0 + rr : 0) * dpad + 4 * v, ok);
+  }
+}
+
+__global__ void __launch_bounds__(SIM_THREADS)
+sim_argmax_planes_kernel(const tome_metric_desc_t d, const float* __restrict__ plane_a, const float* __restrict__ plane_b,
+                         float* __restrict__ node_max, int32_t* __restrict__ node_idx, float* __restrict__ scores_out) {
+  extern __shared__ float4 sm4[];
+  float* sm = reinterpret_cast<float*>(sm4);
+  const int dpad = (d.dim + 3) & ~3, pitch = dpad + 4;
+  float* sa = sm;
+  float* sb0 = sm + SIM_TILE * pitch;
+  const int b = blockIdx.y;
+  const int ta = (d.tokens + 1) / 2, tb = d.tokens / 2;
+  const int a0 = blockIdx.x * SIM_TILE;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const float* pa = plane_a + (long long)b * ta * dpad;
+  const float* pb = plane_b + (long long)b * tb * dpad;
+  const int n_bt = (tb + SIM_TILE - 1) / SIM_TILE;
+
+  load_tile_async(sa, pa, a0, ta, dpad);
+  load_tile_async(sb0, pb, 0, tb, dpad);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+
+  float best_v[4];
+  int best_j[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    best_v[i] = -INFINITY;
+    best_j[i] = 0x7fffffff;
+  }
+  for (int bt = 0; bt < n_bt; ++bt) {
+    const int b0 = bt * SIM_TILE;
+    float* sb = sb0 + (bt & 1) * SIM_TILE * pitch;
+    if (bt + 1 < n_bt) load_tile_async(sb0 + ((bt + 1) & 1) * SIM_TILE * pitch, pb, b0 + SIM_TILE, tb, dpad);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");  // tile bt (and the a tile) have landed; tile bt+1 may be in flight
+    __syncthreads();
+    // packed f32x2 FMAs (scalar FFMA issues at half rate on sm_100): lane .x accumulates the even k, lane .y the odd k
+    float2 acc2[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc2[i][j] = make_float2(0.f, 0.f);
+    // row pointers hoisted out of the k loop: IMAD shares the FMA pipe with FFMA2, so address arithmetic inside the
+    // loop costs FMA throughput one for one
+    const float4* ap[4];
+    const float4* bp[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ap[i] = reinterpret_cast<const float4*>(sa + (ty + 16 * i) * pitch);
+      bp[i] = reinterpret_cast<const float4*>(sb + (tx + 16 * i) * pitch);
+    }
+#pragma unroll 4
+    for (int c4 = 0; c4 < (dpad >> 2); ++c4) {  // one 128-bit shared-memory read feeds 4 k-steps: 8 LDS.128 per 32 FFMA2
+      float4 av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = ap[i][c4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = bp[j][c4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc2[i][j] = __ffma2_rn(make_float2(av[i].x, av[i].y), make_float2(bv[j].x, bv[j].y), acc2[i][j]);
+          acc2[i][j] = __ffma2_rn(make_float2(av[i].z, av[i].w), make_float2(bv[j].z, bv[j].w), acc2[i][j]);
+        }
+    }
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = acc2[i][j].x + acc2[i][j].y;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int ai = a0 + ty + 16 * i;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int bj = b0 + tx + 16 * j;
+        if (ai < ta && bj < tb) {
+          float s = acc[i][j];
+          if ((d.class_token && ai == 0) || (d.distill_token && bj == 0)) s = -INFINITY;  // :77-80
+          if (scores_out) scores_out[((long long)b * ta + ai) * tb + bj] = s;
+          if (argmax_better(s, bj, best_v[i], best_j[i])) {
+            best_v[i] = s;
+            best_j[i] = bj;
+          }
+        }
+      }
+    }
+    __syncthreads();  // tile bt fully consumed before tile bt+2 overwrites its buffer
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best_v[i], o);
+      const int oj = __shfl_xor_sync(0xffffffffu, best_j[i], o);
+      if (argmax_better(ov, oj, best_v[i], best_j[i])) {
+        best_v[i] = ov;
+        best_j[i] = oj;
+      }
+    }
+    const int ai = a0 + ty + 16 * i;
+    if (tx == 0 && ai < ta) {
+      node_max[(long long)b * ta + ai] = best_v[i];
+      node_idx[(long long)b * ta + ai] = best_j[i] == 0x7fffffff ? 0 : best_j[i];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ K2
 // rank order of jnp.argsort(node_max)[:, ::-1]: j precedes i iff key_j "greater" (NaN greatest), ties: larger index.
 __device__ __forceinline__ bool rank_before(float vj, int j, float vi, int i) {
@@ -271,8 +473,13 @@ extern "C" int tome_clamp_r(int tokens, int r, int class_token, int distill_toke
   return r > 0 ? r : 0;
 }
 
+extern "C" size_t tome_sim_argmax_workspace_bytes(const tome_metric_desc_t* d) {
+  if (!d || d->batch <= 0 || d->tokens <= 0 || d->dim <= 0) return 0;
+  return (size_t)d->batch * d->tokens * ((d->dim + 3) & ~3) * sizeof(float);
+}
+
 extern "C" int tome_sim_argmax(const tome_metric_desc_t* d, const void* src, float* node_max, int32_t* node_idx,
-                               float* scores_out, void* stream_) {
+                               float* scores_out, void* workspace, size_t workspace_bytes, void* stream_) {
   clear_error();
   cudaStream_t stream = (cudaStream_t)stream_;
   TOME_CHECK(d && src && node_max && node_idx, TOME_ERR_INVALID, "sim_argmax: null argument");
@@ -284,10 +491,36 @@ extern "C" int tome_sim_argmax(const tome_metric_desc_t* d, const void* src, flo
   TOME_CHECK(d->token_stride % 2 == 0 && d->batch_stride % 2 == 0 && d->head_stride % 2 == 0, TOME_ERR_INVALID,
              "sim_argmax: strides must be even (vector loads)");
   TOME_CHECK(d->batch <= 65535, TOME_ERR_INVALID, "sim_argmax: batch too large for one launch");
-  const int ta = (d->tokens + 1) / 2;
-  const size_t smem = (size_t)2 * SIM_TILE * (((d->dim + 3) & ~3) + 4) * sizeof(float);
-  ProfScope prof(PROF_SIM, 2.0 * d->batch * ((d->tokens + 1) / 2) * (double)(d->tokens / 2) * d->dim, 1, stream);
+  const int ta = (d->tokens + 1) / 2, tb = d->tokens / 2;
+  const int dpad = (d->dim + 3) & ~3;
   dim3 grid(ceil_div(ta, SIM_TILE), d->batch);
+  if (workspace != nullptr) {
+    // ---- normalise once, then stream tiles (see the comment above metric_norm_kernel)
+    TOME_CHECK(workspace_bytes >= tome_sim_argmax_workspace_bytes(d) && ((uintptr_t)workspace & 15) == 0, TOME_ERR_INVALID,
+               "sim_argmax: workspace must be 16-byte aligned and hold %zu bytes (got %zu)", tome_sim_argmax_workspace_bytes(d),
+               workspace_bytes);
+    ProfScope prof(PROF_SIM, 2.0 * d->batch * ta * (double)tb * d->dim, 2, stream);
+    float* plane_a = reinterpret_cast<float*>(workspace);
+    float* plane_b = plane_a + (size_t)d->batch * ta * dpad;
+    const long long toks = (long long)d->batch * d->tokens;
+    const unsigned nblk = (unsigned)((toks + 7) / 8);
+    const bool fast64 = d->dtype == TOME_BF16 && d->dim == 64 && d->token_stride % 8 == 0 && d->batch_stride % 8 == 0 &&
+                        d->head_stride % 8 == 0 && ((uintptr_t)src & 15) == 0;
+    if (fast64)
+      metric_norm64_kernel<<<(unsigned)((toks * 8 + 255) / 256), 256, 0, stream>>>(*d, reinterpret_cast<const __nv_bfloat16*>(src), plane_a, plane_b);
+    else if (d->dtype == TOME_BF16)
+      metric_norm_kernel<__nv_bfloat16><<<nblk, 256, 0, stream>>>(*d, reinterpret_cast<const __nv_bfloat16*>(src), plane_a, plane_b);
+    else
+      metric_norm_kernel<float><<<nblk, 256, 0, stream>>>(*d, reinterpret_cast<const float*>(src), plane_a, plane_b);
+    TOME_CUDA(cudaGetLastError());
+    const size_t smem = (size_t)3 * SIM_TILE * (dpad + 4) * sizeof(float);
+    TOME_CUDA(cudaFuncSetAttribute(sim_argmax_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sim_argmax_planes_kernel<<<grid, SIM_THREADS, smem, stream>>>(*d, plane_a, plane_b, node_max, node_idx, scores_out);
+    TOME_CUDA(cudaGetLastError());
+    return TOME_OK;
+  }
+  const size_t smem = (size_t)2 * SIM_TILE * (dpad + 4) * sizeof(float);
+  ProfScope prof(PROF_SIM, 2.0 * d->batch * ta * (double)tb * d->dim, 1, stream);
   if (d->dtype == TOME_BF16) {
     auto kern = sim_argmax_kernel<__nv_bfloat16>;
     TOME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

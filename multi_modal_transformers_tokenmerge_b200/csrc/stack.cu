@@ -43,8 +43,8 @@ struct StackLayout {
   std::vector<LayerBufs> L;
   __nv_bfloat16 *x1_scratch, *g0, *g1, *g2, *g3, *big;
   float *ws_gemm, *ws_colsum, *ws_ln;
-  uint8_t* ws_attn;
-  size_t ws_attn_bytes;
+  uint8_t *ws_attn, *ws_sim;
+  size_t ws_attn_bytes, ws_sim_bytes;
   int32_t* origin;
   size_t ws_gemm_bytes;
   size_t total;
@@ -186,6 +186,8 @@ static StackLayout make_layout(const tome_stack_cfg_t* c, void* workspace) {
     S.ws_attn_bytes = f > bw ? f : bw;
     S.ws_attn = b.take<uint8_t>(S.ws_attn_bytes);
   }
+  S.ws_sim_bytes = B * T0 * (size_t)((c->head_dim + 3) & ~3) * sizeof(float);  // normalised matching metric (tome_sim_argmax workspace)
+  S.ws_sim = b.take<uint8_t>(S.ws_sim_bytes);
   // split-K workspace: the largest weight gradient, at most 64 splits are ever chosen but 148 tiles bound the product
   size_t wmax = C * 3 * HD;
   if (C * F > wmax) wmax = C * F;
@@ -345,7 +347,7 @@ extern "C" int tome_stack_forward(const tome_stack_cfg_t* c, const tome_stack_io
       md.batch = B; md.tokens = T; md.dim = D; md.heads = H; md.dtype = TOME_BF16;
       md.batch_stride = (long long)T * 3 * HD; md.token_stride = 3 * HD; md.head_stride = D;
       md.class_token = c->class_token; md.distill_token = c->distill_token;
-      RC(tome_sim_argmax(&md, Lb.qkv + HD, Lb.node_max, Lb.node_idx, nullptr, st));
+      RC(tome_sim_argmax(&md, Lb.qkv + HD, Lb.node_max, Lb.node_idx, nullptr, S.ws_sim, S.ws_sim_bytes, st));
       tome_plan_shape_t ps{B, T, r, c->distill_token};
       RC(tome_select_topr(&ps, Lb.node_max, Lb.node_idx, &Lb.plan, st));
       tome_merge_shape_t ms{B, T, C, r, c->distill_token, TOME_BF16, TOME_MERGE_WAVG};

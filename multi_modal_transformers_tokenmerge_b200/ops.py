@@ -74,10 +74,18 @@ class MatchPlan:
                       self.dst_off.data_ptr(), self.dst_src.data_ptr())
 
 
+def _scratch(nbytes: int, device) -> torch.Tensor:
+    """uint8 device scratch of `nbytes` whose data pointer is 256-byte aligned (torch's allocator aligns to 512)."""
+    t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+    assert t.data_ptr() % 256 == 0
+    return t
+
+
 def sim_argmax(src: torch.Tensor, *, heads: int = 1, dim: Optional[int] = None, batch_stride=None, token_stride=None,
                head_stride=None, tokens=None, batch=None, class_token=False, distill_token=False, dump_scores=False,
-               offset_elems: int = 0):
-    """K1.  `src` is either a [B,T,Dm] metric (heads=1) or a packed buffer addressed by the given strides."""
+               offset_elems: int = 0, use_workspace: bool = True):
+    """K1.  `src` is either a [B,T,Dm] metric (heads=1) or a packed buffer addressed by the given strides.
+    `use_workspace=False` takes the library's no-scratch path (every CTA normalises its own rows)."""
     _need_cuda(src)
     if heads == 1 and dim is None:
         assert src.dim() == 3 and src.is_contiguous()
@@ -90,7 +98,9 @@ def sim_argmax(src: torch.Tensor, *, heads: int = 1, dim: Optional[int] = None, 
     d = L.MetricDesc(batch, tokens, dim, heads, _dt(src), batch_stride, token_stride, head_stride,
                      int(bool(class_token)), int(bool(distill_token)))
     base = C.c_void_p(src.data_ptr() + offset_elems * src.element_size())
-    L.check(L.lib().tome_sim_argmax(C.byref(d), base, _ptr(node_max), _ptr(node_idx), _ptr(scores), _stream()))
+    ws = _scratch(L.lib().tome_sim_argmax_workspace_bytes(C.byref(d)), src.device) if use_workspace else None
+    L.check(L.lib().tome_sim_argmax(C.byref(d), base, _ptr(node_max), _ptr(node_idx), _ptr(scores), _ptr(ws),
+                                    0 if ws is None else ws.numel(), _stream()))
     return node_max, node_idx, scores
 
 
@@ -202,13 +212,6 @@ def layernorm_bwd(x, dy, gamma, mean, rstd, dgamma, dbeta, dres=None, axis: int 
 
 
 # ------------------------------------------------------------------------------------------------ attention
-def _scratch(nbytes: int, device) -> torch.Tensor:
-    """uint8 device scratch of `nbytes` whose data pointer is 256-byte aligned (torch's allocator aligns to 512)."""
-    t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
-    assert t.data_ptr() % 256 == 0
-    return t
-
-
 def _attn_desc(q, k, v, out, scale, gid, pos, allow, size):
     b, t, h, d = q.shape
     for x in (q, k, v, out):

@@ -32,7 +32,8 @@ static ffi::Error SimArgmax(cudaStream_t s, ffi::AnyBuffer metric, ffi::Result<f
   auto d = metric.dimensions();
   tome_metric_desc_t m{(int)d[0], (int)d[1], (int)d[2], 1, DType(metric.element_type()), (long long)(d[1] * d[2]), (long long)d[2], 0,
                        class_token, distill_token};
-  return Status(tome_sim_argmax(&m, metric.untyped_data(), node_max->typed_data(), node_idx->typed_data(), nullptr, s));
+  return Status(tome_sim_argmax(&m, metric.untyped_data(), node_max->typed_data(), node_idx->typed_data(), nullptr,
+                                /*workspace=*/nullptr, 0, s));  // no-scratch path; add a u8 Ret buffer to take the faster one
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(TomeSimArgmax, SimArgmax,
                               ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<ffi::AnyBuffer>()

@@ -313,3 +313,22 @@ def test_attention_fwd_lazy_rescale(ops, T, growth):
     logits = torch.where(m, logits, torch.full_like(logits, -1e30))
     ref_lse = torch.logsumexp(logits, -1)
     assert ((lse.cpu() - ref_lse).abs() / ref_lse.abs().clamp_min(1.0)).max().item() <= 2e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T,H,D", [(3, 536, 6, 64), (2, 75, 1, 30), (2, 300, 3, 128)])
+def test_sim_argmax_workspace_and_scratchless_paths_agree(ops, B, T, H, D):
+    """tome_sim_argmax has two code paths (normalise once into a workspace, or normalise inside every CTA); both follow the
+    reference order (normalise, then an ascending-k fp32 dot product), so their scores agree to fp32 rounding of the
+    norm and each path's arg max is the exact first maximum of ITS OWN dumped scores."""
+    rng = np.random.default_rng(B * T + D)
+    src = torch.tensor(rng.standard_normal((B, T, H, D)).astype(np.float32)).cuda().bfloat16()
+    kw = dict(heads=H, dim=D, batch=B, tokens=T, batch_stride=T * H * D, token_stride=H * D, head_stride=D, dump_scores=True)
+    nm1, ni1, sc1 = ops.sim_argmax(src, use_workspace=True, **kw)
+    nm0, ni0, sc0 = ops.sim_argmax(src, use_workspace=False, **kw)
+    torch.cuda.synchronize()
+    assert (sc1 - sc0).abs().max().item() <= 2e-6
+    for nm, ni, sc in ((nm1, ni1, sc1), (nm0, ni0, sc0)):
+        s = sc.cpu().numpy()
+        np.testing.assert_array_equal(ni.cpu().numpy(), s.argmax(-1).astype(np.int32))
+        np.testing.assert_array_equal(nm.cpu().numpy(), s.max(-1))
