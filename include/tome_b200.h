@@ -195,7 +195,8 @@ int tome_attention_fwd(const tome_attn_desc_t* desc, const void* q, const void* 
                        float* lse, void* workspace, size_t workspace_bytes, void* stream);
 
 /* dq,dk,dv share the layout of q,k,v (their own strides below).  workspace: tome_attention_bwd_workspace_bytes(desc)
- * bytes of 256-byte-aligned device scratch (delta = rowsum(dO*O), per-tile mask words); gradients are produced
+ * bytes of 256-byte-aligned device scratch (per-tile mask words, delta = rowsum(dO*O) and lse*log2e padded to 64-token
+ * tiles); gradients are produced
  * without atomics or fp32 staging. */
 typedef struct {
   long long dq_batch_stride, dq_token_stride;

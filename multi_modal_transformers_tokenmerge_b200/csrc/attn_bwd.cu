@@ -2,15 +2,20 @@
 // with the group-table mask and log(size) bias of the forward kernel).  No atomics, no fp32 dQ buffer: two
 // kernels, each owning its outputs.
 //
-//   prep      delta[b,h,q] = sum_d dO*O ; per-token mask words (which groups a query may see)
+//   prep      delta[b,h,q] = sum_d dO*O and lse2 = lse*log2(e), both padded to 64-token tiles ([B,H,Tp]) so a tile is
+//             one aligned 256-byte bulk copy; attn_meta_kernel (attn_meta.cuh) builds the per-tile mask words
 //   dkdv      CTA = (128-key tile, head, batch), thread = key row, loop over 64-query tiles:
 //               S^T = K Q^T, dP^T = V dO^T (TMEM) -> P^T, dS^T (bf16, shared) -> dV += P^T dO, dK += dS^T Q (TMEM)
 //   dq        CTA = (128-query tile, head, batch), thread = query row, loop over 64-key tiles:
-//               S = Q K^T, dP = dO V^T (TMEM) -> dS (bf16, shared) -> dQ += dS K (TMEM)
+//               S = Q K^T, dP = dO V^T (TMEM) -> dS (bf16, shared, double-buffered) -> dQ += dS K (TMEM)
 // P is recomputed from the saved log-sum-exp: P = exp2(s2 - lse2), s2 = q.k*scale*log2e + log2(size_k);
 // dS = P * (dP - delta) * scale.  Each kernel uses 256 TMEM columns, so two CTAs share an SM.
+// Everything a tile needs besides Q/K/V/dO (lse2, delta, positions, mask words, bias) arrives through a small ring of
+// bulk copies issued by the producer warp: the softmax threads run no global loads, ballots or CTA barriers per tile
+// (the first version did, and that dependent-load chain paced the kernels).
 #include <float.h>
 
+#include "attn_meta.cuh"
 #include "common.cuh"
 #include "host_util.h"
 
@@ -21,58 +26,49 @@ int check_attn_desc(const tome_attn_desc_t* d, const char* who);  // attn_fwd.cu
 constexpr int AB_D = 64;
 constexpr int AB_THREADS = 192;
 constexpr uint32_t AB_TMEM_COLS = 256;
+constexpr int AB_MSLOTS = 3;  // metadata ring
 
 struct AttnBwdParams {
-  int batch, tokens, heads;
+  int batch, tokens, heads, tp;  // tp = tokens padded to a multiple of 64
   float scale, scale_log2;
-  const uint8_t* gid;
+  const uint8_t* gid;   // null: no mask
   const int32_t* pos;
-  const uint8_t* allow;
-  int num_groups;
-  const uint2* mwords;  // [B,T] (m_all, m_causal) or null
+  const uint8_t* meta;  // [B][tp/64][ATTN_META_BYTES]
   const float* size;
-  const float* lse;     // [B,H,T]
-  const float* delta;   // [B,H,T]
+  const float* lse2;    // [B,H,tp]  lse * log2(e), +inf past T
+  const float* delta;   // [B,H,tp]  0 past T
   __nv_bfloat16* dq; long long dq_bs, dq_ts;
   __nv_bfloat16* dk; long long dk_bs, dk_ts;
   __nv_bfloat16* dv; long long dv_bs, dv_ts;
 };
 
-__device__ __forceinline__ void named_bar_sync_b(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
 // ------------------------------------------------------------------------------------------------ prep
-__global__ void attn_bwd_prep_kernel(int B, int T, int H, const __nv_bfloat16* __restrict__ o, long long o_bs, long long o_ts,
-                                     const __nv_bfloat16* __restrict__ dout, long long do_bs, long long do_ts,
-                                     float* __restrict__ delta, const uint8_t* __restrict__ gid,
-                                     const uint8_t* __restrict__ allow, int G, uint2* __restrict__ mwords) {
+__global__ void attn_bwd_prep_kernel(int B, int T, int Tp, int H, const __nv_bfloat16* __restrict__ o, long long o_bs,
+                                     long long o_ts, const __nv_bfloat16* __restrict__ dout, long long do_bs, long long do_ts,
+                                     const float* __restrict__ lse, float* __restrict__ delta, float* __restrict__ lse2) {
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;  // (b, t, h, chunk of 8)
-  const long long total = (long long)B * T * H * 8;
-  if (idx < total) {
+  const long long total = (long long)B * Tp * H * 8;
+  if (idx < total) {  // total is a multiple of 8: the 8 lanes of a (b,t,h) group leave together
     const int ch = (int)(idx & 7);
     const long long r = idx >> 3;
     const int h = (int)(r % H);
     const long long bt = r / H;
-    const int t = (int)(bt % T), b = (int)(bt / T);
-    const uint4 ov = __ldg(reinterpret_cast<const uint4*>(o + b * o_bs + t * o_ts + h * AB_D + ch * 8));
-    const uint4 dv = __ldg(reinterpret_cast<const uint4*>(dout + b * do_bs + t * do_ts + h * AB_D + ch * 8));
-    float s = bf16_lo(ov.x) * bf16_lo(dv.x) + bf16_hi(ov.x) * bf16_hi(dv.x) + bf16_lo(ov.y) * bf16_lo(dv.y) +
-              bf16_hi(ov.y) * bf16_hi(dv.y) + bf16_lo(ov.z) * bf16_lo(dv.z) + bf16_hi(ov.z) * bf16_hi(dv.z) +
-              bf16_lo(ov.w) * bf16_lo(dv.w) + bf16_hi(ov.w) * bf16_hi(dv.w);
+    const int t = (int)(bt % Tp), b = (int)(bt / Tp);
+    float s = 0.f;
+    if (t < T) {
+      const uint4 ov = __ldg(reinterpret_cast<const uint4*>(o + b * o_bs + t * o_ts + h * AB_D + ch * 8));
+      const uint4 dv = __ldg(reinterpret_cast<const uint4*>(dout + b * do_bs + t * do_ts + h * AB_D + ch * 8));
+      s = bf16_lo(ov.x) * bf16_lo(dv.x) + bf16_hi(ov.x) * bf16_hi(dv.x) + bf16_lo(ov.y) * bf16_lo(dv.y) +
+          bf16_hi(ov.y) * bf16_hi(dv.y) + bf16_lo(ov.z) * bf16_lo(dv.z) + bf16_hi(ov.z) * bf16_hi(dv.z) +
+          bf16_lo(ov.w) * bf16_lo(dv.w) + bf16_hi(ov.w) * bf16_hi(dv.w);
+    }
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if (ch == 0) delta[((long long)b * H + h) * T + t] = s;
-    if (mwords && h == 0 && ch == 0) {
-      const int gq = gid[bt];
-      uint32_t ma = 0, mc = 0;
-      for (int g = 0; g < G; ++g) {
-        const int a = allow[gq * G + g];
-        ma |= (a == 1 ? 1u : 0u) << g;
-        mc |= (a == 2 ? 1u : 0u) << g;
-      }
-      mwords[bt] = make_uint2(ma, mc);
+    if (ch == 0) {
+      const long long w = ((long long)b * H + h) * Tp + t;
+      delta[w] = s;
+      lse2[w] = t < T ? lse[((long long)b * H + h) * T + t] * 1.4426950408889634f : INFINITY;  // queries past T: exp2(s - inf) = 0
     }
   }
 }
@@ -80,41 +76,42 @@ __global__ void attn_bwd_prep_kernel(int B, int T, int H, const __nv_bfloat16* _
 // ------------------------------------------------------------------------------------------------ dK / dV
 constexpr int DKV_BK = 128;  // keys per CTA
 constexpr int DKV_BQ = 64;   // queries per tile
+static_assert(DKV_BQ == ATTN_META_TILE, "query tiles and metadata tiles must coincide");
 constexpr int DKV_KV_BYTES = DKV_BK * AB_D * 2;  // 16 KB
 constexpr int DKV_Q_BYTES = DKV_BQ * AB_D * 2;   // 8 KB
 constexpr int DKV_PT_BYTES = DKV_BK * DKV_BQ * 2;  // 16 KB
-constexpr int DKV_META = 2 * DKV_BQ * 12 + 2 * 2 * 32 * 2 * 4;  // lse2, delta, pos x 2 parities; query-visibility words (all, causal) per key group x 2 parities
-constexpr int DKV_SMEM = 2 * DKV_KV_BYTES + 2 * 2 * DKV_Q_BYTES + 2 * DKV_PT_BYTES + DKV_META + 256 + 1024;
+constexpr int DKV_META_SLOT = 1280;  // lse2[64] | delta[64] | pos[64] | qvis[32][2] | qvisc[32][2]
+constexpr int DKV_SMEM = 2 * DKV_KV_BYTES + 2 * 2 * DKV_Q_BYTES + 2 * DKV_PT_BYTES + AB_MSLOTS * DKV_META_SLOT + 256 + 1024;
 
 __global__ void __launch_bounds__(AB_THREADS, 2)
 attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                      const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
                      const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1 KB alignment by pointer arithmetic on the __shared__ array itself, so every access below stays LDS/STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_k = smem;
   uint8_t* s_v = s_k + DKV_KV_BYTES;
   uint8_t* s_qdo = s_v + DKV_KV_BYTES;            // stage s: Q at s*16K, dO at s*16K + 8K
   uint8_t* s_pt = s_qdo + 2 * 2 * DKV_Q_BYTES;    // P^T  [128 keys][64 queries] bf16, K-major swizzled
   uint8_t* s_dst = s_pt + DKV_PT_BYTES;           // dS^T
-  float* s_lse = reinterpret_cast<float*>(s_dst + DKV_PT_BYTES);  // [2][64]
-  float* s_delta = s_lse + 2 * DKV_BQ;
-  int* s_posq = reinterpret_cast<int*>(s_delta + 2 * DKV_BQ);
-  uint32_t* s_qvis = reinterpret_cast<uint32_t*>(s_posq + 2 * DKV_BQ);  // [2][32 key groups][2] queries that see the group
-  uint32_t* s_qvisc = s_qvis + 2 * 32 * 2;                              // [2][32][2] ... iff pos_k <= pos_q
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_qvisc + 2 * 32 * 2);
+  uint8_t* s_meta = s_dst + DKV_PT_BYTES;         // slot i at i * DKV_META_SLOT
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_meta + AB_MSLOTS * DKV_META_SLOT);
   uint64_t* kv_full = bars;        // 1
   uint64_t* q_full = bars + 1;     // [2]
   uint64_t* q_empty = bars + 3;    // [2]
   uint64_t* st_full = bars + 5;    // S^T_i and dP^T_i in TMEM
   uint64_t* ps_ready = bars + 6;   // P^T_i, dS^T_i in smem; TMEM S^T/dP^T consumed (128 arrivals)
   uint64_t* pd_free = bars + 7;    // dV/dK MMAs of tile i done: smem P^T/dS^T reusable, accumulators final at the end
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* meta_full = bars + 8;  // [3]
+  uint64_t* meta_empty = bars + 11;  // [3]  128 arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int T = p.tokens;
   const int n_q = (T + DKV_BQ - 1) / DKV_BQ;
+  const bool has_mask = p.gid != nullptr;
 
   if (threadIdx.x == 0) {
     mbar_init(kv_full, 1);
@@ -125,6 +122,10 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     mbar_init(st_full, 1);
     mbar_init(ps_ready, DKV_BK);
     mbar_init(pd_free, 1);
+    for (int i = 0; i < AB_MSLOTS; ++i) {
+      mbar_init(&meta_full[i], 1);
+      mbar_init(&meta_empty[i], DKV_BK);
+    }
     fence_barrier_init();
   }
   if (warp == 4 && lane == 0) {
@@ -145,7 +146,17 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       mbar_expect_tx(kv_full, 2 * DKV_KV_BYTES);
       tma_load_3d(s_k, &tm_k, kv_full, h * AB_D, kt * DKV_BK, b);
       tma_load_3d(s_v, &tm_v, kv_full, h * AB_D, kt * DKV_BK, b);
+      const float* lse_row = p.lse2 + ((size_t)b * p.heads + h) * p.tp;
+      const float* del_row = p.delta + ((size_t)b * p.heads + h) * p.tp;
+      const uint8_t* meta_b = p.meta + (size_t)b * n_q * ATTN_META_BYTES;
       for (int i = 0; i < n_q; ++i) {
+        const int ms = i % AB_MSLOTS;
+        uint8_t* slot = s_meta + ms * DKV_META_SLOT;
+        mbar_wait(&meta_empty[ms], ((i / AB_MSLOTS) & 1) ^ 1);
+        mbar_expect_tx(&meta_full[ms], has_mask ? 1280u : 512u);
+        bulk_g2s(slot, lse_row + i * DKV_BQ, 256, &meta_full[ms]);
+        bulk_g2s(slot + 256, del_row + i * DKV_BQ, 256, &meta_full[ms]);
+        if (has_mask) bulk_g2s(slot + 512, meta_b + (size_t)i * ATTN_META_BYTES + ATTN_META_OFF_POS, 768, &meta_full[ms]);  // pos | qvis | qvisc
         const int st = i & 1;
         mbar_wait(&q_empty[st], ((i >> 1) & 1) ^ 1);
         mbar_expect_tx(&q_full[st], 2 * DKV_Q_BYTES);
@@ -197,7 +208,6 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     const int row = threadIdx.x;  // key row == TMEM lane
     const int kk = kt * DKV_BK + row;
     const uint32_t lane_sel = ((uint32_t)(warp * 32)) << 16;
-    const bool has_mask = p.mwords != nullptr;
     const bool k_valid = kk < T;
     float bias2 = 0.f;
     int gk = 0, pk = 0;
@@ -208,89 +218,69 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         pk = p.pos[(long long)b * T + kk];
       }
     }
+    const float2 scale2 = make_float2(p.scale_log2, p.scale_log2), bias22 = make_float2(bias2, bias2);
+    const float2 sc2 = make_float2(p.scale, p.scale);
     for (int i = 0; i < n_q; ++i) {
-      const int par = i & 1;
-      if (row < DKV_BQ) {  // per-query metadata of this tile (warps 0 and 1: one query per thread)
-        const int q = i * DKV_BQ + row;
-        float l2 = INFINITY, dl = 0.f;    // queries past T: exp2(s - inf) = 0
-        uint32_t ma = 0xffffffffu, mc = 0;
-        int pq = 0;
-        if (q < T) {
-          l2 = p.lse[((long long)b * p.heads + h) * T + q] * 1.4426950408889634f;
-          dl = p.delta[((long long)b * p.heads + h) * T + q];
-          if (has_mask) {
-            const uint2 w = p.mwords[(long long)b * T + q];
-            ma = w.x;
-            mc = w.y;
-            pq = p.pos[(long long)b * T + q];
-          }
-        }
-        s_lse[par * DKV_BQ + row] = l2;
-        s_delta[par * DKV_BQ + row] = dl;
-        if (has_mask) {
-          s_posq[par * DKV_BQ + row] = pq;
-          for (int g = 0; g < p.num_groups; ++g) {  // bit q of word (g, warp): query q sees keys of group g
-            const uint32_t wa = __ballot_sync(0xffffffffu, (ma >> g) & 1u);
-            const uint32_t wc = __ballot_sync(0xffffffffu, (mc >> g) & 1u);
-            if (lane == 0) {
-              s_qvis[(par * 32 + g) * 2 + warp] = wa;
-              s_qvisc[(par * 32 + g) * 2 + warp] = wc;
-            }
-          }
-        }
-      }
-      named_bar_sync_b(1, DKV_BK);
-      uint32_t vw[2] = {0xffffffffu, 0xffffffffu}, vc[2] = {0u, 0u};
+      const int ms = i % AB_MSLOTS;
+      const uint8_t* slot = s_meta + ms * DKV_META_SLOT;
+      mbar_wait(&meta_full[ms], (i / AB_MSLOTS) & 1);
+      uint32_t vw[2] = {0xffffffffu, 0xffffffffu};
       if (has_mask) {
-        vw[0] = s_qvis[(par * 32 + gk) * 2];
-        vw[1] = s_qvis[(par * 32 + gk) * 2 + 1];
-        vc[0] = s_qvisc[(par * 32 + gk) * 2];
-        vc[1] = s_qvisc[(par * 32 + gk) * 2 + 1];
+        const uint2 a = *reinterpret_cast<const uint2*>(slot + 768 + gk * 8);
+        const uint2 c = *reinterpret_cast<const uint2*>(slot + 1024 + gk * 8);
+        vw[0] = a.x; vw[1] = a.y;
+        if (c.x | c.y) {  // rare (Text sets): fold the causal rule into the visibility words
+          const int* posq = reinterpret_cast<const int*>(slot + 512);
+          for (int q = 0; q < 32; ++q) {
+            if (((c.x >> q) & 1u) && pk <= posq[q]) vw[0] |= 1u << q;
+            if (((c.y >> q) & 1u) && pk <= posq[32 + q]) vw[1] |= 1u << q;
+          }
+        }
       }
-      if (!k_valid) vw[0] = vw[1] = vc[0] = vc[1] = 0u;  // rows past T contribute nothing
-      const float4* lse4 = reinterpret_cast<const float4*>(s_lse + par * DKV_BQ);
-      const float4* del4 = reinterpret_cast<const float4*>(s_delta + par * DKV_BQ);
+      if (!k_valid) vw[0] = vw[1] = 0u;  // rows past T contribute nothing
+      const float4* lse4 = reinterpret_cast<const float4*>(slot);
+      const float4* del4 = reinterpret_cast<const float4*>(slot + 256);
       mbar_wait(st_full, i & 1);
       tc_fence_after();
-      if (i >= 1) mbar_wait(pd_free, (i - 1) & 1);  // previous P^T / dS^T fully consumed by the tensor core
 #pragma unroll
       for (int cq = 0; cq < DKV_BQ / 32; ++cq) {
         const int c0 = cq * 32;
-        uint32_t sv[32], dv[32];
-        tmem_ld_x32(tm_st + lane_sel + c0, sv);
-        tmem_ld_x32(tm_dpt + lane_sel + c0, dv);
-        uint32_t word = vw[cq];
-        if (vc[cq]) {  // rare (Text sets): fold the causal rule into the visibility word
-          for (int c = 0; c < 32; ++c)
-            if (((vc[cq] >> c) & 1u) && pk <= s_posq[par * DKV_BQ + c0 + c]) word |= 1u << c;
-        }
+        float sv[32], dv[32];
+        tmem_ld_f32x32(tm_st + lane_sel + c0, sv);
+        tmem_ld_f32x32(tm_dpt + lane_sel + c0, dv);
         tmem_ld_wait();
-        float pv[32], ds[32];
+        const uint32_t word = vw[cq];
+        uint32_t pw[16], dw[16];
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
           const float4 l4 = lse4[cq * 8 + c4], d4 = del4[cq * 8 + c4];
-          const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dl4[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int c = c4 * 4 + u;
-            const float s2 = fmaf(__uint_as_float(sv[c]), p.scale_log2, bias2);
-            const float pe = ((word >> c) & 1u) ? fast_exp2(s2 - lv[u]) : 0.f;
-            pv[c] = pe;
-            ds[c] = pe * p.scale * (__uint_as_float(dv[c]) - dl4[u]);
+          for (int u = 0; u < 2; ++u) {
+            const int c = c4 * 4 + 2 * u;
+            const float2 lv = u ? make_float2(l4.z, l4.w) : make_float2(l4.x, l4.y);
+            const float2 dl = u ? make_float2(d4.z, d4.w) : make_float2(d4.x, d4.y);
+            float2 t = __ffma2_rn(make_float2(sv[c], sv[c + 1]), scale2, bias22);
+            t = __fadd2_rn(t, make_float2(-lv.x, -lv.y));
+            float2 pe = make_float2(fast_exp2(t.x), fast_exp2(t.y));
+            pe.x = ((word >> c) & 1u) ? pe.x : 0.f;
+            pe.y = ((word >> (c + 1)) & 1u) ? pe.y : 0.f;
+            float2 g = __fadd2_rn(make_float2(dv[c], dv[c + 1]), make_float2(-dl.x, -dl.y));
+            g = __fmul2_rn(g, sc2);
+            g = __fmul2_rn(g, pe);
+            pw[c >> 1] = pack_bf16(pe.x, pe.y);
+            dw[c >> 1] = pack_bf16(g.x, g.y);
           }
         }
+        if (cq == 0 && i >= 1) mbar_wait(pd_free, (i - 1) & 1);  // previous P^T / dS^T fully consumed by the tensor core
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           const int chunk = (c0 >> 3) + ch;
           const int off = row * 128 + ((chunk ^ (row & 7)) << 4);
-          *reinterpret_cast<uint4*>(s_pt + off) =
-              make_uint4(pack_bf16(pv[ch * 8 + 0], pv[ch * 8 + 1]), pack_bf16(pv[ch * 8 + 2], pv[ch * 8 + 3]),
-                         pack_bf16(pv[ch * 8 + 4], pv[ch * 8 + 5]), pack_bf16(pv[ch * 8 + 6], pv[ch * 8 + 7]));
-          *reinterpret_cast<uint4*>(s_dst + off) =
-              make_uint4(pack_bf16(ds[ch * 8 + 0], ds[ch * 8 + 1]), pack_bf16(ds[ch * 8 + 2], ds[ch * 8 + 3]),
-                         pack_bf16(ds[ch * 8 + 4], ds[ch * 8 + 5]), pack_bf16(ds[ch * 8 + 6], ds[ch * 8 + 7]));
+          *reinterpret_cast<uint4*>(s_pt + off) = make_uint4(pw[4 * ch], pw[4 * ch + 1], pw[4 * ch + 2], pw[4 * ch + 3]);
+          *reinterpret_cast<uint4*>(s_dst + off) = make_uint4(dw[4 * ch], dw[4 * ch + 1], dw[4 * ch + 2], dw[4 * ch + 3]);
         }
       }
+      mbar_arrive(&meta_empty[ms]);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(ps_ready);
@@ -303,19 +293,17 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       __nv_bfloat16* dvr = p.dv + (long long)b * p.dv_bs + (long long)(k_valid ? kk : 0) * p.dv_ts + h * AB_D;
 #pragma unroll
       for (int c0 = 0; c0 < AB_D; c0 += 32) {
-        uint32_t a[32], c[32];
-        tmem_ld_x32(tm_dk + lane_sel + c0, a);
-        tmem_ld_x32(tm_dv + lane_sel + c0, c);
+        float a[32], c[32];
+        tmem_ld_f32x32(tm_dk + lane_sel + c0, a);
+        tmem_ld_f32x32(tm_dv + lane_sel + c0, c);
         tmem_ld_wait();
         if (k_valid) {
 #pragma unroll
           for (int i = 0; i < 32; i += 8) {
-            *reinterpret_cast<uint4*>(dkr + c0 + i) =
-                make_uint4(pack_bf16(__uint_as_float(a[i]), __uint_as_float(a[i + 1])), pack_bf16(__uint_as_float(a[i + 2]), __uint_as_float(a[i + 3])),
-                           pack_bf16(__uint_as_float(a[i + 4]), __uint_as_float(a[i + 5])), pack_bf16(__uint_as_float(a[i + 6]), __uint_as_float(a[i + 7])));
-            *reinterpret_cast<uint4*>(dvr + c0 + i) =
-                make_uint4(pack_bf16(__uint_as_float(c[i]), __uint_as_float(c[i + 1])), pack_bf16(__uint_as_float(c[i + 2]), __uint_as_float(c[i + 3])),
-                           pack_bf16(__uint_as_float(c[i + 4]), __uint_as_float(c[i + 5])), pack_bf16(__uint_as_float(c[i + 6]), __uint_as_float(c[i + 7])));
+            *reinterpret_cast<uint4*>(dkr + c0 + i) = make_uint4(pack_bf16(a[i], a[i + 1]), pack_bf16(a[i + 2], a[i + 3]),
+                                                                 pack_bf16(a[i + 4], a[i + 5]), pack_bf16(a[i + 6], a[i + 7]));
+            *reinterpret_cast<uint4*>(dvr + c0 + i) = make_uint4(pack_bf16(c[i], c[i + 1]), pack_bf16(c[i + 2], c[i + 3]),
+                                                                 pack_bf16(c[i + 4], c[i + 5]), pack_bf16(c[i + 6], c[i + 7]));
           }
         }
       }
@@ -332,51 +320,54 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 // ------------------------------------------------------------------------------------------------ dQ
 constexpr int DQ_BQ = 128;  // queries per CTA
 constexpr int DQ_BK = 64;   // keys per tile
+static_assert(DQ_BK == ATTN_META_TILE, "key tiles and metadata tiles must coincide");
 constexpr int DQ_Q_BYTES = DQ_BQ * AB_D * 2;   // 16 KB
 constexpr int DQ_K_BYTES = DQ_BK * AB_D * 2;   // 8 KB
-constexpr int DQ_DS_BYTES = DQ_BQ * DQ_BK * 2;  // 16 KB
-constexpr int DQ_META = 2 * DQ_BK * 8 + 2 * 2 * 32 * 2 * 4 + 2 * 32 * 4;  // bias2, pos x 2 parities; key-visibility words per query group; column words
-constexpr int DQ_SMEM = 2 * DQ_Q_BYTES + 2 * 2 * DQ_K_BYTES + DQ_DS_BYTES + DQ_META + 256 + 1024;
+constexpr int DQ_DS_BYTES = DQ_BQ * DQ_BK * 2;  // 16 KB, x2 buffers
+constexpr int DQ_META_SLOT = ATTN_META_KEY_BYTES;  // bias2 | vis | visc | pos
+constexpr int DQ_SMEM = 2 * DQ_Q_BYTES + 2 * 2 * DQ_K_BYTES + 2 * DQ_DS_BYTES + AB_MSLOTS * DQ_META_SLOT + 256 + 1024;
 
 __global__ void __launch_bounds__(AB_THREADS, 2)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                    const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
                    const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_q = smem;
   uint8_t* s_do = s_q + DQ_Q_BYTES;
   uint8_t* s_kv = s_do + DQ_Q_BYTES;             // stage s: K at s*16K, V at s*16K + 8K
-  uint8_t* s_ds = s_kv + 2 * 2 * DQ_K_BYTES;     // dS [128 queries][64 keys] bf16 K-major swizzled
-  float* s_bias = reinterpret_cast<float*>(s_ds + DQ_DS_BYTES);  // [2][64]
-  int* s_pos = reinterpret_cast<int*>(s_bias + 2 * DQ_BK);
-  uint32_t* s_vis = reinterpret_cast<uint32_t*>(s_pos + 2 * DQ_BK);  // [2][32 query groups][2] keys visible to the group
-  uint32_t* s_visc = s_vis + 2 * 32 * 2;                             // [2][32][2] ... iff pos_k <= pos_q
-  uint32_t* s_colw = s_visc + 2 * 32 * 2;                            // [32] query groups that see key group g (code 1)
-  uint32_t* s_colc = s_colw + 32;                                    // [32] (code 2)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_colc + 32);
+  uint8_t* s_ds = s_kv + 2 * 2 * DQ_K_BYTES;     // dS [128 queries][64 keys] bf16 K-major swizzled, buffer i at i * 16 KB
+  uint8_t* s_meta = s_ds + 2 * DQ_DS_BYTES;      // slot i at i * DQ_META_SLOT
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_meta + AB_MSLOTS * DQ_META_SLOT);
   uint64_t* q_full = bars;          // Q and dO
   uint64_t* kv_full = bars + 1;     // [2]
   uint64_t* kv_empty = bars + 3;    // [2]
   uint64_t* s_full = bars + 5;      // S_j, dP_j in TMEM
   uint64_t* ds_ready = bars + 6;    // dS_j in smem, S_j/dP_j consumed (128 arrivals)
-  uint64_t* ds_free = bars + 7;     // dQ MMA of tile j done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* ds_free = bars + 7;     // [2] dQ MMA of tile j done reading dS buffer j&1
+  uint64_t* meta_full = bars + 9;   // [3]
+  uint64_t* meta_empty = bars + 12; // [3] 128 arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int T = p.tokens;
   const int n_k = (T + DQ_BK - 1) / DQ_BK;
+  const bool has_mask = p.gid != nullptr;
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
+      mbar_init(&ds_free[i], 1);
     }
     mbar_init(s_full, 1);
     mbar_init(ds_ready, DQ_BQ);
-    mbar_init(ds_free, 1);
+    for (int i = 0; i < AB_MSLOTS; ++i) {
+      mbar_init(&meta_full[i], 1);
+      mbar_init(&meta_empty[i], DQ_BQ);
+    }
     fence_barrier_init();
   }
   if (warp == 4 && lane == 0) {
@@ -386,18 +377,6 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     tma_prefetch_desc(&tm_do);
   }
   if (warp == 5) tmem_alloc(tmem_slot, AB_TMEM_COLS);
-  if (threadIdx.x < 32) {  // transpose the mask words: which query groups may see keys of group g
-    uint32_t cw = 0, cc = 0;
-    const int g = threadIdx.x;
-    if (p.allow != nullptr && g < p.num_groups)
-      for (int qg = 0; qg < p.num_groups; ++qg) {
-        const int a = p.allow[qg * p.num_groups + g];
-        cw |= (a == 1 ? 1u : 0u) << qg;
-        cc |= (a == 2 ? 1u : 0u) << qg;
-      }
-    s_colw[g] = cw;
-    s_colc[g] = cc;
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -409,7 +388,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       mbar_expect_tx(q_full, 2 * DQ_Q_BYTES);
       tma_load_3d(s_q, &tm_q, q_full, h * AB_D, qt * DQ_BQ, b);
       tma_load_3d(s_do, &tm_do, q_full, h * AB_D, qt * DQ_BQ, b);
+      const uint32_t meta_bytes = has_mask ? ATTN_META_KEY_BYTES : 256u;
+      const uint8_t* meta_b = p.meta + (size_t)b * n_k * ATTN_META_BYTES;
       for (int j = 0; j < n_k; ++j) {
+        const int ms = j % AB_MSLOTS;
+        mbar_wait(&meta_empty[ms], ((j / AB_MSLOTS) & 1) ^ 1);
+        mbar_expect_tx(&meta_full[ms], meta_bytes);
+        bulk_g2s(s_meta + ms * DQ_META_SLOT, meta_b + (size_t)j * ATTN_META_BYTES, meta_bytes, &meta_full[ms]);
         const int st = j & 1;
         mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
         mbar_expect_tx(&kv_full[st], 2 * DQ_K_BYTES);
@@ -443,12 +428,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         }
         if (j >= 1) {
           const int st = (j - 1) & 1;
-          const uint32_t ak = smem_u32(s_kv + st * 2 * DQ_K_BYTES);
+          const uint32_t ak = smem_u32(s_kv + st * 2 * DQ_K_BYTES), adsj = ads + ((j - 1) & 1) * DQ_DS_BYTES;
 #pragma unroll
           for (int k = 0; k < DQ_BK / 16; ++k)  // dQ += dS K
-            umma_bf16(tm_dq, make_smem_desc(ads + k * 32, 16, 1024), make_smem_desc(ak + k * 2048, 8192, 1024), idesc_g,
+            umma_bf16(tm_dq, make_smem_desc(adsj + k * 32, 16, 1024), make_smem_desc(ak + k * 2048, 8192, 1024), idesc_g,
                       (j > 1 || k > 0) ? 1u : 0u);
-          umma_commit(ds_free);
+          umma_commit(&ds_free[(j - 1) & 1]);
           umma_commit(&kv_empty[st]);
         }
       }
@@ -457,110 +442,90 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const int row = threadIdx.x;
     const int q = qt * DQ_BQ + row;
     const uint32_t lane_sel = ((uint32_t)(warp * 32)) << 16;
-    const bool has_mask = p.mwords != nullptr;
     const bool q_valid = q < T;
-    float lse2 = INFINITY, dl = 0.f;
+    const long long lrow = ((long long)b * p.heads + h) * p.tp + (q_valid ? q : 0);
+    const float lse2 = q_valid ? p.lse2[lrow] : INFINITY;   // rows past T: exp2(s - inf) = 0
+    const float dl = q_valid ? p.delta[lrow] : 0.f;
     int gq = 0, pos_q = 0;
-    if (q_valid) {
-      lse2 = p.lse[((long long)b * p.heads + h) * T + q] * 1.4426950408889634f;
-      dl = p.delta[((long long)b * p.heads + h) * T + q];
-      if (has_mask) {
-        gq = p.gid[(long long)b * T + q];
-        pos_q = p.pos[(long long)b * T + q];
-      }
+    if (has_mask && q_valid) {
+      gq = p.gid[(long long)b * T + q];
+      pos_q = p.pos[(long long)b * T + q];
     }
+    const float2 scale2 = make_float2(p.scale_log2, p.scale_log2);
+    const float2 nl2 = make_float2(-lse2, -lse2);
+    const float2 sc2 = make_float2(p.scale, p.scale), nds2 = make_float2(-dl * p.scale, -dl * p.scale);
     for (int j = 0; j < n_k; ++j) {
-      const int par = j & 1;
-      if (row < DQ_BK) {  // per-key metadata (warps 0 and 1: one key per thread)
-        const int kk = j * DQ_BK + row;
-        float bias2 = -INFINITY;  // keys past T contribute nothing (and stay "visible" so the -inf survives)
-        uint32_t cw = 0xffffffffu, cc = 0u;
-        int pk = 0;
-        if (kk < T) {
-          bias2 = p.size ? log2f(p.size[(long long)b * T + kk]) : 0.f;
-          if (has_mask) {
-            const int gk = p.gid[(long long)b * T + kk];
-            cw = s_colw[gk];
-            cc = s_colc[gk];
-            pk = p.pos[(long long)b * T + kk];
-          }
-        }
-        s_bias[par * DQ_BK + row] = bias2;
-        if (has_mask) {
-          s_pos[par * DQ_BK + row] = pk;
-          for (int g = 0; g < p.num_groups; ++g) {
-            const uint32_t wa = __ballot_sync(0xffffffffu, (cw >> g) & 1u);
-            const uint32_t wc = __ballot_sync(0xffffffffu, (cc >> g) & 1u);
-            if (lane == 0) {
-              s_vis[(par * 32 + g) * 2 + warp] = wa;
-              s_visc[(par * 32 + g) * 2 + warp] = wc;
-            }
-          }
-        }
-      }
-      named_bar_sync_b(1, DQ_BQ);
-      uint32_t vw[2] = {0xffffffffu, 0xffffffffu}, vc[2] = {0u, 0u};
+      const int ms = j % AB_MSLOTS;
+      const uint8_t* slot = s_meta + ms * DQ_META_SLOT;
+      mbar_wait(&meta_full[ms], (j / AB_MSLOTS) & 1);
+      uint32_t vw[2] = {0xffffffffu, 0xffffffffu};
       if (has_mask) {
-        vw[0] = s_vis[(par * 32 + gq) * 2];
-        vw[1] = s_vis[(par * 32 + gq) * 2 + 1];
-        vc[0] = s_visc[(par * 32 + gq) * 2];
-        vc[1] = s_visc[(par * 32 + gq) * 2 + 1];
+        const uint2 a = *reinterpret_cast<const uint2*>(slot + ATTN_META_OFF_VIS + gq * 8);
+        const uint2 c = *reinterpret_cast<const uint2*>(slot + ATTN_META_OFF_VISC + gq * 8);
+        vw[0] = a.x; vw[1] = a.y;
+        if (c.x | c.y) {
+          const int* m_pos = reinterpret_cast<const int*>(slot + ATTN_META_OFF_POS);
+          for (int i = 0; i < 32; ++i) {
+            if (((c.x >> i) & 1u) && m_pos[i] <= pos_q) vw[0] |= 1u << i;
+            if (((c.y >> i) & 1u) && m_pos[32 + i] <= pos_q) vw[1] |= 1u << i;
+          }
+        }
       }
-      const float4* bias4 = reinterpret_cast<const float4*>(s_bias + par * DQ_BK);
+      const float4* bias4 = reinterpret_cast<const float4*>(slot);
+      uint8_t* dsb = s_ds + (j & 1) * DQ_DS_BYTES + row * 128;
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      if (j >= 1) mbar_wait(ds_free, (j - 1) & 1);
 #pragma unroll
       for (int cq = 0; cq < DQ_BK / 32; ++cq) {
         const int c0 = cq * 32;
-        uint32_t sv[32], dv[32];
-        tmem_ld_x32(tm_s + lane_sel + c0, sv);
-        tmem_ld_x32(tm_dp + lane_sel + c0, dv);
-        uint32_t word = vw[cq];
-        if (vc[cq]) {
-          for (int c = 0; c < 32; ++c)
-            if (((vc[cq] >> c) & 1u) && s_pos[par * DQ_BK + c0 + c] <= pos_q) word |= 1u << c;
-        }
+        float sv[32], dv[32];
+        tmem_ld_f32x32(tm_s + lane_sel + c0, sv);
+        tmem_ld_f32x32(tm_dp + lane_sel + c0, dv);
         tmem_ld_wait();
-        float ds[32];
+        const uint32_t word = vw[cq];
+        uint32_t dw[16];
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
           const float4 b4 = bias4[cq * 8 + c4];
-          const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int c = c4 * 4 + u;
-            const float s2 = fmaf(__uint_as_float(sv[c]), p.scale_log2, bv[u]);
-            const float pe = ((word >> c) & 1u) ? fast_exp2(s2 - lse2) : 0.f;
-            ds[c] = pe * p.scale * (__uint_as_float(dv[c]) - dl);
+          for (int u = 0; u < 2; ++u) {
+            const int c = c4 * 4 + 2 * u;
+            const float2 bv = u ? make_float2(b4.z, b4.w) : make_float2(b4.x, b4.y);
+            float2 t = __ffma2_rn(make_float2(sv[c], sv[c + 1]), scale2, bv);
+            t = __fadd2_rn(t, nl2);
+            float2 pe = make_float2(fast_exp2(t.x), fast_exp2(t.y));
+            pe.x = ((word >> c) & 1u) ? pe.x : 0.f;
+            pe.y = ((word >> (c + 1)) & 1u) ? pe.y : 0.f;
+            float2 g = __ffma2_rn(make_float2(dv[c], dv[c + 1]), sc2, nds2);  // (dP - delta) * scale
+            g = __fmul2_rn(g, pe);
+            dw[c >> 1] = pack_bf16(g.x, g.y);
           }
         }
+        if (cq == 0 && j >= 2) mbar_wait(&ds_free[j & 1], ((j - 2) >> 1) & 1);  // dQ MMA of tile j-2 has read this buffer
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           const int chunk = (c0 >> 3) + ch;
-          *reinterpret_cast<uint4*>(s_ds + row * 128 + ((chunk ^ (row & 7)) << 4)) =
-              make_uint4(pack_bf16(ds[ch * 8 + 0], ds[ch * 8 + 1]), pack_bf16(ds[ch * 8 + 2], ds[ch * 8 + 3]),
-                         pack_bf16(ds[ch * 8 + 4], ds[ch * 8 + 5]), pack_bf16(ds[ch * 8 + 6], ds[ch * 8 + 7]));
+          *reinterpret_cast<uint4*>(dsb + ((chunk ^ (row & 7)) << 4)) = make_uint4(dw[4 * ch], dw[4 * ch + 1], dw[4 * ch + 2], dw[4 * ch + 3]);
         }
       }
+      mbar_arrive(&meta_empty[ms]);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(ds_ready);
     }
-    mbar_wait(ds_free, (n_k - 1) & 1);
+    mbar_wait(&ds_free[(n_k - 1) & 1], ((n_k - 1) >> 1) & 1);
     tc_fence_after();
     __nv_bfloat16* dqr = p.dq + (long long)b * p.dq_bs + (long long)(q_valid ? q : 0) * p.dq_ts + h * AB_D;
 #pragma unroll
     for (int c0 = 0; c0 < AB_D; c0 += 32) {
-      uint32_t a[32];
-      tmem_ld_x32(tm_dq + lane_sel + c0, a);
+      float a[32];
+      tmem_ld_f32x32(tm_dq + lane_sel + c0, a);
       tmem_ld_wait();
       if (q_valid) {
 #pragma unroll
         for (int i = 0; i < 32; i += 8)
-          *reinterpret_cast<uint4*>(dqr + c0 + i) =
-              make_uint4(pack_bf16(__uint_as_float(a[i]), __uint_as_float(a[i + 1])), pack_bf16(__uint_as_float(a[i + 2]), __uint_as_float(a[i + 3])),
-                         pack_bf16(__uint_as_float(a[i + 4]), __uint_as_float(a[i + 5])), pack_bf16(__uint_as_float(a[i + 6]), __uint_as_float(a[i + 7])));
+          *reinterpret_cast<uint4*>(dqr + c0 + i) = make_uint4(pack_bf16(a[i], a[i + 1]), pack_bf16(a[i + 2], a[i + 3]),
+                                                               pack_bf16(a[i + 4], a[i + 5]), pack_bf16(a[i + 6], a[i + 7]));
       }
     }
   }
@@ -578,10 +543,13 @@ using namespace tome;
 
 static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
+static size_t bwd_pad_elems(const tome_attn_desc_t* d) {
+  return (size_t)d->batch * d->heads * (size_t)(((d->tokens + 63) / 64) * 64);
+}
+
 extern "C" size_t tome_attention_bwd_workspace_bytes(const tome_attn_desc_t* d) {
   if (!d || d->batch <= 0 || d->tokens <= 0 || d->heads <= 0) return 0;
-  const size_t bht = (size_t)d->batch * d->heads * d->tokens;
-  return align256(bht * sizeof(float)) + align256((size_t)d->batch * d->tokens * sizeof(uint2));
+  return align256(attn_meta_bytes(d->batch, d->tokens)) + 2 * align256(bwd_pad_elems(d) * sizeof(float));
 }
 
 extern "C" int tome_attention_bwd(const tome_attn_desc_t* d, const tome_attn_grad_strides_t* gs, const void* q, const void* k,
@@ -600,23 +568,24 @@ extern "C" int tome_attention_bwd(const tome_attn_desc_t* d, const tome_attn_gra
                            gs->dv_batch_stride, gs->dv_token_stride, gs->do_batch_stride, gs->do_token_stride};
   for (int i = 0; i < 8; ++i) TOME_CHECK(st[i] % 8 == 0, TOME_ERR_INVALID, "attention_bwd: strides must be multiples of 8");
   const int B = d->batch, T = d->tokens, H = d->heads;
-  ProfScope prof(PROF_ATTN_BWD, 10.0 * d->batch * d->heads * (double)d->tokens * d->tokens * d->head_dim, 3, stream);
-  float* delta = reinterpret_cast<float*>(workspace);
-  uint2* mwords = d->gid ? reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(workspace) + align256((size_t)B * H * T * sizeof(float)))
-                         : nullptr;
+  ProfScope prof(PROF_ATTN_BWD, 10.0 * d->batch * d->heads * (double)d->tokens * d->tokens * d->head_dim, 4, stream);
+  const int Tp = ((T + 63) / 64) * 64;
+  uint8_t* meta = reinterpret_cast<uint8_t*>(workspace);
+  float* delta = reinterpret_cast<float*>(meta + align256(attn_meta_bytes(B, T)));
+  float* lse2 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(delta) + align256(bwd_pad_elems(d) * sizeof(float)));
+  if (int rc = launch_attn_meta(B, T, d->gid, d->pos, d->allow, d->num_groups, d->size, meta, stream)) return rc;
   {
-    const long long total = (long long)B * T * H * 8;
+    const long long total = (long long)B * Tp * H * 8;
     attn_bwd_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
-        B, T, H, reinterpret_cast<const __nv_bfloat16*>(out), d->o_batch_stride, d->o_token_stride,
-        reinterpret_cast<const __nv_bfloat16*>(dout), gs->do_batch_stride, gs->do_token_stride, delta, d->gid, d->allow,
-        d->num_groups, mwords);
+        B, T, Tp, H, reinterpret_cast<const __nv_bfloat16*>(out), d->o_batch_stride, d->o_token_stride,
+        reinterpret_cast<const __nv_bfloat16*>(dout), gs->do_batch_stride, gs->do_token_stride, lse, delta, lse2);
     TOME_CUDA(cudaGetLastError());
   }
   const uint64_t hd = (uint64_t)H * d->head_dim;
   AttnBwdParams p;
-  p.batch = B; p.tokens = T; p.heads = H;
+  p.batch = B; p.tokens = T; p.heads = H; p.tp = Tp;
   p.scale = d->scale; p.scale_log2 = d->scale * 1.4426950408889634f;
-  p.gid = d->gid; p.pos = d->pos; p.allow = d->gid ? d->allow : nullptr; p.num_groups = d->num_groups; p.mwords = mwords; p.size = d->size; p.lse = lse; p.delta = delta;
+  p.gid = d->gid; p.pos = d->pos; p.meta = meta; p.size = d->size; p.lse2 = lse2; p.delta = delta;
   p.dq = reinterpret_cast<__nv_bfloat16*>(dq); p.dq_bs = gs->dq_batch_stride; p.dq_ts = gs->dq_token_stride;
   p.dk = reinterpret_cast<__nv_bfloat16*>(dk); p.dk_bs = gs->dk_batch_stride; p.dk_ts = gs->dk_token_stride;
   p.dv = reinterpret_cast<__nv_bfloat16*>(dv); p.dv_bs = gs->dv_batch_stride; p.dv_ts = gs->dv_token_stride;
