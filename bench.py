@@ -169,6 +169,10 @@ def main():
     from multi_modal_transformers_tokenmerge_b200.tokenizers.token_sequencer import sequence_groups
 
     lib = L.lib()  # raises if the CUDA library is missing: the product path has no fallback
+    # stdout carries exactly ONE JSON line: anything a library prints meanwhile (NCCL's version banner at N > 1) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -309,10 +313,13 @@ def main():
             out["cpu_baseline"] = {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
                                    "sample": f"3 train steps of 2 samples of the same workload (fp32, torch-CPU restatement of the "
                                              f"reference), {sec:.1f} s/step"}
-        print(json.dumps(out))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    if out is not None:
+        print(json.dumps(out), flush=True)
 
 
 if __name__ == "__main__":

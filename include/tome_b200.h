@@ -144,6 +144,10 @@ int tome_gemm_bf16(const tome_gemm_args_t* args, void* workspace, size_t workspa
 int tome_colsum_workspace_rows(int m);
 int tome_colsum_bf16(int m, int n, const void* x, long long ldx, float* out, int accumulate, float* workspace,
                      void* stream);
+/* y = dropout(x) (dense bf16 [M,N]; the mask of the GEMM epilogue for the same seed / site / element) and
+ * out[n] (+)= sum_m y[m,n] in ONE pass: the backward of "Dropout -> Dense" (attention.py:37,60) needs both. */
+int tome_dropout_colsum_bf16(int m, int n, const void* x, void* y, float rate, uint64_t seed, uint32_t site, float* out,
+                             int accumulate, float* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * 4. LayerNorm as configured          model_configs/attention_blocks/vanilla_decoder.yaml:7-13

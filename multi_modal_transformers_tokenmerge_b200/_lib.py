@@ -126,6 +126,7 @@ def lib() -> C.CDLL:
             "tome_gemm_bf16": [P(GemmArgs), vp, C.c_size_t, vp],
             "tome_colsum_workspace_rows": [i32],
             "tome_colsum_bf16": [i32, i32, vp, ll, vp, i32, vp, vp],
+            "tome_dropout_colsum_bf16": [i32, i32, vp, vp, f32, C.c_uint64, C.c_uint32, vp, i32, vp, vp],
             "tome_layernorm_fwd": [i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp],
             "tome_layernorm_bwd": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
             "tome_attention_workspace_bytes": [P(AttnDesc)],

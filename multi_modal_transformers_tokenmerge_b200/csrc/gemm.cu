@@ -521,11 +521,11 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
 
 using namespace tome;
 
-static int pick_bn(int n) {  // fewest N tiles, then the narrower tile
-  const int t256 = ceil_div(n, 256), t192 = ceil_div(n, 192), t128 = ceil_div(n, 128);
-  if (t128 <= t192 && t128 <= t256) return 128;
-  if (t192 <= t256) return 192;
-  return 256;
+static int pick_bn(int n) {  // least padded MMA work (tiles x width), then the wider tile
+  const int w128 = ceil_div(n, 128) * 128, w192 = ceil_div(n, 192) * 192, w256 = ceil_div(n, 256) * 256;
+  if (w256 <= w192 && w256 <= w128) return 256;
+  if (w192 <= w128) return 192;
+  return 128;
 }
 
 static int pick_splits(const tome_gemm_args_t* a, int bn) {

@@ -73,6 +73,16 @@ int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t 
   return encode(out, base, 3, dims, strides, box);
 }
 
+int make_tmap_3d_bf16_plain(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,
+                            uint64_t stride2, uint32_t box_d0, uint32_t box_d1) {
+  TOME_CHECK((stride1 * 2) % 16 == 0 && (stride2 * 2) % 16 == 0 && (box_d0 * 2) % 16 == 0, TOME_ERR_INVALID,
+             "TMA strides / box width must be multiples of 16 bytes");
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1 * 2, stride2 * 2};
+  cuuint32_t box[3] = {box_d0, box_d1, 1};
+  return encode(out, base, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+
 }  // namespace tome
 
 namespace tome {

@@ -36,6 +36,10 @@ int make_tmap_2d_bf16_store32(CUtensorMap* out, const void* base, uint64_t rows,
 int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,
                       uint64_t stride2, uint32_t box_d1);
 
+// same tensor with a {box_d0, box_d1, 1} box and no swizzle (box_d0 * 2 bytes must be a multiple of 16)
+int make_tmap_3d_bf16_plain(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,
+                            uint64_t stride2, uint32_t box_d0, uint32_t box_d1);
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // ---- launch accounting + optional per-op CUDA-event timing (bench.py's roofline pass; off by default) ----

@@ -171,13 +171,16 @@ ln_seq_bwd_kernel(int B, int T, int C, const __nv_bfloat16* __restrict__ x, cons
   }
 }
 
-// out[n] (+)= sum_r ws[r, n]      (fp32, fixed order)
-__global__ void reduce_rows_kernel(int R, int N, const float* __restrict__ ws, float* __restrict__ out, int accumulate) {
+// out_p[n] (+)= sum_r ws[p][r, n]   for plane p = blockIdx.y (fp32, fixed order); planes are `plane_stride` floats apart
+__global__ void reduce_rows_kernel(int R, int N, const float* __restrict__ ws, long long plane_stride, float* __restrict__ out0,
+                                   float* __restrict__ out1, int accumulate) {
   __shared__ float s[8][33];
   const int n = blockIdx.x * 32 + (threadIdx.x & 31), rgp = threadIdx.x >> 5;
+  const float* w = ws + blockIdx.y * plane_stride;
+  float* out = blockIdx.y ? out1 : out0;
   float a = 0.f;
   if (n < N)
-    for (int r = rgp; r < R; r += 8) a += ws[(long long)r * N + n];
+    for (int r = rgp; r < R; r += 8) a += w[(long long)r * N + n];
   s[rgp][threadIdx.x & 31] = a;
   __syncthreads();
   if (rgp == 0 && n < N) {
@@ -185,6 +188,234 @@ __global__ void reduce_rows_kernel(int R, int N, const float* __restrict__ ws, f
 #pragma unroll
     for (int g = 0; g < 8; ++g) t += s[g][threadIdx.x & 31];
     out[n] = accumulate ? out[n] + t : t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ axis 1, shared-memory slabs
+// The kernels above read their (batch, 64-feature) slab twice through L2 and keep few loads in flight per thread.  When
+// the slab fits in shared memory (T <= LN_SMEM_T_FWD / _BWD) it is instead brought in ONCE by TMA -- 64-row boxes, one
+// mbarrier per box, so the statistics pass starts on the first box while the others are still in flight -- and the
+// second pass runs out of shared memory.  HBM/L2 traffic per element: forward 1 read + 1 write (was 2 + 1), backward
+// 3 reads + 1 write (was 5 + 1).
+constexpr int LN_BOX = 64;                       // token rows per TMA box (box = 64 rows x 128 bytes = 8 KB, 128B swizzle)
+constexpr int LN_SMEM_T_FWD = 1536, LN_SMEM_T_BWD = 640;
+__host__ __device__ constexpr int ln_boxes(int T) { return (T + LN_BOX - 1) / LN_BOX; }
+
+__device__ __forceinline__ uint4 slab_ld(const uint8_t* slab, int t, int ct) {  // row t, 16-byte chunk ct of the swizzled slab
+  return *reinterpret_cast<const uint4*>(slab + (size_t)t * 128 + ((ct ^ (t & 7)) << 4));
+}
+
+__global__ void __launch_bounds__(LN_THREADS)
+ln_seq_fwd_smem_kernel(const __grid_constant__ CUtensorMap tm_x, int T, int C, float eps, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ mean,
+                       float* __restrict__ rstd) {
+  extern __shared__ uint8_t ln_smem_raw[];
+  uint8_t* slab = ln_smem_raw + ((1024u - (smem_u32(ln_smem_raw) & 1023u)) & 1023u);
+  const int nb = ln_boxes(T);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(slab + (size_t)nb * LN_BOX * 128);
+  __shared__ float s_sum[LN_RG][LN_SLAB + 1];
+  __shared__ float s_sq[LN_RG][LN_SLAB + 1];
+  __shared__ float s_mean[LN_SLAB], s_rstd[LN_SLAB];
+  const int b = blockIdx.y, c0 = blockIdx.x * LN_SLAB;
+  const int ct = threadIdx.x & 7, rg = threadIdx.x >> 3;
+  const int c = c0 + ct * 8;
+  const bool active = c < C;
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < nb; ++k) mbar_init(&bars[k], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < nb; ++k) {
+      mbar_expect_tx(&bars[k], LN_BOX * 128);
+      tma_load_3d(slab + (size_t)k * LN_BOX * 128, &tm_x, &bars[k], c0, k * LN_BOX, b);  // rows past T / columns past C arrive as zeros
+    }
+  }
+  float sum[8], sq[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum[i] = sq[i] = 0.f;
+  for (int k = 0; k < nb; ++k) {
+    mbar_wait(&bars[k], 0);
+#pragma unroll
+    for (int u = 0; u < LN_BOX / LN_RG; ++u) {
+      const int t = k * LN_BOX + u * LN_RG + rg;   // zero rows past T add nothing
+      float f[8];
+      unpack8(slab_ld(slab, t, ct), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        sum[i] += f[i];
+        sq[i] = fmaf(f[i], f[i], sq[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    s_sum[rg][ct * 8 + i] = sum[i];
+    s_sq[rg][ct * 8 + i] = sq[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < LN_SLAB) {
+    float a = 0.f, q = 0.f;
+    for (int g = 0; g < LN_RG; ++g) {
+      a += s_sum[g][threadIdx.x];
+      q += s_sq[g][threadIdx.x];
+    }
+    const float mu = a / (float)T;
+    const float var = fmaxf(q / (float)T - mu * mu, 0.f);
+    const float rs = rsqrtf(var + eps);
+    s_mean[threadIdx.x] = mu;
+    s_rstd[threadIdx.x] = rs;
+    if (c0 + threadIdx.x < C) {
+      mean[(long long)b * C + c0 + threadIdx.x] = mu;
+      rstd[(long long)b * C + c0 + threadIdx.x] = rs;
+    }
+  }
+  __syncthreads();
+  if (!active) return;
+  float mu[8], sc[8], sh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    mu[i] = s_mean[ct * 8 + i];
+    sc[i] = s_rstd[ct * 8 + i] * gamma[c + i];
+    sh[i] = beta[c + i];
+  }
+  __nv_bfloat16* yb = y + (long long)b * T * C + c;
+#pragma unroll 4
+  for (int t = rg; t < T; t += LN_RG) {
+    float f[8];
+    unpack8(slab_ld(slab, t, ct), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i] - mu[i], sc[i], sh[i]);
+    st_na_v4(yb + (long long)t * C, pack8(f));
+  }
+}
+
+// Backward keeps TWO slabs (x and dy), so it works on 32-feature slabs: 2 x T x 64 bytes (69 KB at T = 536) lets three
+// CTAs share an SM, and their load / statistics / write phases overlap.  (With 64-feature slabs only one CTA fits and
+// the kernel was slower than the L2 version.)  64-byte rows need no swizzle: 8 consecutive threads read 128 contiguous
+// bytes.  Two CTAs with adjacent slabs fetch the two halves of the same 128-byte lines at about the same time.
+constexpr int LNB_CPR = 4;                      // 16-byte chunks per row
+constexpr int LNB_SLAB = LNB_CPR * 8;           // 32 features
+constexpr int LNB_RG = LN_THREADS / LNB_CPR;    // 64 row groups = one 64-row box per step
+static_assert(LNB_RG == LN_BOX, "one row per thread per box");
+constexpr int LNB_MAX_BOXES = 10;               // the backward slab path keeps one residual row per box in registers: T <= 640
+
+__global__ void __launch_bounds__(LN_THREADS)
+ln_seq_bwd_smem_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dy, int B, int T, int C,
+                       const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+                       const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx, float* __restrict__ partial) {
+  extern __shared__ uint8_t ln_smem_raw[];
+  uint8_t* slab_x = ln_smem_raw + ((128u - (smem_u32(ln_smem_raw) & 127u)) & 127u);
+  const int nb = ln_boxes(T);
+  constexpr int BOX_BYTES = LN_BOX * LNB_SLAB * 2;  // 4 KB
+  uint8_t* slab_d = slab_x + (size_t)nb * BOX_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(slab_d + (size_t)nb * BOX_BYTES);
+  __shared__ float s_a[LN_THREADS / 32][LNB_SLAB + 1];   // per-warp partial sums (the 8 row groups of a warp are shuffle-reduced first)
+  __shared__ float s_b[LN_THREADS / 32][LNB_SLAB + 1];
+  __shared__ float s_A[LNB_SLAB], s_B[LNB_SLAB];
+  const int b = blockIdx.y, c0 = blockIdx.x * LNB_SLAB;
+  const int ct = threadIdx.x & (LNB_CPR - 1), rg = threadIdx.x / LNB_CPR;
+  const int c = c0 + ct * 8;
+  const bool active = c < C;
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < nb; ++k) mbar_init(&bars[k], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < nb; ++k) {
+      mbar_expect_tx(&bars[k], 2 * BOX_BYTES);
+      tma_load_3d(slab_x + (size_t)k * BOX_BYTES, &tm_x, &bars[k], c0, k * LN_BOX, b);  // rows past T / columns past C arrive as zeros
+      tma_load_3d(slab_d + (size_t)k * BOX_BYTES, &tm_dy, &bars[k], c0, k * LN_BOX, b);
+    }
+  }
+  // the residual-branch gradient rows this thread will add in the second pass: requested NOW, so their latency hides
+  // behind the TMA loads and the statistics pass (nb <= LNB_MAX_BOXES on this path)
+  const long long base = (long long)b * T * C + c;
+  uint4 rv[LNB_MAX_BOXES];
+#pragma unroll
+  for (int k = 0; k < LNB_MAX_BOXES; ++k) {
+    const int t = k * LN_BOX + rg;
+    rv[k] = (dres && active && t < T) ? ld_nc_v4(dres + base + (long long)t * C) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  float mu[8], rs[8];
+  float sa[8], sb[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sa[i] = sb[i] = 0.f;
+    mu[i] = active ? mean[(long long)b * C + c + i] : 0.f;
+    rs[i] = active ? rstd[(long long)b * C + c + i] : 0.f;
+  }
+  const size_t my = (size_t)rg * (LNB_SLAB * 2) + ct * 16;  // this thread's 16 bytes inside a box
+  for (int k = 0; k < nb; ++k) {
+    mbar_wait(&bars[k], 0);
+    float fx[8], fd[8];   // row k * 64 + rg; rows past T hold dy = 0 and add nothing
+    unpack8(*reinterpret_cast<const uint4*>(slab_x + (size_t)k * BOX_BYTES + my), fx);
+    unpack8(*reinterpret_cast<const uint4*>(slab_d + (size_t)k * BOX_BYTES + my), fd);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sa[i] += fd[i];
+      sb[i] = fmaf(fd[i], (fx[i] - mu[i]) * rs[i], sb[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {  // lanes l, l^4, l^8, l^16 hold the same features of different row groups
+#pragma unroll
+    for (int o = LNB_CPR; o < 32; o <<= 1) {
+      sa[i] += __shfl_xor_sync(0xffffffffu, sa[i], o);
+      sb[i] += __shfl_xor_sync(0xffffffffu, sb[i], o);
+    }
+  }
+  if ((threadIdx.x & 31) < LNB_CPR) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s_a[threadIdx.x >> 5][ct * 8 + i] = sa[i];
+      s_b[threadIdx.x >> 5][ct * 8 + i] = sb[i];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < LNB_SLAB) {
+    float a = 0.f, q = 0.f;
+#pragma unroll
+    for (int g = 0; g < LN_THREADS / 32; ++g) {
+      a += s_a[g][threadIdx.x];
+      q += s_b[g][threadIdx.x];
+    }
+    s_A[threadIdx.x] = a;
+    s_B[threadIdx.x] = q;
+    if (c0 + threadIdx.x < C) {
+      partial[(long long)b * C + c0 + threadIdx.x] = a;
+      partial[(long long)(B + b) * C + c0 + threadIdx.x] = q;
+    }
+  }
+  __syncthreads();
+  if (!active) return;
+  const float inv_t = 1.0f / (float)T;
+  float k0[8], k1[8], k2[8];  // dx = k0*dy + k1*xhat + k2
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float g = rs[i] * gamma[c + i];
+    k0[i] = g;
+    k1[i] = -g * s_B[ct * 8 + i] * inv_t;
+    k2[i] = -g * s_A[ct * 8 + i] * inv_t;
+  }
+#pragma unroll
+  for (int k = 0; k < LNB_MAX_BOXES; ++k) {
+    const int t = k * LN_BOX + rg;
+    if (t < T) {
+      float fx[8], fd[8], o[8];
+      unpack8(*reinterpret_cast<const uint4*>(slab_x + (size_t)k * BOX_BYTES + my), fx);
+      unpack8(*reinterpret_cast<const uint4*>(slab_d + (size_t)k * BOX_BYTES + my), fd);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = fmaf(k0[i], fd[i], fmaf(k1[i], (fx[i] - mu[i]) * rs[i], k2[i]));
+      if (dres) {
+        float fr[8];
+        unpack8(rv[k], fr);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += fr[i];
+      }
+      st_na_v4(dx + base + (long long)t * C, pack8(o));
+    }
   }
 }
 
@@ -205,6 +436,45 @@ colsum_partial_kernel(int M, int N, long long ldx, int rows_per_chunk, const __n
     for (int m = m0 + rg; m < m1; m += LN_RG) {
       float f[8];
       unpack8(ld_nc_v4(x + (long long)m * ldx + c), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sum[i] += f[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s_sum[rg][ct * 8 + i] = sum[i];
+  __syncthreads();
+  if (threadIdx.x < LN_SLAB && c0 + threadIdx.x < N) {
+    float a = 0.f;
+    for (int g = 0; g < LN_RG; ++g) a += s_sum[g][threadIdx.x];
+    ws[(long long)chunk * N + c0 + threadIdx.x] = a;
+  }
+}
+
+// y = dropout(x) with the GEMM epilogue's stream for element (m, n), and ws[chunk, n] = sum over the chunk's rows of y:
+// the backward of a "dropout -> Dense" pair needs both, and one pass over x serves them (it used to be two kernels
+// and two reads).
+__global__ void __launch_bounds__(LN_THREADS)
+dropout_colsum_kernel(int M, int N, int rows_per_chunk, const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                      DropoutCfg d, float* __restrict__ ws) {
+  __shared__ float s_sum[LN_RG][LN_SLAB + 1];
+  const int chunk = blockIdx.y, c0 = blockIdx.x * LN_SLAB;
+  const int ct = threadIdx.x & 7, rg = threadIdx.x >> 3;
+  const int c = c0 + ct * 8;
+  const int m0 = chunk * rows_per_chunk, m1 = min(M, m0 + rows_per_chunk);
+  float sum[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum[i] = 0.f;
+  if (c < N) {
+#pragma unroll 4
+    for (int m = m0 + rg; m < m1; m += LN_RG) {
+      float f[8];
+      unpack8(ld_nc_v4(x + (long long)m * N + c), f);
+      const uint32_t keep = dropout_keep8(d, (uint32_t)m, (uint32_t)c);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = ((keep >> i) & 1u) ? f[i] * d.inv_keep : 0.f;
+      const uint4 o = pack8(f);
+      st_na_v4(y + (long long)m * N + c, o);
+      unpack8(o, f);  // sum what the GEMMs will read (the bf16-rounded values), like the separate colsum did
 #pragma unroll
       for (int i = 0; i < 8; ++i) sum[i] += f[i];
     }
@@ -352,6 +622,10 @@ using namespace tome;
 
 extern "C" int tome_colsum_workspace_rows(int m) { return colsum_rows(m); }
 
+static int g_ln_smem_fwd = 1, g_ln_smem_bwd = 1;
+/* tuning aid (not part of the public header): bit 0 = forward, bit 1 = backward may take the shared-memory-slab kernels */
+extern "C" void tome_ln_set_smem_path(int mask) { g_ln_smem_fwd = mask & 1; g_ln_smem_bwd = (mask >> 1) & 1; }
+
 extern "C" int tome_colsum_bf16(int m, int n, const void* x, long long ldx, float* out, int accumulate, float* workspace,
                                 void* stream_) {
   clear_error();
@@ -364,7 +638,31 @@ extern "C" int tome_colsum_bf16(int m, int n, const void* x, long long ldx, floa
   dim3 grid(ceil_div(n, LN_SLAB), chunks);
   colsum_partial_kernel<<<grid, LN_THREADS, 0, stream>>>(m, n, ldx, rpc, reinterpret_cast<const __nv_bfloat16*>(x), workspace);
   TOME_CUDA(cudaGetLastError());
-  reduce_rows_kernel<<<ceil_div(n, 32), 256, 0, stream>>>(chunks, n, workspace, out, accumulate);
+  reduce_rows_kernel<<<ceil_div(n, 32), 256, 0, stream>>>(chunks, n, workspace, 0, out, out, accumulate);
+  TOME_CUDA(cudaGetLastError());
+  return TOME_OK;
+}
+
+extern "C" int tome_dropout_colsum_bf16(int m, int n, const void* x, void* y, float rate, uint64_t seed, uint32_t site,
+                                        float* out, int accumulate, float* workspace, void* stream_) {
+  clear_error();
+  cudaStream_t stream = (cudaStream_t)stream_;
+  TOME_CHECK(m > 0 && n > 0 && x && y && out && workspace, TOME_ERR_INVALID, "dropout_colsum: bad argument");
+  TOME_CHECK(n % 8 == 0, TOME_ERR_INVALID, "dropout_colsum: n must be a multiple of 8");
+  TOME_CHECK(rate >= 0.f && rate < 1.f, TOME_ERR_INVALID, "dropout_colsum: rate must be in [0, 1)");
+  DropoutCfg d;
+  d.thresh16 = (uint32_t)(rate * 65536.0f + 0.5f);
+  d.inv_keep = 1.0f / (1.0f - (float)d.thresh16 / 65536.0f);
+  d.seed_lo = (uint32_t)seed; d.seed_hi = (uint32_t)(seed >> 32);
+  d.site = site;
+  const int chunks = colsum_rows(m);
+  ProfScope prof(PROF_COLSUM, (double)m * n * 4.0, 2, stream);
+  const int rpc = ceil_div(m, chunks);
+  dim3 grid(ceil_div(n, LN_SLAB), chunks);
+  dropout_colsum_kernel<<<grid, LN_THREADS, 0, stream>>>(m, n, rpc, reinterpret_cast<const __nv_bfloat16*>(x),
+                                                         reinterpret_cast<__nv_bfloat16*>(y), d, workspace);
+  TOME_CUDA(cudaGetLastError());
+  reduce_rows_kernel<<<ceil_div(n, 32), 256, 0, stream>>>(chunks, n, workspace, 0, out, out, accumulate);
   TOME_CUDA(cudaGetLastError());
   return TOME_OK;
 }
@@ -383,7 +681,19 @@ extern "C" int tome_layernorm_fwd(int batch, int tokens, int channels, int axis,
   if (axis == 1) {
     TOME_CHECK(batch <= 65535, TOME_ERR_INVALID, "layernorm_fwd: batch too large");
     dim3 grid(ceil_div(channels, LN_SLAB), batch);
-    ln_seq_fwd_kernel<<<grid, LN_THREADS, 0, stream>>>(tokens, channels, eps, xp, gamma, beta, yp, mean, rstd);
+    if (g_ln_smem_fwd && tokens <= LN_SMEM_T_FWD && ((uintptr_t)x & 15) == 0) {
+      CUtensorMap tx;
+      if (int rc = make_tmap_3d_bf16(&tx, x, channels, tokens, batch, channels, (uint64_t)tokens * channels, LN_BOX)) return rc;
+      const int smem = ln_boxes(tokens) * LN_BOX * 128 + ln_boxes(tokens) * 8 + 1024;
+      static int smem_set = 0;
+      if (smem > smem_set) {
+        TOME_CUDA(cudaFuncSetAttribute(ln_seq_fwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        smem_set = smem;
+      }
+      ln_seq_fwd_smem_kernel<<<grid, LN_THREADS, smem, stream>>>(tx, tokens, channels, eps, gamma, beta, yp, mean, rstd);
+    } else {
+      ln_seq_fwd_kernel<<<grid, LN_THREADS, 0, stream>>>(tokens, channels, eps, xp, gamma, beta, yp, mean, rstd);
+    }
   } else {
     const long long rows = (long long)batch * tokens;
     ln_feat_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(rows, channels, eps, xp, gamma, beta, yp, mean, rstd);
@@ -410,7 +720,21 @@ extern "C" int tome_layernorm_bwd(int batch, int tokens, int channels, int axis,
   if (axis == 1) {
     TOME_CHECK(batch <= 65535, TOME_ERR_INVALID, "layernorm_bwd: batch too large");
     dim3 grid(ceil_div(channels, LN_SLAB), batch);
-    ln_seq_bwd_kernel<<<grid, LN_THREADS, 0, stream>>>(batch, tokens, channels, xp, dyp, gamma, mean, rstd, drp, dxp, partial);
+    if (g_ln_smem_bwd && tokens <= LN_SMEM_T_BWD && (((uintptr_t)x | (uintptr_t)dy) & 15) == 0) {
+      CUtensorMap tx, tdy;
+      if (int rc = make_tmap_3d_bf16_plain(&tx, x, channels, tokens, batch, channels, (uint64_t)tokens * channels, LNB_SLAB, LN_BOX)) return rc;
+      if (int rc = make_tmap_3d_bf16_plain(&tdy, dy, channels, tokens, batch, channels, (uint64_t)tokens * channels, LNB_SLAB, LN_BOX)) return rc;
+      const int smem = 2 * ln_boxes(tokens) * LN_BOX * LNB_SLAB * 2 + ln_boxes(tokens) * 8 + 128;
+      static int smem_set = 0;
+      if (smem > smem_set) {
+        TOME_CUDA(cudaFuncSetAttribute(ln_seq_bwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        smem_set = smem;
+      }
+      grid = dim3(ceil_div(channels, LNB_SLAB), batch);
+      ln_seq_bwd_smem_kernel<<<grid, LN_THREADS, smem, stream>>>(tx, tdy, batch, tokens, channels, gamma, mean, rstd, drp, dxp, partial);
+    } else {
+      ln_seq_bwd_kernel<<<grid, LN_THREADS, 0, stream>>>(batch, tokens, channels, xp, dyp, gamma, mean, rstd, drp, dxp, partial);
+    }
     chunks = batch;
   } else {
     const long long rows = (long long)batch * tokens;
@@ -422,9 +746,8 @@ extern "C" int tome_layernorm_bwd(int batch, int tokens, int channels, int axis,
     ln_feat_param_grad_kernel<<<grid, LN_THREADS, 0, stream>>>(rows, channels, rpc, chunks, xp, dyp, mean, rstd, partial);
   }
   TOME_CUDA(cudaGetLastError());
-  reduce_rows_kernel<<<ceil_div(channels, 32), 256, 0, stream>>>(chunks, channels, partial, dbeta, 1);
-  reduce_rows_kernel<<<ceil_div(channels, 32), 256, 0, stream>>>(chunks, channels, partial + (long long)chunks * channels,
-                                                                 dgamma, 1);
+  reduce_rows_kernel<<<dim3(ceil_div(channels, 32), 2), 256, 0, stream>>>(chunks, channels, partial, (long long)chunks * channels,
+                                                                          dbeta, dgamma, 1);
   TOME_CUDA(cudaGetLastError());
   return TOME_OK;
 }

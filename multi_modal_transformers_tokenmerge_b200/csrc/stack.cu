@@ -211,25 +211,6 @@ __global__ void broadcast_groups_kernel(int B, int T, const uint8_t* __restrict_
   }
 }
 
-// dy_eff = dy * keep / (1 - rate), same stream as the GEMM epilogue (element (row, col) of the [rows, n] tensor)
-__global__ void dropout_apply_kernel(long long n8_total, int n8_per_row, const __nv_bfloat16* __restrict__ x,
-                                     __nv_bfloat16* __restrict__ y, DropoutCfg d) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8_total; i += (long long)gridDim.x * blockDim.x) {
-    const uint4 v = ld_nc_v4(reinterpret_cast<const uint4*>(x) + i);
-    const uint32_t row = (uint32_t)(i / n8_per_row), col = (uint32_t)(i - (long long)row * n8_per_row) * 8u;
-    const uint32_t keep = dropout_keep8(d, row, col);
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    uint32_t o[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float lo = ((keep >> (2 * j)) & 1u) ? bf16_lo(w[j]) * d.inv_keep : 0.f;
-      const float hi = ((keep >> (2 * j + 1)) & 1u) ? bf16_hi(w[j]) * d.inv_keep : 0.f;
-      o[j] = pack_bf16(lo, hi);
-    }
-    reinterpret_cast<uint4*>(y)[i] = make_uint4(o[0], o[1], o[2], o[3]);
-  }
-}
-
 static DropoutCfg make_drop(const tome_stack_cfg_t* c, uint32_t site) {
   DropoutCfg d;
   d.thresh16 = (uint32_t)(c->dropout_rate * 65536.0f + 0.5f);
@@ -396,14 +377,16 @@ extern "C" int tome_stack_backward(const tome_stack_cfg_t* c, const tome_stack_i
   // dL/dx_final (and the loss value again, harmless) from the readout rows
   RC(tome_readout_mse(B, TL, C, c->n_readout, S.L.back().x_out, S.origin, io->target, io->loss, g0, nullptr, st));
 
-  auto masked = [&](const __nv_bfloat16* src, __nv_bfloat16* dst, long long rows, int ncols, int site) -> const __nv_bfloat16* {
-    if (!drop) return src;
-    const long long n8 = rows * ncols / 8;
-    long long blocks = (n8 + 255) / 256;
-    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-    ProfScope prof(PROF_OTHER, 0.0, 1, st);
-    dropout_apply_kernel<<<(unsigned)blocks, 256, 0, st>>>(n8, ncols / 8, src, dst, make_drop(c, (uint32_t)site));
-    return dst;
+  // dy_eff = dropout mask applied to an incoming gradient + its column sums (the Dense bias gradient), one pass
+  auto masked_colsum = [&](const __nv_bfloat16* src, __nv_bfloat16* dst, int rows, int ncols, int site, float* dbias,
+                           const __nv_bfloat16** out) -> int {
+    if (!drop) {
+      *out = src;
+      return tome_colsum_bf16(rows, ncols, src, ncols, dbias, 1, S.ws_colsum, st);
+    }
+    *out = dst;
+    return tome_dropout_colsum_bf16(rows, ncols, src, dst, c->dropout_rate, c->dropout_seed, (uint32_t)site, dbias, 1,
+                                    S.ws_colsum, st);
   };
 
   for (int l = c->layers - 1; l >= 0; --l) {
@@ -412,8 +395,8 @@ extern "C" int tome_stack_backward(const tome_stack_cfg_t* c, const tome_stack_i
     const int T = S.shapes[l].t_in, r = S.shapes[l].r, To = S.shapes[l].t_out;
     const int M = B * T, Mo = B * To;
     // ---- MLP: y = x1m + drop2(m1 W2 + b2),  m1 = drop1(relu(h2 W1 + b1))          d_out in g0
-    const __nv_bfloat16* dy2 = masked(g0, g2, Mo, C, 3 * l + 2);
-    RC(tome_colsum_bf16(Mo, C, dy2, C, gr + o.b2, 1, S.ws_colsum, st));
+    const __nv_bfloat16* dy2;
+    RC(masked_colsum(g0, g2, Mo, C, 3 * l + 2, gr + o.b2, &dy2));
     RC(gemm(c, S, st, F, C, Mo, Lb.m1, F, TOME_MAJOR_MN, dy2, C, TOME_MAJOR_MN, gr + o.w2, C, TOME_F32, nullptr, 0, nullptr,
             nullptr, 1.f, -1, 1));
     RC(gemm(c, S, st, Mo, F, C, dy2, C, TOME_MAJOR_K, pw + o.w2, C, TOME_MAJOR_K, S.big, F, TOME_BF16, nullptr, 0, nullptr, Lb.m1,
@@ -437,8 +420,8 @@ extern "C" int tome_stack_backward(const tome_stack_cfg_t* c, const tome_stack_i
       __nv_bfloat16* t = g0; g0 = g2; g2 = t;  // keep "dx1 lives in g0"
     }
     // ---- out projection: x1 = x + drop0(o Wo + bo)
-    const __nv_bfloat16* dyo = masked(dx1, g1, M, C, 3 * l + 0);
-    RC(tome_colsum_bf16(M, C, dyo, C, gr + o.bo, 1, S.ws_colsum, st));
+    const __nv_bfloat16* dyo;
+    RC(masked_colsum(dx1, g1, M, C, 3 * l + 0, gr + o.bo, &dyo));
     RC(gemm(c, S, st, HD, C, M, Lb.attn_o, HD, TOME_MAJOR_MN, dyo, C, TOME_MAJOR_MN, gr + o.wo, C, TOME_F32, nullptr, 0, nullptr,
             nullptr, 1.f, -1, 1));
     RC(gemm(c, S, st, M, HD, C, dyo, C, TOME_MAJOR_K, pw + o.wo, C, TOME_MAJOR_K, g3, HD, TOME_BF16, nullptr, 0, nullptr, nullptr,

@@ -120,6 +120,15 @@ def bench_attn():
 
 
 def bench_ln():
+    from multi_modal_transformers_tokenmerge_b200 import _lib
+    for mask in (0, 3):
+        _lib.lib().tome_ln_set_smem_path(mask)
+        print("shared-memory slab path:", "on" if mask else "off")
+        _bench_ln()
+    _lib.lib().tome_ln_set_smem_path(3)
+
+
+def _bench_ln():
     for (B, T, C) in [(256, 536, 384), (256, 536, 768)]:
         x = torch.randn(B, T, C, device="cuda").bfloat16()
         g = torch.ones(C, device="cuda")
@@ -130,8 +139,9 @@ def bench_ln():
             print(f"ln_fwd axis{axis} B{B} T{T} C{C}: {t*1e6:8.1f} us {by/t/1e9:7.1f} GB/s")
             y, mean, rstd = ops.layernorm_fwd(x, g, b, 1e-6, axis)
             dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
-            t = timeit(lambda: ops.layernorm_bwd(x, y, g, mean, rstd, dg, db, None, axis))
-            print(f"ln_bwd axis{axis} B{B} T{T} C{C}: {t*1e6:8.1f} us {1.5*by/t/1e9:7.1f} GB/s")
+            dres = torch.randn_like(x)
+            t = timeit(lambda: ops.layernorm_bwd(x, y, g, mean, rstd, dg, db, dres, axis))
+            print(f"ln_bwd axis{axis} B{B} T{T} C{C}: {t*1e6:8.1f} us {2.0*by/t/1e9:7.1f} GB/s")
 
 
 if __name__ == "__main__":
