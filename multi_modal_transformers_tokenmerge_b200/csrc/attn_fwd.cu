@@ -253,9 +253,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           s[32 + i] = ((vw1 >> i) & 1u) ? s[32 + i] : -FLT_MAX;
         }
       }
-      float m_tile = fmaxf(s[0], s[1]);
+      float mt[4];  // four independent maxima: a single 31-deep dependent chain would serialise on the ALU latency
 #pragma unroll
-      for (int i = 2; i < ATT_BN; i += 2) m_tile = fmaxf(m_tile, fmaxf(s[i], s[i + 1]));
+      for (int c = 0; c < 4; ++c) mt[c] = fmaxf(s[16 * c], s[16 * c + 1]);
+#pragma unroll
+      for (int i = 2; i < 16; i += 2)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) mt[c] = fmaxf(mt[c], fmaxf(s[16 * c + i], s[16 * c + i + 1]));
+      float m_tile = fmaxf(fmaxf(mt[0], mt[1]), fmaxf(mt[2], mt[3]));
       // m_tile >= -FLT_MAX: every tile holds at least one key < T, whose logit is finite or -FLT_MAX
 
       if (j == 0) {
@@ -285,7 +290,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       // P = exp2(s2 - m_run) -> bf16, K-major 128B-swizzled A operand in shared memory buffer j&1
       if (j >= 2) mbar_wait(&pv_done[j & 1], ((j - 2) >> 1) & 1);  // P V_{j-2} has finished reading this buffer
       const float2 nm2 = make_float2(-m_run, -m_run);
-      float2 l2 = make_float2(0.f, 0.f);
+      float2 l2[4];  // four independent partial row sums (same reason as the maxima)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) l2[u] = make_float2(0.f, 0.f);
       uint8_t* prow = s_p + (j & 1) * ATT_P_BYTES + row * 128;
 #pragma unroll
       for (int ch = 0; ch < ATT_BN / 8; ++ch) {  // 8 chunks of 8 keys = 16 bytes
@@ -294,12 +301,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         for (int u = 0; u < 4; ++u) {
           const float2 d = __fadd2_rn(make_float2(s[ch * 8 + 2 * u], s[ch * 8 + 2 * u + 1]), nm2);
           const float2 e = make_float2(fast_exp2(d.x), fast_exp2(d.y));
-          l2 = __fadd2_rn(l2, e);
+          l2[u] = __fadd2_rn(l2[u], e);
           w[u] = pack_bf16(e.x, e.y);
         }
         *reinterpret_cast<uint4*>(prow + ((ch ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
       }
-      l_run += l2.x + l2.y;
+      const float2 lsum = __fadd2_rn(__fadd2_rn(l2[0], l2[1]), __fadd2_rn(l2[2], l2[3]));
+      l_run += lsum.x + lsum.y;
       fence_proxy_async_smem();  // P visible to the tensor core (async proxy)
       tc_fence_before();         // our TMEM reads of S_j / writes of O are ordered before the MMAs that follow
       mbar_arrive(&p_ready[j & 1]);
