@@ -96,12 +96,15 @@ def test_matching_and_merge_golden(ops, name):
     np.testing.assert_array_equal(um.cpu().numpy(), O.unmerge(oplan2, ox2))
 
 
-@pytest.mark.parametrize("T,r,H,D,C", [(536, 16, 6, 64, 384), (75, 10, 2, 32, 64), (1024, 256, 12, 64, 768)])
+# last three: BASELINE configs[3] (T0 = 2080, wrist + primary camera, 4 frames) and configs[4] (block microbench: 4096 x 1024
+# at merge ratios T/2 and T/16)
+@pytest.mark.parametrize("T,r,H,D,C", [(536, 16, 6, 64, 384), (75, 10, 2, 32, 64), (1024, 256, 12, 64, 768),
+                                       (2080, 64, 12, 64, 768), (4096, 2048, 2, 64, 1024), (4096, 256, 2, 64, 1024)])
 def test_matching_from_packed_keys_and_bf16_merge(ops, T, r, H, D, C):
     """metric = keys averaged over heads, read in place from a packed bf16 qkv buffer (the block's call site);
     bf16 merge vs oracle on the bf16-rounded inputs (fp32 arithmetic, one final rounding): bit-exact."""
     rng = np.random.default_rng(7)
-    B = 3
+    B = 3 if T <= 1024 else 2
     qkv = torch.tensor(rng.standard_normal((B, T, 3, H, D)).astype(np.float32)).cuda().bfloat16()
     nm, ni, sc = ops.sim_argmax(qkv, heads=H, dim=D, batch=B, tokens=T, batch_stride=T * 3 * H * D,
                                 token_stride=3 * H * D, head_stride=D, dump_scores=True, offset_elems=H * D)
@@ -214,7 +217,8 @@ def test_gemm_epilogues_and_splitk(ops):
 
 # ------------------------------------------------------------------------------------------------ LayerNorm
 @pytest.mark.parametrize("axis", [1, 2])
-@pytest.mark.parametrize("B,T,C", [(3, 74, 768), (4, 536, 384), (2, 33, 40)])
+# T = 700: forward from the shared-memory slab, backward from the two-pass L2 kernel; T = 1600: both two-pass
+@pytest.mark.parametrize("B,T,C", [(3, 74, 768), (4, 536, 384), (2, 33, 40), (2, 700, 72), (1, 1600, 64)])
 def test_layernorm_fwd_bwd(ops, axis, B, T, C):
     """vs oracle.layer_norm (flax LayerNorm as configured; axis 1 = tokens) + autograd.  bf16 I/O: forward 3e-2 abs,
     dx / dgamma / dbeta within 1e-2 relative L2."""
