@@ -214,6 +214,26 @@ int tome_attention_bwd(const tome_attn_desc_t* desc, const tome_attn_grad_stride
                        void* dv, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * 5b. Per-modality top-k pruning       tokenizers/token_compression.py:15-46 (compute_top_k_tokens): the sibling
+ *                                      compression path of SURVEY.md 8(f) rank 2
+ * ------------------------------------------------------------------------------------------------------------ */
+#define TOME_MAX_TOKEN_SETS 16
+typedef struct {
+  int batch, tokens, channels;
+  int dtype;        /* tome_dtype of the embeddings */
+  int n_sets;       /* token sets ("modalities"), in output order */
+  int set_start[TOME_MAX_TOKEN_SETS]; /* tokenset_idx[s][0] */
+  int set_n[TOME_MAX_TOKEN_SETS];     /* tokenset_idx[s][1] */
+  int set_k[TOME_MAX_TOKEN_SETS];     /* tokenset_k[s]: 0 <= k <= n (jax.lax.top_k raises otherwise) */
+  int score_planes; /* importance is [score_planes, B, T]; planes are summed in order before ranking (1 = plain [B,T]) */
+} tome_prune_desc_t;
+/* For every set keep the k highest-scoring tokens in descending score order (equal scores: lower index first, as
+ * jax.lax.top_k; NaN ranks above every number), sets concatenated in order:
+ * ids i32 [B, sum k] = kept token indices, out [B, sum k, C] = embeddings gathered through ids (bit copies). */
+int tome_topk_prune(const tome_prune_desc_t* desc, const void* embeddings, const float* importance, void* out,
+                    int32_t* ids, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * 6. Small fused steps around the block
  * ------------------------------------------------------------------------------------------------------------ */
 

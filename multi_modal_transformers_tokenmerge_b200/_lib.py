@@ -40,6 +40,11 @@ class PlanShape(C.Structure):
     _fields_ = [("batch", i32), ("tokens", i32), ("r", i32), ("distill_token", i32)]
 
 
+class PruneDesc(C.Structure):
+    _fields_ = [("batch", i32), ("tokens", i32), ("channels", i32), ("dtype", i32), ("n_sets", i32),
+                ("set_start", i32 * 16), ("set_n", i32 * 16), ("set_k", i32 * 16), ("score_planes", i32)]
+
+
 class MergeShape(C.Structure):
     _fields_ = [("batch", i32), ("tokens", i32), ("channels", i32), ("r", i32), ("distill_token", i32),
                 ("dtype", i32), ("mode", i32)]
@@ -122,6 +127,7 @@ def lib() -> C.CDLL:
             "tome_select_topr": [P(PlanShape), vp, vp, P(Plan), vp],
             "tome_merge_fwd": [P(MergeShape), P(Plan), vp, vp, vp, vp, vp, vp, vp, vp, vp],
             "tome_merge_bwd": [P(MergeShape), P(Plan), vp, vp, vp, vp, vp],
+            "tome_topk_prune": [P(PruneDesc), vp, vp, vp, vp, vp],
             "tome_gemm_workspace_bytes": [P(GemmArgs)],
             "tome_gemm_bf16": [P(GemmArgs), vp, C.c_size_t, vp],
             "tome_colsum_workspace_rows": [i32],

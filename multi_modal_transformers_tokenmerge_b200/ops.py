@@ -153,6 +153,25 @@ def merge_bwd(plan: MatchPlan, dy: torch.Tensor, size: Optional[torch.Tensor], s
 
 
 # ------------------------------------------------------------------------------------------------ dense
+def topk_prune(emb: torch.Tensor, importance: torch.Tensor, set_start, set_n, set_k):
+    """K9.  emb [B,T,C] (bf16 / fp32), importance fp32 [B,T] or [P,B,T] (planes summed in order).
+    Returns (out [B, sum k, C], ids int32 [B, sum k])."""
+    _need_cuda(emb, importance)
+    assert emb.dim() == 3 and emb.is_contiguous() and importance.is_contiguous() and importance.dtype == torch.float32
+    b, t, c = emb.shape
+    planes = 1 if importance.dim() == 2 else importance.shape[0]
+    assert tuple(importance.shape[-2:]) == (b, t), (importance.shape, emb.shape)
+    ns = len(set_k)
+    if not (1 <= ns <= 16):
+        raise ValueError(f"between 1 and 16 token sets are supported, got {ns}")
+    d = L.PruneDesc(b, t, c, _dt(emb), ns, (C.c_int32 * 16)(*set_start), (C.c_int32 * 16)(*set_n), (C.c_int32 * 16)(*set_k), planes)
+    ktot = int(sum(set_k))
+    out = torch.empty(b, ktot, c, dtype=emb.dtype, device=emb.device)
+    ids = torch.empty(b, ktot, dtype=torch.int32, device=emb.device)
+    L.check(L.lib().tome_topk_prune(C.byref(d), _ptr(emb), _ptr(importance), _ptr(out), _ptr(ids), _stream()))
+    return out, ids
+
+
 def gemm(a: torch.Tensor, b: torch.Tensor, *, m: int, n: int, k: int, a_major=L.TOME_MAJOR_K, b_major=L.TOME_MAJOR_K,
          lda=None, ldb=None, out: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16, bias=None, residual=None,
          gate=None, gate_scale=1.0, relu=False, dropout_rate=0.0, dropout_seed=0, dropout_site=0, k_splits=0,

@@ -2,6 +2,7 @@
 
 Mirror of multi_modal_transformers/tokenizers/token_compression.py (same names, argument meaning and return shapes):
 
+    x = compute_top_k_tokens(embeddings, importance_scores, tokenset_idx, tokenset_k)      # :15-46
     merge = bipartite_soft_matching(metric, r, class_token=False, distill_token=False)   # :54-112
     y = merge(x, mode="sum")                                                               # :90-109
     x, size = merge_wavg(merge, x, size=None)                                              # :114-129
@@ -30,6 +31,40 @@ import torch
 from .. import _lib as L
 from .. import ops
 
+
+### token pruning methods ###
+
+def compute_top_k_tokens(embeddings: torch.Tensor, importance_scores: torch.Tensor, tokenset_idx, tokenset_k) -> torch.Tensor:
+    """token_compression.py:15-46: top-k tokens per modality by importance score.
+
+    embeddings [T, C] and importance_scores [T] as in the reference (one sequence; its caller vmaps), or batched
+    [B, T, C] / [B, T].  tokenset_idx: (start_idx, num_tokens) per modality; tokenset_k: tokens to keep per modality.
+    Returns the kept embeddings, modalities concatenated in order, each in descending score order (jax.lax.top_k; equal
+    scores keep the lower index first).  One kernel launch (tome_topk_prune); `compute_top_k_tokens.last_ids` holds the
+    kept indices of the most recent call (additive; the reference discards them).
+
+    Note: the reference computes its importance scores as mean(attn_weights, axis=-1) -- a mean
+    over KEYS of rows that sum to one, i.e. the constant 1/T (compressed_attention.py:303-306) -- so with the
+    reference's own scores this function keeps the first k tokens of every modality.  Any score works here.
+    """
+    unbatched = embeddings.dim() == 2
+    if unbatched:
+        embeddings, importance_scores = embeddings.unsqueeze(0), importance_scores.unsqueeze(0)
+    if embeddings.dim() != 3 or importance_scores.shape != embeddings.shape[:2]:
+        raise ValueError(f"embeddings {tuple(embeddings.shape)} / importance_scores {tuple(importance_scores.shape)} do not match")
+    if len(tokenset_idx) != len(tokenset_k):
+        raise ValueError("tokenset_idx and tokenset_k must have one entry per modality")
+    starts, ns = [int(s[0]) for s in tokenset_idx], [int(s[1]) for s in tokenset_idx]
+    for n, k in zip(ns, tokenset_k):
+        if k > n:
+            raise ValueError(f"top_k: k = {k} exceeds the modality's {n} tokens")  # jax.lax.top_k raises likewise
+    out, ids = ops.topk_prune(embeddings.contiguous(), importance_scores.float().contiguous(), starts, ns,
+                              [int(k) for k in tokenset_k])
+    compute_top_k_tokens.last_ids = ids[0] if unbatched else ids
+    return out[0] if unbatched else out
+
+
+### token merging methods ###
 
 def do_nothing(x, mode=None):
     """token_compression.py:51"""

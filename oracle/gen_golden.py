@@ -6,6 +6,7 @@ The committed .npz fixtures are what tests/ read; this script documents how they
 
 Reference entry points executed:
   multi_modal_transformers/tokenizers/token_compression.py:54-129  bipartite_soft_matching, merge, merge_wavg
+  multi_modal_transformers/tokenizers/token_compression.py:15-46   compute_top_k_tokens
   multi_modal_transformers/tokenizers/token_sequencer.py:186-334   TokenSequence.generate_attention_mask,
                                                                    get_modality_idx
 """
@@ -94,6 +95,34 @@ def main():
     out["names"] = np.array(names)
     np.savez_compressed(os.path.join(OUT, "token_compression.npz"), **out)
     print("token_compression.npz:", names)
+
+    # ---------------- per-modality top-k pruning (token_compression.py:15-46) ----------------
+    # written to its own file so the matching goldens above stay byte-identical
+    prng = np.random.default_rng(20261019)
+    pcases = [
+        # name, T, C, tokenset_idx, tokenset_k, kind
+        ("two_sets", 40, 8, ((0, 16), (16, 24)), (4, 6), "normal"),
+        ("octo_like", 74, 16, ((0, 16), (16, 25), (45, 25)), (16, 10, 10), "normal"),   # prefix kept whole, images pruned
+        ("gaps", 64, 4, ((8, 20), (40, 24)), (5, 24), "normal"),                          # sets need not tile the sequence; k == n
+        ("ties", 32, 4, ((0, 32),), (7,), "ties"),                                        # equal scores: lower index first
+        ("constant", 48, 4, ((0, 16), (16, 32)), (3, 5), "constant"),                     # the reference's own 1/T scores
+        ("c2", 536, 32, ((0, 16), (16, 256), (272, 4), (276, 256), (532, 4)), (16, 192, 4, 192, 4), "normal"),
+    ]
+    po = {"names": np.array([c[0] for c in pcases])}
+    for name, T, C, sets, ks, kind in pcases:
+        emb = prng.standard_normal((T, C)).astype(np.float32)
+        if kind == "normal":
+            imp = prng.random(T).astype(np.float32)
+        elif kind == "ties":
+            imp = prng.integers(0, 4, size=T).astype(np.float32)
+        else:
+            imp = np.full(T, 1.0 / T, np.float32)
+        kept = tc.compute_top_k_tokens(jnp.asarray(emb), jnp.asarray(imp), sets, ks)   # the reference function itself
+        po[f"{name}/emb"], po[f"{name}/imp"] = emb, imp
+        po[f"{name}/sets"], po[f"{name}/ks"] = np.asarray(sets, np.int32), np.asarray(ks, np.int32)
+        po[f"{name}/kept"] = np.asarray(kept)
+    np.savez_compressed(os.path.join(OUT, "token_pruning.npz"), **po)
+    print("token_pruning.npz:", [c[0] for c in pcases])
 
     # ---------------- token sequence masks ----------------
     seqs = {

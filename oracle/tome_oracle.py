@@ -141,6 +141,18 @@ def merge_wavg(plan: MatchPlan, x: np.ndarray, size: Optional[np.ndarray] = None
     return x, size
 
 
+def compute_top_k_tokens(embeddings: np.ndarray, importance_scores: np.ndarray, tokenset_idx, tokenset_k):
+    """token_compression.py:15-46 for ONE sequence (embeddings [T, C], scores [T]).  jax.lax.top_k (:31): the k largest
+    values in descending order; equal values keep the lower index first (XLA's TopK is stable).  Returns (kept rows, ids)."""
+    ids = []
+    for k, (start, n) in zip(tokenset_k, tokenset_idx):
+        sub = np.asarray(importance_scores[start:start + n])                # dynamic_slice_in_dim (:41)
+        order = np.argsort(-sub, kind="stable")[:k]                         # top_k (:31)
+        ids.append(order.astype(np.int32) + np.int32(start))                # idx += seq_start_idx (:34)
+    ids = np.concatenate(ids, axis=-1)                                      # :44
+    return np.take(embeddings, ids, axis=0), ids                            # jnp.take(embeddings, ids, axis=0) (:46)
+
+
 def row_map(plan: MatchPlan) -> np.ndarray:
     """For every input row t of the layer, the row of the merged output it lands in.  [B,T] int32.
     (Derived from the concatenation order of token_compression.py:103-108.)"""

@@ -336,3 +336,47 @@ def test_sim_argmax_workspace_and_scratchless_paths_agree(ops, B, T, H, D):
         s = sc.cpu().numpy()
         np.testing.assert_array_equal(ni.cpu().numpy(), s.argmax(-1).astype(np.int32))
         np.testing.assert_array_equal(nm.cpu().numpy(), s.max(-1))
+
+
+# ------------------------------------------------------------------------------------------------ top-k pruning
+TP = np.load(os.path.join(GOLD, "token_pruning.npz"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", [str(n) for n in TP["names"]])
+def test_topk_prune_golden(ops, name):
+    """tome_topk_prune vs the goldens made by the reference's compute_top_k_tokens: kept rows and indices bit-exact, through
+    the reference-shaped Python function (unbatched call) and batched with per-row scores, in fp32 and bf16."""
+    from multi_modal_transformers_tokenmerge_b200.tokenizers import token_compression as TCm
+    emb, imp = TP[f"{name}/emb"], TP[f"{name}/imp"]
+    sets = [tuple(int(v) for v in s) for s in TP[f"{name}/sets"]]
+    ks = [int(k) for k in TP[f"{name}/ks"]]
+    kept = TCm.compute_top_k_tokens(dev(emb), dev(imp), sets, ks)
+    np.testing.assert_array_equal(kept.cpu().numpy(), TP[f"{name}/kept"])
+    _, oid = O.compute_top_k_tokens(emb, imp, sets, ks)
+    np.testing.assert_array_equal(TCm.compute_top_k_tokens.last_ids.cpu().numpy(), oid)
+    # batched, different scores per row, bf16 embeddings (16-byte rows need C % 8 == 0), scores split into two planes
+    if emb.shape[1] % 8 == 0:
+        rng = np.random.default_rng(3)
+        B = 3
+        embb = torch.tensor(rng.standard_normal((B,) + emb.shape).astype(np.float32)).cuda().bfloat16()
+        p0 = rng.integers(0, 3, size=(B, emb.shape[0])).astype(np.float32)
+        p1 = rng.integers(0, 3, size=(B, emb.shape[0])).astype(np.float32)
+        out, ids = ops.topk_prune(embb, dev(np.stack([p0, p1])), [s[0] for s in sets], [s[1] for s in sets], ks)
+        for b in range(B):
+            okept, oid = O.compute_top_k_tokens(embb[b].float().cpu().numpy(), p0[b] + p1[b], sets, ks)
+            np.testing.assert_array_equal(ids[b].cpu().numpy(), oid)
+            np.testing.assert_array_equal(out[b].float().cpu().numpy(), okept)
+
+
+@pytest.mark.gpu
+def test_topk_prune_errors_and_nan(ops):
+    from multi_modal_transformers_tokenmerge_b200 import _lib as L
+    emb = torch.zeros(1, 8, 4, device="cuda")
+    imp = torch.tensor([[0.5, float("nan"), 0.1, 0.9, 0.9, 0.2, 0.3, 0.0]], device="cuda")
+    _, ids = ops.topk_prune(emb, imp, [0], [8], [4])
+    assert ids[0].tolist() == [1, 3, 4, 0]            # NaN ranks above every number; equal scores keep the lower index first
+    with pytest.raises(L.TomeError):
+        ops.topk_prune(emb, imp, [0], [8], [9])       # k > n, as jax.lax.top_k
+    with pytest.raises(L.TomeError):
+        ops.topk_prune(emb, imp, [4], [8], [2])       # set leaves the sequence

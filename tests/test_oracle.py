@@ -112,3 +112,18 @@ def test_block_oracle_runs_and_grads_flow():
     loss.backward()
     assert all(t.grad is not None and torch.isfinite(t.grad).all() for p in params for t in p.tensors())
     assert pe.grad is not None
+
+
+def test_top_k_pruning_matches_reference_goldens():
+    """oracle.compute_top_k_tokens vs tests/golden/token_pruning.npz, which oracle/gen_golden.py produced by executing the
+    reference's own compute_top_k_tokens (token_compression.py:15-46): kept rows bit for bit, incl. tied and constant scores."""
+    g = np.load(os.path.join(GOLD, "token_pruning.npz"))
+    for name in [str(n) for n in g["names"]]:
+        sets = [tuple(int(v) for v in s) for s in g[f"{name}/sets"]]
+        ks = [int(k) for k in g[f"{name}/ks"]]
+        kept, ids = O.compute_top_k_tokens(g[f"{name}/emb"], g[f"{name}/imp"], sets, ks)
+        np.testing.assert_array_equal(kept, g[f"{name}/kept"], err_msg=name)
+        assert ids.shape == (sum(ks),) and len(set(ids.tolist())) == sum(ks)
+        if name == "constant":  # the reference's own importance scores are the constant 1/T: the first k of every set survive
+            want = np.concatenate([np.arange(s, s + k) for (s, _), k in zip(sets, ks)])
+            np.testing.assert_array_equal(ids, want)
