@@ -123,6 +123,16 @@ def cpu_reference_steps(cfgname, steps, warmup, sample_batch):
     return sample_batch * len(times) / sum(times), sum(times) / len(times), torch.get_num_threads(), T0
 
 
+def workload_config(args, world, B, T0):
+    """The `config` object both arms print: the workload is the same, only the implementation differs."""
+    c = CONFIGS[args.config]
+    return {"workload": f"{args.config} ToMe stack train step (BASELINE.json configs[{1 if args.config == 'octo_small' else 2}] shape)",
+            "global_batch": B * world, "per_gpu_batch": B, "tokens": T0, "layers": c["layers"], "channels": c["channels"],
+            "heads": c["heads"], "mlp_dim": c["mlp_dim"], "r_per_layer": c["r"], "mask": "block-causal group table",
+            "ln_axis": "tokens", "hidden_dropout": args.dropout, "attention_dropout": 0.0, "optimizer": "AdamW fp32 master",
+            "parallelism": f"dp{world}", "l2_policy": "inputs and activations (>= 1 GB/step) exceed the 126 MB L2"}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -134,7 +144,9 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.config} ToMe stack train step, restated reference on host CPU", "sample_batch": sb},
+        "config": dict(workload_config(args, int(os.environ.get("WORLD_SIZE", "1")), c["batch"], T0),
+                       reference_note=f"restated reference on the host CPU: each step is a bounded sample of {sb} of the "
+                                      f"{c['batch']} samples, plain SGD, no dropout"),
         "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -303,11 +315,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": f"{args.config} ToMe stack train step (BASELINE.json configs[1] shape)", "global_batch": B * world,
-                       "per_gpu_batch": B, "tokens": T0, "layers": c["layers"], "channels": C, "heads": c["heads"],
-                       "mlp_dim": c["mlp_dim"], "r_per_layer": c["r"], "mask": "block-causal group table", "ln_axis": "tokens",
-                       "hidden_dropout": args.dropout, "attention_dropout": 0.0, "optimizer": "AdamW fp32 master",
-                       "parallelism": f"dp{world}", "l2_policy": "inputs and activations (>= 1 GB/step) exceed the 126 MB L2"},
+            "config": workload_config(args, world, B, T0),
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "merge_roofline": merge_roof,

@@ -206,6 +206,21 @@ def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate=False
     return out
 
 
+def dropout_colsum(x: torch.Tensor, rate: float, seed: int, site: int, out: Optional[torch.Tensor] = None, accumulate=False):
+    """y = dropout(x) with the GEMM epilogue's mask for (seed, site, element) and the column sums of y, in one pass.
+    x bf16 [M, N] contiguous.  Returns (y, colsum fp32 [N])."""
+    _need_cuda(x)
+    assert x.dim() == 2 and x.is_contiguous() and x.dtype == torch.bfloat16
+    m, n = x.shape
+    y = torch.empty_like(x)
+    if out is None:
+        out = torch.zeros(n, dtype=torch.float32, device=x.device)
+    ws = torch.empty(L.lib().tome_colsum_workspace_rows(m), n, dtype=torch.float32, device=x.device)
+    L.check(L.lib().tome_dropout_colsum_bf16(m, n, _ptr(x), _ptr(y), float(rate), int(seed), int(site), _ptr(out), int(accumulate),
+                                             _ptr(ws), _stream()))
+    return y, out
+
+
 def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-6, axis: int = 1):
     _need_cuda(x)
     assert x.dtype == torch.bfloat16 and x.is_contiguous()

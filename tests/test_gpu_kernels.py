@@ -380,3 +380,33 @@ def test_topk_prune_errors_and_nan(ops):
         ops.topk_prune(emb, imp, [0], [8], [9])       # k > n, as jax.lax.top_k
     with pytest.raises(L.TomeError):
         ops.topk_prune(emb, imp, [4], [8], [2])       # set leaves the sequence
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("m,n", [(1000, 384), (4097, 1536), (130, 40)])
+@pytest.mark.parametrize("epilogue", ["specialised", "generic"])
+def test_dropout_mask_identical_in_forward_epilogue_and_backward_pass(ops, m, n, epilogue):
+    """Hidden dropout is never stored: the forward GEMM epilogue and the backward pass (tome_dropout_colsum_bf16) each
+    regenerate the mask from (seed, site, row, column).  A GEMM whose every output is exactly 1 exposes the epilogue's mask;
+    the backward pass over a tensor of ones must reproduce it bit for bit, and its column sums must be those of its output.
+    `generic` adds a ReLU-free, bias-free combination that takes the run-time-flag epilogue instead of a specialised one."""
+    k = 8
+    A = torch.full((m, k), 0.125, device="cuda").bfloat16()
+    W = torch.ones(k, n, device="cuda").bfloat16()
+    bias = torch.zeros(n, device="cuda")
+    resid = torch.zeros(m, n, device="cuda").bfloat16()
+    rate, seed, site = 0.1, 1234567, 17
+    if epilogue == "specialised":   # bias + dropout + residual: the out-projection / MLP-2 forward epilogue
+        fwd = ops.gemm(A, W, m=m, n=n, k=k, b_major=1, bias=bias, residual=resid, dropout_rate=rate, dropout_seed=seed, dropout_site=site)
+    else:                            # dropout alone: no specialisation exists, the generic epilogue runs
+        fwd = ops.gemm(A, W, m=m, n=n, k=k, b_major=1, dropout_rate=rate, dropout_seed=seed, dropout_site=site)
+    bwd, cs = ops.dropout_colsum(torch.ones(m, n, device="cuda").bfloat16(), rate, seed, site)
+    torch.cuda.synchronize()
+    assert torch.equal(fwd, bwd)
+    kept = (fwd != 0).float().mean().item()
+    assert abs(kept - 0.9) < 0.01
+    vals = fwd[fwd != 0].float().unique()
+    assert vals.numel() == 1 and abs(vals.item() - 1.0 / 0.9) < 1e-2      # inverted dropout scaling, rounded to bf16
+    assert (cs - bwd.float().sum(0)).abs().max().item() <= 1e-3 * m
+    other, _ = ops.dropout_colsum(torch.ones(m, n, device="cuda").bfloat16(), rate, seed, site + 1)
+    assert not torch.equal(other, bwd)                                       # another site draws another mask
