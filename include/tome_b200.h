@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TOME_ABI_VERSION 5
+#define TOME_ABI_VERSION 6
 
 enum tome_status { TOME_OK = 0, TOME_ERR_INVALID = 1, TOME_ERR_CUDA = 2, TOME_ERR_UNSUPPORTED = 3 };
 enum tome_dtype { TOME_BF16 = 0, TOME_F32 = 1 };
@@ -189,11 +189,18 @@ typedef struct {
   int num_groups;
   /* proportional attention (ToMe paper; not in the reference): logits += log(size[b,k]) */
   const float* size; /* [B,T] or NULL */
+  /* attention-weight dropout (flax dot_product_attention with dropout_rate > 0 and the default broadcast_dropout=True,
+   * vanilla_decoder.yaml:23): weights *= keep[q,k] / (1 - rate) after the softmax, ONE mask shared by every batch row
+   * and head.  keep[q,k] is regenerated from (seed, site, q, k) in forward and backward; 0 disables. */
+  float dropout_rate;
+  uint64_t dropout_seed;
+  uint32_t dropout_site;
 } tome_attn_desc_t;
 
 /* out [B,T,H,D] bf16, lse f32 [B,H,T] (natural-log sum-exp of the biased, masked, scaled logits).
- * workspace: tome_attention_workspace_bytes(desc) bytes of 16-byte-aligned device scratch (per-tile mask words and
- * log2(size) bias, built once per call and streamed into the kernel by bulk copies); contents need not be kept. */
+ * workspace: tome_attention_workspace_bytes(desc) bytes of 256-byte-aligned device scratch (per-tile mask words,
+ * log2(size) bias and, with dropout, the keep bits: built once per call and streamed into the kernel by bulk copies);
+ * contents need not be kept. */
 size_t tome_attention_workspace_bytes(const tome_attn_desc_t* desc);
 int tome_attention_fwd(const tome_attn_desc_t* desc, const void* q, const void* k, const void* v, void* out,
                        float* lse, void* workspace, size_t workspace_bytes, void* stream);
@@ -279,6 +286,7 @@ typedef struct {
   int n_readout;
   float dropout_rate; /* hidden dropout after out-proj, ReLU and dense_out (attention.py:34,37,60); 0 in parity mode */
   uint64_t dropout_seed;
+  float attn_dropout_rate; /* attention-weight dropout (self_attention.dropout_rate, vanilla_decoder.yaml:23), same seed */
 } tome_stack_cfg_t;
 
 /* Per-layer parameter offsets (elements) into one flat fp32 vector (master weights / gradients / Adam moments)
@@ -331,7 +339,9 @@ enum tome_prof_tag { TOME_PROF_GEMM = 0, TOME_PROF_ATTN_FWD, TOME_PROF_ATTN_BWD,
                      TOME_PROF_SIM, TOME_PROF_SELECT, TOME_PROF_LN, TOME_PROF_COLSUM, TOME_PROF_OTHER, TOME_PROF_NTAGS };
 /* number of kernels this library has launched in this process (reset != 0 zeroes the counter after reading) */
 long long tome_launch_count(int reset);
-/* bracket every op with a pair of CUDA events on its own stream (up to max_records ops) */
+/* record ONE CUDA event at the end of every op on its stream (up to max_records ops): op i is timed from the end of op
+ * i-1 (the first from a start event), so markers perturb short kernels half as much and inter-op gaps are charged to
+ * the op that follows them.  Meant for a single stream (the stack executor's). */
 int tome_profile_enable(int max_records);
 int tome_profile_disable(void);
 /* per tag: total milliseconds, total algorithmic work (FLOPs for GEMM / attention / sim, bytes for merge / LN /

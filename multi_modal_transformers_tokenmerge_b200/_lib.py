@@ -15,7 +15,7 @@ TOME_OK, TOME_ERR_INVALID, TOME_ERR_CUDA, TOME_ERR_UNSUPPORTED = 0, 1, 2, 3
 TOME_BF16, TOME_F32 = 0, 1
 TOME_MAJOR_K, TOME_MAJOR_MN = 0, 1
 TOME_MERGE_SUM, TOME_MERGE_WAVG = 0, 1
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 vp, ll, i32, f32, u64, u32 = C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_uint64, C.c_uint32
 
@@ -69,7 +69,7 @@ class AttnDesc(C.Structure):
                 ("v_batch_stride", ll), ("v_token_stride", ll), ("o_batch_stride", ll), ("o_token_stride", ll),
                 ("scale", f32),
                 ("gid", vp), ("pos", vp), ("allow", vp), ("num_groups", i32),
-                ("size", vp)]
+                ("size", vp), ("dropout_rate", f32), ("dropout_seed", u64), ("dropout_site", C.c_uint32)]
 
 
 class AttnGradStrides(C.Structure):
@@ -81,7 +81,7 @@ class StackCfg(C.Structure):
     _fields_ = [("batch", i32), ("tokens", i32), ("channels", i32), ("heads", i32), ("head_dim", i32),
                 ("mlp_dim", i32), ("layers", i32), ("r", i32), ("ln_axis", i32), ("ln_eps", f32),
                 ("prop_attn", i32), ("class_token", i32), ("distill_token", i32), ("num_groups", i32),
-                ("n_readout", i32), ("dropout_rate", f32), ("dropout_seed", u64)]
+                ("n_readout", i32), ("dropout_rate", f32), ("dropout_seed", u64), ("attn_dropout_rate", f32)]
 
 
 class StackIO(C.Structure):

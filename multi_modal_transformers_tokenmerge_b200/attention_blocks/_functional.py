@@ -108,7 +108,11 @@ def dense(p, x2d: torch.Tensor, *, relu=False, residual=None, dropout=0.0, seed=
                     residual=residual, dropout_rate=dropout, dropout_seed=seed, dropout_site=site)
 
 
-def attention(p, spec: AttentionSpec, x: torch.Tensor, mask: Optional[GroupMask], size: Optional[torch.Tensor]):
+ATTN_DROP_SITE = 0x40000000   # attention-weight dropout of layer l draws from site ATTN_DROP_SITE + l (csrc/stack.cu)
+
+
+def attention(p, spec: AttentionSpec, x: torch.Tensor, mask: Optional[GroupMask], size: Optional[torch.Tensor],
+              dropout_rate: float = 0.0, dropout_seed: int = 0, layer: int = 0):
     """query/key/value DenseGeneral (tome_attention.py:145-164) + dot_product_attention with the group mask and the
     log(size) bias (:259-285).  Returns (o [B,T,H*D] before the `out` projection, packed qkv [B,T,3,H,D])."""
     B, T, C = x.shape
@@ -126,7 +130,8 @@ def attention(p, spec: AttentionSpec, x: torch.Tensor, mask: Optional[GroupMask]
     kw = {}
     if mask is not None:
         kw = dict(gid=mask.gid, pos=mask.pos, allow=mask.allow)
-    o, _ = ops.attention_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], size=size, scale=1.0 / math.sqrt(D), **kw)
+    o, _ = ops.attention_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], size=size, scale=1.0 / math.sqrt(D),
+                             dropout_rate=dropout_rate, dropout_seed=dropout_seed, dropout_site=ATTN_DROP_SITE + layer, **kw)
     return o.view(B, T, H * D), qkv
 
 

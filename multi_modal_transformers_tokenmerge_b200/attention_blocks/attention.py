@@ -12,9 +12,10 @@ them; hydra's DictConfig behaves the same for the keys read here).  Modules are 
 (SURVEY.md A.5).  Inputs and outputs are CUDA torch tensors; activations are bf16, parameters fp32.
 
 Differences from the reference that a caller can observe (all listed in DESIGN.md):
-  * attention-weight dropout (`self_attention.dropout_rate`, yaml:23) is not implemented by the fused attention
-    kernel: with train=True and a non-zero rate the module raises unless `attention_dropout="ignore"` is set;
-    hidden dropout (yaml:17,50) is implemented (Philox, regenerated in backward) but its random stream is not Flax's;
+  * dropout: hidden dropout (yaml:17,50) and attention-weight dropout (`self_attention.dropout_rate`, yaml:23, with
+    flax's default broadcast_dropout=True: one [T,T] mask for all batch rows and heads) are implemented, regenerated in
+    backward from (seed, site, element) and never stored -- but the random stream is a counter-based LCG, not Flax's
+    threefry; `attention_dropout="ignore"` switches the attention-weight dropout off; broadcast_dropout=False raises;
   * `mask` may be the dense boolean array of octo.py:66-68 (converted to a group table on the host) or, on the fast
     path, a `GroupMask` / `TokenSequence`.
 """
@@ -123,10 +124,10 @@ class Encoder1DBlock(Module):
         ln, dr, at, mlp = self._specs()
         if not inputs.is_cuda:
             raise RuntimeError("Encoder1DBlock runs on CUDA (sm_100a) only; there is no CPU fallback")
-        if train and at.dropout_rate > 0.0 and self.attention_dropout != "ignore":
-            raise NotImplementedError(
-                "attention-weight dropout (self_attention.dropout_rate > 0 with train=True) is not implemented by the fused "
-                'attention kernel; set dropout_rate: 0 or construct the block with attention_dropout="ignore"')
+        if train and at.dropout_rate > 0.0 and not at.broadcast_dropout:
+            raise NotImplementedError("attention-weight dropout is implemented for flax's default broadcast_dropout=True (one "
+                                      "mask for all batch rows and heads); broadcast_dropout=False is not")
+        attn_rate = at.dropout_rate if (train and self.attention_dropout != "ignore") else 0.0
         B, T, C = inputs.shape
         x_in = F._bf16(inputs).contiguous()
         st = tome_state if tome_state is not None else F.ToMeState()
@@ -135,7 +136,8 @@ class Encoder1DBlock(Module):
         seed = _seed_of(dropout_rng)
         rate = dr.rate if train else 0.0
         x = F.layer_norm(params["LayerNorm_0"], ln, x_in)                                              # :58
-        o, qkv = F.attention(params[self._attn_name], at, x, st.mask, st.size if prop_attn else None)   # :59
+        o, qkv = F.attention(params[self._attn_name], at, x, st.mask, st.size if prop_attn else None,
+                             dropout_rate=attn_rate, dropout_seed=seed, layer=site // 3)                # :59
         x1 = F.dense(params[self._attn_name]["out"], o.reshape(B * T, -1), residual=x_in.reshape(B * T, C), dropout=rate,
                      seed=seed, site=site).view(B, T, C)                                               # :60-63
         if self.tome and r > 0:
@@ -207,17 +209,18 @@ class StackedEncoder1DBlock(Module):
         hd = at.qkv_features or C
         if abs(mdrop.rate - dr.rate) > 1e-12:
             raise NotImplementedError("the native stack uses one hidden dropout rate (yaml:17 and :50 agree in the reference)")
-        if train and at.dropout_rate > 0.0 and self._extra.get("attention_dropout", "error") != "ignore":
-            raise NotImplementedError("attention-weight dropout is not implemented; see Encoder1DBlock")
+        if train and at.dropout_rate > 0.0 and not at.broadcast_dropout:
+            raise NotImplementedError("attention-weight dropout needs broadcast_dropout=True; see Encoder1DBlock")
+        attn_rate = at.dropout_rate if (train and self._extra.get("attention_dropout", "error") != "ignore") else 0.0
         gm = None if mask is None else (mask if isinstance(mask, F.GroupMask) else F.group_mask_from_dense(mask))
         if gm is not None and gm.gid.dim() != 1:
             raise ValueError("the stack takes one group-id vector [T] (every batch row starts from the same sequence)")
-        key = (B, T, C, r, train, prop_attn, n_readout, dropout_seed, None if gm is None else gm.allow.shape[0])
+        key = (B, T, C, r, train, prop_attn, n_readout, dropout_seed, attn_rate, None if gm is None else gm.allow.shape[0])
         if self._engine is None or self._engine_key != key:
             cfg = StackConfig(batch=B, tokens=T, channels=C, heads=at.num_heads, head_dim=hd // at.num_heads, mlp_dim=d.features,
                               layers=self.num_blocks, r=r, ln_axis=ln.axis, ln_eps=ln.epsilon, prop_attn=prop_attn,
                               num_groups=0 if gm is None else int(gm.allow.shape[0]), n_readout=n_readout,
-                              dropout_rate=dr.rate if train else 0.0, dropout_seed=dropout_seed)
+                              dropout_rate=dr.rate if train else 0.0, dropout_seed=dropout_seed, attn_dropout_rate=attn_rate)
             self._engine = ToMeStackEngine(cfg, gid=None if gm is None else gm.gid.cpu().numpy(),
                                            pos=None if gm is None else gm.pos.cpu().numpy(),
                                            allow=None if gm is None else gm.allow.cpu().numpy(), readout_idx=readout_idx,

@@ -37,6 +37,9 @@ struct AttnBwdParams {
   const float* size;
   const float* lse2;    // [B,H,tp]  lse * log2(e), +inf past T
   const float* delta;   // [B,H,tp]  0 past T
+  const uint8_t* keep_q;  // attention dropout keep words in the dQ tiling [n_q128][n_k64][128][2], or null
+  const uint8_t* keep_k;  // ... in the dK/dV tiling [n_k128][n_q64][128][2]
+  float inv_keep;         // 1 / (1 - rate)
   __nv_bfloat16* dq; long long dq_bs, dq_ts;
   __nv_bfloat16* dk; long long dk_bs, dk_ts;
   __nv_bfloat16* dv; long long dv_bs, dv_ts;
@@ -80,9 +83,10 @@ static_assert(DKV_BQ == ATTN_META_TILE, "query tiles and metadata tiles must coi
 constexpr int DKV_KV_BYTES = DKV_BK * AB_D * 2;  // 16 KB
 constexpr int DKV_Q_BYTES = DKV_BQ * AB_D * 2;   // 8 KB
 constexpr int DKV_PT_BYTES = DKV_BK * DKV_BQ * 2;  // 16 KB
-constexpr int DKV_META_SLOT = 1280;  // lse2[64] | delta[64] | pos[64] | qvis[32][2] | qvisc[32][2]
+constexpr int DKV_META_SLOT = 1280 + ATTN_DROP_TILE_BYTES;  // lse2[64] | delta[64] | pos[64] | qvis[32][2] | qvisc[32][2] | dropout keep words [128 keys][2]
 constexpr int DKV_SMEM = 2 * DKV_KV_BYTES + 2 * 2 * DKV_Q_BYTES + 2 * DKV_PT_BYTES + AB_MSLOTS * DKV_META_SLOT + 256 + 1024;
 
+template <bool DROP>  // attention-weight dropout compiled in or not
 __global__ void __launch_bounds__(AB_THREADS, 2)
 attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                      const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
@@ -153,7 +157,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const int ms = i % AB_MSLOTS;
         uint8_t* slot = s_meta + ms * DKV_META_SLOT;
         mbar_wait(&meta_empty[ms], ((i / AB_MSLOTS) & 1) ^ 1);
-        mbar_expect_tx(&meta_full[ms], has_mask ? 1280u : 512u);
+        mbar_expect_tx(&meta_full[ms], (has_mask ? 1280u : 512u) + (DROP ? ATTN_DROP_TILE_BYTES : 0));
+        if constexpr (DROP) bulk_g2s(slot + 1280, p.keep_k + ((size_t)kt * n_q + i) * ATTN_DROP_TILE_BYTES, ATTN_DROP_TILE_BYTES, &meta_full[ms]);
         bulk_g2s(slot, lse_row + i * DKV_BQ, 256, &meta_full[ms]);
         bulk_g2s(slot + 256, del_row + i * DKV_BQ, 256, &meta_full[ms]);
         if (has_mask) bulk_g2s(slot + 512, meta_b + (size_t)i * ATTN_META_BYTES + ATTN_META_OFF_POS, 768, &meta_full[ms]);  // pos | qvis | qvisc
@@ -219,7 +224,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       }
     }
     const float2 scale2 = make_float2(p.scale_log2, p.scale_log2), bias22 = make_float2(bias2, bias2);
-    const float2 sc2 = make_float2(p.scale, p.scale);
+    const float2 sc2 = make_float2(p.scale, p.scale), ik2 = make_float2(p.inv_keep, p.inv_keep);
     for (int i = 0; i < n_q; ++i) {
       const int ms = i % AB_MSLOTS;
       const uint8_t* slot = s_meta + ms * DKV_META_SLOT;
@@ -238,6 +243,11 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         }
       }
       if (!k_valid) vw[0] = vw[1] = 0u;  // rows past T contribute nothing
+      uint32_t kb[2] = {0xffffffffu, 0xffffffffu};  // dropout keep bits of this key against the tile's 64 queries
+      if constexpr (DROP) {
+        const uint2 t = *reinterpret_cast<const uint2*>(slot + 1280 + row * 8);
+        kb[0] = t.x; kb[1] = t.y;
+      }
       const float4* lse4 = reinterpret_cast<const float4*>(slot);
       const float4* del4 = reinterpret_cast<const float4*>(slot + 256);
       mbar_wait(st_full, i & 1);
@@ -264,10 +274,19 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             float2 pe = make_float2(fast_exp2(t.x), fast_exp2(t.y));
             pe.x = ((word >> c) & 1u) ? pe.x : 0.f;
             pe.y = ((word >> (c + 1)) & 1u) ? pe.y : 0.f;
-            float2 g = __fadd2_rn(make_float2(dv[c], dv[c + 1]), make_float2(-dl.x, -dl.y));
+            // dropout (weights' = weights * keep / (1 - rate)): dP' = dP * keep / (1 - rate) enters dS, P' enters dV
+            float2 dp = make_float2(dv[c], dv[c + 1]), pd = pe;
+            if constexpr (DROP) {
+              const bool k0 = (kb[cq] >> c) & 1u, k1 = (kb[cq] >> (c + 1)) & 1u;
+              dp = __fmul2_rn(dp, ik2);
+              pd = __fmul2_rn(pd, ik2);
+              dp.x = k0 ? dp.x : 0.f; dp.y = k1 ? dp.y : 0.f;
+              pd.x = k0 ? pd.x : 0.f; pd.y = k1 ? pd.y : 0.f;
+            }
+            float2 g = __fadd2_rn(dp, make_float2(-dl.x, -dl.y));
             g = __fmul2_rn(g, sc2);
             g = __fmul2_rn(g, pe);
-            pw[c >> 1] = pack_bf16(pe.x, pe.y);
+            pw[c >> 1] = pack_bf16(pd.x, pd.y);
             dw[c >> 1] = pack_bf16(g.x, g.y);
           }
         }
@@ -324,9 +343,10 @@ static_assert(DQ_BK == ATTN_META_TILE, "key tiles and metadata tiles must coinci
 constexpr int DQ_Q_BYTES = DQ_BQ * AB_D * 2;   // 16 KB
 constexpr int DQ_K_BYTES = DQ_BK * AB_D * 2;   // 8 KB
 constexpr int DQ_DS_BYTES = DQ_BQ * DQ_BK * 2;  // 16 KB, x2 buffers
-constexpr int DQ_META_SLOT = ATTN_META_KEY_BYTES;  // bias2 | vis | visc | pos
+constexpr int DQ_META_SLOT = ATTN_META_KEY_BYTES + ATTN_DROP_TILE_BYTES;  // bias2 | vis | visc | pos | dropout keep words [128 queries][2]
 constexpr int DQ_SMEM = 2 * DQ_Q_BYTES + 2 * 2 * DQ_K_BYTES + 2 * DQ_DS_BYTES + AB_MSLOTS * DQ_META_SLOT + 256 + 1024;
 
+template <bool DROP>
 __global__ void __launch_bounds__(AB_THREADS, 2)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                    const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
@@ -393,8 +413,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       for (int j = 0; j < n_k; ++j) {
         const int ms = j % AB_MSLOTS;
         mbar_wait(&meta_empty[ms], ((j / AB_MSLOTS) & 1) ^ 1);
-        mbar_expect_tx(&meta_full[ms], meta_bytes);
+        mbar_expect_tx(&meta_full[ms], meta_bytes + (DROP ? ATTN_DROP_TILE_BYTES : 0));
         bulk_g2s(s_meta + ms * DQ_META_SLOT, meta_b + (size_t)j * ATTN_META_BYTES, meta_bytes, &meta_full[ms]);
+        if constexpr (DROP)
+          bulk_g2s(s_meta + ms * DQ_META_SLOT + ATTN_META_KEY_BYTES, p.keep_q + ((size_t)qt * n_k + j) * ATTN_DROP_TILE_BYTES,
+                   ATTN_DROP_TILE_BYTES, &meta_full[ms]);
         const int st = j & 1;
         mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
         mbar_expect_tx(&kv_full[st], 2 * DQ_K_BYTES);
@@ -454,6 +477,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const float2 scale2 = make_float2(p.scale_log2, p.scale_log2);
     const float2 nl2 = make_float2(-lse2, -lse2);
     const float2 sc2 = make_float2(p.scale, p.scale), nds2 = make_float2(-dl * p.scale, -dl * p.scale);
+    const float2 ik2 = make_float2(p.inv_keep, p.inv_keep);
     for (int j = 0; j < n_k; ++j) {
       const int ms = j % AB_MSLOTS;
       const uint8_t* slot = s_meta + ms * DQ_META_SLOT;
@@ -470,6 +494,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             if (((c.y >> i) & 1u) && m_pos[32 + i] <= pos_q) vw[1] |= 1u << i;
           }
         }
+      }
+      uint32_t kb[2] = {0xffffffffu, 0xffffffffu};  // dropout keep bits of this query against the tile's 64 keys
+      if constexpr (DROP) {
+        const uint2 t = *reinterpret_cast<const uint2*>(slot + ATTN_META_KEY_BYTES + row * 8);
+        kb[0] = t.x; kb[1] = t.y;
       }
       const float4* bias4 = reinterpret_cast<const float4*>(slot);
       uint8_t* dsb = s_ds + (j & 1) * DQ_DS_BYTES + row * 128;
@@ -496,7 +525,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             float2 pe = make_float2(fast_exp2(t.x), fast_exp2(t.y));
             pe.x = ((word >> c) & 1u) ? pe.x : 0.f;
             pe.y = ((word >> (c + 1)) & 1u) ? pe.y : 0.f;
-            float2 g = __ffma2_rn(make_float2(dv[c], dv[c + 1]), sc2, nds2);  // (dP - delta) * scale
+            float2 dp = make_float2(dv[c], dv[c + 1]);
+            if constexpr (DROP) {  // dP' = dP * keep / (1 - rate)
+              dp = __fmul2_rn(dp, ik2);
+              dp.x = ((kb[cq] >> c) & 1u) ? dp.x : 0.f;
+              dp.y = ((kb[cq] >> (c + 1)) & 1u) ? dp.y : 0.f;
+            }
+            float2 g = __ffma2_rn(dp, sc2, nds2);  // (dP' - delta) * scale
             g = __fmul2_rn(g, pe);
             dw[c >> 1] = pack_bf16(g.x, g.y);
           }
@@ -549,7 +584,8 @@ static size_t bwd_pad_elems(const tome_attn_desc_t* d) {
 
 extern "C" size_t tome_attention_bwd_workspace_bytes(const tome_attn_desc_t* d) {
   if (!d || d->batch <= 0 || d->tokens <= 0 || d->heads <= 0) return 0;
-  return align256(attn_meta_bytes(d->batch, d->tokens)) + 2 * align256(bwd_pad_elems(d) * sizeof(float));
+  return align256(attn_meta_bytes(d->batch, d->tokens)) + 2 * align256(bwd_pad_elems(d) * sizeof(float)) +
+         (d->dropout_rate > 0.f ? attn_dropbits_bytes(d->tokens) : 0);
 }
 
 extern "C" int tome_attention_bwd(const tome_attn_desc_t* d, const tome_attn_grad_strides_t* gs, const void* q, const void* k,
@@ -574,6 +610,17 @@ extern "C" int tome_attention_bwd(const tome_attn_desc_t* d, const tome_attn_gra
   float* delta = reinterpret_cast<float*>(meta + align256(attn_meta_bytes(B, T)));
   float* lse2 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(delta) + align256(bwd_pad_elems(d) * sizeof(float)));
   if (int rc = launch_attn_meta(B, T, d->gid, d->pos, d->allow, d->num_groups, d->size, meta, stream)) return rc;
+  TOME_CHECK(d->dropout_rate >= 0.f && d->dropout_rate < 1.f, TOME_ERR_INVALID, "attention_bwd: dropout_rate must be in [0, 1)");
+  const uint8_t *keep_q = nullptr, *keep_k = nullptr;
+  float inv_keep = 1.0f;
+  if (d->dropout_rate > 0.f) {  // the same (seed, site) as the forward call regenerates the same mask
+    uint8_t* bits = reinterpret_cast<uint8_t*>(lse2) + align256(bwd_pad_elems(d) * sizeof(float));
+    if (int rc = launch_attn_dropbits(T, d->dropout_rate, d->dropout_seed, d->dropout_site, bits, stream)) return rc;
+    keep_q = bits;
+    keep_k = bits + attn_dropbits_bytes(T) / 2;
+    const uint32_t th = (uint32_t)(d->dropout_rate * 65536.0f + 0.5f);
+    inv_keep = 1.0f / (1.0f - (float)th / 65536.0f);
+  }
   {
     const long long total = (long long)B * Tp * H * 8;
     attn_bwd_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
@@ -586,13 +633,16 @@ extern "C" int tome_attention_bwd(const tome_attn_desc_t* d, const tome_attn_gra
   p.batch = B; p.tokens = T; p.heads = H; p.tp = Tp;
   p.scale = d->scale; p.scale_log2 = d->scale * 1.4426950408889634f;
   p.gid = d->gid; p.pos = d->pos; p.meta = meta; p.size = d->size; p.lse2 = lse2; p.delta = delta;
+  p.keep_q = keep_q; p.keep_k = keep_k; p.inv_keep = inv_keep;
   p.dq = reinterpret_cast<__nv_bfloat16*>(dq); p.dq_bs = gs->dq_batch_stride; p.dq_ts = gs->dq_token_stride;
   p.dk = reinterpret_cast<__nv_bfloat16*>(dk); p.dk_bs = gs->dk_batch_stride; p.dk_ts = gs->dk_token_stride;
   p.dv = reinterpret_cast<__nv_bfloat16*>(dv); p.dv_bs = gs->dv_batch_stride; p.dv_ts = gs->dv_token_stride;
   static bool attr_set = false;
   if (!attr_set) {
-    TOME_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
-    TOME_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
+    TOME_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
+    TOME_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
+    TOME_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
+    TOME_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
     attr_set = true;
   }
   {
@@ -602,7 +652,8 @@ extern "C" int tome_attention_bwd(const tome_attn_desc_t* d, const tome_attn_gra
     if (int rc = make_tmap_3d_bf16(&tv, v, hd, T, B, d->v_token_stride, d->v_batch_stride, DKV_BK)) return rc;
     if (int rc = make_tmap_3d_bf16(&tdo, dout, hd, T, B, gs->do_token_stride, gs->do_batch_stride, DKV_BQ)) return rc;
     dim3 grid(ceil_div(T, DKV_BK), H, B);
-    attn_bwd_dkdv_kernel<<<grid, AB_THREADS, DKV_SMEM, stream>>>(tq, tk, tv, tdo, p);
+    if (keep_k) attn_bwd_dkdv_kernel<true><<<grid, AB_THREADS, DKV_SMEM, stream>>>(tq, tk, tv, tdo, p);
+    else attn_bwd_dkdv_kernel<false><<<grid, AB_THREADS, DKV_SMEM, stream>>>(tq, tk, tv, tdo, p);
     TOME_CUDA(cudaGetLastError());
   }
   {
@@ -612,7 +663,8 @@ extern "C" int tome_attention_bwd(const tome_attn_desc_t* d, const tome_attn_gra
     if (int rc = make_tmap_3d_bf16(&tv, v, hd, T, B, d->v_token_stride, d->v_batch_stride, DQ_BK)) return rc;
     if (int rc = make_tmap_3d_bf16(&tdo, dout, hd, T, B, gs->do_token_stride, gs->do_batch_stride, DQ_BQ)) return rc;
     dim3 grid(ceil_div(T, DQ_BQ), H, B);
-    attn_bwd_dq_kernel<<<grid, AB_THREADS, DQ_SMEM, stream>>>(tq, tk, tv, tdo, p);
+    if (keep_q) attn_bwd_dq_kernel<true><<<grid, AB_THREADS, DQ_SMEM, stream>>>(tq, tk, tv, tdo, p);
+    else attn_bwd_dq_kernel<false><<<grid, AB_THREADS, DQ_SMEM, stream>>>(tq, tk, tv, tdo, p);
     TOME_CUDA(cudaGetLastError());
   }
   return TOME_OK;

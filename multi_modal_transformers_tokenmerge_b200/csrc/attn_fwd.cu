@@ -35,7 +35,7 @@ constexpr int ATT_KV_BYTES = ATT_BN * ATT_D * 2;        // 8 KB each for K and V
 constexpr int ATT_P_BYTES = ATT_BM * ATT_BN * 2;        // 16 KB, x2 buffers
 constexpr int ATT_SLOTS = 6;  // ring of 8 KB slots; items are loaded in the order K_0 K_1 V_0 K_2 V_1 ...
 constexpr int ATT_MSLOTS = 4; // metadata ring
-constexpr int ATT_META_SLOT = ATTN_META_KEY_BYTES;  // bias2 | vis[32][2] | visc[32][2] | pos
+constexpr int ATT_META_SLOT = ATTN_META_KEY_BYTES + ATTN_DROP_TILE_BYTES;  // bias2 | vis[32][2] | visc[32][2] | pos | dropout keep words [128][2]
 static_assert(ATT_BN == ATTN_META_TILE, "key tiles and metadata tiles must coincide");
 constexpr int ATT_SMEM = ATT_Q_BYTES + ATT_SLOTS * ATT_KV_BYTES + 2 * ATT_P_BYTES + ATT_MSLOTS * ATT_META_SLOT + 512 + 1024;
 constexpr uint32_t ATT_TMEM_COLS = 256;  // S0 [0,64) S1 [64,128) O [128,192)
@@ -47,6 +47,8 @@ struct AttnFwdParams {
   const uint8_t* gid;   // null: no mask
   const int32_t* pos;
   const uint8_t* meta;  // [B][n_kv][ATTN_META_BYTES]
+  const uint8_t* keep_q;  // attention dropout keep words [n_q128][n_kv][128][2] or null
+  float inv_keep;         // 1 / (1 - rate)
   __nv_bfloat16* out;
   long long o_batch_stride, o_token_stride;
   float* lse;
@@ -69,6 +71,8 @@ __device__ __forceinline__ void tmem_ld_f32x32(uint32_t taddr, float (&r)[N]) {
       : "memory");
 }
 
+// DROP: attention-weight dropout compiled in (the keep words ride in the metadata ring); the rate-0 instantiation carries none of it
+template <bool DROP>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const AttnFwdParams p) {
@@ -144,8 +148,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       for (int j = 0; j < n_kv; ++j) {
         const int ms = j % ATT_MSLOTS;
         mbar_wait(&meta_empty[ms], ((j / ATT_MSLOTS) & 1) ^ 1);
-        mbar_expect_tx(&meta_full[ms], meta_bytes);
+        mbar_expect_tx(&meta_full[ms], meta_bytes + (DROP ? ATTN_DROP_TILE_BYTES : 0));
         bulk_g2s(s_meta + ms * ATT_META_SLOT, meta_b + (size_t)j * ATTN_META_BYTES, meta_bytes, &meta_full[ms]);
+        if constexpr (DROP)
+          bulk_g2s(s_meta + ms * ATT_META_SLOT + ATTN_META_KEY_BYTES, p.keep_q + ((size_t)qt * n_kv + j) * ATTN_DROP_TILE_BYTES,
+                   ATTN_DROP_TILE_BYTES, &meta_full[ms]);
         if (j + 1 < n_kv) load_item(false, j + 1);
         load_item(true, j);
       }
@@ -229,6 +236,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         masked_tile = !__all_sync(0xffffffffu, (vw0 & vw1) == 0xffffffffu);  // warp-uniform: skip the selects when nothing is masked
       }
 
+      uint2 kb = make_uint2(0xffffffffu, 0xffffffffu);  // dropout keep bits of this row's 64 keys
+      if constexpr (DROP) kb = *reinterpret_cast<const uint2*>(mb + ATTN_META_KEY_BYTES + row * 8);
+
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
       float s[ATT_BN];
@@ -300,8 +310,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const float2 d = __fadd2_rn(make_float2(s[ch * 8 + 2 * u], s[ch * 8 + 2 * u + 1]), nm2);
-          const float2 e = make_float2(fast_exp2(d.x), fast_exp2(d.y));
-          l2[u] = __fadd2_rn(l2[u], e);
+          float2 e = make_float2(fast_exp2(d.x), fast_exp2(d.y));
+          l2[u] = __fadd2_rn(l2[u], e);   // the row sum is that of the UNdropped weights (dropout follows the softmax)
+          if constexpr (DROP) {
+            const uint32_t kw = ch < 4 ? kb.x : kb.y;
+            const int bit = (ch & 3) * 8 + 2 * u;
+            e.x = ((kw >> bit) & 1u) ? e.x : 0.f;
+            e.y = ((kw >> (bit + 1)) & 1u) ? e.y : 0.f;
+          }
           w[u] = pack_bf16(e.x, e.y);
         }
         *reinterpret_cast<uint4*>(prow + ((ch ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -316,7 +332,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     mbar_wait(&pv_done[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);
     tc_fence_after();
     if (warp_active) {
-      const float inv_l = 1.0f / l_run;
+      const float inv_l = p.inv_keep / l_run;   // 1 / (1 - rate) of the dropout folded into the normalisation
       __nv_bfloat16* orow = p.out + (long long)b * p.o_batch_stride + (long long)(q < T ? q : 0) * p.o_token_stride + h * ATT_D;
 #pragma unroll
       for (int c0 = 0; c0 < ATT_D; c0 += 32) {
@@ -396,6 +412,51 @@ int launch_attn_meta(int B, int T, const uint8_t* gid, const int32_t* pos, const
   return TOME_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ dropout keep bits (attn_meta.cuh)
+// thread = (query q, 32-key word w), q fastest: a warp holds 32 consecutive queries of one word, so the transposed words
+// come from 32 ballots
+__global__ void __launch_bounds__(256)
+attn_dropbits_kernel(int n128, int n64, DropoutCfg d, uint32_t* __restrict__ keep_q, uint32_t* __restrict__ keep_k) {
+  const int Tq = n128 * 128;                       // padded query / key range: both arrays are written completely
+  const long long t = blockIdx.x * 256ll + threadIdx.x;
+  const int q = (int)(t % Tq), w = (int)(t / Tq);  // w < n128 * 4
+  if (w >= n128 * 4) return;                        // whole warps leave together (Tq % 32 == 0)
+  DropStream st = drop_stream(d, (uint32_t)q, (uint32_t)w);
+  const uint32_t thr = d.thresh16 << 16;
+  uint32_t word = 0;
+#pragma unroll
+  for (int e = 0; e < 32; ++e) word |= (st.next() >= thr ? 1u : 0u) << e;
+  if ((w >> 1) < n64)  // key tile w/2 exists in the 64-wide tiling
+    keep_q[(((long long)(q >> 7) * n64 + (w >> 1)) * 128 + (q & 127)) * 2 + (w & 1)] = word;
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int e = 0; e < 32; ++e) {
+    const uint32_t col = __ballot_sync(0xffffffffu, (word >> e) & 1u);  // bit l: keep(q_base + l, 32 w + e)
+    if (lane == e) {
+      const int kk = 32 * w + e, q0 = q & ~31;   // this lane's q is q0 + e; the word covers queries q0 .. q0 + 31
+      if ((q0 >> 6) < n64)
+        keep_k[(((long long)(kk >> 7) * n64 + (q0 >> 6)) * 128 + (kk & 127)) * 2 + ((q0 >> 5) & 1)] = col;
+    }
+  }
+}
+
+int launch_attn_dropbits(int T, float rate, uint64_t seed, uint32_t site, uint8_t* bits, cudaStream_t stream) {
+  TOME_CHECK(bits != nullptr && ((uintptr_t)bits & 15) == 0, TOME_ERR_INVALID, "attention: dropout workspace must be 16-byte aligned");
+  TOME_CHECK(rate > 0.f && rate < 1.f, TOME_ERR_INVALID, "attention: dropout_rate must be in [0, 1)");
+  const int n128 = (T + 127) / 128, n64 = (T + 63) / 64;
+  DropoutCfg d;
+  d.thresh16 = (uint32_t)(rate * 65536.0f + 0.5f);
+  d.inv_keep = 1.0f / (1.0f - (float)d.thresh16 / 65536.0f);
+  d.seed_lo = (uint32_t)seed; d.seed_hi = (uint32_t)(seed >> 32);
+  d.site = site;
+  uint32_t* kq = reinterpret_cast<uint32_t*>(bits);
+  uint32_t* kk = kq + (size_t)n128 * n64 * (ATTN_DROP_TILE_BYTES / 4);
+  const long long threads = (long long)n128 * 128 * n128 * 4;
+  attn_dropbits_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(n128, n64, d, kq, kk);
+  TOME_CUDA(cudaGetLastError());
+  return TOME_OK;
+}
+
 }  // namespace tome
 
 using namespace tome;
@@ -416,9 +477,14 @@ int check_attn_desc(const tome_attn_desc_t* d, const char* who) {
 }
 }  // namespace tome
 
+static size_t fwd_ws_bytes(const tome_attn_desc_t* d) {
+  const size_t meta = (attn_meta_bytes(d->batch, d->tokens) + 255) & ~size_t(255);
+  return meta + (d->dropout_rate > 0.f ? attn_dropbits_bytes(d->tokens) : 0);
+}
+
 extern "C" size_t tome_attention_workspace_bytes(const tome_attn_desc_t* d) {
   if (!d || d->batch <= 0 || d->tokens <= 0) return 0;
-  return attn_meta_bytes(d->batch, d->tokens);
+  return fwd_ws_bytes(d);
 }
 
 extern "C" int tome_attention_fwd(const tome_attn_desc_t* d, const void* q, const void* k, const void* v, void* out,
@@ -428,9 +494,10 @@ extern "C" int tome_attention_fwd(const tome_attn_desc_t* d, const void* q, cons
   if (int rc = check_attn_desc(d, "attention_fwd")) return rc;
   TOME_CHECK(q && k && v && out, TOME_ERR_INVALID, "attention_fwd: null tensor");
   TOME_CHECK(((uintptr_t)out & 15) == 0, TOME_ERR_INVALID, "attention_fwd: out must be 16-byte aligned");
-  TOME_CHECK(workspace && workspace_bytes >= attn_meta_bytes(d->batch, d->tokens), TOME_ERR_INVALID,
-             "attention_fwd: workspace too small (%zu < %zu, see tome_attention_workspace_bytes)", workspace_bytes,
-             attn_meta_bytes(d->batch, d->tokens));
+  TOME_CHECK(workspace && workspace_bytes >= fwd_ws_bytes(d), TOME_ERR_INVALID,
+             "attention_fwd: workspace too small (%zu < %zu, see tome_attention_workspace_bytes)", workspace_bytes, fwd_ws_bytes(d));
+  TOME_CHECK(((uintptr_t)workspace & 255) == 0, TOME_ERR_INVALID, "attention_fwd: workspace must be 256-byte aligned");
+  TOME_CHECK(d->dropout_rate >= 0.f && d->dropout_rate < 1.f, TOME_ERR_INVALID, "attention_fwd: dropout_rate must be in [0, 1)");
   CUtensorMap tq, tk, tv;
   const uint64_t hd = (uint64_t)d->heads * d->head_dim;
   ProfScope prof(PROF_ATTN_FWD, 4.0 * d->batch * d->heads * (double)d->tokens * d->tokens * d->head_dim, 2, stream);
@@ -443,16 +510,27 @@ extern "C" int tome_attention_fwd(const tome_attn_desc_t* d, const void* q, cons
   p.batch = d->batch; p.tokens = d->tokens; p.heads = d->heads;
   p.scale_log2 = d->scale * 1.4426950408889634f;
   p.gid = d->gid; p.pos = d->pos; p.meta = reinterpret_cast<const uint8_t*>(workspace);
+  p.keep_q = nullptr;
+  p.inv_keep = 1.0f;
+  if (d->dropout_rate > 0.f) {
+    uint8_t* bits = reinterpret_cast<uint8_t*>(workspace) + ((attn_meta_bytes(d->batch, d->tokens) + 255) & ~size_t(255));
+    if (int rc = launch_attn_dropbits(d->tokens, d->dropout_rate, d->dropout_seed, d->dropout_site, bits, stream)) return rc;
+    p.keep_q = bits;
+    const uint32_t th = (uint32_t)(d->dropout_rate * 65536.0f + 0.5f);
+    p.inv_keep = 1.0f / (1.0f - (float)th / 65536.0f);
+  }
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.o_batch_stride = d->o_batch_stride; p.o_token_stride = d->o_token_stride;
   p.lse = lse;
   static bool attr_set = false;
   if (!attr_set) {
-    TOME_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    TOME_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    TOME_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     attr_set = true;
   }
   dim3 grid(ceil_div(d->tokens, ATT_BM), d->heads, d->batch);
-  attn_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tq, tk, tv, p);
+  if (p.keep_q) attn_fwd_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tq, tk, tv, p);
+  else attn_fwd_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tq, tk, tv, p);
   TOME_CUDA(cudaGetLastError());
   return TOME_OK;
 }

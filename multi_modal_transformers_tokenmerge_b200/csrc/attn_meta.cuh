@@ -30,6 +30,21 @@ inline size_t attn_meta_bytes(int batch, int tokens) {
 int launch_attn_meta(int B, int T, const uint8_t* gid, const int32_t* pos, const uint8_t* allow, int G, const float* size,
                      uint8_t* meta, cudaStream_t stream);
 
+// ---- attention-weight dropout (flax broadcast_dropout=True: ONE [Tq, Tk] mask for every batch row and head) ----
+// keep(q, k) = element k % 32 of the LCG stream (seed, site, row = q, chunk = k / 32) of common.cuh -- the generator the GEMM
+// epilogues use.  Because the mask is shared by all (batch, head) pairs it is tiny (T^2 bits = 36 KB at T = 536), so
+// attn_dropbits_kernel materialises it ONCE per call as bit words in the two tilings the kernels stream with one 1 KB
+// bulk copy per tile:
+//   keep_q[q128 tile][k64 tile][128 query rows][2 words]   bit k % 64 of a row: keep(q, k)   (forward, dQ: thread = query row)
+//   keep_k[k128 tile][q64 tile][128 key rows][2 words]     bit q % 64 of a row: keep(q, k)   (dK/dV:    thread = key row)
+constexpr int ATTN_DROP_TILE_BYTES = 128 * 2 * 4;
+inline size_t attn_dropbits_bytes(int tokens) {  // both tilings
+  const size_t n128 = (tokens + 127) / 128, n64 = (tokens + 63) / 64;
+  return 2 * n128 * n64 * ATTN_DROP_TILE_BYTES;
+}
+// keep_q at `bits`, keep_k right after it (n128 * n64 tiles each)
+int launch_attn_dropbits(int T, float rate, uint64_t seed, uint32_t site, uint8_t* bits, cudaStream_t stream);
+
 // global -> shared bulk copy completing on an mbarrier (bytes % 16 == 0, both addresses 16-byte aligned)
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

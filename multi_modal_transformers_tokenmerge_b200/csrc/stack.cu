@@ -22,6 +22,10 @@
 
 namespace tome {
 
+// dropout sites: hidden dropout uses 3 * layer + {0: out-proj, 1: MLP hidden, 2: MLP out}; attention-weight dropout of layer l
+// draws from site kAttnDropSite + l
+constexpr uint32_t kAttnDropSite = 0x40000000u;
+
 struct LayerShape {
   int t_in, r, t_out;
 };
@@ -87,6 +91,7 @@ static int check_cfg(const tome_stack_cfg_t* c) {
   TOME_CHECK(c->r >= 0, TOME_ERR_INVALID, "stack: r must be >= 0");
   TOME_CHECK(c->num_groups >= 0 && c->num_groups <= 32, TOME_ERR_INVALID, "stack: num_groups must be in [0, 32]");
   TOME_CHECK(c->dropout_rate >= 0.f && c->dropout_rate < 1.f, TOME_ERR_INVALID, "stack: dropout_rate must be in [0, 1)");
+  TOME_CHECK(c->attn_dropout_rate >= 0.f && c->attn_dropout_rate < 1.f, TOME_ERR_INVALID, "stack: attn_dropout_rate must be in [0, 1)");
   TOME_CHECK(c->n_readout >= 0, TOME_ERR_INVALID, "stack: n_readout must be >= 0");
   return TOME_OK;
 }
@@ -182,6 +187,7 @@ static StackLayout make_layout(const tome_stack_cfg_t* c, void* workspace) {
     tome_attn_desc_t ad;
     memset(&ad, 0, sizeof(ad));
     ad.batch = c->batch; ad.tokens = c->tokens; ad.heads = c->heads; ad.head_dim = c->head_dim;
+    ad.dropout_rate = c->attn_dropout_rate;
     const size_t f = tome_attention_workspace_bytes(&ad), bw = tome_attention_bwd_workspace_bytes(&ad);
     S.ws_attn_bytes = f > bw ? f : bw;
     S.ws_attn = b.take<uint8_t>(S.ws_attn_bytes);
@@ -319,6 +325,7 @@ extern "C" int tome_stack_forward(const tome_stack_cfg_t* c, const tome_stack_io
     ad.scale = 1.0f / sqrtf((float)D);
     if (c->num_groups) { ad.gid = Lb.gid_in; ad.pos = Lb.pos_in; ad.allow = io->allow; ad.num_groups = c->num_groups; }
     ad.size = c->prop_attn ? Lb.size_in : nullptr;
+    ad.dropout_rate = c->attn_dropout_rate; ad.dropout_seed = c->dropout_seed; ad.dropout_site = kAttnDropSite + (uint32_t)l;
     RC(tome_attention_fwd(&ad, Lb.qkv, Lb.qkv + HD, Lb.qkv + 2 * HD, Lb.attn_o, Lb.lse, S.ws_attn, S.ws_attn_bytes, st));
     __nv_bfloat16* x1 = r > 0 ? S.x1_scratch : Lb.x1m;
     RC(gemm(c, S, st, M, C, HD, Lb.attn_o, HD, TOME_MAJOR_K, pw + o.wo, C, TOME_MAJOR_MN, x1, C, TOME_BF16, pf + o.bo, 0,
@@ -436,6 +443,7 @@ extern "C" int tome_stack_backward(const tome_stack_cfg_t* c, const tome_stack_i
     ad.scale = 1.0f / sqrtf((float)D);
     if (c->num_groups) { ad.gid = Lb.gid_in; ad.pos = Lb.pos_in; ad.allow = io->allow; ad.num_groups = c->num_groups; }
     ad.size = c->prop_attn ? Lb.size_in : nullptr;
+    ad.dropout_rate = c->attn_dropout_rate; ad.dropout_seed = c->dropout_seed; ad.dropout_site = kAttnDropSite + (uint32_t)l;
     tome_attn_grad_strides_t gs;
     gs.dq_batch_stride = gs.dk_batch_stride = gs.dv_batch_stride = (long long)T * 3 * HD;
     gs.dq_token_stride = gs.dk_token_stride = gs.dv_token_stride = 3 * HD;

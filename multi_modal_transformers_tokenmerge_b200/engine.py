@@ -39,11 +39,13 @@ class StackConfig:
     n_readout: int = 0
     dropout_rate: float = 0.0
     dropout_seed: int = 0
+    attn_dropout_rate: float = 0.0   # attention-weight dropout (self_attention.dropout_rate, vanilla_decoder.yaml:23)
 
     def c(self) -> L.StackCfg:
         return L.StackCfg(self.batch, self.tokens, self.channels, self.heads, self.head_dim, self.mlp_dim, self.layers,
                           self.r, self.ln_axis, self.ln_eps, int(self.prop_attn), int(self.class_token),
-                          int(self.distill_token), self.num_groups, self.n_readout, self.dropout_rate, self.dropout_seed)
+                          int(self.distill_token), self.num_groups, self.n_readout, self.dropout_rate, self.dropout_seed,
+                          self.attn_dropout_rate)
 
     def param_shapes(self) -> Dict[str, tuple]:
         c, hd, f = self.channels, self.heads * self.head_dim, self.mlp_dim

@@ -246,7 +246,7 @@ def layernorm_bwd(x, dy, gamma, mean, rstd, dgamma, dbeta, dres=None, axis: int 
 
 
 # ------------------------------------------------------------------------------------------------ attention
-def _attn_desc(q, k, v, out, scale, gid, pos, allow, size):
+def _attn_desc(q, k, v, out, scale, gid, pos, allow, size, dropout=(0.0, 0, 0)):
     b, t, h, d = q.shape
     for x in (q, k, v, out):
         assert x.dtype == torch.bfloat16 and x.stride(3) == 1 and x.stride(2) == d, "heads must be packed [.., H, D]"
@@ -254,24 +254,28 @@ def _attn_desc(q, k, v, out, scale, gid, pos, allow, size):
     return L.AttnDesc(b, t, h, d, q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
                       out.stride(0), out.stride(1), float(scale),
                       None if gid is None else gid.data_ptr(), None if pos is None else pos.data_ptr(),
-                      None if allow is None else allow.data_ptr(), g, None if size is None else size.data_ptr())
+                      None if allow is None else allow.data_ptr(), g, None if size is None else size.data_ptr(),
+                      float(dropout[0]), int(dropout[1]), int(dropout[2]))
 
 
-def attention_fwd(q, k, v, *, gid=None, pos=None, allow=None, size=None, scale=None):
-    """q,k,v: [B,T,H,D] bf16 views (may be slices of a packed qkv buffer).  Returns (out [B,T,H,D], lse [B,H,T])."""
+def attention_fwd(q, k, v, *, gid=None, pos=None, allow=None, size=None, scale=None, dropout_rate=0.0, dropout_seed=0,
+                  dropout_site=0):
+    """q,k,v: [B,T,H,D] bf16 views (may be slices of a packed qkv buffer).  Returns (out [B,T,H,D], lse [B,H,T]).
+    dropout_*: attention-weight dropout, one mask for all batch rows and heads (flax broadcast_dropout=True)."""
     _need_cuda(q, k, v)
     b, t, h, d = q.shape
     scale = 1.0 / math.sqrt(d) if scale is None else scale
     out = torch.empty(b, t, h, d, dtype=torch.bfloat16, device=q.device)
     lse = torch.empty(b, h, t, dtype=torch.float32, device=q.device)
-    desc = _attn_desc(q, k, v, out, scale, gid, pos, allow, size)
+    desc = _attn_desc(q, k, v, out, scale, gid, pos, allow, size, (dropout_rate, dropout_seed, dropout_site))
     ws = _scratch(L.lib().tome_attention_workspace_bytes(C.byref(desc)), q.device)
     L.check(L.lib().tome_attention_fwd(C.byref(desc), _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse), _ptr(ws), ws.numel(),
                                        _stream()))
     return out, lse
 
 
-def attention_bwd(q, k, v, out, lse, dout, *, gid=None, pos=None, allow=None, size=None, scale=None, dqkv=None):
+def attention_bwd(q, k, v, out, lse, dout, *, gid=None, pos=None, allow=None, size=None, scale=None, dqkv=None,
+                  dropout_rate=0.0, dropout_seed=0, dropout_site=0):
     """Returns (dq, dk, dv) [B,T,H,D] bf16 (views of one packed [B,T,3,H,D] buffer unless dqkv views are given)."""
     _need_cuda(q, k, v, out, dout)
     b, t, h, d = q.shape
@@ -281,7 +285,7 @@ def attention_bwd(q, k, v, out, lse, dout, *, gid=None, pos=None, allow=None, si
         dq, dk, dv = buf[:, :, 0], buf[:, :, 1], buf[:, :, 2]
     else:
         dq, dk, dv = dqkv
-    desc = _attn_desc(q, k, v, out, scale, gid, pos, allow, size)
+    desc = _attn_desc(q, k, v, out, scale, gid, pos, allow, size, (dropout_rate, dropout_seed, dropout_site))
     gs = L.AttnGradStrides(dq.stride(0), dq.stride(1), dk.stride(0), dk.stride(1), dv.stride(0), dv.stride(1),
                            dout.stride(0), dout.stride(1))
     ws = _scratch(L.lib().tome_attention_bwd_workspace_bytes(C.byref(desc)), q.device)

@@ -309,6 +309,34 @@ def attention(q, k, v, mask=None, bias=None, drop_keep=None):
     return torch.einsum("bhqk,bkhd->bqhd", w, v)
 
 
+def dropout_keep_mask(rows: int, cols: int, rate: float, seed: int, site: int):
+    """Host restatement of the library's counter-based dropout stream (csrc/common.cuh: drop_stream / DropStream): element
+    (row, col) belongs to the stream (row, col // 32); two lowbias32 hashes give the LCG start state and its odd increment;
+    element col % 32 is kept iff the top 16 bits of the (col % 32 + 1)-th state are >= round(rate * 65536).
+    Returns (keep bool [rows, cols], effective rate).  Used to hand the oracle the exact mask the kernels drew."""
+    M = np.uint64(0xFFFFFFFF)
+
+    def lowbias32(x):
+        x = x ^ (x >> np.uint64(16)); x = (x * np.uint64(0x21f0aaad)) & M
+        x = x ^ (x >> np.uint64(15)); x = (x * np.uint64(0x735a2d97)) & M
+        return x ^ (x >> np.uint64(15))
+
+    thresh16 = int(rate * 65536.0 + 0.5)
+    thr = np.uint64(thresh16 << 16)
+    seed_lo, seed_hi = np.uint64(seed & 0xFFFFFFFF), np.uint64((seed >> 32) & 0xFFFFFFFF)
+    k = (seed_lo ^ ((np.uint64(site) * np.uint64(0x9E3779B9)) & M)) & M
+    nch = (cols + 31) // 32
+    r = np.arange(rows, dtype=np.uint64)[:, None]
+    ch = np.arange(nch, dtype=np.uint64)[None, :]
+    x = lowbias32((r * np.uint64(0x9E3779B1) + ch * np.uint64(0x85EBCA77) + k) & M)
+    c = lowbias32((((r ^ seed_hi) & M) * np.uint64(0xC2B2AE35) + ch * np.uint64(0x27D4EB2F) + (k ^ np.uint64(0x5bd1e995))) & M) | np.uint64(1)
+    keep = np.zeros((rows, nch, 32), bool)
+    for e in range(32):
+        x = (x * np.uint64(0x915F77F5) + c) & M
+        keep[:, :, e] = x >= thr
+    return keep.reshape(rows, nch * 32)[:, :cols], thresh16 / 65536.0
+
+
 def merge_wavg_torch(plan: MatchPlan, x, size):
     """merge_wavg with autograd support; same sequential scatter order as token_compression.py:100-101."""
     torch = _torch()

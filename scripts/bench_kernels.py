@@ -106,6 +106,8 @@ def bench_attn():
         if gm.shape[1] == T:
             t = timeit(lambda: ops.attention_fwd(q, k, v, size=size, gid=gm, pos=pm, allow=am), iters=5)
             print(f"attn_fwd B{B} T{T} H{H} masked: {t*1e6:9.1f} us {fl/t/1e12:7.1f} TF/s")
+            t = timeit(lambda: ops.attention_fwd(q, k, v, size=size, gid=gm, pos=pm, allow=am, dropout_rate=0.1, dropout_seed=3, dropout_site=5), iters=5)
+            print(f"attn_fwd B{B} T{T} H{H} masked + weight dropout 0.1: {t*1e6:9.1f} us {fl/t/1e12:7.1f} TF/s")
         if hasattr(ops, "attention_bwd"):
             try:
                 out, lse = ops.attention_fwd(q, k, v, size=size)
@@ -115,6 +117,8 @@ def bench_attn():
                 if gm.shape[1] == T:
                     t = timeit(lambda: ops.attention_bwd(q, k, v, out, lse, do, size=size, gid=gm, pos=pm, allow=am), iters=5)
                     print(f"attn_bwd B{B} T{T} H{H} masked: {t*1e6:9.1f} us {2.5*fl/t/1e12:7.1f} TF/s")
+                    t = timeit(lambda: ops.attention_bwd(q, k, v, out, lse, do, size=size, gid=gm, pos=pm, allow=am, dropout_rate=0.1, dropout_seed=3, dropout_site=5), iters=5)
+                    print(f"attn_bwd B{B} T{T} H{H} masked + weight dropout 0.1: {t*1e6:9.1f} us {2.5*fl/t/1e12:7.1f} TF/s")
             except Exception as ex:  # not built yet
                 print("attn_bwd unavailable:", ex)
 

@@ -66,6 +66,50 @@ def test_attention_bwd(pkg, T, H, masked, sized):
         assert e <= 2e-2, f"{name}: rel err {e}"
 
 
+@pytest.mark.parametrize("T,H,rate", [(536, 3, 0.1), (150, 2, 0.5), (1000, 1, 0.25)])
+def test_attention_weight_dropout_fwd_bwd(pkg, T, H, rate):
+    """Attention-weight dropout (flax dot_product_attention, broadcast_dropout=True: one [T,T] mask for every batch row and
+    head, applied after the softmax and scaled by 1/(1-rate); vanilla_decoder.yaml:23).  The oracle is handed the EXACT mask
+    the kernels regenerate from (seed, site, q, k) -- oracle.dropout_keep_mask restates the generator on the host -- so the
+    forward output and dq/dk/dv are compared like the rate-0 tests; the same mask also proves forward and both backward
+    kernels (which read it in two different tilings) agree on every bit."""
+    ops, _ = pkg
+    rng = np.random.default_rng(T + H)
+    B, D = 2, 64
+    seed, site = 987654321012, 0x40000003
+    qkv = torch.tensor(rng.standard_normal((B, T, 3, H, D)).astype(np.float32)).cuda().bfloat16()
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    n_img = (T - 16) // 2 - 4
+    g1, p1, allow, _ = O.sequence_groups(f"[TaskDescriptionPrefix{{16}}] [Image{{{n_img}}};Readout{{4}}]*2")
+    pad = T - g1.shape[0]
+    g1 = np.concatenate([g1, np.full(pad, g1[-1], np.uint8)])
+    p1 = np.concatenate([p1, np.arange(pad, dtype=np.int32)])
+    gid = np.stack([g1, rng.permutation(g1)])
+    pos = np.stack([p1, rng.integers(0, 50, size=T).astype(np.int32)])
+    size = rng.integers(1, 4, size=(B, T)).astype(np.float32)
+    dv_ = lambda a: torch.as_tensor(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    kw = dict(gid=dv_(gid), pos=dv_(pos), allow=dv_(allow), size=dv_(size), dropout_rate=rate, dropout_seed=seed, dropout_site=site)
+    out, lse = ops.attention_fwd(q, k, v, **kw)
+    dout = torch.tensor(rng.standard_normal((B, T, H, D)).astype(np.float32)).cuda().bfloat16()
+    dq, dk, dvv = ops.attention_bwd(q, k, v, out, lse, dout, **kw)
+    torch.cuda.synchronize()
+    keep, p_eff = O.dropout_keep_mask(T, T, rate, seed, site)
+    assert abs(keep.mean() - (1 - rate)) < 0.01
+    drop_keep = torch.as_tensor(keep.astype(np.float32) / (1.0 - p_eff))[None, None]
+    qr, kr, vr = (t.float().cpu().requires_grad_(True) for t in (q, k, v))
+    mask = torch.as_tensor(O.dense_mask(gid, pos, gid, pos, allow))[:, None]
+    bias = torch.log(torch.as_tensor(size))[:, None, None, :]
+    ref = O.attention(qr, kr, vr, mask=mask, bias=bias, drop_keep=drop_keep)
+    assert rel_err(out.float().cpu(), ref.detach()) <= 2e-2
+    # the log-sum-exp is that of the UNdropped weights
+    out0, lse0 = ops.attention_fwd(q, k, v, gid=kw["gid"], pos=kw["pos"], allow=kw["allow"], size=kw["size"])
+    assert torch.equal(lse, lse0) and not torch.equal(out, out0)
+    ref.backward(dout.float().cpu())
+    for name, got, want in (("dq", dq, qr.grad), ("dk", dk, kr.grad), ("dv", dvv, vr.grad)):
+        e = rel_err(got.float().cpu(), want)
+        assert e <= 2.5e-2, f"{name}: rel err {e}"
+
+
 def _build(pkg, B, W, P, C, H, Dff, Lyr, r, ln_axis, seed=0, n_ro=2, n_tdp=4):
     ops, engine = pkg
     rng = np.random.default_rng(seed)
@@ -195,7 +239,7 @@ def test_stack_octo_small_shape_runs_and_trains(pkg):
     assert eng.tokens_at(Lyr) == 344
     assert torch.all(eng.final_size().sum(dim=1) == T)
     assert all(math.isfinite(v) for v in losses) and losses[-1] < losses[0], losses
-    cfg2 = engine.StackConfig(**{**cfg.__dict__, "dropout_rate": 0.1, "dropout_seed": 5})
+    cfg2 = engine.StackConfig(**{**cfg.__dict__, "dropout_rate": 0.1, "attn_dropout_rate": 0.1, "dropout_seed": 5})
     e2 = engine.ToMeStackEngine(cfg2, gid=gid, pos=pos, allow=allow, readout_idx=ro)
     e2.init_params(1)
     vals = []
