@@ -15,7 +15,7 @@ from .. import _lib as L
 from .. import ops
 from ._module import AttentionSpec, LayerNormSpec
 
-SUPPORTED_HEAD_DIMS = (64,)
+SUPPORTED_HEAD_DIMS = tuple(range(8, 257, 8))   # 64 runs on the tcgen05 kernels; the others (e.g. the literal 3 x 256) on the generic path
 
 
 @dataclass
@@ -122,7 +122,7 @@ def attention(p, spec: AttentionSpec, x: torch.Tensor, mask: Optional[GroupMask]
         raise ValueError(f"Memory dimension ({qkv_features}) must be divisible by number of heads ({H}).")  # :139-142
     D = qkv_features // H
     if D not in SUPPORTED_HEAD_DIMS:
-        raise NotImplementedError(f"head_dim {D}: this build's tcgen05 attention kernels support {SUPPORTED_HEAD_DIMS}")
+        raise NotImplementedError(f"head_dim {D}: the attention kernels take multiples of 8 up to 256")
     wqkv = torch.cat([_w(p[n]["kernel"]).reshape(C, H * D) for n in ("query", "key", "value")], dim=1).contiguous()
     bqkv = torch.cat([_f(p[n]["bias"]).reshape(-1) for n in ("query", "key", "value")]) if spec.use_bias else None
     qkv = ops.gemm(x.reshape(B * T, C), wqkv, m=B * T, n=3 * H * D, k=C, b_major=L.TOME_MAJOR_MN, bias=bqkv)

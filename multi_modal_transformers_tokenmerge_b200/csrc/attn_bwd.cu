@@ -22,6 +22,8 @@
 namespace tome {
 
 int check_attn_desc(const tome_attn_desc_t* d, const char* who);  // attn_fwd.cu
+int attn_generic_bwd(const tome_attn_desc_t* d, const tome_attn_grad_strides_t* gs, const void* q, const void* k, const void* v,
+                     const void* out, const float* lse, const void* dout, void* dq, void* dk, void* dv, cudaStream_t stream);  // attn_generic.cu
 
 constexpr int AB_D = 64;
 constexpr int AB_THREADS = 192;
@@ -594,8 +596,13 @@ extern "C" int tome_attention_bwd(const tome_attn_desc_t* d, const tome_attn_gra
   clear_error();
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int rc = check_attn_desc(d, "attention_bwd")) return rc;
-  TOME_CHECK(gs && q && k && v && out && lse && dout && dq && dk && dv && workspace, TOME_ERR_INVALID,
-             "attention_bwd: null argument");
+  TOME_CHECK(gs && q && k && v && out && lse && dout && dq && dk && dv, TOME_ERR_INVALID, "attention_bwd: null argument");
+  TOME_CHECK(d->dropout_rate >= 0.f && d->dropout_rate < 1.f, TOME_ERR_INVALID, "attention_bwd: dropout_rate must be in [0, 1)");
+  if (d->head_dim != AB_D) {
+    ProfScope prof(PROF_ATTN_BWD, 10.0 * d->batch * d->heads * (double)d->tokens * d->tokens * d->head_dim, 2, stream);
+    return attn_generic_bwd(d, gs, q, k, v, out, lse, dout, dq, dk, dv, stream);
+  }
+  TOME_CHECK(workspace != nullptr, TOME_ERR_INVALID, "attention_bwd: null workspace");
   TOME_CHECK(((uintptr_t)workspace & 255) == 0, TOME_ERR_INVALID, "attention_bwd: workspace must be 256-byte aligned");
   TOME_CHECK(workspace_bytes >= tome_attention_bwd_workspace_bytes(d), TOME_ERR_INVALID,
              "attention_bwd: workspace too small (%zu < %zu, see tome_attention_bwd_workspace_bytes)", workspace_bytes,

@@ -462,10 +462,14 @@ int launch_attn_dropbits(int T, float rate, uint64_t seed, uint32_t site, uint8_
 using namespace tome;
 
 namespace tome {
+int attn_generic_fwd(const tome_attn_desc_t* d, const void* q, const void* k, const void* v, void* out, float* lse,
+                     cudaStream_t stream);  // attn_generic.cu
 int check_attn_desc(const tome_attn_desc_t* d, const char* who) {
   TOME_CHECK(d != nullptr, TOME_ERR_INVALID, "%s: null descriptor", who);
   TOME_CHECK(d->batch > 0 && d->tokens > 0 && d->heads > 0, TOME_ERR_INVALID, "%s: bad shape", who);
-  TOME_CHECK(d->head_dim == ATT_D, TOME_ERR_UNSUPPORTED, "%s: head_dim %d not supported (this build: 64)", who, d->head_dim);
+  TOME_CHECK(d->head_dim >= 8 && d->head_dim <= 256 && d->head_dim % 8 == 0, TOME_ERR_UNSUPPORTED,
+             "%s: head_dim %d not supported (64 runs on tensor cores; other multiples of 8 up to 256 on the generic path)", who,
+             d->head_dim);
   TOME_CHECK(d->batch <= 65535 && d->heads <= 65535, TOME_ERR_INVALID, "%s: batch/heads exceed grid limits", who);
   TOME_CHECK(!d->gid || (d->pos && d->allow && d->num_groups >= 1 && d->num_groups <= 32), TOME_ERR_INVALID,
              "%s: a group mask needs pos, allow and 1 <= num_groups <= 32 (got %d)", who, d->num_groups);
@@ -494,6 +498,11 @@ extern "C" int tome_attention_fwd(const tome_attn_desc_t* d, const void* q, cons
   if (int rc = check_attn_desc(d, "attention_fwd")) return rc;
   TOME_CHECK(q && k && v && out, TOME_ERR_INVALID, "attention_fwd: null tensor");
   TOME_CHECK(((uintptr_t)out & 15) == 0, TOME_ERR_INVALID, "attention_fwd: out must be 16-byte aligned");
+  TOME_CHECK(d->dropout_rate >= 0.f && d->dropout_rate < 1.f, TOME_ERR_INVALID, "attention_fwd: dropout_rate must be in [0, 1)");
+  if (d->head_dim != ATT_D) {  // e.g. the literal reference config (3 heads x 256): fp32 CUDA-core path, same semantics
+    ProfScope prof(PROF_ATTN_FWD, 4.0 * d->batch * d->heads * (double)d->tokens * d->tokens * d->head_dim, 1, stream);
+    return attn_generic_fwd(d, q, k, v, out, lse, stream);
+  }
   TOME_CHECK(workspace && workspace_bytes >= fwd_ws_bytes(d), TOME_ERR_INVALID,
              "attention_fwd: workspace too small (%zu < %zu, see tome_attention_workspace_bytes)", workspace_bytes, fwd_ws_bytes(d));
   TOME_CHECK(((uintptr_t)workspace & 255) == 0, TOME_ERR_INVALID, "attention_fwd: workspace must be 256-byte aligned");

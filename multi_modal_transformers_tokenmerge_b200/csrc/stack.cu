@@ -85,7 +85,9 @@ static int check_cfg(const tome_stack_cfg_t* c) {
              "stack: need batch > 0, tokens >= 2, 1 <= layers <= 64");
   TOME_CHECK(c->channels % 8 == 0 && c->mlp_dim % 8 == 0 && c->channels > 0 && c->mlp_dim > 0, TOME_ERR_INVALID,
              "stack: channels and mlp_dim must be positive multiples of 8");
-  TOME_CHECK(c->head_dim == 64, TOME_ERR_UNSUPPORTED, "stack: head_dim %d not supported (this build: 64)", c->head_dim);
+  TOME_CHECK(c->head_dim >= 8 && c->head_dim <= 256 && c->head_dim % 8 == 0, TOME_ERR_UNSUPPORTED,
+             "stack: head_dim %d not supported (64 on tensor cores; other multiples of 8 up to 256 on the generic attention path)",
+             c->head_dim);
   TOME_CHECK(c->heads > 0, TOME_ERR_INVALID, "stack: heads must be positive");
   TOME_CHECK(c->ln_axis == 1 || c->ln_axis == 2, TOME_ERR_INVALID, "stack: ln_axis must be 1 (tokens) or 2 (features)");
   TOME_CHECK(c->r >= 0, TOME_ERR_INVALID, "stack: r must be >= 0");

@@ -73,7 +73,7 @@ def test_validation_errors_are_reported_not_thrown(lib):
     shp = L.MergeShape(1, 8, 8, 2, 0, L.TOME_BF16, 7)  # unknown mode (the reference only implements "sum")
     assert lib.tome_merge_fwd(C.byref(shp), C.byref(plan), None, None, None, None, None, None, None, None, None) == L.TOME_ERR_INVALID
     assert b"mode" in lib.tome_last_error()
-    d = L.AttnDesc(1, 8, 1, 256, 0, 0, 0, 0, 0, 0, 0, 0, 1.0, None, None, None, 0, None)  # head_dim 256 not built
+    d = L.AttnDesc(1, 8, 1, 260, 0, 0, 0, 0, 0, 0, 0, 0, 1.0, None, None, None, 0, None)  # head_dim 260: not a multiple of 8
     assert lib.tome_attention_fwd(C.byref(d), None, None, None, None, None, None, 0, None) == L.TOME_ERR_UNSUPPORTED
 
 

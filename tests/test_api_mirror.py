@@ -197,6 +197,39 @@ def test_blocks_chained_in_python_equal_the_native_stack_and_the_oracle(r):
     assert err <= 3e-2, err
 
 
+@gpu
+def test_literal_reference_yaml_values_run_through_the_vanilla_modules():
+    """The reference's own hyper-parameters (vanilla_decoder.yaml: one Encoder1DBlock, flax.linen.SelfAttention with 3 heads over
+    768 features = head_dim 256, MLP 768 -> 768, LayerNorm over tokens; octo_base.yaml:10: 74 tokens) through the
+    reference-shaped modules: the vanilla StackedEncoder1DBlock, eval mode, dense boolean mask as octo.py:66-68 builds it,
+    against the oracle.  head_dim 256 is served by the generic attention path."""
+    cfg = MC.load("attention_blocks/tome_decoder_octo_base")
+    e = dict(cfg["encoder_1d_block"], _target_="multi_modal_transformers.attention_blocks.attention.Encoder1DBlock")
+    e["self_attention"] = dict(e["self_attention"], _target_="flax.linen.SelfAttention", num_heads=3, qkv_features=768)
+    e["mlp_block"] = dict(e["mlp_block"], dense=dict(e["mlp_block"]["dense"], features=768),
+                          dense_out=dict(e["mlp_block"]["dense_out"], features=768))
+    stack = MC.build_stack({"num_blocks": 1, "encoder_1d_block": e})
+    assert type(stack) is A.StackedEncoder1DBlock
+    seq = "[TaskDescriptionPrefix{16}] [Image{25};Readout{4}]*2"
+    ts = TokenSequence(seq)
+    B, T, C = 2, ts.num_tokens, 768
+    assert T == 74
+    rng = np.random.default_rng(5)
+    x = _dev(rng.standard_normal((B, T, C)).astype(np.float32))
+    variables = stack.init(3, x)
+    dense = torch.as_tensor(ts.generate_attention_mask(repeats=3))[None].expand(B, -1, -1, -1)   # [B, H, T, T] booleans
+    y = stack.apply(variables, x, train=False, mask=dense)
+    assert y.shape == (B, T, C)
+    p = variables["params"]
+    gid, pos, allow, _ = O.sequence_groups(seq)
+    layers = A.flax_tree_to_layers(p["ScanEncoder1DBlock_0"], stack._block()._attn_name, 1)
+    rb = lambda a: torch.as_tensor(np.asarray(a)).bfloat16().float()  # noqa: E731
+    params = [O.BlockParams(**{k: (rb(v) if k.startswith("w") else torch.as_tensor(np.asarray(v))) for k, v in layers[0].items()})]
+    xf, _, _ = O.tome_stack(params, torch.as_tensor(p["posembed_input"]["pos_embedding"]), x.cpu(), gid, pos, allow, num_heads=3, r=0)
+    err = (y.float().cpu() - xf).norm() / xf.norm()
+    assert err <= 3e-2, err
+
+
 def _index_tree(tree, l):
     if isinstance(tree, dict):
         return {k: _index_tree(v, l) for k, v in tree.items()}

@@ -410,3 +410,43 @@ def test_dropout_mask_identical_in_forward_epilogue_and_backward_pass(ops, m, n,
     assert (cs - bwd.float().sum(0)).abs().max().item() <= 1e-3 * m
     other, _ = ops.dropout_colsum(torch.ones(m, n, device="cuda").bfloat16(), rate, seed, site + 1)
     assert not torch.equal(other, bwd)                                       # another site draws another mask
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T,H,D,rate", [(74, 3, 256, 0.0), (74, 3, 256, 0.1), (130, 2, 32, 0.0), (90, 2, 40, 0.25)])
+def test_attention_generic_head_dims(ops, T, H, D, rate):
+    """head_dim != 64 (the literal reference config has 3 heads x 256) runs on the generic attention path: forward, lse and
+    dq / dk / dv vs the oracle with mask, log(size) bias and -- handed the exact regenerated mask -- weight dropout."""
+    rng = np.random.default_rng(T * D + H)
+    B = 2
+    qkv = torch.tensor(rng.standard_normal((B, T, 3, H, D)).astype(np.float32)).cuda().bfloat16()
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    n_img = (T - 16) // 2 - 4
+    g1, p1, allow, _ = O.sequence_groups(f"[TaskDescriptionPrefix{{16}}] [Image{{{n_img}}};Readout{{4}}]*2")
+    pad = T - g1.shape[0]
+    g1 = np.concatenate([g1, np.full(pad, g1[-1], np.uint8)])
+    p1 = np.concatenate([p1, np.arange(pad, dtype=np.int32)])
+    gid, pos = np.stack([g1, rng.permutation(g1)]), np.stack([p1, rng.integers(0, 50, size=T).astype(np.int32)])
+    size = rng.integers(1, 4, size=(B, T)).astype(np.float32)
+    seed, site = 4242, 0x40000001
+    kw = dict(gid=dev(gid), pos=dev(pos), allow=dev(allow), size=dev(size), dropout_rate=rate, dropout_seed=seed, dropout_site=site)
+    out, lse = ops.attention_fwd(q, k, v, **kw)
+    dout = torch.tensor(rng.standard_normal((B, T, H, D)).astype(np.float32)).cuda().bfloat16()
+    dq, dk, dvv = ops.attention_bwd(q, k, v, out, lse, dout, **kw)
+    torch.cuda.synchronize()
+    drop_keep = None
+    if rate > 0:
+        keep, p_eff = O.dropout_keep_mask(T, T, rate, seed, site)
+        drop_keep = torch.as_tensor(keep.astype(np.float32) / (1.0 - p_eff))[None, None]
+    qr, kr, vr = (t.float().cpu().requires_grad_(True) for t in (q, k, v))
+    mask = torch.as_tensor(O.dense_mask(gid, pos, gid, pos, allow))[:, None]
+    bias = torch.log(torch.as_tensor(size))[:, None, None, :]
+    ref = O.attention(qr, kr, vr, mask=mask, bias=bias, drop_keep=drop_keep)
+    rel = lambda a, b: ((a.double() - b.double()).norm() / (b.double().norm() + 1e-12)).item()  # noqa: E731
+    assert rel(out.float().cpu(), ref.detach()) <= 1e-2
+    logits = torch.einsum("bqhd,bkhd->bhqk", q.float().cpu() / math.sqrt(D), k.float().cpu()) + bias
+    logits = torch.where(mask, logits, torch.full_like(logits, -1e30))
+    assert (lse.cpu() - torch.logsumexp(logits, -1)).abs().max().item() <= 2e-2
+    ref.backward(dout.float().cpu())
+    for name, got, want in (("dq", dq, qr.grad), ("dk", dk, kr.grad), ("dv", dvv, vr.grad)):
+        assert rel(got.float().cpu(), want) <= 1.5e-2, name

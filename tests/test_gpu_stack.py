@@ -110,13 +110,12 @@ def test_attention_weight_dropout_fwd_bwd(pkg, T, H, rate):
         assert e <= 2.5e-2, f"{name}: rel err {e}"
 
 
-def _build(pkg, B, W, P, C, H, Dff, Lyr, r, ln_axis, seed=0, n_ro=2, n_tdp=4):
+def _build(pkg, B, W, P, C, H, Dff, Lyr, r, ln_axis, seed=0, n_ro=2, n_tdp=4, D=64):
     ops, engine = pkg
     rng = np.random.default_rng(seed)
     seq = f"[TaskDescriptionPrefix{{{n_tdp}}}] [Image{{{P}}};Readout{{{n_ro}}}]*{W}"
     gid, pos, allow, ro = O.sequence_groups(seq)
     T = gid.shape[0]
-    D = 64
     layers = [O.init_block_params(rng, C, H, D, Dff) for _ in range(Lyr)]
     for d in layers:  # non-trivial LN affine so their gradients are exercised
         for k_ in ("ln1_scale", "ln2_scale"):
@@ -175,8 +174,22 @@ def test_stack_forward_backward_vs_oracle(pkg, ln_axis, r, Lyr, b1_shift, tol_fw
     """Whole stack vs the oracle (fp32 arithmetic, activations rounded to bf16 at the points where the kernels store
     them): merge indices bit-exact (the oracle recomputes ranking + split from the GPU's node_max / node_idx), token
     sizes bit-exact, final tokens / readout / loss and every parameter gradient within the tolerances of CASES."""
-    B, W, P, C, H, Dff = 2, 2, 24, 128, 2, 256
-    eng, cfg, layers, pe, x, y, groups = _build(pkg, B, W, P, C, H, Dff, Lyr, r, ln_axis)
+    _stack_vs_oracle(pkg, dict(B=2, W=2, P=24, C=128, H=2, Dff=256), ln_axis, r, Lyr, b1_shift, tol_fwd, tol_grad)
+
+
+@pytest.mark.parametrize("r,b1_shift,tol_grad", [(0, 8.0, 2e-2), (8, 8.0, 2e-2), (0, 0.0, 0.25)])
+def test_stack_literal_reference_config(pkg, r, b1_shift, tol_grad):
+    """C0, the only shape the reference itself defines (octo_base.yaml:10 + vanilla_decoder.yaml): 74 tokens
+    ("[TaskDescriptionPrefix{16}] [Image{25};Readout{4}]*2"), C = 768, 3 heads x 256, Dff = 768, ONE block, LayerNorm over
+    tokens.  head_dim 256 takes the generic attention path; everything else is the same code as octo-small.  r = 0 is the
+    reference as written (its ToMe step is a stub), r = 8 adds the merge."""
+    _stack_vs_oracle(pkg, dict(B=2, W=2, P=25, C=768, H=3, Dff=768, n_ro=4, n_tdp=16, D=256), 1, r, 1, b1_shift, 3e-2, tol_grad)
+
+
+def _stack_vs_oracle(pkg, shape, ln_axis, r, Lyr, b1_shift, tol_fwd, tol_grad):
+    sh = dict(shape)
+    B, W, P, C, H, Dff = (sh.pop(k_) for k_ in ("B", "W", "P", "C", "H", "Dff"))
+    eng, cfg, layers, pe, x, y, groups = _build(pkg, B, W, P, C, H, Dff, Lyr, r, ln_axis, **sh)
     if b1_shift:
         for d in layers:
             d["b1"] = d["b1"] + np.float32(b1_shift)
