@@ -33,11 +33,14 @@ constexpr int ATT_THREADS = 192;
 constexpr int ATT_Q_BYTES = ATT_BM * ATT_D * 2;         // 16 KB
 constexpr int ATT_KV_BYTES = ATT_BN * ATT_D * 2;        // 8 KB each for K and V
 constexpr int ATT_P_BYTES = ATT_BM * ATT_BN * 2;        // 16 KB, x2 buffers
-constexpr int ATT_SLOTS = 6;  // ring of 8 KB slots; items are loaded in the order K_0 K_1 V_0 K_2 V_1 ...
-constexpr int ATT_MSLOTS = 4; // metadata ring
+constexpr int ATT_SLOTS = 5;  // ring of 8 KB slots; items are loaded in the order K_0 K_1 V_0 K_2 V_1 ...
+constexpr int ATT_MSLOTS = 3; // metadata ring
+constexpr int ATT_QAUG_BYTES = ATT_BM * ATTN_AUG_K * 2;   // 4 KB: mask augmentation operand of the query tile (attn_meta.cuh)
+constexpr int ATT_KAUG_BYTES = ATT_BN * ATTN_AUG_K * 2;   // 2 KB per key tile, one per ring slot
 constexpr int ATT_META_SLOT = ATTN_META_KEY_BYTES + ATTN_DROP_TILE_BYTES;  // bias2 | vis[32][2] | visc[32][2] | pos | dropout keep words [128][2]
 static_assert(ATT_BN == ATTN_META_TILE, "key tiles and metadata tiles must coincide");
-constexpr int ATT_SMEM = ATT_Q_BYTES + ATT_SLOTS * ATT_KV_BYTES + 2 * ATT_P_BYTES + ATT_MSLOTS * ATT_META_SLOT + 512 + 1024;
+constexpr int ATT_SMEM = ATT_Q_BYTES + ATT_SLOTS * ATT_KV_BYTES + 2 * ATT_P_BYTES + ATT_QAUG_BYTES + ATT_SLOTS * ATT_KAUG_BYTES +
+                         ATT_MSLOTS * ATT_META_SLOT + 512 + 1024;
 constexpr uint32_t ATT_TMEM_COLS = 256;  // S0 [0,64) S1 [64,128) O [128,192)
 constexpr float ATT_LAZY_LOG2 = 8.0f;    // rescale O only when the row maximum grows by more than 2^8
 
@@ -47,6 +50,7 @@ struct AttnFwdParams {
   const uint8_t* gid;   // null: no mask
   const int32_t* pos;
   const uint8_t* meta;  // [B][n_kv][ATTN_META_BYTES]
+  const uint32_t* aug_flag;  // != 0: the mask is folded into S by one extra K = 16 MMA step (attn_meta.cuh)
   const uint8_t* keep_q;  // attention dropout keep words [n_q128][n_kv][128][2] or null
   float inv_keep;         // 1 / (1 - rate)
   __nv_bfloat16* out;
@@ -75,14 +79,17 @@ __device__ __forceinline__ void tmem_ld_f32x32(uint32_t taddr, float (&r)[N]) {
 template <bool DROP>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                const __grid_constant__ CUtensorMap tm_v, const AttnFwdParams p) {
+                const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_qaug,
+                const __grid_constant__ CUtensorMap tm_kaug, const AttnFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1 KB alignment by pointer arithmetic on the __shared__ array itself, so every access below stays LDS/STS
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_q = smem;
   uint8_t* s_kv = s_q + ATT_Q_BYTES;                        // slot i at i * 8 KB
   uint8_t* s_p = s_kv + ATT_SLOTS * ATT_KV_BYTES;           // buffer i at i * 16 KB
-  uint8_t* s_meta = s_p + 2 * ATT_P_BYTES;                  // metadata slot i at i * ATT_META_SLOT
+  uint8_t* s_qaug = s_p + 2 * ATT_P_BYTES;                  // [128 rows][16] bf16, 32-byte swizzle
+  uint8_t* s_kaug = s_qaug + ATT_QAUG_BYTES;                // slot i at i * 2 KB (only K slots use theirs)
+  uint8_t* s_meta = s_kaug + ATT_SLOTS * ATT_KAUG_BYTES;    // metadata slot i at i * ATT_META_SLOT
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_meta + ATT_MSLOTS * ATT_META_SLOT);
   uint64_t* q_full = bars;                 // 1
   uint64_t* kv_full = bars + 1;            // [6]
@@ -128,6 +135,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_o = tmem_base + 128;   // 64 columns; S buffers at +0 and +64
   const bool has_mask = p.gid != nullptr;
+  // the mask rides in the QK^T contraction (attn_meta.cuh) when the table allows it; CTA-uniform
+  const bool use_aug = has_mask && *p.aug_flag != 0u;
 
   if (warp == 4) {
     // ================================================================= TMA producer: K/V ring + metadata ring
@@ -136,14 +145,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       auto load_item = [&](bool is_v, int tile) {  // ring order K_0 K_1 V_0 K_2 V_1 ... K_{n-1} V_{n-2} V_{n-1}
         const int slot = item % ATT_SLOTS, use = item / ATT_SLOTS;
         mbar_wait(&kv_empty[slot], (use & 1) ^ 1);
-        mbar_expect_tx(&kv_full[slot], ATT_KV_BYTES);
+        const bool aug = use_aug && !is_v;   // a K tile brings its 2 KB one-hot group operand along
+        mbar_expect_tx(&kv_full[slot], ATT_KV_BYTES + (aug ? ATT_KAUG_BYTES : 0));
         tma_load_3d(s_kv + slot * ATT_KV_BYTES, is_v ? &tm_v : &tm_k, &kv_full[slot], h * ATT_D, tile * ATT_BN, b);
+        if (aug) tma_load_3d(s_kaug + slot * ATT_KAUG_BYTES, &tm_kaug, &kv_full[slot], 0, tile * ATT_BN, b);
         ++item;
       };
-      const uint32_t meta_bytes = has_mask ? ATTN_META_KEY_BYTES : 256u;  // without a mask only the bias is read
+      // with the mask folded into S only the bias (and the dropout words) are read from the metadata block
+      const uint32_t meta_bytes = (has_mask && !use_aug) ? ATTN_META_KEY_BYTES : 256u;
       const uint8_t* meta_b = p.meta + (size_t)b * n_kv * ATTN_META_BYTES;
-      mbar_expect_tx(q_full, ATT_Q_BYTES);
+      mbar_expect_tx(q_full, ATT_Q_BYTES + (use_aug ? ATT_QAUG_BYTES : 0));
       tma_load_3d(s_q, &tm_q, q_full, h * ATT_D, qt * ATT_BM, b);
+      if (use_aug) tma_load_3d(s_qaug, &tm_qaug, q_full, 0, qt * ATT_BM, b);
       load_item(false, 0);
       for (int j = 0; j < n_kv; ++j) {
         const int ms = j % ATT_MSLOTS;
@@ -173,6 +186,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         for (int k = 0; k < ATT_D / 16; ++k)
           umma_bf16(tmem_base + (t & 1) * ATT_BN, make_smem_desc(aq + k * 32, 16, 1024), make_smem_desc(ak + k * 32, 16, 1024),
                     idesc_s, k > 0 ? 1u : 0u);
+        if (use_aug)  // S += Mq Ek^T: 0 where the query's group sees the key's group, -2^100 (absorbing) where it does not
+          umma_bf16(tmem_base + (t & 1) * ATT_BN, make_smem_desc_sw32(smem_u32(s_qaug)),
+                    make_smem_desc_sw32(smem_u32(s_kaug + slot * ATT_KAUG_BYTES)), idesc_s, 1u);
         umma_commit(&s_full[t & 1]);
         umma_commit(&kv_empty[slot]);
       };
@@ -222,7 +238,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const float4* bias4 = reinterpret_cast<const float4*>(mb);
       uint32_t vw0 = 0xffffffffu, vw1 = 0xffffffffu;
       bool masked_tile = false;
-      if (has_mask) {
+      if (has_mask && !use_aug) {
         const uint2 vv = *reinterpret_cast<const uint2*>(mb + ATTN_META_OFF_VIS + gq * 8);
         const uint2 vc = *reinterpret_cast<const uint2*>(mb + ATTN_META_OFF_VISC + gq * 8);
         vw0 = vv.x; vw1 = vv.y;
@@ -365,11 +381,34 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 // ------------------------------------------------------------------------------------------------ metadata (attn_meta.cuh)
 __global__ void __launch_bounds__(ATTN_META_TILE)
 attn_meta_kernel(int T, const uint8_t* __restrict__ gid, const int32_t* __restrict__ pos, const uint8_t* __restrict__ allow,
-                 int G, const float* __restrict__ size, uint8_t* __restrict__ meta) {
+                 int G, const float* __restrict__ size, uint8_t* __restrict__ meta, uint32_t* __restrict__ aug_flag,
+                 uint4* __restrict__ aug_q, uint4* __restrict__ aug_k) {
   const int tile = blockIdx.x, b = blockIdx.y, t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int idx = tile * ATTN_META_TILE + t;
   const bool valid = idx < T;
   uint8_t* m = meta + ((size_t)b * gridDim.x + tile) * ATTN_META_BYTES;
+  if (tile == 0 && b == 0 && t == 0) {  // does the augmentation apply?  a mask, at most 16 groups, no positional rule
+    uint32_t ok = (gid != nullptr && G <= ATTN_AUG_K) ? 1u : 0u;
+    for (int i = 0; ok && i < G * G; ++i)
+      if (allow[i] == 2) ok = 0u;
+    *aug_flag = ok;
+  }
+  {  // augmentation operands of this token: 16 bf16 each (two 16-byte stores); zeros past T or without a mask
+    uint32_t qw[8] = {0, 0, 0, 0, 0, 0, 0, 0}, kw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (gid != nullptr && valid && G <= ATTN_AUG_K) {
+      const int g = gid[(long long)b * T + idx];
+      for (int o = 0; o < G; ++o) {
+        const uint32_t mq = allow[g * G + o] == 1 ? 0u : 0xF180u;   // bf16(-2^100)
+        qw[o >> 1] |= mq << ((o & 1) * 16);
+      }
+      kw[g >> 1] |= 0x3F80u << ((g & 1) * 16);                       // bf16(1)
+    }
+    const size_t row = ((size_t)b * gridDim.x + tile) * ATTN_META_TILE + t;
+    aug_q[row * 2] = make_uint4(qw[0], qw[1], qw[2], qw[3]);
+    aug_q[row * 2 + 1] = make_uint4(qw[4], qw[5], qw[6], qw[7]);
+    aug_k[row * 2] = make_uint4(kw[0], kw[1], kw[2], kw[3]);
+    aug_k[row * 2 + 1] = make_uint4(kw[4], kw[5], kw[6], kw[7]);
+  }
   reinterpret_cast<float*>(m)[t] = valid ? (size ? log2f(size[(long long)b * T + idx]) : 0.f) : -INFINITY;
   uint32_t cw = 0xffffffffu, cc = 0u, rw = 0xffffffffu, rc = 0u;  // tokens past T: "visible" (the -inf bias / +inf lse removes them)
   int ps = 0;
@@ -407,7 +446,10 @@ int launch_attn_meta(int B, int T, const uint8_t* gid, const int32_t* pos, const
                      uint8_t* meta, cudaStream_t stream) {
   TOME_CHECK(meta != nullptr && ((uintptr_t)meta & 15) == 0, TOME_ERR_INVALID, "attention: workspace must be non-null and 16-byte aligned");
   dim3 grid((T + ATTN_META_TILE - 1) / ATTN_META_TILE, B);
-  attn_meta_kernel<<<grid, ATTN_META_TILE, 0, stream>>>(T, gid, pos, allow, G, size, meta);
+  attn_meta_kernel<<<grid, ATTN_META_TILE, 0, stream>>>(
+      T, gid, pos, allow, G, size, meta, const_cast<uint32_t*>(attn_aug_flag(meta, B, T)),
+      reinterpret_cast<uint4*>(const_cast<uint8_t*>(attn_aug_q(meta, B, T))),
+      reinterpret_cast<uint4*>(const_cast<uint8_t*>(attn_aug_k(meta, B, T))));
   TOME_CUDA(cudaGetLastError());
   return TOME_OK;
 }
@@ -519,6 +561,13 @@ extern "C" int tome_attention_fwd(const tome_attn_desc_t* d, const void* q, cons
   p.batch = d->batch; p.tokens = d->tokens; p.heads = d->heads;
   p.scale_log2 = d->scale * 1.4426950408889634f;
   p.gid = d->gid; p.pos = d->pos; p.meta = reinterpret_cast<const uint8_t*>(workspace);
+  p.aug_flag = attn_aug_flag(p.meta, d->batch, d->tokens);
+  CUtensorMap tqa, tka;
+  {
+    const uint64_t tp = attn_tiles(d->tokens) * ATTN_META_TILE;
+    if (int rc = make_tmap_3d_bf16_sw32(&tqa, attn_aug_q(p.meta, d->batch, d->tokens), tp, d->batch, ATT_BM)) return rc;
+    if (int rc = make_tmap_3d_bf16_sw32(&tka, attn_aug_k(p.meta, d->batch, d->tokens), tp, d->batch, ATT_BN)) return rc;
+  }
   p.keep_q = nullptr;
   p.inv_keep = 1.0f;
   if (d->dropout_rate > 0.f) {
@@ -538,8 +587,8 @@ extern "C" int tome_attention_fwd(const tome_attn_desc_t* d, const void* q, cons
     attr_set = true;
   }
   dim3 grid(ceil_div(d->tokens, ATT_BM), d->heads, d->batch);
-  if (p.keep_q) attn_fwd_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tq, tk, tv, p);
-  else attn_fwd_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tq, tk, tv, p);
+  if (p.keep_q) attn_fwd_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tq, tk, tv, tqa, tka, p);
+  else attn_fwd_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tq, tk, tv, tqa, tka, p);
   TOME_CUDA(cudaGetLastError());
   return TOME_OK;
 }

@@ -23,8 +23,25 @@ constexpr int ATTN_META_KEY_BYTES = 1024;   // bias2 | vis | visc | pos : what a
 constexpr int ATTN_META_OFF_VIS = 256, ATTN_META_OFF_VISC = 512, ATTN_META_OFF_POS = 768, ATTN_META_OFF_QVIS = 1024,
               ATTN_META_OFF_QVISC = 1280;
 
-inline size_t attn_meta_bytes(int batch, int tokens) {
-  return (size_t)batch * ((tokens + ATTN_META_TILE - 1) / ATTN_META_TILE) * ATTN_META_BYTES;
+// ---- the mask as part of the QK^T contraction ("augmentation") ----
+// mask[q,k] depends only on (group of q, group of k), i.e. it has rank <= G.  With G <= 16 and no positional (code 2)
+// rule, S' = [Q | Mq] [K | Ek]^T where Ek[k] = one-hot(group of k) and Mq[q][g] = 0 if group(q) sees group g else -2^100
+// adds exactly 0 to visible logits and -2^100 (which absorbs any q.k in fp32) to masked ones: ONE extra K = 16 MMA step per
+// S tile and the softmax threads do no mask work at all.  attn_meta_kernel writes the two [B, Tp, 16] bf16 operand arrays
+// (32-byte rows, loaded by TMA with the 32-byte swizzle) and a flag word saying whether the trick applies to this table.
+constexpr int ATTN_AUG_K = 16;
+constexpr float ATTN_AUG_BIG = 1.2676506002282294e30f;   // 2^100, exact in bf16
+inline size_t attn_tiles(int tokens) { return (size_t)(tokens + ATTN_META_TILE - 1) / ATTN_META_TILE; }
+inline size_t attn_blocks_bytes(int batch, int tokens) { return (size_t)batch * attn_tiles(tokens) * ATTN_META_BYTES; }
+inline size_t attn_aug_array_bytes(int batch, int tokens) { return (size_t)batch * attn_tiles(tokens) * ATTN_META_TILE * ATTN_AUG_K * 2; }
+// workspace of launch_attn_meta: [per-tile blocks][flag, 256 B][q operand][k operand]
+inline size_t attn_meta_bytes(int batch, int tokens) { return attn_blocks_bytes(batch, tokens) + 256 + 2 * attn_aug_array_bytes(batch, tokens); }
+inline const uint32_t* attn_aug_flag(const uint8_t* meta, int batch, int tokens) {
+  return reinterpret_cast<const uint32_t*>(meta + attn_blocks_bytes(batch, tokens));
+}
+inline const uint8_t* attn_aug_q(const uint8_t* meta, int batch, int tokens) { return meta + attn_blocks_bytes(batch, tokens) + 256; }
+inline const uint8_t* attn_aug_k(const uint8_t* meta, int batch, int tokens) {
+  return attn_aug_q(meta, batch, tokens) + attn_aug_array_bytes(batch, tokens);
 }
 // launches attn_meta_kernel (attn_fwd.cu); meta must be 16-byte aligned
 int launch_attn_meta(int B, int T, const uint8_t* gid, const int32_t* pos, const uint8_t* allow, int G, const float* size,

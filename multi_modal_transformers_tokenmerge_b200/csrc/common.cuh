@@ -135,6 +135,17 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= (uint64_t)2 << 61;
   return d;
 }
+// K-major operand of ONE K = 16 step stored as dense 32-byte rows with the 32-byte swizzle (layout_type = 6): 8-row atoms of
+// 256 bytes stacked along M/N (SBO = 256); what TMA writes for a {16 x rows} bf16 box with CU_TENSOR_MAP_SWIZZLE_32B.
+__device__ __forceinline__ uint64_t make_smem_desc_sw32(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;            // LBO: unused for a swizzled K-major operand that is one atom wide
+  d |= (uint64_t)(256 >> 4) << 32;   // SBO
+  d |= (uint64_t)1 << 46;            // version 1 (Blackwell)
+  d |= (uint64_t)6 << 61;            // SWIZZLE_32B
+  return d;
+}
 // Instruction descriptor for kind::f16, bf16 inputs, fp32 accumulator.
 //   [4,6) c_format=1(F32)  [7,10) a_format=1(BF16)  [10,13) b_format=1(BF16)  [15] a_major  [16] b_major
 //   [17,23) N>>3   [24,29) M>>4

@@ -83,6 +83,13 @@ int make_tmap_3d_bf16_plain(CUtensorMap* out, const void* base, uint64_t d0, uin
   return encode(out, base, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
+int make_tmap_3d_bf16_sw32(CUtensorMap* out, const void* base, uint64_t d1, uint64_t d2, uint32_t box_d1) {
+  cuuint64_t dims[3] = {16, d1, d2};
+  cuuint64_t strides[2] = {32, d1 * 32};
+  cuuint32_t box[3] = {16, box_d1, 1};
+  return encode(out, base, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
 }  // namespace tome
 
 namespace tome {

@@ -40,6 +40,9 @@ int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t 
 int make_tmap_3d_bf16_plain(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1,
                             uint64_t stride2, uint32_t box_d0, uint32_t box_d1);
 
+// [d2, d1, 16] bf16 tensor of 32-byte rows (dense), box {16, box_d1, 1}, 32-byte swizzle: the K = 16 "mask augmentation" operand
+int make_tmap_3d_bf16_sw32(CUtensorMap* out, const void* base, uint64_t d1, uint64_t d2, uint32_t box_d1);
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // ---- launch accounting + optional per-op CUDA-event timing (bench.py's roofline pass; off by default) ----
