@@ -36,7 +36,6 @@ struct AttnBwdParams {
   const uint8_t* gid;   // null: no mask
   const int32_t* pos;
   const uint8_t* meta;  // [B][tp/64][ATTN_META_BYTES]
-  const uint32_t* aug_flag;  // != 0: the mask is folded into S / S^T by one extra K = 16 MMA step (attn_meta.cuh)
   const float* size;
   const float* lse2;    // [B,H,tp]  lse * log2(e), +inf past T
   const float* delta;   // [B,H,tp]  0 past T
@@ -87,16 +86,12 @@ constexpr int DKV_KV_BYTES = DKV_BK * AB_D * 2;  // 16 KB
 constexpr int DKV_Q_BYTES = DKV_BQ * AB_D * 2;   // 8 KB
 constexpr int DKV_PT_BYTES = DKV_BK * DKV_BQ * 2;  // 16 KB
 constexpr int DKV_META_SLOT = 1280 + ATTN_DROP_TILE_BYTES;  // lse2[64] | delta[64] | pos[64] | qvis[32][2] | qvisc[32][2] | dropout keep words [128 keys][2]
-constexpr int DKV_KAUG_BYTES = DKV_BK * ATTN_AUG_K * 2;   // 4 KB: one-hot key groups of this CTA's 128 keys
-constexpr int DKV_QAUG_BYTES = DKV_BQ * ATTN_AUG_K * 2;   // 2 KB per query tile stage
-constexpr int DKV_SMEM = 2 * DKV_KV_BYTES + 2 * 2 * DKV_Q_BYTES + 2 * DKV_PT_BYTES + DKV_KAUG_BYTES + 2 * DKV_QAUG_BYTES +
-                         AB_MSLOTS * DKV_META_SLOT + 256 + 1024;
+constexpr int DKV_SMEM = 2 * DKV_KV_BYTES + 2 * 2 * DKV_Q_BYTES + 2 * DKV_PT_BYTES + AB_MSLOTS * DKV_META_SLOT + 256 + 1024;
 
 template <bool DROP>  // attention-weight dropout compiled in or not
 __global__ void __launch_bounds__(AB_THREADS, 2)
 attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                      const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
-                     const __grid_constant__ CUtensorMap tm_qaug, const __grid_constant__ CUtensorMap tm_kaug,
                      const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1 KB alignment by pointer arithmetic on the __shared__ array itself, so every access below stays LDS/STS
@@ -106,9 +101,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   uint8_t* s_qdo = s_v + DKV_KV_BYTES;            // stage s: Q at s*16K, dO at s*16K + 8K
   uint8_t* s_pt = s_qdo + 2 * 2 * DKV_Q_BYTES;    // P^T  [128 keys][64 queries] bf16, K-major swizzled
   uint8_t* s_dst = s_pt + DKV_PT_BYTES;           // dS^T
-  uint8_t* s_kaug = s_dst + DKV_PT_BYTES;         // [128 keys][16] bf16, 32-byte swizzle
-  uint8_t* s_qaug = s_kaug + DKV_KAUG_BYTES;      // stage s at s * 2 KB
-  uint8_t* s_meta = s_qaug + 2 * DKV_QAUG_BYTES;  // slot i at i * DKV_META_SLOT
+  uint8_t* s_meta = s_dst + DKV_PT_BYTES;         // slot i at i * DKV_META_SLOT
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_meta + AB_MSLOTS * DKV_META_SLOT);
   uint64_t* kv_full = bars;        // 1
   uint64_t* q_full = bars + 1;     // [2]
@@ -125,7 +118,6 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   const int T = p.tokens;
   const int n_q = (T + DKV_BQ - 1) / DKV_BQ;
   const bool has_mask = p.gid != nullptr;
-  const bool use_aug = has_mask && *p.aug_flag != 0u;   // CTA-uniform
 
   if (threadIdx.x == 0) {
     mbar_init(kv_full, 1);
@@ -157,10 +149,9 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 
   if (warp == 4) {
     if (lane == 0) {
-      mbar_expect_tx(kv_full, 2 * DKV_KV_BYTES + (use_aug ? DKV_KAUG_BYTES : 0));
+      mbar_expect_tx(kv_full, 2 * DKV_KV_BYTES);
       tma_load_3d(s_k, &tm_k, kv_full, h * AB_D, kt * DKV_BK, b);
       tma_load_3d(s_v, &tm_v, kv_full, h * AB_D, kt * DKV_BK, b);
-      if (use_aug) tma_load_3d(s_kaug, &tm_kaug, kv_full, 0, kt * DKV_BK, b);
       const float* lse_row = p.lse2 + ((size_t)b * p.heads + h) * p.tp;
       const float* del_row = p.delta + ((size_t)b * p.heads + h) * p.tp;
       const uint8_t* meta_b = p.meta + (size_t)b * n_q * ATTN_META_BYTES;
@@ -168,16 +159,14 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const int ms = i % AB_MSLOTS;
         uint8_t* slot = s_meta + ms * DKV_META_SLOT;
         mbar_wait(&meta_empty[ms], ((i / AB_MSLOTS) & 1) ^ 1);
-        const bool mask_words = has_mask && !use_aug;
-        mbar_expect_tx(&meta_full[ms], (mask_words ? 1280u : 512u) + (DROP ? ATTN_DROP_TILE_BYTES : 0));
+        mbar_expect_tx(&meta_full[ms], (has_mask ? 1280u : 512u) + (DROP ? ATTN_DROP_TILE_BYTES : 0));
         if constexpr (DROP) bulk_g2s(slot + 1280, p.keep_k + ((size_t)kt * n_q + i) * ATTN_DROP_TILE_BYTES, ATTN_DROP_TILE_BYTES, &meta_full[ms]);
         bulk_g2s(slot, lse_row + i * DKV_BQ, 256, &meta_full[ms]);
         bulk_g2s(slot + 256, del_row + i * DKV_BQ, 256, &meta_full[ms]);
-        if (mask_words) bulk_g2s(slot + 512, meta_b + (size_t)i * ATTN_META_BYTES + ATTN_META_OFF_POS, 768, &meta_full[ms]);  // pos | qvis | qvisc
+        if (has_mask) bulk_g2s(slot + 512, meta_b + (size_t)i * ATTN_META_BYTES + ATTN_META_OFF_POS, 768, &meta_full[ms]);  // pos | qvis | qvisc
         const int st = i & 1;
         mbar_wait(&q_empty[st], ((i >> 1) & 1) ^ 1);
-        mbar_expect_tx(&q_full[st], 2 * DKV_Q_BYTES + (use_aug ? DKV_QAUG_BYTES : 0));
-        if (use_aug) tma_load_3d(s_qaug + st * DKV_QAUG_BYTES, &tm_qaug, &q_full[st], 0, i * DKV_BQ, b);
+        mbar_expect_tx(&q_full[st], 2 * DKV_Q_BYTES);
         tma_load_3d(s_qdo + st * 2 * DKV_Q_BYTES, &tm_q, &q_full[st], h * AB_D, i * DKV_BQ, b);
         tma_load_3d(s_qdo + st * 2 * DKV_Q_BYTES + DKV_Q_BYTES, &tm_do, &q_full[st], h * AB_D, i * DKV_BQ, b);
       }
@@ -201,8 +190,6 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 #pragma unroll
           for (int k = 0; k < AB_D / 16; ++k)
             umma_bf16(tm_st, make_smem_desc(ak + k * 32, 16, 1024), make_smem_desc(aq + k * 32, 16, 1024), idesc_s, k > 0);
-          if (use_aug)  // S^T += Ek Mq^T: -2^100 where the query's group does not see the key's group
-            umma_bf16(tm_st, make_smem_desc_sw32(smem_u32(s_kaug)), make_smem_desc_sw32(smem_u32(s_qaug + st * DKV_QAUG_BYTES)), idesc_s, 1u);
 #pragma unroll
           for (int k = 0; k < AB_D / 16; ++k)
             umma_bf16(tm_dpt, make_smem_desc(av + k * 32, 16, 1024), make_smem_desc(ado + k * 32, 16, 1024), idesc_s, k > 0);
@@ -245,7 +232,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       const uint8_t* slot = s_meta + ms * DKV_META_SLOT;
       mbar_wait(&meta_full[ms], (i / AB_MSLOTS) & 1);
       uint32_t vw[2] = {0xffffffffu, 0xffffffffu};
-      if (has_mask && !use_aug) {
+      if (has_mask) {
         const uint2 a = *reinterpret_cast<const uint2*>(slot + 768 + gk * 8);
         const uint2 c = *reinterpret_cast<const uint2*>(slot + 1024 + gk * 8);
         vw[0] = a.x; vw[1] = a.y;
@@ -257,8 +244,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           }
         }
       }
-      if (!k_valid) vw[0] = vw[1] = 0u;  // rows past T contribute nothing (their dK / dV rows are never stored either)
-      const bool select_mask = !use_aug || !k_valid;   // warp-divergent only in the one warp that straddles T
+      if (!k_valid) vw[0] = vw[1] = 0u;  // rows past T contribute nothing
       uint32_t kb[2] = {0xffffffffu, 0xffffffffu};  // dropout keep bits of this key against the tile's 64 queries
       if constexpr (DROP) {
         const uint2 t = *reinterpret_cast<const uint2*>(slot + 1280 + row * 8);
@@ -288,10 +274,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             float2 t = __ffma2_rn(make_float2(sv[c], sv[c + 1]), scale2, bias22);
             t = __fadd2_rn(t, make_float2(-lv.x, -lv.y));
             float2 pe = make_float2(fast_exp2(t.x), fast_exp2(t.y));
-            if (select_mask) {
-              pe.x = ((word >> c) & 1u) ? pe.x : 0.f;
-              pe.y = ((word >> (c + 1)) & 1u) ? pe.y : 0.f;
-            }
+            pe.x = ((word >> c) & 1u) ? pe.x : 0.f;
+            pe.y = ((word >> (c + 1)) & 1u) ? pe.y : 0.f;
             // dropout (weights' = weights * keep / (1 - rate)): dP' = dP * keep / (1 - rate) enters dS, P' enters dV
             float2 dp = make_float2(dv[c], dv[c + 1]), pd = pe;
             if constexpr (DROP) {
@@ -362,16 +346,12 @@ constexpr int DQ_Q_BYTES = DQ_BQ * AB_D * 2;   // 16 KB
 constexpr int DQ_K_BYTES = DQ_BK * AB_D * 2;   // 8 KB
 constexpr int DQ_DS_BYTES = DQ_BQ * DQ_BK * 2;  // 16 KB, x2 buffers
 constexpr int DQ_META_SLOT = ATTN_META_KEY_BYTES + ATTN_DROP_TILE_BYTES;  // bias2 | vis | visc | pos | dropout keep words [128 queries][2]
-constexpr int DQ_QAUG_BYTES = DQ_BQ * ATTN_AUG_K * 2;   // 4 KB
-constexpr int DQ_KAUG_BYTES = DQ_BK * ATTN_AUG_K * 2;   // 2 KB per K/V stage
-constexpr int DQ_SMEM = 2 * DQ_Q_BYTES + 2 * 2 * DQ_K_BYTES + 2 * DQ_DS_BYTES + DQ_QAUG_BYTES + 2 * DQ_KAUG_BYTES +
-                        AB_MSLOTS * DQ_META_SLOT + 256 + 1024;
+constexpr int DQ_SMEM = 2 * DQ_Q_BYTES + 2 * 2 * DQ_K_BYTES + 2 * DQ_DS_BYTES + AB_MSLOTS * DQ_META_SLOT + 256 + 1024;
 
 template <bool DROP>
 __global__ void __launch_bounds__(AB_THREADS, 2)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                    const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
-                   const __grid_constant__ CUtensorMap tm_qaug, const __grid_constant__ CUtensorMap tm_kaug,
                    const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -379,9 +359,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   uint8_t* s_do = s_q + DQ_Q_BYTES;
   uint8_t* s_kv = s_do + DQ_Q_BYTES;             // stage s: K at s*16K, V at s*16K + 8K
   uint8_t* s_ds = s_kv + 2 * 2 * DQ_K_BYTES;     // dS [128 queries][64 keys] bf16 K-major swizzled, buffer i at i * 16 KB
-  uint8_t* s_qaug = s_ds + 2 * DQ_DS_BYTES;      // [128 queries][16] bf16, 32-byte swizzle
-  uint8_t* s_kaug = s_qaug + DQ_QAUG_BYTES;      // stage s at s * 2 KB
-  uint8_t* s_meta = s_kaug + 2 * DQ_KAUG_BYTES;  // slot i at i * DQ_META_SLOT
+  uint8_t* s_meta = s_ds + 2 * DQ_DS_BYTES;      // slot i at i * DQ_META_SLOT
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_meta + AB_MSLOTS * DQ_META_SLOT);
   uint64_t* q_full = bars;          // Q and dO
   uint64_t* kv_full = bars + 1;     // [2]
@@ -398,7 +376,6 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   const int T = p.tokens;
   const int n_k = (T + DQ_BK - 1) / DQ_BK;
   const bool has_mask = p.gid != nullptr;
-  const bool use_aug = has_mask && *p.aug_flag != 0u;   // CTA-uniform
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
@@ -430,11 +407,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 
   if (warp == 4) {
     if (lane == 0) {
-      mbar_expect_tx(q_full, 2 * DQ_Q_BYTES + (use_aug ? DQ_QAUG_BYTES : 0));
+      mbar_expect_tx(q_full, 2 * DQ_Q_BYTES);
       tma_load_3d(s_q, &tm_q, q_full, h * AB_D, qt * DQ_BQ, b);
       tma_load_3d(s_do, &tm_do, q_full, h * AB_D, qt * DQ_BQ, b);
-      if (use_aug) tma_load_3d(s_qaug, &tm_qaug, q_full, 0, qt * DQ_BQ, b);
-      const uint32_t meta_bytes = (has_mask && !use_aug) ? ATTN_META_KEY_BYTES : 256u;
+      const uint32_t meta_bytes = has_mask ? ATTN_META_KEY_BYTES : 256u;
       const uint8_t* meta_b = p.meta + (size_t)b * n_k * ATTN_META_BYTES;
       for (int j = 0; j < n_k; ++j) {
         const int ms = j % AB_MSLOTS;
@@ -446,8 +422,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                    ATTN_DROP_TILE_BYTES, &meta_full[ms]);
         const int st = j & 1;
         mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
-        mbar_expect_tx(&kv_full[st], 2 * DQ_K_BYTES + (use_aug ? DQ_KAUG_BYTES : 0));
-        if (use_aug) tma_load_3d(s_kaug + st * DQ_KAUG_BYTES, &tm_kaug, &kv_full[st], 0, j * DQ_BK, b);
+        mbar_expect_tx(&kv_full[st], 2 * DQ_K_BYTES);
         tma_load_3d(s_kv + st * 2 * DQ_K_BYTES, &tm_k, &kv_full[st], h * AB_D, j * DQ_BK, b);
         tma_load_3d(s_kv + st * 2 * DQ_K_BYTES + DQ_K_BYTES, &tm_v, &kv_full[st], h * AB_D, j * DQ_BK, b);
       }
@@ -471,8 +446,6 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 #pragma unroll
           for (int k = 0; k < AB_D / 16; ++k)
             umma_bf16(tm_s, make_smem_desc(aq + k * 32, 16, 1024), make_smem_desc(ak + k * 32, 16, 1024), idesc_s, k > 0);
-          if (use_aug)  // S += Mq Ek^T
-            umma_bf16(tm_s, make_smem_desc_sw32(smem_u32(s_qaug)), make_smem_desc_sw32(smem_u32(s_kaug + st * DQ_KAUG_BYTES)), idesc_s, 1u);
 #pragma unroll
           for (int k = 0; k < AB_D / 16; ++k)
             umma_bf16(tm_dp, make_smem_desc(ado + k * 32, 16, 1024), make_smem_desc(av + k * 32, 16, 1024), idesc_s, k > 0);
@@ -512,7 +485,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       const uint8_t* slot = s_meta + ms * DQ_META_SLOT;
       mbar_wait(&meta_full[ms], (j / AB_MSLOTS) & 1);
       uint32_t vw[2] = {0xffffffffu, 0xffffffffu};
-      if (has_mask && !use_aug) {
+      if (has_mask) {
         const uint2 a = *reinterpret_cast<const uint2*>(slot + ATTN_META_OFF_VIS + gq * 8);
         const uint2 c = *reinterpret_cast<const uint2*>(slot + ATTN_META_OFF_VISC + gq * 8);
         vw[0] = a.x; vw[1] = a.y;
@@ -552,10 +525,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             float2 t = __ffma2_rn(make_float2(sv[c], sv[c + 1]), scale2, bv);
             t = __fadd2_rn(t, nl2);
             float2 pe = make_float2(fast_exp2(t.x), fast_exp2(t.y));
-            if (!use_aug) {
-              pe.x = ((word >> c) & 1u) ? pe.x : 0.f;
-              pe.y = ((word >> (c + 1)) & 1u) ? pe.y : 0.f;
-            }
+            pe.x = ((word >> c) & 1u) ? pe.x : 0.f;
+            pe.y = ((word >> (c + 1)) & 1u) ? pe.y : 0.f;
             float2 dp = make_float2(dv[c], dv[c + 1]);
             if constexpr (DROP) {  // dP' = dP * keep / (1 - rate)
               dp = __fmul2_rn(dp, ik2);
@@ -669,8 +640,6 @@ extern "C" int tome_attention_bwd(const tome_attn_desc_t* d, const tome_attn_gra
   p.batch = B; p.tokens = T; p.heads = H; p.tp = Tp;
   p.scale = d->scale; p.scale_log2 = d->scale * 1.4426950408889634f;
   p.gid = d->gid; p.pos = d->pos; p.meta = meta; p.size = d->size; p.lse2 = lse2; p.delta = delta;
-  p.aug_flag = attn_aug_flag(meta, B, T);
-  const uint64_t tp_aug = attn_tiles(T) * ATTN_META_TILE;
   p.keep_q = keep_q; p.keep_k = keep_k; p.inv_keep = inv_keep;
   p.dq = reinterpret_cast<__nv_bfloat16*>(dq); p.dq_bs = gs->dq_batch_stride; p.dq_ts = gs->dq_token_stride;
   p.dk = reinterpret_cast<__nv_bfloat16*>(dk); p.dk_bs = gs->dk_batch_stride; p.dk_ts = gs->dk_token_stride;
@@ -689,12 +658,9 @@ extern "C" int tome_attention_bwd(const tome_attn_desc_t* d, const tome_attn_gra
     if (int rc = make_tmap_3d_bf16(&tk, k, hd, T, B, d->k_token_stride, d->k_batch_stride, DKV_BK)) return rc;
     if (int rc = make_tmap_3d_bf16(&tv, v, hd, T, B, d->v_token_stride, d->v_batch_stride, DKV_BK)) return rc;
     if (int rc = make_tmap_3d_bf16(&tdo, dout, hd, T, B, gs->do_token_stride, gs->do_batch_stride, DKV_BQ)) return rc;
-    CUtensorMap tqa, tka;
-    if (int rc = make_tmap_3d_bf16_sw32(&tqa, attn_aug_q(meta, B, T), tp_aug, B, DKV_BQ)) return rc;
-    if (int rc = make_tmap_3d_bf16_sw32(&tka, attn_aug_k(meta, B, T), tp_aug, B, DKV_BK)) return rc;
     dim3 grid(ceil_div(T, DKV_BK), H, B);
-    if (keep_k) attn_bwd_dkdv_kernel<true><<<grid, AB_THREADS, DKV_SMEM, stream>>>(tq, tk, tv, tdo, tqa, tka, p);
-    else attn_bwd_dkdv_kernel<false><<<grid, AB_THREADS, DKV_SMEM, stream>>>(tq, tk, tv, tdo, tqa, tka, p);
+    if (keep_k) attn_bwd_dkdv_kernel<true><<<grid, AB_THREADS, DKV_SMEM, stream>>>(tq, tk, tv, tdo, p);
+    else attn_bwd_dkdv_kernel<false><<<grid, AB_THREADS, DKV_SMEM, stream>>>(tq, tk, tv, tdo, p);
     TOME_CUDA(cudaGetLastError());
   }
   {
@@ -703,12 +669,9 @@ extern "C" int tome_attention_bwd(const tome_attn_desc_t* d, const tome_attn_gra
     if (int rc = make_tmap_3d_bf16(&tk, k, hd, T, B, d->k_token_stride, d->k_batch_stride, DQ_BK)) return rc;
     if (int rc = make_tmap_3d_bf16(&tv, v, hd, T, B, d->v_token_stride, d->v_batch_stride, DQ_BK)) return rc;
     if (int rc = make_tmap_3d_bf16(&tdo, dout, hd, T, B, gs->do_token_stride, gs->do_batch_stride, DQ_BQ)) return rc;
-    CUtensorMap tqa, tka;
-    if (int rc = make_tmap_3d_bf16_sw32(&tqa, attn_aug_q(meta, B, T), tp_aug, B, DQ_BQ)) return rc;
-    if (int rc = make_tmap_3d_bf16_sw32(&tka, attn_aug_k(meta, B, T), tp_aug, B, DQ_BK)) return rc;
     dim3 grid(ceil_div(T, DQ_BQ), H, B);
-    if (keep_q) attn_bwd_dq_kernel<true><<<grid, AB_THREADS, DQ_SMEM, stream>>>(tq, tk, tv, tdo, tqa, tka, p);
-    else attn_bwd_dq_kernel<false><<<grid, AB_THREADS, DQ_SMEM, stream>>>(tq, tk, tv, tdo, tqa, tka, p);
+    if (keep_q) attn_bwd_dq_kernel<true><<<grid, AB_THREADS, DQ_SMEM, stream>>>(tq, tk, tv, tdo, p);
+    else attn_bwd_dq_kernel<false><<<grid, AB_THREADS, DQ_SMEM, stream>>>(tq, tk, tv, tdo, p);
     TOME_CUDA(cudaGetLastError());
   }
   return TOME_OK;
