@@ -6,7 +6,7 @@
 
 A "step" is one full training step of the octo-small-style ToMe stack (BASELINE.json configs[1]: batch 256 per GPU,
 T0 = 536 tokens, 12 layers, r = 16 / layer, block-causal readout mask, bf16) on synthetic embeddings: zero grads,
-forward, synthetic readout loss, full backward, (N > 1: overlapped NCCL gradient all-reduce), AdamW.
+forward, action head + l2 loss on the readouts (or the synthetic readout MSE), full backward, (N > 1: overlapped NCCL gradient all-reduce), AdamW.
 One JSON line is printed by rank 0.  See DESIGN.md "Measurement" for every field.
 """
 from __future__ import annotations
@@ -91,7 +91,10 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ reference arm / cpu baseline
-def cpu_reference_steps(cfgname, steps, warmup, sample_batch):
+ACTION_DIM, MAX_ACTION = 8, 1.0   # action_heads/diffusion.yaml dense_out features: 8; continuous.py:13 max_action
+
+
+def cpu_reference_steps(cfgname, steps, warmup, sample_batch, loss_kind="continuous"):
     """The reference's algorithm for this path, restated (oracle/tome_oracle.py: sequential scatter loop, double merge
     call, dense [B,H,T,T] mask, fp32) as a torch-CPU train step with autograd + SGD, all host threads.  JAX/Flax are
     not installable here (no wheels, no network), so this is the port ("kind": "port"), not the JAX program."""
@@ -109,13 +112,21 @@ def cpu_reference_steps(cfgname, steps, warmup, sample_batch):
     x = torch.tensor(np.random.default_rng(0).standard_normal((sample_batch, T0, c["channels"])).astype(np.float32))
     y = torch.tensor(np.random.default_rng(2).standard_normal((sample_batch, len(ro), c["channels"])).astype(np.float32))
     leaves = [t for p in params for t in p.tensors()] + [pe]
+    if loss_kind == "continuous":   # ContinuousActionHead + compute_l2_loss (continuous.py:16-25, octo.py:157-165, 253-263)
+        hk = torch.tensor((rng.standard_normal((c["channels"], ACTION_DIM)) * (2.0 / c["channels"]) ** 0.5).astype(np.float32),
+                          requires_grad=True)
+        hb = torch.zeros(ACTION_DIM, requires_grad=True)
+        actions = torch.tensor(np.random.default_rng(3).uniform(-1, 1, (sample_batch, ACTION_DIM)).astype(np.float32))
+        leaves += [hk, hb]
     opt = torch.optim.SGD(leaves, lr=1e-4)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         opt.zero_grad(set_to_none=True)
         xf, size, origin = O.tome_stack(params, pe, x, gid, pos, allow, num_heads=c["heads"], r=c["r"])
-        loss, _ = O.readout_loss(xf, origin, ro, y)
+        loss, readouts = O.readout_loss(xf, origin, ro, y)
+        if loss_kind == "continuous":
+            loss = O.l2_loss(O.continuous_action_head(readouts, hk, hb, MAX_ACTION), actions).mean()
         loss.backward()
         opt.step()
         if i >= warmup:
@@ -129,7 +140,10 @@ def workload_config(args, world, B, T0):
     return {"workload": f"{args.config} ToMe stack train step (BASELINE.json configs[{1 if args.config == 'octo_small' else 2}] shape)",
             "global_batch": B * world, "per_gpu_batch": B, "tokens": T0, "layers": c["layers"], "channels": c["channels"],
             "heads": c["heads"], "mlp_dim": c["mlp_dim"], "r_per_layer": c["r"], "mask": "block-causal group table",
-            "ln_axis": "tokens", "hidden_dropout": args.dropout, "attention_dropout": args.attn_dropout, "optimizer": "AdamW fp32 master",
+            "ln_axis": "tokens",
+            "loss": ("continuous action head + l2 loss on the pooled readouts (continuous_train_step, octo.py:242-280)"
+                     if args.loss == "continuous" else "synthetic MSE on the readout rows"),
+            "hidden_dropout": args.dropout, "attention_dropout": args.attn_dropout, "optimizer": "AdamW fp32 master",
             "parallelism": f"dp{world}", "l2_policy": "inputs and activations (>= 1 GB/step) exceed the 126 MB L2"}
 
 
@@ -137,7 +151,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     sb = 2 if (args.steps + args.warmup) <= 12 else 1
-    sps, sec, cores, T0 = cpu_reference_steps(args.config, args.steps, args.warmup, sb)
+    sps, sec, cores, T0 = cpu_reference_steps(args.config, args.steps, args.warmup, sb, args.loss)
     c = CONFIGS[args.config]
     sample = f"{sb} samples/step of the {args.config} workload (T0={T0}, {c['layers']} layers, r={c['r']}), fp32, train step"
     print(json.dumps({
@@ -163,6 +177,9 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override (default: the config's 256)")
     ap.add_argument("--dropout", type=float, default=0.1, help="hidden dropout rate (vanilla_decoder.yaml:17,50)")
     ap.add_argument("--attn-dropout", type=float, default=0.1, help="attention-weight dropout rate (vanilla_decoder.yaml:23)")
+    ap.add_argument("--loss", default="continuous", choices=["continuous", "synthetic"],
+                    help="continuous: ContinuousActionHead + l2 loss on the pooled readouts, the reference's "
+                         "continuous_train_step; synthetic: MSE on the readout rows")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "tome_b200" else args.warmup
@@ -197,13 +214,15 @@ def main():
     T0, B, C = len(gid), c["batch"], c["channels"]
     cfg = StackConfig(batch=B, tokens=T0, channels=C, heads=c["heads"], head_dim=c["head_dim"], mlp_dim=c["mlp_dim"],
                       layers=c["layers"], r=c["r"], ln_axis=1, num_groups=allow.shape[0], n_readout=len(ro),
-                      dropout_rate=args.dropout, dropout_seed=1234 + rank, attn_dropout_rate=args.attn_dropout)
+                      dropout_rate=args.dropout, dropout_seed=1234 + rank, attn_dropout_rate=args.attn_dropout,
+                      **(dict(head="continuous", head_features=ACTION_DIM, max_action=MAX_ACTION) if args.loss == "continuous" else {}))
     eng = ToMeStackEngine(cfg, gid=gid, pos=pos, allow=allow, readout_idx=ro)
     eng.init_params(seed=1)  # same weights on every rank
     trainer = DataParallelTrainer(eng)
     g = torch.Generator(device="cuda").manual_seed(100 + rank)
     x = torch.randn(B, T0, C, device="cuda", generator=g).bfloat16()      # synthetic block inputs (embeddings)
-    y = torch.randn(B, len(ro), C, device="cuda", generator=g)
+    tshape = (B, ACTION_DIM) if args.loss == "continuous" else (B, len(ro), C)   # target actions / synthetic readout targets
+    y = torch.rand(*tshape, device="cuda", generator=g) * 2 - 1 if args.loss == "continuous" else torch.randn(*tshape, device="cuda", generator=g)
 
     def barrier():
         if world > 1:
@@ -235,7 +254,7 @@ def main():
 
     # ---- end to end through the public API: pinned host inputs -> H2D -> step -> D2H loss, every step ----
     xh = [torch.randn(B, T0, C).bfloat16().pin_memory() for _ in range(2)]
-    yh = [torch.randn(B, len(ro), C).pin_memory() for _ in range(2)]
+    yh = [(torch.rand(*tshape) * 2 - 1 if args.loss == "continuous" else torch.randn(*tshape)).pin_memory() for _ in range(2)]
     xd = [torch.empty_like(x) for _ in range(2)]
     yd = [torch.empty_like(y) for _ in range(2)]
     loss_h = torch.zeros(1).pin_memory()
@@ -356,7 +375,7 @@ def main():
             "kernels": kernels, "model_tflops": value / world * fl / 1e12, "loss": loss_dev,
         }
         if world == 1 and not args.no_cpu_baseline:
-            sps, sec, cores, _ = cpu_reference_steps(args.config, 3, 1, 2)
+            sps, sec, cores, _ = cpu_reference_steps(args.config, 3, 1, 2, args.loss)
             out["cpu_baseline"] = {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
                                    "sample": f"3 train steps of 2 samples of the same workload (fp32, torch-CPU restatement of the "
                                              f"reference), {sec:.1f} s/step"}

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TOME_ABI_VERSION 6
+#define TOME_ABI_VERSION 7
 
 enum tome_status { TOME_OK = 0, TOME_ERR_INVALID = 1, TOME_ERR_CUDA = 2, TOME_ERR_UNSUPPORTED = 3 };
 enum tome_dtype { TOME_BF16 = 0, TOME_F32 = 1 };
@@ -263,6 +263,40 @@ int tome_chain_row_maps(int batch, int layers, const int32_t* const* row_maps_ho
 int tome_readout_mse(int batch, int tokens, int channels, int n_readout, const void* x, const int32_t* origin,
                      const float* target, float* loss, void* dx, float* out, void* stream);
 
+/* Action heads on the pooled readout rows and their training losses.
+ *   TOME_HEAD_CONTINUOUS_L2:  action_heads/continuous.py:16-25 + models/octo/octo.py:157-165, 253-263
+ *       pooled = mean over all n_readout rows; z = pooled W + b; out = tanh(z / max_action) * max_action  (f32 [B, features]);
+ *       loss_b = sum_a (out - actions[b,a])^2, loss[0] = mean_b loss_b.  groups must be 1; actions f32 [B, features].
+ *   TOME_HEAD_CATEGORICAL_CE: action_heads/categorical.py:12-40 + models/octo/octo.py:178-190, 292-303
+ *       readout i belongs to action group i / (n_readout / groups) ("(action timestep)"); pooled[g] = mean of the group;
+ *       out = logits = pooled[g] W + b (f32 [B, groups, features], features = num_bins);
+ *       label = one_hot(digitize(actions[b,g], linspace(-max_action, max_action, features + 1)), features) -- literally:
+ *       digitize is 1-based, so bin k maps to class k + 1 and the top bin / out-of-range values to an all-zero label, whose
+ *       cross-entropy is 0; loss[0] = mean over (b, g) of -sum_f label_f log_softmax(logits)_f.  actions f32 [B, groups].
+ * x is the FINAL sequence of the stack ([B, tokens, C], bf16 or f32) and origin i32 [B, n_readout] the row each readout
+ * token ended up in (tome_chain_row_maps; arange(n_readout) for an already gathered readout tensor, tokens = n_readout).
+ * w f32 [C, features] (Flax Dense kernel layout), bias f32 [features] or NULL.  loss f32 [1 + B] as tome_readout_mse
+ * (NULL: inference).  workspace (tome_action_head_workspace_bytes; NULL when no backward follows) keeps pooled and
+ * dL/dz for tome_action_head_bwd, which ACCUMULATES into dw [C, features] / dbias [features] (summed over the batch in a
+ * fixed order) and OVERWRITES dx (x's dtype and shape; zero except the readout rows; NULL to skip). */
+#define TOME_HEAD_CONTINUOUS_L2 0
+#define TOME_HEAD_CATEGORICAL_CE 1
+typedef struct {
+  int batch, tokens, channels;
+  int x_dtype;      /* tome_dtype of x / dx */
+  int n_readout;
+  int groups;       /* 1 (continuous) or action_space_dim (categorical) */
+  int features;     /* Dense features: action dimensions (continuous) or num_bins (categorical) */
+  int kind;         /* TOME_HEAD_* */
+  float max_action;
+} tome_head_desc_t;
+size_t tome_action_head_workspace_bytes(const tome_head_desc_t* desc);
+int tome_action_head_fwd(const tome_head_desc_t* desc, const void* x, const int32_t* origin, const float* w,
+                         const float* bias, const float* actions, float* out, float* loss, void* workspace,
+                         size_t workspace_bytes, void* stream);
+int tome_action_head_bwd(const tome_head_desc_t* desc, const int32_t* origin, const float* w, const void* workspace,
+                         float* dw, float* dbias, void* dx, void* stream);
+
 /* AdamW on an fp32 master vector with a bf16 working copy refreshed in the same pass (bf16_copy may be NULL).
  * grad_scale multiplies the gradient first (1/world_size after a sum all-reduce). */
 int tome_adamw_step(long long n, float* param, const float* grad, float* m, float* v, void* bf16_copy, float lr,
@@ -287,14 +321,21 @@ typedef struct {
   float dropout_rate; /* hidden dropout after out-proj, ReLU and dense_out (attention.py:34,37,60); 0 in parity mode */
   uint64_t dropout_seed;
   float attn_dropout_rate; /* attention-weight dropout (self_attention.dropout_rate, vanilla_decoder.yaml:23), same seed */
+  int head;           /* loss on the readout rows: 0 = synthetic MSE against target [B,n_readout,C] (tome_readout_mse);
+                         1 + TOME_HEAD_*: that action head and its loss (tome_action_head_*), target = actions */
+  int head_groups;    /* tome_head_desc_t.groups */
+  int head_features;  /* tome_head_desc_t.features */
+  float max_action;
 } tome_stack_cfg_t;
 
 /* Per-layer parameter offsets (elements) into one flat fp32 vector (master weights / gradients / Adam moments)
  * and the same offsets into a flat bf16 working copy.  Kernels are stored [in, out] (Flax layout):
  * wqkv [C, 3*H*D] = concat(query, key, value kernels), wo [H*D, C], w1 [C, Dff], w2 [Dff, C].
  * Layout of one layer: ln1_scale[C] ln1_bias[C] wqkv bqkv[3HD] wo bo[C] ln2_scale[C] ln2_bias[C] w1 b1[Dff] w2 b2[C];
- * the vector starts with pos_embedding [T0, C].  tome_stack_param_count gives the total. */
+ * the vector starts with pos_embedding [T0, C]; with cfg.head > 0 it ends with the head's Dense kernel [C, features] and
+ * bias [features] (tome_stack_head_offset; -1 without a head).  tome_stack_param_count gives the total. */
 long long tome_stack_param_count(const tome_stack_cfg_t* cfg);
+long long tome_stack_head_offset(const tome_stack_cfg_t* cfg);
 long long tome_stack_layer_offset(const tome_stack_cfg_t* cfg, int layer); /* offset of ln1_scale of `layer` */
 
 /* bytes of activation workspace the executor needs (saved activations for backward + scratch) */
@@ -309,7 +350,8 @@ typedef struct {
   const int32_t* pos;         /* [T0] */
   const uint8_t* allow;       /* [G,G] */
   const int32_t* readout_idx; /* [n_readout] original positions of the readout tokens */
-  const float* target;        /* [B,n_readout,C] (loss) or NULL */
+  const float* target;        /* loss target or NULL: [B,n_readout,C] (head 0), actions [B,features] (continuous head)
+                                 or [B,groups] (categorical head) */
   void* workspace; size_t workspace_bytes;
   /* outputs */
   void* x_final;              /* bf16 [B,T_L,C] (points into workspace when NULL is passed: see tome_stack_final) */
@@ -318,6 +360,8 @@ typedef struct {
   float* grads_f32;           /* flat fp32 gradient vector (backward; accumulated into, caller zeroes) */
   void* const* layer_done_events; /* optional host array [layers+1] of cudaEvent_t recorded as each layer's (and
                                      finally the pos-embedding's) gradients become final, for all-reduce overlap */
+  float* head_out;            /* f32 [B, head_groups, head_features]: actions (continuous) or logits (categorical);
+                                 required when cfg.head > 0 */
 } tome_stack_io_t;
 
 int tome_stack_forward(const tome_stack_cfg_t* cfg, const tome_stack_io_t* io, void* stream);

@@ -15,7 +15,7 @@ TOME_OK, TOME_ERR_INVALID, TOME_ERR_CUDA, TOME_ERR_UNSUPPORTED = 0, 1, 2, 3
 TOME_BF16, TOME_F32 = 0, 1
 TOME_MAJOR_K, TOME_MAJOR_MN = 0, 1
 TOME_MERGE_SUM, TOME_MERGE_WAVG = 0, 1
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 vp, ll, i32, f32, u64, u32 = C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_uint64, C.c_uint32
 
@@ -81,7 +81,16 @@ class StackCfg(C.Structure):
     _fields_ = [("batch", i32), ("tokens", i32), ("channels", i32), ("heads", i32), ("head_dim", i32),
                 ("mlp_dim", i32), ("layers", i32), ("r", i32), ("ln_axis", i32), ("ln_eps", f32),
                 ("prop_attn", i32), ("class_token", i32), ("distill_token", i32), ("num_groups", i32),
-                ("n_readout", i32), ("dropout_rate", f32), ("dropout_seed", u64), ("attn_dropout_rate", f32)]
+                ("n_readout", i32), ("dropout_rate", f32), ("dropout_seed", u64), ("attn_dropout_rate", f32),
+                ("head", i32), ("head_groups", i32), ("head_features", i32), ("max_action", f32)]
+
+
+HEAD_CONTINUOUS_L2, HEAD_CATEGORICAL_CE = 0, 1
+
+
+class HeadDesc(C.Structure):
+    _fields_ = [("batch", i32), ("tokens", i32), ("channels", i32), ("x_dtype", i32), ("n_readout", i32),
+                ("groups", i32), ("features", i32), ("kind", i32), ("max_action", f32)]
 
 
 class StackIO(C.Structure):
@@ -89,7 +98,7 @@ class StackIO(C.Structure):
                 ("gid", vp), ("pos", vp), ("allow", vp), ("readout_idx", vp), ("target", vp),
                 ("workspace", vp), ("workspace_bytes", C.c_size_t),
                 ("x_final", vp), ("readout", vp), ("loss", vp), ("grads_f32", vp),
-                ("layer_done_events", C.POINTER(vp))]
+                ("layer_done_events", C.POINTER(vp)), ("head_out", vp)]
 
 
 _lib = None
@@ -109,10 +118,10 @@ def lib() -> C.CDLL:
         if L.tome_abi_version() != ABI_VERSION:
             raise ImportError(f"libtome_b200.so has ABI {L.tome_abi_version()}, python binding expects {ABI_VERSION}: rebuild")
         for name in ("tome_gemm_workspace_bytes", "tome_stack_workspace_bytes", "tome_attention_workspace_bytes", "tome_sim_argmax_workspace_bytes",
-                     "tome_attention_bwd_workspace_bytes"):
+                     "tome_attention_bwd_workspace_bytes", "tome_action_head_workspace_bytes"):
             if hasattr(L, name):
                 getattr(L, name).restype = C.c_size_t
-        for name in ("tome_stack_param_count", "tome_stack_layer_offset", "tome_launch_count"):
+        for name in ("tome_stack_param_count", "tome_stack_layer_offset", "tome_stack_head_offset", "tome_launch_count"):
             if hasattr(L, name):
                 getattr(L, name).restype = ll
         for name in ("tome_stack_final_x", "tome_stack_final_size", "tome_stack_layer_edge_idx", "tome_stack_layer_dst_idx",
@@ -143,6 +152,10 @@ def lib() -> C.CDLL:
             "tome_pos_embedding_bwd": [i32, i32, i32, vp, vp, vp],
             "tome_chain_row_maps": [i32, i32, P(vp), P(i32), vp, i32, vp, vp],
             "tome_readout_mse": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp],
+            "tome_action_head_workspace_bytes": [P(HeadDesc)],
+            "tome_action_head_fwd": [P(HeadDesc), vp, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp],
+            "tome_action_head_bwd": [P(HeadDesc), vp, vp, vp, vp, vp, vp, vp],
+            "tome_stack_head_offset": [P(StackCfg)],
             "tome_adamw_step": [ll, vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, f32, i32, vp],
             "tome_cast_f32_to_bf16": [ll, vp, vp, vp],
             "tome_launch_count": [i32],

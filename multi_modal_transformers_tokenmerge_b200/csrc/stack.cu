@@ -50,6 +50,8 @@ struct StackLayout {
   uint8_t *ws_attn, *ws_sim;
   size_t ws_attn_bytes, ws_sim_bytes;
   int32_t* origin;
+  uint8_t* ws_head;      // pooled readouts + dL/dz of the action head (cfg.head > 0)
+  size_t ws_head_bytes;
   size_t ws_gemm_bytes;
   size_t total;
 };
@@ -79,6 +81,15 @@ static ParamOffsets layer_offsets(const tome_stack_cfg_t* c, int layer) {
   return o;
 }
 
+// descriptor of the action head over the final sequence of `tokens` rows (cfg.head = 1 + TOME_HEAD_*)
+static tome_head_desc_t head_desc(const tome_stack_cfg_t* c, int tokens) {
+  tome_head_desc_t h;
+  h.batch = c->batch; h.tokens = tokens; h.channels = c->channels; h.x_dtype = TOME_BF16;
+  h.n_readout = c->n_readout; h.groups = c->head_groups; h.features = c->head_features;
+  h.kind = c->head - 1; h.max_action = c->max_action;
+  return h;
+}
+
 static int check_cfg(const tome_stack_cfg_t* c) {
   TOME_CHECK(c != nullptr, TOME_ERR_INVALID, "stack: null config");
   TOME_CHECK(c->batch > 0 && c->tokens >= 2 && c->layers >= 1 && c->layers <= 64, TOME_ERR_INVALID,
@@ -95,6 +106,13 @@ static int check_cfg(const tome_stack_cfg_t* c) {
   TOME_CHECK(c->dropout_rate >= 0.f && c->dropout_rate < 1.f, TOME_ERR_INVALID, "stack: dropout_rate must be in [0, 1)");
   TOME_CHECK(c->attn_dropout_rate >= 0.f && c->attn_dropout_rate < 1.f, TOME_ERR_INVALID, "stack: attn_dropout_rate must be in [0, 1)");
   TOME_CHECK(c->n_readout >= 0, TOME_ERR_INVALID, "stack: n_readout must be >= 0");
+  TOME_CHECK(c->head >= 0 && c->head <= 2, TOME_ERR_INVALID,
+             "stack: head must be 0 (synthetic readout MSE), 1 (continuous l2) or 2 (categorical cross-entropy)");
+  if (c->head > 0) {
+    TOME_CHECK(c->n_readout > 0, TOME_ERR_INVALID, "stack: an action head needs readout tokens");
+    tome_head_desc_t h = head_desc(c, 1);
+    if (tome_action_head_workspace_bytes(&h) == 0) return TOME_ERR_INVALID;  // message set by the head's own check
+  }
   return TOME_OK;
 }
 
@@ -206,6 +224,13 @@ static StackLayout make_layout(const tome_stack_cfg_t* c, void* workspace) {
   const size_t ln_rows = c->ln_axis == 1 ? B : 256;
   S.ws_ln = b.take<float>(2 * ln_rows * C);
   S.origin = b.take<int32_t>(B * (c->n_readout > 0 ? c->n_readout : 1));
+  S.ws_head_bytes = 0;
+  S.ws_head = nullptr;
+  if (c->head > 0) {
+    tome_head_desc_t h = head_desc(c, 1);
+    S.ws_head_bytes = tome_action_head_workspace_bytes(&h);
+    S.ws_head = b.take<uint8_t>(S.ws_head_bytes);
+  }
   S.total = (b.off + 255) & ~size_t(255);
   return S;
 }
@@ -262,8 +287,17 @@ static int gemm(const tome_stack_cfg_t* c, const StackLayout& S, cudaStream_t st
 
 using namespace tome;
 
+// the action head's Dense kernel [C, features] and bias [features] follow the last layer (so they ride in the last
+// layer's all-reduce bucket: their gradients are the first to become final)
+static long long head_param_count(const tome_stack_cfg_t* c) {
+  return c->head > 0 ? (long long)c->channels * c->head_features + c->head_features : 0;
+}
 extern "C" long long tome_stack_param_count(const tome_stack_cfg_t* c) {
   if (check_cfg(c)) return -1;
+  return layer_offsets(c, c->layers).ln1_scale + head_param_count(c);
+}
+extern "C" long long tome_stack_head_offset(const tome_stack_cfg_t* c) {
+  if (check_cfg(c) || c->head == 0) return -1;
   return layer_offsets(c, c->layers).ln1_scale;
 }
 extern "C" long long tome_stack_layer_offset(const tome_stack_cfg_t* c, int layer) {
@@ -361,7 +395,17 @@ extern "C" int tome_stack_forward(const tome_stack_cfg_t* c, const tome_stack_io
       toks[l] = S.shapes[l].t_in;
     }
     RC(tome_chain_row_maps(B, c->layers, maps, toks, io->readout_idx, c->n_readout, S.origin, st));
-    if (io->readout || (io->target && io->loss))
+    if (c->head > 0) {
+      // action head on the pooled readout rows + its loss (continuous.py / categorical.py, octo.py:157-190)
+      tome_head_desc_t h = head_desc(c, TL);
+      const long long ho = layer_offsets(c, c->layers).ln1_scale;
+      const bool with_loss = io->target && io->loss;
+      TOME_CHECK(io->head_out, TOME_ERR_INVALID, "stack: head_out missing");
+      RC(tome_action_head_fwd(&h, S.L.back().x_out, S.origin, io->params_f32 + ho, io->params_f32 + ho + (long long)C * c->head_features,
+                              with_loss ? io->target : nullptr, io->head_out, with_loss ? io->loss : nullptr, S.ws_head,
+                              S.ws_head_bytes, st));
+      if (io->readout) RC(tome_readout_mse(B, TL, C, c->n_readout, S.L.back().x_out, S.origin, nullptr, nullptr, nullptr, io->readout, st));
+    } else if (io->readout || (io->target && io->loss))
       RC(tome_readout_mse(B, TL, C, c->n_readout, S.L.back().x_out, S.origin, (io->target && io->loss) ? io->target : nullptr,
                           (io->target && io->loss) ? io->loss : nullptr, nullptr, io->readout, st));
   }
@@ -383,8 +427,15 @@ extern "C" int tome_stack_backward(const tome_stack_cfg_t* c, const tome_stack_i
   const int TL = S.shapes.back().t_out;
 
   __nv_bfloat16 *g0 = S.g0, *g1 = S.g1, *g2 = S.g2, *g3 = S.g3;
-  // dL/dx_final (and the loss value again, harmless) from the readout rows
-  RC(tome_readout_mse(B, TL, C, c->n_readout, S.L.back().x_out, S.origin, io->target, io->loss, g0, nullptr, st));
+  // dL/dx_final from the readout rows: through the action head (pooled / dL/dz saved by forward), or the synthetic MSE
+  // (which recomputes the loss value, harmless)
+  if (c->head > 0) {
+    tome_head_desc_t h = head_desc(c, TL);
+    const long long ho = layer_offsets(c, c->layers).ln1_scale;
+    RC(tome_action_head_bwd(&h, S.origin, pf + ho, S.ws_head, gr + ho, gr + ho + (long long)C * c->head_features, g0, st));
+  } else {
+    RC(tome_readout_mse(B, TL, C, c->n_readout, S.L.back().x_out, S.origin, io->target, io->loss, g0, nullptr, st));
+  }
 
   // dy_eff = dropout mask applied to an incoming gradient + its column sums (the Dense bias gradient), one pass
   auto masked_colsum = [&](const __nv_bfloat16* src, __nv_bfloat16* dst, int rows, int ncols, int site, float* dbias,

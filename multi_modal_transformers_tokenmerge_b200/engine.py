@@ -40,12 +40,18 @@ class StackConfig:
     dropout_rate: float = 0.0
     dropout_seed: int = 0
     attn_dropout_rate: float = 0.0   # attention-weight dropout (self_attention.dropout_rate, vanilla_decoder.yaml:23)
+    head: str = "none"          # loss on the readouts: "none" = synthetic MSE, "continuous" (continuous.py + l2 loss,
+                                # octo.py:157-165) or "categorical" (categorical.py + cross-entropy, octo.py:178-190)
+    head_groups: int = 1        # categorical: action_space_dim
+    head_features: int = 0      # continuous: action dimensions; categorical: num_bins
+    max_action: float = 1.0
 
     def c(self) -> L.StackCfg:
         return L.StackCfg(self.batch, self.tokens, self.channels, self.heads, self.head_dim, self.mlp_dim, self.layers,
                           self.r, self.ln_axis, self.ln_eps, int(self.prop_attn), int(self.class_token),
                           int(self.distill_token), self.num_groups, self.n_readout, self.dropout_rate, self.dropout_seed,
-                          self.attn_dropout_rate)
+                          self.attn_dropout_rate, {"none": 0, "continuous": 1, "categorical": 2}[self.head],
+                          self.head_groups, self.head_features, self.max_action)
 
     def param_shapes(self) -> Dict[str, tuple]:
         c, hd, f = self.channels, self.heads * self.head_dim, self.mlp_dim
@@ -82,6 +88,8 @@ class ToMeStackEngine:
         self.loss = torch.zeros(1 + cfg.batch, dtype=torch.float32, device=self.dev)
         self.readout = (torch.empty(cfg.batch, cfg.n_readout, cfg.channels, dtype=torch.float32, device=self.dev)
                         if cfg.n_readout else None)
+        self.head_out = (torch.empty(cfg.batch, cfg.head_groups, cfg.head_features, dtype=torch.float32, device=self.dev)
+                         if cfg.head != "none" else None)
         self._x = self._target = None
         self._events = None
 
@@ -102,9 +110,14 @@ class ToMeStackEngine:
                 d[name] = flat[off: off + n].view(*shapes[name])
                 off += n
             out["layers"].append(d)
+        if cfg.head != "none":  # Dense kernel [C, features] + bias [features] of the action head, after the last layer
+            off = int(self.lib.tome_stack_head_offset(C.byref(self.ccfg)))
+            n = cfg.channels * cfg.head_features
+            out["head"] = {"kernel": flat[off: off + n].view(cfg.channels, cfg.head_features),
+                           "bias": flat[off + n: off + n + cfg.head_features]}
         return out
 
-    def load_params(self, pos_embedding, layers: Sequence[dict]) -> None:
+    def load_params(self, pos_embedding, layers: Sequence[dict], head: Optional[dict] = None) -> None:
         """`layers[l]` uses the oracle / Flax names: ln1_scale, ln1_bias, wq, bq, wk, bk, wv, bv, wo, bo, ln2_*, w1, b1, w2, b2
         (kernels [in, out]); or already-fused wqkv / bqkv."""
         v = self.param_views(self.params)
@@ -116,6 +129,9 @@ class ToMeStackEngine:
                 src["bqkv"] = torch.cat([src["bq"], src["bk"], src["bv"]], dim=0)
             for name in PARAM_ORDER:
                 v["layers"][l][name].copy_(src[name])
+        if head is not None:
+            v["head"]["kernel"].copy_(torch.as_tensor(np.asarray(head["kernel"], np.float32)))
+            v["head"]["bias"].copy_(torch.as_tensor(np.asarray(head["bias"], np.float32)))
         self.sync_bf16()
 
     def init_params(self, seed: int = 1) -> None:
@@ -135,6 +151,9 @@ class ToMeStackEngine:
                     t.zero_()
                 else:
                     t.normal_(0.0, 0.01, generator=g)
+        if "head" in v:
+            v["head"]["kernel"].normal_(0.0, (2.0 / self.cfg.channels) ** 0.5, generator=g)
+            v["head"]["bias"].normal_(0.0, 0.01, generator=g)
         self.sync_bf16()
 
     def sync_bf16(self) -> None:
@@ -158,14 +177,17 @@ class ToMeStackEngine:
                          self.workspace.data_ptr() + self._ws_off, self._ws_bytes, None,
                          None if self.readout is None else self.readout.data_ptr(), self.loss.data_ptr(),
                          None if self.grads is None else self.grads.data_ptr(),
-                         None if ev is None else C.cast(ev, C.POINTER(C.c_void_p)))
+                         None if ev is None else C.cast(ev, C.POINTER(C.c_void_p)),
+                         None if self.head_out is None else self.head_out.data_ptr())
 
     def forward(self, x: torch.Tensor, target: Optional[torch.Tensor] = None):
         cfg = self.cfg
         assert x.is_cuda and x.is_contiguous() and tuple(x.shape) == (cfg.batch, cfg.tokens, cfg.channels), x.shape
         assert x.dtype in (torch.float32, torch.bfloat16)
         if target is not None:
-            assert target.dtype == torch.float32 and tuple(target.shape) == (cfg.batch, cfg.n_readout, cfg.channels)
+            want = {"none": (cfg.batch, cfg.n_readout, cfg.channels), "continuous": (cfg.batch, cfg.head_features),
+                    "categorical": (cfg.batch, cfg.head_groups)}[cfg.head]
+            assert target.dtype == torch.float32 and tuple(target.shape) == want, (target.shape, want)
         self._x, self._target = x, target
         io = self._io(x, target)
         L.check(self.lib.tome_stack_forward(C.byref(self.ccfg), C.byref(io), self._stream()))

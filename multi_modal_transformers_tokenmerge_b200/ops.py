@@ -292,3 +292,62 @@ def attention_bwd(q, k, v, out, lse, dout, *, gid=None, pos=None, allow=None, si
     L.check(L.lib().tome_attention_bwd(C.byref(desc), C.byref(gs), _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse),
                                        _ptr(dout), _ptr(dq), _ptr(dk), _ptr(dv), _ptr(ws), ws.numel(), _stream()))
     return dq, dk, dv
+
+
+# ------------------------------------------------------------------------------------------------ action heads
+@dataclass
+class HeadState:
+    """What tome_action_head_fwd leaves behind for the backward call."""
+
+    desc: "L.HeadDesc"
+    origin: torch.Tensor
+    w: torch.Tensor
+    workspace: torch.Tensor
+    off: int
+
+
+def action_head_fwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], *, kind: int, max_action: float,
+                    groups: int = 1, origin: Optional[torch.Tensor] = None, actions: Optional[torch.Tensor] = None,
+                    keep_for_backward: bool = False):
+    """Pooled-readout action head + loss (continuous.py:16-25 / categorical.py:30-40, octo.py:157-190).
+
+    x [B, tokens, C] bf16 / f32; origin i32 [B, n_readout] = rows of x holding the readouts (default: every row).
+    Returns (out f32 [B, groups, features], loss f32 [1 + B] or None, HeadState or None)."""
+    _need_cuda(x, w, bias, origin, actions)
+    B, T, Cc = x.shape
+    assert x.is_contiguous() and w.dtype == torch.float32 and w.is_contiguous() and w.shape[0] == Cc
+    if origin is None:
+        origin = torch.arange(T, dtype=torch.int32, device=x.device).repeat(B, 1)
+    assert origin.dtype == torch.int32 and origin.is_contiguous() and origin.shape[0] == B
+    feats = int(w.shape[1])
+    d = L.HeadDesc(B, T, Cc, _dt(x), int(origin.shape[1]), int(groups), feats, int(kind), float(max_action))
+    out = torch.empty(B, groups, feats, dtype=torch.float32, device=x.device)
+    loss = None
+    if actions is not None:
+        assert actions.dtype == torch.float32 and actions.is_contiguous()
+        want = (B, feats) if kind == L.HEAD_CONTINUOUS_L2 else (B, groups)
+        assert tuple(actions.shape) == want, (actions.shape, want)
+        loss = torch.zeros(1 + B, dtype=torch.float32, device=x.device)
+    ws, off, nbytes = None, 0, 0
+    if keep_for_backward:
+        nbytes = int(L.lib().tome_action_head_workspace_bytes(C.byref(d)))
+        if nbytes == 0:
+            L.check(1)
+        ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=x.device)
+        off = (-ws.data_ptr()) % 256
+    L.check(L.lib().tome_action_head_fwd(C.byref(d), _ptr(x), _ptr(origin), _ptr(w), _ptr(bias), _ptr(actions), _ptr(out),
+                                         _ptr(loss), None if ws is None else C.c_void_p(ws.data_ptr() + off), nbytes, _stream()))
+    return out, loss, (HeadState(d, origin, w, ws, off) if keep_for_backward else None)
+
+
+def action_head_bwd(state: HeadState, dw: torch.Tensor, dbias: Optional[torch.Tensor], want_dx: bool = True):
+    """Accumulates into dw [C, features] / dbias [features]; returns dx (x's dtype and shape) or None."""
+    d = state.desc
+    dx = None
+    if want_dx:
+        dx = torch.empty(d.batch, d.tokens, d.channels, dtype=torch.bfloat16 if d.x_dtype == L.TOME_BF16 else torch.float32,
+                         device=dw.device)
+    L.check(L.lib().tome_action_head_bwd(C.byref(d), _ptr(state.origin), _ptr(state.w),
+                                         C.c_void_p(state.workspace.data_ptr() + state.off), _ptr(dw), _ptr(dbias), _ptr(dx),
+                                         _stream()))
+    return dx

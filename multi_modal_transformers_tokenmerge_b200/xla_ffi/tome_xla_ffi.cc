@@ -176,7 +176,8 @@ static ffi::Error StackFwd(cudaStream_t s, ffi::Buffer<ffi::F32> params_f32, ffi
                            ffi::Buffer<ffi::U8> gid, ffi::Buffer<ffi::S32> pos, ffi::Buffer<ffi::U8> allow,
                            ffi::Buffer<ffi::S32> readout_idx, ffi::Buffer<ffi::F32> target, ffi::Result<ffi::Buffer<ffi::U8>> workspace,
                            ffi::Result<ffi::AnyBuffer> x_final, ffi::Result<ffi::Buffer<ffi::F32>> readout,
-                           ffi::Result<ffi::Buffer<ffi::F32>> loss, std::string_view cfg_bytes) {
+                           ffi::Result<ffi::Buffer<ffi::F32>> loss, ffi::Result<ffi::Buffer<ffi::F32>> head_out,
+                           std::string_view cfg_bytes) {
   if (cfg_bytes.size() != sizeof(tome_stack_cfg_t)) return ffi::Error(ffi::ErrorCode::kInvalidArgument, "bad tome_stack_cfg_t attribute");
   tome_stack_cfg_t cfg;
   memcpy(&cfg, cfg_bytes.data(), sizeof(cfg));
@@ -188,6 +189,7 @@ static ffi::Error StackFwd(cudaStream_t s, ffi::Buffer<ffi::F32> params_f32, ffi
   io.readout_idx = readout_idx.typed_data(); io.target = target.typed_data();
   io.workspace = workspace->typed_data(); io.workspace_bytes = workspace->element_count();
   io.x_final = x_final->untyped_data(); io.readout = readout->typed_data(); io.loss = loss->typed_data();
+  io.head_out = cfg.head > 0 ? head_out->typed_data() : nullptr;   // actions / logits of the action head ([1] dummy without one)
   return Status(tome_stack_forward(&cfg, &io, s));
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(TomeStackFwd, StackFwd,
@@ -195,4 +197,4 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(TomeStackFwd, StackFwd,
                                   .Arg<ffi::AnyBuffer>().Arg<ffi::Buffer<ffi::U8>>().Arg<ffi::Buffer<ffi::S32>>()
                                   .Arg<ffi::Buffer<ffi::U8>>().Arg<ffi::Buffer<ffi::S32>>().Arg<ffi::Buffer<ffi::F32>>()
                                   .Ret<ffi::Buffer<ffi::U8>>().Ret<ffi::AnyBuffer>().Ret<ffi::Buffer<ffi::F32>>()
-                                  .Ret<ffi::Buffer<ffi::F32>>().Attr<std::string_view>("cfg"));
+                                  .Ret<ffi::Buffer<ffi::F32>>().Ret<ffi::Buffer<ffi::F32>>().Attr<std::string_view>("cfg"));

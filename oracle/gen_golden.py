@@ -9,6 +9,10 @@ Reference entry points executed:
   multi_modal_transformers/tokenizers/token_compression.py:15-46   compute_top_k_tokens
   multi_modal_transformers/tokenizers/token_sequencer.py:186-334   TokenSequence.generate_attention_mask,
                                                                    get_modality_idx
+  multi_modal_transformers/action_heads/continuous.py:12-25        ContinuousActionHead.__call__
+  multi_modal_transformers/action_heads/categorical.py:12-40       assign_bins, CategoricalActionHead.__call__
+  (the two loss expressions live inside the Octo class, which needs the whole model: octo.py:163-165 and :183-187 are
+   restated here in numpy float64 on the executed heads' outputs)
 """
 import importlib.util
 import os
@@ -142,6 +146,49 @@ def main():
         mo[f"{name}/readout_idx"] = np.asarray(seq.get_modality_idx("readouts")).astype(np.int32)
     np.savez_compressed(os.path.join(OUT, "token_sequencer.npz"), **mo)
     print("token_sequencer.npz:", list(seqs))
+
+    # ---------------- action heads (continuous.py, categorical.py) ----------------
+    cont = _load("ref_continuous", f"{REF}/multi_modal_transformers/action_heads/continuous.py")
+    cat = _load("ref_categorical", f"{REF}/multi_modal_transformers/action_heads/categorical.py")
+    hrng = np.random.default_rng(20261020)
+    ho = {}
+    ccases = [("cont_small", 3, 4, 16, 7, 1.0), ("cont_octo", 4, 8, 768, 8, 2.0), ("cont_saturated", 2, 4, 32, 5, 0.25)]
+    for name, B, n, C, A, mx in ccases:
+        readouts = hrng.standard_normal((B, n, C)).astype(np.float32)
+        kernel = (hrng.standard_normal((C, A)) * np.sqrt(2.0 / C)).astype(np.float32)
+        bias = (hrng.standard_normal(A) * 0.01).astype(np.float32)
+        actions = (hrng.uniform(-mx, mx, size=(B, A))).astype(np.float32)
+        dense = {"_target_": "flax.linen.Dense", "features": A, "kernel": kernel, "bias": bias}
+        head = cont.ContinuousActionHead(max_action=mx, attention_pooling={}, dense=dense)
+        pred = np.asarray(head(jnp.asarray(readouts)))                     # the reference module itself, [B, 1, A]
+        p64 = np.squeeze(pred).astype(np.float64)                           # octo.py:163
+        loss = np.sum(np.square(p64 - actions), axis=-1)                    # octo.py:165
+        ho.update({f"{name}/readouts": readouts, f"{name}/kernel": kernel, f"{name}/bias": bias, f"{name}/actions": actions,
+                   f"{name}/max_action": np.float32(mx), f"{name}/pred": pred, f"{name}/loss": loss.astype(np.float32)})
+    kcases = [("cat_small", 3, 2, 3, 16, 8, 1.0), ("cat_octo", 4, 8, 1, 768, 256, 2.0), ("cat_edges", 2, 4, 2, 32, 4, 1.0)]
+    for name, B, A, ts_, C, bins, mx in kcases:
+        n = A * ts_
+        readouts = hrng.standard_normal((B, n, C)).astype(np.float32)
+        kernel = (hrng.standard_normal((C, bins)) * np.sqrt(2.0 / C)).astype(np.float32)
+        bias = (hrng.standard_normal(bins) * 0.01).astype(np.float32)
+        actions = (hrng.uniform(-mx, mx, size=(B, A))).astype(np.float32)
+        if name == "cat_edges":   # values on bin edges, at both bounds and outside them
+            actions = np.array([[-1.0, -0.5, 0.0, 0.5], [1.0, 1.5, -1.5, 0.999]], np.float32)
+        dense = {"_target_": "flax.linen.Dense", "features": bins, "kernel": kernel, "bias": bias}
+        head = cat.CategoricalActionHead(num_bins=bins, max_action=mx, action_space_dim=A, dense=dense)
+        logits = np.asarray(head(jnp.asarray(readouts)))                    # the reference module itself, [B, A, bins]
+        target_bin = np.asarray(cat.assign_bins(jnp.asarray(actions), (-mx, mx), bins))   # the reference function itself
+        onehot = (target_bin[..., None] == np.arange(bins)).astype(np.float64)   # jax.nn.one_hot: out of range -> zeros
+        z = logits.astype(np.float64)
+        logsm = z - z.max(-1, keepdims=True) - np.log(np.exp(z - z.max(-1, keepdims=True)).sum(-1, keepdims=True))
+        loss = -(onehot * logsm).sum(-1)                                    # optax.softmax_cross_entropy, octo.py:187
+        ho.update({f"{name}/readouts": readouts, f"{name}/kernel": kernel, f"{name}/bias": bias, f"{name}/actions": actions,
+                   f"{name}/max_action": np.float32(mx), f"{name}/cfg": np.array([A, bins], np.int32), f"{name}/logits": logits,
+                   f"{name}/target_bin": target_bin.astype(np.int32), f"{name}/loss": loss.astype(np.float32)})
+    ho["continuous"] = np.array([c[0] for c in ccases])
+    ho["categorical"] = np.array([c[0] for c in kcases])
+    np.savez_compressed(os.path.join(OUT, "action_heads.npz"), **ho)
+    print("action_heads.npz:", list(ho["continuous"]), list(ho["categorical"]))
 
 
 if __name__ == "__main__":

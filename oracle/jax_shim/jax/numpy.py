@@ -67,7 +67,7 @@ def _lift(name):
 
 for _n in ("matmul", "swapaxes", "take_along_axis", "concatenate", "ones_like", "zeros_like", "arange", "ones",
            "zeros", "hstack", "vstack", "squeeze", "take", "ravel", "sum", "expand_dims", "repeat", "tile",
-           "where", "stack", "sqrt", "log", "exp", "maximum", "minimum", "abs", "mean"):
+           "where", "stack", "sqrt", "log", "exp", "maximum", "minimum", "abs", "mean", "tanh", "digitize"):
     globals()[_n] = _lift(_n)
 
 
@@ -85,3 +85,8 @@ class linalg:
     def norm(x, axis=None, keepdims=False):
         x = _np.asarray(x)
         return _wrap(_np.sqrt(_np.sum(x * x, axis=axis, keepdims=keepdims)))
+
+
+def linspace(start, stop, num=50, dtype=None):
+    """jnp.linspace with x64 disabled: computed in fp32 (start + i * step, last point = stop)."""
+    return _wrap(_np.linspace(_np.float32(start), _np.float32(stop), num, dtype=_np.float32))

@@ -12,14 +12,16 @@ It restates, line by line, the reference's algorithm for the hot path (paths rel
   * hyper-parameters, LN axes .... model_configs/attention_blocks/vanilla_decoder.yaml:1-59
   * mask rules ................... tokenizers/token_sequencer.py:55-183, 199-253, 313-334
   * mask use / readout gather .... models/octo/octo.py:66-68, 116-126
+  * action heads + losses ........ action_heads/continuous.py:16-25, action_heads/categorical.py:12-40,
+                                   models/octo/octo.py:157-165, 178-190 (l2 / cross-entropy), :253-263, 292-303 (mean)
 
 Third-party arithmetic that is NOT under /root/reference and is restated from its published behaviour:
 flax ^0.8.2 (`dot_product_attention`, `DenseGeneral`, `LayerNorm(use_fast_variance=True)`, `Dropout`),
 jax ^0.4.26 (`argsort` stable, `argmax` first-max, `.at[].add`), see pyproject.toml:27-47.
 
 Parity pinning: the matching/merge functions are checked against golden vectors produced by EXECUTING the
-reference's own `token_compression.py` / `token_sequencer.py` under a numpy shim of jax (oracle/gen_golden.py ->
-tests/golden/*.npz) and against the hand-checked vector of SURVEY.md Appendix B.  The block-level pieces that do
+reference's own `token_compression.py` / `token_sequencer.py` / `action_heads/continuous.py` /
+`action_heads/categorical.py` under a numpy shim of jax + flax (oracle/gen_golden.py -> tests/golden/*.npz) and against the hand-checked vector of SURVEY.md Appendix B.  The block-level pieces that do
 not exist in runnable form in the reference (ToMe placement, `unmerge`, proportional `log size` bias -- the
 reference's tome_attention.py is a SyntaxError and has no tests) are DEFINED here following the ToMe paper;
 for those rows parity is "unpinned by the reference" and this file is the only pin.
@@ -524,3 +526,51 @@ def block_params_to_torch(d: dict, dtype=None, requires_grad=False) -> BlockPara
         t.requires_grad_(requires_grad)
         kw[k] = t
     return BlockParams(**kw)
+
+
+# --------------------------------------------------------------------------------------------------------
+# 5. action heads on the readouts + their losses   (torch CPU: autograd gives the gradients)
+# --------------------------------------------------------------------------------------------------------
+
+
+def continuous_action_head(readouts, kernel, bias, max_action: float):
+    """ContinuousActionHead.__call__ (action_heads/continuous.py:16-25): mean over the readout axis, Dense,
+    reshape to [B, 1, A], tanh(mean / max_action) * max_action.  readouts [B, n, C]; kernel [C, A]; bias [A]."""
+    torch = _torch()
+    emb = readouts.mean(dim=-2)                                   # :17
+    mean = emb @ kernel + bias                                    # :21  flax Dense
+    mean = mean.reshape(mean.shape[0], 1, -1)                     # :22  "batch (seq mean) -> batch seq mean", seq = 1
+    return torch.tanh(mean / max_action) * max_action             # :24
+
+
+def l2_loss(predictions, actions):
+    """Octo.compute_l2_loss (octo.py:161-165) -> [B]; the train step takes its mean (:253-263)."""
+    torch = _torch()
+    predictions = torch.squeeze(predictions)                      # :163
+    return ((predictions - actions) ** 2).sum(dim=-1)             # :165
+
+
+def assign_bins(x: np.ndarray, bounds, num_bins: int) -> np.ndarray:
+    """categorical.py:12-22: jnp.digitize against linspace(lo, hi, num_bins + 1) in fp32 -- 1-based for in-range values."""
+    bins = np.linspace(np.float32(bounds[0]), np.float32(bounds[1]), num_bins + 1, dtype=np.float32)
+    return np.digitize(np.asarray(x, np.float32), bins).astype(np.int32)
+
+
+def categorical_action_head(readouts, kernel, bias, action_space_dim: int):
+    """CategoricalActionHead.__call__ (categorical.py:30-40): "(action timestep)" groups, mean over the timestep axis,
+    squeeze, Dense -> logits [B, action, num_bins]."""
+    torch = _torch()
+    B, n, C = readouts.shape
+    emb = readouts.reshape(B, action_space_dim, n // action_space_dim, C)   # :31-35
+    emb = torch.squeeze(emb.mean(dim=-2))                                    # :37
+    return emb @ kernel + bias                                              # :38
+
+
+def ce_loss(logits, actions: np.ndarray, max_action: float, num_bins: int):
+    """Octo.compute_ce_loss (octo.py:182-190): labels = one_hot(assign_bins(actions)), out-of-range index -> all-zero row
+    (jax.nn.one_hot); optax.softmax_cross_entropy = -sum(labels * log_softmax(logits), -1) -> [B, action]."""
+    torch = _torch()
+    idx = assign_bins(actions, (-max_action, max_action), num_bins)         # :182
+    onehot = (idx[..., None] == np.arange(num_bins)).astype(np.float32)      # :183
+    labels = torch.as_tensor(onehot, dtype=logits.dtype)
+    return -(labels * torch.log_softmax(logits, dim=-1)).sum(dim=-1)         # :187

@@ -63,6 +63,27 @@ def test_stack_shape_arithmetic_on_host(lib):
     assert b"multiples of 8" in lib.tome_last_error()
 
 
+def test_action_head_shapes_on_host(lib):
+    """Head descriptors are validated on the host, and a stack with a head carries the head's Dense kernel + bias at the
+    end of the flat parameter vector (continuous.py:21 / categorical.py:38)."""
+    from multi_modal_transformers_tokenmerge_b200 import _lib as L
+    from multi_modal_transformers_tokenmerge_b200.engine import StackConfig
+    d = L.HeadDesc(256, 344, 384, L.TOME_BF16, 8, 1, 7, L.HEAD_CONTINUOUS_L2, 1.0)
+    assert lib.tome_action_head_workspace_bytes(C.byref(d)) >= 256 * (384 + 7) * 4
+    d = L.HeadDesc(4, 10, 32, L.TOME_BF16, 8, 3, 16, L.HEAD_CATEGORICAL_CE, 1.0)   # 8 readouts / 3 actions
+    assert lib.tome_action_head_workspace_bytes(C.byref(d)) == 0 and b"do not split" in lib.tome_last_error()
+    d = L.HeadDesc(4, 10, 32, L.TOME_BF16, 8, 2, 16, L.HEAD_CONTINUOUS_L2, 1.0)
+    assert lib.tome_action_head_workspace_bytes(C.byref(d)) == 0 and b"groups must be 1" in lib.tome_last_error()
+    base = dict(batch=8, tokens=74, channels=768, heads=12, head_dim=64, mlp_dim=3072, layers=2, r=4, num_groups=5, n_readout=8)
+    n0 = lib.tome_stack_param_count(C.byref(StackConfig(**base).c()))
+    assert lib.tome_stack_head_offset(C.byref(StackConfig(**base).c())) == -1
+    cfg = StackConfig(**base, head="categorical", head_groups=8, head_features=256, max_action=1.0).c()
+    assert lib.tome_stack_param_count(C.byref(cfg)) == n0 + 768 * 256 + 256
+    assert lib.tome_stack_head_offset(C.byref(cfg)) == n0
+    bad = StackConfig(**base, head="continuous", head_groups=2, head_features=7).c()
+    assert lib.tome_stack_param_count(C.byref(bad)) == -1 and b"groups must be 1" in lib.tome_last_error()
+
+
 def test_validation_errors_are_reported_not_thrown(lib):
     from multi_modal_transformers_tokenmerge_b200 import _lib as L
     assert lib.tome_gemm_bf16(None, None, 0, None) == L.TOME_ERR_INVALID

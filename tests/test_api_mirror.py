@@ -15,6 +15,7 @@ from multi_modal_transformers_tokenmerge_b200 import model_configs as MC  # noqa
 from multi_modal_transformers_tokenmerge_b200.attention_blocks import _functional as F  # noqa: E402
 from multi_modal_transformers_tokenmerge_b200.attention_blocks import attention as A  # noqa: E402
 from multi_modal_transformers_tokenmerge_b200.attention_blocks import tome_attention as TA  # noqa: E402
+from multi_modal_transformers_tokenmerge_b200 import action_heads as AH  # noqa: E402
 from multi_modal_transformers_tokenmerge_b200.tokenizers import token_compression as TCm  # noqa: E402
 from multi_modal_transformers_tokenmerge_b200.tokenizers.token_sequencer import TokenSequence  # noqa: E402
 from oracle import tome_oracle as O  # noqa: E402  (checker only)
@@ -276,3 +277,42 @@ def test_mha_module_and_hidden_dropout_site_parity():
     torch.testing.assert_close(h, y_stack, rtol=0, atol=0)
     y_eval = stack.apply(variables, xs, train=False, mask=gm)
     assert not torch.equal(y_eval, y_stack)
+
+
+@gpu
+def test_action_head_modules_against_reference_goldens():
+    """ContinuousActionHead / CategoricalActionHead constructed and called as the reference's modules are
+    (continuous.py:12-25, categorical.py:24-40; the Dense node is the one diffusion.yaml / vanilla_decoder.yaml use), on
+    the inputs and parameters of goldens made by executing those modules: same shapes, same numbers (fp32, 1e-5), and
+    the losses of octo.py:157-190 on top."""
+    g = np.load(os.path.join(GOLD, "action_heads.npz"))
+    dense = lambda f: {"_target_": "flax.linen.Dense", "features": f, "use_bias": True,  # noqa: E731
+                       "kernel_init": {"_target_": "flax.linen.initializers.he_normal"},
+                       "bias_init": {"_target_": "flax.linen.initializers.normal"}}
+    for name in g["continuous"]:
+        ro, act = _dev(g[f"{name}/readouts"]), _dev(g[f"{name}/actions"])
+        A_ = g[f"{name}/kernel"].shape[1]
+        head = AH.ContinuousActionHead(max_action=float(g[f"{name}/max_action"]), attention_pooling=None, dense=dense(A_))
+        v = head.init(0, ro)
+        assert v["params"]["Dense_0"]["kernel"].shape == g[f"{name}/kernel"].shape       # Flax's auto-name for the Dense
+        v = {"params": {"Dense_0": {"kernel": g[f"{name}/kernel"], "bias": g[f"{name}/bias"]}}}
+        pred = head.apply(v, ro)
+        assert tuple(pred.shape) == g[f"{name}/pred"].shape                              # [B, 1, A] (continuous.py:22)
+        np.testing.assert_allclose(pred.cpu().numpy(), g[f"{name}/pred"], rtol=1e-5, atol=1e-6)
+        per_row, mean = AH.l2_loss(head, v, ro, act)
+        np.testing.assert_allclose(per_row.cpu().numpy(), g[f"{name}/loss"], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(mean.item(), g[f"{name}/loss"].mean(), rtol=1e-4)
+    for name in g["categorical"]:
+        A_, bins = (int(x) for x in g[f"{name}/cfg"])
+        ro, act = _dev(g[f"{name}/readouts"]), _dev(g[f"{name}/actions"])
+        mx = float(g[f"{name}/max_action"])
+        head = AH.CategoricalActionHead(num_bins=bins, max_action=mx, action_space_dim=A_, dense=dense(bins))
+        v = {"params": {"Dense_0": {"kernel": g[f"{name}/kernel"], "bias": g[f"{name}/bias"]}}}
+        logits = head.apply(v, ro)
+        np.testing.assert_allclose(logits.cpu().numpy().reshape(g[f"{name}/logits"].shape), g[f"{name}/logits"], rtol=1e-5, atol=2e-6)
+        np.testing.assert_array_equal(AH.categorical.assign_bins(act, (-mx, mx), bins), g[f"{name}/target_bin"])
+        per_row, mean = AH.ce_loss(head, v, ro, act)
+        np.testing.assert_allclose(per_row.cpu().numpy(), g[f"{name}/loss"].sum(-1), rtol=1e-4, atol=1e-5)
+    with pytest.raises(ValueError, match="num_bins"):
+        AH.CategoricalActionHead(num_bins=8, max_action=1.0, action_space_dim=2, dense=dense(7)).apply(
+            {"params": {"Dense_0": {"kernel": np.zeros((16, 7), np.float32)}}}, torch.zeros(1, 4, 16, device="cuda"))

@@ -450,3 +450,109 @@ def test_attention_generic_head_dims(ops, T, H, D, rate):
     ref.backward(dout.float().cpu())
     for name, got, want in (("dq", dq, qr.grad), ("dk", dk, kr.grad), ("dv", dvv, vr.grad)):
         assert rel(got.float().cpu(), want) <= 1.5e-2, name
+
+
+# ------------------------------------------------------------------------------------------------ action heads
+def rel_err(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+def _head_golden():
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "action_heads.npz"))
+
+
+@pytest.mark.parametrize("name", ["cont_small", "cont_octo", "cont_saturated"])
+def test_continuous_head_matches_reference_goldens(ops, name):
+    """tome_action_head_fwd (continuous) against outputs of the reference's own ContinuousActionHead.__call__
+    (continuous.py:16-25, executed under the numpy shim) and the l2 loss of octo.py:163-165: fp32, 1e-5."""
+    from multi_modal_transformers_tokenmerge_b200 import _lib as L
+    g = _head_golden()
+    ro = torch.tensor(g[f"{name}/readouts"]).cuda()
+    w, b = torch.tensor(g[f"{name}/kernel"]).cuda(), torch.tensor(g[f"{name}/bias"]).cuda()
+    act = torch.tensor(g[f"{name}/actions"]).cuda()
+    out, loss, _ = ops.action_head_fwd(ro, w, b, kind=L.HEAD_CONTINUOUS_L2, max_action=float(g[f"{name}/max_action"]), actions=act)
+    np.testing.assert_allclose(out.cpu().numpy(), g[f"{name}/pred"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(loss[1:].cpu().numpy(), g[f"{name}/loss"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(loss[0].item(), g[f"{name}/loss"].mean(), rtol=1e-4)
+
+
+@pytest.mark.parametrize("name", ["cat_small", "cat_octo", "cat_edges"])
+def test_categorical_head_matches_reference_goldens(ops, name):
+    """tome_action_head_fwd (categorical) against the reference's CategoricalActionHead.__call__ and assign_bins
+    (categorical.py:12-40, executed) + the cross-entropy of octo.py:183-187; cat_edges sits on bin edges and outside the
+    range, where the reference's 1-based digitize gives all-zero labels (loss 0) or class 0."""
+    from multi_modal_transformers_tokenmerge_b200 import _lib as L
+    g = _head_golden()
+    A, bins = (int(v) for v in g[f"{name}/cfg"])
+    ro = torch.tensor(g[f"{name}/readouts"]).cuda()
+    w, b = torch.tensor(g[f"{name}/kernel"]).cuda(), torch.tensor(g[f"{name}/bias"]).cuda()
+    act = torch.tensor(g[f"{name}/actions"]).cuda()
+    out, loss, _ = ops.action_head_fwd(ro, w, b, kind=L.HEAD_CATEGORICAL_CE, max_action=float(g[f"{name}/max_action"]), groups=A,
+                                       actions=act)
+    np.testing.assert_allclose(out.cpu().numpy(), g[f"{name}/logits"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(loss[1:].cpu().numpy(), g[f"{name}/loss"].sum(-1), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(loss[0].item(), g[f"{name}/loss"].mean(), rtol=1e-4)
+
+
+@pytest.mark.parametrize("kind,dtype", [("continuous", torch.float32), ("categorical", torch.float32), ("continuous", torch.bfloat16),
+                                        ("categorical", torch.bfloat16)])
+def test_action_head_backward_vs_oracle_autograd(ops, kind, dtype):
+    """dW, db and dx of the head + loss against autograd of the oracle, with the readouts scattered over a longer sequence
+    through `origin` -- including two readouts that share a row (merged tokens), whose gradients must add."""
+    from multi_modal_transformers_tokenmerge_b200 import _lib as L
+    rng = np.random.default_rng(5)
+    B, T, C, n = 5, 40, 96, 8
+    groups, feats = (1, 6) if kind == "continuous" else (4, 12)
+    mx = 2.0
+    x = torch.tensor(rng.standard_normal((B, T, C)).astype(np.float32)).to(dtype)
+    origin = np.stack([rng.choice(T, size=n, replace=False) for _ in range(B)]).astype(np.int32)
+    origin[1, 3] = origin[1, 2]          # two readouts merged into the same row
+    origin[2, 7] = origin[2, 0]
+    w = (rng.standard_normal((C, feats)) * 0.2).astype(np.float32)
+    b = (rng.standard_normal(feats) * 0.1).astype(np.float32)
+    if kind == "continuous":
+        act = rng.uniform(-mx, mx, size=(B, feats)).astype(np.float32)
+    else:
+        act = rng.uniform(-mx * 1.2, mx, size=(B, groups)).astype(np.float32)
+    k = L.HEAD_CONTINUOUS_L2 if kind == "continuous" else L.HEAD_CATEGORICAL_CE
+    out, loss, st = ops.action_head_fwd(x.cuda(), torch.tensor(w).cuda(), torch.tensor(b).cuda(), kind=k, max_action=mx,
+                                        groups=groups, origin=torch.tensor(origin).cuda(), actions=torch.tensor(act).cuda(),
+                                        keep_for_backward=True)
+    dw = torch.zeros(C, feats, device="cuda")
+    db = torch.zeros(feats, device="cuda")
+    dx = ops.action_head_bwd(st, dw, db)
+    torch.cuda.synchronize()
+    xr = x.float().clone().requires_grad_(True)
+    wr, br = torch.tensor(w, requires_grad=True), torch.tensor(b, requires_grad=True)
+    ro = torch.gather(xr, 1, torch.as_tensor(origin, dtype=torch.long)[..., None].expand(-1, -1, C))
+    if kind == "continuous":
+        want = O.continuous_action_head(ro, wr, br, mx)
+        ref = O.l2_loss(want, torch.tensor(act)).mean()
+    else:
+        want = O.categorical_action_head(ro, wr, br, groups)
+        ref = O.ce_loss(want, act, mx, feats).mean()
+    ref.backward()
+    np.testing.assert_allclose(out.cpu().numpy().reshape(want.shape), want.detach().numpy(), rtol=2e-5, atol=2e-5)
+    assert abs(loss[0].item() - ref.item()) <= 1e-5 * abs(ref.item()) + 1e-7
+    tol = 1e-5 if dtype == torch.float32 else 1e-2      # dx is stored in x's dtype
+    assert rel_err(dw.cpu(), wr.grad) <= 1e-5 and rel_err(db.cpu(), br.grad) <= 1e-5
+    assert rel_err(dx.float().cpu(), xr.grad) <= tol
+    rows = torch.zeros(B, T, dtype=torch.bool)
+    rows.scatter_(1, torch.as_tensor(origin, dtype=torch.long), True)
+    assert torch.all(dx.float().cpu()[~rows] == 0)
+    # accumulate semantics of dw / db
+    ops.action_head_bwd(st, dw, db, want_dx=False)
+    assert rel_err(dw.cpu(), 2 * wr.grad) <= 1e-5
+
+
+def test_action_head_rejects_bad_arguments(ops):
+    from multi_modal_transformers_tokenmerge_b200 import _lib as L
+    x = torch.zeros(2, 6, 16, device="cuda")
+    w = torch.zeros(16, 4, device="cuda")
+    with pytest.raises(L.TomeError, match="groups must be 1"):
+        ops.action_head_fwd(x, w, None, kind=L.HEAD_CONTINUOUS_L2, max_action=1.0, groups=2)
+    with pytest.raises(L.TomeError, match="do not split"):
+        ops.action_head_fwd(x, w, None, kind=L.HEAD_CATEGORICAL_CE, max_action=1.0, groups=4)
+    with pytest.raises(L.TomeError, match="max_action"):
+        ops.action_head_fwd(x, w, None, kind=L.HEAD_CONTINUOUS_L2, max_action=0.0)

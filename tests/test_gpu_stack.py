@@ -263,3 +263,94 @@ def test_stack_octo_small_shape_runs_and_trains(pkg):
         torch.cuda.synchronize()
         vals.append((e2.loss[0].item(), e2.grads.norm().item()))
     assert vals[0] == vals[1] and math.isfinite(vals[0][1])
+
+
+@pytest.mark.parametrize("head,r", [("continuous", 4), ("categorical", 4), ("continuous", 0)])
+def test_stack_with_action_head_vs_oracle(pkg, head, r):
+    """The real losses of the reference's train steps instead of the synthetic MSE: the readout rows
+    of the final sequence are pooled, pushed through the action head (continuous.py / categorical.py) and into
+    compute_l2_loss / compute_ce_loss (octo.py:157-190), whose batch mean is the training loss (:253-263, 292-303).
+    Head output, loss, the head's own gradients and every stack gradient against the oracle's autograd; the head
+    parameters live at the end of the flat vector (tome_stack_head_offset) and are updated by AdamW with the rest."""
+    ops, engine = pkg
+    B, W, P, C, H, Dff, Lyr, n_ro = 3, 2, 24, 128, 2, 256, 2, 4
+    rng = np.random.default_rng(11)
+    seq = f"[TaskDescriptionPrefix{{4}}] [Image{{{P}}};Readout{{{n_ro}}}]*{W}"
+    gid, pos, allow, ro = O.sequence_groups(seq)
+    T = gid.shape[0]
+    layers = [O.init_block_params(rng, C, H, 64, Dff) for _ in range(Lyr)]
+    for d in layers:
+        d["b1"] = d["b1"] + np.float32(8.0)   # open the ReLU gates: measure the kernels, not bf16 gate flips (see CASES)
+    pe = (rng.standard_normal((1, T, C)) * 0.02).astype(np.float32)
+    x = rng.standard_normal((B, T, C)).astype(np.float32)
+    mx = 1.5
+    if head == "continuous":
+        groups, feats = 1, 7
+        actions = rng.uniform(-mx, mx, size=(B, feats)).astype(np.float32)
+    else:
+        groups, feats = 4, 16     # 8 readouts = 4 actions x 2 timesteps
+        actions = rng.uniform(-mx, mx * 0.8, size=(B, groups)).astype(np.float32)
+    hk = (rng.standard_normal((C, feats)) * math.sqrt(2.0 / C)).astype(np.float32)
+    hb = (rng.standard_normal(feats) * 0.01).astype(np.float32)
+    cfg = engine.StackConfig(batch=B, tokens=T, channels=C, heads=H, head_dim=64, mlp_dim=Dff, layers=Lyr, r=r, ln_axis=2,
+                             num_groups=allow.shape[0], n_readout=len(ro), head=head, head_groups=groups, head_features=feats,
+                             max_action=mx)
+    eng = engine.ToMeStackEngine(cfg, gid=gid, pos=pos, allow=allow, readout_idx=ro)
+    assert eng.n_params == eng.layer_offset(Lyr - 1) + (eng.layer_offset(1) - eng.layer_offset(0)) + C * feats + feats
+    eng.load_params(pe[0], layers, head={"kernel": hk, "bias": hb})
+    xd, ad = torch.tensor(x).cuda(), torch.tensor(actions).cuda()
+    eng.zero_grad()
+    eng.forward(xd, ad)
+    eng.backward()
+    torch.cuda.synchronize()
+    node_override = []
+    for l in range(Lyr):
+        pl = eng.layer_plan(l)
+        node_override.append(None if pl is None else (pl[0].cpu().numpy(), pl[1].cpu().numpy()))
+    # oracle: same bf16-rounded GEMM weights; the head runs in fp32 on both sides
+    y_dummy = np.zeros((B, len(ro), C), np.float32)
+    v = eng.param_views(eng.params_bf16.float().cpu())
+    vf = eng.param_views(eng.params.cpu())
+    params = []
+    hd = H * 64
+    for l in range(Lyr):
+        src, srcf = v["layers"][l], vf["layers"][l]
+        d = dict(ln1_scale=srcf["ln1_scale"], ln1_bias=srcf["ln1_bias"], ln2_scale=srcf["ln2_scale"], ln2_bias=srcf["ln2_bias"],
+                 wq=src["wqkv"][:, :hd], wk=src["wqkv"][:, hd:2 * hd], wv=src["wqkv"][:, 2 * hd:],
+                 bq=srcf["bqkv"][:hd], bk=srcf["bqkv"][hd:2 * hd], bv=srcf["bqkv"][2 * hd:],
+                 wo=src["wo"], bo=srcf["bo"], w1=src["w1"], b1=srcf["b1"], w2=src["w2"], b2=srcf["b2"])
+        params.append(O.BlockParams(**{k_: t.clone().contiguous().requires_grad_(True) for k_, t in d.items()}))
+    pet = vf["pos_embedding"].clone()[None].requires_grad_(True)
+    kt = vf["head"]["kernel"].clone().requires_grad_(True)
+    bt = vf["head"]["bias"].clone().requires_grad_(True)
+    xf, size, origin = O.tome_stack(params, pet, torch.tensor(x), gid, pos, allow, num_heads=H, r=r, ln_axis="feature",
+                                    node_override=node_override, act_dtype=torch.bfloat16)
+    _, readouts = O.readout_loss(xf, origin, ro, torch.tensor(y_dummy))
+    if head == "continuous":
+        want_out = O.continuous_action_head(readouts, kt, bt, mx)
+        loss = O.l2_loss(want_out, torch.tensor(actions)).mean()
+    else:
+        want_out = O.categorical_action_head(readouts, kt, bt, groups)
+        loss = O.ce_loss(want_out, actions, mx, feats).mean()
+    loss.backward()
+    assert rel_err(eng.head_out.cpu().reshape(want_out.shape), want_out.detach()) <= 1e-2
+    assert abs(eng.loss[0].item() - loss.item()) <= 2e-2 * abs(loss.item())
+    g = eng.param_views(eng.grads.cpu())
+    assert rel_err(g["head"]["kernel"], kt.grad) <= 2e-2
+    assert rel_err(g["head"]["bias"], bt.grad) <= 2e-2
+    assert rel_err(g["pos_embedding"], pet.grad[0]) <= 3e-2
+    for l in range(Lyr):
+        p, gl = params[l], g["layers"][l]
+        ref = dict(wqkv=torch.cat([p.wq.grad, p.wk.grad, p.wv.grad], 1), wo=p.wo.grad, w1=p.w1.grad, w2=p.w2.grad,
+                   b1=p.b1.grad, b2=p.b2.grad, ln1_scale=p.ln1_scale.grad, ln2_bias=p.ln2_bias.grad)
+        for name, want in ref.items():
+            e = rel_err(gl[name], want)
+            assert e <= 3e-2, f"layer {l} grad {name}: rel err {e}"
+    # the head trains with the stack
+    l0 = eng.loss[0].item()
+    for _ in range(10):
+        eng.zero_grad()
+        eng.forward(xd, ad)
+        eng.backward()
+        eng.adamw_step(lr=1e-3)
+    assert eng.loss[0].item() < l0

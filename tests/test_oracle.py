@@ -127,3 +127,26 @@ def test_top_k_pruning_matches_reference_goldens():
         if name == "constant":  # the reference's own importance scores are the constant 1/T: the first k of every set survive
             want = np.concatenate([np.arange(s, s + k) for (s, _), k in zip(sets, ks)])
             np.testing.assert_array_equal(ids, want)
+
+
+def test_action_heads_match_reference_goldens():
+    """oracle.continuous_action_head / categorical_action_head / assign_bins / l2_loss / ce_loss against outputs of the
+    reference's own action_heads/continuous.py and categorical.py (executed by oracle/gen_golden.py under the shim)."""
+    torch = pytest.importorskip("torch")
+    g = np.load(os.path.join(GOLD, "action_heads.npz"))
+    t = lambda a: torch.tensor(np.asarray(a))  # noqa: E731
+    for name in g["continuous"]:
+        mx = float(g[f"{name}/max_action"])
+        pred = O.continuous_action_head(t(g[f"{name}/readouts"]), t(g[f"{name}/kernel"]), t(g[f"{name}/bias"]), mx)
+        assert tuple(pred.shape) == g[f"{name}/pred"].shape                      # [B, 1, A]
+        np.testing.assert_allclose(pred.numpy(), g[f"{name}/pred"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(O.l2_loss(pred, t(g[f"{name}/actions"])).numpy(), g[f"{name}/loss"], rtol=1e-4, atol=1e-6)
+    for name in g["categorical"]:
+        A, bins = (int(v) for v in g[f"{name}/cfg"])
+        mx = float(g[f"{name}/max_action"])
+        logits = O.categorical_action_head(t(g[f"{name}/readouts"]), t(g[f"{name}/kernel"]), t(g[f"{name}/bias"]), A)
+        np.testing.assert_allclose(logits.numpy(), g[f"{name}/logits"], rtol=1e-5, atol=2e-6)
+        np.testing.assert_array_equal(O.assign_bins(g[f"{name}/actions"], (-mx, mx), bins), g[f"{name}/target_bin"])   # exact
+        np.testing.assert_allclose(O.ce_loss(logits, g[f"{name}/actions"], mx, bins).numpy(), g[f"{name}/loss"], rtol=1e-4, atol=1e-5)
+    # the reference's 1-based digitize: the top bin and everything above the range have no class at all
+    assert O.assign_bins(np.array([0.999, 1.0, 7.0, -7.0], np.float32), (-1.0, 1.0), 4).tolist() == [4, 5, 5, 0]
