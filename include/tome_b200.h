@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TOME_ABI_VERSION 7
+#define TOME_ABI_VERSION 8
 
 enum tome_status { TOME_OK = 0, TOME_ERR_INVALID = 1, TOME_ERR_CUDA = 2, TOME_ERR_UNSUPPORTED = 3 };
 enum tome_dtype { TOME_BF16 = 0, TOME_F32 = 1 };
@@ -297,6 +297,40 @@ int tome_action_head_fwd(const tome_head_desc_t* desc, const void* x, const int3
 int tome_action_head_bwd(const tome_head_desc_t* desc, const int32_t* origin, const float* w, const void* workspace,
                          float* dw, float* dbias, void* dx, void* stream);
 
+/* Diffusion action head, training path: DiffusionActionHead.denoise_loss over OctoDenoise / FourierFeatures / MLPBlock
+ * (action_heads/diffusion.py:29-64, 94-143; the head octo_base.yaml selects).  The random draws are the caller's:
+ * time i32 [B] in [0, diffusion_steps), noise f32 [B, A]; alpha_hats f32 [diffusion_steps] is the cumulative product of
+ * 1 - cosine_beta_schedule (diffusion.py:16-26, 85-92).
+ *   noisy = sqrt(ah[t]) actions + sqrt(1 - ah[t]) noise;  emb = mean over the readout rows (x / origin as tome_action_head_fwd);
+ *   ff = [cos | sin](2 pi t fourier_kernel);  te = Dense_1(relu(Dense_0(ff)))          time encoder MLPBlock
+ *   pred = Dense_1(relu(Dense_0([noisy | te | emb])))                                  denoiser MLPBlock (num_blocks = 1)
+ *   loss[0] = mean_b sum_a 0.5 (pred - noise)^2, loss[1 + b] = per-row sums            optax.l2_loss
+ * The MLPBlocks' Dropouts are inactive, as in the reference (OctoDenoise calls them without `train`).
+ * Parameters: one flat fp32 vector + its bf16 copy (GEMM operands), layout
+ *   fourier_kernel [F/2] | tw1 [F, Ht] tb1 [Ht] | tw2 [Ht, To] tb2 [To] | w1 [A + To + C, H] b1 [H] | w2 [H, A] b2 [A]
+ * (kernels [in, out] as Flax stores them; tome_diffusion_head_param_offset(desc, i) gives the offset of the i-th array,
+ * i = 9: the total).  backward ACCUMULATES into grads_f32 (same layout) and OVERWRITES dx (bf16 [B, tokens, C], zero
+ * except the readout rows; NULL to skip); it needs the workspace forward wrote. */
+typedef struct {
+  int batch, tokens, channels;   /* x bf16 [B, tokens, C]; channels % 8 == 0 */
+  int n_readout;
+  int action_dim;                /* A: denoiser mlp_block.dense_out.features; multiple of 8 (diffusion.yaml: 8) */
+  int fourier_dim;               /* F: FourierFeatures.output_dim, multiple of 16 */
+  int time_hidden, time_out;     /* Ht, To: time_encoder.mlp_block dense / dense_out features */
+  int hidden;                    /* H: denoiser mlp_block.dense.features */
+  int diffusion_steps;
+} tome_diffusion_desc_t;
+long long tome_diffusion_head_param_count(const tome_diffusion_desc_t* desc);
+long long tome_diffusion_head_param_offset(const tome_diffusion_desc_t* desc, int which);
+size_t tome_diffusion_head_workspace_bytes(const tome_diffusion_desc_t* desc);
+int tome_diffusion_head_fwd(const tome_diffusion_desc_t* desc, const float* params_f32, const void* params_bf16, const void* x,
+                            const int32_t* origin, const float* actions, const float* noise, const int32_t* time,
+                            const float* alpha_hats, float* pred, float* loss, void* workspace, size_t workspace_bytes,
+                            void* stream);
+int tome_diffusion_head_bwd(const tome_diffusion_desc_t* desc, const float* params_f32, const void* params_bf16,
+                            const int32_t* origin, const int32_t* time, void* workspace, float* grads_f32, void* dx,
+                            void* stream);
+
 /* AdamW on an fp32 master vector with a bf16 working copy refreshed in the same pass (bf16_copy may be NULL).
  * grad_scale multiplies the gradient first (1/world_size after a sum all-reduce). */
 int tome_adamw_step(long long n, float* param, const float* grad, float* m, float* v, void* bf16_copy, float lr,
@@ -322,18 +356,20 @@ typedef struct {
   uint64_t dropout_seed;
   float attn_dropout_rate; /* attention-weight dropout (self_attention.dropout_rate, vanilla_decoder.yaml:23), same seed */
   int head;           /* loss on the readout rows: 0 = synthetic MSE against target [B,n_readout,C] (tome_readout_mse);
-                         1 + TOME_HEAD_*: that action head and its loss (tome_action_head_*), target = actions */
+                         1 + TOME_HEAD_*: that action head and its loss (tome_action_head_*), target = actions;
+                         3: the diffusion head's denoise loss (tome_diffusion_head_*), target = [actions | noise] */
   int head_groups;    /* tome_head_desc_t.groups */
-  int head_features;  /* tome_head_desc_t.features */
+  int head_features;  /* tome_head_desc_t.features / tome_diffusion_desc_t.action_dim */
   float max_action;
+  int head_fourier_dim, head_time_hidden, head_time_out, head_hidden, diffusion_steps; /* tome_diffusion_desc_t (head 3) */
 } tome_stack_cfg_t;
 
 /* Per-layer parameter offsets (elements) into one flat fp32 vector (master weights / gradients / Adam moments)
  * and the same offsets into a flat bf16 working copy.  Kernels are stored [in, out] (Flax layout):
  * wqkv [C, 3*H*D] = concat(query, key, value kernels), wo [H*D, C], w1 [C, Dff], w2 [Dff, C].
  * Layout of one layer: ln1_scale[C] ln1_bias[C] wqkv bqkv[3HD] wo bo[C] ln2_scale[C] ln2_bias[C] w1 b1[Dff] w2 b2[C];
- * the vector starts with pos_embedding [T0, C]; with cfg.head > 0 it ends with the head's Dense kernel [C, features] and
- * bias [features] (tome_stack_head_offset; -1 without a head).  tome_stack_param_count gives the total. */
+ * the vector starts with pos_embedding [T0, C]; with cfg.head > 0 it ends with the head's parameters (tome_stack_head_offset;
+ * -1 without a head): Dense kernel [C, features] and bias [features], or the diffusion head's vector (its own layout).  tome_stack_param_count gives the total. */
 long long tome_stack_param_count(const tome_stack_cfg_t* cfg);
 long long tome_stack_head_offset(const tome_stack_cfg_t* cfg);
 long long tome_stack_layer_offset(const tome_stack_cfg_t* cfg, int layer); /* offset of ln1_scale of `layer` */
@@ -350,8 +386,8 @@ typedef struct {
   const int32_t* pos;         /* [T0] */
   const uint8_t* allow;       /* [G,G] */
   const int32_t* readout_idx; /* [n_readout] original positions of the readout tokens */
-  const float* target;        /* loss target or NULL: [B,n_readout,C] (head 0), actions [B,features] (continuous head)
-                                 or [B,groups] (categorical head) */
+  const float* target;        /* loss target or NULL: [B,n_readout,C] (head 0), actions [B,features] (continuous head),
+                                 [B,groups] (categorical head), [2,B,A] = actions then noise (diffusion head) */
   void* workspace; size_t workspace_bytes;
   /* outputs */
   void* x_final;              /* bf16 [B,T_L,C] (points into workspace when NULL is passed: see tome_stack_final) */
@@ -360,8 +396,10 @@ typedef struct {
   float* grads_f32;           /* flat fp32 gradient vector (backward; accumulated into, caller zeroes) */
   void* const* layer_done_events; /* optional host array [layers+1] of cudaEvent_t recorded as each layer's (and
                                      finally the pos-embedding's) gradients become final, for all-reduce overlap */
-  float* head_out;            /* f32 [B, head_groups, head_features]: actions (continuous) or logits (categorical);
-                                 required when cfg.head > 0 */
+  float* head_out;            /* f32 [B, head_groups, head_features]: actions (continuous), logits (categorical) or the
+                                 predicted denoise term [B, A] (diffusion); required when cfg.head > 0 */
+  const int32_t* head_time;   /* diffusion head: i32 [B] sampled time steps */
+  const float* head_alpha_hats; /* diffusion head: f32 [diffusion_steps] */
 } tome_stack_io_t;
 
 int tome_stack_forward(const tome_stack_cfg_t* cfg, const tome_stack_io_t* io, void* stream);

@@ -15,7 +15,7 @@ TOME_OK, TOME_ERR_INVALID, TOME_ERR_CUDA, TOME_ERR_UNSUPPORTED = 0, 1, 2, 3
 TOME_BF16, TOME_F32 = 0, 1
 TOME_MAJOR_K, TOME_MAJOR_MN = 0, 1
 TOME_MERGE_SUM, TOME_MERGE_WAVG = 0, 1
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 vp, ll, i32, f32, u64, u32 = C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_uint64, C.c_uint32
 
@@ -82,7 +82,17 @@ class StackCfg(C.Structure):
                 ("mlp_dim", i32), ("layers", i32), ("r", i32), ("ln_axis", i32), ("ln_eps", f32),
                 ("prop_attn", i32), ("class_token", i32), ("distill_token", i32), ("num_groups", i32),
                 ("n_readout", i32), ("dropout_rate", f32), ("dropout_seed", u64), ("attn_dropout_rate", f32),
-                ("head", i32), ("head_groups", i32), ("head_features", i32), ("max_action", f32)]
+                ("head", i32), ("head_groups", i32), ("head_features", i32), ("max_action", f32),
+                ("head_fourier_dim", i32), ("head_time_hidden", i32), ("head_time_out", i32), ("head_hidden", i32),
+                ("diffusion_steps", i32)]
+
+
+class DiffusionDesc(C.Structure):
+    _fields_ = [("batch", i32), ("tokens", i32), ("channels", i32), ("n_readout", i32), ("action_dim", i32),
+                ("fourier_dim", i32), ("time_hidden", i32), ("time_out", i32), ("hidden", i32), ("diffusion_steps", i32)]
+
+
+DIFFUSION_PARAMS = ["fourier_kernel", "tw1", "tb1", "tw2", "tb2", "w1", "b1", "w2", "b2"]
 
 
 HEAD_CONTINUOUS_L2, HEAD_CATEGORICAL_CE = 0, 1
@@ -98,7 +108,7 @@ class StackIO(C.Structure):
                 ("gid", vp), ("pos", vp), ("allow", vp), ("readout_idx", vp), ("target", vp),
                 ("workspace", vp), ("workspace_bytes", C.c_size_t),
                 ("x_final", vp), ("readout", vp), ("loss", vp), ("grads_f32", vp),
-                ("layer_done_events", C.POINTER(vp)), ("head_out", vp)]
+                ("layer_done_events", C.POINTER(vp)), ("head_out", vp), ("head_time", vp), ("head_alpha_hats", vp)]
 
 
 _lib = None
@@ -118,10 +128,11 @@ def lib() -> C.CDLL:
         if L.tome_abi_version() != ABI_VERSION:
             raise ImportError(f"libtome_b200.so has ABI {L.tome_abi_version()}, python binding expects {ABI_VERSION}: rebuild")
         for name in ("tome_gemm_workspace_bytes", "tome_stack_workspace_bytes", "tome_attention_workspace_bytes", "tome_sim_argmax_workspace_bytes",
-                     "tome_attention_bwd_workspace_bytes", "tome_action_head_workspace_bytes"):
+                     "tome_attention_bwd_workspace_bytes", "tome_action_head_workspace_bytes", "tome_diffusion_head_workspace_bytes"):
             if hasattr(L, name):
                 getattr(L, name).restype = C.c_size_t
-        for name in ("tome_stack_param_count", "tome_stack_layer_offset", "tome_stack_head_offset", "tome_launch_count"):
+        for name in ("tome_stack_param_count", "tome_stack_layer_offset", "tome_stack_head_offset", "tome_launch_count",
+                     "tome_diffusion_head_param_count", "tome_diffusion_head_param_offset"):
             if hasattr(L, name):
                 getattr(L, name).restype = ll
         for name in ("tome_stack_final_x", "tome_stack_final_size", "tome_stack_layer_edge_idx", "tome_stack_layer_dst_idx",
@@ -156,6 +167,11 @@ def lib() -> C.CDLL:
             "tome_action_head_fwd": [P(HeadDesc), vp, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp],
             "tome_action_head_bwd": [P(HeadDesc), vp, vp, vp, vp, vp, vp, vp],
             "tome_stack_head_offset": [P(StackCfg)],
+            "tome_diffusion_head_param_count": [P(DiffusionDesc)],
+            "tome_diffusion_head_param_offset": [P(DiffusionDesc), i32],
+            "tome_diffusion_head_workspace_bytes": [P(DiffusionDesc)],
+            "tome_diffusion_head_fwd": [P(DiffusionDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp],
+            "tome_diffusion_head_bwd": [P(DiffusionDesc), vp, vp, vp, vp, vp, vp, vp, vp],
             "tome_adamw_step": [ll, vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, f32, i32, vp],
             "tome_cast_f32_to_bf16": [ll, vp, vp, vp],
             "tome_launch_count": [i32],

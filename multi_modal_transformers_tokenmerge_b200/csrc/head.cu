@@ -143,22 +143,32 @@ __global__ void head_loss_final_kernel(int B, float inv_count, float* loss) {
   loss[0] = t * inv_count;
 }
 
-// dW[c, f] += sum_{b, g} pooled[b, g, c] * dz[b, g, f];  db[f] += sum_{b, g} dz[b, g, f]   (fixed order over b, g)
+// dW[c, f] += sum_{b, g} pooled[b, g, c] * dz[b, g, f];  db[f] += sum_{b, g} dz[b, g, f].
+// A CTA owns 32 consecutive outputs; its 8 warps each sum one contiguous slice of the B*G rows and the slices are added
+// in warp order through shared memory, so the result does not depend on the launch (no atomics).
 __global__ void __launch_bounds__(HEAD_THREADS)
 head_wgrad_kernel(const tome_head_desc_t d, const float* __restrict__ pooled, const float* __restrict__ dz,
                   float* __restrict__ dw, float* __restrict__ dbias) {
+  __shared__ float part[HEAD_THREADS / 32][32];
   const int C = d.channels, F = d.features, BG = d.batch * d.groups;
-  const long long i = blockIdx.x * (long long)HEAD_THREADS + threadIdx.x;
-  if (i < (long long)C * F) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = HEAD_THREADS / 32;
+  const long long i = blockIdx.x * 32LL + lane, n_w = (long long)C * F;
+  const int r0 = (int)((long long)BG * warp / nw), r1 = (int)((long long)BG * (warp + 1) / nw);
+  float s = 0.f;
+  if (i < n_w) {
     const int c = (int)(i / F), f = (int)(i - (long long)c * F);
-    float s = 0.f;
-    for (int r = 0; r < BG; ++r) s = fmaf(pooled[(long long)r * C + c], dz[(long long)r * F + f], s);
-    dw[i] += s;
-  } else if (dbias && i < (long long)C * F + F) {
-    const int f = (int)(i - (long long)C * F);
-    float s = 0.f;
-    for (int r = 0; r < BG; ++r) s += dz[(long long)r * F + f];
-    dbias[f] += s;
+    for (int r = r0; r < r1; ++r) s = fmaf(pooled[(long long)r * C + c], dz[(long long)r * F + f], s);
+  } else if (i < n_w + F) {
+    const int f = (int)(i - n_w);
+    for (int r = r0; r < r1; ++r) s += dz[(long long)r * F + f];
+  }
+  part[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0) {
+    float t = 0.f;
+    for (int w = 0; w < nw; ++w) t += part[w][lane];
+    if (i < n_w) dw[i] += t;
+    else if (dbias && i < n_w + F) dbias[i - n_w] += t;
   }
 }
 
@@ -261,7 +271,7 @@ extern "C" int tome_action_head_bwd(const tome_head_desc_t* d, const int32_t* or
   HeadWs ws = head_ws(d, const_cast<void*>(workspace));
   ProfScope prof(PROF_OTHER, 0.0, dx ? 3 : 1, stream);
   const long long n = (long long)d->channels * d->features + d->features;
-  head_wgrad_kernel<<<(unsigned)((n + HEAD_THREADS - 1) / HEAD_THREADS), HEAD_THREADS, 0, stream>>>(*d, ws.pooled, ws.dz, dw, dbias);
+  head_wgrad_kernel<<<(unsigned)((n + 31) / 32), HEAD_THREADS, 0, stream>>>(*d, ws.pooled, ws.dz, dw, dbias);
   TOME_CUDA(cudaGetLastError());
   if (dx) {
     const size_t esz = d->x_dtype == TOME_BF16 ? 2 : 4;

@@ -90,6 +90,14 @@ static tome_head_desc_t head_desc(const tome_stack_cfg_t* c, int tokens) {
   return h;
 }
 
+static tome_diffusion_desc_t diffusion_desc(const tome_stack_cfg_t* c, int tokens) {
+  tome_diffusion_desc_t d;
+  d.batch = c->batch; d.tokens = tokens; d.channels = c->channels; d.n_readout = c->n_readout;
+  d.action_dim = c->head_features; d.fourier_dim = c->head_fourier_dim; d.time_hidden = c->head_time_hidden;
+  d.time_out = c->head_time_out; d.hidden = c->head_hidden; d.diffusion_steps = c->diffusion_steps;
+  return d;
+}
+
 static int check_cfg(const tome_stack_cfg_t* c) {
   TOME_CHECK(c != nullptr, TOME_ERR_INVALID, "stack: null config");
   TOME_CHECK(c->batch > 0 && c->tokens >= 2 && c->layers >= 1 && c->layers <= 64, TOME_ERR_INVALID,
@@ -106,9 +114,13 @@ static int check_cfg(const tome_stack_cfg_t* c) {
   TOME_CHECK(c->dropout_rate >= 0.f && c->dropout_rate < 1.f, TOME_ERR_INVALID, "stack: dropout_rate must be in [0, 1)");
   TOME_CHECK(c->attn_dropout_rate >= 0.f && c->attn_dropout_rate < 1.f, TOME_ERR_INVALID, "stack: attn_dropout_rate must be in [0, 1)");
   TOME_CHECK(c->n_readout >= 0, TOME_ERR_INVALID, "stack: n_readout must be >= 0");
-  TOME_CHECK(c->head >= 0 && c->head <= 2, TOME_ERR_INVALID,
-             "stack: head must be 0 (synthetic readout MSE), 1 (continuous l2) or 2 (categorical cross-entropy)");
-  if (c->head > 0) {
+  TOME_CHECK(c->head >= 0 && c->head <= 3, TOME_ERR_INVALID,
+             "stack: head must be 0 (synthetic readout MSE), 1 (continuous l2), 2 (categorical cross-entropy) or 3 (diffusion)");
+  if (c->head == 3) {
+    TOME_CHECK(c->n_readout > 0, TOME_ERR_INVALID, "stack: an action head needs readout tokens");
+    tome_diffusion_desc_t d = diffusion_desc(c, 1);
+    if (tome_diffusion_head_param_count(&d) < 0) return TOME_ERR_INVALID;  // message set by the head's own check
+  } else if (c->head > 0) {
     TOME_CHECK(c->n_readout > 0, TOME_ERR_INVALID, "stack: an action head needs readout tokens");
     tome_head_desc_t h = head_desc(c, 1);
     if (tome_action_head_workspace_bytes(&h) == 0) return TOME_ERR_INVALID;  // message set by the head's own check
@@ -226,7 +238,11 @@ static StackLayout make_layout(const tome_stack_cfg_t* c, void* workspace) {
   S.origin = b.take<int32_t>(B * (c->n_readout > 0 ? c->n_readout : 1));
   S.ws_head_bytes = 0;
   S.ws_head = nullptr;
-  if (c->head > 0) {
+  if (c->head == 3) {
+    tome_diffusion_desc_t d = diffusion_desc(c, 1);
+    S.ws_head_bytes = tome_diffusion_head_workspace_bytes(&d);
+    S.ws_head = b.take<uint8_t>(S.ws_head_bytes);
+  } else if (c->head > 0) {
     tome_head_desc_t h = head_desc(c, 1);
     S.ws_head_bytes = tome_action_head_workspace_bytes(&h);
     S.ws_head = b.take<uint8_t>(S.ws_head_bytes);
@@ -290,6 +306,10 @@ using namespace tome;
 // the action head's Dense kernel [C, features] and bias [features] follow the last layer (so they ride in the last
 // layer's all-reduce bucket: their gradients are the first to become final)
 static long long head_param_count(const tome_stack_cfg_t* c) {
+  if (c->head == 3) {
+    tome_diffusion_desc_t d = diffusion_desc(c, 1);
+    return tome_diffusion_head_param_count(&d);
+  }
   return c->head > 0 ? (long long)c->channels * c->head_features + c->head_features : 0;
 }
 extern "C" long long tome_stack_param_count(const tome_stack_cfg_t* c) {
@@ -395,7 +415,17 @@ extern "C" int tome_stack_forward(const tome_stack_cfg_t* c, const tome_stack_io
       toks[l] = S.shapes[l].t_in;
     }
     RC(tome_chain_row_maps(B, c->layers, maps, toks, io->readout_idx, c->n_readout, S.origin, st));
-    if (c->head > 0) {
+    if (c->head == 3) {
+      // diffusion head: denoise_loss on the pooled readout rows (diffusion.py:94-143); target = [actions | noise]
+      tome_diffusion_desc_t d = diffusion_desc(c, TL);
+      const long long ho = layer_offsets(c, c->layers).ln1_scale;
+      TOME_CHECK(io->head_out && io->target && io->loss && io->head_time && io->head_alpha_hats, TOME_ERR_INVALID,
+                 "stack: the diffusion head needs head_out, target ([B, 2A] = actions | noise), loss, head_time and head_alpha_hats");
+      RC(tome_diffusion_head_fwd(&d, io->params_f32 + ho, reinterpret_cast<const __nv_bfloat16*>(io->params_bf16) + ho,
+                                 S.L.back().x_out, S.origin, io->target, io->target + (size_t)B * c->head_features, io->head_time,
+                                 io->head_alpha_hats, io->head_out, io->loss, S.ws_head, S.ws_head_bytes, st));
+      if (io->readout) RC(tome_readout_mse(B, TL, C, c->n_readout, S.L.back().x_out, S.origin, nullptr, nullptr, nullptr, io->readout, st));
+    } else if (c->head > 0) {
       // action head on the pooled readout rows + its loss (continuous.py / categorical.py, octo.py:157-190)
       tome_head_desc_t h = head_desc(c, TL);
       const long long ho = layer_offsets(c, c->layers).ln1_scale;
@@ -429,7 +459,12 @@ extern "C" int tome_stack_backward(const tome_stack_cfg_t* c, const tome_stack_i
   __nv_bfloat16 *g0 = S.g0, *g1 = S.g1, *g2 = S.g2, *g3 = S.g3;
   // dL/dx_final from the readout rows: through the action head (pooled / dL/dz saved by forward), or the synthetic MSE
   // (which recomputes the loss value, harmless)
-  if (c->head > 0) {
+  if (c->head == 3) {
+    tome_diffusion_desc_t d = diffusion_desc(c, TL);
+    const long long ho = layer_offsets(c, c->layers).ln1_scale;
+    TOME_CHECK(io->head_time, TOME_ERR_INVALID, "stack_backward: head_time missing");
+    RC(tome_diffusion_head_bwd(&d, pf + ho, pw + ho, S.origin, io->head_time, S.ws_head, gr + ho, g0, st));
+  } else if (c->head > 0) {
     tome_head_desc_t h = head_desc(c, TL);
     const long long ho = layer_offsets(c, c->layers).ln1_scale;
     RC(tome_action_head_bwd(&h, S.origin, pf + ho, S.ws_head, gr + ho, gr + ho + (long long)C * c->head_features, g0, st));

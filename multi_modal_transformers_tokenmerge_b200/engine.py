@@ -41,17 +41,33 @@ class StackConfig:
     dropout_seed: int = 0
     attn_dropout_rate: float = 0.0   # attention-weight dropout (self_attention.dropout_rate, vanilla_decoder.yaml:23)
     head: str = "none"          # loss on the readouts: "none" = synthetic MSE, "continuous" (continuous.py + l2 loss,
-                                # octo.py:157-165) or "categorical" (categorical.py + cross-entropy, octo.py:178-190)
+                                # octo.py:157-165), "categorical" (categorical.py + cross-entropy, octo.py:178-190) or
+                                # "diffusion" (diffusion.py:94-143 denoise loss)
     head_groups: int = 1        # categorical: action_space_dim
-    head_features: int = 0      # continuous: action dimensions; categorical: num_bins
+    head_features: int = 0      # continuous / diffusion: action dimensions; categorical: num_bins
     max_action: float = 1.0
+    head_fourier_dim: int = 0   # diffusion: FourierFeatures.output_dim, time-encoder MLP widths, denoiser hidden width
+    head_time_hidden: int = 0
+    head_time_out: int = 0
+    head_hidden: int = 0
+    diffusion_steps: int = 0
 
     def c(self) -> L.StackCfg:
         return L.StackCfg(self.batch, self.tokens, self.channels, self.heads, self.head_dim, self.mlp_dim, self.layers,
                           self.r, self.ln_axis, self.ln_eps, int(self.prop_attn), int(self.class_token),
                           int(self.distill_token), self.num_groups, self.n_readout, self.dropout_rate, self.dropout_seed,
-                          self.attn_dropout_rate, {"none": 0, "continuous": 1, "categorical": 2}[self.head],
-                          self.head_groups, self.head_features, self.max_action)
+                          self.attn_dropout_rate, {"none": 0, "continuous": 1, "categorical": 2, "diffusion": 3}[self.head],
+                          self.head_groups, self.head_features, self.max_action, self.head_fourier_dim, self.head_time_hidden,
+                          self.head_time_out, self.head_hidden, self.diffusion_steps)
+
+    def diffusion_desc(self, tokens: int = 1) -> L.DiffusionDesc:
+        return L.DiffusionDesc(self.batch, tokens, self.channels, self.n_readout, self.head_features, self.head_fourier_dim,
+                               self.head_time_hidden, self.head_time_out, self.head_hidden, self.diffusion_steps)
+
+    def diffusion_param_shapes(self) -> Dict[str, tuple]:
+        a, f, ht, to, h = self.head_features, self.head_fourier_dim, self.head_time_hidden, self.head_time_out, self.head_hidden
+        return dict(fourier_kernel=(f // 2, 1), tw1=(f, ht), tb1=(ht,), tw2=(ht, to), tb2=(to,),
+                    w1=(a + to + self.channels, h), b1=(h,), w2=(h, a), b2=(a,))
 
     def param_shapes(self) -> Dict[str, tuple]:
         c, hd, f = self.channels, self.heads * self.head_dim, self.mlp_dim
@@ -90,6 +106,7 @@ class ToMeStackEngine:
                         if cfg.n_readout else None)
         self.head_out = (torch.empty(cfg.batch, cfg.head_groups, cfg.head_features, dtype=torch.float32, device=self.dev)
                          if cfg.head != "none" else None)
+        self.head_time = self.alpha_hats = None     # diffusion head: set_diffusion_draws()
         self._x = self._target = None
         self._events = None
 
@@ -110,7 +127,15 @@ class ToMeStackEngine:
                 d[name] = flat[off: off + n].view(*shapes[name])
                 off += n
             out["layers"].append(d)
-        if cfg.head != "none":  # Dense kernel [C, features] + bias [features] of the action head, after the last layer
+        if cfg.head == "diffusion":   # the diffusion head's own vector (include/tome_b200.h), after the last layer
+            off = int(self.lib.tome_stack_head_offset(C.byref(self.ccfg)))
+            dd = cfg.diffusion_desc()
+            shapes_d = cfg.diffusion_param_shapes()
+            out["head"] = {}
+            for i, name in enumerate(L.DIFFUSION_PARAMS):
+                o = off + int(self.lib.tome_diffusion_head_param_offset(C.byref(dd), i))
+                out["head"][name] = flat[o: o + int(np.prod(shapes_d[name]))].view(*shapes_d[name])
+        elif cfg.head != "none":  # Dense kernel [C, features] + bias [features] of the action head, after the last layer
             off = int(self.lib.tome_stack_head_offset(C.byref(self.ccfg)))
             n = cfg.channels * cfg.head_features
             out["head"] = {"kernel": flat[off: off + n].view(cfg.channels, cfg.head_features),
@@ -130,8 +155,8 @@ class ToMeStackEngine:
             for name in PARAM_ORDER:
                 v["layers"][l][name].copy_(src[name])
         if head is not None:
-            v["head"]["kernel"].copy_(torch.as_tensor(np.asarray(head["kernel"], np.float32)))
-            v["head"]["bias"].copy_(torch.as_tensor(np.asarray(head["bias"], np.float32)))
+            for name, t in v["head"].items():
+                t.copy_(torch.as_tensor(np.asarray(head[name], np.float32)).reshape(t.shape))
         self.sync_bf16()
 
     def init_params(self, seed: int = 1) -> None:
@@ -151,9 +176,11 @@ class ToMeStackEngine:
                     t.zero_()
                 else:
                     t.normal_(0.0, 0.01, generator=g)
-        if "head" in v:
-            v["head"]["kernel"].normal_(0.0, (2.0 / self.cfg.channels) ** 0.5, generator=g)
-            v["head"]["bias"].normal_(0.0, 0.01, generator=g)
+        for name, t in v.get("head", {}).items():   # he_normal kernels / normal(0.01) biases (diffusion.yaml, vanilla_decoder.yaml)
+            if t.dim() == 2:
+                t.normal_(0.0, (2.0 / t.shape[0]) ** 0.5, generator=g)
+            else:
+                t.normal_(0.0, 0.01, generator=g)
         self.sync_bf16()
 
     def sync_bf16(self) -> None:
@@ -178,7 +205,16 @@ class ToMeStackEngine:
                          None if self.readout is None else self.readout.data_ptr(), self.loss.data_ptr(),
                          None if self.grads is None else self.grads.data_ptr(),
                          None if ev is None else C.cast(ev, C.POINTER(C.c_void_p)),
-                         None if self.head_out is None else self.head_out.data_ptr())
+                         None if self.head_out is None else self.head_out.data_ptr(),
+                         None if self.head_time is None else self.head_time.data_ptr(),
+                         None if self.alpha_hats is None else self.alpha_hats.data_ptr())
+
+    def set_diffusion_draws(self, time: torch.Tensor, alpha_hats) -> None:
+        """Diffusion head: the sampled time steps (i32 [B], diffusion.py:125) and the alpha_hat table (:88-92)."""
+        assert time.dtype == torch.int32 and tuple(time.shape) == (self.cfg.batch,) and time.is_cuda
+        self.head_time = time.contiguous()
+        self.alpha_hats = torch.as_tensor(np.asarray(alpha_hats, np.float32)).to(self.dev)
+        assert self.alpha_hats.numel() == self.cfg.diffusion_steps
 
     def forward(self, x: torch.Tensor, target: Optional[torch.Tensor] = None):
         cfg = self.cfg
@@ -186,7 +222,9 @@ class ToMeStackEngine:
         assert x.dtype in (torch.float32, torch.bfloat16)
         if target is not None:
             want = {"none": (cfg.batch, cfg.n_readout, cfg.channels), "continuous": (cfg.batch, cfg.head_features),
-                    "categorical": (cfg.batch, cfg.head_groups)}[cfg.head]
+                    "categorical": (cfg.batch, cfg.head_groups), "diffusion": (2, cfg.batch, cfg.head_features)}[cfg.head]
+            if cfg.head == "diffusion":
+                assert self.head_time is not None, "set_diffusion_draws(time, alpha_hats) first"
             assert target.dtype == torch.float32 and tuple(target.shape) == want, (target.shape, want)
         self._x, self._target = x, target
         io = self._io(x, target)

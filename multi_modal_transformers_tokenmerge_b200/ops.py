@@ -351,3 +351,50 @@ def action_head_bwd(state: HeadState, dw: torch.Tensor, dbias: Optional[torch.Te
                                          C.c_void_p(state.workspace.data_ptr() + state.off), _ptr(dw), _ptr(dbias), _ptr(dx),
                                          _stream()))
     return dx
+
+
+@dataclass
+class DiffusionState:
+    desc: "L.DiffusionDesc"
+    params: torch.Tensor
+    params_bf16: torch.Tensor
+    origin: torch.Tensor
+    time: torch.Tensor
+    workspace: torch.Tensor
+    off: int
+
+
+def diffusion_head_fwd(x: torch.Tensor, params: torch.Tensor, desc: "L.DiffusionDesc", actions: torch.Tensor, noise: torch.Tensor,
+                       time: torch.Tensor, alpha_hats: torch.Tensor, origin: Optional[torch.Tensor] = None):
+    """DiffusionActionHead.denoise_loss (diffusion.py:114-143) on the final sequence x bf16 [B, tokens, C].
+    params: flat fp32 vector in the layout of include/tome_b200.h.  Returns (pred [B, A], loss [1 + B], state)."""
+    _need_cuda(x, params, actions, noise, time, alpha_hats, origin)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and params.dtype == torch.float32
+    B, T, _ = x.shape
+    if origin is None:
+        origin = torch.arange(T, dtype=torch.int32, device=x.device).repeat(B, 1)
+    n = int(L.lib().tome_diffusion_head_param_count(C.byref(desc)))
+    if n < 0:
+        L.check(1)
+    assert params.numel() == n, (params.numel(), n)
+    p16 = params.to(torch.bfloat16)
+    nbytes = int(L.lib().tome_diffusion_head_workspace_bytes(C.byref(desc)))
+    ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=x.device)
+    off = (-ws.data_ptr()) % 256
+    pred = torch.empty(B, desc.action_dim, dtype=torch.float32, device=x.device)
+    loss = torch.zeros(1 + B, dtype=torch.float32, device=x.device)
+    for t, dt in ((actions, torch.float32), (noise, torch.float32), (time, torch.int32), (alpha_hats, torch.float32)):
+        assert t.dtype == dt and t.is_contiguous()
+    L.check(L.lib().tome_diffusion_head_fwd(C.byref(desc), _ptr(params), _ptr(p16), _ptr(x), _ptr(origin), _ptr(actions), _ptr(noise),
+                                            _ptr(time), _ptr(alpha_hats), _ptr(pred), _ptr(loss), C.c_void_p(ws.data_ptr() + off),
+                                            nbytes, _stream()))
+    return pred, loss, DiffusionState(desc, params, p16, origin, time, ws, off)
+
+
+def diffusion_head_bwd(state: DiffusionState, grads: torch.Tensor, want_dx: bool = True):
+    d = state.desc
+    dx = torch.empty(d.batch, d.tokens, d.channels, dtype=torch.bfloat16, device=grads.device) if want_dx else None
+    L.check(L.lib().tome_diffusion_head_bwd(C.byref(d), _ptr(state.params), _ptr(state.params_bf16), _ptr(state.origin),
+                                            _ptr(state.time), C.c_void_p(state.workspace.data_ptr() + state.off), _ptr(grads),
+                                            _ptr(dx), _stream()))
+    return dx

@@ -11,6 +11,8 @@ Reference entry points executed:
                                                                    get_modality_idx
   multi_modal_transformers/action_heads/continuous.py:12-25        ContinuousActionHead.__call__
   multi_modal_transformers/action_heads/categorical.py:12-40       assign_bins, CategoricalActionHead.__call__
+  multi_modal_transformers/action_heads/diffusion.py:16-64         cosine_beta_schedule, FourierFeatures, OctoDenoise
+  multi_modal_transformers/attention_blocks/attention.py:20-39     MLPBlock (instantiated by OctoDenoise)
   (the two loss expressions live inside the Octo class, which needs the whole model: octo.py:163-165 and :183-187 are
    restated here in numpy float64 on the executed heads' outputs)
 """
@@ -34,6 +36,7 @@ def _load(name, path):
 
 
 def main():
+    sys.dont_write_bytecode = True
     sys.path.insert(0, os.path.join(HERE, "jax_shim"))
     sys.path.insert(0, REF)
     import jax.numpy as jnp  # the shim
@@ -185,6 +188,42 @@ def main():
         ho.update({f"{name}/readouts": readouts, f"{name}/kernel": kernel, f"{name}/bias": bias, f"{name}/actions": actions,
                    f"{name}/max_action": np.float32(mx), f"{name}/cfg": np.array([A, bins], np.int32), f"{name}/logits": logits,
                    f"{name}/target_bin": target_bin.astype(np.int32), f"{name}/loss": loss.astype(np.float32)})
+    # ---------------- diffusion head: schedule + denoiser network (diffusion.py:16-64) ----------------
+    import flax.linen as nn
+    import multi_modal_transformers.action_heads.diffusion as dif     # imported as a package module: its config nodes
+    #                                                                   name FourierFeatures / MLPBlock by _target_ path
+    for steps in (8, 32):
+        betas = np.asarray(dif.cosine_beta_schedule(steps))
+        alphas = 1 - betas
+        ho[f"diff_schedule{steps}/betas"] = betas
+        ho[f"diff_schedule{steps}/alpha_hats"] = np.array([np.prod(alphas[: i + 1]) for i in range(steps)], np.float32)  # :88-92
+    dcases = [("diff_small", 4, 3, 8, 32, 32, 48, 40, 64, 8), ("diff_mid", 8, 4, 8, 384, 128, 192, 128, 256, 32)]
+    for name, B, n, A, C, F, Ht, To, H, steps in dcases:
+        r_ = lambda *sh: (hrng.standard_normal(sh) * 0.1).astype(np.float32)  # noqa: E731
+        p = dict(fourier_kernel=r_(F // 2, 1), tw1=r_(F, Ht), tb1=r_(Ht), tw2=r_(Ht, To), tb2=r_(To),
+                 w1=(r_(A + To + C, H) * 0.5), b1=r_(H), w2=r_(H, A), b2=r_(A))
+        dense = lambda k, b: {"_target_": "flax.linen.Dense", "features": k.shape[1], "kernel": k, "bias": b}  # noqa: E731
+        mlp = lambda k0, b0, k1, b1: {"_target_": "multi_modal_transformers.attention_blocks.attention.MLPBlock",  # noqa: E731
+                                      "dense": dense(k0, b0), "activation": {"_partial_": True, "_target_": "flax.linen.relu"},
+                                      "norm": {"_target_": "flax.linen.Dropout", "rate": 0.1}, "dense_out": dense(k1, b1)}
+        nn.Module.shim_params = {"fourier_kernel": p["fourier_kernel"]}
+        te = {"_target_": "multi_modal_transformers.action_heads.diffusion.FourierFeatures", "output_dim": F,
+              "kernel_init": {"_target_": "flax.linen.initializers.he_normal"}, "mlp_block": mlp(p["tw1"], p["tb1"], p["tw2"], p["tb2"])}
+        den = dif.OctoDenoise(num_blocks=1, time_encoder=te, mlp_block=mlp(p["w1"], p["b1"], p["w2"], p["b2"]))
+        readouts = hrng.standard_normal((B, n, C)).astype(np.float32)
+        actions = hrng.uniform(-1, 1, (B, A)).astype(np.float32)
+        noise = hrng.standard_normal((B, A)).astype(np.float32)
+        time = hrng.integers(0, steps, (B, 1)).astype(np.int32)
+        ah = ho[f"diff_schedule{steps}/alpha_hats"][time]                           # diffusion.py:131
+        noisy = (np.sqrt(ah) * actions + np.sqrt(1 - ah) * noise).astype(np.float32)   # :132-134 (restated)
+        emb = np.asarray(jnp.mean(jnp.asarray(readouts), axis=-2))                  # :107
+        pred = np.asarray(den(jnp.asarray(noisy), jnp.asarray(time), jnp.asarray(emb)))   # the reference modules themselves
+        loss = np.mean(np.sum(0.5 * (pred.astype(np.float64) - noise) ** 2, axis=-1))    # :141-142 (restated)
+        for k_, v_ in p.items():
+            ho[f"{name}/p/{k_}"] = v_
+        ho.update({f"{name}/readouts": readouts, f"{name}/actions": actions, f"{name}/noise": noise, f"{name}/time": time,
+                   f"{name}/steps": np.int32(steps), f"{name}/noisy": noisy, f"{name}/pred": pred, f"{name}/loss": np.float32(loss)})
+    ho["diffusion"] = np.array([c[0] for c in dcases])
     ho["continuous"] = np.array([c[0] for c in ccases])
     ho["categorical"] = np.array([c[0] for c in kcases])
     np.savez_compressed(os.path.join(OUT, "action_heads.npz"), **ho)

@@ -13,11 +13,44 @@ def make_causal_mask(x, extra_batch_dims=0, dtype=_np.float32):
 
 
 class Module:
-    """flax.linen.Module is a dataclass over the class annotations; that is all the action heads need."""
+    """flax.linen.Module is a dataclass over the class annotations.  The shim has no variable collections: `self.param`
+    returns the array the generator script registered under that name in `Module.shim_params`."""
+
+    shim_params = {}
 
     def __init_subclass__(cls, **kw):
         super().__init_subclass__(**kw)
         _dc.dataclass(cls)
+
+    def param(self, name, init_fn, *shape_args):
+        return _wrap(_np.asarray(Module.shim_params[name], _np.float32))
+
+
+class _Initializers:
+    """flax.linen.initializers: only looked up (he_normal / normal nodes are `call`ed), never used for values here."""
+
+    @staticmethod
+    def he_normal(*a, **k):
+        return lambda *a_, **k_: None
+
+    normal = zeros_init = lecun_normal = xavier_uniform = he_normal
+
+
+initializers = _Initializers()
+
+
+def relu(x):
+    return _wrap(_np.maximum(_np.asarray(x), 0))
+
+
+@_dc.dataclass
+class Dropout:
+    """flax.linen.Dropout: identity when deterministic (the only way the files we execute call it)."""
+    rate: float = 0.0
+
+    def __call__(self, x, deterministic=True):
+        assert deterministic, "the shim has no RNG: stochastic dropout is not executed"
+        return x
 
 
 def compact(fn):

@@ -5,8 +5,16 @@ import importlib
 
 
 def _resolve(path):
-    mod, _, name = path.rpartition(".")
-    return getattr(importlib.import_module(mod), name)
+    parts = path.split(".")
+    for i in range(len(parts) - 1, 0, -1):      # longest importable prefix, then attribute access
+        try:
+            obj = importlib.import_module(".".join(parts[:i]))
+        except ModuleNotFoundError:
+            continue
+        for name in parts[i:]:
+            obj = getattr(obj, name)
+        return obj
+    raise ImportError(path)
 
 
 def instantiate(cfg, *args, _recursive_=True, **extra):

@@ -2,6 +2,7 @@
 import numpy as _np
 
 inf = _np.inf
+pi = _np.pi
 float32 = _np.float32
 int32 = _np.int32
 bool_ = _np.bool_
@@ -67,7 +68,7 @@ def _lift(name):
 
 for _n in ("matmul", "swapaxes", "take_along_axis", "concatenate", "ones_like", "zeros_like", "arange", "ones",
            "zeros", "hstack", "vstack", "squeeze", "take", "ravel", "sum", "expand_dims", "repeat", "tile",
-           "where", "stack", "sqrt", "log", "exp", "maximum", "minimum", "abs", "mean", "tanh", "digitize"):
+           "where", "stack", "sqrt", "log", "exp", "maximum", "minimum", "abs", "mean", "tanh", "digitize", "cos", "sin", "clip", "prod"):
     globals()[_n] = _lift(_n)
 
 

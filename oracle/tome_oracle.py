@@ -13,7 +13,8 @@ It restates, line by line, the reference's algorithm for the hot path (paths rel
   * mask rules ................... tokenizers/token_sequencer.py:55-183, 199-253, 313-334
   * mask use / readout gather .... models/octo/octo.py:66-68, 116-126
   * action heads + losses ........ action_heads/continuous.py:16-25, action_heads/categorical.py:12-40,
-                                   models/octo/octo.py:157-165, 178-190 (l2 / cross-entropy), :253-263, 292-303 (mean)
+                                   models/octo/octo.py:157-165, 178-190 (l2 / cross-entropy), :253-263, 292-303 (mean);
+                                   action_heads/diffusion.py:16-64, 85-143 (schedule, Fourier features, denoiser, loss)
 
 Third-party arithmetic that is NOT under /root/reference and is restated from its published behaviour:
 flax ^0.8.2 (`dot_product_attention`, `DenseGeneral`, `LayerNorm(use_fast_variance=True)`, `Dropout`),
@@ -21,7 +22,7 @@ jax ^0.4.26 (`argsort` stable, `argmax` first-max, `.at[].add`), see pyproject.t
 
 Parity pinning: the matching/merge functions are checked against golden vectors produced by EXECUTING the
 reference's own `token_compression.py` / `token_sequencer.py` / `action_heads/continuous.py` /
-`action_heads/categorical.py` under a numpy shim of jax + flax (oracle/gen_golden.py -> tests/golden/*.npz) and against the hand-checked vector of SURVEY.md Appendix B.  The block-level pieces that do
+`action_heads/categorical.py` / `action_heads/diffusion.py` under a numpy shim of jax + flax (oracle/gen_golden.py -> tests/golden/*.npz) and against the hand-checked vector of SURVEY.md Appendix B.  The block-level pieces that do
 not exist in runnable form in the reference (ToMe placement, `unmerge`, proportional `log size` bias -- the
 reference's tome_attention.py is a SyntaxError and has no tests) are DEFINED here following the ToMe paper;
 for those rows parity is "unpinned by the reference" and this file is the only pin.
@@ -574,3 +575,47 @@ def ce_loss(logits, actions: np.ndarray, max_action: float, num_bins: int):
     onehot = (idx[..., None] == np.arange(num_bins)).astype(np.float32)      # :183
     labels = torch.as_tensor(onehot, dtype=logits.dtype)
     return -(labels * torch.log_softmax(logits, dim=-1)).sum(dim=-1)         # :187
+
+
+def cosine_beta_schedule(timesteps: int, s: float = 0.008) -> np.ndarray:
+    """diffusion.py:16-26 in fp32 (jnp with x64 disabled)."""
+    f = np.float32
+    t = np.linspace(f(0), f(timesteps), timesteps + 1, dtype=np.float32) / f(timesteps)
+    ac = np.cos((t + f(s)) / f(1 + s) * f(np.pi) * f(0.5)) ** 2
+    ac = ac / ac[0]
+    return np.clip(f(1) - ac[1:] / ac[:-1], 0, 0.999).astype(np.float32)
+
+
+def alpha_hats(diffusion_steps: int) -> np.ndarray:
+    """DiffusionActionHead.setup (diffusion.py:85-92): cumulative products of 1 - beta."""
+    alphas = np.float32(1) - cosine_beta_schedule(diffusion_steps)
+    return np.array([np.prod(alphas[: i + 1]) for i in range(diffusion_steps)], np.float32)
+
+
+def _mlp_block(x, k0, b0, k1, b1):
+    """MLPBlock (attention.py:20-39) with train=False: Dense -> relu -> Dense (both Dropouts deterministic)."""
+    torch = _torch()
+    return torch.relu(x @ k0 + b0) @ k1 + b1
+
+
+def octo_denoise(noisy_action, time, readout_embedding, p):
+    """OctoDenoise.__call__ with FourierFeatures (diffusion.py:29-64), num_blocks = 1.  time int [B, 1];
+    p: dict of torch tensors fourier_kernel [F/2, 1], tw1, tb1, tw2, tb2, w1, b1, w2, b2 (kernels [in, out])."""
+    torch = _torch()
+    x = 2 * math.pi * time.to(torch.float32) @ p["fourier_kernel"].T          # :45
+    x = torch.cat([torch.cos(x), torch.sin(x)], dim=-1)                        # :46
+    time_embedding = _mlp_block(x, p["tw1"], p["tb1"], p["tw2"], p["tb2"])    # :47
+    x = torch.cat([noisy_action, time_embedding, readout_embedding], dim=-1)   # :61
+    return _mlp_block(x, p["w1"], p["b1"], p["w2"], p["b2"])                  # :62-63
+
+
+def denoise_loss(readouts, actions, time, noise, ah: np.ndarray, p):
+    """DiffusionActionHead.denoise_loss (diffusion.py:114-143) with the random draws (time int [B, 1], noise [B, A])
+    supplied by the caller.  Returns (loss, predictions)."""
+    torch = _torch()
+    alpha_hat = torch.as_tensor(ah)[time.long()]                               # :131  [B, 1]
+    noisy = torch.sqrt(alpha_hat) * actions + torch.sqrt(1 - alpha_hat) * noise   # :132-134
+    emb = readouts.mean(dim=-2)                                                # :107
+    pred = octo_denoise(noisy, time, emb, p)                                   # :110
+    loss = (0.5 * (pred - noise) ** 2).sum(dim=-1).mean()                      # :141-142 optax.l2_loss
+    return loss, pred

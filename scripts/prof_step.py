@@ -9,7 +9,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from bench import CONFIGS, SEQ  # noqa: E402
+from bench import ACTION_DIM, CONFIGS, MAX_ACTION, SEQ  # noqa: E402
 from multi_modal_transformers_tokenmerge_b200.engine import StackConfig, ToMeStackEngine  # noqa: E402
 from multi_modal_transformers_tokenmerge_b200.tokenizers.token_sequencer import sequence_groups  # noqa: E402
 
@@ -20,11 +20,11 @@ gid, pos, allow, ro = sequence_groups(SEQ)
 T0, B, C = len(gid), c["batch"], c["channels"]
 cfg = StackConfig(batch=B, tokens=T0, channels=C, heads=c["heads"], head_dim=c["head_dim"], mlp_dim=c["mlp_dim"],
                   layers=layers, r=c["r"], ln_axis=1, num_groups=allow.shape[0], n_readout=len(ro), dropout_rate=0.1,
-                  dropout_seed=1)
+                  dropout_seed=1, attn_dropout_rate=0.1, head="continuous", head_features=ACTION_DIM, max_action=MAX_ACTION)
 eng = ToMeStackEngine(cfg, gid=gid, pos=pos, allow=allow, readout_idx=ro)
 eng.init_params(seed=1)
 x = torch.randn(B, T0, C, device="cuda").bfloat16()
-y = torch.randn(B, len(ro), C, device="cuda")
+y = torch.rand(B, ACTION_DIM, device="cuda") * 2 - 1   # target actions (bench.py --loss continuous)
 
 
 def step():

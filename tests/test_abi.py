@@ -84,6 +84,25 @@ def test_action_head_shapes_on_host(lib):
     assert lib.tome_stack_param_count(C.byref(bad)) == -1 and b"groups must be 1" in lib.tome_last_error()
 
 
+def test_diffusion_head_shapes_on_host(lib):
+    """diffusion.yaml's literal widths: parameter layout and its place at the end of the stack's flat vector."""
+    from multi_modal_transformers_tokenmerge_b200 import _lib as L
+    from multi_modal_transformers_tokenmerge_b200.engine import StackConfig
+    d = L.DiffusionDesc(8, 74, 768, 8, 8, 768, 768, 768, 768, 32)
+    n = 384 + (768 * 768 + 768) * 2 + (8 + 768 + 768) * 768 + 768 + 768 * 8 + 8
+    assert lib.tome_diffusion_head_param_count(C.byref(d)) == n
+    assert lib.tome_diffusion_head_param_offset(C.byref(d), 0) == 0 and lib.tome_diffusion_head_param_offset(C.byref(d), 1) == 384
+    assert lib.tome_diffusion_head_param_offset(C.byref(d), 9) == n
+    assert lib.tome_diffusion_head_workspace_bytes(C.byref(d)) > 0
+    bad = L.DiffusionDesc(8, 74, 768, 8, 7, 768, 768, 768, 768, 32)      # action_dim 7: rows of the concatenated input unaligned
+    assert lib.tome_diffusion_head_param_count(C.byref(bad)) == -1 and b"action_dim" in lib.tome_last_error()
+    base = dict(batch=8, tokens=74, channels=768, heads=12, head_dim=64, mlp_dim=3072, layers=1, num_groups=5, n_readout=8)
+    n0 = lib.tome_stack_param_count(C.byref(StackConfig(**base).c()))
+    cfg = StackConfig(**base, head="diffusion", head_features=8, head_fourier_dim=768, head_time_hidden=768, head_time_out=768,
+                      head_hidden=768, diffusion_steps=32).c()
+    assert lib.tome_stack_param_count(C.byref(cfg)) == n0 + n and lib.tome_stack_head_offset(C.byref(cfg)) == n0
+
+
 def test_validation_errors_are_reported_not_thrown(lib):
     from multi_modal_transformers_tokenmerge_b200 import _lib as L
     assert lib.tome_gemm_bf16(None, None, 0, None) == L.TOME_ERR_INVALID

@@ -316,3 +316,56 @@ def test_action_head_modules_against_reference_goldens():
     with pytest.raises(ValueError, match="num_bins"):
         AH.CategoricalActionHead(num_bins=8, max_action=1.0, action_space_dim=2, dense=dense(7)).apply(
             {"params": {"Dense_0": {"kernel": np.zeros((16, 7), np.float32)}}}, torch.zeros(1, 4, 16, device="cuda"))
+
+
+def _diffusion_node(A, F, Ht, To, H):
+    dense = lambda f: {"_target_": "flax.linen.Dense", "features": f, "use_bias": True,  # noqa: E731
+                       "kernel_init": {"_target_": "flax.linen.initializers.he_normal"},
+                       "bias_init": {"_target_": "flax.linen.initializers.normal"}}
+    mlp = lambda f0, f1: {"_target_": "multi_modal_transformers.attention_blocks.attention.MLPBlock", "dense": dense(f0),  # noqa: E731
+                          "activation": {"_partial_": True, "_target_": "flax.linen.relu"},
+                          "norm": {"_target_": "flax.linen.Dropout", "rate": 0.1}, "dense_out": dense(f1)}
+    return {"_target_": "multi_modal_transformers.action_heads.diffusion.OctoDenoise", "num_blocks": 1,
+            "time_encoder": {"_target_": "multi_modal_transformers.action_heads.diffusion.FourierFeatures", "output_dim": F,
+                             "kernel_init": {"_target_": "flax.linen.initializers.he_normal"}, "mlp_block": mlp(Ht, To)},
+            "mlp_block": mlp(H, A)}
+
+
+def test_diffusion_head_module_schedule_and_param_tree():
+    """DiffusionActionHead built from a diffusion.yaml-shaped node: the cosine schedule of :16-26 / :85-92 equals the
+    reference's own (golden), and init() yields Flax's parameter tree with the yaml's literal widths."""
+    g = np.load(os.path.join(GOLD, "action_heads.npz"))
+    head = AH.DiffusionActionHead(diffusion_steps=32, attention_pooling=None, denoising_model=_diffusion_node(8, 768, 768, 768, 768))
+    np.testing.assert_array_equal(head.betas, g["diff_schedule32/betas"])
+    np.testing.assert_array_equal(head.alpha_hats, g["diff_schedule32/alpha_hats"])
+    v = head.init(0, np.zeros((2, 8, 768), np.float32))["params"]["denoiser"]
+    assert v["FourierFeatures_0"]["fourier_kernel"].shape == (384, 1)
+    assert v["FourierFeatures_0"]["MLPBlock_0"]["Dense_1"]["kernel"].shape == (768, 768)
+    assert v["MLPBlock_0"]["Dense_0"]["kernel"].shape == (8 + 768 + 768, 768)        # [noisy | time | readout] (:61)
+    assert v["MLPBlock_0"]["Dense_1"]["kernel"].shape == (768, 8)
+    with pytest.raises(NotImplementedError):
+        AH.DiffusionActionHead(32, None, {**_diffusion_node(8, 32, 32, 32, 32), "num_blocks": 2})
+
+
+@gpu
+def test_diffusion_head_module_against_reference_goldens():
+    """denoise_loss / predict_denoise_term of the module, on the parameters and draws of the goldens made by executing
+    the reference's OctoDenoise (bf16 tensor-core GEMMs inside: 2e-2 relative)."""
+    g = np.load(os.path.join(GOLD, "action_heads.npz"))
+    for name in g["diffusion"]:
+        p = {k: g[f"{name}/p/{k}"] for k in ("fourier_kernel", "tw1", "tb1", "tw2", "tb2", "w1", "b1", "w2", "b2")}
+        A, F, Ht, To, H = p["w2"].shape[1], p["tw1"].shape[0], p["tw1"].shape[1], p["tw2"].shape[1], p["w1"].shape[1]
+        head = AH.DiffusionActionHead(int(g[f"{name}/steps"]), None, _diffusion_node(A, F, Ht, To, H))
+        v = {"params": {"denoiser": {
+            "FourierFeatures_0": {"fourier_kernel": p["fourier_kernel"],
+                                  "MLPBlock_0": {"Dense_0": {"kernel": p["tw1"], "bias": p["tb1"]}, "Dense_1": {"kernel": p["tw2"], "bias": p["tb2"]}}},
+            "MLPBlock_0": {"Dense_0": {"kernel": p["w1"], "bias": p["b1"]}, "Dense_1": {"kernel": p["w2"], "bias": p["b2"]}}}}}
+        ro, act = _dev(g[f"{name}/readouts"]), _dev(g[f"{name}/actions"])
+        loss = head.denoise_loss(v, ro, act, time=_dev(g[f"{name}/time"]), noise=_dev(g[f"{name}/noise"]))
+        assert abs(loss.item() - float(g[f"{name}/loss"])) <= 2e-2 * float(g[f"{name}/loss"])
+        pred = head.predict_denoise_term(v, ro, _dev(g[f"{name}/time"]), _dev(g[f"{name}/noisy"]))
+        want = torch.tensor(g[f"{name}/pred"])
+        assert ((pred.cpu() - want).norm() / want.norm()).item() <= 2e-2
+        # drawn internally: finite, reproducible for a seed, different for another
+        l1, l2, l3 = (head.denoise_loss(v, ro, act, rng=s).item() for s in (1, 1, 2))
+        assert np.isfinite(l1) and l1 == l2 and l1 != l3

@@ -354,3 +354,79 @@ def test_stack_with_action_head_vs_oracle(pkg, head, r):
         eng.backward()
         eng.adamw_step(lr=1e-3)
     assert eng.loss[0].item() < l0
+
+
+def test_stack_with_diffusion_head_vs_oracle(pkg):
+    """The loss octo_base.yaml actually selects (action_heads: diffusion): stack -> pooled readouts -> denoise loss
+    (diffusion.py:94-143) with the draws supplied; loss, the head's gradients and the stack's against the oracle."""
+    ops, engine = pkg
+    B, W, P, C, H, Dff, Lyr, n_ro, r = 8, 2, 24, 128, 2, 256, 2, 4, 4
+    A, F, Ht, To, Hd, steps = 8, 64, 96, 64, 128, 32
+    rng = np.random.default_rng(13)
+    gid, pos, allow, ro = O.sequence_groups(f"[TaskDescriptionPrefix{{4}}] [Image{{{P}}};Readout{{{n_ro}}}]*{W}")
+    T = gid.shape[0]
+    layers = [O.init_block_params(rng, C, H, 64, Dff) for _ in range(Lyr)]
+    for d in layers:
+        d["b1"] = d["b1"] + np.float32(8.0)
+    pe = (rng.standard_normal((1, T, C)) * 0.02).astype(np.float32)
+    x = rng.standard_normal((B, T, C)).astype(np.float32)
+    cfg = engine.StackConfig(batch=B, tokens=T, channels=C, heads=H, head_dim=64, mlp_dim=Dff, layers=Lyr, r=r, ln_axis=2,
+                             num_groups=allow.shape[0], n_readout=len(ro), head="diffusion", head_features=A, head_fourier_dim=F,
+                             head_time_hidden=Ht, head_time_out=To, head_hidden=Hd, diffusion_steps=steps)
+    eng = engine.ToMeStackEngine(cfg, gid=gid, pos=pos, allow=allow, readout_idx=ro)
+    shapes = cfg.diffusion_param_shapes()
+    hp = {k: (rng.standard_normal(s) * (0.05 if k == "fourier_kernel" else 0.1)).astype(np.float32) for k, s in shapes.items()}
+    hp["tb1"] += np.float32(12.0)     # open every ReLU gate of the head too (see CASES)
+    hp["b1"] += np.float32(12.0)
+    eng.load_params(pe[0], layers, head=hp)
+    actions = rng.uniform(-1, 1, (B, A)).astype(np.float32)
+    noise = rng.standard_normal((B, A)).astype(np.float32)
+    time = rng.integers(0, steps, B).astype(np.int32)
+    ah = O.alpha_hats(steps)
+    eng.set_diffusion_draws(torch.tensor(time).cuda(), ah)
+    xd, tgt = torch.tensor(x).cuda(), torch.tensor(np.stack([actions, noise])).cuda()
+    eng.zero_grad()
+    eng.forward(xd, tgt)
+    eng.backward()
+    torch.cuda.synchronize()
+    node_override = []
+    for l in range(Lyr):
+        pl = eng.layer_plan(l)
+        node_override.append(None if pl is None else (pl[0].cpu().numpy(), pl[1].cpu().numpy()))
+    v = eng.param_views(eng.params_bf16.float().cpu())
+    vf = eng.param_views(eng.params.cpu())
+    params, hd = [], H * 64
+    for l in range(Lyr):
+        src, srcf = v["layers"][l], vf["layers"][l]
+        d = dict(ln1_scale=srcf["ln1_scale"], ln1_bias=srcf["ln1_bias"], ln2_scale=srcf["ln2_scale"], ln2_bias=srcf["ln2_bias"],
+                 wq=src["wqkv"][:, :hd], wk=src["wqkv"][:, hd:2 * hd], wv=src["wqkv"][:, 2 * hd:],
+                 bq=srcf["bqkv"][:hd], bk=srcf["bqkv"][hd:2 * hd], bv=srcf["bqkv"][2 * hd:],
+                 wo=src["wo"], bo=srcf["bo"], w1=src["w1"], b1=srcf["b1"], w2=src["w2"], b2=srcf["b2"])
+        params.append(O.BlockParams(**{k_: t.clone().contiguous().requires_grad_(True) for k_, t in d.items()}))
+    pet = vf["pos_embedding"].clone()[None].requires_grad_(True)
+    pt = {k: (v["head"][k] if k in ("tw1", "tw2", "w1") else vf["head"][k]).clone().requires_grad_(True) for k in shapes}
+    xf, size, origin = O.tome_stack(params, pet, torch.tensor(x), gid, pos, allow, num_heads=H, r=r, ln_axis="feature",
+                                    node_override=node_override, act_dtype=torch.bfloat16)
+    _, readouts = O.readout_loss(xf, origin, ro, torch.zeros(B, len(ro), C))
+    loss, want = O.denoise_loss(readouts, torch.tensor(actions), torch.tensor(time)[:, None], torch.tensor(noise), ah, pt)
+    loss.backward()
+    assert rel_err(eng.head_out.cpu().reshape(want.shape), want.detach()) <= 2e-2
+    assert abs(eng.loss[0].item() - loss.item()) <= 2e-2 * abs(loss.item())
+    g = eng.param_views(eng.grads.cpu())
+    for k in shapes:
+        e = rel_err(g["head"][k], pt[k].grad)
+        # the Fourier-kernel gradient is a sum over the batch of terms of both signs scaled by 2 pi t: cancellation
+        assert e <= (0.1 if k == "fourier_kernel" else 3e-2), f"head grad {k}: rel err {e}"
+    assert rel_err(g["pos_embedding"], pet.grad[0]) <= 4e-2
+    for l in range(Lyr):
+        p, gl = params[l], g["layers"][l]
+        for name, want_g in dict(wqkv=torch.cat([p.wq.grad, p.wk.grad, p.wv.grad], 1), wo=p.wo.grad, w1=p.w1.grad, w2=p.w2.grad).items():
+            e = rel_err(gl[name], want_g)
+            assert e <= 4e-2, f"layer {l} grad {name}: rel err {e}"
+    l0 = eng.loss[0].item()
+    for _ in range(10):
+        eng.zero_grad()
+        eng.forward(xd, tgt)
+        eng.backward()
+        eng.adamw_step(lr=1e-3)
+    assert eng.loss[0].item() < l0

@@ -150,3 +150,22 @@ def test_action_heads_match_reference_goldens():
         np.testing.assert_allclose(O.ce_loss(logits, g[f"{name}/actions"], mx, bins).numpy(), g[f"{name}/loss"], rtol=1e-4, atol=1e-5)
     # the reference's 1-based digitize: the top bin and everything above the range have no class at all
     assert O.assign_bins(np.array([0.999, 1.0, 7.0, -7.0], np.float32), (-1.0, 1.0), 4).tolist() == [4, 5, 5, 0]
+
+
+def test_diffusion_head_matches_reference_goldens():
+    """oracle.cosine_beta_schedule / alpha_hats / octo_denoise / denoise_loss against the reference's own
+    cosine_beta_schedule, FourierFeatures, OctoDenoise and MLPBlock (diffusion.py:16-64, attention.py:20-39), executed by
+    oracle/gen_golden.py under the shim; the noisy-action and loss lines (:131-142) are restated there on those outputs."""
+    torch = pytest.importorskip("torch")
+    g = np.load(os.path.join(GOLD, "action_heads.npz"))
+    for steps in (8, 32):
+        np.testing.assert_array_equal(O.cosine_beta_schedule(steps), g[f"diff_schedule{steps}/betas"])
+        np.testing.assert_array_equal(O.alpha_hats(steps), g[f"diff_schedule{steps}/alpha_hats"])
+    assert O.cosine_beta_schedule(32)[-1] == np.float32(0.999)             # the clip of :26
+    for name in g["diffusion"]:
+        p = {k: torch.tensor(g[f"{name}/p/{k}"]) for k in ("fourier_kernel", "tw1", "tb1", "tw2", "tb2", "w1", "b1", "w2", "b2")}
+        loss, pred = O.denoise_loss(torch.tensor(g[f"{name}/readouts"]), torch.tensor(g[f"{name}/actions"]),
+                                    torch.tensor(g[f"{name}/time"]), torch.tensor(g[f"{name}/noise"]),
+                                    O.alpha_hats(int(g[f"{name}/steps"])), p)
+        np.testing.assert_allclose(pred.numpy(), g[f"{name}/pred"], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(loss.item(), g[f"{name}/loss"], rtol=1e-5)
