@@ -144,7 +144,7 @@ def workload_config(args, world, B, T0):
             "loss": ("continuous action head + l2 loss on the pooled readouts (continuous_train_step, octo.py:242-280)"
                      if args.loss == "continuous" else "synthetic MSE on the readout rows"),
             "hidden_dropout": args.dropout, "attention_dropout": args.attn_dropout, "optimizer": "AdamW fp32 master",
-            "parallelism": f"dp{world}", "l2_policy": "inputs and activations (>= 1 GB/step) exceed the 126 MB L2"}
+            "parallelism": f"dp{world}", "comm_sms": args.comm_sms if world > 1 else 0, "l2_policy": "inputs and activations (>= 1 GB/step) exceed the 126 MB L2"}
 
 
 def run_reference(args, rank):
@@ -180,6 +180,9 @@ def main():
     ap.add_argument("--loss", default="continuous", choices=["continuous", "synthetic"],
                     help="continuous: ContinuousActionHead + l2 loss on the pooled readouts, the reference's "
                          "continuous_train_step; synthetic: MSE on the readout rows")
+    ap.add_argument("--comm-sms", type=int, default=0,
+                    help="N > 1: SMs reserved for the NCCL all-reduce kernels during backward (NCCL max_ctas = this, the "
+                         "persistent GEMM grid shrinks by this); 0 = NCCL's default and the full grid")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "tome_b200" else args.warmup
@@ -195,7 +198,7 @@ def main():
 
     from multi_modal_transformers_tokenmerge_b200 import _lib as L
     from multi_modal_transformers_tokenmerge_b200.engine import StackConfig, ToMeStackEngine
-    from multi_modal_transformers_tokenmerge_b200.parallel import DataParallelTrainer
+    from multi_modal_transformers_tokenmerge_b200.parallel import DataParallelTrainer, nccl_options
     from multi_modal_transformers_tokenmerge_b200.tokenizers.token_sequencer import sequence_groups
 
     lib = L.lib()  # raises if the CUDA library is missing: the product path has no fallback
@@ -206,7 +209,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=nccl_options(args.comm_sms))
     c = dict(CONFIGS[args.config])
     if args.batch:
         c["batch"] = args.batch
@@ -218,7 +221,7 @@ def main():
                       **(dict(head="continuous", head_features=ACTION_DIM, max_action=MAX_ACTION) if args.loss == "continuous" else {}))
     eng = ToMeStackEngine(cfg, gid=gid, pos=pos, allow=allow, readout_idx=ro)
     eng.init_params(seed=1)  # same weights on every rank
-    trainer = DataParallelTrainer(eng)
+    trainer = DataParallelTrainer(eng, comm_sms=args.comm_sms if world > 1 else 0)
     g = torch.Generator(device="cuda").manual_seed(100 + rank)
     x = torch.randn(B, T0, C, device="cuda", generator=g).bfloat16()      # synthetic block inputs (embeddings)
     tshape = (B, ACTION_DIM) if args.loss == "continuous" else (B, len(ro), C)   # target actions / synthetic readout targets

@@ -137,6 +137,9 @@ typedef struct {
 } tome_gemm_args_t;
 
 size_t tome_gemm_workspace_bytes(const tome_gemm_args_t* args);
+/* SMs the persistent GEMM grid may occupy from now on (process-wide; 0 = all 148).  Lowered by the data-parallel trainer
+ * during backward so the overlapped NCCL all-reduce kernels have SMs of their own. */
+int tome_gemm_set_sm_limit(int sms);
 int tome_gemm_bf16(const tome_gemm_args_t* args, void* workspace, size_t workspace_bytes, void* stream);
 
 /* out[n] (+)= sum_m x[m,n]   (bias gradients).  x bf16 [M, ldx]; out f32 [N].  workspace: f32 [ws_rows, N] with

@@ -150,6 +150,7 @@ def lib() -> C.CDLL:
             "tome_topk_prune": [P(PruneDesc), vp, vp, vp, vp, vp],
             "tome_gemm_workspace_bytes": [P(GemmArgs)],
             "tome_gemm_bf16": [P(GemmArgs), vp, C.c_size_t, vp],
+            "tome_gemm_set_sm_limit": [i32],
             "tome_colsum_workspace_rows": [i32],
             "tome_colsum_bf16": [i32, i32, vp, ll, vp, i32, vp, vp],
             "tome_dropout_colsum_bf16": [i32, i32, vp, vp, f32, C.c_uint64, C.c_uint32, vp, i32, vp, vp],

@@ -485,6 +485,12 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __re
   }
 }
 
+// SMs the persistent grid may occupy (0 = all).  The data-parallel trainer lowers it during backward so that the NCCL
+// all-reduce kernels running beside it own their SMs: a persistent CTA that cannot be scheduled until a long collective
+// kernel leaves its SM would hold back the whole GEMM (tiles are assigned statically).
+static int g_gemm_sm_limit = 0;
+static inline int gemm_sms() { return g_gemm_sm_limit > 0 && g_gemm_sm_limit < kNumSMs ? g_gemm_sm_limit : kNumSMs; }
+
 template <int BN, bool A_MN, bool B_MN, bool MC, int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmShape& s, const GemmEpilogue& e,
                        cudaStream_t stream) {
@@ -502,7 +508,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   if (MC) {
-    const int clusters = items < kNumSMs / 2 ? items : kNumSMs / 2;
+    const int clusters = items < gemm_sms() / 2 ? items : gemm_sms() / 2;
     cfg.gridDim = dim3(2 * clusters);
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
@@ -511,7 +517,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     cfg.attrs = attr;
     cfg.numAttrs = 1;
   } else {
-    cfg.gridDim = dim3(items < kNumSMs ? items : kNumSMs);
+    cfg.gridDim = dim3(items < gemm_sms() ? items : gemm_sms());
   }
   TOME_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, s, e));
   return TOME_OK;
@@ -539,6 +545,13 @@ static int pick_splits(const tome_gemm_args_t* a, int bn) {
   if (s > kb / 8) s = kb / 8 > 0 ? kb / 8 : 1;  // keep >= 8 k-blocks per split
   if (s > 64) s = 64;
   return s;
+}
+
+extern "C" int tome_gemm_set_sm_limit(int sms) {
+  clear_error();
+  TOME_CHECK(sms >= 0, TOME_ERR_INVALID, "gemm_set_sm_limit: sms must be >= 0 (0 = all)");
+  g_gemm_sm_limit = sms >= 2 || sms == 0 ? sms : 2;
+  return TOME_OK;
 }
 
 extern "C" size_t tome_gemm_workspace_bytes(const tome_gemm_args_t* a) {

@@ -56,11 +56,24 @@ class GradBucketReducer:
         main.wait_stream(self.comm_stream)
 
 
+def nccl_options(max_ctas: int):
+    """ProcessGroupNCCL options capping the CTAs (= SMs) one collective may occupy; None when max_ctas == 0."""
+    if not max_ctas:
+        return None
+    opts = dist.ProcessGroupNCCL.Options()
+    opts.config.max_ctas = int(max_ctas)
+    opts.config.min_ctas = 1
+    return opts
+
+
 class DataParallelTrainer:
     """forward + backward + overlapped gradient all-reduce + AdamW for one rank's shard of the batch."""
 
-    def __init__(self, engine, group=None):
+    def __init__(self, engine, group=None, comm_sms: int = 0):
+        """comm_sms > 0: SMs left to the NCCL kernels while backward runs (the persistent GEMM grid shrinks by that many;
+        pair it with an NCCL CTA cap of the same size, see `nccl_options`)."""
         self.engine = engine
+        self.comm_sms = int(comm_sms)
         offs = [engine.layer_offset(l) for l in range(engine.cfg.layers)]
         self.reducer = GradBucketReducer(engine.grads, layer_buckets(offs, engine.n_params), group)
         self.world = self.reducer.world
@@ -74,7 +87,11 @@ class DataParallelTrainer:
         e.zero_grad()
         e.forward(x, target)
         if self.world > 1:
+            if self.comm_sms:
+                e.lib.tome_gemm_set_sm_limit(148 - self.comm_sms)
             e.backward(events=self.events)  # events[l] <- layer l done; events[L] <- everything done
+            if self.comm_sms:
+                e.lib.tome_gemm_set_sm_limit(0)
             L = e.cfg.layers
             order = [self.events[l] for l in range(L - 1, -1, -1)] + [self.events[L]]
             self.reducer.reduce(order)
