@@ -34,7 +34,7 @@ constexpr int ATT_Q_BYTES = ATT_BM * ATT_D * 2;         // 16 KB
 constexpr int ATT_KV_BYTES = ATT_BN * ATT_D * 2;        // 8 KB each for K and V
 constexpr int ATT_P_BYTES = ATT_BM * ATT_BN * 2;        // 16 KB, x2 buffers
 constexpr int ATT_SLOTS = 5;  // ring of 8 KB slots; items are loaded in the order K_0 K_1 V_0 K_2 V_1 ...
-constexpr int ATT_MSLOTS = 3; // metadata ring
+constexpr int ATT_MSLOTS = 4; // metadata ring
 constexpr int ATT_QAUG_BYTES = ATT_BM * ATTN_AUG_K * 2;   // 4 KB: mask augmentation operand of the query tile (attn_meta.cuh)
 constexpr int ATT_KAUG_BYTES = ATT_BN * ATTN_AUG_K * 2;   // 2 KB per key tile, one per ring slot
 constexpr int ATT_META_SLOT = ATTN_META_KEY_BYTES + ATTN_DROP_TILE_BYTES;  // bias2 | vis[32][2] | visc[32][2] | pos | dropout keep words [128][2]
@@ -271,7 +271,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const float2 t1 = __ffma2_rn(make_float2(s[4 * i4 + 2], s[4 * i4 + 3]), scale2, make_float2(bb.z, bb.w));
         s[4 * i4] = t0.x; s[4 * i4 + 1] = t0.y; s[4 * i4 + 2] = t1.x; s[4 * i4 + 3] = t1.y;
       }
-      mbar_arrive(&meta_empty[ms]);  // last read of this tile's metadata
       if (masked_tile) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -340,6 +339,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
       const float2 lsum = __fadd2_rn(__fadd2_rn(l2[0], l2[1]), __fadd2_rn(l2[2], l2[3]));
       l_run += lsum.x + lsum.y;
+      // Release the metadata slot only HERE, after the P stores above: they consume every value loaded from the slot (bias,
+      // visibility words, keep bits), so all those shared-memory loads have returned.  An arrive placed right after the
+      // loads were merely ISSUED let the producer's next bulk copy overwrite the slot under loads still queued behind the
+      // MUFU / tcgen05.ld traffic: rows then saw the bias of the tile three ahead (-inf past T) -- wrong, and different
+      // from run to run.  Found by the full-size reproducibility test; invisible at small batch.
+      mbar_arrive(&meta_empty[ms]);
       fence_proxy_async_smem();  // P visible to the tensor core (async proxy)
       tc_fence_before();         // our TMEM reads of S_j / writes of O are ordered before the MMAs that follow
       mbar_arrive(&p_ready[j & 1]);

@@ -430,3 +430,51 @@ def test_stack_with_diffusion_head_vs_oracle(pkg):
         eng.backward()
         eng.adamw_step(lr=1e-3)
     assert eng.loss[0].item() < l0
+
+
+def test_full_size_bench_shape_properties(pkg):
+    """BASELINE.json configs[1] at FULL size (B = 256 / GPU, T0 = 536, 12 layers, r = 16, bf16, hidden + attention dropout
+    0.1, continuous action head) -- too large for the oracle, so size-independent properties are checked instead:
+    token counts follow 536 - 16 l; token sizes are integer-valued and conserve T0 in every row; every row of every layer's
+    matching plan is a valid index split (edge ranking a permutation of the even tokens, destinations inside the odd set);
+    the step is bit-reproducible for a fixed dropout seed; the loss is finite and falls under AdamW."""
+    ops, engine = pkg
+    gid, pos, allow, ro = O.sequence_groups("[TaskDescriptionPrefix{16}] [Image{256};Readout{4}]*2")
+    B, T, C, H, Dff, Lyr, r, A = 256, 536, 384, 6, 1536, 12, 16, 8
+    cfg = engine.StackConfig(batch=B, tokens=T, channels=C, heads=H, head_dim=64, mlp_dim=Dff, layers=Lyr, r=r,
+                             num_groups=allow.shape[0], n_readout=len(ro), dropout_rate=0.1, attn_dropout_rate=0.1, dropout_seed=7,
+                             head="continuous", head_features=A, max_action=1.0)
+    eng = engine.ToMeStackEngine(cfg, gid=gid, pos=pos, allow=allow, readout_idx=ro)
+    eng.init_params(1)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(B, T, C, device="cuda", generator=g).bfloat16()
+    act = torch.rand(B, A, device="cuda", generator=g) * 2 - 1
+    runs = []
+    for _ in range(2):
+        eng.zero_grad()
+        eng.forward(x, act)
+        eng.backward()
+        torch.cuda.synchronize()
+        runs.append((eng.loss.clone(), eng.grads.clone(), eng.final_x().clone()))
+    assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1]) and torch.equal(runs[0][2], runs[1][2])
+    assert [eng.tokens_at(l) for l in range(Lyr + 1)] == [T - r * l for l in range(Lyr + 1)]
+    size = eng.final_size()
+    assert torch.all(size == size.round()) and torch.all(size >= 1) and torch.all(size.sum(dim=1) == T)
+    for l in range(Lyr):
+        nm, ni, ei, di = eng.layer_plan(l)
+        t = eng.tokens_at(l)
+        ta, tb = (t + 1) // 2, t // 2
+        assert torch.equal(ei.sort(dim=1).values, torch.arange(ta, device="cuda", dtype=torch.int32).expand(B, ta))
+        assert int(di.min()) >= 0 and int(di.max()) < tb and int(ni.min()) >= 0 and int(ni.max()) < tb
+        top = torch.gather(nm, 1, ei[:, :r].long())          # the r merged edges are the r largest row maxima
+        rest = torch.gather(nm, 1, ei[:, r:].long())
+        assert torch.all(top.min(dim=1).values >= rest.max(dim=1).values)
+    assert torch.isfinite(eng.grads).all()
+    losses = []
+    for _ in range(4):
+        eng.zero_grad()
+        eng.forward(x, act)
+        eng.backward()
+        eng.adamw_step(lr=3e-4)
+        losses.append(eng.loss[0].item())
+    assert all(math.isfinite(v) for v in losses) and losses[-1] < losses[0], losses
