@@ -628,3 +628,46 @@ def test_diffusion_head_backward_vs_oracle_autograd(ops):
         assert e <= (0.1 if k == "fourier_kernel" else 3e-2), f"grad {k}: rel err {e}"
         off += nel
     assert rel_err(dx.float().cpu(), xr.grad) <= 3e-2
+
+
+# ------------------------------------------------------------------------------------------------ full-batch behaviour
+@pytest.mark.parametrize("T", [536, 600])
+def test_attention_full_batch_reproducible_and_accurate(ops, T):
+    """At the bench batch (256 x 6 heads: 7 680 CTAs, several waves, two CTAs per SM) the forward must be bit-reproducible
+    and as accurate as at small batch.  This is the test that exposes a shared-memory ring slot released before the loads
+    from it have returned (profiles/r01c_attention.md): invisible at small batch and for T a multiple of 64.  The reference
+    here is torch's fp32 attention on the same bf16 inputs (checker only); masked / dropout variants and the backward are
+    checked for reproducibility."""
+    torch.manual_seed(T)
+    B, H, D = 256, 6, 64
+    qkv = torch.randn(B, T, 3, H, D, device="cuda").bfloat16()
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    ref = torch.nn.functional.scaled_dot_product_attention(q.transpose(1, 2).float(), k.transpose(1, 2).float(),
+                                                           v.transpose(1, 2).float()).transpose(1, 2)
+    runs = []
+    for _ in range(4):
+        o, l = ops.attention_fwd(q, k, v)
+        torch.cuda.synchronize()
+        runs.append((o.clone(), l.clone()))
+    assert (runs[0][0].float() - ref).abs().max().item() <= 0.02
+    for o, l in runs[1:]:
+        assert torch.equal(o, runs[0][0]) and torch.equal(l, runs[0][1])
+    # masked (+ sizes, + weight dropout): reproducible forward and backward
+    n_img = (T - 16) // 2 - 4
+    g1, p1, allow, _ = O.sequence_groups(f"[TaskDescriptionPrefix{{16}}] [Image{{{n_img}}};Readout{{4}}]*2")
+    pad = T - g1.shape[0]
+    gid = torch.tensor(np.concatenate([g1, np.full(pad, g1[-1], np.uint8)])).cuda().repeat(B, 1).contiguous()
+    pos = torch.tensor(np.concatenate([p1, np.arange(pad, dtype=np.int32)])).cuda().repeat(B, 1).contiguous()
+    size = torch.randint(1, 4, (B, T), device="cuda").float()
+    kw = dict(gid=gid, pos=pos, allow=torch.tensor(allow).cuda(), size=size)
+    dout = torch.randn(B, T, H, D, device="cuda").bfloat16()
+    for extra in (dict(), dict(dropout_rate=0.1, dropout_seed=11, dropout_site=0x40000001)):
+        outs = []
+        for _ in range(3):
+            o, l = ops.attention_fwd(q, k, v, **kw, **extra)
+            dq, dk, dv = ops.attention_bwd(q, k, v, o, l, dout, **kw, **extra)
+            torch.cuda.synchronize()
+            outs.append([t.clone() for t in (o, l, dq, dk, dv)])
+        for other in outs[1:]:
+            for a, b in zip(outs[0], other):
+                assert torch.equal(a, b)

@@ -437,7 +437,7 @@ def test_full_size_bench_shape_properties(pkg):
     0.1, continuous action head) -- too large for the oracle, so size-independent properties are checked instead:
     token counts follow 536 - 16 l; token sizes are integer-valued and conserve T0 in every row; every row of every layer's
     matching plan is a valid index split (edge ranking a permutation of the even tokens, destinations inside the odd set);
-    the step is bit-reproducible for a fixed dropout seed; the loss is finite and falls under AdamW."""
+    the step is bit-reproducible for a fixed dropout seed; the loss is finite and (dropout off) falls under AdamW."""
     ops, engine = pkg
     gid, pos, allow, ro = O.sequence_groups("[TaskDescriptionPrefix{16}] [Image{256};Readout{4}]*2")
     B, T, C, H, Dff, Lyr, r, A = 256, 536, 384, 6, 1536, 12, 16, 8
@@ -470,11 +470,18 @@ def test_full_size_bench_shape_properties(pkg):
         rest = torch.gather(nm, 1, ei[:, r:].long())
         assert torch.all(top.min(dim=1).values >= rest.max(dim=1).values)
     assert torch.isfinite(eng.grads).all()
+    # training on one batch lowers its loss (dropout off for this part: with it every step sees the same masks but a
+    # noisier objective, and four steps without warm-up need not be monotone)
+    del eng
+    torch.cuda.empty_cache()
+    cfg0 = engine.StackConfig(**{**cfg.__dict__, "dropout_rate": 0.0, "attn_dropout_rate": 0.0})
+    eng = engine.ToMeStackEngine(cfg0, gid=gid, pos=pos, allow=allow, readout_idx=ro)
+    eng.init_params(1)
     losses = []
-    for _ in range(4):
+    for _ in range(5):
         eng.zero_grad()
         eng.forward(x, act)
         eng.backward()
-        eng.adamw_step(lr=3e-4)
+        eng.adamw_step(lr=1e-4)
         losses.append(eng.loss[0].item())
     assert all(math.isfinite(v) for v in losses) and losses[-1] < losses[0], losses
