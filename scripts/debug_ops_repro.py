@@ -51,8 +51,25 @@ q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
 check("attention fwd", lambda: ops.attention_fwd(q, k, v))
 gamma, beta = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
 check("layernorm fwd axis1", lambda: ops.layernorm_fwd(x, gamma, beta, axis=1))
-#check("sim_argmax", lambda: ops.sim_argmax(qkv[:, :, 1], heads=H, dim=D)[:2])
-nm, ni = ops.sim_argmax(qkv[:, :, 1].reshape(B, T, H * D), heads=H, dim=D)[:2]
+kk = qkv[:, :, 1].reshape(B, T, H * D).contiguous()
+check("sim_argmax", lambda: ops.sim_argmax(kk, heads=H, dim=D, batch_stride=T * H * D, token_stride=H * D, head_stride=D, tokens=T, batch=B)[:2])
+nm, ni = ops.sim_argmax(kk, heads=H, dim=D, batch_stride=T * H * D, token_stride=H * D, head_stride=D, tokens=T, batch=B)[:2]
 plan = ops.select_topr(nm, ni, T, 16)
+check("select_topr", lambda: (lambda p: (p.edge_idx, p.dst_idx, p.row_map))(ops.select_topr(nm, ni, T, 16)))
 size = torch.ones(B, T, device="cuda")
 check("merge fwd", lambda: ops.merge_fwd(plan, x, size, 1)[:2])
+x1, s1 = ops.merge_fwd(plan, x, size, 1)[:2]
+dyo = torch.randn_like(x1)
+check("merge bwd", lambda: ops.merge_bwd(plan, dyo, size, s1, 1))
+y, mean, rstd = ops.layernorm_fwd(x, gamma, beta, axis=1)
+dyl = torch.randn_like(x)
+def ln_bwd():
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dx = ops.layernorm_bwd(x, dyl, gamma, mean, rstd, dg, db, axis=1)
+    return dx, dg, db
+check("layernorm bwd axis1", ln_bwd)
+check("colsum", lambda: ops.colsum(h1))
+check("dropout_colsum", lambda: ops.dropout_colsum(x2, 0.1, 3, 7))
+o, l = ops.attention_fwd(q, k, v)
+do = torch.randn(B, T, H, D, device="cuda").bfloat16()
+check("attention bwd", lambda: ops.attention_bwd(q, k, v, o, l, do))

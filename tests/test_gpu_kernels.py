@@ -671,3 +671,63 @@ def test_attention_full_batch_reproducible_and_accurate(ops, T):
         for other in outs[1:]:
             for a, b in zip(outs[0], other):
                 assert torch.equal(a, b)
+
+
+def test_full_batch_ops_match_torch(ops):
+    """The hot ops at the bench's full size (B = 256, T = 536, C = 384: 137 216 rows), against torch on the same bf16 inputs
+    (checker only; far too large for the CPU oracle): attention backward, the projection / MLP GEMMs with their fused
+    epilogues, token-axis LayerNorm, and merge_wavg on sampled batch rows against the oracle."""
+    torch.manual_seed(1)
+    B, T, C, H, D, F = 256, 536, 384, 6, 64, 1536
+    M = B * T
+    # attention backward vs autograd of fp32 attention
+    qkv = torch.randn(B, T, 3, H, D, device="cuda").bfloat16()
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    o, l = ops.attention_fwd(q, k, v)
+    do = torch.randn(B, T, H, D, device="cuda").bfloat16()
+    dq, dk, dv = ops.attention_bwd(q, k, v, o, l, do)
+    qf, kf, vf = (t.transpose(1, 2).float().detach().requires_grad_(True) for t in (q, k, v))
+    ref = torch.nn.functional.scaled_dot_product_attention(qf, kf, vf)
+    ref.backward(do.transpose(1, 2).float())
+    for name, got, want in (("dq", dq, qf.grad), ("dk", dk, kf.grad), ("dv", dv, vf.grad)):
+        e = rel_err(got.float(), want.transpose(1, 2))
+        assert e <= 2e-2, f"{name}: rel err {e}"
+    del qf, kf, vf, ref
+    # GEMMs: bias + relu (fc1), bias + residual (fc2), gated dgrad, weight gradient over all 137 216 rows
+    x = torch.randn(M, C, device="cuda").bfloat16()
+    w1 = (torch.randn(C, F, device="cuda") * 0.05).bfloat16()
+    b1 = torch.randn(F, device="cuda") * 0.1
+    h1 = ops.gemm(x, w1, m=M, n=F, k=C, b_major=1, bias=b1, relu=True)
+    want = torch.relu(x.float() @ w1.float() + b1)
+    assert rel_err(h1.float(), want) <= 1e-2
+    w2 = (torch.randn(F, C, device="cuda") * 0.05).bfloat16()
+    b2 = torch.randn(C, device="cuda") * 0.1
+    y2 = ops.gemm(h1, w2, m=M, n=C, k=F, b_major=1, bias=b2, residual=x)
+    assert rel_err(y2.float(), h1.float() @ w2.float() + b2 + x.float()) <= 1e-2
+    dy = torch.randn(M, C, device="cuda").bfloat16()
+    dh = ops.gemm(dy, w2, m=M, n=F, k=C, gate=h1, gate_scale=1.0)
+    assert rel_err(dh.float(), (dy.float() @ w2.float().t()) * (h1 > 0)) <= 1e-2
+    dw = ops.gemm(x, dh, m=C, n=F, k=M, a_major=1, b_major=1, out_dtype=torch.float32)
+    assert rel_err(dw, x.float().t() @ dh.float()) <= 1e-2
+    del want
+    # LayerNorm over tokens
+    x3 = x.view(B, T, C)
+    gamma, beta = torch.rand(C, device="cuda") + 0.5, torch.randn(C, device="cuda") * 0.1
+    y, mean, rstd = ops.layernorm_fwd(x3, gamma, beta, axis=1)
+    xf = x3.float()
+    mu = xf.mean(dim=1, keepdim=True)
+    var = (xf * xf).mean(dim=1, keepdim=True) - mu * mu
+    assert rel_err(y.float(), (xf - mu) * torch.rsqrt(var.clamp_min(0) + 1e-6) * gamma + beta) <= 1e-2
+    # matching + merge_wavg: sampled batch rows against the oracle, bit-exact given the GPU's own scores
+    kk = qkv[:, :, 1].reshape(B, T, H * D).contiguous()
+    nm, ni, _ = ops.sim_argmax(kk, heads=H, dim=D, batch_stride=T * H * D, token_stride=H * D, head_stride=D, tokens=T, batch=B)
+    plan = ops.select_topr(nm, ni, T, 16)
+    xs = torch.randn(B, T, C, device="cuda")
+    size = torch.randint(1, 4, (B, T), device="cuda").float()
+    x1, s1, _, _ = ops.merge_fwd(plan, xs, size, 1)
+    for b_ in (0, 37, 128, 255):
+        oplan = O.plan_from_node(nm[b_:b_ + 1].cpu().numpy(), ni[b_:b_ + 1].cpu().numpy(), T, 16)
+        np.testing.assert_array_equal(plan.edge_idx[b_:b_ + 1].cpu().numpy(), oplan.edge_idx)
+        ox1, os1 = O.merge_wavg(oplan, xs[b_:b_ + 1].cpu().numpy(), size[b_:b_ + 1].cpu().numpy()[..., None])
+        np.testing.assert_array_equal(x1[b_:b_ + 1].cpu().numpy(), ox1)
+        np.testing.assert_array_equal(s1[b_:b_ + 1].cpu().numpy(), os1[..., 0])
