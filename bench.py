@@ -317,17 +317,17 @@ def main():
             ent["gbs"] = work / (kms * 1e-3) / 1e9
         kernels[k_] = ent
     gms, gwork, gcnt = prof["gemm"]
-    # DRAM read + write per launch from the committed ncu captures (profiles/r01c_layer0_launch_metrics.txt: mean of the 12
-    # GEMM launches of layer 0; profiles/r01c_ncu_full_summary.txt: merge_fwd at layer 0); only for the captured configuration
+    # DRAM read + write per launch from the committed ncu captures (profiles/r01d_ncu_full_summary.txt: mean of the 12
+    # GEMM launches of layer 0, and merge_fwd at layer 0); only for the captured configuration
     captured = args.config == "octo_small" and B == 256
     roof = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)", "achieved": gwork / (gms * 1e-3) / 1e12,
             "peak": P["tf_sust"], "unit": "TFLOP/s", "frac": gwork / (gms * 1e-3) / 1e12 / P["tf_sust"],
-            "traffic": 441.4e6 if captured else None, "traffic_unit": "bytes per launch (ncu dram read+write, layer-0 shapes)",
+            "traffic": 445.8e6 if captured else None, "traffic_unit": "bytes per launch (ncu dram read+write, layer-0 shapes)",
             "peak_source": f"{P['src']} bf16_tflops_sustained", "launches_per_step": gcnt // nprof,
             "avg_launch_us": gms / gcnt * 1e3, "share_of_step": gms / tot_ms}
     mms, mwork, mcnt = prof["merge_fwd"]
     merge_roof = {"bound": "hbm", "kernel": "merge_fwd_kernel", "achieved": mwork / (mms * 1e-3) / 1e9, "peak": P["hbm"],
-                  "unit": "GB/s", "frac": mwork / (mms * 1e-3) / 1e9 / P["hbm"], "traffic": 157.5e6 if captured else None,
+                  "unit": "GB/s", "frac": mwork / (mms * 1e-3) / 1e9 / P["hbm"], "traffic": 159.0e6 if captured else None,
                   "traffic_unit": "bytes per launch (ncu dram read+write, layer 0: 207.6 MB algorithmic, part of the output still in L2)",
                   "peak_source": f"{P['src']} hbm_gbs", "avg_launch_us": mms / mcnt * 1e3} if mcnt else None
 
