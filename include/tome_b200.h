@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TOME_ABI_VERSION 8
+#define TOME_ABI_VERSION 9
 
 enum tome_status { TOME_OK = 0, TOME_ERR_INVALID = 1, TOME_ERR_CUDA = 2, TOME_ERR_UNSUPPORTED = 3 };
 enum tome_dtype { TOME_BF16 = 0, TOME_F32 = 1 };
@@ -134,6 +134,13 @@ typedef struct {
   int k_splits;
   int accumulate;
   int no_multicast; /* debugging aid: 1 disables the CTA-pair TMA multicast of the B operand */
+  /* The ReLU gate as one bit per element instead of bf16 rows ([M, ld_bits] u32 words, bit j of word w = column 32 w + j):
+   * a ReLU epilogue with relu_bits_out != NULL also writes bit = (output > 0) (after dropout, so the dropped elements are
+   * gated too); a later GEMM with gate_bits != NULL multiplies by (bit ? gate_scale : 0) exactly as `gate` would, reading
+   * 1/16 of the bytes.  ld_bits >= ceil(n / 32). */
+  const void* gate_bits;
+  void* relu_bits_out;
+  long long ld_bits;
 } tome_gemm_args_t;
 
 size_t tome_gemm_workspace_bytes(const tome_gemm_args_t* args);

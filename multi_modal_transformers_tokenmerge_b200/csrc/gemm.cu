@@ -43,6 +43,11 @@ struct GemmEpilogue {
   DropoutCfg drop;     // applied after ReLU, before residual
   long long split_stride;  // elements between split-K partial outputs (c_is_f32 only)
   int accumulate;          // c_is_f32 only: C += result
+  // one bit per output element, [M, ldw] u32 words of 32 columns: written by a ReLU epilogue (bit = output > 0), read by a
+  // gate epilogue in place of the bf16 gate rows (16x less traffic for the ReLU backward)
+  uint32_t* bits_out;
+  const uint32_t* bits_in;
+  long long ldw;
 };
 
 struct GemmShape {
@@ -230,16 +235,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         // ---- everything the epilogue reads from memory is fetched while the tensor core still works on this tile
         if (kBias && etid < BN) s_bias[acc * BN + etid] = (n0 + etid < s.n) ? __ldg(e.bias + n0 + etid) : 0.f;
         uint4 pre[(kResid || kGate) ? NCH : 1][4];
+        uint32_t gw[kGate ? NCH : 1];
+        const bool gate_by_bits = kGate && e.bits_in != nullptr;   // CTA-uniform
+        if constexpr (kGate) {
+          if (gate_by_bits) {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c)
+              gw[c] = (row_ok && cbase + c * 32 < s.n) ? __ldg(e.bits_in + row * e.ldw + ((cbase >> 5) + c)) : 0u;
+          }
+        }
         if constexpr (kResid || kGate) {
-          const __nv_bfloat16* src = kResid ? resid : gate;
-          const long long ld = kResid ? e.ldr : e.ldg;
+          if (!gate_by_bits) {
+            const __nv_bfloat16* src = kResid ? resid : gate;
+            const long long ld = kResid ? e.ldr : e.ldg;
 #pragma unroll
-          for (int c = 0; c < NCH; ++c)
+            for (int c = 0; c < NCH; ++c)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int col = cbase + c * 32 + i * 8;
-              pre[c][i] = (row_ok && col < s.n) ? __ldg(reinterpret_cast<const uint4*>(src + row * ld + col)) : make_uint4(0u, 0u, 0u, 0u);
-            }
+              for (int i = 0; i < 4; ++i) {
+                const int col = cbase + c * 32 + i * 8;
+                pre[c][i] = (row_ok && col < s.n) ? __ldg(reinterpret_cast<const uint4*>(src + row * ld + col)) : make_uint4(0u, 0u, 0u, 0u);
+              }
+          }
         }
         if (kBias) asm volatile("bar.sync 1, %0;" ::"r"(32 * GEMM_EPI_WARPS) : "memory");  // bias tile visible to all epilogue warps
         mbar_wait(&tmem_full[acc], acc_phase);
@@ -262,12 +278,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             }
           }
           if constexpr (kGate) {  // acc *= (gate > 0 ? gate_scale : 0): the sign/zero test runs on the raw bf16 bits
+            if (gate_by_bits) {
+              const uint32_t w = gw[c];
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const uint32_t w = reinterpret_cast<const uint32_t*>(&pre[c][i / 8])[(i / 2) & 3];
-              const float2 t = __fmul2_rn(make_float2(v[i], v[i + 1]), gs2);
-              v[i] = ((int)(w << 16) > 0) ? t.x : 0.f;
-              v[i + 1] = ((int)w > 0xffff) ? t.y : 0.f;
+              for (int i = 0; i < 32; i += 2) {
+                const float2 t = __fmul2_rn(make_float2(v[i], v[i + 1]), gs2);
+                v[i] = ((w >> i) & 1u) ? t.x : 0.f;
+                v[i + 1] = ((w >> (i + 1)) & 1u) ? t.y : 0.f;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                const uint32_t w = reinterpret_cast<const uint32_t*>(&pre[c][i / 8])[(i / 2) & 3];
+                const float2 t = __fmul2_rn(make_float2(v[i], v[i + 1]), gs2);
+                v[i] = ((int)(w << 16) > 0) ? t.x : 0.f;
+                v[i + 1] = ((int)w > 0xffff) ? t.y : 0.f;
+              }
             }
           }
           if (drop_on) {
@@ -288,6 +314,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               const uint32_t w = reinterpret_cast<const uint32_t*>(&pre[c][i / 8])[(i / 2) & 3];
               const float2 t = __fadd2_rn(make_float2(v[i], v[i + 1]), make_float2(bf16_lo(w), bf16_hi(w)));
               v[i] = t.x; v[i + 1] = t.y;
+            }
+          }
+          if constexpr (kRelu) {
+            if (e.bits_out != nullptr) {  // the ReLU (and dropout) gate of this chunk, one bit per column, for the backward GEMM
+              uint32_t word = 0u;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) word |= (v[i] > 0.f) ? (1u << i) : 0u;
+              if (row_ok && col < s.n) e.bits_out[row * e.ldw + (col >> 5)] = word;
             }
           }
           uint32_t pk[16];
@@ -376,7 +410,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 32; ++i) acc_f[i] = fmaxf(acc_f[i], 0.f);
         }
-        if (gate) {
+        if (e.bits_in) {
+          const uint32_t w = active ? __ldg(e.bits_in + row * e.ldw + (col >> 5)) : 0u;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc_f[i] *= ((w >> i) & 1u) ? e.gate_scale : 0.f;
+        } else if (gate) {
 #pragma unroll
           for (int i = 0; i < 32; i += 8) {
             uint4 gq = pre[c][i / 8];
@@ -398,6 +436,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               for (int j = 0; j < 8; ++j) acc_f[i + j] = ((keep >> j) & 1u) ? acc_f[i + j] * e.drop.inv_keep : 0.f;
             }
           }
+        }
+        if (e.bits_out && active) {  // after ReLU and dropout: bit = the element survives (columns past N read as 0)
+          uint32_t word = 0u;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) word |= (i < ncols && acc_f[i] > 0.f) ? (1u << i) : 0u;
+          e.bits_out[row * e.ldw + (col >> 5)] = word;
         }
         if (resid) {
 #pragma unroll
@@ -537,7 +581,7 @@ static int pick_bn(int n) {  // least padded MMA work (tiles x width), then the 
 static int pick_splits(const tome_gemm_args_t* a, int bn) {
   if (a->k_splits > 0) return a->k_splits;
   if (a->c_dtype != TOME_F32 || a->ldc != a->n) return 1;  // split-K only for dense fp32 outputs (weight gradients)
-  if (a->bias || a->residual || a->gate || a->relu || a->dropout_rate > 0.f) return 1;
+  if (a->bias || a->residual || a->gate || a->gate_bits || a->relu || a->dropout_rate > 0.f) return 1;
   const int tiles = ceil_div(a->m, GEMM_BM) * ceil_div(a->n, bn);
   const int kb = ceil_div(a->k, GEMM_BK);
   int s = kNumSMs / (tiles > 0 ? tiles : 1);
@@ -573,6 +617,10 @@ extern "C" int tome_gemm_bf16(const tome_gemm_args_t* a, void* workspace, size_t
   TOME_CHECK(a->ldc % (a->c_dtype == TOME_F32 ? 4 : 8) == 0, TOME_ERR_INVALID, "gemm: ldc must keep rows 16-byte aligned");
   TOME_CHECK(!a->residual || a->ldr % 8 == 0, TOME_ERR_INVALID, "gemm: ldr must be a multiple of 8");
   TOME_CHECK(!a->gate || a->ldg % 8 == 0, TOME_ERR_INVALID, "gemm: ldg must be a multiple of 8");
+  TOME_CHECK(!(a->gate && a->gate_bits), TOME_ERR_INVALID, "gemm: pass the gate as bf16 rows or as bits, not both");
+  TOME_CHECK(!(a->gate_bits || a->relu_bits_out) || a->ld_bits * 32 >= a->n, TOME_ERR_INVALID,
+             "gemm: ld_bits (%lld words) does not cover n = %d columns", a->ld_bits, a->n);
+  TOME_CHECK(!a->relu_bits_out || a->relu, TOME_ERR_INVALID, "gemm: relu_bits_out needs the ReLU epilogue");
   TOME_CHECK(a->dropout_rate >= 0.f && a->dropout_rate < 1.f, TOME_ERR_INVALID, "gemm: dropout_rate must be in [0,1)");
 
   const int bn = pick_bn(a->n);
@@ -590,6 +638,8 @@ extern "C" int tome_gemm_bf16(const tome_gemm_args_t* a, void* workspace, size_t
 
   GemmEpilogue e;
   e.c = a->c; e.bias = a->bias; e.residual = a->residual; e.gate = a->gate;
+  e.bits_out = reinterpret_cast<uint32_t*>(a->relu_bits_out); e.bits_in = reinterpret_cast<const uint32_t*>(a->gate_bits);
+  e.ldw = a->ld_bits;
   e.ldc = a->ldc; e.ldr = a->ldr; e.ldg = a->ldg;
   e.gate_scale = a->gate_scale; e.relu = a->relu; e.c_is_f32 = (a->c_dtype == TOME_F32);
   e.drop.thresh16 = (uint32_t)(a->dropout_rate * 65536.0f + 0.5f);
@@ -602,7 +652,7 @@ extern "C" int tome_gemm_bf16(const tome_gemm_args_t* a, void* workspace, size_t
   if (s.k_splits > 1) {
     TOME_CHECK(e.c_is_f32, TOME_ERR_INVALID, "gemm: split-K requires an fp32 output");
     TOME_CHECK(a->ldc == a->n, TOME_ERR_INVALID, "gemm: split-K requires a dense output (ldc == n)");
-    TOME_CHECK(!a->bias && !a->residual && !a->gate && !a->relu && e.drop.thresh16 == 0, TOME_ERR_INVALID,
+    TOME_CHECK(!a->bias && !a->residual && !a->gate && !a->gate_bits && !a->relu && e.drop.thresh16 == 0, TOME_ERR_INVALID,
                "gemm: split-K supports a plain epilogue only");
     const size_t need = (size_t)s.k_splits * (size_t)a->m * (size_t)a->ldc * sizeof(float);
     TOME_CHECK(workspace && workspace_bytes >= need, TOME_ERR_INVALID, "gemm: split-K workspace too small (%zu < %zu)",
@@ -632,7 +682,7 @@ extern "C" int tome_gemm_bf16(const tome_gemm_args_t* a, void* workspace, size_t
   // which epilogue: a compile-time specialisation when the combination is one the stack uses, else the generic one
   int epi = EPI_GENERIC;
   if (!e.c_is_f32 && s.k_splits == 1 && !a->accumulate) {
-    const int flags = (a->bias ? EPI_BIAS : 0) | (a->relu ? EPI_RELU : 0) | (a->gate ? EPI_GATE : 0) |
+    const int flags = (a->bias ? EPI_BIAS : 0) | (a->relu ? EPI_RELU : 0) | ((a->gate || a->gate_bits) ? EPI_GATE : 0) |
                       (e.drop.thresh16 ? EPI_DROP : 0) | (a->residual ? EPI_RESID : 0);
     if (!amn && bmn) {  // forward layers: A = activations (K-major), B = Flax kernel [in, out] (MN-major)
       if (flags == EPI_BIAS) epi = EPI_BIAS;

@@ -33,6 +33,7 @@ struct LayerShape {
 struct LayerBufs {
   // saved for backward
   __nv_bfloat16 *x_in, *h, *qkv, *attn_o, *x1m, *h2, *m1, *x_out;
+  uint32_t* m1_bits;  // [B*To, F/32]: one bit per element of m1 (ReLU and dropout survive), the gate of the MLP dgrad
   float *ln1_mean, *ln1_rstd, *ln2_mean, *ln2_rstd, *lse;
   float *size_in, *size_out;  // size_in == nullptr at layer 0 (all ones)
   uint8_t *gid_in, *gid_out;
@@ -203,6 +204,7 @@ static StackLayout make_layout(const tome_stack_cfg_t* c, void* workspace) {
     Lb.ln2_rstd = b.take<float>(st_out);
     Lb.h2 = b.take<__nv_bfloat16>(B * To * C);
     Lb.m1 = b.take<__nv_bfloat16>(B * To * F);
+    Lb.m1_bits = b.take<uint32_t>(B * To * ((F + 31) / 32));
     Lb.x_out = b.take<__nv_bfloat16>(B * To * C);
     x_prev = Lb.x_out;
     size_prev = Lb.size_out;
@@ -279,7 +281,7 @@ static DropoutCfg make_drop(const tome_stack_cfg_t* c, uint32_t site) {
 static int gemm(const tome_stack_cfg_t* c, const StackLayout& S, cudaStream_t st, int m, int n, int k, const void* a,
                 long long lda, int a_major, const void* b, long long ldb, int b_major, void* out, long long ldc, int c_dtype,
                 const float* bias, int relu, const void* residual, const void* gate, float gate_scale, int drop_site,
-                int accumulate) {
+                int accumulate, const void* gate_bits = nullptr, void* relu_bits_out = nullptr) {
   tome_gemm_args_t g;
   memset(&g, 0, sizeof(g));
   g.m = m; g.n = n; g.k = k;
@@ -289,6 +291,7 @@ static int gemm(const tome_stack_cfg_t* c, const StackLayout& S, cudaStream_t st
   g.bias = bias; g.relu = relu;
   g.residual = residual; g.ldr = n;
   g.gate = gate; g.ldg = n; g.gate_scale = gate_scale;
+  g.gate_bits = gate_bits; g.relu_bits_out = relu_bits_out; g.ld_bits = (n + 31) / 32;
   if (drop_site >= 0 && c->dropout_rate > 0.f) {
     g.dropout_rate = c->dropout_rate;
     g.dropout_seed = c->dropout_seed;
@@ -400,7 +403,7 @@ extern "C" int tome_stack_forward(const tome_stack_cfg_t* c, const tome_stack_io
     RC(tome_layernorm_fwd(B, To, C, c->ln_axis, c->ln_eps, Lb.x1m, pf + o.ln2_scale, pf + o.ln2_bias, Lb.h2, Lb.ln2_mean,
                           Lb.ln2_rstd, st));
     RC(gemm(c, S, st, Mo, F, C, Lb.h2, C, TOME_MAJOR_K, pw + o.w1, F, TOME_MAJOR_MN, Lb.m1, F, TOME_BF16, pf + o.b1, 1, nullptr,
-            nullptr, 1.f, 3 * l + 1, 0));
+            nullptr, 1.f, 3 * l + 1, 0, nullptr, Lb.m1_bits));
     RC(gemm(c, S, st, Mo, C, F, Lb.m1, F, TOME_MAJOR_K, pw + o.w2, C, TOME_MAJOR_MN, Lb.x_out, C, TOME_BF16, pf + o.b2, 0, Lb.x1m,
             nullptr, 1.f, 3 * l + 2, 0));
   }
@@ -494,8 +497,8 @@ extern "C" int tome_stack_backward(const tome_stack_cfg_t* c, const tome_stack_i
     RC(masked_colsum(g0, g2, Mo, C, 3 * l + 2, gr + o.b2, &dy2));
     RC(gemm(c, S, st, F, C, Mo, Lb.m1, F, TOME_MAJOR_MN, dy2, C, TOME_MAJOR_MN, gr + o.w2, C, TOME_F32, nullptr, 0, nullptr,
             nullptr, 1.f, -1, 1));
-    RC(gemm(c, S, st, Mo, F, C, dy2, C, TOME_MAJOR_K, pw + o.w2, C, TOME_MAJOR_K, S.big, F, TOME_BF16, nullptr, 0, nullptr, Lb.m1,
-            inv_keep, -1, 0));  // dm1 (pre-activation): relu and dropout masks both read off the saved m1
+    RC(gemm(c, S, st, Mo, F, C, dy2, C, TOME_MAJOR_K, pw + o.w2, C, TOME_MAJOR_K, S.big, F, TOME_BF16, nullptr, 0, nullptr, nullptr,
+            inv_keep, -1, 0, Lb.m1_bits));  // dm1 (pre-activation): the relu and dropout masks are the bits MLP-1 forward wrote
     RC(tome_colsum_bf16(Mo, F, S.big, F, gr + o.b1, 1, S.ws_colsum, st));
     RC(gemm(c, S, st, C, F, Mo, Lb.h2, C, TOME_MAJOR_MN, S.big, F, TOME_MAJOR_MN, gr + o.w1, F, TOME_F32, nullptr, 0, nullptr,
             nullptr, 1.f, -1, 1));

@@ -175,8 +175,10 @@ def topk_prune(emb: torch.Tensor, importance: torch.Tensor, set_start, set_n, se
 def gemm(a: torch.Tensor, b: torch.Tensor, *, m: int, n: int, k: int, a_major=L.TOME_MAJOR_K, b_major=L.TOME_MAJOR_K,
          lda=None, ldb=None, out: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16, bias=None, residual=None,
          gate=None, gate_scale=1.0, relu=False, dropout_rate=0.0, dropout_seed=0, dropout_site=0, k_splits=0,
-         accumulate=False, no_multicast=False) -> torch.Tensor:
-    """C[M,N] = epilogue(A * B^T) on tcgen05.  a/b are 2-D bf16 tensors whose rows are M/N (K-major) or K (MN-major)."""
+         accumulate=False, no_multicast=False, gate_bits: Optional[torch.Tensor] = None,
+         relu_bits_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """C[M,N] = epilogue(A * B^T) on tcgen05.  a/b are 2-D bf16 tensors whose rows are M/N (K-major) or K (MN-major).
+    gate_bits / relu_bits_out: int32 [M, ceil(N/32)] one-bit-per-element ReLU gates (see include/tome_b200.h)."""
     _need_cuda(a, b)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     lda = a.stride(0) if lda is None else lda
@@ -188,7 +190,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, m: int, n: int, k: int, a_major=L.
                       None if residual is None else residual.data_ptr(), 0 if residual is None else residual.stride(0),
                       None if gate is None else gate.data_ptr(), 0 if gate is None else gate.stride(0),
                       float(gate_scale), int(relu), float(dropout_rate), int(dropout_seed), int(dropout_site),
-                      int(k_splits), int(accumulate), int(no_multicast))
+                      int(k_splits), int(accumulate), int(no_multicast),
+                      None if gate_bits is None else gate_bits.data_ptr(),
+                      None if relu_bits_out is None else relu_bits_out.data_ptr(),
+                      0 if (gate_bits is None and relu_bits_out is None) else (gate_bits if gate_bits is not None else relu_bits_out).stride(0))
     ws_bytes = L.lib().tome_gemm_workspace_bytes(C.byref(args))
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=a.device) if ws_bytes else None
     L.check(L.lib().tome_gemm_bf16(C.byref(args), _ptr(ws), ws_bytes, _stream()))

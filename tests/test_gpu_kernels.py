@@ -731,3 +731,37 @@ def test_full_batch_ops_match_torch(ops):
         ox1, os1 = O.merge_wavg(oplan, xs[b_:b_ + 1].cpu().numpy(), size[b_:b_ + 1].cpu().numpy()[..., None])
         np.testing.assert_array_equal(x1[b_:b_ + 1].cpu().numpy(), ox1)
         np.testing.assert_array_equal(s1[b_:b_ + 1].cpu().numpy(), os1[..., 0])
+
+
+@pytest.mark.parametrize("m,n,k,rate", [(1000, 384, 256, 0.0), (4097, 1536, 384, 0.1), (130, 160, 64, 0.25)])
+def test_gemm_relu_gate_bits(ops, m, n, k, rate):
+    """A ReLU epilogue can emit its gate as one bit per element (after dropout, so dropped elements are gated too), and a
+    later GEMM gated by those bits must equal, bit for bit, the same GEMM gated by the bf16 output itself -- for the
+    specialised epilogues (K-major A, the stack's layouts) and the generic one (fp32 output)."""
+    rng = np.random.default_rng(m + n)
+    A = dev(rng.standard_normal((m, k)).astype(np.float32) * 0.3, torch.bfloat16)
+    W = dev(rng.standard_normal((k, n)).astype(np.float32) * 0.3, torch.bfloat16)
+    bias = dev(rng.standard_normal(n).astype(np.float32) * 0.1)
+    words = (n + 31) // 32
+    bits = torch.full((m, words), -1, dtype=torch.int32, device="cuda")
+    h = ops.gemm(A, W, m=m, n=n, k=k, b_major=1, bias=bias, relu=True, dropout_rate=rate, dropout_seed=5, dropout_site=9,
+                 relu_bits_out=bits)
+    h_plain = ops.gemm(A, W, m=m, n=n, k=k, b_major=1, bias=bias, relu=True, dropout_rate=rate, dropout_seed=5, dropout_site=9)
+    assert torch.equal(h, h_plain)                      # asking for the bits does not change the output
+    want = (h > 0).cpu().numpy()
+    got = np.unpackbits(bits.cpu().numpy().view(np.uint8).reshape(m, words * 4), axis=1, bitorder="little")[:, :n].astype(bool)
+    np.testing.assert_array_equal(got, want)
+    if rate:
+        assert 0.3 < want.mean() < 0.5                  # about half the pre-activations positive, a tenth of those dropped
+    dy = dev(rng.standard_normal((m, 64)).astype(np.float32), torch.bfloat16)
+    W2 = dev(rng.standard_normal((n, 64)).astype(np.float32) * 0.3, torch.bfloat16)       # [N, K] K-major: the dgrad layout
+    g_rows = ops.gemm(dy, W2, m=m, n=n, k=64, gate=h, gate_scale=1.25)
+    g_bits = ops.gemm(dy, W2, m=m, n=n, k=64, gate_bits=bits, gate_scale=1.25)
+    assert torch.equal(g_rows, g_bits)
+    f_rows = ops.gemm(dy, W2, m=m, n=n, k=64, gate=h, gate_scale=1.25, out_dtype=torch.float32)      # generic epilogue
+    f_bits = ops.gemm(dy, W2, m=m, n=n, k=64, gate_bits=bits, gate_scale=1.25, out_dtype=torch.float32)
+    assert torch.equal(f_rows, f_bits)
+    bits2 = torch.zeros_like(bits)
+    ops.gemm(A, W, m=m, n=n, k=k, b_major=1, bias=bias, relu=True, out_dtype=torch.float32, relu_bits_out=bits2)   # generic writer
+    if rate == 0.0:
+        assert torch.equal(bits2, bits)
