@@ -317,12 +317,12 @@ def main():
             ent["gbs"] = work / (kms * 1e-3) / 1e9
         kernels[k_] = ent
     gms, gwork, gcnt = prof["gemm"]
-    # DRAM read + write per launch from the committed ncu captures (profiles/r01d_ncu_full_summary.txt: mean of the 12
-    # GEMM launches of layer 0, and merge_fwd at layer 0); only for the captured configuration
+    # DRAM read + write per launch from the committed ncu captures (profiles/r01d_ncu_final_kernels.txt: mean of the 12
+    # GEMM launches of layer 0; profiles/r01d_ncu_full_summary.txt: merge_fwd at layer 0); only for the captured configuration
     captured = args.config == "octo_small" and B == 256
     roof = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)", "achieved": gwork / (gms * 1e-3) / 1e12,
             "peak": P["tf_sust"], "unit": "TFLOP/s", "frac": gwork / (gms * 1e-3) / 1e12 / P["tf_sust"],
-            "traffic": 445.8e6 if captured else None, "traffic_unit": "bytes per launch (ncu dram read+write, layer-0 shapes)",
+            "traffic": 414.6e6 if captured else None, "traffic_unit": "bytes per launch (ncu dram read+write, layer-0 shapes)",
             "peak_source": f"{P['src']} bf16_tflops_sustained", "launches_per_step": gcnt // nprof,
             "avg_launch_us": gms / gcnt * 1e3, "share_of_step": gms / tot_ms}
     mms, mwork, mcnt = prof["merge_fwd"]
