@@ -92,13 +92,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint8_t* s_meta = s_kaug + ATT_SLOTS * ATT_KAUG_BYTES;    // metadata slot i at i * ATT_META_SLOT
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_meta + ATT_MSLOTS * ATT_META_SLOT);
   uint64_t* q_full = bars;                 // 1
-  uint64_t* kv_full = bars + 1;            // [6]
-  uint64_t* kv_empty = bars + 7;           // [6]
+  uint64_t* kv_full = bars + 1;            // [ATT_SLOTS] (room for 6)
+  uint64_t* kv_empty = bars + 7;           // [ATT_SLOTS] (room for 6)
   uint64_t* s_full = bars + 13;            // [2]  S_j ready in TMEM buffer j&1
   uint64_t* p_ready = bars + 15;           // [2]  P_j in smem buffer j&1, S_j consumed, O corrected (128 arrivals)
   uint64_t* pv_done = bars + 17;           // [2]  O += P_j V_j retired: P buffer j&1 reusable, O readable
-  uint64_t* meta_full = bars + 19;         // [4]  bulk copy of the tile's metadata block landed
-  uint64_t* meta_empty = bars + 23;        // [4]  128 arrivals (softmax threads)
+  uint64_t* meta_full = bars + 19;         // [ATT_MSLOTS]  bulk copy of the tile's metadata block landed
+  uint64_t* meta_empty = bars + 23;        // [ATT_MSLOTS]  128 arrivals (softmax threads), after the P stores of the tile
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -765,3 +765,37 @@ def test_gemm_relu_gate_bits(ops, m, n, k, rate):
     ops.gemm(A, W, m=m, n=n, k=k, b_major=1, bias=bias, relu=True, out_dtype=torch.float32, relu_bits_out=bits2)   # generic writer
     if rate == 0.0:
         assert torch.equal(bits2, bits)
+
+
+@pytest.mark.parametrize("T,rate", [(536, 0.0), (300, 0.1), (74, 0.0)])
+def test_attention_bwd_dq_paths_agree(ops, T, rate):
+    """dQ as a batched GEMM over the dS^T tiles stored by the dK/dV kernel (the default up to 3 072 tokens) against the
+    recomputing dQ kernel: same bf16 dS, same accumulation order, so dq must agree bit for bit; dk / dv come from the same
+    kernel in both modes."""
+    import ctypes
+    from multi_modal_transformers_tokenmerge_b200 import _lib as L
+    setter = L.lib().tome_attention_set_dq_from_ds
+    setter.argtypes = [ctypes.c_int]
+    setter.restype = None
+    rng = np.random.default_rng(T)
+    B, H, D = 4, 3, 64
+    qkv = dev(rng.standard_normal((B, T, 3, H, D)).astype(np.float32), torch.bfloat16)
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    n_img = (T - 16) // 2 - 4
+    g1, p1, allow, _ = O.sequence_groups(f"[TaskDescriptionPrefix{{16}}] [Image{{{n_img}}};Readout{{4}}]*2")
+    pad = T - g1.shape[0]
+    gid = dev(np.tile(np.concatenate([g1, np.full(pad, g1[-1], np.uint8)]), (B, 1)))
+    pos = dev(np.tile(np.concatenate([p1, np.arange(pad, dtype=np.int32)]), (B, 1)))
+    size = dev(rng.integers(1, 4, size=(B, T)).astype(np.float32))
+    kw = dict(gid=gid, pos=pos, allow=dev(allow), size=size, dropout_rate=rate, dropout_seed=3, dropout_site=0x40000002)
+    o, l = ops.attention_fwd(q, k, v, **kw)
+    do = dev(rng.standard_normal((B, T, H, D)).astype(np.float32), torch.bfloat16)
+    try:
+        setter(0)
+        a = [t.clone() for t in ops.attention_bwd(q, k, v, o, l, do, **kw)]
+        setter(1)
+        b = [t.clone() for t in ops.attention_bwd(q, k, v, o, l, do, **kw)]
+    finally:
+        setter(-1)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
