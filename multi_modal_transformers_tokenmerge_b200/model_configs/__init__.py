@@ -1,5 +1,6 @@
-"""Config loading for the block stack: the YAML schema of the reference's model_configs/attention_blocks/*.yaml
-(plain PyYAML here; hydra's `compose` yields the same mapping for these files)."""
+"""Config loading for the block stack and the action heads: the YAML schema of the reference's
+model_configs/attention_blocks/*.yaml and model_configs/action_heads/*.yaml (plain PyYAML here; hydra's `compose` yields the
+same mapping for these files)."""
 from __future__ import annotations
 
 import os
@@ -30,3 +31,26 @@ def build_stack(cfg: Dict[str, Any]):
         return tome_attention.StackedEncoder1DBlock(cfg["num_blocks"], cfg["encoder_1d_block"], tome_r=r,
                                                     prop_attn=bool(cfg.get("prop_attn", True)))
     return attention.StackedEncoder1DBlock(cfg["num_blocks"], cfg["encoder_1d_block"])
+
+
+_HEAD_TARGETS = {"ContinuousActionHead": ("continuous", ("max_action", "attention_pooling", "dense")),
+                 "CategoricalActionHead": ("categorical", ("num_bins", "max_action", "action_space_dim", "dense")),
+                 "DiffusionActionHead": ("diffusion", ("diffusion_steps", "attention_pooling", "denoising_model", "rng_collection"))}
+
+
+def build_action_head(node: Dict[str, Any]):
+    """What octo.py:82-86 does with `instantiate(action_head...)`: the head module named by the node's `_target_`
+    (multi_modal_transformers.action_heads.{continuous,categorical,diffusion}.*ActionHead), built from the node's own keys.
+    Accepts the head node itself or the one-entry mapping a head YAML holds (`diffusion_action_head: {...}`)."""
+    from .. import action_heads
+
+    if "_target_" not in node and len(node) == 1:
+        node = next(iter(node.values()))
+    cls = str(node.get("_target_", "")).rsplit(".", 1)[-1]
+    if cls not in _HEAD_TARGETS:
+        raise ValueError(f"unsupported action head _target_ {node.get('_target_')!r} (supported: {sorted(_HEAD_TARGETS)})")
+    _, keys = _HEAD_TARGETS[cls]
+    kw = {k: node[k] for k in keys if k in node}
+    if "attention_pooling" in keys:
+        kw.setdefault("attention_pooling", None)
+    return getattr(action_heads, cls)(**kw)

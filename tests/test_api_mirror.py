@@ -369,3 +369,21 @@ def test_diffusion_head_module_against_reference_goldens():
         # drawn internally: finite, reproducible for a seed, different for another
         l1, l2, l3 = (head.denoise_loss(v, ro, act, rng=s).item() for s in (1, 1, 2))
         assert np.isfinite(l1) and l1 == l2 and l1 != l3
+
+
+def test_action_head_configs_build_the_mirror_modules():
+    """model_configs.build_action_head on the reference's head schema (`_target_` strings of
+    multi_modal_transformers.action_heads.*): the diffusion YAML shipped here, and continuous / categorical nodes."""
+    head = MC.build_action_head(MC.load("action_heads/diffusion_octo_small"))
+    assert isinstance(head, AH.DiffusionActionHead) and head.diffusion_steps == 32 and head.rng_collection == "diffusion"
+    v = head.init(0, np.zeros((2, 8, 384), np.float32))["params"]["denoiser"]
+    assert v["MLPBlock_0"]["Dense_0"]["kernel"].shape == (8 + 384 + 384, 384) and v["MLPBlock_0"]["Dense_1"]["kernel"].shape == (384, 8)
+    dense = {"_target_": "flax.linen.Dense", "features": 7}
+    c = MC.build_action_head({"_target_": "multi_modal_transformers.action_heads.continuous.ContinuousActionHead", "max_action": 2.0,
+                              "attention_pooling": {"ignored": True}, "dense": dense})
+    assert isinstance(c, AH.ContinuousActionHead) and c.max_action == 2.0
+    k = MC.build_action_head({"_target_": "multi_modal_transformers.action_heads.categorical.CategoricalActionHead", "num_bins": 256,
+                              "max_action": 1.0, "action_space_dim": 8, "dense": {**dense, "features": 256}})
+    assert isinstance(k, AH.CategoricalActionHead) and k.action_space_dim == 8
+    with pytest.raises(ValueError, match="unsupported action head"):
+        MC.build_action_head({"_target_": "somewhere.OtherHead"})
