@@ -112,7 +112,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   uint64_t* pd_free = bars + 7;    // dV/dK MMAs of tile i done: smem P^T/dS^T reusable, accumulators final at the end
   uint64_t* meta_full = bars + 8;  // [3]
   uint64_t* meta_empty = bars + 11;  // [3]  128 arrivals
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* ds_stored = bars + 14;   // store_ds: the TMA store of dS^T_i has read the tile out of shared memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -129,6 +130,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     mbar_init(st_full, 1);
     mbar_init(ps_ready, DKV_BK);
     mbar_init(pd_free, 1);
+    mbar_init(ds_stored, 1);
     for (int i = 0; i < AB_MSLOTS; ++i) {
       mbar_init(&meta_full[i], 1);
       mbar_init(&meta_empty[i], DKV_BK);
@@ -212,9 +214,12 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           for (int k = 0; k < DKV_BQ / 16; ++k)  // dK += dS^T Q
             umma_bf16(tm_dk, make_smem_desc(adst + k * 32, 16, 1024), make_smem_desc(aq + k * 2048, 8192, 1024), idesc_g,
                       (i > 1 || k > 0) ? 1u : 0u);
-          if (p.store_ds) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the store has read dS^T out of smem
           umma_commit(pd_free);
           umma_commit(&q_empty[st]);
+          if (p.store_ds) {  // after the commits, so neither the softmax warps nor the producer wait for the store's read
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            mbar_arrive(ds_stored);
+          }
         }
       }
       if (p.store_ds) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before the CTA exits
@@ -300,7 +305,10 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             dw[c >> 1] = pack_bf16(g.x, g.y);
           }
         }
-        if (cq == 0 && i >= 1) mbar_wait(pd_free, (i - 1) & 1);  // previous P^T / dS^T fully consumed by the tensor core
+        if (cq == 0 && i >= 1) {
+          mbar_wait(pd_free, (i - 1) & 1);  // previous P^T / dS^T fully consumed by the tensor core
+          if (p.store_ds) mbar_wait(ds_stored, (i - 1) & 1);  // ... and dS^T by its TMA store
+        }
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           const int chunk = (c0 >> 3) + ch;
