@@ -700,17 +700,18 @@ attn_bwd_dq_gemm_kernel(const __grid_constant__ CUtensorMap tm_ds, const __grid_
   }
 }
 
-// dQ from the dS^T tiles the dK/dV kernel stores (a batched GEMM: 902 vs 1 025 us at B=256 T=536 H=6, 2 477 vs 2 552 at
-// T=2080) or the recomputing dQ kernel (which wins once the T^2 traffic dominates: 4 397 vs 4 495 us at T=4096).
-// -1: by sequence length (default); 0 / 1: force.  Process-wide tuning aid, not part of the public header.
+// dQ from the dS^T tiles the dK/dV kernel stores (a batched GEMM: 884 vs 1 023 us at B=256 T=536 H=6, 2 383 vs 2 575 at
+// T=2080, 4 340 vs 4 433 at T=4096, 4 912 vs 4 977 at T=6144) or the recomputing dQ kernel, which needs no B*H*T^2 buffer.
+// -1 (default): the GEMM path while that buffer stays under 8 GiB; 0 / 1: force.  Process-wide tuning aid, not part of
+// the public header.
 static int g_attn_dq_from_ds = -1;
-static inline bool dq_from_ds(const tome_attn_desc_t* d) {
-  if (d->head_dim != AB_D) return false;
-  return g_attn_dq_from_ds < 0 ? d->tokens <= 3072 : g_attn_dq_from_ds != 0;
-}
 static inline size_t ds_buffer_bytes(const tome_attn_desc_t* d) {
   const size_t tq = ((size_t)d->tokens + 63) / 64 * 64, tk = ((size_t)d->tokens + 127) / 128 * 128;
   return align256((size_t)d->batch * d->heads * tq * tk * 2);
+}
+static inline bool dq_from_ds(const tome_attn_desc_t* d) {
+  if (d->head_dim != AB_D) return false;
+  return g_attn_dq_from_ds < 0 ? ds_buffer_bytes(d) <= ((size_t)8 << 30) : g_attn_dq_from_ds != 0;
 }
 
 extern "C" void tome_attention_set_dq_from_ds(int mode) { g_attn_dq_from_ds = mode < 0 ? -1 : (mode ? 1 : 0); }
