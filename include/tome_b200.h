@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TOME_ABI_VERSION 9
+#define TOME_ABI_VERSION 10
 
 enum tome_status { TOME_OK = 0, TOME_ERR_INVALID = 1, TOME_ERR_CUDA = 2, TOME_ERR_UNSUPPORTED = 3 };
 enum tome_dtype { TOME_BF16 = 0, TOME_F32 = 1 };
@@ -147,6 +147,8 @@ size_t tome_gemm_workspace_bytes(const tome_gemm_args_t* args);
 /* SMs the persistent GEMM grid may occupy from now on (process-wide; 0 = all 148).  Lowered by the data-parallel trainer
  * during backward so the overlapped NCCL all-reduce kernels have SMs of their own. */
 int tome_gemm_set_sm_limit(int sms);
+/* number of SMs the kernels of this library size their persistent grids for (148 on B200) */
+int tome_num_sms(void);
 int tome_gemm_bf16(const tome_gemm_args_t* args, void* workspace, size_t workspace_bytes, void* stream);
 
 /* out[n] (+)= sum_m x[m,n]   (bias gradients).  x bf16 [M, ldx]; out f32 [N].  workspace: f32 [ws_rows, N] with
@@ -410,6 +412,9 @@ typedef struct {
                                  predicted denoise term [B, A] (diffusion); required when cfg.head > 0 */
   const int32_t* head_time;   /* diffusion head: i32 [B] sampled time steps */
   const float* head_alpha_hats; /* diffusion head: f32 [diffusion_steps] */
+  void* grad_trace;           /* optional (parity tests), bf16 [layers, B * T0 * C]: backward copies dL/dx_out of layer l (its
+                                 first B * T_out(l) * C elements) into slot l before it consumes it, so a checker can run
+                                 each layer's backward on the implementation's own incoming gradient */
 } tome_stack_io_t;
 
 int tome_stack_forward(const tome_stack_cfg_t* cfg, const tome_stack_io_t* io, void* stream);
@@ -418,11 +423,18 @@ int tome_stack_backward(const tome_stack_cfg_t* cfg, const tome_stack_io_t* io, 
 /* device pointers into the workspace, valid after forward: final tokens/sizes and per-layer plan dumps (tests) */
 int tome_stack_tokens_at(const tome_stack_cfg_t* cfg, int layer); /* T entering `layer`; layer == layers: final T */
 const void* tome_stack_final_x(const tome_stack_cfg_t* cfg, const tome_stack_io_t* io);
+/* bf16 [B, T_in(layer), C]: the tokens entering `layer` (after the position embedding for layer 0); layer == layers: final x */
+const void* tome_stack_layer_x_in(const tome_stack_cfg_t* cfg, const tome_stack_io_t* io, int layer);
+/* f32 [B, T_in(layer)] token sizes entering `layer`, or NULL while every size is still 1 */
+const float* tome_stack_layer_size_in(const tome_stack_cfg_t* cfg, const tome_stack_io_t* io, int layer);
 const float* tome_stack_final_size(const tome_stack_cfg_t* cfg, const tome_stack_io_t* io);
 const int32_t* tome_stack_layer_edge_idx(const tome_stack_cfg_t* cfg, const tome_stack_io_t* io, int layer);
 const int32_t* tome_stack_layer_dst_idx(const tome_stack_cfg_t* cfg, const tome_stack_io_t* io, int layer);
 const float* tome_stack_layer_node_max(const tome_stack_cfg_t* cfg, const tome_stack_io_t* io, int layer);
 const int32_t* tome_stack_layer_node_idx(const tome_stack_cfg_t* cfg, const tome_stack_io_t* io, int layer);
+/* u32 [B * T_out(layer), ceil(mlp_dim / 32)]: bit j of word w = element 32 w + j of MLP-1's output survived ReLU (and hidden
+ * dropout), i.e. the gate the MLP backward of attention.py:32-34 uses; lets a checker take the SAME gate decisions. */
+const uint32_t* tome_stack_layer_relu_bits(const tome_stack_cfg_t* cfg, const tome_stack_io_t* io, int layer);
 
 /* ------------------------------------------------------------------------------------------------------------
  * 8. Launch accounting and per-op timing (measurement aid; off by default, never on the product path's hot loop)

@@ -15,7 +15,7 @@ TOME_OK, TOME_ERR_INVALID, TOME_ERR_CUDA, TOME_ERR_UNSUPPORTED = 0, 1, 2, 3
 TOME_BF16, TOME_F32 = 0, 1
 TOME_MAJOR_K, TOME_MAJOR_MN = 0, 1
 TOME_MERGE_SUM, TOME_MERGE_WAVG = 0, 1
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 vp, ll, i32, f32, u64, u32 = C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_uint64, C.c_uint32
 
@@ -109,7 +109,8 @@ class StackIO(C.Structure):
                 ("gid", vp), ("pos", vp), ("allow", vp), ("readout_idx", vp), ("target", vp),
                 ("workspace", vp), ("workspace_bytes", C.c_size_t),
                 ("x_final", vp), ("readout", vp), ("loss", vp), ("grads_f32", vp),
-                ("layer_done_events", C.POINTER(vp)), ("head_out", vp), ("head_time", vp), ("head_alpha_hats", vp)]
+                ("layer_done_events", C.POINTER(vp)), ("head_out", vp), ("head_time", vp), ("head_alpha_hats", vp),
+                ("grad_trace", vp)]
 
 
 _lib = None
@@ -137,7 +138,8 @@ def lib() -> C.CDLL:
             if hasattr(L, name):
                 getattr(L, name).restype = ll
         for name in ("tome_stack_final_x", "tome_stack_final_size", "tome_stack_layer_edge_idx", "tome_stack_layer_dst_idx",
-                     "tome_stack_layer_node_max", "tome_stack_layer_node_idx"):
+                     "tome_stack_layer_node_max", "tome_stack_layer_node_idx", "tome_stack_layer_relu_bits",
+                     "tome_stack_layer_x_in", "tome_stack_layer_size_in"):
             if hasattr(L, name):
                 getattr(L, name).restype = vp
         P = C.POINTER
@@ -192,6 +194,10 @@ def lib() -> C.CDLL:
             "tome_stack_layer_dst_idx": [P(StackCfg), P(StackIO), i32],
             "tome_stack_layer_node_max": [P(StackCfg), P(StackIO), i32],
             "tome_stack_layer_node_idx": [P(StackCfg), P(StackIO), i32],
+            "tome_stack_layer_relu_bits": [P(StackCfg), P(StackIO), i32],
+            "tome_stack_layer_x_in": [P(StackCfg), P(StackIO), i32],
+            "tome_stack_layer_size_in": [P(StackCfg), P(StackIO), i32],
+            "tome_num_sms": [],
         }
         for name, args in sig.items():
             if hasattr(L, name):

@@ -184,6 +184,7 @@ class StackedEncoder1DBlock(Module):
         self._extra = extra
         self._engine = None
         self._engine_key = None
+        self._loaded_params = None
 
     def _block(self, train=None, mask=None):
         cfg = {k: v for k, v in self.encoder_1d_block.items() if k != "_target_"}
@@ -215,7 +216,9 @@ class StackedEncoder1DBlock(Module):
         gm = None if mask is None else (mask if isinstance(mask, F.GroupMask) else F.group_mask_from_dense(mask))
         if gm is not None and gm.gid.dim() != 1:
             raise ValueError("the stack takes one group-id vector [T] (every batch row starts from the same sequence)")
-        key = (B, T, C, r, train, prop_attn, n_readout, dropout_seed, attn_rate, None if gm is None else gm.allow.shape[0])
+        # the dropout seed is NOT part of the key: a caller that passes a fresh dropout rng per step (as the reference does)
+        # must not tear down the engine (workspace, parameters, gradients) on every apply; it is updated in place below
+        key = (B, T, C, r, train, prop_attn, n_readout, attn_rate, None if gm is None else gm.allow.shape[0])
         if self._engine is None or self._engine_key != key:
             cfg = StackConfig(batch=B, tokens=T, channels=C, heads=at.num_heads, head_dim=hd // at.num_heads, mlp_dim=d.features,
                               layers=self.num_blocks, r=r, ln_axis=ln.axis, ln_eps=ln.epsilon, prop_attn=prop_attn,
@@ -226,8 +229,12 @@ class StackedEncoder1DBlock(Module):
                                            allow=None if gm is None else gm.allow.cpu().numpy(), readout_idx=readout_idx,
                                            training=train)
             self._engine_key = key
-        self._engine.load_params(np.asarray(_np(params["posembed_input"]["pos_embedding"])).reshape(T, C),
-                                 flax_tree_to_layers(params["ScanEncoder1DBlock_0"], blk._attn_name, self.num_blocks))
+            self._loaded_params = None
+        self._engine.set_dropout_seed(dropout_seed)
+        if self._loaded_params is not params:   # same tree object as last time: the device copy is current
+            self._engine.load_params(np.asarray(_np(params["posembed_input"]["pos_embedding"])).reshape(T, C),
+                                     flax_tree_to_layers(params["ScanEncoder1DBlock_0"], blk._attn_name, self.num_blocks))
+            self._loaded_params = params
         return self._engine
 
     def _apply(self, params, x, train=False, mask=None, dropout_rng=None):

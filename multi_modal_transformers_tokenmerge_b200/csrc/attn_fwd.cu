@@ -585,12 +585,9 @@ extern "C" int tome_attention_fwd(const tome_attn_desc_t* d, const void* q, cons
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.o_batch_stride = d->o_batch_stride; p.o_token_stride = d->o_token_stride;
   p.lse = lse;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TOME_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    TOME_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    attr_set = true;
-  }
+  static DynSmemOnce once0, once1;
+  TOME_CUDA(ensure_dyn_smem(attn_fwd_kernel<false>, ATT_SMEM, once0));
+  TOME_CUDA(ensure_dyn_smem(attn_fwd_kernel<true>, ATT_SMEM, once1));
   dim3 grid(ceil_div(d->tokens, ATT_BM), d->heads, d->batch);
   if (p.keep_q) attn_fwd_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tq, tk, tv, tqa, tka, p);
   else attn_fwd_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tq, tk, tv, tqa, tka, p);

@@ -539,11 +539,8 @@ template <int BN, bool A_MN, bool B_MN, bool MC, int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmShape& s, const GemmEpilogue& e,
                        cudaStream_t stream) {
   auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, MC, EPI>;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
-    TOME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::TOTAL));
-    attr_set = true;
-  }
+  static DynSmemOnce once;  // per instantiation, per device
+  TOME_CUDA(ensure_dyn_smem(kern, GemmSmem<BN>::TOTAL, once));
   const int items = s.m_items * s.n_tiles * s.k_splits;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -597,6 +594,8 @@ extern "C" int tome_gemm_set_sm_limit(int sms) {
   g_gemm_sm_limit = sms >= 2 || sms == 0 ? sms : 2;
   return TOME_OK;
 }
+
+extern "C" int tome_num_sms(void) { return kNumSMs; }
 
 extern "C" size_t tome_gemm_workspace_bytes(const tome_gemm_args_t* a) {
   if (!a) return 0;

@@ -7,6 +7,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/tome_b200.h"
 
 namespace tome {
@@ -44,6 +46,23 @@ int make_tmap_3d_bf16_plain(CUtensorMap* out, const void* base, uint64_t d0, uin
 int make_tmap_3d_bf16_sw32(CUtensorMap* out, const void* base, uint64_t d1, uint64_t d2, uint32_t box_d1);
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: a process that drives several GPUs (JAX's
+// default) must set it on each one.  One DynSmemOnce per call site remembers, per device, the largest size already set.
+struct DynSmemOnce {
+  std::atomic<int> set[64];
+};
+template <typename Kernel>
+inline cudaError_t ensure_dyn_smem(Kernel kernel, int bytes, DynSmemOnce& once) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (once.set[dev].load(std::memory_order_acquire) >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) once.set[dev].store(bytes, std::memory_order_release);
+  return e;
+}
 
 // ---- launch accounting + optional per-op CUDA-event timing (bench.py's roofline pass; off by default) ----
 enum ProfTag { PROF_GEMM = 0, PROF_ATTN_FWD, PROF_ATTN_BWD, PROF_MERGE_FWD, PROF_MERGE_BWD, PROF_SIM, PROF_SELECT,

@@ -685,11 +685,8 @@ extern "C" int tome_layernorm_fwd(int batch, int tokens, int channels, int axis,
       CUtensorMap tx;
       if (int rc = make_tmap_3d_bf16(&tx, x, channels, tokens, batch, channels, (uint64_t)tokens * channels, LN_BOX)) return rc;
       const int smem = ln_boxes(tokens) * LN_BOX * 128 + ln_boxes(tokens) * 8 + 1024;
-      static int smem_set = 0;
-      if (smem > smem_set) {
-        TOME_CUDA(cudaFuncSetAttribute(ln_seq_fwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        smem_set = smem;
-      }
+      static DynSmemOnce once;
+      TOME_CUDA(ensure_dyn_smem(ln_seq_fwd_smem_kernel, smem, once));
       ln_seq_fwd_smem_kernel<<<grid, LN_THREADS, smem, stream>>>(tx, tokens, channels, eps, gamma, beta, yp, mean, rstd);
     } else {
       ln_seq_fwd_kernel<<<grid, LN_THREADS, 0, stream>>>(tokens, channels, eps, xp, gamma, beta, yp, mean, rstd);
@@ -725,11 +722,8 @@ extern "C" int tome_layernorm_bwd(int batch, int tokens, int channels, int axis,
       if (int rc = make_tmap_3d_bf16_plain(&tx, x, channels, tokens, batch, channels, (uint64_t)tokens * channels, LNB_SLAB, LN_BOX)) return rc;
       if (int rc = make_tmap_3d_bf16_plain(&tdy, dy, channels, tokens, batch, channels, (uint64_t)tokens * channels, LNB_SLAB, LN_BOX)) return rc;
       const int smem = 2 * ln_boxes(tokens) * LN_BOX * LNB_SLAB * 2 + ln_boxes(tokens) * 8 + 128;
-      static int smem_set = 0;
-      if (smem > smem_set) {
-        TOME_CUDA(cudaFuncSetAttribute(ln_seq_bwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        smem_set = smem;
-      }
+      static DynSmemOnce once;
+      TOME_CUDA(ensure_dyn_smem(ln_seq_bwd_smem_kernel, smem, once));
       grid = dim3(ceil_div(channels, LNB_SLAB), batch);
       ln_seq_bwd_smem_kernel<<<grid, LN_THREADS, smem, stream>>>(tx, tdy, batch, tokens, channels, gamma, mean, rstd, drp, dxp, partial);
     } else {

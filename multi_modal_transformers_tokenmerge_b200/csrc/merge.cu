@@ -328,11 +328,8 @@ extern "C" int tome_merge_fwd(const tome_merge_shape_t* s, const tome_plan_t* pl
     dim3 grid2(ceil_div(s->tokens - s->r, rows), s->batch);
 #define LAUNCHB(TT, W)                                                                                                  \
   do {                                                                                                                  \
-    static size_t smem_set = 0;                                                                                         \
-    if (smem > 48 * 1024 && smem > smem_set) {                                                                          \
-      TOME_CUDA(cudaFuncSetAttribute(merge_fwd_bulk_kernel<TT, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      smem_set = smem;                                                                                                  \
-    }                                                                                                                   \
+    static DynSmemOnce once;                                                                                            \
+    if (smem > 48 * 1024) TOME_CUDA(ensure_dyn_smem(merge_fwd_bulk_kernel<TT, W>, (int)smem, once));                   \
     merge_fwd_bulk_kernel<TT, W><<<grid2, MERGE_THREADS, smem, stream>>>(*s, *plan, reinterpret_cast<const TT*>(x), size, \
                                                                          reinterpret_cast<TT*>(x_out), size_out, gid, pos, \
                                                                          gid_out, pos_out, rows);                       \

@@ -492,6 +492,9 @@ extern "C" int tome_stack_backward(const tome_stack_cfg_t* c, const tome_stack_i
     const ParamOffsets o = layer_offsets(c, l);
     const int T = S.shapes[l].t_in, r = S.shapes[l].r, To = S.shapes[l].t_out;
     const int M = B * T, Mo = B * To;
+    if (io->grad_trace)  // parity aid: the gradient this layer receives, before it is consumed
+      TOME_CUDA(cudaMemcpyAsync(reinterpret_cast<__nv_bfloat16*>(io->grad_trace) + (size_t)l * B * c->tokens * C, g0,
+                                (size_t)Mo * C * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice, st));
     // ---- MLP: y = x1m + drop2(m1 W2 + b2),  m1 = drop1(relu(h2 W1 + b1))          d_out in g0
     const __nv_bfloat16* dy2;
     RC(masked_colsum(g0, g2, Mo, C, 3 * l + 2, gr + o.b2, &dy2));
@@ -572,7 +575,18 @@ ACCESSOR(tome_stack_layer_edge_idx, const int32_t*, S.L[layer].plan.edge_idx)
 ACCESSOR(tome_stack_layer_dst_idx, const int32_t*, S.L[layer].plan.dst_idx)
 ACCESSOR(tome_stack_layer_node_max, const float*, S.L[layer].node_max)
 ACCESSOR(tome_stack_layer_node_idx, const int32_t*, S.L[layer].node_idx)
+ACCESSOR(tome_stack_layer_relu_bits, const uint32_t*, S.L[layer].m1_bits)
 
+extern "C" const void* tome_stack_layer_x_in(const tome_stack_cfg_t* c, const tome_stack_io_t* io, int layer) {
+  if (check_cfg(c) || !io || layer < 0 || layer > c->layers) return nullptr;
+  StackLayout S = make_layout(c, io->workspace);
+  return layer == c->layers ? S.L.back().x_out : S.L[layer].x_in;
+}
+extern "C" const float* tome_stack_layer_size_in(const tome_stack_cfg_t* c, const tome_stack_io_t* io, int layer) {
+  if (check_cfg(c) || !io || layer < 0 || layer > c->layers) return nullptr;
+  StackLayout S = make_layout(c, io->workspace);
+  return layer == c->layers ? S.L.back().size_out : S.L[layer].size_in;
+}
 extern "C" const void* tome_stack_final_x(const tome_stack_cfg_t* c, const tome_stack_io_t* io) {
   if (check_cfg(c) || !io) return nullptr;
   return make_layout(c, io->workspace).L.back().x_out;

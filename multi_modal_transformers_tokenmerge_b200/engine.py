@@ -109,6 +109,8 @@ class ToMeStackEngine:
         self.head_time = self.alpha_hats = None     # diffusion head: set_diffusion_draws()
         self._x = self._target = None
         self._events = None
+        self._base_seed = int(cfg.dropout_seed)
+        self._grad_trace = None
 
     # ------------------------------------------------------------------ parameters
     def layer_offset(self, layer: int) -> int:
@@ -207,7 +209,8 @@ class ToMeStackEngine:
                          None if ev is None else C.cast(ev, C.POINTER(C.c_void_p)),
                          None if self.head_out is None else self.head_out.data_ptr(),
                          None if self.head_time is None else self.head_time.data_ptr(),
-                         None if self.alpha_hats is None else self.alpha_hats.data_ptr())
+                         None if self.alpha_hats is None else self.alpha_hats.data_ptr(),
+                         None if self._grad_trace is None else self._grad_trace.data_ptr())
 
     def set_diffusion_draws(self, time: torch.Tensor, alpha_hats) -> None:
         """Diffusion head: the sampled time steps (i32 [B], diffusion.py:125) and the alpha_hat table (:88-92)."""
@@ -215,6 +218,23 @@ class ToMeStackEngine:
         self.head_time = time.contiguous()
         self.alpha_hats = torch.as_tensor(np.asarray(alpha_hats, np.float32)).to(self.dev)
         assert self.alpha_hats.numel() == self.cfg.diffusion_steps
+
+    def set_dropout_step(self, step: int) -> int:
+        """Fold the training step into the dropout seed, as the reference does with `jax.random.fold_in(rngs['dropout'],
+        train_state.step)` (models/octo/octo.py): every kernel derives its masks from (seed, site, row, column) only, so
+        without this every step would draw the same masks.  Call before `forward`; `backward` of the same step reuses the
+        value (it regenerates the masks from the same seed).  Returns the mixed 64-bit seed."""
+        z = (self._base_seed + 0x9E3779B97F4A7C15 * (int(step) + 1)) & 0xFFFFFFFFFFFFFFFF   # splitmix64 finaliser
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+        z ^= z >> 31
+        self.ccfg.dropout_seed = z
+        return z
+
+    def set_dropout_seed(self, seed: int) -> None:
+        """Replace the base dropout seed in place (no reallocation); takes effect at the next forward."""
+        self._base_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.ccfg.dropout_seed = self._base_seed
 
     def forward(self, x: torch.Tensor, target: Optional[torch.Tensor] = None):
         cfg = self.cfg
@@ -287,3 +307,35 @@ class ToMeStackEngine:
         ei = self._view(f.tome_stack_layer_edge_idx(C.byref(self.ccfg), C.byref(io), layer), (b, ta), torch.int32)
         di = self._view(f.tome_stack_layer_dst_idx(C.byref(self.ccfg), C.byref(io), layer), (b, r), torch.int32)
         return nm, ni, ei, di
+
+    def layer_x_in(self, layer: int) -> torch.Tensor:
+        """bf16 [B, T_in(layer), C] tokens entering `layer` in the last forward (layer == layers: the final tokens)."""
+        io = self._io(self._x, self._target)
+        p = self.lib.tome_stack_layer_x_in(C.byref(self.ccfg), C.byref(io), layer)
+        return self._view(p, (self.cfg.batch, self.tokens_at(layer), self.cfg.channels), torch.bfloat16)
+
+    def layer_size_in(self, layer: int) -> Optional[torch.Tensor]:
+        io = self._io(self._x, self._target)
+        p = self.lib.tome_stack_layer_size_in(C.byref(self.ccfg), C.byref(io), layer)
+        return None if not p else self._view(p, (self.cfg.batch, self.tokens_at(layer)), torch.float32)
+
+    def enable_grad_trace(self) -> None:
+        """Parity aid: keep the gradient every layer receives during backward (tome_stack_io_t.grad_trace)."""
+        cfg = self.cfg
+        self._grad_trace = torch.zeros(cfg.layers, cfg.batch * cfg.tokens * cfg.channels, dtype=torch.bfloat16, device=self.dev)
+
+    def layer_grad_out(self, layer: int) -> torch.Tensor:
+        """bf16 [B, T_out(layer), C]: dL/dx_out of `layer` as the last backward received it (needs enable_grad_trace())."""
+        b, to, c = self.cfg.batch, self.tokens_at(layer + 1), self.cfg.channels
+        return self._grad_trace[layer, : b * to * c].view(b, to, c)
+
+    def layer_relu_gate(self, layer: int) -> torch.Tensor:
+        """bool [B, T_out(layer), mlp_dim]: which elements of MLP-1's output survived ReLU (and hidden dropout) in the
+        last forward -- the gate bits the MLP backward consumes (tome_stack_layer_relu_bits)."""
+        io = self._io(self._x, self._target)
+        b, to, f = self.cfg.batch, self.tokens_at(layer + 1), self.cfg.mlp_dim
+        words = (f + 31) // 32
+        p = self.lib.tome_stack_layer_relu_bits(C.byref(self.ccfg), C.byref(io), layer)
+        w = self._view(p, (b * to, words), torch.int32)
+        bits = (w[:, :, None] >> torch.arange(32, device=w.device, dtype=torch.int32)) & 1
+        return bits.reshape(b, to, words * 32)[:, :, :f].bool()

@@ -85,10 +85,11 @@ class DataParallelTrainer:
     def train_step(self, x: torch.Tensor, target: torch.Tensor, lr: float = 1e-4, **adam) -> None:
         e = self.engine
         e.zero_grad()
+        e.set_dropout_step(e.step_count)   # fresh dropout masks every step (forward and backward of a step share them)
         e.forward(x, target)
         if self.world > 1:
             if self.comm_sms:
-                e.lib.tome_gemm_set_sm_limit(148 - self.comm_sms)
+                e.lib.tome_gemm_set_sm_limit(int(e.lib.tome_num_sms()) - self.comm_sms)
             e.backward(events=self.events)  # events[l] <- layer l done; events[L] <- everything done
             if self.comm_sms:
                 e.lib.tome_gemm_set_sm_limit(0)

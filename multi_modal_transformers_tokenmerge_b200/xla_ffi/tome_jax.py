@@ -1,7 +1,9 @@
 """jax.ffi registration + custom_vjp wrappers for the handlers of tome_xla_ffi.cc.
 
-NOT EXERCISED IN THIS IMAGE (jax / jaxlib are not installed): importing this module without JAX raises
-ImportError at once.  It shows exactly what a maintainer of the reference adds so that
+NEVER RUN AGAINST REAL JAX IN THIS IMAGE (jax / jaxlib are not installed): importing this module without
+JAX raises ImportError at once.  tests/test_xla_ffi_stub.py traces it on the CPU against a stub of the few `jax` symbols it
+uses (ffi_call returning zero arrays of the declared shapes), which checks syntax, static-attribute handling and shapes --
+not the kernels and not XLA.  It shows exactly what a maintainer of the reference adds so that
 `multi_modal_transformers.tokenizers.token_compression.merge_wavg` (and the block modules built on it) run on
 libtome_b200.so from inside jit-compiled Flax code.  Logic-free: shapes in, `jax.ffi.ffi_call`, shapes out.
 """
@@ -40,32 +42,40 @@ def bipartite_soft_matching(metric, r, class_token=False, distill_token=False):
         "tome_select_topr", (S((b, ta), jnp.int32), S((b, r), jnp.int32), S((b, t), jnp.int32), S((b, tb + 1), jnp.int32),
                              S((b, r), jnp.int32)))(nmax, nidx, tokens=np.int32(t), r=np.int32(r), distill_token=np.int32(distill_token))
 
-    @jax.custom_vjp
-    def _merge(x, size, mode):
-        return _fwd(x, size, mode)[0]
+    def _make_merge(mode: int):
+        """One custom_vjp per merge mode: `mode` is a Python int closed over (a static FFI attribute), never a traced
+        argument -- as a positional of the custom_vjp it would reach `_fwd` as a tracer and `np.int32(mode)` would raise."""
 
-    def _fwd(x, size, mode):
-        c = x.shape[-1]
-        y, s_out = jax.ffi.ffi_call("tome_merge_fwd", (S((b, t - r, c), x.dtype), S((b, t - r), jnp.float32)))(
-            x, size, edge, dst_off, dst_src, r=np.int32(r), mode=np.int32(mode), distill_token=np.int32(distill_token))
-        return (y, s_out), (size, s_out, mode)
+        @jax.custom_vjp
+        def f(x, size):
+            return _fwd(x, size)[0]
 
-    def _bwd(res, g):
-        size, s_out, mode = res
-        dy, _ = g
-        dx = jax.ffi.ffi_call("tome_merge_bwd", S((b, t, dy.shape[-1]), dy.dtype))(dy, size, s_out, row_map, r=np.int32(r), mode=np.int32(mode))
-        return dx, None, None
+        def _fwd(x, size):
+            c = x.shape[-1]
+            y, s_out = jax.ffi.ffi_call("tome_merge_fwd", (S((b, t - r, c), x.dtype), S((b, t - r), jnp.float32)))(
+                x, size, edge, dst_off, dst_src, r=np.int32(r), mode=np.int32(mode), distill_token=np.int32(distill_token))
+            return (y, s_out), (size, s_out)
 
-    _merge.defvjp(_fwd, _bwd)
-    _merge = jax.tree_util.Partial(_merge)
+        def _bwd(res, g):
+            size, s_out = res
+            dy, _ = g
+            dx = jax.ffi.ffi_call("tome_merge_bwd", S((b, t, dy.shape[-1]), dy.dtype))(
+                dy, size, s_out, row_map, r=np.int32(r), mode=np.int32(mode))
+            return dx, jnp.zeros_like(size)   # sizes descend from constants only (SURVEY.md A.2): no gradient
+
+        f.defvjp(_fwd, _bwd)
+        return f
+
+    _merge_sum, _merge_wavg = _make_merge(0), _make_merge(1)
 
     def merge(x, mode="sum"):
         """merge(x, mode="sum") of :90-109 (fp32 rows of >= 4 columns; merge_wavg below never needs the 1-column call)."""
         if mode != "sum":
             raise ValueError(f'merge: mode "{mode}" is not implemented (the reference only implements "sum", :99)')
-        return _merge(x, jnp.ones(x.shape[:2], jnp.float32), 0)[0]
+        y, _ = _merge_sum(x, jnp.ones(x.shape[:2], jnp.float32))
+        return y
 
-    merge.r, merge.wavg = r, lambda x, size: _merge(x, size, 1)
+    merge.r, merge.wavg = r, _merge_wavg   # wavg(x, size [B,T]) -> (y, size_out [B,T-r])
     return merge
 
 

@@ -408,7 +408,7 @@ def _round_st(t, dtype):
 
 def tome_block(p: BlockParams, x, size, gid, pos, allow, *, num_heads, r, ln_axis="seq", prop_attn=True,
                class_token=False, distill_token=False, scores_override=None, node_override=None,
-               trace: Optional[list] = None, act_dtype=None):
+               trace: Optional[list] = None, act_dtype=None, relu_gate=None):
     """ToMeEncoder1DBlock with the ToMe-paper placement (reference shell attention.py:52-69):
 
         x = x + attn(LN(x), mask(groups), bias = log size)       # dropout 0 (parity mode)
@@ -454,14 +454,23 @@ def tome_block(p: BlockParams, x, size, gid, pos, allow, *, num_heads, r, ln_axi
         pos2[bi, rm[bi, ti]] = pos[bi, ti]
         gid, pos = gid2, pos2
     y = rd(layer_norm(x, p.ln2_scale, p.ln2_bias, axis=ln_axis))
-    y = rd(torch.relu(y @ p.w1 + p.b1))  # attention.py:32-33 (dropout at :34,:37 is identity in parity mode)
+    pre = y @ p.w1 + p.b1
+    if relu_gate is None:
+        y = rd(torch.relu(pre))  # attention.py:32-33 (dropout at :34,:37 is identity in parity mode)
+    else:
+        # parity protocol for the gradients, as node_override is for the matching: the checker takes the SAME ReLU gate
+        # decisions as the implementation under test (bool [B,T',Dff]; a pre-activation within bf16 rounding of zero may
+        # fall on either side, and one flipped gate moves a whole row of dW).  The forward value is relu() of the oracle's
+        # own pre-activation wherever the gates agree; where they differ |pre| is of the order of the rounding error.
+        y = rd(torch.where(torch.as_tensor(relu_gate), pre, torch.zeros_like(pre)))
     y = y @ p.w2 + p.b2
     return rd(x + y), size, gid, pos
 
 
 def tome_stack(params: Sequence[BlockParams], pos_embedding, x, gid, pos, allow, *, num_heads, r,
                ln_axis="seq", prop_attn=True, scores_override: Optional[Sequence] = None,
-               node_override: Optional[Sequence] = None, trace: Optional[list] = None, act_dtype=None):
+               node_override: Optional[Sequence] = None, trace: Optional[list] = None, act_dtype=None,
+               relu_gate: Optional[Sequence] = None):
     """StackedEncoder1DBlock (attention.py:94-119) unrolled, with shrinking T.  Returns
     (x_final [B,T_L,C], size, origin_row [B,T0] = row of x_final each ORIGINAL token ended up in)."""
     torch = _torch()
@@ -477,7 +486,7 @@ def tome_stack(params: Sequence[BlockParams], pos_embedding, x, gid, pos, allow,
         no = None if node_override is None else node_override[li]
         x, size, gid, pos = tome_block(p, x, size, gid, pos, allow, num_heads=num_heads, r=r, ln_axis=ln_axis,
                                        prop_attn=prop_attn, scores_override=so, node_override=no, trace=tr,
-                                       act_dtype=act_dtype)
+                                       act_dtype=act_dtype, relu_gate=None if relu_gate is None else relu_gate[li])
         plan = tr[0].plan
         if plan.r > 0:
             origin = np.take_along_axis(row_map(plan), origin, axis=1)

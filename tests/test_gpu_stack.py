@@ -29,14 +29,20 @@ def rel_err(a, b):
     return ((a - b).norm() / (b.norm() + 1e-12)).item()
 
 
-@pytest.mark.parametrize("T,H,masked,sized", [(74, 3, True, True), (536, 6, True, True), (128, 2, False, False),
-                                              (200, 2, True, False), (333, 4, False, True)])
-def test_attention_bwd(pkg, T, H, masked, sized):
+# (536, 12): octo-base heads; (2080, 12) = BASELINE.json configs[3]; (4096, 2) = configs[4].  dq_mode: -1 = the library's
+# choice (dQ as a GEMM over the stored dS^T tiles at these sizes), 0 = force the recomputing dQ kernel (the path taken by
+# default once the dS^T buffer would exceed 8 GiB), so both backward paths are pinned at the long-sequence shapes
+@pytest.mark.parametrize("T,H,masked,sized,dq_mode", [(74, 3, True, True, -1), (536, 6, True, True, -1), (128, 2, False, False, -1),
+                                                      (200, 2, True, False, -1), (333, 4, False, True, -1),
+                                                      (536, 12, True, True, -1), (2080, 12, True, True, -1),
+                                                      (2080, 12, True, True, 0), (4096, 2, True, True, -1),
+                                                      (4096, 2, True, True, 0)])
+def test_attention_bwd(pkg, T, H, masked, sized, dq_mode):
     """dq/dk/dv vs autograd of oracle.attention on the same bf16-rounded inputs; relative L2 error <= 2e-2 per tensor
     (bf16 P / dS operands and bf16 gradient outputs)."""
     ops, _ = pkg
     rng = np.random.default_rng(T * 7 + H)
-    B, D = 2, 64
+    B, D = (2, 64) if T < 2000 else (1, 64)
     qkv = torch.tensor(rng.standard_normal((B, T, 3, H, D)).astype(np.float32)).cuda().bfloat16()
     q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
     gid = pos = allow = size = None
@@ -46,16 +52,23 @@ def test_attention_bwd(pkg, T, H, masked, sized):
         pad = T - g1.shape[0]
         g1 = np.concatenate([g1, np.full(pad, g1[-1], np.uint8)])
         p1 = np.concatenate([p1, np.arange(pad, dtype=np.int32)])
-        gid = np.stack([g1, rng.permutation(g1)])
-        pos = np.stack([p1, rng.integers(0, 50, size=T).astype(np.int32)])
+        gid = np.stack([g1, rng.permutation(g1)])[:B]
+        pos = np.stack([p1, rng.integers(0, 50, size=T).astype(np.int32)])[:B]
+        if B == 1:
+            gid, pos = np.stack([rng.permutation(g1)]), np.stack([rng.integers(0, 50, size=T).astype(np.int32)])
     if sized:
         size = rng.integers(1, 6, size=(B, T)).astype(np.float32)
     dv_ = lambda a: None if a is None else torch.as_tensor(np.ascontiguousarray(a)).cuda()  # noqa: E731
     kw = dict(gid=dv_(gid), pos=dv_(pos), allow=dv_(allow), size=dv_(size))
     out, lse = ops.attention_fwd(q, k, v, **kw)
     dout = torch.tensor(rng.standard_normal((B, T, H, D)).astype(np.float32)).cuda().bfloat16()
-    dq, dk, dvv = ops.attention_bwd(q, k, v, out, lse, dout, **kw)
-    torch.cuda.synchronize()
+    from multi_modal_transformers_tokenmerge_b200 import _lib
+    _lib.lib().tome_attention_set_dq_from_ds(dq_mode)
+    try:
+        dq, dk, dvv = ops.attention_bwd(q, k, v, out, lse, dout, **kw)
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().tome_attention_set_dq_from_ds(-1)
     qr, kr, vr = (t.float().cpu().requires_grad_(True) for t in (q, k, v))
     mask = None if gid is None else torch.as_tensor(O.dense_mask(gid, pos, gid, pos, allow))[:, None]
     bias = None if size is None else torch.log(torch.as_tensor(size))[:, None, None, :]
@@ -110,6 +123,9 @@ def test_attention_weight_dropout_fwd_bwd(pkg, T, H, rate):
         assert e <= 2.5e-2, f"{name}: rel err {e}"
 
 
+TOL_SEQ_LN = 4e-2   # gradient bar of the reference-literal (token-axis LayerNorm) rows once the oracle follows the GPU's gates
+
+
 def _build(pkg, B, W, P, C, H, Dff, Lyr, r, ln_axis, seed=0, n_ro=2, n_tdp=4, D=64):
     ops, engine = pkg
     rng = np.random.default_rng(seed)
@@ -132,7 +148,7 @@ def _build(pkg, B, W, P, C, H, Dff, Lyr, r, ln_axis, seed=0, n_ro=2, n_tdp=4, D=
     return eng, cfg, layers, pe, x, y, (gid, pos, allow, ro)
 
 
-def _oracle_run(eng, cfg, layers, pe, x, y, groups, node_override, act_dtype=None):
+def _oracle_run(eng, cfg, layers, pe, x, y, groups, node_override, act_dtype=None, relu_gate=None):
     gid, pos, allow, ro = groups
     # the oracle sees exactly the bf16-rounded weights the GPU GEMMs consume (biases / LN params stay fp32)
     v = eng.param_views(eng.params_bf16.float().cpu())
@@ -152,7 +168,7 @@ def _oracle_run(eng, cfg, layers, pe, x, y, groups, node_override, act_dtype=Non
     tr = []
     xf, size, origin = O.tome_stack(params, pet, xt, gid, pos, allow, num_heads=cfg.heads, r=cfg.r,
                                     ln_axis="seq" if cfg.ln_axis == 1 else "feature", node_override=node_override, trace=tr,
-                                    act_dtype=act_dtype)
+                                    act_dtype=act_dtype, relu_gate=relu_gate)
     loss, out = O.readout_loss(xf, origin, ro, torch.tensor(y))
     loss.backward()
     return params, pet, xf, size, origin, loss, out, tr
@@ -161,12 +177,14 @@ def _oracle_run(eng, cfg, layers, pe, x, y, groups, node_override, act_dtype=Non
 # (ln_axis, r, layers, b1 shift, tolerance on the forward, tolerance on every parameter gradient)
 #  * b1 + 8 opens every ReLU gate and ln_axis = 2 avoids the token-axis cancellation, so those rows measure the
 #    kernels themselves: gradients within 2e-2 relative L2 of the fp32 oracle (observed <= 6e-3);
-#  * the reference-literal rows (ReLU active, LayerNorm over tokens) are dominated by two effects that are properties
-#    of bf16 storage, not of the kernels: a ReLU gate whose pre-activation is within bf16 rounding of zero flips
-#    (relative L2 error = sqrt(fraction flipped), ~0.4 % of gates -> ~6 %), and with reduction_axes=[1] the token sums
-#    in the weight gradients cancel (sum_t xhat = 0), which amplifies rounding noise.  Observed <= 0.17; bar 0.25.
-CASES = [(2, 4, 2, 8.0, 1e-2, 2e-2), (2, 0, 1, 8.0, 1e-2, 2e-2), (2, 6, 3, 8.0, 1e-2, 2e-2), (1, 4, 2, 8.0, 1e-2, 0.12),
-         (1, 4, 2, 0.0, 3e-2, 0.25), (2, 4, 2, 0.0, 3e-2, 0.25), (1, 0, 1, 0.0, 3e-2, 0.25), (1, 6, 3, 0.0, 3e-2, 0.25)]
+#  * the reference-literal rows (ReLU active, LayerNorm over tokens): a ReLU gate whose pre-activation is within bf16
+#    rounding of zero can fall on either side, and one flipped gate moves a whole row of dW (round 1 measured up to 0.17
+#    from that alone).  The oracle therefore takes the GPU's gate bits (tome_stack_layer_relu_bits -> relu_gate), exactly
+#    as it takes the GPU's node_max / node_idx for the matching; what is left is bf16 rounding, amplified in the
+#    token-axis LayerNorm rows by the cancelling token sums (sum_t xhat = 0) and by ~1.4x per layer of depth: observed
+#    <= 0.030 at 3 layers (bar 4e-2; round 1 needed 0.25 here), <= 0.043 at 3 layers of the real widths (bar 6e-2).
+CASES = [(2, 4, 2, 8.0, 1e-2, 2e-2), (2, 0, 1, 8.0, 1e-2, 2e-2), (2, 6, 3, 8.0, 1e-2, 2e-2), (1, 4, 2, 8.0, 1e-2, TOL_SEQ_LN),
+         (1, 4, 2, 0.0, 1e-2, TOL_SEQ_LN), (2, 4, 2, 0.0, 1e-2, 2e-2), (1, 0, 1, 0.0, 1e-2, TOL_SEQ_LN), (1, 6, 3, 0.0, 1e-2, TOL_SEQ_LN)]
 
 
 @pytest.mark.parametrize("ln_axis,r,Lyr,b1_shift,tol_fwd,tol_grad", CASES)
@@ -177,7 +195,7 @@ def test_stack_forward_backward_vs_oracle(pkg, ln_axis, r, Lyr, b1_shift, tol_fw
     _stack_vs_oracle(pkg, dict(B=2, W=2, P=24, C=128, H=2, Dff=256), ln_axis, r, Lyr, b1_shift, tol_fwd, tol_grad)
 
 
-@pytest.mark.parametrize("r,b1_shift,tol_grad", [(0, 8.0, 2e-2), (8, 8.0, 2e-2), (0, 0.0, 0.25)])
+@pytest.mark.parametrize("r,b1_shift,tol_grad", [(0, 8.0, 2e-2), (8, 8.0, 2e-2), (0, 0.0, TOL_SEQ_LN)])
 def test_stack_literal_reference_config(pkg, r, b1_shift, tol_grad):
     """C0, the only shape the reference itself defines (octo_base.yaml:10 + vanilla_decoder.yaml): 74 tokens
     ("[TaskDescriptionPrefix{16}] [Image{25};Readout{4}]*2"), C = 768, 3 heads x 256, Dff = 768, ONE block, LayerNorm over
@@ -204,8 +222,9 @@ def _stack_vs_oracle(pkg, shape, ln_axis, r, Lyr, b1_shift, tol_fwd, tol_grad):
         pl = eng.layer_plan(l)
         plans.append(pl)
         node_override.append(None if pl is None else (pl[0].cpu().numpy(), pl[1].cpu().numpy()))
+    gates = [eng.layer_relu_gate(l).cpu().numpy() for l in range(Lyr)]
     params, pet, xf, size, origin, loss, out, tr = _oracle_run(eng, cfg, layers, pe, x, y, groups, node_override,
-                                                               torch.bfloat16)
+                                                               torch.bfloat16, relu_gate=gates)
     for l in range(Lyr):
         if plans[l] is None:
             continue
@@ -214,19 +233,116 @@ def _stack_vs_oracle(pkg, shape, ln_axis, r, Lyr, b1_shift, tol_fwd, tol_grad):
     fs = eng.final_size()
     if fs is not None:
         np.testing.assert_array_equal(fs.cpu().numpy(), size.detach().numpy()[..., 0])
-    assert rel_err(eng.final_x().float().cpu(), xf.detach()) <= tol_fwd
-    assert rel_err(eng.readout.cpu(), out.detach()) <= tol_fwd
-    assert abs(eng.loss[0].item() - loss.item()) <= tol_fwd * abs(loss.item())
+    e_fwd = dict(final_x=rel_err(eng.final_x().float().cpu(), xf.detach()), readout=rel_err(eng.readout.cpu(), out.detach()),
+                 loss=abs(eng.loss[0].item() - loss.item()) / abs(loss.item()))
     g = eng.param_views(eng.grads.cpu())
-    assert rel_err(g["pos_embedding"], pet.grad[0]) <= tol_grad
+    e_grad = {"pos_embedding": rel_err(g["pos_embedding"], pet.grad[0])}
     for l in range(Lyr):
         p, gl = params[l], g["layers"][l]
         ref = dict(ln1_scale=p.ln1_scale.grad, ln1_bias=p.ln1_bias.grad, ln2_scale=p.ln2_scale.grad, ln2_bias=p.ln2_bias.grad,
                    wqkv=torch.cat([p.wq.grad, p.wk.grad, p.wv.grad], 1), bqkv=torch.cat([p.bq.grad, p.bk.grad, p.bv.grad]),
                    wo=p.wo.grad, bo=p.bo.grad, w1=p.w1.grad, b1=p.b1.grad, w2=p.w2.grad, b2=p.b2.grad)
         for name, want in ref.items():
-            e = rel_err(gl[name], want)
-            assert e <= tol_grad, f"layer {l} grad {name}: rel err {e}"
+            e_grad[f"layer {l} grad {name}"] = rel_err(gl[name], want)
+    worst = max(e_grad, key=e_grad.get)
+    print(f"\n[stack parity] {shape} ln_axis={ln_axis} r={r} L={Lyr} b1+{b1_shift}: fwd {e_fwd}; worst grad {worst} = {e_grad[worst]:.4f}")
+    for k_, v in e_fwd.items():
+        assert v <= tol_fwd, f"{k_}: rel err {v}"
+    for k_, v in e_grad.items():
+        assert v <= tol_grad, f"{k_}: rel err {v}"
+
+
+REAL = {"octo_small": dict(C=384, H=6, Dff=1536, r=16), "octo_base": dict(C=768, H=12, Dff=3072, r=32)}
+
+
+@pytest.mark.parametrize("name,ln_axis,Lyr,tol_fwd,tol_grad", [("octo_small", 2, 12, 2e-2, 3e-2), ("octo_base", 2, 12, 2e-2, 3e-2),
+                                                                ("octo_small", 1, 3, 2e-2, 6e-2), ("octo_base", 1, 3, 2e-2, 6e-2)])
+def test_stack_real_dims_end_to_end_vs_oracle(pkg, name, ln_axis, Lyr, tol_fwd, tol_grad):
+    """BASELINE.json configs[1] (octo-small: C = 384, 6 heads, Dff = 1536, r = 16) and configs[2] (octo-base: C = 768, 12
+    heads, Dff = 3072, r = 32) at their REAL widths, T0 = 536, block-causal group mask, proportional attention, B = 2:
+    merge indices and token sizes bit-exact, final tokens / readout / loss and every parameter gradient end to end.
+    The whole 12-layer depth is compared end to end with feature-axis LayerNorm; with the reference's token-axis LayerNorm
+    the comparison stops at 3 layers, because that configuration amplifies ANY rounding difference by ~1.4x per layer
+    (the oracle against itself, bf16-rounded vs fp32 activations, is 27 % apart after 12 layers: DESIGN.md section 2) --
+    its full depth is covered layer by layer in test_stack_real_dims_layer_by_layer."""
+    d = REAL[name]
+    _stack_vs_oracle(pkg, dict(B=2, W=2, P=256, C=d["C"], H=d["H"], Dff=d["Dff"], n_ro=4, n_tdp=16), ln_axis, d["r"], Lyr, 0.0,
+                     tol_fwd, tol_grad)
+
+
+@pytest.mark.parametrize("name", ["octo_small", "octo_base"])
+def test_stack_real_dims_layer_by_layer(pkg, name):
+    """The reference-literal configuration (LayerNorm over tokens, vanilla_decoder.yaml:7-13) at real widths and FULL depth
+    (12 layers, T0 = 536 -> 344 / 152), one layer at a time: the oracle's block l is run on the tokens the GPU's layer l
+    received (tome_stack_layer_x_in) and, for backward, on the gradient the GPU's layer l received (grad_trace), following
+    the GPU's matching scores and ReLU gates.  Per layer: merge indices and token sizes bit-exact, block output within 1e-2,
+    every parameter gradient of the layer and the gradient handed to the layer below within 3e-2 (relative L2).  This pins
+    every kernel at every depth without the ~1.4x-per-layer amplification of the end-to-end comparison."""
+    ops, engine = pkg
+    d = REAL[name]
+    Lyr, B = 12, 2
+    eng, cfg, layers, pe, x, y, groups = _build(pkg, B, 2, 256, d["C"], d["H"], d["Dff"], Lyr, d["r"], 1, n_ro=4, n_tdp=16)
+    gid, pos, allow, ro = groups
+    eng.enable_grad_trace()
+    eng.zero_grad()
+    eng.forward(torch.tensor(x).cuda(), torch.tensor(y).cuda())
+    eng.backward()
+    torch.cuda.synchronize()
+    v = eng.param_views(eng.params_bf16.float().cpu())
+    vf = eng.param_views(eng.params.cpu())
+    g = eng.param_views(eng.grads.cpu())
+    hd = cfg.heads * cfg.head_dim
+    T = cfg.tokens
+    size = torch.ones(B, T, 1)
+    gid_l = np.broadcast_to(gid, (B, T)).copy()
+    pos_l = np.broadcast_to(pos, (B, T)).copy()
+    worst = {}
+    for l in range(Lyr):
+        src, srcf = v["layers"][l], vf["layers"][l]
+        dd = dict(ln1_scale=srcf["ln1_scale"], ln1_bias=srcf["ln1_bias"], ln2_scale=srcf["ln2_scale"], ln2_bias=srcf["ln2_bias"],
+                  wq=src["wqkv"][:, :hd], wk=src["wqkv"][:, hd:2 * hd], wv=src["wqkv"][:, 2 * hd:],
+                  bq=srcf["bqkv"][:hd], bk=srcf["bqkv"][hd:2 * hd], bv=srcf["bqkv"][2 * hd:],
+                  wo=src["wo"], bo=srcf["bo"], w1=src["w1"], b1=srcf["b1"], w2=src["w2"], b2=srcf["b2"])
+        p = O.BlockParams(**{k_: t.clone().contiguous().requires_grad_(True) for k_, t in dd.items()})
+        x_in = eng.layer_x_in(l).float().cpu().requires_grad_(True)
+        s_gpu = eng.layer_size_in(l)
+        if s_gpu is not None:
+            np.testing.assert_array_equal(s_gpu.cpu().numpy(), size.numpy()[..., 0])
+        pl = eng.layer_plan(l)
+        tr = []
+        x_out, size2, gid2, pos2 = O.tome_block(p, x_in, size, gid_l, pos_l, allow, num_heads=cfg.heads, r=cfg.r, ln_axis="seq",
+                                                node_override=(pl[0].cpu().numpy(), pl[1].cpu().numpy()), trace=tr,
+                                                act_dtype=torch.bfloat16, relu_gate=eng.layer_relu_gate(l).cpu().numpy())
+        np.testing.assert_array_equal(pl[2].cpu().numpy(), tr[0].plan.edge_idx)
+        np.testing.assert_array_equal(pl[3].cpu().numpy(), tr[0].plan.dst_idx)
+        errs = {"x_out": rel_err(eng.layer_x_in(l + 1).float().cpu(), x_out.detach())}
+        x_out.backward(eng.layer_grad_out(l).float().cpu())
+        ref = dict(ln1_scale=p.ln1_scale.grad, ln1_bias=p.ln1_bias.grad, ln2_scale=p.ln2_scale.grad, ln2_bias=p.ln2_bias.grad,
+                   wqkv=torch.cat([p.wq.grad, p.wk.grad, p.wv.grad], 1), bqkv=torch.cat([p.bq.grad, p.bk.grad, p.bv.grad]),
+                   wo=p.wo.grad, bo=p.bo.grad, w1=p.w1.grad, b1=p.b1.grad, w2=p.w2.grad, b2=p.b2.grad)
+        for nm_, want in ref.items():
+            errs[nm_] = rel_err(g["layers"][l][nm_], want)
+        # d(bo) = sum over tokens of dL/dx1, and with LayerNorm over TOKENS the LN2 branch of that gradient sums to zero over
+        # the tokens of every (batch, feature) by construction: what survives is the residual-path part, of the size of
+        # d(b2) (the same column sum without the cancelling branch), while the rounding noise of the cancelled part stays.
+        # Its error is therefore measured against |d(b2)|, the un-cancelled column sum of this layer (plain relative error
+        # reads 0.17 - 0.31 at layer 0, where the surviving part is smallest).
+        errs["bo"] = ((g["layers"][l]["bo"].double() - p.bo.grad.double()).norm() / p.b2.grad.double().norm()).item()
+        errs["bo_plain_rel"] = rel_err(g["layers"][l]["bo"], p.bo.grad)
+        if l > 0:
+            errs["dx_in"] = rel_err(eng.layer_grad_out(l - 1).float().cpu(), x_in.grad)
+        else:
+            errs["pos_embedding"] = rel_err(g["pos_embedding"], x_in.grad.sum(0))
+        for k_, e in errs.items():
+            if e > worst.get(k_, (0.0, 0))[0]:
+                worst[k_] = (e, l)
+        size, gid_l, pos_l = size2.detach(), gid2, pos2
+    print(f"\n[layer-by-layer parity] {name}: worst (rel err, layer) per quantity: "
+          + ", ".join(f"{k_} {e:.4f}@{l}" for k_, (e, l) in worst.items()))
+    np.testing.assert_array_equal(eng.final_size().cpu().numpy(), size.numpy()[..., 0])
+    for k_, (e, l) in worst.items():
+        if k_ != "bo_plain_rel":   # reported only
+            assert e <= (1e-2 if k_ == "x_out" else 3e-2), f"layer {l} {k_}: rel err {e}"
 
 
 def test_stack_octo_small_shape_runs_and_trains(pkg):
@@ -485,3 +601,40 @@ def test_full_size_bench_shape_properties(pkg):
         eng.adamw_step(lr=1e-4)
         losses.append(eng.loss[0].item())
     assert all(math.isfinite(v) for v in losses) and losses[-1] < losses[0], losses
+
+
+def test_dropout_masks_change_every_step_and_repeat_for_the_same_step(pkg):
+    """the kernels derive dropout masks from (seed, site, row, column) only, so the trainer folds the step into the
+    seed (the reference: jax.random.fold_in(rngs['dropout'], train_state.step)).  Two steps draw different masks; the same
+    step index reproduces its masks bit for bit; forward and backward of one step share the seed (ccfg is read by both)."""
+    ops, engine = pkg
+    from multi_modal_transformers_tokenmerge_b200.parallel import DataParallelTrainer
+    gid, pos, allow, ro = O.sequence_groups("[TaskDescriptionPrefix{4}] [Image{24};Readout{2}]*2")
+    B, T, C = 4, gid.shape[0], 128
+    cfg = engine.StackConfig(batch=B, tokens=T, channels=C, heads=2, head_dim=64, mlp_dim=256, layers=2, r=4,
+                             num_groups=allow.shape[0], n_readout=len(ro), dropout_rate=0.2, attn_dropout_rate=0.2, dropout_seed=77)
+    eng = engine.ToMeStackEngine(cfg, gid=gid, pos=pos, allow=allow, readout_idx=ro)
+    eng.init_params(1)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(B, T, C, device="cuda", generator=g)
+    y = torch.randn(B, len(ro), C, device="cuda", generator=g)
+
+    def run(step):
+        seed = eng.set_dropout_step(step)
+        eng.zero_grad()
+        eng.forward(x, y)
+        assert eng.ccfg.dropout_seed == seed
+        eng.backward()
+        torch.cuda.synchronize()
+        return eng.loss[0].item(), eng.final_x().clone(), eng.grads.clone()
+
+    a, b, a2 = run(0), run(1), run(0)
+    assert a[0] != b[0] and not torch.equal(a[1], b[1])
+    assert a[0] == a2[0] and torch.equal(a[1], a2[1]) and torch.equal(a[2], a2[2])
+    # the trainer advances the step by itself: with lr = 0 the parameters stay put, so only the masks can change the loss
+    tr = DataParallelTrainer(eng)
+    losses = []
+    for _ in range(3):
+        tr.train_step(x, y, lr=0.0)
+        losses.append(eng.loss[0].item())
+    assert len(set(losses)) == 3, losses
