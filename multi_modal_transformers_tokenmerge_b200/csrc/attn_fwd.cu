@@ -39,9 +39,14 @@ constexpr int ATT_QAUG_BYTES = ATT_BM * ATTN_AUG_K * 2;   // 4 KB: mask augmenta
 constexpr int ATT_KAUG_BYTES = ATT_BN * ATTN_AUG_K * 2;   // 2 KB per key tile, one per ring slot
 constexpr int ATT_META_SLOT = ATTN_META_KEY_BYTES + ATTN_DROP_TILE_BYTES;  // bias2 | vis[32][2] | visc[32][2] | pos | dropout keep words [128][2]
 static_assert(ATT_BN == ATTN_META_TILE, "key tiles and metadata tiles must coincide");
-constexpr int ATT_SMEM = ATT_Q_BYTES + ATT_SLOTS * ATT_KV_BYTES + 2 * ATT_P_BYTES + ATT_QAUG_BYTES + ATT_SLOTS * ATT_KAUG_BYTES +
-                         ATT_MSLOTS * ATT_META_SLOT + 512 + 1024;
-constexpr uint32_t ATT_TMEM_COLS = 256;  // S0 [0,64) S1 [64,128) O [128,192)
+// TS = both MMAs take their A operand from tensor memory: Q is copied there once per CTA and P_j overwrites the first 32
+// columns of S_j (two bf16 per column), so no P buffer exists in shared memory
+template <bool TS>
+constexpr int att_smem() {
+  return ATT_Q_BYTES + ATT_SLOTS * ATT_KV_BYTES + (TS ? 0 : 2 * ATT_P_BYTES) + ATT_QAUG_BYTES + ATT_SLOTS * ATT_KAUG_BYTES +
+         ATT_MSLOTS * ATT_META_SLOT + 512 + 1024;
+}
+constexpr uint32_t ATT_TMEM_COLS = 256;  // S0 [0,64) S1 [64,128) O [128,192) Q [192,224)
 constexpr float ATT_LAZY_LOG2 = 8.0f;    // rescale O only when the row maximum grows by more than 2^8
 
 struct AttnFwdParams {
@@ -76,7 +81,7 @@ __device__ __forceinline__ void tmem_ld_f32x32(uint32_t taddr, float (&r)[N]) {
 }
 
 // DROP: attention-weight dropout compiled in (the keep words ride in the metadata ring); the rate-0 instantiation carries none of it
-template <bool DROP>
+template <bool DROP, bool TS>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_qaug,
@@ -86,8 +91,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_q = smem;
   uint8_t* s_kv = s_q + ATT_Q_BYTES;                        // slot i at i * 8 KB
-  uint8_t* s_p = s_kv + ATT_SLOTS * ATT_KV_BYTES;           // buffer i at i * 16 KB
-  uint8_t* s_qaug = s_p + 2 * ATT_P_BYTES;                  // [128 rows][16] bf16, 32-byte swizzle
+  uint8_t* s_p = s_kv + ATT_SLOTS * ATT_KV_BYTES;           // buffer i at i * 16 KB (absent with TS)
+  uint8_t* s_qaug = s_p + (TS ? 0 : 2 * ATT_P_BYTES);       // [128 rows][16] bf16, 32-byte swizzle
   uint8_t* s_kaug = s_qaug + ATT_QAUG_BYTES;                // slot i at i * 2 KB (only K slots use theirs)
   uint8_t* s_meta = s_kaug + ATT_SLOTS * ATT_KAUG_BYTES;    // metadata slot i at i * ATT_META_SLOT
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_meta + ATT_MSLOTS * ATT_META_SLOT);
@@ -99,7 +104,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint64_t* pv_done = bars + 17;           // [2]  O += P_j V_j retired: P buffer j&1 reusable, O readable
   uint64_t* meta_full = bars + 19;         // [ATT_MSLOTS]  bulk copy of the tile's metadata block landed
   uint64_t* meta_empty = bars + 23;        // [ATT_MSLOTS]  128 arrivals (softmax threads), after the P stores of the tile
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
+  uint64_t* q_ready = bars + 27;           // TS: the query tile has been copied into tensor memory (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -108,6 +114,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
+    mbar_init(q_ready, ATT_BM);
     for (int i = 0; i < ATT_SLOTS; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
@@ -134,6 +141,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_o = tmem_base + 128;   // 64 columns; S buffers at +0 and +64
+  const uint32_t tmem_q = tmem_base + 192;   // TS: 32 columns = 128 x 64 bf16
   const bool has_mask = p.gid != nullptr;
   // the mask rides in the QK^T contraction (attn_meta.cuh) when the table allows it; CTA-uniform
   const bool use_aug = has_mask && *p.aug_flag != 0u;
@@ -183,16 +191,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tc_fence_after();
         const uint32_t ak = smem_u32(s_kv + slot * ATT_KV_BYTES);
 #pragma unroll
-        for (int k = 0; k < ATT_D / 16; ++k)
-          umma_bf16(tmem_base + (t & 1) * ATT_BN, make_smem_desc(aq + k * 32, 16, 1024), make_smem_desc(ak + k * 32, 16, 1024),
-                    idesc_s, k > 0 ? 1u : 0u);
+        for (int k = 0; k < ATT_D / 16; ++k) {
+          if constexpr (TS)
+            umma_bf16_ts(tmem_base + (t & 1) * ATT_BN, tmem_q + k * 8, make_smem_desc(ak + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+          else
+            umma_bf16(tmem_base + (t & 1) * ATT_BN, make_smem_desc(aq + k * 32, 16, 1024), make_smem_desc(ak + k * 32, 16, 1024),
+                      idesc_s, k > 0 ? 1u : 0u);
+        }
         if (use_aug)  // S += Mq Ek^T: 0 where the query's group sees the key's group, -2^100 (absorbing) where it does not
           umma_bf16(tmem_base + (t & 1) * ATT_BN, make_smem_desc_sw32(smem_u32(s_qaug)),
                     make_smem_desc_sw32(smem_u32(s_kaug + slot * ATT_KAUG_BYTES)), idesc_s, 1u);
         umma_commit(&s_full[t & 1]);
         umma_commit(&kv_empty[slot]);
       };
-      mbar_wait(q_full, 0);
+      if constexpr (TS) {
+        mbar_wait(q_ready, 0);
+        tc_fence_after();
+      } else {
+        mbar_wait(q_full, 0);
+      }
       issue_s(0);
       if (n_kv > 1) issue_s(1);
       for (int j = 0; j < n_kv; ++j) {
@@ -203,9 +220,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tc_fence_after();
         const uint32_t av = smem_u32(s_kv + slot * ATT_KV_BYTES), apj = ap + (j & 1) * ATT_P_BYTES;
 #pragma unroll
-        for (int k = 0; k < ATT_BN / 16; ++k)  // O += P_j V_j
-          umma_bf16(tmem_o, make_smem_desc(apj + k * 32, 16, 1024), make_smem_desc(av + k * 2048, 8192, 1024), idesc_o,
-                    (j > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < ATT_BN / 16; ++k) {  // O += P_j V_j
+          if constexpr (TS)
+            umma_bf16_ts(tmem_o, tmem_base + (j & 1) * ATT_BN + k * 8, make_smem_desc(av + k * 2048, 8192, 1024), idesc_o,
+                         (j > 0 || k > 0) ? 1u : 0u);
+          else
+            umma_bf16(tmem_o, make_smem_desc(apj + k * 32, 16, 1024), make_smem_desc(av + k * 2048, 8192, 1024), idesc_o,
+                      (j > 0 || k > 0) ? 1u : 0u);
+        }
         umma_commit(&pv_done[j & 1]);
         umma_commit(&kv_empty[slot]);
         if (j + 2 < n_kv) issue_s(j + 2);
@@ -224,6 +246,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
     float m_run = -INFINITY, l_run = 0.f;
     const float2 scale2 = make_float2(p.scale_log2, p.scale_log2);
+    if constexpr (TS) {  // this thread's query row: shared memory (128B-swizzled, as TMA wrote it) -> 32 TMEM columns
+      mbar_wait(q_full, 0);
+      uint32_t qw[32];
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        const uint4 t = *reinterpret_cast<const uint4*>(s_q + row * 128 + ((ch ^ (row & 7)) << 4));
+        qw[4 * ch] = t.x; qw[4 * ch + 1] = t.y; qw[4 * ch + 2] = t.z; qw[4 * ch + 3] = t.w;
+      }
+      tmem_st_x32(tmem_q + lane_sel, qw);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(q_ready);
+    }
 
     for (int j = 0; j < n_kv; ++j) {
       const int ms = j % ATT_MSLOTS;
@@ -312,13 +347,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
       }
 
-      // P = exp2(s2 - m_run) -> bf16, K-major 128B-swizzled A operand in shared memory buffer j&1
-      if (j >= 2) mbar_wait(&pv_done[j & 1], ((j - 2) >> 1) & 1);  // P V_{j-2} has finished reading this buffer
+      // P = exp2(s2 - m_run) -> bf16: the A operand of the PV product.  TS: written over the first 32 columns of S_j in
+      // tensor memory (every logit of this row is already in registers; S_{j+2}, which reuses the buffer, is issued behind
+      // P_j V_j).  Otherwise: K-major 128B-swizzled rows of shared-memory buffer j&1.
+      if constexpr (!TS) {
+        if (j >= 2) mbar_wait(&pv_done[j & 1], ((j - 2) >> 1) & 1);  // P V_{j-2} has finished reading this buffer
+      }
       const float2 nm2 = make_float2(-m_run, -m_run);
       float2 l2[4];  // four independent partial row sums (same reason as the maxima)
 #pragma unroll
       for (int u = 0; u < 4; ++u) l2[u] = make_float2(0.f, 0.f);
       uint8_t* prow = s_p + (j & 1) * ATT_P_BYTES + row * 128;
+      uint32_t pw[TS ? 32 : 1];
 #pragma unroll
       for (int ch = 0; ch < ATT_BN / 8; ++ch) {  // 8 chunks of 8 keys = 16 bytes
         uint32_t w[4];
@@ -335,7 +375,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           }
           w[u] = pack_bf16(e.x, e.y);
         }
-        *reinterpret_cast<uint4*>(prow + ((ch ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        if constexpr (TS) {
+          pw[4 * ch] = w[0]; pw[4 * ch + 1] = w[1]; pw[4 * ch + 2] = w[2]; pw[4 * ch + 3] = w[3];
+        } else {
+          *reinterpret_cast<uint4*>(prow + ((ch ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+      if constexpr (TS) {
+        tmem_st_x32(ts, pw);
+        tmem_st_wait();
       }
       const float2 lsum = __fadd2_rn(__fadd2_rn(l2[0], l2[1]), __fadd2_rn(l2[2], l2[3]));
       l_run += lsum.x + lsum.y;
@@ -345,8 +393,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       // MUFU / tcgen05.ld traffic: rows then saw the bias of the tile three ahead (-inf past T) -- wrong, and different
       // from run to run.  Found by the full-size reproducibility test; invisible at small batch.
       mbar_arrive(&meta_empty[ms]);
-      fence_proxy_async_smem();  // P visible to the tensor core (async proxy)
-      tc_fence_before();         // our TMEM reads of S_j / writes of O are ordered before the MMAs that follow
+      if constexpr (!TS) fence_proxy_async_smem();  // P visible to the tensor core (async proxy)
+      tc_fence_before();         // our TMEM reads of S_j / writes of O (and P_j) are ordered before the MMAs that follow
       mbar_arrive(&p_ready[j & 1]);
     }
     // O is final once the last P V retires
@@ -528,6 +576,11 @@ int check_attn_desc(const tome_attn_desc_t* d, const char* who) {
 }
 }  // namespace tome
 
+// 1 (default): A operands (Q, P) in tensor memory; 0: both operands of both products in shared memory (round-1 kernel, kept
+// as the A/B cross-check).  Process-wide tuning aid, not part of the public header.
+static int g_attn_fwd_ts = 1;
+extern "C" void tome_attention_set_fwd_ts(int on) { g_attn_fwd_ts = on ? 1 : 0; }
+
 static size_t fwd_ws_bytes(const tome_attn_desc_t* d) {
   const size_t meta = (attn_meta_bytes(d->batch, d->tokens) + 255) & ~size_t(255);
   return meta + (d->dropout_rate > 0.f ? attn_dropbits_bytes(d->tokens) : 0);
@@ -585,12 +638,21 @@ extern "C" int tome_attention_fwd(const tome_attn_desc_t* d, const void* q, cons
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.o_batch_stride = d->o_batch_stride; p.o_token_stride = d->o_token_stride;
   p.lse = lse;
-  static DynSmemOnce once0, once1;
-  TOME_CUDA(ensure_dyn_smem(attn_fwd_kernel<false>, ATT_SMEM, once0));
-  TOME_CUDA(ensure_dyn_smem(attn_fwd_kernel<true>, ATT_SMEM, once1));
   dim3 grid(ceil_div(d->tokens, ATT_BM), d->heads, d->batch);
-  if (p.keep_q) attn_fwd_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tq, tk, tv, tqa, tka, p);
-  else attn_fwd_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tq, tk, tv, tqa, tka, p);
+#define TOME_ATT_LAUNCH(DROP_, TS_)                                                                          \
+  do {                                                                                                       \
+    static DynSmemOnce once;                                                                                 \
+    TOME_CUDA(ensure_dyn_smem(attn_fwd_kernel<DROP_, TS_>, att_smem<TS_>(), once));                          \
+    attn_fwd_kernel<DROP_, TS_><<<grid, ATT_THREADS, att_smem<TS_>(), stream>>>(tq, tk, tv, tqa, tka, p);    \
+  } while (0)
+  if (g_attn_fwd_ts) {
+    if (p.keep_q) TOME_ATT_LAUNCH(true, true);
+    else TOME_ATT_LAUNCH(false, true);
+  } else {
+    if (p.keep_q) TOME_ATT_LAUNCH(true, false);
+    else TOME_ATT_LAUNCH(false, false);
+  }
+#undef TOME_ATT_LAUNCH
   TOME_CUDA(cudaGetLastError());
   return TOME_OK;
 }

@@ -107,6 +107,19 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same with the A operand read from TENSOR MEMORY (K-major, lane = row, one 32-bit column = two consecutive bf16 of K, so a
+// K = 16 step is 8 columns): the operand costs no shared-memory bandwidth.  128 x N x 16 with both operands in shared
+// memory reads (128 + N) * 32 B per step, which at N = 64 is more than the 128 B/clk the SM's shared memory delivers in
+// the 32 cycles the step takes on the tensor pipe.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // mbarrier arrives once every previously issued UMMA of this thread has completed (implies fence::before).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
