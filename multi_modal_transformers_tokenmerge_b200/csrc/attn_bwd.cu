@@ -36,7 +36,8 @@ struct AttnBwdParams {
   const uint8_t* gid;   // null: no mask
   const int32_t* pos;
   const uint8_t* meta;  // [B][tp/64][ATTN_META_BYTES]
-  int store_ds;         // dK/dV kernel: also TMA-store every dS^T tile (the dQ GEMM kernel consumes them)
+  int store_ds;         // dK/dV kernel: also store every dS^T tile (the dQ GEMM kernel consumes them)
+
   const float* size;
   const float* lse2;    // [B,H,tp]  lse * log2(e), +inf past T
   const float* delta;   // [B,H,tp]  0 past T
@@ -354,6 +355,316 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   }
 }
 
+// ------------------------------------------------------------------------------------------------ dK / dV, P^T and dS^T in tensor memory
+// Same tiling and arithmetic as attn_bwd_dkdv_kernel, but the two products that consume what the softmax threads produce
+// take their A operand from TENSOR MEMORY (tcgen05.mma with [tmem] A): once a thread has read its row of dP^T_i, it
+// writes dS^T_i (two bf16 per column) over columns [64, 96) and P^T_i over [96, 128) of that very accumulator, and
+// dV += P^T dO / dK += dS^T Q read them from there.  Nothing the threads produce passes through shared memory any more:
+// per 128 x 64 tile the shared-memory traffic falls from 160 KB (four SS products 96 KB, P^T / dS^T staging 32 KB, TMA in
+// 16 KB, TMA store read 16 KB) to 80 KB, and with two CTAs per SM that traffic -- 2 x 1280 cycles of the SM's 128 B/clk
+// against ~5000 measured per tile pair -- was the largest single term of the kernel.  dS^T for the dQ GEMM is written to
+// global memory straight from the registers (a thread owns one 128-byte line per tile).
+// S^T lives in columns [0, 64) and is free again as soon as every thread has read it (s_free), so S^T_{i+1} is computed
+// while the threads are still busy with dP^T_i; the order on the tensor pipe is S^T_{i+1}, dV_i, dK_i, dP^T_{i+1}.
+constexpr int DKT_SMEM = 2 * DKV_KV_BYTES + 2 * 2 * DKV_Q_BYTES + DKV_PT_BYTES + AB_MSLOTS * DKV_META_SLOT + 256 + 1024;
+
+template <bool DROP>
+__global__ void __launch_bounds__(AB_THREADS, 2)
+attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                        const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
+                        const __grid_constant__ CUtensorMap tm_ds, const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* s_k = smem;
+  uint8_t* s_v = s_k + DKV_KV_BYTES;
+  uint8_t* s_qdo = s_v + DKV_KV_BYTES;            // stage s: Q at s*16K, dO at s*16K + 8K
+  uint8_t* s_dst = s_qdo + 2 * 2 * DKV_Q_BYTES;   // dS^T [128 keys][64 queries] bf16, 128B-swizzled rows: staging of the TMA store
+  uint8_t* s_meta = s_dst + DKV_PT_BYTES;         // slot i at i * DKV_META_SLOT
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_meta + AB_MSLOTS * DKV_META_SLOT);
+  uint64_t* kv_full = bars;        // 1
+  uint64_t* q_full = bars + 1;     // [2]
+  uint64_t* q_empty = bars + 3;    // [2]
+  uint64_t* s_full = bars + 5;     // S^T_i in TMEM
+  uint64_t* dp_full = bars + 6;    // dP^T_i in TMEM
+  uint64_t* s_free = bars + 7;     // every thread has read its row of S^T_i (128 arrivals)
+  uint64_t* ps_ready = bars + 8;   // P^T_i, dS^T_i written over dP^T_i (128 arrivals)
+  uint64_t* pd_free = bars + 9;    // dV/dK MMAs of a tile retired (accumulators final after the last one)
+  uint64_t* meta_full = bars + 10;   // [3]
+  uint64_t* meta_empty = bars + 13;  // [3]  128 arrivals
+  uint64_t* ds_stored = bars + 16;   // store_ds: the TMA store of dS^T_i has read the tile out of shared memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int T = p.tokens;
+  const int n_q = (T + DKV_BQ - 1) / DKV_BQ;
+  const bool has_mask = p.gid != nullptr;
+
+  if (threadIdx.x == 0) {
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(dp_full, 1);
+    mbar_init(s_free, DKV_BK);
+    mbar_init(ps_ready, DKV_BK);
+    mbar_init(pd_free, 1);
+    mbar_init(ds_stored, 1);
+    for (int i = 0; i < AB_MSLOTS; ++i) {
+      mbar_init(&meta_full[i], 1);
+      mbar_init(&meta_empty[i], DKV_BK);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+    tma_prefetch_desc(&tm_do);
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, AB_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_st = tmem_base, tm_dpt = tmem_base + 64, tm_dk = tmem_base + 128, tm_dv = tmem_base + 192;
+  const uint32_t tm_dsa = tm_dpt, tm_pa = tm_dpt + 32;   // A operands: dS^T over dP^T[0,32), P^T over dP^T[32,64)
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, 2 * DKV_KV_BYTES);
+      tma_load_3d(s_k, &tm_k, kv_full, h * AB_D, kt * DKV_BK, b);
+      tma_load_3d(s_v, &tm_v, kv_full, h * AB_D, kt * DKV_BK, b);
+      const float* lse_row = p.lse2 + ((size_t)b * p.heads + h) * p.tp;
+      const float* del_row = p.delta + ((size_t)b * p.heads + h) * p.tp;
+      const uint8_t* meta_b = p.meta + (size_t)b * n_q * ATTN_META_BYTES;
+      for (int i = 0; i < n_q; ++i) {
+        const int ms = i % AB_MSLOTS;
+        uint8_t* slot = s_meta + ms * DKV_META_SLOT;
+        mbar_wait(&meta_empty[ms], ((i / AB_MSLOTS) & 1) ^ 1);
+        mbar_expect_tx(&meta_full[ms], (has_mask ? 1280u : 512u) + (DROP ? ATTN_DROP_TILE_BYTES : 0));
+        if constexpr (DROP) bulk_g2s(slot + 1280, p.keep_k + ((size_t)kt * n_q + i) * ATTN_DROP_TILE_BYTES, ATTN_DROP_TILE_BYTES, &meta_full[ms]);
+        bulk_g2s(slot, lse_row + i * DKV_BQ, 256, &meta_full[ms]);
+        bulk_g2s(slot + 256, del_row + i * DKV_BQ, 256, &meta_full[ms]);
+        if (has_mask) bulk_g2s(slot + 512, meta_b + (size_t)i * ATTN_META_BYTES + ATTN_META_OFF_POS, 768, &meta_full[ms]);  // pos | qvis | qvisc
+        const int st = i & 1;
+        mbar_wait(&q_empty[st], ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(&q_full[st], 2 * DKV_Q_BYTES);
+        tma_load_3d(s_qdo + st * 2 * DKV_Q_BYTES, &tm_q, &q_full[st], h * AB_D, i * DKV_BQ, b);
+        tma_load_3d(s_qdo + st * 2 * DKV_Q_BYTES + DKV_Q_BYTES, &tm_do, &q_full[st], h * AB_D, i * DKV_BQ, b);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(DKV_BK, DKV_BQ, false, false);  // K/V K-major, Q/dO K-major
+      constexpr uint32_t idesc_g = make_idesc_bf16(DKV_BK, AB_D, false, true);     // P^T/dS^T from TMEM (K-major), dO/Q MN-major
+      const uint32_t ak = smem_u32(s_k), av = smem_u32(s_v);
+      mbar_wait(kv_full, 0);
+      for (int i = 0; i <= n_q; ++i) {
+        if (i < n_q) {
+          const int st = i & 1;
+          if (i >= 1) {
+            mbar_wait(s_free, (i - 1) & 1);   // S^T_{i-1} has been read by every thread
+            tc_fence_after();
+          }
+          mbar_wait(&q_full[st], (i >> 1) & 1);
+          tc_fence_after();
+          const uint32_t aq = smem_u32(s_qdo + st * 2 * DKV_Q_BYTES);
+#pragma unroll
+          for (int k = 0; k < AB_D / 16; ++k)
+            umma_bf16(tm_st, make_smem_desc(ak + k * 32, 16, 1024), make_smem_desc(aq + k * 32, 16, 1024), idesc_s, k > 0);
+          umma_commit(s_full);
+        }
+        if (i >= 1) {
+          mbar_wait(ps_ready, (i - 1) & 1);
+          tc_fence_after();
+          const int st = (i - 1) & 1;
+          const uint32_t aq = smem_u32(s_qdo + st * 2 * DKV_Q_BYTES), ado = aq + DKV_Q_BYTES;
+          if (p.store_ds) {  // dS^T tile (keys kt*128.., queries (i-1)*64..) -> global, in the layout it has in shared memory
+            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                         ::"l"(&tm_ds), "r"(smem_u32(s_dst)), "r"((i - 1) * DKV_BQ), "r"(kt * DKV_BK), "r"(b * p.heads + h) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+#pragma unroll
+          for (int k = 0; k < DKV_BQ / 16; ++k)  // dV += P^T dO
+            umma_bf16_ts(tm_dv, tm_pa + k * 8, make_smem_desc(ado + k * 2048, 8192, 1024), idesc_g, (i > 1 || k > 0) ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < DKV_BQ / 16; ++k)  // dK += dS^T Q
+            umma_bf16_ts(tm_dk, tm_dsa + k * 8, make_smem_desc(aq + k * 2048, 8192, 1024), idesc_g, (i > 1 || k > 0) ? 1u : 0u);
+          umma_commit(pd_free);
+          umma_commit(&q_empty[st]);
+        }
+        if (i < n_q) {  // dP^T_i = V dO_i^T, behind the products that read P^T_{i-1} / dS^T_{i-1} out of the same columns
+          const int st = i & 1;
+          const uint32_t ado = smem_u32(s_qdo + st * 2 * DKV_Q_BYTES) + DKV_Q_BYTES;
+#pragma unroll
+          for (int k = 0; k < AB_D / 16; ++k)
+            umma_bf16(tm_dpt, make_smem_desc(av + k * 32, 16, 1024), make_smem_desc(ado + k * 32, 16, 1024), idesc_s, k > 0);
+          umma_commit(dp_full);
+        }
+        if (i >= 1 && p.store_ds) {  // after the issue work of this round, so nobody waits for the store's shared-memory read
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          mbar_arrive(ds_stored);
+        }
+      }
+      if (p.store_ds) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before the CTA exits
+    }
+  } else {
+    const int row = threadIdx.x;  // key row == TMEM lane
+    const int kk = kt * DKV_BK + row;
+    const uint32_t lane_sel = ((uint32_t)(warp * 32)) << 16;
+    const bool k_valid = kk < T;
+    float bias2 = 0.f;
+    int gk = 0, pk = 0;
+    if (k_valid) {
+      if (p.size) bias2 = log2f(p.size[(long long)b * T + kk]);
+      if (has_mask) {
+        gk = p.gid[(long long)b * T + kk];
+        pk = p.pos[(long long)b * T + kk];
+      }
+    }
+    const float2 scale2 = make_float2(p.scale_log2, p.scale_log2), bias22 = make_float2(bias2, bias2);
+    const float2 sc2 = make_float2(p.scale, p.scale), ik2 = make_float2(p.inv_keep, p.inv_keep);
+    for (int i = 0; i < n_q; ++i) {
+      const int ms = i % AB_MSLOTS;
+      const uint8_t* slot = s_meta + ms * DKV_META_SLOT;
+      mbar_wait(&meta_full[ms], (i / AB_MSLOTS) & 1);
+      uint32_t vw[2] = {0xffffffffu, 0xffffffffu};
+      if (has_mask) {
+        const uint2 a = *reinterpret_cast<const uint2*>(slot + 768 + gk * 8);
+        const uint2 c = *reinterpret_cast<const uint2*>(slot + 1024 + gk * 8);
+        vw[0] = a.x; vw[1] = a.y;
+        if (c.x | c.y) {  // rare (Text sets): fold the causal rule into the visibility words
+          const int* posq = reinterpret_cast<const int*>(slot + 512);
+          for (int q = 0; q < 32; ++q) {
+            if (((c.x >> q) & 1u) && pk <= posq[q]) vw[0] |= 1u << q;
+            if (((c.y >> q) & 1u) && pk <= posq[32 + q]) vw[1] |= 1u << q;
+          }
+        }
+      }
+      if (!k_valid) vw[0] = vw[1] = 0u;  // rows past T contribute nothing (and store zeros into dS^T)
+      uint32_t kb[2] = {0xffffffffu, 0xffffffffu};  // dropout keep bits of this key against the tile's 64 queries
+      if constexpr (DROP) {
+        const uint2 t = *reinterpret_cast<const uint2*>(slot + 1280 + row * 8);
+        kb[0] = t.x; kb[1] = t.y;
+      }
+      const float4* lse4 = reinterpret_cast<const float4*>(slot);
+      const float4* del4 = reinterpret_cast<const float4*>(slot + 256);
+      // ---- phase 1: P = exp2(s2 - lse2) from S^T_i, kept as packed bf16 (what the dV product consumes, before dropout)
+      uint32_t pe[32];
+      mbar_wait(s_full, i & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int cq = 0; cq < DKV_BQ / 32; ++cq) {
+        float sv[32];
+        tmem_ld_f32x32(tm_st + lane_sel + cq * 32, sv);
+        tmem_ld_wait();
+        if (cq == 1) {       // the whole row of S^T_i is in registers: the next S^T may overwrite it
+          tc_fence_before();
+          mbar_arrive(s_free);
+        }
+        const uint32_t word = vw[cq];
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 l4 = lse4[cq * 8 + c4];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int c = c4 * 4 + 2 * u;
+            const float2 lv = u ? make_float2(l4.z, l4.w) : make_float2(l4.x, l4.y);
+            float2 t = __ffma2_rn(make_float2(sv[c], sv[c + 1]), scale2, bias22);
+            t = __fadd2_rn(t, make_float2(-lv.x, -lv.y));
+            float2 e = make_float2(fast_exp2(t.x), fast_exp2(t.y));
+            e.x = ((word >> c) & 1u) ? e.x : 0.f;
+            e.y = ((word >> (c + 1)) & 1u) ? e.y : 0.f;
+            pe[cq * 16 + (c >> 1)] = pack_bf16(e.x, e.y);
+          }
+        }
+      }
+      // ---- phase 2: dS = P (dP' - delta) scale from dP^T_i; the upper half of the row first, so that by the time the
+      // packed results are written over columns [64, 128) both halves of dP^T_i are in registers
+      uint32_t dw[32], pw[DROP ? 32 : 1];
+      mbar_wait(dp_full, i & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int cq = DKV_BQ / 32 - 1; cq >= 0; --cq) {
+        float dv[32];
+        tmem_ld_f32x32(tm_dpt + lane_sel + cq * 32, dv);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 d4 = del4[cq * 8 + c4];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int c = c4 * 4 + 2 * u;
+            const float2 dl = u ? make_float2(d4.z, d4.w) : make_float2(d4.x, d4.y);
+            const uint32_t pwv = pe[cq * 16 + (c >> 1)];
+            const float2 pf = make_float2(bf16_lo(pwv), bf16_hi(pwv));
+            float2 dp = make_float2(dv[c], dv[c + 1]);
+            if constexpr (DROP) {  // weights' = weights keep / (1 - rate): dP' = dP keep / (1 - rate) enters dS, P' enters dV
+              const bool k0 = (kb[cq] >> c) & 1u, k1 = (kb[cq] >> (c + 1)) & 1u;
+              dp = __fmul2_rn(dp, ik2);
+              float2 pd = __fmul2_rn(pf, ik2);
+              dp.x = k0 ? dp.x : 0.f; dp.y = k1 ? dp.y : 0.f;
+              pd.x = k0 ? pd.x : 0.f; pd.y = k1 ? pd.y : 0.f;
+              pw[cq * 16 + (c >> 1)] = pack_bf16(pd.x, pd.y);
+            }
+            float2 g = __fadd2_rn(dp, make_float2(-dl.x, -dl.y));
+            g = __fmul2_rn(g, sc2);
+            g = __fmul2_rn(g, pf);
+            dw[cq * 16 + (c >> 1)] = pack_bf16(g.x, g.y);
+          }
+        }
+      }
+      tmem_st_x32(tm_dsa + lane_sel, dw);
+      if constexpr (DROP) tmem_st_x32(tm_pa + lane_sel, pw);
+      else tmem_st_x32(tm_pa + lane_sel, pe);
+      if (p.store_ds) {  // the dS^T tile the dQ GEMM consumes, staged for one TMA store (a direct 16-byte-per-lane global
+                         // store of these rows cost 330 us per call: 32 partial sectors per instruction)
+        if (i >= 1) mbar_wait(ds_stored, (i - 1) & 1);
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch)
+          *reinterpret_cast<uint4*>(s_dst + row * 128 + ((ch ^ (row & 7)) << 4)) = make_uint4(dw[4 * ch], dw[4 * ch + 1], dw[4 * ch + 2], dw[4 * ch + 3]);
+        fence_proxy_async_smem();
+      }
+      tmem_st_wait();
+      mbar_arrive(&meta_empty[ms]);
+      tc_fence_before();
+      mbar_arrive(ps_ready);
+    }
+    mbar_wait(pd_free, (n_q - 1) & 1);  // accumulators final
+    tc_fence_after();
+    {
+      // tcgen05.ld is warp-collective: rows past T take part in the loads and only skip the stores
+      __nv_bfloat16* dkr = p.dk + (long long)b * p.dk_bs + (long long)(k_valid ? kk : 0) * p.dk_ts + h * AB_D;
+      __nv_bfloat16* dvr = p.dv + (long long)b * p.dv_bs + (long long)(k_valid ? kk : 0) * p.dv_ts + h * AB_D;
+#pragma unroll
+      for (int c0 = 0; c0 < AB_D; c0 += 32) {
+        float a[32], c[32];
+        tmem_ld_f32x32(tm_dk + lane_sel + c0, a);
+        tmem_ld_f32x32(tm_dv + lane_sel + c0, c);
+        tmem_ld_wait();
+        if (k_valid) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            *reinterpret_cast<uint4*>(dkr + c0 + i) = make_uint4(pack_bf16(a[i], a[i + 1]), pack_bf16(a[i + 2], a[i + 3]),
+                                                                 pack_bf16(a[i + 4], a[i + 5]), pack_bf16(a[i + 6], a[i + 7]));
+            *reinterpret_cast<uint4*>(dvr + c0 + i) = make_uint4(pack_bf16(c[i], c[i + 1]), pack_bf16(c[i + 2], c[i + 3]),
+                                                                 pack_bf16(c[i + 4], c[i + 5]), pack_bf16(c[i + 6], c[i + 7]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, AB_TMEM_COLS);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ dQ
 constexpr int DQ_BQ = 128;  // queries per CTA
 constexpr int DQ_BK = 64;   // keys per tile
@@ -494,7 +805,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     }
     const float2 scale2 = make_float2(p.scale_log2, p.scale_log2);
     const float2 nl2 = make_float2(-lse2, -lse2);
-    const float2 sc2 = make_float2(p.scale, p.scale), nds2 = make_float2(-dl * p.scale, -dl * p.scale);
+    const float2 sc2 = make_float2(p.scale, p.scale);
     const float2 ik2 = make_float2(p.inv_keep, p.inv_keep);
     for (int j = 0; j < n_k; ++j) {
       const int ms = j % AB_MSLOTS;
@@ -549,8 +860,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
               dp.x = ((kb[cq] >> c) & 1u) ? dp.x : 0.f;
               dp.y = ((kb[cq] >> (c + 1)) & 1u) ? dp.y : 0.f;
             }
-            float2 g = __ffma2_rn(dp, sc2, nds2);  // (dP' - delta) * scale
-            g = __fmul2_rn(g, pe);
+            // the dK/dV kernel forms dS from the bf16-rounded P it feeds to the dV product (and so does the forward's P V):
+            // the same rounding and the same operation order here keep the two dQ paths bit-identical
+            const uint32_t pr = pack_bf16(pe.x, pe.y);
+            float2 g = __fadd2_rn(dp, make_float2(-dl, -dl));
+            g = __fmul2_rn(g, sc2);
+            g = __fmul2_rn(g, make_float2(bf16_lo(pr), bf16_hi(pr)));
             dw[c >> 1] = pack_bf16(g.x, g.y);
           }
         }
@@ -714,6 +1029,10 @@ static inline bool dq_from_ds(const tome_attn_desc_t* d) {
   return g_attn_dq_from_ds < 0 ? ds_buffer_bytes(d) <= ((size_t)8 << 30) : g_attn_dq_from_ds != 0;
 }
 
+// 1 (default): the dK/dV kernel keeps P^T / dS^T in tensor memory (attn_bwd_dkdv_ts_kernel); 0: the shared-memory version.
+static int g_attn_bwd_ts = 1;
+extern "C" void tome_attention_set_bwd_ts(int on) { g_attn_bwd_ts = on ? 1 : 0; }
+
 extern "C" void tome_attention_set_dq_from_ds(int mode) { g_attn_dq_from_ds = mode < 0 ? -1 : (mode ? 1 : 0); }
 
 extern "C" size_t tome_attention_bwd_workspace_bytes(const tome_attn_desc_t* d) {
@@ -776,12 +1095,14 @@ extern "C" int tome_attention_bwd(const tome_attn_desc_t* d, const tome_attn_gra
   p.keep_q = keep_q; p.keep_k = keep_k; p.inv_keep = inv_keep;
   const bool from_ds = dq_from_ds(d);
   p.store_ds = from_ds ? 1 : 0;
+
   // dS^T [B*H][ceil128(T) keys][ceil64(T) queries] bf16, after the (possibly absent) dropout bit tilings
   uint8_t* ds_buf = reinterpret_cast<uint8_t*>(lse2) + align256(bwd_pad_elems(d) * sizeof(float)) +
                     align256(d->dropout_rate > 0.f ? attn_dropbits_bytes(T) : 0);
   const uint64_t ds_tq = ((uint64_t)T + 63) / 64 * 64, ds_tk = ((uint64_t)T + 127) / 128 * 128;
   CUtensorMap tds_store, tds_load;
   if (from_ds) {
+
     if (int rc = make_tmap_3d_bf16(&tds_store, ds_buf, ds_tq, ds_tk, (uint64_t)B * H, ds_tq, ds_tq * ds_tk, DKV_BK)) return rc;
     if (int rc = make_tmap_3d_bf16(&tds_load, ds_buf, ds_tq, ds_tk, (uint64_t)B * H, ds_tq, ds_tq * ds_tk, DQG_BK)) return rc;
   } else {
@@ -796,6 +1117,9 @@ extern "C" int tome_attention_bwd(const tome_attn_desc_t* d, const tome_attn_gra
   TOME_CUDA(ensure_dyn_smem(attn_bwd_dq_kernel<false>, DQ_SMEM, once[2]));
   TOME_CUDA(ensure_dyn_smem(attn_bwd_dq_kernel<true>, DQ_SMEM, once[3]));
   TOME_CUDA(ensure_dyn_smem(attn_bwd_dq_gemm_kernel, DQG_SMEM, once[4]));
+  static DynSmemOnce once_ts[2];
+  TOME_CUDA(ensure_dyn_smem(attn_bwd_dkdv_ts_kernel<false>, DKT_SMEM, once_ts[0]));
+  TOME_CUDA(ensure_dyn_smem(attn_bwd_dkdv_ts_kernel<true>, DKT_SMEM, once_ts[1]));
   {
     CUtensorMap tq, tk, tv, tdo;
     if (int rc = make_tmap_3d_bf16(&tq, q, hd, T, B, d->q_token_stride, d->q_batch_stride, DKV_BQ)) return rc;
@@ -803,7 +1127,10 @@ extern "C" int tome_attention_bwd(const tome_attn_desc_t* d, const tome_attn_gra
     if (int rc = make_tmap_3d_bf16(&tv, v, hd, T, B, d->v_token_stride, d->v_batch_stride, DKV_BK)) return rc;
     if (int rc = make_tmap_3d_bf16(&tdo, dout, hd, T, B, gs->do_token_stride, gs->do_batch_stride, DKV_BQ)) return rc;
     dim3 grid(ceil_div(T, DKV_BK), H, B);
-    if (keep_k) attn_bwd_dkdv_kernel<true><<<grid, AB_THREADS, DKV_SMEM, stream>>>(tq, tk, tv, tdo, tds_store, p);
+    if (g_attn_bwd_ts) {
+      if (keep_k) attn_bwd_dkdv_ts_kernel<true><<<grid, AB_THREADS, DKT_SMEM, stream>>>(tq, tk, tv, tdo, tds_store, p);
+      else attn_bwd_dkdv_ts_kernel<false><<<grid, AB_THREADS, DKT_SMEM, stream>>>(tq, tk, tv, tdo, tds_store, p);
+    } else if (keep_k) attn_bwd_dkdv_kernel<true><<<grid, AB_THREADS, DKV_SMEM, stream>>>(tq, tk, tv, tdo, tds_store, p);
     else attn_bwd_dkdv_kernel<false><<<grid, AB_THREADS, DKV_SMEM, stream>>>(tq, tk, tv, tdo, tds_store, p);
     TOME_CUDA(cudaGetLastError());
   }

@@ -408,7 +408,7 @@ def _round_st(t, dtype):
 
 def tome_block(p: BlockParams, x, size, gid, pos, allow, *, num_heads, r, ln_axis="seq", prop_attn=True,
                class_token=False, distill_token=False, scores_override=None, node_override=None,
-               trace: Optional[list] = None, act_dtype=None, relu_gate=None):
+               trace: Optional[list] = None, act_dtype=None, relu_gate=None, taps: Optional[dict] = None):
     """ToMeEncoder1DBlock with the ToMe-paper placement (reference shell attention.py:52-69):
 
         x = x + attn(LN(x), mask(groups), bias = log size)       # dropout 0 (parity mode)
@@ -429,6 +429,10 @@ def tome_block(p: BlockParams, x, size, gid, pos, allow, *, num_heads, r, ln_axi
     bias = torch.log(size[:, None, None, :, 0]) if prop_attn else None
     o = rd(attention(q, k, v, mask=mask, bias=bias).reshape(B, T, -1))
     x = rd(x + (o @ p.wo + p.bo))
+    if taps is not None:   # checker hook: the post-attention residual stream (its gradient is dL/dx1, whose column sum is d bo)
+        if x.requires_grad:
+            x.retain_grad()
+        taps["x1"] = x
     # --- ToMe (intended call site tome_attention.py:249-256): metric = keys reduced over heads
     metric = k.detach().mean(dim=2).to(torch.float32).numpy()
     plan = bipartite_soft_matching(metric, r, class_token, distill_token, scores_override=scores_override,

@@ -48,9 +48,8 @@ def main():
             out, lse = ops.attention_fwd(q, k, v, **kw, **drop)
             do = torch.randn_like(out)
             ref = None
-            for ts in ((0, 1) if hasattr(lib, "tome_attention_set_bwd_ts") else (0,)):
-                if hasattr(lib, "tome_attention_set_bwd_ts"):
-                    lib.tome_attention_set_bwd_ts(ts)
+            for ts in (0, 1):
+                lib.tome_attention_set_bwd_ts(ts)
                 t0 = timeit(lambda: ops.attention_bwd(q, k, v, out, lse, do, **kw), iters=5)
                 t1 = timeit(lambda: ops.attention_bwd(q, k, v, out, lse, do, **kw, **drop), iters=5)
                 g = ops.attention_bwd(q, k, v, out, lse, do, **kw, **drop)

@@ -777,8 +777,8 @@ def test_gemm_relu_gate_bits(ops, m, n, k, rate):
 @pytest.mark.parametrize("T,rate", [(536, 0.0), (300, 0.1), (74, 0.0)])
 def test_attention_bwd_dq_paths_agree(ops, T, rate):
     """dQ as a batched GEMM over the dS^T tiles stored by the dK/dV kernel (the default up to 3 072 tokens) against the
-    recomputing dQ kernel: same bf16 dS, same accumulation order, so dq must agree bit for bit; dk / dv come from the same
-    kernel in both modes."""
+    recomputing dQ kernel: same bf16 dS (both form it from the bf16-rounded P, in the same operation order), same accumulation
+    order, so dq must agree bit for bit; dk / dv come from the same kernel in both modes."""
     import ctypes
     from multi_modal_transformers_tokenmerge_b200 import _lib as L
     setter = L.lib().tome_attention_set_dq_from_ds
