@@ -24,11 +24,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SEQ = "[TaskDescriptionPrefix{16}] [Image{256};Readout{4}]*2"   # T0 = 536 (form of octo_base.yaml:10)
+SEQ_C3 = "[TaskDescriptionPrefix{16}] [Image{256};Image{256};Readout{4}]*4"   # T0 = 2080: wrist + primary camera, 4-frame history
 CONFIGS = {
     # BASELINE.json configs[1]: octo-small train step bf16, batch 256 / GPU, r = 16
-    "octo_small": dict(channels=384, heads=6, head_dim=64, mlp_dim=1536, layers=12, r=16, batch=256),
+    "octo_small": dict(channels=384, heads=6, head_dim=64, mlp_dim=1536, layers=12, r=16, batch=256, seq=SEQ, baseline_cfg=1),
     # BASELINE.json configs[2] per-GPU shard: octo-base, 256 / GPU (2048 on 8 GPUs), r = 32
-    "octo_base": dict(channels=768, heads=12, head_dim=64, mlp_dim=3072, layers=12, r=32, batch=256),
+    "octo_base": dict(channels=768, heads=12, head_dim=64, mlp_dim=3072, layers=12, r=32, batch=256, seq=SEQ, baseline_cfg=2),
+    # BASELINE.json configs[3]: octo-base with wrist + primary cameras (2x image tokens), 4-frame history; sweep with --r 0..64
+    "c3": dict(channels=768, heads=12, head_dim=64, mlp_dim=3072, layers=12, r=32, batch=32, seq=SEQ_C3, baseline_cfg=3),
 }
 METRIC = "ToMe-transformer train samples/sec"
 
@@ -94,16 +97,19 @@ class ClockSampler:
 ACTION_DIM, MAX_ACTION = 8, 1.0   # action_heads/diffusion.yaml dense_out features: 8; continuous.py:13 max_action
 
 
-def cpu_reference_steps(cfgname, steps, warmup, sample_batch, loss_kind="continuous"):
+def cpu_reference_steps(cfgname, steps, warmup, sample_batch, loss_kind="continuous", r=None, dropout=0.0, attn_dropout=0.0):
     """The reference's algorithm for this path, restated (oracle/tome_oracle.py: sequential scatter loop, double merge
-    call, dense [B,H,T,T] mask, fp32) as a torch-CPU train step with autograd + SGD, all host threads.  JAX/Flax are
-    not installable here (no wheels, no network), so this is the port ("kind": "port"), not the JAX program."""
+    call, dense [B,H,T,T] mask, fp32) as a torch-CPU train step with autograd + AdamW and the same dropout sites, all host
+    threads.  JAX/Flax are not installable here (no wheels, no network), so this is the port ("kind": "port"), not the
+    JAX program."""
     import numpy as np
     import torch
     from oracle import tome_oracle as O
 
-    c = CONFIGS[cfgname]
-    gid, pos, allow, ro = O.sequence_groups(SEQ)
+    c = dict(CONFIGS[cfgname])
+    if r is not None:
+        c["r"] = r
+    gid, pos, allow, ro = O.sequence_groups(c["seq"])
     T0 = gid.shape[0]
     rng = np.random.default_rng(1)
     params = [O.block_params_to_torch(O.init_block_params(rng, c["channels"], c["heads"], c["head_dim"], c["mlp_dim"]),
@@ -118,12 +124,13 @@ def cpu_reference_steps(cfgname, steps, warmup, sample_batch, loss_kind="continu
         hb = torch.zeros(ACTION_DIM, requires_grad=True)
         actions = torch.tensor(np.random.default_rng(3).uniform(-1, 1, (sample_batch, ACTION_DIM)).astype(np.float32))
         leaves += [hk, hb]
-    opt = torch.optim.SGD(leaves, lr=1e-4)
+    opt = torch.optim.AdamW(leaves, lr=1e-4, weight_decay=0.0)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         opt.zero_grad(set_to_none=True)
-        xf, size, origin = O.tome_stack(params, pe, x, gid, pos, allow, num_heads=c["heads"], r=c["r"])
+        xf, size, origin = O.tome_stack(params, pe, x, gid, pos, allow, num_heads=c["heads"], r=c["r"], dropout_rate=dropout,
+                                        attn_dropout_rate=attn_dropout)
         loss, readouts = O.readout_loss(xf, origin, ro, y)
         if loss_kind == "continuous":
             loss = O.l2_loss(O.continuous_action_head(readouts, hk, hb, MAX_ACTION), actions).mean()
@@ -134,10 +141,22 @@ def cpu_reference_steps(cfgname, steps, warmup, sample_batch, loss_kind="continu
     return sample_batch * len(times) / sum(times), sum(times) / len(times), torch.get_num_threads(), T0
 
 
+def cfg_of(args):
+    c = dict(CONFIGS[args.config])
+    if getattr(args, "r", None) is not None:
+        c["r"] = args.r
+    if getattr(args, "batch", 0):
+        c["batch"] = args.batch
+    return c
+
+
+REF_SAMPLE_BATCH = 8   # the reference's own CPU-runnable case is batch 8
+
+
 def workload_config(args, world, B, T0):
     """The `config` object both arms print: the workload is the same, only the implementation differs."""
-    c = CONFIGS[args.config]
-    return {"workload": f"{args.config} ToMe stack train step (BASELINE.json configs[{1 if args.config == 'octo_small' else 2}] shape)",
+    c = cfg_of(args)
+    return {"workload": f"{args.config} ToMe stack train step (BASELINE.json configs[{c['baseline_cfg']}] shape)",
             "global_batch": B * world, "per_gpu_batch": B, "tokens": T0, "layers": c["layers"], "channels": c["channels"],
             "heads": c["heads"], "mlp_dim": c["mlp_dim"], "r_per_layer": c["r"], "mask": "block-causal group table",
             "ln_axis": "tokens",
@@ -150,70 +169,148 @@ def workload_config(args, world, B, T0):
 def run_reference(args, rank):
     if rank != 0:
         return
-    sb = 2 if (args.steps + args.warmup) <= 12 else 1
-    sps, sec, cores, T0 = cpu_reference_steps(args.config, args.steps, args.warmup, sb, args.loss)
-    c = CONFIGS[args.config]
-    sample = f"{sb} samples/step of the {args.config} workload (T0={T0}, {c['layers']} layers, r={c['r']}), fp32, train step"
+    sb = REF_SAMPLE_BATCH   # the same bounded sample whatever --steps / --warmup say
+    c = cfg_of(args)
+    sps, sec, cores, T0 = cpu_reference_steps(args.config, args.steps, args.warmup, sb, args.loss, r=c["r"], dropout=args.dropout,
+                                              attn_dropout=args.attn_dropout)
+    sample = (f"{sb} samples/step of the {args.config} workload (T0={T0}, {c['layers']} layers, r={c['r']}), fp32, train step "
+              f"(forward, loss, backward, AdamW; hidden dropout {args.dropout}, attention dropout {args.attn_dropout})")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": dict(workload_config(args, int(os.environ.get("WORLD_SIZE", "1")), c["batch"], T0),
                        reference_note=f"restated reference on the host CPU: each step is a bounded sample of {sb} of the "
-                                      f"{c['batch']} samples, plain SGD, no dropout"),
+                                      f"{c['batch']} samples per GPU, same loss, AdamW and dropout sites as the GPU arm"),
         "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-# ------------------------------------------------------------------------------------------------ this repo's arm
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="tome_b200", choices=["tome_b200", "reference"])
-    ap.add_argument("--config", default="octo_small", choices=list(CONFIGS))
-    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override (default: the config's 256)")
-    ap.add_argument("--dropout", type=float, default=0.1, help="hidden dropout rate (vanilla_decoder.yaml:17,50)")
-    ap.add_argument("--attn-dropout", type=float, default=0.1, help="attention-weight dropout rate (vanilla_decoder.yaml:23)")
-    ap.add_argument("--loss", default="continuous", choices=["continuous", "synthetic"],
-                    help="continuous: ContinuousActionHead + l2 loss on the pooled readouts, the reference's "
-                         "continuous_train_step; synthetic: MSE on the readout rows")
-    ap.add_argument("--comm-sms", type=int, default=0,
-                    help="N > 1: SMs reserved for the NCCL all-reduce kernels during backward (NCCL max_ctas = this, the "
-                         "persistent GEMM grid shrinks by this); 0 = NCCL's default and the full grid")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "tome_b200" else args.warmup
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        return run_reference(args, rank)
+def tracked_traffic():
+    """DRAM read + write per launch of the two roofline kernels, from the tracked summary of this round's ncu --set full
+    captures (profiles/roofline_traffic.json: written by scripts/ncu_summaries.py traffic, never typed in by hand)."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
 
+
+# ------------------------------------------------------------------------------------------------ configs[4]: block microbench
+def microbench(args):
+    """BASELINE.json configs[4]: the kernels of one ToMe block, standalone, at 1k - 8k tokens and d = 768 / 1024, with a merge
+    ratio sweep, each against the roofline that bounds it.  Every kernel is timed ALONE (CUDA events, L2 flushed by writing
+    256 MB between launches, 3 warm-up + 5 timed launches), so the denominators are the burst peaks of MEASURED_PEAKS.json.
+    B is chosen so that B * T = 32 768 tokens.  Algorithmic work per launch: attention 4 T^2 D / 10 T^2 D flop per (b, h);
+    sim 2 Ta Tb D flop per sample; GEMM 2 M N K; merge / LayerNorm bytes as in DESIGN.md section 4."""
     import numpy as np
+    import torch
+
+    from multi_modal_transformers_tokenmerge_b200 import ops
+    from multi_modal_transformers_tokenmerge_b200.tokenizers.token_sequencer import sequence_groups
+
+    P = peaks()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def timeit(fn, iters=5, warmup=3):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        tot = 0.0
+        for _ in range(iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / iters * 1e-3
+
+    rows = []
+
+    def add(kernel, T, C, r, sec, flops=None, nbytes=None):
+        row = {"kernel": kernel, "tokens": T, "channels": C, "r": r, "us": sec * 1e6}
+        if flops is not None:
+            row.update(bound="tensor", achieved_tflops=flops / sec / 1e12, frac=flops / sec / 1e12 / P["tf_burst"])
+        else:
+            row.update(bound="hbm", achieved_gbs=nbytes / sec / 1e9, frac=nbytes / sec / 1e9 / P["hbm"])
+        rows.append(row)
+
+    rng = np.random.default_rng(0)
+    for T in (1024, 2048, 4096, 8192):
+        for C in (768, 1024):
+            B, H, D = 32768 // T, C // 64, 64
+            M = B * T
+            x = torch.randn(B, T, C, device="cuda").bfloat16()
+            qkv = torch.randn(B, T, 3, H, D, device="cuda").bfloat16()
+            q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+            n_img = (T - 16) // 2 - 4
+            g1, p1, allow, _ = sequence_groups(f"[TaskDescriptionPrefix{{16}}] [Image{{{n_img}}};Readout{{4}}]*2")
+            gid = torch.tensor(np.stack([rng.permutation(g1) for _ in range(B)])).cuda()   # scrambled, as after a merge
+            pos = torch.tensor(np.broadcast_to(p1, (B, T)).copy()).cuda()
+            kw = dict(gid=gid, pos=pos, allow=torch.tensor(allow).cuda(), size=torch.randint(1, 4, (B, T), device="cuda").float())
+            # --- attention (masked, proportional bias)
+            fl = 4.0 * B * H * T * T * D
+            add("attn_fwd", T, C, None, timeit(lambda: ops.attention_fwd(q, k, v, **kw)), flops=fl)
+            out, lse = ops.attention_fwd(q, k, v, **kw)
+            do = torch.randn_like(out)
+            add("attn_bwd", T, C, None, timeit(lambda: ops.attention_bwd(q, k, v, out, lse, do, **kw)), flops=2.5 * fl)
+            # --- dense layers of the block (forward shapes)
+            for name, n_, k_ in (("gemm_qkv", 3 * C, C), ("gemm_mlp1", 4 * C, C), ("gemm_mlp2", C, 4 * C)):
+                a = torch.randn(M, k_, device="cuda").bfloat16()
+                w = torch.randn(k_, n_, device="cuda").bfloat16()
+                o_ = torch.empty(M, n_, device="cuda", dtype=torch.bfloat16)
+                add(name, T, C, None, timeit(lambda: ops.gemm(a, w, m=M, n=n_, k=k_, b_major=1, out=o_)), flops=2.0 * M * n_ * k_)
+                del a, w, o_
+            # --- LayerNorm over tokens
+            gm, bt = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
+            add("ln_fwd", T, C, None, timeit(lambda: ops.layernorm_fwd(x, gm, bt, 1e-6, 1)), nbytes=2.0 * M * C * 2)
+            y_, mean, rstd = ops.layernorm_fwd(x, gm, bt, 1e-6, 1)
+            dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+            add("ln_bwd", T, C, None, timeit(lambda: ops.layernorm_bwd(x, y_, gm, mean, rstd, dg, db, None, 1)), nbytes=3.0 * M * C * 2)
+            # --- matching + merge, ratio sweep
+            ta, tb = (T + 1) // 2, T // 2
+            kwm = dict(heads=H, dim=D, batch=B, tokens=T, batch_stride=T * 3 * H * D, token_stride=3 * H * D, head_stride=D,
+                       offset_elems=H * D)   # the keys, read in place from the packed qkv buffer
+            add("sim_argmax", T, C, None, timeit(lambda: ops.sim_argmax(qkv, **kwm)), flops=2.0 * B * ta * tb * D)
+            nm, ni, _ = ops.sim_argmax(qkv, **kwm)
+            size = torch.ones(B, T, device="cuda")
+            for r in (T // 16, T // 8, T // 4, T // 2):
+                add("select_topr", T, C, r, timeit(lambda: ops.select_topr(nm, ni, T, r)), nbytes=B * (8.0 * ta + 4 * (ta + r + T + tb + 1 + r)))
+                plan = ops.select_topr(nm, ni, T, r)
+                add("merge_fwd", T, C, r, timeit(lambda: ops.merge_fwd(plan, x, size, 1)),
+                    nbytes=B * (T * C * 2.0 + 4 * T + 4 * (ta + r) + (T - r) * C * 2 + 4 * (T - r)))
+                x1, s1, _, _ = ops.merge_fwd(plan, x, size, 1)
+                dy = torch.randn_like(x1)
+                add("merge_bwd", T, C, r, timeit(lambda: ops.merge_bwd(plan, dy, size, s1, 1)),
+                    nbytes=B * ((T - r) * C * 2.0 + T * C * 2 + 4 * T))
+                del plan, x1, s1, dy
+            del x, qkv, out, lse, do
+            torch.cuda.empty_cache()
+    return {"metric": "ToMe block microbench (BASELINE.json configs[4]): per-kernel time against its roofline",
+            "unit": "us per launch; frac = achieved / measured burst peak", "n_gpus": 1, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "standalone ToMe block kernels, B * T = 32768 tokens, T in 1k..8k, d in {768, 1024}, heads = d / 64, "
+                                   "r in T/16..T/2, block-causal group mask in post-merge order, log-size bias",
+                       "l2_policy": "256 MB written between timed launches"},
+            "peaks": {"hbm_gbs": P["hbm"], "bf16_tflops_burst": P["tf_burst"], "source": P["src"]}, "rows": rows}
+
+
+# ------------------------------------------------------------------------------------------------ this repo's arm
+def measure_workload(args, cfgname, rank, world, local, steps, warmup, with_extras=True):
+    """One workload measured three ways on this rank's GPU (max over ranks): device-timed steps with resident inputs
+    (`value`), end to end through the public trainer API with pinned-host inputs (`e2e`), and a per-op CUDA-event pass
+    (`kernels`, `roofline`).  Returns the dict rank 0 prints (None on other ranks)."""
     import torch
     import torch.distributed as dist
 
     from multi_modal_transformers_tokenmerge_b200 import _lib as L
     from multi_modal_transformers_tokenmerge_b200.engine import StackConfig, ToMeStackEngine
-    from multi_modal_transformers_tokenmerge_b200.parallel import DataParallelTrainer, nccl_options
+    from multi_modal_transformers_tokenmerge_b200.parallel import DataParallelTrainer
     from multi_modal_transformers_tokenmerge_b200.tokenizers.token_sequencer import sequence_groups
 
-    lib = L.lib()  # raises if the CUDA library is missing: the product path has no fallback
-    # stdout carries exactly ONE JSON line: anything a library prints meanwhile (NCCL's version banner at N > 1) goes to stderr
-    sys.stdout.flush()
-    real_stdout = os.dup(1)
-    os.dup2(2, 1)
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=nccl_options(args.comm_sms))
-    c = dict(CONFIGS[args.config])
-    if args.batch:
-        c["batch"] = args.batch
-    gid, pos, allow, ro = sequence_groups(SEQ)
+    lib = L.lib()
+    a2 = argparse.Namespace(**{**vars(args), "config": cfgname})
+    c = cfg_of(a2)
+    gid, pos, allow, ro = sequence_groups(c["seq"])
     T0, B, C = len(gid), c["batch"], c["channels"]
     cfg = StackConfig(batch=B, tokens=T0, channels=C, heads=c["heads"], head_dim=c["head_dim"], mlp_dim=c["mlp_dim"],
                       layers=c["layers"], r=c["r"], ln_axis=1, num_groups=allow.shape[0], n_readout=len(ro),
@@ -246,14 +343,24 @@ def main():
         return ms.item()
 
     step = lambda: trainer.train_step(x, y, lr=1e-4)  # noqa: E731
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     lib.tome_launch_count(1)
     with ClockSampler(local) as clk:
-        ms = timed(args.steps, step)
+        ms = timed(steps, step)
     launches = int(lib.tome_launch_count(1))
     loss_dev = float(eng.loss[0].item())
-    value = world * B * args.steps / (ms * 1e-3)
+    value = world * B * steps / (ms * 1e-3)
+
+    # every rank started from the same weights and applied the same summed gradients: the parameter vectors must be
+    # bit-identical (a checksum of the fp32 bit patterns, min == max over the ranks)
+    in_sync = None
+    if world > 1:
+        chk = eng.params.view(torch.int32).to(torch.int64).sum().reshape(1)
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        in_sync = bool(lo.item() == hi.item())
 
     # ---- end to end through the public API: pinned host inputs -> H2D -> step -> D2H loss, every step ----
     xh = [torch.randn(B, T0, C).bfloat16().pin_memory() for _ in range(2)]
@@ -267,22 +374,22 @@ def main():
     state = {"i": 0}
 
     def prefetch(i):
-        s = i & 1
+        s_ = i & 1
         with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[s])
-            xd[s].copy_(xh[s], non_blocking=True)
-            yd[s].copy_(yh[s], non_blocking=True)
-            ready[s].record(copy_stream)
+            copy_stream.wait_event(consumed[s_])
+            xd[s_].copy_(xh[s_], non_blocking=True)
+            yd[s_].copy_(yh[s_], non_blocking=True)
+            ready[s_].record(copy_stream)
 
     def e2e_step():
         i = state["i"]
-        s = i & 1
+        s_ = i & 1
         if i == 0:
             prefetch(0)
         prefetch(i + 1)                       # next step's inputs stream in under this step's compute
-        torch.cuda.current_stream().wait_event(ready[s])
-        trainer.train_step(xd[s], yd[s], lr=1e-4)
-        consumed[s].record()
+        torch.cuda.current_stream().wait_event(ready[s_])
+        trainer.train_step(xd[s_], yd[s_], lr=1e-4)
+        consumed[s_].record()
         loss_h.copy_(eng.loss[:1], non_blocking=True)
         torch.cuda.current_stream().synchronize()   # the step's result is read on the host every step
         state["i"] = i + 1
@@ -291,8 +398,8 @@ def main():
         ev.record()
     for _ in range(2):
         e2e_step()
-    ms_e2e = timed(args.steps, e2e_step)
-    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+    ms_e2e = timed(steps, e2e_step)
+    e2e_value = world * B * steps / (ms_e2e * 1e-3)
     h2d = xh[0].numel() * 2 + yh[0].numel() * 4
     d2h = 4
 
@@ -313,28 +420,33 @@ def main():
         ent = {"ms_per_step": kms / nprof, "share": kms / tot_ms, "ops_per_step": cnt // nprof}
         if k_ in ("gemm", "attn_fwd", "attn_bwd", "sim_argmax") and kms > 0:
             ent["tflops"] = work / (kms * 1e-3) / 1e12
+            ent["frac_of_sustained_bf16_peak"] = ent["tflops"] / P["tf_sust"]
         elif work > 0 and kms > 0:
             ent["gbs"] = work / (kms * 1e-3) / 1e9
+            ent["frac_of_hbm_peak"] = ent["gbs"] / P["hbm"]
         kernels[k_] = ent
     gms, gwork, gcnt = prof["gemm"]
-    # DRAM read + write per launch from the committed ncu captures (profiles/r01d_ncu_final_kernels.txt: mean of the 12
-    # GEMM launches of layer 0; profiles/r01d_ncu_full_summary.txt: merge_fwd at layer 0); only for the captured configuration
-    captured = args.config == "octo_small" and B == 256
+    # DRAM read + write per launch from the tracked summary of this round's ncu captures; only for the captured configuration
+    tr = tracked_traffic()
+    captured = cfgname == "octo_small" and B == 256 and c["r"] == 16
+    gt, mt = tr.get("gemm_bf16_kernel", {}), tr.get("merge_fwd_bulk_kernel", {})
     roof = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)", "achieved": gwork / (gms * 1e-3) / 1e12,
             "peak": P["tf_sust"], "unit": "TFLOP/s", "frac": gwork / (gms * 1e-3) / 1e12 / P["tf_sust"],
-            "traffic": 414.6e6 if captured else None, "traffic_unit": "bytes per launch (ncu dram read+write, layer-0 shapes)",
+            "traffic": gt.get("bytes_per_launch") if captured else None,
+            "traffic_unit": "bytes per launch (ncu dram read+write, mean over the GEMM launches of layer 0)",
+            "traffic_source": gt.get("source") if captured else None,
             "peak_source": f"{P['src']} bf16_tflops_sustained", "launches_per_step": gcnt // nprof,
             "avg_launch_us": gms / gcnt * 1e3, "share_of_step": gms / tot_ms}
     mms, mwork, mcnt = prof["merge_fwd"]
     merge_roof = {"bound": "hbm", "kernel": "merge_fwd_kernel", "achieved": mwork / (mms * 1e-3) / 1e9, "peak": P["hbm"],
-                  "unit": "GB/s", "frac": mwork / (mms * 1e-3) / 1e9 / P["hbm"], "traffic": 159.0e6 if captured else None,
-                  "traffic_unit": "bytes per launch (ncu dram read+write, layer 0: 207.6 MB algorithmic, part of the output still in L2)",
+                  "unit": "GB/s", "frac": mwork / (mms * 1e-3) / 1e9 / P["hbm"],
+                  "traffic": mt.get("bytes_per_launch") if captured else None,
+                  "traffic_unit": "bytes per launch (ncu dram read+write, layer 0)", "traffic_source": mt.get("source") if captured else None,
                   "peak_source": f"{P['src']} hbm_gbs", "avg_launch_us": mms / mcnt * 1e3} if mcnt else None
 
     # ---- the same merge kernel timed back to back (no per-launch event pair): three disjoint input/output sets of the
-    # layer-0 shape (3 x 208 MB > the 126 MB L2), 30 launches between ONE pair of events.  The in-step figure above carries
-    # the cost of an event pair per ~35 us launch; this one does not.
-    if merge_roof is not None and c["r"] > 0:
+    # layer-0 shape (> the 126 MB L2), 30 launches between ONE pair of events.
+    if with_extras and merge_roof is not None and c["r"] > 0:
         from multi_modal_transformers_tokenmerge_b200 import ops as O_
         r0 = lib.tome_clamp_r(T0, c["r"], 0, 0)
         metric = torch.randn(B, T0, c["head_dim"], device="cuda", generator=g)
@@ -360,7 +472,7 @@ def main():
         bytes_m = B * (T0 * C * 2 + 4 * T0 + 4 * ((T0 + 1) // 2 + r0) + (T0 - r0) * C * 2 + 4 * (T0 - r0))
         gbs = bytes_m / (ms_m / n_rep * 1e-3) / 1e9
         merge_roof["back_to_back"] = {"achieved": gbs, "frac": gbs / P["hbm"], "avg_launch_us": ms_m / n_rep * 1e3,
-                                      "note": "layer-0 shape through the C ABI, 3 rotating input/output buffer sets (624 MB > L2), "
+                                      "note": "layer-0 shape through the C ABI, 3 rotating input/output buffer sets (> L2), "
                                               "one event pair around 30 launches"}
         del sets
 
@@ -368,23 +480,98 @@ def main():
     if rank == 0:
         fl = flops_per_sample(c, T0) * 3
         out = {
-            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": workload_config(args, world, B, T0),
+            "config": workload_config(a2, world, B, T0),
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / steps},
             "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "merge_roofline": merge_roof,
-            "kernels": kernels, "model_tflops": value / world * fl / 1e12, "loss": loss_dev,
+            "kernels": kernels, "model_tflops": value / world * fl / 1e12,
+            "model_frac_of_sustained_bf16_peak": value / world * fl / 1e12 / P["tf_sust"], "loss": loss_dev,
         }
-        if world == 1 and not args.no_cpu_baseline:
-            sps, sec, cores, _ = cpu_reference_steps(args.config, 3, 1, 2, args.loss)
+        if in_sync is not None:
+            out["params_in_sync"] = in_sync
+    del trainer, eng, x, y, xd, yd
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="tome_b200", choices=["tome_b200", "reference"])
+    ap.add_argument("--config", default="octo_small", choices=list(CONFIGS),
+                    help="octo_small = BASELINE.json configs[1] (the metric's configuration), octo_base = configs[2] per-GPU shard, "
+                         "c3 = configs[3] (two cameras, 4-frame history, T0 = 2080; sweep it with --r)")
+    ap.add_argument("--r", type=int, default=None, help="tokens merged per layer (default: the config's; configs[3] sweeps 0..64)")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override (default: the config's)")
+    ap.add_argument("--dropout", type=float, default=0.1, help="hidden dropout rate (vanilla_decoder.yaml:17,50)")
+    ap.add_argument("--attn-dropout", type=float, default=0.1, help="attention-weight dropout rate (vanilla_decoder.yaml:23)")
+    ap.add_argument("--loss", default="continuous", choices=["continuous", "synthetic"],
+                    help="continuous: ContinuousActionHead + l2 loss on the pooled readouts, the reference's "
+                         "continuous_train_step; synthetic: MSE on the readout rows")
+    ap.add_argument("--comm-sms", type=int, default=0,
+                    help="N > 1: SMs reserved for the NCCL all-reduce kernels during backward (NCCL max_ctas = this, the "
+                         "persistent GEMM grid shrinks by this); 0 = NCCL's default and the full grid")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--octo-base", default="auto", choices=["auto", "on", "off"],
+                    help="also measure the octo_base shard (BASELINE.json configs[2]) and attach it as `octo_base`; auto = at 8 GPUs")
+    ap.add_argument("--microbench", action="store_true",
+                    help="BASELINE.json configs[4]: standalone ToMe block kernels at 1k-8k tokens, d = 768 / 1024, merge-ratio "
+                         "sweep, each against its roofline (one JSON object; N = 1 only)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "tome_b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+
+    import torch
+    import torch.distributed as dist
+
+    from multi_modal_transformers_tokenmerge_b200 import _lib as L
+    from multi_modal_transformers_tokenmerge_b200.parallel import nccl_options
+
+    L.lib()  # raises if the CUDA library is missing: the product path has no fallback
+    # stdout carries exactly ONE JSON line: anything a library prints meanwhile (NCCL's version banner at N > 1) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    torch.cuda.set_device(local)
+    if args.microbench:
+        out = microbench(args) if rank == 0 else None
+    else:
+        if world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=nccl_options(args.comm_sms))
+        out = measure_workload(args, args.config, rank, world, local, args.steps, args.warmup)
+        want_base = args.octo_base == "on" or (args.octo_base == "auto" and world == 8)
+        if want_base and args.config == "octo_small":
+            # BASELINE.json configs[2] (octo-base, batch 2048 over 8 GPUs) rides on the same line, so that the driver's scaling
+            # run carries a measured number for it; fewer steps, same protocol
+            a3 = argparse.Namespace(**{**vars(args), "r": None, "batch": 0})
+            base = measure_workload(a3, "octo_base", rank, world, local, max(3, args.steps // 2), 3, with_extras=False)
+            if out is not None:
+                out["octo_base"] = {k_: base[k_] for k_ in ("value", "unit", "n_gpus", "steps", "ms_per_step", "config", "e2e", "roofline",
+                                                            "kernels", "model_tflops", "model_frac_of_sustained_bf16_peak", "clocks")
+                                    if k_ in base}
+                if "params_in_sync" in base:
+                    out["octo_base"]["params_in_sync"] = base["params_in_sync"]
+        if out is not None and world == 1 and not args.no_cpu_baseline:
+            c = cfg_of(args)
+            sps, sec, cores, _ = cpu_reference_steps(args.config, 2, 1, REF_SAMPLE_BATCH if args.config != "c3" else 2, args.loss, r=c["r"],
+                                                     dropout=args.dropout, attn_dropout=args.attn_dropout)
             out["cpu_baseline"] = {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
-                                   "sample": f"3 train steps of 2 samples of the same workload (fp32, torch-CPU restatement of the "
-                                             f"reference), {sec:.1f} s/step"}
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+                                   "sample": f"2 train steps (after 1 warm-up) of {REF_SAMPLE_BATCH if args.config != 'c3' else 2} samples of the "
+                                             f"same workload (fp32, torch-CPU restatement of the reference, AdamW, same dropout sites), "
+                                             f"{sec:.1f} s/step"}
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
     sys.stdout.flush()
     os.dup2(real_stdout, 1)
     if out is not None:

@@ -408,7 +408,8 @@ def _round_st(t, dtype):
 
 def tome_block(p: BlockParams, x, size, gid, pos, allow, *, num_heads, r, ln_axis="seq", prop_attn=True,
                class_token=False, distill_token=False, scores_override=None, node_override=None,
-               trace: Optional[list] = None, act_dtype=None, relu_gate=None, taps: Optional[dict] = None):
+               trace: Optional[list] = None, act_dtype=None, relu_gate=None, taps: Optional[dict] = None,
+               dropout_rate: float = 0.0, attn_dropout_rate: float = 0.0):
     """ToMeEncoder1DBlock with the ToMe-paper placement (reference shell attention.py:52-69):
 
         x = x + attn(LN(x), mask(groups), bias = log size)       # dropout 0 (parity mode)
@@ -416,10 +417,15 @@ def tome_block(p: BlockParams, x, size, gid, pos, allow, *, num_heads, r, ln_axi
         x, size = merge_wavg(plan, x, size);  groups follow the merge (dst keeps its own group/pos)
         x = x + MLP(LN'(x))
 
-    x [B,T,C] torch; size [B,T,1] torch; gid/pos numpy [B,T]; returns (x, size, gid, pos)."""
+    x [B,T,C] torch; size [B,T,1] torch; gid/pos numpy [B,T]; returns (x, size, gid, pos).
+    dropout_rate / attn_dropout_rate > 0 (training, `octo.py:120` always passes train=True) draw torch's own masks at the
+    reference's four sites -- attention weights (one [T,T] mask for all batch rows and heads: flax broadcast_dropout), after
+    the out projection (attention.py:60), after the ReLU and after dense_out (:34, :37); used by bench.py's CPU arm, never by
+    a parity test (the kernels' counter-based masks are compared through dropout_keep_mask instead)."""
     torch = _torch()
     B, T, C = x.shape
     H = num_heads
+    drop = (lambda t: torch.nn.functional.dropout(t, dropout_rate)) if dropout_rate > 0 else (lambda t: t)
     rd = lambda t: _round_st(t, act_dtype)  # noqa: E731
     h = rd(layer_norm(x, p.ln1_scale, p.ln1_bias, axis=ln_axis))
     q = rd(h @ p.wq + p.bq).reshape(B, T, H, -1)
@@ -427,8 +433,11 @@ def tome_block(p: BlockParams, x, size, gid, pos, allow, *, num_heads, r, ln_axi
     v = rd(h @ p.wv + p.bv).reshape(B, T, H, -1)
     mask = torch.as_tensor(dense_mask(gid, pos, gid, pos, allow))[:, None, :, :]
     bias = torch.log(size[:, None, None, :, 0]) if prop_attn else None
-    o = rd(attention(q, k, v, mask=mask, bias=bias).reshape(B, T, -1))
-    x = rd(x + (o @ p.wo + p.bo))
+    keep = None
+    if attn_dropout_rate > 0:
+        keep = (torch.rand(1, 1, T, T) >= attn_dropout_rate).to(x.dtype) / (1.0 - attn_dropout_rate)
+    o = rd(attention(q, k, v, mask=mask, bias=bias, drop_keep=keep).reshape(B, T, -1))
+    x = rd(x + drop(o @ p.wo + p.bo))
     if taps is not None:   # checker hook: the post-attention residual stream (its gradient is dL/dx1, whose column sum is d bo)
         if x.requires_grad:
             x.retain_grad()
@@ -460,21 +469,21 @@ def tome_block(p: BlockParams, x, size, gid, pos, allow, *, num_heads, r, ln_axi
     y = rd(layer_norm(x, p.ln2_scale, p.ln2_bias, axis=ln_axis))
     pre = y @ p.w1 + p.b1
     if relu_gate is None:
-        y = rd(torch.relu(pre))  # attention.py:32-33 (dropout at :34,:37 is identity in parity mode)
+        y = rd(drop(torch.relu(pre)))  # attention.py:32-34 (dropout at :34,:37 is the identity in parity mode)
     else:
         # parity protocol for the gradients, as node_override is for the matching: the checker takes the SAME ReLU gate
         # decisions as the implementation under test (bool [B,T',Dff]; a pre-activation within bf16 rounding of zero may
         # fall on either side, and one flipped gate moves a whole row of dW).  The forward value is relu() of the oracle's
         # own pre-activation wherever the gates agree; where they differ |pre| is of the order of the rounding error.
         y = rd(torch.where(torch.as_tensor(relu_gate), pre, torch.zeros_like(pre)))
-    y = y @ p.w2 + p.b2
+    y = drop(y @ p.w2 + p.b2)
     return rd(x + y), size, gid, pos
 
 
 def tome_stack(params: Sequence[BlockParams], pos_embedding, x, gid, pos, allow, *, num_heads, r,
                ln_axis="seq", prop_attn=True, scores_override: Optional[Sequence] = None,
                node_override: Optional[Sequence] = None, trace: Optional[list] = None, act_dtype=None,
-               relu_gate: Optional[Sequence] = None):
+               relu_gate: Optional[Sequence] = None, dropout_rate: float = 0.0, attn_dropout_rate: float = 0.0):
     """StackedEncoder1DBlock (attention.py:94-119) unrolled, with shrinking T.  Returns
     (x_final [B,T_L,C], size, origin_row [B,T0] = row of x_final each ORIGINAL token ended up in)."""
     torch = _torch()
@@ -490,7 +499,8 @@ def tome_stack(params: Sequence[BlockParams], pos_embedding, x, gid, pos, allow,
         no = None if node_override is None else node_override[li]
         x, size, gid, pos = tome_block(p, x, size, gid, pos, allow, num_heads=num_heads, r=r, ln_axis=ln_axis,
                                        prop_attn=prop_attn, scores_override=so, node_override=no, trace=tr,
-                                       act_dtype=act_dtype, relu_gate=None if relu_gate is None else relu_gate[li])
+                                       act_dtype=act_dtype, relu_gate=None if relu_gate is None else relu_gate[li],
+                                       dropout_rate=dropout_rate, attn_dropout_rate=attn_dropout_rate)
         plan = tr[0].plan
         if plan.r > 0:
             origin = np.take_along_axis(row_map(plan), origin, axis=1)

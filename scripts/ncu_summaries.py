@@ -62,5 +62,23 @@ def raw(path, note):
         print("top stalls (warps per issue): " + ", ".join(f"{k.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', '')} {v:.2f}" for k, v in top))
 
 
+def traffic(path, note):
+    """profiles/roofline_traffic.json: mean dram read + write bytes per launch of every kernel in an ncu --set full report."""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ix = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    agg = collections.OrderedDict()
+    for r in rows[2:]:
+        name = short(r[ix["Kernel Name"]]).split("<")[0]
+        b = sum(float(r[ix[m]].replace(",", "")) * scale[units[ix[m]]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += b
+    print(json.dumps({k: {"bytes_per_launch": v[1] / v[0], "launches": v[0], "source": f"{note} ({path}, ncu --set full)"} for k, v in agg.items()}, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "")
+    {"launches": launches, "raw": raw, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "")
