@@ -364,48 +364,75 @@ sim_argmax_planes_kernel(const tome_metric_desc_t d, const float* __restrict__ p
 }
 
 // ------------------------------------------------------------------------------------------------ K2
-// rank order of jnp.argsort(node_max)[:, ::-1]: j precedes i iff key_j "greater" (NaN greatest), ties: larger index.
-__device__ __forceinline__ bool rank_before(float vj, int j, float vi, int i) {
-  const bool nj = vj != vj, ni = vi != vi;
-  if (nj || ni) return nj && (!ni || j > i);
-  return vj > vi || (vj == vi && j > i);
+// Rank order of jnp.argsort(node_max)[:, ::-1] (token_compression.py:84): value descending with NaN greatest, ties by
+// index DEscending.  One CTA per batch row sorts 64-bit keys (order-preserving image of the float in the high word, index in
+// the low word) with a bitonic network in shared memory -- O(n log^2 n) compare-exchanges instead of the round-1 rank-by-
+// count (n^2 comparisons: 1.2 ms per call at T = 8192) -- and a second sort of (destination, rank) pairs gives every merged
+// source its slot in the CSR lists, keeping the rank order inside a destination that the reference's sequential adds need.
+__device__ __forceinline__ unsigned long long rank_key(float v, int i) {
+  uint32_t u = __float_as_uint(v);
+  if (v != v) u = 0xFFFFFFFFu;                 // NaN sorts above every number (numpy / jax argsort order)
+  else if (v == 0.f) u = 0x80000000u;          // -0 == +0
+  else u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return ((unsigned long long)u << 32) | (uint32_t)i;
+}
+
+// in-place bitonic sort of n (a power of two) keys, DEscending; every thread of the CTA takes part
+__device__ __forceinline__ void bitonic_sort_desc(unsigned long long* keys, int n, int tid, int nt) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < n; i += nt) {
+        const int l = i ^ j;
+        if (l > i) {
+          const unsigned long long a = keys[i], b = keys[l];
+          const bool desc = (i & k) == 0;
+          if (desc ? a < b : a > b) {
+            keys[i] = b;
+            keys[l] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
 }
 
 constexpr int SEL_THREADS = 1024;
+__host__ __device__ inline int sel_pow2(int n) { int p = 1; while (p < n) p <<= 1; return p; }
 
 __global__ void __launch_bounds__(SEL_THREADS)
 select_topr_kernel(const tome_plan_shape_t s, const float* __restrict__ node_max, const int32_t* __restrict__ node_idx,
                    const tome_plan_t p) {
-  extern __shared__ int sel_sm[];
+  extern __shared__ __align__(8) unsigned char sel_raw[];
   const int T = s.tokens, r = s.r;
   const int ta = (T + 1) / 2, tb = T / 2;
-  float* vals = reinterpret_cast<float*>(sel_sm);  // [ta]
-  int* nidx = sel_sm + ta;                         // [ta]
+  const int n2 = sel_pow2(ta);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(sel_raw);  // [n2]
+  int* nidx = reinterpret_cast<int*>(keys + n2);   // [ta]
   int* rnk = nidx + ta;                            // [ta]   rank of even token i
-  int* edge = rnk + ta;                            // [ta]   edge[rank] = i
-  int* dstr = edge + ta;                           // [r]    destination of rank i
-  int* cnt = dstr + r;                             // [tb+1] counts then exclusive offsets
+  int* cnt = rnk + ta;                             // [tb+1] counts then exclusive offsets
   int* part = cnt + tb + 1;                        // [SEL_THREADS] scan partials
   const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
 
-  for (int i = tid; i < ta; i += nt) {
-    vals[i] = node_max[(long long)b * ta + i];
-    nidx[i] = node_idx[(long long)b * ta + i];
+  for (int i = tid; i < n2; i += nt) {
+    if (i < ta) {
+      keys[i] = rank_key(node_max[(long long)b * ta + i], i);
+      nidx[i] = node_idx[(long long)b * ta + i];
+    } else {
+      keys[i] = 0ull;   // below every real key (the smallest real high word is that of -inf, 0x007FFFFF)
+    }
   }
   for (int j = tid; j <= tb; j += nt) cnt[j] = 0;
   __syncthreads();
-  for (int i = tid; i < ta; i += nt) {
-    const float vi = vals[i];
-    int rk = 0;
-    for (int j = 0; j < ta; ++j) rk += rank_before(vals[j], j, vi, i) ? 1 : 0;
+  bitonic_sort_desc(keys, n2, tid, nt);
+  for (int rk = tid; rk < ta; rk += nt) {
+    const int i = (int)(uint32_t)keys[rk];
     rnk[i] = rk;
-    edge[rk] = i;
     p.edge_idx[(long long)b * ta + rk] = i;
   }
   __syncthreads();
   for (int i = tid; i < r; i += nt) {
-    const int d = nidx[edge[i]];
-    dstr[i] = d;
+    const int d = nidx[(int)(uint32_t)keys[i]];
     p.dst_idx[(long long)b * r + i] = d;
     atomicAdd(&cnt[d], 1);
   }
@@ -434,12 +461,26 @@ select_topr_kernel(const tome_plan_shape_t s, const float* __restrict__ node_max
     __syncthreads();
   }
   for (int j = tid; j <= tb; j += nt) p.dst_off[(long long)b * (tb + 1) + j] = cnt[j];
-  // placement: sources of one destination keep their rank order (the reference adds them in that order, :100-101)
-  for (int i = tid; i < r; i += nt) {
-    const int d = dstr[i];
-    int k = 0;
-    for (int i2 = 0; i2 < i; ++i2) k += (dstr[i2] == d) ? 1 : 0;
-    p.dst_src[(long long)b * r + cnt[d] + k] = edge[i];
+  // placement: the merged sources sorted by (destination, rank) are the CSR lists in order -- sources of one destination
+  // keep their rank order (the reference adds them in that order, :100-101).  Descending sort of the complemented key.
+  {
+    const int r2 = sel_pow2(r);
+    // entry i is rebuilt in place from the ranking key at the same index (read and written by the same thread only)
+    for (int i = tid; i < r2; i += nt) {
+      unsigned long long k = 0ull;
+      if (i < r) {
+        const int src = (int)(uint32_t)keys[i];
+        const int d = nidx[src];
+        // (d, rank i) ascending == ~(d, i) descending; the even-token index rides along through part of the key: 20 bits of
+        // destination, 20 bits of rank, 24 bits of source index (T <= 2^20 is far beyond the shared-memory limit anyway)
+        k = ~(((unsigned long long)d << 44) | ((unsigned long long)i << 24)) & ~0xFFFFFFull;
+        k |= (unsigned long long)src;
+      }
+      keys[i] = k;
+    }
+    __syncthreads();
+    bitonic_sort_desc(keys, r2, tid, nt);
+    for (int q = tid; q < r; q += nt) p.dst_src[(long long)b * r + q] = (int)(keys[q] & 0xFFFFFFull);
   }
   // row map: where every input token lands in the concatenation [unm | dst] (:103-108)
   const int n_unm = ta - r;
@@ -547,9 +588,9 @@ extern "C" int tome_select_topr(const tome_plan_shape_t* s, const float* node_ma
   TOME_CHECK(s->r >= 1 && s->r <= tb && s->r <= ta, TOME_ERR_INVALID,
              "select_topr: r (%d) must be clamped to [1, %d] first (tome_clamp_r; r == 0 is the identity, no plan needed)",
              s->r, tb);
-  const size_t smem = sizeof(int) * ((size_t)4 * ta + s->r + tb + 1 + SEL_THREADS);
-  TOME_CHECK(smem <= 220 * 1024, TOME_ERR_UNSUPPORTED, "select_topr: tokens (%d) too large for the shared-memory ranking",
-             s->tokens);
+  const size_t smem = sizeof(unsigned long long) * (size_t)sel_pow2(ta) + sizeof(int) * ((size_t)2 * ta + tb + 1 + SEL_THREADS);
+  TOME_CHECK(smem <= 220 * 1024 && s->tokens < (1 << 20), TOME_ERR_UNSUPPORTED,
+             "select_topr: tokens (%d) too large for the shared-memory ranking", s->tokens);
   TOME_CUDA(cudaFuncSetAttribute(select_topr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope prof(PROF_SELECT, 0.0, 1, stream);
   select_topr_kernel<<<s->batch, SEL_THREADS, smem, stream>>>(*s, node_max, node_idx, *plan);
