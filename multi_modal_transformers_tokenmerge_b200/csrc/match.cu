@@ -9,6 +9,8 @@
 // numpy), so indices are bit-exact given the same fp32 scores.  The similarity product is fp32 FMA on CUDA cores
 // on purpose: it is 0.1 % of the block's FLOPs and fp32 keeps the arg max aligned with the fp32
 // reference; the scores tile lives in registers and never reaches HBM unless scores_out is given.
+#include <string.h>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -23,6 +25,10 @@ __device__ __forceinline__ bool argmax_better(float v, int j, float bv, int bj) 
 
 constexpr int SIM_TILE = 64;
 constexpr int SIM_THREADS = 256;
+
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
 
 template <typename T>
 __device__ __forceinline__ float2 load2(const T* p);
@@ -363,6 +369,256 @@ sim_argmax_planes_kernel(const tome_metric_desc_t d, const float* __restrict__ p
   }
 }
 
+// ------------------------------------------------------------------------------------------------ K1 on the tensor cores
+// scores = a b^T is a dense contraction, so it belongs on tcgen05 -- but the arg max must come out of fp32 scores that
+// agree with the reference's fp32 arithmetic (scores within 1e-5, indices exact from the scores the kernel itself used).
+// A bf16 MMA alone cannot do that; a SPLIT one can: every normalised fp32 value is written as v = h + m + l with h = bf16(v),
+// m = bf16(v - h), l = bf16(v - h - m) (3 x 8 bits: the 24-bit significand exactly), and
+//   a . b  =  sum over (hh, hm, mh, hl, lh, mm) products  +  terms below 2^-24 |a||b|,
+// each bf16 x bf16 product exact in the fp32 accumulator.  metric_split64_kernel writes every row as the three 64-wide chunks
+// [h | m | l] (384 bytes per token; fp32 would be 256), and the score tile is six chunk products accumulated into ONE TMEM
+// tile -- 24 tcgen05.mma 128 x 128 x 16 steps -- double-buffered so the epilogue warps (thread = a row) take the running row
+// max / first arg max of tile j from tensor memory while tile j + 1 is being computed.  (A first version stored the six
+// operand chunks per row explicitly, 768 B per token: its 295 MB of L2 -> SM traffic per call, not the tensor pipe, set
+// its 93 us -- profiles/r02_sim_argmax_tc.md.)
+// The a tiles of one batch element form a thread-block cluster (up to 8 CTAs): every b chunk is fetched from L2 by ONE of
+// them (round robin) and TMA-multicast into the ring slot of all, so the b rows cross the L2 -> SM path once per cluster
+// instead of once per a tile (32 times at T = 8192).
+//   warp 4  TMA: the a tile's three chunks once (48 KB, resident), then the b tiles chunk by chunk through a 3-slot ring
+//   warp 5  MMA issuer: per b chunk h: a_h, a_m, a_l;  m: a_h, a_m;  l: a_h        warps 0..3  epilogue
+constexpr int SIMT_BM = 128, SIMT_BN = 128, SIMT_CHUNKS = 3, SIMT_SLOTS = 3, SIMT_ROW = 192;
+constexpr int SIMT_CHUNK_BYTES = 128 * 64 * 2;   // 16 KB: 128 rows x 64 bf16, 128B-swizzled
+constexpr int SIMT_SMEM = (SIMT_CHUNKS + SIMT_SLOTS) * SIMT_CHUNK_BYTES + 256 + 1024;
+constexpr int SIMT_THREADS = 192;
+
+// bf16, dim == 64, 16-byte aligned rows: 8 lanes per token row; head mean, L2 norm (no epsilon), three-way bf16 split
+__global__ void __launch_bounds__(256)
+metric_split64_kernel(const tome_metric_desc_t d, const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ plane_a,
+                      __nv_bfloat16* __restrict__ plane_b) {
+  const long long tok = ((long long)blockIdx.x * 256 + threadIdx.x) >> 3;   // b * T + t
+  const int sub = threadIdx.x & 7;
+  const bool valid = tok < (long long)d.batch * d.tokens;   // every lane stays for the shuffles
+  const long long tk = valid ? tok : 0;
+  const int b = (int)(tk / d.tokens), t = (int)(tk % d.tokens);
+  const int ta = (d.tokens + 1) / 2, tb = d.tokens / 2;
+  const __nv_bfloat16* base = src + (long long)b * d.batch_stride + (long long)t * d.token_stride + sub * 8;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int h = 0; h < d.heads; ++h) {
+    const uint4 v = ld_nc_v4(base + (long long)h * d.head_stride);
+    acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
+    acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z); acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
+  }
+  float ss = 0.f;
+  const float inv_h = 1.0f / (float)d.heads;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (d.heads > 1) acc[i] *= inv_h;
+    ss += acc[i] * acc[i];
+  }
+  ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+  ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+  ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+  const float nrm = sqrtf(ss);
+  if (!valid) return;
+  float hi[8], mi[8], lo[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float v = acc[i] / nrm;
+    hi[i] = __bfloat162float(__float2bfloat16_rn(v));
+    const float r1 = v - hi[i];                       // exact: v and hi agree in their leading bits
+    mi[i] = __bfloat162float(__float2bfloat16_rn(r1));
+    lo[i] = __bfloat162float(__float2bfloat16_rn(r1 - mi[i]));
+  }
+  const uint4 wh = pack8(hi), wm = pack8(mi), wl = pack8(lo);
+  const bool odd = t & 1;
+  uint4* out = reinterpret_cast<uint4*>((odd ? plane_b + ((long long)b * tb + (t >> 1)) * SIMT_ROW : plane_a + ((long long)b * ta + (t >> 1)) * SIMT_ROW)) + sub;
+  out[0] = wh;    // chunk c starts 64 elements = 8 uint4 further
+  out[8] = wm;
+  out[16] = wl;
+}
+
+// any dtype / even strides, dim == 64: one warp per token row, two columns per lane (the fp32 `metric` argument of
+// bipartite_soft_matching takes this one)
+template <typename T>
+__global__ void __launch_bounds__(256)
+metric_split_kernel(const tome_metric_desc_t d, const T* __restrict__ src, __nv_bfloat16* __restrict__ plane_a,
+                    __nv_bfloat16* __restrict__ plane_b) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long tok = (long long)blockIdx.x * 8 + warp;   // b * T + t
+  if (tok >= (long long)d.batch * d.tokens) return;
+  const int b = (int)(tok / d.tokens), t = (int)(tok % d.tokens);
+  const int ta = (d.tokens + 1) / 2, tb = d.tokens / 2;
+  const T* base = src + (long long)b * d.batch_stride + (long long)t * d.token_stride + 2 * lane;
+  float2 acc = make_float2(0.f, 0.f);
+  for (int h = 0; h < d.heads; ++h) {
+    const float2 v = load2<T>(base + (long long)h * d.head_stride);
+    acc.x += v.x;
+    acc.y += v.y;
+  }
+  if (d.heads > 1) {
+    const float inv_h = 1.0f / (float)d.heads;
+    acc.x *= inv_h;
+    acc.y *= inv_h;
+  }
+  const float nrm = sqrtf(warp_sum(acc.x * acc.x + acc.y * acc.y));
+  float v[2] = {acc.x / nrm, acc.y / nrm}, hi[2], mi[2], lo[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    hi[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
+    const float r1 = v[i] - hi[i];
+    mi[i] = __bfloat162float(__float2bfloat16_rn(r1));
+    lo[i] = __bfloat162float(__float2bfloat16_rn(r1 - mi[i]));
+  }
+  const uint32_t wh = pack_bf16(hi[0], hi[1]), wm = pack_bf16(mi[0], mi[1]), wl = pack_bf16(lo[0], lo[1]);
+  const bool odd = t & 1;
+  uint32_t* out = reinterpret_cast<uint32_t*>(odd ? plane_b + ((long long)b * tb + (t >> 1)) * SIMT_ROW : plane_a + ((long long)b * ta + (t >> 1)) * SIMT_ROW) + lane;
+  out[0] = wh;            // chunk c starts 64 elements = 32 words further
+  out[32] = wm;
+  out[64] = wl;
+}
+
+__global__ void __launch_bounds__(SIMT_THREADS, 2)
+sim_argmax_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const tome_metric_desc_t d,
+                     float* __restrict__ node_max, int32_t* __restrict__ node_idx, float* __restrict__ scores_out, const int csize) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* s_a = smem;                                   // chunk c at c * 16 KB
+  uint8_t* s_b = s_a + SIMT_CHUNKS * SIMT_CHUNK_BYTES;   // ring slot i at i * 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_b + SIMT_SLOTS * SIMT_CHUNK_BYTES);
+  uint64_t* a_full = bars;            // 1
+  uint64_t* b_full = bars + 1;        // [SIMT_SLOTS] (room for 4)
+  uint64_t* b_empty = bars + 5;       // [SIMT_SLOTS] (room for 4)
+  uint64_t* s_full = bars + 9;        // [2] score tile in TMEM buffer jt & 1
+  uint64_t* s_free = bars + 11;       // [2] 128 arrivals: the epilogue has read it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int at = blockIdx.x, b = blockIdx.y;
+  const int ta = (d.tokens + 1) / 2, tb = d.tokens / 2;
+  const int n_bt = (tb + SIMT_BN - 1) / SIMT_BN;
+
+  if (threadIdx.x == 0) {
+    mbar_init(a_full, 1);
+    for (int i = 0; i < SIMT_SLOTS; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], csize);   // one commit from the MMA issuer of every CTA of the cluster
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], SIMT_BM);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  if (csize > 1) cluster_sync_all();   // the peers' barriers exist before anything is multicast at them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t crank = csize > 1 ? cluster_ctarank() : 0u;
+  const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_expect_tx(a_full, SIMT_CHUNKS * SIMT_CHUNK_BYTES);
+      for (int c = 0; c < SIMT_CHUNKS; ++c) tma_load_3d(s_a + c * SIMT_CHUNK_BYTES, &tm_a, a_full, c * 64, at * SIMT_BM, b);
+      int item = 0;
+      for (int jt = 0; jt < n_bt; ++jt)
+        for (int c = 0; c < SIMT_CHUNKS; ++c, ++item) {
+          const int slot = item % SIMT_SLOTS;
+          mbar_wait(&b_empty[slot], ((item / SIMT_SLOTS) & 1) ^ 1);   // every CTA of the cluster has drained the slot
+          mbar_expect_tx(&b_full[slot], SIMT_CHUNK_BYTES);
+          if (csize == 1) tma_load_3d(s_b + slot * SIMT_CHUNK_BYTES, &tm_b, &b_full[slot], c * 64, jt * SIMT_BN, b);
+          else if ((uint32_t)(item % csize) == crank)   // this chunk is ours to fetch, for everybody
+            tma_load_3d_mc(s_b + slot * SIMT_CHUNK_BYTES, &tm_b, &b_full[slot], c * 64, jt * SIMT_BN, b, cmask);
+        }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(SIMT_BM, SIMT_BN, false, false);
+      mbar_wait(a_full, 0);
+      int item = 0;
+      for (int jt = 0; jt < n_bt; ++jt) {
+        if (jt >= 2) {
+          mbar_wait(&s_free[jt & 1], ((jt - 2) >> 1) & 1);
+          tc_fence_after();
+        }
+        const uint32_t td = tmem_base + (jt & 1) * SIMT_BN;
+        for (int c = 0; c < SIMT_CHUNKS; ++c, ++item) {   // b chunk c (h, m, l) meets the a chunks 0 .. 2 - c: hh mh lh | hm mm | hl
+          const int slot = item % SIMT_SLOTS;
+          mbar_wait(&b_full[slot], (item / SIMT_SLOTS) & 1);
+          tc_fence_after();
+          const uint32_t ab = smem_u32(s_b + slot * SIMT_CHUNK_BYTES);
+          for (int ca = 0; ca < SIMT_CHUNKS - c; ++ca) {
+            const uint32_t aa = smem_u32(s_a + ca * SIMT_CHUNK_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(td, make_smem_desc(aa + k * 32, 16, 1024), make_smem_desc(ab + k * 32, 16, 1024), idesc,
+                        (c > 0 || ca > 0 || k > 0) ? 1u : 0u);
+          }
+          if (csize == 1) umma_commit(&b_empty[slot]);
+          else umma_commit_mc(&b_empty[slot], cmask);   // tell every producer of the cluster
+        }
+        umma_commit(&s_full[jt & 1]);
+      }
+    }
+  } else {
+    const int row = threadIdx.x;  // TMEM lane
+    const int ai = at * SIMT_BM + row;
+    const uint32_t lane_sel = ((uint32_t)(warp * 32)) << 16;
+    const bool row_ok = ai < ta;
+    const bool row_protected = d.class_token && ai == 0;   // :77-78
+    float bv = -INFINITY;
+    int bj = 0x7fffffff;
+    float* dump = (scores_out && row_ok) ? scores_out + ((long long)b * ta + ai) * tb : nullptr;
+    for (int jt = 0; jt < n_bt; ++jt) {
+      mbar_wait(&s_full[jt & 1], (jt >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < SIMT_BN; c0 += 32) {
+        float v[32];
+        tmem_ld_f32x32(tmem_base + (jt & 1) * SIMT_BN + lane_sel + c0, v);
+        tmem_ld_wait();
+        const int j0 = jt * SIMT_BN + c0;
+        if (j0 < tb) {   // uniform
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int j = j0 + i;
+            float sc = v[i];
+            if (row_protected || (d.distill_token && j == 0)) sc = -INFINITY;  // :77-80
+            if (j < tb) {
+              if (dump) dump[j] = sc;
+              // first maximum; NaN is the greatest and the first NaN stays (numpy / jax argmax)
+              if (sc > bv || (sc != sc && bv == bv)) {
+                bv = sc;
+                bj = j;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&s_free[jt & 1]);
+    }
+    if (row_ok) {
+      node_max[(long long)b * ta + ai] = bv;
+      node_idx[(long long)b * ta + ai] = bj == 0x7fffffff ? 0 : bj;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (csize > 1) cluster_sync_all();   // peers may still multicast into this CTA's ring / arrive on its barriers
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ K2
 // Rank order of jnp.argsort(node_max)[:, ::-1] (token_compression.py:84): value descending with NaN greatest, ties by
 // index DEscending.  One CTA per batch row sorts 64-bit keys (order-preserving image of the float in the high word, index in
@@ -514,9 +770,22 @@ extern "C" int tome_clamp_r(int tokens, int r, int class_token, int distill_toke
   return r > 0 ? r : 0;
 }
 
+// 1 (default): the tensor-core path (split-bf16 K = 384 contraction) whenever the input allows it; 0: fp32 CUDA-core planes.
+// Process-wide tuning aid (A/B measurements, cross-check), not part of the public header.
+static int g_sim_tc = 1, g_sim_mc = 1;
+extern "C" void tome_sim_argmax_set_tc(int on) { g_sim_tc = on ? 1 : 0; g_sim_mc = on == 2 ? 0 : 1; }   // 2: tensor cores without the cluster multicast
+
+static bool sim_tc_eligible(const tome_metric_desc_t* d) { return d->dim == 64; }
+static bool sim_fast64(const tome_metric_desc_t* d, const void* src) {   // 128-bit loads, 8 lanes per row
+  return d->dtype == TOME_BF16 && d->dim == 64 && d->token_stride % 8 == 0 && d->batch_stride % 8 == 0 &&
+         d->head_stride % 8 == 0 && ((uintptr_t)src & 15) == 0;
+}
+
 extern "C" size_t tome_sim_argmax_workspace_bytes(const tome_metric_desc_t* d) {
   if (!d || d->batch <= 0 || d->tokens <= 0 || d->dim <= 0) return 0;
-  return (size_t)d->batch * d->tokens * ((d->dim + 3) & ~3) * sizeof(float);
+  const size_t f32_planes = (size_t)d->batch * d->tokens * ((d->dim + 3) & ~3) * sizeof(float);
+  const size_t split_planes = (size_t)d->batch * d->tokens * SIMT_ROW * 2;   // three bf16 chunks of 64 per token (dim 64 only)
+  return d->dim == 64 && split_planes > f32_planes ? split_planes : f32_planes;
 }
 
 extern "C" int tome_sim_argmax(const tome_metric_desc_t* d, const void* src, float* node_max, int32_t* node_idx,
@@ -541,13 +810,48 @@ extern "C" int tome_sim_argmax(const tome_metric_desc_t* d, const void* src, flo
                "sim_argmax: workspace must be 16-byte aligned and hold %zu bytes (got %zu)", tome_sim_argmax_workspace_bytes(d),
                workspace_bytes);
     ProfScope prof(PROF_SIM, 2.0 * d->batch * ta * (double)tb * d->dim, 2, stream);
+    if (g_sim_tc && sim_tc_eligible(d)) {
+      __nv_bfloat16* pa = reinterpret_cast<__nv_bfloat16*>(workspace);
+      __nv_bfloat16* pb = pa + (size_t)d->batch * ta * SIMT_ROW;
+      const long long toks = (long long)d->batch * d->tokens;
+      if (sim_fast64(d, src))
+        metric_split64_kernel<<<(unsigned)((toks * 8 + 255) / 256), 256, 0, stream>>>(*d, reinterpret_cast<const __nv_bfloat16*>(src), pa, pb);
+      else if (d->dtype == TOME_BF16)
+        metric_split_kernel<__nv_bfloat16><<<(unsigned)((toks + 7) / 8), 256, 0, stream>>>(*d, reinterpret_cast<const __nv_bfloat16*>(src), pa, pb);
+      else
+        metric_split_kernel<float><<<(unsigned)((toks + 7) / 8), 256, 0, stream>>>(*d, reinterpret_cast<const float*>(src), pa, pb);
+      TOME_CUDA(cudaGetLastError());
+      CUtensorMap tma_a, tma_b;
+      if (int rc = make_tmap_3d_bf16(&tma_a, pa, SIMT_ROW, ta, d->batch, SIMT_ROW, (uint64_t)ta * SIMT_ROW, SIMT_BM)) return rc;
+      if (int rc = make_tmap_3d_bf16(&tma_b, pb, SIMT_ROW, tb, d->batch, SIMT_ROW, (uint64_t)tb * SIMT_ROW, SIMT_BN)) return rc;
+      static DynSmemOnce once;
+      TOME_CUDA(ensure_dyn_smem(sim_argmax_tc_kernel, SIMT_SMEM, once));
+      const int n_at = ceil_div(ta, SIMT_BM);
+      int csize = 1;   // the largest cluster size <= 8 that divides the number of a tiles
+      for (int c = 8; c > 1; --c)
+        if (n_at % c == 0) { csize = c; break; }
+      if (!g_sim_mc) csize = 1;
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(n_at, d->batch);
+      cfg.blockDim = dim3(SIMT_THREADS);
+      cfg.dynamicSmemBytes = SIMT_SMEM;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = csize;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      TOME_CUDA(cudaLaunchKernelEx(&cfg, sim_argmax_tc_kernel, tma_a, tma_b, *d, node_max, node_idx, scores_out, csize));
+      return TOME_OK;
+    }
     float* plane_a = reinterpret_cast<float*>(workspace);
     float* plane_b = plane_a + (size_t)d->batch * ta * dpad;
     const long long toks = (long long)d->batch * d->tokens;
     const unsigned nblk = (unsigned)((toks + 7) / 8);
-    const bool fast64 = d->dtype == TOME_BF16 && d->dim == 64 && d->token_stride % 8 == 0 && d->batch_stride % 8 == 0 &&
-                        d->head_stride % 8 == 0 && ((uintptr_t)src & 15) == 0;
-    if (fast64)
+    if (sim_fast64(d, src))
       metric_norm64_kernel<<<(unsigned)((toks * 8 + 255) / 256), 256, 0, stream>>>(*d, reinterpret_cast<const __nv_bfloat16*>(src), plane_a, plane_b);
     else if (d->dtype == TOME_BF16)
       metric_norm_kernel<__nv_bfloat16><<<nblk, 256, 0, stream>>>(*d, reinterpret_cast<const __nv_bfloat16*>(src), plane_a, plane_b);

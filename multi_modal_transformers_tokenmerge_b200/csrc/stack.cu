@@ -226,7 +226,12 @@ static StackLayout make_layout(const tome_stack_cfg_t* c, void* workspace) {
     S.ws_attn_bytes = f > bw ? f : bw;
     S.ws_attn = b.take<uint8_t>(S.ws_attn_bytes);
   }
-  S.ws_sim_bytes = B * T0 * (size_t)((c->head_dim + 3) & ~3) * sizeof(float);  // normalised matching metric (tome_sim_argmax workspace)
+  {  // normalised (and, on the tensor-core path, bf16-split) matching metric: tome_sim_argmax's workspace
+    tome_metric_desc_t md;
+    memset(&md, 0, sizeof(md));
+    md.batch = c->batch; md.tokens = c->tokens; md.dim = c->head_dim; md.heads = c->heads; md.dtype = TOME_BF16;
+    S.ws_sim_bytes = tome_sim_argmax_workspace_bytes(&md);
+  }
   S.ws_sim = b.take<uint8_t>(S.ws_sim_bytes);
   // split-K workspace: the largest weight gradient, at most 64 splits are ever chosen but 148 tiles bound the product
   size_t wmax = C * 3 * HD;

@@ -13,6 +13,15 @@ Reference entry points executed:
   multi_modal_transformers/action_heads/categorical.py:12-40       assign_bins, CategoricalActionHead.__call__
   multi_modal_transformers/action_heads/diffusion.py:16-64         cosine_beta_schedule, FourierFeatures, OctoDenoise
   multi_modal_transformers/attention_blocks/attention.py:20-39     MLPBlock (instantiated by OctoDenoise)
+  multi_modal_transformers/attention_blocks/attention.py:41-119    Encoder1DBlock.__call__, AddPositionEmbedding,
+                                                                   StackedEncoder1DBlock.__call__ (nn.scan over the block) with
+                                                                   the config nodes of model_configs/attention_blocks/
+                                                                   vanilla_decoder.yaml: the reference's OWN control flow --
+                                                                   which LayerNorm instance feeds what, where the residuals and
+                                                                   the (deterministic) dropouts sit, how the scan threads the
+                                                                   carry and slices the stacked parameters -- with the Flax
+                                                                   leaf modules (LayerNorm, SelfAttention, Dense) restated in
+                                                                   oracle/jax_shim/flax/linen.py  -> encoder_blocks.npz
   (the two loss expressions live inside the Octo class, which needs the whole model: octo.py:163-165 and :183-187 are
    restated here in numpy float64 on the executed heads' outputs)
 """
@@ -230,5 +239,83 @@ def main():
     print("action_heads.npz:", list(ho["continuous"]), list(ho["categorical"]))
 
 
+def gen_blocks():
+    """encoder_blocks.npz: StackedEncoder1DBlock / Encoder1DBlock of the reference, executed (attention.py:41-119)."""
+    sys.dont_write_bytecode = True
+    for pth in (os.path.join(HERE, "jax_shim"), REF):
+        if pth not in sys.path:
+            sys.path.insert(0, pth)
+    import flax.linen as nn
+    import jax.numpy as jnp
+    import multi_modal_transformers.attention_blocks.attention as att
+    ts = _load("ref_token_sequencer2", f"{REF}/multi_modal_transformers/tokenizers/token_sequencer.py")
+
+    rng = np.random.default_rng(20261019)
+    out = {}
+    # (name, B, sequence grammar or None, T if no grammar, C, H, Dff, num_blocks, reduction axis)
+    cases = [("lit_seq", 2, "[TaskDescriptionPrefix{4}] [Image{6};Readout{2}]*2", 0, 64, 2, 64, 2, 1),   # yaml as written: LN over tokens
+             ("allones_1blk", 3, None, 17, 32, 4, 48, 1, 1),   # nn.merge_param refuses mask=None (attention.py:55): all-ones mask
+             ("feature_ln", 2, "[TaskDescriptionPrefix{3}] [Image{5};Readout{1}]*3", 0, 64, 2, 128, 3, -1)]
+    for name, B, seq, T, C, H, Dff, N, ax in cases:
+        mask = None
+        if seq is not None:
+            tseq = ts.TokenSequence(seq)
+            m = np.asarray(tseq.generate_attention_mask(repeats=1))          # [1, T, T] bool, the reference's own rule table
+            T = m.shape[-1]
+            mask = np.broadcast_to(m[None], (B, 1, T, T)).copy()             # octo.py:119 adds the batch axis
+        else:
+            mask = np.ones((B, 1, T, T), bool)
+        D = C // H
+        r_ = lambda *sh, s_=1.0: (rng.standard_normal(sh) * s_).astype(np.float32)  # noqa: E731
+        blk = {"LayerNorm_0": {"scale": 1 + r_(N, C, s_=0.1), "bias": r_(N, C, s_=0.1)},
+               "LayerNorm_1": {"scale": 1 + r_(N, C, s_=0.1), "bias": r_(N, C, s_=0.1)},
+               "SelfAttention_0": {k_: {"kernel": r_(N, C, H, D, s_=(2.0 / C) ** 0.5), "bias": r_(N, H, D, s_=0.01)} for k_ in ("query", "key", "value")},
+               "MLPBlock_0": {"Dense_0": {"kernel": r_(N, C, Dff, s_=(2.0 / C) ** 0.5), "bias": r_(N, Dff, s_=0.01)},
+                              "Dense_1": {"kernel": r_(N, Dff, C, s_=(2.0 / Dff) ** 0.5), "bias": r_(N, C, s_=0.01)}}}
+        blk["SelfAttention_0"]["out"] = {"kernel": r_(N, H, D, C, s_=(2.0 / C) ** 0.5), "bias": r_(N, C, s_=0.01)}
+        tree = {"posembed_input": {"pos_embedding": r_(1, T, C, s_=0.02)}, "ScanEncoder1DBlock_0": blk}
+        dense = lambda f: {"_target_": "flax.linen.Dense", "features": f, "use_bias": True,  # noqa: E731
+                           "kernel_init": {"_target_": "flax.linen.initializers.he_normal"},
+                           "bias_init": {"_target_": "flax.linen.initializers.normal"}}
+        enc = {  # model_configs/attention_blocks/vanilla_decoder.yaml:4-59, widths scaled down
+            "_target_": "multi_modal_transformers.attention_blocks.attention.Encoder1DBlock",
+            "layer_norm": {"_target_": "flax.linen.LayerNorm", "epsilon": 1e-6, "reduction_axes": [ax], "feature_axes": [-1],
+                           "dtype": None, "param_dtype": None},
+            "dropout": {"_target_": "flax.linen.Dropout", "rate": 0.1},
+            "self_attention": {"_target_": "flax.linen.SelfAttention", "num_heads": H, "qkv_features": C, "dropout_rate": 0.1,
+                               "decode": False, "kernel_init": {"_target_": "flax.linen.initializers.he_normal"}, "use_bias": True,
+                               "bias_init": {"_target_": "flax.linen.initializers.normal"}, "dtype": "float32", "param_dtype": "float32"},
+            "mlp_block": {"_target_": "multi_modal_transformers.attention_blocks.attention.MLPBlock", "dense": dense(Dff),
+                          "activation": {"_partial_": True, "_target_": "flax.linen.relu"},
+                          "norm": {"_target_": "flax.linen.Dropout", "rate": 0.1}, "dense_out": dense(C)}}
+        x = r_(B, T, C)
+        stack = att.StackedEncoder1DBlock(num_blocks=N, encoder_1d_block=enc)
+        with nn.shim_scope({"StackedEncoder1DBlock_0": tree}):
+            y = np.asarray(stack(jnp.asarray(x), train=False, mask=None if mask is None else jnp.asarray(mask)))
+        # one block alone (layer 0's parameters), the Encoder1DBlock entry point itself
+        one = att.Encoder1DBlock(layer_norm=enc["layer_norm"], dropout=enc["dropout"], self_attention=enc["self_attention"],
+                                 mlp_block=enc["mlp_block"])
+        with nn.shim_scope({"Encoder1DBlock_0": nn._tree_index(blk, 0)}):
+            y1, none = one(jnp.asarray(x), mask=None if mask is None else jnp.asarray(mask), train=False)
+        assert none is None
+        out[f"{name}/x"], out[f"{name}/y"], out[f"{name}/y_block0"] = x, y.astype(np.float32), np.asarray(y1, np.float32)
+        out[f"{name}/meta"] = np.array([B, T, C, H, Dff, N, ax], np.int32)
+        out[f"{name}/mask"] = mask
+        if seq is not None:
+            out[f"{name}/seq"] = np.array(seq)
+
+        def flat(prefix, t):
+            for k_, v_ in t.items():
+                if isinstance(v_, dict):
+                    flat(f"{prefix}/{k_}", v_)
+                else:
+                    out[f"{prefix}/{k_}"] = v_
+        flat(f"{name}/params", tree)
+    out["cases"] = np.array([c[0] for c in cases])
+    np.savez_compressed(os.path.join(OUT, "encoder_blocks.npz"), **out)
+    print("encoder_blocks.npz:", [c[0] for c in cases])
+
+
 if __name__ == "__main__":
     main()
+    gen_blocks()

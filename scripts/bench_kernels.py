@@ -62,6 +62,20 @@ def bench_merge():
         t = timeit(lambda: ops.sim_argmax(metric))
         t2 = timeit(lambda: ops.select_topr(nm, ni, T, r))
         print(f"   sim_argmax {t*1e6:8.1f} us   select_topr {t2*1e6:8.1f} us")
+        H = C // 64   # the stack's call: keys read in place from the packed bf16 qkv buffer, mean over heads
+        qkv = torch.randn(B, T, 3, H, 64, device="cuda").bfloat16()
+        kwm = dict(heads=H, dim=64, batch=B, tokens=T, batch_stride=T * 3 * H * 64, token_stride=3 * H * 64, head_stride=64, offset_elems=H * 64)
+        ref = None
+        for tc in (0, 2, 1):
+            _lib.lib().tome_sim_argmax_set_tc(tc)
+            t = timeit(lambda: ops.sim_argmax(qkv, **kwm))
+            nm2, ni2, _ = ops.sim_argmax(qkv, **kwm)
+            if ref is None:
+                ref = (nm2.clone(), ni2.clone())
+            same = (ni2 == ref[1]).float().mean().item()
+            print(f"   sim_argmax from packed bf16 keys, {H} heads, {('fp32 CUDA cores', 'tensor cores + cluster multicast', 'tensor cores')[tc]}: {t*1e6:8.1f} us"
+                  f"  (arg max equal to fp32 path: {same:.5f}, max |node_max diff| {(nm2 - ref[0]).abs().max().item():.2e})")
+        _lib.lib().tome_sim_argmax_set_tc(1)
 
 
 def bench_gemm():

@@ -387,3 +387,36 @@ def test_action_head_configs_build_the_mirror_modules():
     assert isinstance(k, AH.CategoricalActionHead) and k.action_space_dim == 8
     with pytest.raises(ValueError, match="unsupported action head"):
         MC.build_action_head({"_target_": "somewhere.OtherHead"})
+
+
+@gpu
+@pytest.mark.parametrize("name", ["lit_seq", "allones_1blk", "feature_ln"])
+def test_vanilla_stack_module_against_the_executed_reference_blocks(name):
+    """The drop-in StackedEncoder1DBlock (CUDA path) fed the SAME Flax parameter tree and inputs as the reference's own
+    StackedEncoder1DBlock.__call__ (attention.py:87-119, executed under the shim by oracle/gen_golden.py ->
+    tests/golden/encoder_blocks.npz): position embedding, scan over the stacked block parameters, pre-LN attention and MLP
+    branches with their residuals, dense boolean mask as octo.py:66-68 / :119 builds it.  bf16 kernels vs the fp32 fixture:
+    relative L2 error <= 2e-2."""
+    EB = np.load(os.path.join(os.path.dirname(__file__), "golden", "encoder_blocks.npz"))
+    B, T, C, H, Dff, N, ax = [int(v) for v in EB[f"{name}/meta"]]
+    tree, pre = {}, f"{name}/params/"
+    for k in EB.files:
+        if k.startswith(pre):
+            node, parts = tree, k[len(pre):].split("/")
+            for p_ in parts[:-1]:
+                node = node.setdefault(p_, {})
+            node[parts[-1]] = EB[k]
+    cfg = MC.load("attention_blocks/tome_decoder_octo_base")
+    e = dict(cfg["encoder_1d_block"], _target_="multi_modal_transformers.attention_blocks.attention.Encoder1DBlock")
+    e["layer_norm"] = dict(e["layer_norm"], reduction_axes=[ax])
+    e["self_attention"] = dict(e["self_attention"], _target_="flax.linen.SelfAttention", num_heads=H, qkv_features=C)
+    e["mlp_block"] = dict(e["mlp_block"], dense=dict(e["mlp_block"]["dense"], features=Dff),
+                          dense_out=dict(e["mlp_block"]["dense_out"], features=C))
+    stack = MC.build_stack({"num_blocks": N, "encoder_1d_block": e})
+    assert type(stack) is A.StackedEncoder1DBlock
+    x = _dev(EB[f"{name}/x"])
+    mask = torch.as_tensor(EB[f"{name}/mask"]).expand(B, H, T, T)
+    y = stack.apply({"params": tree}, x, train=False, mask=mask)
+    want = torch.as_tensor(EB[f"{name}/y"])
+    err = ((y.float().cpu() - want).norm() / want.norm()).item()
+    assert err <= 2e-2, err

@@ -169,3 +169,73 @@ def test_diffusion_head_matches_reference_goldens():
                                     O.alpha_hats(int(g[f"{name}/steps"])), p)
         np.testing.assert_allclose(pred.numpy(), g[f"{name}/pred"], rtol=1e-4, atol=1e-5)
         np.testing.assert_allclose(loss.item(), g[f"{name}/loss"], rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ block composition
+EB = np.load(os.path.join(GOLD, "encoder_blocks.npz"))
+
+
+def _eb_tree(name):
+    """the Flax parameter tree of an encoder_blocks.npz case, rebuilt from its flattened keys"""
+    tree = {}
+    pre = f"{name}/params/"
+    for k in EB.files:
+        if k.startswith(pre):
+            node = tree
+            parts = k[len(pre):].split("/")
+            for p_ in parts[:-1]:
+                node = node.setdefault(p_, {})
+            node[parts[-1]] = EB[k]
+    return tree
+
+
+def _eb_oracle_params(blk, layer, C):
+    import torch
+    a = blk["SelfAttention_0"]
+    g = lambda t: torch.tensor(np.asarray(t[layer], np.float32))  # noqa: E731
+    return O.BlockParams(
+        ln1_scale=g(blk["LayerNorm_0"]["scale"]), ln1_bias=g(blk["LayerNorm_0"]["bias"]),
+        ln2_scale=g(blk["LayerNorm_1"]["scale"]), ln2_bias=g(blk["LayerNorm_1"]["bias"]),
+        wq=g(a["query"]["kernel"]).reshape(C, -1), bq=g(a["query"]["bias"]).reshape(-1),
+        wk=g(a["key"]["kernel"]).reshape(C, -1), bk=g(a["key"]["bias"]).reshape(-1),
+        wv=g(a["value"]["kernel"]).reshape(C, -1), bv=g(a["value"]["bias"]).reshape(-1),
+        wo=g(a["out"]["kernel"]).reshape(-1, C), bo=g(a["out"]["bias"]),
+        w1=g(blk["MLPBlock_0"]["Dense_0"]["kernel"]), b1=g(blk["MLPBlock_0"]["Dense_0"]["bias"]),
+        w2=g(blk["MLPBlock_0"]["Dense_1"]["kernel"]), b2=g(blk["MLPBlock_0"]["Dense_1"]["bias"]))
+
+
+def _eb_groups(name, B, T):
+    if f"{name}/seq" in EB.files:
+        gid, pos, allow, _ = O.sequence_groups(str(EB[f"{name}/seq"]))
+    else:
+        gid, pos, allow = np.zeros(T, np.uint8), np.arange(T, dtype=np.int32), np.ones((1, 1), np.uint8)
+    # the mask the reference itself built (TokenSequence.generate_attention_mask) is what the group table must expand to
+    dense = O.dense_mask(np.broadcast_to(gid, (B, T)), np.broadcast_to(pos, (B, T)), np.broadcast_to(gid, (B, T)),
+                         np.broadcast_to(pos, (B, T)), allow)
+    np.testing.assert_array_equal(dense, EB[f"{name}/mask"][:, 0])
+    return gid, pos, allow
+
+
+@pytest.mark.parametrize("name", [str(n) for n in EB["cases"]])
+def test_block_and_stack_follow_the_reference_control_flow(name):
+    """oracle.tome_block / tome_stack (r = 0, no size bias: the reference as written) against the outputs of the reference's
+    OWN Encoder1DBlock.__call__ and StackedEncoder1DBlock.__call__ (attention.py:41-119), executed by oracle/gen_golden.py
+    with the vanilla_decoder.yaml config nodes: which LayerNorm instance feeds what, where the residual adds sit, the MLP
+    block's order, the position embedding, the scan over stacked parameters.  fp32 on both sides: 2e-5 relative."""
+    import torch
+    B, T, C, H, Dff, N, ax = [int(v) for v in EB[f"{name}/meta"]]
+    tree = _eb_tree(name)
+    blk = tree["ScanEncoder1DBlock_0"]
+    gid, pos, allow = _eb_groups(name, B, T)
+    x = torch.tensor(EB[f"{name}/x"])
+    ln_axis = "seq" if ax == 1 else "feature"
+    params = [_eb_oracle_params(blk, l, C) for l in range(N)]
+    with torch.no_grad():
+        y, size, _ = O.tome_stack(params, torch.tensor(tree["posembed_input"]["pos_embedding"]), x, gid, pos, allow, num_heads=H,
+                                  r=0, ln_axis=ln_axis, prop_attn=False)
+        g2, p2 = np.broadcast_to(gid, (B, T)).copy(), np.broadcast_to(pos, (B, T)).copy()
+        y1, _, _, _ = O.tome_block(params[0], x, torch.ones(B, T, 1), g2, p2, allow, num_heads=H, r=0, ln_axis=ln_axis, prop_attn=False)
+    rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))  # noqa: E731
+    assert rel(y.numpy(), EB[f"{name}/y"]) <= 2e-5
+    assert rel(y1.numpy(), EB[f"{name}/y_block0"]) <= 2e-5
+    assert float(size.min()) == 1.0 == float(size.max())
