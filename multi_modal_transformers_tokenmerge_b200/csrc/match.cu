@@ -381,9 +381,10 @@ sim_argmax_planes_kernel(const tome_metric_desc_t d, const float* __restrict__ p
 // max / first arg max of tile j from tensor memory while tile j + 1 is being computed.  (A first version stored the six
 // operand chunks per row explicitly, 768 B per token: its 295 MB of L2 -> SM traffic per call, not the tensor pipe, set
 // its 93 us -- profiles/r02_sim_argmax_tc.md.)
-// The a tiles of one batch element form a thread-block cluster (up to 8 CTAs): every b chunk is fetched from L2 by ONE of
-// them (round robin) and TMA-multicast into the ring slot of all, so the b rows cross the L2 -> SM path once per cluster
-// instead of once per a tile (32 times at T = 8192).
+// Optional (tome_sim_argmax_set_tc(2), off by default): the a tiles of one batch element form a thread-block cluster (up to
+// 8 CTAs) and every b chunk is fetched from L2 by ONE of them and TMA-multicast into the ring slot of all.  Measured: no
+// gain (93 vs 89 us at B = 256, T = 536; 393 vs 390 us at T = 8192) -- after the three-chunk layout the kernel is bound by
+// the per-CTA latency chain (ncu: the epilogue warps wait for the first score tile, 25 % tensor pipe), not by L2 -> SM bytes.
 //   warp 4  TMA: the a tile's three chunks once (48 KB, resident), then the b tiles chunk by chunk through a 3-slot ring
 //   warp 5  MMA issuer: per b chunk h: a_h, a_m, a_l;  m: a_h, a_m;  l: a_h        warps 0..3  epilogue
 constexpr int SIMT_BM = 128, SIMT_BN = 128, SIMT_CHUNKS = 3, SIMT_SLOTS = 3, SIMT_ROW = 192;
@@ -772,8 +773,8 @@ extern "C" int tome_clamp_r(int tokens, int r, int class_token, int distill_toke
 
 // 1 (default): the tensor-core path (split-bf16 K = 384 contraction) whenever the input allows it; 0: fp32 CUDA-core planes.
 // Process-wide tuning aid (A/B measurements, cross-check), not part of the public header.
-static int g_sim_tc = 1, g_sim_mc = 1;
-extern "C" void tome_sim_argmax_set_tc(int on) { g_sim_tc = on ? 1 : 0; g_sim_mc = on == 2 ? 0 : 1; }   // 2: tensor cores without the cluster multicast
+static int g_sim_tc = 1, g_sim_mc = 0;
+extern "C" void tome_sim_argmax_set_tc(int on) { g_sim_tc = on ? 1 : 0; g_sim_mc = on == 2 ? 1 : 0; }   // 2: tensor cores + cluster multicast of the b rows
 
 static bool sim_tc_eligible(const tome_metric_desc_t* d) { return d->dim == 64; }
 static bool sim_fast64(const tome_metric_desc_t* d, const void* src) {   // 128-bit loads, 8 lanes per row

@@ -73,7 +73,7 @@ def bench_merge():
             if ref is None:
                 ref = (nm2.clone(), ni2.clone())
             same = (ni2 == ref[1]).float().mean().item()
-            print(f"   sim_argmax from packed bf16 keys, {H} heads, {('fp32 CUDA cores', 'tensor cores + cluster multicast', 'tensor cores')[tc]}: {t*1e6:8.1f} us"
+            print(f"   sim_argmax from packed bf16 keys, {H} heads, {('fp32 CUDA cores', 'tensor cores', 'tensor cores + cluster multicast')[tc]}: {t*1e6:8.1f} us"
                   f"  (arg max equal to fp32 path: {same:.5f}, max |node_max diff| {(nm2 - ref[0]).abs().max().item():.2e})")
         _lib.lib().tome_sim_argmax_set_tc(1)
 
