@@ -16,7 +16,7 @@ BUILD = os.path.join(CSRC, "_build")
 LIB = os.path.join(HERE, "libtome_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
-         "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+         "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("TOME_NVCC_EXTRA", "").split()   # e.g. -DTOME_GEMM_EPI_WARPS=16 (A/B builds)
 
 
 def _sources():

@@ -27,7 +27,12 @@ namespace tome {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_EPI_WARPS = 8;
+#ifndef TOME_GEMM_EPI_WARPS
+#define TOME_GEMM_EPI_WARPS 8
+#endif
+constexpr int GEMM_EPI_WARPS = TOME_GEMM_EPI_WARPS;   // 4 per TMEM lane quadrant x NSPLIT column groups
+constexpr int GEMM_NSPLIT = GEMM_EPI_WARPS / 4;
+static_assert(GEMM_EPI_WARPS % 4 == 0 && GEMM_NSPLIT >= 1 && GEMM_NSPLIT <= 4, "epilogue warps come in groups of four (one per lane quadrant)");
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 
 
@@ -61,7 +66,8 @@ struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN <= 128) ? 6 : (BN <= 192) ? 5 : 4;  // 6 x 32 KB, 5 x 40 KB, 4 x 48 KB
+  // 6 x 32 KB, 5 x 40 KB, 4 x 48 KB; with 16 epilogue warps the staging tiles take 32 KB and the widest tile keeps 3 stages
+  static constexpr int STAGES = (BN <= 128) ? 6 : (BN <= 192) ? (GEMM_EPI_WARPS > 8 ? 4 : 5) : (GEMM_EPI_WARPS > 8 ? 3 : 4);
   static constexpr int STORE_BYTES = GEMM_EPI_WARPS * 2048;  // per epilogue warp: 32 rows x 64 B staging tile for TMA stores
   static constexpr int BAR_BYTES = 256 + 2 * BN * 4;  // barriers + double-buffered bias tile
   static constexpr int TOTAL = STAGES * STAGE_BYTES + STORE_BYTES + BAR_BYTES + 1024;  // +1024: manual 1 KB alignment
@@ -206,11 +212,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
   } else {
     // ================================================================= epilogue (warps 2..9)
-    constexpr int HALF = BN / 2;                 // columns per epilogue warp
-    constexpr int NCH = HALF / 32;               // 32-column chunks per warp
+    // the tile's BN / 32 column chunks are dealt round-robin to the GEMM_NSPLIT warps of a lane quadrant: warp `part` owns
+    // chunks part, part + NSPLIT, ... (chunk index = column / 32 inside the tile)
+    constexpr int NCHUNKS = BN / 32;
+    constexpr int NCH = (NCHUNKS + GEMM_NSPLIT - 1) / GEMM_NSPLIT;   // most chunks one warp owns
     const int ew = warp - 2;
     const int quad = warp & 3;                   // TMEM lane quadrant this warp may access
-    const int half = ew >> 2;                    // which half of the tile's columns
+    const int part = ew >> 2;                    // which column group of the tile
+#define TOME_CHUNK(c) (part + (c) * GEMM_NSPLIT)
+#define TOME_CHUNK_OK(c) (NCHUNKS % GEMM_NSPLIT == 0 || TOME_CHUNK(c) < NCHUNKS)
     const int row_in_tile = quad * 32 + lane;
     const int etid = threadIdx.x - 64;           // 0..255
     const __nv_bfloat16* resid = reinterpret_cast<const __nv_bfloat16*>(e.residual);
@@ -230,7 +240,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const int m_blk = (tile / s.n_tiles) * (MC ? 2 : 1) + (int)crank;
         const long long row = (long long)m_blk * GEMM_BM + row_in_tile;
         const int n0 = n_blk * BN;
-        const int cbase = n0 + half * HALF;
         const bool row_ok = row < s.m;
         // ---- everything the epilogue reads from memory is fetched while the tensor core still works on this tile
         if (kBias && etid < BN) s_bias[acc * BN + etid] = (n0 + etid < s.n) ? __ldg(e.bias + n0 + etid) : 0.f;
@@ -240,8 +249,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         if constexpr (kGate) {
           if (gate_by_bits) {
 #pragma unroll
-            for (int c = 0; c < NCH; ++c)
-              gw[c] = (row_ok && cbase + c * 32 < s.n) ? __ldg(e.bits_in + row * e.ldw + ((cbase >> 5) + c)) : 0u;
+            for (int c = 0; c < NCH; ++c) {
+              const int col = n0 + TOME_CHUNK(c) * 32;
+              gw[c] = (TOME_CHUNK_OK(c) && row_ok && col < s.n) ? __ldg(e.bits_in + row * e.ldw + (col >> 5)) : 0u;
+            }
           }
         }
         if constexpr (kResid || kGate) {
@@ -252,23 +263,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             for (int c = 0; c < NCH; ++c)
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const int col = cbase + c * 32 + i * 8;
-                pre[c][i] = (row_ok && col < s.n) ? __ldg(reinterpret_cast<const uint4*>(src + row * ld + col)) : make_uint4(0u, 0u, 0u, 0u);
+                const int col = n0 + TOME_CHUNK(c) * 32 + i * 8;
+                pre[c][i] = (TOME_CHUNK_OK(c) && row_ok && col < s.n) ? __ldg(reinterpret_cast<const uint4*>(src + row * ld + col)) : make_uint4(0u, 0u, 0u, 0u);
               }
           }
         }
         if (kBias) asm volatile("bar.sync 1, %0;" ::"r"(32 * GEMM_EPI_WARPS) : "memory");  // bias tile visible to all epilogue warps
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
-        const uint32_t t_addr = tmem_base + acc * BN + half * HALF + ((uint32_t)(quad * 32) << 16);
+        const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
+          if (!TOME_CHUNK_OK(c)) break;   // warp-uniform: this warp owns one chunk fewer
           float v[32];
-          tmem_ld_f32x32(t_addr + c * 32, v);
+          tmem_ld_f32x32(t_addr + TOME_CHUNK(c) * 32, v);
           tmem_ld_wait();
-          const int col = cbase + c * 32;
+          const int col = n0 + TOME_CHUNK(c) * 32;
           if constexpr (kBias) {
-            const float4* b4p = reinterpret_cast<const float4*>(s_bias + acc * BN + half * HALF + c * 32);
+            const float4* b4p = reinterpret_cast<const float4*>(s_bias + acc * BN + TOME_CHUNK(c) * 32);
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
               const float4 b4 = b4p[i / 4];
@@ -366,7 +378,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const int m_blk = (tile / (s.k_splits * s.n_tiles)) * (MC ? 2 : 1) + (int)crank;
       const long long row = (long long)m_blk * GEMM_BM + row_in_tile;
       const int n0 = n_blk * BN;
-      const int cbase = n0 + half * HALF;
       const bool row_ok = row < s.m;
       // ---- prefetch everything the epilogue reads, while the tensor core is still working on this tile
       if (e.bias && etid < BN) s_bias[acc * BN + etid] = (n0 + etid < s.n) ? __ldg(e.bias + n0 + etid) : 0.f;
@@ -379,27 +390,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       for (int c = 0; c < NCH; ++c)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int col = cbase + c * 32 + i * 8;
-          pre[c][i] = (pre_src && row_ok && col < s.n) ? __ldg(reinterpret_cast<const uint4*>(pre_src + row * pre_ld + col))
-                                                      : make_uint4(0u, 0u, 0u, 0u);
+          const int col = n0 + TOME_CHUNK(c) * 32 + i * 8;
+          pre[c][i] = (TOME_CHUNK_OK(c) && pre_src && row_ok && col < s.n) ? __ldg(reinterpret_cast<const uint4*>(pre_src + row * pre_ld + col))
+                                                                            : make_uint4(0u, 0u, 0u, 0u);
         }
       asm volatile("bar.sync 1, %0;" ::"r"(32 * GEMM_EPI_WARPS) : "memory");  // bias tile visible to all epilogue warps
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + acc * BN + half * HALF + ((uint32_t)(quad * 32) << 16);
+      const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
+        if (!TOME_CHUNK_OK(c)) break;   // warp-uniform
         uint32_t v[32];
-        tmem_ld_x32(t_addr + c * 32, v);
+        tmem_ld_x32(t_addr + TOME_CHUNK(c) * 32, v);
         tmem_ld_wait();
-        const int col = cbase + c * 32;
+        const int col = n0 + TOME_CHUNK(c) * 32;
         const bool active = row_ok && col < s.n;  // rows / columns past the edge are computed but never stored
         float acc_f[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc_f[i] = __uint_as_float(v[i]);
         const int ncols = min(32, s.n - col);  // multiple of 8 (host checks n % 8 == 0); <= 0 past the edge
         if (e.bias) {
-          const float4* b4p = reinterpret_cast<const float4*>(s_bias + acc * BN + half * HALF + c * 32);
+          const float4* b4p = reinterpret_cast<const float4*>(s_bias + acc * BN + TOME_CHUNK(c) * 32);
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             const float4 b4 = b4p[i / 4];
@@ -499,6 +511,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all of this warp's TMA stores are complete
+#undef TOME_CHUNK
+#undef TOME_CHUNK_OK
   }
 
   tc_fence_before();
