@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtome_b200.so")
+LIB_PATH = os.path.join(HERE, f"libtome_b200{os.environ.get('TOME_LIB_SUFFIX', '')}.so")   # suffix: experimental A/B builds (build.py)
 
 TOME_OK, TOME_ERR_INVALID, TOME_ERR_CUDA, TOME_ERR_UNSUPPORTED = 0, 1, 2, 3
 TOME_BF16, TOME_F32 = 0, 1

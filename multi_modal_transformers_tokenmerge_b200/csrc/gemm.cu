@@ -59,15 +59,24 @@ struct GemmShape {
   int m, n, k;
   int m_tiles, n_tiles, k_splits, kb_per_split, kb_total;
   int m_items;  // m_tiles, or ceil(m_tiles / 2) when CTA pairs share the B operand
+  int ablate;   // TOME_GEMM_ABLATE builds only: 1 = no output stores, 2 = no operand loads, 4 = no MMAs (wrong results; timing probes)
 };
+#ifdef TOME_GEMM_ABLATE
+#define TOME_ABL(bit) ((s.ablate & (bit)) != 0)
+#else
+#define TOME_ABL(bit) false
+#endif
 
-template <int BN>
+template <int BN, bool PAIR = false>
 struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  // pair MMA: this CTA holds half of the tile's columns, as whole 64-column atoms (BN = 192: 96 columns in two atoms)
+  static constexpr int B_ATOMS = PAIR ? (BN / 2 + 63) / 64 : BN / 64;
+  static constexpr int B_BYTES = B_ATOMS * 64 * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // 6 x 32 KB, 5 x 40 KB, 4 x 48 KB; with 16 epilogue warps the staging tiles take 32 KB and the widest tile keeps 3 stages
-  static constexpr int STAGES = (BN <= 128) ? 6 : (BN <= 192) ? (GEMM_EPI_WARPS > 8 ? 4 : 5) : (GEMM_EPI_WARPS > 8 ? 3 : 4);
+  static constexpr int STAGES = PAIR ? ((BN <= 128) ? 8 : 6)   // 8 x 24 KB, 6 x 32 KB (BN = 192 and 256)
+                                     : (BN <= 128) ? 6 : (BN <= 192) ? (GEMM_EPI_WARPS > 8 ? 4 : 5) : (GEMM_EPI_WARPS > 8 ? 3 : 4);
   static constexpr int STORE_BYTES = GEMM_EPI_WARPS * 2048;  // per epilogue warp: 32 rows x 64 B staging tile for TMA stores
   static constexpr int BAR_BYTES = 256 + 2 * BN * 4;  // barriers + double-buffered bias tile
   static constexpr int TOTAL = STAGES * STAGE_BYTES + STORE_BYTES + BAR_BYTES + 1024;  // +1024: manual 1 KB alignment
@@ -81,11 +90,12 @@ struct GemmSmem {
 // carry no flag tests or per-8-column edge tests.  The stack's own GEMMs all take one of these paths.
 constexpr int EPI_GENERIC = -1, EPI_BIAS = 1, EPI_RELU = 2, EPI_GATE = 4, EPI_DROP = 8, EPI_RESID = 16;
 
-template <int BN, bool A_MN, bool B_MN, bool MC, int EPI>
+template <int BN, bool A_MN, bool B_MN, int MC, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const __grid_constant__ CUtensorMap tma_c, const GemmShape s, const GemmEpilogue e) {
-  using L = GemmSmem<BN>;
+  constexpr bool PAIR = MC == 2;   // one 256-row cta_group::2 MMA per cluster pair (MC == 1: two 128-row MMAs sharing a multicast B)
+  using L = GemmSmem<BN, PAIR>;
   constexpr int STAGES = L::STAGES;
   constexpr uint32_t TMEM_COLS = BN <= 64 ? 128 : BN <= 128 ? 256 : 512;  // two accumulator stages of BN columns
   static_assert(2 * BN <= 512 && BN % 64 == 0, "two BN-column accumulators must fit the 512 TMEM columns");
@@ -107,6 +117,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const uint32_t crank = MC ? cluster_ctarank() : 0u;
   const int first_item = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int item_step = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const bool leader = crank == 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -116,15 +127,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], MC ? 2 : 1);
+      mbar_init(&empty_bar[i], MC == 1 ? 2 : 1);   // MC == 1: both CTAs' MMAs drain a multicast stage; pair: one commit
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], GEMM_EPI_WARPS);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], PAIR ? 2 * GEMM_EPI_WARPS : GEMM_EPI_WARPS);  // one arrive per epilogue warp (pair: of both CTAs, at the leader)
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 2) {
+    if constexpr (PAIR) tmem_alloc2(tmem_slot, TMEM_COLS);
+    else tmem_alloc(tmem_slot, TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
   if (MC) cluster_sync_all();  // the peer's barriers exist before anything is multicast at them
@@ -147,8 +161,40 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
-          mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
           const int k0 = kb * GEMM_BK;
+          if constexpr (PAIR) {
+            // both CTAs' loads are counted on the LEADER's barrier: its MMA thread is the only consumer
+            const uint32_t fb = map_to_cta(&full_bar[stage], 0);
+            if (TOME_ABL(2)) {
+              if (leader) mbar_arrive(&full_bar[stage]);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+              continue;
+            }
+            // bytes both CTAs' boxes deliver (a K-major half of BN = 192 is one 96-row box: 12 KB of the 16 KB slot)
+            constexpr uint32_t kPairTx = 2 * (L::A_BYTES + (B_MN ? L::B_BYTES : (BN / 2) * GEMM_BK * 2));
+            if (leader) mbar_expect_tx(&full_bar[stage], kPairTx);
+            if (!A_MN) {
+              tma_load_2d_pair(sa, &tma_a, fb, k0, TOME_ABL(32) ? (m0 & 1023) : m0);   // 32: operand stream from 1024 rows (L2-resident)
+            } else {
+#pragma unroll
+              for (int j = 0; j < GEMM_BM / 64; ++j) tma_load_2d_pair(sa + j * 8192, &tma_a, fb, m0 + 64 * j, k0);
+            }
+            const int nh = n0 + (int)crank * (BN / 2);   // this CTA's half of the tile's columns
+            if (!B_MN) {
+              tma_load_2d_pair(sb, &tma_b, fb, k0, nh);  // box {64 k, BN/2 n}
+            } else {
+#pragma unroll
+              for (int j = 0; j < L::B_ATOMS; ++j) tma_load_2d_pair(sb + j * 8192, &tma_b, fb, nh + 64 * j, k0);   // BN = 192: the second atom is half used
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          if (TOME_ABL(2) && !MC) {
+            mbar_arrive(&full_bar[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
           if (!A_MN) {
             tma_load_2d(sa, &tma_a, &full_bar[stage], k0, m0);  // box {64 k, 128 m}
           } else {
@@ -178,8 +224,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
   } else if (warp == 1) {
     // ================================================================= UMMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, A_MN, B_MN);
+    if (lane == 0 && (!PAIR || leader)) {
+      constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * GEMM_BM : GEMM_BM, BN, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -198,15 +244,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           const uint32_t sb = sa + L::A_BYTES;
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
+            if (TOME_ABL(4)) break;
             const uint64_t da = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
             const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (PAIR) umma2_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          if (MC) umma_commit_mc(&empty_bar[stage], (uint16_t)3);  // both CTAs' producers may refill this stage
+          if constexpr (PAIR) umma2_commit_mc(&empty_bar[stage], (uint16_t)3);   // both producers may refill their halves
+          else if (MC) umma_commit_mc(&empty_bar[stage], (uint16_t)3);  // both CTAs' producers may refill this stage
           else umma_commit(&empty_bar[stage]);                     // smem slot reusable once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if constexpr (PAIR) umma2_commit_mc(&tmem_full[acc], (uint16_t)3);  // both CTAs' epilogues read their 128 rows
+        else umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -272,12 +322,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
+        // the TMEM read of chunk c + 1 is in flight while chunk c is processed (two register sets, compile-time ping-pong)
+        float va[32], vb[32];
+        if (!TOME_ABL(8)) tmem_ld_f32x32(t_addr + TOME_CHUNK(0) * 32, va);
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-          if (!TOME_CHUNK_OK(c)) break;   // warp-uniform: this warp owns one chunk fewer
-          float v[32];
-          tmem_ld_f32x32(t_addr + TOME_CHUNK(c) * 32, v);
+          if (!TOME_CHUNK_OK(c) || TOME_ABL(8)) break;   // warp-uniform: this warp owns one chunk fewer
+          float (&v)[32] = (c & 1) ? vb : va;
           tmem_ld_wait();
+          if (c + 1 < NCH && TOME_CHUNK_OK(c + 1)) tmem_ld_f32x32(t_addr + TOME_CHUNK(c + 1) * 32, (c & 1) ? va : vb);
           const int col = n0 + TOME_CHUNK(c) * 32;
           if constexpr (kBias) {
             const float4* b4p = reinterpret_cast<const float4*>(s_bias + acc * BN + TOME_CHUNK(c) * 32);
@@ -347,7 +400,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             }
           }
           // stage this warp's 32 rows x 32 columns in shared memory (64-byte swizzled rows) and hand the box to TMA,
-          // which writes whole lines and clips rows >= M / columns >= N
+          // which writes whole lines and clips rows >= M / columns >= N.  (Reading the tile back and storing it with
+          // 128-bit LSU stores, 8 rows x 64 B per instruction, was measured slower: 108 vs 78 us for the stores of the
+          // 133120 x 1536 output alone, 154 vs 142 us for the whole GEMM without CTA pairs.)
           uint8_t* stg = s_store + ew * 2048;
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous box has left smem
           __syncwarp();
@@ -358,8 +413,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            const int row0 = m_blk * GEMM_BM + quad * 32;
-            if (col < s.n && row0 < s.m) {
+            const int row0 = (TOME_ABL(16) ? (m_blk & 7) : m_blk) * GEMM_BM + quad * 32;   // 16: all stores into 1024 rows (L2-resident)
+            if (col < s.n && row0 < s.m && !TOME_ABL(1)) {
               asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                            ::"l"(&tma_c), "r"(smem_u32(stg)), "r"(col), "r"(row0) : "memory");
             }
@@ -368,7 +423,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (lane == 0) {
+          if constexpr (PAIR) mbar_arrive_cluster(map_to_cta(&tmem_empty[acc], 0));   // the leader's MMA thread waits for both CTAs
+          else mbar_arrive(&tmem_empty[acc]);
+        }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     } else
@@ -507,7 +565,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(map_to_cta(&tmem_empty[acc], 0));
+        else mbar_arrive(&tmem_empty[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all of this warp's TMA stores are complete
@@ -520,7 +581,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   if (MC) cluster_sync_all();  // the peer may still multicast into this CTA's smem / arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (PAIR) tmem_dealloc2(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -549,17 +611,17 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __re
 static int g_gemm_sm_limit = 0;
 static inline int gemm_sms() { return g_gemm_sm_limit > 0 && g_gemm_sm_limit < kNumSMs ? g_gemm_sm_limit : kNumSMs; }
 
-template <int BN, bool A_MN, bool B_MN, bool MC, int EPI>
+template <int BN, bool A_MN, bool B_MN, int MC, int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmShape& s, const GemmEpilogue& e,
                        cudaStream_t stream) {
   auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, MC, EPI>;
   static DynSmemOnce once;  // per instantiation, per device
-  TOME_CUDA(ensure_dyn_smem(kern, GemmSmem<BN>::TOTAL, once));
+  TOME_CUDA(ensure_dyn_smem(kern, GemmSmem<BN, MC == 2>::TOTAL, once));
   const int items = s.m_items * s.n_tiles * s.k_splits;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = GemmSmem<BN>::TOTAL;
+  cfg.dynamicSmemBytes = GemmSmem<BN, MC == 2>::TOTAL;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   if (MC) {
@@ -589,6 +651,40 @@ static int pick_bn(int n) {  // least padded MMA work (tiles x width), then the 
   return 128;
 }
 
+static int g_gemm_force_mode = -1, g_gemm_force_bn = 0;
+// tuning aid: force the CTA mode (0 single, 1 multicast pairs, 2 pair MMA; -1 = automatic) and the tile width (0 = automatic)
+extern "C" void tome_gemm_force_tile(int mode, int bn) { g_gemm_force_mode = mode; g_gemm_force_bn = bn; }
+// g_gemm_pair = 1 (default): CTA pairs may run one cta_group::2 MMA per k-step (256 x BN tile, each CTA holding half of B);
+// 0: never (two 128-row MMAs sharing a TMA-multicast B tile, round 1).  Process-wide tuning aid, not in the public header.
+static int g_gemm_pair = 1;
+extern "C" void tome_gemm_set_pair_mma(int on) { g_gemm_pair = on ? 1 : 0; }
+static int g_gemm_ablate = 0;
+extern "C" void tome_gemm_set_ablate(int bits) { g_gemm_ablate = bits; }   // has an effect in TOME_GEMM_ABLATE builds only
+
+struct TileChoice { int bn, mode; };   // mode 0: one CTA per tile; 1: CTA pairs, multicast B; 2: CTA pairs, one 256-row MMA
+static TileChoice pick_tile(const tome_gemm_args_t* a) {
+  const int m_tiles = ceil_div(a->m, GEMM_BM);
+  // CTA pairs: worth it unless an odd, small tile count would leave a large share of dummy tiles
+  const bool pairs_ok = a->no_multicast == 0 && m_tiles >= 2 && (m_tiles % 2 == 0 || m_tiles >= 16);
+  TileChoice t;
+  t.bn = pick_bn(a->n);
+  t.mode = pairs_ok ? 1 : 0;
+  // The pair MMA halves each SM's B traffic (L2 -> shared memory and shared memory -> tensor core).  Measured on B200 over
+  // every GEMM of an octo-small / octo-base layer with the stack's epilogues (scripts/sweep_gemm_tiles.py,
+  // profiles/r02_gemm_tile_sweep.md): with the tile width below it is the fastest or within 2 % of the fastest mode at every
+  // shape that can form pairs (octo-base: 1.46 - 1.56 PF/s against 1.31 - 1.41 for multicast pairs, above cuBLAS).  A pair
+  // MMA narrower than 192 columns is not: 256 x 128 x 16 occupies the tensor pipe as long as 256 x 256 x 16 does.
+  if (pairs_ok && g_gemm_pair) {
+    t.mode = 2;
+    // activations x weights with a wide output: the 256-wide pair tile beats the exactly fitting 192 (qkv, N = 1152: 112 vs 121 us)
+    if (t.bn == 192 && a->n >= 1024 && a->a_major == TOME_MAJOR_K) t.bn = 256;
+    if (t.bn == 128) t.mode = 1;
+  }
+  if (g_gemm_force_bn == 128 || g_gemm_force_bn == 192 || g_gemm_force_bn == 256) t.bn = g_gemm_force_bn;
+  if (g_gemm_force_mode == 0 || (g_gemm_force_mode > 0 && g_gemm_force_mode <= 2 && pairs_ok)) t.mode = g_gemm_force_mode;
+  return t;
+}
+
 static int pick_splits(const tome_gemm_args_t* a, int bn) {
   if (a->k_splits > 0) return a->k_splits;
   if (a->c_dtype != TOME_F32 || a->ldc != a->n) return 1;  // split-K only for dense fp32 outputs (weight gradients)
@@ -613,7 +709,7 @@ extern "C" int tome_num_sms(void) { return kNumSMs; }
 
 extern "C" size_t tome_gemm_workspace_bytes(const tome_gemm_args_t* a) {
   if (!a) return 0;
-  const int splits = pick_splits(a, pick_bn(a->n));
+  const int splits = pick_splits(a, pick_tile(a).bn);
   if (splits <= 1) return 0;
   return (size_t)splits * (size_t)a->m * (size_t)a->ldc * sizeof(float);
 }
@@ -636,7 +732,9 @@ extern "C" int tome_gemm_bf16(const tome_gemm_args_t* a, void* workspace, size_t
   TOME_CHECK(!a->relu_bits_out || a->relu, TOME_ERR_INVALID, "gemm: relu_bits_out needs the ReLU epilogue");
   TOME_CHECK(a->dropout_rate >= 0.f && a->dropout_rate < 1.f, TOME_ERR_INVALID, "gemm: dropout_rate must be in [0,1)");
 
-  const int bn = pick_bn(a->n);
+  const TileChoice tile = pick_tile(a);
+  const int bn = tile.bn, mode = tile.mode;
+  const bool mc = mode != 0;
   GemmShape s;
   s.m = a->m; s.n = a->n; s.k = a->k;
   s.m_tiles = ceil_div(a->m, GEMM_BM);
@@ -645,9 +743,8 @@ extern "C" int tome_gemm_bf16(const tome_gemm_args_t* a, void* workspace, size_t
   s.k_splits = pick_splits(a, bn);
   s.kb_per_split = ceil_div(s.kb_total, s.k_splits);
   s.k_splits = ceil_div(s.kb_total, s.kb_per_split);  // drop empty splits
-  // CTA pairs sharing B: worth it unless an odd, small tile count would leave a large share of dummy tiles
-  const bool mc = a->no_multicast == 0 && s.m_tiles >= 2 && (s.m_tiles % 2 == 0 || s.m_tiles >= 16);
   s.m_items = mc ? ceil_div(s.m_tiles, 2) : s.m_tiles;
+  s.ablate = g_gemm_ablate;
 
   GemmEpilogue e;
   e.c = a->c; e.bias = a->bias; e.residual = a->residual; e.gate = a->gate;
@@ -706,30 +803,21 @@ extern "C" int tome_gemm_bf16(const tome_gemm_args_t* a, void* workspace, size_t
       else if (flags == EPI_GATE) epi = EPI_GATE;
     }
   }
+#define TOME_GEMM_MODE(BN_, AMN_, BMN_, EPI_)                                                        \
+  do {                                                                                              \
+    if (mode == 2) rc = launch_gemm<BN_, AMN_, BMN_, 2, EPI_>(ta, tb, tc, s, e, stream);            \
+    else if (mode == 1) rc = launch_gemm<BN_, AMN_, BMN_, 1, EPI_>(ta, tb, tc, s, e, stream);     \
+    else rc = launch_gemm<BN_, AMN_, BMN_, 0, EPI_>(ta, tb, tc, s, e, stream);                      \
+  } while (0)
 #define TOME_GEMM_LAYOUTS(BN_, EPI_)                                                                \
   do {                                                                                              \
-    if (mc) {                                                                                       \
-      if (!amn && !bmn) rc = launch_gemm<BN_, false, false, true, EPI_>(ta, tb, tc, s, e, stream);  \
-      else if (!amn && bmn) rc = launch_gemm<BN_, false, true, true, EPI_>(ta, tb, tc, s, e, stream); \
-      else if (amn && !bmn) rc = launch_gemm<BN_, true, false, true, EPI_>(ta, tb, tc, s, e, stream); \
-      else rc = launch_gemm<BN_, true, true, true, EPI_>(ta, tb, tc, s, e, stream);                 \
-    } else {                                                                                        \
-      if (!amn && !bmn) rc = launch_gemm<BN_, false, false, false, EPI_>(ta, tb, tc, s, e, stream); \
-      else if (!amn && bmn) rc = launch_gemm<BN_, false, true, false, EPI_>(ta, tb, tc, s, e, stream); \
-      else if (amn && !bmn) rc = launch_gemm<BN_, true, false, false, EPI_>(ta, tb, tc, s, e, stream); \
-      else rc = launch_gemm<BN_, true, true, false, EPI_>(ta, tb, tc, s, e, stream);                \
-    }                                                                                               \
+    if (!amn && !bmn) TOME_GEMM_MODE(BN_, false, false, EPI_);                                      \
+    else if (!amn && bmn) TOME_GEMM_MODE(BN_, false, true, EPI_);                                   \
+    else if (amn && !bmn) TOME_GEMM_MODE(BN_, true, false, EPI_);                                   \
+    else TOME_GEMM_MODE(BN_, true, true, EPI_);                                                     \
   } while (0)
-#define TOME_GEMM_FWD(BN_, EPI_)                                                                    \
-  do {                                                                                              \
-    if (mc) rc = launch_gemm<BN_, false, true, true, EPI_>(ta, tb, tc, s, e, stream);               \
-    else rc = launch_gemm<BN_, false, true, false, EPI_>(ta, tb, tc, s, e, stream);                 \
-  } while (0)
-#define TOME_GEMM_DGRAD(BN_, EPI_)                                                                  \
-  do {                                                                                              \
-    if (mc) rc = launch_gemm<BN_, false, false, true, EPI_>(ta, tb, tc, s, e, stream);              \
-    else rc = launch_gemm<BN_, false, false, false, EPI_>(ta, tb, tc, s, e, stream);                \
-  } while (0)
+#define TOME_GEMM_FWD(BN_, EPI_) TOME_GEMM_MODE(BN_, false, true, EPI_)
+#define TOME_GEMM_DGRAD(BN_, EPI_) TOME_GEMM_MODE(BN_, false, false, EPI_)
 #define TOME_GEMM_DISPATCH(BN_)                                                                     \
   do {                                                                                              \
     switch (epi) {                                                                                  \
@@ -744,6 +832,7 @@ extern "C" int tome_gemm_bf16(const tome_gemm_args_t* a, void* workspace, size_t
   if (bn == 128) TOME_GEMM_DISPATCH(128);
   else if (bn == 192) TOME_GEMM_DISPATCH(192);
   else TOME_GEMM_DISPATCH(256);
+#undef TOME_GEMM_MODE
 #undef TOME_GEMM_LAYOUTS
 #undef TOME_GEMM_FWD
 #undef TOME_GEMM_DGRAD

@@ -79,6 +79,15 @@ def bench_merge():
 
 
 def bench_gemm():
+    from multi_modal_transformers_tokenmerge_b200 import _lib
+    for pair in (1, 0):
+        _lib.lib().tome_gemm_set_pair_mma(pair)
+        print("cta_group::2 pair MMA:", "on" if pair else "off (two 128-row MMAs, multicast B)")
+        _bench_gemm()
+    _lib.lib().tome_gemm_set_pair_mma(1)
+
+
+def _bench_gemm():
     for (m, n, k, bmn) in [(137216, 1152, 384, 1), (137216, 384, 384, 1), (133120, 1536, 384, 1), (133120, 384, 1536, 1),
                            (137216, 2304, 768, 1), (129024, 3072, 768, 1), (129024, 768, 3072, 1), (8192, 8192, 8192, 0)]:
         a = torch.randn(m, k, device="cuda").bfloat16()
