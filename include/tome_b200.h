@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TOME_ABI_VERSION 10
+#define TOME_ABI_VERSION 11
 
 enum tome_status { TOME_OK = 0, TOME_ERR_INVALID = 1, TOME_ERR_CUDA = 2, TOME_ERR_UNSUPPORTED = 3 };
 enum tome_dtype { TOME_BF16 = 0, TOME_F32 = 1 };
@@ -141,6 +141,11 @@ typedef struct {
   const void* gate_bits;
   void* relu_bits_out;
   long long ld_bits;
+  /* Bias gradient of the layer that produced this GEMM's input gradient, without a second pass over C: when not NULL
+   * (bf16 C, no split-K), row i of colsum_partial (f32 [ceil(m / 128), n], dense) receives the column sums of the
+   * bf16-rounded rows 128 i .. 128 i + 127 of C, in a fixed order; tome_reduce_rows_f32 adds the rows up.
+   * (MLPBlock Dense bias: attention.py:32-37 under autodiff.) */
+  float* colsum_partial;
 } tome_gemm_args_t;
 
 size_t tome_gemm_workspace_bytes(const tome_gemm_args_t* args);
@@ -153,6 +158,8 @@ int tome_gemm_bf16(const tome_gemm_args_t* args, void* workspace, size_t workspa
 
 /* out[n] (+)= sum_m x[m,n]   (bias gradients).  x bf16 [M, ldx]; out f32 [N].  workspace: f32 [ws_rows, N] with
  * ws_rows = tome_colsum_workspace_rows(m). */
+/* out[n] (+)= sum_r partial[r, n]   (f32, rows added in a fixed order: the second stage of every column sum here) */
+int tome_reduce_rows_f32(int rows, int n, const float* partial, float* out, int accumulate, void* stream);
 int tome_colsum_workspace_rows(int m);
 int tome_colsum_bf16(int m, int n, const void* x, long long ldx, float* out, int accumulate, float* workspace,
                      void* stream);
@@ -226,6 +233,13 @@ typedef struct {
   long long dk_batch_stride, dk_token_stride;
   long long dv_batch_stride, dv_token_stride;
   long long do_batch_stride, do_token_stride;
+  /* Optional (head_dim 64 only): the q/k/v projection's bias gradient without a second pass over dq/dk/dv.  When not NULL,
+   * row b * ceil(T / 128) + t of bias_partial (f32, leading dimension bias_partial_ld) receives the column sums of the t-th
+   * 128-token tile of batch row b: dq at columns [q_col, q_col + H*D), dk at [k_col, ...), dv at [v_col, ...), each laid out
+   * [head][d]; tome_reduce_rows_f32 adds the B * ceil(T / 128) rows up.  (DenseGeneral bias, tome_attention.py:145-164.) */
+  float* bias_partial;
+  long long bias_partial_ld;
+  int bias_q_col, bias_k_col, bias_v_col;
 } tome_attn_grad_strides_t;
 size_t tome_attention_bwd_workspace_bytes(const tome_attn_desc_t* desc);
 int tome_attention_bwd(const tome_attn_desc_t* desc, const tome_attn_grad_strides_t* gs, const void* q, const void* k,

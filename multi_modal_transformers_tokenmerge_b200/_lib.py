@@ -15,7 +15,7 @@ TOME_OK, TOME_ERR_INVALID, TOME_ERR_CUDA, TOME_ERR_UNSUPPORTED = 0, 1, 2, 3
 TOME_BF16, TOME_F32 = 0, 1
 TOME_MAJOR_K, TOME_MAJOR_MN = 0, 1
 TOME_MERGE_SUM, TOME_MERGE_WAVG = 0, 1
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 vp, ll, i32, f32, u64, u32 = C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_uint64, C.c_uint32
 
@@ -61,7 +61,7 @@ class GemmArgs(C.Structure):
                 ("gate_scale", f32), ("relu", i32),
                 ("dropout_rate", f32), ("dropout_seed", u64), ("dropout_site", u32),
                 ("k_splits", i32), ("accumulate", i32), ("no_multicast", i32),
-                ("gate_bits", vp), ("relu_bits_out", vp), ("ld_bits", ll)]
+                ("gate_bits", vp), ("relu_bits_out", vp), ("ld_bits", ll), ("colsum_partial", vp)]
 
 
 class AttnDesc(C.Structure):
@@ -75,7 +75,8 @@ class AttnDesc(C.Structure):
 
 class AttnGradStrides(C.Structure):
     _fields_ = [("dq_batch_stride", ll), ("dq_token_stride", ll), ("dk_batch_stride", ll), ("dk_token_stride", ll),
-                ("dv_batch_stride", ll), ("dv_token_stride", ll), ("do_batch_stride", ll), ("do_token_stride", ll)]
+                ("dv_batch_stride", ll), ("dv_token_stride", ll), ("do_batch_stride", ll), ("do_token_stride", ll),
+                ("bias_partial", vp), ("bias_partial_ld", ll), ("bias_q_col", i32), ("bias_k_col", i32), ("bias_v_col", i32)]
 
 
 class StackCfg(C.Structure):
@@ -155,6 +156,7 @@ def lib() -> C.CDLL:
             "tome_gemm_bf16": [P(GemmArgs), vp, C.c_size_t, vp],
             "tome_gemm_set_sm_limit": [i32],
             "tome_colsum_workspace_rows": [i32],
+            "tome_reduce_rows_f32": [i32, i32, vp, vp, i32, vp],
             "tome_colsum_bf16": [i32, i32, vp, ll, vp, i32, vp, vp],
             "tome_dropout_colsum_bf16": [i32, i32, vp, vp, f32, C.c_uint64, C.c_uint32, vp, i32, vp, vp],
             "tome_layernorm_fwd": [i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp],

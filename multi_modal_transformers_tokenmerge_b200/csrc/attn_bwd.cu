@@ -47,7 +47,57 @@ struct AttnBwdParams {
   __nv_bfloat16* dq; long long dq_bs, dq_ts;
   __nv_bfloat16* dk; long long dk_bs, dk_ts;
   __nv_bfloat16* dv; long long dv_bs, dv_ts;
+  // bias-gradient partials (or null): row (b * n_tiles128 + tile) of an f32 matrix with leading dimension cs_ld receives the
+  // column sums of that 128-token tile of dq / dk / dv at columns cs_q / cs_k / cs_v + h * 64
+  float* cs;
+  long long cs_ld;
+  int cs_q, cs_k, cs_v, n_t128;
 };
+
+// Epilogue shared by the four kernels below.  The 128 threads of warps 0-3 each own one row of a [128 x 64] fp32 accumulator in
+// tensor memory.  The rows are rounded to bf16 and staged in shared memory (16 KB, 128-byte swizzled rows), then written out
+// by whole 128-byte lines (8 lanes per row, 4 rows per store instruction; a thread storing its own row scatters 32 partial
+// sectors per instruction) and, when asked, summed per column over the valid rows -- the Dense bias gradient of the q/k/v
+// projection -- without a second pass over dq/dk/dv in HBM.  `part`: 1 KB of shared memory.  Named barrier `bar`, 128 threads.
+__device__ __forceinline__ void ab_store_tile(uint8_t* stage, float* part, uint32_t tm_row, int rows_valid, __nv_bfloat16* gtile,
+                                              long long row_stride, float* colsum_out, int bar) {
+  const int row = threadIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    float a[32], c[32];
+    tmem_ld_f32x32(tm_row, a);
+    tmem_ld_f32x32(tm_row + 32, c);
+    tmem_ld_wait();
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch)
+      *reinterpret_cast<uint4*>(stage + row * 128 + ((ch ^ (row & 7)) << 4)) =
+          make_uint4(pack_bf16(a[8 * ch], a[8 * ch + 1]), pack_bf16(a[8 * ch + 2], a[8 * ch + 3]),
+                     pack_bf16(a[8 * ch + 4], a[8 * ch + 5]), pack_bf16(a[8 * ch + 6], a[8 * ch + 7]));
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch)
+      *reinterpret_cast<uint4*>(stage + row * 128 + (((ch + 4) ^ (row & 7)) << 4)) =
+          make_uint4(pack_bf16(c[8 * ch], c[8 * ch + 1]), pack_bf16(c[8 * ch + 2], c[8 * ch + 3]),
+                     pack_bf16(c[8 * ch + 4], c[8 * ch + 5]), pack_bf16(c[8 * ch + 6], c[8 * ch + 7]));
+  }
+  asm volatile("bar.sync %0, 128;" ::"r"(bar) : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int pce = threadIdx.x + 128 * i, r = pce >> 3, ch = pce & 7;
+    const uint4 w = *reinterpret_cast<const uint4*>(stage + r * 128 + ((ch ^ (r & 7)) << 4));
+    if (r < rows_valid) *reinterpret_cast<uint4*>(gtile + (long long)r * row_stride + ch * 8) = w;
+  }
+  if (colsum_out != nullptr) {   // CTA-uniform
+    float s0 = 0.f, s1 = 0.f;   // lane = column pair, warp = 32-row group; a warp reads one row per step: no bank conflict
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) {
+      const int r = warp * 32 + i;
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(stage + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
+      if (r < rows_valid) { s0 += bf16_lo(w); s1 += bf16_hi(w); }
+    }
+    *reinterpret_cast<float2*>(part + warp * 64 + 2 * lane) = make_float2(s0, s1);
+    asm volatile("bar.sync %0, 128;" ::"r"(bar) : "memory");
+    if (threadIdx.x < 64) colsum_out[threadIdx.x] = (part[threadIdx.x] + part[64 + threadIdx.x]) + (part[128 + threadIdx.x] + part[192 + threadIdx.x]);
+  }
+}
 
 // ------------------------------------------------------------------------------------------------ prep
 __global__ void attn_bwd_prep_kernel(int B, int T, int Tp, int H, const __nv_bfloat16* __restrict__ o, long long o_bs,
@@ -326,25 +376,13 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     mbar_wait(pd_free, (n_q - 1) & 1);  // accumulators final
     tc_fence_after();
     {
-      // tcgen05.ld is warp-collective: rows past T take part in the loads and only skip the stores
-      __nv_bfloat16* dkr = p.dk + (long long)b * p.dk_bs + (long long)(k_valid ? kk : 0) * p.dk_ts + h * AB_D;
-      __nv_bfloat16* dvr = p.dv + (long long)b * p.dv_bs + (long long)(k_valid ? kk : 0) * p.dv_ts + h * AB_D;
-#pragma unroll
-      for (int c0 = 0; c0 < AB_D; c0 += 32) {
-        float a[32], c[32];
-        tmem_ld_f32x32(tm_dk + lane_sel + c0, a);
-        tmem_ld_f32x32(tm_dv + lane_sel + c0, c);
-        tmem_ld_wait();
-        if (k_valid) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            *reinterpret_cast<uint4*>(dkr + c0 + i) = make_uint4(pack_bf16(a[i], a[i + 1]), pack_bf16(a[i + 2], a[i + 3]),
-                                                                 pack_bf16(a[i + 4], a[i + 5]), pack_bf16(a[i + 6], a[i + 7]));
-            *reinterpret_cast<uint4*>(dvr + c0 + i) = make_uint4(pack_bf16(c[i], c[i + 1]), pack_bf16(c[i + 2], c[i + 3]),
-                                                                 pack_bf16(c[i + 4], c[i + 5]), pack_bf16(c[i + 6], c[i + 7]));
-          }
-        }
-      }
+      // every MMA has retired: the K and V tiles serve as staging for dK and dV, the Q/dO ring for the column-sum scratch
+      const int rows_valid = min(DKV_BK, T - kt * DKV_BK);
+      float* cs_row = p.cs ? p.cs + ((long long)b * p.n_t128 + kt) * p.cs_ld + h * AB_D : nullptr;
+      ab_store_tile(s_k, reinterpret_cast<float*>(s_qdo), tm_dk + lane_sel, rows_valid,
+                    p.dk + (long long)b * p.dk_bs + (long long)kt * DKV_BK * p.dk_ts + h * AB_D, p.dk_ts, cs_row ? cs_row + p.cs_k : nullptr, 1);
+      ab_store_tile(s_v, reinterpret_cast<float*>(s_qdo) + 256, tm_dv + lane_sel, rows_valid,
+                    p.dv + (long long)b * p.dv_bs + (long long)kt * DKV_BK * p.dv_ts + h * AB_D, p.dv_ts, cs_row ? cs_row + p.cs_v : nullptr, 1);
     }
   }
   tc_fence_before();
@@ -636,25 +674,13 @@ attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     mbar_wait(pd_free, (n_q - 1) & 1);  // accumulators final
     tc_fence_after();
     {
-      // tcgen05.ld is warp-collective: rows past T take part in the loads and only skip the stores
-      __nv_bfloat16* dkr = p.dk + (long long)b * p.dk_bs + (long long)(k_valid ? kk : 0) * p.dk_ts + h * AB_D;
-      __nv_bfloat16* dvr = p.dv + (long long)b * p.dv_bs + (long long)(k_valid ? kk : 0) * p.dv_ts + h * AB_D;
-#pragma unroll
-      for (int c0 = 0; c0 < AB_D; c0 += 32) {
-        float a[32], c[32];
-        tmem_ld_f32x32(tm_dk + lane_sel + c0, a);
-        tmem_ld_f32x32(tm_dv + lane_sel + c0, c);
-        tmem_ld_wait();
-        if (k_valid) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            *reinterpret_cast<uint4*>(dkr + c0 + i) = make_uint4(pack_bf16(a[i], a[i + 1]), pack_bf16(a[i + 2], a[i + 3]),
-                                                                 pack_bf16(a[i + 4], a[i + 5]), pack_bf16(a[i + 6], a[i + 7]));
-            *reinterpret_cast<uint4*>(dvr + c0 + i) = make_uint4(pack_bf16(c[i], c[i + 1]), pack_bf16(c[i + 2], c[i + 3]),
-                                                                 pack_bf16(c[i + 4], c[i + 5]), pack_bf16(c[i + 6], c[i + 7]));
-          }
-        }
-      }
+      // every MMA has retired: the K and V tiles serve as staging for dK and dV, the Q/dO ring for the column-sum scratch
+      const int rows_valid = min(DKV_BK, T - kt * DKV_BK);
+      float* cs_row = p.cs ? p.cs + ((long long)b * p.n_t128 + kt) * p.cs_ld + h * AB_D : nullptr;
+      ab_store_tile(s_k, reinterpret_cast<float*>(s_qdo), tm_dk + lane_sel, rows_valid,
+                    p.dk + (long long)b * p.dk_bs + (long long)kt * DKV_BK * p.dk_ts + h * AB_D, p.dk_ts, cs_row ? cs_row + p.cs_k : nullptr, 1);
+      ab_store_tile(s_v, reinterpret_cast<float*>(s_qdo) + 256, tm_dv + lane_sel, rows_valid,
+                    p.dv + (long long)b * p.dv_bs + (long long)kt * DKV_BK * p.dv_ts + h * AB_D, p.dv_ts, cs_row ? cs_row + p.cs_v : nullptr, 1);
     }
   }
   tc_fence_before();
@@ -883,19 +909,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     }
     mbar_wait(&ds_free[(n_k - 1) & 1], ((n_k - 1) >> 1) & 1);
     tc_fence_after();
-    __nv_bfloat16* dqr = p.dq + (long long)b * p.dq_bs + (long long)(q_valid ? q : 0) * p.dq_ts + h * AB_D;
-#pragma unroll
-    for (int c0 = 0; c0 < AB_D; c0 += 32) {
-      float a[32];
-      tmem_ld_f32x32(tm_dq + lane_sel + c0, a);
-      tmem_ld_wait();
-      if (q_valid) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 8)
-          *reinterpret_cast<uint4*>(dqr + c0 + i) = make_uint4(pack_bf16(a[i], a[i + 1]), pack_bf16(a[i + 2], a[i + 3]),
-                                                               pack_bf16(a[i + 4], a[i + 5]), pack_bf16(a[i + 6], a[i + 7]));
-      }
-    }
+    ab_store_tile(s_q, reinterpret_cast<float*>(s_do), tm_dq + lane_sel, min(DQ_BQ, T - qt * DQ_BQ),
+                  p.dq + (long long)b * p.dq_bs + (long long)qt * DQ_BQ * p.dq_ts + h * AB_D, p.dq_ts,
+                  p.cs ? p.cs + ((long long)b * p.n_t128 + qt) * p.cs_ld + h * AB_D + p.cs_q : nullptr, 1);   // Q / dO tiles: free now
   }
   tc_fence_before();
   __syncthreads();
@@ -991,21 +1007,10 @@ attn_bwd_dq_gemm_kernel(const __grid_constant__ CUtensorMap tm_ds, const __grid_
     const uint32_t lane_sel = ((uint32_t)(warp * 32)) << 16;
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    if (qt * DQG_BQ + warp * 32 < T) {
-      __nv_bfloat16* dqr = p.dq + (long long)b * p.dq_bs + (long long)(q < T ? q : 0) * p.dq_ts + h * AB_D;
-#pragma unroll
-      for (int c0 = 0; c0 < AB_D; c0 += 32) {
-        float a[32];
-        tmem_ld_f32x32(tmem_base + lane_sel + c0, a);
-        tmem_ld_wait();
-        if (q < T) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 8)
-            *reinterpret_cast<uint4*>(dqr + c0 + i) = make_uint4(pack_bf16(a[i], a[i + 1]), pack_bf16(a[i + 2], a[i + 3]),
-                                                                 pack_bf16(a[i + 4], a[i + 5]), pack_bf16(a[i + 6], a[i + 7]));
-        }
-      }
-    }
+    // every stage has been consumed: stage 0 (24 KB) holds the staging tile and the column-sum scratch
+    ab_store_tile(smem, reinterpret_cast<float*>(smem + DQG_BQ * 128), tmem_base + lane_sel, min(DQG_BQ, T - qt * DQG_BQ),
+                  p.dq + (long long)b * p.dq_bs + (long long)qt * DQG_BQ * p.dq_ts + h * AB_D, p.dq_ts,
+                  p.cs ? p.cs + ((long long)b * p.n_t128 + qt) * p.cs_ld + h * AB_D + p.cs_q : nullptr, 1);
   }
   tc_fence_before();
   __syncthreads();
@@ -1050,6 +1055,8 @@ extern "C" int tome_attention_bwd(const tome_attn_desc_t* d, const tome_attn_gra
   if (int rc = check_attn_desc(d, "attention_bwd")) return rc;
   TOME_CHECK(gs && q && k && v && out && lse && dout && dq && dk && dv, TOME_ERR_INVALID, "attention_bwd: null argument");
   TOME_CHECK(d->dropout_rate >= 0.f && d->dropout_rate < 1.f, TOME_ERR_INVALID, "attention_bwd: dropout_rate must be in [0, 1)");
+  TOME_CHECK(!gs->bias_partial || d->head_dim == AB_D, TOME_ERR_INVALID, "attention_bwd: bias_partial needs head_dim 64");
+  TOME_CHECK(!gs->bias_partial || gs->bias_partial_ld >= 0, TOME_ERR_INVALID, "attention_bwd: bad bias_partial_ld");
   if (d->head_dim != AB_D) {
     ProfScope prof(PROF_ATTN_BWD, 10.0 * d->batch * d->heads * (double)d->tokens * d->tokens * d->head_dim, 2, stream);
     return attn_generic_bwd(d, gs, q, k, v, out, lse, dout, dq, dk, dv, stream);
@@ -1095,6 +1102,9 @@ extern "C" int tome_attention_bwd(const tome_attn_desc_t* d, const tome_attn_gra
   p.keep_q = keep_q; p.keep_k = keep_k; p.inv_keep = inv_keep;
   const bool from_ds = dq_from_ds(d);
   p.store_ds = from_ds ? 1 : 0;
+  p.cs = gs->bias_partial; p.cs_ld = gs->bias_partial_ld;
+  p.cs_q = gs->bias_q_col; p.cs_k = gs->bias_k_col; p.cs_v = gs->bias_v_col;
+  p.n_t128 = ceil_div(T, 128);
 
   // dS^T [B*H][ceil128(T) keys][ceil64(T) queries] bf16, after the (possibly absent) dropout bit tilings
   uint8_t* ds_buf = reinterpret_cast<uint8_t*>(lse2) + align256(bwd_pad_elems(d) * sizeof(float)) +

@@ -53,6 +53,7 @@ struct GemmEpilogue {
   uint32_t* bits_out;
   const uint32_t* bits_in;
   long long ldw;
+  float* colsum_part;      // [m_tiles, n] column sums of each 128-row tile of the bf16 output (specialised epilogues), or null
 };
 
 struct GemmShape {
@@ -79,7 +80,9 @@ struct GemmSmem {
                                      : (BN <= 128) ? 6 : (BN <= 192) ? (GEMM_EPI_WARPS > 8 ? 4 : 5) : (GEMM_EPI_WARPS > 8 ? 3 : 4);
   static constexpr int STORE_BYTES = GEMM_EPI_WARPS * 2048;  // per epilogue warp: 32 rows x 64 B staging tile for TMA stores
   static constexpr int BAR_BYTES = 256 + 2 * BN * 4;  // barriers + double-buffered bias tile
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + STORE_BYTES + BAR_BYTES + 1024;  // +1024: manual 1 KB alignment
+  static constexpr int COL_BYTES = 2 * 4 * BN * 4;    // column sums: [accumulator stage][lane quadrant][BN] f32
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + STORE_BYTES + BAR_BYTES + COL_BYTES + 1024;  // +1024: manual 1 KB alignment
+  static_assert(TOTAL <= 232448, "shared memory per CTA");
 };
 
 // MC: clusters of two CTAs work on vertically adjacent tiles (same n_blk); each CTA fetches half of the shared B tile
@@ -110,6 +113,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* s_bias = reinterpret_cast<float*>(s_store + L::STORE_BYTES + 256);  // [2][BN]
+  float* s_col = s_bias + 2 * BN;                                             // [2][4][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -293,30 +297,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const bool row_ok = row < s.m;
         // ---- everything the epilogue reads from memory is fetched while the tensor core still works on this tile
         if (kBias && etid < BN) s_bias[acc * BN + etid] = (n0 + etid < s.n) ? __ldg(e.bias + n0 + etid) : 0.f;
-        uint4 pre[(kResid || kGate) ? NCH : 1][4];
+        uint4 pre[kResid ? NCH : 1][4];
         uint32_t gw[kGate ? NCH : 1];
-        const bool gate_by_bits = kGate && e.bits_in != nullptr;   // CTA-uniform
-        if constexpr (kGate) {
-          if (gate_by_bits) {
+        if constexpr (kGate) {   // the gate arrives as one bit per element (a bf16 gate tensor takes the generic epilogue)
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-              const int col = n0 + TOME_CHUNK(c) * 32;
-              gw[c] = (TOME_CHUNK_OK(c) && row_ok && col < s.n) ? __ldg(e.bits_in + row * e.ldw + (col >> 5)) : 0u;
-            }
+          for (int c = 0; c < NCH; ++c) {
+            const int col = n0 + TOME_CHUNK(c) * 32;
+            gw[c] = (TOME_CHUNK_OK(c) && row_ok && col < s.n) ? __ldg(e.bits_in + row * e.ldw + (col >> 5)) : 0u;
           }
         }
-        if constexpr (kResid || kGate) {
-          if (!gate_by_bits) {
-            const __nv_bfloat16* src = kResid ? resid : gate;
-            const long long ld = kResid ? e.ldr : e.ldg;
+        if constexpr (kResid) {
 #pragma unroll
-            for (int c = 0; c < NCH; ++c)
+          for (int c = 0; c < NCH; ++c)
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int col = n0 + TOME_CHUNK(c) * 32 + i * 8;
-                pre[c][i] = (TOME_CHUNK_OK(c) && row_ok && col < s.n) ? __ldg(reinterpret_cast<const uint4*>(src + row * ld + col)) : make_uint4(0u, 0u, 0u, 0u);
-              }
-          }
+            for (int i = 0; i < 4; ++i) {
+              const int col = n0 + TOME_CHUNK(c) * 32 + i * 8;
+              pre[c][i] = (TOME_CHUNK_OK(c) && row_ok && col < s.n) ? __ldg(reinterpret_cast<const uint4*>(resid + row * e.ldr + col)) : make_uint4(0u, 0u, 0u, 0u);
+            }
         }
         if (kBias) asm volatile("bar.sync 1, %0;" ::"r"(32 * GEMM_EPI_WARPS) : "memory");  // bias tile visible to all epilogue warps
         mbar_wait(&tmem_full[acc], acc_phase);
@@ -342,23 +339,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               v[i] = t0.x; v[i + 1] = t0.y; v[i + 2] = t1.x; v[i + 3] = t1.y;
             }
           }
-          if constexpr (kGate) {  // acc *= (gate > 0 ? gate_scale : 0): the sign/zero test runs on the raw bf16 bits
-            if (gate_by_bits) {
-              const uint32_t w = gw[c];
+          if constexpr (kGate) {  // acc *= (bit ? gate_scale : 0)
+            const uint32_t w = gw[c];
 #pragma unroll
-              for (int i = 0; i < 32; i += 2) {
-                const float2 t = __fmul2_rn(make_float2(v[i], v[i + 1]), gs2);
-                v[i] = ((w >> i) & 1u) ? t.x : 0.f;
-                v[i + 1] = ((w >> (i + 1)) & 1u) ? t.y : 0.f;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; i += 2) {
-                const uint32_t w = reinterpret_cast<const uint32_t*>(&pre[c][i / 8])[(i / 2) & 3];
-                const float2 t = __fmul2_rn(make_float2(v[i], v[i + 1]), gs2);
-                v[i] = ((int)(w << 16) > 0) ? t.x : 0.f;
-                v[i + 1] = ((int)w > 0xffff) ? t.y : 0.f;
-              }
+            for (int i = 0; i < 32; i += 2) {
+              const float2 t = __fmul2_rn(make_float2(v[i], v[i + 1]), gs2);
+              v[i] = ((w >> i) & 1u) ? t.x : 0.f;
+              v[i + 1] = ((w >> (i + 1)) & 1u) ? t.y : 0.f;
             }
           }
           if (drop_on) {
@@ -420,9 +407,51 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
+          if (e.colsum_part != nullptr) {
+            // column sums of what was just staged (the bf16-rounded outputs, like a separate pass over C would read):
+            // lane = (half h, column pair j) adds 16 rows; the halves walk rows of opposite parity (no bank conflict)
+            const int j = lane & 15, h = lane >> 4;
+            const int rlim = s.m - (m_blk * GEMM_BM + quad * 32);   // rows of this warp's slab that exist
+            float2 sum = make_float2(0.f, 0.f);
+            const uint8_t* sp = stg + (j & 3) * 4;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int r = h * 16 + (i ^ h);
+              uint32_t w = *reinterpret_cast<const uint32_t*>(sp + r * 64 + (((j >> 2) ^ ((r >> 1) & 3)) << 4));
+              if (r >= rlim) w = 0u;
+              sum = __fadd2_rn(sum, make_float2(bf16_lo(w), bf16_hi(w)));
+            }
+            sum.x += __shfl_xor_sync(0xffffffffu, sum.x, 16);
+            sum.y += __shfl_xor_sync(0xffffffffu, sum.y, 16);
+            if (h == 0) *reinterpret_cast<float2*>(s_col + (acc * 4 + quad) * BN + TOME_CHUNK(c) * 32 + 2 * j) = sum;
+          }
         }
         tc_fence_before();
         __syncwarp();
+        if (e.colsum_part != nullptr) {   // CTA-uniform
+          // The four lane quadrants' sums of this tile -> one row of partials, by the first epilogue warp; the other seven only
+          // signal (bar.arrive) and go on to their next tile.  One barrier per accumulator stage: no warp can be two tiles
+          // ahead of another (the MMA of tile i + 2 waits for every warp's release of tile i), and warp 2 releases its
+          // accumulator only after it has read the sums, so a stage's slots are never rewritten under it.
+          if (ew == 0) {
+            asm volatile("bar.sync %0, %1;" ::"r"(2 + acc), "r"(32 * GEMM_EPI_WARPS) : "memory");
+            if (m_blk < s.m_tiles) {
+#pragma unroll
+              for (int cidx = lane * 2; cidx < BN; cidx += 64) {
+                if (n0 + cidx < s.n) {
+                  const float* sc = s_col + acc * 4 * BN + cidx;
+                  const float2 q0 = *reinterpret_cast<const float2*>(sc), q1 = *reinterpret_cast<const float2*>(sc + BN),
+                               q2 = *reinterpret_cast<const float2*>(sc + 2 * BN), q3 = *reinterpret_cast<const float2*>(sc + 3 * BN);
+                  *reinterpret_cast<float2*>(e.colsum_part + (long long)m_blk * s.n + n0 + cidx) =
+                      make_float2((q0.x + q1.x) + (q2.x + q3.x), (q0.y + q1.y) + (q2.y + q3.y));
+                }
+              }
+            }
+            __syncwarp();
+          } else {
+            asm volatile("bar.arrive %0, %1;" ::"r"(2 + acc), "r"(32 * GEMM_EPI_WARPS) : "memory");
+          }
+        }
         if (lane == 0) {
           if constexpr (PAIR) mbar_arrive_cluster(map_to_cta(&tmem_empty[acc], 0));   // the leader's MMA thread waits for both CTAs
           else mbar_arrive(&tmem_empty[acc]);
@@ -750,6 +779,7 @@ extern "C" int tome_gemm_bf16(const tome_gemm_args_t* a, void* workspace, size_t
   e.c = a->c; e.bias = a->bias; e.residual = a->residual; e.gate = a->gate;
   e.bits_out = reinterpret_cast<uint32_t*>(a->relu_bits_out); e.bits_in = reinterpret_cast<const uint32_t*>(a->gate_bits);
   e.ldw = a->ld_bits;
+  e.colsum_part = a->colsum_partial;
   e.ldc = a->ldc; e.ldr = a->ldr; e.ldg = a->ldg;
   e.gate_scale = a->gate_scale; e.relu = a->relu; e.c_is_f32 = (a->c_dtype == TOME_F32);
   e.drop.thresh16 = (uint32_t)(a->dropout_rate * 65536.0f + 0.5f);
@@ -800,9 +830,12 @@ extern "C" int tome_gemm_bf16(const tome_gemm_args_t* a, void* workspace, size_t
       else if (flags == (EPI_BIAS | EPI_RELU) || flags == (EPI_BIAS | EPI_RELU | EPI_DROP)) epi = EPI_BIAS | EPI_RELU | EPI_DROP;
     } else if (!amn && !bmn) {  // data gradients: B = the same kernel read K-major
       if (flags == 0) epi = 0;
-      else if (flags == EPI_GATE) epi = EPI_GATE;
+      else if (flags == EPI_GATE && a->gate_bits) epi = EPI_GATE;   // bf16 gate rows: generic epilogue
     }
   }
+  TOME_CHECK(!a->colsum_partial || epi != EPI_GENERIC, TOME_ERR_INVALID,
+             "gemm: colsum_partial needs a bf16 output without split-K and one of the stack's epilogues (plain or gated data "
+             "gradient, bias / bias+ReLU(+dropout) / bias(+dropout)+residual forward)");
 #define TOME_GEMM_MODE(BN_, AMN_, BMN_, EPI_)                                                        \
   do {                                                                                              \
     if (mode == 2) rc = launch_gemm<BN_, AMN_, BMN_, 2, EPI_>(ta, tb, tc, s, e, stream);            \

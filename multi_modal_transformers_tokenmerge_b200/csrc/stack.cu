@@ -48,6 +48,7 @@ struct StackLayout {
   std::vector<LayerBufs> L;
   __nv_bfloat16 *x1_scratch, *g0, *g1, *g2, *g3, *big;
   float *ws_gemm, *ws_colsum, *ws_ln;
+  float* ws_colpart;   // [ceil(B T0 / 128), widest N]: per-row-tile column sums written by a GEMM epilogue
   uint8_t *ws_attn, *ws_sim;
   size_t ws_attn_bytes, ws_sim_bytes;
   int32_t* origin;
@@ -240,6 +241,10 @@ static StackLayout make_layout(const tome_stack_cfg_t* c, void* workspace) {
   S.ws_gemm_bytes = wmax * sizeof(float) * 64;
   S.ws_gemm = b.take<float>(wmax * 64);
   S.ws_colsum = b.take<float>(256 * wide);
+  {  // rows: 128-row tiles of the flattened [B T0, N] GEMM outputs, or (batch row, 128-token tile) pairs of attention backward
+    const size_t r1 = (B * T0 + 127) / 128, r2 = B * ((T0 + 127) / 128);
+    S.ws_colpart = b.take<float>((r1 > r2 ? r1 : r2) * wide);
+  }
   const size_t ln_rows = c->ln_axis == 1 ? B : 256;
   S.ws_ln = b.take<float>(2 * ln_rows * C);
   S.origin = b.take<int32_t>(B * (c->n_readout > 0 ? c->n_readout : 1));
@@ -286,7 +291,7 @@ static DropoutCfg make_drop(const tome_stack_cfg_t* c, uint32_t site) {
 static int gemm(const tome_stack_cfg_t* c, const StackLayout& S, cudaStream_t st, int m, int n, int k, const void* a,
                 long long lda, int a_major, const void* b, long long ldb, int b_major, void* out, long long ldc, int c_dtype,
                 const float* bias, int relu, const void* residual, const void* gate, float gate_scale, int drop_site,
-                int accumulate, const void* gate_bits = nullptr, void* relu_bits_out = nullptr) {
+                int accumulate, const void* gate_bits = nullptr, void* relu_bits_out = nullptr, float* colsum_partial = nullptr) {
   tome_gemm_args_t g;
   memset(&g, 0, sizeof(g));
   g.m = m; g.n = n; g.k = k;
@@ -297,6 +302,7 @@ static int gemm(const tome_stack_cfg_t* c, const StackLayout& S, cudaStream_t st
   g.residual = residual; g.ldr = n;
   g.gate = gate; g.ldg = n; g.gate_scale = gate_scale;
   g.gate_bits = gate_bits; g.relu_bits_out = relu_bits_out; g.ld_bits = (n + 31) / 32;
+  g.colsum_partial = colsum_partial;
   if (drop_site >= 0 && c->dropout_rate > 0.f) {
     g.dropout_rate = c->dropout_rate;
     g.dropout_seed = c->dropout_seed;
@@ -506,8 +512,9 @@ extern "C" int tome_stack_backward(const tome_stack_cfg_t* c, const tome_stack_i
     RC(gemm(c, S, st, F, C, Mo, Lb.m1, F, TOME_MAJOR_MN, dy2, C, TOME_MAJOR_MN, gr + o.w2, C, TOME_F32, nullptr, 0, nullptr,
             nullptr, 1.f, -1, 1));
     RC(gemm(c, S, st, Mo, F, C, dy2, C, TOME_MAJOR_K, pw + o.w2, C, TOME_MAJOR_K, S.big, F, TOME_BF16, nullptr, 0, nullptr, nullptr,
-            inv_keep, -1, 0, Lb.m1_bits));  // dm1 (pre-activation): the relu and dropout masks are the bits MLP-1 forward wrote
-    RC(tome_colsum_bf16(Mo, F, S.big, F, gr + o.b1, 1, S.ws_colsum, st));
+            inv_keep, -1, 0, Lb.m1_bits, nullptr, S.ws_colpart));  // dm1 (pre-activation): the relu and dropout masks are the bits
+    // MLP-1 forward wrote; the same epilogue leaves dm1's column sums per 128-row tile (no second pass over the 400 MB)
+    RC(tome_reduce_rows_f32((Mo + 127) / 128, F, S.ws_colpart, gr + o.b1, 1, st));
     RC(gemm(c, S, st, C, F, Mo, Lb.h2, C, TOME_MAJOR_MN, S.big, F, TOME_MAJOR_MN, gr + o.w1, F, TOME_F32, nullptr, 0, nullptr,
             nullptr, 1.f, -1, 1));
     RC(gemm(c, S, st, Mo, C, F, S.big, F, TOME_MAJOR_K, pw + o.w1, F, TOME_MAJOR_K, g1, C, TOME_BF16, nullptr, 0, nullptr, nullptr,
@@ -544,13 +551,18 @@ extern "C" int tome_stack_backward(const tome_stack_cfg_t* c, const tome_stack_i
     ad.size = c->prop_attn ? Lb.size_in : nullptr;
     ad.dropout_rate = c->attn_dropout_rate; ad.dropout_seed = c->dropout_seed; ad.dropout_site = kAttnDropSite + (uint32_t)l;
     tome_attn_grad_strides_t gs;
+    memset(&gs, 0, sizeof(gs));
     gs.dq_batch_stride = gs.dk_batch_stride = gs.dv_batch_stride = (long long)T * 3 * HD;
     gs.dq_token_stride = gs.dk_token_stride = gs.dv_token_stride = 3 * HD;
     gs.do_batch_stride = (long long)T * HD; gs.do_token_stride = HD;
+    const bool fused_bias = D == 64;   // the tcgen05 kernels leave dqkv's column sums per 128-token tile
+    gs.bias_partial = fused_bias ? S.ws_colpart : nullptr;
+    gs.bias_partial_ld = 3 * HD; gs.bias_q_col = 0; gs.bias_k_col = HD; gs.bias_v_col = 2 * HD;
     RC(tome_attention_bwd(&ad, &gs, Lb.qkv, Lb.qkv + HD, Lb.qkv + 2 * HD, Lb.attn_o, Lb.lse, g3, S.big, S.big + HD,
                           S.big + 2 * HD, S.ws_attn, S.ws_attn_bytes, st));
     // ---- qkv projection
-    RC(tome_colsum_bf16(M, 3 * HD, S.big, 3 * HD, gr + o.bqkv, 1, S.ws_colsum, st));
+    if (fused_bias) RC(tome_reduce_rows_f32(B * ((T + 127) / 128), 3 * HD, S.ws_colpart, gr + o.bqkv, 1, st));
+    else RC(tome_colsum_bf16(M, 3 * HD, S.big, 3 * HD, gr + o.bqkv, 1, S.ws_colsum, st));
     RC(gemm(c, S, st, C, 3 * HD, M, Lb.h, C, TOME_MAJOR_MN, S.big, 3 * HD, TOME_MAJOR_MN, gr + o.wqkv, 3 * HD, TOME_F32, nullptr, 0,
             nullptr, nullptr, 1.f, -1, 1));
     RC(gemm(c, S, st, M, C, 3 * HD, S.big, 3 * HD, TOME_MAJOR_K, pw + o.wqkv, 3 * HD, TOME_MAJOR_K, g1, C, TOME_BF16, nullptr, 0,

@@ -176,7 +176,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, m: int, n: int, k: int, a_major=L.
          lda=None, ldb=None, out: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16, bias=None, residual=None,
          gate=None, gate_scale=1.0, relu=False, dropout_rate=0.0, dropout_seed=0, dropout_site=0, k_splits=0,
          accumulate=False, no_multicast=False, gate_bits: Optional[torch.Tensor] = None,
-         relu_bits_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+         relu_bits_out: Optional[torch.Tensor] = None, colsum_partial: Optional[torch.Tensor] = None) -> torch.Tensor:
     """C[M,N] = epilogue(A * B^T) on tcgen05.  a/b are 2-D bf16 tensors whose rows are M/N (K-major) or K (MN-major).
     gate_bits / relu_bits_out: int32 [M, ceil(N/32)] one-bit-per-element ReLU gates (see include/tome_b200.h)."""
     _need_cuda(a, b)
@@ -193,10 +193,22 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, m: int, n: int, k: int, a_major=L.
                       int(k_splits), int(accumulate), int(no_multicast),
                       None if gate_bits is None else gate_bits.data_ptr(),
                       None if relu_bits_out is None else relu_bits_out.data_ptr(),
-                      0 if (gate_bits is None and relu_bits_out is None) else (gate_bits if gate_bits is not None else relu_bits_out).stride(0))
+                      0 if (gate_bits is None and relu_bits_out is None) else (gate_bits if gate_bits is not None else relu_bits_out).stride(0),
+                      None if colsum_partial is None else colsum_partial.data_ptr())
     ws_bytes = L.lib().tome_gemm_workspace_bytes(C.byref(args))
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=a.device) if ws_bytes else None
     L.check(L.lib().tome_gemm_bf16(C.byref(args), _ptr(ws), ws_bytes, _stream()))
+    return out
+
+
+def reduce_rows(partial: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate=False) -> torch.Tensor:
+    """out[n] (+)= sum_r partial[r, n] (f32, fixed order): second stage of the column sums a GEMM epilogue leaves."""
+    _need_cuda(partial)
+    assert partial.dtype == torch.float32 and partial.is_contiguous() and partial.dim() == 2
+    rows, n = partial.shape
+    if out is None:
+        out = torch.zeros(n, dtype=torch.float32, device=partial.device)
+    L.check(L.lib().tome_reduce_rows_f32(rows, n, _ptr(partial), _ptr(out), int(accumulate), _stream()))
     return out
 
 
@@ -280,8 +292,10 @@ def attention_fwd(q, k, v, *, gid=None, pos=None, allow=None, size=None, scale=N
 
 
 def attention_bwd(q, k, v, out, lse, dout, *, gid=None, pos=None, allow=None, size=None, scale=None, dqkv=None,
-                  dropout_rate=0.0, dropout_seed=0, dropout_site=0):
-    """Returns (dq, dk, dv) [B,T,H,D] bf16 (views of one packed [B,T,3,H,D] buffer unless dqkv views are given)."""
+                  dropout_rate=0.0, dropout_seed=0, dropout_site=0, bias_partial: Optional[torch.Tensor] = None):
+    """Returns (dq, dk, dv) [B,T,H,D] bf16 (views of one packed [B,T,3,H,D] buffer unless dqkv views are given).
+    bias_partial: optional f32 [B * ceil(T / 128), 3 * H * D]; receives per-128-token-tile column sums of dq | dk | dv (the
+    packed projection's bias gradient once reduced over rows with reduce_rows)."""
     _need_cuda(q, k, v, out, dout)
     b, t, h, d = q.shape
     scale = 1.0 / math.sqrt(d) if scale is None else scale
@@ -293,6 +307,11 @@ def attention_bwd(q, k, v, out, lse, dout, *, gid=None, pos=None, allow=None, si
     desc = _attn_desc(q, k, v, out, scale, gid, pos, allow, size, (dropout_rate, dropout_seed, dropout_site))
     gs = L.AttnGradStrides(dq.stride(0), dq.stride(1), dk.stride(0), dk.stride(1), dv.stride(0), dv.stride(1),
                            dout.stride(0), dout.stride(1))
+    if bias_partial is not None:
+        assert bias_partial.dtype == torch.float32 and bias_partial.is_contiguous()
+        assert bias_partial.shape == (b * ((t + 127) // 128), 3 * h * d)
+        gs.bias_partial, gs.bias_partial_ld = bias_partial.data_ptr(), 3 * h * d
+        gs.bias_q_col, gs.bias_k_col, gs.bias_v_col = 0, h * d, 2 * h * d
     ws = _scratch(L.lib().tome_attention_bwd_workspace_bytes(C.byref(desc)), q.device)
     L.check(L.lib().tome_attention_bwd(C.byref(desc), C.byref(gs), _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse),
                                        _ptr(dout), _ptr(dq), _ptr(dk), _ptr(dv), _ptr(ws), ws.numel(), _stream()))

@@ -806,3 +806,77 @@ def test_attention_bwd_dq_paths_agree(ops, T, rate):
         setter(-1)
     for x, y in zip(a, b):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("m,n,k", [(4097, 1536, 384), (1000, 384, 256), (130, 160, 64), (70000, 768, 128)])
+def test_gemm_epilogue_column_sums(ops, m, n, k):
+    """A GEMM epilogue can leave the column sums of its bf16 output per 128-row tile (the Dense bias gradient without a second
+    pass over the tensor): reduced over the tiles they must equal the column sums of the output it wrote -- rows past M
+    excluded even when the epilogue adds a bias to them -- for the gated data gradient, the plain one and a forward layer, in
+    every CTA mode; asking for them must not change the output; and the result is reproducible bit for bit."""
+    import ctypes
+    from multi_modal_transformers_tokenmerge_b200 import _lib as L
+    rng = np.random.default_rng(m + n + k)
+    A = dev(rng.standard_normal((m, k)).astype(np.float32) * 0.5, torch.bfloat16)
+    Wk = dev(rng.standard_normal((n, k)).astype(np.float32) * 0.5, torch.bfloat16)       # K-major (dgrad layout)
+    Wf = dev(rng.standard_normal((k, n)).astype(np.float32) * 0.5, torch.bfloat16)       # [in, out] (forward layout)
+    bias = dev(rng.standard_normal(n).astype(np.float32))
+    words = (n + 31) // 32
+    bits = torch.randint(-2**31, 2**31 - 1, (m, words), dtype=torch.int32, device="cuda")
+    tiles = (m + 127) // 128
+    cases = [dict(b=Wk, b_major=0, gate_bits=bits, gate_scale=1.25), dict(b=Wk, b_major=0), dict(b=Wf, b_major=1, bias=bias),
+             dict(b=Wf, b_major=1, bias=bias, relu=True, dropout_rate=0.1, dropout_seed=3, dropout_site=2)]
+    try:
+        for mode in (-1, 0, 1, 2):
+            L.lib().tome_gemm_force_tile(mode, 0)
+            for kw in cases:
+                kw = dict(kw)
+                b = kw.pop("b")
+                plain = ops.gemm(A, b, m=m, n=n, k=k, **kw)
+                part = torch.full((tiles, n), float("nan"), device="cuda")
+                out = ops.gemm(A, b, m=m, n=n, k=k, colsum_partial=part, **kw)
+                assert torch.equal(out, plain)
+                got = ops.reduce_rows(part)
+                want = out.double().sum(0)
+                scale = out.double().abs().sum(0).max().item()
+                assert (got.double() - want).abs().max().item() <= 2e-6 * scale + 1e-6, (mode, list(kw))
+                part2 = torch.zeros_like(part)
+                ops.gemm(A, b, m=m, n=n, k=k, colsum_partial=part2, **kw)
+                assert torch.equal(part, part2)
+    finally:
+        L.lib().tome_gemm_force_tile(-1, 0)
+    with pytest.raises(Exception):   # fp32 outputs take the generic epilogue, which has no column sums
+        ops.gemm(A, Wk, m=m, n=n, k=k, out_dtype=torch.float32, colsum_partial=torch.zeros(tiles, n, device="cuda"))
+
+
+@pytest.mark.parametrize("T,H,rate,from_ds", [(536, 3, 0.0, 1), (300, 2, 0.1, 1), (74, 2, 0.0, 0), (257, 1, 0.1, 0)])
+def test_attention_bwd_bias_partials(ops, T, H, rate, from_ds):
+    """The attention-backward epilogues can leave the column sums of every 128-token tile of dq / dk / dv (the packed q/k/v
+    projection's bias gradient): reduced over the tiles they equal the column sums of the gradients written, on both dQ paths,
+    and asking for them changes no gradient bit."""
+    import ctypes
+    from multi_modal_transformers_tokenmerge_b200 import _lib as L
+    setter = L.lib().tome_attention_set_dq_from_ds
+    setter.argtypes = [ctypes.c_int]
+    setter.restype = None
+    rng = np.random.default_rng(T + H)
+    B, D = 3, 64
+    qkv = dev(rng.standard_normal((B, T, 3, H, D)).astype(np.float32), torch.bfloat16)
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    size = dev(rng.integers(1, 4, size=(B, T)).astype(np.float32))
+    kw = dict(size=size, dropout_rate=rate, dropout_seed=11, dropout_site=3)
+    out, lse = ops.attention_fwd(q, k, v, **kw)
+    do = dev(rng.standard_normal((B, T, H, D)).astype(np.float32), torch.bfloat16)
+    try:
+        setter(from_ds)
+        ref = [t.clone() for t in ops.attention_bwd(q, k, v, out, lse, do, **kw)]
+        part = torch.full((B * ((T + 127) // 128), 3 * H * D), float("nan"), device="cuda")
+        got = ops.attention_bwd(q, k, v, out, lse, do, bias_partial=part, **kw)
+    finally:
+        setter(-1)
+    for a, b_ in zip(ref, got):
+        assert torch.equal(a, b_)
+    sums = ops.reduce_rows(part).double().cpu()
+    want = torch.cat([g.double().sum((0, 1)).reshape(-1) for g in got]).cpu()
+    scale = torch.cat([g.double().abs().sum((0, 1)).reshape(-1) for g in got]).max().item()
+    assert (sums - want).abs().max().item() <= 2e-6 * scale + 1e-6
