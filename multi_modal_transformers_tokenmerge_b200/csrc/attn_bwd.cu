@@ -565,10 +565,30 @@ attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     }
     const float2 scale2 = make_float2(p.scale_log2, p.scale_log2), bias22 = make_float2(bias2, bias2);
     const float2 sc2 = make_float2(p.scale, p.scale), ik2 = make_float2(p.inv_keep, p.inv_keep);
+    // a warp whose 32 key rows are all past T (three of the four in the last tile when T mod 128 <= 32) only keeps the barriers
+    // moving: its rows of the A operands stay whatever tensor memory holds (row i of A reaches row i of dK / dV only, and
+    // those rows are never stored), its rows of the stored dS^T tile are zeros (the dQ GEMM sums over them)
+    const bool warp_active = kt * DKV_BK + warp * 32 < T;
     for (int i = 0; i < n_q; ++i) {
       const int ms = i % AB_MSLOTS;
       const uint8_t* slot = s_meta + ms * DKV_META_SLOT;
       mbar_wait(&meta_full[ms], (i / AB_MSLOTS) & 1);
+      if (!warp_active) {
+        mbar_wait(s_full, i & 1);
+        tc_fence_before();
+        mbar_arrive(s_free);
+        mbar_wait(dp_full, i & 1);
+        if (p.store_ds) {
+          if (i >= 1) mbar_wait(ds_stored, (i - 1) & 1);
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) *reinterpret_cast<uint4*>(s_dst + row * 128 + (ch << 4)) = make_uint4(0u, 0u, 0u, 0u);
+          fence_proxy_async_smem();
+        }
+        mbar_arrive(&meta_empty[ms]);
+        tc_fence_before();
+        mbar_arrive(ps_ready);
+        continue;
+      }
       uint32_t vw[2] = {0xffffffffu, 0xffffffffu};
       if (has_mask) {
         const uint2 a = *reinterpret_cast<const uint2*>(slot + 768 + gk * 8);
@@ -936,13 +956,22 @@ static size_t bwd_pad_elems(const tome_attn_desc_t* d) {
 // the alternative to attn_bwd_dq_kernel, which recomputes S, dP and the softmax.  CTA = (128-query tile, head, batch);
 // per 64-key step the A operand is the dS^T block read MN-major (two 64-query atoms), the B operand the K tile read
 // MN-major (as V is in the forward P V product); the accumulator sits in 64 TMEM columns.
-constexpr int DQG_BQ = 128, DQG_BK = 64, DQG_STAGES = 4;
+// 3 stages x 3 CTAs per SM: the kernel is a short stream of dS^T tiles (9 k-steps at T = 536), so more resident CTAs to
+// overlap one CTA's prologue / epilogue with another's loads beat a deeper ring (4 x 2: 892 us for the whole backward at the
+// bench shape, 2 x 4: 870, 3 x 3: 865)
+#ifndef TOME_DQG_STAGES
+#define TOME_DQG_STAGES 3
+#endif
+#ifndef TOME_DQG_CTAS
+#define TOME_DQG_CTAS 3
+#endif
+constexpr int DQG_BQ = 128, DQG_BK = 64, DQG_STAGES = TOME_DQG_STAGES;
 constexpr int DQG_A_BYTES = 2 * DQG_BK * 128;   // 16 KB: two [64 keys][64 queries] atoms
 constexpr int DQG_B_BYTES = DQG_BK * AB_D * 2;  // 8 KB
 constexpr int DQG_STAGE = DQG_A_BYTES + DQG_B_BYTES;
 constexpr int DQG_SMEM = DQG_STAGES * DQG_STAGE + 256 + 1024;
 
-__global__ void __launch_bounds__(AB_THREADS, 2)
+__global__ void __launch_bounds__(AB_THREADS, TOME_DQG_CTAS)
 attn_bwd_dq_gemm_kernel(const __grid_constant__ CUtensorMap tm_ds, const __grid_constant__ CUtensorMap tm_k,
                         const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -1026,7 +1055,9 @@ attn_bwd_dq_gemm_kernel(const __grid_constant__ CUtensorMap tm_ds, const __grid_
 // the public header.
 static int g_attn_dq_from_ds = -1;
 static inline size_t ds_buffer_bytes(const tome_attn_desc_t* d) {
-  const size_t tq = ((size_t)d->tokens + 63) / 64 * 64, tk = ((size_t)d->tokens + 127) / 128 * 128;
+  // [B*H][T keys][T queries, rows pitched to 16 bytes]: the TMA stores clip the tiles' rows / columns past T and the loads
+  // zero-fill them, so no padding is written or read (T = 536: 575 KB per head instead of the 737 KB of whole 128 x 64 tiles)
+  const size_t tq = ((size_t)d->tokens + 7) / 8 * 8, tk = (size_t)d->tokens;
   return align256((size_t)d->batch * d->heads * tq * tk * 2);
 }
 static inline bool dq_from_ds(const tome_attn_desc_t* d) {
@@ -1109,12 +1140,12 @@ extern "C" int tome_attention_bwd(const tome_attn_desc_t* d, const tome_attn_gra
   // dS^T [B*H][ceil128(T) keys][ceil64(T) queries] bf16, after the (possibly absent) dropout bit tilings
   uint8_t* ds_buf = reinterpret_cast<uint8_t*>(lse2) + align256(bwd_pad_elems(d) * sizeof(float)) +
                     align256(d->dropout_rate > 0.f ? attn_dropbits_bytes(T) : 0);
-  const uint64_t ds_tq = ((uint64_t)T + 63) / 64 * 64, ds_tk = ((uint64_t)T + 127) / 128 * 128;
+  const uint64_t ds_tq = ((uint64_t)T + 7) / 8 * 8, ds_tk = (uint64_t)T;   // row pitch, rows (see ds_buffer_bytes)
   CUtensorMap tds_store, tds_load;
   if (from_ds) {
 
-    if (int rc = make_tmap_3d_bf16(&tds_store, ds_buf, ds_tq, ds_tk, (uint64_t)B * H, ds_tq, ds_tq * ds_tk, DKV_BK)) return rc;
-    if (int rc = make_tmap_3d_bf16(&tds_load, ds_buf, ds_tq, ds_tk, (uint64_t)B * H, ds_tq, ds_tq * ds_tk, DQG_BK)) return rc;
+    if (int rc = make_tmap_3d_bf16(&tds_store, ds_buf, (uint64_t)T, ds_tk, (uint64_t)B * H, ds_tq, ds_tq * ds_tk, DKV_BK)) return rc;
+    if (int rc = make_tmap_3d_bf16(&tds_load, ds_buf, (uint64_t)T, ds_tk, (uint64_t)B * H, ds_tq, ds_tq * ds_tk, DQG_BK)) return rc;
   } else {
     memset(&tds_store, 0, sizeof(tds_store));
   }

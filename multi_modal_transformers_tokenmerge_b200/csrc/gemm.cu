@@ -68,20 +68,26 @@ struct GemmShape {
 #define TOME_ABL(bit) false
 #endif
 
-template <int BN, bool PAIR = false>
+constexpr int GEMM_BRES_KB = 6;   // k-blocks (of 64) a resident B operand may have: K <= 384
+
+// BRES (pair MMA only): the CTA's half of the B operand -- all of K, up to GEMM_BRES_KB k-blocks -- stays in shared memory for
+// the whole kernel (a cluster works on ONE column tile), and the ring carries A alone.
+template <int BN, bool PAIR = false, bool BRES = false>
 struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   // pair MMA: this CTA holds half of the tile's columns, as whole 64-column atoms (BN = 192: 96 columns in two atoms)
   static constexpr int B_ATOMS = PAIR ? (BN / 2 + 63) / 64 : BN / 64;
   static constexpr int B_BYTES = B_ATOMS * 64 * GEMM_BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = BRES ? A_BYTES : A_BYTES + B_BYTES;
+  static constexpr int RES_BYTES = BRES ? GEMM_BRES_KB * B_BYTES : 0;
   // 6 x 32 KB, 5 x 40 KB, 4 x 48 KB; with 16 epilogue warps the staging tiles take 32 KB and the widest tile keeps 3 stages
-  static constexpr int STAGES = PAIR ? ((BN <= 128) ? 8 : 6)   // 8 x 24 KB, 6 x 32 KB (BN = 192 and 256)
+  static constexpr int STAGES = BRES ? 6                        // 6 x 16 KB of A (one whole K = 384 tile ahead) + 96 KB of B
+                              : PAIR ? ((BN <= 128) ? 8 : 6)   // 8 x 24 KB, 6 x 32 KB (BN = 192 and 256)
                                      : (BN <= 128) ? 6 : (BN <= 192) ? (GEMM_EPI_WARPS > 8 ? 4 : 5) : (GEMM_EPI_WARPS > 8 ? 3 : 4);
   static constexpr int STORE_BYTES = GEMM_EPI_WARPS * 2048;  // per epilogue warp: 32 rows x 64 B staging tile for TMA stores
   static constexpr int BAR_BYTES = 256 + 2 * BN * 4;  // barriers + double-buffered bias tile
   static constexpr int COL_BYTES = 2 * 4 * BN * 4;    // column sums: [accumulator stage][lane quadrant][BN] f32
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + STORE_BYTES + BAR_BYTES + COL_BYTES + 1024;  // +1024: manual 1 KB alignment
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + RES_BYTES + STORE_BYTES + BAR_BYTES + COL_BYTES + 1024;  // +1024: manual 1 KB alignment
   static_assert(TOTAL <= 232448, "shared memory per CTA");
 };
 
@@ -97,8 +103,9 @@ template <int BN, bool A_MN, bool B_MN, int MC, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const __grid_constant__ CUtensorMap tma_c, const GemmShape s, const GemmEpilogue e) {
-  constexpr bool PAIR = MC == 2;   // one 256-row cta_group::2 MMA per cluster pair (MC == 1: two 128-row MMAs sharing a multicast B)
-  using L = GemmSmem<BN, PAIR>;
+  constexpr bool PAIR = MC >= 2;   // one 256-row cta_group::2 MMA per cluster pair (MC == 1: two 128-row MMAs sharing a multicast B)
+  constexpr bool BRES = MC == 3;   // ... with the B operand resident in shared memory (K <= 384)
+  using L = GemmSmem<BN, PAIR, BRES>;
   constexpr int STAGES = L::STAGES;
   constexpr uint32_t TMEM_COLS = BN <= 64 ? 128 : BN <= 128 ? 256 : 512;  // two accumulator stages of BN columns
   static_assert(2 * BN <= 512 && BN % 64 == 0, "two BN-column accumulators must fit the 512 TMEM columns");
@@ -106,22 +113,32 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   // 1 KB alignment by pointer arithmetic on the __shared__ array itself, so the epilogue's accesses stay LDS/STS
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* s_store = smem + STAGES * L::STAGE_BYTES;  // 1 KB aligned (stage sizes are multiples of 1 KB)
+  uint8_t* s_bres = smem + STAGES * L::STAGE_BYTES;   // resident B: k-block kb at kb * B_BYTES (BRES only)
+  uint8_t* s_store = s_bres + L::RES_BYTES;           // 1 KB aligned (stage sizes are multiples of 1 KB)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_store + L::STORE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* bres_full = tmem_empty + 2;                // BRES: the resident B operand has landed (both CTAs', at the leader)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_full + 1);
   float* s_bias = reinterpret_cast<float*>(s_store + L::STORE_BYTES + 256);  // [2][BN]
   float* s_col = s_bias + 2 * BN;                                             // [2][4][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = s.m_items * s.n_tiles * s.k_splits;  // work items (tile, or vertical tile pair)
   const uint32_t crank = MC ? cluster_ctarank() : 0u;
-  const int first_item = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int item_step = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const bool leader = crank == 0;
+  // Work items (tile, or vertical tile pair), dealt round-robin to the CTAs / clusters.  BRES: cluster c keeps column tile
+  // c % n_tiles and walks the row-tile pairs c / n_tiles, + clusters / n_tiles, ... (the host launches a multiple of n_tiles
+  // clusters), so the n_tiles clusters working on one row-tile pair read its A tile at the same time (one HBM read, L2 hits
+  // for the rest); an item is then just the row-tile pair.
+  const int bres_groups = BRES ? (int)(gridDim.x >> 1) / s.n_tiles : 1;
+  const int bres_nblk = BRES ? (int)(blockIdx.x >> 1) % s.n_tiles : 0;
+  const int num_tiles = BRES ? s.m_items : s.m_items * s.n_tiles * s.k_splits;
+  const int first_item = BRES ? (int)(blockIdx.x >> 1) / s.n_tiles : MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int item_step = BRES ? bres_groups : MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+#define TOME_ITEM_NBLK(tile) (BRES ? bres_nblk : ((tile) / s.k_splits) % s.n_tiles)
+#define TOME_ITEM_MROW(tile) (BRES ? (tile) : (tile) / (s.k_splits * s.n_tiles))
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -137,6 +154,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], PAIR ? 2 * GEMM_EPI_WARPS : GEMM_EPI_WARPS);  // one arrive per epilogue warp (pair: of both CTAs, at the leader)
     }
+    mbar_init(bres_full, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -154,10 +172,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if constexpr (BRES) {   // this CTA's half of the column tile, every k-block, once
+        constexpr uint32_t kResTx = 2 * (B_MN ? L::B_BYTES : (BN / 2) * GEMM_BK * 2);
+        const uint32_t rb = map_to_cta(bres_full, 0);
+        if (leader) mbar_expect_tx(bres_full, kResTx * (uint32_t)s.kb_total);
+        const int nh = bres_nblk * BN + (int)crank * (BN / 2);
+        for (int kb = 0; kb < s.kb_total; ++kb) {
+          uint8_t* sb = s_bres + kb * L::B_BYTES;
+          if (!B_MN) {
+            tma_load_2d_pair(sb, &tma_b, rb, kb * GEMM_BK, nh);
+          } else {
+#pragma unroll
+            for (int j = 0; j < L::B_ATOMS; ++j) tma_load_2d_pair(sb + j * 8192, &tma_b, rb, nh + 64 * j, kb * GEMM_BK);
+          }
+        }
+      }
       for (int tile = first_item; tile < num_tiles; tile += item_step) {
-        const int split = tile % s.k_splits;
-        const int n_blk = (tile / s.k_splits) % s.n_tiles;
-        const int m_blk = (tile / (s.k_splits * s.n_tiles)) * (MC ? 2 : 1) + (int)crank;
+        const int split = BRES ? 0 : tile % s.k_splits;
+        const int n_blk = TOME_ITEM_NBLK(tile);
+        const int m_blk = TOME_ITEM_MROW(tile) * (MC ? 2 : 1) + (int)crank;
         const int m0 = m_blk * GEMM_BM, n0 = n_blk * BN;
         const int kb0 = split * s.kb_per_split;
         const int kb1 = min(kb0 + s.kb_per_split, s.kb_total);
@@ -166,6 +199,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
           const int k0 = kb * GEMM_BK;
+          if constexpr (BRES) {   // the ring carries A alone
+            const uint32_t fb = map_to_cta(&full_bar[stage], 0);
+            if (leader) mbar_expect_tx(&full_bar[stage], 2 * L::A_BYTES);
+            tma_load_2d_pair(sa, &tma_a, fb, k0, m0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           if constexpr (PAIR) {
             // both CTAs' loads are counted on the LEADER's barrier: its MMA thread is the only consumer
             const uint32_t fb = map_to_cta(&full_bar[stage], 0);
@@ -234,8 +274,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if constexpr (BRES) {
+        mbar_wait(bres_full, 0);
+        tc_fence_after();
+      }
       for (int tile = first_item; tile < num_tiles; tile += item_step) {
-        const int split = tile % s.k_splits;
+        const int split = BRES ? 0 : tile % s.k_splits;
         const int kb0 = split * s.kb_per_split;
         const int kb1 = min(kb0 + s.kb_per_split, s.kb_total);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -245,7 +289,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
-          const uint32_t sb = sa + L::A_BYTES;
+          const uint32_t sb = BRES ? smem_u32(s_bres + kb * L::B_BYTES) : sa + L::A_BYTES;
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             if (TOME_ABL(4)) break;
@@ -290,8 +334,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const uint32_t thr32 = e.drop.thresh16 << 16;
       const float2 gs2 = make_float2(e.gate_scale, e.gate_scale);
       for (int tile = first_item; tile < num_tiles; tile += item_step) {
-        const int n_blk = tile % s.n_tiles;
-        const int m_blk = (tile / s.n_tiles) * (MC ? 2 : 1) + (int)crank;
+        const int n_blk = TOME_ITEM_NBLK(tile);   // k_splits == 1 here
+        const int m_blk = TOME_ITEM_MROW(tile) * (MC ? 2 : 1) + (int)crank;
         const long long row = (long long)m_blk * GEMM_BM + row_in_tile;
         const int n0 = n_blk * BN;
         const bool row_ok = row < s.m;
@@ -604,6 +648,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #undef TOME_CHUNK
 #undef TOME_CHUNK_OK
   }
+#undef TOME_ITEM_NBLK
+#undef TOME_ITEM_MROW
 
   tc_fence_before();
   __syncthreads();
@@ -640,21 +686,30 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __re
 static int g_gemm_sm_limit = 0;
 static inline int gemm_sms() { return g_gemm_sm_limit > 0 && g_gemm_sm_limit < kNumSMs ? g_gemm_sm_limit : kNumSMs; }
 
+// B-resident launches: groups of n_tiles clusters (one per column tile), as many groups as fit and have work
+static inline int bres_clusters(int n_tiles, int m_items) {
+  int groups = (gemm_sms() / 2) / n_tiles;
+  if (groups > m_items) groups = m_items;
+  return groups * n_tiles;
+}
+
 template <int BN, bool A_MN, bool B_MN, int MC, int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmShape& s, const GemmEpilogue& e,
                        cudaStream_t stream) {
   auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, MC, EPI>;
+  using SM = GemmSmem<BN, MC >= 2, MC == 3>;
   static DynSmemOnce once;  // per instantiation, per device
-  TOME_CUDA(ensure_dyn_smem(kern, GemmSmem<BN, MC == 2>::TOTAL, once));
+  TOME_CUDA(ensure_dyn_smem(kern, SM::TOTAL, once));
   const int items = s.m_items * s.n_tiles * s.k_splits;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = GemmSmem<BN, MC == 2>::TOTAL;
+  cfg.dynamicSmemBytes = SM::TOTAL;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   if (MC) {
-    const int clusters = items < gemm_sms() / 2 ? items : gemm_sms() / 2;
+    int clusters = items < gemm_sms() / 2 ? items : gemm_sms() / 2;
+    if (MC == 3) clusters = bres_clusters(s.n_tiles, s.m_items);   // a multiple of the column tiles
     cfg.gridDim = dim3(2 * clusters);
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
@@ -687,6 +742,8 @@ extern "C" void tome_gemm_force_tile(int mode, int bn) { g_gemm_force_mode = mod
 // 0: never (two 128-row MMAs sharing a TMA-multicast B tile, round 1).  Process-wide tuning aid, not in the public header.
 static int g_gemm_pair = 1;
 extern "C" void tome_gemm_set_pair_mma(int on) { g_gemm_pair = on ? 1 : 0; }
+static int g_gemm_bres = 1;   // tuning aid: 0 = never keep B resident
+extern "C" void tome_gemm_set_b_resident(int on) { g_gemm_bres = on ? 1 : 0; }
 static int g_gemm_ablate = 0;
 extern "C" void tome_gemm_set_ablate(int bits) { g_gemm_ablate = bits; }   // has an effect in TOME_GEMM_ABLATE builds only
 
@@ -709,8 +766,12 @@ static TileChoice pick_tile(const tome_gemm_args_t* a) {
     if (t.bn == 192 && a->n >= 1024 && a->a_major == TOME_MAJOR_K) t.bn = 256;
     if (t.bn == 128) t.mode = 1;
   }
+  // K <= 384 with a specialised epilogue: keep B in shared memory (mode 3; the caller checks the epilogue)
+  if (t.mode == 2 && g_gemm_bres && a->k <= GEMM_BRES_KB * GEMM_BK && a->a_major == TOME_MAJOR_K && ceil_div(a->n, t.bn) <= gemm_sms() / 2)
+    t.mode = 3;
   if (g_gemm_force_bn == 128 || g_gemm_force_bn == 192 || g_gemm_force_bn == 256) t.bn = g_gemm_force_bn;
   if (g_gemm_force_mode == 0 || (g_gemm_force_mode > 0 && g_gemm_force_mode <= 2 && pairs_ok)) t.mode = g_gemm_force_mode;
+  if (g_gemm_force_mode == 3 && pairs_ok && t.bn >= 192 && a->k <= GEMM_BRES_KB * GEMM_BK && a->a_major == TOME_MAJOR_K) t.mode = 3;
   return t;
 }
 
@@ -762,7 +823,8 @@ extern "C" int tome_gemm_bf16(const tome_gemm_args_t* a, void* workspace, size_t
   TOME_CHECK(a->dropout_rate >= 0.f && a->dropout_rate < 1.f, TOME_ERR_INVALID, "gemm: dropout_rate must be in [0,1)");
 
   const TileChoice tile = pick_tile(a);
-  const int bn = tile.bn, mode = tile.mode;
+  const int bn = tile.bn;
+  int mode = tile.mode;
   const bool mc = mode != 0;
   GemmShape s;
   s.m = a->m; s.n = a->n; s.k = a->k;
@@ -833,12 +895,16 @@ extern "C" int tome_gemm_bf16(const tome_gemm_args_t* a, void* workspace, size_t
       else if (flags == EPI_GATE && a->gate_bits) epi = EPI_GATE;   // bf16 gate rows: generic epilogue
     }
   }
+  if (mode == 3 && (epi == EPI_GENERIC || bn == 128)) mode = 2;   // the resident-B kernels exist for the specialised epilogues only
   TOME_CHECK(!a->colsum_partial || epi != EPI_GENERIC, TOME_ERR_INVALID,
              "gemm: colsum_partial needs a bf16 output without split-K and one of the stack's epilogues (plain or gated data "
              "gradient, bias / bias+ReLU(+dropout) / bias(+dropout)+residual forward)");
 #define TOME_GEMM_MODE(BN_, AMN_, BMN_, EPI_)                                                        \
   do {                                                                                              \
-    if (mode == 2) rc = launch_gemm<BN_, AMN_, BMN_, 2, EPI_>(ta, tb, tc, s, e, stream);            \
+    if (mode == 3) {                                                                                \
+      if constexpr (!(AMN_) && (EPI_) >= 0 && (BN_) >= 192) rc = launch_gemm<BN_, AMN_, BMN_, 3, EPI_>(ta, tb, tc, s, e, stream); \
+      else rc = TOME_ERR_INVALID;                                                                   \
+    } else if (mode == 2) rc = launch_gemm<BN_, AMN_, BMN_, 2, EPI_>(ta, tb, tc, s, e, stream);     \
     else if (mode == 1) rc = launch_gemm<BN_, AMN_, BMN_, 1, EPI_>(ta, tb, tc, s, e, stream);     \
     else rc = launch_gemm<BN_, AMN_, BMN_, 0, EPI_>(ta, tb, tc, s, e, stream);                      \
   } while (0)
