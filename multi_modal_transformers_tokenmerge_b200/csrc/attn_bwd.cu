@@ -15,6 +15,8 @@
 // (the first version did, and that dependent-load chain paced the kernels).
 #include <float.h>
 
+#include <stdlib.h>
+
 #include "attn_meta.cuh"
 #include "common.cuh"
 #include "host_util.h"
@@ -27,6 +29,8 @@ int attn_generic_bwd(const tome_attn_desc_t* d, const tome_attn_grad_strides_t* 
 
 constexpr int AB_D = 64;
 constexpr int AB_THREADS = 192;
+constexpr int DKT_SOFTMAX_WARPS = 8;
+constexpr int DKT_THREADS = 320;   // attn_bwd_dkdv_ts_kernel: eight softmax warps + producer + MMA issuer
 constexpr uint32_t AB_TMEM_COLS = 256;
 constexpr int AB_MSLOTS = 3;  // metadata ring
 
@@ -52,7 +56,20 @@ struct AttnBwdParams {
   float* cs;
   long long cs_ld;
   int cs_q, cs_k, cs_v, n_t128;
+  int ablate;   // TOME_ATTN_ABLATE builds only (timing probes, wrong results): 1 = no softmax arithmetic, 2 = no MMAs
 };
+#ifdef TOME_ATTN_ABLATE
+#define AB_ABL(bit) ((p.ablate & (bit)) != 0)
+#else
+#define AB_ABL(bit) false
+#endif
+
+// one mbarrier arrival for the whole warp, after every lane has got here (the lanes' tensor-memory accesses are warp-collective
+// and already waited for; their shared-memory stores are ordered by the __syncwarp)
+__device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
 
 // Epilogue shared by the four kernels below.  The 128 threads of warps 0-3 each own one row of a [128 x 64] fp32 accumulator in
 // tensor memory.  The rows are rounded to bf16 and staged in shared memory (16 KB, 128-byte swizzled rows), then written out
@@ -61,7 +78,7 @@ struct AttnBwdParams {
 // projection -- without a second pass over dq/dk/dv in HBM.  `part`: 1 KB of shared memory.  Named barrier `bar`, 128 threads.
 __device__ __forceinline__ void ab_store_tile(uint8_t* stage, float* part, uint32_t tm_row, int rows_valid, __nv_bfloat16* gtile,
                                               long long row_stride, float* colsum_out, int bar) {
-  const int row = threadIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tid = threadIdx.x & 127, row = tid, warp = tid >> 5, lane = tid & 31;   // callers: one or two groups of 128 threads
   {
     float a[32], c[32];
     tmem_ld_f32x32(tm_row, a);
@@ -81,7 +98,7 @@ __device__ __forceinline__ void ab_store_tile(uint8_t* stage, float* part, uint3
   asm volatile("bar.sync %0, 128;" ::"r"(bar) : "memory");
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int pce = threadIdx.x + 128 * i, r = pce >> 3, ch = pce & 7;
+    const int pce = tid + 128 * i, r = pce >> 3, ch = pce & 7;
     const uint4 w = *reinterpret_cast<const uint4*>(stage + r * 128 + ((ch ^ (r & 7)) << 4));
     if (r < rows_valid) *reinterpret_cast<uint4*>(gtile + (long long)r * row_stride + ch * 8) = w;
   }
@@ -95,7 +112,7 @@ __device__ __forceinline__ void ab_store_tile(uint8_t* stage, float* part, uint3
     }
     *reinterpret_cast<float2*>(part + warp * 64 + 2 * lane) = make_float2(s0, s1);
     asm volatile("bar.sync %0, 128;" ::"r"(bar) : "memory");
-    if (threadIdx.x < 64) colsum_out[threadIdx.x] = (part[threadIdx.x] + part[64 + threadIdx.x]) + (part[128 + threadIdx.x] + part[192 + threadIdx.x]);
+    if (tid < 64) colsum_out[tid] = (part[tid] + part[64 + tid]) + (part[128 + tid] + part[192 + tid]);
   }
 }
 
@@ -404,10 +421,10 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 // global memory straight from the registers (a thread owns one 128-byte line per tile).
 // S^T lives in columns [0, 64) and is free again as soon as every thread has read it (s_free), so S^T_{i+1} is computed
 // while the threads are still busy with dP^T_i; the order on the tensor pipe is S^T_{i+1}, dV_i, dK_i, dP^T_{i+1}.
-constexpr int DKT_SMEM = 2 * DKV_KV_BYTES + 2 * 2 * DKV_Q_BYTES + DKV_PT_BYTES + AB_MSLOTS * DKV_META_SLOT + 256 + 1024;
+constexpr int DKT_SMEM = 2 * DKV_KV_BYTES + 2 * 2 * DKV_Q_BYTES + 2 * DKV_PT_BYTES + AB_MSLOTS * DKV_META_SLOT + 256 + 1024;
 
 template <bool DROP>
-__global__ void __launch_bounds__(AB_THREADS, 2)
+__global__ void __launch_bounds__(DKT_THREADS, 2)
 attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                         const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
                         const __grid_constant__ CUtensorMap tm_ds, const AttnBwdParams p) {
@@ -416,8 +433,8 @@ attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   uint8_t* s_k = smem;
   uint8_t* s_v = s_k + DKV_KV_BYTES;
   uint8_t* s_qdo = s_v + DKV_KV_BYTES;            // stage s: Q at s*16K, dO at s*16K + 8K
-  uint8_t* s_dst = s_qdo + 2 * 2 * DKV_Q_BYTES;   // dS^T [128 keys][64 queries] bf16, 128B-swizzled rows: staging of the TMA store
-  uint8_t* s_meta = s_dst + DKV_PT_BYTES;         // slot i at i * DKV_META_SLOT
+  uint8_t* s_dst = s_qdo + 2 * 2 * DKV_Q_BYTES;   // dS^T [128 keys][64 queries] bf16, 128B-swizzled rows: staging of the TMA store, tile i in buffer i & 1
+  uint8_t* s_meta = s_dst + 2 * DKV_PT_BYTES;     // slot i at i * DKV_META_SLOT
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_meta + AB_MSLOTS * DKV_META_SLOT);
   uint64_t* kv_full = bars;        // 1
   uint64_t* q_full = bars + 1;     // [2]
@@ -429,8 +446,8 @@ attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   uint64_t* pd_free = bars + 9;    // dV/dK MMAs of a tile retired (accumulators final after the last one)
   uint64_t* meta_full = bars + 10;   // [3]
   uint64_t* meta_empty = bars + 13;  // [3]  128 arrivals
-  uint64_t* ds_stored = bars + 16;   // store_ds: the TMA store of dS^T_i has read the tile out of shared memory
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* ds_stored = bars + 16;   // [2] store_ds: the TMA store of dS^T_i has read buffer i & 1 out of shared memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -446,31 +463,36 @@ attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     }
     mbar_init(s_full, 1);
     mbar_init(dp_full, 1);
-    mbar_init(s_free, DKV_BK);
-    mbar_init(ps_ready, DKV_BK);
+    mbar_init(s_free, DKT_SOFTMAX_WARPS);       // one arrival per softmax warp (elected lane) instead of one per thread
+    mbar_init(ps_ready, DKT_SOFTMAX_WARPS);     // (fewer barrier transactions; measured neutral on the kernel's duration)
     mbar_init(pd_free, 1);
-    mbar_init(ds_stored, 1);
+    mbar_init(&ds_stored[0], 1);
+    mbar_init(&ds_stored[1], 1);
     for (int i = 0; i < AB_MSLOTS; ++i) {
       mbar_init(&meta_full[i], 1);
-      mbar_init(&meta_empty[i], DKV_BK);
+      mbar_init(&meta_empty[i], DKT_SOFTMAX_WARPS);
     }
     fence_barrier_init();
   }
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
     tma_prefetch_desc(&tm_do);
   }
-  if (warp == 5) tmem_alloc(tmem_slot, AB_TMEM_COLS);
+  if (warp == 9) tmem_alloc(tmem_slot, AB_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tm_st = tmem_base, tm_dpt = tmem_base + 64, tm_dk = tmem_base + 128, tm_dv = tmem_base + 192;
-  const uint32_t tm_dsa = tm_dpt, tm_pa = tm_dpt + 32;   // A operands: dS^T over dP^T[0,32), P^T over dP^T[32,64)
+  // A operands, written by each thread over the 32 columns of dP^T it has just read: the thread of query half g leaves dS^T
+  // (16 columns = 32 bf16) at dP^T[32 g, 32 g + 16) and P^T at dP^T[32 g + 16, 32 g + 32); k-step k of the two products reads
+  // its 8 columns at tm_dsa(k) / tm_pa(k)
+  auto tm_dsa = [&](int k) { return tm_dpt + (uint32_t)((k >> 1) * 32 + (k & 1) * 8); };
+  auto tm_pa = [&](int k) { return tm_dpt + (uint32_t)((k >> 1) * 32 + 16 + (k & 1) * 8); };
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       mbar_expect_tx(kv_full, 2 * DKV_KV_BYTES);
       tma_load_3d(s_k, &tm_k, kv_full, h * AB_D, kt * DKV_BK, b);
@@ -494,7 +516,7 @@ attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         tma_load_3d(s_qdo + st * 2 * DKV_Q_BYTES + DKV_Q_BYTES, &tm_do, &q_full[st], h * AB_D, i * DKV_BQ, b);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(DKV_BK, DKV_BQ, false, false);  // K/V K-major, Q/dO K-major
       constexpr uint32_t idesc_g = make_idesc_bf16(DKV_BK, AB_D, false, true);     // P^T/dS^T from TMEM (K-major), dO/Q MN-major
@@ -512,7 +534,7 @@ attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           const uint32_t aq = smem_u32(s_qdo + st * 2 * DKV_Q_BYTES);
 #pragma unroll
           for (int k = 0; k < AB_D / 16; ++k)
-            umma_bf16(tm_st, make_smem_desc(ak + k * 32, 16, 1024), make_smem_desc(aq + k * 32, 16, 1024), idesc_s, k > 0);
+            if (!AB_ABL(2)) umma_bf16(tm_st, make_smem_desc(ak + k * 32, 16, 1024), make_smem_desc(aq + k * 32, 16, 1024), idesc_s, k > 0);
           umma_commit(s_full);
         }
         if (i >= 1) {
@@ -521,16 +543,17 @@ attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           const int st = (i - 1) & 1;
           const uint32_t aq = smem_u32(s_qdo + st * 2 * DKV_Q_BYTES), ado = aq + DKV_Q_BYTES;
           if (p.store_ds) {  // dS^T tile (keys kt*128.., queries (i-1)*64..) -> global, in the layout it has in shared memory
+            if (!AB_ABL(4))
             asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                         ::"l"(&tm_ds), "r"(smem_u32(s_dst)), "r"((i - 1) * DKV_BQ), "r"(kt * DKV_BK), "r"(b * p.heads + h) : "memory");
+                         ::"l"(&tm_ds), "r"(smem_u32(s_dst + ((i - 1) & 1) * DKV_PT_BYTES)), "r"((i - 1) * DKV_BQ), "r"(kt * DKV_BK), "r"(b * p.heads + h) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
 #pragma unroll
           for (int k = 0; k < DKV_BQ / 16; ++k)  // dV += P^T dO
-            umma_bf16_ts(tm_dv, tm_pa + k * 8, make_smem_desc(ado + k * 2048, 8192, 1024), idesc_g, (i > 1 || k > 0) ? 1u : 0u);
+            if (!AB_ABL(2)) umma_bf16_ts(tm_dv, tm_pa(k), make_smem_desc(ado + k * 2048, 8192, 1024), idesc_g, (i > 1 || k > 0) ? 1u : 0u);
 #pragma unroll
           for (int k = 0; k < DKV_BQ / 16; ++k)  // dK += dS^T Q
-            umma_bf16_ts(tm_dk, tm_dsa + k * 8, make_smem_desc(aq + k * 2048, 8192, 1024), idesc_g, (i > 1 || k > 0) ? 1u : 0u);
+            if (!AB_ABL(2)) umma_bf16_ts(tm_dk, tm_dsa(k), make_smem_desc(aq + k * 2048, 8192, 1024), idesc_g, (i > 1 || k > 0) ? 1u : 0u);
           umma_commit(pd_free);
           umma_commit(&q_empty[st]);
         }
@@ -539,20 +562,27 @@ attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           const uint32_t ado = smem_u32(s_qdo + st * 2 * DKV_Q_BYTES) + DKV_Q_BYTES;
 #pragma unroll
           for (int k = 0; k < AB_D / 16; ++k)
-            umma_bf16(tm_dpt, make_smem_desc(av + k * 32, 16, 1024), make_smem_desc(ado + k * 32, 16, 1024), idesc_s, k > 0);
+            if (!AB_ABL(2)) umma_bf16(tm_dpt, make_smem_desc(av + k * 32, 16, 1024), make_smem_desc(ado + k * 32, 16, 1024), idesc_s, k > 0);
           umma_commit(dp_full);
         }
-        if (i >= 1 && p.store_ds) {  // after the issue work of this round, so nobody waits for the store's shared-memory read
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          mbar_arrive(ds_stored);
+        if (i >= 2 && p.store_ds) {  // all but the newest store have left shared memory: buffer i & 1 (tile i - 2) is free again
+          if (!AB_ABL(16)) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          mbar_arrive(&ds_stored[i & 1]);
         }
       }
       if (p.store_ds) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before the CTA exits
     }
   } else {
-    const int row = threadIdx.x;  // key row == TMEM lane
+    // warps 0-7: thread = (key row, query half): warp w owns TMEM lanes 32 (w & 3) .. + 31 and the 32 queries of half w >> 2 of
+    // every tile.  Nothing is reduced along a row here (lse and delta arrive precomputed), so the two halves of a row never
+    // talk to each other.  Measured (profiles/r02_attention_bwd.md): eight warps at 96 registers run exactly as fast as four
+    // at 168 (857 vs 865 us for the whole backward at the bench shape) -- the kernel is paced by the hand-offs between the
+    // softmax threads and the single MMA thread (two dependent hops per tile), not by issue slots or latency hiding; kept
+    // because the smaller register footprint leaves room for the dK / dV epilogues to run side by side.
+    const int row = (warp & 3) * 32 + lane;  // key row == TMEM lane
+    const int hq = warp >> 2;                // query half
     const int kk = kt * DKV_BK + row;
-    const uint32_t lane_sel = ((uint32_t)(warp * 32)) << 16;
+    const uint32_t lane_sel = ((uint32_t)((warp & 3) * 32)) << 16;
     const bool k_valid = kk < T;
     float bias2 = 0.f;
     int gk = 0, pk = 0;
@@ -565,68 +595,60 @@ attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     }
     const float2 scale2 = make_float2(p.scale_log2, p.scale_log2), bias22 = make_float2(bias2, bias2);
     const float2 sc2 = make_float2(p.scale, p.scale), ik2 = make_float2(p.inv_keep, p.inv_keep);
-    // a warp whose 32 key rows are all past T (three of the four in the last tile when T mod 128 <= 32) only keeps the barriers
-    // moving: its rows of the A operands stay whatever tensor memory holds (row i of A reaches row i of dK / dV only, and
-    // those rows are never stored), its rows of the stored dS^T tile are zeros (the dQ GEMM sums over them)
-    const bool warp_active = kt * DKV_BK + warp * 32 < T;
+    // a warp whose 32 key rows are all past T (three of the four quadrants in the last tile when T mod 128 <= 32) only keeps the
+    // barriers moving: its rows of the A operands stay whatever tensor memory holds (row i of A reaches row i of dK / dV only,
+    // and those rows are never stored), its rows of the stored dS^T tile are zeros (the dQ GEMM sums over them)
+    const bool warp_active = kt * DKV_BK + (warp & 3) * 32 < T;
+    uint8_t* dst_row0 = s_dst + row * 128;
     for (int i = 0; i < n_q; ++i) {
       const int ms = i % AB_MSLOTS;
       const uint8_t* slot = s_meta + ms * DKV_META_SLOT;
       mbar_wait(&meta_full[ms], (i / AB_MSLOTS) & 1);
-      if (!warp_active) {
+      if (!warp_active || AB_ABL(1)) {
         mbar_wait(s_full, i & 1);
         tc_fence_before();
-        mbar_arrive(s_free);
+        warp_arrive(s_free, lane);
         mbar_wait(dp_full, i & 1);
         if (p.store_ds) {
-          if (i >= 1) mbar_wait(ds_stored, (i - 1) & 1);
+          uint8_t* dst_row = dst_row0 + (i & 1) * DKV_PT_BYTES;
+          if (i >= 2) mbar_wait(&ds_stored[i & 1], ((i - 2) >> 1) & 1);
 #pragma unroll
-          for (int ch = 0; ch < 8; ++ch) *reinterpret_cast<uint4*>(s_dst + row * 128 + (ch << 4)) = make_uint4(0u, 0u, 0u, 0u);
-          fence_proxy_async_smem();
+          for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<uint4*>(dst_row + ((hq * 4 + ch) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+          if (!AB_ABL(8)) fence_proxy_async_smem();
         }
-        mbar_arrive(&meta_empty[ms]);
+        warp_arrive(&meta_empty[ms], lane);
         tc_fence_before();
-        mbar_arrive(ps_ready);
+        warp_arrive(ps_ready, lane);
         continue;
       }
-      uint32_t vw[2] = {0xffffffffu, 0xffffffffu};
+      uint32_t vw = 0xffffffffu;
       if (has_mask) {
-        const uint2 a = *reinterpret_cast<const uint2*>(slot + 768 + gk * 8);
-        const uint2 c = *reinterpret_cast<const uint2*>(slot + 1024 + gk * 8);
-        vw[0] = a.x; vw[1] = a.y;
-        if (c.x | c.y) {  // rare (Text sets): fold the causal rule into the visibility words
-          const int* posq = reinterpret_cast<const int*>(slot + 512);
-          for (int q = 0; q < 32; ++q) {
-            if (((c.x >> q) & 1u) && pk <= posq[q]) vw[0] |= 1u << q;
-            if (((c.y >> q) & 1u) && pk <= posq[32 + q]) vw[1] |= 1u << q;
-          }
+        vw = *reinterpret_cast<const uint32_t*>(slot + 768 + gk * 8 + hq * 4);
+        const uint32_t c = *reinterpret_cast<const uint32_t*>(slot + 1024 + gk * 8 + hq * 4);
+        if (c) {  // rare (Text sets): fold the causal rule into the visibility word
+          const int* posq = reinterpret_cast<const int*>(slot + 512) + hq * 32;
+          for (int q = 0; q < 32; ++q)
+            if (((c >> q) & 1u) && pk <= posq[q]) vw |= 1u << q;
         }
       }
-      if (!k_valid) vw[0] = vw[1] = 0u;  // rows past T contribute nothing (and store zeros into dS^T)
-      uint32_t kb[2] = {0xffffffffu, 0xffffffffu};  // dropout keep bits of this key against the tile's 64 queries
-      if constexpr (DROP) {
-        const uint2 t = *reinterpret_cast<const uint2*>(slot + 1280 + row * 8);
-        kb[0] = t.x; kb[1] = t.y;
-      }
-      const float4* lse4 = reinterpret_cast<const float4*>(slot);
-      const float4* del4 = reinterpret_cast<const float4*>(slot + 256);
+      if (!k_valid) vw = 0u;  // rows past T contribute nothing (and store zeros into dS^T)
+      uint32_t kb = 0xffffffffu;  // dropout keep bits of this key against this half's 32 queries
+      if constexpr (DROP) kb = *reinterpret_cast<const uint32_t*>(slot + 1280 + row * 8 + hq * 4);
+      const float4* lse4 = reinterpret_cast<const float4*>(slot) + hq * 8;
+      const float4* del4 = reinterpret_cast<const float4*>(slot + 256) + hq * 8;
       // ---- phase 1: P = exp2(s2 - lse2) from S^T_i, kept as packed bf16 (what the dV product consumes, before dropout)
-      uint32_t pe[32];
+      uint32_t pe[16];
       mbar_wait(s_full, i & 1);
       tc_fence_after();
-#pragma unroll
-      for (int cq = 0; cq < DKV_BQ / 32; ++cq) {
+      {
         float sv[32];
-        tmem_ld_f32x32(tm_st + lane_sel + cq * 32, sv);
+        tmem_ld_f32x32(tm_st + lane_sel + hq * 32, sv);
         tmem_ld_wait();
-        if (cq == 1) {       // the whole row of S^T_i is in registers: the next S^T may overwrite it
-          tc_fence_before();
-          mbar_arrive(s_free);
-        }
-        const uint32_t word = vw[cq];
+        tc_fence_before();
+        warp_arrive(s_free, lane);   // this thread's part of S^T_i is in registers: the next S^T may overwrite it
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
-          const float4 l4 = lse4[cq * 8 + c4];
+          const float4 l4 = lse4[c4];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const int c = c4 * 4 + 2 * u;
@@ -634,78 +656,80 @@ attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             float2 t = __ffma2_rn(make_float2(sv[c], sv[c + 1]), scale2, bias22);
             t = __fadd2_rn(t, make_float2(-lv.x, -lv.y));
             float2 e = make_float2(fast_exp2(t.x), fast_exp2(t.y));
-            e.x = ((word >> c) & 1u) ? e.x : 0.f;
-            e.y = ((word >> (c + 1)) & 1u) ? e.y : 0.f;
-            pe[cq * 16 + (c >> 1)] = pack_bf16(e.x, e.y);
+            e.x = ((vw >> c) & 1u) ? e.x : 0.f;
+            e.y = ((vw >> (c + 1)) & 1u) ? e.y : 0.f;
+            pe[c >> 1] = pack_bf16(e.x, e.y);
           }
         }
       }
-      // ---- phase 2: dS = P (dP' - delta) scale from dP^T_i; the upper half of the row first, so that by the time the
-      // packed results are written over columns [64, 128) both halves of dP^T_i are in registers
-      uint32_t dw[32], pw[DROP ? 32 : 1];
+      // ---- phase 2: dS = P (dP' - delta) scale from dP^T_i
+      uint32_t dw[16], pw[DROP ? 16 : 1];
       mbar_wait(dp_full, i & 1);
       tc_fence_after();
-#pragma unroll
-      for (int cq = DKV_BQ / 32 - 1; cq >= 0; --cq) {
+      {
         float dv[32];
-        tmem_ld_f32x32(tm_dpt + lane_sel + cq * 32, dv);
+        tmem_ld_f32x32(tm_dpt + lane_sel + hq * 32, dv);
         tmem_ld_wait();
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
-          const float4 d4 = del4[cq * 8 + c4];
+          const float4 d4 = del4[c4];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const int c = c4 * 4 + 2 * u;
             const float2 dl = u ? make_float2(d4.z, d4.w) : make_float2(d4.x, d4.y);
-            const uint32_t pwv = pe[cq * 16 + (c >> 1)];
+            const uint32_t pwv = pe[c >> 1];
             const float2 pf = make_float2(bf16_lo(pwv), bf16_hi(pwv));
             float2 dp = make_float2(dv[c], dv[c + 1]);
             if constexpr (DROP) {  // weights' = weights keep / (1 - rate): dP' = dP keep / (1 - rate) enters dS, P' enters dV
-              const bool k0 = (kb[cq] >> c) & 1u, k1 = (kb[cq] >> (c + 1)) & 1u;
+              const bool k0 = (kb >> c) & 1u, k1 = (kb >> (c + 1)) & 1u;
               dp = __fmul2_rn(dp, ik2);
               float2 pd = __fmul2_rn(pf, ik2);
               dp.x = k0 ? dp.x : 0.f; dp.y = k1 ? dp.y : 0.f;
               pd.x = k0 ? pd.x : 0.f; pd.y = k1 ? pd.y : 0.f;
-              pw[cq * 16 + (c >> 1)] = pack_bf16(pd.x, pd.y);
+              pw[c >> 1] = pack_bf16(pd.x, pd.y);
             }
             float2 g = __fadd2_rn(dp, make_float2(-dl.x, -dl.y));
             g = __fmul2_rn(g, sc2);
             g = __fmul2_rn(g, pf);
-            dw[cq * 16 + (c >> 1)] = pack_bf16(g.x, g.y);
+            dw[c >> 1] = pack_bf16(g.x, g.y);
           }
         }
       }
-      tmem_st_x32(tm_dsa + lane_sel, dw);
-      if constexpr (DROP) tmem_st_x32(tm_pa + lane_sel, pw);
-      else tmem_st_x32(tm_pa + lane_sel, pe);
+      tmem_st_x16(tm_dpt + lane_sel + hq * 32, dw);
+      if constexpr (DROP) tmem_st_x16(tm_dpt + lane_sel + hq * 32 + 16, pw);
+      else tmem_st_x16(tm_dpt + lane_sel + hq * 32 + 16, pe);
       if (p.store_ds) {  // the dS^T tile the dQ GEMM consumes, staged for one TMA store (a direct 16-byte-per-lane global
                          // store of these rows cost 330 us per call: 32 partial sectors per instruction)
-        if (i >= 1) mbar_wait(ds_stored, (i - 1) & 1);
+        uint8_t* dst_row = dst_row0 + (i & 1) * DKV_PT_BYTES;
+        if (i >= 2) mbar_wait(&ds_stored[i & 1], ((i - 2) >> 1) & 1);   // the store of tile i - 2 has read this buffer
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch)
-          *reinterpret_cast<uint4*>(s_dst + row * 128 + ((ch ^ (row & 7)) << 4)) = make_uint4(dw[4 * ch], dw[4 * ch + 1], dw[4 * ch + 2], dw[4 * ch + 3]);
-        fence_proxy_async_smem();
+        for (int ch = 0; ch < 4; ++ch)
+          *reinterpret_cast<uint4*>(dst_row + (((hq * 4 + ch) ^ (row & 7)) << 4)) = make_uint4(dw[4 * ch], dw[4 * ch + 1], dw[4 * ch + 2], dw[4 * ch + 3]);
+        if (!AB_ABL(8)) fence_proxy_async_smem();
       }
       tmem_st_wait();
-      mbar_arrive(&meta_empty[ms]);
+      warp_arrive(&meta_empty[ms], lane);
       tc_fence_before();
-      mbar_arrive(ps_ready);
+      warp_arrive(ps_ready, lane);
     }
     mbar_wait(pd_free, (n_q - 1) & 1);  // accumulators final
     tc_fence_after();
     {
-      // every MMA has retired: the K and V tiles serve as staging for dK and dV, the Q/dO ring for the column-sum scratch
+      // every MMA has retired: the K and V tiles serve as staging for dK and dV, the Q/dO ring for the column-sum scratch;
+      // warps 0-3 write dK while warps 4-7 write dV (own staging tile, scratch and named barrier each)
       const int rows_valid = min(DKV_BK, T - kt * DKV_BK);
       float* cs_row = p.cs ? p.cs + ((long long)b * p.n_t128 + kt) * p.cs_ld + h * AB_D : nullptr;
-      ab_store_tile(s_k, reinterpret_cast<float*>(s_qdo), tm_dk + lane_sel, rows_valid,
-                    p.dk + (long long)b * p.dk_bs + (long long)kt * DKV_BK * p.dk_ts + h * AB_D, p.dk_ts, cs_row ? cs_row + p.cs_k : nullptr, 1);
-      ab_store_tile(s_v, reinterpret_cast<float*>(s_qdo) + 256, tm_dv + lane_sel, rows_valid,
-                    p.dv + (long long)b * p.dv_bs + (long long)kt * DKV_BK * p.dv_ts + h * AB_D, p.dv_ts, cs_row ? cs_row + p.cs_v : nullptr, 1);
+      if (hq == 0)
+        ab_store_tile(s_k, reinterpret_cast<float*>(s_qdo), tm_dk + lane_sel, rows_valid,
+                      p.dk + (long long)b * p.dk_bs + (long long)kt * DKV_BK * p.dk_ts + h * AB_D, p.dk_ts, cs_row ? cs_row + p.cs_k : nullptr, 1);
+      else
+        ab_store_tile(s_v, reinterpret_cast<float*>(s_qdo) + 256, tm_dv + lane_sel, rows_valid,
+                      p.dv + (long long)b * p.dv_bs + (long long)kt * DKV_BK * p.dv_ts + h * AB_D, p.dv_ts, cs_row ? cs_row + p.cs_v : nullptr, 2);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, AB_TMEM_COLS);
   }
@@ -1136,6 +1160,10 @@ extern "C" int tome_attention_bwd(const tome_attn_desc_t* d, const tome_attn_gra
   p.cs = gs->bias_partial; p.cs_ld = gs->bias_partial_ld;
   p.cs_q = gs->bias_q_col; p.cs_k = gs->bias_k_col; p.cs_v = gs->bias_v_col;
   p.n_t128 = ceil_div(T, 128);
+  p.ablate = 0;
+#ifdef TOME_ATTN_ABLATE
+  if (const char* e = getenv("TOME_ATTN_ABLATE")) p.ablate = atoi(e);
+#endif
 
   // dS^T [B*H][ceil128(T) keys][ceil64(T) queries] bf16, after the (possibly absent) dropout bit tilings
   uint8_t* ds_buf = reinterpret_cast<uint8_t*>(lse2) + align256(bwd_pad_elems(d) * sizeof(float)) +
@@ -1169,8 +1197,8 @@ extern "C" int tome_attention_bwd(const tome_attn_desc_t* d, const tome_attn_gra
     if (int rc = make_tmap_3d_bf16(&tdo, dout, hd, T, B, gs->do_token_stride, gs->do_batch_stride, DKV_BQ)) return rc;
     dim3 grid(ceil_div(T, DKV_BK), H, B);
     if (g_attn_bwd_ts) {
-      if (keep_k) attn_bwd_dkdv_ts_kernel<true><<<grid, AB_THREADS, DKT_SMEM, stream>>>(tq, tk, tv, tdo, tds_store, p);
-      else attn_bwd_dkdv_ts_kernel<false><<<grid, AB_THREADS, DKT_SMEM, stream>>>(tq, tk, tv, tdo, tds_store, p);
+      if (keep_k) attn_bwd_dkdv_ts_kernel<true><<<grid, DKT_THREADS, DKT_SMEM, stream>>>(tq, tk, tv, tdo, tds_store, p);
+      else attn_bwd_dkdv_ts_kernel<false><<<grid, DKT_THREADS, DKT_SMEM, stream>>>(tq, tk, tv, tdo, tds_store, p);
     } else if (keep_k) attn_bwd_dkdv_kernel<true><<<grid, AB_THREADS, DKV_SMEM, stream>>>(tq, tk, tv, tdo, tds_store, p);
     else attn_bwd_dkdv_kernel<false><<<grid, AB_THREADS, DKV_SMEM, stream>>>(tq, tk, tv, tdo, tds_store, p);
     TOME_CUDA(cudaGetLastError());
