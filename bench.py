@@ -6,7 +6,7 @@
 
 A "step" is one full training step of the octo-small-style ToMe stack (BASELINE.json configs[1]: batch 256 per GPU,
 T0 = 536 tokens, 12 layers, r = 16 / layer, block-causal readout mask, bf16) on synthetic embeddings: zero grads,
-forward, action head + l2 loss on the readouts (or the synthetic readout MSE), full backward, (N > 1: overlapped NCCL gradient all-reduce), AdamW.
+forward, action head + l2 loss on the readouts (or the synthetic readout MSE), full backward, (N > 1: NCCL gradient all-reduce, see --overlap), AdamW.
 One JSON line is printed by rank 0.  See DESIGN.md "Measurement" for every field.
 """
 from __future__ import annotations
@@ -163,7 +163,7 @@ def workload_config(args, world, B, T0):
             "loss": ("continuous action head + l2 loss on the pooled readouts (continuous_train_step, octo.py:242-280)"
                      if args.loss == "continuous" else "synthetic MSE on the readout rows"),
             "hidden_dropout": args.dropout, "attention_dropout": args.attn_dropout, "optimizer": "AdamW fp32 master",
-            "parallelism": f"dp{world}", "comm_sms": args.comm_sms if world > 1 else 0, "l2_policy": "inputs and activations (>= 1 GB/step) exceed the 126 MB L2"}
+            "parallelism": f"dp{world}", "allreduce": (args.overlap if world > 1 else None), "comm_sms": args.comm_sms if world > 1 else 0, "l2_policy": "inputs and activations (>= 1 GB/step) exceed the 126 MB L2"}
 
 
 def run_reference(args, rank):
@@ -318,7 +318,7 @@ def measure_workload(args, cfgname, rank, world, local, steps, warmup, with_extr
                       **(dict(head="continuous", head_features=ACTION_DIM, max_action=MAX_ACTION) if args.loss == "continuous" else {}))
     eng = ToMeStackEngine(cfg, gid=gid, pos=pos, allow=allow, readout_idx=ro)
     eng.init_params(seed=1)  # same weights on every rank
-    trainer = DataParallelTrainer(eng, comm_sms=args.comm_sms if world > 1 else 0)
+    trainer = DataParallelTrainer(eng, comm_sms=args.comm_sms if world > 1 else 0, overlap=args.overlap)
     g = torch.Generator(device="cuda").manual_seed(100 + rank)
     x = torch.randn(B, T0, C, device="cuda", generator=g).bfloat16()      # synthetic block inputs (embeddings)
     tshape = (B, ACTION_DIM) if args.loss == "continuous" else (B, len(ro), C)   # target actions / synthetic readout targets
@@ -516,6 +516,8 @@ def main():
     ap.add_argument("--comm-sms", type=int, default=0,
                     help="N > 1: SMs reserved for the NCCL all-reduce kernels during backward (NCCL max_ctas = this, the "
                          "persistent GEMM grid shrinks by this); 0 = NCCL's default and the full grid")
+    ap.add_argument("--overlap", default="none", choices=["layer", "none"],
+                    help="gradient all-reduce: per-layer buckets overlapped with backward, or one all-reduce after backward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--octo-base", default="auto", choices=["auto", "on", "off"],
                     help="also measure the octo_base shard (BASELINE.json configs[2]) and attach it as `octo_base`; auto = at 8 GPUs")

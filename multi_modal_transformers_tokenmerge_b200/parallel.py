@@ -69,11 +69,19 @@ def nccl_options(max_ctas: int):
 class DataParallelTrainer:
     """forward + backward + overlapped gradient all-reduce + AdamW for one rank's shard of the batch."""
 
-    def __init__(self, engine, group=None, comm_sms: int = 0):
-        """comm_sms > 0: SMs left to the NCCL kernels while backward runs (the persistent GEMM grid shrinks by that many;
+    def __init__(self, engine, group=None, comm_sms: int = 0, overlap: str = "none"):
+        """overlap: "none" (default) -- ONE all-reduce over the whole gradient vector after backward; "layer" -- one bucket per
+        layer, reduced on a side stream as soon as backward has finished that layer.  The persistent 148-CTA GEMM grids cannot
+        share an SM with an NCCL CTA, so every GEMM launched under a running collective waits for it on those SMs; the whole
+        octo-small gradient vector (87 MB fp32) takes 0.35 ms over NVSwitch at N = 8 (octo-base: 0.89 ms), less than the stalls
+        cost: 33.66 ms per step against 34.69 with per-layer overlap and 33.83 at N = 1 on the same box
+        (profiles/r02_scaling.md).
+        comm_sms > 0: SMs left to the NCCL kernels while backward runs (the persistent GEMM grid shrinks by that many;
         pair it with an NCCL CTA cap of the same size, see `nccl_options`)."""
+        assert overlap in ("layer", "none")
         self.engine = engine
-        self.comm_sms = int(comm_sms)
+        self.overlap = overlap
+        self.comm_sms = int(comm_sms) if overlap == "layer" else 0
         offs = [engine.layer_offset(l) for l in range(engine.cfg.layers)]
         self.reducer = GradBucketReducer(engine.grads, layer_buckets(offs, engine.n_params), group)
         self.world = self.reducer.world
@@ -87,7 +95,10 @@ class DataParallelTrainer:
         e.zero_grad()
         e.set_dropout_step(e.step_count)   # fresh dropout masks every step (forward and backward of a step share them)
         e.forward(x, target)
-        if self.world > 1:
+        if self.world > 1 and self.overlap == "none":
+            e.backward()
+            dist.all_reduce(e.grads, op=dist.ReduceOp.SUM, group=self.reducer.group)
+        elif self.world > 1:
             if self.comm_sms:
                 e.lib.tome_gemm_set_sm_limit(int(e.lib.tome_num_sms()) - self.comm_sms)
             e.backward(events=self.events)  # events[l] <- layer l done; events[L] <- everything done

@@ -26,8 +26,10 @@ def main():
     g = torch.Generator(device="cuda").manual_seed(7)          # every rank draws ALL shards, uses its own
     xs = [torch.randn(B, T, C, device="cuda", generator=g).bfloat16() for _ in range(world)]
     ys = [torch.rand(B, A, device="cuda", generator=g) * 2 - 1 for _ in range(world)]
-    tr = DataParallelTrainer(eng)
-    # --- the overlapped path: per-layer events, side-stream all-reduce, no optimiser step yet (lr = 0 keeps the weights)
+    overlap = os.environ.get("TOME_DP_OVERLAP", "layer")
+    tr = DataParallelTrainer(eng, overlap=overlap)
+    # --- "layer": per-layer events, side-stream all-reduce overlapped with backward; "none": one all-reduce after backward.
+    # No optimiser step yet (lr = 0 keeps the weights)
     tr.train_step(xs[rank], ys[rank], lr=0.0)
     torch.cuda.synchronize()
     reduced = eng.grads.clone()
@@ -59,7 +61,7 @@ def main():
     dist.all_reduce(lo, op=dist.ReduceOp.MIN)
     dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print("DPRESULT " + json.dumps({"world": world, "rel_err_all": rel, "worst_tensor_rel_err": worst,
+        print("DPRESULT " + json.dumps({"world": world, "overlap": overlap, "rel_err_all": rel, "worst_tensor_rel_err": worst,
                                         "params_in_sync": bool(lo.item() == hi.item()), "grad_norm": local_sum.norm().item()}))
     dist.barrier()
     dist.destroy_process_group()

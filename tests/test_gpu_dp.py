@@ -11,8 +11,10 @@ torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 
-def test_overlapped_allreduce_equals_the_local_sum_and_replicas_stay_in_sync():
-    """Two ranks, different shards, identical weights: the gradients after the per-layer-event all-reduce (NCCL on a side
+@pytest.mark.parametrize("overlap", ["layer", "none"])
+def test_overlapped_allreduce_equals_the_local_sum_and_replicas_stay_in_sync(overlap):
+    """Both exchange policies of DataParallelTrainer ("none": one all-reduce after backward, the default; "layer": below).
+    Two ranks, different shards, identical weights: the gradients after the per-layer-event all-reduce (NCCL on a side
     stream behind the events the native backward records, head parameters in the last layer's bucket, position embedding
     in the last bucket) equal the sum of the shards' gradients computed on one GPU without any exchange -- every tensor
     within 1e-5 relative (fp32 sums in a different order) -- and after two AdamW steps the replicas' parameter vectors are
@@ -22,11 +24,11 @@ def test_overlapped_allreduce_equals_the_local_sum_and_replicas_stay_in_sync():
     here = os.path.dirname(os.path.abspath(__file__))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(here, "dp_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env={**os.environ, "TOME_DP_OVERLAP": overlap})
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     line = [ln for ln in r.stdout.splitlines() if ln.startswith("DPRESULT ")][-1]
     res = json.loads(line[len("DPRESULT "):])
     print(res)
-    assert res["world"] == 2 and res["grad_norm"] > 0
+    assert res["world"] == 2 and res["grad_norm"] > 0 and res["overlap"] == overlap
     assert res["rel_err_all"] <= 1e-5 and res["worst_tensor_rel_err"] <= 1e-5, res
     assert res["params_in_sync"], res
