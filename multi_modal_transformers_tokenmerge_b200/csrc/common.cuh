@@ -160,6 +160,11 @@ __device__ __forceinline__ uint32_t map_to_cta(const void* p, uint32_t rank) {
 // arrive on a barrier that may live in the peer CTA.  Relaxed: the only data the waiter depends on is tensor memory already
 // read by tcgen05.ld (ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync); a .release here costs a
 // MEMBAR + ERRBAR per arrive that waits for every store of the epilogue warp still in flight (22 % of all stall samples)
+__device__ __forceinline__ float ld_shared_cluster_f32(uint32_t cluster_addr) {   // distributed shared memory read (address from map_to_cta)
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }

@@ -5,6 +5,8 @@
 // HBM-bound.  axis 1: one CTA owns a (batch, 64-feature) slab = T rows x 128 bytes; 8 threads x 16 bytes cover a
 // row segment (one full 128-byte line), 32 row groups stride over T.  The slab (T x 128 B <= 1 MB) is read twice, the
 // second time from L2.  Also here: column sums (bias gradients) with the same slab walk.
+#include <string.h>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -217,17 +219,23 @@ __device__ __forceinline__ uint4 slab_ld(const uint8_t* slab, int t, int ct) {  
   return *reinterpret_cast<const uint4*>(slab + (size_t)t * 128 + ((ct ^ (t & 7)) << 4));
 }
 
+// CL: the tokens of one (batch, slab) are split over the gridDim.z CTAs of a thread-block cluster, `nb` boxes each (long
+// sequences with few batch rows: one CTA per slab left most of the machine idle -- 0.08 of the HBM peak at T = 8192, B = 4).
+// Every CTA reduces its own rows, the partial sums are exchanged through distributed shared memory and added in rank
+// order by every CTA (identical statistics everywhere, deterministic), rank 0 stores them.
+template <bool CL>
 __global__ void __launch_bounds__(LN_THREADS)
-ln_seq_fwd_smem_kernel(const __grid_constant__ CUtensorMap tm_x, int T, int C, float eps, const float* __restrict__ gamma,
+ln_seq_fwd_smem_kernel(const __grid_constant__ CUtensorMap tm_x, int T, int C, int nb, float eps, const float* __restrict__ gamma,
                        const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ mean,
                        float* __restrict__ rstd) {
   extern __shared__ uint8_t ln_smem_raw[];
   uint8_t* slab = ln_smem_raw + ((1024u - (smem_u32(ln_smem_raw) & 1023u)) & 1023u);
-  const int nb = ln_boxes(T);
+  const int t0 = CL ? (int)blockIdx.z * nb * LN_BOX : 0;   // first token row of this CTA
   uint64_t* bars = reinterpret_cast<uint64_t*>(slab + (size_t)nb * LN_BOX * 128);
   __shared__ float s_sum[LN_RG][LN_SLAB + 1];
   __shared__ float s_sq[LN_RG][LN_SLAB + 1];
   __shared__ float s_mean[LN_SLAB], s_rstd[LN_SLAB];
+  __shared__ float s_part[2][LN_SLAB];   // CL: this CTA's partial sums, read by its cluster peers
   const int b = blockIdx.y, c0 = blockIdx.x * LN_SLAB;
   const int ct = threadIdx.x & 7, rg = threadIdx.x >> 3;
   const int c = c0 + ct * 8;
@@ -240,7 +248,7 @@ ln_seq_fwd_smem_kernel(const __grid_constant__ CUtensorMap tm_x, int T, int C, f
   if (threadIdx.x == 0) {
     for (int k = 0; k < nb; ++k) {
       mbar_expect_tx(&bars[k], LN_BOX * 128);
-      tma_load_3d(slab + (size_t)k * LN_BOX * 128, &tm_x, &bars[k], c0, k * LN_BOX, b);  // rows past T / columns past C arrive as zeros
+      tma_load_3d(slab + (size_t)k * LN_BOX * 128, &tm_x, &bars[k], c0, t0 + k * LN_BOX, b);  // rows past T / columns past C arrive as zeros
     }
   }
   float sum[8], sq[8];
@@ -266,23 +274,43 @@ ln_seq_fwd_smem_kernel(const __grid_constant__ CUtensorMap tm_x, int T, int C, f
     s_sq[rg][ct * 8 + i] = sq[i];
   }
   __syncthreads();
+  if (CL) {
+    if (threadIdx.x < LN_SLAB) {
+      float a = 0.f, q = 0.f;
+      for (int g = 0; g < LN_RG; ++g) {
+        a += s_sum[g][threadIdx.x];
+        q += s_sq[g][threadIdx.x];
+      }
+      s_part[0][threadIdx.x] = a;
+      s_part[1][threadIdx.x] = q;
+    }
+    cluster_sync_all();   // every CTA's partials are in its shared memory
+  }
   if (threadIdx.x < LN_SLAB) {
     float a = 0.f, q = 0.f;
-    for (int g = 0; g < LN_RG; ++g) {
-      a += s_sum[g][threadIdx.x];
-      q += s_sq[g][threadIdx.x];
+    if (CL) {
+      for (uint32_t r = 0; r < gridDim.z; ++r) {
+        a += ld_shared_cluster_f32(map_to_cta(&s_part[0][threadIdx.x], r));
+        q += ld_shared_cluster_f32(map_to_cta(&s_part[1][threadIdx.x], r));
+      }
+    } else {
+      for (int g = 0; g < LN_RG; ++g) {
+        a += s_sum[g][threadIdx.x];
+        q += s_sq[g][threadIdx.x];
+      }
     }
     const float mu = a / (float)T;
     const float var = fmaxf(q / (float)T - mu * mu, 0.f);
     const float rs = rsqrtf(var + eps);
     s_mean[threadIdx.x] = mu;
     s_rstd[threadIdx.x] = rs;
-    if (c0 + threadIdx.x < C) {
+    if (c0 + threadIdx.x < C && (!CL || blockIdx.z == 0)) {
       mean[(long long)b * C + c0 + threadIdx.x] = mu;
       rstd[(long long)b * C + c0 + threadIdx.x] = rs;
     }
   }
-  __syncthreads();
+  if (CL) cluster_sync_all();   // nobody leaves (or reuses s_part) while a peer may still read it
+  else __syncthreads();
   if (!active) return;
   float mu[8], sc[8], sh[8];
 #pragma unroll
@@ -292,13 +320,14 @@ ln_seq_fwd_smem_kernel(const __grid_constant__ CUtensorMap tm_x, int T, int C, f
     sh[i] = beta[c + i];
   }
   __nv_bfloat16* yb = y + (long long)b * T * C + c;
+  const int t_end = min(T - t0, nb * LN_BOX);   // rows of this CTA that exist
 #pragma unroll 4
-  for (int t = rg; t < T; t += LN_RG) {
+  for (int t = rg; t < t_end; t += LN_RG) {
     float f[8];
     unpack8(slab_ld(slab, t, ct), f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i] - mu[i], sc[i], sh[i]);
-    st_na_v4(yb + (long long)t * C, pack8(f));
+    st_na_v4(yb + (long long)(t0 + t) * C, pack8(f));
   }
 }
 
@@ -312,19 +341,21 @@ constexpr int LNB_RG = LN_THREADS / LNB_CPR;    // 64 row groups = one 64-row bo
 static_assert(LNB_RG == LN_BOX, "one row per thread per box");
 constexpr int LNB_MAX_BOXES = 10;               // the backward slab path keeps one residual row per box in registers: T <= 640
 
+template <bool CL>   // as in the forward kernel: tokens split over a cluster, `nb` boxes (<= LNB_MAX_BOXES) per CTA
 __global__ void __launch_bounds__(LN_THREADS)
-ln_seq_bwd_smem_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dy, int B, int T, int C,
+ln_seq_bwd_smem_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dy, int B, int T, int C, int nb,
                        const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                        const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx, float* __restrict__ partial) {
   extern __shared__ uint8_t ln_smem_raw[];
   uint8_t* slab_x = ln_smem_raw + ((128u - (smem_u32(ln_smem_raw) & 127u)) & 127u);
-  const int nb = ln_boxes(T);
+  const int t0 = CL ? (int)blockIdx.z * nb * LN_BOX : 0;   // first token row of this CTA
   constexpr int BOX_BYTES = LN_BOX * LNB_SLAB * 2;  // 4 KB
   uint8_t* slab_d = slab_x + (size_t)nb * BOX_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(slab_d + (size_t)nb * BOX_BYTES);
   __shared__ float s_a[LN_THREADS / 32][LNB_SLAB + 1];   // per-warp partial sums (the 8 row groups of a warp are shuffle-reduced first)
   __shared__ float s_b[LN_THREADS / 32][LNB_SLAB + 1];
   __shared__ float s_A[LNB_SLAB], s_B[LNB_SLAB];
+  __shared__ float s_part[2][LNB_SLAB];   // CL: this CTA's partial sums, read by its cluster peers
   const int b = blockIdx.y, c0 = blockIdx.x * LNB_SLAB;
   const int ct = threadIdx.x & (LNB_CPR - 1), rg = threadIdx.x / LNB_CPR;
   const int c = c0 + ct * 8;
@@ -337,8 +368,8 @@ ln_seq_bwd_smem_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
   if (threadIdx.x == 0) {
     for (int k = 0; k < nb; ++k) {
       mbar_expect_tx(&bars[k], 2 * BOX_BYTES);
-      tma_load_3d(slab_x + (size_t)k * BOX_BYTES, &tm_x, &bars[k], c0, k * LN_BOX, b);  // rows past T / columns past C arrive as zeros
-      tma_load_3d(slab_d + (size_t)k * BOX_BYTES, &tm_dy, &bars[k], c0, k * LN_BOX, b);
+      tma_load_3d(slab_x + (size_t)k * BOX_BYTES, &tm_x, &bars[k], c0, t0 + k * LN_BOX, b);  // rows past T / columns past C arrive as zeros
+      tma_load_3d(slab_d + (size_t)k * BOX_BYTES, &tm_dy, &bars[k], c0, t0 + k * LN_BOX, b);
     }
   }
   // the residual-branch gradient rows this thread will add in the second pass: requested NOW, so their latency hides
@@ -347,8 +378,8 @@ ln_seq_bwd_smem_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
   uint4 rv[LNB_MAX_BOXES];
 #pragma unroll
   for (int k = 0; k < LNB_MAX_BOXES; ++k) {
-    const int t = k * LN_BOX + rg;
-    rv[k] = (dres && active && t < T) ? ld_nc_v4(dres + base + (long long)t * C) : make_uint4(0u, 0u, 0u, 0u);
+    const int t = t0 + k * LN_BOX + rg;
+    rv[k] = (dres && active && k < nb && t < T) ? ld_nc_v4(dres + base + (long long)t * C) : make_uint4(0u, 0u, 0u, 0u);
   }
   float mu[8], rs[8];
   float sa[8], sb[8];
@@ -386,21 +417,42 @@ ln_seq_bwd_smem_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     }
   }
   __syncthreads();
+  if (CL) {
+    if (threadIdx.x < LNB_SLAB) {
+      float a = 0.f, q = 0.f;
+#pragma unroll
+      for (int g = 0; g < LN_THREADS / 32; ++g) {
+        a += s_a[g][threadIdx.x];
+        q += s_b[g][threadIdx.x];
+      }
+      s_part[0][threadIdx.x] = a;
+      s_part[1][threadIdx.x] = q;
+    }
+    cluster_sync_all();
+  }
   if (threadIdx.x < LNB_SLAB) {
     float a = 0.f, q = 0.f;
+    if (CL) {
+      for (uint32_t r = 0; r < gridDim.z; ++r) {
+        a += ld_shared_cluster_f32(map_to_cta(&s_part[0][threadIdx.x], r));
+        q += ld_shared_cluster_f32(map_to_cta(&s_part[1][threadIdx.x], r));
+      }
+    } else {
 #pragma unroll
-    for (int g = 0; g < LN_THREADS / 32; ++g) {
-      a += s_a[g][threadIdx.x];
-      q += s_b[g][threadIdx.x];
+      for (int g = 0; g < LN_THREADS / 32; ++g) {
+        a += s_a[g][threadIdx.x];
+        q += s_b[g][threadIdx.x];
+      }
     }
     s_A[threadIdx.x] = a;
     s_B[threadIdx.x] = q;
-    if (c0 + threadIdx.x < C) {
+    if (c0 + threadIdx.x < C && (!CL || blockIdx.z == 0)) {
       partial[(long long)b * C + c0 + threadIdx.x] = a;
       partial[(long long)(B + b) * C + c0 + threadIdx.x] = q;
     }
   }
-  __syncthreads();
+  if (CL) cluster_sync_all();   // nobody leaves while a peer may still read its partial sums
+  else __syncthreads();
   if (!active) return;
   const float inv_t = 1.0f / (float)T;
   float k0[8], k1[8], k2[8];  // dx = k0*dy + k1*xhat + k2
@@ -413,8 +465,8 @@ ln_seq_bwd_smem_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
   }
 #pragma unroll
   for (int k = 0; k < LNB_MAX_BOXES; ++k) {
-    const int t = k * LN_BOX + rg;
-    if (t < T) {
+    const int t = t0 + k * LN_BOX + rg;
+    if (k < nb && t < T) {
       float fx[8], fd[8], o[8];
       unpack8(*reinterpret_cast<const uint4*>(slab_x + (size_t)k * BOX_BYTES + my), fx);
       unpack8(*reinterpret_cast<const uint4*>(slab_d + (size_t)k * BOX_BYTES + my), fd);
@@ -635,6 +687,35 @@ using namespace tome;
 extern "C" int tome_colsum_workspace_rows(int m) { return colsum_rows(m); }
 
 static int g_ln_smem_fwd = 1, g_ln_smem_bwd = 1;
+static int g_ln_force_cluster = 0;
+/* testing aid (not in the public header): 1 = take the cluster kernels even when one CTA per slab would do; n > 1 = split the
+ * tokens over exactly n CTAs */
+extern "C" void tome_ln_force_cluster(int n) { g_ln_force_cluster = n < 0 ? 0 : n > 8 ? 8 : n; }
+
+// CTAs per (batch, slab): about nine 64-row boxes per CTA (what the T = 536 shape has), at most a portable cluster of 8
+static inline int ln_token_split(int boxes) {
+  int s = (boxes + 8) / 9;
+  return s < 1 ? 1 : s > 8 ? 8 : s;
+}
+
+template <typename K, typename... Args>
+static int launch_cluster_z(K kern, dim3 grid, int smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(LN_THREADS);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = grid.z;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TOME_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
+  return TOME_OK;
+}
 /* tuning aid (not part of the public header): bit 0 = forward, bit 1 = backward may take the shared-memory-slab kernels */
 extern "C" void tome_ln_set_smem_path(int mask) { g_ln_smem_fwd = mask & 1; g_ln_smem_bwd = (mask >> 1) & 1; }
 
@@ -703,13 +784,23 @@ extern "C" int tome_layernorm_fwd(int batch, int tokens, int channels, int axis,
   if (axis == 1) {
     TOME_CHECK(batch <= 65535, TOME_ERR_INVALID, "layernorm_fwd: batch too large");
     dim3 grid(ceil_div(channels, LN_SLAB), batch);
-    if (g_ln_smem_fwd && tokens <= LN_SMEM_T_FWD && ((uintptr_t)x & 15) == 0) {
+    const int nb_all = ln_boxes(tokens);
+    const int split = g_ln_force_cluster > 1 ? g_ln_force_cluster : ln_token_split(nb_all);   // CTAs (one cluster) per (batch, slab)
+    const int nb = ceil_div(nb_all, split);
+    if (g_ln_smem_fwd && ((uintptr_t)x & 15) == 0 && nb * LN_BOX <= LN_SMEM_T_FWD) {
       CUtensorMap tx;
       if (int rc = make_tmap_3d_bf16(&tx, x, channels, tokens, batch, channels, (uint64_t)tokens * channels, LN_BOX)) return rc;
-      const int smem = ln_boxes(tokens) * LN_BOX * 128 + ln_boxes(tokens) * 8 + 1024;
-      static DynSmemOnce once;
-      TOME_CUDA(ensure_dyn_smem(ln_seq_fwd_smem_kernel, smem, once));
-      ln_seq_fwd_smem_kernel<<<grid, LN_THREADS, smem, stream>>>(tx, tokens, channels, eps, gamma, beta, yp, mean, rstd);
+      const int smem = nb * LN_BOX * 128 + nb * 8 + 1024;
+      if (split == 1 && !g_ln_force_cluster) {
+        static DynSmemOnce once;
+        TOME_CUDA(ensure_dyn_smem(ln_seq_fwd_smem_kernel<false>, smem, once));
+        ln_seq_fwd_smem_kernel<false><<<grid, LN_THREADS, smem, stream>>>(tx, tokens, channels, nb, eps, gamma, beta, yp, mean, rstd);
+      } else {
+        static DynSmemOnce once;
+        TOME_CUDA(ensure_dyn_smem(ln_seq_fwd_smem_kernel<true>, smem, once));
+        if (int rc = launch_cluster_z(ln_seq_fwd_smem_kernel<true>, dim3(grid.x, grid.y, split), smem, stream, tx, tokens, channels, nb,
+                                      eps, gamma, beta, yp, mean, rstd)) return rc;
+      }
     } else {
       ln_seq_fwd_kernel<<<grid, LN_THREADS, 0, stream>>>(tokens, channels, eps, xp, gamma, beta, yp, mean, rstd);
     }
@@ -739,15 +830,25 @@ extern "C" int tome_layernorm_bwd(int batch, int tokens, int channels, int axis,
   if (axis == 1) {
     TOME_CHECK(batch <= 65535, TOME_ERR_INVALID, "layernorm_bwd: batch too large");
     dim3 grid(ceil_div(channels, LN_SLAB), batch);
-    if (g_ln_smem_bwd && tokens <= LN_SMEM_T_BWD && (((uintptr_t)x | (uintptr_t)dy) & 15) == 0) {
+    const int nb_all = ln_boxes(tokens);
+    const int split = g_ln_force_cluster > 1 ? g_ln_force_cluster : ln_token_split(nb_all);
+    const int nb = ceil_div(nb_all, split);
+    if (g_ln_smem_bwd && nb <= LNB_MAX_BOXES && (((uintptr_t)x | (uintptr_t)dy) & 15) == 0) {
       CUtensorMap tx, tdy;
       if (int rc = make_tmap_3d_bf16_plain(&tx, x, channels, tokens, batch, channels, (uint64_t)tokens * channels, LNB_SLAB, LN_BOX)) return rc;
       if (int rc = make_tmap_3d_bf16_plain(&tdy, dy, channels, tokens, batch, channels, (uint64_t)tokens * channels, LNB_SLAB, LN_BOX)) return rc;
-      const int smem = 2 * ln_boxes(tokens) * LN_BOX * LNB_SLAB * 2 + ln_boxes(tokens) * 8 + 128;
-      static DynSmemOnce once;
-      TOME_CUDA(ensure_dyn_smem(ln_seq_bwd_smem_kernel, smem, once));
+      const int smem = 2 * nb * LN_BOX * LNB_SLAB * 2 + nb * 8 + 128;
       grid = dim3(ceil_div(channels, LNB_SLAB), batch);
-      ln_seq_bwd_smem_kernel<<<grid, LN_THREADS, smem, stream>>>(tx, tdy, batch, tokens, channels, gamma, mean, rstd, drp, dxp, partial);
+      if (split == 1 && !g_ln_force_cluster) {
+        static DynSmemOnce once;
+        TOME_CUDA(ensure_dyn_smem(ln_seq_bwd_smem_kernel<false>, smem, once));
+        ln_seq_bwd_smem_kernel<false><<<grid, LN_THREADS, smem, stream>>>(tx, tdy, batch, tokens, channels, nb, gamma, mean, rstd, drp, dxp, partial);
+      } else {
+        static DynSmemOnce once;
+        TOME_CUDA(ensure_dyn_smem(ln_seq_bwd_smem_kernel<true>, smem, once));
+        if (int rc = launch_cluster_z(ln_seq_bwd_smem_kernel<true>, dim3(grid.x, grid.y, split), smem, stream, tx, tdy, batch, tokens,
+                                      channels, nb, gamma, mean, rstd, drp, dxp, partial)) return rc;
+      }
     } else {
       ln_seq_bwd_kernel<<<grid, LN_THREADS, 0, stream>>>(batch, tokens, channels, xp, dyp, gamma, mean, rstd, drp, dxp, partial);
     }

@@ -220,8 +220,10 @@ def test_gemm_epilogues_and_splitk(ops):
 
 # ------------------------------------------------------------------------------------------------ LayerNorm
 @pytest.mark.parametrize("axis", [1, 2])
-# T = 700: forward from the shared-memory slab, backward from the two-pass L2 kernel; T = 1600: both two-pass
-@pytest.mark.parametrize("B,T,C", [(3, 74, 768), (4, 536, 384), (2, 33, 40), (2, 700, 72), (1, 1600, 64)])
+# T <= 576: one CTA per (batch, slab); 700 / 1600 / 2080 / 4100: the tokens split over a cluster of 2 / 3 / 4 / 8 CTAs whose
+# partial sums meet in distributed shared memory; 6000: forward cluster of 8, backward the two-pass L2 kernel (> 10 boxes / CTA)
+@pytest.mark.parametrize("B,T,C", [(3, 74, 768), (4, 536, 384), (2, 33, 40), (2, 700, 72), (1, 1600, 64), (2, 2080, 96),
+                                   (1, 4100, 64), (1, 6000, 40)])
 def test_layernorm_fwd_bwd(ops, axis, B, T, C):
     """vs oracle.layer_norm (flax LayerNorm as configured; axis 1 = tokens) + autograd.  bf16 I/O: forward 3e-2 abs,
     dx / dgamma / dbeta within 1e-2 relative L2."""
@@ -246,6 +248,42 @@ def test_layernorm_fwd_bwd(ops, axis, B, T, C):
     assert rel(dx.float().cpu(), ref_dx) <= 1e-2
     assert rel(dgamma.cpu(), gr.grad) <= 1e-2
     assert rel(dbeta.cpu(), br.grad) <= 1e-2
+
+
+@pytest.mark.parametrize("split", [1, 2, 3, 5])
+def test_layernorm_token_split_matches_single_cta(ops, split):
+    """The cluster kernels (tokens of a slab split over `split` CTAs, statistics exchanged through distributed shared memory)
+    against the one-CTA-per-slab kernels on a shape both can run: y and dx bit-identical up to the summation order of the
+    statistics (<= 1 bf16 ulp on y), saved statistics and parameter gradients to 1e-5, and the run is reproducible."""
+    from multi_modal_transformers_tokenmerge_b200 import _lib as L
+    rng = np.random.default_rng(split)
+    B, T, C = 3, 536, 200
+    x = dev((rng.standard_normal((B, T, C)) * 2 + 0.5).astype(np.float32), torch.bfloat16)
+    g = dev((1 + 0.1 * rng.standard_normal(C)).astype(np.float32))
+    bta = dev((0.1 * rng.standard_normal(C)).astype(np.float32))
+    dy = dev(rng.standard_normal((B, T, C)).astype(np.float32), torch.bfloat16)
+    dres = dev(rng.standard_normal((B, T, C)).astype(np.float32), torch.bfloat16)
+
+    def run():
+        y, mean, rstd = ops.layernorm_fwd(x, g, bta, 1e-6, 1)
+        dgamma, dbeta = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+        dx = ops.layernorm_bwd(x, dy, g, mean, rstd, dgamma, dbeta, dres, 1)
+        return y, mean, rstd, dx, dgamma, dbeta
+
+    ref = run()
+    try:
+        L.lib().tome_ln_force_cluster(split)
+        got = run()
+        again = run()
+    finally:
+        L.lib().tome_ln_force_cluster(0)
+    for a, b_ in zip(got, again):
+        assert torch.equal(a, b_)
+    rel = lambda a, b_: ((a.double() - b_.double()).norm() / b_.double().norm()).item()  # noqa: E731
+    assert rel(got[1], ref[1]) <= 1e-5 and rel(got[2], ref[2]) <= 1e-5
+    assert (got[0].float() - ref[0].float()).abs().max().item() <= 2 ** -5      # one bf16 ulp at |y| < 8
+    assert rel(got[3].float(), ref[3].float()) <= 2e-3
+    assert rel(got[4], ref[4]) <= 1e-5 and rel(got[5], ref[5]) <= 1e-5
 
 
 # ------------------------------------------------------------------------------------------------ attention
