@@ -120,6 +120,7 @@ __device__ __forceinline__ void ab_store_tile(uint8_t* stage, float* part, uint3
 __global__ void attn_bwd_prep_kernel(int B, int T, int Tp, int H, const __nv_bfloat16* __restrict__ o, long long o_bs,
                                      long long o_ts, const __nv_bfloat16* __restrict__ dout, long long do_bs, long long do_ts,
                                      const float* __restrict__ lse, float* __restrict__ delta, float* __restrict__ lse2) {
+  pdl_prologue();
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;  // (b, t, h, chunk of 8)
   const long long total = (long long)B * Tp * H * 8;
   if (idx < total) {  // total is a multiple of 8: the 8 lanes of a (b,t,h) group leave together
@@ -162,6 +163,7 @@ __global__ void __launch_bounds__(AB_THREADS, 2)
 attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                      const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
                      const __grid_constant__ CUtensorMap tm_ds, const AttnBwdParams p) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   // 1 KB alignment by pointer arithmetic on the __shared__ array itself, so every access below stays LDS/STS
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -428,6 +430,7 @@ __global__ void __launch_bounds__(DKT_THREADS, 2)
 attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                         const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
                         const __grid_constant__ CUtensorMap tm_ds, const AttnBwdParams p) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_k = smem;
@@ -750,6 +753,7 @@ __global__ void __launch_bounds__(AB_THREADS, 2)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                    const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
                    const AttnBwdParams p) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_q = smem;
@@ -998,6 +1002,7 @@ constexpr int DQG_SMEM = DQG_STAGES * DQG_STAGE + 256 + 1024;
 __global__ void __launch_bounds__(AB_THREADS, TOME_DQG_CTAS)
 attn_bwd_dq_gemm_kernel(const __grid_constant__ CUtensorMap tm_ds, const __grid_constant__ CUtensorMap tm_k,
                         const AttnBwdParams p) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQG_STAGES * DQG_STAGE);
@@ -1144,7 +1149,7 @@ extern "C" int tome_attention_bwd(const tome_attn_desc_t* d, const tome_attn_gra
   }
   {
     const long long total = (long long)B * Tp * H * 8;
-    attn_bwd_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+    launch_k(attn_bwd_prep_kernel, (unsigned)((total + 255) / 256), 256, 0, stream, 
         B, T, Tp, H, reinterpret_cast<const __nv_bfloat16*>(out), d->o_batch_stride, d->o_token_stride,
         reinterpret_cast<const __nv_bfloat16*>(dout), gs->do_batch_stride, gs->do_token_stride, lse, delta, lse2);
     TOME_CUDA(cudaGetLastError());
@@ -1197,17 +1202,17 @@ extern "C" int tome_attention_bwd(const tome_attn_desc_t* d, const tome_attn_gra
     if (int rc = make_tmap_3d_bf16(&tdo, dout, hd, T, B, gs->do_token_stride, gs->do_batch_stride, DKV_BQ)) return rc;
     dim3 grid(ceil_div(T, DKV_BK), H, B);
     if (g_attn_bwd_ts) {
-      if (keep_k) attn_bwd_dkdv_ts_kernel<true><<<grid, DKT_THREADS, DKT_SMEM, stream>>>(tq, tk, tv, tdo, tds_store, p);
-      else attn_bwd_dkdv_ts_kernel<false><<<grid, DKT_THREADS, DKT_SMEM, stream>>>(tq, tk, tv, tdo, tds_store, p);
-    } else if (keep_k) attn_bwd_dkdv_kernel<true><<<grid, AB_THREADS, DKV_SMEM, stream>>>(tq, tk, tv, tdo, tds_store, p);
-    else attn_bwd_dkdv_kernel<false><<<grid, AB_THREADS, DKV_SMEM, stream>>>(tq, tk, tv, tdo, tds_store, p);
+      if (keep_k) launch_k(attn_bwd_dkdv_ts_kernel<true>, grid, DKT_THREADS, DKT_SMEM, stream, tq, tk, tv, tdo, tds_store, p);
+      else launch_k(attn_bwd_dkdv_ts_kernel<false>, grid, DKT_THREADS, DKT_SMEM, stream, tq, tk, tv, tdo, tds_store, p);
+    } else if (keep_k) launch_k(attn_bwd_dkdv_kernel<true>, grid, AB_THREADS, DKV_SMEM, stream, tq, tk, tv, tdo, tds_store, p);
+    else launch_k(attn_bwd_dkdv_kernel<false>, grid, AB_THREADS, DKV_SMEM, stream, tq, tk, tv, tdo, tds_store, p);
     TOME_CUDA(cudaGetLastError());
   }
   if (from_ds) {
     CUtensorMap tk;
     if (int rc = make_tmap_3d_bf16(&tk, k, hd, T, B, d->k_token_stride, d->k_batch_stride, DQG_BK)) return rc;
     dim3 grid(ceil_div(T, DQG_BQ), H, B);
-    attn_bwd_dq_gemm_kernel<<<grid, AB_THREADS, DQG_SMEM, stream>>>(tds_load, tk, p);
+    launch_k(attn_bwd_dq_gemm_kernel, grid, AB_THREADS, DQG_SMEM, stream, tds_load, tk, p);
     TOME_CUDA(cudaGetLastError());
   } else {
     CUtensorMap tq, tk, tv, tdo;
@@ -1216,8 +1221,8 @@ extern "C" int tome_attention_bwd(const tome_attn_desc_t* d, const tome_attn_gra
     if (int rc = make_tmap_3d_bf16(&tv, v, hd, T, B, d->v_token_stride, d->v_batch_stride, DQ_BK)) return rc;
     if (int rc = make_tmap_3d_bf16(&tdo, dout, hd, T, B, gs->do_token_stride, gs->do_batch_stride, DQ_BQ)) return rc;
     dim3 grid(ceil_div(T, DQ_BQ), H, B);
-    if (keep_q) attn_bwd_dq_kernel<true><<<grid, AB_THREADS, DQ_SMEM, stream>>>(tq, tk, tv, tdo, p);
-    else attn_bwd_dq_kernel<false><<<grid, AB_THREADS, DQ_SMEM, stream>>>(tq, tk, tv, tdo, p);
+    if (keep_q) launch_k(attn_bwd_dq_kernel<true>, grid, AB_THREADS, DQ_SMEM, stream, tq, tk, tv, tdo, p);
+    else launch_k(attn_bwd_dq_kernel<false>, grid, AB_THREADS, DQ_SMEM, stream, tq, tk, tv, tdo, p);
     TOME_CUDA(cudaGetLastError());
   }
   return TOME_OK;

@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_qaug,
                 const __grid_constant__ CUtensorMap tm_kaug, const AttnFwdParams p) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   // 1 KB alignment by pointer arithmetic on the __shared__ array itself, so every access below stays LDS/STS
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -436,6 +437,7 @@ __global__ void __launch_bounds__(ATTN_META_TILE)
 attn_meta_kernel(int T, const uint8_t* __restrict__ gid, const int32_t* __restrict__ pos, const uint8_t* __restrict__ allow,
                  int G, const float* __restrict__ size, uint8_t* __restrict__ meta, uint32_t* __restrict__ aug_flag,
                  uint4* __restrict__ aug_q, uint4* __restrict__ aug_k) {
+  pdl_prologue();
   const int tile = blockIdx.x, b = blockIdx.y, t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int idx = tile * ATTN_META_TILE + t;
   const bool valid = idx < T;
@@ -499,7 +501,7 @@ int launch_attn_meta(int B, int T, const uint8_t* gid, const int32_t* pos, const
                      uint8_t* meta, cudaStream_t stream) {
   TOME_CHECK(meta != nullptr && ((uintptr_t)meta & 15) == 0, TOME_ERR_INVALID, "attention: workspace must be non-null and 16-byte aligned");
   dim3 grid((T + ATTN_META_TILE - 1) / ATTN_META_TILE, B);
-  attn_meta_kernel<<<grid, ATTN_META_TILE, 0, stream>>>(
+  launch_k(attn_meta_kernel, grid, ATTN_META_TILE, 0, stream, 
       T, gid, pos, allow, G, size, meta, const_cast<uint32_t*>(attn_aug_flag(meta, B, T)),
       reinterpret_cast<uint4*>(const_cast<uint8_t*>(attn_aug_q(meta, B, T))),
       reinterpret_cast<uint4*>(const_cast<uint8_t*>(attn_aug_k(meta, B, T))));
@@ -512,6 +514,7 @@ int launch_attn_meta(int B, int T, const uint8_t* gid, const int32_t* pos, const
 // come from 32 ballots
 __global__ void __launch_bounds__(256)
 attn_dropbits_kernel(int n128, int n64, DropoutCfg d, uint32_t* __restrict__ keep_q, uint32_t* __restrict__ keep_k) {
+  pdl_prologue();
   const int Tq = n128 * 128;                       // padded query / key range: both arrays are written completely
   const long long t = blockIdx.x * 256ll + threadIdx.x;
   const int q = (int)(t % Tq), w = (int)(t / Tq);  // w < n128 * 4
@@ -547,7 +550,7 @@ int launch_attn_dropbits(int T, float rate, uint64_t seed, uint32_t site, uint8_
   uint32_t* kq = reinterpret_cast<uint32_t*>(bits);
   uint32_t* kk = kq + (size_t)n128 * n64 * (ATTN_DROP_TILE_BYTES / 4);
   const long long threads = (long long)n128 * 128 * n128 * 4;
-  attn_dropbits_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(n128, n64, d, kq, kk);
+  launch_k(attn_dropbits_kernel, (unsigned)((threads + 255) / 256), 256, 0, stream, n128, n64, d, kq, kk);
   TOME_CUDA(cudaGetLastError());
   return TOME_OK;
 }
@@ -643,7 +646,7 @@ extern "C" int tome_attention_fwd(const tome_attn_desc_t* d, const void* q, cons
   do {                                                                                                       \
     static DynSmemOnce once;                                                                                 \
     TOME_CUDA(ensure_dyn_smem(attn_fwd_kernel<DROP_, TS_>, att_smem<TS_>(), once));                          \
-    attn_fwd_kernel<DROP_, TS_><<<grid, ATT_THREADS, att_smem<TS_>(), stream>>>(tq, tk, tv, tqa, tka, p);    \
+    launch_k(attn_fwd_kernel<DROP_, TS_>, grid, ATT_THREADS, att_smem<TS_>(), stream, tq, tk, tv, tqa, tka, p);    \
   } while (0)
   if (g_attn_fwd_ts) {
     if (p.keep_q) TOME_ATT_LAUNCH(true, true);

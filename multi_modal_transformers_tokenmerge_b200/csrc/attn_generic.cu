@@ -46,6 +46,7 @@ __device__ __forceinline__ bool ag_keep(const AttnGenericParams& p, DropStream& 
 // ------------------------------------------------------------------------------------------------ forward: warp = query row
 __global__ void __launch_bounds__(AG_WARPS * 32)
 attn_generic_fwd_kernel(const AttnGenericParams p) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int q = blockIdx.x * AG_WARPS + (threadIdx.x >> 5), h = blockIdx.y, b = blockIdx.z;
   if (q >= p.tokens) return;
@@ -99,6 +100,7 @@ attn_generic_fwd_kernel(const AttnGenericParams p) {
 // ------------------------------------------------------------------------------------------------ dQ: warp = query row
 __global__ void __launch_bounds__(AG_WARPS * 32)
 attn_generic_dq_kernel(const AttnGenericParams p) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int q = blockIdx.x * AG_WARPS + (threadIdx.x >> 5), h = blockIdx.y, b = blockIdx.z;
   if (q >= p.tokens) return;
@@ -158,6 +160,7 @@ attn_generic_dq_kernel(const AttnGenericParams p) {
 // ------------------------------------------------------------------------------------------------ dK / dV: warp = key row
 __global__ void __launch_bounds__(AG_WARPS * 32)
 attn_generic_dkdv_kernel(const AttnGenericParams p) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int kk = blockIdx.x * AG_WARPS + (threadIdx.x >> 5), h = blockIdx.y, b = blockIdx.z;
   if (kk >= p.tokens) return;
@@ -251,7 +254,7 @@ int attn_generic_fwd(const tome_attn_desc_t* d, const void* q, const void* k, co
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.lse = lse;
   dim3 grid(ceil_div(d->tokens, AG_WARPS), d->heads, d->batch);
-  attn_generic_fwd_kernel<<<grid, AG_WARPS * 32, 0, stream>>>(p);
+  launch_k(attn_generic_fwd_kernel, grid, AG_WARPS * 32, 0, stream, p);
   TOME_CUDA(cudaGetLastError());
   return TOME_OK;
 }
@@ -270,8 +273,8 @@ int attn_generic_bwd(const tome_attn_desc_t* d, const tome_attn_grad_strides_t* 
   p.dq_bs = gs->dq_batch_stride; p.dq_ts = gs->dq_token_stride; p.dk_bs = gs->dk_batch_stride; p.dk_ts = gs->dk_token_stride;
   p.dv_bs = gs->dv_batch_stride; p.dv_ts = gs->dv_token_stride;
   dim3 grid(ceil_div(d->tokens, AG_WARPS), d->heads, d->batch);
-  attn_generic_dq_kernel<<<grid, AG_WARPS * 32, 0, stream>>>(p);
-  attn_generic_dkdv_kernel<<<grid, AG_WARPS * 32, 0, stream>>>(p);
+  launch_k(attn_generic_dq_kernel, grid, AG_WARPS * 32, 0, stream, p);
+  launch_k(attn_generic_dkdv_kernel, grid, AG_WARPS * 32, 0, stream, p);
   TOME_CUDA(cudaGetLastError());
   return TOME_OK;
 }

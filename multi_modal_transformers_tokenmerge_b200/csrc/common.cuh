@@ -49,6 +49,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ programmatic dependent launch
+// First statement of every kernel of this library.  Launched with the programmatic-stream-serialization attribute
+// (host_util.h launch_k) a grid may be scheduled onto SMs while its predecessor in the stream is still draining; `wait` then
+// blocks until that predecessor has completed and its memory is visible, so nothing below it ever runs early -- what could be
+// saved is the launch latency between dependent kernels (~500 launches per training step).  Without the attribute both
+// instructions do nothing.  The trigger follows the wait, so a kernel never runs more than one grid ahead.
+// Measured on the octo-small step (TOME_PDL=1 / 0 alternating on one box): 33.52 / 33.76 / 33.67 / 33.65 ms -- no gain, so
+// the attribute is off by default; the step's distance from the sum of its kernels is the power-capped clock, not gaps.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");

@@ -87,6 +87,7 @@ diff_prep_kernel(const tome_diffusion_desc_t d, const __nv_bfloat16* __restrict_
                  const float* __restrict__ fourier, const float* __restrict__ actions, const float* __restrict__ noise,
                  const int32_t* __restrict__ time, const float* __restrict__ alpha_hats, __nv_bfloat16* __restrict__ ff,
                  __nv_bfloat16* __restrict__ cat) {
+  pdl_prologue();
   const int b = blockIdx.x, C = d.channels, A = d.action_dim, F2 = d.fourier_dim / 2, n = d.n_readout;
   const long long Dc = (long long)A + d.time_out + C;
   const int t = min(max(time[b], 0), d.diffusion_steps - 1);
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(DH_THREADS)
 diff_out_kernel(const tome_diffusion_desc_t d, const __nv_bfloat16* __restrict__ h, const float* __restrict__ w2,
                 const float* __restrict__ b2, const float* __restrict__ noise, float* __restrict__ pred,
                 float* __restrict__ loss, float* __restrict__ dpred) {
+  pdl_prologue();
   __shared__ float lsum[DH_THREADS / 32];
   const int b = blockIdx.x, H = d.hidden, A = d.action_dim;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -141,6 +143,7 @@ diff_out_kernel(const tome_diffusion_desc_t d, const __nv_bfloat16* __restrict__
   }
 }
 __global__ void diff_loss_final_kernel(int B, float* loss) {
+  pdl_prologue();
   float t = 0.f;
   for (int b = 0; b < B; ++b) t += loss[1 + b];
   loss[0] = t / (float)B;
@@ -151,6 +154,7 @@ __global__ void __launch_bounds__(DH_THREADS)
 diff_out_bwd_kernel(const tome_diffusion_desc_t d, const __nv_bfloat16* __restrict__ h, const float* __restrict__ w2,
                     const float* __restrict__ dpred, float* __restrict__ dw2, float* __restrict__ db2,
                     __nv_bfloat16* __restrict__ dh) {
+  pdl_prologue();
   const int H = d.hidden, A = d.action_dim, B = d.batch;
   const long long i = blockIdx.x * (long long)DH_THREADS + threadIdx.x;
   if (i < (long long)H * A) {                       // weight gradient, fixed order over the batch
@@ -177,6 +181,7 @@ diff_out_bwd_kernel(const tome_diffusion_desc_t d, const __nv_bfloat16* __restri
 __global__ void __launch_bounds__(DH_THREADS)
 diff_scatter_kernel(const tome_diffusion_desc_t d, const int32_t* __restrict__ origin, const __nv_bfloat16* __restrict__ dcat,
                     __nv_bfloat16* __restrict__ dx) {
+  pdl_prologue();
   const int b = blockIdx.x, C = d.channels, n = d.n_readout;
   const long long Dc = (long long)d.action_dim + d.time_out + C;
   const float inv_n = 1.0f / (float)n;
@@ -191,6 +196,7 @@ diff_scatter_kernel(const tome_diffusion_desc_t d, const int32_t* __restrict__ o
 __global__ void __launch_bounds__(DH_THREADS)
 diff_fourier_bwd_kernel(const tome_diffusion_desc_t d, const int32_t* __restrict__ time, const float* __restrict__ fourier,
                         const float* __restrict__ dff, float* __restrict__ dfourier) {
+  pdl_prologue();
   const int j = blockIdx.x * DH_THREADS + threadIdx.x, F2 = d.fourier_dim / 2;
   if (j >= F2) return;
   const float w = fourier[j];
@@ -278,7 +284,7 @@ extern "C" int tome_diffusion_head_fwd(const tome_diffusion_desc_t* d, const flo
   const int B = (int)s.B;
   {
     ProfScope prof(PROF_OTHER, 0.0, 1, st);
-    diff_prep_kernel<<<B, DH_THREADS, 0, st>>>(*d, reinterpret_cast<const __nv_bfloat16*>(x), origin, params_f32 + o.fourier, actions,
+    launch_k(diff_prep_kernel, B, DH_THREADS, 0, st, *d, reinterpret_cast<const __nv_bfloat16*>(x), origin, params_f32 + o.fourier, actions,
                                                noise, time, alpha_hats, w.ff, w.cat);
     TOME_CUDA(cudaGetLastError());
   }
@@ -291,10 +297,10 @@ extern "C" int tome_diffusion_head_fwd(const tome_diffusion_desc_t* d, const flo
   DH_RC(diff_gemm(st, B, (int)s.H, (int)s.Dc, w.cat, s.Dc, TOME_MAJOR_K, pw + o.w1, s.H, TOME_MAJOR_MN, w.h, s.H, TOME_BF16,
                   params_f32 + o.b1, 1, nullptr, 0, 0));
   ProfScope prof(PROF_OTHER, 0.0, loss ? 2 : 1, st);
-  diff_out_kernel<<<B, DH_THREADS, 0, st>>>(*d, w.h, params_f32 + o.w2, params_f32 + o.b2, noise, pred, loss, w.dpred);
+  launch_k(diff_out_kernel, B, DH_THREADS, 0, st, *d, w.h, params_f32 + o.w2, params_f32 + o.b2, noise, pred, loss, w.dpred);
   TOME_CUDA(cudaGetLastError());
   if (loss) {
-    diff_loss_final_kernel<<<1, 1, 0, st>>>(B, loss);
+    launch_k(diff_loss_final_kernel, 1, 1, 0, st, B, loss);
     TOME_CUDA(cudaGetLastError());
   }
   return TOME_OK;
@@ -317,7 +323,7 @@ extern "C" int tome_diffusion_head_bwd(const tome_diffusion_desc_t* d, const flo
   {
     ProfScope prof(PROF_OTHER, 0.0, 1, st);
     const long long nthr = s.H * s.A + s.A > s.B * s.H ? s.H * s.A + s.A : s.B * s.H;
-    diff_out_bwd_kernel<<<(unsigned)((nthr + DH_THREADS - 1) / DH_THREADS), DH_THREADS, 0, st>>>(
+    launch_k(diff_out_bwd_kernel, (unsigned)((nthr + DH_THREADS - 1) / DH_THREADS), DH_THREADS, 0, st, 
         *d, w.h, params_f32 + o.w2, w.dpred, gr + o.w2, gr + o.b2, w.dh);
     TOME_CUDA(cudaGetLastError());
   }
@@ -330,7 +336,7 @@ extern "C" int tome_diffusion_head_bwd(const tome_diffusion_desc_t* d, const flo
   if (dx) {
     ProfScope prof(PROF_OTHER, 0.0, 2, st);
     TOME_CUDA(cudaMemsetAsync(dx, 0, (size_t)s.B * s.T * s.C * 2, st));
-    diff_scatter_kernel<<<B, DH_THREADS, 0, st>>>(*d, origin, w.dcat, reinterpret_cast<__nv_bfloat16*>(dx));
+    launch_k(diff_scatter_kernel, B, DH_THREADS, 0, st, *d, origin, w.dcat, reinterpret_cast<__nv_bfloat16*>(dx));
     TOME_CUDA(cudaGetLastError());
   }
   // time encoder: dte = dcat[:, A:A+To];  dW_t2 += th^T dte, db_t2 += colsum(dte), dth = relu'(th) * (dte W_t2^T)
@@ -346,7 +352,7 @@ extern "C" int tome_diffusion_head_bwd(const tome_diffusion_desc_t* d, const flo
   DH_RC(diff_gemm(st, B, (int)s.F, (int)s.Ht, w.dth, s.Ht, TOME_MAJOR_K, pw + o.tw1, s.Ht, TOME_MAJOR_K, w.dff, s.F, TOME_F32, nullptr, 0,
                   nullptr, 0, 0));
   ProfScope prof(PROF_OTHER, 0.0, 1, st);
-  diff_fourier_bwd_kernel<<<(unsigned)((s.F / 2 + DH_THREADS - 1) / DH_THREADS), DH_THREADS, 0, st>>>(*d, time, params_f32 + o.fourier,
+  launch_k(diff_fourier_bwd_kernel, (unsigned)((s.F / 2 + DH_THREADS - 1) / DH_THREADS), DH_THREADS, 0, st, *d, time, params_f32 + o.fourier,
                                                                                                       w.dff, gr + o.fourier);
   TOME_CUDA(cudaGetLastError());
   return TOME_OK;

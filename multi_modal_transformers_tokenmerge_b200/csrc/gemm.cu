@@ -103,6 +103,7 @@ template <int BN, bool A_MN, bool B_MN, int MC, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const __grid_constant__ CUtensorMap tma_c, const GemmShape s, const GemmEpilogue e) {
+  pdl_prologue();
   constexpr bool PAIR = MC >= 2;   // one 256-row cta_group::2 MMA per cluster pair (MC == 1: two 128-row MMAs sharing a multicast B)
   constexpr bool BRES = MC == 3;   // ... with the B operand resident in shared memory (K <= 384)
   using L = GemmSmem<BN, PAIR, BRES>;
@@ -664,6 +665,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 // sum split-K partials: out[i] = sum_s part[s*stride + i]      (fp32, deterministic order)
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, long long n4,
                                      long long stride4, int splits, int accumulate) {
+  pdl_prologue();
   const float4* p = reinterpret_cast<const float4*>(part);
   float4* o = reinterpret_cast<float4*>(out);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -706,17 +708,18 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = SM::TOTAL;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_attr(&attr[0]);
   if (MC) {
     int clusters = items < gemm_sms() / 2 ? items : gemm_sms() / 2;
     if (MC == 3) clusters = bres_clusters(s.n_tiles, s.m_items);   // a multiple of the column tiles
     cfg.gridDim = dim3(2 * clusters);
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cudaLaunchAttribute& ca = attr[cfg.numAttrs++];
+    ca.id = cudaLaunchAttributeClusterDimension;
+    ca.val.clusterDim.x = 2;
+    ca.val.clusterDim.y = 1;
+    ca.val.clusterDim.z = 1;
   } else {
     cfg.gridDim = dim3(items < gemm_sms() ? items : gemm_sms());
   }
@@ -945,7 +948,7 @@ extern "C" int tome_gemm_bf16(const tome_gemm_args_t* a, void* workspace, size_t
     const long long n4 = (long long)a->m * a->ldc / 4;
     int blocks = (int)((n4 + 255) / 256);
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float*>(workspace),
+    launch_k(splitk_reduce_kernel, blocks, 256, 0, stream, reinterpret_cast<const float*>(workspace),
                                                      reinterpret_cast<float*>(a->c), n4, n4, s.k_splits, a->accumulate);
     TOME_CUDA(cudaGetLastError());
   }

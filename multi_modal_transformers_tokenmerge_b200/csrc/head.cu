@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(HEAD_THREADS)
 head_fwd_kernel(const tome_head_desc_t d, const void* __restrict__ x, const int32_t* __restrict__ origin,
                 const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ actions,
                 float* __restrict__ out, float* __restrict__ loss, float* __restrict__ pooled_g, float* __restrict__ dz_g) {
+  pdl_prologue();
   extern __shared__ float head_sm[];
   const int b = blockIdx.x, C = d.channels, G = d.groups, F = d.features, m = d.n_readout / d.groups;
   float* pooled = head_sm;        // [G*C]
@@ -138,6 +139,7 @@ head_fwd_kernel(const tome_head_desc_t d, const void* __restrict__ x, const int3
 }
 
 __global__ void head_loss_final_kernel(int B, float inv_count, float* loss) {
+  pdl_prologue();
   float t = 0.f;
   for (int b = 0; b < B; ++b) t += loss[1 + b];
   loss[0] = t * inv_count;
@@ -149,6 +151,7 @@ __global__ void head_loss_final_kernel(int B, float inv_count, float* loss) {
 __global__ void __launch_bounds__(HEAD_THREADS)
 head_wgrad_kernel(const tome_head_desc_t d, const float* __restrict__ pooled, const float* __restrict__ dz,
                   float* __restrict__ dw, float* __restrict__ dbias) {
+  pdl_prologue();
   __shared__ float part[HEAD_THREADS / 32][32];
   const int C = d.channels, F = d.features, BG = d.batch * d.groups;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = HEAD_THREADS / 32;
@@ -177,6 +180,7 @@ template <bool BF16>
 __global__ void __launch_bounds__(HEAD_THREADS)
 head_dgrad_kernel(const tome_head_desc_t d, const int32_t* __restrict__ origin, const float* __restrict__ w,
                   const float* __restrict__ dz, void* __restrict__ dx) {
+  pdl_prologue();
   extern __shared__ float head_sm[];
   const int b = blockIdx.x, C = d.channels, G = d.groups, F = d.features, m = d.n_readout / d.groups;
   float* dzs = head_sm;  // [G*F]
@@ -247,15 +251,15 @@ extern "C" int tome_action_head_fwd(const tome_head_desc_t* d, const void* x, co
   ProfScope prof(PROF_OTHER, 0.0, loss ? 2 : 1, stream);
   if (d->x_dtype == TOME_BF16) {
     TOME_CUDA(cudaFuncSetAttribute(head_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    head_fwd_kernel<true><<<d->batch, HEAD_THREADS, smem, stream>>>(*d, x, origin, w, bias, actions, out, loss, ws.pooled, ws.dz);
+    launch_k(head_fwd_kernel<true>, d->batch, HEAD_THREADS, smem, stream, *d, x, origin, w, bias, actions, out, loss, ws.pooled, ws.dz);
   } else {
     TOME_CUDA(cudaFuncSetAttribute(head_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    head_fwd_kernel<false><<<d->batch, HEAD_THREADS, smem, stream>>>(*d, x, origin, w, bias, actions, out, loss, ws.pooled, ws.dz);
+    launch_k(head_fwd_kernel<false>, d->batch, HEAD_THREADS, smem, stream, *d, x, origin, w, bias, actions, out, loss, ws.pooled, ws.dz);
   }
   TOME_CUDA(cudaGetLastError());
   if (loss) {
     const float count = d->kind == TOME_HEAD_CONTINUOUS_L2 ? (float)d->batch : (float)d->batch * (float)d->groups;
-    head_loss_final_kernel<<<1, 1, 0, stream>>>(d->batch, 1.0f / count, loss);
+    launch_k(head_loss_final_kernel, 1, 1, 0, stream, d->batch, 1.0f / count, loss);
     TOME_CUDA(cudaGetLastError());
   }
   return TOME_OK;
@@ -271,7 +275,7 @@ extern "C" int tome_action_head_bwd(const tome_head_desc_t* d, const int32_t* or
   HeadWs ws = head_ws(d, const_cast<void*>(workspace));
   ProfScope prof(PROF_OTHER, 0.0, dx ? 3 : 1, stream);
   const long long n = (long long)d->channels * d->features + d->features;
-  head_wgrad_kernel<<<(unsigned)((n + 31) / 32), HEAD_THREADS, 0, stream>>>(*d, ws.pooled, ws.dz, dw, dbias);
+  launch_k(head_wgrad_kernel, (unsigned)((n + 31) / 32), HEAD_THREADS, 0, stream, *d, ws.pooled, ws.dz, dw, dbias);
   TOME_CUDA(cudaGetLastError());
   if (dx) {
     const size_t esz = d->x_dtype == TOME_BF16 ? 2 : 4;
@@ -279,10 +283,10 @@ extern "C" int tome_action_head_bwd(const tome_head_desc_t* d, const int32_t* or
     const size_t smem = (size_t)d->groups * d->features * sizeof(float);
     if (d->x_dtype == TOME_BF16) {
       TOME_CUDA(cudaFuncSetAttribute(head_dgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      head_dgrad_kernel<true><<<d->batch, HEAD_THREADS, smem, stream>>>(*d, origin, w, ws.dz, dx);
+      launch_k(head_dgrad_kernel<true>, d->batch, HEAD_THREADS, smem, stream, *d, origin, w, ws.dz, dx);
     } else {
       TOME_CUDA(cudaFuncSetAttribute(head_dgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      head_dgrad_kernel<false><<<d->batch, HEAD_THREADS, smem, stream>>>(*d, origin, w, ws.dz, dx);
+      launch_k(head_dgrad_kernel<false>, d->batch, HEAD_THREADS, smem, stream, *d, origin, w, ws.dz, dx);
     }
     TOME_CUDA(cudaGetLastError());
   }

@@ -6,6 +6,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include <atomic>
 
@@ -62,6 +63,27 @@ inline cudaError_t ensure_dyn_smem(Kernel kernel, int bytes, DynSmemOnce& once) 
   e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e == cudaSuccess) once.set[dev].store(bytes, std::memory_order_release);
   return e;
+}
+
+// ---- kernel launches with programmatic dependent launch (common.cuh pdl_prologue) ----
+bool pdl_enabled();   // TOME_PDL=1 in the environment, or tome_set_pdl(1), turns the attribute on (off by default: measured neutral)
+inline int pdl_attr(cudaLaunchAttribute* a) {   // fills *a; returns the number of attributes to pass (0 or 1)
+  a->id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  a->val.programmaticStreamSerializationAllowed = 1;
+  return pdl_enabled() ? 1 : 0;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  cfg.numAttrs = pdl_attr(attr);
+  cfg.attrs = attr;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 // ---- launch accounting + optional per-op CUDA-event timing (bench.py's roofline pass; off by default) ----

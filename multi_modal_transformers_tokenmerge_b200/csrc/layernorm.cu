@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(LN_THREADS)
 ln_seq_fwd_kernel(int T, int C, float eps, const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                   const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ mean,
                   float* __restrict__ rstd) {
+  pdl_prologue();
   __shared__ float s_sum[LN_RG][LN_SLAB + 1];
   __shared__ float s_sq[LN_RG][LN_SLAB + 1];
   __shared__ float s_mean[LN_SLAB], s_rstd[LN_SLAB];
@@ -99,6 +100,7 @@ __global__ void __launch_bounds__(LN_THREADS)
 ln_seq_bwd_kernel(int B, int T, int C, const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                   const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                   const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx, float* __restrict__ partial) {
+  pdl_prologue();
   __shared__ float s_a[LN_RG][LN_SLAB + 1];
   __shared__ float s_b[LN_RG][LN_SLAB + 1];
   __shared__ float s_A[LN_SLAB], s_B[LN_SLAB];
@@ -181,6 +183,7 @@ template <int G>
 __global__ void __launch_bounds__(32 * G)
 reduce_rows_kernel(int R, int N, const float* __restrict__ ws, long long plane_stride, float* __restrict__ out0,
                    float* __restrict__ out1, int accumulate) {
+  pdl_prologue();
   __shared__ float s[G][33];
   const int n = blockIdx.x * 32 + (threadIdx.x & 31), rgp = threadIdx.x >> 5;
   const float* w = ws + blockIdx.y * plane_stride;
@@ -228,6 +231,7 @@ __global__ void __launch_bounds__(LN_THREADS)
 ln_seq_fwd_smem_kernel(const __grid_constant__ CUtensorMap tm_x, int T, int C, int nb, float eps, const float* __restrict__ gamma,
                        const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ mean,
                        float* __restrict__ rstd) {
+  pdl_prologue();
   extern __shared__ uint8_t ln_smem_raw[];
   uint8_t* slab = ln_smem_raw + ((1024u - (smem_u32(ln_smem_raw) & 1023u)) & 1023u);
   const int t0 = CL ? (int)blockIdx.z * nb * LN_BOX : 0;   // first token row of this CTA
@@ -346,6 +350,7 @@ __global__ void __launch_bounds__(LN_THREADS)
 ln_seq_bwd_smem_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dy, int B, int T, int C, int nb,
                        const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                        const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx, float* __restrict__ partial) {
+  pdl_prologue();
   extern __shared__ uint8_t ln_smem_raw[];
   uint8_t* slab_x = ln_smem_raw + ((128u - (smem_u32(ln_smem_raw) & 127u)) & 127u);
   const int t0 = CL ? (int)blockIdx.z * nb * LN_BOX : 0;   // first token row of this CTA
@@ -488,6 +493,7 @@ ln_seq_bwd_smem_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
 __global__ void __launch_bounds__(LN_THREADS)
 colsum_partial_kernel(int M, int N, long long ldx, int rows_per_chunk, const __nv_bfloat16* __restrict__ x,
                       float* __restrict__ ws) {
+  pdl_prologue();
   __shared__ float s_sum[LN_RG][LN_SLAB + 1];
   const int chunk = blockIdx.y, c0 = blockIdx.x * LN_SLAB;
   const int ct = threadIdx.x & 7, rg = threadIdx.x >> 3;
@@ -520,6 +526,7 @@ colsum_partial_kernel(int M, int N, long long ldx, int rows_per_chunk, const __n
 __global__ void __launch_bounds__(LN_THREADS)
 dropout_colsum_kernel(int M, int N, int rows_per_chunk, const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                       DropoutCfg d, float* __restrict__ ws) {
+  pdl_prologue();
   __shared__ float s_sum[LN_RG][LN_SLAB + 1];
   const int chunk = blockIdx.y, c0 = blockIdx.x * LN_SLAB;
   const int ct = threadIdx.x & 7, rg = threadIdx.x >> 3;
@@ -559,6 +566,7 @@ __global__ void __launch_bounds__(256)
 ln_feat_fwd_kernel(long long rows, int C, float eps, const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                    const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ mean,
                    float* __restrict__ rstd) {
+  pdl_prologue();
   const long long row = blockIdx.x * 8ll + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -595,6 +603,7 @@ __global__ void __launch_bounds__(256)
 ln_feat_bwd_kernel(long long rows, int C, const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                    const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                    const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx) {
+  pdl_prologue();
   const long long row = blockIdx.x * 8ll + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -634,6 +643,7 @@ __global__ void __launch_bounds__(LN_THREADS)
 ln_feat_param_grad_kernel(long long rows, int C, int rows_per_chunk, int n_chunks, const __nv_bfloat16* __restrict__ x,
                           const __nv_bfloat16* __restrict__ dy, const float* __restrict__ mean,
                           const float* __restrict__ rstd, float* __restrict__ ws) {
+  pdl_prologue();
   __shared__ float s_a[LN_RG][LN_SLAB + 1];
   __shared__ float s_b[LN_RG][LN_SLAB + 1];
   const int chunk = blockIdx.y, c0 = blockIdx.x * LN_SLAB;
@@ -706,13 +716,14 @@ static int launch_cluster_z(K kern, dim3 grid, int smem, cudaStream_t stream, Ar
   cfg.blockDim = dim3(LN_THREADS);
   cfg.dynamicSmemBytes = (size_t)smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = grid.z;
+  cudaLaunchAttribute attr[2];
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_attr(&attr[0]);
+  cudaLaunchAttribute& ca = attr[cfg.numAttrs++];
+  ca.id = cudaLaunchAttributeClusterDimension;
+  ca.val.clusterDim.x = 1;
+  ca.val.clusterDim.y = 1;
+  ca.val.clusterDim.z = grid.z;
   TOME_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
   return TOME_OK;
 }
@@ -723,8 +734,8 @@ extern "C" int tome_reduce_rows_f32(int rows, int n, const float* partial, float
   clear_error();
   cudaStream_t stream = (cudaStream_t)stream_;
   TOME_CHECK(rows > 0 && n > 0 && partial && out, TOME_ERR_INVALID, "reduce_rows: bad argument");
-  if (rows >= 256) reduce_rows_kernel<32><<<ceil_div(n, 32), 1024, 0, stream>>>(rows, n, partial, 0, out, out, accumulate);
-  else reduce_rows_kernel<8><<<ceil_div(n, 32), 256, 0, stream>>>(rows, n, partial, 0, out, out, accumulate);
+  if (rows >= 256) launch_k(reduce_rows_kernel<32>, ceil_div(n, 32), 1024, 0, stream, rows, n, partial, 0, out, out, accumulate);
+  else launch_k(reduce_rows_kernel<8>, ceil_div(n, 32), 256, 0, stream, rows, n, partial, 0, out, out, accumulate);
   TOME_CUDA(cudaGetLastError());
   return TOME_OK;
 }
@@ -739,9 +750,9 @@ extern "C" int tome_colsum_bf16(int m, int n, const void* x, long long ldx, floa
   ProfScope prof(PROF_COLSUM, (double)m * n * 2.0, 2, stream);
   const int rpc = ceil_div(m, chunks);
   dim3 grid(ceil_div(n, LN_SLAB), chunks);
-  colsum_partial_kernel<<<grid, LN_THREADS, 0, stream>>>(m, n, ldx, rpc, reinterpret_cast<const __nv_bfloat16*>(x), workspace);
+  launch_k(colsum_partial_kernel, grid, LN_THREADS, 0, stream, m, n, ldx, rpc, reinterpret_cast<const __nv_bfloat16*>(x), workspace);
   TOME_CUDA(cudaGetLastError());
-  reduce_rows_kernel<8><<<ceil_div(n, 32), 256, 0, stream>>>(chunks, n, workspace, 0, out, out, accumulate);
+  launch_k(reduce_rows_kernel<8>, ceil_div(n, 32), 256, 0, stream, chunks, n, workspace, 0, out, out, accumulate);
   TOME_CUDA(cudaGetLastError());
   return TOME_OK;
 }
@@ -762,10 +773,10 @@ extern "C" int tome_dropout_colsum_bf16(int m, int n, const void* x, void* y, fl
   ProfScope prof(PROF_COLSUM, (double)m * n * 4.0, 2, stream);
   const int rpc = ceil_div(m, chunks);
   dim3 grid(ceil_div(n, LN_SLAB), chunks);
-  dropout_colsum_kernel<<<grid, LN_THREADS, 0, stream>>>(m, n, rpc, reinterpret_cast<const __nv_bfloat16*>(x),
+  launch_k(dropout_colsum_kernel, grid, LN_THREADS, 0, stream, m, n, rpc, reinterpret_cast<const __nv_bfloat16*>(x),
                                                          reinterpret_cast<__nv_bfloat16*>(y), d, workspace);
   TOME_CUDA(cudaGetLastError());
-  reduce_rows_kernel<8><<<ceil_div(n, 32), 256, 0, stream>>>(chunks, n, workspace, 0, out, out, accumulate);
+  launch_k(reduce_rows_kernel<8>, ceil_div(n, 32), 256, 0, stream, chunks, n, workspace, 0, out, out, accumulate);
   TOME_CUDA(cudaGetLastError());
   return TOME_OK;
 }
@@ -794,7 +805,7 @@ extern "C" int tome_layernorm_fwd(int batch, int tokens, int channels, int axis,
       if (split == 1 && !g_ln_force_cluster) {
         static DynSmemOnce once;
         TOME_CUDA(ensure_dyn_smem(ln_seq_fwd_smem_kernel<false>, smem, once));
-        ln_seq_fwd_smem_kernel<false><<<grid, LN_THREADS, smem, stream>>>(tx, tokens, channels, nb, eps, gamma, beta, yp, mean, rstd);
+        launch_k(ln_seq_fwd_smem_kernel<false>, grid, LN_THREADS, smem, stream, tx, tokens, channels, nb, eps, gamma, beta, yp, mean, rstd);
       } else {
         static DynSmemOnce once;
         TOME_CUDA(ensure_dyn_smem(ln_seq_fwd_smem_kernel<true>, smem, once));
@@ -802,11 +813,11 @@ extern "C" int tome_layernorm_fwd(int batch, int tokens, int channels, int axis,
                                       eps, gamma, beta, yp, mean, rstd)) return rc;
       }
     } else {
-      ln_seq_fwd_kernel<<<grid, LN_THREADS, 0, stream>>>(tokens, channels, eps, xp, gamma, beta, yp, mean, rstd);
+      launch_k(ln_seq_fwd_kernel, grid, LN_THREADS, 0, stream, tokens, channels, eps, xp, gamma, beta, yp, mean, rstd);
     }
   } else {
     const long long rows = (long long)batch * tokens;
-    ln_feat_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(rows, channels, eps, xp, gamma, beta, yp, mean, rstd);
+    launch_k(ln_feat_fwd_kernel, (unsigned)((rows + 7) / 8), 256, 0, stream, rows, channels, eps, xp, gamma, beta, yp, mean, rstd);
   }
   TOME_CUDA(cudaGetLastError());
   return TOME_OK;
@@ -842,7 +853,7 @@ extern "C" int tome_layernorm_bwd(int batch, int tokens, int channels, int axis,
       if (split == 1 && !g_ln_force_cluster) {
         static DynSmemOnce once;
         TOME_CUDA(ensure_dyn_smem(ln_seq_bwd_smem_kernel<false>, smem, once));
-        ln_seq_bwd_smem_kernel<false><<<grid, LN_THREADS, smem, stream>>>(tx, tdy, batch, tokens, channels, nb, gamma, mean, rstd, drp, dxp, partial);
+        launch_k(ln_seq_bwd_smem_kernel<false>, grid, LN_THREADS, smem, stream, tx, tdy, batch, tokens, channels, nb, gamma, mean, rstd, drp, dxp, partial);
       } else {
         static DynSmemOnce once;
         TOME_CUDA(ensure_dyn_smem(ln_seq_bwd_smem_kernel<true>, smem, once));
@@ -850,20 +861,20 @@ extern "C" int tome_layernorm_bwd(int batch, int tokens, int channels, int axis,
                                       channels, nb, gamma, mean, rstd, drp, dxp, partial)) return rc;
       }
     } else {
-      ln_seq_bwd_kernel<<<grid, LN_THREADS, 0, stream>>>(batch, tokens, channels, xp, dyp, gamma, mean, rstd, drp, dxp, partial);
+      launch_k(ln_seq_bwd_kernel, grid, LN_THREADS, 0, stream, batch, tokens, channels, xp, dyp, gamma, mean, rstd, drp, dxp, partial);
     }
     chunks = batch;
   } else {
     const long long rows = (long long)batch * tokens;
-    ln_feat_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(rows, channels, xp, dyp, gamma, mean, rstd, drp, dxp);
+    launch_k(ln_feat_bwd_kernel, (unsigned)((rows + 7) / 8), 256, 0, stream, rows, channels, xp, dyp, gamma, mean, rstd, drp, dxp);
     TOME_CUDA(cudaGetLastError());
     chunks = colsum_rows(rows);
     const int rpc = (int)((rows + chunks - 1) / chunks);
     dim3 grid(ceil_div(channels, LN_SLAB), chunks);
-    ln_feat_param_grad_kernel<<<grid, LN_THREADS, 0, stream>>>(rows, channels, rpc, chunks, xp, dyp, mean, rstd, partial);
+    launch_k(ln_feat_param_grad_kernel, grid, LN_THREADS, 0, stream, rows, channels, rpc, chunks, xp, dyp, mean, rstd, partial);
   }
   TOME_CUDA(cudaGetLastError());
-  reduce_rows_kernel<8><<<dim3(ceil_div(channels, 32), 2), 256, 0, stream>>>(chunks, channels, partial, (long long)chunks * channels,
+  launch_k(reduce_rows_kernel<8>, dim3(ceil_div(channels, 32), 2), 256, 0, stream, chunks, channels, partial, (long long)chunks * channels,
                                                                           dbeta, dgamma, 1);
   TOME_CUDA(cudaGetLastError());
   return TOME_OK;

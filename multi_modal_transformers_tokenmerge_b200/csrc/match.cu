@@ -84,6 +84,7 @@ template <typename T>
 __global__ void __launch_bounds__(SIM_THREADS)
 sim_argmax_kernel(const tome_metric_desc_t d, const T* __restrict__ src, float* __restrict__ node_max,
                   int32_t* __restrict__ node_idx, float* __restrict__ scores_out) {
+  pdl_prologue();
   extern __shared__ float4 sm4[];
   float* sm = reinterpret_cast<float*>(sm4);
   const int dpad = (d.dim + 3) & ~3, pitch = dpad + 4;
@@ -178,6 +179,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 metric_norm_kernel(const tome_metric_desc_t d, const T* __restrict__ src, float* __restrict__ plane_a,
                    float* __restrict__ plane_b) {
+  pdl_prologue();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long tok = (long long)blockIdx.x * 8 + warp;   // b * T + t
   if (tok >= (long long)d.batch * d.tokens) return;
@@ -214,6 +216,7 @@ metric_norm_kernel(const tome_metric_desc_t d, const T* __restrict__ src, float*
 __global__ void __launch_bounds__(256)
 metric_norm64_kernel(const tome_metric_desc_t d, const __nv_bfloat16* __restrict__ src, float* __restrict__ plane_a,
                      float* __restrict__ plane_b) {
+  pdl_prologue();
   const long long tok = ((long long)blockIdx.x * 256 + threadIdx.x) >> 3;   // b * T + t
   const int sub = threadIdx.x & 7;
   const bool valid = tok < (long long)d.batch * d.tokens;   // every lane stays for the shuffles
@@ -265,6 +268,7 @@ __device__ __forceinline__ void load_tile_async(float* dst, const float* plane, 
 __global__ void __launch_bounds__(SIM_THREADS)
 sim_argmax_planes_kernel(const tome_metric_desc_t d, const float* __restrict__ plane_a, const float* __restrict__ plane_b,
                          float* __restrict__ node_max, int32_t* __restrict__ node_idx, float* __restrict__ scores_out) {
+  pdl_prologue();
   extern __shared__ float4 sm4[];
   float* sm = reinterpret_cast<float*>(sm4);
   const int dpad = (d.dim + 3) & ~3, pitch = dpad + 4;
@@ -396,6 +400,7 @@ constexpr int SIMT_THREADS = 192;
 __global__ void __launch_bounds__(256)
 metric_split64_kernel(const tome_metric_desc_t d, const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ plane_a,
                       __nv_bfloat16* __restrict__ plane_b) {
+  pdl_prologue();
   const long long tok = ((long long)blockIdx.x * 256 + threadIdx.x) >> 3;   // b * T + t
   const int sub = threadIdx.x & 7;
   const bool valid = tok < (long long)d.batch * d.tokens;   // every lane stays for the shuffles
@@ -446,6 +451,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 metric_split_kernel(const tome_metric_desc_t d, const T* __restrict__ src, __nv_bfloat16* __restrict__ plane_a,
                     __nv_bfloat16* __restrict__ plane_b) {
+  pdl_prologue();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long tok = (long long)blockIdx.x * 8 + warp;   // b * T + t
   if (tok >= (long long)d.batch * d.tokens) return;
@@ -483,6 +489,7 @@ metric_split_kernel(const tome_metric_desc_t d, const T* __restrict__ src, __nv_
 __global__ void __launch_bounds__(SIMT_THREADS, 2)
 sim_argmax_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const tome_metric_desc_t d,
                      float* __restrict__ node_max, int32_t* __restrict__ node_idx, float* __restrict__ scores_out, const int csize) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_a = smem;                                   // chunk c at c * 16 KB
@@ -660,6 +667,7 @@ __host__ __device__ inline int sel_pow2(int n) { int p = 1; while (p < n) p <<= 
 __global__ void __launch_bounds__(SEL_THREADS)
 select_topr_kernel(const tome_plan_shape_t s, const float* __restrict__ node_max, const int32_t* __restrict__ node_idx,
                    const tome_plan_t p) {
+  pdl_prologue();
   extern __shared__ __align__(8) unsigned char sel_raw[];
   const int T = s.tokens, r = s.r;
   const int ta = (T + 1) / 2, tb = T / 2;
@@ -816,11 +824,11 @@ extern "C" int tome_sim_argmax(const tome_metric_desc_t* d, const void* src, flo
       __nv_bfloat16* pb = pa + (size_t)d->batch * ta * SIMT_ROW;
       const long long toks = (long long)d->batch * d->tokens;
       if (sim_fast64(d, src))
-        metric_split64_kernel<<<(unsigned)((toks * 8 + 255) / 256), 256, 0, stream>>>(*d, reinterpret_cast<const __nv_bfloat16*>(src), pa, pb);
+        launch_k(metric_split64_kernel, (unsigned)((toks * 8 + 255) / 256), 256, 0, stream, *d, reinterpret_cast<const __nv_bfloat16*>(src), pa, pb);
       else if (d->dtype == TOME_BF16)
-        metric_split_kernel<__nv_bfloat16><<<(unsigned)((toks + 7) / 8), 256, 0, stream>>>(*d, reinterpret_cast<const __nv_bfloat16*>(src), pa, pb);
+        launch_k(metric_split_kernel<__nv_bfloat16>, (unsigned)((toks + 7) / 8), 256, 0, stream, *d, reinterpret_cast<const __nv_bfloat16*>(src), pa, pb);
       else
-        metric_split_kernel<float><<<(unsigned)((toks + 7) / 8), 256, 0, stream>>>(*d, reinterpret_cast<const float*>(src), pa, pb);
+        launch_k(metric_split_kernel<float>, (unsigned)((toks + 7) / 8), 256, 0, stream, *d, reinterpret_cast<const float*>(src), pa, pb);
       TOME_CUDA(cudaGetLastError());
       CUtensorMap tma_a, tma_b;
       if (int rc = make_tmap_3d_bf16(&tma_a, pa, SIMT_ROW, ta, d->batch, SIMT_ROW, (uint64_t)ta * SIMT_ROW, SIMT_BM)) return rc;
@@ -838,13 +846,14 @@ extern "C" int tome_sim_argmax(const tome_metric_desc_t* d, const void* src, flo
       cfg.blockDim = dim3(SIMT_THREADS);
       cfg.dynamicSmemBytes = SIMT_SMEM;
       cfg.stream = stream;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = csize;
-      attr[0].val.clusterDim.y = 1;
-      attr[0].val.clusterDim.z = 1;
+      cudaLaunchAttribute attr[2];
       cfg.attrs = attr;
-      cfg.numAttrs = 1;
+      cfg.numAttrs = pdl_attr(&attr[0]);
+      cudaLaunchAttribute& ca = attr[cfg.numAttrs++];
+      ca.id = cudaLaunchAttributeClusterDimension;
+      ca.val.clusterDim.x = csize;
+      ca.val.clusterDim.y = 1;
+      ca.val.clusterDim.z = 1;
       TOME_CUDA(cudaLaunchKernelEx(&cfg, sim_argmax_tc_kernel, tma_a, tma_b, *d, node_max, node_idx, scores_out, csize));
       return TOME_OK;
     }
@@ -853,15 +862,15 @@ extern "C" int tome_sim_argmax(const tome_metric_desc_t* d, const void* src, flo
     const long long toks = (long long)d->batch * d->tokens;
     const unsigned nblk = (unsigned)((toks + 7) / 8);
     if (sim_fast64(d, src))
-      metric_norm64_kernel<<<(unsigned)((toks * 8 + 255) / 256), 256, 0, stream>>>(*d, reinterpret_cast<const __nv_bfloat16*>(src), plane_a, plane_b);
+      launch_k(metric_norm64_kernel, (unsigned)((toks * 8 + 255) / 256), 256, 0, stream, *d, reinterpret_cast<const __nv_bfloat16*>(src), plane_a, plane_b);
     else if (d->dtype == TOME_BF16)
-      metric_norm_kernel<__nv_bfloat16><<<nblk, 256, 0, stream>>>(*d, reinterpret_cast<const __nv_bfloat16*>(src), plane_a, plane_b);
+      launch_k(metric_norm_kernel<__nv_bfloat16>, nblk, 256, 0, stream, *d, reinterpret_cast<const __nv_bfloat16*>(src), plane_a, plane_b);
     else
-      metric_norm_kernel<float><<<nblk, 256, 0, stream>>>(*d, reinterpret_cast<const float*>(src), plane_a, plane_b);
+      launch_k(metric_norm_kernel<float>, nblk, 256, 0, stream, *d, reinterpret_cast<const float*>(src), plane_a, plane_b);
     TOME_CUDA(cudaGetLastError());
     const size_t smem = (size_t)3 * SIM_TILE * (dpad + 4) * sizeof(float);
     TOME_CUDA(cudaFuncSetAttribute(sim_argmax_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sim_argmax_planes_kernel<<<grid, SIM_THREADS, smem, stream>>>(*d, plane_a, plane_b, node_max, node_idx, scores_out);
+    launch_k(sim_argmax_planes_kernel, grid, SIM_THREADS, smem, stream, *d, plane_a, plane_b, node_max, node_idx, scores_out);
     TOME_CUDA(cudaGetLastError());
     return TOME_OK;
   }
@@ -870,12 +879,12 @@ extern "C" int tome_sim_argmax(const tome_metric_desc_t* d, const void* src, flo
   if (d->dtype == TOME_BF16) {
     auto kern = sim_argmax_kernel<__nv_bfloat16>;
     TOME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, SIM_THREADS, smem, stream>>>(*d, reinterpret_cast<const __nv_bfloat16*>(src), node_max, node_idx,
+    launch_k(kern, grid, SIM_THREADS, smem, stream, *d, reinterpret_cast<const __nv_bfloat16*>(src), node_max, node_idx,
                                               scores_out);
   } else {
     auto kern = sim_argmax_kernel<float>;
     TOME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, SIM_THREADS, smem, stream>>>(*d, reinterpret_cast<const float*>(src), node_max, node_idx, scores_out);
+    launch_k(kern, grid, SIM_THREADS, smem, stream, *d, reinterpret_cast<const float*>(src), node_max, node_idx, scores_out);
   }
   TOME_CUDA(cudaGetLastError());
   return TOME_OK;
@@ -898,7 +907,7 @@ extern "C" int tome_select_topr(const tome_plan_shape_t* s, const float* node_ma
              "select_topr: tokens (%d) too large for the shared-memory ranking", s->tokens);
   TOME_CUDA(cudaFuncSetAttribute(select_topr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope prof(PROF_SELECT, 0.0, 1, stream);
-  select_topr_kernel<<<s->batch, SEL_THREADS, smem, stream>>>(*s, node_max, node_idx, *plan);
+  launch_k(select_topr_kernel, s->batch, SEL_THREADS, smem, stream, *s, node_max, node_idx, *plan);
   TOME_CUDA(cudaGetLastError());
   return TOME_OK;
 }

@@ -46,6 +46,7 @@ merge_fwd_kernel(const tome_merge_shape_t s, const tome_plan_t p, const T* __res
                  const float* __restrict__ size, T* __restrict__ x_out, float* __restrict__ size_out,
                  const uint8_t* __restrict__ gid, const int32_t* __restrict__ pos, uint8_t* __restrict__ gid_out,
                  int32_t* __restrict__ pos_out) {
+  pdl_prologue();
   constexpr int N = Vec<T>::N;
   const int Tn = s.tokens, r = s.r, C = s.channels;
   const int ta = (Tn + 1) / 2, tb = Tn / 2, n_unm = ta - r, To = Tn - r;
@@ -134,6 +135,7 @@ merge_fwd_bulk_kernel(const tome_merge_shape_t s, const tome_plan_t p, const T* 
                       const float* __restrict__ size, T* __restrict__ x_out, float* __restrict__ size_out,
                       const uint8_t* __restrict__ gid, const int32_t* __restrict__ pos, uint8_t* __restrict__ gid_out,
                       int32_t* __restrict__ pos_out, int rows_per_cta) {
+  pdl_prologue();
   constexpr int N = Vec<T>::N;
   extern __shared__ __align__(128) uint8_t smem_merge[];
   const int Tn = s.tokens, r = s.r, C = s.channels;
@@ -255,6 +257,7 @@ template <typename T, bool WAVG>
 __global__ void __launch_bounds__(MERGE_THREADS)
 merge_bwd_kernel(const tome_merge_shape_t s, const int32_t* __restrict__ row_map, const float* __restrict__ size,
                  const float* __restrict__ size_out, const T* __restrict__ dy, T* __restrict__ dx) {
+  pdl_prologue();
   constexpr int N = Vec<T>::N;
   const int Tn = s.tokens, C = s.channels, To = Tn - s.r;
   const int vpr = C / N;
@@ -330,7 +333,7 @@ extern "C" int tome_merge_fwd(const tome_merge_shape_t* s, const tome_plan_t* pl
   do {                                                                                                                  \
     static DynSmemOnce once;                                                                                            \
     if (smem > 48 * 1024) TOME_CUDA(ensure_dyn_smem(merge_fwd_bulk_kernel<TT, W>, (int)smem, once));                   \
-    merge_fwd_bulk_kernel<TT, W><<<grid2, MERGE_THREADS, smem, stream>>>(*s, *plan, reinterpret_cast<const TT*>(x), size, \
+    launch_k(merge_fwd_bulk_kernel<TT, W>, grid2, MERGE_THREADS, smem, stream, *s, *plan, reinterpret_cast<const TT*>(x), size, \
                                                                          reinterpret_cast<TT*>(x_out), size_out, gid, pos, \
                                                                          gid_out, pos_out, rows);                       \
   } while (0)
@@ -342,7 +345,7 @@ extern "C" int tome_merge_fwd(const tome_merge_shape_t* s, const tome_plan_t* pl
   }
   const int grid = merge_grid(items);  // rows wider than 32 KB: thread-per-vector kernel
 #define LAUNCH(TT, W)                                                                                              \
-  merge_fwd_kernel<TT, W><<<grid, MERGE_THREADS, 0, stream>>>(*s, *plan, reinterpret_cast<const TT*>(x), size,     \
+  launch_k(merge_fwd_kernel<TT, W>, grid, MERGE_THREADS, 0, stream, *s, *plan, reinterpret_cast<const TT*>(x), size,     \
                                                               reinterpret_cast<TT*>(x_out), size_out, gid, pos,   \
                                                               gid_out, pos_out)
   if (s->dtype == TOME_BF16) { if (wavg) LAUNCH(__nv_bfloat16, true); else LAUNCH(__nv_bfloat16, false); }
@@ -370,7 +373,7 @@ extern "C" int tome_merge_bwd(const tome_merge_shape_t* s, const tome_plan_t* pl
   ProfScope prof(PROF_MERGE_BWD, (double)s->batch * ((double)(s->tokens - s->r) * s->channels * esz + (double)s->tokens * s->channels * esz + 4.0 * s->tokens), 1, stream);
   const int grid = merge_grid(items);
 #define LAUNCH(TT, W)                                                                                               \
-  merge_bwd_kernel<TT, W><<<grid, MERGE_THREADS, 0, stream>>>(*s, plan->row_map, size, size_out,                    \
+  launch_k(merge_bwd_kernel<TT, W>, grid, MERGE_THREADS, 0, stream, *s, plan->row_map, size, size_out,                    \
                                                               reinterpret_cast<const TT*>(dy), reinterpret_cast<TT*>(dx))
   if (s->dtype == TOME_BF16) { if (wavg) LAUNCH(__nv_bfloat16, true); else LAUNCH(__nv_bfloat16, false); }
   else { if (wavg) LAUNCH(float, true); else LAUNCH(float, false); }

@@ -16,6 +16,7 @@ __device__ __forceinline__ uint4 pack8m(const float (&f)[8]) {
 template <bool X_F32>
 __global__ void add_pos_kernel(long long n8, long long tc8, const void* __restrict__ x, const float* __restrict__ pe,
                                __nv_bfloat16* __restrict__ y) {
+  pdl_prologue();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     float f[8];
     if (X_F32) {
@@ -32,6 +33,7 @@ __global__ void add_pos_kernel(long long n8, long long tc8, const void* __restri
 }
 
 __global__ void pos_bwd_kernel(int B, long long tc8, const __nv_bfloat16* __restrict__ dy, float* __restrict__ dpe) {
+  pdl_prologue();
   const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (j >= tc8) return;
   float a[8];
@@ -56,6 +58,7 @@ struct ChainArgs {
 };
 __global__ void chain_kernel(int B, int layers, const ChainArgs a, const int32_t* __restrict__ readout_idx, int n,
                              int32_t* __restrict__ origin) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * n) return;
   const int b = i / n;
@@ -70,6 +73,7 @@ __global__ void __launch_bounds__(256)
 readout_mse_kernel(int B, int T, int C, int n, const __nv_bfloat16* __restrict__ x, const int32_t* __restrict__ origin,
                    const float* __restrict__ target, float* __restrict__ loss, __nv_bfloat16* __restrict__ dx,
                    float* __restrict__ out) {
+  pdl_prologue();
   __shared__ float red[8];
   const int b = blockIdx.x;
   const float gscale = 2.0f / ((float)B * (float)n * (float)C);
@@ -95,6 +99,7 @@ readout_mse_kernel(int B, int T, int C, int n, const __nv_bfloat16* __restrict__
   }
 }
 __global__ void loss_final_kernel(int B, float inv_count, float* loss) {
+  pdl_prologue();
   float t = 0.f;
   for (int b = 0; b < B; ++b) t += loss[1 + b];
   loss[0] = t * inv_count;
@@ -103,6 +108,7 @@ __global__ void loss_final_kernel(int B, float inv_count, float* loss) {
 __global__ void adamw_kernel(long long n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, __nv_bfloat16* __restrict__ w16, float lr, float b1, float b2, float eps,
                              float wd, float gs, float bc1, float bc2) {
+  pdl_prologue();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float gi = g[i] * gs;
     const float mi = b1 * m[i] + (1.f - b1) * gi;
@@ -117,6 +123,7 @@ __global__ void adamw_kernel(long long n, float* __restrict__ p, const float* __
 }
 
 __global__ void cast_kernel(long long n, const float* __restrict__ s, __nv_bfloat16* __restrict__ d) {
+  pdl_prologue();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     d[i] = __float2bfloat16(s[i]);
 }
@@ -142,9 +149,9 @@ extern "C" int tome_add_pos_embedding(int batch, int tokens, int channels, const
   const long long tc8 = (long long)tokens * channels / 8, n8 = tc8 * batch;
   ProfScope prof(PROF_OTHER, 0.0, 1, stream);
   if (x_dtype == TOME_F32)
-    add_pos_kernel<true><<<ew_grid(n8, 256), 256, 0, stream>>>(n8, tc8, x, pos_embedding, reinterpret_cast<__nv_bfloat16*>(y));
+    launch_k(add_pos_kernel<true>, ew_grid(n8, 256), 256, 0, stream, n8, tc8, x, pos_embedding, reinterpret_cast<__nv_bfloat16*>(y));
   else
-    add_pos_kernel<false><<<ew_grid(n8, 256), 256, 0, stream>>>(n8, tc8, x, pos_embedding, reinterpret_cast<__nv_bfloat16*>(y));
+    launch_k(add_pos_kernel<false>, ew_grid(n8, 256), 256, 0, stream, n8, tc8, x, pos_embedding, reinterpret_cast<__nv_bfloat16*>(y));
   TOME_CUDA(cudaGetLastError());
   return TOME_OK;
 }
@@ -156,7 +163,7 @@ extern "C" int tome_pos_embedding_bwd(int batch, int tokens, int channels, const
              "pos_embedding_bwd: bad argument");
   const long long tc8 = (long long)tokens * channels / 8;
   ProfScope prof(PROF_OTHER, 0.0, 1, stream);
-  pos_bwd_kernel<<<(unsigned)((tc8 + 127) / 128), 128, 0, stream>>>(batch, tc8, reinterpret_cast<const __nv_bfloat16*>(dy), dpe);
+  launch_k(pos_bwd_kernel, (unsigned)((tc8 + 127) / 128), 128, 0, stream, batch, tc8, reinterpret_cast<const __nv_bfloat16*>(dy), dpe);
   TOME_CUDA(cudaGetLastError());
   return TOME_OK;
 }
@@ -175,7 +182,7 @@ extern "C" int tome_chain_row_maps(int batch, int layers, const int32_t* const* 
   }
   const int n = batch * n_readout;
   ProfScope prof(PROF_OTHER, 0.0, 1, stream);
-  chain_kernel<<<ceil_div(n, 128), 128, 0, stream>>>(batch, layers, a, readout_idx, n_readout, origin);
+  launch_k(chain_kernel, ceil_div(n, 128), 128, 0, stream, batch, layers, a, readout_idx, n_readout, origin);
   TOME_CUDA(cudaGetLastError());
   return TOME_OK;
 }
@@ -188,11 +195,11 @@ extern "C" int tome_readout_mse(int batch, int tokens, int channels, int n_reado
   TOME_CHECK(!(loss || dx) || target, TOME_ERR_INVALID, "readout_mse: loss / dx need a target");
   ProfScope prof(PROF_OTHER, 0.0, loss ? 2 : 1, stream);
   if (dx) TOME_CUDA(cudaMemsetAsync(dx, 0, (size_t)batch * tokens * channels * 2, stream));
-  readout_mse_kernel<<<batch, 256, 0, stream>>>(batch, tokens, channels, n_readout, reinterpret_cast<const __nv_bfloat16*>(x),
+  launch_k(readout_mse_kernel, batch, 256, 0, stream, batch, tokens, channels, n_readout, reinterpret_cast<const __nv_bfloat16*>(x),
                                                 origin, target, loss, reinterpret_cast<__nv_bfloat16*>(dx), out);
   TOME_CUDA(cudaGetLastError());
   if (loss) {
-    loss_final_kernel<<<1, 1, 0, stream>>>(batch, 1.0f / ((float)batch * n_readout * channels), loss);
+    launch_k(loss_final_kernel, 1, 1, 0, stream, batch, 1.0f / ((float)batch * n_readout * channels), loss);
     TOME_CUDA(cudaGetLastError());
   }
   return TOME_OK;
@@ -206,7 +213,7 @@ extern "C" int tome_adamw_step(long long n, float* param, const float* grad, flo
   TOME_CHECK(n > 0 && param && grad && m && v && step >= 1, TOME_ERR_INVALID, "adamw_step: bad argument");
   ProfScope prof(PROF_OTHER, 0.0, 1, stream);
   const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
-  adamw_kernel<<<ew_grid(n, 256), 256, 0, stream>>>(n, param, grad, m, v, reinterpret_cast<__nv_bfloat16*>(bf16_copy), lr, beta1,
+  launch_k(adamw_kernel, ew_grid(n, 256), 256, 0, stream, n, param, grad, m, v, reinterpret_cast<__nv_bfloat16*>(bf16_copy), lr, beta1,
                                                     beta2, eps, weight_decay, grad_scale, bc1, bc2);
   TOME_CUDA(cudaGetLastError());
   return TOME_OK;
@@ -217,7 +224,7 @@ extern "C" int tome_cast_f32_to_bf16(long long n, const float* src, void* dst, v
   cudaStream_t stream = (cudaStream_t)stream_;
   TOME_CHECK(n > 0 && src && dst, TOME_ERR_INVALID, "cast: bad argument");
   ProfScope prof(PROF_OTHER, 0.0, 1, stream);
-  cast_kernel<<<ew_grid(n, 256), 256, 0, stream>>>(n, src, reinterpret_cast<__nv_bfloat16*>(dst));
+  launch_k(cast_kernel, ew_grid(n, 256), 256, 0, stream, n, src, reinterpret_cast<__nv_bfloat16*>(dst));
   TOME_CUDA(cudaGetLastError());
   return TOME_OK;
 }

@@ -26,6 +26,7 @@ __device__ __forceinline__ bool topk_before(float vj, int j, float vi, int i) {
 __global__ void __launch_bounds__(PRUNE_THREADS)
 topk_prune_kernel(const tome_prune_desc_t d, const uint8_t* __restrict__ emb, const float* __restrict__ score,
                   uint8_t* __restrict__ out, int32_t* __restrict__ ids) {
+  pdl_prologue();
   extern __shared__ float prune_sm[];
   const int s = blockIdx.x, b = blockIdx.y;
   const int start = d.set_start[s], n = d.set_n[s], k = d.set_k[s];
@@ -94,7 +95,7 @@ extern "C" int tome_topk_prune(const tome_prune_desc_t* d, const void* embedding
   ProfScope prof(PROF_OTHER, 0.0, 1, stream);
   TOME_CUDA(cudaFuncSetAttribute(topk_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(d->n_sets, d->batch);
-  topk_prune_kernel<<<grid, PRUNE_THREADS, smem, stream>>>(*d, reinterpret_cast<const uint8_t*>(embeddings), importance,
+  launch_k(topk_prune_kernel, grid, PRUNE_THREADS, smem, stream, *d, reinterpret_cast<const uint8_t*>(embeddings), importance,
                                                           reinterpret_cast<uint8_t*>(out), ids);
   TOME_CUDA(cudaGetLastError());
   return TOME_OK;

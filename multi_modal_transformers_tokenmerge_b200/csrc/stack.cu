@@ -265,6 +265,7 @@ static StackLayout make_layout(const tome_stack_cfg_t* c, void* workspace) {
 
 __global__ void broadcast_groups_kernel(int B, int T, const uint8_t* __restrict__ gid, const int32_t* __restrict__ pos,
                                         uint8_t* __restrict__ gid_out, int32_t* __restrict__ pos_out) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B * T) {
     gid_out[i] = gid[i % T];
@@ -374,7 +375,7 @@ extern "C" int tome_stack_forward(const tome_stack_cfg_t* c, const tome_stack_io
   if (c->num_groups) {
     const int n = B * c->tokens;
     ProfScope prof(PROF_OTHER, 0.0, 1, st);
-    broadcast_groups_kernel<<<ceil_div(n, 256), 256, 0, st>>>(B, c->tokens, io->gid, io->pos, S.L[0].gid_in, S.L[0].pos_in);
+    launch_k(broadcast_groups_kernel, ceil_div(n, 256), 256, 0, st, B, c->tokens, io->gid, io->pos, S.L[0].gid_in, S.L[0].pos_in);
     TOME_CUDA(cudaGetLastError());
   }
   for (int l = 0; l < c->layers; ++l) {
