@@ -22,6 +22,13 @@ Reference entry points executed:
                                                                    carry and slices the stacked parameters -- with the Flax
                                                                    leaf modules (LayerNorm, SelfAttention, Dense) restated in
                                                                    oracle/jax_shim/flax/linen.py  -> encoder_blocks.npz
+  multi_modal_transformers/tokenizers/images/image_tokenizer.py:35-309  image_to_patches, encode_patch_position (train=False),
+                                                                   ResNetV2Block.__call__, ImageTokenizer.__call__ with config
+                                                                   nodes of the form of model_configs/tokenizers/images/
+                                                                   gato_resnet.yaml at small widths (the literal 28 224 x 768 Dense
+                                                                   kernel alone would be 87 MB); Flax leaves (Conv, GroupNorm,
+                                                                   max_pool, gelu, Embed, Dense) restated in the shim
+                                                                   -> image_tokenizer.npz
   (the two loss expressions live inside the Octo class, which needs the whole model: octo.py:163-165 and :183-187 are
    restated here in numpy float64 on the executed heads' outputs)
 """
@@ -316,6 +323,70 @@ def gen_blocks():
     print("encoder_blocks.npz:", [c[0] for c in cases])
 
 
+def gen_image_tokenizer():
+    """image_tokenizer.npz: the reference's ImageTokenizer executed in evaluation mode (train=False: the training mode draws
+    the position tokens from jax.random, which no stand-in can reproduce)."""
+    sys.dont_write_bytecode = True
+    for pth in (os.path.join(HERE, "jax_shim"), REF):
+        if pth not in sys.path:
+            sys.path.insert(0, pth)
+    import flax.linen as nn
+    it = _load("ref_image_tokenizer", f"{REF}/multi_modal_transformers/tokenizers/images/image_tokenizer.py")
+    rng = np.random.default_rng(20261019)
+    # name, B, N, H, patch, C_in, features, groups, embed, position_interval, num_blocks, normalize
+    cases = [("two_frames", 2, 2, 56, 28, 3, 16, 4, 32, 16, 2, True),
+             ("nine_patches_one_block", 1, 3, 84, 28, 3, 8, 2, 24, 128, 1, True),
+             ("group_size_one_raw_pixels", 3, 1, 40, 20, 3, 32, 32, 16, 64, 2, False)]
+    out = {}
+    for (name, B, N, H, P, Cin, F, G, E, PI, NB, norm) in cases:
+        o2 = (P - 12) // 2 + 1 - 2
+        f32 = lambda a: a.astype(np.float32)  # noqa: E731
+        conv = lambda kh, cin: {"kernel": f32(rng.standard_normal((kh, kh, cin, F)) * (0.05 if kh == 12 else 0.1)),  # noqa: E731
+                                "bias": f32(rng.standard_normal(F) * 0.01)}
+        ef = {"Conv_0": conv(12, Cin), "Dense_0": {"kernel": f32(rng.standard_normal((o2 * o2 * F, E)) * 0.05),
+                                                    "bias": f32(rng.standard_normal(E) * 0.01)}}
+        for i in range(NB):
+            ef[f"GroupNorm_{i}"] = {"scale": f32(1 + 0.1 * rng.standard_normal(F)), "bias": f32(0.1 * rng.standard_normal(F))}
+            ef[f"Conv_{i + 1}"] = conv(3, F)
+        tree = {"embedding_function": ef,
+                "image_row_position_embedding": {"embedding": f32(rng.standard_normal((PI, E)) * 0.1)},
+                "image_col_position_embedding": {"embedding": f32(rng.standard_normal((PI, E)) * 0.1)}}
+        node = lambda t, **kw: dict(_target_=t, **kw)  # noqa: E731
+        cfg = dict(image_size=(H, H, Cin), patch_size=P, normalize=norm, position_interval=PI, rng_collection="patch_encoding",
+                   embedding_dim=E,
+                   row_position_embedding=node("flax.linen.Embed", name="image_row_position_embedding", num_embeddings=PI, features=E),
+                   col_position_embedding=node("flax.linen.Embed", name="image_col_position_embedding", num_embeddings=PI, features=E),
+                   resnet=node("ref_image_tokenizer.ResNetV2Block", num_blocks=NB,
+                               input_conv=node("flax.linen.Conv", features=F, kernel_size=[12, 12], strides=[2, 2], padding="VALID", use_bias=True),
+                               input_pool=dict(_partial_=True, _target_="flax.linen.max_pool", window_shape=[3, 3], strides=[1, 1], padding="VALID"),
+                               resnet_norm=node("flax.linen.GroupNorm", num_groups=G, epsilon=1e-6),
+                               resnet_activation=dict(_partial_=True, _target_="flax.linen.gelu"),
+                               resnet_conv=node("flax.linen.Conv", features=F, kernel_size=[3, 3], strides=[1, 1], padding="SAME", use_bias=True),
+                               output_dense=node("flax.linen.Dense", features=E)))
+        img = rng.integers(0, 256, size=(B, N, H, H, Cin)).astype(np.uint8)
+        tok = it.ImageTokenizer(**cfg)
+        with nn.shim_scope({"ImageTokenizer_0": tree}):
+            y = np.asarray(tok(img.astype(np.float32), train=False), np.float32)
+        # the pieces on their own: patches of the first image, evaluation-mode position tokens
+        out[f"{name}/patches00"] = np.asarray(it.image_to_patches(img[0, 0].astype(np.float32), P, norm), np.float32)
+        rt, ct = it.encode_patch_position(img[0, 0].astype(np.float32), None, P, PI, False)
+        out[f"{name}/row_tokens"], out[f"{name}/col_tokens"] = np.asarray(rt, np.int32), np.asarray(ct, np.int32)
+        out[f"{name}/image"], out[f"{name}/out"] = img, y
+        out[f"{name}/meta"] = np.array([B, N, H, P, Cin, F, G, E, PI, NB, int(norm)], np.int32)
+
+        def flat(prefix, t):
+            for k_, v_ in t.items():
+                if isinstance(v_, dict):
+                    flat(f"{prefix}/{k_}", v_)
+                else:
+                    out[f"{prefix}/{k_}"] = v_
+        flat(f"{name}/params", tree)
+    out["cases"] = np.array([c[0] for c in cases])
+    np.savez_compressed(os.path.join(OUT, "image_tokenizer.npz"), **out)
+    print("image_tokenizer.npz:", [c[0] for c in cases])
+
+
 if __name__ == "__main__":
     main()
     gen_blocks()
+    gen_image_tokenizer()

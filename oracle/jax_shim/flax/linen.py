@@ -75,6 +75,16 @@ class Module:
                     return __call(self, *a, **k)
                 with shim_scope(_child_params(self, type(self).__name__)) as sc:
                     self._shim_scope = sc
+                    if hasattr(self, "setup") and not getattr(self, "_shim_setup_done", False):
+                        # setup()-style module: children are attributes and take the attribute's name unless given one
+                        object.__setattr__(self, "_shim_setup_done", True)
+                        self.setup()
+                        for attr, val in list(vars(self).items()):
+                            if hasattr(val, "name") and getattr(val, "name", None) is None and not attr.startswith("_"):
+                                try:
+                                    object.__setattr__(val, "name", attr)
+                                except Exception:
+                                    pass
                     return __call(self, *a, **k)
             cls.__call__ = wrapped
 
@@ -91,7 +101,7 @@ class _Initializers:
     def he_normal(*a, **k):
         return lambda *a_, **k_: None
 
-    normal = zeros_init = lecun_normal = xavier_uniform = he_normal
+    normal = zeros_init = lecun_normal = xavier_uniform = variance_scaling = he_normal
 
 
 initializers = _Initializers()
@@ -236,3 +246,116 @@ def scan(target, variable_axes=None, variable_broadcast=False, split_rngs=None, 
 
 def _tree_index(tree, i):
     return {k: _tree_index(v, i) for k, v in tree.items()} if isinstance(tree, dict) else _np.asarray(tree)[i]
+
+
+# ---- image front end (tokenizers/images/image_tokenizer.py): Conv, GroupNorm, max_pool, gelu, Embed ------------------------
+def gelu(x, approximate=True):
+    """flax.linen.gelu = jax.nn.gelu, default approximate=True: 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))."""
+    x = _np.asarray(x, _np.float32)
+    if approximate:
+        c = _np.float32(_np.sqrt(2.0 / _np.pi))
+        return _wrap((0.5 * x * (1.0 + _np.tanh(c * (x + _np.float32(0.044715) * x * x * x)))).astype(_np.float32))
+    from math import erf
+    return _wrap((0.5 * x * (1.0 + _np.vectorize(erf)(x / _np.sqrt(2.0)))).astype(_np.float32))
+
+
+def max_pool(inputs, window_shape, strides=None, padding="VALID"):
+    """flax.linen.max_pool on [batch dims..., spatial..., features]: every leading dimension beyond the window's is batch."""
+    assert padding == "VALID", "the shim pools without padding only"
+    x = _np.asarray(inputs, _np.float32)
+    wh, ww = window_shape
+    sh, sw = strides or (1, 1)
+    H, W = x.shape[-3], x.shape[-2]
+    oh, ow = (H - wh) // sh + 1, (W - ww) // sw + 1
+    out = _np.full(x.shape[:-3] + (oh, ow, x.shape[-1]), -_np.inf, _np.float32)
+    for dy in range(wh):
+        for dx in range(ww):
+            out = _np.maximum(out, x[..., dy:dy + sh * oh:sh, dx:dx + sw * ow:sw, :])
+    return _wrap(out)
+
+
+@_dc.dataclass
+class Conv:
+    """flax.linen.Conv, 2-D, NHWC, kernel [kh, kw, in, features]; leading dimensions beyond (H, W, C) are batch (flattened and
+    restored, as Flax does); padding VALID or SAME (SAME: total padding k - 1 for stride 1, low side (k - 1) // 2)."""
+    features: int = 0
+    kernel_size: object = (3, 3)
+    strides: object = (1, 1)
+    padding: str = "SAME"
+    use_bias: bool = True
+    dtype: object = None
+    param_dtype: object = None
+    kernel_init: object = None
+    bias_init: object = None
+    name: object = None
+
+    def __call__(self, x):
+        p = _child_params(self, "Conv")
+        x = _np.asarray(x, _np.float32)
+        lead = x.shape[:-3]
+        x = x.reshape((-1,) + x.shape[-3:])
+        k = _np.asarray(p["kernel"], _np.float32)
+        kh, kw = k.shape[:2]
+        sh, sw = self.strides
+        if self.padding == "SAME":
+            assert (sh, sw) == (1, 1)
+            x = _np.pad(x, ((0, 0), ((kh - 1) // 2, kh - 1 - (kh - 1) // 2), ((kw - 1) // 2, kw - 1 - (kw - 1) // 2), (0, 0)))
+        else:
+            assert self.padding == "VALID"
+        H, W = x.shape[1:3]
+        oh, ow = (H - kh) // sh + 1, (W - kw) // sw + 1
+        out = _np.zeros((x.shape[0], oh, ow, k.shape[3]), _np.float32)
+        for dy in range(kh):
+            for dx in range(kw):
+                out += _np.einsum("bhwc,cf->bhwf", x[:, dy:dy + sh * oh:sh, dx:dx + sw * ow:sw, :], k[dy, dx], dtype=_np.float32)
+        if self.use_bias:
+            out = out + _np.asarray(p["bias"], _np.float32)
+        assert out.shape[-1] == self.features
+        return _wrap(out.reshape(lead + out.shape[1:]).astype(_np.float32))
+
+
+@_dc.dataclass
+class GroupNorm:
+    """flax.linen.GroupNorm (0.8.x): reduction_axes default = every axis except the FIRST (batch) one, i.e. on a
+    [B, images, patches, H, W, C] input the statistics of a group run over images x patches x H x W x (C / groups) for each
+    batch row; use_fast_variance (var = max(0, E[x^2] - E[x]^2)); scale / bias per channel."""
+    num_groups: object = 32
+    group_size: object = None
+    epsilon: float = 1e-6
+    dtype: object = None
+    param_dtype: object = None
+    use_bias: bool = True
+    use_scale: bool = True
+    name: object = None
+
+    def __call__(self, x):
+        p = _child_params(self, "GroupNorm")
+        x = _np.asarray(x, _np.float32)
+        C = x.shape[-1]
+        G = self.num_groups if self.num_groups is not None else C // self.group_size
+        assert C % G == 0
+        g = x.reshape(x.shape[:-1] + (G, C // G))
+        ax = tuple(range(1, g.ndim - 2)) + (g.ndim - 1,)
+        mu = g.mean(axis=ax, keepdims=True, dtype=_np.float32)
+        var = _np.maximum((g * g).mean(axis=ax, keepdims=True, dtype=_np.float32) - mu * mu, 0)
+        y = ((g - mu) * (1.0 / _np.sqrt(var + _np.float32(self.epsilon))).astype(_np.float32)).reshape(x.shape)
+        if self.use_scale:
+            y = y * _np.asarray(p["scale"], _np.float32)
+        if self.use_bias:
+            y = y + _np.asarray(p["bias"], _np.float32)
+        return _wrap(y.astype(_np.float32))
+
+
+@_dc.dataclass
+class Embed:
+    """flax.linen.Embed: rows of the [num_embeddings, features] table."""
+    num_embeddings: int = 0
+    features: int = 0
+    dtype: object = None
+    param_dtype: object = None
+    embedding_init: object = None
+    name: object = None
+
+    def __call__(self, idx):
+        p = _child_params(self, "Embed")
+        return _wrap(_np.asarray(p["embedding"], _np.float32)[_np.asarray(idx, _np.int64)])

@@ -20,6 +20,8 @@ def vmap(fn, in_axes=0, out_axes=0):
         axes = in_axes if isinstance(in_axes, (tuple, list)) else (in_axes,) * len(args)
         n = next(a.shape[ax] for a, ax in zip(args, axes) if ax is not None)
         outs = [fn(*[a if ax is None else _np.take(a, i, axis=ax) for a, ax in zip(args, axes)]) for i in range(n)]
+        if isinstance(outs[0], tuple):   # functions returning several arrays: map each
+            return tuple(numpy._wrap(_np.stack([o[j] for o in outs], axis=out_axes)) for j in range(len(outs[0])))
         return numpy._wrap(_np.stack(outs, axis=out_axes))
 
     return mapped

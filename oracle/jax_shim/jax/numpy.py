@@ -68,7 +68,8 @@ def _lift(name):
 
 for _n in ("matmul", "swapaxes", "take_along_axis", "concatenate", "ones_like", "zeros_like", "arange", "ones",
            "zeros", "hstack", "vstack", "squeeze", "take", "ravel", "sum", "expand_dims", "repeat", "tile",
-           "where", "stack", "sqrt", "log", "exp", "maximum", "minimum", "abs", "mean", "tanh", "digitize", "cos", "sin", "clip", "prod"):
+           "where", "stack", "sqrt", "log", "exp", "maximum", "minimum", "abs", "mean", "tanh", "digitize", "cos", "sin", "clip", "prod",
+           "floor", "reshape"):
     globals()[_n] = _lift(_n)
 
 

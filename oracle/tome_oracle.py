@@ -642,3 +642,110 @@ def denoise_loss(readouts, actions, time, noise, ah: np.ndarray, p):
     pred = octo_denoise(noisy, time, emb, p)                                   # :110
     loss = (0.5 * (pred - noise) ** 2).sum(dim=-1).mean()                      # :141-142 optax.l2_loss
     return loss, pred
+
+
+# ------------------------------------------------------------------------------------------------ image patch-embed front end
+# multi_modal_transformers/tokenizers/images/image_tokenizer.py.  Pinned by tests/golden/image_tokenizer.npz,
+# made by EXECUTING the reference's ImageTokenizer / ResNetV2Block / image_to_patches / encode_patch_position (train=False)
+# under the shim, whose Conv / GroupNorm / max_pool / gelu / Embed / Dense leaves restate Flax 0.8.x from memory
+# (oracle/jax_shim/flax/linen.py) -- the same "reference control flow, restated leaves" footing as encoder_blocks.npz.
+def image_to_patches(image: np.ndarray, patch_size: int, normalize: bool) -> np.ndarray:
+    """image_tokenizer.py:35-71.  image [H, W, C] (square, divisible by the patch) -> [(H/p)*(W/p), p, p, C], patches in
+    row-major (h, w) order; normalize: 2 * (x / 255) - 1."""
+    h, w, c = image.shape
+    assert h == w and h % patch_size == 0
+    n = h // patch_size
+    pt = image.reshape(n, patch_size, n, patch_size, c).transpose(0, 2, 1, 3, 4).reshape(n * n, patch_size, patch_size, c)
+    pt = pt.astype(np.float32)
+    if normalize:
+        pt = (np.float32(2) * (pt / np.float32(255.0))) - np.float32(1.0)                                   # :67
+    return pt
+
+
+def patch_position_tokens(image_size: int, patch_size: int, num_tokens: int):
+    """encode_patch_position with train=False (image_tokenizer.py:74-140): for patch k the pixel interval of index
+    k % patches_per_dim ("row", :94 -- the fastest-varying index of the (h w) patch order, i.e. the horizontal one) and of
+    k // patches_per_dim ("col", :95) is normalised by the image size, scaled to num_tokens - 1, floored (:100, fp32) and the
+    midpoint of the quantised interval taken with a floor division (:112-113).  Returns int32 (row_tokens, col_tokens) [n]."""
+    ppd = image_size // patch_size
+    f = np.float32
+    edges = np.arange(0, image_size + patch_size, patch_size)
+    q = np.floor((edges.astype(f) / f(image_size)) * f(num_tokens - 1)).astype(f)
+    mid = np.floor_divide(q[:-1] + q[1:], f(2)).astype(np.int32)          # per interval
+    k = np.arange(ppd * ppd)
+    return mid[k % ppd].astype(np.int32), mid[k // ppd].astype(np.int32)
+
+
+def _conv2d_nhwc(x, kernel, bias, stride, same):
+    """flax.linen.Conv (NHWC, kernel [kh, kw, in, out]); SAME pads (k - 1) // 2 low, the rest high (stride 1)."""
+    kh, kw = kernel.shape[:2]
+    if same:
+        x = np.pad(x, ((0, 0), ((kh - 1) // 2, kh - 1 - (kh - 1) // 2), ((kw - 1) // 2, kw - 1 - (kw - 1) // 2), (0, 0)))
+    H, W = x.shape[1:3]
+    oh, ow = (H - kh) // stride + 1, (W - kw) // stride + 1
+    cols = np.empty((x.shape[0], oh, ow, kh * kw * x.shape[3]), np.float32)
+    for dy in range(kh):
+        for dx in range(kw):
+            t = dy * kw + dx
+            cols[..., t * x.shape[3]:(t + 1) * x.shape[3]] = x[:, dy:dy + stride * oh:stride, dx:dx + stride * ow:stride, :]
+    return (cols.reshape(-1, cols.shape[-1]) @ kernel.reshape(-1, kernel.shape[3]).astype(np.float32)).reshape(
+        x.shape[0], oh, ow, kernel.shape[3]) + bias.astype(np.float32)
+
+
+def gelu_tanh(x):
+    """flax.linen.gelu (approximate=True)."""
+    x = x.astype(np.float32)
+    c = np.float32(np.sqrt(2.0 / np.pi))
+    return (np.float32(0.5) * x * (np.float32(1) + np.tanh(c * (x + np.float32(0.044715) * x * x * x)))).astype(np.float32)
+
+
+def group_norm_flax(x, scale, bias, groups: int, eps: float):
+    """flax.linen.GroupNorm with default reduction axes on x [B, ..., C]: per (batch row, group) statistics over EVERY other
+    axis (images, patches, H, W and the group's channels), fast variance, per-channel scale / bias."""
+    B, C = x.shape[0], x.shape[-1]
+    g = x.reshape(B, -1, groups, C // groups).astype(np.float32)
+    mu = g.mean(axis=(1, 3), keepdims=True, dtype=np.float32)
+    var = np.maximum((g * g).mean(axis=(1, 3), keepdims=True, dtype=np.float32) - mu * mu, 0)
+    y = ((g - mu) * (np.float32(1) / np.sqrt(var + np.float32(eps))).astype(np.float32)).reshape(x.shape)
+    return (y * scale.astype(np.float32) + bias.astype(np.float32)).astype(np.float32)
+
+
+def image_tokenizer_fwd(p: dict, image: np.ndarray, *, patch_size: int, position_interval: int, num_groups: int,
+                        conv_stride: int = 2, pool_window: int = 3, gn_eps: float = 1e-6, normalize: bool = True) -> np.ndarray:
+    """ImageTokenizer.__call__ with train=False (image_tokenizer.py:216-309) around ResNetV2Block.__call__ (:148-190):
+    patches -> Conv (VALID, stride 2) -> max_pool (3x3, stride 1, VALID) -> num_blocks x [GroupNorm -> gelu -> Conv 3x3 SAME]
+    -> + residual (the pooled tensor) -> flatten -> Dense -> + row / column position embeddings.
+    image [B, N, H, W, C] (pixel values 0..255); p: conv0_kernel [k, k, C, F], conv0_bias, blocks = [(gn_scale, gn_bias,
+    conv_kernel [3, 3, F, F], conv_bias), ...], dense_kernel [o*o*F, E], dense_bias, row_embedding / col_embedding
+    [position_interval, E].  Returns [B, N, n_patches, E] fp32."""
+    B, N, H, W, C = image.shape
+    pt = np.stack([np.stack([image_to_patches(image[b, i], patch_size, normalize) for i in range(N)]) for b in range(B)])
+    n = pt.shape[2]
+    x = _conv2d_nhwc(pt.reshape((-1,) + pt.shape[3:]), p["conv0_kernel"], p["conv0_bias"], conv_stride, same=False)
+    o1 = x.shape[1]
+    o2 = o1 - pool_window + 1
+    pooled = np.full((x.shape[0], o2, o2, x.shape[3]), -np.inf, np.float32)
+    for dy in range(pool_window):
+        for dx in range(pool_window):
+            pooled = np.maximum(pooled, x[:, dy:dy + o2, dx:dx + o2, :])
+    x = pooled
+    for (gs, gb, ck, cb) in p["blocks"]:
+        h = group_norm_flax(x.reshape(B, N, n, o2, o2, -1), gs, gb, num_groups, gn_eps).reshape(x.shape)
+        x = _conv2d_nhwc(gelu_tanh(h), ck, cb, 1, same=True)
+    x = x + pooled                                                             # :170 (shapes agree: no projection of the residual)
+    tok = x.reshape(B, N, n, -1) @ p["dense_kernel"].astype(np.float32) + p["dense_bias"].astype(np.float32)
+    rt, ct = patch_position_tokens(H, patch_size, position_interval)
+    return (tok + p["row_embedding"].astype(np.float32)[rt] + p["col_embedding"].astype(np.float32)[ct]).astype(np.float32)
+
+
+def image_tokenizer_params_from_flax(tree: dict, num_blocks: int) -> dict:
+    """Flax parameter tree of ImageTokenizer (setup-style children named by attribute / explicit `name`, ResNetV2Block's
+    compact children auto-named Conv_i / GroupNorm_i / Dense_0) -> the dict image_tokenizer_fwd takes."""
+    ef = tree["embedding_function"]
+    g = lambda a: np.asarray(a, np.float32)  # noqa: E731
+    return dict(conv0_kernel=g(ef["Conv_0"]["kernel"]), conv0_bias=g(ef["Conv_0"]["bias"]),
+                blocks=[(g(ef[f"GroupNorm_{i}"]["scale"]), g(ef[f"GroupNorm_{i}"]["bias"]), g(ef[f"Conv_{i + 1}"]["kernel"]),
+                         g(ef[f"Conv_{i + 1}"]["bias"])) for i in range(num_blocks)],
+                dense_kernel=g(ef["Dense_0"]["kernel"]), dense_bias=g(ef["Dense_0"]["bias"]),
+                row_embedding=g(tree["image_row_position_embedding"]["embedding"]),
+                col_embedding=g(tree["image_col_position_embedding"]["embedding"]))

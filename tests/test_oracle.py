@@ -239,3 +239,35 @@ def test_block_and_stack_follow_the_reference_control_flow(name):
     assert rel(y.numpy(), EB[f"{name}/y"]) <= 2e-5
     assert rel(y1.numpy(), EB[f"{name}/y_block0"]) <= 2e-5
     assert float(size.min()) == 1.0 == float(size.max())
+
+
+def _golden_tree(Z, prefix):
+    """rebuild the nested parameter dict stored under `prefix/...` keys of an .npz"""
+    tree = {}
+    for k in Z.files:
+        if k.startswith(prefix + "/"):
+            node = tree
+            parts = k[len(prefix) + 1:].split("/")
+            for q in parts[:-1]:
+                node = node.setdefault(q, {})
+            node[parts[-1]] = Z[k]
+    return tree
+
+
+@pytest.mark.parametrize("name", ["two_frames", "nine_patches_one_block", "group_size_one_raw_pixels"])
+def test_image_tokenizer_oracle_matches_the_executed_reference(name):
+    """oracle.image_to_patches / patch_position_tokens / image_tokenizer_fwd against fixtures made by executing the reference's
+    image_tokenizer.py (image_to_patches, encode_patch_position with train=False, ResNetV2Block, ImageTokenizer) under the
+    shim: patches and position tokens bit for bit, tokens to 2e-5 (fp32 sums in a different order)."""
+    Z = np.load(os.path.join(GOLD, "image_tokenizer.npz"))
+    B, N, H, P, Cin, F, G, E, PI, NB, norm = [int(v) for v in Z[f"{name}/meta"]]
+    img = Z[f"{name}/image"]
+    np.testing.assert_array_equal(O.image_to_patches(img[0, 0].astype(np.float32), P, bool(norm)), Z[f"{name}/patches00"])
+    rt, ct = O.patch_position_tokens(H, P, PI)
+    np.testing.assert_array_equal(rt, Z[f"{name}/row_tokens"])
+    np.testing.assert_array_equal(ct, Z[f"{name}/col_tokens"])
+    p = O.image_tokenizer_params_from_flax(_golden_tree(Z, f"{name}/params"), NB)
+    got = O.image_tokenizer_fwd(p, img.astype(np.float32), patch_size=P, position_interval=PI, num_groups=G, normalize=bool(norm))
+    want = Z[f"{name}/out"]
+    assert got.shape == want.shape == (B, N, (H // P) ** 2, E)
+    assert np.abs(got - want).max() <= 2e-5 * max(1.0, np.abs(want).max())
