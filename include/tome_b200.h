@@ -26,10 +26,10 @@
 extern "C" {
 #endif
 
-#define TOME_ABI_VERSION 11
+#define TOME_ABI_VERSION 12
 
 enum tome_status { TOME_OK = 0, TOME_ERR_INVALID = 1, TOME_ERR_CUDA = 2, TOME_ERR_UNSUPPORTED = 3 };
-enum tome_dtype { TOME_BF16 = 0, TOME_F32 = 1 };
+enum tome_dtype { TOME_BF16 = 0, TOME_F32 = 1, TOME_U8 = 2 /* raw pixels: image front end only */ };
 enum tome_major { TOME_MAJOR_K = 0, TOME_MAJOR_MN = 1 };
 enum tome_merge_mode { TOME_MERGE_SUM = 0, TOME_MERGE_WAVG = 1 };
 
@@ -449,6 +449,51 @@ const int32_t* tome_stack_layer_node_idx(const tome_stack_cfg_t* cfg, const tome
 /* u32 [B * T_out(layer), ceil(mlp_dim / 32)]: bit j of word w = element 32 w + j of MLP-1's output survived ReLU (and hidden
  * dropout), i.e. the gate the MLP backward of attention.py:32-34 uses; lets a checker take the SAME gate decisions. */
 const uint32_t* tome_stack_layer_relu_bits(const tome_stack_cfg_t* cfg, const tome_stack_io_t* io, int layer);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 7b. Image patch-embed front end (forward)   tokenizers/images/image_tokenizer.py:35-71 (image_to_patches), :74-140
+ *     (encode_patch_position), :148-190 (ResNetV2Block), :216-309 (ImageTokenizer); config form of
+ *     model_configs/tokenizers/images/gato_resnet.yaml.  SURVEY.md 8(f) rank 4: the compute ahead of the block.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int batch, n_images;   /* images [B, N, H, W, C_in], square */
+  int image_size;        /* H = W, a multiple of patch_size */
+  int channels_in;
+  int image_dtype;       /* TOME_U8 (raw pixels 0..255) or TOME_F32 (the reference's float pixels) */
+  int normalize;         /* 2 * (x / 255) - 1 before the first convolution (image_tokenizer.py:67) */
+  int patch_size;        /* patches in row-major (h, w) order, each embedded on its own */
+  int conv_kernel, conv_stride;   /* input convolution, padding VALID (gato_resnet.yaml: 12, 2) */
+  int features;          /* channels of every convolution (64); a multiple of 8 and of num_groups */
+  int pool_window;       /* max pool, stride 1, VALID (3) */
+  int num_blocks;        /* x [GroupNorm -> gelu(tanh) -> Conv 3x3 SAME]; the pooled tensor is added back after the last */
+  int num_groups;        /* GroupNorm groups (32).  Flax semantics: the statistics of a group run over EVERY axis but the
+                            batch one, i.e. over the N images, all patches, H, W and the group's channels of a batch row */
+  float gn_eps;
+  int embed_dim;         /* output Dense features (768); a multiple of 8 */
+  int position_interval; /* rows of the two position-embedding tables */
+  int token_rows;        /* position tokens are given per patch for every image alike (1: evaluation mode, the interval
+                            midpoints) or per (batch row, image) (batch * n_images: training mode, sampled by the caller) */
+  int out_dtype;         /* TOME_BF16 or TOME_F32 */
+  int chunk_rows;        /* batch rows processed per pass (bounds the workspace); 0 = the library chooses (~1 GiB of im2col rows).
+                            GroupNorm statistics are per batch row, so the result does not depend on it */
+} tome_image_tokenizer_desc_t;
+
+/* Flat parameter vector (f32 master and bf16 working copy, same offsets): conv0 kernel [k*k*C_in, F] (= Flax [k, k, C_in, F]),
+ * conv0 bias [F]; per block: GroupNorm scale [F], bias [F], conv kernel [9F, F], conv bias [F]; dense kernel [o*o*F, E],
+ * dense bias [E]; row embedding [P, E]; column embedding [P, E]   (o = (patch - k) / stride + 1 - (pool_window - 1)). */
+enum tome_image_tokenizer_param { TOME_IT_CONV0_KERNEL = 0, TOME_IT_CONV0_BIAS, TOME_IT_DENSE_KERNEL, TOME_IT_DENSE_BIAS,
+                                  TOME_IT_ROW_EMBED, TOME_IT_COL_EMBED,
+                                  TOME_IT_BLOCK0 = 16 /* + 4 * block + {0: gn scale, 1: gn bias, 2: conv kernel, 3: conv bias} */ };
+long long tome_image_tokenizer_param_count(const tome_image_tokenizer_desc_t* desc);
+long long tome_image_tokenizer_param_offset(const tome_image_tokenizer_desc_t* desc, int which);
+size_t tome_image_tokenizer_workspace_bytes(const tome_image_tokenizer_desc_t* desc);
+/* out [B, N, n_patches, E] = ImageTokenizer(image).  row_tokens / col_tokens: i32 [token_rows, n_patches] indices into the
+ * embedding tables (evaluation mode: image_tokenizer.py:111-113; the Python mirror computes them).  The convolutions and the
+ * Dense run on the tcgen05 GEMM (im2col rows written by the preceding normalise / activate kernel), bf16 activations, fp32
+ * accumulation.  workspace: 256-byte aligned, tome_image_tokenizer_workspace_bytes(desc) bytes. */
+int tome_image_tokenizer_fwd(const tome_image_tokenizer_desc_t* desc, const void* image, const float* params_f32,
+                             const void* params_bf16, const int32_t* row_tokens, const int32_t* col_tokens, void* out,
+                             void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * 8. Launch accounting and per-op timing (measurement aid; off by default, never on the product path's hot loop)

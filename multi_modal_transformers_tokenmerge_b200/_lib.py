@@ -12,10 +12,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, f"libtome_b200{os.environ.get('TOME_LIB_SUFFIX', '')}.so")   # suffix: experimental A/B builds (build.py)
 
 TOME_OK, TOME_ERR_INVALID, TOME_ERR_CUDA, TOME_ERR_UNSUPPORTED = 0, 1, 2, 3
-TOME_BF16, TOME_F32 = 0, 1
+TOME_BF16, TOME_F32, TOME_U8 = 0, 1, 2
 TOME_MAJOR_K, TOME_MAJOR_MN = 0, 1
 TOME_MERGE_SUM, TOME_MERGE_WAVG = 0, 1
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 vp, ll, i32, f32, u64, u32 = C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_uint64, C.c_uint32
 
@@ -100,6 +100,16 @@ DIFFUSION_PARAMS = ["fourier_kernel", "tw1", "tb1", "tw2", "tb2", "w1", "b1", "w
 HEAD_CONTINUOUS_L2, HEAD_CATEGORICAL_CE = 0, 1
 
 
+class ImageTokenizerDesc(C.Structure):
+    _fields_ = [("batch", i32), ("n_images", i32), ("image_size", i32), ("channels_in", i32), ("image_dtype", i32),
+                ("normalize", i32), ("patch_size", i32), ("conv_kernel", i32), ("conv_stride", i32), ("features", i32),
+                ("pool_window", i32), ("num_blocks", i32), ("num_groups", i32), ("gn_eps", f32), ("embed_dim", i32),
+                ("position_interval", i32), ("token_rows", i32), ("out_dtype", i32), ("chunk_rows", i32)]
+
+
+IT_CONV0_KERNEL, IT_CONV0_BIAS, IT_DENSE_KERNEL, IT_DENSE_BIAS, IT_ROW_EMBED, IT_COL_EMBED, IT_BLOCK0 = 0, 1, 2, 3, 4, 5, 16
+
+
 class HeadDesc(C.Structure):
     _fields_ = [("batch", i32), ("tokens", i32), ("channels", i32), ("x_dtype", i32), ("n_readout", i32),
                 ("groups", i32), ("features", i32), ("kind", i32), ("max_action", f32)]
@@ -131,11 +141,13 @@ def lib() -> C.CDLL:
         if L.tome_abi_version() != ABI_VERSION:
             raise ImportError(f"libtome_b200.so has ABI {L.tome_abi_version()}, python binding expects {ABI_VERSION}: rebuild")
         for name in ("tome_gemm_workspace_bytes", "tome_stack_workspace_bytes", "tome_attention_workspace_bytes", "tome_sim_argmax_workspace_bytes",
-                     "tome_attention_bwd_workspace_bytes", "tome_action_head_workspace_bytes", "tome_diffusion_head_workspace_bytes"):
+                     "tome_attention_bwd_workspace_bytes", "tome_action_head_workspace_bytes", "tome_diffusion_head_workspace_bytes",
+                     "tome_image_tokenizer_workspace_bytes"):
             if hasattr(L, name):
                 getattr(L, name).restype = C.c_size_t
         for name in ("tome_stack_param_count", "tome_stack_layer_offset", "tome_stack_head_offset", "tome_launch_count",
-                     "tome_diffusion_head_param_count", "tome_diffusion_head_param_offset"):
+                     "tome_diffusion_head_param_count", "tome_diffusion_head_param_offset",
+                     "tome_image_tokenizer_param_count", "tome_image_tokenizer_param_offset"):
             if hasattr(L, name):
                 getattr(L, name).restype = ll
         for name in ("tome_stack_final_x", "tome_stack_final_size", "tome_stack_layer_edge_idx", "tome_stack_layer_dst_idx",
@@ -178,6 +190,10 @@ def lib() -> C.CDLL:
             "tome_diffusion_head_workspace_bytes": [P(DiffusionDesc)],
             "tome_diffusion_head_fwd": [P(DiffusionDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp],
             "tome_diffusion_head_bwd": [P(DiffusionDesc), vp, vp, vp, vp, vp, vp, vp, vp],
+            "tome_image_tokenizer_param_count": [P(ImageTokenizerDesc)],
+            "tome_image_tokenizer_param_offset": [P(ImageTokenizerDesc), i32],
+            "tome_image_tokenizer_workspace_bytes": [P(ImageTokenizerDesc)],
+            "tome_image_tokenizer_fwd": [P(ImageTokenizerDesc), vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp],
             "tome_adamw_step": [ll, vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, f32, i32, vp],
             "tome_cast_f32_to_bf16": [ll, vp, vp, vp],
             "tome_launch_count": [i32],

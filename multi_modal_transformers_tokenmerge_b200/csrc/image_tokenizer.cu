@@ -1,0 +1,452 @@
+// K12: image patch-embed front end (forward).   tokenizers/images/image_tokenizer.py:35-71 (image_to_patches), :74-140
+// (encode_patch_position), :148-190 (ResNetV2Block), :216-309 (ImageTokenizer); SURVEY.md 8(f) rank 4.
+//
+//   image [B, N, H, W, C_in] -> patches (p x p, row-major) -> Conv k x k / stride s VALID -> max pool w x w / 1 VALID
+//   -> num_blocks x [GroupNorm -> gelu(tanh) -> Conv 3x3 SAME] -> + pooled -> flatten (h, w, c) -> Dense -> + row / column
+//   position embeddings -> tokens [B, N, n_patches, E].
+//
+// The three contractions (input convolution, block convolutions, Dense) run on the tcgen05 GEMM of gemm.cu with bf16
+// operands and fp32 accumulation; the kernels here produce their A operands and consume their outputs:
+//   it_im2col0_kernel      pixels (u8 / f32) -> normalise -> im2col rows [M0, k*k*C_in] bf16 (patch extraction is index
+//                          arithmetic: no patch tensor is ever written)
+//   it_pool_kernel         conv0 output [.., o1, o1, F] -> max over w x w windows -> [.., o2, o2, F]
+//   it_gn_partial_kernel / it_gn_final_kernel   GroupNorm statistics.  Flax's GroupNorm reduces over EVERY axis but the
+//                          batch one, so a (batch row, group) statistic spans all N images and all patches of that row:
+//                          per-CTA per-channel partial sums in a fixed order, then one thread per (row, group)
+//   it_gn_gelu_im2col_kernel   (x - mean) * rstd * scale + bias -> gelu -> the nine shifted copies of the 3x3 SAME
+//                          im2col row, zero outside the o2 x o2 window; one 16-byte store per thread
+//   it_posadd_kernel       Dense output + row_embedding[row_token] + col_embedding[col_token] -> out dtype
+// The last block convolution adds the pooled tensor through the GEMM's residual epilogue (image_tokenizer.py:170) and
+// the flatten is free ([.., o2, o2, F] rows ARE the Dense's K-major A operand).  HBM-bound: the im2col rows dominate the
+// traffic (k*k*C_in / (s*s*C_in) = 36x the pixels for the input convolution, 9x the activations for the blocks); the
+// batch is processed in chunks of whole batch rows so the im2col buffer stays near 1 GiB whatever the batch.
+#include <algorithm>
+
+#include "common.cuh"
+#include "host_util.h"
+
+namespace tome {
+
+constexpr int IT_THREADS = 256;
+constexpr int IT_GN_MAX_CTAS = 64;      // CTAs per batch row in the statistics pass
+constexpr size_t IT_COL_TARGET = (size_t)1 << 30;   // im2col buffer target per chunk of batch rows
+
+struct ItGeom {
+  int ppd, np;          // patches per image side / per image
+  int o1, o2;           // side after the input convolution / after the pool
+  int k0;               // k*k*C_in
+  int kd;               // o2*o2*F (Dense fan-in)
+  long long imgs;       // B*N
+  int chunk_rows;       // batch rows per chunk
+  int gn_ctas;
+  // workspace offsets (bytes) of one chunk
+  size_t off_col, off_y0, off_pool, off_xa, off_xb, off_dense, off_part, off_stats, total;
+};
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static int it_geometry(const tome_image_tokenizer_desc_t* d, ItGeom* g, const char* who) {
+  TOME_CHECK(d != nullptr, TOME_ERR_INVALID, "%s: null descriptor", who);
+  TOME_CHECK(d->batch > 0 && d->n_images > 0 && d->image_size > 0 && d->channels_in > 0, TOME_ERR_INVALID, "%s: bad image shape", who);
+  TOME_CHECK(d->patch_size > 0 && d->image_size % d->patch_size == 0, TOME_ERR_INVALID,
+             "%s: image_size (%d) must be a multiple of patch_size (%d) (image_tokenizer.py:52)", who, d->image_size, d->patch_size);
+  TOME_CHECK(d->image_dtype == TOME_U8 || d->image_dtype == TOME_F32, TOME_ERR_INVALID, "%s: image_dtype must be u8 or f32", who);
+  TOME_CHECK(d->out_dtype == TOME_BF16 || d->out_dtype == TOME_F32, TOME_ERR_INVALID, "%s: out_dtype must be bf16 or f32", who);
+  TOME_CHECK(d->conv_kernel > 0 && d->conv_stride > 0 && d->patch_size >= d->conv_kernel, TOME_ERR_INVALID,
+             "%s: the input convolution (%d, stride %d) does not fit a %d-pixel patch", who, d->conv_kernel, d->conv_stride, d->patch_size);
+  TOME_CHECK(d->pool_window >= 1, TOME_ERR_INVALID, "%s: pool_window must be >= 1", who);
+  TOME_CHECK(d->num_blocks >= 1, TOME_ERR_UNSUPPORTED, "%s: num_blocks must be >= 1", who);
+  TOME_CHECK(d->features > 0 && d->features % 8 == 0 && d->features <= 2048, TOME_ERR_UNSUPPORTED,
+             "%s: features (%d) must be a multiple of 8, at most 2048", who, d->features);
+  TOME_CHECK(d->num_groups > 0 && d->features % d->num_groups == 0, TOME_ERR_INVALID,
+             "%s: features (%d) must be a multiple of num_groups (%d)", who, d->features, d->num_groups);
+  TOME_CHECK(d->embed_dim > 0 && d->embed_dim % 8 == 0, TOME_ERR_UNSUPPORTED, "%s: embed_dim (%d) must be a multiple of 8", who, d->embed_dim);
+  TOME_CHECK(d->position_interval > 0, TOME_ERR_INVALID, "%s: position_interval must be positive", who);
+  TOME_CHECK(d->token_rows == 1 || d->token_rows == d->batch * d->n_images, TOME_ERR_INVALID,
+             "%s: token_rows must be 1 or batch * n_images (got %d)", who, d->token_rows);
+  g->ppd = d->image_size / d->patch_size;
+  g->np = g->ppd * g->ppd;
+  g->o1 = (d->patch_size - d->conv_kernel) / d->conv_stride + 1;
+  g->o2 = g->o1 - (d->pool_window - 1);
+  TOME_CHECK(g->o2 >= 1, TOME_ERR_INVALID, "%s: a %d-wide pool does not fit the %d x %d convolution output", who, d->pool_window, g->o1, g->o1);
+  g->k0 = d->conv_kernel * d->conv_kernel * d->channels_in;
+  TOME_CHECK(g->k0 % 8 == 0, TOME_ERR_UNSUPPORTED, "%s: conv_kernel^2 * channels_in (%d) must be a multiple of 8", who, g->k0);
+  g->kd = g->o2 * g->o2 * d->features;
+  g->imgs = (long long)d->batch * d->n_images;
+  const long long m0_row = (long long)d->n_images * g->np * g->o1 * g->o1;   // im2col rows per batch row
+  const long long m2_row = (long long)d->n_images * g->np * g->o2 * g->o2;
+  const size_t col_row = 2 * (size_t)std::max(m0_row * g->k0, m2_row * 9 * d->features);
+  long long cr = (long long)(IT_COL_TARGET / col_row);
+  TOME_CHECK(d->chunk_rows >= 0, TOME_ERR_INVALID, "%s: chunk_rows must be >= 0", who);
+  if (d->chunk_rows > 0) cr = d->chunk_rows;
+  if (cr < 1) cr = 1;
+  if (cr > d->batch) cr = d->batch;
+  TOME_CHECK(m0_row * cr < (1ll << 31) && m2_row * cr * 9 * (d->features / 8) < (1ll << 40), TOME_ERR_UNSUPPORTED, "%s: batch row too large", who);
+  g->chunk_rows = (int)cr;
+  long long want = m2_row * (d->features / 8) / (IT_THREADS * 4);
+  g->gn_ctas = (int)std::min<long long>(IT_GN_MAX_CTAS, std::max<long long>(1, want));
+  size_t o = 0;
+  g->off_col = o;   o += align256(col_row * cr);
+  g->off_y0 = o;    o += align256((size_t)2 * m0_row * cr * d->features);
+  g->off_pool = o;  o += align256((size_t)2 * m2_row * cr * d->features);
+  g->off_xa = o;    o += align256((size_t)2 * m2_row * cr * d->features);
+  g->off_xb = o;    o += align256((size_t)2 * m2_row * cr * d->features);
+  g->off_dense = o; o += align256((size_t)4 * cr * d->n_images * g->np * d->embed_dim);
+  g->off_part = o;  o += align256((size_t)4 * cr * g->gn_ctas * d->features * 2);
+  g->off_stats = o; o += align256((size_t)4 * cr * d->num_groups * 2);
+  g->total = o;
+  return TOME_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// pixels -> im2col rows of the input convolution.  Row m = ((img * np + patch) * o1 + oy) * o1 + ox, column
+// (dy * k + dx) * C_in + c  <-  image[img, py * p + oy * s + dy, px * p + ox * s + dx, c]: for one dy the (dx, c) run
+// is contiguous in the image.  One thread writes 8 consecutive columns (16 bytes).
+template <typename PixT>
+__global__ void __launch_bounds__(IT_THREADS)
+it_im2col0_kernel(const PixT* __restrict__ image, __nv_bfloat16* __restrict__ col, long long n_vec, int k0, int np, int ppd,
+                  int o1, int psize, int stride, int kw_c /* k * C_in */, int img_w_c /* W * C_in */, int c_in, int normalize) {
+  pdl_prologue();
+  const long long v = (long long)blockIdx.x * IT_THREADS + threadIdx.x;
+  if (v >= n_vec) return;
+  const int vpr = k0 >> 3;
+  const long long m = v / vpr;
+  const int kk = (int)(v - m * vpr) << 3;
+  const int ox = (int)(m % o1);
+  long long t = m / o1;
+  const int oy = (int)(t % o1);
+  t /= o1;
+  const int patch = (int)(t % np);
+  const long long img = t / np;
+  const int py = patch / ppd, px = patch - py * ppd;
+  const PixT* base = image + img * (long long)(img_w_c / c_in) * img_w_c   // H == W
+                     + (long long)(py * psize + oy * stride) * img_w_c + (long long)(px * psize + ox * stride) * c_in;
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = kk + j;
+    const int dy = k / kw_c, rem = k - dy * kw_c;
+    float x = (float)base[(long long)dy * img_w_c + rem];
+    if (normalize) x = 2.0f * __fdiv_rn(x, 255.0f) - 1.0f;   // image_tokenizer.py:67
+    f[j] = x;
+  }
+  uint4 o;
+  o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+  st_na_v4(col + v * 8, o);
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+
+// max pool, stride 1, VALID (flax.linen.max_pool).  Thread = (output pixel, 8 channels).
+__global__ void __launch_bounds__(IT_THREADS)
+it_pool_kernel(const __nv_bfloat16* __restrict__ y0, __nv_bfloat16* __restrict__ pooled, long long n_vec, int nchunk, int o1,
+               int o2, int window) {
+  pdl_prologue();
+  const long long v = (long long)blockIdx.x * IT_THREADS + threadIdx.x;
+  if (v >= n_vec) return;
+  const int c = (int)(v % nchunk);
+  long long t = v / nchunk;
+  const int ox = (int)(t % o2);
+  t /= o2;
+  const int oy = (int)(t % o2);
+  const long long ip = t / o2;
+  const int F = nchunk << 3;
+  const __nv_bfloat16* src = y0 + ((ip * o1 + oy) * o1 + ox) * F + (c << 3);
+  float best[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) best[j] = -INFINITY;
+  for (int dy = 0; dy < window; ++dy)
+    for (int dx = 0; dx < window; ++dx) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(src + ((long long)dy * o1 + dx) * F), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) best[j] = fmaxf(best[j], f[j]);
+    }
+  uint4 o;
+  o.x = pack_bf16(best[0], best[1]); o.y = pack_bf16(best[2], best[3]); o.z = pack_bf16(best[4], best[5]); o.w = pack_bf16(best[6], best[7]);
+  *reinterpret_cast<uint4*>(pooled + v * 8) = o;
+}
+
+// GroupNorm statistics, stage 1: x [rows_b, R, F] bf16; CTA (j, b) sums x and x^2 per CHANNEL over its slice of the R rows
+// of batch row b -> part [rows_b, gridDim.x, F, 2].  Thread = (8-channel chunk, row lane); lanes are added in lane order.
+__global__ void __launch_bounds__(IT_THREADS)
+it_gn_partial_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ part, long long R, int nchunk) {
+  pdl_prologue();
+  __shared__ float sm[2][IT_THREADS * 8];
+  const int F = nchunk << 3;
+  const int lanes = blockDim.x / nchunk;
+  const int c = threadIdx.x % nchunk, rl = threadIdx.x / nchunk;
+  const long long r0 = R * blockIdx.x / gridDim.x, r1 = R * (blockIdx.x + 1) / gridDim.x;
+  const __nv_bfloat16* xb = x + (long long)blockIdx.y * R * F + (c << 3);
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  for (long long r = r0 + rl; r < r1; r += lanes) {
+    float f[8];
+    unpack8(ld_nc_v4(xb + r * F), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] = fmaf(f[j], f[j], q[j]); }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sm[0][rl * F + (c << 3) + j] = s[j];
+    sm[1][rl * F + (c << 3) + j] = q[j];
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < F; ch += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int l = 0; l < lanes; ++l) { a += sm[0][l * F + ch]; b += sm[1][l * F + ch]; }
+    float* o = part + (((long long)blockIdx.y * gridDim.x + blockIdx.x) * F + ch) * 2;
+    o[0] = a; o[1] = b;
+  }
+}
+
+// stage 2: thread = (batch row, group): the CTA partials of the group's channels added in (CTA, channel) order ->
+// stats [rows_b, G, 2] = (mean, 1 / sqrt(var + eps)), var = E[x^2] - mean^2 clamped at 0 (Flax's fast variance).
+__global__ void it_gn_final_kernel(const float* __restrict__ part, float* __restrict__ stats, int rows_b, int n_ctas, int F,
+                                   int G, long long R, float eps) {
+  pdl_prologue();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows_b * G) return;
+  const int b = i / G, g = i - b * G, cg = F / G;
+  float s = 0.f, q = 0.f;
+  for (int j = 0; j < n_ctas; ++j) {
+    const float* p = part + (((long long)b * n_ctas + j) * F + g * cg) * 2;
+    for (int ch = 0; ch < cg; ++ch) { s += p[2 * ch]; q += p[2 * ch + 1]; }
+  }
+  const float inv_n = 1.0f / ((float)R * (float)cg);
+  const float mean = s * inv_n;
+  const float var = fmaxf(q * inv_n - mean * mean, 0.f);
+  stats[2 * i] = mean;
+  stats[2 * i + 1] = 1.0f / sqrtf(var + eps);
+}
+
+__device__ __forceinline__ float gelu_tanh(float x) {   // flax.linen.gelu, approximate=True
+  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  const float t = 1.0f - 2.0f / (1.0f + __expf(2.0f * u));   // tanh(u); saturates cleanly at +-1
+  return 0.5f * x * (1.0f + t);
+}
+
+// GroupNorm -> gelu -> im2col rows of the 3x3 SAME convolution.  Thread = (pixel, tap, 8 channels): output vector index
+// == thread index, so the stores are one contiguous stream; the activation is recomputed for each of the nine taps that
+// read a pixel (exp on the SFU, far below the store bandwidth this kernel is bound by).
+__global__ void __launch_bounds__(IT_THREADS)
+it_gn_gelu_im2col_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ scale,
+                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ col, long long n_vec, int nchunk, int o2,
+                         long long pix_per_row /* N * np * o2 * o2 */, int G) {
+  pdl_prologue();
+  const long long v = (long long)blockIdx.x * IT_THREADS + threadIdx.x;
+  if (v >= n_vec) return;
+  const int c = (int)(v % nchunk);
+  long long t = v / nchunk;
+  const int tap = (int)(t % 9);
+  const long long m = t / 9;
+  const int ox = (int)(m % o2), oy = (int)((m / o2) % o2);
+  const int sy = oy + tap / 3 - 1, sx = ox + tap % 3 - 1;
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  if (sy >= 0 && sy < o2 && sx >= 0 && sx < o2) {
+    const int F = nchunk << 3, cg = F / G;
+    const long long ms = m + (long long)(sy - oy) * o2 + (sx - ox);
+    const int b = (int)(m / pix_per_row);
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + ms * F + (c << 3)), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ch = (c << 3) + j;
+      const float* st = stats + 2 * ((long long)b * G + ch / cg);
+      f[j] = gelu_tanh((f[j] - st[0]) * st[1] * __ldg(scale + ch) + __ldg(bias + ch));
+    }
+    o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+  }
+  st_na_v4(col + v * 8, o);
+}
+
+// tokens + row / column position embeddings (image_tokenizer.py:296-305), 4 features per thread.
+__global__ void __launch_bounds__(IT_THREADS)
+it_posadd_kernel(const float* __restrict__ dense, const float* __restrict__ row_emb, const float* __restrict__ col_emb,
+                 const int32_t* __restrict__ row_tok, const int32_t* __restrict__ col_tok, void* __restrict__ out, long long n_vec,
+                 int E, int np, long long img0, int per_image_tokens, int P, int out_bf16) {
+  pdl_prologue();
+  const long long v = (long long)blockIdx.x * IT_THREADS + threadIdx.x;
+  if (v >= n_vec) return;
+  const int e4 = E >> 2;
+  const long long m = v / e4;
+  const int e = (int)(v - m * e4) << 2;
+  const int p = (int)(m % np);
+  const long long ti = (per_image_tokens ? (img0 + m / np) * np : 0) + p;
+  int rt = row_tok[ti], ct = col_tok[ti];
+  rt = min(max(rt, 0), P - 1);   // jnp indexing clamps out-of-range indices
+  ct = min(max(ct, 0), P - 1);
+  const float4 d = *reinterpret_cast<const float4*>(dense + m * E + e);
+  const float4 r = *reinterpret_cast<const float4*>(row_emb + (long long)rt * E + e);
+  const float4 c = *reinterpret_cast<const float4*>(col_emb + (long long)ct * E + e);
+  const float4 y = make_float4((d.x + r.x) + c.x, (d.y + r.y) + c.y, (d.z + r.z) + c.z, (d.w + r.w) + c.w);
+  if (out_bf16) {
+    uint2 w = make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + m * E + e) = w;
+  } else {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + m * E + e) = y;
+  }
+}
+
+static long long it_offset(const tome_image_tokenizer_desc_t* d, const ItGeom& g, int which) {
+  const long long F = d->features, E = d->embed_dim, P = d->position_interval;
+  const long long conv0 = (long long)g.k0 * F + F;
+  const long long block = 2 * F + 9 * F * F + F;
+  const long long blocks_end = conv0 + block * d->num_blocks;
+  switch (which) {
+    case TOME_IT_CONV0_KERNEL: return 0;
+    case TOME_IT_CONV0_BIAS: return (long long)g.k0 * F;
+    case TOME_IT_DENSE_KERNEL: return blocks_end;
+    case TOME_IT_DENSE_BIAS: return blocks_end + (long long)g.kd * E;
+    case TOME_IT_ROW_EMBED: return blocks_end + (long long)g.kd * E + E;
+    case TOME_IT_COL_EMBED: return blocks_end + (long long)g.kd * E + E + P * E;
+    default: break;
+  }
+  if (which >= TOME_IT_BLOCK0 && which < TOME_IT_BLOCK0 + 4 * d->num_blocks) {
+    const int b = (which - TOME_IT_BLOCK0) / 4, f = (which - TOME_IT_BLOCK0) % 4;
+    const long long base = conv0 + block * b;
+    return base + (f == 0 ? 0 : f == 1 ? F : f == 2 ? 2 * F : 2 * F + 9 * F * F);
+  }
+  return -1;
+}
+
+}  // namespace tome
+
+using namespace tome;
+
+extern "C" long long tome_image_tokenizer_param_count(const tome_image_tokenizer_desc_t* d) {
+  clear_error();
+  ItGeom g;
+  if (it_geometry(d, &g, "image_tokenizer_param_count") != TOME_OK) return -1;
+  return it_offset(d, g, TOME_IT_COL_EMBED) + (long long)d->position_interval * d->embed_dim;
+}
+
+extern "C" long long tome_image_tokenizer_param_offset(const tome_image_tokenizer_desc_t* d, int which) {
+  clear_error();
+  ItGeom g;
+  if (it_geometry(d, &g, "image_tokenizer_param_offset") != TOME_OK) return -1;
+  const long long o = it_offset(d, g, which);
+  if (o < 0) set_error(TOME_ERR_INVALID, "image_tokenizer_param_offset: no parameter %d", which);
+  return o;
+}
+
+extern "C" size_t tome_image_tokenizer_workspace_bytes(const tome_image_tokenizer_desc_t* d) {
+  clear_error();
+  ItGeom g;
+  if (it_geometry(d, &g, "image_tokenizer_workspace_bytes") != TOME_OK) return 0;
+  return g.total;
+}
+
+static int it_gemm(int m, int n, int k, const void* a, const void* b, void* c, int c_dtype, const float* bias, const void* residual,
+                   cudaStream_t stream) {
+  tome_gemm_args_t ga;
+  memset(&ga, 0, sizeof(ga));
+  ga.m = m; ga.n = n; ga.k = k;
+  ga.a = a; ga.lda = k; ga.a_major = TOME_MAJOR_K;
+  ga.b = b; ga.ldb = n; ga.b_major = TOME_MAJOR_MN;    // the Flax kernel layout [in, out] as is
+  ga.c = c; ga.ldc = n; ga.c_dtype = c_dtype;
+  ga.bias = bias;
+  ga.residual = residual; ga.ldr = n;
+  ga.k_splits = 1;
+  return tome_gemm_bf16(&ga, nullptr, 0, stream);
+}
+
+extern "C" int tome_image_tokenizer_fwd(const tome_image_tokenizer_desc_t* d, const void* image, const float* pf, const void* pb_,
+                                        const int32_t* row_tokens, const int32_t* col_tokens, void* out, void* workspace,
+                                        size_t workspace_bytes, void* stream_) {
+  clear_error();
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ItGeom g;
+  int rc = it_geometry(d, &g, "image_tokenizer_fwd");
+  if (rc != TOME_OK) return rc;
+  TOME_CHECK(image && pf && pb_ && row_tokens && col_tokens && out && workspace, TOME_ERR_INVALID, "image_tokenizer_fwd: null argument");
+  TOME_CHECK(workspace_bytes >= g.total, TOME_ERR_INVALID, "image_tokenizer_fwd: workspace too small (%zu < %zu)", workspace_bytes, g.total);
+  TOME_CHECK((((uintptr_t)workspace) & 255) == 0 && (((uintptr_t)pb_ | (uintptr_t)pf | (uintptr_t)out) & 15) == 0, TOME_ERR_INVALID,
+             "image_tokenizer_fwd: workspace must be 256-byte aligned, parameters / out 16-byte aligned");
+  const __nv_bfloat16* pb = reinterpret_cast<const __nv_bfloat16*>(pb_);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  __nv_bfloat16* col = reinterpret_cast<__nv_bfloat16*>(ws + g.off_col);
+  __nv_bfloat16* y0 = reinterpret_cast<__nv_bfloat16*>(ws + g.off_y0);
+  __nv_bfloat16* pooled = reinterpret_cast<__nv_bfloat16*>(ws + g.off_pool);
+  __nv_bfloat16* xbuf[2] = {reinterpret_cast<__nv_bfloat16*>(ws + g.off_xa), reinterpret_cast<__nv_bfloat16*>(ws + g.off_xb)};
+  float* dense = reinterpret_cast<float*>(ws + g.off_dense);
+  float* part = reinterpret_cast<float*>(ws + g.off_part);
+  float* stats = reinterpret_cast<float*>(ws + g.off_stats);
+  const int F = d->features, E = d->embed_dim, nchunk = F / 8;
+  const int gn_threads = nchunk * std::max(1, IT_THREADS / nchunk);
+  const long long pix_img = (long long)d->image_size * d->image_size * d->channels_in;
+  const size_t pix_bytes = d->image_dtype == TOME_U8 ? 1 : 4;
+  const size_t out_bytes = d->out_dtype == TOME_BF16 ? 2 : 4;
+  auto nblk = [](long long n) { return (unsigned)((n + IT_THREADS - 1) / IT_THREADS); };
+
+  for (int b0 = 0; b0 < d->batch; b0 += g.chunk_rows) {
+    const int rows_b = std::min(g.chunk_rows, d->batch - b0);
+    const long long imgs = (long long)rows_b * d->n_images, img0 = (long long)b0 * d->n_images;
+    const long long m0 = imgs * g.np * g.o1 * g.o1, m2 = imgs * g.np * g.o2 * g.o2, mt = imgs * g.np;
+    const long long R = (long long)d->n_images * g.np * g.o2 * g.o2;   // rows of one batch row in the GroupNorm reduction
+    const uint8_t* img = reinterpret_cast<const uint8_t*>(image) + (size_t)img0 * pix_img * pix_bytes;
+    {
+      const long long nv = m0 * (g.k0 / 8);
+      ProfScope prof(PROF_OTHER, (double)nv * 16, 1, stream);
+      if (d->image_dtype == TOME_U8)
+        launch_k(it_im2col0_kernel<uint8_t>, nblk(nv), IT_THREADS, 0, stream, img, col, nv, g.k0, g.np, g.ppd, g.o1, d->patch_size,
+                 d->conv_stride, d->conv_kernel * d->channels_in, d->image_size * d->channels_in, d->channels_in, d->normalize);
+      else
+        launch_k(it_im2col0_kernel<float>, nblk(nv), IT_THREADS, 0, stream, reinterpret_cast<const float*>(img), col, nv, g.k0, g.np,
+                 g.ppd, g.o1, d->patch_size, d->conv_stride, d->conv_kernel * d->channels_in, d->image_size * d->channels_in,
+                 d->channels_in, d->normalize);
+      TOME_CUDA(cudaGetLastError());
+    }
+    rc = it_gemm((int)m0, F, g.k0, col, pb + it_offset(d, g, TOME_IT_CONV0_KERNEL), y0, TOME_BF16, pf + it_offset(d, g, TOME_IT_CONV0_BIAS),
+                 nullptr, stream);
+    if (rc != TOME_OK) return rc;
+    {
+      const long long nv = m2 * nchunk;
+      ProfScope prof(PROF_OTHER, (double)nv * 16 * (d->pool_window * d->pool_window + 1), 1, stream);
+      launch_k(it_pool_kernel, nblk(nv), IT_THREADS, 0, stream, y0, pooled, nv, nchunk, g.o1, g.o2, d->pool_window);
+      TOME_CUDA(cudaGetLastError());
+    }
+    const __nv_bfloat16* x = pooled;
+    for (int blk = 0; blk < d->num_blocks; ++blk) {
+      const int pi = TOME_IT_BLOCK0 + 4 * blk;
+      {
+        ProfScope prof(PROF_OTHER, (double)m2 * F * 2, 2, stream);
+        launch_k(it_gn_partial_kernel, dim3(g.gn_ctas, rows_b), gn_threads, 0, stream, x, part, R, nchunk);
+        TOME_CUDA(cudaGetLastError());
+        launch_k(it_gn_final_kernel, (unsigned)ceil_div(rows_b * d->num_groups, 128), 128, 0, stream, part, stats, rows_b, g.gn_ctas, F,
+                 d->num_groups, R, d->gn_eps);
+        TOME_CUDA(cudaGetLastError());
+      }
+      {
+        const long long nv = m2 * 9 * nchunk;
+        ProfScope prof(PROF_OTHER, (double)nv * 16, 1, stream);
+        launch_k(it_gn_gelu_im2col_kernel, nblk(nv), IT_THREADS, 0, stream, x, stats, pf + it_offset(d, g, pi + 0),
+                 pf + it_offset(d, g, pi + 1), col, nv, nchunk, g.o2, R, d->num_groups);
+        TOME_CUDA(cudaGetLastError());
+      }
+      __nv_bfloat16* y = xbuf[blk & 1];
+      const bool last = blk == d->num_blocks - 1;
+      rc = it_gemm((int)m2, F, 9 * F, col, pb + it_offset(d, g, pi + 2), y, TOME_BF16, pf + it_offset(d, g, pi + 3),
+                   last ? pooled : nullptr, stream);   // image_tokenizer.py:170: x + residual after the LAST block
+      if (rc != TOME_OK) return rc;
+      x = y;
+    }
+    rc = it_gemm((int)mt, E, g.kd, x, pb + it_offset(d, g, TOME_IT_DENSE_KERNEL), dense, TOME_F32, pf + it_offset(d, g, TOME_IT_DENSE_BIAS),
+                 nullptr, stream);
+    if (rc != TOME_OK) return rc;
+    {
+      const long long nv = mt * (E / 4);
+      ProfScope prof(PROF_OTHER, (double)nv * 16 * 2, 1, stream);
+      launch_k(it_posadd_kernel, nblk(nv), IT_THREADS, 0, stream, dense, pf + it_offset(d, g, TOME_IT_ROW_EMBED),
+               pf + it_offset(d, g, TOME_IT_COL_EMBED), row_tokens, col_tokens,
+               reinterpret_cast<uint8_t*>(out) + (size_t)img0 * g.np * E * out_bytes, nv, E, g.np, img0, d->token_rows == 1 ? 0 : 1,
+               d->position_interval, d->out_dtype == TOME_BF16 ? 1 : 0);
+      TOME_CUDA(cudaGetLastError());
+    }
+  }
+  return TOME_OK;
+}

@@ -422,3 +422,31 @@ def diffusion_head_bwd(state: DiffusionState, grads: torch.Tensor, want_dx: bool
                                             _ptr(state.time), C.c_void_p(state.workspace.data_ptr() + state.off), _ptr(grads),
                                             _ptr(dx), _stream()))
     return dx
+
+
+# ------------------------------------------------------------------------------------------------ image front end
+def image_tokenizer_fwd(image: torch.Tensor, params: torch.Tensor, desc: "L.ImageTokenizerDesc", row_tokens: torch.Tensor,
+                        col_tokens: torch.Tensor, params_bf16: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None):
+    """ImageTokenizer.__call__ (tokenizers/images/image_tokenizer.py:216-309) on image [B, N, H, W, C] (uint8 or fp32 pixels).
+    params: flat fp32 vector in the layout of include/tome_b200.h section 7b; row_tokens / col_tokens i32 [token_rows, n_patches].
+    Returns tokens [B, N, n_patches, E] in desc.out_dtype."""
+    _need_cuda(image, params, row_tokens, col_tokens, params_bf16)
+    assert image.is_contiguous() and image.dim() == 5 and params.dtype == torch.float32
+    assert image.dtype == (torch.uint8 if desc.image_dtype == L.TOME_U8 else torch.float32)
+    n = int(L.lib().tome_image_tokenizer_param_count(C.byref(desc)))
+    if n < 0:
+        L.check(1)
+    assert params.numel() == n, (params.numel(), n)
+    p16 = params.to(torch.bfloat16) if params_bf16 is None else params_bf16
+    nbytes = int(L.lib().tome_image_tokenizer_workspace_bytes(C.byref(desc)))
+    ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=image.device) if workspace is None else workspace
+    assert ws.numel() >= nbytes + 256
+    off = (-ws.data_ptr()) % 256
+    n_patches = (desc.image_size // desc.patch_size) ** 2
+    for t in (row_tokens, col_tokens):
+        assert t.dtype == torch.int32 and t.is_contiguous() and t.numel() == desc.token_rows * n_patches
+    out = torch.empty(desc.batch, desc.n_images, n_patches, desc.embed_dim, device=image.device,
+                      dtype=torch.bfloat16 if desc.out_dtype == L.TOME_BF16 else torch.float32)
+    L.check(L.lib().tome_image_tokenizer_fwd(C.byref(desc), _ptr(image), _ptr(params), _ptr(p16), _ptr(row_tokens), _ptr(col_tokens),
+                                             _ptr(out), C.c_void_p(ws.data_ptr() + off), nbytes, _stream()))
+    return out

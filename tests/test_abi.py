@@ -130,3 +130,31 @@ def test_product_path_has_no_cpu_fallback():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f"{f} imports the oracle"
+
+
+def test_image_tokenizer_shapes_on_host(lib):
+    """gato_resnet.yaml's literal geometry (280 x 280 x 3, 56-pixel patches, 12 x 12 / 2 convolution, 3 x 3 pool, 2 blocks of
+    64 features, Dense 768, 128 position tokens): parameter layout, workspace, argument checks -- no GPU."""
+    from multi_modal_transformers_tokenmerge_b200 import _lib as L
+    d = L.ImageTokenizerDesc(batch=4, n_images=2, image_size=280, channels_in=3, image_dtype=L.TOME_U8, normalize=1, patch_size=56,
+                             conv_kernel=12, conv_stride=2, features=64, pool_window=3, num_blocks=2, num_groups=32, gn_eps=1e-6,
+                             embed_dim=768, position_interval=128, token_rows=1, out_dtype=L.TOME_BF16)
+    conv0 = 12 * 12 * 3 * 64 + 64
+    block = 64 + 64 + 9 * 64 * 64 + 64
+    kd = 21 * 21 * 64                                   # (56 - 12) / 2 + 1 = 23 -> pool -> 21
+    n = conv0 + 2 * block + kd * 768 + 768 + 2 * 128 * 768
+    assert lib.tome_image_tokenizer_param_count(C.byref(d)) == n
+    off = lambda w: lib.tome_image_tokenizer_param_offset(C.byref(d), w)  # noqa: E731
+    assert off(L.IT_CONV0_KERNEL) == 0 and off(L.IT_CONV0_BIAS) == conv0 - 64
+    assert off(L.IT_BLOCK0) == conv0 and off(L.IT_BLOCK0 + 2) == conv0 + 128 and off(L.IT_BLOCK0 + 4) == conv0 + block
+    assert off(L.IT_DENSE_KERNEL) == conv0 + 2 * block and off(L.IT_COL_EMBED) == n - 128 * 768
+    assert off(L.IT_BLOCK0 + 8) == -1 and b"no parameter" in lib.tome_last_error()
+    ws = lib.tome_image_tokenizer_workspace_bytes(C.byref(d))
+    assert ws >= 2 * 4 * 2 * 25 * 23 * 23 * 432          # at least the input convolution's im2col rows of the 4 batch rows
+    d.batch = 4096                                       # the workspace is per chunk of batch rows, not per batch
+    assert lib.tome_image_tokenizer_workspace_bytes(C.byref(d)) < (3 << 30)
+    for field, value, msg in (("patch_size", 57, b"multiple of patch_size"), ("features", 60, b"multiple of 8"),
+                              ("num_groups", 7, b"num_groups"), ("token_rows", 3, b"token_rows"), ("pool_window", 30, b"pool")):
+        bad = L.ImageTokenizerDesc.from_buffer_copy(d)
+        setattr(bad, field, value)
+        assert lib.tome_image_tokenizer_param_count(C.byref(bad)) == -1 and msg in lib.tome_last_error(), field

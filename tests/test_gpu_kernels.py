@@ -918,3 +918,89 @@ def test_attention_bwd_bias_partials(ops, T, H, rate, from_ds):
     want = torch.cat([g.double().sum((0, 1)).reshape(-1) for g in got]).cpu()
     scale = torch.cat([g.double().abs().sum((0, 1)).reshape(-1) for g in got]).max().item()
     assert (sums - want).abs().max().item() <= 2e-6 * scale + 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ image front end
+def _it_nodes(H, P, Cin, F, G, E, PI, NB, norm):
+    node = lambda t, **kw: dict(_target_=t, **kw)  # noqa: E731
+    return dict(image_size=(H, H, Cin), patch_size=P, normalize=bool(norm), position_interval=PI, rng_collection="patch_encoding", embedding_dim=E,
+                row_position_embedding=node("flax.linen.Embed", name="image_row_position_embedding", num_embeddings=PI, features=E),
+                col_position_embedding=node("flax.linen.Embed", name="image_col_position_embedding", num_embeddings=PI, features=E),
+                resnet=node("multi_modal_transformers.tokenizers.images.image_tokenizer.ResNetV2Block", num_blocks=NB,
+                            input_conv=node("flax.linen.Conv", features=F, kernel_size=[12, 12], strides=[2, 2], padding="VALID", use_bias=True),
+                            input_pool=dict(_partial_=True, _target_="flax.linen.max_pool", window_shape=[3, 3], strides=[1, 1], padding="VALID"),
+                            resnet_norm=node("flax.linen.GroupNorm", num_groups=G, epsilon=1e-6),
+                            resnet_activation=dict(_partial_=True, _target_="flax.linen.gelu"),
+                            resnet_conv=node("flax.linen.Conv", features=F, kernel_size=[3, 3], strides=[1, 1], padding="SAME", use_bias=True),
+                            output_dense=node("flax.linen.Dense", features=E)))
+
+
+def _golden_tree(Z, prefix):
+    tree = {}
+    for k in Z.files:
+        if k.startswith(prefix + "/"):
+            node = tree
+            parts = k[len(prefix) + 1:].split("/")
+            for q in parts[:-1]:
+                node = node.setdefault(q, {})
+            node[parts[-1]] = Z[k]
+    return tree
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["two_frames", "nine_patches_one_block", "group_size_one_raw_pixels"])
+@pytest.mark.parametrize("pixels", ["f32", "u8"])
+def test_image_tokenizer_golden(ops, name, pixels):
+    """ImageTokenizer mirror (csrc/image_tokenizer.cu) against the tokens the reference's own ImageTokenizer produced under the
+    shim (tests/golden/image_tokenizer.npz; image_tokenizer.py:216-309, train=False).  bf16 operands, fp32 accumulation through
+    three chained contractions: |err| <= 3e-2 * max|want| (observed ~1e-2), mean |err| <= 5e-3 * max|want|."""
+    from multi_modal_transformers_tokenmerge_b200.tokenizers.images import ImageTokenizer
+    Z = np.load(os.path.join(GOLD, "image_tokenizer.npz"))
+    B, N, H, P, Cin, F, G, E, PI, NB, norm = [int(v) for v in Z[f"{name}/meta"]]
+    tok = ImageTokenizer(**_it_nodes(H, P, Cin, F, G, E, PI, NB, norm), out_dtype=torch.float32)
+    img = torch.from_numpy(Z[f"{name}/image"]).cuda()
+    if pixels == "f32":
+        img = img.float()
+    got = tok.apply({"params": _golden_tree(Z, f"{name}/params")}, img, train=False).cpu().numpy()
+    want = Z[f"{name}/out"]
+    assert got.shape == want.shape
+    scale = np.abs(want).max()
+    assert np.abs(got - want).max() <= 3e-2 * scale, (np.abs(got - want).max(), scale)
+    assert np.abs(got - want).mean() <= 5e-3 * scale
+
+
+@pytest.mark.gpu
+def test_image_tokenizer_gato_geometry_vs_oracle(ops):
+    """gato_resnet.yaml's literal geometry (280 x 280 x 3 uint8 pixels, 56-pixel patches, 64 features in 32 groups, 2 blocks,
+    Dense 768, 128 position tokens), 3 batch rows x 2 images, against the oracle (pinned by the goldens above): bf16 output;
+    one pass over the batch and one batch row per pass give the SAME bits (GroupNorm statistics are per batch row);
+    training-mode position tokens (one row per image) select the embedding rows the host drew."""
+    from multi_modal_transformers_tokenmerge_b200.tokenizers.images import ImageTokenizer, encode_patch_position
+    rng = np.random.default_rng(11)
+    H, P, F, G, E, PI, NB = 280, 56, 64, 32, 768, 128, 2
+    nodes = _it_nodes(H, P, 3, F, G, E, PI, NB, True)
+    tok = ImageTokenizer(**nodes)
+    variables = tok.init(5, None)
+    ef = variables["params"]["embedding_function"]
+    for i in range(NB):
+        ef[f"GroupNorm_{i}"]["scale"] = (1 + 0.1 * rng.standard_normal(F)).astype(np.float32)
+        ef[f"GroupNorm_{i}"]["bias"] = (0.1 * rng.standard_normal(F)).astype(np.float32)
+    img = rng.integers(0, 256, size=(3, 2, H, H, 3)).astype(np.uint8)
+    got = tok.apply(variables, torch.from_numpy(img).cuda(), train=False)
+    assert got.dtype == torch.bfloat16 and tuple(got.shape) == (3, 2, 25, E)
+    p = O.image_tokenizer_params_from_flax(variables["params"], NB)
+    want = O.image_tokenizer_fwd(p, img.astype(np.float32), patch_size=P, position_interval=PI, num_groups=G, normalize=True)
+    scale = np.abs(want).max()
+    err = np.abs(got.float().cpu().numpy() - want)
+    assert err.max() <= 3e-2 * scale and err.mean() <= 5e-3 * scale, (err.max(), err.mean(), scale)
+    tok1 = ImageTokenizer(**nodes, chunk_rows=1)
+    got1 = tok1.apply(variables, torch.from_numpy(img).cuda(), train=False)
+    assert torch.equal(got, got1)
+    # training mode: tokens per (batch row, image); the embedding rows are the only thing that changes
+    gt = tok.apply(variables, torch.from_numpy(img).cuda(), train=True, rngs={"patch_encoding": 9})
+    row, col = encode_patch_position(H, P, PI, True, np.random.default_rng(9), images=6)
+    r0, c0 = encode_patch_position(H, P, PI, False)
+    re_, ce = variables["params"]["image_row_position_embedding"]["embedding"], variables["params"]["image_col_position_embedding"]["embedding"]
+    delta = (re_[row] + ce[col] - re_[r0][None] - ce[c0][None]).reshape(3, 2, 25, E)
+    d_got = gt.float().cpu().numpy() - got.float().cpu().numpy()
+    assert np.abs(d_got - delta).max() <= 2 ** -7 * max(1.0, scale)      # two bf16 roundings

@@ -42,3 +42,32 @@ def test_assemble_embeddings_and_compressed_grammar():
     assert tc.generate_attention_mask(1, layer=3).shape == (1, 16, 28)  # rectangular, as in the reference
     with pytest.raises(ValueError):
         TokenSequence("[Bogus{3}]")
+
+
+def test_image_patch_position_tokens_match_the_executed_reference():
+    """tokenizers/images mirror: evaluation-mode position tokens against the reference's own encode_patch_position
+    (tests/golden/image_tokenizer.npz), the patch origin table against image_to_patches' (h w) order, and the training-mode
+    draws inside their quantised intervals."""
+    import os
+    from multi_modal_transformers_tokenmerge_b200.tokenizers.images import encode_patch_position, image_to_patches_index
+    Z = np.load(os.path.join(os.path.dirname(__file__), "golden", "image_tokenizer.npz"))
+    for name in Z["cases"]:
+        B, N, H, P, Cin, F, G, E, PI, NB, norm = [int(v) for v in Z[f"{name}/meta"]]
+        rt, ct = encode_patch_position(H, P, PI, train=False)
+        np.testing.assert_array_equal(rt, Z[f"{name}/row_tokens"])
+        np.testing.assert_array_equal(ct, Z[f"{name}/col_tokens"])
+        org = image_to_patches_index(H, P)
+        img = Z[f"{name}/image"][0, 0].astype(np.float32)
+        want = Z[f"{name}/patches00"]
+        for k, (y, x) in enumerate(org):
+            px = img[y:y + P, x:x + P]
+            if norm:
+                px = np.float32(2) * (px / np.float32(255)) - np.float32(1)
+            np.testing.assert_array_equal(px, want[k])
+        r2, c2 = encode_patch_position(H, P, PI, train=True, rng=np.random.default_rng(3), images=5)
+        ppd = H // P
+        q = np.floor((np.arange(0, H + P, P, dtype=np.float32) / np.float32(H)) * np.float32(PI - 1)).astype(np.int64)
+        k = np.arange(ppd * ppd)
+        assert r2.shape == c2.shape == (5, ppd * ppd)
+        assert (r2 >= q[k % ppd]).all() and (r2 < np.maximum(q[k % ppd + 1], q[k % ppd] + 1)).all()
+        assert (c2 >= q[k // ppd]).all() and (c2 < np.maximum(q[k // ppd + 1], q[k // ppd] + 1)).all()
