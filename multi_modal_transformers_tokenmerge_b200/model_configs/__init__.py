@@ -54,3 +54,27 @@ def build_action_head(node: Dict[str, Any]):
     if "attention_pooling" in keys:
         kw.setdefault("attention_pooling", None)
     return getattr(action_heads, cls)(**kw)
+
+
+def build_image_tokenizer(node: Dict[str, Any], **overrides):
+    """What the reference does with `instantiate(config.tokenizers.images.encoder)`: the ImageTokenizer named by the node
+    (the `encoder` mapping of gato_resnet.yaml, or the YAML's top level holding it).  Hydra interpolations of the reference file
+    (`${tokenizers.images.encoder.position_interval}`, `${dtype}`) are resolved the way its composed config resolves them:
+    num_embeddings = position_interval; dtype keys are dropped (activations are bf16, parameters fp32 here)."""
+    from ..tokenizers.images import ImageTokenizer
+
+    if "_target_" not in node and "encoder" in node:
+        node = node["encoder"]
+    if not str(node.get("_target_", "")).endswith("ImageTokenizer"):
+        raise ValueError(f"unsupported image tokenizer _target_ {node.get('_target_')!r}")
+
+    def resolve(v):
+        if isinstance(v, dict):
+            return {k: resolve(x) for k, x in v.items() if k not in ("dtype", "param_dtype")}
+        if isinstance(v, str) and v.startswith("${") and v.endswith("position_interval}"):
+            return int(node["position_interval"])
+        return v
+
+    kw = {k: resolve(v) for k, v in node.items() if k != "_target_"}
+    kw.update(overrides)
+    return ImageTokenizer(**kw)

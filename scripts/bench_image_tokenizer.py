@@ -9,13 +9,12 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from multi_modal_transformers_tokenmerge_b200 import _lib as L  # noqa: E402
-from multi_modal_transformers_tokenmerge_b200.tokenizers.images import ImageTokenizer  # noqa: E402
-from tests.test_gpu_kernels import _it_nodes  # noqa: E402
+from multi_modal_transformers_tokenmerge_b200 import model_configs  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 H, P, F, G, E, PI, NB = 280, 56, 64, 32, 768, 128, 2
-tok = ImageTokenizer(**_it_nodes(H, P, 3, F, G, E, PI, NB, True))
+tok = model_configs.build_image_tokenizer(model_configs.load("tokenizers/images/gato_resnet_octo"))
 variables = tok.init(5, None)
 img = torch.randint(0, 256, (B, N, H, H, 3), dtype=torch.uint8, device="cuda")
 for _ in range(3):

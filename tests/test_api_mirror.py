@@ -420,3 +420,27 @@ def test_vanilla_stack_module_against_the_executed_reference_blocks(name):
     want = torch.as_tensor(EB[f"{name}/y"])
     err = ((y.float().cpu() - want).norm() / want.norm()).item()
     assert err <= 2e-2, err
+
+
+def test_image_tokenizer_config_nodes():
+    """model_configs.build_image_tokenizer: the package's gato_resnet_octo.yaml and (when the reference tree is present) the
+    reference's own gato_resnet.yaml with its hydra interpolations give the same front end; unsupported nodes raise."""
+    import os
+    import pytest
+    import yaml
+    from multi_modal_transformers_tokenmerge_b200 import model_configs as M
+    tok = M.build_image_tokenizer(M.load("tokenizers/images/gato_resnet_octo"))
+    assert tok.image_size == (280, 280, 3) and tok.patch_size == 56 and tok._geometry() == (23, 21)
+    assert (tok.resnet.num_blocks, tok.resnet.num_groups, tok.resnet.pool_window, tok.resnet.dense_features) == (2, 32, 3, 768)
+    ref = "/root/reference/multi_modal_transformers/model_configs/tokenizers/images/gato_resnet.yaml"
+    if os.path.exists(ref):
+        t2 = M.build_image_tokenizer(yaml.safe_load(open(ref)))
+        assert (t2.image_size, t2.patch_size, t2.position_interval, t2.embedding_dim) == (tok.image_size, tok.patch_size, 128, 768)
+        assert t2.resnet.input_conv == tok.resnet.input_conv and t2.resnet.resnet_conv == tok.resnet.resnet_conv
+    node = M.load("tokenizers/images/gato_resnet_octo")["encoder"]
+    bad = dict(node, resnet=dict(node["resnet"], input_pool=dict(node["resnet"]["input_pool"], strides=[2, 2])))
+    with pytest.raises(NotImplementedError):
+        M.build_image_tokenizer(bad)
+    v = tok.init(0, None)["params"]
+    assert v["embedding_function"]["Conv_0"]["kernel"].shape == (12, 12, 3, 64) and v["embedding_function"]["Dense_0"]["kernel"].shape == (21 * 21 * 64, 768)
+    assert set(v) == {"embedding_function", "image_row_position_embedding", "image_col_position_embedding"}
