@@ -265,6 +265,25 @@ typedef struct {
  * ids i32 [B, sum k] = kept token indices, out [B, sum k, C] = embeddings gathered through ids (bit copies). */
 int tome_topk_prune(const tome_prune_desc_t* desc, const void* embeddings, const float* importance, void* out,
                     int32_t* ids, void* stream);
+/* What a stack of pruning layers needs around the gather (compressed_attention.py:396-402, one prune per layer):
+ * row_map i32 [B, T] = output row of every token, -1 for a pruned one (the inverse of ids [B, kept]); gid_out / pos_out
+ * (optional) = the mask group / position of the kept tokens, carried with them. */
+int tome_prune_row_map(int batch, int tokens, int kept, const int32_t* ids, const uint8_t* gid, const int32_t* pos,
+                       int32_t* row_map, uint8_t* gid_out, int32_t* pos_out, void* stream);
+/* Backward of the gather (autodiff of token_compression.py:41-44): dx [B, T, C] = dy [B, kept, C] rows through row_map,
+ * zero rows for pruned tokens. */
+int tome_prune_bwd(int batch, int tokens, int kept, int channels, int dtype, const int32_t* row_map, const void* dy, void* dx,
+                   void* stream);
+
+/* Token importance from the attention weights   attention_blocks/compressed_attention.py:303-306:
+ *   importance [B, T] = mean over heads ( mean over one token axis ( softmax weights [B, H, Tq, Tk] ) ).
+ * TOME_IMPORTANCE_ROW_MEAN: the inner mean runs over the KEYS, the expression as the reference writes it (rows of a
+ * softmax sum to one, so every score is 1 / T up to rounding; kept for fidelity).  TOME_IMPORTANCE_RECEIVED: over the
+ * QUERIES -- the attention a token receives, a usable ranking for tome_topk_prune.  desc / q / k as tome_attention_fwd
+ * (mask and log(size) bias included), lse [B, H, T] = what that call wrote; weights are the undropped ones. */
+enum tome_importance_mode { TOME_IMPORTANCE_ROW_MEAN = 0, TOME_IMPORTANCE_RECEIVED = 1 };
+int tome_attention_importance(const tome_attn_desc_t* desc, const void* q, const void* k, const float* lse, int mode,
+                              float* importance, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * 6. Small fused steps around the block
@@ -388,6 +407,17 @@ typedef struct {
   int head_features;  /* tome_head_desc_t.features / tome_diffusion_desc_t.action_dim */
   float max_action;
   int head_fourier_dim, head_time_hidden, head_time_out, head_hidden, diffusion_steps; /* tome_diffusion_desc_t (head 3) */
+  /* Per-modality top-k PRUNING per layer instead of merging (the sibling compression path: token_compression.py:15-46 applied
+   * by every layer, compressed_attention.py:303-308, 396-402; grammar of token_sequencer.py:222-238).  prune_sets > 0 selects it
+   * (r must be 0, prop_attn 0): the sequence is prune_sets consecutive token sets; set i holds prune_set_n[i] tokens at layer 0
+   * and every layer drops its prune_set_c[i] least important ones (scores: prune_importance, a tome_importance_mode), keeping
+   * the rest in descending score order.  The reference prunes the attention output before the out projection and then adds
+   * the UNPRUNED residual (a shape error as written); here the same token choice is applied after the residual add, which is
+   * what pruning both branches alike gives. */
+  int prune_sets;
+  int prune_set_n[TOME_MAX_TOKEN_SETS];
+  int prune_set_c[TOME_MAX_TOKEN_SETS];
+  int prune_importance;
 } tome_stack_cfg_t;
 
 /* Per-layer parameter offsets (elements) into one flat fp32 vector (master weights / gradients / Adam moments)
@@ -429,6 +459,12 @@ typedef struct {
   void* grad_trace;           /* optional (parity tests), bf16 [layers, B * T0 * C]: backward copies dL/dx_out of layer l (its
                                  first B * T_out(l) * C elements) into slot l before it consumes it, so a checker can run
                                  each layer's backward on the implementation's own incoming gradient */
+  /* Pruning stacks: the per-layer attention masks of the compression grammar (TokenSequence.generate_attention_mask(layer = l),
+   * token_sequencer.py:222-238, 313-321, what compressed_attention.py:399 passes as masks[layer_idx]) as group ids / positions:
+   * u8 / i32 [sum over layers of T_in(l)], layer after layer, the same for every batch row.  NULL: the layer-0 gid / pos are
+   * carried with the kept tokens instead (a kept token keeps its own group and position). */
+  const uint8_t* layer_gid;
+  const int32_t* layer_pos;
 } tome_stack_io_t;
 
 int tome_stack_forward(const tome_stack_cfg_t* cfg, const tome_stack_io_t* io, void* stream);
@@ -449,6 +485,9 @@ const int32_t* tome_stack_layer_node_idx(const tome_stack_cfg_t* cfg, const tome
 /* u32 [B * T_out(layer), ceil(mlp_dim / 32)]: bit j of word w = element 32 w + j of MLP-1's output survived ReLU (and hidden
  * dropout), i.e. the gate the MLP backward of attention.py:32-34 uses; lets a checker take the SAME gate decisions. */
 const uint32_t* tome_stack_layer_relu_bits(const tome_stack_cfg_t* cfg, const tome_stack_io_t* io, int layer);
+/* pruning stacks: f32 [B, T_in(layer)] importance scores the layer ranked, i32 [B, T_out(layer)] the token indices it kept */
+const float* tome_stack_layer_importance(const tome_stack_cfg_t* cfg, const tome_stack_io_t* io, int layer);
+const int32_t* tome_stack_layer_prune_ids(const tome_stack_cfg_t* cfg, const tome_stack_io_t* io, int layer);
 
 /* ------------------------------------------------------------------------------------------------------------
  * 7b. Image patch-embed front end (forward)   tokenizers/images/image_tokenizer.py:35-71 (image_to_patches), :74-140

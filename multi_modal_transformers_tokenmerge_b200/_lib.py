@@ -86,7 +86,11 @@ class StackCfg(C.Structure):
                 ("n_readout", i32), ("dropout_rate", f32), ("dropout_seed", u64), ("attn_dropout_rate", f32),
                 ("head", i32), ("head_groups", i32), ("head_features", i32), ("max_action", f32),
                 ("head_fourier_dim", i32), ("head_time_hidden", i32), ("head_time_out", i32), ("head_hidden", i32),
-                ("diffusion_steps", i32)]
+                ("diffusion_steps", i32),
+                ("prune_sets", i32), ("prune_set_n", i32 * 16), ("prune_set_c", i32 * 16), ("prune_importance", i32)]
+
+
+IMPORTANCE_ROW_MEAN, IMPORTANCE_RECEIVED = 0, 1
 
 
 class DiffusionDesc(C.Structure):
@@ -121,7 +125,7 @@ class StackIO(C.Structure):
                 ("workspace", vp), ("workspace_bytes", C.c_size_t),
                 ("x_final", vp), ("readout", vp), ("loss", vp), ("grads_f32", vp),
                 ("layer_done_events", C.POINTER(vp)), ("head_out", vp), ("head_time", vp), ("head_alpha_hats", vp),
-                ("grad_trace", vp)]
+                ("grad_trace", vp), ("layer_gid", vp), ("layer_pos", vp)]
 
 
 _lib = None
@@ -152,7 +156,7 @@ def lib() -> C.CDLL:
                 getattr(L, name).restype = ll
         for name in ("tome_stack_final_x", "tome_stack_final_size", "tome_stack_layer_edge_idx", "tome_stack_layer_dst_idx",
                      "tome_stack_layer_node_max", "tome_stack_layer_node_idx", "tome_stack_layer_relu_bits",
-                     "tome_stack_layer_x_in", "tome_stack_layer_size_in"):
+                     "tome_stack_layer_x_in", "tome_stack_layer_size_in", "tome_stack_layer_importance", "tome_stack_layer_prune_ids"):
             if hasattr(L, name):
                 getattr(L, name).restype = vp
         P = C.POINTER
@@ -164,6 +168,11 @@ def lib() -> C.CDLL:
             "tome_merge_fwd": [P(MergeShape), P(Plan), vp, vp, vp, vp, vp, vp, vp, vp, vp],
             "tome_merge_bwd": [P(MergeShape), P(Plan), vp, vp, vp, vp, vp],
             "tome_topk_prune": [P(PruneDesc), vp, vp, vp, vp, vp],
+            "tome_prune_row_map": [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp],
+            "tome_prune_bwd": [i32, i32, i32, i32, i32, vp, vp, vp, vp],
+            "tome_attention_importance": [P(AttnDesc), vp, vp, vp, i32, vp, vp],
+            "tome_stack_layer_importance": [P(StackCfg), P(StackIO), i32],
+            "tome_stack_layer_prune_ids": [P(StackCfg), P(StackIO), i32],
             "tome_gemm_workspace_bytes": [P(GemmArgs)],
             "tome_gemm_bf16": [P(GemmArgs), vp, C.c_size_t, vp],
             "tome_gemm_set_sm_limit": [i32],

@@ -64,7 +64,7 @@ __global__ void chain_kernel(int B, int layers, const ChainArgs a, const int32_t
   const int b = i / n;
   int pidx = readout_idx[i % n];
   for (int l = 0; l < layers; ++l)
-    if (a.maps[l]) pidx = a.maps[l][(long long)b * a.tokens[l] + pidx];
+    if (a.maps[l] && pidx >= 0) pidx = a.maps[l][(long long)b * a.tokens[l] + pidx];   // -1: pruned away by a pruning layer
   origin[i] = pidx;
 }
 

@@ -64,9 +64,74 @@ topk_prune_kernel(const tome_prune_desc_t d, const uint8_t* __restrict__ emb, co
   }
 }
 
+// row_map[b, t] = output row of token t, -1 when it was pruned; gid / pos follow the kept tokens.  row_map is pre-filled with
+// -1 by the caller (cudaMemsetAsync 0xFF); ids are distinct per batch row, so the scatter has no collisions.
+__global__ void prune_row_map_kernel(int B, int T, int K, const int32_t* __restrict__ ids, const uint8_t* __restrict__ gid,
+                                     const int32_t* __restrict__ pos, int32_t* __restrict__ row_map, uint8_t* __restrict__ gid_out,
+                                     int32_t* __restrict__ pos_out) {
+  pdl_prologue();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * K) return;
+  const int b = (int)(i / K), j = (int)(i - (long long)b * K);
+  const int t = ids[i];
+  row_map[(long long)b * T + t] = j;
+  if (gid_out) gid_out[i] = gid[(long long)b * T + t];
+  if (pos_out) pos_out[i] = pos[(long long)b * T + t];
+}
+
+// backward of the gather: dx[b, t] = dy[b, row_map[b, t]], zero for a pruned token.  Thread = 16 bytes.
+__global__ void __launch_bounds__(256)
+prune_bwd_kernel(long long n_vec, int T, int K, int vpr, const int32_t* __restrict__ row_map, const uint4* __restrict__ dy,
+                 uint4* __restrict__ dx) {
+  pdl_prologue();
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n_vec; i += (long long)gridDim.x * 256) {
+    const long long rowg = i / vpr;
+    const int v = (int)(i - rowg * vpr);
+    const int b = (int)(rowg / T);
+    const int r = row_map[rowg];
+    dx[i] = r >= 0 ? ld_nc_v4(dy + ((long long)b * K + r) * vpr + v) : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 }  // namespace tome
 
 using namespace tome;
+
+extern "C" int tome_prune_row_map(int batch, int tokens, int kept, const int32_t* ids, const uint8_t* gid, const int32_t* pos,
+                                  int32_t* row_map, uint8_t* gid_out, int32_t* pos_out, void* stream_) {
+  clear_error();
+  cudaStream_t stream = (cudaStream_t)stream_;
+  TOME_CHECK(batch > 0 && tokens > 0 && kept >= 0 && kept <= tokens && ids && row_map, TOME_ERR_INVALID, "prune_row_map: bad argument");
+  TOME_CHECK((!gid_out || gid) && (!pos_out || pos), TOME_ERR_INVALID, "prune_row_map: gid_out / pos_out need gid / pos");
+  ProfScope prof(PROF_OTHER, 0.0, 2, stream);
+  TOME_CUDA(cudaMemsetAsync(row_map, 0xFF, (size_t)batch * tokens * sizeof(int32_t), stream));
+  if (kept == 0) return TOME_OK;
+  const long long n = (long long)batch * kept;
+  launch_k(prune_row_map_kernel, (unsigned)((n + 255) / 256), 256, 0, stream, batch, tokens, kept, ids, gid, pos, row_map, gid_out, pos_out);
+  TOME_CUDA(cudaGetLastError());
+  return TOME_OK;
+}
+
+extern "C" int tome_prune_bwd(int batch, int tokens, int kept, int channels, int dtype, const int32_t* row_map, const void* dy,
+                              void* dx, void* stream_) {
+  clear_error();
+  cudaStream_t stream = (cudaStream_t)stream_;
+  TOME_CHECK(batch > 0 && tokens > 0 && kept > 0 && kept <= tokens && channels > 0 && row_map && dy && dx, TOME_ERR_INVALID,
+             "prune_bwd: bad argument");
+  TOME_CHECK(dtype == TOME_BF16 || dtype == TOME_F32, TOME_ERR_INVALID, "prune_bwd: dtype must be bf16 or f32");
+  const int row_bytes = channels * (dtype == TOME_BF16 ? 2 : 4);
+  TOME_CHECK(row_bytes % 16 == 0 && ((((uintptr_t)dy | (uintptr_t)dx) & 15) == 0), TOME_ERR_INVALID,
+             "prune_bwd: rows must be multiples of 16 bytes, 16-byte aligned");
+  const int vpr = row_bytes / 16;
+  const long long n_vec = (long long)batch * tokens * vpr;
+  long long blocks = (n_vec + 255) / 256;
+  if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
+  ProfScope prof(PROF_MERGE_BWD, (double)batch * ((double)tokens + kept) * row_bytes, 1, stream);
+  launch_k(prune_bwd_kernel, (unsigned)blocks, 256, 0, stream, n_vec, tokens, kept, vpr, row_map, reinterpret_cast<const uint4*>(dy),
+           reinterpret_cast<uint4*>(dx));
+  TOME_CUDA(cudaGetLastError());
+  return TOME_OK;
+}
 
 extern "C" int tome_topk_prune(const tome_prune_desc_t* d, const void* embeddings, const float* importance, void* out,
                                int32_t* ids, void* stream_) {

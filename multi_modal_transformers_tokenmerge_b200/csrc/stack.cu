@@ -41,6 +41,8 @@ struct LayerBufs {
   float* node_max;
   int32_t* node_idx;
   tome_plan_t plan;
+  float* importance;     // pruning stacks: [B, T] scores ranked by this layer
+  int32_t* prune_ids;    // pruning stacks: [B, To] kept token indices
 };
 
 struct StackLayout {
@@ -116,6 +118,27 @@ static int check_cfg(const tome_stack_cfg_t* c) {
   TOME_CHECK(c->dropout_rate >= 0.f && c->dropout_rate < 1.f, TOME_ERR_INVALID, "stack: dropout_rate must be in [0, 1)");
   TOME_CHECK(c->attn_dropout_rate >= 0.f && c->attn_dropout_rate < 1.f, TOME_ERR_INVALID, "stack: attn_dropout_rate must be in [0, 1)");
   TOME_CHECK(c->n_readout >= 0, TOME_ERR_INVALID, "stack: n_readout must be >= 0");
+  TOME_CHECK(c->prune_sets >= 0 && c->prune_sets <= TOME_MAX_TOKEN_SETS, TOME_ERR_INVALID, "stack: prune_sets must be in [0, %d]",
+             TOME_MAX_TOKEN_SETS);
+  if (c->prune_sets > 0) {
+    TOME_CHECK(c->r == 0 && c->prop_attn == 0 && !c->class_token && !c->distill_token, TOME_ERR_INVALID,
+               "stack: a pruning stack (prune_sets > 0) takes r = 0, prop_attn = 0 and no class / distill token");
+    TOME_CHECK(c->prune_importance == TOME_IMPORTANCE_ROW_MEAN || c->prune_importance == TOME_IMPORTANCE_RECEIVED, TOME_ERR_INVALID,
+               "stack: unknown prune_importance %d", c->prune_importance);
+    TOME_CHECK(c->head_dim == 64 || c->head_dim == 128 || c->head_dim == 256, TOME_ERR_UNSUPPORTED,
+               "stack: pruning stacks need head_dim 64, 128 or 256 (tome_attention_importance)");
+    long long total = 0;
+    for (int i = 0; i < c->prune_sets; ++i) {
+      TOME_CHECK(c->prune_set_n[i] >= 1 && c->prune_set_c[i] >= 0, TOME_ERR_INVALID, "stack: token set %d: n >= 1, c >= 0", i);
+      // the grammar's token count at the last layer's input must stay positive and its top_k valid (token_compression.py:31)
+      TOME_CHECK((long long)c->prune_set_n[i] - (long long)c->layers * c->prune_set_c[i] >= 0 &&
+                 (long long)c->prune_set_n[i] - (long long)(c->layers - 1) * c->prune_set_c[i] >= 1, TOME_ERR_INVALID,
+                 "stack: token set %d (%d tokens) cannot drop %d tokens in each of %d layers", i, c->prune_set_n[i],
+                 c->prune_set_c[i], c->layers);
+      total += c->prune_set_n[i];
+    }
+    TOME_CHECK(total == c->tokens, TOME_ERR_INVALID, "stack: the token sets hold %lld tokens, the sequence %d", total, c->tokens);
+  }
   TOME_CHECK(c->head >= 0 && c->head <= 3, TOME_ERR_INVALID,
              "stack: head must be 0 (synthetic readout MSE), 1 (continuous l2), 2 (categorical cross-entropy) or 3 (diffusion)");
   if (c->head == 3) {
@@ -136,6 +159,10 @@ static std::vector<LayerShape> layer_shapes(const tome_stack_cfg_t* c) {
   for (int l = 0; l < c->layers; ++l) {
     s[l].t_in = t;
     s[l].r = tome_clamp_r(t, c->r, c->class_token, c->distill_token);
+    if (c->prune_sets > 0) {
+      s[l].r = 0;
+      for (int i = 0; i < c->prune_sets; ++i) s[l].r += c->prune_set_c[i];
+    }
     s[l].t_out = t - s[l].r;
     t = s[l].t_out;
   }
@@ -185,7 +212,16 @@ static StackLayout make_layout(const tome_stack_cfg_t* c, void* workspace) {
     memset(&Lb.plan, 0, sizeof(Lb.plan));
     Lb.node_max = nullptr;
     Lb.node_idx = nullptr;
-    if (r > 0) {
+    Lb.importance = nullptr;
+    Lb.prune_ids = nullptr;
+    if (r > 0 && c->prune_sets > 0) {
+      Lb.importance = b.take<float>(B * T);
+      Lb.prune_ids = b.take<int32_t>(B * To);
+      Lb.plan.row_map = b.take<int32_t>(B * T);
+      Lb.size_out = nullptr;
+      Lb.gid_out = c->num_groups ? b.take<uint8_t>(B * To) : nullptr;
+      Lb.pos_out = c->num_groups ? b.take<int32_t>(B * To) : nullptr;
+    } else if (r > 0) {
       Lb.node_max = b.take<float>(B * ta);
       Lb.node_idx = b.take<int32_t>(B * ta);
       Lb.plan.edge_idx = b.take<int32_t>(B * ta);
@@ -354,7 +390,10 @@ static int check_io(const tome_stack_cfg_t* c, const tome_stack_io_t* io, const 
   TOME_CHECK(io->params_f32 && io->params_bf16 && io->x && io->workspace, TOME_ERR_INVALID, "stack: null params / x / workspace");
   TOME_CHECK(io->workspace_bytes >= S.total, TOME_ERR_INVALID, "stack: workspace too small (%zu < %zu)", io->workspace_bytes, S.total);
   TOME_CHECK(((uintptr_t)io->workspace & 255) == 0, TOME_ERR_INVALID, "stack: workspace must be 256-byte aligned");
-  TOME_CHECK(c->num_groups == 0 || (io->gid && io->pos && io->allow), TOME_ERR_INVALID, "stack: a group mask needs gid, pos and allow");
+  TOME_CHECK(c->num_groups == 0 || (((io->gid && io->pos) || (io->layer_gid && io->layer_pos)) && io->allow), TOME_ERR_INVALID,
+             "stack: a group mask needs gid, pos (or layer_gid, layer_pos) and allow");
+  TOME_CHECK(!(io->layer_gid || io->layer_pos) || (c->prune_sets > 0 && c->num_groups > 0 && io->layer_gid && io->layer_pos), TOME_ERR_INVALID,
+             "stack: layer_gid / layer_pos are the per-layer masks of a pruning stack with a group mask (both or neither)");
   TOME_CHECK(c->n_readout == 0 || io->readout_idx, TOME_ERR_INVALID, "stack: readout_idx missing");
   if (backward) TOME_CHECK(io->grads_f32 && io->target && io->loss && c->n_readout > 0, TOME_ERR_INVALID,
                            "stack_backward: needs grads_f32, target, loss and n_readout > 0");
@@ -375,9 +414,11 @@ extern "C" int tome_stack_forward(const tome_stack_cfg_t* c, const tome_stack_io
   if (c->num_groups) {
     const int n = B * c->tokens;
     ProfScope prof(PROF_OTHER, 0.0, 1, st);
-    launch_k(broadcast_groups_kernel, ceil_div(n, 256), 256, 0, st, B, c->tokens, io->gid, io->pos, S.L[0].gid_in, S.L[0].pos_in);
+    launch_k(broadcast_groups_kernel, ceil_div(n, 256), 256, 0, st, B, c->tokens, io->layer_gid ? io->layer_gid : io->gid,
+             io->layer_pos ? io->layer_pos : io->pos, S.L[0].gid_in, S.L[0].pos_in);
     TOME_CUDA(cudaGetLastError());
   }
+  long long grammar_off = 0;   // pruning stacks with per-layer grammar masks: offset of the NEXT layer's rows in layer_gid / layer_pos
   for (int l = 0; l < c->layers; ++l) {
     const LayerBufs& Lb = S.L[l];
     const ParamOffsets o = layer_offsets(c, l);
@@ -401,7 +442,30 @@ extern "C" int tome_stack_forward(const tome_stack_cfg_t* c, const tome_stack_io
     __nv_bfloat16* x1 = r > 0 ? S.x1_scratch : Lb.x1m;
     RC(gemm(c, S, st, M, C, HD, Lb.attn_o, HD, TOME_MAJOR_K, pw + o.wo, C, TOME_MAJOR_MN, x1, C, TOME_BF16, pf + o.bo, 0,
             Lb.x_in, nullptr, 1.f, 3 * l + 0, 0));
-    if (r > 0) {
+    grammar_off += T;
+    if (r > 0 && c->prune_sets > 0) {
+      // importance from this layer's attention weights, per-set top-k, gather (compressed_attention.py:303-308)
+      RC(tome_attention_importance(&ad, Lb.qkv, Lb.qkv + HD, Lb.lse, c->prune_importance, Lb.importance, st));
+      tome_prune_desc_t pd;
+      memset(&pd, 0, sizeof(pd));
+      pd.batch = B; pd.tokens = T; pd.channels = C; pd.dtype = TOME_BF16; pd.n_sets = c->prune_sets; pd.score_planes = 1;
+      for (int i = 0, start = 0; i < c->prune_sets; ++i) {
+        pd.set_start[i] = start;
+        pd.set_n[i] = c->prune_set_n[i] - l * c->prune_set_c[i];
+        pd.set_k[i] = pd.set_n[i] - c->prune_set_c[i];
+        start += pd.set_n[i];
+      }
+      RC(tome_topk_prune(&pd, x1, Lb.importance, Lb.x1m, Lb.prune_ids, st));
+      const bool grammar = io->layer_gid != nullptr && c->num_groups > 0;
+      RC(tome_prune_row_map(B, T, To, Lb.prune_ids, Lb.gid_in, Lb.pos_in, Lb.plan.row_map, grammar ? nullptr : Lb.gid_out,
+                            grammar ? nullptr : Lb.pos_out, st));
+      if (grammar && l + 1 < c->layers) {   // masks[layer + 1] of the compression grammar, the same for every batch row
+        ProfScope prof(PROF_OTHER, 0.0, 1, st);
+        launch_k(broadcast_groups_kernel, ceil_div(B * To, 256), 256, 0, st, B, To, io->layer_gid + grammar_off,
+                 io->layer_pos + grammar_off, Lb.gid_out, Lb.pos_out);
+        TOME_CUDA(cudaGetLastError());
+      }
+    } else if (r > 0) {
       tome_metric_desc_t md;
       md.batch = B; md.tokens = T; md.dim = D; md.heads = H; md.dtype = TOME_BF16;
       md.batch_stride = (long long)T * 3 * HD; md.token_stride = 3 * HD; md.head_stride = D;
@@ -426,7 +490,7 @@ extern "C" int tome_stack_forward(const tome_stack_cfg_t* c, const tome_stack_io
     const int32_t* maps[64];
     int toks[64];
     for (int l = 0; l < c->layers; ++l) {
-      maps[l] = S.shapes[l].r > 0 ? S.L[l].plan.row_map : nullptr;
+      maps[l] = S.shapes[l].r > 0 ? S.L[l].plan.row_map : nullptr;   // merge and prune layers both leave token -> output row
       toks[l] = S.shapes[l].t_in;
     }
     RC(tome_chain_row_maps(B, c->layers, maps, toks, io->readout_idx, c->n_readout, S.origin, st));
@@ -525,7 +589,10 @@ extern "C" int tome_stack_backward(const tome_stack_cfg_t* c, const tome_stack_i
                           gr + o.ln2_scale, gr + o.ln2_bias, S.ws_ln, st));
     // ---- merge backward -> dx1 in g0
     const __nv_bfloat16* dx1;
-    if (r > 0) {
+    if (r > 0 && c->prune_sets > 0) {
+      RC(tome_prune_bwd(B, T, To, C, TOME_BF16, Lb.plan.row_map, g2, g0, st));
+      dx1 = g0;
+    } else if (r > 0) {
       tome_merge_shape_t ms{B, T, C, r, c->distill_token, TOME_BF16, TOME_MERGE_WAVG};
       RC(tome_merge_bwd(&ms, &Lb.plan, Lb.size_in, Lb.size_out, g2, g0, st));
       dx1 = g0;
@@ -594,6 +661,8 @@ ACCESSOR(tome_stack_layer_dst_idx, const int32_t*, S.L[layer].plan.dst_idx)
 ACCESSOR(tome_stack_layer_node_max, const float*, S.L[layer].node_max)
 ACCESSOR(tome_stack_layer_node_idx, const int32_t*, S.L[layer].node_idx)
 ACCESSOR(tome_stack_layer_relu_bits, const uint32_t*, S.L[layer].m1_bits)
+ACCESSOR(tome_stack_layer_importance, const float*, S.L[layer].importance)
+ACCESSOR(tome_stack_layer_prune_ids, const int32_t*, S.L[layer].prune_ids)
 
 extern "C" const void* tome_stack_layer_x_in(const tome_stack_cfg_t* c, const tome_stack_io_t* io, int layer) {
   if (check_cfg(c) || !io || layer < 0 || layer > c->layers) return nullptr;

@@ -51,6 +51,11 @@ class StackConfig:
     head_time_out: int = 0
     head_hidden: int = 0
     diffusion_steps: int = 0
+    # per-modality top-k pruning per layer instead of merging (include/tome_b200.h: tome_stack_cfg_t.prune_*): token sets as
+    # (tokens at layer 0, tokens dropped by every layer), in sequence order; importance: "row_mean" (compressed_attention.py:303-306
+    # as written) or "received"
+    prune_sets: tuple = ()
+    prune_importance: str = "received"
 
     def c(self) -> L.StackCfg:
         return L.StackCfg(self.batch, self.tokens, self.channels, self.heads, self.head_dim, self.mlp_dim, self.layers,
@@ -58,7 +63,9 @@ class StackConfig:
                           int(self.distill_token), self.num_groups, self.n_readout, self.dropout_rate, self.dropout_seed,
                           self.attn_dropout_rate, {"none": 0, "continuous": 1, "categorical": 2, "diffusion": 3}[self.head],
                           self.head_groups, self.head_features, self.max_action, self.head_fourier_dim, self.head_time_hidden,
-                          self.head_time_out, self.head_hidden, self.diffusion_steps)
+                          self.head_time_out, self.head_hidden, self.diffusion_steps, len(self.prune_sets),
+                          (C.c_int * 16)(*[int(n) for n, _ in self.prune_sets]), (C.c_int * 16)(*[int(c) for _, c in self.prune_sets]),
+                          {"row_mean": L.IMPORTANCE_ROW_MEAN, "received": L.IMPORTANCE_RECEIVED}[self.prune_importance])
 
     def diffusion_desc(self, tokens: int = 1) -> L.DiffusionDesc:
         return L.DiffusionDesc(self.batch, tokens, self.channels, self.n_readout, self.head_features, self.head_fourier_dim,
@@ -77,7 +84,7 @@ class StackConfig:
 
 class ToMeStackEngine:
     def __init__(self, cfg: StackConfig, device="cuda", gid=None, pos=None, allow=None, readout_idx=None,
-                 training: bool = True):
+                 training: bool = True, layer_gid=None, layer_pos=None):
         if not torch.cuda.is_available():
             raise RuntimeError("ToMeStackEngine needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = L.lib()
@@ -101,6 +108,9 @@ class ToMeStackEngine:
         self.pos = None if pos is None else torch.as_tensor(np.asarray(pos, np.int32)).to(self.dev)
         self.allow = None if allow is None else torch.as_tensor(np.asarray(allow, np.uint8)).contiguous().to(self.dev)
         self.readout_idx = None if readout_idx is None else torch.as_tensor(np.asarray(readout_idx, np.int32)).to(self.dev)
+        # pruning stacks: the compression grammar's per-layer masks, layer after layer (token_sequencer.py:222-238)
+        self.layer_gid = None if layer_gid is None else torch.as_tensor(np.concatenate([np.asarray(g, np.uint8) for g in layer_gid])).to(self.dev)
+        self.layer_pos = None if layer_pos is None else torch.as_tensor(np.concatenate([np.asarray(g, np.int32) for g in layer_pos])).to(self.dev)
         self.loss = torch.zeros(1 + cfg.batch, dtype=torch.float32, device=self.dev)
         self.readout = (torch.empty(cfg.batch, cfg.n_readout, cfg.channels, dtype=torch.float32, device=self.dev)
                         if cfg.n_readout else None)
@@ -210,7 +220,9 @@ class ToMeStackEngine:
                          None if self.head_out is None else self.head_out.data_ptr(),
                          None if self.head_time is None else self.head_time.data_ptr(),
                          None if self.alpha_hats is None else self.alpha_hats.data_ptr(),
-                         None if self._grad_trace is None else self._grad_trace.data_ptr())
+                         None if self._grad_trace is None else self._grad_trace.data_ptr(),
+                         None if self.layer_gid is None else self.layer_gid.data_ptr(),
+                         None if self.layer_pos is None else self.layer_pos.data_ptr())
 
     def set_diffusion_draws(self, time: torch.Tensor, alpha_hats) -> None:
         """Diffusion head: the sampled time steps (i32 [B], diffusion.py:125) and the alpha_hat table (:88-92)."""
@@ -307,6 +319,16 @@ class ToMeStackEngine:
         ei = self._view(f.tome_stack_layer_edge_idx(C.byref(self.ccfg), C.byref(io), layer), (b, ta), torch.int32)
         di = self._view(f.tome_stack_layer_dst_idx(C.byref(self.ccfg), C.byref(io), layer), (b, r), torch.int32)
         return nm, ni, ei, di
+
+    def layer_prune(self, layer: int):
+        """Pruning stacks: (importance f32 [B, T_in], kept token indices i32 [B, T_out]) of `layer` in the last forward."""
+        io = self._io(self._x, self._target)
+        b, t, to = self.cfg.batch, self.tokens_at(layer), self.tokens_at(layer + 1)
+        pi = self.lib.tome_stack_layer_importance(C.byref(self.ccfg), C.byref(io), layer)
+        pk = self.lib.tome_stack_layer_prune_ids(C.byref(self.ccfg), C.byref(io), layer)
+        if not pi or not pk:
+            return None
+        return self._view(pi, (b, t), torch.float32), self._view(pk, (b, to), torch.int32)
 
     def layer_x_in(self, layer: int) -> torch.Tensor:
         """bf16 [B, T_in(layer), C] tokens entering `layer` in the last forward (layer == layers: the final tokens)."""

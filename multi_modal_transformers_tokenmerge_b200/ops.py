@@ -450,3 +450,50 @@ def image_tokenizer_fwd(image: torch.Tensor, params: torch.Tensor, desc: "L.Imag
     L.check(L.lib().tome_image_tokenizer_fwd(C.byref(desc), _ptr(image), _ptr(params), _ptr(p16), _ptr(row_tokens), _ptr(col_tokens),
                                              _ptr(out), C.c_void_p(ws.data_ptr() + off), nbytes, _stream()))
     return out
+
+
+# ------------------------------------------------------------------------------------------------ pruning path
+def attention_importance(q: torch.Tensor, k: torch.Tensor, lse: torch.Tensor, mode: str = "received", size: Optional[torch.Tensor] = None,
+                         gid: Optional[torch.Tensor] = None, pos: Optional[torch.Tensor] = None, allow: Optional[torch.Tensor] = None,
+                         scale: Optional[float] = None) -> torch.Tensor:
+    """compressed_attention.py:303-306 on q, k bf16 [B, T, H, D] (views into a packed qkv are fine) and the lse [B, H, T] of
+    attention_fwd: importance f32 [B, T] = mean over heads of the mean over keys ("row_mean", as written) or over queries
+    ("received") of the softmax weights.  gid / pos are per batch row [B, T]."""
+    _need_cuda(q, k, lse, size, gid, pos, allow)
+    B, T, H, D = q.shape
+    assert q.dtype == k.dtype == torch.bfloat16 and q.stride(3) == 1 and k.stride(3) == 1 and q.stride(2) == D and k.stride(2) == D
+    assert lse.dtype == torch.float32 and lse.is_contiguous() and tuple(lse.shape) == (B, H, T)
+    d = L.AttnDesc(batch=B, tokens=T, heads=H, head_dim=D, q_batch_stride=q.stride(0), q_token_stride=q.stride(1),
+                   k_batch_stride=k.stride(0), k_token_stride=k.stride(1), scale=float(scale if scale is not None else D ** -0.5))
+    if gid is not None:
+        assert gid.dtype == torch.uint8 and pos.dtype == torch.int32 and allow.dtype == torch.uint8
+        assert tuple(gid.shape) == (B, T) and tuple(pos.shape) == (B, T) and gid.is_contiguous() and pos.is_contiguous()
+        d.gid, d.pos, d.allow, d.num_groups = gid.data_ptr(), pos.data_ptr(), allow.data_ptr(), int(allow.shape[0])
+    if size is not None:
+        assert size.dtype == torch.float32 and size.is_contiguous() and tuple(size.shape) == (B, T)
+        d.size = size.data_ptr()
+    out = torch.empty(B, T, dtype=torch.float32, device=q.device)
+    L.check(L.lib().tome_attention_importance(C.byref(d), _ptr(q), _ptr(k), _ptr(lse),
+                                              {"row_mean": L.IMPORTANCE_ROW_MEAN, "received": L.IMPORTANCE_RECEIVED}[mode], _ptr(out), _stream()))
+    return out
+
+
+def prune_row_map(ids: torch.Tensor, tokens: int, gid: Optional[torch.Tensor] = None, pos: Optional[torch.Tensor] = None):
+    """ids i32 [B, kept] -> (row_map i32 [B, tokens] with -1 for pruned tokens, gid_out, pos_out of the kept tokens)."""
+    _need_cuda(ids, gid, pos)
+    B, K = ids.shape
+    rm = torch.empty(B, tokens, dtype=torch.int32, device=ids.device)
+    go = None if gid is None else torch.empty(B, K, dtype=torch.uint8, device=ids.device)
+    po = None if pos is None else torch.empty(B, K, dtype=torch.int32, device=ids.device)
+    L.check(L.lib().tome_prune_row_map(B, tokens, K, _ptr(ids), _ptr(gid), _ptr(pos), _ptr(rm), _ptr(go), _ptr(po), _stream()))
+    return rm, go, po
+
+
+def prune_bwd(row_map: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+    """Backward of the top-k gather: dx [B, T, C] from dy [B, kept, C] (zero rows for pruned tokens)."""
+    _need_cuda(row_map, dy)
+    B, T = row_map.shape
+    assert dy.is_contiguous() and dy.shape[0] == B
+    dx = torch.empty(B, T, dy.shape[2], dtype=dy.dtype, device=dy.device)
+    L.check(L.lib().tome_prune_bwd(B, T, dy.shape[1], dy.shape[2], _dt(dy), _ptr(row_map), _ptr(dy), _ptr(dx), _stream()))
+    return dx

@@ -151,6 +151,22 @@ class TokenSequence:
         pos = np.concatenate([np.arange(s.num_tokens, dtype=np.int32) for s in self.token_sequence])
         return gid, pos
 
+    def layer_group_ids(self, layer: int) -> Tuple[np.ndarray, np.ndarray]:
+        """group_ids() of the compression grammar at `layer` (the rows of generate_attention_mask(layer=layer), :222-238,
+        313-321, as group ids / positions): what a pruning stack passes as tome_stack_io_t.layer_gid / layer_pos."""
+        sets = self._parse(layer=layer)
+        gid = np.concatenate([np.full(s.num_tokens, g, np.uint8) for g, s in enumerate(sets)])
+        pos = np.concatenate([np.arange(s.num_tokens, dtype=np.int32) for s in sets])
+        return gid, pos
+
+    def prune_sets(self) -> List[Tuple[int, int]]:
+        """[(tokens at layer 0, tokens dropped by every layer)] per token set, in sequence order: tome_stack_cfg_t.prune_set_n /
+        prune_set_c (the grammar's `num_tokens - layer * num_compressed_tokens`, :236)."""
+        if self.token_compression_sequence_str is None:
+            raise ValueError("no token_compression_sequence was given")
+        l0, l1 = self._parse(layer=0), self._parse(layer=1)
+        return [(a.num_tokens, a.num_tokens - b.num_tokens) for a, b in zip(l0, l1)]
+
     def allow_table(self) -> np.ndarray:
         """uint8 [G, G]: rule code of (query group, key group)."""
         sets = self.token_sequence

@@ -509,6 +509,106 @@ def tome_stack(params: Sequence[BlockParams], pos_embedding, x, gid, pos, allow,
     return x, size, origin
 
 
+def attention_weights(q, k, mask=None, bias=None):
+    """The softmax weights of `attention` [B,H,Tq,Tk] (flax dot_product_attention_weights, before dropout)."""
+    torch = _torch()
+    logits = torch.einsum("bqhd,bkhd->bhqk", q / math.sqrt(q.shape[-1]), k)
+    if bias is not None:
+        logits = logits + bias
+    if mask is not None:
+        logits = torch.where(mask, logits, torch.full_like(logits, torch.finfo(logits.dtype).min))
+    return torch.softmax(logits, dim=-1)
+
+
+def attention_importance(w, mode: str = "row_mean"):
+    """compressed_attention.py:303-306: mean over heads of the mean over the LAST axis (keys) of attn_weights [B,H,Tq,Tk]
+    -> [B,T] ("row_mean": 1/T for every token, rows of a softmax sum to one).  "received": the inner mean over queries."""
+    inner = w.mean(dim=-1) if mode == "row_mean" else w.mean(dim=-2)          # [B,H,T]
+    return inner.mean(dim=-2)
+
+
+def prune_sets_at(sets, layer: int):
+    """Token sets of a pruning stack entering `layer`: sets = [(n at layer 0, c dropped per layer)] -> tokenset_idx
+    [(start, n)], tokenset_k (token_sequencer.py:222-238: num_tokens - layer * num_compressed_tokens)."""
+    idx, ks, start = [], [], 0
+    for n0, c in sets:
+        n = n0 - layer * c
+        idx.append((start, n))
+        ks.append(n - c)
+        start += n
+    return idx, ks
+
+
+def prune_block(p: BlockParams, x, gid, pos, allow, *, num_heads, tokenset_idx, tokenset_k, importance="received",
+                ln_axis="seq", act_dtype=None, relu_gate=None, ids_override=None, next_groups=None, trace: Optional[dict] = None):
+    """The pruning sibling of tome_block (compressed_attention.py:328-358 with :303-308): attention, importance scores from
+    its weights, per-set top-k (compute_top_k_tokens) of the post-residual tokens, MLP on the kept ones.  The reference
+    prunes the attention output before the out projection and then adds the unpruned residual (shapes cannot agree); the
+    same token choice applied to both branches is a gather after the residual add, which is what this does.
+    ids_override [B, kept]: take the implementation's keep decisions (scores within rounding of each other may swap).
+    next_groups = (gid, pos) of the compression grammar's next layer, else the kept tokens carry their own."""
+    torch = _torch()
+    B, T, C = x.shape
+    H = num_heads
+    rd = lambda t: _round_st(t, act_dtype)  # noqa: E731
+    h = rd(layer_norm(x, p.ln1_scale, p.ln1_bias, axis=ln_axis))
+    q = rd(h @ p.wq + p.bq).reshape(B, T, H, -1)
+    k = rd(h @ p.wk + p.bk).reshape(B, T, H, -1)
+    v = rd(h @ p.wv + p.bv).reshape(B, T, H, -1)
+    mask = torch.as_tensor(dense_mask(gid, pos, gid, pos, allow))[:, None, :, :]
+    w = attention_weights(q, k, mask=mask)
+    o = rd(torch.einsum("bhqk,bkhd->bqhd", w, v).reshape(B, T, -1))
+    x = rd(x + (o @ p.wo + p.bo))
+    imp = attention_importance(w.detach(), importance).to(torch.float32).numpy()
+    if ids_override is None:
+        ids = np.stack([compute_top_k_tokens(np.zeros((T, 1), np.float32), imp[b], tokenset_idx, tokenset_k)[1] for b in range(B)])
+    else:
+        ids = np.asarray(ids_override)
+    if trace is not None:
+        trace["importance"], trace["ids"] = imp, ids
+    x = torch.gather(x, 1, torch.as_tensor(ids.astype(np.int64))[:, :, None].expand(B, ids.shape[1], C))   # jnp.take (:46)
+    if next_groups is not None:
+        gid, pos = (np.broadcast_to(a, (B, ids.shape[1])).copy() for a in next_groups)
+    else:
+        gid, pos = np.take_along_axis(gid, ids, axis=1), np.take_along_axis(pos, ids, axis=1)
+    y = rd(layer_norm(x, p.ln2_scale, p.ln2_bias, axis=ln_axis))
+    pre = y @ p.w1 + p.b1
+    y = rd(torch.relu(pre) if relu_gate is None else torch.where(torch.as_tensor(relu_gate), pre, torch.zeros_like(pre)))
+    return rd(x + (y @ p.w2 + p.b2)), gid, pos, ids
+
+
+def prune_stack(params: Sequence[BlockParams], pos_embedding, x, gid, pos, allow, *, num_heads, sets, importance="received",
+                ln_axis="seq", act_dtype=None, relu_gate: Optional[Sequence] = None, ids_override: Optional[Sequence] = None,
+                layer_groups: Optional[Sequence] = None, trace: Optional[list] = None):
+    """StackedCompressedEncoder1DBlock (compressed_attention.py:377-404) with shrinking T.  layer_groups[l] = (gid, pos) of
+    TokenSequence.generate_attention_mask(layer=l) (masks[layer_idx], :399); None: groups are carried with the kept tokens.
+    Returns (x_final, origin [B,T0] = row of x_final each original token ended in, -1 when pruned)."""
+    B, T0, C = x.shape
+    x = _round_st(x + pos_embedding, act_dtype)
+    g0, p0 = (gid, pos) if layer_groups is None else layer_groups[0]
+    gid = np.broadcast_to(g0, (B, T0)).copy()
+    pos = np.broadcast_to(p0, (B, T0)).copy()
+    origin = np.broadcast_to(np.arange(T0, dtype=np.int32), (B, T0)).copy()
+    for li, p in enumerate(params):
+        idx, ks = prune_sets_at(sets, li)
+        tr: dict = {}
+        nxt = None if layer_groups is None or li + 1 >= len(params) else layer_groups[li + 1]
+        T = x.shape[1]
+        x, gid2, pos2, ids = prune_block(p, x, gid, pos, allow, num_heads=num_heads, tokenset_idx=idx, tokenset_k=ks,
+                                         importance=importance, ln_axis=ln_axis, act_dtype=act_dtype,
+                                         relu_gate=None if relu_gate is None else relu_gate[li],
+                                         ids_override=None if ids_override is None else ids_override[li], next_groups=nxt, trace=tr)
+        if layer_groups is not None and li + 1 >= len(params):
+            gid2, pos2 = gid2, pos2          # after the last layer no mask is consumed
+        gid, pos = gid2, pos2
+        rm = np.full((B, T), -1, np.int32)
+        np.put_along_axis(rm, ids, np.broadcast_to(np.arange(ids.shape[1], dtype=np.int32), ids.shape), axis=1)
+        origin = np.where(origin >= 0, np.take_along_axis(rm, np.maximum(origin, 0), axis=1), -1)
+        if trace is not None:
+            trace.append(tr)
+    return x, origin
+
+
 def readout_loss(x_final, origin, readout_idx, target):
     """Stand-in for octo.py:123-124 + :167-174: gather the rows the readout tokens ended up in (unmerge to the
     original positions, then jnp.take), mean squared error against `target` [B, n_readout, C]."""

@@ -4,6 +4,8 @@ import ctypes as C
 import os
 import re
 
+import numpy as np
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -158,3 +160,25 @@ def test_image_tokenizer_shapes_on_host(lib):
         bad = L.ImageTokenizerDesc.from_buffer_copy(d)
         setattr(bad, field, value)
         assert lib.tome_image_tokenizer_param_count(C.byref(bad)) == -1 and msg in lib.tome_last_error(), field
+
+
+def test_pruning_stack_shapes_on_host(lib):
+    """tome_stack_cfg_t.prune_*: token counts per layer follow the compression grammar (n - layer * c), the argument checks
+    name what is wrong -- no GPU."""
+    from multi_modal_transformers_tokenmerge_b200.engine import StackConfig
+    from multi_modal_transformers_tokenmerge_b200.tokenizers.token_sequencer import TokenSequence
+    ts = TokenSequence("[TaskDescriptionPrefix{16}] [Image{256};Readout{4}]*2", "[TaskDescriptionPrefix{0}] [Image{8};Readout{0}]*2")
+    sets = ts.prune_sets()
+    assert sets == [(16, 0), (256, 8), (4, 0), (256, 8), (4, 0)]
+    g3, p3 = ts.layer_group_ids(3)
+    assert g3.shape == (536 - 48,) and list(np.bincount(g3)) == [16, 232, 4, 232, 4] and p3[16 + 231] == 231
+    base = dict(batch=2, tokens=536, channels=384, heads=6, head_dim=64, mlp_dim=1536, layers=12, prop_attn=False, num_groups=5, n_readout=8)
+    cfg = StackConfig(**base, prune_sets=tuple(sets)).c()
+    assert [lib.tome_stack_tokens_at(C.byref(cfg), l) for l in (0, 1, 12)] == [536, 520, 344]
+    assert lib.tome_stack_workspace_bytes(C.byref(cfg)) > 0
+    for kw, msg in ((dict(prune_sets=tuple(sets), r=4), b"r = 0"), (dict(prune_sets=((16, 0), (256, 30), (4, 0), (256, 8), (4, 0))), b"cannot drop"),
+                    (dict(prune_sets=((16, 0), (256, 8))), b"token sets hold")):
+        b2 = dict(base)
+        b2.update(kw)
+        bad = StackConfig(**b2).c()
+        assert lib.tome_stack_param_count(C.byref(bad)) == -1 and msg in lib.tome_last_error(), kw

@@ -1,0 +1,193 @@
+"""The pruning sibling of the merge path on the GPU: importance scores from the attention weights
+(compressed_attention.py:303-306), per-set top-k (token_compression.py:15-46), the gather's row map / backward, and the
+stack executor running one prune per layer with the compression grammar's per-layer masks (token_sequencer.py:222-238,
+compressed_attention.py:396-402) -- against the oracle.  Needs a B200: `-m gpu`.
+
+Protocol, as for the matching: kept-token indices must be bit-exact when the oracle ranks the GPU's OWN fp32 importance
+scores; the scores themselves, the outputs and the gradients are compared within the tolerance written in each test, with
+the oracle following the GPU's keep decisions and ReLU gates."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import tome_oracle as O  # noqa: E402
+from multi_modal_transformers_tokenmerge_b200.tokenizers.token_sequencer import TokenSequence  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from multi_modal_transformers_tokenmerge_b200 import _lib, engine, ops
+    _lib.lib()
+    return ops, engine
+
+
+def rel_err(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+@pytest.mark.parametrize("T,H,D,masked,sized", [(536, 6, 64, True, False), (74, 3, 256, True, True), (200, 2, 128, False, False),
+                                                (333, 4, 64, False, True), (1000, 2, 64, True, True)])
+def test_attention_importance(pkg, T, H, D, masked, sized):
+    """mean over heads of the mean over keys ("row_mean", the reference's expression: 1 / T) or over queries ("received") of
+    the softmax weights, from q, k and the lse the attention forward saved, vs the oracle's dense weights: relative L2 <= 1e-2
+    (bf16 logits through exp; observed ~2e-3), row_mean within 1e-3 of 1 / T, bit-reproducible."""
+    ops, _ = pkg
+    rng = np.random.default_rng(T + H)
+    B = 2
+    qkv = torch.tensor(rng.standard_normal((B, T, 3, H, D)).astype(np.float32)).cuda().bfloat16()
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    gid = pos = allow = size = None
+    if masked:
+        n_img = (T - 16) // 2 - 4
+        g1, p1, allow, _ = O.sequence_groups(f"[TaskDescriptionPrefix{{16}}] [Image{{{n_img}}};Readout{{4}}]*2")
+        pad = T - g1.shape[0]
+        g1 = np.concatenate([g1, np.full(pad, g1[-1], np.uint8)])
+        p1 = np.concatenate([p1, np.arange(pad, dtype=np.int32)])
+        gid, pos = np.stack([g1, g1]), np.stack([p1, p1])
+    if sized:
+        size = rng.integers(1, 6, size=(B, T)).astype(np.float32)
+    dv_ = lambda a: None if a is None else torch.as_tensor(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    kw = dict(gid=dv_(gid), pos=dv_(pos), allow=dv_(allow), size=dv_(size))
+    if D == 64:
+        _, lse = ops.attention_fwd(q, k, v, **kw)
+    else:   # the generic path's lse has the same definition; take the oracle's so this test pins the importance kernel alone
+        lse = None
+    mask = None if gid is None else torch.as_tensor(O.dense_mask(gid, pos, gid, pos, allow))[:, None]
+    bias = None if size is None else torch.log(torch.as_tensor(size))[:, None, None, :]
+    qf, kf = q.float().cpu(), k.float().cpu()
+    w = O.attention_weights(qf, kf, mask=mask, bias=bias)
+    if lse is None:
+        logits = torch.einsum("bqhd,bkhd->bhqk", qf / np.sqrt(D), kf)
+        if bias is not None:
+            logits = logits + bias
+        if mask is not None:
+            logits = torch.where(mask, logits, torch.full_like(logits, torch.finfo(torch.float32).min))
+        lse = torch.logsumexp(logits, dim=-1).cuda().contiguous()
+    for mode in ("row_mean", "received"):
+        got = ops.attention_importance(q, k, lse, mode, **kw)
+        again = ops.attention_importance(q, k, lse, mode, **kw)
+        assert torch.equal(got, again)
+        want = O.attention_importance(w, mode)
+        e = rel_err(got.cpu(), want)
+        assert e <= 1e-2, f"{mode}: rel err {e}"
+        if mode == "row_mean":
+            assert (got.cpu() * T - 1).abs().max() <= 1e-3
+        else:
+            assert abs(got.sum(dim=1).cpu() - 1.0).max() <= 1e-3       # the weights of a batch row sum to H * T before the means
+
+
+def test_prune_row_map_and_backward(pkg):
+    """Inverse of the kept-index list (-1 for pruned tokens), group / position carried with the kept tokens, and the gather's
+    backward (zero rows for pruned tokens): index work, bit-exact against numpy."""
+    ops, _ = pkg
+    rng = np.random.default_rng(5)
+    B, T, K, C = 3, 61, 40, 64
+    ids = np.stack([rng.permutation(T)[:K] for _ in range(B)]).astype(np.int32)
+    gid = rng.integers(0, 5, size=(B, T)).astype(np.uint8)
+    pos = rng.integers(0, 30, size=(B, T)).astype(np.int32)
+    rm, go, po = ops.prune_row_map(torch.as_tensor(ids).cuda(), T, torch.as_tensor(gid).cuda(), torch.as_tensor(pos).cuda())
+    want = np.full((B, T), -1, np.int32)
+    np.put_along_axis(want, ids, np.broadcast_to(np.arange(K, dtype=np.int32), (B, K)), axis=1)
+    np.testing.assert_array_equal(rm.cpu().numpy(), want)
+    np.testing.assert_array_equal(go.cpu().numpy(), np.take_along_axis(gid, ids, axis=1))
+    np.testing.assert_array_equal(po.cpu().numpy(), np.take_along_axis(pos, ids, axis=1))
+    for dtype in (torch.bfloat16, torch.float32):
+        dy = torch.tensor(rng.standard_normal((B, K, C)).astype(np.float32)).cuda().to(dtype)
+        dx = ops.prune_bwd(rm, dy)
+        ref = torch.zeros(B, T, C, dtype=dtype)
+        ref.scatter_(1, torch.as_tensor(ids.astype(np.int64))[:, :, None].expand(B, K, C), dy.cpu())
+        assert torch.equal(dx.cpu(), ref)
+
+
+SEQ = "[TaskDescriptionPrefix{8}] [Image{40};Readout{2}]*2"
+COMP = "[TaskDescriptionPrefix{0}] [Image{6};Readout{0}]*2"
+
+
+@pytest.mark.parametrize("importance,grammar_masks,ln_axis,Lyr", [("received", True, 2, 3), ("received", False, 2, 3), ("row_mean", True, 2, 2),
+                                                                  ("received", True, 1, 2)])
+def test_prune_stack_forward_backward_vs_oracle(pkg, importance, grammar_masks, ln_axis, Lyr):
+    """A pruning stack (StackConfig.prune_sets) vs oracle.prune_stack: every layer drops 6 of each image set's tokens (92 -> 80 ->
+    68 -> 56), masks either from the compression grammar at each layer (layer_gid / layer_pos, what compressed_attention.py:399
+    passes) or carried with the kept tokens.  Kept indices bit-exact from the GPU's own importance scores; importance within
+    1e-2 of the oracle's; final tokens / readout / loss within 1e-2 (2e-2 for token-axis LayerNorm) and every parameter gradient
+    within 2e-2 (4e-2) with the oracle following the GPU's keep decisions and ReLU gates; readout rows tracked through the
+    row maps."""
+    ops, engine = pkg
+    rng = np.random.default_rng(17)
+    B, C, H, D, Dff = 2, 128, 2, 64, 256
+    ts = TokenSequence(SEQ, COMP)
+    gid, pos = ts.group_ids()
+    allow, ro = ts.allow_table(), ts.get_modality_idx("readouts")
+    T = gid.shape[0]
+    sets = ts.prune_sets()
+    assert sets == [(8, 0), (40, 6), (2, 0), (40, 6), (2, 0)]
+    layer_groups = [ts.layer_group_ids(l) for l in range(Lyr)] if grammar_masks else None
+    layers = [O.init_block_params(rng, C, H, D, Dff) for _ in range(Lyr)]
+    for d in layers:
+        d["ln1_scale"] = (d["ln1_scale"] + 0.1 * rng.standard_normal(C)).astype(np.float32)
+        d["ln2_bias"] = (0.1 * rng.standard_normal(C)).astype(np.float32)
+    pe = (rng.standard_normal((1, T, C)) * 0.02).astype(np.float32)
+    x = rng.standard_normal((B, T, C)).astype(np.float32)
+    y = rng.standard_normal((B, len(ro), C)).astype(np.float32)
+    cfg = engine.StackConfig(batch=B, tokens=T, channels=C, heads=H, head_dim=D, mlp_dim=Dff, layers=Lyr, r=0, ln_axis=ln_axis,
+                             prop_attn=False, num_groups=allow.shape[0], n_readout=len(ro), prune_sets=tuple(sets),
+                             prune_importance=importance)
+    eng = engine.ToMeStackEngine(cfg, gid=gid, pos=pos, allow=allow, readout_idx=ro,
+                                 layer_gid=None if layer_groups is None else [g for g, _ in layer_groups],
+                                 layer_pos=None if layer_groups is None else [p for _, p in layer_groups])
+    eng.load_params(pe[0], layers)
+    assert [eng.tokens_at(l) for l in range(Lyr + 1)] == [T - 12 * l for l in range(Lyr + 1)]
+    eng.zero_grad()
+    eng.forward(torch.tensor(x).cuda(), torch.tensor(y).cuda())
+    eng.backward()
+    torch.cuda.synchronize()
+    imps, ids = zip(*[tuple(t.cpu().numpy() for t in eng.layer_prune(l)) for l in range(Lyr)])
+    for l in range(Lyr):    # the oracle's top-k of the GPU's own scores reproduces the GPU's kept indices bit for bit
+        idx, ks = O.prune_sets_at(sets, l)
+        for b in range(B):
+            np.testing.assert_array_equal(O.compute_top_k_tokens(np.zeros((imps[l].shape[1], 1), np.float32), imps[l][b], idx, ks)[1], ids[l][b])
+    gates = [eng.layer_relu_gate(l).cpu().numpy() for l in range(Lyr)]
+    v, vf = eng.param_views(eng.params_bf16.float().cpu()), eng.param_views(eng.params.cpu())
+    params = []
+    hd = H * D
+    for l in range(Lyr):
+        src, srcf = v["layers"][l], vf["layers"][l]
+        d = dict(ln1_scale=srcf["ln1_scale"], ln1_bias=srcf["ln1_bias"], ln2_scale=srcf["ln2_scale"], ln2_bias=srcf["ln2_bias"],
+                 wq=src["wqkv"][:, :hd], wk=src["wqkv"][:, hd:2 * hd], wv=src["wqkv"][:, 2 * hd:], bq=srcf["bqkv"][:hd],
+                 bk=srcf["bqkv"][hd:2 * hd], bv=srcf["bqkv"][2 * hd:], wo=src["wo"], bo=srcf["bo"], w1=src["w1"], b1=srcf["b1"],
+                 w2=src["w2"], b2=srcf["b2"])
+        params.append(O.BlockParams(**{k_: t.clone().contiguous().requires_grad_(True) for k_, t in d.items()}))
+    pet = vf["pos_embedding"].clone()[None].requires_grad_(True)
+    tr = []
+    xf, origin = O.prune_stack(params, pet, torch.tensor(x), gid, pos, allow, num_heads=H, sets=sets, importance=importance,
+                               ln_axis="seq" if ln_axis == 1 else "feature", act_dtype=torch.bfloat16, relu_gate=gates,
+                               ids_override=ids, layer_groups=layer_groups, trace=tr)
+    for l in range(Lyr):
+        e = rel_err(torch.as_tensor(imps[l]), torch.as_tensor(tr[l]["importance"]))
+        assert e <= 1e-2, f"layer {l} importance: rel err {e}"
+    assert (origin[:, ro] >= 0).all()
+    loss, out = O.readout_loss(xf, origin, ro, torch.tensor(y))
+    loss.backward()
+    tol_f, tol_g = (1e-2, 2e-2) if ln_axis == 2 else (2e-2, 4e-2)
+    e_fwd = dict(final_x=rel_err(eng.final_x().float().cpu(), xf.detach()), readout=rel_err(eng.readout.cpu(), out.detach()),
+                 loss=abs(eng.loss[0].item() - loss.item()) / abs(loss.item()))
+    g = eng.param_views(eng.grads.cpu())
+    e_grad = {"pos_embedding": rel_err(g["pos_embedding"], pet.grad[0])}
+    for l in range(Lyr):
+        p, gl = params[l], g["layers"][l]
+        ref = dict(ln1_scale=p.ln1_scale.grad, ln1_bias=p.ln1_bias.grad, ln2_scale=p.ln2_scale.grad, ln2_bias=p.ln2_bias.grad,
+                   wqkv=torch.cat([p.wq.grad, p.wk.grad, p.wv.grad], 1), bqkv=torch.cat([p.bq.grad, p.bk.grad, p.bv.grad]),
+                   wo=p.wo.grad, bo=p.bo.grad, w1=p.w1.grad, b1=p.b1.grad, w2=p.w2.grad, b2=p.b2.grad)
+        for name, want in ref.items():
+            e_grad[f"layer {l} grad {name}"] = rel_err(gl[name], want)
+    worst = max(e_grad, key=e_grad.get)
+    print(f"\n[prune stack] {importance} grammar={grammar_masks} ln_axis={ln_axis}: fwd {e_fwd}; worst grad {worst} = {e_grad[worst]:.4f}")
+    for k_, val in e_fwd.items():
+        assert val <= tol_f, f"{k_}: rel err {val}"
+    for k_, val in e_grad.items():
+        assert val <= tol_g, f"{k_}: rel err {val}"
