@@ -13,8 +13,10 @@
 //   it_gn_partial_kernel / it_gn_final_kernel   GroupNorm statistics.  Flax's GroupNorm reduces over EVERY axis but the
 //                          batch one, so a (batch row, group) statistic spans all N images and all patches of that row:
 //                          per-CTA per-channel partial sums in a fixed order, then one thread per (row, group)
-//   it_gn_gelu_im2col_kernel   (x - mean) * rstd * scale + bias -> gelu -> the nine shifted copies of the 3x3 SAME
-//                          im2col row, zero outside the o2 x o2 window; one 16-byte store per thread
+//   it_gn_gelu_kernel      (x - mean) * rstd * scale + bias -> gelu, once per element (the statistics folded into a
+//                          per-(batch row, channel) multiply-add by it_gn_fold_kernel)
+//   it_im2col3_kernel      the nine shifted copies of the 3x3 SAME im2col row, zero outside the o2 x o2 window; one
+//                          16-byte load and one 16-byte store per thread
 //   it_posadd_kernel       Dense output + row_embedding[row_token] + col_embedding[col_token] -> out dtype
 // The last block convolution adds the pooled tensor through the GEMM's residual epilogue (image_tokenizer.py:170) and
 // the flatten is free ([.., o2, o2, F] rows ARE the Dense's K-major A operand).  HBM-bound: the im2col rows dominate the
@@ -40,7 +42,7 @@ struct ItGeom {
   int chunk_rows;       // batch rows per chunk
   int gn_ctas;
   // workspace offsets (bytes) of one chunk
-  size_t off_col, off_y0, off_pool, off_xa, off_xb, off_dense, off_part, off_stats, total;
+  size_t off_col, off_y0, off_pool, off_xa, off_xb, off_h, off_dense, off_part, off_stats, off_ab, total;
 };
 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -81,7 +83,8 @@ static int it_geometry(const tome_image_tokenizer_desc_t* d, ItGeom* g, const ch
   if (d->chunk_rows > 0) cr = d->chunk_rows;
   if (cr < 1) cr = 1;
   if (cr > d->batch) cr = d->batch;
-  TOME_CHECK(m0_row * cr < (1ll << 31) && m2_row * cr * 9 * (d->features / 8) < (1ll << 40), TOME_ERR_UNSUPPORTED, "%s: batch row too large", who);
+  TOME_CHECK(m0_row * cr * (g->k0 / 8) < (1ll << 31) && m2_row * cr * 9 * (d->features / 8) < (1ll << 31), TOME_ERR_UNSUPPORTED,
+             "%s: %lld batch rows per pass need more than 2^31 16-byte vectors of im2col rows: lower chunk_rows", who, cr);
   g->chunk_rows = (int)cr;
   long long want = m2_row * (d->features / 8) / (IT_THREADS * 4);
   g->gn_ctas = (int)std::min<long long>(IT_GN_MAX_CTAS, std::max<long long>(1, want));
@@ -91,48 +94,83 @@ static int it_geometry(const tome_image_tokenizer_desc_t* d, ItGeom* g, const ch
   g->off_pool = o;  o += align256((size_t)2 * m2_row * cr * d->features);
   g->off_xa = o;    o += align256((size_t)2 * m2_row * cr * d->features);
   g->off_xb = o;    o += align256((size_t)2 * m2_row * cr * d->features);
+  g->off_h = o;     o += align256((size_t)2 * m2_row * cr * d->features);
   g->off_dense = o; o += align256((size_t)4 * cr * d->n_images * g->np * d->embed_dim);
   g->off_part = o;  o += align256((size_t)4 * cr * g->gn_ctas * d->features * 2);
   g->off_stats = o; o += align256((size_t)4 * cr * d->num_groups * 2);
+  g->off_ab = o;    o += align256((size_t)4 * cr * d->features * 2);
   g->total = o;
   return TOME_OK;
 }
 
+// Division of an index below 2^31 by a runtime constant, as one multiply-high and a shift (the index decodes below would
+// otherwise spend more instructions on dividing than on moving their 16 bytes).
+struct FastDiv {
+  uint32_t mul, shift, d;
+  __device__ __forceinline__ uint32_t div(uint32_t n) const { return d == 1 ? n : __umulhi(n, mul) >> shift; }
+  __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const { q = div(n); r = n - q * d; }
+};
+static FastDiv make_fastdiv(uint32_t d) {   // exact for n < 2^31: mul = ceil(2^(31+s) / d), s = ceil(log2 d)
+  FastDiv f;
+  f.d = d;
+  uint32_t s = 0;
+  while ((1ull << s) < d) ++s;
+  f.mul = d == 1 ? 0u : (uint32_t)(((1ull << (31 + s)) + d - 1) / d);
+  f.shift = d == 1 ? 0u : s - 1;
+  return f;
+}
+
+struct Im2col0Args {
+  FastDiv vpr, o1, np, ppd, kw_c;
+  int psize, stride, img_w_c, c_in, normalize;
+  long long img_elems;   // H * W * C_in
+};
+
 // ---------------------------------------------------------------------------------------------------------------
 // pixels -> im2col rows of the input convolution.  Row m = ((img * np + patch) * o1 + oy) * o1 + ox, column
 // (dy * k + dx) * C_in + c  <-  image[img, py * p + oy * s + dy, px * p + ox * s + dx, c]: for one dy the (dx, c) run
-// is contiguous in the image.  One thread writes 8 consecutive columns (16 bytes).
+// is contiguous in the image.  One thread writes 8 consecutive columns (16 bytes), which span at most two dy rows.
+// uint8 pixels go through a 256-entry table of the normalised bf16 values (2 * (x / 255) - 1, image_tokenizer.py:67).
 template <typename PixT>
 __global__ void __launch_bounds__(IT_THREADS)
-it_im2col0_kernel(const PixT* __restrict__ image, __nv_bfloat16* __restrict__ col, long long n_vec, int k0, int np, int ppd,
-                  int o1, int psize, int stride, int kw_c /* k * C_in */, int img_w_c /* W * C_in */, int c_in, int normalize) {
+it_im2col0_kernel(const PixT* __restrict__ image, __nv_bfloat16* __restrict__ col, uint32_t n_vec, const Im2col0Args a) {
   pdl_prologue();
-  const long long v = (long long)blockIdx.x * IT_THREADS + threadIdx.x;
+  __shared__ uint16_t lut[256];
+  if (sizeof(PixT) == 1) {
+    float x = (float)threadIdx.x;
+    if (a.normalize) x = 2.0f * __fdiv_rn(x, 255.0f) - 1.0f;
+    __nv_bfloat16 h = __float2bfloat16(x);
+    lut[threadIdx.x] = *reinterpret_cast<uint16_t*>(&h);
+    __syncthreads();
+  }
+  const uint32_t v = blockIdx.x * IT_THREADS + threadIdx.x;
   if (v >= n_vec) return;
-  const int vpr = k0 >> 3;
-  const long long m = v / vpr;
-  const int kk = (int)(v - m * vpr) << 3;
-  const int ox = (int)(m % o1);
-  long long t = m / o1;
-  const int oy = (int)(t % o1);
-  t /= o1;
-  const int patch = (int)(t % np);
-  const long long img = t / np;
-  const int py = patch / ppd, px = patch - py * ppd;
-  const PixT* base = image + img * (long long)(img_w_c / c_in) * img_w_c   // H == W
-                     + (long long)(py * psize + oy * stride) * img_w_c + (long long)(px * psize + ox * stride) * c_in;
-  float f[8];
+  uint32_t m, kc, ox, oy, patch, img, py, px, dy, rem, t;
+  a.vpr.divmod(v, m, kc);
+  a.o1.divmod(m, t, ox);
+  a.o1.divmod(t, t, oy);
+  a.np.divmod(t, img, patch);
+  a.ppd.divmod(patch, py, px);
+  a.kw_c.divmod(kc << 3, dy, rem);
+  const PixT* base = image + img * a.img_elems + (long long)(py * a.psize + oy * a.stride + dy) * a.img_w_c +
+                     (long long)(px * a.psize + ox * a.stride) * a.c_in;
+  uint32_t w[4];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int k = kk + j;
-    const int dy = k / kw_c, rem = k - dy * kw_c;
-    float x = (float)base[(long long)dy * img_w_c + rem];
-    if (normalize) x = 2.0f * __fdiv_rn(x, 255.0f) - 1.0f;   // image_tokenizer.py:67
-    f[j] = x;
+    if (rem >= a.kw_c.d) { rem -= a.kw_c.d; base += a.img_w_c; }
+    uint32_t h16;
+    if (sizeof(PixT) == 1) {
+      h16 = lut[(uint32_t)base[rem]];
+    } else {
+      float x = (float)base[rem];
+      if (a.normalize) x = 2.0f * __fdiv_rn(x, 255.0f) - 1.0f;
+      __nv_bfloat16 h = __float2bfloat16(x);
+      h16 = *reinterpret_cast<uint16_t*>(&h);
+    }
+    if (j & 1) w[j >> 1] |= h16 << 16; else w[j >> 1] = h16;
+    ++rem;
   }
-  uint4 o;
-  o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
-  st_na_v4(col + v * 8, o);
+  st_na_v4(col + (size_t)v * 8, make_uint4(w[0], w[1], w[2], w[3]));
 }
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
@@ -142,32 +180,30 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
 
 // max pool, stride 1, VALID (flax.linen.max_pool).  Thread = (output pixel, 8 channels).
 __global__ void __launch_bounds__(IT_THREADS)
-it_pool_kernel(const __nv_bfloat16* __restrict__ y0, __nv_bfloat16* __restrict__ pooled, long long n_vec, int nchunk, int o1,
-               int o2, int window) {
+it_pool_kernel(const __nv_bfloat16* __restrict__ y0, __nv_bfloat16* __restrict__ pooled, uint32_t n_vec, FastDiv nchunk, int o1,
+               FastDiv o2, int window) {
   pdl_prologue();
-  const long long v = (long long)blockIdx.x * IT_THREADS + threadIdx.x;
+  const uint32_t v = blockIdx.x * IT_THREADS + threadIdx.x;
   if (v >= n_vec) return;
-  const int c = (int)(v % nchunk);
-  long long t = v / nchunk;
-  const int ox = (int)(t % o2);
-  t /= o2;
-  const int oy = (int)(t % o2);
-  const long long ip = t / o2;
-  const int F = nchunk << 3;
-  const __nv_bfloat16* src = y0 + ((ip * o1 + oy) * o1 + ox) * F + (c << 3);
+  uint32_t c, t, ox, oy, ip;
+  nchunk.divmod(v, t, c);
+  o2.divmod(t, t, ox);
+  o2.divmod(t, ip, oy);
+  const int F = nchunk.d << 3;
+  const __nv_bfloat16* src = y0 + (((size_t)ip * o1 + oy) * o1 + ox) * F + (c << 3);
   float best[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) best[j] = -INFINITY;
   for (int dy = 0; dy < window; ++dy)
     for (int dx = 0; dx < window; ++dx) {
       float f[8];
-      unpack8(*reinterpret_cast<const uint4*>(src + ((long long)dy * o1 + dx) * F), f);
+      unpack8(*reinterpret_cast<const uint4*>(src + ((size_t)dy * o1 + dx) * F), f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) best[j] = fmaxf(best[j], f[j]);
     }
   uint4 o;
   o.x = pack_bf16(best[0], best[1]); o.y = pack_bf16(best[2], best[3]); o.z = pack_bf16(best[4], best[5]); o.w = pack_bf16(best[6], best[7]);
-  *reinterpret_cast<uint4*>(pooled + v * 8) = o;
+  *reinterpret_cast<uint4*>(pooled + (size_t)v * 8) = o;
 }
 
 // GroupNorm statistics, stage 1: x [rows_b, R, F] bf16; CTA (j, b) sums x and x^2 per CHANNEL over its slice of the R rows
@@ -204,24 +240,30 @@ it_gn_partial_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ pa
   }
 }
 
-// stage 2: thread = (batch row, group): the CTA partials of the group's channels added in (CTA, channel) order ->
-// stats [rows_b, G, 2] = (mean, 1 / sqrt(var + eps)), var = E[x^2] - mean^2 clamped at 0 (Flax's fast variance).
-__global__ void it_gn_final_kernel(const float* __restrict__ part, float* __restrict__ stats, int rows_b, int n_ctas, int F,
-                                   int G, long long R, float eps) {
+// stage 2: warp = (batch row, group): lane j adds the group's channels of CTA partials j, j + 32, ... in order, then a
+// fixed butterfly over the lanes -> stats [rows_b, G, 2] = (mean, 1 / sqrt(var + eps)), var = E[x^2] - mean^2 clamped at 0
+// (Flax's fast variance).
+__global__ void __launch_bounds__(128)
+it_gn_final_kernel(const float* __restrict__ part, float* __restrict__ stats, int rows_b, int n_ctas, int F, int G, long long R,
+                   float eps) {
   pdl_prologue();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (i >= rows_b * G) return;
   const int b = i / G, g = i - b * G, cg = F / G;
   float s = 0.f, q = 0.f;
-  for (int j = 0; j < n_ctas; ++j) {
+  for (int j = lane; j < n_ctas; j += 32) {
     const float* p = part + (((long long)b * n_ctas + j) * F + g * cg) * 2;
     for (int ch = 0; ch < cg; ++ch) { s += p[2 * ch]; q += p[2 * ch + 1]; }
   }
-  const float inv_n = 1.0f / ((float)R * (float)cg);
-  const float mean = s * inv_n;
-  const float var = fmaxf(q * inv_n - mean * mean, 0.f);
-  stats[2 * i] = mean;
-  stats[2 * i + 1] = 1.0f / sqrtf(var + eps);
+  s = warp_sum(s);
+  q = warp_sum(q);
+  if (lane == 0) {
+    const float inv_n = 1.0f / ((float)R * (float)cg);
+    const float mean = s * inv_n;
+    const float var = fmaxf(q * inv_n - mean * mean, 0.f);
+    stats[2 * i] = mean;
+    stats[2 * i + 1] = 1.0f / sqrtf(var + eps);
+  }
 }
 
 __device__ __forceinline__ float gelu_tanh(float x) {   // flax.linen.gelu, approximate=True
@@ -230,38 +272,64 @@ __device__ __forceinline__ float gelu_tanh(float x) {   // flax.linen.gelu, appr
   return 0.5f * x * (1.0f + t);
 }
 
-// GroupNorm -> gelu -> im2col rows of the 3x3 SAME convolution.  Thread = (pixel, tap, 8 channels): output vector index
-// == thread index, so the stores are one contiguous stream; the activation is recomputed for each of the nine taps that
-// read a pixel (exp on the SFU, far below the store bandwidth this kernel is bound by).
-__global__ void __launch_bounds__(IT_THREADS)
-it_gn_gelu_im2col_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ scale,
-                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ col, long long n_vec, int nchunk, int o2,
-                         long long pix_per_row /* N * np * o2 * o2 */, int G) {
+// h = gelu(GroupNorm(x)), once per element.  Thread = (pixel, 8 channels); ab [rows_b, F, 2] holds the per-(batch row,
+// channel) affine (rstd * scale, bias - mean * rstd * scale) the preceding tiny kernel folded the statistics into.
+__global__ void it_gn_fold_kernel(const float* __restrict__ stats, const float* __restrict__ scale, const float* __restrict__ bias,
+                                  float* __restrict__ ab, int rows_b, int F, int G) {
   pdl_prologue();
-  const long long v = (long long)blockIdx.x * IT_THREADS + threadIdx.x;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows_b * F) return;
+  const int b = i / F, ch = i - b * F;
+  const float* st = stats + 2 * ((long long)b * G + ch / (F / G));
+  const float a = st[1] * scale[ch];
+  ab[2 * i] = a;
+  ab[2 * i + 1] = bias[ch] - st[0] * a;
+}
+
+__global__ void __launch_bounds__(IT_THREADS)
+it_gn_gelu_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ ab, __nv_bfloat16* __restrict__ h, uint32_t n_vec,
+                  FastDiv nchunk, FastDiv pix_per_row) {
+  pdl_prologue();
+  const uint32_t v = blockIdx.x * IT_THREADS + threadIdx.x;
   if (v >= n_vec) return;
-  const int c = (int)(v % nchunk);
-  long long t = v / nchunk;
-  const int tap = (int)(t % 9);
-  const long long m = t / 9;
-  const int ox = (int)(m % o2), oy = (int)((m / o2) % o2);
-  const int sy = oy + tap / 3 - 1, sx = ox + tap % 3 - 1;
-  uint4 o = make_uint4(0u, 0u, 0u, 0u);
-  if (sy >= 0 && sy < o2 && sx >= 0 && sx < o2) {
-    const int F = nchunk << 3, cg = F / G;
-    const long long ms = m + (long long)(sy - oy) * o2 + (sx - ox);
-    const int b = (int)(m / pix_per_row);
-    float f[8];
-    unpack8(*reinterpret_cast<const uint4*>(x + ms * F + (c << 3)), f);
+  uint32_t m, c;
+  nchunk.divmod(v, m, c);
+  const uint32_t b = pix_per_row.div(m);
+  const float4* abp = reinterpret_cast<const float4*>(ab + ((size_t)b * (nchunk.d << 3) + (c << 3)) * 2);
+  float f[8];
+  unpack8(ld_nc_v4(x + (size_t)v * 8), f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int ch = (c << 3) + j;
-      const float* st = stats + 2 * ((long long)b * G + ch / cg);
-      f[j] = gelu_tanh((f[j] - st[0]) * st[1] * __ldg(scale + ch) + __ldg(bias + ch));
-    }
-    o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+  for (int j = 0; j < 4; ++j) {
+    const float4 t = __ldg(abp + j);   // (a, b) of channels 2j and 2j + 1
+    f[2 * j] = gelu_tanh(fmaf(f[2 * j], t.x, t.y));
+    f[2 * j + 1] = gelu_tanh(fmaf(f[2 * j + 1], t.z, t.w));
   }
-  st_na_v4(col + v * 8, o);
+  uint4 o;
+  o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+  *reinterpret_cast<uint4*>(h + (size_t)v * 8) = o;
+}
+
+// im2col rows of the 3x3 SAME convolution: the nine shifted copies of h, zero outside the o2 x o2 window.  Thread =
+// (pixel, tap, 8 channels): output vector index == thread index, so the stores are one contiguous stream.
+__global__ void __launch_bounds__(IT_THREADS)
+it_im2col3_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict__ col, uint32_t n_vec, FastDiv nchunk, FastDiv o2) {
+  pdl_prologue();
+  const uint32_t v = blockIdx.x * IT_THREADS + threadIdx.x;
+  if (v >= n_vec) return;
+  uint32_t c, t, tap, m, ox, oy, q;
+  nchunk.divmod(v, t, c);
+  m = t / 9u;
+  tap = t - m * 9u;
+  o2.divmod(m, q, ox);
+  oy = q - o2.div(q) * o2.d;
+  const int ty = (int)(tap / 3u), tx = (int)(tap - (tap / 3u) * 3u);
+  const int sy = (int)oy + ty - 1, sx = (int)ox + tx - 1;
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  if (sy >= 0 && sy < (int)o2.d && sx >= 0 && sx < (int)o2.d) {
+    const long long ms = (long long)m + (long long)(ty - 1) * (int)o2.d + (tx - 1);
+    o = *reinterpret_cast<const uint4*>(h + (size_t)ms * (nchunk.d << 3) + (c << 3));
+  }
+  st_na_v4(col + (size_t)v * 8, o);
 }
 
 // tokens + row / column position embeddings (image_tokenizer.py:296-305), 4 features per thread.
@@ -376,6 +444,8 @@ extern "C" int tome_image_tokenizer_fwd(const tome_image_tokenizer_desc_t* d, co
   float* dense = reinterpret_cast<float*>(ws + g.off_dense);
   float* part = reinterpret_cast<float*>(ws + g.off_part);
   float* stats = reinterpret_cast<float*>(ws + g.off_stats);
+  float* ab = reinterpret_cast<float*>(ws + g.off_ab);
+  __nv_bfloat16* hbuf = reinterpret_cast<__nv_bfloat16*>(ws + g.off_h);
   const int F = d->features, E = d->embed_dim, nchunk = F / 8;
   const int gn_threads = nchunk * std::max(1, IT_THREADS / nchunk);
   const long long pix_img = (long long)d->image_size * d->image_size * d->channels_in;
@@ -391,41 +461,52 @@ extern "C" int tome_image_tokenizer_fwd(const tome_image_tokenizer_desc_t* d, co
     const uint8_t* img = reinterpret_cast<const uint8_t*>(image) + (size_t)img0 * pix_img * pix_bytes;
     {
       const long long nv = m0 * (g.k0 / 8);
+      Im2col0Args ia;
+      ia.vpr = make_fastdiv(g.k0 / 8); ia.o1 = make_fastdiv(g.o1); ia.np = make_fastdiv(g.np); ia.ppd = make_fastdiv(g.ppd);
+      ia.kw_c = make_fastdiv(d->conv_kernel * d->channels_in);
+      ia.psize = d->patch_size; ia.stride = d->conv_stride; ia.img_w_c = d->image_size * d->channels_in; ia.c_in = d->channels_in;
+      ia.normalize = d->normalize; ia.img_elems = pix_img;
       ProfScope prof(PROF_OTHER, (double)nv * 16, 1, stream);
       if (d->image_dtype == TOME_U8)
-        launch_k(it_im2col0_kernel<uint8_t>, nblk(nv), IT_THREADS, 0, stream, img, col, nv, g.k0, g.np, g.ppd, g.o1, d->patch_size,
-                 d->conv_stride, d->conv_kernel * d->channels_in, d->image_size * d->channels_in, d->channels_in, d->normalize);
+        launch_k(it_im2col0_kernel<uint8_t>, nblk(nv), IT_THREADS, 0, stream, img, col, (uint32_t)nv, ia);
       else
-        launch_k(it_im2col0_kernel<float>, nblk(nv), IT_THREADS, 0, stream, reinterpret_cast<const float*>(img), col, nv, g.k0, g.np,
-                 g.ppd, g.o1, d->patch_size, d->conv_stride, d->conv_kernel * d->channels_in, d->image_size * d->channels_in,
-                 d->channels_in, d->normalize);
+        launch_k(it_im2col0_kernel<float>, nblk(nv), IT_THREADS, 0, stream, reinterpret_cast<const float*>(img), col, (uint32_t)nv, ia);
       TOME_CUDA(cudaGetLastError());
     }
     rc = it_gemm((int)m0, F, g.k0, col, pb + it_offset(d, g, TOME_IT_CONV0_KERNEL), y0, TOME_BF16, pf + it_offset(d, g, TOME_IT_CONV0_BIAS),
                  nullptr, stream);
     if (rc != TOME_OK) return rc;
+    const FastDiv fd_chunk = make_fastdiv(nchunk), fd_o2 = make_fastdiv(g.o2);
     {
       const long long nv = m2 * nchunk;
       ProfScope prof(PROF_OTHER, (double)nv * 16 * (d->pool_window * d->pool_window + 1), 1, stream);
-      launch_k(it_pool_kernel, nblk(nv), IT_THREADS, 0, stream, y0, pooled, nv, nchunk, g.o1, g.o2, d->pool_window);
+      launch_k(it_pool_kernel, nblk(nv), IT_THREADS, 0, stream, y0, pooled, (uint32_t)nv, fd_chunk, g.o1, fd_o2, d->pool_window);
       TOME_CUDA(cudaGetLastError());
     }
     const __nv_bfloat16* x = pooled;
     for (int blk = 0; blk < d->num_blocks; ++blk) {
       const int pi = TOME_IT_BLOCK0 + 4 * blk;
       {
-        ProfScope prof(PROF_OTHER, (double)m2 * F * 2, 2, stream);
+        ProfScope prof(PROF_OTHER, (double)m2 * F * 2, 3, stream);
         launch_k(it_gn_partial_kernel, dim3(g.gn_ctas, rows_b), gn_threads, 0, stream, x, part, R, nchunk);
         TOME_CUDA(cudaGetLastError());
-        launch_k(it_gn_final_kernel, (unsigned)ceil_div(rows_b * d->num_groups, 128), 128, 0, stream, part, stats, rows_b, g.gn_ctas, F,
+        launch_k(it_gn_final_kernel, (unsigned)ceil_div(rows_b * d->num_groups, 4), 128, 0, stream, part, stats, rows_b, g.gn_ctas, F,
                  d->num_groups, R, d->gn_eps);
+        TOME_CUDA(cudaGetLastError());
+        launch_k(it_gn_fold_kernel, (unsigned)ceil_div(rows_b * F, 256), 256, 0, stream, stats, pf + it_offset(d, g, pi + 0),
+                 pf + it_offset(d, g, pi + 1), ab, rows_b, F, d->num_groups);
+        TOME_CUDA(cudaGetLastError());
+      }
+      {
+        const long long nv = m2 * nchunk;
+        ProfScope prof(PROF_OTHER, (double)nv * 32, 1, stream);
+        launch_k(it_gn_gelu_kernel, nblk(nv), IT_THREADS, 0, stream, x, ab, hbuf, (uint32_t)nv, fd_chunk, make_fastdiv((uint32_t)R));
         TOME_CUDA(cudaGetLastError());
       }
       {
         const long long nv = m2 * 9 * nchunk;
         ProfScope prof(PROF_OTHER, (double)nv * 16, 1, stream);
-        launch_k(it_gn_gelu_im2col_kernel, nblk(nv), IT_THREADS, 0, stream, x, stats, pf + it_offset(d, g, pi + 0),
-                 pf + it_offset(d, g, pi + 1), col, nv, nchunk, g.o2, R, d->num_groups);
+        launch_k(it_im2col3_kernel, nblk(nv), IT_THREADS, 0, stream, hbuf, col, (uint32_t)nv, fd_chunk, fd_o2);
         TOME_CUDA(cudaGetLastError());
       }
       __nv_bfloat16* y = xbuf[blk & 1];
