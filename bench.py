@@ -14,6 +14,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import re
 import statistics
 import subprocess
 import sys
@@ -159,6 +160,8 @@ def workload_config(args, world, B, T0):
     return {"workload": f"{args.config} ToMe stack train step (BASELINE.json configs[{c['baseline_cfg']}] shape)",
             "global_batch": B * world, "per_gpu_batch": B, "tokens": T0, "layers": c["layers"], "channels": c["channels"],
             "heads": c["heads"], "mlp_dim": c["mlp_dim"], "r_per_layer": c["r"], "mask": "block-causal group table",
+            "compression": ("per-modality top-k pruning per layer (attention-received importance)" if getattr(args, "compress", "merge") == "prune"
+                            else "ToMe bipartite merge per layer"),
             "ln_axis": "tokens",
             "loss": ("continuous action head + l2 loss on the pooled readouts (continuous_train_step, octo.py:242-280)"
                      if args.loss == "continuous" else "synthetic MSE on the readout rows"),
@@ -312,11 +315,23 @@ def measure_workload(args, cfgname, rank, world, local, steps, warmup, with_extr
     c = cfg_of(a2)
     gid, pos, allow, ro = sequence_groups(c["seq"])
     T0, B, C = len(gid), c["batch"], c["channels"]
+    prune_kw, eng_kw = {}, {}
+    if getattr(args, "compress", "merge") == "prune":
+        # the sibling compression path: every layer DROPS r tokens, split evenly over the image sets, by
+        # attention-received importance + per-set top-k, masks from the compression grammar at each layer
+        from multi_modal_transformers_tokenmerge_b200.tokenizers.token_sequencer import TokenSequence
+        n_img = c["seq"].count("Image{")
+        assert c["r"] % n_img == 0, "--compress prune: r must split evenly over the image sets"
+        comp = re.sub(r"Image\{\d+\}", "Image{%d}" % (c["r"] // n_img), re.sub(r"(TaskDescriptionPrefix|Readout)\{\d+\}", r"\1{0}", c["seq"]))
+        ts = TokenSequence(c["seq"], comp)
+        lg = [ts.layer_group_ids(l) for l in range(c["layers"])]
+        prune_kw = dict(prune_sets=tuple(ts.prune_sets()), prune_importance="received", prop_attn=False)
+        eng_kw = dict(layer_gid=[g_ for g_, _ in lg], layer_pos=[p_ for _, p_ in lg])
     cfg = StackConfig(batch=B, tokens=T0, channels=C, heads=c["heads"], head_dim=c["head_dim"], mlp_dim=c["mlp_dim"],
-                      layers=c["layers"], r=c["r"], ln_axis=1, num_groups=allow.shape[0], n_readout=len(ro),
-                      dropout_rate=args.dropout, dropout_seed=1234 + rank, attn_dropout_rate=args.attn_dropout,
+                      layers=c["layers"], r=0 if prune_kw else c["r"], ln_axis=1, num_groups=allow.shape[0], n_readout=len(ro),
+                      dropout_rate=args.dropout, dropout_seed=1234 + rank, attn_dropout_rate=args.attn_dropout, **prune_kw,
                       **(dict(head="continuous", head_features=ACTION_DIM, max_action=MAX_ACTION) if args.loss == "continuous" else {}))
-    eng = ToMeStackEngine(cfg, gid=gid, pos=pos, allow=allow, readout_idx=ro)
+    eng = ToMeStackEngine(cfg, gid=gid, pos=pos, allow=allow, readout_idx=ro, **eng_kw)
     eng.init_params(seed=1)  # same weights on every rank
     trainer = DataParallelTrainer(eng, comm_sms=args.comm_sms if world > 1 else 0, overlap=args.overlap)
     g = torch.Generator(device="cuda").manual_seed(100 + rank)
@@ -418,7 +433,7 @@ def measure_workload(args, cfgname, rank, world, local, steps, warmup, with_extr
         if cnt == 0:
             continue
         ent = {"ms_per_step": kms / nprof, "share": kms / tot_ms, "ops_per_step": cnt // nprof}
-        if k_ in ("gemm", "attn_fwd", "attn_bwd", "sim_argmax") and kms > 0:
+        if k_ in ("gemm", "attn_fwd", "attn_bwd", "sim_argmax", "importance") and kms > 0:
             ent["tflops"] = work / (kms * 1e-3) / 1e12
             ent["frac_of_sustained_bf16_peak"] = ent["tflops"] / P["tf_sust"]
         elif work > 0 and kms > 0:
@@ -446,7 +461,7 @@ def measure_workload(args, cfgname, rank, world, local, steps, warmup, with_extr
 
     # ---- the same merge kernel timed back to back (no per-launch event pair): three disjoint input/output sets of the
     # layer-0 shape (> the 126 MB L2), 30 launches between ONE pair of events.
-    if with_extras and merge_roof is not None and c["r"] > 0:
+    if with_extras and merge_roof is not None and c["r"] > 0 and not prune_kw:
         from multi_modal_transformers_tokenmerge_b200 import ops as O_
         r0 = lib.tome_clamp_r(T0, c["r"], 0, 0)
         metric = torch.randn(B, T0, c["head_dim"], device="cuda", generator=g)
@@ -518,6 +533,9 @@ def main():
                          "persistent GEMM grid shrinks by this); 0 = NCCL's default and the full grid")
     ap.add_argument("--overlap", default="none", choices=["layer", "none"],
                     help="gradient all-reduce: per-layer buckets overlapped with backward, or one all-reduce after backward")
+    ap.add_argument("--compress", default="merge", choices=["merge", "prune"],
+                    help="merge: ToMe bipartite soft matching + merge_wavg per layer (the metric's path); prune: the sibling path, "
+                         "per-modality top-k pruning of r tokens per layer (compressed_attention.py / token_compression.py:15-46)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--octo-base", default="auto", choices=["auto", "on", "off"],
                     help="also measure the octo_base shard (BASELINE.json configs[2]) and attach it as `octo_base`; auto = at 8 GPUs")

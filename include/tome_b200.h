@@ -538,7 +538,8 @@ int tome_image_tokenizer_fwd(const tome_image_tokenizer_desc_t* desc, const void
  * 8. Launch accounting and per-op timing (measurement aid; off by default, never on the product path's hot loop)
  * ------------------------------------------------------------------------------------------------------------ */
 enum tome_prof_tag { TOME_PROF_GEMM = 0, TOME_PROF_ATTN_FWD, TOME_PROF_ATTN_BWD, TOME_PROF_MERGE_FWD, TOME_PROF_MERGE_BWD,
-                     TOME_PROF_SIM, TOME_PROF_SELECT, TOME_PROF_LN, TOME_PROF_COLSUM, TOME_PROF_OTHER, TOME_PROF_NTAGS };
+                     TOME_PROF_SIM, TOME_PROF_SELECT, TOME_PROF_LN, TOME_PROF_COLSUM, TOME_PROF_OTHER, TOME_PROF_IMPORTANCE,
+                     TOME_PROF_PRUNE, TOME_PROF_NTAGS };
 /* number of kernels this library has launched in this process (reset != 0 zeroes the counter after reading) */
 long long tome_launch_count(int reset);
 /* record ONE CUDA event at the end of every op on its stream (up to max_records ops): op i is timed from the end of op

@@ -234,7 +234,7 @@ def lib() -> C.CDLL:
 
 
 PROF_TAGS = ["gemm", "attn_fwd", "attn_bwd", "merge_fwd", "merge_bwd", "sim_argmax", "select_topr", "layernorm", "colsum",
-             "other"]
+             "other", "importance", "prune"]
 
 
 def profile_collect() -> dict:

@@ -88,7 +88,7 @@ inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
 
 // ---- launch accounting + optional per-op CUDA-event timing (bench.py's roofline pass; off by default) ----
 enum ProfTag { PROF_GEMM = 0, PROF_ATTN_FWD, PROF_ATTN_BWD, PROF_MERGE_FWD, PROF_MERGE_BWD, PROF_SIM, PROF_SELECT,
-               PROF_LN, PROF_COLSUM, PROF_OTHER, PROF_NTAGS };
+               PROF_LN, PROF_COLSUM, PROF_OTHER, PROF_IMPORTANCE, PROF_PRUNE, PROF_NTAGS };
 struct ProfScope {  // RAII around one C-ABI op: `kernels` launches doing `work` algorithmic FLOPs or bytes
   cudaStream_t st;
   bool rec;

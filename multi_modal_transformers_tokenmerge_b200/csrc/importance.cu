@@ -151,7 +151,7 @@ extern "C" int tome_attention_importance(const tome_attn_desc_t* d, const void* 
   p.out = importance;
   const dim3 grid(ceil_div(d->tokens, 16 * IMP_WARPS), d->batch);
   const double flops = 2.0 * d->batch * d->heads * (double)d->tokens * d->tokens * d->head_dim;
-  ProfScope prof(PROF_OTHER, flops, 1, stream);
+  ProfScope prof(PROF_IMPORTANCE, flops, 1, stream);
 #define IMP_LAUNCH(DD)                                                                                          \
   if (mode == TOME_IMPORTANCE_RECEIVED) launch_k(attn_importance_kernel<DD, true>, grid, IMP_WARPS * 32, 0, stream, p); \
   else launch_k(attn_importance_kernel<DD, false>, grid, IMP_WARPS * 32, 0, stream, p)

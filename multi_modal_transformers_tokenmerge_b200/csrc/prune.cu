@@ -126,7 +126,7 @@ extern "C" int tome_prune_bwd(int batch, int tokens, int kept, int channels, int
   const long long n_vec = (long long)batch * tokens * vpr;
   long long blocks = (n_vec + 255) / 256;
   if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
-  ProfScope prof(PROF_MERGE_BWD, (double)batch * ((double)tokens + kept) * row_bytes, 1, stream);
+  ProfScope prof(PROF_PRUNE, (double)batch * ((double)tokens + kept) * row_bytes, 1, stream);
   launch_k(prune_bwd_kernel, (unsigned)blocks, 256, 0, stream, n_vec, tokens, kept, vpr, row_map, reinterpret_cast<const uint4*>(dy),
            reinterpret_cast<uint4*>(dx));
   TOME_CUDA(cudaGetLastError());
@@ -155,9 +155,12 @@ extern "C" int tome_topk_prune(const tome_prune_desc_t* d, const void* embedding
                "topk_prune: token set %d keeps k = %d of %d tokens (top_k needs 0 <= k <= n)", s, d->set_k[s], d->set_n[s]);
     if (d->set_n[s] > nmax) nmax = d->set_n[s];
   }
+  int ktot_host = 0;
+  for (int s = 0; s < d->n_sets; ++s) ktot_host += d->set_k[s];
+  const double row_bytes_host = d->channels * (d->dtype == TOME_BF16 ? 2.0 : 4.0);
   const size_t smem = (size_t)2 * nmax * sizeof(float);
   TOME_CHECK(smem <= 200 * 1024, TOME_ERR_UNSUPPORTED, "topk_prune: token set of %d tokens is too large for the shared-memory ranking", nmax);
-  ProfScope prof(PROF_OTHER, 0.0, 1, stream);
+  ProfScope prof(PROF_PRUNE, (double)d->batch * ((double)d->tokens * 4 + 2.0 * ktot_host * row_bytes_host), 1, stream);
   TOME_CUDA(cudaFuncSetAttribute(topk_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(d->n_sets, d->batch);
   launch_k(topk_prune_kernel, grid, PRUNE_THREADS, smem, stream, *d, reinterpret_cast<const uint8_t*>(embeddings), importance,
