@@ -11,7 +11,7 @@
 // The contraction s = q . k is the one place here that is a matrix product, and it is small and feeds a transcendental
 // epilogue: 16-row tiles per warp on the warp-level bf16 MMA (mma.sync m16n8k16, fp32 accumulate -- the same operand
 // rounding as the attention kernels' S), A fragments of the warp's 16 rows held in registers across the sweep over the
-// other axis, B fragments read straight from global memory (L1 / L2 resident: every warp of a CTA sweeps the same rows).
+// other axis, the swept operand staged through shared memory (cp.async, double-buffered) and read with ldmatrix.
 // Sums run in a fixed order (thread-sequential over heads and column tiles, then a 4-lane butterfly) => deterministic.
 // Weights are the UNDROPPED ones (the ranking must not depend on the dropout stream).
 #include <float.h>
@@ -40,22 +40,43 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+
 // ROWS_ARE_KEYS: the warp's 16 rows are keys and it sweeps the queries (RECEIVED); otherwise rows are queries, sweep over keys.
+// CTA = 4 warps x 16 rows.  The swept operand goes through shared memory in 64-row blocks (cp.async, two buffers; rows padded
+// by 16 bytes so the 8 x 8 ldmatrix tiles are conflict-free) together with its per-column terms (lse or log size, group,
+// position); B fragments come from ldmatrix (a row-major [n][k] tile IS the "col" B operand of m16n8k16).
 template <int D, bool ROWS_ARE_KEYS>
 __global__ void __launch_bounds__(IMP_WARPS * 32)
 attn_importance_kernel(const ImpParams p) {
   pdl_prologue();
+  constexpr int PITCH = D + 8;   // bf16 elements per staged row
+  constexpr int IMP_COLS = D > 128 ? 32 : 64;   // rows of the swept operand staged per step (static shared memory <= 48 KB)
+  __shared__ __align__(16) __nv_bfloat16 ys[2][IMP_COLS * PITCH];
+  __shared__ float c_term_s[2][IMP_COLS];
+  __shared__ int c_gp_s[2][IMP_COLS];     // group | position << 8
+  __shared__ uint8_t allow_s[32 * 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int b = blockIdx.y, T = p.tokens;
+  const int b = blockIdx.y, T = p.tokens, G = p.num_groups;
   const int r0 = (blockIdx.x * IMP_WARPS + warp) * 16;
-  if (r0 >= T) return;
   const __nv_bfloat16* X = (ROWS_ARE_KEYS ? p.k + b * p.k_bs : p.q + b * p.q_bs);
   const __nv_bfloat16* Y = (ROWS_ARE_KEYS ? p.q + b * p.q_bs : p.k + b * p.k_bs);
   const long long x_ts = ROWS_ARE_KEYS ? p.k_ts : p.q_ts, y_ts = ROWS_ARE_KEYS ? p.q_ts : p.k_ts;
   const int row[2] = {r0 + g, r0 + g + 8};
   const bool row_ok[2] = {row[0] < T, row[1] < T};
   const long long bt = (long long)b * T;
+  if (p.gid)
+    for (int i = threadIdx.x; i < G * G; i += IMP_WARPS * 32) allow_s[i] = p.allow[i];
   int rg[2] = {0, 0}, rp[2] = {0, 0};
   float r_lsz[2] = {0.f, 0.f};
 #pragma unroll
@@ -64,53 +85,80 @@ attn_importance_kernel(const ImpParams p) {
       if (p.gid) { rg[i] = p.gid[bt + row[i]]; rp[i] = p.pos[bt + row[i]]; }
       if (ROWS_ARE_KEYS && p.size) r_lsz[i] = log2f(p.size[bt + row[i]]);
     }
+  const int nblk = (T + IMP_COLS - 1) / IMP_COLS, n_it = p.heads * nblk;
+
+  auto stage = [&](int it, int buf) {   // block `it` = (head, 64-row block) of the swept operand -> buffer buf
+    const int h = it / nblk, c0 = (it - h * nblk) * IMP_COLS;
+    constexpr int VPR = D / 8;          // 16-byte vectors per row
+    for (int v = threadIdx.x; v < IMP_COLS * VPR; v += IMP_WARPS * 32) {
+      const int r = v / VPR, c = v - r * VPR;
+      const int yrow = min(c0 + r, T - 1);
+      cp_async16(smem_u32(&ys[buf][r * PITCH + c * 8]), Y + (long long)yrow * y_ts + h * D + c * 8);
+    }
+    cp_async_commit();
+    if (threadIdx.x < IMP_COLS) {
+      const int col = min(c0 + (int)threadIdx.x, T - 1);
+      c_term_s[buf][threadIdx.x] = ROWS_ARE_KEYS ? -p.lse[((long long)b * p.heads + h) * T + col] * 1.4426950408889634f
+                                                  : (p.size ? log2f(p.size[bt + col]) : 0.f);
+      c_gp_s[buf][threadIdx.x] = p.gid ? ((int)p.gid[bt + col] | (p.pos[bt + col] << 8)) : 0;
+    }
+  };
+
   float acc[2] = {0.f, 0.f};
-  for (int h = 0; h < p.heads; ++h) {
-    uint32_t a[D / 16][4];
+  uint32_t a[D / 16][4];
+  float r_lse2[2] = {0.f, 0.f};
+  stage(0, 0);
+  for (int it = 0; it < n_it; ++it) {
+    const int buf = it & 1;
+    const int h = it / nblk, c0 = (it - h * nblk) * IMP_COLS;
+    if (c0 == 0) {   // a new head: this warp's 16 rows of the fixed operand
 #pragma unroll
-    for (int kk = 0; kk < D / 16; ++kk) {
+      for (int kk = 0; kk < D / 16; ++kk)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int ri = i & 1;
-        a[kk][i] = row_ok[ri] ? *reinterpret_cast<const uint32_t*>(X + (long long)row[ri] * x_ts + h * D + kk * 16 + (i >> 1) * 8 + 2 * t) : 0u;
+        for (int i = 0; i < 4; ++i) {
+          const int ri = i & 1;
+          a[kk][i] = row_ok[ri] ? *reinterpret_cast<const uint32_t*>(X + (long long)row[ri] * x_ts + h * D + kk * 16 + (i >> 1) * 8 + 2 * t) : 0u;
+        }
+      if (!ROWS_ARE_KEYS) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          r_lse2[i] = row_ok[i] ? p.lse[((long long)b * p.heads + h) * T + row[i]] * 1.4426950408889634f : 0.f;
       }
     }
-    const float* lse_h = p.lse + ((long long)b * p.heads + h) * T;
-    float r_lse2[2] = {0.f, 0.f};
-    if (!ROWS_ARE_KEYS) {
+    cp_async_wait<0>();
+    __syncthreads();                       // block `it` has landed; every warp is done with the other buffer
+    if (it + 1 < n_it) stage(it + 1, buf ^ 1);
+    if (r0 < T) {
+      const uint32_t ybase = smem_u32(&ys[buf][0]) + ((lane & 7) * PITCH + (lane >> 3) * 8) * 2;
+#pragma unroll 2
+      for (int j = 0; j < IMP_COLS / 8; ++j) {
+        if (c0 + j * 8 >= T) break;
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int i = 0; i < 2; ++i) r_lse2[i] = row_ok[i] ? lse_h[row[i]] * 1.4426950408889634f : 0.f;
-    }
-    for (int c0 = 0; c0 < T; c0 += 8) {
-      float c[4] = {0.f, 0.f, 0.f, 0.f};
-      const int yrow = c0 + g;
-      const __nv_bfloat16* yr = Y + (long long)(yrow < T ? yrow : T - 1) * y_ts + h * D + 2 * t;
+        for (int kp = 0; kp < D / 32; ++kp) {
+          uint32_t bf[4];
+          ldmatrix_x4(bf, ybase + (j * 8 * PITCH + kp * 32) * 2);
+          mma_bf16_16816(c, a[2 * kp], bf[0], bf[1]);
+          mma_bf16_16816(c, a[2 * kp + 1], bf[2], bf[3]);
+        }
 #pragma unroll
-      for (int kk = 0; kk < D / 16; ++kk) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(yr + kk * 16);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(yr + kk * 16 + 8);
-        mma_bf16_16816(c, a[kk], b0, b1);
-      }
+        for (int jj = 0; jj < 2; ++jj) {
+          const int cl = j * 8 + 2 * t + jj;
+          if (c0 + cl >= T) continue;
+          const float c_term = c_term_s[buf][cl];
+          const int gp = c_gp_s[buf][cl], cg = gp & 255, cp = gp >> 8;
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int col = c0 + 2 * t + j;
-        if (col >= T) continue;
-        int cg = 0, cp = 0;
-        if (p.gid) { cg = p.gid[bt + col]; cp = p.pos[bt + col]; }
-        const float c_term = ROWS_ARE_KEYS ? -lse_h[col] * 1.4426950408889634f : (p.size ? log2f(p.size[bt + col]) : 0.f);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          if (!row_ok[i]) continue;
-          const int qg = ROWS_ARE_KEYS ? cg : rg[i], qp = ROWS_ARE_KEYS ? cp : rp[i];
-          const int kg = ROWS_ARE_KEYS ? rg[i] : cg, kp = ROWS_ARE_KEYS ? rp[i] : cp;
-          bool vis = true;
-          if (p.gid) {
-            const int al = p.allow[qg * p.num_groups + kg];
-            vis = al == 1 || (al == 2 && kp <= qp);
+          for (int i = 0; i < 2; ++i) {
+            bool vis = row_ok[i];
+            if (p.gid) {
+              const int al = ROWS_ARE_KEYS ? allow_s[cg * G + rg[i]] : allow_s[rg[i] * G + cg];
+              const bool causal_ok = ROWS_ARE_KEYS ? rp[i] <= cp : cp <= rp[i];
+              vis = vis && (al == 1 || (al == 2 && causal_ok));
+            }
+            const float r_term = ROWS_ARE_KEYS ? r_lsz[i] : -r_lse2[i];
+            const float s2 = fmaf(c[2 * i + jj], p.scale_log2, c_term + r_term);
+            acc[i] += vis ? fast_exp2(s2) : 0.f;
           }
-          const float r_term = ROWS_ARE_KEYS ? r_lsz[i] : -r_lse2[i];
-          const float s2 = fmaf(c[2 * i + j], p.scale_log2, c_term + r_term);
-          acc[i] += vis ? exp2f(s2) : 0.f;
         }
       }
     }
@@ -138,8 +186,9 @@ extern "C" int tome_attention_importance(const tome_attn_desc_t* d, const void* 
   TOME_CHECK(d->head_dim == 64 || d->head_dim == 128 || d->head_dim == 256, TOME_ERR_UNSUPPORTED,
              "attention_importance: head_dim %d not supported (64, 128, 256)", d->head_dim);
   TOME_CHECK(mode == TOME_IMPORTANCE_ROW_MEAN || mode == TOME_IMPORTANCE_RECEIVED, TOME_ERR_INVALID, "attention_importance: unknown mode %d", mode);
-  TOME_CHECK((d->q_token_stride | d->k_token_stride | d->q_batch_stride | d->k_batch_stride) % 2 == 0 &&
-             (((uintptr_t)q | (uintptr_t)k) & 3) == 0, TOME_ERR_INVALID, "attention_importance: q / k rows must be 4-byte aligned");
+  TOME_CHECK((d->q_token_stride | d->k_token_stride | d->q_batch_stride | d->k_batch_stride) % 8 == 0 &&
+             (((uintptr_t)q | (uintptr_t)k) & 15) == 0, TOME_ERR_INVALID, "attention_importance: q / k rows must be 16-byte aligned");
+  TOME_CHECK(d->num_groups <= 32, TOME_ERR_INVALID, "attention_importance: at most 32 groups");
   TOME_CHECK(!d->gid || (d->pos && d->allow && d->num_groups > 0), TOME_ERR_INVALID, "attention_importance: gid needs pos, allow, num_groups");
   ImpParams p;
   p.batch = d->batch; p.tokens = d->tokens; p.heads = d->heads;
