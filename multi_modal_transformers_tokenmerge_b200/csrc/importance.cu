@@ -55,7 +55,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // CTA = 4 warps x 16 rows.  The swept operand goes through shared memory in 64-row blocks (cp.async, two buffers; rows padded
 // by 16 bytes so the 8 x 8 ldmatrix tiles are conflict-free) together with its per-column terms (lse or log size, group,
 // position); B fragments come from ldmatrix (a row-major [n][k] tile IS the "col" B operand of m16n8k16).
-template <int D, bool ROWS_ARE_KEYS>
+template <int D, bool ROWS_ARE_KEYS, bool MASKED>
 __global__ void __launch_bounds__(IMP_WARPS * 32)
 attn_importance_kernel(const ImpParams p) {
   pdl_prologue();
@@ -64,7 +64,6 @@ attn_importance_kernel(const ImpParams p) {
   __shared__ __align__(16) __nv_bfloat16 ys[2][IMP_COLS * PITCH];
   __shared__ float c_term_s[2][IMP_COLS];
   __shared__ int c_gp_s[2][IMP_COLS];     // group | position << 8
-  __shared__ uint8_t allow_s[32 * 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int b = blockIdx.y, T = p.tokens, G = p.num_groups;
@@ -75,15 +74,25 @@ attn_importance_kernel(const ImpParams p) {
   const int row[2] = {r0 + g, r0 + g + 8};
   const bool row_ok[2] = {row[0] < T, row[1] < T};
   const long long bt = (long long)b * T;
-  if (p.gid)
-    for (int i = threadIdx.x; i < G * G; i += IMP_WARPS * 32) allow_s[i] = p.allow[i];
-  int rg[2] = {0, 0}, rp[2] = {0, 0};
-  float r_lsz[2] = {0.f, 0.f};
+  // Visibility of a column group for each of this thread's two rows, as bit masks over the (<= 32) groups: bit cg of vis1 =
+  // the pair is always visible, of vis2 = visible when the key's position does not exceed the query's (causal-intra sets).
+  int rp[2] = {0, 0};
+  uint32_t vis1[2] = {0xffffffffu, 0xffffffffu}, vis2[2] = {0u, 0u};
+  float r_term[2] = {0.f, 0.f};   // log2 size of a key row; -lse2 of a query row is set per head below
 #pragma unroll
   for (int i = 0; i < 2; ++i)
     if (row_ok[i]) {
-      if (p.gid) { rg[i] = p.gid[bt + row[i]]; rp[i] = p.pos[bt + row[i]]; }
-      if (ROWS_ARE_KEYS && p.size) r_lsz[i] = log2f(p.size[bt + row[i]]);
+      if (MASKED) {
+        const int rg = p.gid[bt + row[i]];
+        rp[i] = p.pos[bt + row[i]];
+        vis1[i] = 0u;
+        for (int cg = 0; cg < G; ++cg) {
+          const int al = ROWS_ARE_KEYS ? p.allow[cg * G + rg] : p.allow[rg * G + cg];
+          vis1[i] |= (al == 1 ? 1u : 0u) << cg;
+          vis2[i] |= (al == 2 ? 1u : 0u) << cg;
+        }
+      }
+      if (ROWS_ARE_KEYS && p.size) r_term[i] = log2f(p.size[bt + row[i]]);
     }
   const int nblk = (T + IMP_COLS - 1) / IMP_COLS, n_it = p.heads * nblk;
 
@@ -97,16 +106,17 @@ attn_importance_kernel(const ImpParams p) {
     }
     cp_async_commit();
     if (threadIdx.x < IMP_COLS) {
+      const bool ok = c0 + (int)threadIdx.x < T;   // a column past T contributes exp2(-inf) = 0
       const int col = min(c0 + (int)threadIdx.x, T - 1);
-      c_term_s[buf][threadIdx.x] = ROWS_ARE_KEYS ? -p.lse[((long long)b * p.heads + h) * T + col] * 1.4426950408889634f
-                                                  : (p.size ? log2f(p.size[bt + col]) : 0.f);
-      c_gp_s[buf][threadIdx.x] = p.gid ? ((int)p.gid[bt + col] | (p.pos[bt + col] << 8)) : 0;
+      const float ct = ROWS_ARE_KEYS ? -p.lse[((long long)b * p.heads + h) * T + col] * 1.4426950408889634f
+                                     : (p.size ? log2f(p.size[bt + col]) : 0.f);
+      c_term_s[buf][threadIdx.x] = ok ? ct : -INFINITY;
+      c_gp_s[buf][threadIdx.x] = MASKED ? ((int)p.gid[bt + col] | (p.pos[bt + col] << 8)) : 0;
     }
   };
 
   float acc[2] = {0.f, 0.f};
   uint32_t a[D / 16][4];
-  float r_lse2[2] = {0.f, 0.f};
   stage(0, 0);
   for (int it = 0; it < n_it; ++it) {
     const int buf = it & 1;
@@ -122,7 +132,7 @@ attn_importance_kernel(const ImpParams p) {
       if (!ROWS_ARE_KEYS) {
 #pragma unroll
         for (int i = 0; i < 2; ++i)
-          r_lse2[i] = row_ok[i] ? p.lse[((long long)b * p.heads + h) * T + row[i]] * 1.4426950408889634f : 0.f;
+          r_term[i] = row_ok[i] ? -p.lse[((long long)b * p.heads + h) * T + row[i]] * 1.4426950408889634f : 0.f;
       }
     }
     cp_async_wait<0>();
@@ -144,20 +154,18 @@ attn_importance_kernel(const ImpParams p) {
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
           const int cl = j * 8 + 2 * t + jj;
-          if (c0 + cl >= T) continue;
           const float c_term = c_term_s[buf][cl];
-          const int gp = c_gp_s[buf][cl], cg = gp & 255, cp = gp >> 8;
+          const int gp = MASKED ? c_gp_s[buf][cl] : 0;
+          const int cg = gp & 255, cp = gp >> 8;
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
-            bool vis = row_ok[i];
-            if (p.gid) {
-              const int al = ROWS_ARE_KEYS ? allow_s[cg * G + rg[i]] : allow_s[rg[i] * G + cg];
+            float s2 = fmaf(c[2 * i + jj], p.scale_log2, c_term + r_term[i]);
+            if (MASKED) {
               const bool causal_ok = ROWS_ARE_KEYS ? rp[i] <= cp : cp <= rp[i];
-              vis = vis && (al == 1 || (al == 2 && causal_ok));
+              const bool vis = ((vis1[i] >> cg) & 1u) || (((vis2[i] >> cg) & 1u) && causal_ok);
+              s2 = vis ? s2 : -INFINITY;
             }
-            const float r_term = ROWS_ARE_KEYS ? r_lsz[i] : -r_lse2[i];
-            const float s2 = fmaf(c[2 * i + jj], p.scale_log2, c_term + r_term);
-            acc[i] += vis ? fast_exp2(s2) : 0.f;
+            acc[i] += fast_exp2(s2);
           }
         }
       }
@@ -201,13 +209,17 @@ extern "C" int tome_attention_importance(const tome_attn_desc_t* d, const void* 
   const dim3 grid(ceil_div(d->tokens, 16 * IMP_WARPS), d->batch);
   const double flops = 2.0 * d->batch * d->heads * (double)d->tokens * d->tokens * d->head_dim;
   ProfScope prof(PROF_IMPORTANCE, flops, 1, stream);
-#define IMP_LAUNCH(DD)                                                                                          \
-  if (mode == TOME_IMPORTANCE_RECEIVED) launch_k(attn_importance_kernel<DD, true>, grid, IMP_WARPS * 32, 0, stream, p); \
-  else launch_k(attn_importance_kernel<DD, false>, grid, IMP_WARPS * 32, 0, stream, p)
+#define IMP_LAUNCH2(DD, RK)                                                                              \
+  if (d->gid) launch_k(attn_importance_kernel<DD, RK, true>, grid, IMP_WARPS * 32, 0, stream, p);        \
+  else launch_k(attn_importance_kernel<DD, RK, false>, grid, IMP_WARPS * 32, 0, stream, p)
+#define IMP_LAUNCH(DD)                                                     \
+  if (mode == TOME_IMPORTANCE_RECEIVED) { IMP_LAUNCH2(DD, true); }         \
+  else { IMP_LAUNCH2(DD, false); }
   if (d->head_dim == 64) { IMP_LAUNCH(64); }
   else if (d->head_dim == 128) { IMP_LAUNCH(128); }
   else { IMP_LAUNCH(256); }
 #undef IMP_LAUNCH
+#undef IMP_LAUNCH2
   TOME_CUDA(cudaGetLastError());
   return TOME_OK;
 }
