@@ -342,6 +342,17 @@ int tome_action_head_fwd(const tome_head_desc_t* desc, const void* x, const int3
 int tome_action_head_bwd(const tome_head_desc_t* desc, const int32_t* origin, const float* w, const void* workspace,
                          float* dw, float* dbias, void* dx, void* stream);
 
+/* The attention step of MultiHeadAttentionPooling (attention_blocks/attention.py:139-147; forward): the learnt query
+ * [embed_dim] is projected once (wq f32 [embed_dim, heads * head_dim] = the Flax query kernel [E, H, D] flattened, bq f32
+ * [H * D] or NULL; scaled by 1 / sqrt(head_dim)), then one softmax over the n_keys (<= 64) key rows of every (batch row, head)
+ * and the weighted sum of the value rows.  kv: bf16 [batch, n_keys, kv_ld], keys at column 0, values at column v_col (each
+ * [H, D] wide: the output of one GEMM over the concatenated key | value kernels).  q_scratch f32 [H * D]; out bf16
+ * [batch, H * D], the input of the out projection (:147), LayerNorm (:148) and MLPBlock (:149) -- the library's GEMM /
+ * LayerNorm entry points. */
+int tome_attention_pool_fwd(int batch, int n_keys, int heads, int head_dim, int embed_dim, const float* learnt_q,
+                            const float* wq, const float* bq, const void* kv, long long kv_ld, int v_col, float* q_scratch,
+                            void* out, void* stream);
+
 /* Diffusion action head, training path: DiffusionActionHead.denoise_loss over OctoDenoise / FourierFeatures / MLPBlock
  * (action_heads/diffusion.py:29-64, 94-143; the head octo_base.yaml selects).  The random draws are the caller's:
  * time i32 [B] in [0, diffusion_steps), noise f32 [B, A]; alpha_hats f32 [diffusion_steps] is the cumulative product of

@@ -193,6 +193,7 @@ def lib() -> C.CDLL:
             "tome_action_head_workspace_bytes": [P(HeadDesc)],
             "tome_action_head_fwd": [P(HeadDesc), vp, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp],
             "tome_action_head_bwd": [P(HeadDesc), vp, vp, vp, vp, vp, vp, vp],
+            "tome_attention_pool_fwd": [i32, i32, i32, i32, i32, vp, vp, vp, vp, ll, i32, vp, vp, vp],
             "tome_stack_head_offset": [P(StackCfg)],
             "tome_diffusion_head_param_count": [P(DiffusionDesc)],
             "tome_diffusion_head_param_offset": [P(DiffusionDesc), i32],

@@ -76,6 +76,77 @@ class MLPBlock(Module):
         return y.view(*shp[:-1], do.features)
 
 
+class MultiHeadAttentionPooling(Module):
+    """Multihead attention pooling (attention.py:122-150): a learnt query attends over the tokens, then LayerNorm -> MLPBlock on
+    the pooled token with the residual.  Forward (the reference's heads keep its call commented out: continuous.py:18-19,
+    diffusion.py:99-100).  Parameters, Flax names: learnt_q_input [1, 1, E], MultiHeadDotProductAttention_0/{query, key, value,
+    out}, LayerNorm_0, MLPBlock_0.  Key / value / out projections, LayerNorm and the MLP are the library's GEMM / LayerNorm
+    kernels; the one-query attention itself is csrc/attn_pool.cu."""
+
+    def __init__(self, query_map_input: Dict[str, Any], dot_product_attention: Dict[str, Any], layer_norm: Dict[str, Any],
+                 mlp_block: Dict[str, Any]):
+        self.query_map_input, self.dot_product_attention = query_map_input, dot_product_attention
+        self.layer_norm, self.mlp_block = layer_norm, mlp_block
+
+    def _specs(self):
+        at, ln = instantiate(self.dot_product_attention), instantiate(self.layer_norm)
+        assert isinstance(at, AttentionSpec) and isinstance(ln, LayerNormSpec)
+        if at.tome:
+            raise ValueError("MultiHeadAttentionPooling.dot_product_attention must be a flax attention node")
+        return at, ln, MLPBlock(**{k: v for k, v in self.mlp_block.items() if k != "_target_"})
+
+    def _init(self, rng, x, train=False):
+        at, ln, mlp = self._specs()
+        E = x.shape[-1]
+        H = at.num_heads
+        D = (at.qkv_features or E) // H
+        from ._module import _init_name
+        qinit = make_init(_init_name(self.query_map_input.get("kernel_init"), "lecun_normal"))
+        proj = lambda: {"kernel": make_init(at.kernel_init)(rng, (E, H, D), E, H * D), "bias": make_init(at.bias_init)(rng, (H, D))}  # noqa: E731
+        attn = {"query": proj(), "key": proj(), "value": proj(),
+                "out": {"kernel": make_init(at.kernel_init)(rng, (H, D, E), H * D, E), "bias": make_init(at.bias_init)(rng, (E,))}}
+        return {"learnt_q_input": qinit(rng, (1, 1, E), E, E), "MultiHeadDotProductAttention_0": attn,
+                "LayerNorm_0": {"scale": np.ones(E, np.float32), "bias": np.zeros(E, np.float32)},
+                "MLPBlock_0": mlp._init(rng, np.zeros((1, 1, E), np.float32))}
+
+    def _apply(self, params, x, train=False, dropout_rng=None):
+        import ctypes as C_
+
+        from .. import _lib as L_
+        at, ln, mlp = self._specs()
+        if not x.is_cuda:
+            raise RuntimeError("MultiHeadAttentionPooling runs on CUDA (sm_100a) only: got a CPU tensor.  There is no CPU fallback.")
+        if x.dim() != 3:
+            raise ValueError("x must be [batch, sequence, embedding] (attention.py:135)")
+        if train and at.dropout_rate > 0.0:
+            raise NotImplementedError("attention-weight dropout inside the pooling attention is not implemented")
+        B, n, E = x.shape
+        H = at.num_heads
+        hd = at.qkv_features or E
+        if hd % H:
+            raise ValueError(f"Memory dimension ({hd}) must be divisible by number of heads ({H}).")
+        D = hd // H
+        a = params["MultiHeadDotProductAttention_0"]
+        dev = x.device
+        # key | value projections of the tokens in one GEMM (flax DenseGeneral [E, H, D] kernels side by side)
+        wkv = torch.cat([F._w(a[k_]["kernel"]).reshape(E, hd) for k_ in ("key", "value")], dim=1).contiguous()
+        bkv = torch.cat([F._f(a[k_]["bias"]).reshape(-1) for k_ in ("key", "value")])
+        kv = ops.gemm(F._bf16(x).reshape(B * n, E).contiguous(), wkv, m=B * n, n=2 * hd, k=E, b_major=L_.TOME_MAJOR_MN, bias=bkv)
+        learnt = F._f(params["learnt_q_input"]).reshape(E).contiguous()
+        wq = F._f(a["query"]["kernel"]).reshape(E, hd).contiguous()
+        bq = F._f(a["query"]["bias"]).reshape(hd).contiguous()
+        q_scratch = torch.empty(hd, dtype=torch.float32, device=dev)
+        o = torch.empty(B, hd, dtype=torch.bfloat16, device=dev)
+        L_.check(L_.lib().tome_attention_pool_fwd(B, n, H, D, E, C_.c_void_p(learnt.data_ptr()), C_.c_void_p(wq.data_ptr()),
+                                                C_.c_void_p(bq.data_ptr()), C_.c_void_p(kv.data_ptr()), 2 * hd, hd,
+                                                C_.c_void_p(q_scratch.data_ptr()), C_.c_void_p(o.data_ptr()),
+                                                C_.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        x1 = F.dense(a["out"], o)                                                        # [B, E]            (:147)
+        y = F.layer_norm(params["LayerNorm_0"], ln, x1.view(B, 1, E))                    # (:148)
+        y = mlp._apply(params["MLPBlock_0"], y, train=train, residual=x1.view(B, 1, E), dropout_rng=dropout_rng)   # (:149-151)
+        return y
+
+
 class Encoder1DBlock(Module):
     """Transformer encoder layer (attention.py:41-69); returns `(x + y, None)` like the scanned reference block."""
 

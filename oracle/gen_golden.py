@@ -386,7 +386,65 @@ def gen_image_tokenizer():
     print("image_tokenizer.npz:", [c[0] for c in cases])
 
 
+class _Cfg(dict):
+    """omegaconf.DictConfig lets the reference write `self.query_map_input.kernel_init` (attention.py:141): attribute access."""
+    __getattr__ = dict.__getitem__
+
+
+def gen_attention_pooling():
+    """attention_pooling.npz: the reference's MultiHeadAttentionPooling (attention.py:122-150) executed in evaluation mode with
+    config nodes of the form of model_configs/action_heads/diffusion.yaml:6-51 (widths scaled down)."""
+    sys.dont_write_bytecode = True
+    for pth in (os.path.join(HERE, "jax_shim"), REF):
+        if pth not in sys.path:
+            sys.path.insert(0, pth)
+    import flax.linen as nn
+    import jax.numpy as jnp
+    import multi_modal_transformers.attention_blocks.attention as att
+    rng = np.random.default_rng(20261020)
+    out = {}
+    # name, B, readouts, E, heads, Dff, LayerNorm reduction axis (diffusion.yaml says [1]: the single pooled token)
+    cases = [("yaml_axes", 3, 4, 64, 2, 96, 1), ("feature_ln", 2, 8, 128, 4, 128, -1), ("one_readout", 2, 1, 64, 1, 64, -1)]
+    for name, B, n, E, H, Dff, ax in cases:
+        D = E // H
+        r_ = lambda *sh, s_=1.0: (rng.standard_normal(sh) * s_).astype(np.float32)  # noqa: E731
+        tree = {"learnt_q_input": r_(1, 1, E, s_=0.5),
+                "MultiHeadDotProductAttention_0": {k_: {"kernel": r_(E, H, D, s_=(2.0 / E) ** 0.5), "bias": r_(H, D, s_=0.01)} for k_ in ("query", "key", "value")},
+                "LayerNorm_0": {"scale": 1 + r_(E, s_=0.1), "bias": r_(E, s_=0.1)},
+                "MLPBlock_0": {"Dense_0": {"kernel": r_(E, Dff, s_=(2.0 / E) ** 0.5), "bias": r_(Dff, s_=0.01)},
+                               "Dense_1": {"kernel": r_(Dff, E, s_=(2.0 / Dff) ** 0.5), "bias": r_(E, s_=0.01)}}}
+        tree["MultiHeadDotProductAttention_0"]["out"] = {"kernel": r_(H, D, E, s_=(2.0 / E) ** 0.5), "bias": r_(E, s_=0.01)}
+        he = {"_target_": "flax.linen.initializers.he_normal"}
+        dense = lambda f: {"_target_": "flax.linen.Dense", "features": f, "use_bias": True, "kernel_init": he,  # noqa: E731
+                           "bias_init": {"_target_": "flax.linen.initializers.normal"}}
+        pool = att.MultiHeadAttentionPooling(
+            query_map_input=_Cfg(kernel_init=he),
+            dot_product_attention={"_target_": "flax.linen.MultiHeadDotProductAttention", "num_heads": H, "kernel_init": he},
+            layer_norm={"_target_": "flax.linen.LayerNorm", "epsilon": 1e-6, "reduction_axes": [ax], "feature_axes": [-1]},
+            mlp_block={"_target_": "multi_modal_transformers.attention_blocks.attention.MLPBlock", "dense": dense(Dff),
+                       "activation": {"_partial_": True, "_target_": "flax.linen.relu"},
+                       "norm": {"_target_": "flax.linen.Dropout", "rate": 0.1}, "dense_out": dense(E)})
+        x = r_(B, n, E)
+        with nn.shim_scope({"MultiHeadAttentionPooling_0": tree}):
+            y = np.asarray(pool(jnp.asarray(x), train=False), np.float32)
+        assert y.shape == (B, 1, E)
+        out[f"{name}/x"], out[f"{name}/y"] = x, y
+        out[f"{name}/meta"] = np.array([B, n, E, H, Dff, ax], np.int32)
+
+        def flat(prefix, t):
+            for k_, v_ in t.items():
+                if isinstance(v_, dict):
+                    flat(f"{prefix}/{k_}", v_)
+                else:
+                    out[f"{prefix}/{k_}"] = v_
+        flat(f"{name}/params", tree)
+    out["cases"] = np.array([c[0] for c in cases])
+    np.savez_compressed(os.path.join(OUT, "attention_pooling.npz"), **out)
+    print("attention_pooling.npz:", [c[0] for c in cases])
+
+
 if __name__ == "__main__":
     main()
     gen_blocks()
     gen_image_tokenizer()
+    gen_attention_pooling()

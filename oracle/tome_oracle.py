@@ -849,3 +849,35 @@ def image_tokenizer_params_from_flax(tree: dict, num_blocks: int) -> dict:
                 dense_kernel=g(ef["Dense_0"]["kernel"]), dense_bias=g(ef["Dense_0"]["bias"]),
                 row_embedding=g(tree["image_row_position_embedding"]["embedding"]),
                 col_embedding=g(tree["image_col_position_embedding"]["embedding"]))
+
+
+# ------------------------------------------------------------------------------------------------ attention pooling
+def attention_pooling(x: np.ndarray, p: dict, num_heads: int, ln_axis: int = 1, eps: float = 1e-6) -> np.ndarray:
+    """MultiHeadAttentionPooling.__call__ in evaluation mode (attention_blocks/attention.py:122-150): a learnt
+    query [1, 1, E] tiled over the batch (:139-144) attends over the tokens x [B, n, E] (flax MultiHeadDotProductAttention: per-head
+    Dense projections, q / sqrt(D), softmax over the n keys, out projection; :147), then LayerNorm (:148) -> MLPBlock (:149) on
+    the pooled token, returned with the residual (:151).  ln_axis: the configured reduction axis (diffusion.yaml:21 says [1] -- the
+    single pooled token, whose normalised value is 0, so LayerNorm returns its bias; -1 = features).
+    p: Flax tree {learnt_q_input, MultiHeadDotProductAttention_0: {query, key, value, out}, LayerNorm_0, MLPBlock_0: {Dense_0, Dense_1}}.
+    Pinned by tests/golden/attention_pooling.npz (the reference's own module executed under the shim).  Returns [B, 1, E]."""
+    f = np.float32
+    x = np.asarray(x, f)
+    B, n, E = x.shape
+    a = p["MultiHeadDotProductAttention_0"]
+    g = lambda t: np.asarray(t, f)  # noqa: E731
+    q = np.einsum("btc,chd->bthd", np.broadcast_to(g(p["learnt_q_input"]), (B, 1, E)), g(a["query"]["kernel"])) + g(a["query"]["bias"])
+    k = np.einsum("btc,chd->bthd", x, g(a["key"]["kernel"])) + g(a["key"]["bias"])
+    v = np.einsum("btc,chd->bthd", x, g(a["value"]["kernel"])) + g(a["value"]["bias"])
+    logits = np.einsum("bqhd,bkhd->bhqk", q / np.sqrt(f(q.shape[-1])), k)
+    w = np.exp(logits - logits.max(-1, keepdims=True))
+    w = (w / w.sum(-1, keepdims=True)).astype(f)
+    o = np.einsum("bhqk,bkhd->bqhd", w, v)
+    x1 = (np.einsum("bthd,hdc->btc", o, g(a["out"]["kernel"])) + g(a["out"]["bias"])).astype(f)       # [B, 1, E]
+    ax = 1 if ln_axis == 1 else 2
+    mu = x1.mean(axis=ax, keepdims=True, dtype=f)
+    var = np.maximum((x1 * x1).mean(axis=ax, keepdims=True, dtype=f) - mu * mu, 0)
+    y = ((x1 - mu) / np.sqrt(var + f(eps))).astype(f) * g(p["LayerNorm_0"]["scale"]) + g(p["LayerNorm_0"]["bias"])
+    m = p["MLPBlock_0"]
+    y = np.maximum(y @ g(m["Dense_0"]["kernel"]) + g(m["Dense_0"]["bias"]), 0)
+    y = y @ g(m["Dense_1"]["kernel"]) + g(m["Dense_1"]["bias"])
+    return (x1 + y).astype(f)

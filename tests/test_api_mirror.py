@@ -444,3 +444,49 @@ def test_image_tokenizer_config_nodes():
     v = tok.init(0, None)["params"]
     assert v["embedding_function"]["Conv_0"]["kernel"].shape == (12, 12, 3, 64) and v["embedding_function"]["Dense_0"]["kernel"].shape == (21 * 21 * 64, 768)
     assert set(v) == {"embedding_function", "image_row_position_embedding", "image_col_position_embedding"}
+
+
+def _pool_nodes(H, Dff, E, ax):
+    he = {"_target_": "flax.linen.initializers.he_normal"}
+    dense = lambda f: {"_target_": "flax.linen.Dense", "features": f, "use_bias": True, "kernel_init": he,  # noqa: E731
+                       "bias_init": {"_target_": "flax.linen.initializers.normal"}}
+    return dict(query_map_input={"kernel_init": he},
+                dot_product_attention={"_target_": "flax.linen.MultiHeadDotProductAttention", "num_heads": H, "kernel_init": he},
+                layer_norm={"_target_": "flax.linen.LayerNorm", "epsilon": 1e-6, "reduction_axes": [ax], "feature_axes": [-1]},
+                mlp_block={"_target_": "multi_modal_transformers.attention_blocks.attention.MLPBlock", "dense": dense(Dff),
+                           "activation": {"_partial_": True, "_target_": "flax.linen.relu"},
+                           "norm": {"_target_": "flax.linen.Dropout", "rate": 0.1}, "dense_out": dense(E)})
+
+
+def test_attention_pooling_param_tree():
+    """MultiHeadAttentionPooling.init: Flax's names and shapes (attention.py:139-149), config nodes of diffusion.yaml:6-51."""
+    pool = A.MultiHeadAttentionPooling(**_pool_nodes(3, 768, 768, 1))
+    v = pool.init(0, np.zeros((2, 4, 768), np.float32))["params"]
+    assert set(v) == {"learnt_q_input", "MultiHeadDotProductAttention_0", "LayerNorm_0", "MLPBlock_0"}
+    assert v["learnt_q_input"].shape == (1, 1, 768)
+    a = v["MultiHeadDotProductAttention_0"]
+    assert a["query"]["kernel"].shape == (768, 3, 256) and a["key"]["bias"].shape == (3, 256) and a["out"]["kernel"].shape == (3, 256, 768)
+    assert v["MLPBlock_0"]["Dense_0"]["kernel"].shape == (768, 768)
+
+
+@gpu
+@pytest.mark.parametrize("name", ["yaml_axes", "feature_ln", "one_readout"])
+def test_attention_pooling_module_against_the_executed_reference(name):
+    """MultiHeadAttentionPooling (CUDA path: key | value GEMM, csrc/attn_pool.cu, out GEMM, LayerNorm, MLP GEMMs) fed the SAME Flax
+    parameter tree and tokens as the reference's own module (attention.py:122-150, executed under the shim ->
+    tests/golden/attention_pooling.npz).  bf16 kernels vs the fp32 fixture: relative L2 error <= 2e-2."""
+    Z = np.load(os.path.join(GOLD, "attention_pooling.npz"))
+    B, n, E, H, Dff, ax = [int(v) for v in Z[f"{name}/meta"]]
+    tree, pre = {}, f"{name}/params/"
+    for k in Z.files:
+        if k.startswith(pre):
+            node, parts = tree, k[len(pre):].split("/")
+            for p_ in parts[:-1]:
+                node = node.setdefault(p_, {})
+            node[parts[-1]] = Z[k]
+    pool = A.MultiHeadAttentionPooling(**_pool_nodes(H, Dff, E, ax))
+    y = pool.apply({"params": tree}, _dev(Z[f"{name}/x"]), train=False)
+    want = torch.as_tensor(Z[f"{name}/y"])
+    assert tuple(y.shape) == (B, 1, E)
+    err = ((y.float().cpu() - want).norm() / want.norm()).item()
+    assert err <= 2e-2, err

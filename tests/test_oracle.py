@@ -271,3 +271,15 @@ def test_image_tokenizer_oracle_matches_the_executed_reference(name):
     want = Z[f"{name}/out"]
     assert got.shape == want.shape == (B, N, (H // P) ** 2, E)
     assert np.abs(got - want).max() <= 2e-5 * max(1.0, np.abs(want).max())
+
+
+@pytest.mark.parametrize("name", ["yaml_axes", "feature_ln", "one_readout"])
+def test_attention_pooling_oracle_matches_the_executed_reference(name):
+    """oracle.attention_pooling against the output of the reference's own MultiHeadAttentionPooling (attention.py:122-150)
+    executed under the shim (tests/golden/attention_pooling.npz): 2e-5 (fp32 sums in a different order)."""
+    Z = np.load(os.path.join(GOLD, "attention_pooling.npz"))
+    B, n, E, H, Dff, ax = [int(v) for v in Z[f"{name}/meta"]]
+    got = O.attention_pooling(Z[f"{name}/x"], _golden_tree(Z, f"{name}/params"), H, ln_axis=ax)
+    want = Z[f"{name}/y"]
+    assert got.shape == want.shape == (B, 1, E)
+    assert np.abs(got - want).max() <= 2e-5 * max(1.0, np.abs(want).max())
