@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TOME_ABI_VERSION 12
+#define TOME_ABI_VERSION 13
 
 enum tome_status { TOME_OK = 0, TOME_ERR_INVALID = 1, TOME_ERR_CUDA = 2, TOME_ERR_UNSUPPORTED = 3 };
 enum tome_dtype { TOME_BF16 = 0, TOME_F32 = 1, TOME_U8 = 2 /* raw pixels: image front end only */ };
@@ -120,6 +120,7 @@ int tome_merge_bwd(const tome_merge_shape_t* shape, const tome_plan_t* plan, con
  * epilogue, in order: + bias[N]; ReLU; * (gate > 0 ? gate_scale : 0); dropout; + residual; cast to c_dtype.
  * k_splits > 1 (fp32 C only) splits the reduction and sums the partials in a fixed order (weight gradients);
  * k_splits == 0 lets the library choose; with accumulate != 0 the result is ADDED to C (fp32 C only). */
+#define TOME_GEMM_MAX_SHIFTS 16
 typedef struct {
   int m, n, k;
   const void* a; long long lda; int a_major;
@@ -146,6 +147,14 @@ typedef struct {
    * bf16-rounded rows 128 i .. 128 i + 127 of C, in a fixed order; tome_reduce_rows_f32 adds the rows up.
    * (MLPBlock Dense bias: attention.py:32-37 under autodiff.) */
   float* colsum_partial;
+  /* Row-shifted A windows: a convolution over a zero-bordered, flattened activation grid without materialising im2col rows.
+   * With a_row_shift != NULL (host array of a_shift_groups <= TOME_GEMM_MAX_SHIFTS ints; K-major A, no split-K), A is
+   * [m, k / a_shift_groups] and the reduction runs over the groups g: C[i, :] = sum_g A[i + a_row_shift[g], :] * B[g-th block
+   * of k / a_shift_groups rows, :], rows outside [0, m) reading as zero.  For a 3 x 3 SAME convolution on a grid of width W
+   * (zero border included) a_row_shift[3 ty + tx] = (ty - 1) W + (tx - 1) and B is the Flax kernel [3, 3, in, out] as it is.
+   * k / a_shift_groups must be a multiple of 64. */
+  const int* a_row_shift;
+  int a_shift_groups;
 } tome_gemm_args_t;
 
 size_t tome_gemm_workspace_bytes(const tome_gemm_args_t* args);

@@ -61,6 +61,10 @@ struct GemmShape {
   int m_tiles, n_tiles, k_splits, kb_per_split, kb_total;
   int m_items;  // m_tiles, or ceil(m_tiles / 2) when CTA pairs share the B operand
   int ablate;   // TOME_GEMM_ABLATE builds only: 1 = no output stores, 2 = no operand loads, 4 = no MMAs (wrong results; timing probes)
+  // Row-shifted A windows (tome_gemm_args_t.a_row_shift): K is a_groups groups of a_group_kb k-blocks; group g reads columns
+  // [0, a_group_kb * 64) of A at rows m0 + a_shift[g] (TMA zero-fills rows outside the matrix).  a_groups == 0: plain GEMM.
+  int a_groups, a_group_kb;
+  int a_shift[TOME_GEMM_MAX_SHIFTS];
 };
 #ifdef TOME_GEMM_ABLATE
 #define TOME_ABL(bit) ((s.ablate & (bit)) != 0)
@@ -200,10 +204,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
           const int k0 = kb * GEMM_BK;
+          int ka = k0, ma = m0;   // coordinates of the A tile (K-major A): shifted windows re-read the same columns at other rows
+          if (s.a_groups) {
+            const int g = kb / s.a_group_kb;
+            ka = (kb - g * s.a_group_kb) * GEMM_BK;
+            ma = m0 + s.a_shift[g];
+          }
           if constexpr (BRES) {   // the ring carries A alone
             const uint32_t fb = map_to_cta(&full_bar[stage], 0);
             if (leader) mbar_expect_tx(&full_bar[stage], 2 * L::A_BYTES);
-            tma_load_2d_pair(sa, &tma_a, fb, k0, m0);
+            if (!A_MN) tma_load_2d_pair(sa, &tma_a, fb, ka, ma);
+            else tma_load_2d_pair(sa, &tma_a, fb, k0, m0);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
             continue;
           }
@@ -219,7 +230,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             constexpr uint32_t kPairTx = 2 * (L::A_BYTES + (B_MN ? L::B_BYTES : (BN / 2) * GEMM_BK * 2));
             if (leader) mbar_expect_tx(&full_bar[stage], kPairTx);
             if (!A_MN) {
-              tma_load_2d_pair(sa, &tma_a, fb, k0, TOME_ABL(32) ? (m0 & 1023) : m0);   // 32: operand stream from 1024 rows (L2-resident)
+              tma_load_2d_pair(sa, &tma_a, fb, ka, TOME_ABL(32) ? (m0 & 1023) : ma);   // 32: operand stream from 1024 rows (L2-resident)
             } else {
 #pragma unroll
               for (int j = 0; j < GEMM_BM / 64; ++j) tma_load_2d_pair(sa + j * 8192, &tma_a, fb, m0 + 64 * j, k0);
@@ -241,7 +252,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           }
           mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
           if (!A_MN) {
-            tma_load_2d(sa, &tma_a, &full_bar[stage], k0, m0);  // box {64 k, 128 m}
+            tma_load_2d(sa, &tma_a, &full_bar[stage], ka, ma);  // box {64 k, 128 m}
           } else {
 #pragma unroll
             for (int j = 0; j < GEMM_BM / 64; ++j)  // box {64 m, 64 k} per 64-wide M atom
@@ -783,6 +794,7 @@ static TileChoice pick_tile(const tome_gemm_args_t* a) {
 
 static int pick_splits(const tome_gemm_args_t* a, int bn) {
   if (a->k_splits > 0) return a->k_splits;
+  if (a->a_row_shift) return 1;
   if (a->c_dtype != TOME_F32 || a->ldc != a->n) return 1;  // split-K only for dense fp32 outputs (weight gradients)
   if (a->bias || a->residual || a->gate || a->gate_bits || a->relu || a->dropout_rate > 0.f) return 1;
   const int tiles = ceil_div(a->m, GEMM_BM) * ceil_div(a->n, bn);
@@ -842,6 +854,16 @@ extern "C" int tome_gemm_bf16(const tome_gemm_args_t* a, void* workspace, size_t
   s.k_splits = ceil_div(s.kb_total, s.kb_per_split);  // drop empty splits
   s.m_items = mc ? ceil_div(s.m_tiles, 2) : s.m_tiles;
   s.ablate = g_gemm_ablate;
+  s.a_groups = 0; s.a_group_kb = 1;
+  if (a->a_row_shift) {
+    TOME_CHECK(a->a_shift_groups >= 1 && a->a_shift_groups <= TOME_GEMM_MAX_SHIFTS && a->k % a->a_shift_groups == 0 &&
+               (a->k / a->a_shift_groups) % GEMM_BK == 0, TOME_ERR_INVALID,
+               "gemm: a_row_shift needs 1 <= a_shift_groups <= %d and k / a_shift_groups a multiple of %d", TOME_GEMM_MAX_SHIFTS, GEMM_BK);
+    TOME_CHECK(a->a_major == TOME_MAJOR_K && s.k_splits == 1, TOME_ERR_INVALID, "gemm: a_row_shift needs a K-major A and no split-K");
+    s.a_groups = a->a_shift_groups;
+    s.a_group_kb = a->k / a->a_shift_groups / GEMM_BK;
+    for (int g = 0; g < a->a_shift_groups; ++g) s.a_shift[g] = a->a_row_shift[g];
+  }
 
   GemmEpilogue e;
   e.c = a->c; e.bias = a->bias; e.residual = a->residual; e.gate = a->gate;
@@ -872,7 +894,7 @@ extern "C" int tome_gemm_bf16(const tome_gemm_args_t* a, void* workspace, size_t
 
   CUtensorMap ta, tb;
   int rc;
-  if (a->a_major == TOME_MAJOR_K) rc = make_tmap_2d_bf16(&ta, a->a, a->m, a->k, a->lda, GEMM_BM);
+  if (a->a_major == TOME_MAJOR_K) rc = make_tmap_2d_bf16(&ta, a->a, a->m, s.a_groups ? a->k / s.a_groups : a->k, a->lda, GEMM_BM);
   else rc = make_tmap_2d_bf16(&ta, a->a, a->k, a->m, a->lda, GEMM_BK);
   if (rc) return rc;
   if (a->b_major == TOME_MAJOR_K) rc = make_tmap_2d_bf16(&tb, a->b, a->n, a->k, a->ldb, mc ? bn / 2 : bn);

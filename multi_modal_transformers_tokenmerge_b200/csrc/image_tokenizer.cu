@@ -15,8 +15,12 @@
 //                          per-CTA per-channel partial sums in a fixed order, then one thread per (row, group)
 //   it_gn_gelu_kernel      (x - mean) * rstd * scale + bias -> gelu, once per element (the statistics folded into a
 //                          per-(batch row, channel) multiply-add by it_gn_fold_kernel)
-//   it_im2col3_kernel      the nine shifted copies of the 3x3 SAME im2col row, zero outside the o2 x o2 window; one
-//                          16-byte load and one 16-byte store per thread
+//   3 x 3 convolutions     features % 64 == 0 (the reference's 64): the block activations live on a (o2 + 2)^2 grid with a zero
+//                          border, and the convolution is ONE GEMM whose nine k-blocks read the SAME matrix at rows shifted by
+//                          (ty - 1)(o2 + 2) + (tx - 1) (tome_gemm_args_t.a_row_shift: a TMA row coordinate per k-block; no
+//                          im2col rows, the activation is re-read from L2); it_compact_kernel then gathers the interior
+//   it_im2col3_kernel      other widths: the nine shifted copies of the 3x3 SAME im2col row, zero outside the o2 x o2
+//                          window; one 16-byte load and one 16-byte store per thread
 //   it_posadd_kernel       Dense output + row_embedding[row_token] + col_embedding[col_token] -> out dtype
 // The last block convolution adds the pooled tensor through the GEMM's residual epilogue (image_tokenizer.py:170) and
 // the flatten is free ([.., o2, o2, F] rows ARE the Dense's K-major A operand).  HBM-bound: the im2col rows dominate the
@@ -36,6 +40,8 @@ constexpr size_t IT_COL_TARGET = (size_t)1 << 30;   // im2col buffer target per 
 struct ItGeom {
   int ppd, np;          // patches per image side / per image
   int o1, o2;           // side after the input convolution / after the pool
+  int wp, pad;          // side of the grid the block activations live on: o2 + 2 with a zero border (pad = 1) when the 3 x 3
+                        // convolutions run as row-shifted GEMMs (features % 64 == 0), else o2 (pad = 0, im2col rows)
   int k0;               // k*k*C_in
   int kd;               // o2*o2*F (Dense fan-in)
   long long imgs;       // B*N
@@ -74,16 +80,19 @@ static int it_geometry(const tome_image_tokenizer_desc_t* d, ItGeom* g, const ch
   g->k0 = d->conv_kernel * d->conv_kernel * d->channels_in;
   TOME_CHECK(g->k0 % 16 == 0, TOME_ERR_UNSUPPORTED, "%s: conv_kernel^2 * channels_in (%d) must be a multiple of 16", who, g->k0);
   g->kd = g->o2 * g->o2 * d->features;
+  g->pad = d->features % 64 == 0 ? 1 : 0;
+  g->wp = g->o2 + 2 * g->pad;
   g->imgs = (long long)d->batch * d->n_images;
   const long long m0_row = (long long)d->n_images * g->np * g->o1 * g->o1;   // im2col rows per batch row
   const long long m2_row = (long long)d->n_images * g->np * g->o2 * g->o2;
-  const size_t col_row = 2 * (size_t)std::max(m0_row * g->k0, m2_row * 9 * d->features);
+  const long long m2p_row = (long long)d->n_images * g->np * g->wp * g->wp;   // rows of the (bordered) activation grid
+  const size_t col_row = 2 * (size_t)std::max(m0_row * g->k0, g->pad ? 0ll : m2_row * 9 * d->features);
   long long cr = (long long)(IT_COL_TARGET / col_row);
   TOME_CHECK(d->chunk_rows >= 0, TOME_ERR_INVALID, "%s: chunk_rows must be >= 0", who);
   if (d->chunk_rows > 0) cr = d->chunk_rows;
   if (cr < 1) cr = 1;
   if (cr > d->batch) cr = d->batch;
-  TOME_CHECK(m0_row * cr * (g->k0 / 8) < (1ll << 31) && m2_row * cr * 9 * (d->features / 8) < (1ll << 31), TOME_ERR_UNSUPPORTED,
+  TOME_CHECK(m0_row * cr * (g->k0 / 8) < (1ll << 31) && m2p_row * cr * 9 * (d->features / 8) < (1ll << 31), TOME_ERR_UNSUPPORTED,
              "%s: %lld batch rows per pass need more than 2^31 16-byte vectors of im2col rows: lower chunk_rows", who, cr);
   g->chunk_rows = (int)cr;
   long long want = m2_row * (d->features / 8) / (IT_THREADS * 4);
@@ -91,9 +100,9 @@ static int it_geometry(const tome_image_tokenizer_desc_t* d, ItGeom* g, const ch
   size_t o = 0;
   g->off_col = o;   o += align256(col_row * cr);
   g->off_y0 = o;    o += align256((size_t)2 * m0_row * cr * d->features);
-  g->off_pool = o;  o += align256((size_t)2 * m2_row * cr * d->features);
-  g->off_xa = o;    o += align256((size_t)2 * m2_row * cr * d->features);
-  g->off_xb = o;    o += align256((size_t)2 * m2_row * cr * d->features);
+  g->off_pool = o;  o += align256((size_t)2 * m2p_row * cr * d->features);
+  g->off_xa = o;    o += align256((size_t)2 * m2p_row * cr * d->features);
+  g->off_xb = o;    o += align256((size_t)2 * m2p_row * cr * d->features);
   g->off_h = o;     o += align256((size_t)2 * m2_row * cr * d->features);
   g->off_dense = o; o += align256((size_t)4 * cr * d->n_images * g->np * d->embed_dim);
   g->off_part = o;  o += align256((size_t)4 * cr * g->gn_ctas * d->features * 2);
@@ -188,7 +197,7 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
 // max pool, stride 1, VALID (flax.linen.max_pool).  Thread = (output pixel, 8 channels).
 __global__ void __launch_bounds__(IT_THREADS)
 it_pool_kernel(const __nv_bfloat16* __restrict__ y0, __nv_bfloat16* __restrict__ pooled, uint32_t n_vec, FastDiv nchunk, int o1,
-               FastDiv o2, int window) {
+               FastDiv o2, int window, int wp, int pad) {
   pdl_prologue();
   const uint32_t v = blockIdx.x * IT_THREADS + threadIdx.x;
   if (v >= n_vec) return;
@@ -206,13 +215,13 @@ it_pool_kernel(const __nv_bfloat16* __restrict__ y0, __nv_bfloat16* __restrict__
       best.x = bf16x2_max(best.x, u.x); best.y = bf16x2_max(best.y, u.y);
       best.z = bf16x2_max(best.z, u.z); best.w = bf16x2_max(best.w, u.w);
     }
-  *reinterpret_cast<uint4*>(pooled + (size_t)v * 8) = best;
+  *reinterpret_cast<uint4*>(pooled + ((((size_t)ip * wp + oy + pad) * wp + ox + pad) * nchunk.d + c) * 8) = best;
 }
 
 // GroupNorm statistics, stage 1: x [rows_b, R, F] bf16; CTA (j, b) sums x and x^2 per CHANNEL over its slice of the R rows
 // of batch row b -> part [rows_b, gridDim.x, F, 2].  Thread = (8-channel chunk, row lane); lanes are added in lane order.
 __global__ void __launch_bounds__(IT_THREADS)
-it_gn_partial_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ part, long long R, int nchunk) {
+it_gn_partial_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ part, long long R, int nchunk, FastDiv wp, int pad) {
   pdl_prologue();
   __shared__ float sm[2][IT_THREADS * 8];
   const int F = nchunk << 3;
@@ -224,6 +233,12 @@ it_gn_partial_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ pa
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
   for (long long r = r0 + rl; r < r1; r += lanes) {
+    if (pad) {   // bordered grid: only the interior pixels are data
+      uint32_t q, xx, yy;
+      wp.divmod((uint32_t)r, q, xx);
+      yy = q - wp.div(q) * wp.d;
+      if (xx < (uint32_t)pad || xx >= wp.d - pad || yy < (uint32_t)pad || yy >= wp.d - pad) continue;
+    }
     float f[8];
     unpack8(ld_nc_v4(xb + r * F), f);
 #pragma unroll
@@ -292,13 +307,22 @@ __global__ void it_gn_fold_kernel(const float* __restrict__ stats, const float* 
 
 __global__ void __launch_bounds__(IT_THREADS)
 it_gn_gelu_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ ab, __nv_bfloat16* __restrict__ h, uint32_t n_vec,
-                  FastDiv nchunk, FastDiv pix_per_row) {
+                  FastDiv nchunk, FastDiv pix_per_row, FastDiv wp, int pad) {
   pdl_prologue();
   const uint32_t v = blockIdx.x * IT_THREADS + threadIdx.x;
   if (v >= n_vec) return;
   uint32_t m, c;
   nchunk.divmod(v, m, c);
   const uint32_t b = pix_per_row.div(m);
+  if (pad) {   // the zero border the row-shifted convolution reads as SAME padding
+    uint32_t q, xx, yy;
+    wp.divmod(m, q, xx);
+    yy = q - wp.div(q) * wp.d;
+    if (xx < (uint32_t)pad || xx >= wp.d - pad || yy < (uint32_t)pad || yy >= wp.d - pad) {
+      *reinterpret_cast<uint4*>(h + (size_t)v * 8) = make_uint4(0u, 0u, 0u, 0u);
+      return;
+    }
+  }
   const float4* abp = reinterpret_cast<const float4*>(ab + ((size_t)b * (nchunk.d << 3) + (c << 3)) * 2);
   float f[8];
   unpack8(ld_nc_v4(x + (size_t)v * 8), f);
@@ -334,6 +358,20 @@ it_im2col3_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict
     o = *reinterpret_cast<const uint4*>(h + (size_t)ms * (nchunk.d << 3) + (c << 3));
   }
   st_na_v4(col + (size_t)v * 8, o);
+}
+
+// interior of the bordered grid -> dense [pixels, F] rows (the flatten the Dense consumes).  Thread = 16 bytes of output.
+__global__ void __launch_bounds__(IT_THREADS)
+it_compact_kernel(const __nv_bfloat16* __restrict__ xp, __nv_bfloat16* __restrict__ out, uint32_t n_vec, FastDiv nchunk, FastDiv o2,
+                  int wp, int pad) {
+  pdl_prologue();
+  const uint32_t v = blockIdx.x * IT_THREADS + threadIdx.x;
+  if (v >= n_vec) return;
+  uint32_t c, t, ox, oy, ip;
+  nchunk.divmod(v, t, c);
+  o2.divmod(t, t, ox);
+  o2.divmod(t, ip, oy);
+  st_na_v4(out + (size_t)v * 8, ld_nc_v4(xp + ((((size_t)ip * wp + oy + pad) * wp + ox + pad) * nchunk.d + c) * 8));
 }
 
 // tokens + row / column position embeddings (image_tokenizer.py:296-305), 4 features per thread.
@@ -414,11 +452,12 @@ extern "C" size_t tome_image_tokenizer_workspace_bytes(const tome_image_tokenize
 }
 
 static int it_gemm(int m, int n, int k, const void* a, const void* b, void* c, int c_dtype, const float* bias, const void* residual,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, const int* a_row_shift = nullptr, int shift_groups = 0) {
   tome_gemm_args_t ga;
   memset(&ga, 0, sizeof(ga));
   ga.m = m; ga.n = n; ga.k = k;
-  ga.a = a; ga.lda = k; ga.a_major = TOME_MAJOR_K;
+  ga.a = a; ga.lda = shift_groups ? k / shift_groups : k; ga.a_major = TOME_MAJOR_K;
+  ga.a_row_shift = a_row_shift; ga.a_shift_groups = shift_groups;
   ga.b = b; ga.ldb = n; ga.b_major = TOME_MAJOR_MN;    // the Flax kernel layout [in, out] as is
   ga.c = c; ga.ldc = n; ga.c_dtype = c_dtype;
   ga.bias = bias;
@@ -461,7 +500,12 @@ extern "C" int tome_image_tokenizer_fwd(const tome_image_tokenizer_desc_t* d, co
     const int rows_b = std::min(g.chunk_rows, d->batch - b0);
     const long long imgs = (long long)rows_b * d->n_images, img0 = (long long)b0 * d->n_images;
     const long long m0 = imgs * g.np * g.o1 * g.o1, m2 = imgs * g.np * g.o2 * g.o2, mt = imgs * g.np;
-    const long long R = (long long)d->n_images * g.np * g.o2 * g.o2;   // rows of one batch row in the GroupNorm reduction
+    const long long R = (long long)d->n_images * g.np * g.o2 * g.o2;   // pixels of one batch row in the GroupNorm reduction
+    const long long Rp = (long long)d->n_images * g.np * g.wp * g.wp;  // rows of one batch row on the (bordered) activation grid
+    const long long m2p = imgs * g.np * g.wp * g.wp;
+    const FastDiv fd_wp = make_fastdiv(g.wp);
+    int shifts[9];
+    for (int t9 = 0; t9 < 9; ++t9) shifts[t9] = (t9 / 3 - 1) * g.wp + (t9 % 3 - 1);
     const uint8_t* img = reinterpret_cast<const uint8_t*>(image) + (size_t)img0 * pix_img * pix_bytes;
     {
       const long long nv = m0 * (g.k0 / 8);
@@ -484,7 +528,7 @@ extern "C" int tome_image_tokenizer_fwd(const tome_image_tokenizer_desc_t* d, co
     {
       const long long nv = m2 * nchunk;
       ProfScope prof(PROF_OTHER, (double)nv * 16 * (d->pool_window * d->pool_window + 1), 1, stream);
-      launch_k(it_pool_kernel, nblk(nv), IT_THREADS, 0, stream, y0, pooled, (uint32_t)nv, fd_chunk, g.o1, fd_o2, d->pool_window);
+      launch_k(it_pool_kernel, nblk(nv), IT_THREADS, 0, stream, y0, pooled, (uint32_t)nv, fd_chunk, g.o1, fd_o2, d->pool_window, g.wp, g.pad);
       TOME_CUDA(cudaGetLastError());
     }
     const __nv_bfloat16* x = pooled;
@@ -492,7 +536,7 @@ extern "C" int tome_image_tokenizer_fwd(const tome_image_tokenizer_desc_t* d, co
       const int pi = TOME_IT_BLOCK0 + 4 * blk;
       {
         ProfScope prof(PROF_OTHER, (double)m2 * F * 2, 3, stream);
-        launch_k(it_gn_partial_kernel, dim3(g.gn_ctas, rows_b), gn_threads, 0, stream, x, part, R, nchunk);
+        launch_k(it_gn_partial_kernel, dim3(g.gn_ctas, rows_b), gn_threads, 0, stream, x, part, Rp, nchunk, fd_wp, g.pad);
         TOME_CUDA(cudaGetLastError());
         launch_k(it_gn_final_kernel, (unsigned)ceil_div(rows_b * d->num_groups, 4), 128, 0, stream, part, stats, rows_b, g.gn_ctas, F,
                  d->num_groups, R, d->gn_eps);
@@ -502,23 +546,37 @@ extern "C" int tome_image_tokenizer_fwd(const tome_image_tokenizer_desc_t* d, co
         TOME_CUDA(cudaGetLastError());
       }
       {
-        const long long nv = m2 * nchunk;
+        const long long nv = m2p * nchunk;
         ProfScope prof(PROF_OTHER, (double)nv * 32, 1, stream);
-        launch_k(it_gn_gelu_kernel, nblk(nv), IT_THREADS, 0, stream, x, ab, hbuf, (uint32_t)nv, fd_chunk, make_fastdiv((uint32_t)R));
-        TOME_CUDA(cudaGetLastError());
-      }
-      {
-        const long long nv = m2 * 9 * nchunk;
-        ProfScope prof(PROF_OTHER, (double)nv * 16, 1, stream);
-        launch_k(it_im2col3_kernel, nblk(nv), IT_THREADS, 0, stream, hbuf, col, (uint32_t)nv, fd_chunk, fd_o2);
+        launch_k(it_gn_gelu_kernel, nblk(nv), IT_THREADS, 0, stream, x, ab, hbuf, (uint32_t)nv, fd_chunk, make_fastdiv((uint32_t)Rp), fd_wp, g.pad);
         TOME_CUDA(cudaGetLastError());
       }
       __nv_bfloat16* y = xbuf[blk & 1];
       const bool last = blk == d->num_blocks - 1;
-      rc = it_gemm((int)m2, F, 9 * F, col, pb + it_offset(d, g, pi + 2), y, TOME_BF16, pf + it_offset(d, g, pi + 3),
-                   last ? pooled : nullptr, stream);   // image_tokenizer.py:170: x + residual after the LAST block
+      if (g.pad) {
+        // 3 x 3 SAME convolution as ONE GEMM over nine row-shifted windows of the bordered activation (no im2col rows): tap
+        // (ty, tx) reads h at rows + (ty - 1) wp + (tx - 1); outputs on border positions are never read
+        rc = it_gemm((int)m2p, F, 9 * F, hbuf, pb + it_offset(d, g, pi + 2), y, TOME_BF16, pf + it_offset(d, g, pi + 3),
+                     last ? pooled : nullptr, stream, shifts, 9);   // image_tokenizer.py:170: x + residual after the LAST block
+      } else {
+        const long long nv = m2 * 9 * nchunk;
+        {
+          ProfScope prof(PROF_OTHER, (double)nv * 16, 1, stream);
+          launch_k(it_im2col3_kernel, nblk(nv), IT_THREADS, 0, stream, hbuf, col, (uint32_t)nv, fd_chunk, fd_o2);
+          TOME_CUDA(cudaGetLastError());
+        }
+        rc = it_gemm((int)m2, F, 9 * F, col, pb + it_offset(d, g, pi + 2), y, TOME_BF16, pf + it_offset(d, g, pi + 3),
+                     last ? pooled : nullptr, stream);
+      }
       if (rc != TOME_OK) return rc;
       x = y;
+    }
+    if (g.pad) {   // the Dense flattens (h, w, c) of the interior
+      const long long nv = m2 * nchunk;
+      ProfScope prof(PROF_OTHER, (double)nv * 32, 1, stream);
+      launch_k(it_compact_kernel, nblk(nv), IT_THREADS, 0, stream, x, hbuf, (uint32_t)nv, fd_chunk, fd_o2, g.wp, g.pad);
+      TOME_CUDA(cudaGetLastError());
+      x = hbuf;
     }
     rc = it_gemm((int)mt, E, g.kd, x, pb + it_offset(d, g, TOME_IT_DENSE_KERNEL), dense, TOME_F32, pf + it_offset(d, g, TOME_IT_DENSE_BIAS),
                  nullptr, stream);

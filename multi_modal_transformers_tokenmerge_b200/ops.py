@@ -176,9 +176,12 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, m: int, n: int, k: int, a_major=L.
          lda=None, ldb=None, out: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16, bias=None, residual=None,
          gate=None, gate_scale=1.0, relu=False, dropout_rate=0.0, dropout_seed=0, dropout_site=0, k_splits=0,
          accumulate=False, no_multicast=False, gate_bits: Optional[torch.Tensor] = None,
-         relu_bits_out: Optional[torch.Tensor] = None, colsum_partial: Optional[torch.Tensor] = None) -> torch.Tensor:
+         relu_bits_out: Optional[torch.Tensor] = None, colsum_partial: Optional[torch.Tensor] = None,
+         a_row_shift=None) -> torch.Tensor:
     """C[M,N] = epilogue(A * B^T) on tcgen05.  a/b are 2-D bf16 tensors whose rows are M/N (K-major) or K (MN-major).
-    gate_bits / relu_bits_out: int32 [M, ceil(N/32)] one-bit-per-element ReLU gates (see include/tome_b200.h)."""
+    gate_bits / relu_bits_out: int32 [M, ceil(N/32)] one-bit-per-element ReLU gates (see include/tome_b200.h).
+    a_row_shift: list of row shifts, one per group of k / len(a_row_shift) reduction columns (row-shifted A windows: a
+    convolution over a flattened, zero-bordered grid without im2col rows; a is [M, k / groups])."""
     _need_cuda(a, b)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     lda = a.stride(0) if lda is None else lda
@@ -195,6 +198,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, m: int, n: int, k: int, a_major=L.
                       None if relu_bits_out is None else relu_bits_out.data_ptr(),
                       0 if (gate_bits is None and relu_bits_out is None) else (gate_bits if gate_bits is not None else relu_bits_out).stride(0),
                       None if colsum_partial is None else colsum_partial.data_ptr())
+    if a_row_shift is not None:
+        shifts = (C.c_int * len(a_row_shift))(*[int(v) for v in a_row_shift])
+        args.a_row_shift, args.a_shift_groups = C.cast(shifts, C.c_void_p), len(a_row_shift)
     ws_bytes = L.lib().tome_gemm_workspace_bytes(C.byref(args))
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=a.device) if ws_bytes else None
     L.check(L.lib().tome_gemm_bf16(C.byref(args), _ptr(ws), ws_bytes, _stream()))

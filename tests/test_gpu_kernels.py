@@ -1004,3 +1004,30 @@ def test_image_tokenizer_gato_geometry_vs_oracle(ops):
     delta = (re_[row] + ce[col] - re_[r0][None] - ce[c0][None]).reshape(3, 2, 25, E)
     d_got = gt.float().cpu().numpy() - got.float().cpu().numpy()
     assert np.abs(d_got - delta).max() <= 2 ** -7 * max(1.0, scale)      # two bf16 roundings
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("m,n,cols,shifts", [(1000, 64, 64, [-24, -23, -22, -1, 0, 1, 22, 23, 24]), (4096, 128, 128, [0, 5, -700]),
+                                             (300, 256, 64, [-400, 400, 0, 1])])
+def test_gemm_row_shifted_windows(ops, m, n, cols, shifts):
+    """tome_gemm_args_t.a_row_shift: C[i] = sum_g A[i + shift_g] B_g with rows outside [0, m) reading as zero -- the 3 x 3
+    convolution of the image front end as one GEMM (first case: its nine shifts on a 23-wide grid).  Against an fp32 torch sum
+    over explicitly shifted, zero-filled copies of the same bf16 operands: |err| <= 2e-2 * sqrt(k) / 16."""
+    rng = np.random.default_rng(m + n)
+    G = len(shifts)
+    A = torch.tensor(rng.standard_normal((m, cols)).astype(np.float32)).cuda().bfloat16()
+    W = torch.tensor(rng.standard_normal((G * cols, n)).astype(np.float32)).cuda().bfloat16()
+    bias = torch.tensor(rng.standard_normal(n).astype(np.float32)).cuda()
+    out = ops.gemm(A, W, m=m, n=n, k=G * cols, b_major=1, bias=bias, out_dtype=torch.float32, a_row_shift=shifts)
+    out16 = ops.gemm(A, W, m=m, n=n, k=G * cols, b_major=1, bias=bias, a_row_shift=shifts)
+    Af, Wf = A.float().cpu(), W.float().cpu()
+    ref = bias.cpu()[None].repeat(m, 1)
+    for g_, sh in enumerate(shifts):
+        sa = torch.zeros_like(Af)
+        lo, hi = max(0, -sh), min(m, m - sh)
+        if hi > lo:
+            sa[lo:hi] = Af[lo + sh:hi + sh]
+        ref = ref + sa @ Wf[g_ * cols:(g_ + 1) * cols]
+    tol = 2e-2 * math.sqrt(G * cols) / 16
+    assert (out.cpu() - ref).abs().max().item() <= tol
+    assert (out16.float().cpu() - ref).abs().max().item() <= tol + 2 ** -7 * ref.abs().max().item()
