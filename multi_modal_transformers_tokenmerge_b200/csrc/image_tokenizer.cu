@@ -26,6 +26,8 @@
 // the flatten is free ([.., o2, o2, F] rows ARE the Dense's K-major A operand).  HBM-bound: the im2col rows dominate the
 // traffic (k*k*C_in / (s*s*C_in) = 36x the pixels for the input convolution, 9x the activations for the blocks); the
 // batch is processed in chunks of whole batch rows so the im2col buffer stays near 1 GiB whatever the batch.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -85,9 +87,11 @@ static int it_geometry(const tome_image_tokenizer_desc_t* d, ItGeom* g, const ch
   g->k0 = d->conv_kernel * d->conv_kernel * d->channels_in;
   // (checked below once the path is known: the im2col path needs conv_kernel^2 * channels_in to be a multiple of 16)
   g->kd = g->o2 * g->o2 * d->features;
-  g->pad = d->features % 64 == 0 ? 1 : 0;
+  // TOME_IT_NO_SHIFT / TOME_IT_NO_S2D (environment; A/B measurements and bisection only) force the im2col paths
+  static const bool no_shift = getenv("TOME_IT_NO_SHIFT") != nullptr, no_s2d = getenv("TOME_IT_NO_S2D") != nullptr;
+  g->pad = (d->features % 64 == 0 && !no_shift) ? 1 : 0;
   g->s2d = (d->patch_size % d->conv_stride == 0 && d->conv_kernel % d->conv_stride == 0 &&
-            d->conv_stride * d->conv_stride * d->channels_in <= IT_S2D_CH && d->conv_kernel / d->conv_stride <= IT_S2D_TX) ? 1 : 0;
+            d->conv_stride * d->conv_stride * d->channels_in <= IT_S2D_CH && d->conv_kernel / d->conv_stride <= IT_S2D_TX && !no_s2d) ? 1 : 0;
   g->gs = d->patch_size / d->conv_stride;
   g->ks = d->conv_kernel / d->conv_stride;
   g->g1 = g->s2d ? g->gs : g->o1;
@@ -114,7 +118,7 @@ static int it_geometry(const tome_image_tokenizer_desc_t* d, ItGeom* g, const ch
   g->off_pool = o;  o += align256((size_t)2 * m2p_row * cr * d->features);
   g->off_xa = o;    o += align256((size_t)2 * m2p_row * cr * d->features);
   g->off_xb = o;    o += align256((size_t)2 * m2p_row * cr * d->features);
-  g->off_h = o;     o += align256((size_t)2 * m2_row * cr * d->features);
+  g->off_h = o;     o += align256((size_t)2 * m2p_row * cr * d->features);
   g->off_dense = o; o += align256((size_t)4 * cr * d->n_images * g->np * d->embed_dim);
   g->off_w0 = o;    o += align256((size_t)2 * IT_S2D_CH * IT_S2D_TX * IT_S2D_TX * d->features);   // repacked input-convolution kernel
   g->off_part = o;  o += align256((size_t)4 * cr * g->gn_ctas * d->features * 2);
