@@ -36,17 +36,12 @@
 namespace tome {
 
 constexpr int IT_THREADS = 256;
-constexpr int IT_S2D_CH = 16;   // channels of a space-to-depth pixel, zero-padded (stride^2 * C_in <= 16)
-constexpr int IT_S2D_TX = 8;    // horizontal taps packed per row of the x-expanded operand (kernel / stride <= 8): 8 x 16 = 128 columns
 constexpr int IT_GN_MAX_CTAS = 64;      // CTAs per batch row in the statistics pass
 constexpr size_t IT_COL_TARGET = (size_t)1 << 30;   // im2col buffer target per chunk of batch rows
 
 struct ItGeom {
   int ppd, np;          // patches per image side / per image
   int o1, o2;           // side after the input convolution / after the pool
-  int s2d;              // 1: the input convolution runs on the space-to-depth grid as a row-shifted GEMM (see it_s2d_xcol_kernel)
-  int gs, ks;           // that grid's side (patch / stride) and the taps per side on it (kernel / stride)
-  int g1;               // row pitch (pixels) of the input convolution's output: gs on the s2d path, else o1
   int wp, pad;          // side of the grid the block activations live on: o2 + 2 with a zero border (pad = 1) when the 3 x 3
                         // convolutions run as row-shifted GEMMs (features % 64 == 0), else o2 (pad = 0, im2col rows)
   int k0;               // k*k*C_in
@@ -55,7 +50,7 @@ struct ItGeom {
   int chunk_rows;       // batch rows per chunk
   int gn_ctas;
   // workspace offsets (bytes) of one chunk
-  size_t off_col, off_y0, off_pool, off_xa, off_xb, off_h, off_dense, off_w0, off_part, off_stats, off_ab, total;
+  size_t off_col, off_y0, off_pool, off_xa, off_xb, off_h, off_dense, off_part, off_stats, off_ab, total;
 };
 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -85,29 +80,23 @@ static int it_geometry(const tome_image_tokenizer_desc_t* d, ItGeom* g, const ch
   g->o2 = g->o1 - (d->pool_window - 1);
   TOME_CHECK(g->o2 >= 1, TOME_ERR_INVALID, "%s: a %d-wide pool does not fit the %d x %d convolution output", who, d->pool_window, g->o1, g->o1);
   g->k0 = d->conv_kernel * d->conv_kernel * d->channels_in;
-  // (checked below once the path is known: the im2col path needs conv_kernel^2 * channels_in to be a multiple of 16)
   g->kd = g->o2 * g->o2 * d->features;
-  // TOME_IT_NO_SHIFT / TOME_IT_NO_S2D (environment; A/B measurements and bisection only) force the im2col paths
-  static const bool no_shift = getenv("TOME_IT_NO_SHIFT") != nullptr, no_s2d = getenv("TOME_IT_NO_S2D") != nullptr;
+  // TOME_IT_NO_SHIFT (environment; A/B measurements and bisection only) forces the im2col path of the 3 x 3 convolutions
+  static const bool no_shift = getenv("TOME_IT_NO_SHIFT") != nullptr;
   g->pad = (d->features % 64 == 0 && !no_shift) ? 1 : 0;
-  g->s2d = (d->patch_size % d->conv_stride == 0 && d->conv_kernel % d->conv_stride == 0 &&
-            d->conv_stride * d->conv_stride * d->channels_in <= IT_S2D_CH && d->conv_kernel / d->conv_stride <= IT_S2D_TX && !no_s2d) ? 1 : 0;
-  g->gs = d->patch_size / d->conv_stride;
-  g->ks = d->conv_kernel / d->conv_stride;
-  g->g1 = g->s2d ? g->gs : g->o1;
-  TOME_CHECK(g->s2d || g->k0 % 16 == 0, TOME_ERR_UNSUPPORTED, "%s: conv_kernel^2 * channels_in (%d) must be a multiple of 16", who, g->k0);
+  TOME_CHECK(g->k0 % 16 == 0, TOME_ERR_UNSUPPORTED, "%s: conv_kernel^2 * channels_in (%d) must be a multiple of 16", who, g->k0);
   g->wp = g->o2 + 2 * g->pad;
   g->imgs = (long long)d->batch * d->n_images;
-  const long long m0_row = (long long)d->n_images * g->np * g->g1 * g->g1;   // rows of the input convolution's GEMM per batch row
+  const long long m0_row = (long long)d->n_images * g->np * g->o1 * g->o1;   // im2col rows of the input convolution per batch row
   const long long m2_row = (long long)d->n_images * g->np * g->o2 * g->o2;
   const long long m2p_row = (long long)d->n_images * g->np * g->wp * g->wp;   // rows of the (bordered) activation grid
-  const size_t col_row = 2 * (size_t)std::max(m0_row * (g->s2d ? IT_S2D_CH * IT_S2D_TX : g->k0), g->pad ? 0ll : m2_row * 9 * d->features);
+  const size_t col_row = 2 * (size_t)std::max(m0_row * g->k0, g->pad ? 0ll : m2_row * 9 * d->features);
   long long cr = (long long)(IT_COL_TARGET / col_row);
   TOME_CHECK(d->chunk_rows >= 0, TOME_ERR_INVALID, "%s: chunk_rows must be >= 0", who);
   if (d->chunk_rows > 0) cr = d->chunk_rows;
   if (cr < 1) cr = 1;
   if (cr > d->batch) cr = d->batch;
-  TOME_CHECK(m0_row * cr * ((g->s2d ? IT_S2D_CH * IT_S2D_TX : g->k0) / 8) < (1ll << 31) && m2p_row * cr * 9 * (d->features / 8) < (1ll << 31), TOME_ERR_UNSUPPORTED,
+  TOME_CHECK(m0_row * cr * (g->k0 / 8) < (1ll << 31) && m2p_row * cr * 9 * (d->features / 8) < (1ll << 31), TOME_ERR_UNSUPPORTED,
              "%s: %lld batch rows per pass need more than 2^31 16-byte vectors of im2col rows: lower chunk_rows", who, cr);
   g->chunk_rows = (int)cr;
   long long want = m2_row * (d->features / 8) / (IT_THREADS * 4);
@@ -120,7 +109,6 @@ static int it_geometry(const tome_image_tokenizer_desc_t* d, ItGeom* g, const ch
   g->off_xb = o;    o += align256((size_t)2 * m2p_row * cr * d->features);
   g->off_h = o;     o += align256((size_t)2 * m2p_row * cr * d->features);
   g->off_dense = o; o += align256((size_t)4 * cr * d->n_images * g->np * d->embed_dim);
-  g->off_w0 = o;    o += align256((size_t)2 * IT_S2D_CH * IT_S2D_TX * IT_S2D_TX * d->features);   // repacked input-convolution kernel
   g->off_part = o;  o += align256((size_t)4 * cr * g->gn_ctas * d->features * 2);
   g->off_stats = o; o += align256((size_t)4 * cr * d->num_groups * 2);
   g->off_ab = o;    o += align256((size_t)4 * cr * d->features * 2);
@@ -202,81 +190,6 @@ it_im2col0_kernel(const PixT* __restrict__ image, __nv_bfloat16* __restrict__ co
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
   f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
-}
-
-// Input convolution without im2col rows.  A k x k / stride-s convolution is a (k/s) x (k/s) / stride-1 convolution over the
-// space-to-depth grid (side gs = p / s, s*s*C_in channels per pixel, here zero-padded to 16).  Row (y, x) of the operand this
-// kernel writes holds the 8 pixels x .. x + 7 of grid row y (8 x 16 = 128 columns, zeros past the row end): the horizontal
-// taps.  The vertical taps are row shifts of that SAME matrix by ty * gs -- tome_gemm_args_t.a_row_shift -- so the GEMM reads
-// 128 columns x (k/s) shifted windows instead of k*k*C_in im2col columns: 256 B written per grid pixel instead of 864 B per
-// output pixel, re-read from L2.  Outputs land on the gs-wide grid; those with x or y > gs - k/s are never read.
-// Thread = (grid pixel, horizontal tap): 2 rows x (s * C_in) contiguous pixels bytes -> 16 bf16 (two 16-byte stores).
-struct S2dArgs {
-  FastDiv gs, np, ppd;
-  int psize, stride, c_in, img_w_c, normalize, row_elems /* s * C_in */;
-  long long img_elems;
-};
-template <typename PixT>
-__global__ void __launch_bounds__(IT_THREADS)
-it_s2d_xcol_kernel(const PixT* __restrict__ image, __nv_bfloat16* __restrict__ q, uint32_t n_items, const S2dArgs a) {
-  pdl_prologue();
-  __shared__ uint16_t lut[256];
-  if (sizeof(PixT) == 1) {
-    float x = (float)threadIdx.x;
-    if (a.normalize) x = 2.0f * __fdiv_rn(x, 255.0f) - 1.0f;
-    __nv_bfloat16 h = __float2bfloat16(x);
-    lut[threadIdx.x] = *reinterpret_cast<uint16_t*>(&h);
-    __syncthreads();
-  }
-  const uint32_t it = blockIdx.x * IT_THREADS + threadIdx.x;
-  if (it >= n_items) return;
-  const uint32_t tx = it & (IT_S2D_TX - 1);
-  uint32_t m = it >> 3, x, y, t, patch, img, py, px;
-  a.gs.divmod(m, t, x);
-  a.gs.divmod(t, t, y);
-  a.np.divmod(t, img, patch);
-  a.ppd.divmod(patch, py, px);
-  uint32_t w[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-  const uint32_t xs = x + tx;
-  if (xs < a.gs.d) {
-    const PixT* base = image + img * a.img_elems + (long long)(py * a.psize + y * a.stride) * a.img_w_c +
-                       (long long)(px * a.psize + xs * a.stride) * a.c_in;
-    int e = 0;   // channel index (sy, sx, c) of the space-to-depth pixel
-    for (int sy = 0; sy < a.stride; ++sy)
-      for (int j = 0; j < a.row_elems; ++j, ++e) {
-        uint32_t h16;
-        if (sizeof(PixT) == 1) {
-          h16 = lut[(uint32_t)base[(long long)sy * a.img_w_c + j]];
-        } else {
-          float v = (float)base[(long long)sy * a.img_w_c + j];
-          if (a.normalize) v = 2.0f * __fdiv_rn(v, 255.0f) - 1.0f;
-          __nv_bfloat16 h = __float2bfloat16(v);
-          h16 = *reinterpret_cast<uint16_t*>(&h);
-        }
-        w[e >> 1] |= h16 << ((e & 1) * 16);
-      }
-  }
-  __nv_bfloat16* dst = q + (size_t)it * IT_S2D_CH;
-  st_na_v4(dst, make_uint4(w[0], w[1], w[2], w[3]));
-  st_na_v4(dst + 8, make_uint4(w[4], w[5], w[6], w[7]));
-}
-
-// Flax kernel [k, k, C_in, F] -> the operand of that GEMM: row (ty * 8 + tx) * 16 + (sy * s + sx) * C_in + c  <-  kernel
-// [ty * s + sy, tx * s + sx, c, :], zero rows for tx >= k / s and for the padded channels.
-__global__ void it_w0_repack_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ out, int ks, int stride,
-                                    int c_in, int kdim, int F) {
-  pdl_prologue();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int rows = ks * IT_S2D_TX * IT_S2D_CH;
-  if (i >= rows * F) return;
-  const int r = i / F, f = i - r * F;
-  const int e = r % IT_S2D_CH, tx = (r / IT_S2D_CH) % IT_S2D_TX, ty = r / (IT_S2D_CH * IT_S2D_TX);
-  __nv_bfloat16 v = __float2bfloat16(0.f);
-  if (tx < ks && e < stride * stride * c_in) {
-    const int sy = e / (stride * c_in), rem = e - sy * stride * c_in, sx = rem / c_in, c = rem - sx * c_in;
-    v = w[(((long long)(ty * stride + sy) * kdim + (tx * stride + sx)) * c_in + c) * F + f];
-  }
-  out[i] = v;
 }
 
 __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
@@ -451,10 +364,11 @@ it_im2col3_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict
   st_na_v4(col + (size_t)v * 8, o);
 }
 
-// interior of the bordered grid -> dense [pixels, F] rows (the flatten the Dense consumes).  Thread = 16 bytes of output.
+// interior of the bordered grid + the residual (the pooled tensor) -> dense [pixels, F] rows (the flatten the Dense consumes).
+// Thread = 16 bytes of output.
 __global__ void __launch_bounds__(IT_THREADS)
-it_compact_kernel(const __nv_bfloat16* __restrict__ xp, __nv_bfloat16* __restrict__ out, uint32_t n_vec, FastDiv nchunk, FastDiv o2,
-                  int wp, int pad) {
+it_compact_kernel(const __nv_bfloat16* __restrict__ xp, const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ out,
+                  uint32_t n_vec, FastDiv nchunk, FastDiv o2, int wp, int pad) {
   pdl_prologue();
   const uint32_t v = blockIdx.x * IT_THREADS + threadIdx.x;
   if (v >= n_vec) return;
@@ -462,7 +376,14 @@ it_compact_kernel(const __nv_bfloat16* __restrict__ xp, __nv_bfloat16* __restric
   nchunk.divmod(v, t, c);
   o2.divmod(t, t, ox);
   o2.divmod(t, ip, oy);
-  st_na_v4(out + (size_t)v * 8, ld_nc_v4(xp + ((((size_t)ip * wp + oy + pad) * wp + ox + pad) * nchunk.d + c) * 8));
+  const size_t src = ((((size_t)ip * wp + oy + pad) * wp + ox + pad) * nchunk.d + c) * 8;
+  float f[8], r[8];
+  unpack8(ld_nc_v4(xp + src), f);
+  unpack8(ld_nc_v4(res + src), r);   // x + residual (image_tokenizer.py:170), added here instead of in the convolution's epilogue
+  uint4 o;
+  o.x = pack_bf16(f[0] + r[0], f[1] + r[1]); o.y = pack_bf16(f[2] + r[2], f[3] + r[3]);
+  o.z = pack_bf16(f[4] + r[4], f[5] + r[5]); o.w = pack_bf16(f[6] + r[6], f[7] + r[7]);
+  st_na_v4(out + (size_t)v * 8, o);
 }
 
 // tokens + row / column position embeddings (image_tokenizer.py:296-305), 4 features per thread.
@@ -590,7 +511,7 @@ extern "C" int tome_image_tokenizer_fwd(const tome_image_tokenizer_desc_t* d, co
   for (int b0 = 0; b0 < d->batch; b0 += g.chunk_rows) {
     const int rows_b = std::min(g.chunk_rows, d->batch - b0);
     const long long imgs = (long long)rows_b * d->n_images, img0 = (long long)b0 * d->n_images;
-    const long long m0 = imgs * g.np * g.g1 * g.g1, m2 = imgs * g.np * g.o2 * g.o2, mt = imgs * g.np;
+    const long long m0 = imgs * g.np * g.o1 * g.o1, m2 = imgs * g.np * g.o2 * g.o2, mt = imgs * g.np;
     const long long R = (long long)d->n_images * g.np * g.o2 * g.o2;   // pixels of one batch row in the GroupNorm reduction
     const long long Rp = (long long)d->n_images * g.np * g.wp * g.wp;  // rows of one batch row on the (bordered) activation grid
     const long long m2p = imgs * g.np * g.wp * g.wp;
@@ -598,34 +519,7 @@ extern "C" int tome_image_tokenizer_fwd(const tome_image_tokenizer_desc_t* d, co
     int shifts[9];
     for (int t9 = 0; t9 < 9; ++t9) shifts[t9] = (t9 / 3 - 1) * g.wp + (t9 % 3 - 1);
     const uint8_t* img = reinterpret_cast<const uint8_t*>(image) + (size_t)img0 * pix_img * pix_bytes;
-    if (g.s2d) {
-      // input convolution on the space-to-depth grid: x-expanded operand [m0, 128] + (k / s) row-shifted windows (see the kernel)
-      __nv_bfloat16* w0 = reinterpret_cast<__nv_bfloat16*>(ws + g.off_w0);
-      const int krows = g.ks * IT_S2D_TX * IT_S2D_CH;
-      if (b0 == 0) {
-        ProfScope prof(PROF_OTHER, 0.0, 1, stream);
-        launch_k(it_w0_repack_kernel, (unsigned)ceil_div(krows * F, 256), 256, 0, stream, pb + it_offset(d, g, TOME_IT_CONV0_KERNEL), w0,
-                 g.ks, d->conv_stride, d->channels_in, d->conv_kernel, F);
-        TOME_CUDA(cudaGetLastError());
-      }
-      S2dArgs sa;
-      sa.gs = make_fastdiv(g.gs); sa.np = make_fastdiv(g.np); sa.ppd = make_fastdiv(g.ppd);
-      sa.psize = d->patch_size; sa.stride = d->conv_stride; sa.c_in = d->channels_in; sa.img_w_c = d->image_size * d->channels_in;
-      sa.normalize = d->normalize; sa.row_elems = d->conv_stride * d->channels_in; sa.img_elems = pix_img;
-      const long long ni = m0 * IT_S2D_TX;
-      {
-        ProfScope prof(PROF_OTHER, (double)ni * 32, 1, stream);
-        if (d->image_dtype == TOME_U8)
-          launch_k(it_s2d_xcol_kernel<uint8_t>, nblk(ni), IT_THREADS, 0, stream, img, col, (uint32_t)ni, sa);
-        else
-          launch_k(it_s2d_xcol_kernel<float>, nblk(ni), IT_THREADS, 0, stream, reinterpret_cast<const float*>(img), col, (uint32_t)ni, sa);
-        TOME_CUDA(cudaGetLastError());
-      }
-      int sh0[IT_S2D_TX];
-      for (int ty = 0; ty < g.ks; ++ty) sh0[ty] = ty * g.gs;
-      rc = it_gemm((int)m0, F, krows, col, w0, y0, TOME_BF16, pf + it_offset(d, g, TOME_IT_CONV0_BIAS), nullptr, stream, sh0, g.ks);
-      if (rc != TOME_OK) return rc;
-    } else {
+    {
       const long long nv = m0 * (g.k0 / 8);
       Im2col0Args ia;
       ia.vpr = make_fastdiv(g.k0 / 8); ia.o1 = make_fastdiv(g.o1); ia.np = make_fastdiv(g.np); ia.ppd = make_fastdiv(g.ppd);
@@ -648,7 +542,7 @@ extern "C" int tome_image_tokenizer_fwd(const tome_image_tokenizer_desc_t* d, co
     {
       const long long nv = m2 * nchunk;
       ProfScope prof(PROF_OTHER, (double)nv * 16 * (d->pool_window * d->pool_window + 1), 1, stream);
-      launch_k(it_pool_kernel, nblk(nv), IT_THREADS, 0, stream, y0, pooled, (uint32_t)nv, fd_chunk, g.g1, fd_o2, d->pool_window, g.wp, g.pad);
+      launch_k(it_pool_kernel, nblk(nv), IT_THREADS, 0, stream, y0, pooled, (uint32_t)nv, fd_chunk, g.o1, fd_o2, d->pool_window, g.wp, g.pad);
       TOME_CUDA(cudaGetLastError());
     }
     const __nv_bfloat16* x = pooled;
@@ -677,7 +571,7 @@ extern "C" int tome_image_tokenizer_fwd(const tome_image_tokenizer_desc_t* d, co
         // 3 x 3 SAME convolution as ONE GEMM over nine row-shifted windows of the bordered activation (no im2col rows): tap
         // (ty, tx) reads h at rows + (ty - 1) wp + (tx - 1); outputs on border positions are never read
         rc = it_gemm((int)m2p, F, 9 * F, hbuf, pb + it_offset(d, g, pi + 2), y, TOME_BF16, pf + it_offset(d, g, pi + 3),
-                     last ? pooled : nullptr, stream, shifts, 9);   // image_tokenizer.py:170: x + residual after the LAST block
+                     nullptr, stream, shifts, 9);   // the residual of image_tokenizer.py:170 is added by it_compact_kernel
       } else {
         const long long nv = m2 * 9 * nchunk;
         {
@@ -691,10 +585,10 @@ extern "C" int tome_image_tokenizer_fwd(const tome_image_tokenizer_desc_t* d, co
       if (rc != TOME_OK) return rc;
       x = y;
     }
-    if (g.pad) {   // the Dense flattens (h, w, c) of the interior
+    if (g.pad) {   // the Dense flattens (h, w, c) of the interior of x + pooled
       const long long nv = m2 * nchunk;
-      ProfScope prof(PROF_OTHER, (double)nv * 32, 1, stream);
-      launch_k(it_compact_kernel, nblk(nv), IT_THREADS, 0, stream, x, hbuf, (uint32_t)nv, fd_chunk, fd_o2, g.wp, g.pad);
+      ProfScope prof(PROF_OTHER, (double)nv * 48, 1, stream);
+      launch_k(it_compact_kernel, nblk(nv), IT_THREADS, 0, stream, x, pooled, hbuf, (uint32_t)nv, fd_chunk, fd_o2, g.wp, g.pad);
       TOME_CUDA(cudaGetLastError());
       x = hbuf;
     }

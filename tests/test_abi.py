@@ -152,11 +152,11 @@ def test_image_tokenizer_shapes_on_host(lib):
     assert off(L.IT_DENSE_KERNEL) == conv0 + 2 * block and off(L.IT_COL_EMBED) == n - 128 * 768
     assert off(L.IT_BLOCK0 + 8) == -1 and b"no parameter" in lib.tome_last_error()
     ws = lib.tome_image_tokenizer_workspace_bytes(C.byref(d))
-    assert ws >= 2 * 4 * 2 * 25 * 28 * 28 * 128          # at least the input convolution's x-expanded operand of the 4 batch rows
-    # every buffer of a pass at its size: x-expanded operand, conv0 output on the 28-wide grid, four bordered (23 x 23) activation
+    assert ws >= 2 * 4 * 2 * 25 * 23 * 23 * 432          # at least the input convolution's im2col rows of the 4 batch rows
+    # every buffer of a pass at its size: im2col rows and output of the input convolution, four bordered (23 x 23) activation
     # buffers, the Dense output (an undersized one here once let a kernel write into its neighbour)
     n_patch = 4 * 2 * 25
-    assert ws >= n_patch * (784 * 128 * 2 + 784 * 64 * 2 + 4 * 529 * 64 * 2 + 768 * 4)
+    assert ws >= n_patch * (529 * 432 * 2 + 529 * 64 * 2 + 4 * 529 * 64 * 2 + 768 * 4)
     d.batch = 4096                                       # the workspace is per chunk of batch rows, not per batch
     assert lib.tome_image_tokenizer_workspace_bytes(C.byref(d)) < (3 << 30)
     for field, value, msg in (("patch_size", 57, b"multiple of patch_size"), ("features", 60, b"multiple of 8"),
