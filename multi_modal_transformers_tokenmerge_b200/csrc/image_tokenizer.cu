@@ -50,7 +50,7 @@ struct ItGeom {
   int chunk_rows;       // batch rows per chunk
   int gn_ctas;
   // workspace offsets (bytes) of one chunk
-  size_t off_col, off_y0, off_pool, off_xa, off_xb, off_h, off_dense, off_part, off_stats, off_ab, total;
+  size_t off_col, off_y0, off_pool, off_xa, off_xb, off_h, off_pix, off_dense, off_part, off_stats, off_ab, total;
 };
 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -108,6 +108,7 @@ static int it_geometry(const tome_image_tokenizer_desc_t* d, ItGeom* g, const ch
   g->off_xa = o;    o += align256((size_t)2 * m2p_row * cr * d->features);
   g->off_xb = o;    o += align256((size_t)2 * m2p_row * cr * d->features);
   g->off_h = o;     o += align256((size_t)2 * m2p_row * cr * d->features);
+  g->off_pix = o;   o += align256((size_t)2 * cr * d->n_images * d->image_size * d->image_size * d->channels_in + 16);
   g->off_dense = o; o += align256((size_t)4 * cr * d->n_images * g->np * d->embed_dim);
   g->off_part = o;  o += align256((size_t)4 * cr * g->gn_ctas * d->features * 2);
   g->off_stats = o; o += align256((size_t)4 * cr * d->num_groups * 2);
@@ -182,6 +183,54 @@ it_im2col0_kernel(const PixT* __restrict__ image, __nv_bfloat16* __restrict__ co
     }
     if (j & 1) w[j >> 1] |= h16 << 16; else w[j >> 1] = h16;
     ++rem;
+  }
+  st_na_v4(col + (size_t)v * 8, make_uint4(w[0], w[1], w[2], w[3]));
+  st_na_v4(col + (size_t)v * 8 + 8, make_uint4(w[4], w[5], w[6], w[7]));
+}
+
+// pixels (u8 / f32) -> normalised bf16, once (8 pixels values per thread); the im2col below then moves whole 32-bit words.
+template <typename PixT>
+__global__ void __launch_bounds__(IT_THREADS)
+it_pixels_bf16_kernel(const PixT* __restrict__ image, __nv_bfloat16* __restrict__ out, long long n, int normalize) {
+  pdl_prologue();
+  const long long i = ((long long)blockIdx.x * IT_THREADS + threadIdx.x) * 8;
+  if (i >= n) return;
+  uint32_t w[4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float x = i + j < n ? (float)image[i + j] : 0.f;
+    if (normalize) x = 2.0f * __fdiv_rn(x, 255.0f) - 1.0f;   // image_tokenizer.py:67
+    __nv_bfloat16 h = __float2bfloat16(x);
+    const uint32_t h16 = *reinterpret_cast<uint16_t*>(&h);
+    if (j & 1) w[j >> 1] |= h16 << 16; else w[j >> 1] = h16;
+  }
+  if (i + 8 <= n) *reinterpret_cast<uint4*>(out + i) = make_uint4(w[0], w[1], w[2], w[3]);
+  else for (int j = 0; i + j < n; ++j) reinterpret_cast<uint16_t*>(out)[i + j] = (uint16_t)(w[j >> 1] >> ((j & 1) * 16));
+}
+
+// im2col rows of the input convolution from the bf16 pixels, two elements (one 32-bit word) at a time: every offset involved
+// is even (host-checked: k * C_in, W * C_in, stride * C_in and patch * C_in even), so a word never straddles a (dy) row.
+__global__ void __launch_bounds__(IT_THREADS)
+it_im2col0_words_kernel(const uint32_t* __restrict__ pix, __nv_bfloat16* __restrict__ col, uint32_t n_vec, const Im2col0Args a) {
+  pdl_prologue();
+  const uint32_t v = (blockIdx.x * IT_THREADS + threadIdx.x) * 2;   // two consecutive 16-byte vectors of one row
+  if (v >= n_vec) return;
+  uint32_t m, kc, ox, oy, patch, img, py, px, dy, rem, t;
+  a.vpr.divmod(v, m, kc);
+  a.o1.divmod(m, t, ox);
+  a.o1.divmod(t, t, oy);
+  a.np.divmod(t, img, patch);
+  a.ppd.divmod(patch, py, px);
+  a.kw_c.divmod(kc << 3, dy, rem);
+  const uint32_t* base = pix + ((img * a.img_elems + (long long)(py * a.psize + oy * a.stride + dy) * a.img_w_c +
+                                 (long long)(px * a.psize + ox * a.stride) * a.c_in) >> 1);
+  const uint32_t row_words = (uint32_t)a.img_w_c >> 1, kw_words = a.kw_c.d >> 1;
+  uint32_t rw = rem >> 1, w[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (rw >= kw_words) { rw -= kw_words; base += row_words; }
+    w[j] = __ldg(base + rw);
+    ++rw;
   }
   st_na_v4(col + (size_t)v * 8, make_uint4(w[0], w[1], w[2], w[3]));
   st_na_v4(col + (size_t)v * 8 + 8, make_uint4(w[4], w[5], w[6], w[7]));
@@ -526,7 +575,21 @@ extern "C" int tome_image_tokenizer_fwd(const tome_image_tokenizer_desc_t* d, co
       ia.kw_c = make_fastdiv(d->conv_kernel * d->channels_in);
       ia.psize = d->patch_size; ia.stride = d->conv_stride; ia.img_w_c = d->image_size * d->channels_in; ia.c_in = d->channels_in;
       ia.normalize = d->normalize; ia.img_elems = pix_img;
-      {
+      const bool words = (d->conv_kernel * d->channels_in) % 2 == 0 && (d->image_size * d->channels_in) % 2 == 0 &&
+                         (d->conv_stride * d->channels_in) % 2 == 0 && (d->patch_size * d->channels_in) % 2 == 0 && (pix_img % 2) == 0;
+      if (words) {
+        // pixels -> normalised bf16 once, then the im2col moves 32-bit words (no per-byte loads, table lookups or packing)
+        __nv_bfloat16* pix = reinterpret_cast<__nv_bfloat16*>(ws + g.off_pix);
+        const long long np_ = imgs * pix_img;
+        ProfScope prof(PROF_OTHER, (double)np_ * 3 + (double)nv * 16, 2, stream);
+        if (d->image_dtype == TOME_U8)
+          launch_k(it_pixels_bf16_kernel<uint8_t>, nblk((np_ + 7) / 8), IT_THREADS, 0, stream, img, pix, np_, d->normalize);
+        else
+          launch_k(it_pixels_bf16_kernel<float>, nblk((np_ + 7) / 8), IT_THREADS, 0, stream, reinterpret_cast<const float*>(img), pix, np_, d->normalize);
+        TOME_CUDA(cudaGetLastError());
+        launch_k(it_im2col0_words_kernel, nblk(nv / 2), IT_THREADS, 0, stream, reinterpret_cast<const uint32_t*>(pix), col, (uint32_t)nv, ia);
+        TOME_CUDA(cudaGetLastError());
+      } else {
         ProfScope prof(PROF_OTHER, (double)nv * 16, 1, stream);
         if (d->image_dtype == TOME_U8)
           launch_k(it_im2col0_kernel<uint8_t>, nblk(nv / 2), IT_THREADS, 0, stream, img, col, (uint32_t)nv, ia);

@@ -1031,3 +1031,27 @@ def test_gemm_row_shifted_windows(ops, m, n, cols, shifts):
     tol = 2e-2 * math.sqrt(G * cols) / 16
     assert (out.cpu() - ref).abs().max().item() <= tol
     assert (out16.float().cpu() - ref).abs().max().item() <= tol + 2 ** -7 * ref.abs().max().item()
+
+
+@pytest.mark.gpu
+def test_image_tokenizer_other_geometry_vs_oracle(ops):
+    """A geometry none of the reference-made goldens has -- one input channel, a 4 x 4 / stride-1 input convolution, a 2 x 2 pool,
+    three blocks of 64 features (the row-shifted 3 x 3 path) -- against the oracle: exercises the byte-wise pixel im2col (odd
+    element offsets rule out the 32-bit path) and the general index arithmetic.  Same tolerance as the golden test."""
+    from multi_modal_transformers_tokenmerge_b200.tokenizers.images import ImageTokenizer
+    rng = np.random.default_rng(23)
+    H, P, Cin, F, G, E, PI, NB = 36, 12, 1, 64, 8, 64, 32, 3
+    nodes = _it_nodes(H, P, Cin, F, G, E, PI, NB, True)
+    nodes["resnet"]["input_conv"].update(kernel_size=[4, 4], strides=[1, 1])
+    nodes["resnet"]["input_pool"].update(window_shape=[2, 2])
+    tok = ImageTokenizer(**nodes, out_dtype=torch.float32)
+    variables = tok.init(3, None)
+    img = rng.integers(0, 256, size=(2, 3, H, H, Cin)).astype(np.uint8)
+    got = tok.apply(variables, torch.from_numpy(img).cuda(), train=False).cpu().numpy()
+    p = O.image_tokenizer_params_from_flax(variables["params"], NB)
+    want = O.image_tokenizer_fwd(p, img.astype(np.float32), patch_size=P, position_interval=PI, num_groups=G, conv_stride=1,
+                                 pool_window=2, normalize=True)
+    assert got.shape == want.shape == (2, 3, 9, E)
+    scale = np.abs(want).max()
+    err = np.abs(got - want)
+    assert err.max() <= 3e-2 * scale and err.mean() <= 5e-3 * scale, (err.max(), err.mean(), scale)
