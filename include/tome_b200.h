@@ -396,6 +396,12 @@ int tome_diffusion_head_bwd(const tome_diffusion_desc_t* desc, const float* para
                             const int32_t* origin, const int32_t* time, void* workspace, float* grads_f32, void* dx,
                             void* stream);
 
+/* One update of the diffusion head's sampling loop (action_heads/diffusion.py:182-190, inference): out = clip(c1 * (sample - c2 *
+ * denoise_term) + c3 * noise, -clip, clip) over n floats; the denoise term of each step is tome_diffusion_head_fwd with an
+ * alpha_hat table of ones (noisy = the current sample) -- the Python mirror's predict_action strings the steps together. */
+int tome_ddpm_step(long long n, const float* sample, const float* denoise_term, const float* noise, float c1, float c2, float c3,
+                   float clip, float* out, void* stream);
+
 /* AdamW on an fp32 master vector with a bf16 working copy refreshed in the same pass (bf16_copy may be NULL).
  * grad_scale multiplies the gradient first (1/world_size after a sum all-reduce). */
 int tome_adamw_step(long long n, float* param, const float* grad, float* m, float* v, void* bf16_copy, float lr,

@@ -205,6 +205,7 @@ def lib() -> C.CDLL:
             "tome_image_tokenizer_param_offset": [P(ImageTokenizerDesc), i32],
             "tome_image_tokenizer_workspace_bytes": [P(ImageTokenizerDesc)],
             "tome_image_tokenizer_fwd": [P(ImageTokenizerDesc), vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp],
+            "tome_ddpm_step": [ll, vp, vp, vp, f32, f32, f32, f32, vp, vp],
             "tome_adamw_step": [ll, vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, f32, i32, vp],
             "tome_cast_f32_to_bf16": [ll, vp, vp, vp],
             "tome_launch_count": [i32],

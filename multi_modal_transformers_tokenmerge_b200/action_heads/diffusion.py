@@ -107,5 +107,39 @@ class DiffusionActionHead(Module):
                                             time.to(torch.int32).reshape(-1).contiguous(), ones)
         return pred
 
+    def predict_action(self, variables, readouts, rng=0, train=True, init=None, noise=None, clip: float = 5.0):
+        """:146-213 -- the sampling loop (inference): start from Gaussian noise [B, A], and for time = steps - 1 .. 0 take the
+        denoise term and apply algorithm 2 of arXiv:2006.11239 with the schedule's coefficients, clipping to [-5, 5] (:190).
+        The reference draws its step noise from the SAME per-sample keys at every step (:179, "TODO: check keys here"), i.e. one
+        noise tensor [B, A] reused by all steps; `noise` may also be [steps, B, A].  `init` / `noise` default to draws from `rng`
+        (numpy's generator, not jax.random's stream).  Every floating-point operation runs in the kernels."""
+        import ctypes as C_
+        g = as_rng(rng)
+        x = readouts.to(torch.bfloat16).contiguous()
+        dev = x.device
+        B, A = x.shape[0], self._d1.features
+        if init is None:
+            init = torch.as_tensor(g.standard_normal((B, A)).astype(np.float32))
+        if noise is None:
+            noise = torch.as_tensor(g.standard_normal((B, A)).astype(np.float32))
+        sample = init.to(dev).float().contiguous().clone()
+        noise = noise.to(dev).float().contiguous()
+        desc, flat = self._desc(readouts), self._flat(variables["params"], dev)
+        ones = torch.ones(self.diffusion_steps, dtype=torch.float32, device=dev)
+        zeros = torch.zeros(B, A, dtype=torch.float32, device=dev)
+        strm = lambda: C_.c_void_p(torch.cuda.current_stream().cuda_stream)  # noqa: E731
+        for t in range(self.diffusion_steps - 1, -1, -1):                                              # :207-211
+            time = torch.full((B,), t, dtype=torch.int32, device=dev)
+            eps, _, _ = ops.diffusion_head_fwd(x, flat, desc, sample, zeros, time, ones)             # predict_denoise_term (:167-173)
+            c1 = 1.0 / float(np.sqrt(self.alphas[t]))                                                   # :183-185
+            c2 = float((np.float32(1) - self.alphas[t]) / np.sqrt(np.float32(1) - self.alpha_hats[t]))
+            c3 = float(np.sqrt(self.betas[t]))
+            nz = noise[self.diffusion_steps - 1 - t] if noise.dim() == 3 else noise
+            out = torch.empty_like(sample)
+            L.check(L.lib().tome_ddpm_step(B * A, C_.c_void_p(sample.data_ptr()), C_.c_void_p(eps.data_ptr()),
+                                           C_.c_void_p(nz.data_ptr()), c1, c2, c3, float(clip), C_.c_void_p(out.data_ptr()), strm()))
+            sample = out
+        return sample
+
     def _apply(self, params, readouts, time, noisy_actions, dropout_rng=None):
         return self.predict_denoise_term({"params": params}, readouts, time, noisy_actions)

@@ -357,3 +357,30 @@ extern "C" int tome_diffusion_head_bwd(const tome_diffusion_desc_t* d, const flo
   TOME_CUDA(cudaGetLastError());
   return TOME_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// One step of the sampler's update (DiffusionActionHead.predict_action, action_heads/diffusion.py:182-190; algorithm 2 of
+// arXiv:2006.11239):  out = clip(c1 * (sample - c2 * denoise_term) + c3 * noise, -clip, clip), the coefficients taken from
+// the schedule by the caller (c1 = 1 / sqrt(alpha_t), c2 = (1 - alpha_t) / sqrt(1 - alpha_hat_t), c3 = sqrt(beta_t)).
+namespace tome {
+__global__ void ddpm_step_kernel(long long n, const float* __restrict__ sample, const float* __restrict__ eps,
+                                 const float* __restrict__ noise, float c1, float c2, float c3, float clip, float* __restrict__ out) {
+  pdl_prologue();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = c1 * (sample[i] - c2 * eps[i]) + c3 * noise[i];
+  out[i] = fminf(fmaxf(v, -clip), clip);
+}
+}  // namespace tome
+
+extern "C" int tome_ddpm_step(long long n, const float* sample, const float* denoise_term, const float* noise, float c1, float c2,
+                              float c3, float clip, float* out, void* stream_) {
+  clear_error();
+  cudaStream_t st = (cudaStream_t)stream_;
+  TOME_CHECK(n > 0 && sample && denoise_term && noise && out, TOME_ERR_INVALID, "ddpm_step: bad argument");
+  TOME_CHECK(clip > 0.f, TOME_ERR_INVALID, "ddpm_step: clip must be positive");
+  ProfScope prof(PROF_OTHER, 0.0, 1, st);
+  launch_k(tome::ddpm_step_kernel, (unsigned)((n + 255) / 256), 256, 0, st, n, sample, denoise_term, noise, c1, c2, c3, clip, out);
+  TOME_CUDA(cudaGetLastError());
+  return TOME_OK;
+}

@@ -744,6 +744,29 @@ def denoise_loss(readouts, actions, time, noise, ah: np.ndarray, p):
     return loss, pred
 
 
+def diffusion_predict_action(readouts, init, noise, betas: np.ndarray, p, clip: float = 5.0):
+    """DiffusionActionHead.predict_action (diffusion.py:146-213) with the random draws supplied: init [B, A] (the Gaussian start,
+    :203) and noise [B, A] -- the reference draws the step noise from the SAME per-sample keys at every step (:179), so one
+    tensor serves all steps -- or [steps, B, A].  time runs steps - 1 .. 0 (:210); algorithm 2 of arXiv:2006.11239 with
+    c1 = 1 / sqrt(alpha_t), c2 = (1 - alpha_t) / sqrt(1 - alpha_hat_t), c3 = sqrt(beta_t) (:183-186); clip to [-5, 5] (:189)."""
+    torch = _torch()
+    betas = np.asarray(betas, np.float32)
+    alphas = np.float32(1) - betas
+    ah = np.array([np.prod(alphas[: i + 1]) for i in range(len(betas))], np.float32)
+    emb = readouts.mean(dim=-2)
+    x = init.clone()
+    steps = len(betas)
+    for t in range(steps - 1, -1, -1):
+        time = torch.full((x.shape[0], 1), t, dtype=torch.int64)
+        eps = octo_denoise(x, time, emb, p)
+        c1 = float(np.float32(1) / np.sqrt(alphas[t]))
+        c2 = float((np.float32(1) - alphas[t]) / np.sqrt(np.float32(1) - ah[t]))
+        c3 = float(np.sqrt(betas[t]))
+        nz = noise[steps - 1 - t] if noise.dim() == 3 else noise
+        x = torch.clamp(c1 * (x - c2 * eps) + c3 * nz, -clip, clip)
+    return x
+
+
 # ------------------------------------------------------------------------------------------------ image patch-embed front end
 # SURVEY 8(f) rank 4: multi_modal_transformers/tokenizers/images/image_tokenizer.py.  Pinned by tests/golden/image_tokenizer.npz,
 # made by EXECUTING the reference's ImageTokenizer / ResNetV2Block / image_to_patches / encode_patch_position (train=False)

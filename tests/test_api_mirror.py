@@ -490,3 +490,35 @@ def test_attention_pooling_module_against_the_executed_reference(name):
     assert tuple(y.shape) == (B, 1, E)
     err = ((y.float().cpu() - want).norm() / want.norm()).item()
     assert err <= 2e-2, err
+
+
+@gpu
+def test_diffusion_head_sampler_against_the_oracle():
+    """DiffusionActionHead.predict_action (diffusion.py:146-213, the inference loop) on the golden denoiser parameters with the
+    start sample and the step noise supplied: vs oracle.diffusion_predict_action (fp32 restatement over the reference-pinned
+    OctoDenoise).  bf16 GEMMs inside every one of the steps, each step scaling the running error by 1 / sqrt(alpha_t) >= 1:
+    |err| <= 5e-2 of the clip range; results stay inside [-5, 5] and are reproducible."""
+    g = np.load(os.path.join(GOLD, "action_heads.npz"))
+    for name in g["diffusion"]:
+        p = {k: g[f"{name}/p/{k}"] for k in ("fourier_kernel", "tw1", "tb1", "tw2", "tb2", "w1", "b1", "w2", "b2")}
+        A, F, Ht, To, H = p["w2"].shape[1], p["tw1"].shape[0], p["tw1"].shape[1], p["tw2"].shape[1], p["w1"].shape[1]
+        steps = int(g[f"{name}/steps"])
+        head = AH.DiffusionActionHead(steps, None, _diffusion_node(A, F, Ht, To, H))
+        v = {"params": {"denoiser": {
+            "FourierFeatures_0": {"fourier_kernel": p["fourier_kernel"],
+                                  "MLPBlock_0": {"Dense_0": {"kernel": p["tw1"], "bias": p["tb1"]}, "Dense_1": {"kernel": p["tw2"], "bias": p["tb2"]}}},
+            "MLPBlock_0": {"Dense_0": {"kernel": p["w1"], "bias": p["b1"]}, "Dense_1": {"kernel": p["w2"], "bias": p["b2"]}}}}}
+        ro = g[f"{name}/readouts"]
+        rng = np.random.default_rng(5)
+        B = ro.shape[0]
+        init = rng.standard_normal((B, A)).astype(np.float32)
+        noise = rng.standard_normal((B, A)).astype(np.float32)
+        got = head.predict_action(v, _dev(ro), init=torch.tensor(init), noise=torch.tensor(noise))
+        again = head.predict_action(v, _dev(ro), init=torch.tensor(init), noise=torch.tensor(noise))
+        assert torch.equal(got, again) and got.abs().max().item() <= 5.0
+        pt = {k: torch.tensor(a) for k, a in p.items()}
+        want = O.diffusion_predict_action(torch.tensor(ro).to(torch.bfloat16).float(), torch.tensor(init), torch.tensor(noise), head.betas, pt)
+        err = (got.cpu() - want).abs().max().item()
+        assert err <= 5e-2 * 5.0, (name, err)
+        drawn = head.predict_action(v, _dev(ro), rng=3)
+        assert tuple(drawn.shape) == (B, A) and torch.isfinite(drawn).all()
