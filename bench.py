@@ -418,6 +418,57 @@ def measure_workload(args, cfgname, rank, world, local, steps, warmup, with_extr
     h2d = xh[0].numel() * 2 + yh[0].numel() * 4
     d2h = 4
 
+    # ---- from pixels (extra, N = 1 line only): the image patch-embed front end (csrc/image_tokenizer.cu, forward) produces the
+    # image tokens of the step from uint8 frames -- 256 x 256 x 3 per frame, 16-pixel patches = 256 tokens per frame, the named
+    # shape -- which are assembled with the language / readout token embeddings (TokenSequence.assemble_embeddings) into the
+    # block's input; then the same train step.  The front end has no backward here (the reference trains it), so this is an
+    # observations -> loss throughput of the block's step with its inputs computed on the device, not a second headline.
+    from_pixels = None
+    if with_extras and getattr(args, "from_pixels", "auto") != "off" and c["seq"] == SEQ:
+        from multi_modal_transformers_tokenmerge_b200.tokenizers.images import ImageTokenizer
+        from multi_modal_transformers_tokenmerge_b200.tokenizers.token_sequencer import TokenEmbeddings, TokenSequence
+        node = lambda t_, **kw: dict(_target_=t_, **kw)  # noqa: E731
+        tok = ImageTokenizer(image_size=(256, 256, 3), patch_size=16, normalize=True, position_interval=128, rng_collection="patch_encoding",
+                             embedding_dim=C, out_dtype=torch.bfloat16,
+                             row_position_embedding=node("flax.linen.Embed", name="image_row_position_embedding", num_embeddings=128, features=C),
+                             col_position_embedding=node("flax.linen.Embed", name="image_col_position_embedding", num_embeddings=128, features=C),
+                             resnet=dict(num_blocks=2,
+                                         input_conv=node("flax.linen.Conv", features=64, kernel_size=[12, 12], strides=[2, 2], padding="VALID"),
+                                         input_pool=node("flax.linen.max_pool", window_shape=[3, 3], strides=[1, 1], padding="VALID"),
+                                         resnet_norm=node("flax.linen.GroupNorm", num_groups=32, epsilon=1e-6),
+                                         resnet_activation=node("flax.linen.gelu"),
+                                         resnet_conv=node("flax.linen.Conv", features=64, kernel_size=[3, 3], strides=[1, 1], padding="SAME"),
+                                         output_dense=node("flax.linen.Dense", features=C)))
+        tvars = tok.init(3, None)
+        ts = TokenSequence(c["seq"])
+        frames = torch.randint(0, 256, (B, 2, 256, 256, 3), dtype=torch.uint8, device="cuda", generator=g)
+        text = torch.randn(B, 16, C, device="cuda", generator=g).bfloat16()
+        readouts = torch.randn(B, 8, C, device="cuda", generator=g).bfloat16()
+        state_px = {}
+
+        def pixel_step():
+            img_tok = tok.apply(tvars, frames, train=False).reshape(B, 2 * 256, C)
+            xin = ts.assemble_embeddings(TokenEmbeddings(text=text, images=img_tok, readouts=readouts)).contiguous()
+            state_px["x"] = xin
+            trainer.train_step(xin, y, lr=1e-4)
+
+        for _ in range(3):
+            pixel_step()
+        lib.tome_launch_count(1)
+        ms_px = timed(steps, pixel_step)
+        launches_px = int(lib.tome_launch_count(1))
+        e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0_.record()
+        for _ in range(steps):
+            tok.apply(tvars, frames, train=False)
+        e1_.record()
+        torch.cuda.synchronize()
+        from_pixels = {"value": world * B * steps / (ms_px * 1e-3), "unit": "samples/s", "ms_per_step": ms_px / steps,
+                       "front_end_ms": e0_.elapsed_time(e1_) / steps, "frames_per_sample": 2, "frame": "256 x 256 x 3 uint8, 16-pixel patches -> 256 tokens",
+                       "pixel_bytes_per_step": int(frames.numel()), "gpu_launches": launches_px,
+                       "note": "image front end forward (no backward) + token assembly + the same train step"}
+        del frames, text, readouts, state_px
+
     # ---- roofline pass: same step, every op bracketed by CUDA events on its own stream ----
     P = peaks()
     L.check(lib.tome_profile_enable(4096))
@@ -505,6 +556,8 @@ def measure_workload(args, cfgname, rank, world, local, steps, warmup, with_extr
             "kernels": kernels, "model_tflops": value / world * fl / 1e12,
             "model_frac_of_sustained_bf16_peak": value / world * fl / 1e12 / P["tf_sust"], "loss": loss_dev,
         }
+        if from_pixels is not None:
+            out["from_pixels"] = from_pixels
         if in_sync is not None:
             out["params_in_sync"] = in_sync
     del trainer, eng, x, y, xd, yd
@@ -536,6 +589,9 @@ def main():
     ap.add_argument("--compress", default="merge", choices=["merge", "prune"],
                     help="merge: ToMe bipartite soft matching + merge_wavg per layer (the metric's path); prune: the sibling path, "
                          "per-modality top-k pruning of r tokens per layer (compressed_attention.py / token_compression.py:15-46)")
+    ap.add_argument("--from-pixels", default="auto", choices=["auto", "off"],
+                    help="also time the step with its image tokens computed from uint8 frames by the image front end (sub-object "
+                         "`from_pixels`; octo_small / octo_base sequences)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--octo-base", default="auto", choices=["auto", "on", "off"],
                     help="also measure the octo_base shard (BASELINE.json configs[2]) and attach it as `octo_base`; auto = at 8 GPUs")
