@@ -7,25 +7,27 @@
 //
 // The three contractions (input convolution, block convolutions, Dense) run on the tcgen05 GEMM of gemm.cu with bf16
 // operands and fp32 accumulation; the kernels here produce their A operands and consume their outputs:
-//   it_im2col0_kernel      pixels (u8 / f32) -> normalise -> im2col rows [M0, k*k*C_in] bf16 (patch extraction is index
-//                          arithmetic: no patch tensor is ever written)
-//   it_pool_kernel         conv0 output [.., o1, o1, F] -> max over w x w windows -> [.., o2, o2, F]
+//   it_pixels_bf16_kernel + it_im2col0_words_kernel   pixels (u8 / f32) -> normalised bf16 once, then the im2col rows
+//                          [M0, k*k*C_in] of the input convolution by 32-bit words (patch extraction is index arithmetic: no
+//                          patch tensor is ever written); it_im2col0_kernel does both per byte through a 256-entry table
+//                          when an odd element offset rules the word path out
+//   it_pool_kernel         conv0 output [.., o1, o1, F] -> max over w x w windows (packed bf16x2 max) -> the activation grid
 //   it_gn_partial_kernel / it_gn_final_kernel   GroupNorm statistics.  Flax's GroupNorm reduces over EVERY axis but the
 //                          batch one, so a (batch row, group) statistic spans all N images and all patches of that row:
-//                          per-CTA per-channel partial sums in a fixed order, then one thread per (row, group)
+//                          per-CTA per-channel partial sums in a fixed order, then one warp per (row, group)
 //   it_gn_gelu_kernel      (x - mean) * rstd * scale + bias -> gelu, once per element (the statistics folded into a
-//                          per-(batch row, channel) multiply-add by it_gn_fold_kernel)
+//                          per-(batch row, channel) multiply-add by it_gn_fold_kernel); zeroes the grid's border
 //   3 x 3 convolutions     features % 64 == 0 (the reference's 64): the block activations live on a (o2 + 2)^2 grid with a zero
 //                          border, and the convolution is ONE GEMM whose nine k-blocks read the SAME matrix at rows shifted by
 //                          (ty - 1)(o2 + 2) + (tx - 1) (tome_gemm_args_t.a_row_shift: a TMA row coordinate per k-block; no
-//                          im2col rows, the activation is re-read from L2); it_compact_kernel then gathers the interior
+//                          im2col rows, the activation is re-read from L2); it_compact_kernel then gathers the interior and
+//                          adds the pooled tensor (the residual of image_tokenizer.py:170)
 //   it_im2col3_kernel      other widths: the nine shifted copies of the 3x3 SAME im2col row, zero outside the o2 x o2
-//                          window; one 16-byte load and one 16-byte store per thread
+//                          window; one 16-byte load and one 16-byte store per thread; residual in the last GEMM's epilogue
 //   it_posadd_kernel       Dense output + row_embedding[row_token] + col_embedding[col_token] -> out dtype
-// The last block convolution adds the pooled tensor through the GEMM's residual epilogue (image_tokenizer.py:170) and
-// the flatten is free ([.., o2, o2, F] rows ARE the Dense's K-major A operand).  HBM-bound: the im2col rows dominate the
-// traffic (k*k*C_in / (s*s*C_in) = 36x the pixels for the input convolution, 9x the activations for the blocks); the
-// batch is processed in chunks of whole batch rows so the im2col buffer stays near 1 GiB whatever the batch.
+// What is left HBM-bound is the input convolution (its im2col rows are k*k*C_in / (s*s*C_in) = 36x the pixels); the batch
+// is processed in chunks of whole batch rows so that buffer stays near 1 GiB whatever the batch.  Measurements and the
+// versions that led here: DESIGN.md 4.5, profiles/r02c_image_tokenizer.md.
 #include <stdlib.h>
 
 #include <algorithm>
