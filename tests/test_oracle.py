@@ -283,3 +283,23 @@ def test_attention_pooling_oracle_matches_the_executed_reference(name):
     want = Z[f"{name}/y"]
     assert got.shape == want.shape == (B, 1, E)
     assert np.abs(got - want).max() <= 2e-5 * max(1.0, np.abs(want).max())
+
+
+def test_image_tokenizer_known_answers_of_the_reference_tests():
+    """The reference's own unit tests for this file (tokenizers/images/tests/test_image_tokenizer.py), restated on the oracle and
+    on the mirror's host functions: image_to_patches on a 280 x 280 image of sixteen constant 70 x 70 patches in raster order
+    (:22-37), encode_patch_position on a 128-pixel image with one-pixel patches and 128 tokens -- row_encoding[123] == 122,
+    shape (128^2,) (:40-55) -- and the stochastic case's bound |row_encoding[123] - 122| <= 70 on a 280-pixel image (:58-72)."""
+    from multi_modal_transformers_tokenmerge_b200.tokenizers.images import encode_patch_position, image_to_patches_index
+    patches = np.ones((16, 70, 70, 3), np.float32) * (np.arange(16, dtype=np.float32) + 1)[:, None, None, None]
+    image = patches.reshape(4, 4, 70, 70, 3).transpose(0, 2, 1, 3, 4).reshape(280, 280, 3)      # '(row col) h w c -> (row h) (col w) c'
+    np.testing.assert_array_equal(O.image_to_patches(image, 70, normalize=False), patches)
+    org = image_to_patches_index(280, 70)
+    for k, (y, x) in enumerate(org):
+        assert (image[y:y + 70, x:x + 70] == k + 1).all()
+    for fn in (lambda: O.patch_position_tokens(128, 1, 128), lambda: encode_patch_position(128, 1, 128, train=False)):
+        row, col = fn()
+        assert row.shape == col.shape == (128 * 128,) and row.dtype == np.int32
+        assert row[123] == 122
+    row, col = encode_patch_position(280, 1, 128, train=True, rng=np.random.default_rng(0), images=1)
+    assert row.shape == (1, 280 * 280) and abs(int(row[0, 123]) - 122) <= 70
