@@ -1055,3 +1055,30 @@ def test_image_tokenizer_other_geometry_vs_oracle(ops):
     scale = np.abs(want).max()
     err = np.abs(got - want)
     assert err.max() <= 3e-2 * scale and err.mean() <= 5e-3 * scale, (err.max(), err.mean(), scale)
+
+
+@pytest.mark.gpu
+def test_image_tokenizer_full_batch_properties(ops):
+    """The image front end at a full batch (256 batch rows x 2 frames of 256 x 256 x 3, 16-pixel patches -> 131 072 tokens), where
+    the oracle is too slow: size-independent properties.  GroupNorm statistics are per batch row, so (i) one pass and 32-row
+    passes give identical bits, (ii) permuting the batch rows permutes the output rows bit for bit, (iii) a batch row computed
+    alone equals its rows in the batch; and the first two batch rows agree with the oracle."""
+    from multi_modal_transformers_tokenmerge_b200.tokenizers.images import ImageTokenizer
+    rng = np.random.default_rng(31)
+    H, P, F, G, E, PI, NB, B = 256, 16, 64, 32, 384, 128, 2, 256
+    nodes = _it_nodes(H, P, 3, F, G, E, PI, NB, True)
+    tok = ImageTokenizer(**nodes)
+    variables = tok.init(9, None)
+    img = torch.from_numpy(rng.integers(0, 256, size=(B, 2, H, H, 3)).astype(np.uint8)).cuda()
+    full = tok.apply(variables, img, train=False)
+    assert tuple(full.shape) == (B, 2, 256, E) and torch.isfinite(full.float()).all()
+    chunked = ImageTokenizer(**nodes, chunk_rows=32).apply(variables, img, train=False)
+    assert torch.equal(full, chunked)
+    perm = torch.from_numpy(rng.permutation(B)).cuda()
+    assert torch.equal(tok.apply(variables, img[perm].contiguous(), train=False), full[perm])
+    assert torch.equal(tok.apply(variables, img[5:6].contiguous(), train=False), full[5:6])
+    p = O.image_tokenizer_params_from_flax(variables["params"], NB)
+    want = O.image_tokenizer_fwd(p, img[:2].cpu().numpy().astype(np.float32), patch_size=P, position_interval=PI, num_groups=G, normalize=True)
+    err = np.abs(full[:2].float().cpu().numpy() - want)
+    scale = np.abs(want).max()
+    assert err.max() <= 3e-2 * scale and err.mean() <= 5e-3 * scale, (err.max(), err.mean(), scale)

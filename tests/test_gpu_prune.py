@@ -191,3 +191,58 @@ def test_prune_stack_forward_backward_vs_oracle(pkg, importance, grammar_masks, 
         assert val <= tol_f, f"{k_}: rel err {val}"
     for k_, val in e_grad.items():
         assert val <= tol_g, f"{k_}: rel err {val}"
+
+
+def test_prune_stack_full_size_properties(pkg):
+    """The pruning stack at the metric's shape (octo-small: B = 256, T0 = 536, 12 layers, two image sets dropping 8 tokens each per
+    layer), where the oracle is too slow to follow: size-independent properties.  Every layer keeps, per token set, distinct
+    indices inside the set and exactly n - c of them, in non-increasing score order; text and readout sets are kept whole; the
+    readout rows the loss reads are the original readout tokens; the step is bit-reproducible and three AdamW steps lower the loss."""
+    ops, engine = pkg
+    ts = TokenSequence("[TaskDescriptionPrefix{16}] [Image{256};Readout{4}]*2", "[TaskDescriptionPrefix{0}] [Image{8};Readout{0}]*2")
+    gid, pos = ts.group_ids()
+    allow, ro = ts.allow_table(), ts.get_modality_idx("readouts")
+    sets = ts.prune_sets()
+    B, T, C, Lyr = 256, 536, 384, 12
+    lg = [ts.layer_group_ids(l) for l in range(Lyr)]
+    cfg = engine.StackConfig(batch=B, tokens=T, channels=C, heads=6, head_dim=64, mlp_dim=1536, layers=Lyr, r=0, ln_axis=1, prop_attn=False,
+                             num_groups=allow.shape[0], n_readout=len(ro), prune_sets=tuple(sets), prune_importance="received",
+                             head="continuous", head_features=7, max_action=1.0)
+    eng = engine.ToMeStackEngine(cfg, gid=gid, pos=pos, allow=allow, readout_idx=ro, layer_gid=[g for g, _ in lg], layer_pos=[p for _, p in lg])
+    eng.init_params(seed=2)
+    g_ = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.randn(B, T, C, device="cuda", generator=g_).bfloat16()
+    y = torch.rand(B, 7, device="cuda", generator=g_) * 2 - 1
+    eng.zero_grad()
+    eng.forward(x, y)
+    loss0 = eng.loss[0].item()
+    ids0 = [eng.layer_prune(l)[1].clone() for l in range(Lyr)]
+    for l in range(Lyr):
+        imp, ids = (t.cpu().numpy() for t in eng.layer_prune(l))
+        idx, ks = O.prune_sets_at(sets, l)
+        assert ids.shape == (B, sum(ks)) and imp.shape == (B, sum(n for _, n in idx))
+        assert np.allclose(imp.sum(axis=1), 1.0, atol=2e-3)          # attention received, averaged: sums to one per sequence
+        off = 0
+        for (start, n), k in zip(idx, ks):
+            part = ids[:, off:off + k]
+            assert ((part >= start) & (part < start + n)).all()
+            assert (np.sort(part, axis=1)[:, 1:] != np.sort(part, axis=1)[:, :-1]).all()             # distinct
+            sc = np.take_along_axis(imp, part, axis=1)
+            assert (sc[:, 1:] <= sc[:, :-1]).all()                                                   # top_k order
+            if k == n:
+                assert (np.sort(part, axis=1) == np.arange(start, start + n)).all()                   # kept whole
+            off += k
+    eng.backward()
+    eng.zero_grad()
+    eng.forward(x, y)                                   # same parameters, same inputs: same bits
+    assert eng.loss[0].item() == loss0
+    assert all(torch.equal(a, eng.layer_prune(l)[1]) for l, a in enumerate(ids0))
+    eng.backward()
+    losses = [loss0]
+    for _ in range(3):
+        eng.adamw_step(lr=3e-4)
+        eng.zero_grad()
+        eng.forward(x, y)
+        eng.backward()
+        losses.append(eng.loss[0].item())
+    assert np.isfinite(losses).all() and losses[-1] < losses[0], losses
