@@ -554,8 +554,8 @@ long long tome_image_tokenizer_param_offset(const tome_image_tokenizer_desc_t* d
 size_t tome_image_tokenizer_workspace_bytes(const tome_image_tokenizer_desc_t* desc);
 /* out [B, N, n_patches, E] = ImageTokenizer(image).  row_tokens / col_tokens: i32 [token_rows, n_patches] indices into the
  * embedding tables (evaluation mode: image_tokenizer.py:111-113; the Python mirror computes them).  The convolutions and the
- * Dense run on the tcgen05 GEMM (im2col rows written by the preceding normalise / activate kernel), bf16 activations, fp32
- * accumulation.  workspace: 256-byte aligned, tome_image_tokenizer_workspace_bytes(desc) bytes. */
+ * Dense run on the tcgen05 GEMM (input convolution: im2col rows; 3 x 3 convolutions with features % 64 == 0: row-shifted windows
+ * of the zero-bordered activation, tome_gemm_args_t.a_row_shift), bf16 activations, fp32 accumulation.  workspace: 256-byte aligned, tome_image_tokenizer_workspace_bytes(desc) bytes. */
 int tome_image_tokenizer_fwd(const tome_image_tokenizer_desc_t* desc, const void* image, const float* params_f32,
                              const void* params_bf16, const int32_t* row_tokens, const int32_t* col_tokens, void* out,
                              void* workspace, size_t workspace_bytes, void* stream);
