@@ -287,8 +287,39 @@ def microbench(args):
                 add("merge_bwd", T, C, r, timeit(lambda: ops.merge_bwd(plan, dy, size, s1, 1)),
                     nbytes=B * ((T - r) * C * 2.0 + T * C * 2 + 4 * T))
                 del plan, x1, s1, dy
-            del x, qkv, out, lse, do
+            # --- the sibling compression path: importance from the attention weights, per-set top-k + gather, its backward
+            add("importance", T, C, None, timeit(lambda: ops.attention_importance(q, k, lse, "received", **kw)), flops=2.0 * B * H * T * T * D)
+            imp = ops.attention_importance(q, k, lse, "received", **kw)
+            for r in (T // 16, T // 4):
+                c_img = r // 2
+                ss, sn = [0, 16, 16 + n_img, 20 + n_img, 20 + 2 * n_img], [16, n_img, 4, n_img, 4]
+                sk = [16, n_img - c_img, 4, n_img - c_img, 4]
+                kept = sum(sk)
+                add("topk_prune", T, C, 2 * c_img, timeit(lambda: ops.topk_prune(x, imp, ss, sn, sk)), nbytes=B * (4.0 * T + 2.0 * kept * C * 2 + 4 * kept))
+                _, ids = ops.topk_prune(x, imp, ss, sn, sk)
+                rm, _, _ = ops.prune_row_map(ids, T)
+                dy = torch.randn(B, kept, C, device="cuda").bfloat16()
+                add("prune_bwd", T, C, 2 * c_img, timeit(lambda: ops.prune_bwd(rm, dy)), nbytes=B * (kept * C * 2.0 + T * C * 2 + 4 * T))
+                del ids, rm, dy
+            del x, qkv, out, lse, do, imp
             torch.cuda.empty_cache()
+    # --- the image patch-embed front end (forward): gato_resnet.yaml's geometry and the named shape's (256 x 256, 16-pixel patches)
+    from multi_modal_transformers_tokenmerge_b200 import model_configs
+    for label, image, patch, E_, nb in (("gato 280/56", 280, 56, 768, 64), ("named shape 256/16", 256, 16, 768, 256)):
+        node = dict(model_configs.load("tokenizers/images/gato_resnet_octo")["encoder"])
+        node.update(image_size=[image, image, 3], patch_size=patch)
+        tok = model_configs.build_image_tokenizer(node)
+        tv = tok.init(1, None)
+        frames = torch.randint(0, 256, (nb, 2, image, image, 3), dtype=torch.uint8, device="cuda")
+        o1 = (patch - 12) // 2 + 1
+        o2 = o1 - 2
+        npatch = (image // patch) ** 2
+        fl = 2.0 * nb * 2 * npatch * (o1 * o1 * 432 * 64 + 2 * o2 * o2 * 576 * 64 + o2 * o2 * 64 * E_)
+        sec = timeit(lambda: tok.apply(tv, frames, train=False))
+        rows.append({"kernel": "image_front_end", "geometry": label, "frames": nb * 2, "us": sec * 1e6, "frames_per_s": nb * 2 / sec,
+                     "bound": "tensor", "achieved_tflops": fl / sec / 1e12, "frac": fl / sec / 1e12 / P["tf_burst"]})
+        del frames, tok, tv
+        torch.cuda.empty_cache()
     return {"metric": "ToMe block microbench (BASELINE.json configs[4]): per-kernel time against its roofline",
             "unit": "us per launch; frac = achieved / measured burst peak", "n_gpus": 1, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "standalone ToMe block kernels, B * T = 32768 tokens, T in 1k..8k, d in {768, 1024}, heads = d / 64, "
