@@ -6,8 +6,9 @@
 // and vmapped by its caller; here the batch is a grid dimension.
 //
 // One CTA per (token set, batch row): the set's scores go to shared memory, every token counts how many tokens of its
-// set beat it (its rank; n <= a few hundred, so the n^2 comparisons are cheaper than a sort and exact by
+// set beat it (its rank; for n up to a few hundred the n^2 comparisons are cheaper than a sort and exact by
 // construction), ranks < k publish their index, and the CTA then copies the k selected rows with 128-bit accesses.
+// Token sets of 768 tokens or more take a bitonic sort of (score, index) keys and a grid-wide gather instead (below).
 // Index arithmetic only: the gathered rows are bit-identical to the source rows.
 #include "common.cuh"
 #include "host_util.h"
@@ -61,6 +62,72 @@ topk_prune_kernel(const tome_prune_desc_t d, const uint8_t* __restrict__ emb, co
   for (int i = threadIdx.x; i < k * vpr; i += PRUNE_THREADS) {
     const int r = i / vpr, v = i - r * vpr;
     st_na_v4(ob + (long long)r * row_bytes + v * 16, ld_nc_v4(eb + (long long)sel[r] * row_bytes + v * 16));
+  }
+}
+
+// ---- long token sets: sort instead of rank-by-count (n^2 comparisons: 3.8 ms per call at n = 4076 against 0.1 ms at 500) ----
+// 64-bit keys (orderable score bits, complemented index) sorted DEscending in shared memory reproduce top_k's order: larger
+// score first, NaN above every number, -0 == +0, equal scores by LOWER index.  One CTA per (token set, batch row) writes the
+// ids; the rows are then gathered by a grid-wide kernel (one CTA per set would copy megabytes alone).
+constexpr int PRUNE_SORT_THREADS = 1024;
+constexpr int PRUNE_SORT_MIN_N = 768;     // token sets at least this long take the sort path
+
+__device__ __forceinline__ unsigned long long prune_key(float v, int i) {
+  uint32_t u = __float_as_uint(v);
+  if (v != v) u = 0xFFFFFFFFu;
+  else if (v == 0.f) u = 0x80000000u;
+  else u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return ((unsigned long long)u << 32) | (uint32_t)(0x7FFFFFFF - i);
+}
+
+__global__ void __launch_bounds__(PRUNE_SORT_THREADS)
+topk_sort_kernel(const tome_prune_desc_t d, const float* __restrict__ score, int32_t* __restrict__ ids) {
+  pdl_prologue();
+  extern __shared__ __align__(8) unsigned char prune_sort_raw[];
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(prune_sort_raw);
+  const int s = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
+  const int start = d.set_start[s], n = d.set_n[s], k = d.set_k[s];
+  int off = 0;
+  for (int i = 0; i < s; ++i) off += d.set_k[i];
+  int ktot = off;
+  for (int i = s; i < d.n_sets; ++i) ktot += d.set_k[i];
+  int n2 = 1;
+  while (n2 < n) n2 <<= 1;
+  for (int i = tid; i < n2; i += nt) {
+    unsigned long long key = 0ull;   // below every real key
+    if (i < n) {
+      float v = 0.f;
+      for (int p = 0; p < d.score_planes; ++p) v += score[((long long)p * d.batch + b) * d.tokens + start + i];
+      key = prune_key(v, i);
+    }
+    keys[i] = key;
+  }
+  __syncthreads();
+  for (int kk = 2; kk <= n2; kk <<= 1)
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < n2; i += nt) {
+        const int l = i ^ j;
+        if (l > i) {
+          const unsigned long long a = keys[i], c = keys[l];
+          const bool desc = (i & kk) == 0;
+          if (desc ? a < c : a > c) { keys[i] = c; keys[l] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  for (int rk = tid; rk < k; rk += nt) ids[(long long)b * ktot + off + rk] = start + (0x7FFFFFFF - (int)(uint32_t)keys[rk]);
+}
+
+// out[b, j] = emb[b, ids[b, j]] (bit copies), thread = 16 bytes
+__global__ void __launch_bounds__(256)
+prune_gather_kernel(long long n_vec, int T, int K, int vpr, const int32_t* __restrict__ ids, const uint4* __restrict__ emb,
+                    uint4* __restrict__ out) {
+  pdl_prologue();
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n_vec; i += (long long)gridDim.x * 256) {
+    const long long rowg = i / vpr;           // b * K + j
+    const int v = (int)(i - rowg * vpr);
+    const int b = (int)(rowg / K);
+    st_na_v4(out + i, ld_nc_v4(emb + ((long long)b * T + ids[rowg]) * vpr + v));
   }
 }
 
@@ -159,10 +226,30 @@ extern "C" int tome_topk_prune(const tome_prune_desc_t* d, const void* embedding
   for (int s = 0; s < d->n_sets; ++s) ktot_host += d->set_k[s];
   const double row_bytes_host = d->channels * (d->dtype == TOME_BF16 ? 2.0 : 4.0);
   const size_t smem = (size_t)2 * nmax * sizeof(float);
-  TOME_CHECK(smem <= 200 * 1024, TOME_ERR_UNSUPPORTED, "topk_prune: token set of %d tokens is too large for the shared-memory ranking", nmax);
+  TOME_CHECK(nmax >= PRUNE_SORT_MIN_N || smem <= 200 * 1024, TOME_ERR_UNSUPPORTED, "topk_prune: token set of %d tokens is too large for the shared-memory ranking", nmax);
+  dim3 grid(d->n_sets, d->batch);
+  if (nmax >= PRUNE_SORT_MIN_N) {   // long token sets: sort + grid-wide gather
+    int n2 = 1;
+    while (n2 < nmax) n2 <<= 1;
+    const size_t smem_sort = (size_t)n2 * sizeof(unsigned long long);
+    TOME_CHECK(smem_sort <= 200 * 1024, TOME_ERR_UNSUPPORTED, "topk_prune: token set of %d tokens is too large for the shared-memory sort", nmax);
+    ProfScope prof(PROF_PRUNE, (double)d->batch * ((double)d->tokens * 4 + 2.0 * ktot_host * row_bytes_host), 2, stream);
+    TOME_CUDA(cudaFuncSetAttribute(topk_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sort));
+    launch_k(topk_sort_kernel, grid, PRUNE_SORT_THREADS, smem_sort, stream, *d, importance, ids);
+    TOME_CUDA(cudaGetLastError());
+    if (ktot_host > 0) {
+      const int vpr = (int)row_bytes_host / 16;
+      const long long n_vec = (long long)d->batch * ktot_host * vpr;
+      long long blocks = (n_vec + 255) / 256;
+      if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
+      launch_k(prune_gather_kernel, (unsigned)blocks, 256, 0, stream, n_vec, d->tokens, ktot_host, vpr, ids,
+               reinterpret_cast<const uint4*>(embeddings), reinterpret_cast<uint4*>(out));
+      TOME_CUDA(cudaGetLastError());
+    }
+    return TOME_OK;
+  }
   ProfScope prof(PROF_PRUNE, (double)d->batch * ((double)d->tokens * 4 + 2.0 * ktot_host * row_bytes_host), 1, stream);
   TOME_CUDA(cudaFuncSetAttribute(topk_prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(d->n_sets, d->batch);
   launch_k(topk_prune_kernel, grid, PRUNE_THREADS, smem, stream, *d, reinterpret_cast<const uint8_t*>(embeddings), importance,
                                                           reinterpret_cast<uint8_t*>(out), ids);
   TOME_CUDA(cudaGetLastError());

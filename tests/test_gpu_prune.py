@@ -246,3 +246,26 @@ def test_prune_stack_full_size_properties(pkg):
         eng.backward()
         losses.append(eng.loss[0].item())
     assert np.isfinite(losses).all() and losses[-1] < losses[0], losses
+
+
+@pytest.mark.parametrize("quantised", [False, True])
+def test_topk_prune_long_token_sets(pkg, quantised):
+    """Token sets of thousands of tokens take the sort path of tome_topk_prune (bitonic sort of (score, index) keys + grid-wide
+    gather) instead of rank-by-count: kept indices and rows bit-exact against the oracle's compute_top_k_tokens, with heavy ties
+    (scores quantised to 7 levels: equal scores keep the lower index first, jax.lax.top_k's order), -0 / +0, a kept-whole set and
+    a set that keeps nothing."""
+    ops, _ = pkg
+    rng = np.random.default_rng(41)
+    B, T, C = 3, 4096, 128
+    starts, ns, ks = [0, 16, 2046, 2050, 4092], [16, 2030, 4, 2042, 4], [16, 1500, 0, 777, 4]
+    emb = rng.standard_normal((B, T, C)).astype(np.float32)
+    score = rng.standard_normal((B, T)).astype(np.float32)
+    if quantised:
+        score = np.round(score * 2) / 2
+        score[score == 0] = np.where(rng.random((score == 0).sum()) < 0.5, -0.0, 0.0).astype(np.float32)
+    out, ids = ops.topk_prune(torch.tensor(emb).cuda().bfloat16(), torch.tensor(score).cuda(), starts, ns, ks)
+    embb = torch.tensor(emb).bfloat16()
+    for b in range(B):
+        _, oid = O.compute_top_k_tokens(emb[b], score[b], list(zip(starts, ns)), ks)
+        np.testing.assert_array_equal(ids[b].cpu().numpy(), oid)
+        assert torch.equal(out[b].cpu(), embb[b][torch.as_tensor(oid.astype(np.int64))])
