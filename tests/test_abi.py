@@ -186,3 +186,17 @@ def test_pruning_stack_shapes_on_host(lib):
         b2.update(kw)
         bad = StackConfig(**b2).c()
         assert lib.tome_stack_param_count(C.byref(bad)) == -1 and msg in lib.tome_last_error(), kw
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/tome_b200.h is the drop-in boundary: it must compile as C99 on its own (no C++, no CUDA, no torch types)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "h.c"
+    src.write_text('#include "include/tome_b200.h"\nint main(void) { tome_gemm_args_t g; tome_stack_cfg_t c; tome_image_tokenizer_desc_t d; '
+                   '(void)g; (void)c; (void)d; return TOME_ABI_VERSION > 0 ? 0 : 1; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", f"-I{root}", str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
