@@ -522,3 +522,66 @@ def test_diffusion_head_sampler_against_the_oracle():
         assert err <= 5e-2 * 5.0, (name, err)
         drawn = head.predict_action(v, _dev(ro), rng=3)
         assert tuple(drawn.shape) == (B, A) and torch.isfinite(drawn).all()
+
+
+def _compressed_stack(num_blocks=3, C=128, H=2, Dff=256, ln_axis=-1):
+    import functools
+    from multi_modal_transformers_tokenmerge_b200.attention_blocks import compressed_attention as CA
+    cfg = MC.load("attention_blocks/tome_decoder_octo_small")
+    e = dict(cfg["encoder_1d_block"], _target_="multi_modal_transformers.attention_blocks.compressed_attention.CompressedEncoder1DBlock")
+    e["layer_norm"] = dict(e["layer_norm"], reduction_axes=[ln_axis])
+    e["self_attention"] = dict(e["self_attention"], num_heads=H, qkv_features=C)
+    e["mlp_block"] = dict(e["mlp_block"], dense=dict(e["mlp_block"]["dense"], features=Dff), dense_out=dict(e["mlp_block"]["dense_out"], features=C))
+    ts = TokenSequence("[TaskDescriptionPrefix{8}] [Image{40};Readout{2}]*2", "[TaskDescriptionPrefix{0}] [Image{6};Readout{0}]*2")
+    fns = []
+    for l in range(num_blocks):     # what the reference's caller builds: partial(compute_top_k_tokens, tokenset_idx=..., tokenset_k=...)
+        idx, ks = O.prune_sets_at(ts.prune_sets(), l)
+        fns.append(functools.partial(TCm.compute_top_k_tokens, tokenset_idx=idx, tokenset_k=ks))
+    return CA.StackedCompressedEncoder1DBlock(num_blocks, e, prune_fns=fns, merge_fns=[None] * num_blocks), ts, fns
+
+
+def test_compressed_stack_module_arguments():
+    """StackedCompressedEncoder1DBlock (compressed_attention.py:377-404): prune_fns as the reference builds them, token sets
+    that must follow the compression grammar, merge_fns rejected (commented out in the reference, :310-311)."""
+    from multi_modal_transformers_tokenmerge_b200.attention_blocks import compressed_attention as CA
+    stack, ts, fns = _compressed_stack()
+    assert stack.prune_sets == ((8, 0), (40, 6), (2, 0), (40, 6), (2, 0)) == tuple(ts.prune_sets())
+    e = stack.encoder_1d_block
+    with pytest.raises(ValueError, match="compression grammar"):
+        CA.StackedCompressedEncoder1DBlock(3, e, prune_fns=[fns[0], fns[0], fns[2]])
+    with pytest.raises(ValueError, match="one compute_top_k_tokens"):
+        CA.StackedCompressedEncoder1DBlock(3, e, prune_fns=fns[:2])
+    with pytest.raises(NotImplementedError):
+        CA.StackedCompressedEncoder1DBlock(3, e, prune_fns=fns, merge_fns=[object()] * 3)
+    v = stack.init(0, torch.zeros(2, 92, 128))["params"]
+    assert set(v) == {"posembed_input", "ScanEncoder1DBlock_0"} and v["posembed_input"]["pos_embedding"].shape == (1, 92, 128)
+
+
+@gpu
+def test_compressed_stack_module_against_the_oracle():
+    """The drop-in StackedCompressedEncoder1DBlock: masks[layer] from the compression grammar, one per-set top-k per layer
+    (92 -> 80 -> 68 -> 56 tokens), against oracle.prune_stack following the module's keep decisions and ReLU gates: <= 2e-2."""
+    stack, ts, _ = _compressed_stack()
+    rng = np.random.default_rng(2)
+    B, T, C = 2, 92, 128
+    variables = stack.init(4, torch.zeros(B, T, C))
+    x = rng.standard_normal((B, T, C)).astype(np.float32)
+    masks = [ts.layer_group_ids(l) for l in range(3)]
+    y = stack.apply(variables, _dev(x), masks=masks, allow=ts.allow_table(), train=False)
+    assert tuple(y.shape) == (B, 56, C) and [tuple(i.shape) for i in stack.last_ids] == [(B, 80), (B, 68), (B, 56)]
+    eng = stack._engine
+    v, vf = eng.param_views(eng.params_bf16.float().cpu()), eng.param_views(eng.params.cpu())
+    params, hd = [], 128
+    for l in range(3):
+        s_, f_ = v["layers"][l], vf["layers"][l]
+        d = dict(ln1_scale=f_["ln1_scale"], ln1_bias=f_["ln1_bias"], ln2_scale=f_["ln2_scale"], ln2_bias=f_["ln2_bias"],
+                 wq=s_["wqkv"][:, :hd], wk=s_["wqkv"][:, hd:2 * hd], wv=s_["wqkv"][:, 2 * hd:], bq=f_["bqkv"][:hd], bk=f_["bqkv"][hd:2 * hd],
+                 bv=f_["bqkv"][2 * hd:], wo=s_["wo"], bo=f_["bo"], w1=s_["w1"], b1=f_["b1"], w2=s_["w2"], b2=f_["b2"])
+        params.append(O.BlockParams(**{k_: t.clone().contiguous() for k_, t in d.items()}))
+    gid, pos = ts.group_ids()
+    want, _ = O.prune_stack(params, vf["pos_embedding"].clone()[None], torch.tensor(x), gid, pos, ts.allow_table(), num_heads=2,
+                            sets=ts.prune_sets(), importance="received", ln_axis="feature", act_dtype=torch.bfloat16,
+                            relu_gate=[eng.layer_relu_gate(l).cpu().numpy() for l in range(3)],
+                            ids_override=[i.cpu().numpy() for i in stack.last_ids], layer_groups=masks)
+    err = ((y.float().cpu() - want).norm() / want.norm()).item()
+    assert err <= 2e-2, err
