@@ -111,6 +111,20 @@ COMP = "[TaskDescriptionPrefix{0}] [Image{6};Readout{0}]*2"
 @pytest.mark.parametrize("importance,grammar_masks,ln_axis,Lyr", [("received", True, 2, 3), ("received", False, 2, 3), ("row_mean", True, 2, 2),
                                                                   ("received", True, 1, 2)])
 def test_prune_stack_forward_backward_vs_oracle(pkg, importance, grammar_masks, ln_axis, Lyr):
+    _prune_stack_vs_oracle(pkg, importance, grammar_masks, ln_axis, Lyr, SEQ, COMP, dict(C=128, H=2, Dff=256))
+
+
+@pytest.mark.parametrize("name,dims", [("octo_small", dict(C=384, H=6, Dff=1536)), ("octo_base", dict(C=768, H=12, Dff=3072))])
+def test_prune_stack_real_dims_vs_oracle(pkg, name, dims):
+    """The pruning stack at the REAL widths of BASELINE.json configs[1] / configs[2] and the metric's sequence (T0 = 536, two image
+    sets dropping 8 tokens each per layer, 12 layers: 536 -> 344 tokens), B = 2, feature-axis LayerNorm (the token-axis one
+    amplifies any rounding difference ~1.4x per layer: DESIGN.md section 2), grammar masks per layer: kept indices bit-exact from
+    the GPU's own scores at every layer, forward within 2e-2, every parameter gradient within 3e-2."""
+    _prune_stack_vs_oracle(pkg, "received", True, 2, 12, "[TaskDescriptionPrefix{16}] [Image{256};Readout{4}]*2",
+                           "[TaskDescriptionPrefix{0}] [Image{8};Readout{0}]*2", dims, tol=(2e-2, 3e-2))
+
+
+def _prune_stack_vs_oracle(pkg, importance, grammar_masks, ln_axis, Lyr, seq, comp, dims, tol=None):
     """A pruning stack (StackConfig.prune_sets) vs oracle.prune_stack: every layer drops 6 of each image set's tokens (92 -> 80 ->
     68 -> 56), masks either from the compression grammar at each layer (layer_gid / layer_pos, what compressed_attention.py:399
     passes) or carried with the kept tokens.  Kept indices bit-exact from the GPU's own importance scores; importance within
@@ -119,13 +133,13 @@ def test_prune_stack_forward_backward_vs_oracle(pkg, importance, grammar_masks, 
     row maps."""
     ops, engine = pkg
     rng = np.random.default_rng(17)
-    B, C, H, D, Dff = 2, 128, 2, 64, 256
-    ts = TokenSequence(SEQ, COMP)
+    B, C, H, D, Dff = 2, dims["C"], dims["H"], 64, dims["Dff"]
+    ts = TokenSequence(seq, comp)
     gid, pos = ts.group_ids()
     allow, ro = ts.allow_table(), ts.get_modality_idx("readouts")
     T = gid.shape[0]
     sets = ts.prune_sets()
-    assert sets == [(8, 0), (40, 6), (2, 0), (40, 6), (2, 0)]
+    drop = sum(c_ for _, c_ in sets)
     layer_groups = [ts.layer_group_ids(l) for l in range(Lyr)] if grammar_masks else None
     layers = [O.init_block_params(rng, C, H, D, Dff) for _ in range(Lyr)]
     for d in layers:
@@ -141,7 +155,7 @@ def test_prune_stack_forward_backward_vs_oracle(pkg, importance, grammar_masks, 
                                  layer_gid=None if layer_groups is None else [g for g, _ in layer_groups],
                                  layer_pos=None if layer_groups is None else [p for _, p in layer_groups])
     eng.load_params(pe[0], layers)
-    assert [eng.tokens_at(l) for l in range(Lyr + 1)] == [T - 12 * l for l in range(Lyr + 1)]
+    assert [eng.tokens_at(l) for l in range(Lyr + 1)] == [T - drop * l for l in range(Lyr + 1)]
     eng.zero_grad()
     eng.forward(torch.tensor(x).cuda(), torch.tensor(y).cuda())
     eng.backward()
@@ -173,7 +187,7 @@ def test_prune_stack_forward_backward_vs_oracle(pkg, importance, grammar_masks, 
     assert (origin[:, ro] >= 0).all()
     loss, out = O.readout_loss(xf, origin, ro, torch.tensor(y))
     loss.backward()
-    tol_f, tol_g = (1e-2, 2e-2) if ln_axis == 2 else (2e-2, 4e-2)
+    tol_f, tol_g = tol if tol is not None else ((1e-2, 2e-2) if ln_axis == 2 else (2e-2, 4e-2))
     e_fwd = dict(final_x=rel_err(eng.final_x().float().cpu(), xf.detach()), readout=rel_err(eng.readout.cpu(), out.detach()),
                  loss=abs(eng.loss[0].item() - loss.item()) / abs(loss.item()))
     g = eng.param_views(eng.grads.cpu())
