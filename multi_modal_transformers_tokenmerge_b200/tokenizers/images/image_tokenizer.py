@@ -29,6 +29,15 @@ from ... import ops
 from ...attention_blocks._module import Module, _init_name, make_init
 
 
+def _leaf_ids(tree):
+    for k in sorted(tree):
+        v = tree[k]
+        if isinstance(v, dict):
+            yield from _leaf_ids(v)
+        else:
+            yield id(v)
+
+
 def _pair(v, what):
     v = list(v) if isinstance(v, (list, tuple)) else [v, v]
     if len(v) != 2 or v[0] != v[1]:
@@ -215,7 +224,9 @@ class ImageTokenizer(Module):
                                              images=B * N)
         else:
             row, col = encode_patch_position(self.image_size[0], self.patch_size, self.position_interval, False)
-        key = id(params)
+        # the packed device copy is cached per parameter-tree OBJECT and per leaf object: replacing a leaf (what an optimiser
+        # update of a Flax tree does) repacks; arrays mutated in place are not noticed -- call clear_cache() after doing that
+        key = (id(params),) + (() if isinstance(params, torch.Tensor) else tuple(_leaf_ids(params)))
         if self._packed is None or self._packed[0] != key:
             flat = params if isinstance(params, torch.Tensor) else self.pack_params(params, image.device)
             self._packed = (key, flat, flat.to(torch.bfloat16))
@@ -224,6 +235,10 @@ class ImageTokenizer(Module):
         dev = image.device
         return ops.image_tokenizer_fwd(image.contiguous(), flat, d, torch.from_numpy(np.ascontiguousarray(row)).to(dev),
                                        torch.from_numpy(np.ascontiguousarray(col)).to(dev), params_bf16=flat16)
+
+    def clear_cache(self) -> None:
+        """Drop the packed device copy of the parameters (needed only after mutating parameter arrays in place)."""
+        self._packed = None
 
     def apply(self, variables, image, train: bool = True, rngs=None, **kw):
         if rngs is not None and self.rng_collection in rngs:
